@@ -1,0 +1,98 @@
+/*
+ * vido_b200.h -- C-ABI of libvido_b200.so: the B200 (sm_100a) implementation of VIDO-SLAM's
+ * per-frame tracking-and-optimisation hot path.
+ *
+ * The reference (bxh1/VIDO-SLAM) has no FFI: its hot path lives behind C++ classes of
+ * libvido_slam.so.  Each entry point below replaces one of those C++ interfaces (cited as
+ * file:line under /root/reference/vido_slam/); the C++ host facade (vido-slam_b200/host/System.h)
+ * keeps the reference's System/Tracking/Optimizer call surface and forwards to these functions.
+ *
+ * Conventions: plain C structs, caller-owned buffers, int status (0 ok, <0 error; text via
+ * vido_last_error), no exceptions across the boundary, one context per CUDA device, thread-
+ * compatible (not thread-safe), no CPU fallback: every call fails with VIDO_ERR_CUDA when no
+ * sm_100 device / driver is present.  "_dev" variants take device pointers (inputs already in HBM).
+ */
+#ifndef VIDO_B200_H
+#define VIDO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VIDO_OK 0
+#define VIDO_ERR_ARG (-1)
+#define VIDO_ERR_CUDA (-2)
+#define VIDO_ERR_CAPACITY (-3)
+#define VIDO_ERR_STATE (-4)
+
+typedef struct vido_ctx vido_ctx;
+
+/* cv::KeyPoint mirror: pt.x, pt.y, size, angle, response, octave (include/ORBextractor.h, cv::KeyPoint) */
+typedef struct vido_keypoint {
+  float x, y, size, angle, response;
+  int32_t octave;
+} vido_keypoint;
+
+/* Settings the reference reads from its YAML in Tracking::Tracking (src/Tracking.cc:45-171). */
+typedef struct vido_config {
+  int32_t width, height;          /* Camera.width / Camera.height */
+  float fx, fy, cx, cy, bf;       /* Camera.fx .. Camera.bf */
+  int32_t choose_data;            /* ChooseData: 1 OMD, 2 KITTI, 3 KAIST */
+  float depth_map_factor;         /* DepthMapFactor */
+  float th_depth_bg, th_depth_obj;/* ThDepthBG / ThDepthOBJ */
+  int32_t max_track_bg, max_track_obj; /* MaxTrackPointBG / MaxTrackPointOBJ */
+  int32_t window_size;            /* WINDOW_SIZE */
+  int32_t nfeatures;              /* ORBextractor.nFeatures */
+  float scale_factor;             /* ORBextractor.scaleFactor */
+  int32_t nlevels;                /* ORBextractor.nLevels (<= 8) */
+  int32_t ini_th_fast, min_th_fast; /* ORBextractor.iniThFAST / minThFAST */
+  int32_t rgb;                    /* Camera.RGB: 1 = RGB order, 0 = BGR (3-channel input only) */
+  int32_t max_batch;              /* frames the ORB front-end processes per launch (>=1) */
+  int32_t device;                 /* CUDA device ordinal */
+} vido_config;
+
+void vido_default_config(vido_config* cfg);  /* reference's kitti_config.yaml values at 1242x375 */
+
+/* lifetime: replaces System::Init -> new Tracking / new ORBextractor (src/System.cc:23-48, src/Tracking.cc:39-172) */
+vido_ctx* vido_create(const vido_config* cfg);
+void vido_destroy(vido_ctx* ctx);
+const char* vido_last_error(vido_ctx* ctx); /* ctx may be NULL: error of the failed vido_create */
+int vido_version(void);
+/* number of this library's kernels launched since creation (bench.py's gpu_launches) */
+int64_t vido_kernel_launches(vido_ctx* ctx);
+/* pyramid geometry (ORBextractor::ComputePyramid, src/ORBextractor.cc:1107-1132) */
+int vido_orb_level_info(vido_ctx* ctx, int32_t* w, int32_t* h, int32_t* quota, float* scale);
+
+/*
+ * ORB front-end: replaces ORBextractor::operator() (src/ORBextractor.cc:1034-1105), i.e.
+ * ComputePyramid + ComputeKeyPointsOctTree (:755-843) + DistributeOctTree (:529-753) + IC_Angle (:67-94).
+ * gray: nframes images of height x width CV_8UC1, row stride `stride` bytes, frame stride `frame_stride`.
+ * out: nframes * cap_per_frame keypoints (frame f at out + f*cap_per_frame), n_out[f] = count,
+ * keypoints bit-identical to the reference order (level 0..7, quad-tree list order).
+ */
+int vido_orb_extract(vido_ctx* ctx, const uint8_t* gray, int nframes, size_t frame_stride, int stride,
+                     vido_keypoint* out, int cap_per_frame, int32_t* n_out);
+/* same with gray / out / n_out in device memory; asynchronous on the context stream unless sync!=0 */
+int vido_orb_extract_dev(vido_ctx* ctx, const uint8_t* d_gray, int nframes, size_t frame_stride, int stride,
+                         vido_keypoint* d_out, int cap_per_frame, int32_t* d_n_out, int sync);
+/* 3-channel 8-bit -> gray with OpenCV 4.x fixed-point coefficients (cvtColor in Tracking::GrabImageRGBD,
+ * src/Tracking.cc:327-340); rgb order from the config.  Device pointers. */
+int vido_bgr_to_gray_dev(vido_ctx* ctx, const uint8_t* d_bgr, int nframes, size_t frame_stride, int stride,
+                         uint8_t* d_gray, size_t gray_frame_stride, int gray_stride);
+/* debug/inspection: copy pyramid level `level` of batch slot `frame` of the last extraction to host (tight rows) */
+int vido_orb_get_level(vido_ctx* ctx, int frame, int level, uint8_t* out);
+/* debug/inspection: FAST candidates (x,y relative to minBorder, score) of (frame, level) in reference order */
+int vido_orb_get_candidates(vido_ctx* ctx, int frame, int level, int32_t* xs, int32_t* ys, int32_t* scores,
+                            int cap, int32_t* n);
+
+/* stream handle (cudaStream_t) the context launches on, for event timing in bench.py */
+void* vido_stream(vido_ctx* ctx);
+int vido_sync(vido_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

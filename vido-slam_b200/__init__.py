@@ -1,0 +1,154 @@
+"""ctypes binding of libvido_b200.so -- thin: every call goes straight to the C-ABI in include/vido_b200.h.
+
+There is no CPU fallback: importing works without a GPU (so the symbol table can be checked), but creating a
+context raises when the CUDA library or an sm_100 device is missing.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvido_b200.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4")])
+
+
+class VidoConfig(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float),
+                ("choose_data", C.c_int32), ("depth_map_factor", C.c_float),
+                ("th_depth_bg", C.c_float), ("th_depth_obj", C.c_float),
+                ("max_track_bg", C.c_int32), ("max_track_obj", C.c_int32), ("window_size", C.c_int32),
+                ("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
+                ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32), ("rgb", C.c_int32),
+                ("max_batch", C.c_int32), ("device", C.c_int32)]
+
+
+class VidoError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree CUDA library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VidoError(f"{LIB_PATH} is missing: run __graft_entry__.build() (nvcc, sm_100a)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32p, f32p = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_float)
+    lib.vido_version.restype = C.c_int
+    lib.vido_default_config.argtypes = [C.POINTER(VidoConfig)]
+    lib.vido_create.restype = vp
+    lib.vido_create.argtypes = [C.POINTER(VidoConfig)]
+    lib.vido_destroy.argtypes = [vp]
+    lib.vido_last_error.restype = C.c_char_p
+    lib.vido_last_error.argtypes = [vp]
+    lib.vido_kernel_launches.restype = C.c_int64
+    lib.vido_kernel_launches.argtypes = [vp]
+    lib.vido_stream.restype = vp
+    lib.vido_stream.argtypes = [vp]
+    lib.vido_sync.argtypes = [vp]
+    lib.vido_orb_level_info.argtypes = [vp, vp, vp, vp, vp]
+    lib.vido_orb_extract.argtypes = [vp, vp, C.c_int, C.c_size_t, C.c_int, vp, C.c_int, vp]
+    lib.vido_orb_extract_dev.argtypes = [vp, vp, C.c_int, C.c_size_t, C.c_int, vp, C.c_int, vp, C.c_int]
+    lib.vido_bgr_to_gray_dev.argtypes = [vp, vp, C.c_int, C.c_size_t, C.c_int, vp, C.c_size_t, C.c_int]
+    lib.vido_orb_get_level.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.vido_orb_get_candidates.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp]
+    _lib = lib
+    return lib
+
+
+def default_config(**kw):
+    cfg = VidoConfig()
+    load_library().vido_default_config(C.byref(cfg))
+    for k, v in kw.items():
+        if not hasattr(cfg, k):
+            raise KeyError(k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One context per CUDA device (vido_create / vido_destroy)."""
+
+    def __init__(self, cfg=None, **kw):
+        self.lib = load_library()
+        self.cfg = cfg if cfg is not None else default_config(**kw)
+        self.h = self.lib.vido_create(C.byref(self.cfg))
+        if not self.h:
+            raise VidoError("vido_create failed: " + self.lib.vido_last_error(None).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vido_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise VidoError(f"rc={rc}: " + self.lib.vido_last_error(self.h).decode())
+
+    @property
+    def launches(self):
+        return int(self.lib.vido_kernel_launches(self.h))
+
+    @property
+    def stream(self):
+        return self.lib.vido_stream(self.h)
+
+    def sync(self):
+        self._check(self.lib.vido_sync(self.h))
+
+    def level_info(self):
+        n = self.cfg.nlevels
+        w = np.zeros(n, np.int32); h = np.zeros(n, np.int32); q = np.zeros(n, np.int32); s = np.zeros(n, np.float32)
+        self.lib.vido_orb_level_info(self.h, _ptr(w), _ptr(h), _ptr(q), _ptr(s))
+        return w, h, q, s
+
+    def orb_extract(self, gray, cap=None):
+        """gray: [H,W] or [B,H,W] uint8 numpy (host).  Returns list of keypoint arrays (KP_DTYPE)."""
+        g = np.ascontiguousarray(gray, np.uint8)
+        if g.ndim == 2:
+            g = g[None]
+        B, H, W = g.shape
+        assert H == self.cfg.height and W == self.cfg.width
+        cap = cap or (self.cfg.nfeatures + 64)
+        out = np.zeros((B, cap), KP_DTYPE)
+        n = np.zeros(B, np.int32)
+        self._check(self.lib.vido_orb_extract(self.h, _ptr(g), B, H * W, W, _ptr(out), cap, _ptr(n)))
+        return [out[b, :n[b]].copy() for b in range(B)]
+
+    def orb_extract_dev(self, d_gray_ptr, nframes, frame_stride, stride, d_out_ptr, cap, d_n_ptr, sync=False):
+        self._check(self.lib.vido_orb_extract_dev(self.h, d_gray_ptr, nframes, frame_stride, stride, d_out_ptr, cap,
+                                                  d_n_ptr, 1 if sync else 0))
+
+    def bgr_to_gray_dev(self, d_bgr, nframes, frame_stride, stride, d_gray, gray_frame_stride, gray_stride):
+        self._check(self.lib.vido_bgr_to_gray_dev(self.h, d_bgr, nframes, frame_stride, stride, d_gray,
+                                                  gray_frame_stride, gray_stride))
+
+    def get_level(self, frame, level):
+        w, h, _, _ = self.level_info()
+        out = np.zeros((h[level], w[level]), np.uint8)
+        self._check(self.lib.vido_orb_get_level(self.h, frame, level, _ptr(out)))
+        return out
+
+    def get_candidates(self, frame, level, cap=1 << 18):
+        xs = np.zeros(cap, np.int32); ys = np.zeros(cap, np.int32); sc = np.zeros(cap, np.int32)
+        n = np.zeros(1, np.int32)
+        self._check(self.lib.vido_orb_get_candidates(self.h, frame, level, _ptr(xs), _ptr(ys), _ptr(sc), cap, _ptr(n)))
+        return xs[:n[0]].copy(), ys[:n[0]].copy(), sc[:n[0]].copy()

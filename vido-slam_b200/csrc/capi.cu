@@ -1,0 +1,203 @@
+// capi.cu -- C-ABI entry points of libvido_b200.so (declared in include/vido_b200.h).
+#include <cstring>
+#include <new>
+
+#include "ctx.h"
+
+static thread_local std::string g_create_err;
+
+extern "C" {
+
+int vido_version(void) { return 100; }
+
+void vido_default_config(vido_config* c) {
+  // src/config/kitti_config.yaml of the reference, with the full-resolution KITTI camera the 1242x375
+  // configurations of BASELINE.json use
+  memset(c, 0, sizeof *c);
+  c->width = 1242; c->height = 375;
+  c->fx = 718.856f; c->fy = 718.856f; c->cx = 607.1928f; c->cy = 185.2157f; c->bf = 386.1448f;
+  c->choose_data = 2;
+  c->depth_map_factor = 256.f;
+  c->th_depth_bg = 5000.f; c->th_depth_obj = 25.f;
+  c->max_track_bg = 1000; c->max_track_obj = 500;
+  c->window_size = 20;
+  c->nfeatures = 2500; c->scale_factor = 1.2f; c->nlevels = 8; c->ini_th_fast = 20; c->min_th_fast = 7;
+  c->rgb = 0;
+  c->max_batch = 8;
+  c->device = 0;
+}
+
+const char* vido_last_error(vido_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+vido_ctx* vido_create(const vido_config* cfg) {
+  if (!cfg) { g_create_err = "null config"; return nullptr; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    // no CPU fallback by design: the product path is CUDA only
+    g_create_err = std::string("no CUDA device available: ") + cudaGetErrorString(e);
+    return nullptr;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { g_create_err = "bad device ordinal"; return nullptr; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, cfg->device);
+  if (prop.major < 10) {
+    g_create_err = "libvido_b200 is built for sm_100a (Blackwell) only; found " + std::string(prop.name);
+    return nullptr;
+  }
+  vido_ctx* ctx = new (std::nothrow) vido_ctx();
+  if (!ctx) { g_create_err = "out of memory"; return nullptr; }
+  ctx->cfg = *cfg;
+  if (ctx->cfg.max_batch < 1) ctx->cfg.max_batch = 1;
+  ctx->device = cfg->device;
+  ctx->num_sms = prop.multiProcessorCount;
+  if (cudaSetDevice(cfg->device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    g_create_err = "cudaSetDevice/cudaStreamCreate failed";
+    delete ctx;
+    return nullptr;
+  }
+  int rc = orb_setup(ctx);
+  if (rc != VIDO_OK) {
+    g_create_err = ctx->err;
+    orb_teardown(ctx);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return nullptr;
+  }
+  return ctx;
+}
+
+void vido_destroy(vido_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  orb_teardown(ctx);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int64_t vido_kernel_launches(vido_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* vido_stream(vido_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int vido_sync(vido_ctx* ctx) {
+  if (!ctx) return VIDO_ERR_ARG;
+  VIDO_CUDA(cudaStreamSynchronize(ctx->stream));
+  return VIDO_OK;
+}
+
+int vido_orb_level_info(vido_ctx* ctx, int32_t* w, int32_t* h, int32_t* quota, float* scale) {
+  if (!ctx) return VIDO_ERR_ARG;
+  for (int l = 0; l < ctx->nlevels; l++) {
+    if (w) w[l] = ctx->lv[l].w;
+    if (h) h[l] = ctx->lv[l].h;
+    if (quota) quota[l] = ctx->lv[l].quota;
+    if (scale) scale[l] = ctx->lv[l].scale;
+  }
+  return ctx->nlevels;
+}
+
+static int check_dev_err(vido_ctx* ctx) {
+  int32_t flag = 0;
+  VIDO_CUDA(cudaMemcpyAsync(&flag, ctx->d_err, sizeof flag, cudaMemcpyDeviceToHost, ctx->stream));
+  VIDO_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (flag) {
+    char buf[128];
+    snprintf(buf, sizeof buf, "ORB front-end capacity flag 0x%x (1: >65535 candidates/level, 2-16: quad-tree arrays, 32: output cap)", flag);
+    ctx->err = buf;
+    cudaMemsetAsync(ctx->d_err, 0, sizeof flag, ctx->stream);
+    return VIDO_ERR_CAPACITY;
+  }
+  return VIDO_OK;
+}
+
+int vido_orb_extract_dev(vido_ctx* ctx, const uint8_t* d_gray, int nframes, size_t frame_stride, int stride,
+                         vido_keypoint* d_out, int cap_per_frame, int32_t* d_n_out, int sync) {
+  if (!ctx || !d_gray || !d_out || !d_n_out || cap_per_frame < 1 || stride < ctx->cfg.width) {
+    if (ctx) ctx->err = "vido_orb_extract_dev: bad argument";
+    return VIDO_ERR_ARG;
+  }
+  cudaSetDevice(ctx->device);
+  int rc = orb_run(ctx, d_gray, nframes, frame_stride, stride, d_out, cap_per_frame, d_n_out);
+  if (rc != VIDO_OK) return rc;
+  if (sync) return check_dev_err(ctx);
+  return VIDO_OK;
+}
+
+int vido_orb_extract(vido_ctx* ctx, const uint8_t* gray, int nframes, size_t frame_stride, int stride, vido_keypoint* out,
+                     int cap_per_frame, int32_t* n_out) {
+  if (!ctx || !gray || !out || !n_out || cap_per_frame < 1 || stride < ctx->cfg.width) {
+    if (ctx) ctx->err = "vido_orb_extract: bad argument";
+    return VIDO_ERR_ARG;
+  }
+  cudaSetDevice(ctx->device);
+  const vido_config& c = ctx->cfg;
+  int done = 0;
+  while (done < nframes) {
+    const int B = std::min(c.max_batch, nframes - done);
+    for (int b = 0; b < B; b++)
+      VIDO_CUDA(cudaMemcpy2DAsync(ctx->d_in + (size_t)b * ctx->in_pitch * c.height, ctx->in_pitch,
+                                  gray + (size_t)(done + b) * frame_stride, stride, c.width, c.height,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    int rc = orb_run(ctx, ctx->d_in, B, (size_t)ctx->in_pitch * c.height, ctx->in_pitch, ctx->d_kp, ctx->kp_cap, ctx->d_nkp);
+    if (rc != VIDO_OK) return rc;
+    VIDO_CUDA(cudaMemcpyAsync(n_out + done, ctx->d_nkp, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, ctx->stream));
+    rc = check_dev_err(ctx);  // synchronises
+    if (rc != VIDO_OK) return rc;
+    for (int b = 0; b < B; b++) {
+      int n = n_out[done + b];
+      if (n > cap_per_frame) { ctx->err = "vido_orb_extract: cap_per_frame too small"; return VIDO_ERR_CAPACITY; }
+      VIDO_CUDA(cudaMemcpyAsync(out + (size_t)(done + b) * cap_per_frame, ctx->d_kp + (size_t)b * ctx->kp_cap,
+                                sizeof(vido_keypoint) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    VIDO_CUDA(cudaStreamSynchronize(ctx->stream));
+    done += B;
+  }
+  return VIDO_OK;
+}
+
+int vido_bgr_to_gray_dev(vido_ctx* ctx, const uint8_t* d_bgr, int nframes, size_t frame_stride, int stride, uint8_t* d_gray,
+                         size_t gray_frame_stride, int gray_stride) {
+  if (!ctx || !d_bgr || !d_gray) return VIDO_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  return orb_bgr_to_gray(ctx, d_bgr, nframes, frame_stride, stride, d_gray, gray_frame_stride, gray_stride);
+}
+
+int vido_orb_get_level(vido_ctx* ctx, int frame, int level, uint8_t* out) {
+  if (!ctx || !out || level < 0 || level >= ctx->nlevels || frame < 0 || frame >= ctx->cfg.max_batch) return VIDO_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  const OrbLevel& L = ctx->lv[level];
+  VIDO_CUDA(cudaMemcpy2DAsync(out, L.w, ctx->d_pyr + L.base + (size_t)frame * L.frame_stride, L.pitch, L.w, L.h,
+                              cudaMemcpyDeviceToHost, ctx->stream));
+  VIDO_CUDA(cudaStreamSynchronize(ctx->stream));
+  return VIDO_OK;
+}
+
+int vido_orb_get_candidates(vido_ctx* ctx, int frame, int level, int32_t* xs, int32_t* ys, int32_t* scores, int cap,
+                            int32_t* n) {
+  if (!ctx || level < 0 || level >= ctx->nlevels || frame < 0 || frame >= ctx->cfg.max_batch || !n) return VIDO_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  const OrbLevel& L = ctx->lv[level];
+  std::vector<int32_t> cnt(std::max(L.ncells, 1));
+  std::vector<uint32_t> slots(ctx->slots_per_frame);
+  VIDO_CUDA(cudaMemcpyAsync(cnt.data(), ctx->d_cell_count + (size_t)frame * ctx->cells_per_frame + L.cell_begin,
+                            sizeof(int32_t) * L.ncells, cudaMemcpyDeviceToHost, ctx->stream));
+  VIDO_CUDA(cudaMemcpyAsync(slots.data(), ctx->d_slots + (size_t)frame * ctx->slots_per_frame,
+                            sizeof(uint32_t) * ctx->slots_per_frame, cudaMemcpyDeviceToHost, ctx->stream));
+  VIDO_CUDA(cudaStreamSynchronize(ctx->stream));
+  int k = 0;
+  for (int i = 0; i < L.ncells; i++) {
+    const OrbCell& cell = ctx->cells[L.cell_begin + i];
+    for (int j = 0; j < cnt[i]; j++, k++) {
+      if (k < cap) {
+        uint32_t v = slots[cell.slot_base + j];
+        xs[k] = (int)(v >> 20);
+        ys[k] = (int)((v >> 8) & 0xfff);
+        scores[k] = (int)(v & 0xff);
+      }
+    }
+  }
+  *n = k;
+  return VIDO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+// ctx.h -- device context shared by the C-ABI translation units of libvido_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/vido_b200.h"
+
+#define VIDO_MAX_LEVELS 8
+#define VIDO_EDGE 19       // EDGE_THRESHOLD   (src/ORBextractor.cc:63)
+#define VIDO_MINB 16       // EDGE_THRESHOLD-3 (src/ORBextractor.cc:763)
+
+struct OrbLevel {
+  int w, h, pitch;            // level size and row pitch (bytes, multiple of 64)
+  size_t frame_stride;        // bytes between batch slots of this level
+  size_t base;                // byte offset of the level inside the pyramid allocation
+  int quota;                  // mnFeaturesPerLevel
+  float scale;                // mvScaleFactor
+  int nCols, nRows, wCell, hCell;
+  int cell_begin, ncells;     // range in the cell table
+  int maxBX, maxBY;           // cols-16, rows-16
+  int nIni;                   // DistributeOctTree root count
+  float hX;
+  int boxW, boxH;             // TMA box (bytes x rows) of the FAST tile
+  int cand_cap;               // upper bound on FAST candidates of this level (sum of cell slot caps)
+  size_t cand_base;           // element offset of this level inside a frame's octree scratch
+  int out_base;               // slot offset of this level in the per-frame level-output array
+  int out_cap;                // quota + 4
+};
+
+struct OrbCell {  // one cv::FAST call of ComputeKeyPointsOctTree (src/ORBextractor.cc:779-819)
+  int x0, y0;      // ROI origin in level coordinates
+  int rw, rh;      // ROI size (detection zone is its interior minus 3 px)
+  int offx, offy;  // j*wCell, i*hCell added to ROI-relative coordinates
+  int slot_base;   // first candidate slot of this cell inside a frame's slot array
+  int slot_cap;
+};
+
+struct vido_ctx {
+  vido_config cfg;
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+
+  // ---- ORB front-end ----
+  int nlevels = 0;
+  OrbLevel lv[VIDO_MAX_LEVELS];
+  std::vector<OrbCell> cells;  // host copy
+  int cells_per_frame = 0;
+  int slots_per_frame = 0;     // candidate slots per frame (u32 each)
+  size_t octree_keys_per_frame = 0;
+  int out_slots_per_frame = 0; // sum of out_cap
+  uint8_t* d_pyr = nullptr;    // all levels, all batch slots
+  size_t pyr_bytes = 0;
+  OrbCell* d_cells = nullptr;
+  uint32_t* d_slots = nullptr;      // [B][slots_per_frame] packed x|y|score
+  int32_t* d_cell_count = nullptr;  // [B][cells_per_frame]
+  uint32_t* d_oct_keys = nullptr;   // [B][octree_keys_per_frame] ordered candidates per level (global scratch)
+  uint16_t* d_oct_perm = nullptr;   // [B][2*octree_keys_per_frame] (only used when a level overflows shared memory)
+  uint32_t* d_level_out = nullptr;  // [B][out_slots_per_frame] packed x|y|score of kept keypoints (list order)
+  int32_t* d_level_cnt = nullptr;   // [B][nlevels] kept count, and [B][nlevels] candidate count after it
+  int32_t* d_xofs[VIDO_MAX_LEVELS] = {};   // resize tables (level l built from l-1)
+  int16_t* d_xa[VIDO_MAX_LEVELS] = {};
+  int32_t* d_yofs[VIDO_MAX_LEVELS] = {};
+  int16_t* d_ya[VIDO_MAX_LEVELS] = {};
+  CUtensorMap tmap[VIDO_MAX_LEVELS];
+  vido_keypoint* d_kp = nullptr;    // [B][kp_cap] staging for the host-pointer API
+  int32_t* d_nkp = nullptr;         // [B]
+  int kp_cap = 0;
+  uint8_t* d_in = nullptr;          // staging for host inputs [B][H][in_pitch]
+  int in_pitch = 0;
+  int32_t* d_err = nullptr;         // device error flag
+  int last_batch = 0;
+  int oct_smem_keys = 0;            // shared-memory key capacity of the octree kernel
+  size_t oct_smem_bytes = 0;
+};
+
+#define VIDO_CUDA(call)                                                                     \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      char buf_[512];                                                                       \
+      snprintf(buf_, sizeof buf_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      ctx->err = buf_;                                                                      \
+      return VIDO_ERR_CUDA;                                                                 \
+    }                                                                                       \
+  } while (0)
+
+// orb_kernels.cu
+int orb_setup(vido_ctx* ctx);
+void orb_teardown(vido_ctx* ctx);
+int orb_run(vido_ctx* ctx, const uint8_t* d_gray, int nframes, size_t frame_stride, int stride,
+            vido_keypoint* d_out, int cap_per_frame, int32_t* d_n_out);
+int orb_bgr_to_gray(vido_ctx* ctx, const uint8_t* d_bgr, int nframes, size_t frame_stride, int stride,
+                    uint8_t* d_gray, size_t gray_frame_stride, int gray_stride);
