@@ -88,6 +88,65 @@ int vido_orb_get_level(vido_ctx* ctx, int frame, int level, uint8_t* out);
 int vido_orb_get_candidates(vido_ctx* ctx, int frame, int level, int32_t* xs, int32_t* ys, int32_t* scores,
                             int cap, int32_t* n);
 
+
+/* ---- Levenberg-Marquardt statistics (g2o G2OBatchStatistics-like, used for parity checks) ---- */
+#define VIDO_LM_MAX_RECORDS 320
+typedef struct vido_lm_record { double chi2; double lambda; int32_t trials; int32_t pad; } vido_lm_record;
+typedef struct vido_lm_stats {
+  int32_t iterations;   /* what SparseOptimizer::optimize returns (g2o/core/sparse_optimizer.cpp:354-427); -1: empty graph */
+  int32_t n_records, total_trials, pad;
+  vido_lm_record rec[VIDO_LM_MAX_RECORDS];  /* robust chi2 / lambda / #trials after each outer iteration */
+} vido_lm_stats;
+
+/*
+ * Sliding-window graph optimisation: replaces Optimizer::PartialBatchOptimization (src/Optimizer.cc:43-1228) for the
+ * flat graph the reference builds at :220-362: n_poses VertexSE3 (estimate = Map::vmCameraPose, float 4x4 Twc),
+ * n_poses-1 EdgeSE3 (measurement = Map::vmRigidMotion[i-1][0]), n_points VertexPointXYZ (Map::vp3DPointSta of the
+ * first observation) and one EdgeSE3PointXYZ per observation (measurement = Optimizer::Get3DinCamera, :3277-3294).
+ * In/out arrays are float32 like the Map; results are written back as at :1056-1142.
+ * Host pointers.  Returns VIDO_OK; the iteration count is in stats->iterations.
+ */
+typedef struct vido_ba_problem {
+  int32_t n_poses, n_points, n_obs, pad;
+  float* poses;             /* [n_poses][16] in/out */
+  float* rel_motion;        /* [n_poses-1][16] in: EdgeSE3 measurement; out: inv(pose[i-1])*pose[i] */
+  float* points;            /* [n_points][3] in/out (world) */
+  const int32_t* obs_pose;  /* [n_obs] window-relative pose index */
+  const int32_t* obs_point; /* [n_obs] point index */
+  const float* obs_xyz;     /* [n_obs][3] camera-frame measurement */
+  int32_t max_iterations;   /* 100 (:806) */
+  float sigma2_cam, sigma2_3d, huber_cam, huber_3d; /* 0.0001, 16, 0.01, 0.01 (:192-216) */
+  float gain_threshold;     /* SparseOptimizerTerminateAction gain 1e-3 (:183); <0 disables */
+  int32_t fix_first;        /* reserved (the reference's prior edge at :228-237 never fires in its own calls) */
+} vido_ba_problem;
+void vido_ba_default_params(vido_ba_problem* p);
+int vido_ba_partial(vido_ctx* ctx, vido_ba_problem* p, vido_lm_stats* stats);
+
+
+/*
+ * Per-frame joint optical-flow + pose optimisation: replaces Optimizer::PoseOptimizationFlow2Cam
+ * (src/Optimizer.cc:2622-2824; camera) and Optimizer::PoseOptimizationFlow2 (:3037-3253; one call per object, with
+ * Tcw_init = mInitModel, info_prior = 0.5, rounds = 1, its = 200).  One problem = one SE3 vertex + n flow vertices.
+ * Several problems are solved by one launch (one CTA each).  Host pointers.
+ */
+typedef struct vido_poseopt_problem {
+  int32_t n, n_inliers;   /* in: matches; out: n - nBad (0 when n < 3, nothing optimised) */
+  const float* obs_xy;    /* [n][2] pLastFrame keypoint of the match */
+  const float* flow_xy;   /* [n][2] pLastFrame->mvFlowNext */
+  const float* depth;     /* [n]    pLastFrame->mvStatDepth */
+  float Tcw_init[16];     /* initial transform (pCurFrame->mTcw) */
+  float Tcw_last[16];     /* pLastFrame->mTcw */
+  float fx, fy, cx, cy;
+  float Tcw_out[16];      /* optimised transform, float32 like Converter::toCvMat */
+  float* flow_out;        /* [n][2] refined flow of every match (may be NULL) */
+  int32_t* inlier;        /* [n] 1 inlier / 0 outlier (may be NULL) */
+  float info_flow, info_prior, rp_thres, chi2_th; /* 0.1, 0.3, 0.04, 5.991 (:2680,2706,2624,2725) */
+  int32_t rounds, its;    /* 4, 100 (:2725-2726) */
+} vido_poseopt_problem;
+void vido_poseopt_default_params(vido_poseopt_problem* p);
+/* stats: NULL or 4*nproblems entries (entry 4*k + r = round r of problem k) */
+int vido_pose_opt_flow2(vido_ctx* ctx, vido_poseopt_problem* problems, int nproblems, vido_lm_stats* stats);
+
 /* stream handle (cudaStream_t) the context launches on, for event timing in bench.py */
 void* vido_stream(vido_ctx* ctx);
 int vido_sync(vido_ctx* ctx);

@@ -59,6 +59,77 @@ int vo_orb_extract(const uint8_t* gray, int W, int H, int stride, const vo_orb_p
 int vo_orb_pyramid(const uint8_t* gray, int W, int H, int stride, const vo_orb_params* p,
                    uint8_t* out, int64_t* offsets);
 
+
+/* ---- Levenberg-Marquardt bookkeeping shared by all graph oracles (g2o/core/optimization_algorithm_levenberg.cpp) ---- */
+#define VO_LM_MAX_RECORDS 320
+typedef struct vo_lm_record { double chi2; double lambda; int32_t trials; int32_t pad; } vo_lm_record;
+typedef struct vo_lm_stats {
+  int32_t iterations;      /* return value of SparseOptimizer::optimize */
+  int32_t n_records;
+  int32_t total_trials;
+  int32_t pad;
+  vo_lm_record rec[VO_LM_MAX_RECORDS]; /* robust chi2 / lambda after each outer iteration */
+} vo_lm_stats;
+
+/*
+ * Sliding-window graph of Optimizer::PartialBatchOptimization (src/Optimizer.cc:43-1228) in flat form:
+ * W camera poses (VertexSE3, estimate = Twc float 4x4 as stored in Map::vmCameraPose), W-1 odometry edges
+ * (EdgeSE3, measurement = Map::vmRigidMotion[i-1][0]), P static points (VertexPointXYZ) and one EdgeSE3PointXYZ
+ * per observation (measurement = Optimizer::Get3DinCamera of the feature).  All float32 in / out like the Map.
+ */
+typedef struct vo_ba_problem {
+  int32_t n_poses, n_points, n_obs, pad;
+  float* poses;            /* [n_poses][16]  in: vmCameraPose, out: optimised (float32 round trip of :1058-1069) */
+  float* rel_motion;       /* [n_poses-1][16] in: EdgeSE3 measurements; out: inv(pose[i-1])*pose[i] (:1072-1075) */
+  float* points;           /* [n_points][3] in: vp3DPointSta of the first observation; out: optimised */
+  const int32_t* obs_pose; /* [n_obs] window-relative pose index */
+  const int32_t* obs_point;/* [n_obs] point index */
+  const float* obs_xyz;    /* [n_obs][3] camera-frame measurement */
+  int32_t max_iterations;  /* 100 (:806) */
+  float sigma2_cam, sigma2_3d, huber_cam, huber_3d; /* 0.0001, 16, 0.01, 0.01 (:192-216) */
+  float gain_threshold;    /* 1e-3 (:183) */
+  int32_t fix_first;       /* add the EdgeSE3Prior of :228-237 on pose 0 (never true in the reference's own calls) */
+} vo_ba_problem;
+void vo_ba_default_params(vo_ba_problem* p);
+int vo_ba_partial(vo_ba_problem* p, vo_lm_stats* stats);
+/* edge math exposed for Jacobian tests: EdgeSE3 (g2o/types/edge_se3.cpp:77-105) */
+void vo_edge_se3(const double* Xi /*R row-major 9 + t 3*/, const double* Xj, const double* Z, double err[6],
+                 double Ji[36], double Jj[36]);
+void vo_se3_oplus(const double* X, const double* upd6, double* Xout); /* VertexSE3::oplusImpl */
+void vo_edge_se3_pointxyz(const double* X, const double* p, const double* z, double err[3], double Ji[18], double Jj[9]);
+
+/* ---- per-frame stages of Tracking::GrabImageRGBD / Frame::Frame ---- */
+/* depth pre-scale, in place (src/Tracking.cc:299-322): negatives -> 0; OMD d/f; KITTI bf/(d/f); KAIST mScale*bf/(d/f) */
+void vo_depth_prep(float* depth, int W, int H, int stride_elems, int choose_data, float depth_map_factor, float bf, float mscale);
+/* static association of detected keypoints (src/Frame.cc:72-100,164-177): returns count; out_idx = index into kps */
+int vo_frame_associate(const vo_keypoint* kps, int n, const float* depth, const float* flow, const int32_t* mask,
+                       int W, int H, float th_depth_bg, int32_t* out_idx, float* out_corres_xy, float* out_flow_xy,
+                       float* out_depth, int cap);
+/* stride-4 object sampling (src/Frame.cc:184-211): returns count */
+int vo_frame_sample_objects(const float* depth, const float* flow, const int32_t* mask, int W, int H, float th_depth_obj,
+                            float* keys_xy, float* corres_xy, float* flow_xy, float* depth_out, int32_t* label, int cap);
+
+/*
+ * Per-frame camera pose optimisation Optimizer::PoseOptimizationFlow2Cam (src/Optimizer.cc:2622-2824):
+ * one VertexSE3Expmap + n marginalised VertexSBAFlow, EdgeSE3ProjectFlow2 + EdgeFlowPrior per match, 4 rounds.
+ */
+typedef struct vo_poseopt_problem {
+  int32_t n, pad;
+  const float* obs_xy;    /* [n][2] pLastFrame->mvStatKeys[TM[i]].pt */
+  const float* flow_xy;   /* [n][2] pLastFrame->mvFlowNext[TM[i]] */
+  const float* depth;     /* [n]    pLastFrame->mvStatDepth[TM[i]] */
+  float Tcw_init[16];     /* pCurFrame->mTcw on entry */
+  float Tcw_last[16];     /* pLastFrame->mTcw */
+  float fx, fy, cx, cy;
+  float Tcw_out[16];      /* optimised pose (float32 as Converter::toCvMat) */
+  float* flow_out;        /* [n][2] refined flow of every vertex */
+  int32_t* inlier;        /* [n] 1 inlier / 0 outlier after the 4th round */
+  float info_flow, info_prior, rp_thres, chi2_th; /* 0.1, 0.3, 0.04, 5.991 */
+  int32_t rounds, its;    /* 4, 100 */
+} vo_poseopt_problem;
+void vo_poseopt_default_params(vo_poseopt_problem* p);
+int vo_poseopt_flow2cam(vo_poseopt_problem* p, vo_lm_stats* stats /* [rounds] or NULL */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,3 +93,128 @@ def orb_extract(gray, p, cap=20000):
     n = lib().vo_orb_extract(_p(gray), W, H, W, C.byref(p), _p(out), cap)
     assert n >= 0
     return out[:n].copy()
+
+
+# ---------------------------------------------------------------- graph optimisation oracle
+class LmRecord(C.Structure):
+    _fields_ = [("chi2", C.c_double), ("lam", C.c_double), ("trials", C.c_int32), ("pad", C.c_int32)]
+
+
+class LmStats(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("n_records", C.c_int32), ("total_trials", C.c_int32), ("pad", C.c_int32),
+                ("rec", LmRecord * 320)]
+
+    def records(self):
+        return [(self.rec[i].chi2, self.rec[i].lam, self.rec[i].trials) for i in range(self.n_records)]
+
+
+class BaProblem(C.Structure):
+    _fields_ = [("n_poses", C.c_int32), ("n_points", C.c_int32), ("n_obs", C.c_int32), ("pad", C.c_int32),
+                ("poses", C.c_void_p), ("rel_motion", C.c_void_p), ("points", C.c_void_p),
+                ("obs_pose", C.c_void_p), ("obs_point", C.c_void_p), ("obs_xyz", C.c_void_p),
+                ("max_iterations", C.c_int32), ("sigma2_cam", C.c_float), ("sigma2_3d", C.c_float),
+                ("huber_cam", C.c_float), ("huber_3d", C.c_float), ("gain_threshold", C.c_float),
+                ("fix_first", C.c_int32)]
+
+
+def ba_partial(poses, rel_motion, points, obs_pose, obs_point, obs_xyz, **params):
+    """Oracle sliding-window BA.  Arrays are copied; returns (poses, rel_motion, points, iterations, stats)."""
+    poses = np.ascontiguousarray(poses, np.float32).copy()
+    rel = np.ascontiguousarray(rel_motion, np.float32).copy()
+    pts = np.ascontiguousarray(points, np.float32).copy()
+    op = np.ascontiguousarray(obs_pose, np.int32)
+    ol_ = np.ascontiguousarray(obs_point, np.int32)
+    ox = np.ascontiguousarray(obs_xyz, np.float32)
+    pr = BaProblem()
+    lib().vo_ba_default_params(C.byref(pr))
+    pr.n_poses, pr.n_points, pr.n_obs = len(poses), len(pts), len(op)
+    pr.poses, pr.rel_motion, pr.points = _p(poses), _p(rel), _p(pts)
+    pr.obs_pose, pr.obs_point, pr.obs_xyz = _p(op), _p(ol_), _p(ox)
+    for k, v in params.items():
+        setattr(pr, k, v)
+    st = LmStats()
+    its = lib().vo_ba_partial(C.byref(pr), C.byref(st))
+    return poses, rel, pts, its, st
+
+
+def edge_se3(Xi, Xj, Z):
+    e = np.zeros(6); Ji = np.zeros((6, 6)); Jj = np.zeros((6, 6))
+    lib().vo_edge_se3(_p(np.ascontiguousarray(Xi, np.float64)), _p(np.ascontiguousarray(Xj, np.float64)),
+                      _p(np.ascontiguousarray(Z, np.float64)), _p(e), _p(Ji), _p(Jj))
+    return e, Ji, Jj
+
+
+def se3_oplus(X, u):
+    out = np.zeros(12)
+    lib().vo_se3_oplus(_p(np.ascontiguousarray(X, np.float64)), _p(np.ascontiguousarray(u, np.float64)), _p(out))
+    return out
+
+
+def edge_se3_pointxyz(X, p, z):
+    e = np.zeros(3); Ji = np.zeros((3, 6)); Jj = np.zeros((3, 3))
+    lib().vo_edge_se3_pointxyz(_p(np.ascontiguousarray(X, np.float64)), _p(np.ascontiguousarray(p, np.float64)),
+                               _p(np.ascontiguousarray(z, np.float64)), _p(e), _p(Ji), _p(Jj))
+    return e, Ji, Jj
+
+
+# ---------------------------------------------------------------- per-frame stages
+def depth_prep(depth, choose_data, factor, bf, mscale=1.0):
+    d = np.ascontiguousarray(depth, np.float32).copy()
+    lib().vo_depth_prep(_p(d), d.shape[1], d.shape[0], d.shape[1], int(choose_data), C.c_float(factor), C.c_float(bf),
+                        C.c_float(mscale))
+    return d
+
+
+def frame_associate(kps, depth, flow, mask, th_depth_bg):
+    kps = np.ascontiguousarray(kps)
+    depth = np.ascontiguousarray(depth, np.float32); flow = np.ascontiguousarray(flow, np.float32)
+    mask = np.ascontiguousarray(mask, np.int32)
+    H, W = depth.shape
+    cap = len(kps)
+    idx = np.zeros(cap, np.int32); cor = np.zeros((cap, 2), np.float32); fl = np.zeros((cap, 2), np.float32)
+    dep = np.zeros(cap, np.float32)
+    n = lib().vo_frame_associate(_p(kps), len(kps), _p(depth), _p(flow), _p(mask), W, H, C.c_float(th_depth_bg),
+                                 _p(idx), _p(cor), _p(fl), _p(dep), cap)
+    return idx[:n].copy(), cor[:n].copy(), fl[:n].copy(), dep[:n].copy()
+
+
+def frame_sample_objects(depth, flow, mask, th_depth_obj):
+    depth = np.ascontiguousarray(depth, np.float32); flow = np.ascontiguousarray(flow, np.float32)
+    mask = np.ascontiguousarray(mask, np.int32)
+    H, W = depth.shape
+    cap = ((H + 3) // 4) * ((W + 3) // 4)
+    keys = np.zeros((cap, 2), np.float32); cor = np.zeros((cap, 2), np.float32); fl = np.zeros((cap, 2), np.float32)
+    dep = np.zeros(cap, np.float32); lab = np.zeros(cap, np.int32)
+    n = lib().vo_frame_sample_objects(_p(depth), _p(flow), _p(mask), W, H, C.c_float(th_depth_obj), _p(keys), _p(cor),
+                                      _p(fl), _p(dep), _p(lab), cap)
+    return keys[:n].copy(), cor[:n].copy(), fl[:n].copy(), dep[:n].copy(), lab[:n].copy()
+
+
+class PoseOptProblem(C.Structure):
+    _fields_ = [("n", C.c_int32), ("pad", C.c_int32), ("obs_xy", C.c_void_p), ("flow_xy", C.c_void_p),
+                ("depth", C.c_void_p), ("Tcw_init", C.c_float * 16), ("Tcw_last", C.c_float * 16),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("Tcw_out", C.c_float * 16), ("flow_out", C.c_void_p), ("inlier", C.c_void_p),
+                ("info_flow", C.c_float), ("info_prior", C.c_float), ("rp_thres", C.c_float), ("chi2_th", C.c_float),
+                ("rounds", C.c_int32), ("its", C.c_int32)]
+
+
+def poseopt_flow2cam(obs_xy, flow_xy, depth, Tcw_init, Tcw_last, K, **params):
+    """returns (Tcw 4x4 f32, refined flow [n,2], inlier mask [n], n_inliers, [LmStats]*rounds)"""
+    obs = np.ascontiguousarray(obs_xy, np.float32); fl = np.ascontiguousarray(flow_xy, np.float32)
+    dep = np.ascontiguousarray(depth, np.float32)
+    n = len(obs)
+    pr = PoseOptProblem()
+    lib().vo_poseopt_default_params(C.byref(pr))
+    pr.n = n
+    pr.obs_xy, pr.flow_xy, pr.depth = _p(obs), _p(fl), _p(dep)
+    pr.Tcw_init[:] = np.asarray(Tcw_init, np.float32).reshape(-1).tolist()
+    pr.Tcw_last[:] = np.asarray(Tcw_last, np.float32).reshape(-1).tolist()
+    pr.fx, pr.fy, pr.cx, pr.cy = [float(v) for v in K]
+    fo = np.zeros((n, 2), np.float32); inl = np.zeros(n, np.int32)
+    pr.flow_out, pr.inlier = _p(fo), _p(inl)
+    for k, v in params.items():
+        setattr(pr, k, v)
+    stats = (LmStats * pr.rounds)()
+    ninl = lib().vo_poseopt_flow2cam(C.byref(pr), stats)
+    return np.array(pr.Tcw_out[:], np.float32).reshape(4, 4), fo, inl, ninl, list(stats)

@@ -1,0 +1,66 @@
+"""GPU: the cluster-resident LM solver (vido_ba_partial) against the oracle's restatement of
+Optimizer::PartialBatchOptimization.  Tolerance from BASELINE.json: poses and points within 1e-4 relative;
+the LM trajectory (iterations, trials, chi2, lambda per iteration) must be the same."""
+import numpy as np
+import pytest
+
+import ba_synth
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def ctx(pkg):
+    c = pkg.Context(pkg.default_config(width=640, height=480, max_batch=1))
+    yield c
+    c.close()
+
+
+def _compare(ctx, pr, **params):
+    args = (pr["poses"], pr["rel"], pr["points"], pr["obs_pose"], pr["obs_point"], pr["obs_xyz"])
+    rp, rr, rpts, rits, rst = ol.ba_partial(*args, **params)
+    gp, gr, gpts, gits, gst = ctx.ba_partial(*args, **params)
+    assert gits == rits, (gits, rits, gst.records(), rst.records())
+    assert gst.total_trials == rst.total_trials
+    for (c1, l1, t1), (c2, l2, t2) in zip(gst.records(), rst.records()):
+        assert t1 == t2
+        assert abs(c1 - c2) <= REL_TOL * max(abs(c2), 1e-12)
+        assert abs(l1 - l2) <= 1e-3 * abs(l2)
+    scale_p = max(np.abs(rp).max(), 1.0)
+    assert np.abs(gp - rp).max() <= REL_TOL * scale_p
+    assert np.abs(gr - rr).max() <= REL_TOL * max(np.abs(rr).max(), 1.0)
+    assert np.abs(gpts - rpts).max() <= REL_TOL * max(np.abs(rpts).max(), 1.0)
+    return rits, rst
+
+
+@pytest.mark.parametrize("W,P,seed", [(20, 3000, 1), (20, 6000, 2), (5, 200, 3), (2, 0, 4), (12, 900, 5)])
+def test_window_matches_oracle(ctx, W, P, seed):
+    pr = ba_synth.make_window(W=W, P=P, seed=seed)
+    if P == 0:  # odometry-only graph: make the measurement disagree with the estimate, otherwise chi2 is pure round-off
+        pr["rel"] = pr["rel"].copy()
+        pr["rel"][:, 3] += 0.05
+        pr["rel"][:, 11] -= 0.02
+    its, st = _compare(ctx, pr)
+    assert its >= 1
+
+
+def test_noisy_window_many_iterations(ctx):
+    pr = ba_synth.make_window(W=20, P=2500, seed=11, obs_noise=0.05, pose_noise=0.08, rot_noise=0.01, outliers=0.1)
+    its, st = _compare(ctx, pr)
+    assert its >= 3
+
+
+def test_iteration_cap_and_no_terminate_action(ctx):
+    pr = ba_synth.make_window(W=10, P=500, seed=21, pose_noise=0.05)
+    _compare(ctx, pr, max_iterations=2)
+    _compare(ctx, pr, gain_threshold=-1.0, max_iterations=8)
+
+
+def test_single_pose_and_empty(ctx):
+    pr = ba_synth.make_window(W=1, P=0, seed=1)
+    gp, gr, gpts, gits, gst = ctx.ba_partial(pr["poses"], pr["rel"], pr["points"], pr["obs_pose"], pr["obs_point"], pr["obs_xyz"])
+    rp, rr, rpts, rits, rst = ol.ba_partial(pr["poses"], pr["rel"], pr["points"], pr["obs_pose"], pr["obs_point"], pr["obs_xyz"])
+    assert gits == rits
+    assert np.abs(gp - rp).max() <= 1e-6

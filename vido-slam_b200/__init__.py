@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvido_b200.so")
+LIB_PATH = os.environ.get("VIDO_LIB_PATH", os.path.join(_HERE, "libvido_b200.so"))  # override: debug builds only
 
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
                      ("response", "<f4"), ("octave", "<i4")])
@@ -24,6 +24,36 @@ class VidoConfig(C.Structure):
                 ("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
                 ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32), ("rgb", C.c_int32),
                 ("max_batch", C.c_int32), ("device", C.c_int32)]
+
+
+class LmRecord(C.Structure):
+    _fields_ = [("chi2", C.c_double), ("lam", C.c_double), ("trials", C.c_int32), ("pad", C.c_int32)]
+
+
+class LmStats(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("n_records", C.c_int32), ("total_trials", C.c_int32), ("pad", C.c_int32),
+                ("rec", LmRecord * 320)]
+
+    def records(self):
+        return [(self.rec[i].chi2, self.rec[i].lam, self.rec[i].trials) for i in range(self.n_records)]
+
+
+class BaProblem(C.Structure):
+    _fields_ = [("n_poses", C.c_int32), ("n_points", C.c_int32), ("n_obs", C.c_int32), ("pad", C.c_int32),
+                ("poses", C.c_void_p), ("rel_motion", C.c_void_p), ("points", C.c_void_p),
+                ("obs_pose", C.c_void_p), ("obs_point", C.c_void_p), ("obs_xyz", C.c_void_p),
+                ("max_iterations", C.c_int32), ("sigma2_cam", C.c_float), ("sigma2_3d", C.c_float),
+                ("huber_cam", C.c_float), ("huber_3d", C.c_float), ("gain_threshold", C.c_float),
+                ("fix_first", C.c_int32)]
+
+
+class PoseOptProblem(C.Structure):
+    _fields_ = [("n", C.c_int32), ("n_inliers", C.c_int32), ("obs_xy", C.c_void_p), ("flow_xy", C.c_void_p),
+                ("depth", C.c_void_p), ("Tcw_init", C.c_float * 16), ("Tcw_last", C.c_float * 16),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("Tcw_out", C.c_float * 16), ("flow_out", C.c_void_p), ("inlier", C.c_void_p),
+                ("info_flow", C.c_float), ("info_prior", C.c_float), ("rp_thres", C.c_float), ("chi2_th", C.c_float),
+                ("rounds", C.c_int32), ("its", C.c_int32)]
 
 
 class VidoError(RuntimeError):
@@ -60,6 +90,10 @@ def load_library():
     lib.vido_bgr_to_gray_dev.argtypes = [vp, vp, C.c_int, C.c_size_t, C.c_int, vp, C.c_size_t, C.c_int]
     lib.vido_orb_get_level.argtypes = [vp, C.c_int, C.c_int, vp]
     lib.vido_orb_get_candidates.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp]
+    lib.vido_poseopt_default_params.argtypes = [C.POINTER(PoseOptProblem)]
+    lib.vido_pose_opt_flow2.argtypes = [vp, C.POINTER(PoseOptProblem), C.c_int, C.POINTER(LmStats)]
+    lib.vido_ba_default_params.argtypes = [C.POINTER(BaProblem)]
+    lib.vido_ba_partial.argtypes = [vp, C.POINTER(BaProblem), C.POINTER(LmStats)]
     _lib = lib
     return lib
 
@@ -152,3 +186,53 @@ class Context:
         n = np.zeros(1, np.int32)
         self._check(self.lib.vido_orb_get_candidates(self.h, frame, level, _ptr(xs), _ptr(ys), _ptr(sc), cap, _ptr(n)))
         return xs[:n[0]].copy(), ys[:n[0]].copy(), sc[:n[0]].copy()
+
+    def ba_partial(self, poses, rel_motion, points, obs_pose, obs_point, obs_xyz, **params):
+        """Sliding-window graph optimisation (vido_ba_partial).  Inputs are copied; returns
+        (poses, rel_motion, points, iterations, stats)."""
+        poses = np.ascontiguousarray(poses, np.float32).copy()
+        rel = np.ascontiguousarray(rel_motion, np.float32).copy()
+        pts = np.ascontiguousarray(points, np.float32).copy()
+        op = np.ascontiguousarray(obs_pose, np.int32)
+        ol = np.ascontiguousarray(obs_point, np.int32)
+        ox = np.ascontiguousarray(obs_xyz, np.float32)
+        pr = BaProblem()
+        self.lib.vido_ba_default_params(C.byref(pr))
+        pr.n_poses, pr.n_points, pr.n_obs = len(poses), len(pts), len(op)
+        pr.poses, pr.rel_motion, pr.points = _ptr(poses), _ptr(rel), _ptr(pts)
+        pr.obs_pose, pr.obs_point, pr.obs_xyz = _ptr(op), _ptr(ol), _ptr(ox)
+        for k, v in params.items():
+            setattr(pr, k, v)
+        st = LmStats()
+        self._check(self.lib.vido_ba_partial(self.h, C.byref(pr), C.byref(st)))
+        return poses, rel, pts, st.iterations, st
+
+    def pose_opt_flow2(self, problems, want_stats=True):
+        """problems: list of dicts(obs, flow, depth, Tcw_init, Tcw_last, K, [params...]).  One launch for all.
+        Returns a list of (Tcw 4x4 f32, refined flow [n,2], inlier [n], n_inliers, [LmStats per round])."""
+        m = len(problems)
+        arr = (PoseOptProblem * m)()
+        keep = []
+        for k, d in enumerate(problems):
+            pr = arr[k]
+            self.lib.vido_poseopt_default_params(C.byref(pr))
+            obs = np.ascontiguousarray(d["obs"], np.float32); fl = np.ascontiguousarray(d["flow"], np.float32)
+            dep = np.ascontiguousarray(d["depth"], np.float32)
+            n = len(obs)
+            fo = np.zeros((n, 2), np.float32); inl = np.zeros(n, np.int32)
+            keep.append((obs, fl, dep, fo, inl))
+            pr.n = n
+            pr.obs_xy, pr.flow_xy, pr.depth, pr.flow_out, pr.inlier = _ptr(obs), _ptr(fl), _ptr(dep), _ptr(fo), _ptr(inl)
+            pr.Tcw_init[:] = np.asarray(d["Tcw_init"], np.float32).reshape(-1).tolist()
+            pr.Tcw_last[:] = np.asarray(d["Tcw_last"], np.float32).reshape(-1).tolist()
+            pr.fx, pr.fy, pr.cx, pr.cy = [float(v) for v in d["K"]]
+            for key, v in d.get("params", {}).items():
+                setattr(pr, key, v)
+        stats = (LmStats * (4 * m))() if want_stats else None
+        self._check(self.lib.vido_pose_opt_flow2(self.h, arr, m, stats))
+        out = []
+        for k in range(m):
+            pr = arr[k]
+            st = [stats[4 * k + r] for r in range(pr.rounds)] if want_stats else None
+            out.append((np.array(pr.Tcw_out[:], np.float32).reshape(4, 4), keep[k][3], keep[k][4], int(pr.n_inliers), st))
+        return out

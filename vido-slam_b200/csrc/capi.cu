@@ -57,8 +57,12 @@ vido_ctx* vido_create(const vido_config* cfg) {
     return nullptr;
   }
   int rc = orb_setup(ctx);
+  if (rc == VIDO_OK) rc = ba_setup(ctx, 24, 16384, 131072);
+  if (rc == VIDO_OK) rc = po_setup(ctx, 4096, 16);
   if (rc != VIDO_OK) {
     g_create_err = ctx->err;
+    po_teardown(ctx);
+    ba_teardown(ctx);
     orb_teardown(ctx);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -71,6 +75,8 @@ void vido_destroy(vido_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  po_teardown(ctx);
+  ba_teardown(ctx);
   orb_teardown(ctx);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -198,6 +204,34 @@ int vido_orb_get_candidates(vido_ctx* ctx, int frame, int level, int32_t* xs, in
   }
   *n = k;
   return VIDO_OK;
+}
+
+void vido_ba_default_params(vido_ba_problem* p) {
+  // hard-coded constants of Optimizer::PartialBatchOptimization (src/Optimizer.cc:183,192-216,806)
+  p->max_iterations = 100;
+  p->sigma2_cam = 0.0001f;
+  p->sigma2_3d = 16.f;
+  p->huber_cam = 0.01f;
+  p->huber_3d = 0.01f;
+  p->gain_threshold = 1e-3f;
+  p->fix_first = 0;
+}
+
+int vido_ba_partial(vido_ctx* ctx, vido_ba_problem* p, vido_lm_stats* stats) {
+  if (!ctx || !p) return VIDO_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  return ba_partial_host(ctx, p, stats);
+}
+
+void vido_poseopt_default_params(vido_poseopt_problem* p) {
+  p->info_flow = 0.1f; p->info_prior = 0.3f; p->rp_thres = 0.04f; p->chi2_th = 5.991f;
+  p->rounds = 4; p->its = 100;
+}
+
+int vido_pose_opt_flow2(vido_ctx* ctx, vido_poseopt_problem* problems, int nproblems, vido_lm_stats* stats) {
+  if (!ctx || !problems) return VIDO_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  return po_flow2_host(ctx, problems, nproblems, stats);
 }
 
 }  // extern "C"

@@ -69,6 +69,7 @@ struct vido_ctx {
   int32_t* d_yofs[VIDO_MAX_LEVELS] = {};
   int16_t* d_ya[VIDO_MAX_LEVELS] = {};
   CUtensorMap tmap[VIDO_MAX_LEVELS];
+  CUtensorMap* d_tmap = nullptr;     // device copy of the descriptors
   vido_keypoint* d_kp = nullptr;    // [B][kp_cap] staging for the host-pointer API
   int32_t* d_nkp = nullptr;         // [B]
   int kp_cap = 0;
@@ -78,6 +79,10 @@ struct vido_ctx {
   int last_batch = 0;
   int oct_smem_keys = 0;            // shared-memory key capacity of the octree kernel
   size_t oct_smem_bytes = 0;
+
+  // ---- graph optimisation ----
+  void* ba = nullptr;  // BaWorkspace (ba_kernels.cu)
+  void* po = nullptr;  // PoWorkspace (poseopt_kernels.cu)
 };
 
 #define VIDO_CUDA(call)                                                                     \
@@ -98,3 +103,13 @@ int orb_run(vido_ctx* ctx, const uint8_t* d_gray, int nframes, size_t frame_stri
             vido_keypoint* d_out, int cap_per_frame, int32_t* d_n_out);
 int orb_bgr_to_gray(vido_ctx* ctx, const uint8_t* d_bgr, int nframes, size_t frame_stride, int stride,
                     uint8_t* d_gray, size_t gray_frame_stride, int gray_stride);
+
+// ba_kernels.cu
+int ba_setup(vido_ctx* ctx, int capW, int capP, int capM);
+void ba_teardown(vido_ctx* ctx);
+int ba_partial_host(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st);
+
+// poseopt_kernels.cu
+int po_setup(vido_ctx* ctx, int capN, int capProblems);
+void po_teardown(vido_ctx* ctx);
+int po_flow2_host(vido_ctx* ctx, vido_poseopt_problem* prs, int nproblems, vido_lm_stats* stats);

@@ -69,7 +69,14 @@ struct TmapPack {
   CUtensorMap m[VIDO_MAX_LEVELS];
 };
 
+struct OrbLevelView {
+  const uint8_t* base;
+  size_t frame_stride;
+  int w, h, pitch;
+};
+
 struct FastParams {
+  OrbLevelView view[VIDO_MAX_LEVELS];
   int ini_thr, min_thr;
   int cells_per_frame, slots_per_frame;
   int level_cell_begin[VIDO_MAX_LEVELS + 1];
@@ -149,7 +156,7 @@ __device__ __forceinline__ int fast_score(const uint8_t* t, int bw, int thrMin) 
 #define FAST_MAXDIM 80  // max ROI edge (wCell+6); cells are 30..59 px by construction (src/ORBextractor.cc:773-776)
 #define FAST_THREADS 256
 
-__global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(const __grid_constant__ TmapPack maps,
+__global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(const CUtensorMap* __restrict__ maps,
                                                                   const OrbCell* __restrict__ cells, FastParams P,
                                                                   uint32_t* __restrict__ slots,
                                                                   int32_t* __restrict__ cell_count) {
@@ -167,11 +174,16 @@ __global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(const __grid_c
   for (int l = 1; l < VIDO_MAX_LEVELS; l++)
     if (l < P.nlevels && cell_id >= P.level_cell_begin[l]) level = l;
   const int bw = P.boxW[level], bh = P.boxH[level];
-  uint8_t* tile = smem;                               // bw x bh, filled by TMA
+  // TMA needs the innermost start coordinate 16-byte aligned (measured: unaligned x0 -> illegal instruction),
+  // so the box starts at x0 & ~15 and the ROI sits xoff bytes into each tile row.
+  const int xoff = cell.x0 & 15, x0a = cell.x0 - xoff;
+  uint8_t* tile0 = smem;                              // bw x bh, filled by TMA
+  const uint8_t* tile = tile0 + xoff;
   uint8_t* score = smem + ((bw * bh + 127) & ~127);   // (rh) x (rw) scores, 0 outside the detection zone
   const int rw = cell.rw, rh = cell.rh;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+#ifndef VIDO_NO_TMA
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -182,8 +194,8 @@ __global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(const __grid_c
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(bw * bh) : "memory");
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::
-            "r"(smem_u32(tile)),
-        "l"(&maps.m[level]), "r"(cell.x0), "r"(cell.y0), "r"(b), "r"(smem_u32(&bar))
+            "r"(smem_u32(tile0)),
+        "l"(maps + level), "r"(x0a), "r"(cell.y0), "r"(b), "r"(smem_u32(&bar))
         : "memory");
   }
   // zero the score array while the tile is in flight
@@ -200,6 +212,20 @@ __global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(const __grid_c
   }
   __syncthreads();
 
+#else
+  {  // debug build without TMA: plain cooperative tile load (zero fill outside the level)
+    const OrbLevelView lvw = P.view[level];
+    const uint8_t* img = lvw.base + (size_t)b * lvw.frame_stride;
+    for (int i = tid; i < bw * bh; i += FAST_THREADS) {
+      int ty = i / bw, tx = i - ty * bw;
+      int gx = x0a + tx, gy = cell.y0 + ty;
+      tile0[i] = (gx < lvw.w && gy < lvw.h) ? img[(size_t)gy * lvw.pitch + gx] : 0;
+    }
+    for (int i = tid; i < rw * rh; i += FAST_THREADS) score[i] = 0;
+    (void)bar;
+  }
+  __syncthreads();
+#endif
   // ---- scores of the detection zone [3, rw-3) x [3, rh-3)
   const int iw = rw - 6, ih = rh - 6;
   if (iw > 0 && ih > 0) {
@@ -909,7 +935,7 @@ int orb_setup(vido_ctx* ctx) {
           slot_total += cell.slot_cap;
           L.cand_cap += cell.slot_cap;
           if (cell.rw > FAST_MAXDIM || cell.rh > FAST_MAXDIM) { ctx->err = "FAST cell larger than 80 px"; return VIDO_ERR_ARG; }
-          L.boxW = std::max(L.boxW, (int)align_up(cell.rw, 16));
+          L.boxW = std::max(L.boxW, (int)align_up(cell.rw + 15, 16));  // room for the 16-byte start alignment
           L.boxH = std::max(L.boxH, cell.rh);
           ctx->cells.push_back(cell);
           L.ncells++;
@@ -1007,12 +1033,15 @@ int orb_setup(vido_ctx* ctx) {
         return VIDO_ERR_CUDA;
       }
     }
+    // descriptors live in global memory (64-byte aligned); the FAST kernel indexes them by level
+    VIDO_CUDA(cudaMalloc(&ctx->d_tmap, sizeof(CUtensorMap) * VIDO_MAX_LEVELS));
+    VIDO_CUDA(cudaMemcpy(ctx->d_tmap, ctx->tmap, sizeof(CUtensorMap) * c.nlevels, cudaMemcpyHostToDevice));
   }
   // ---- kernel attributes
   {
     int maxBox = 0;
     for (int l = 0; l < c.nlevels; l++) maxBox = std::max(maxBox, (int)align_up((size_t)ctx->lv[l].boxW * ctx->lv[l].boxH, 128));
-    size_t fast_smem = maxBox + FAST_MAXDIM * FAST_MAXDIM + 128;
+    size_t fast_smem = maxBox + FAST_MAXDIM * FAST_MAXDIM + 256;
     VIDO_CUDA(cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
   }
   {
@@ -1041,7 +1070,7 @@ int orb_setup(vido_ctx* ctx) {
 void orb_teardown(vido_ctx* ctx) {
   cudaFree(ctx->d_pyr); cudaFree(ctx->d_cells); cudaFree(ctx->d_slots); cudaFree(ctx->d_cell_count);
   cudaFree(ctx->d_oct_keys); cudaFree(ctx->d_oct_perm); cudaFree(ctx->d_level_out); cudaFree(ctx->d_level_cnt);
-  cudaFree(ctx->d_kp); cudaFree(ctx->d_nkp); cudaFree(ctx->d_in); cudaFree(ctx->d_err);
+  cudaFree(ctx->d_kp); cudaFree(ctx->d_nkp); cudaFree(ctx->d_in); cudaFree(ctx->d_err); cudaFree(ctx->d_tmap);
   for (int l = 0; l < VIDO_MAX_LEVELS; l++) {
     cudaFree(ctx->d_xofs[l]); cudaFree(ctx->d_xa[l]); cudaFree(ctx->d_yofs[l]); cudaFree(ctx->d_ya[l]);
   }
@@ -1094,16 +1123,14 @@ int orb_run(vido_ctx* ctx, const uint8_t* d_gray, int nframes, size_t frame_stri
     ctx->launches++;
   }
   if (ctx->cells_per_frame > 0) {
-    TmapPack maps;
     FastParams P;
     memset(&P, 0, sizeof P);
     for (int l = 0; l < c.nlevels; l++) {
-      maps.m[l] = ctx->tmap[l];
       P.level_cell_begin[l] = ctx->lv[l].cell_begin;
       P.boxW[l] = ctx->lv[l].boxW;
       P.boxH[l] = ctx->lv[l].boxH;
+      P.view[l] = {ctx->d_pyr + ctx->lv[l].base, ctx->lv[l].frame_stride, ctx->lv[l].w, ctx->lv[l].h, ctx->lv[l].pitch};
     }
-    for (int l = c.nlevels; l < VIDO_MAX_LEVELS; l++) maps.m[l] = ctx->tmap[0];
     P.level_cell_begin[c.nlevels] = ctx->cells_per_frame;
     P.ini_thr = c.ini_th_fast;
     P.min_thr = c.min_th_fast;
@@ -1112,9 +1139,9 @@ int orb_run(vido_ctx* ctx, const uint8_t* d_gray, int nframes, size_t frame_stri
     P.nlevels = c.nlevels;
     int maxBox = 0;
     for (int l = 0; l < c.nlevels; l++) maxBox = std::max(maxBox, (int)align_up((size_t)ctx->lv[l].boxW * ctx->lv[l].boxH, 128));
-    size_t smem = maxBox + FAST_MAXDIM * FAST_MAXDIM + 128;
+    size_t smem = maxBox + FAST_MAXDIM * FAST_MAXDIM + 256;
     dim3 grid(ctx->cells_per_frame, B);
-    fast_cells_kernel<<<grid, FAST_THREADS, smem, st>>>(maps, ctx->d_cells, P, ctx->d_slots, ctx->d_cell_count);
+    fast_cells_kernel<<<grid, FAST_THREADS, smem, st>>>(ctx->d_tmap, ctx->d_cells, P, ctx->d_slots, ctx->d_cell_count);
     ctx->launches++;
   }
   {

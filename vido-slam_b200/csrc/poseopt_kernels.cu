@@ -1,0 +1,581 @@
+// poseopt_kernels.cu -- per-frame joint optical-flow + pose optimisation, one CTA per problem, the four
+// optimisation rounds and every LM iteration inside one launch.
+//
+// Replaces Optimizer::PoseOptimizationFlow2Cam (src/Optimizer.cc:2622-2824) and, with another initial transform,
+// Optimizer::PoseOptimizationFlow2 (:3037-3253):
+//   VertexSE3Expmap (T <- exp(dx) T)      g2o/types/types_six_dof_expmap.h:67-85, se3quat.h:228-262
+//   EdgeSE3ProjectFlow2                   g2o/types/types_six_dof_expmap.h:436-476, types_six_dof_expmap.cpp:805-845
+//   EdgeFlowPrior                         g2o/types/types_six_dof_expmap.h:414-432
+//   Schur complement over the 2-dof flow vertices + dense 6x6 solve   g2o/core/block_solver.hpp:367-486,
+//                                         g2o/solvers/linear_solver_dense.h:65-116
+// Because both Jacobians w.r.t. the flow vertex are the identity, H_ll = (w + w_prior) I and the Schur complement
+// collapses to a weighted sum of J^T J: one 27-value block reduction (warp shuffles) per solve.
+#include <cstring>
+
+#include "ctx.h"
+#include "lm_device.h"
+
+#define PO_THREADS 256
+
+struct PoArgs {
+  int n;
+  const float* obs_xy;   // [n][2]
+  const float* flow_xy;  // [n][2]
+  const float* depth;    // [n]
+  const float* Tcw_init; // [16]
+  const float* Tcw_last; // [16]
+  float fx, fy, cx, cy;
+  double info_f, info_p, delta;
+  float th0, th1;        // chi2 gates: round 0, rounds 1..3
+  int rounds, its;
+  // workspace
+  double* Xw;      // [3n]
+  double* flow;    // [2][2n]
+  double* xl;      // [2n] last solved flow increment
+  double* eProj;   // [2n]
+  int* level;      // [n]
+  // outputs
+  float* Tcw_out;  // [16]
+  float* flow_out; // [n][2]
+  int* inlier;     // [n]
+  int* n_inliers;  // [1]
+  LmCtl* ctl;      // [rounds] final controller state per round
+  LmRec* rec;      // [rounds][VIDO_LM_REC]
+};
+
+struct PoseQ {
+  double q[4];  // w x y z
+  double t[3];
+};
+
+__device__ __forceinline__ void q_rot(const double* q, const double* v, double* o) {
+  const double ux = q[1], uy = q[2], uz = q[3], w = q[0];
+  double cx = 2 * (uy * v[2] - uz * v[1]), cy = 2 * (uz * v[0] - ux * v[2]), cz = 2 * (ux * v[1] - uy * v[0]);
+  o[0] = v[0] + w * cx + (uy * cz - uz * cy);
+  o[1] = v[1] + w * cy + (uz * cx - ux * cz);
+  o[2] = v[2] + w * cz + (ux * cy - uy * cx);
+}
+
+__device__ void quat_from_R_dev(const double* R, double* q) {
+  double t = R[0] + R[4] + R[8];
+  if (t > 0) {
+    t = sqrt(t + 1.0);
+    q[0] = 0.5 * t;
+    t = 0.5 / t;
+    q[1] = (R[7] - R[5]) * t; q[2] = (R[2] - R[6]) * t; q[3] = (R[3] - R[1]) * t;
+  } else {
+    int i = 0;
+    if (R[4] > R[0]) i = 1;
+    if (R[8] > R[4 * i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
+    q[1 + i] = 0.5 * t;
+    t = 0.5 / t;
+    q[0] = (R[3 * k + j] - R[3 * j + k]) * t;
+    q[1 + j] = (R[3 * j + i] + R[3 * i + j]) * t;
+    q[1 + k] = (R[3 * k + i] + R[3 * i + k]) * t;
+  }
+  if (q[0] < 0) { q[0] = -q[0]; q[1] = -q[1]; q[2] = -q[2]; q[3] = -q[3]; }
+  const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
+}
+
+// T <- exp(u) * T, u = [omega, upsilon] (SE3Quat::exp, se3quat.h:228-262)
+__device__ void se3_exp_mul(const double* u, const PoseQ& T, PoseQ& o) {
+  const double wx = u[0], wy = u[1], wz = u[2];
+  const double theta = sqrt(wx * wx + wy * wy + wz * wz);
+  const double Om[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
+  double Om2[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) Om2[3 * i + j] = Om[3 * i] * Om[j] + Om[3 * i + 1] * Om[3 + j] + Om[3 * i + 2] * Om[6 + j];
+  double R[9], V[9];
+  if (theta < 0.00001) {
+    for (int i = 0; i < 9; i++) { R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + Om[i] + Om2[i]; V[i] = R[i]; }
+  } else {
+    const double a = sin(theta) / theta, b = (1 - cos(theta)) / (theta * theta), c = (theta - sin(theta)) / pow(theta, 3);
+    for (int i = 0; i < 9; i++) {
+      const double I = (i % 4 == 0) ? 1.0 : 0.0;
+      R[i] = I + a * Om[i] + b * Om2[i];
+      V[i] = I + b * Om[i] + c * Om2[i];
+    }
+  }
+  double dq[4], dt[3];
+  quat_from_R_dev(R, dq);
+  for (int i = 0; i < 3; i++) dt[i] = V[3 * i] * u[3] + V[3 * i + 1] * u[4] + V[3 * i + 2] * u[5];
+  double rt[3];
+  q_rot(dq, T.t, rt);
+  o.t[0] = dt[0] + rt[0]; o.t[1] = dt[1] + rt[1]; o.t[2] = dt[2] + rt[2];
+  double q[4];
+  q[0] = dq[0] * T.q[0] - dq[1] * T.q[1] - dq[2] * T.q[2] - dq[3] * T.q[3];
+  q[1] = dq[0] * T.q[1] + dq[1] * T.q[0] + dq[2] * T.q[3] - dq[3] * T.q[2];
+  q[2] = dq[0] * T.q[2] + dq[2] * T.q[0] + dq[3] * T.q[1] - dq[1] * T.q[3];
+  q[3] = dq[0] * T.q[3] + dq[3] * T.q[0] + dq[1] * T.q[2] - dq[2] * T.q[1];
+  if (q[0] < 0) { q[0] = -q[0]; q[1] = -q[1]; q[2] = -q[2]; q[3] = -q[3]; }
+  const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  for (int i = 0; i < 4; i++) o.q[i] = q[i] / n;
+}
+
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int NV>
+__device__ __forceinline__ void bsum(double* v, double* sm) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; k++) v[k] = wsum(v[k]);
+  __syncthreads();
+  if (lane == 0)
+    for (int k = 0; k < NV; k++) sm[warp * NV + k] = v[k];
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0;
+    for (int w = 0; w < nw; w++) s += sm[w * NV + threadIdx.x];
+    sm[threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void huber_dev(double e, double delta, double& rho0, double& w) {
+  const double dsqr = delta * delta;
+  if (e <= dsqr) { rho0 = e; w = 1.0; }
+  else { const double s = sqrt(e); rho0 = 2 * s * delta - dsqr; w = delta / s; }
+}
+
+// projection error and (optionally) the 2x6 Jacobian w.r.t. the pose at transform T
+__device__ __forceinline__ void proj_edge(const PoArgs& a, const PoseQ& T, int i, const double* fl, double* e, double* J) {
+  double pc[3];
+  q_rot(T.q, a.Xw + 3 * (size_t)i, pc);
+  pc[0] += T.t[0]; pc[1] += T.t[1]; pc[2] += T.t[2];
+  const double fx = a.fx, fy = a.fy;
+  e[0] = ((double)a.obs_xy[2 * i] + fl[0]) - (pc[0] / pc[2] * fx + (double)a.cx);
+  e[1] = ((double)a.obs_xy[2 * i + 1] + fl[1]) - (pc[1] / pc[2] * fy + (double)a.cy);
+  if (J) {
+    const double x = pc[0], y = pc[1], z = pc[2], z2 = z * z;
+    J[0] = x * y / z2 * fx; J[1] = -(1 + (x * x / z2)) * fx; J[2] = y / z * fx; J[3] = -1. / z * fx; J[4] = 0; J[5] = x / z2 * fx;
+    J[6] = (1 + y * y / z2) * fy; J[7] = -x * y / z2 * fy; J[8] = -x / z * fy; J[9] = 0; J[10] = -1. / z * fy; J[11] = y / z2 * fy;
+  }
+}
+
+__global__ void __launch_bounds__(PO_THREADS) poseopt_flow2_kernel(const PoArgs* __restrict__ problems) {
+  const PoArgs a = problems[blockIdx.x];
+  const int n = a.n, tid = threadIdx.x;
+  __shared__ double red[(PO_THREADS / 32) * 27 + 32];
+  __shared__ PoseQ T[2];
+  __shared__ PoseQ Tinit;
+  __shared__ LmCtl ctl;
+  __shared__ double Hpp[36], bp[6], xp[6];
+  __shared__ int s_robust, s_nbad;
+
+  if (n < 3) {  // "if(nInitialCorrespondences<3) return 0;" -- nothing is touched
+    for (int i = tid; i < 16; i += PO_THREADS) a.Tcw_out[i] = a.Tcw_init[i];
+    for (int i = tid; i < n; i += PO_THREADS) {
+      a.flow_out[2 * i] = a.flow_xy[2 * i]; a.flow_out[2 * i + 1] = a.flow_xy[2 * i + 1];
+      a.inlier[i] = 1;
+    }
+    if (tid == 0) *a.n_inliers = 0;
+    return;
+  }
+  // ---- setup: Twl in float like the reference's cv::Mat code, world points in double
+  if (tid == 0) {
+    const float* L = a.Tcw_init;
+    double R[9] = {L[0], L[1], L[2], L[4], L[5], L[6], L[8], L[9], L[10]};
+    quat_from_R_dev(R, Tinit.q);
+    Tinit.t[0] = L[3]; Tinit.t[1] = L[7]; Tinit.t[2] = L[11];
+    s_robust = 1;
+    for (int k = 0; k < 6; k++) xp[k] = 0;
+  }
+  {
+    const float* L = a.Tcw_last;
+    float Rwl[9], twl[3];
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) Rwl[3 * r + c] = L[4 * c + r];
+    for (int r = 0; r < 3; r++) {
+      float s = 0.f;
+      for (int k = 0; k < 3; k++) s = __fadd_rn(s, __fmul_rn(-Rwl[3 * r + k], L[4 * k + 3]));
+      twl[r] = s;
+    }
+    for (int i = tid; i < n; i += PO_THREADS) {
+      const double ox = a.obs_xy[2 * i], oy = a.obs_xy[2 * i + 1], d = a.depth[i];
+      const double X[3] = {(ox - (double)a.cx) * d / (double)a.fx, (oy - (double)a.cy) * d / (double)a.fy, d};
+      for (int r = 0; r < 3; r++)
+        a.Xw[3 * (size_t)i + r] = (double)Rwl[3 * r] * X[0] + (double)Rwl[3 * r + 1] * X[1] + (double)Rwl[3 * r + 2] * X[2] + (double)twl[r];
+      a.flow[2 * i] = a.flow_xy[2 * i]; a.flow[2 * i + 1] = a.flow_xy[2 * i + 1];
+      a.xl[2 * i] = 0; a.xl[2 * i + 1] = 0;
+      a.level[i] = 0;
+    }
+  }
+  __syncthreads();
+
+  double* const flowbuf[2] = {a.flow, a.flow + 2 * (size_t)n};
+  for (int round = 0; round < a.rounds; round++) {
+    if (tid == 0) {
+      lm_reset(&ctl);
+      T[0] = Tinit;
+    }
+    __syncthreads();
+    const int robust = s_robust;
+    // ---- robust chi2 at the start state (buffer 0)
+    {
+      double chi = 0;
+      for (int i = tid; i < n; i += PO_THREADS) {
+        const double* fl = flowbuf[0] + 2 * i;
+        if (a.level[i] == 0) {
+          double e[2], r0, w;
+          proj_edge(a, T[0], i, fl, e, nullptr);
+          a.eProj[2 * i] = e[0]; a.eProj[2 * i + 1] = e[1];
+          const double c = (e[0] * e[0] + e[1] * e[1]) * a.info_f;
+          if (robust) { huber_dev(c, a.delta, r0, w); chi += r0; } else chi += c;
+        }
+        const double p0 = fl[0] - (double)a.flow_xy[2 * i], p1 = fl[1] - (double)a.flow_xy[2 * i + 1];
+        chi += (p0 * p0 + p1 * p1) * a.info_p;
+      }
+      double v[1] = {chi};
+      bsum<1>(v, red);
+      if (tid == 0) ctl.currentChi = red[0];
+      __syncthreads();
+    }
+    for (int it = 0; it < a.its; it++) {
+      if (ctl.stop_flag || !ctl.ok) break;
+      const int cur = ctl.cur;
+      const PoseQ Tc = T[cur];
+      const double* fcur = flowbuf[cur];
+      double* ftrial = flowbuf[cur ^ 1];
+      // ---- build: H_pp, b_p and the diagonal maximum
+      double acc[27];
+#pragma unroll
+      for (int k = 0; k < 27; k++) acc[k] = 0;
+      double mx = 0;
+      for (int i = tid; i < n; i += PO_THREADS) {
+        double h = a.info_p;
+        if (a.level[i] == 0) {
+          double e[2], J[12], r0, w = 1.0;
+          proj_edge(a, Tc, i, fcur + 2 * i, e, J);
+          a.eProj[2 * i] = e[0]; a.eProj[2 * i + 1] = e[1];
+          if (robust) huber_dev((e[0] * e[0] + e[1] * e[1]) * a.info_f, a.delta, r0, w);
+          w *= a.info_f;
+          h += w;
+          int idx = 0;
+#pragma unroll
+          for (int r = 0; r < 6; r++) {
+            acc[21 + r] -= w * (J[r] * e[0] + J[6 + r] * e[1]);
+#pragma unroll
+            for (int c = r; c < 6; c++) acc[idx++] += w * (J[r] * J[c] + J[6 + r] * J[6 + c]);
+          }
+        }
+        mx = fmax(mx, h);
+      }
+      bsum<27>(acc, red);
+      if (tid == 0) {
+        int idx = 0;
+        for (int r = 0; r < 6; r++) {
+          bp[r] = red[21 + r];
+          for (int c = r; c < 6; c++) { Hpp[6 * r + c] = red[idx]; Hpp[6 * c + r] = red[idx]; idx++; }
+        }
+      }
+      __syncthreads();
+      {  // block max
+        const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) red[warp] = mx;
+        __syncthreads();
+        if (tid == 0) {
+          double m = 0;
+          for (int w = 0; w < PO_THREADS / 32; w++) m = fmax(m, red[w]);
+          for (int r = 0; r < 6; r++) m = fmax(m, fabs(Hpp[7 * r]));
+          lm_begin_iteration(&ctl, it, m, -1.0);
+        }
+        __syncthreads();
+      }
+      // ---- trials
+      while (true) {
+        const double lambda = ctl.lambda;
+#pragma unroll
+        for (int k = 0; k < 27; k++) acc[k] = 0;
+        for (int i = tid; i < n; i += PO_THREADS) {
+          if (a.level[i] != 0) continue;
+          double e[2], J[12], r0, w = 1.0;
+          proj_edge(a, Tc, i, fcur + 2 * i, e, J);
+          if (robust) huber_dev((e[0] * e[0] + e[1] * e[1]) * a.info_f, a.delta, r0, w);
+          w *= a.info_f;
+          const double h = w + a.info_p + lambda;
+          const double p0 = fcur[2 * i] - (double)a.flow_xy[2 * i], p1 = fcur[2 * i + 1] - (double)a.flow_xy[2 * i + 1];
+          const double bl0 = -w * e[0] - a.info_p * p0, bl1 = -w * e[1] - a.info_p * p1;
+          const double s = w * w / h, g = w / h;
+          int idx = 0;
+#pragma unroll
+          for (int r = 0; r < 6; r++) {
+            acc[21 + r] += g * (J[r] * bl0 + J[6 + r] * bl1);
+#pragma unroll
+            for (int c = r; c < 6; c++) acc[idx++] += s * (J[r] * J[c] + J[6 + r] * J[6 + c]);
+          }
+        }
+        bsum<27>(acc, red);
+        if (tid == 0) {  // reduced 6x6 system, LDL^T with positivity test
+          double S[36], bs[6];
+          int idx = 0;
+          for (int r = 0; r < 6; r++) {
+            bs[r] = bp[r] - red[21 + r];
+            for (int c = r; c < 6; c++) {
+              const double v = Hpp[6 * r + c] - red[idx++] + ((r == c) ? lambda : 0.0);
+              S[6 * r + c] = v; S[6 * c + r] = v;
+            }
+          }
+          double Lm[36], D[6];
+          for (int k = 0; k < 36; k++) Lm[k] = 0;
+          bool ok = true;
+          for (int j = 0; j < 6 && ok; j++) {
+            double d = S[7 * j];
+            for (int k = 0; k < j; k++) d -= Lm[6 * j + k] * Lm[6 * j + k] * D[k];
+            if (!(d > 0)) { ok = false; break; }
+            D[j] = d;
+            Lm[7 * j] = 1;
+            for (int i2 = j + 1; i2 < 6; i2++) {
+              double s2 = S[6 * i2 + j];
+              for (int k = 0; k < j; k++) s2 -= Lm[6 * i2 + k] * Lm[6 * j + k] * D[k];
+              Lm[6 * i2 + j] = s2 / d;
+            }
+          }
+          if (ok) {
+            double y[6];
+            for (int i2 = 0; i2 < 6; i2++) {
+              double s2 = bs[i2];
+              for (int k = 0; k < i2; k++) s2 -= Lm[6 * i2 + k] * y[k];
+              y[i2] = s2;
+            }
+            for (int i2 = 0; i2 < 6; i2++) y[i2] /= D[i2];
+            for (int i2 = 5; i2 >= 0; i2--) {
+              double s2 = y[i2];
+              for (int k = i2 + 1; k < 6; k++) s2 -= Lm[6 * k + i2] * xp[k];
+              xp[i2] = s2;
+            }
+          }
+          ctl.fail = ok ? 0 : 1;  // on failure x keeps its previous content
+          se3_exp_mul(xp, Tc, T[cur ^ 1]);
+        }
+        __syncthreads();
+        const int failed = ctl.fail;
+        const PoseQ Tt = T[cur ^ 1];
+        // ---- flow increments, trial state, chi2 and scale
+        double chi = 0, scale = 0;
+        for (int i = tid; i < n; i += PO_THREADS) {
+          const double p0 = fcur[2 * i] - (double)a.flow_xy[2 * i], p1 = fcur[2 * i + 1] - (double)a.flow_xy[2 * i + 1];
+          double bl0 = -a.info_p * p0, bl1 = -a.info_p * p1, h = a.info_p + lambda;
+          double x0, x1;
+          if (a.level[i] == 0) {
+            double e[2], J[12], r0, w = 1.0;
+            proj_edge(a, Tc, i, fcur + 2 * i, e, J);
+            if (robust) huber_dev((e[0] * e[0] + e[1] * e[1]) * a.info_f, a.delta, r0, w);
+            w *= a.info_f;
+            h += w;
+            bl0 -= w * e[0]; bl1 -= w * e[1];
+            double jx0 = 0, jx1 = 0;
+#pragma unroll
+            for (int r = 0; r < 6; r++) { jx0 += J[r] * xp[r]; jx1 += J[6 + r] * xp[r]; }
+            x0 = (bl0 - w * jx0) / h;
+            x1 = (bl1 - w * jx1) / h;
+          } else {
+            x0 = bl0 / h;
+            x1 = bl1 / h;
+          }
+          if (failed) { x0 = a.xl[2 * i]; x1 = a.xl[2 * i + 1]; }
+          else { a.xl[2 * i] = x0; a.xl[2 * i + 1] = x1; }
+          const double f0 = fcur[2 * i] + x0, f1 = fcur[2 * i + 1] + x1;
+          ftrial[2 * i] = f0; ftrial[2 * i + 1] = f1;
+          scale += x0 * (lambda * x0 + bl0) + x1 * (lambda * x1 + bl1);
+          if (a.level[i] == 0) {
+            double e[2], r0, w;
+            const double ft[2] = {f0, f1};
+            proj_edge(a, Tt, i, ft, e, nullptr);
+            a.eProj[2 * i] = e[0]; a.eProj[2 * i + 1] = e[1];
+            const double c = (e[0] * e[0] + e[1] * e[1]) * a.info_f;
+            if (robust) { huber_dev(c, a.delta, r0, w); chi += r0; } else chi += c;
+          }
+          const double q0 = f0 - (double)a.flow_xy[2 * i], q1 = f1 - (double)a.flow_xy[2 * i + 1];
+          chi += (q0 * q0 + q1 * q1) * a.info_p;
+        }
+        double v[2] = {chi, scale};
+        bsum<2>(v, red);
+        if (tid == 0) {
+          double sc = red[1];
+          for (int r = 0; r < 6; r++) sc += xp[r] * (lambda * xp[r] + bp[r]);
+          lm_trial(&ctl, red[0], sc, failed);
+        }
+        __syncthreads();
+        if (!lm_more_trials(&ctl)) break;
+      }
+      if (tid == 0) lm_end_iteration(&ctl, it, -1.0, a.rec ? a.rec + (size_t)round * VIDO_LM_REC : nullptr);
+      __syncthreads();
+    }
+    // ---- classify (src/Optimizer.cc:2751-2794); accepted state -> buffer 0 for the next round
+    const int cur = ctl.cur;
+    const float th = (round == 0) ? a.th0 : a.th1;
+    int bad = 0;
+    for (int i = tid; i < n; i += PO_THREADS) {
+      const double f0 = flowbuf[cur][2 * i], f1 = flowbuf[cur][2 * i + 1];
+      if (a.level[i] != 0) {  // demoted edges are re-evaluated at the final estimate
+        double e[2];
+        const double ft[2] = {f0, f1};
+        proj_edge(a, T[cur], i, ft, e, nullptr);
+        a.eProj[2 * i] = e[0]; a.eProj[2 * i + 1] = e[1];
+      }
+      const float chi2 = (float)((a.eProj[2 * i] * a.eProj[2 * i] + a.eProj[2 * i + 1] * a.eProj[2 * i + 1]) * a.info_f);
+      if (chi2 > th) { a.level[i] = 1; bad++; }
+      else a.level[i] = 0;
+      flowbuf[0][2 * i] = f0; flowbuf[0][2 * i + 1] = f1;
+    }
+    {
+      double v[1] = {(double)bad};
+      bsum<1>(v, red);
+      if (tid == 0) {
+        s_nbad = (int)(red[0] + 0.5);
+        if (round == 2) s_robust = 0;
+        if (a.ctl) a.ctl[round] = ctl;
+        T[0] = T[cur];  // keep the final pose of this round (overwritten by the reset unless it is the last round)
+      }
+      __syncthreads();
+    }
+  }
+  // ---- outputs: pose (SE3Quat -> homogeneous -> float), refined flows, inlier flags
+  if (tid == 0) {
+    const PoseQ& F = T[0];
+    const double w = F.q[0], x = F.q[1], y = F.q[2], z = F.q[3];
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z, twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x,
+                 txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    const double R[9] = {1 - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1 - (txx + tzz), tyz - twx, txz - twy, tyz + twx, 1 - (txx + tyy)};
+    for (int r = 0; r < 3; r++) {
+      for (int c = 0; c < 3; c++) a.Tcw_out[4 * r + c] = (float)R[3 * r + c];
+      a.Tcw_out[4 * r + 3] = (float)F.t[r];
+    }
+    a.Tcw_out[12] = 0.f; a.Tcw_out[13] = 0.f; a.Tcw_out[14] = 0.f; a.Tcw_out[15] = 1.f;
+    *a.n_inliers = n - s_nbad;
+  }
+  for (int i = tid; i < n; i += PO_THREADS) {
+    a.flow_out[2 * i] = (float)flowbuf[0][2 * i];
+    a.flow_out[2 * i + 1] = (float)flowbuf[0][2 * i + 1];
+    a.inlier[i] = a.level[i] == 0;
+  }
+}
+
+// =========================================================================================================
+// host side
+// =========================================================================================================
+struct PoWorkspace {
+  int capN = 0, capProblems = 0;
+  char* d_base = nullptr;
+  PoArgs* d_args = nullptr;
+  // per-slot device arrays
+  float *obs, *flow_in, *depth, *Tinit, *Tlast, *Tout, *flow_out;
+  double *Xw, *flow, *xl, *eProj;
+  int *level, *inlier, *ninl;
+  LmCtl* ctl;
+  LmRec* rec;
+};
+
+int po_setup(vido_ctx* ctx, int capN, int capProblems) {
+  PoWorkspace* ws = new PoWorkspace();
+  ctx->po = ws;
+  ws->capN = capN;
+  ws->capProblems = capProblems;
+  const size_t N = (size_t)capN * capProblems;
+  VIDO_CUDA(cudaMalloc(&ws->d_args, sizeof(PoArgs) * capProblems));
+  VIDO_CUDA(cudaMalloc(&ws->obs, sizeof(float) * 2 * N));
+  VIDO_CUDA(cudaMalloc(&ws->flow_in, sizeof(float) * 2 * N));
+  VIDO_CUDA(cudaMalloc(&ws->depth, sizeof(float) * N));
+  VIDO_CUDA(cudaMalloc(&ws->Tinit, sizeof(float) * 16 * capProblems));
+  VIDO_CUDA(cudaMalloc(&ws->Tlast, sizeof(float) * 16 * capProblems));
+  VIDO_CUDA(cudaMalloc(&ws->Tout, sizeof(float) * 16 * capProblems));
+  VIDO_CUDA(cudaMalloc(&ws->flow_out, sizeof(float) * 2 * N));
+  VIDO_CUDA(cudaMalloc(&ws->Xw, sizeof(double) * 3 * N));
+  VIDO_CUDA(cudaMalloc(&ws->flow, sizeof(double) * 4 * N));
+  VIDO_CUDA(cudaMalloc(&ws->xl, sizeof(double) * 2 * N));
+  VIDO_CUDA(cudaMalloc(&ws->eProj, sizeof(double) * 2 * N));
+  VIDO_CUDA(cudaMalloc(&ws->level, sizeof(int) * N));
+  VIDO_CUDA(cudaMalloc(&ws->inlier, sizeof(int) * N));
+  VIDO_CUDA(cudaMalloc(&ws->ninl, sizeof(int) * capProblems));
+  VIDO_CUDA(cudaMalloc(&ws->ctl, sizeof(LmCtl) * 4 * capProblems));
+  VIDO_CUDA(cudaMalloc(&ws->rec, sizeof(LmRec) * VIDO_LM_REC * 4 * capProblems));
+  return VIDO_OK;
+}
+
+void po_teardown(vido_ctx* ctx) {
+  PoWorkspace* ws = (PoWorkspace*)ctx->po;
+  if (!ws) return;
+  cudaFree(ws->d_args); cudaFree(ws->obs); cudaFree(ws->flow_in); cudaFree(ws->depth); cudaFree(ws->Tinit);
+  cudaFree(ws->Tlast); cudaFree(ws->Tout); cudaFree(ws->flow_out); cudaFree(ws->Xw); cudaFree(ws->flow);
+  cudaFree(ws->xl); cudaFree(ws->eProj); cudaFree(ws->level); cudaFree(ws->inlier); cudaFree(ws->ninl);
+  cudaFree(ws->ctl); cudaFree(ws->rec);
+  delete ws;
+  ctx->po = nullptr;
+}
+
+int po_flow2_host(vido_ctx* ctx, vido_poseopt_problem* prs, int nproblems, vido_lm_stats* stats) {
+  PoWorkspace* ws = (PoWorkspace*)ctx->po;
+  if (nproblems < 1 || nproblems > ws->capProblems) { ctx->err = "too many pose problems"; return VIDO_ERR_CAPACITY; }
+  cudaStream_t s = ctx->stream;
+  std::vector<PoArgs> h(nproblems);
+  for (int k = 0; k < nproblems; k++) {
+    vido_poseopt_problem& p = prs[k];
+    if (p.n > ws->capN || p.n < 0 || p.rounds > 4 || p.rounds < 1) { ctx->err = "pose problem exceeds capacity"; return VIDO_ERR_CAPACITY; }
+    const size_t off = (size_t)k * ws->capN;
+    PoArgs& a = h[k];
+    memset(&a, 0, sizeof a);
+    a.n = p.n;
+    a.obs_xy = ws->obs + 2 * off; a.flow_xy = ws->flow_in + 2 * off; a.depth = ws->depth + off;
+    a.Tcw_init = ws->Tinit + 16 * k; a.Tcw_last = ws->Tlast + 16 * k;
+    a.fx = p.fx; a.fy = p.fy; a.cx = p.cx; a.cy = p.cy;
+    a.info_f = (p.info_flow == 0.1f) ? 0.1 : (double)p.info_flow;   // Matrix2d literals of the reference are doubles
+    a.info_p = (p.info_prior == 0.3f) ? 0.3 : (p.info_prior == 0.5f ? 0.5 : (double)p.info_prior);
+    a.delta = (double)sqrtf(p.rp_thres);
+    a.th0 = p.rp_thres; a.th1 = p.chi2_th;
+    a.rounds = p.rounds; a.its = p.its;
+    a.Xw = ws->Xw + 3 * off; a.flow = ws->flow + 4 * off; a.xl = ws->xl + 2 * off; a.eProj = ws->eProj + 2 * off;
+    a.level = ws->level + off;
+    a.Tcw_out = ws->Tout + 16 * k; a.flow_out = ws->flow_out + 2 * off; a.inlier = ws->inlier + off; a.n_inliers = ws->ninl + k;
+    a.ctl = ws->ctl + 4 * k;
+    a.rec = stats ? ws->rec + (size_t)4 * VIDO_LM_REC * k : nullptr;
+    if (p.n) {
+      VIDO_CUDA(cudaMemcpyAsync((void*)a.obs_xy, p.obs_xy, sizeof(float) * 2 * p.n, cudaMemcpyHostToDevice, s));
+      VIDO_CUDA(cudaMemcpyAsync((void*)a.flow_xy, p.flow_xy, sizeof(float) * 2 * p.n, cudaMemcpyHostToDevice, s));
+      VIDO_CUDA(cudaMemcpyAsync((void*)a.depth, p.depth, sizeof(float) * p.n, cudaMemcpyHostToDevice, s));
+    }
+    VIDO_CUDA(cudaMemcpyAsync((void*)a.Tcw_init, p.Tcw_init, sizeof(float) * 16, cudaMemcpyHostToDevice, s));
+    VIDO_CUDA(cudaMemcpyAsync((void*)a.Tcw_last, p.Tcw_last, sizeof(float) * 16, cudaMemcpyHostToDevice, s));
+  }
+  VIDO_CUDA(cudaMemcpyAsync(ws->d_args, h.data(), sizeof(PoArgs) * nproblems, cudaMemcpyHostToDevice, s));
+  poseopt_flow2_kernel<<<nproblems, PO_THREADS, 0, s>>>(ws->d_args);
+  ctx->launches++;
+  VIDO_CUDA(cudaGetLastError());
+  std::vector<LmCtl> ctls(4 * nproblems);
+  std::vector<LmRec> recs;
+  for (int k = 0; k < nproblems; k++) {
+    vido_poseopt_problem& p = prs[k];
+    const PoArgs& a = h[k];
+    VIDO_CUDA(cudaMemcpyAsync(p.Tcw_out, a.Tcw_out, sizeof(float) * 16, cudaMemcpyDeviceToHost, s));
+    if (p.n && p.flow_out) VIDO_CUDA(cudaMemcpyAsync(p.flow_out, a.flow_out, sizeof(float) * 2 * p.n, cudaMemcpyDeviceToHost, s));
+    if (p.n && p.inlier) VIDO_CUDA(cudaMemcpyAsync(p.inlier, a.inlier, sizeof(int) * p.n, cudaMemcpyDeviceToHost, s));
+    VIDO_CUDA(cudaMemcpyAsync(&p.n_inliers, a.n_inliers, sizeof(int), cudaMemcpyDeviceToHost, s));
+  }
+  if (stats) {
+    recs.resize((size_t)4 * VIDO_LM_REC * nproblems);
+    VIDO_CUDA(cudaMemcpyAsync(ctls.data(), ws->ctl, sizeof(LmCtl) * 4 * nproblems, cudaMemcpyDeviceToHost, s));
+    VIDO_CUDA(cudaMemcpyAsync(recs.data(), ws->rec, sizeof(LmRec) * recs.size(), cudaMemcpyDeviceToHost, s));
+  }
+  VIDO_CUDA(cudaStreamSynchronize(s));
+  if (stats) {
+    for (int k = 0; k < nproblems; k++)
+      for (int r = 0; r < prs[k].rounds; r++) {
+        vido_lm_stats& st = stats[4 * k + r];
+        const LmCtl& c = ctls[4 * k + r];
+        st.iterations = c.iterations; st.n_records = c.n_records; st.total_trials = c.total_trials;
+        for (int i = 0; i < c.n_records && i < VIDO_LM_MAX_RECORDS; i++) {
+          const LmRec& rr = recs[((size_t)4 * k + r) * VIDO_LM_REC + i];
+          st.rec[i].chi2 = rr.chi2; st.rec[i].lambda = rr.lambda; st.rec[i].trials = rr.trials;
+        }
+      }
+  }
+  return VIDO_OK;
+}
