@@ -147,6 +147,93 @@ void vido_poseopt_default_params(vido_poseopt_problem* p);
 /* stats: NULL or 4*nproblems entries (entry 4*k + r = round r of problem k) */
 int vido_pose_opt_flow2(vido_ctx* ctx, vido_poseopt_problem* problems, int nproblems, vido_lm_stats* stats);
 
+
+/*
+ * Initial camera / object model: replaces Tracking::GetInitModelCam (src/Tracking.cc:1914-2028) and GetInitModelObj
+ * (:2030-2162): PnP-RANSAC (500 iterations, 0.4 px, confidence 0.98) against the constant-velocity model, the model
+ * with more inliers wins.  The RANSAC is the deterministic variant documented in oracle/vido_oracle.h (OpenCV's
+ * cv::solvePnPRansac internals are un-vendored and not reproducible bit for bit).  Host pointers.
+ */
+typedef struct vido_pnp_problem {
+  int32_t n, pad;
+  const float* cur_xy;     /* [n][2] current keypoints */
+  const float* pts3d;      /* [n][3] world points of the last frame (Frame::UnprojectStereoStat) */
+  const int32_t* valid;    /* [n] 0 where the depth was negative (excluded from RANSAC); may be NULL */
+  float Tcw_motion[16];    /* mVelocity * mpLastFrame->mTcw */
+  float fx, fy, cx, cy;
+  int32_t iters;           /* 500 */
+  float reproj_err, confidence; /* 0.4, 0.98 */
+  float Tcw_out[16];
+  int32_t* inlier_ids;     /* [n] out: indices of the winning model's inliers, ascending */
+  int32_t n_inliers, winner /* 0 RANSAC, 1 motion model */, ransac_inliers, mm_inliers;
+} vido_pnp_problem;
+void vido_pnp_default_params(vido_pnp_problem* p);
+int vido_init_model(vido_ctx* ctx, vido_pnp_problem* p);
+
+
+/*
+ * Per-frame gather stages.  Device pointers ("_dev"): depth f32 [B][H][W], flow f32 [B][H][W][2], mask i32 [B][H][W],
+ * tight rows.  raw_depth != 0: the depth map still holds the caller's raw values and the conversion of
+ * Tracking::GrabImageRGBD (src/Tracking.cc:299-322) is applied on the fly at the gather points (bit-identical).
+ */
+/* in-place depth pre-scale (src/Tracking.cc:299-322) */
+int vido_depth_prep_dev(vido_ctx* ctx, float* d_depth, int nframes, size_t frame_stride_elems, int stride_elems);
+/* static association of Frame::Frame (src/Frame.cc:72-100,164-177) for nframes frames; keypoints as produced by
+ * vido_orb_extract_dev.  Outputs per frame f at offset f*out_cap: index into the frame's keypoints, corres xy,
+ * flow xy, depth; d_n[f] = count */
+int vido_frame_associate_dev(vido_ctx* ctx, const vido_keypoint* d_kps, const int32_t* d_nkp, int kp_cap,
+                             const float* d_depth, const float* d_flow, const int32_t* d_mask, int nframes, int raw_depth,
+                             int32_t* d_idx, float* d_corres_xy, float* d_flow_xy, float* d_depth_out, int32_t* d_n, int out_cap);
+/* stride-4 object sampling of Frame::Frame (src/Frame.cc:184-211) */
+int vido_frame_sample_objects_dev(vido_ctx* ctx, const float* d_depth, const float* d_flow, const int32_t* d_mask, int nframes,
+                                  int raw_depth, float* d_keys_xy, float* d_corres_xy, float* d_flow_xy, float* d_depth_out,
+                                  int32_t* d_label, int32_t* d_n, int out_cap);
+/* (mask, depth, flow) at truncated query coordinates of frame `frame` (lookups of src/Tracking.cc:369-421,2976-3010);
+ * queries outside the image return mask -1 */
+int vido_gather_dev(vido_ctx* ctx, const float* d_depth, const float* d_flow, const int32_t* d_mask, int frame, int raw_depth,
+                    const float* d_xy, int n, int32_t* d_mask_out, float* d_depth_out, float* d_flow_out);
+/* KAIST depth scale mScale (src/Tracking.cc:318), 1 by default */
+int vido_set_depth_scale(vido_ctx* ctx, float mscale);
+
+
+/*
+ * Per-frame driver: replaces System::TrackRGBD -> Tracking::GrabImageRGBD -> Tracking::Track
+ * (src/System.cc:51-63, src/Tracking.cc:283-456, 1081-1509) including the PartialBatchOptimization of every frame.
+ * This version covers sensor = RGBD (VO), bJoint = true, UseSampleFeature = 0 and a static scene (all-zero mask).
+ * A chunk of frames is passed at once so that the frame-independent front-end (gray conversion, ORB, association)
+ * runs batched; results are identical to calling it frame by frame.
+ */
+typedef struct vido_frame_inputs {
+  const uint8_t* image;   /* height x width x channels, tight rows (CV_8UC1 or CV_8UC3 in Camera.RGB order) */
+  int32_t channels;       /* 1 or 3 */
+  int32_t on_device;      /* 0: host pointers (copied H2D inside the call), 1: device pointers */
+  const float* depth;     /* height x width CV_32F, raw (pre-scaled on the fly as in src/Tracking.cc:299-322) */
+  const float* flow;      /* height x width x 2 CV_32FC2 */
+  const int32_t* mask;    /* height x width CV_32SC1 */
+  int32_t write_back_depth; /* 1: also write the pre-scaled depth back into `depth` like the reference does */
+  int32_t pad;
+  double timestamp;
+} vido_frame_inputs;
+typedef struct vido_track_stats {
+  double ms_orb, ms_assoc, ms_init, ms_poseopt, ms_renew, ms_ba; /* host wall time per stage (ms_orb: front-end share) */
+  int32_t n_keypoints, n_matches, n_init_inliers, init_winner, n_pose_inliers, n_static;
+  int32_t ba_iterations, ba_trials, ba_points, ba_obs;
+} vido_track_stats;
+/* Tcw_out: nframes x 16 floats (what TrackRGBD returns per frame); stats may be NULL.  Returns VIDO_OK or <0. */
+int vido_track_frames(vido_ctx* ctx, const vido_frame_inputs* frames, int nframes, float* Tcw_out, vido_track_stats* stats);
+int vido_track_reset(vido_ctx* ctx);
+/* Map accessors (include/Map.h:44-97): number of frames, vmCameraPose (Twc, refined by the window optimisation),
+ * per-frame static features vpFeatSta / vfDepSta / vp3DPointSta / vnAssoSta */
+int vido_map_num_frames(vido_ctx* ctx);
+int vido_map_get_poses(vido_ctx* ctx, float* poses, int cap);
+int vido_map_get_static(vido_ctx* ctx, int frame, float* xy, float* depth, float* p3, int32_t* asso, int cap);
+
+/* accumulated device time (CUDA events on the context stream) of the kernel groups: ms[0] ORB front-end launches,
+ * ms[1] init-model kernels, ms[2] pose-optimisation kernel, ms[3] window-BA kernel; launches[k] = timed regions;
+ * ba_alg_bytes = algorithmic bytes of the BA launches (296 B per edge per linearisation + 152 B per edge per
+ * residual pass) */
+int vido_get_kernel_times(vido_ctx* ctx, double* ms, int64_t* launches, double* ba_alg_bytes);
+
 /* stream handle (cudaStream_t) the context launches on, for event timing in bench.py */
 void* vido_stream(vido_ctx* ctx);
 int vido_sync(vido_ctx* ctx);

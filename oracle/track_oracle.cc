@@ -1,0 +1,453 @@
+// track_oracle.cc -- CPU restatement of the per-frame driver (VO, static scene).  TEST INFRASTRUCTURE ONLY.
+//
+// Follows, for sensor = RGBD, bJoint = true, UseSampleFeature = 0 and an all-zero object mask:
+//   Tracking::GrabImageRGBD          src/Tracking.cc:283-456   (depth pre-scale, Frame, carry-over of correspondences)
+//   Frame::Frame                     src/Frame.cc:36-241       (ORB, static association)
+//   Tracking::Track                  src/Tracking.cc:1081-1509 (init model, pose optimisation, motion model, renewal,
+//                                                                map bookkeeping, PartialBatchOptimization every frame)
+//   Tracking::Initialization         src/Tracking.cc:1512-1580
+//   Tracking::RenewFrameInfo         src/Tracking.cc:2959-3135 (static part)
+//   Tracking::GetStaticTrack         src/Tracking.cc:2514-2613 (rebuilt from frame 0 every frame, like the reference)
+//   Optimizer::PartialBatchOptimization graph construction   src/Optimizer.cc:43-362, write-back :1056-1142
+// Not covered (documented in DESIGN.md): dynamic objects (DynObjTracking, object motion), IMU, FullBatch.
+// float 4x4 products follow cv::Mat CV_32F gemm (double accumulation, one rounding).
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "vido_oracle.h"
+
+namespace {
+
+struct P2 { float x, y; };
+struct P3 { float x, y, z; };
+
+void mul44(const float* A, const float* B, float* C) {
+  float o[16];
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) {
+      double s = 0;
+      for (int k = 0; k < 4; k++) s += (double)A[4 * r + k] * (double)B[4 * k + c];
+      o[4 * r + c] = (float)s;
+    }
+  memcpy(C, o, sizeof o);
+}
+
+void inv44(const float* T, float* Ti) {  // Converter::toInvMatrix (src/Converter.cc:155-170)
+  float o[16] = {0};
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) o[4 * r + c] = T[4 * c + r];
+  for (int r = 0; r < 3; r++) {
+    double s = 0;
+    for (int k = 0; k < 3; k++) s += (double)(-o[4 * r + k]) * (double)T[4 * k + 3];
+    o[4 * r + 3] = (float)s;
+  }
+  o[15] = 1.f;
+  memcpy(Ti, o, sizeof o);
+}
+
+void eye44(float* T) { memset(T, 0, sizeof(float) * 16); T[0] = T[5] = T[10] = T[15] = 1.f; }
+
+struct Frame {
+  std::vector<vo_keypoint> mvKeys;
+  std::vector<P2> mvStatKeysTmp, mvCorres, mvFlowNext, mvStatKeys;
+  std::vector<float> mvStatDepthTmp, mvStatDepth;
+  std::vector<P3> mvStat3DPointTmp;
+  std::vector<int> nStaInlierID;
+  float Tcw[16];
+};
+
+struct Map {
+  std::vector<std::vector<P2>> vpFeatSta;
+  std::vector<std::vector<float>> vfDepSta;
+  std::vector<std::vector<P3>> vp3DPointSta;
+  std::vector<std::vector<int>> vnAssoSta;
+  std::vector<std::vector<std::pair<int, int>>> TrackletSta;
+  std::vector<std::vector<float>> vmCameraPose;   // 16 floats each (Twc)
+  std::vector<std::vector<float>> vmRigidMotion;  // camera motion [f-1][0]
+};
+
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct Tracker {
+  vo_track_config cfg;
+  Map map;
+  Frame* last = nullptr;
+  Frame* cur = nullptr;
+  bool has_velocity = false;
+  float mVelocity[16];
+  int f_id = 0;
+  bool initialised = false;
+  // incremental tracklet state (rebuild_tracklets == 0)
+  std::vector<int> trackOfPrev;
+
+  ~Tracker() { delete last; if (cur != last) delete cur; }
+
+  P3 unproject_cam(const P2& kp, float z) const {  // Optimizer::Get3DinCamera
+    const float invfx = 1.0f / cfg.fx, invfy = 1.0f / cfg.fy;
+    return {(kp.x - cfg.cx) * z * invfx, (kp.y - cfg.cy) * z * invfy, z};
+  }
+  P3 to_world(const P3& xc, const float* Twc) const {  // cv::Mat  R*x + t
+    P3 o;
+    float* po = &o.x;
+    for (int r = 0; r < 3; r++)
+      po[r] = (float)((double)Twc[4 * r] * xc.x + (double)Twc[4 * r + 1] * xc.y + (double)Twc[4 * r + 2] * xc.z) + Twc[4 * r + 3];
+    return o;
+  }
+
+  // ---- Tracking::GetStaticTrack
+  void rebuild_tracklets() {
+    auto& TM = map.vnAssoSta;
+    const int N = (int)TM.size();
+    std::vector<int> pre;
+    std::vector<std::vector<std::pair<int, int>>> T;
+    for (int i = 0; i < N; i++) {
+      std::vector<int> curc(TM[i].size(), -1);
+      for (size_t j = 0; j < TM[i].size(); j++) {
+        if (TM[i][j] == -1) continue;
+        if (i > 0 && pre[TM[i][j]] != -1) {
+          T[pre[TM[i][j]]].push_back({i + 1, (int)j});
+          curc[j] = pre[TM[i][j]];
+        } else {
+          T.push_back({{i, TM[i][j]}, {i + 1, (int)j}});
+          curc[j] = (int)T.size() - 1;
+        }
+      }
+      pre = curc;
+    }
+    map.TrackletSta.swap(T);
+  }
+  void extend_tracklets() {  // same result, O(features) per frame ("fixed bookkeeping" baseline)
+    auto& TM = map.vnAssoSta;
+    const int i = (int)TM.size() - 1;
+    std::vector<int> curc(TM[i].size(), -1);
+    for (size_t j = 0; j < TM[i].size(); j++) {
+      if (TM[i][j] == -1) continue;
+      if (i > 0 && trackOfPrev[TM[i][j]] != -1) {
+        map.TrackletSta[trackOfPrev[TM[i][j]]].push_back({i + 1, (int)j});
+        curc[j] = trackOfPrev[TM[i][j]];
+      } else {
+        map.TrackletSta.push_back({{i, TM[i][j]}, {i + 1, (int)j}});
+        curc[j] = (int)map.TrackletSta.size() - 1;
+      }
+    }
+    trackOfPrev = curc;
+  }
+
+  // ---- Optimizer::PartialBatchOptimization
+  void partial_batch(int WINDOW, vo_track_stats* st) {
+    const int N = (int)map.vpFeatSta.size();
+    if (st) { st->ba_iterations = -1; st->ba_points = 0; st->ba_obs = 0; }
+    if (WINDOW <= 0) return;
+    const auto& Tr = map.TrackletSta;  // (the reference copies it, :46)
+    std::vector<std::vector<int>> lab(N), mak(N);
+    for (int i = 0; i < N; i++) { lab[i].assign(map.vpFeatSta[i].size(), -1); mak[i] = lab[i]; }
+    for (size_t t = 0; t < Tr.size(); t++) {
+      if (Tr[t].size() < 3) continue;
+      for (auto& e : Tr[t]) lab[e.first][e.second] = (int)t;
+    }
+    const int start = N - WINDOW;
+    std::vector<float> poses, rel, pts, oxyz;
+    std::vector<int> op, ol;
+    std::vector<std::pair<int, int>> ptOwner;  // first (frame, feat) of every point
+    for (int i = start; i < N; i++) {
+      poses.insert(poses.end(), map.vmCameraPose[i].begin(), map.vmCameraPose[i].end());
+      if (i != start) rel.insert(rel.end(), map.vmRigidMotion[i - 1].begin(), map.vmRigidMotion[i - 1].end());
+      for (size_t j = 0; j < lab[i].size(); j++) {
+        const int t = lab[i][j];
+        if (t == -1) continue;
+        int pos = -1;
+        for (size_t k = 0; k < Tr[t].size(); k++)
+          if (Tr[t][k].first == i && Tr[t][k].second == (int)j) { pos = (int)k; break; }
+        if (pos == -1) continue;
+        int pid;
+        if (pos == 0) {
+          pid = (int)ptOwner.size();
+          ptOwner.push_back({i, (int)j});
+          const P3& Xw = map.vp3DPointSta[i][j];
+          pts.push_back(Xw.x); pts.push_back(Xw.y); pts.push_back(Xw.z);
+        } else {
+          pid = mak[Tr[t][pos - 1].first][Tr[t][pos - 1].second];
+          if (pid == -1) continue;
+        }
+        mak[i][j] = pid;
+        const P3 xc = unproject_cam(map.vpFeatSta[i][j], map.vfDepSta[i][j]);
+        op.push_back(i - start); ol.push_back(pid);
+        oxyz.push_back(xc.x); oxyz.push_back(xc.y); oxyz.push_back(xc.z);
+      }
+    }
+    vo_ba_problem pr;
+    memset(&pr, 0, sizeof pr);
+    vo_ba_default_params(&pr);
+    pr.n_poses = WINDOW; pr.n_points = (int)ptOwner.size(); pr.n_obs = (int)op.size();
+    pr.poses = poses.data(); pr.rel_motion = rel.data(); pr.points = pts.data();
+    pr.obs_pose = op.data(); pr.obs_point = ol.data(); pr.obs_xyz = oxyz.data();
+    vo_lm_stats ls;
+    const int its = vo_ba_partial(&pr, &ls);
+    if (st) { st->ba_iterations = its; st->ba_points = pr.n_points; st->ba_obs = pr.n_obs; st->ba_trials = ls.total_trials; }
+    for (int i = start; i < N; i++) {
+      std::copy(poses.begin() + 16 * (i - start), poses.begin() + 16 * (i - start + 1), map.vmCameraPose[i].begin());
+      if (i > start) std::copy(rel.begin() + 16 * (i - start - 1), rel.begin() + 16 * (i - start), map.vmRigidMotion[i - 1].begin());
+    }
+    for (int i = start; i < N; i++)
+      for (size_t j = 0; j < mak[i].size(); j++)
+        if (mak[i][j] != -1) map.vp3DPointSta[i][j] = {pts[3 * mak[i][j]], pts[3 * mak[i][j] + 1], pts[3 * mak[i][j] + 2]};
+  }
+
+  // ---- Tracking::RenewFrameInfo (static part)
+  void renew(const std::vector<int>& TM_sta, const float* depth, const float* flow, const int32_t* mask) {
+    const int W = cfg.width, H = cfg.height, maxn = cfg.max_track_bg;
+    std::vector<P2> keys, corres, fl;
+    std::vector<int> inl;
+    auto try_add = [&](const P2& kp, int inlier_id) -> bool {
+      const int x = (int)kp.x, y = (int)kp.y;
+      if (x >= W || y >= H || x <= 0 || y <= 0) return false;
+      const size_t k = (size_t)y * W + x;
+      if (mask[k] != 0) return false;
+      if (depth[k] > 40 || depth[k] <= 0) return false;
+      const float fx = flow[2 * k], fy = flow[2 * k + 1];
+      if (fx != 0 && fy != 0) {
+        if (kp.x + fx < W && kp.y + fy < H && kp.x + fx > 0 && kp.y + fy > 0) {
+          keys.push_back(kp);
+          corres.push_back({kp.x + fx, kp.y + fy});
+          fl.push_back({fx, fy});
+          inl.push_back(inlier_id);
+          return true;
+        }
+      }
+      return false;
+    };
+    for (size_t i = 0; i < TM_sta.size(); i++) {
+      if (TM_sta[i] == -1) continue;
+      try_add(cur->mvStatKeys[TM_sta[i]], TM_sta[i]);
+      if ((int)keys.size() > maxn) break;
+    }
+    int tot = (int)keys.size(), start_id = 0;
+    const int step = 20;
+    const std::vector<P2> check = keys;
+    while (tot < maxn) {
+      if (start_id == step) break;
+      for (size_t i = start_id; i < cur->mvKeys.size(); i += step) {
+        const P2 s = {cur->mvKeys[i].x, cur->mvKeys[i].y};
+        float min_dist = 100;
+        bool used = false;
+        for (size_t j = 0; j < check.size(); j++) {
+          const float d = std::sqrt((check[j].x - s.x) * (check[j].x - s.x) + (check[j].y - s.y) * (check[j].y - s.y));
+          if (d < min_dist) min_dist = d;
+          if (min_dist < 1.0) { used = true; break; }
+        }
+        if (used) continue;
+        if (try_add(s, -1)) tot++;
+        if (tot >= maxn) break;
+      }
+      start_id++;
+    }
+    const size_t n = keys.size();
+    std::vector<float> dep(n, -1.f);
+    std::vector<P3> p3(n);
+    float Twc[16];
+    inv44(cur->Tcw, Twc);
+    for (size_t i = 0; i < n; i++) {
+      const float d = depth[(size_t)(int)keys[i].y * W + (int)keys[i].x];
+      if (d > 0) dep[i] = d;
+      p3[i] = to_world(unproject_cam(keys[i], dep[i]), Twc);
+    }
+    cur->nStaInlierID = inl;
+    cur->mvStatKeysTmp = keys;
+    cur->mvStatDepthTmp = dep;
+    cur->mvStat3DPointTmp = p3;
+    cur->mvFlowNext = fl;
+    cur->mvCorres = corres;
+  }
+
+  int track(const uint8_t* gray, float* depth, const float* flow, const int32_t* mask, float* Tcw_out, vo_track_stats* st) {
+    const int W = cfg.width, H = cfg.height;
+    if (st) memset(st, 0, sizeof *st);
+    double t0 = now_ms();
+    vo_depth_prep(depth, W, H, W, cfg.choose_data, cfg.depth_map_factor, cfg.bf, 1.0f);
+    cur = new Frame();
+    eye44(cur->Tcw);
+    cur->mvKeys.resize(cfg.orb.nfeatures + 64);
+    int nk = vo_orb_extract(gray, W, H, W, &cfg.orb, cur->mvKeys.data(), (int)cur->mvKeys.size());
+    cur->mvKeys.resize(nk < 0 ? 0 : nk);
+    double t1 = now_ms();
+    {  // Frame ctor association
+      const int n = (int)cur->mvKeys.size();
+      std::vector<int> idx(n);
+      std::vector<float> cor(2 * (size_t)n), fl(2 * (size_t)n), dep(n);
+      const int m = vo_frame_associate(cur->mvKeys.data(), n, depth, flow, mask, W, H, cfg.th_depth_bg, idx.data(), cor.data(),
+                                       fl.data(), dep.data(), n);
+      for (int i = 0; i < m; i++) {
+        cur->mvStatKeysTmp.push_back({cur->mvKeys[idx[i]].x, cur->mvKeys[idx[i]].y});
+        cur->mvCorres.push_back({cor[2 * i], cor[2 * i + 1]});
+        cur->mvFlowNext.push_back({fl[2 * i], fl[2 * i + 1]});
+        cur->mvStatDepthTmp.push_back(dep[i]);
+      }
+    }
+    if (initialised) {  // GrabImageRGBD :369-389
+      cur->mvStatKeys = last->mvCorres;
+      cur->mvStatDepth.assign(cur->mvStatKeys.size(), -1.f);
+      for (size_t i = 0; i < cur->mvStatKeys.size(); i++) {
+        const int v = (int)cur->mvStatKeys[i].y, u = (int)cur->mvStatKeys[i].x;
+        if (u < (W - 1) && u > 0 && v < (H - 1) && v > 0) {
+          const float d = depth[(size_t)v * W + u];
+          if (d > 0) cur->mvStatDepth[i] = d;
+        }
+      }
+    }
+    double t2 = now_ms();
+    if (st) { st->ms_orb = t1 - t0; st->ms_assoc = t2 - t1; st->n_keypoints = (int)cur->mvKeys.size(); }
+    int rc = 0;
+    if (!initialised) {
+      // ---- Tracking::Initialization
+      for (size_t i = 0; i < cur->mvStatKeysTmp.size(); i++)
+        cur->mvStat3DPointTmp.push_back(unproject_cam(cur->mvStatKeysTmp[i], cur->mvStatDepthTmp[i]));
+      map.vpFeatSta.push_back(cur->mvStatKeysTmp);
+      map.vfDepSta.push_back(cur->mvStatDepthTmp);
+      map.vp3DPointSta.push_back(cur->mvStat3DPointTmp);
+      std::vector<float> I(16, 0.f);
+      I[0] = I[5] = I[10] = I[15] = 1.f;
+      map.vmCameraPose.push_back(I);
+      eye44(cur->Tcw);
+      last = cur;
+      last->mvStatKeys = cur->mvStatKeysTmp;
+      last->mvStatDepth = cur->mvStatDepthTmp;
+      initialised = true;
+    } else {
+      const int Ns = (int)cur->mvStatKeys.size();
+      if (Ns < 2) { rc = 1; }
+      else {
+        // ---- GetInitModelCam
+        std::vector<float> cur2d(2 * (size_t)Ns), p3d(3 * (size_t)Ns, 0.f);
+        std::vector<int> valid(Ns, 1), ids(Ns);
+        float Twl[16];
+        inv44(last->Tcw, Twl);
+        for (int i = 0; i < Ns; i++) {
+          cur2d[2 * i] = cur->mvStatKeys[i].x; cur2d[2 * i + 1] = cur->mvStatKeys[i].y;
+          const float z = last->mvStatDepth[i];
+          if (z < 0) { valid[i] = 0; continue; }
+          const P3 xw = to_world(unproject_cam(last->mvStatKeys[i], z), Twl);
+          p3d[3 * i] = xw.x; p3d[3 * i + 1] = xw.y; p3d[3 * i + 2] = xw.z;
+        }
+        vo_pnp_problem pp;
+        memset(&pp, 0, sizeof pp);
+        vo_pnp_default_params(&pp);
+        pp.n = Ns; pp.cur_xy = cur2d.data(); pp.pts3d = p3d.data(); pp.valid = valid.data(); pp.inlier_ids = ids.data();
+        if (has_velocity) mul44(mVelocity, last->Tcw, pp.Tcw_motion);
+        else memcpy(pp.Tcw_motion, last->Tcw, sizeof(float) * 16);
+        pp.fx = cfg.fx; pp.fy = cfg.fy; pp.cx = cfg.cx; pp.cy = cfg.cy;
+        vo_init_model_cam(&pp);
+        std::vector<int> TM_sub(ids.begin(), ids.begin() + pp.n_inliers);
+        memcpy(cur->Tcw, pp.Tcw_out, sizeof(float) * 16);
+        double t3 = now_ms();
+        // ---- PoseOptimizationFlow2Cam
+        const int n = (int)TM_sub.size();
+        std::vector<float> obs(2 * (size_t)n), fl(2 * (size_t)n), dep(n), fo(2 * (size_t)n);
+        std::vector<int> inl(n);
+        for (int i = 0; i < n; i++) {
+          const int k = TM_sub[i];
+          obs[2 * i] = last->mvStatKeys[k].x; obs[2 * i + 1] = last->mvStatKeys[k].y;
+          fl[2 * i] = last->mvFlowNext[k].x; fl[2 * i + 1] = last->mvFlowNext[k].y;
+          dep[i] = last->mvStatDepth[k];
+        }
+        vo_poseopt_problem po;
+        memset(&po, 0, sizeof po);
+        vo_poseopt_default_params(&po);
+        po.n = n; po.obs_xy = obs.data(); po.flow_xy = fl.data(); po.depth = dep.data();
+        memcpy(po.Tcw_init, cur->Tcw, sizeof(float) * 16);
+        memcpy(po.Tcw_last, last->Tcw, sizeof(float) * 16);
+        po.fx = cfg.fx; po.fy = cfg.fy; po.cx = cfg.cx; po.cy = cfg.cy;
+        po.flow_out = fo.data(); po.inlier = inl.data();
+        const int ninl = vo_poseopt_flow2cam(&po, nullptr);
+        memcpy(cur->Tcw, po.Tcw_out, sizeof(float) * 16);
+        if (n >= 3) {
+          for (int i = 0; i < n; i++) {
+            if (inl[i]) {
+              const int k = TM_sub[i];
+              cur->mvStatKeys[k].x = (float)((double)last->mvStatKeys[k].x + (double)fo[2 * i]);
+              cur->mvStatKeys[k].y = (float)((double)last->mvStatKeys[k].y + (double)fo[2 * i + 1]);
+            } else TM_sub[i] = -1;
+          }
+        }
+        double t4 = now_ms();
+        // ---- motion model (src/Tracking.cc:1142-1148)
+        float LastTwc[16];
+        inv44(last->Tcw, LastTwc);
+        mul44(cur->Tcw, LastTwc, mVelocity);
+        has_velocity = true;
+        // ---- RenewFrameInfo + map bookkeeping
+        renew(TM_sub, depth, flow, mask);
+        Frame* old = last;
+        last = cur;
+        last->mvStatKeys = cur->mvStatKeysTmp;
+        last->mvStatDepth = cur->mvStatDepthTmp;
+        delete old;
+        map.vpFeatSta.push_back(cur->mvStatKeysTmp);
+        map.vfDepSta.push_back(cur->mvStatDepthTmp);
+        map.vp3DPointSta.push_back(cur->mvStat3DPointTmp);
+        map.vnAssoSta.push_back(cur->nStaInlierID);
+        if (cfg.rebuild_tracklets) rebuild_tracklets();
+        else extend_tracklets();
+        std::vector<float> Twc(16), mot(16);
+        inv44(cur->Tcw, Twc.data());
+        inv44(mVelocity, mot.data());
+        map.vmCameraPose.push_back(Twc);
+        map.vmRigidMotion.push_back(mot);
+        double t5 = now_ms();
+        if (st) {
+          st->ms_init = t3 - t2; st->ms_poseopt = t4 - t3; st->ms_renew = t5 - t4;
+          st->n_matches = Ns; st->n_init_inliers = pp.n_inliers; st->init_winner = pp.winner; st->n_pose_inliers = ninl;
+          st->n_static = (int)cur->mvStatKeysTmp.size();
+        }
+      }
+    }
+    memcpy(Tcw_out, cur->Tcw, sizeof(float) * 16);
+    // ---- PartialBatchOptimization, every frame (src/Tracking.cc:1428-1451)
+    double t6 = now_ms();
+    const int window = f_id < cfg.window_size ? f_id : cfg.window_size;
+    if (rc == 0) partial_batch(window, st);
+    if (st) st->ms_ba = now_ms() - t6;
+    f_id++;
+    if (rc != 0 && cur != last) { delete cur; cur = last; }
+    return rc;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+void* vo_tracker_create(const vo_track_config* cfg) {
+  Tracker* t = new Tracker();
+  t->cfg = *cfg;
+  return t;
+}
+void vo_tracker_destroy(void* h) { delete (Tracker*)h; }
+int vo_tracker_track(void* h, const uint8_t* gray, float* depth, const float* flow, const int32_t* mask, float* Tcw_out,
+                     vo_track_stats* st) {
+  return ((Tracker*)h)->track(gray, depth, flow, mask, Tcw_out, st);
+}
+int vo_tracker_num_frames(void* h) { return (int)((Tracker*)h)->map.vmCameraPose.size(); }
+int vo_tracker_get_map_poses(void* h, float* poses, int cap) {
+  Tracker* t = (Tracker*)h;
+  int n = (int)t->map.vmCameraPose.size();
+  for (int i = 0; i < n && i < cap; i++) memcpy(poses + 16 * i, t->map.vmCameraPose[i].data(), sizeof(float) * 16);
+  return n;
+}
+int vo_tracker_get_static(void* h, int frame, float* xy, float* depth, float* p3, int32_t* asso, int cap) {
+  Tracker* t = (Tracker*)h;
+  if (frame < 0 || frame >= (int)t->map.vpFeatSta.size()) return -1;
+  const int n = (int)t->map.vpFeatSta[frame].size();
+  for (int i = 0; i < n && i < cap; i++) {
+    xy[2 * i] = t->map.vpFeatSta[frame][i].x; xy[2 * i + 1] = t->map.vpFeatSta[frame][i].y;
+    depth[i] = t->map.vfDepSta[frame][i];
+    p3[3 * i] = t->map.vp3DPointSta[frame][i].x; p3[3 * i + 1] = t->map.vp3DPointSta[frame][i].y; p3[3 * i + 2] = t->map.vp3DPointSta[frame][i].z;
+    asso[i] = frame > 0 ? t->map.vnAssoSta[frame - 1][i] : -1;
+  }
+  return n;
+}
+
+}  // extern "C"

@@ -130,6 +130,54 @@ typedef struct vo_poseopt_problem {
 void vo_poseopt_default_params(vo_poseopt_problem* p);
 int vo_poseopt_flow2cam(vo_poseopt_problem* p, vo_lm_stats* stats /* [rounds] or NULL */);
 
+/*
+ * Initial camera model of Tracking::GetInitModelCam (src/Tracking.cc:1914-2028): PnP-RANSAC over the previous frame's
+ * 3-D points and the current 2-D points versus the constant-velocity model, the one with more inliers wins.
+ * cv::solvePnPRansac(500, 0.4 px, 0.98, SOLVEPNP_P3P) lives in un-vendored OpenCV and is not reproducible bit for
+ * bit (internal RNG, minimal solver, EPnP refit: "parity unpinned"); the restatement fixes a deterministic variant:
+ * counter-based sampling of 4 points, minimal solve by Gauss-Newton from the motion-model pose, OpenCV's adaptive
+ * iteration count, refit on the consensus set.  Cross-checked loosely against cv2.solvePnPRansac in the tests.
+ */
+typedef struct vo_pnp_problem {
+  int32_t n, pad;
+  const float* cur_xy;     /* [n][2] current keypoints */
+  const float* pts3d;      /* [n][3] world points of the last frame (UnprojectStereoStat, float) */
+  const int32_t* valid;    /* [n] 0 where the depth was negative (excluded from RANSAC) */
+  float Tcw_motion[16];    /* mVelocity * mpLastFrame->mTcw (float) */
+  float fx, fy, cx, cy;
+  int32_t iters;           /* 500 */
+  float reproj_err, confidence; /* 0.4, 0.98 */
+  float Tcw_out[16];
+  int32_t* inlier_ids;     /* [n] indices of the winning model's inliers, ascending */
+  int32_t n_inliers, winner /* 0 RANSAC, 1 motion model */, ransac_inliers, mm_inliers;
+} vo_pnp_problem;
+void vo_pnp_default_params(vo_pnp_problem* p);
+int vo_init_model_cam(vo_pnp_problem* p);
+
+/* ---- per-frame driver (VO, static scene): System::TrackRGBD -> Tracking::GrabImageRGBD -> Track ---- */
+typedef struct vo_track_config {
+  int32_t width, height;
+  float fx, fy, cx, cy, bf;
+  int32_t choose_data;
+  float depth_map_factor, th_depth_bg, th_depth_obj;
+  int32_t max_track_bg, window_size;
+  vo_orb_params orb;
+  int32_t rebuild_tracklets; /* 1: rebuild all tracklets from frame 0 every frame like the reference (O(T)/frame) */
+} vo_track_config;
+typedef struct vo_track_stats {
+  double ms_orb, ms_assoc, ms_init, ms_poseopt, ms_renew, ms_ba;
+  int32_t n_keypoints, n_matches, n_init_inliers, init_winner, n_pose_inliers, n_static;
+  int32_t ba_iterations, ba_trials, ba_points, ba_obs;
+} vo_track_stats;
+void* vo_tracker_create(const vo_track_config* cfg);
+void vo_tracker_destroy(void* h);
+/* depth is modified in place (pre-scale) like the reference; returns 0 ok, 1 frame skipped (< 2 matches) */
+int vo_tracker_track(void* h, const uint8_t* gray, float* depth, const float* flow, const int32_t* mask, float* Tcw_out,
+                     vo_track_stats* st);
+int vo_tracker_num_frames(void* h);
+int vo_tracker_get_map_poses(void* h, float* poses /* [n][16] Map::vmCameraPose (Twc, BA-refined) */, int cap);
+int vo_tracker_get_static(void* h, int frame, float* xy, float* depth, float* p3, int32_t* asso, int cap);
+
 #ifdef __cplusplus
 }
 #endif

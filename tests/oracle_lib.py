@@ -218,3 +218,106 @@ def poseopt_flow2cam(obs_xy, flow_xy, depth, Tcw_init, Tcw_last, K, **params):
     stats = (LmStats * pr.rounds)()
     ninl = lib().vo_poseopt_flow2cam(C.byref(pr), stats)
     return np.array(pr.Tcw_out[:], np.float32).reshape(4, 4), fo, inl, ninl, list(stats)
+
+
+class PnpProblem(C.Structure):
+    _fields_ = [("n", C.c_int32), ("pad", C.c_int32), ("cur_xy", C.c_void_p), ("pts3d", C.c_void_p),
+                ("valid", C.c_void_p), ("Tcw_motion", C.c_float * 16),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("iters", C.c_int32), ("reproj_err", C.c_float), ("confidence", C.c_float),
+                ("Tcw_out", C.c_float * 16), ("inlier_ids", C.c_void_p),
+                ("n_inliers", C.c_int32), ("winner", C.c_int32), ("ransac_inliers", C.c_int32), ("mm_inliers", C.c_int32)]
+
+
+def fill_pnp(pr, cur_xy, pts3d, valid, Tcw_motion, K):
+    cur = np.ascontiguousarray(cur_xy, np.float32); pts = np.ascontiguousarray(pts3d, np.float32)
+    val = np.ascontiguousarray(valid, np.int32) if valid is not None else np.ones(len(cur), np.int32)
+    ids = np.zeros(len(cur), np.int32)
+    pr.n = len(cur)
+    pr.cur_xy, pr.pts3d, pr.valid, pr.inlier_ids = _p(cur), _p(pts), _p(val), _p(ids)
+    pr.Tcw_motion[:] = np.asarray(Tcw_motion, np.float32).reshape(-1).tolist()
+    pr.fx, pr.fy, pr.cx, pr.cy = [float(v) for v in K]
+    return cur, pts, val, ids
+
+
+def init_model_cam(cur_xy, pts3d, valid, Tcw_motion, K, **params):
+    """returns (Tcw 4x4 f32, inlier ids, winner, ransac_inliers, mm_inliers)"""
+    pr = PnpProblem()
+    lib().vo_pnp_default_params(C.byref(pr))
+    keep = fill_pnp(pr, cur_xy, pts3d, valid, Tcw_motion, K)
+    for k, v in params.items():
+        setattr(pr, k, v)
+    n = lib().vo_init_model_cam(C.byref(pr))
+    return (np.array(pr.Tcw_out[:], np.float32).reshape(4, 4), keep[3][:n].copy(), pr.winner, pr.ransac_inliers,
+            pr.mm_inliers)
+
+
+# ---------------------------------------------------------------- tracking pipeline oracle
+class TrackConfig(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float),
+                ("cy", C.c_float), ("bf", C.c_float), ("choose_data", C.c_int32), ("depth_map_factor", C.c_float),
+                ("th_depth_bg", C.c_float), ("th_depth_obj", C.c_float), ("max_track_bg", C.c_int32),
+                ("window_size", C.c_int32), ("orb", OrbParams), ("rebuild_tracklets", C.c_int32)]
+
+
+class TrackStats(C.Structure):
+    _fields_ = [("ms_orb", C.c_double), ("ms_assoc", C.c_double), ("ms_init", C.c_double), ("ms_poseopt", C.c_double),
+                ("ms_renew", C.c_double), ("ms_ba", C.c_double),
+                ("n_keypoints", C.c_int32), ("n_matches", C.c_int32), ("n_init_inliers", C.c_int32),
+                ("init_winner", C.c_int32), ("n_pose_inliers", C.c_int32), ("n_static", C.c_int32),
+                ("ba_iterations", C.c_int32), ("ba_trials", C.c_int32), ("ba_points", C.c_int32), ("ba_obs", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def track_config(cam, nfeatures=2500, window=20, max_track_bg=1000, rebuild=1, choose_data=2, depth_map_factor=256.0,
+                 th_depth_bg=5000.0, th_depth_obj=25.0):
+    c = TrackConfig()
+    c.width, c.height = cam["width"], cam["height"]
+    c.fx, c.fy, c.cx, c.cy, c.bf = cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["bf"]
+    c.choose_data, c.depth_map_factor, c.th_depth_bg, c.th_depth_obj = choose_data, depth_map_factor, th_depth_bg, th_depth_obj
+    c.max_track_bg, c.window_size = max_track_bg, window
+    c.orb = default_orb_params(nfeatures)
+    c.rebuild_tracklets = rebuild
+    return c
+
+
+class OracleTracker:
+    def __init__(self, cfg):
+        L = lib()
+        L.vo_tracker_create.restype = C.c_void_p
+        L.vo_tracker_create.argtypes = [C.POINTER(TrackConfig)]
+        L.vo_tracker_destroy.argtypes = [C.c_void_p]
+        L.vo_tracker_track.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [C.POINTER(TrackStats)]
+        L.vo_tracker_get_map_poses.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.vo_tracker_num_frames.argtypes = [C.c_void_p]
+        L.vo_tracker_get_static.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int]
+        self.cfg = cfg
+        self.h = L.vo_tracker_create(C.byref(cfg))
+
+    def track(self, gray, depth_in, flow, mask):
+        """depth_in is copied (the oracle pre-scales its copy in place).  Returns (Tcw 4x4, stats dict, rc)."""
+        g = np.ascontiguousarray(gray, np.uint8); d = np.ascontiguousarray(depth_in, np.float32).copy()
+        f = np.ascontiguousarray(flow, np.float32); m = np.ascontiguousarray(mask, np.int32)
+        T = np.zeros(16, np.float32)
+        st = TrackStats()
+        rc = lib().vo_tracker_track(self.h, _p(g), _p(d), _p(f), _p(m), _p(T), C.byref(st))
+        return T.reshape(4, 4), st.as_dict(), rc
+
+    def map_poses(self):
+        n = lib().vo_tracker_num_frames(self.h)
+        P = np.zeros((n, 16), np.float32)
+        lib().vo_tracker_get_map_poses(self.h, _p(P), n)
+        return P.reshape(n, 4, 4)
+
+    def static_features(self, frame, cap=4096):
+        xy = np.zeros((cap, 2), np.float32); dep = np.zeros(cap, np.float32); p3 = np.zeros((cap, 3), np.float32)
+        asso = np.zeros(cap, np.int32)
+        n = lib().vo_tracker_get_static(self.h, frame, _p(xy), _p(dep), _p(p3), _p(asso), cap)
+        return xy[:n].copy(), dep[:n].copy(), p3[:n].copy(), asso[:n].copy()
+
+    def close(self):
+        if self.h:
+            lib().vo_tracker_destroy(self.h)
+            self.h = None

@@ -30,3 +30,26 @@ def make_poseopt(n=800, seed=0, flow_noise=0.1, outliers=0.05, cam=(718.856, 718
     init[:3, 3] = Tcw[:3, 3] + init_noise * rng.normal(size=3)
     return dict(obs=obs.astype(np.float32), flow=flow.astype(np.float32), depth=depth.astype(np.float32),
                 Tcw_init=init.astype(np.float32), Tcw_last=Tlw.astype(np.float32), K=cam, Tcw_gt=Tcw, bad=bad)
+
+
+def make_pnp(n=1000, seed=0, px_noise=0.1, outliers=0.2, motion_err=0.3, cam=(718.856, 718.856, 607.1928, 185.2157),
+             W=1242, H=375):
+    """3-D world points of the last frame, their (noisy) projections in the current frame, and a constant-velocity
+    guess that is off by `motion_err` metres."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy = cam
+    Twc = np.eye(4)
+    Twc[:3, :3] = ba_synth.rot([0.05, 1, 0.02], 0.08)
+    Twc[:3, 3] = [0.4, -0.05, 7.0]
+    Tcw = np.linalg.inv(Twc)
+    uv = np.stack([rng.uniform(10, W - 10, n), rng.uniform(10, H - 10, n)], 1)
+    z = rng.uniform(4, 50, n)
+    Xc = np.stack([(uv[:, 0] - cx) * z / fx, (uv[:, 1] - cy) * z / fy, z], 1)
+    Xw = Xc @ Twc[:3, :3].T + Twc[:3, 3]
+    obs = uv + px_noise * rng.normal(size=(n, 2))
+    bad = rng.uniform(size=n) < outliers
+    obs[bad] += rng.normal(size=(bad.sum(), 2)) * 15
+    mm = Tcw.copy()
+    mm[:3, 3] += motion_err * np.array([0.2, 0.05, 1.0])
+    return dict(cur=obs.astype(np.float32), pts=Xw.astype(np.float32), Tcw_motion=mm.astype(np.float32), K=cam,
+                Tcw_gt=Tcw, bad=bad)

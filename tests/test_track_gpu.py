@@ -1,0 +1,90 @@
+"""GPU: the per-frame driver (vido_track_frames: batched front-end + sequential back-end incl. the window BA of every
+frame) against the oracle's restatement of Tracking::GrabImageRGBD / Track on seeded synthetic sequences."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import synth
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-4
+
+
+def _sequence(cam, seed, n, **kw):
+    sc = synth.Scene(cam=cam, seed=seed, **kw)
+    return [sc.frame(k) for k in range(n)]
+
+
+def _run_both(pkg, cam, frames, max_batch, nfeatures=2500, window=20):
+    otr = ol.OracleTracker(ol.track_config(cam, nfeatures=nfeatures, window=window))
+    ref = [otr.track(f["gray"].numpy(), f["depth_in"].numpy(), f["flow"].numpy(), f["mask"].numpy()) for f in frames]
+    ctx = pkg.Context(pkg.default_config(width=cam["width"], height=cam["height"], fx=cam["fx"], fy=cam["fy"], cx=cam["cx"],
+                                         cy=cam["cy"], bf=cam["bf"], max_batch=max_batch, nfeatures=nfeatures,
+                                         window_size=window))
+    T, st = ctx.track_frames([dict(image=f["gray"].numpy(), depth=f["depth_in"].numpy(), flow=f["flow"].numpy(),
+                                   mask=f["mask"].numpy()) for f in frames])
+    return otr, ref, ctx, T, st
+
+
+@pytest.mark.parametrize("cam_name,n,batch", [("small", 10, 4), ("kitti", 26, 8)])
+def test_sequence_matches_oracle(pkg, cam_name, n, batch):
+    cam = synth.SMALL if cam_name == "small" else synth.KITTI
+    frames = _sequence(cam, 1234, n, flow_noise=0.1, depth_noise=0.01)
+    otr, ref, ctx, T, st = _run_both(pkg, cam, frames, batch)
+    for k in range(n):
+        T0, s0, rc0 = ref[k]
+        assert rc0 == 0
+        for key in ("n_keypoints", "n_matches", "n_init_inliers", "init_winner", "n_pose_inliers", "n_static",
+                    "ba_iterations", "ba_trials", "ba_points", "ba_obs"):
+            assert st[k][key] == s0[key], (k, key, st[k][key], s0[key])
+        assert np.abs(T[k] - T0).max() <= REL_TOL * max(np.abs(T0).max(), 1.0), k
+    P0, P = otr.map_poses(), ctx.map_poses()
+    assert P.shape == P0.shape
+    assert np.abs(P - P0).max() <= REL_TOL * max(np.abs(P0).max(), 1.0)
+    for fr in (0, n // 2, n - 1):
+        a, b = ctx.map_static(fr), otr.static_features(fr)
+        assert np.array_equal(a[3], b[3])                      # vnAssoSta
+        assert np.abs(a[0] - b[0]).max() <= 1e-3               # vpFeatSta (refined flows)
+        assert np.abs(a[2] - b[2]).max() <= REL_TOL * max(np.abs(b[2]).max(), 1.0)  # vp3DPointSta after BA
+    # the trajectory is also right in absolute terms (ground truth of the generator, frame 0 = origin)
+    G0 = frames[0]["Twc"].numpy()
+    for k in (n - 1,):
+        Tcw_gt = np.linalg.inv(np.linalg.inv(G0) @ frames[k]["Twc"].numpy())
+        assert np.abs(T[k][:3, 3] - Tcw_gt[:3, 3]).max() < 0.05 * max(1.0, k * 0.1)
+    otr.close(); ctx.close()
+
+
+def test_chunking_does_not_change_results(pkg):
+    cam = synth.SMALL
+    frames = _sequence(cam, 77, 7, flow_noise=0.05, depth_noise=0.005)
+    outs = []
+    for batch in (1, 3, 7):
+        ctx = pkg.Context(pkg.default_config(width=640, height=480, fx=cam["fx"], fy=cam["fy"], cx=cam["cx"], cy=cam["cy"],
+                                             bf=cam["bf"], max_batch=batch))
+        T, _ = ctx.track_frames([dict(image=f["gray"].numpy(), depth=f["depth_in"].numpy(), flow=f["flow"].numpy(),
+                                      mask=f["mask"].numpy()) for f in frames], want_stats=False)
+        outs.append((T.copy(), ctx.map_poses().copy()))
+        ctx.close()
+    for T, P in outs[1:]:
+        assert np.array_equal(T, outs[0][0]) and np.array_equal(P, outs[0][1])
+
+
+def test_rgb_input_and_depth_write_back(pkg):
+    """3-channel input goes through the gray conversion kernel; write_back_depth reproduces the reference's in-place
+    depth pre-scale"""
+    cam = synth.SMALL
+    frames = _sequence(cam, 5, 3)
+    ctx = pkg.Context(pkg.default_config(width=640, height=480, fx=cam["fx"], fy=cam["fy"], cx=cam["cx"], cy=cam["cy"],
+                                         bf=cam["bf"], max_batch=2))
+    gray = [f["gray"].numpy() for f in frames]
+    bgr = [np.repeat(g[:, :, None], 3, axis=2) for g in gray]   # B=G=R=g  ->  gray' == g for the OpenCV coefficients
+    deps = [f["depth_in"].numpy().copy() for f in frames]
+    T3, _ = ctx.track_frames([dict(image=b, depth=d, flow=f["flow"].numpy(), mask=f["mask"].numpy(), write_back_depth=1)
+                              for b, d, f in zip(bgr, deps, frames)], want_stats=False)
+    ctx.track_reset()
+    T1, _ = ctx.track_frames([dict(image=g, depth=f["depth_in"].numpy(), flow=f["flow"].numpy(), mask=f["mask"].numpy())
+                              for g, f in zip(gray, frames)], want_stats=False)
+    assert np.array_equal(T1, T3)
+    ref = ol.depth_prep(frames[1]["depth_in"].numpy(), 2, 256.0, cam["bf"])
+    assert np.array_equal(deps[1], ref)
+    ctx.close()

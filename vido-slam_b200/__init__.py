@@ -56,6 +56,32 @@ class PoseOptProblem(C.Structure):
                 ("rounds", C.c_int32), ("its", C.c_int32)]
 
 
+class PnpProblem(C.Structure):
+    _fields_ = [("n", C.c_int32), ("pad", C.c_int32), ("cur_xy", C.c_void_p), ("pts3d", C.c_void_p),
+                ("valid", C.c_void_p), ("Tcw_motion", C.c_float * 16),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("iters", C.c_int32), ("reproj_err", C.c_float), ("confidence", C.c_float),
+                ("Tcw_out", C.c_float * 16), ("inlier_ids", C.c_void_p),
+                ("n_inliers", C.c_int32), ("winner", C.c_int32), ("ransac_inliers", C.c_int32), ("mm_inliers", C.c_int32)]
+
+
+class FrameInputs(C.Structure):
+    _fields_ = [("image", C.c_void_p), ("channels", C.c_int32), ("on_device", C.c_int32), ("depth", C.c_void_p),
+                ("flow", C.c_void_p), ("mask", C.c_void_p), ("write_back_depth", C.c_int32), ("pad", C.c_int32),
+                ("timestamp", C.c_double)]
+
+
+class TrackStats(C.Structure):
+    _fields_ = [("ms_orb", C.c_double), ("ms_assoc", C.c_double), ("ms_init", C.c_double), ("ms_poseopt", C.c_double),
+                ("ms_renew", C.c_double), ("ms_ba", C.c_double),
+                ("n_keypoints", C.c_int32), ("n_matches", C.c_int32), ("n_init_inliers", C.c_int32),
+                ("init_winner", C.c_int32), ("n_pose_inliers", C.c_int32), ("n_static", C.c_int32),
+                ("ba_iterations", C.c_int32), ("ba_trials", C.c_int32), ("ba_points", C.c_int32), ("ba_obs", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 class VidoError(RuntimeError):
     pass
 
@@ -90,6 +116,14 @@ def load_library():
     lib.vido_bgr_to_gray_dev.argtypes = [vp, vp, C.c_int, C.c_size_t, C.c_int, vp, C.c_size_t, C.c_int]
     lib.vido_orb_get_level.argtypes = [vp, C.c_int, C.c_int, vp]
     lib.vido_orb_get_candidates.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp]
+    lib.vido_get_kernel_times.argtypes = [vp, vp, vp, vp]
+    lib.vido_track_frames.argtypes = [vp, C.POINTER(FrameInputs), C.c_int, vp, C.POINTER(TrackStats)]
+    lib.vido_track_reset.argtypes = [vp]
+    lib.vido_map_num_frames.argtypes = [vp]
+    lib.vido_map_get_poses.argtypes = [vp, vp, C.c_int]
+    lib.vido_map_get_static.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int]
+    lib.vido_pnp_default_params.argtypes = [C.POINTER(PnpProblem)]
+    lib.vido_init_model.argtypes = [vp, C.POINTER(PnpProblem)]
     lib.vido_poseopt_default_params.argtypes = [C.POINTER(PoseOptProblem)]
     lib.vido_pose_opt_flow2.argtypes = [vp, C.POINTER(PoseOptProblem), C.c_int, C.POINTER(LmStats)]
     lib.vido_ba_default_params.argtypes = [C.POINTER(BaProblem)]
@@ -236,3 +270,69 @@ class Context:
             st = [stats[4 * k + r] for r in range(pr.rounds)] if want_stats else None
             out.append((np.array(pr.Tcw_out[:], np.float32).reshape(4, 4), keep[k][3], keep[k][4], int(pr.n_inliers), st))
         return out
+
+    def init_model(self, cur_xy, pts3d, valid, Tcw_motion, K, **params):
+        """vido_init_model: returns (Tcw 4x4 f32, inlier ids, winner, ransac_inliers, mm_inliers)"""
+        pr = PnpProblem()
+        self.lib.vido_pnp_default_params(C.byref(pr))
+        cur = np.ascontiguousarray(cur_xy, np.float32); pts = np.ascontiguousarray(pts3d, np.float32)
+        val = np.ascontiguousarray(valid, np.int32) if valid is not None else None
+        ids = np.zeros(max(len(cur), 1), np.int32)
+        pr.n = len(cur)
+        pr.cur_xy, pr.pts3d, pr.inlier_ids = _ptr(cur), _ptr(pts), _ptr(ids)
+        pr.valid = _ptr(val) if val is not None else None
+        pr.Tcw_motion[:] = np.asarray(Tcw_motion, np.float32).reshape(-1).tolist()
+        pr.fx, pr.fy, pr.cx, pr.cy = [float(v) for v in K]
+        for k, v in params.items():
+            setattr(pr, k, v)
+        self._check(self.lib.vido_init_model(self.h, C.byref(pr)))
+        return (np.array(pr.Tcw_out[:], np.float32).reshape(4, 4), ids[:pr.n_inliers].copy(), pr.winner,
+                pr.ransac_inliers, pr.mm_inliers)
+
+    # ---- per-frame driver
+    def track_frames(self, frames, want_stats=True):
+        """frames: list of dicts {image, depth, flow, mask} holding either numpy host arrays or integer device
+        pointers (then pass on_device=True and channels).  Returns (Tcw [n,4,4] f32, [stats dict] or None)."""
+        n = len(frames)
+        arr = (FrameInputs * n)()
+        keep = []
+        for k, f in enumerate(frames):
+            fi = arr[k]
+            if f.get("on_device"):
+                fi.image, fi.depth, fi.flow, fi.mask = f["image"], f["depth"], f["flow"], f["mask"]
+                fi.channels, fi.on_device = int(f["channels"]), 1
+            else:
+                img = np.ascontiguousarray(f["image"], np.uint8); dep = np.ascontiguousarray(f["depth"], np.float32)
+                flo = np.ascontiguousarray(f["flow"], np.float32); msk = np.ascontiguousarray(f["mask"], np.int32)
+                keep.append((img, dep, flo, msk))
+                fi.image, fi.depth, fi.flow, fi.mask = _ptr(img), _ptr(dep), _ptr(flo), _ptr(msk)
+                fi.channels, fi.on_device = (1 if img.ndim == 2 else img.shape[2]), 0
+            fi.write_back_depth = int(f.get("write_back_depth", 0))
+            fi.timestamp = float(f.get("timestamp", 0.1 * k))
+        T = np.zeros((n, 16), np.float32)
+        st = (TrackStats * n)() if want_stats else None
+        self._check(self.lib.vido_track_frames(self.h, arr, n, _ptr(T), st))
+        return T.reshape(n, 4, 4), ([s.as_dict() for s in st] if want_stats else None)
+
+    def track_reset(self):
+        self._check(self.lib.vido_track_reset(self.h))
+
+    def map_poses(self):
+        n = self.lib.vido_map_num_frames(self.h)
+        P = np.zeros((max(n, 1), 16), np.float32)
+        self.lib.vido_map_get_poses(self.h, _ptr(P), n)
+        return P[:n].reshape(n, 4, 4)
+
+    def map_static(self, frame, cap=4096):
+        xy = np.zeros((cap, 2), np.float32); dep = np.zeros(cap, np.float32); p3 = np.zeros((cap, 3), np.float32)
+        asso = np.zeros(cap, np.int32)
+        n = self.lib.vido_map_get_static(self.h, frame, _ptr(xy), _ptr(dep), _ptr(p3), _ptr(asso), cap)
+        if n < 0:
+            raise VidoError("bad frame index")
+        return xy[:n].copy(), dep[:n].copy(), p3[:n].copy(), asso[:n].copy()
+
+    def kernel_times(self):
+        """device ms / timed regions of (ORB front-end, init model, pose optimisation, window BA) + BA algorithmic bytes"""
+        ms = np.zeros(4, np.float64); n = np.zeros(4, np.int64); b = np.zeros(1, np.float64)
+        self._check(self.lib.vido_get_kernel_times(self.h, _ptr(ms), _ptr(n), _ptr(b)))
+        return ms, n, float(b[0])

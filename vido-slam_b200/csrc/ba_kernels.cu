@@ -858,7 +858,9 @@ int ba_partial_host(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st) {
   VIDO_CUDA(cudaMemcpyAsync((void*)a.pt_start, h_pt_start, sizeof(int) * (P + 1), cudaMemcpyHostToDevice, s));
   VIDO_CUDA(cudaMemcpyAsync((void*)a.pose_start, h_pose_start, sizeof(int) * (W + 1), cudaMemcpyHostToDevice, s));
   const size_t smem = sizeof(double) * ((size_t)36 * W * W + 6 * W);
+  cudaEventRecord(ctx->ev0, s);
   ba_window_kernel<<<BA_CLUSTER, BA_THREADS, smem, s>>>(a);
+  cudaEventRecord(ctx->ev1, s);
   ctx->launches++;
   VIDO_CUDA(cudaGetLastError());
   BaCtl ctl;
@@ -869,6 +871,12 @@ int ba_partial_host(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st) {
   static BaRec recs[BA_MAX_REC];
   if (st) VIDO_CUDA(cudaMemcpyAsync(recs, a.rec, sizeof(BaRec) * BA_MAX_REC, cudaMemcpyDeviceToHost, s));
   VIDO_CUDA(cudaStreamSynchronize(s));
+  {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) { ctx->t_ms[3] += ms; ctx->t_n[3]++; }
+    const double edges = (double)M + (double)std::max(W - 1, 0);
+    ctx->ba_alg_bytes += edges * (296.0 * std::max(ctl.iterations, 0) + 152.0 * (ctl.total_trials + 1));
+  }
   if (getenv("VIDO_BA_TIMING"))
     fprintf(stderr, "[ba] its=%d trials=%d ns: linearize=%llu prepare=%llu schur=%llu chol=%llu update=%llu errors=%llu decide=%llu total=%llu\n",
             ctl.iterations, ctl.total_trials, ctl.t_phase[0], ctl.t_phase[1], ctl.t_phase[2], ctl.t_phase[3], ctl.t_phase[4],

@@ -56,11 +56,17 @@ vido_ctx* vido_create(const vido_config* cfg) {
     delete ctx;
     return nullptr;
   }
+  cudaEventCreate(&ctx->ev0);
+  cudaEventCreate(&ctx->ev1);
   int rc = orb_setup(ctx);
   if (rc == VIDO_OK) rc = ba_setup(ctx, 24, 16384, 131072);
   if (rc == VIDO_OK) rc = po_setup(ctx, 4096, 16);
+  if (rc == VIDO_OK) rc = pnp_setup(ctx, 8192, 2048);
+  if (rc == VIDO_OK) rc = trk_setup(ctx);
   if (rc != VIDO_OK) {
     g_create_err = ctx->err;
+    trk_teardown(ctx);
+    pnp_teardown(ctx);
     po_teardown(ctx);
     ba_teardown(ctx);
     orb_teardown(ctx);
@@ -75,6 +81,8 @@ void vido_destroy(vido_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  trk_teardown(ctx);
+  pnp_teardown(ctx);
   po_teardown(ctx);
   ba_teardown(ctx);
   orb_teardown(ctx);
@@ -232,6 +240,70 @@ int vido_pose_opt_flow2(vido_ctx* ctx, vido_poseopt_problem* problems, int nprob
   if (!ctx || !problems) return VIDO_ERR_ARG;
   cudaSetDevice(ctx->device);
   return po_flow2_host(ctx, problems, nproblems, stats);
+}
+
+void vido_pnp_default_params(vido_pnp_problem* p) { p->iters = 500; p->reproj_err = 0.4f; p->confidence = 0.98f; }
+
+int vido_init_model(vido_ctx* ctx, vido_pnp_problem* p) {
+  if (!ctx || !p) return VIDO_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  return pnp_init_model_host(ctx, p);
+}
+
+int vido_depth_prep_dev(vido_ctx* ctx, float* d_depth, int nframes, size_t frame_stride_elems, int stride_elems) {
+  if (!ctx || !d_depth) return VIDO_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  return assoc_depth_prep(ctx, d_depth, nframes, frame_stride_elems, stride_elems);
+}
+
+int vido_frame_associate_dev(vido_ctx* ctx, const vido_keypoint* d_kps, const int32_t* d_nkp, int kp_cap, const float* d_depth,
+                             const float* d_flow, const int32_t* d_mask, int nframes, int raw_depth, int32_t* d_idx,
+                             float* d_corres_xy, float* d_flow_xy, float* d_depth_out, int32_t* d_n, int out_cap) {
+  if (!ctx || !d_kps || !d_nkp || !d_depth || !d_flow || !d_mask) return VIDO_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  return assoc_frame_associate(ctx, d_kps, d_nkp, kp_cap, d_depth, d_flow, d_mask, nframes, raw_depth, d_idx, d_corres_xy,
+                               d_flow_xy, d_depth_out, d_n, out_cap);
+}
+
+int vido_frame_sample_objects_dev(vido_ctx* ctx, const float* d_depth, const float* d_flow, const int32_t* d_mask, int nframes,
+                                  int raw_depth, float* d_keys_xy, float* d_corres_xy, float* d_flow_xy, float* d_depth_out,
+                                  int32_t* d_label, int32_t* d_n, int out_cap) {
+  if (!ctx || !d_depth || !d_flow || !d_mask) return VIDO_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  return assoc_sample_objects(ctx, d_depth, d_flow, d_mask, nframes, raw_depth, d_keys_xy, d_corres_xy, d_flow_xy, d_depth_out,
+                              d_label, d_n, out_cap);
+}
+
+int vido_gather_dev(vido_ctx* ctx, const float* d_depth, const float* d_flow, const int32_t* d_mask, int frame, int raw_depth,
+                    const float* d_xy, int n, int32_t* d_mask_out, float* d_depth_out, float* d_flow_out) {
+  if (!ctx) return VIDO_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  return assoc_gather(ctx, d_depth, d_flow, d_mask, frame, raw_depth, d_xy, n, d_mask_out, d_depth_out, d_flow_out);
+}
+
+int vido_set_depth_scale(vido_ctx* ctx, float mscale) {
+  if (!ctx) return VIDO_ERR_ARG;
+  ctx->mscale = mscale;
+  return VIDO_OK;
+}
+
+int vido_track_frames(vido_ctx* ctx, const vido_frame_inputs* frames, int nframes, float* Tcw_out, vido_track_stats* stats) {
+  if (!ctx || !frames || !Tcw_out || nframes < 1) return VIDO_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  return trk_track_chunk(ctx, frames, nframes, Tcw_out, stats);
+}
+int vido_track_reset(vido_ctx* ctx) { return ctx ? trk_reset(ctx) : VIDO_ERR_ARG; }
+int vido_map_num_frames(vido_ctx* ctx) { return ctx ? trk_num_frames(ctx) : VIDO_ERR_ARG; }
+int vido_map_get_poses(vido_ctx* ctx, float* poses, int cap) { return (ctx && poses) ? trk_get_map_poses(ctx, poses, cap) : VIDO_ERR_ARG; }
+int vido_map_get_static(vido_ctx* ctx, int frame, float* xy, float* depth, float* p3, int32_t* asso, int cap) {
+  return ctx ? trk_get_static(ctx, frame, xy, depth, p3, asso, cap) : VIDO_ERR_ARG;
+}
+
+int vido_get_kernel_times(vido_ctx* ctx, double* ms, int64_t* launches, double* ba_alg_bytes) {
+  if (!ctx) return VIDO_ERR_ARG;
+  for (int k = 0; k < 4; k++) { if (ms) ms[k] = ctx->t_ms[k]; if (launches) launches[k] = ctx->t_n[k]; }
+  if (ba_alg_bytes) *ba_alg_bytes = ctx->ba_alg_bytes;
+  return VIDO_OK;
 }
 
 }  // extern "C"

@@ -46,6 +46,12 @@ struct vido_ctx {
   cudaStream_t stream = nullptr;
   std::string err;
   int64_t launches = 0;
+  float mscale = 1.f;  // Tracking::mScale (KAIST depth scale)
+  // device-time accounting (CUDA events on `stream`), see vido_get_kernel_times
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double t_ms[4] = {0, 0, 0, 0};   // 0 ORB front-end, 1 init model, 2 pose optimisation, 3 window BA
+  int64_t t_n[4] = {0, 0, 0, 0};
+  double ba_alg_bytes = 0;         // algorithmic bytes of the BA launches so far (SURVEY.md 8d accounting)
 
   // ---- ORB front-end ----
   int nlevels = 0;
@@ -83,6 +89,8 @@ struct vido_ctx {
   // ---- graph optimisation ----
   void* ba = nullptr;  // BaWorkspace (ba_kernels.cu)
   void* po = nullptr;  // PoWorkspace (poseopt_kernels.cu)
+  void* pnp = nullptr; // PnpWorkspace (pnp_kernels.cu)
+  void* trk = nullptr; // TrackState (track.cu)
 };
 
 #define VIDO_CUDA(call)                                                                     \
@@ -113,3 +121,27 @@ int ba_partial_host(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st);
 int po_setup(vido_ctx* ctx, int capN, int capProblems);
 void po_teardown(vido_ctx* ctx);
 int po_flow2_host(vido_ctx* ctx, vido_poseopt_problem* prs, int nproblems, vido_lm_stats* stats);
+
+// pnp_kernels.cu
+int pnp_setup(vido_ctx* ctx, int capN, int capIters);
+void pnp_teardown(vido_ctx* ctx);
+int pnp_init_model_host(vido_ctx* ctx, vido_pnp_problem* p);
+
+// assoc_kernels.cu
+int assoc_depth_prep(vido_ctx* ctx, float* d_depth, int nframes, size_t frame_stride, int stride);
+int assoc_frame_associate(vido_ctx* ctx, const vido_keypoint* d_kps, const int32_t* d_nkp, int kp_cap, const float* d_depth,
+                          const float* d_flow, const int32_t* d_mask, int nframes, int raw, int32_t* d_idx, float* d_corres,
+                          float* d_oflow, float* d_odepth, int32_t* d_n, int out_cap);
+int assoc_sample_objects(vido_ctx* ctx, const float* d_depth, const float* d_flow, const int32_t* d_mask, int nframes, int raw,
+                         float* d_keys, float* d_corres, float* d_oflow, float* d_odepth, int32_t* d_label, int32_t* d_n, int out_cap);
+int assoc_gather(vido_ctx* ctx, const float* d_depth, const float* d_flow, const int32_t* d_mask, int frame, int raw,
+                 const float* d_xy, int n, int32_t* d_omask, float* d_odepth, float* d_oflow);
+
+// track.cu
+int trk_setup(vido_ctx* ctx);
+void trk_teardown(vido_ctx* ctx);
+int trk_reset(vido_ctx* ctx);
+int trk_track_chunk(vido_ctx* ctx, const vido_frame_inputs* in, int nframes, float* Tcw_out, vido_track_stats* stats);
+int trk_num_frames(vido_ctx* ctx);
+int trk_get_map_poses(vido_ctx* ctx, float* poses, int cap);
+int trk_get_static(vido_ctx* ctx, int frame, float* xy, float* depth, float* p3, int32_t* asso, int cap);

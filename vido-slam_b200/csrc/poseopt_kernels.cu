@@ -546,7 +546,9 @@ int po_flow2_host(vido_ctx* ctx, vido_poseopt_problem* prs, int nproblems, vido_
     VIDO_CUDA(cudaMemcpyAsync((void*)a.Tcw_last, p.Tcw_last, sizeof(float) * 16, cudaMemcpyHostToDevice, s));
   }
   VIDO_CUDA(cudaMemcpyAsync(ws->d_args, h.data(), sizeof(PoArgs) * nproblems, cudaMemcpyHostToDevice, s));
+  cudaEventRecord(ctx->ev0, s);
   poseopt_flow2_kernel<<<nproblems, PO_THREADS, 0, s>>>(ws->d_args);
+  cudaEventRecord(ctx->ev1, s);
   ctx->launches++;
   VIDO_CUDA(cudaGetLastError());
   std::vector<LmCtl> ctls(4 * nproblems);
@@ -565,6 +567,10 @@ int po_flow2_host(vido_ctx* ctx, vido_poseopt_problem* prs, int nproblems, vido_
     VIDO_CUDA(cudaMemcpyAsync(recs.data(), ws->rec, sizeof(LmRec) * recs.size(), cudaMemcpyDeviceToHost, s));
   }
   VIDO_CUDA(cudaStreamSynchronize(s));
+  {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) { ctx->t_ms[2] += ms; ctx->t_n[2]++; }
+  }
   if (stats) {
     for (int k = 0; k < nproblems; k++)
       for (int r = 0; r < prs[k].rounds; r++) {

@@ -1,0 +1,641 @@
+// track.cu -- per-sequence driver of the hot path (VO, static scene): the host-side state machine of
+// Tracking::GrabImageRGBD / Track around the CUDA stages, with the Map kept as flat per-frame arrays and
+// tracklets maintained incrementally (O(features) per frame instead of the reference's rebuild from frame 0).
+//
+// Replaces (paths under /root/reference/vido_slam/src):
+//   Tracking::GrabImageRGBD    Tracking.cc:283-456    Tracking::Track            Tracking.cc:1081-1509
+//   Tracking::Initialization   Tracking.cc:1512-1580  Tracking::RenewFrameInfo   Tracking.cc:2959-3135 (static part)
+//   Tracking::GetStaticTrack   Tracking.cc:2514-2613  (incremental form, same tracklets)
+//   Optimizer::PartialBatchOptimization graph construction / write-back  Optimizer.cc:43-362, 1056-1142
+// The front-end (gray conversion, pyramid, FAST, quad-tree, orientation, association, per-keypoint map lookups) is run
+// for a whole chunk of frames at once -- it has no inter-frame dependency -- the back-end is sequential per frame.
+// Scope of this version: sensor RGBD, bJoint = true, UseSampleFeature = 0, all-zero object mask (no dynamic objects),
+// no IMU.  float 4x4 products use double accumulation + one rounding like cv::Mat CV_32F gemm.
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+
+#include "ctx.h"
+
+namespace {
+
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+void mul44(const float* A, const float* B, float* C) {
+  float o[16];
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) {
+      double s = 0;
+      for (int k = 0; k < 4; k++) s += (double)A[4 * r + k] * (double)B[4 * k + c];
+      o[4 * r + c] = (float)s;
+    }
+  memcpy(C, o, sizeof o);
+}
+void inv44(const float* T, float* Ti) {
+  float o[16] = {0};
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) o[4 * r + c] = T[4 * c + r];
+  for (int r = 0; r < 3; r++) {
+    double s = 0;
+    for (int k = 0; k < 3; k++) s += (double)(-o[4 * r + k]) * (double)T[4 * k + 3];
+    o[4 * r + 3] = (float)s;
+  }
+  o[15] = 1.f;
+  memcpy(Ti, o, sizeof o);
+}
+void eye44(float* T) { memset(T, 0, sizeof(float) * 16); T[0] = T[5] = T[10] = T[15] = 1.f; }
+
+struct MapFrame {           // Map::vpFeatSta / vfDepSta / vp3DPointSta / vnAssoSta of one frame + its pose
+  std::vector<float> xy, depth, p3;
+  std::vector<int> asso, track, pos;
+  float Twc[16];            // vmCameraPose
+  float rel[16];            // vmRigidMotion[f-1][0]
+};
+struct TrackInfo { int first_frame, len; };
+
+struct FrontFrame {         // front-end results of one frame, on the host
+  std::vector<vido_keypoint> kps;
+  std::vector<int32_t> kp_mask;          // per keypoint: mask / depth / flow at its truncated position
+  std::vector<float> kp_depth, kp_flow;
+  std::vector<int32_t> as_idx;           // Frame-ctor association
+  std::vector<float> as_corres, as_flow, as_depth;
+};
+
+}  // namespace
+
+struct TrackState {
+  // sequence state
+  std::vector<MapFrame> map;
+  std::vector<TrackInfo> tracks;
+  bool initialised = false, has_velocity = false;
+  float mVelocity[16];
+  float lastTcw[16];
+  std::vector<float> last_keys, last_depth, last_corres, last_flow;  // mpLastFrame mvStatKeys / mvStatDepth / mvCorres / mvFlowNext
+  int f_id = 0;
+  // device buffers of one chunk
+  int capB = 0;
+  uint8_t* d_img = nullptr;      // [B][H][W*3] or gray
+  uint8_t* d_gray = nullptr;     // [B][H][W]
+  float* d_depth = nullptr;      // [B][H][W]
+  float* d_flow = nullptr;       // [B][H][W][2]
+  int32_t* d_mask = nullptr;     // [B][H][W]
+  vido_keypoint* d_kp = nullptr; int32_t* d_nkp = nullptr;
+  int32_t* d_kpmask = nullptr; float* d_kpdepth = nullptr; float* d_kpflow = nullptr;
+  int32_t* d_asidx = nullptr; float* d_ascor = nullptr; float* d_asflow = nullptr; float* d_asdepth = nullptr; int32_t* d_asn = nullptr;
+  float* d_q = nullptr; int32_t* d_qmask = nullptr; float* d_qdepth = nullptr; float* d_qflow = nullptr;  // per-frame queries
+  float* d_check = nullptr; uint8_t* d_used = nullptr;
+  // pinned host mirrors
+  char* h_pin = nullptr; size_t h_pin_bytes = 0;
+  int kp_cap = 0, q_cap = 8192;
+};
+
+// ---- per-keypoint map lookups for the renewal top-up (Tracking.cc:3044-3062): mask, depth, flow at (int)pt
+__global__ void kp_lookup_kernel(const vido_keypoint* __restrict__ kps, const int32_t* __restrict__ nkp, int kp_cap, int w, int h,
+                                 const float* __restrict__ depth, const float* __restrict__ flow, const int32_t* __restrict__ mask,
+                                 size_t img_fs, int mode, float factor, float bf, float mscale, int32_t* __restrict__ omask,
+                                 float* __restrict__ odepth, float* __restrict__ oflow) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nkp[b]) return;
+  const size_t o = (size_t)b * kp_cap + i;
+  const int x = (int)kps[o].x, y = (int)kps[o].y;
+  if (x < 0 || y < 0 || x >= w || y >= h) { omask[o] = -1; odepth[o] = 0; oflow[2 * o] = 0; oflow[2 * o + 1] = 0; return; }
+  const size_t k = b * img_fs + (size_t)y * w + x;
+  float d = depth[k];
+  if (mode) {
+    if (d < 0) d = 0.f;
+    else if (mode == 1) d = __fdiv_rn(d, factor);
+    else if (mode == 2) d = __fdiv_rn(bf, __fdiv_rn(d, factor));
+    else d = __fdiv_rn(__fmul_rn(mscale, bf), __fdiv_rn(d, factor));
+  }
+  omask[o] = mask[k];
+  odepth[o] = d;
+  oflow[2 * o] = flow[2 * k];
+  oflow[2 * o + 1] = flow[2 * k + 1];
+}
+
+// used[i] = 1 if keypoint i lies within 1 px (Euclidean, float) of any already selected feature (Tracking.cc:3030-3040)
+__global__ void topup_used_kernel(const vido_keypoint* __restrict__ kps, int n, const float* __restrict__ check, int m,
+                                  uint8_t* __restrict__ used) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float sx = kps[i].x, sy = kps[i].y;
+  bool u = false;
+  for (int j = 0; j < m && !u; j++) {
+    const float dx = __fsub_rn(check[2 * j], sx), dy = __fsub_rn(check[2 * j + 1], sy);
+    const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    u = d < 1.0f;
+  }
+  used[i] = u ? 1 : 0;
+}
+
+int trk_setup(vido_ctx* ctx) {
+  TrackState* ts = new TrackState();
+  ctx->trk = ts;
+  const vido_config& c = ctx->cfg;
+  const int B = c.max_batch;
+  ts->capB = B;
+  ts->kp_cap = ctx->kp_cap;
+  const size_t px = (size_t)c.width * c.height;
+  VIDO_CUDA(cudaMalloc(&ts->d_img, px * 3 * B));
+  VIDO_CUDA(cudaMalloc(&ts->d_gray, px * B));
+  VIDO_CUDA(cudaMalloc(&ts->d_depth, px * 4 * B));
+  VIDO_CUDA(cudaMalloc(&ts->d_flow, px * 8 * B));
+  VIDO_CUDA(cudaMalloc(&ts->d_mask, px * 4 * B));
+  const size_t K = (size_t)ts->kp_cap * B;
+  VIDO_CUDA(cudaMalloc(&ts->d_kp, sizeof(vido_keypoint) * K));
+  VIDO_CUDA(cudaMalloc(&ts->d_nkp, sizeof(int32_t) * B));
+  VIDO_CUDA(cudaMalloc(&ts->d_kpmask, 4 * K)); VIDO_CUDA(cudaMalloc(&ts->d_kpdepth, 4 * K)); VIDO_CUDA(cudaMalloc(&ts->d_kpflow, 8 * K));
+  VIDO_CUDA(cudaMalloc(&ts->d_asidx, 4 * K)); VIDO_CUDA(cudaMalloc(&ts->d_ascor, 8 * K)); VIDO_CUDA(cudaMalloc(&ts->d_asflow, 8 * K));
+  VIDO_CUDA(cudaMalloc(&ts->d_asdepth, 4 * K)); VIDO_CUDA(cudaMalloc(&ts->d_asn, 4 * B));
+  VIDO_CUDA(cudaMalloc(&ts->d_q, 8 * ts->q_cap)); VIDO_CUDA(cudaMalloc(&ts->d_qmask, 4 * ts->q_cap));
+  VIDO_CUDA(cudaMalloc(&ts->d_qdepth, 4 * ts->q_cap)); VIDO_CUDA(cudaMalloc(&ts->d_qflow, 8 * ts->q_cap));
+  VIDO_CUDA(cudaMalloc(&ts->d_check, 8 * ts->q_cap)); VIDO_CUDA(cudaMalloc(&ts->d_used, ts->kp_cap));
+  return VIDO_OK;
+}
+
+void trk_teardown(vido_ctx* ctx) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  if (!ts) return;
+  cudaFree(ts->d_img); cudaFree(ts->d_gray); cudaFree(ts->d_depth); cudaFree(ts->d_flow); cudaFree(ts->d_mask);
+  cudaFree(ts->d_kp); cudaFree(ts->d_nkp); cudaFree(ts->d_kpmask); cudaFree(ts->d_kpdepth); cudaFree(ts->d_kpflow);
+  cudaFree(ts->d_asidx); cudaFree(ts->d_ascor); cudaFree(ts->d_asflow); cudaFree(ts->d_asdepth); cudaFree(ts->d_asn);
+  cudaFree(ts->d_q); cudaFree(ts->d_qmask); cudaFree(ts->d_qdepth); cudaFree(ts->d_qflow); cudaFree(ts->d_check); cudaFree(ts->d_used);
+  delete ts;
+  ctx->trk = nullptr;
+}
+
+int trk_reset(vido_ctx* ctx) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  ts->map.clear(); ts->tracks.clear();
+  ts->initialised = false; ts->has_velocity = false; ts->f_id = 0;
+  ts->last_keys.clear(); ts->last_depth.clear(); ts->last_corres.clear(); ts->last_flow.clear();
+  return VIDO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// front-end of a chunk: inputs resident on the device
+// ---------------------------------------------------------------------------------------------------------
+static int front_end(vido_ctx* ctx, int B, const uint8_t* d_img, int channels, const float* d_depth, const float* d_flow,
+                     const int32_t* d_mask, std::vector<FrontFrame>& out) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  const vido_config& c = ctx->cfg;
+  cudaStream_t s = ctx->stream;
+  const size_t px = (size_t)c.width * c.height;
+  const uint8_t* d_gray = d_img;
+  cudaEventRecord(ctx->ev0, s);
+  if (channels == 3) {
+    int rc = orb_bgr_to_gray(ctx, d_img, B, px * 3, c.width * 3, ts->d_gray, px, c.width);
+    if (rc) return rc;
+    d_gray = ts->d_gray;
+  }
+  int rc = orb_run(ctx, d_gray, B, px, c.width, ts->d_kp, ts->kp_cap, ts->d_nkp);
+  if (rc) return rc;
+  rc = assoc_frame_associate(ctx, ts->d_kp, ts->d_nkp, ts->kp_cap, d_depth, d_flow, d_mask, B, 1, ts->d_asidx, ts->d_ascor,
+                             ts->d_asflow, ts->d_asdepth, ts->d_asn, ts->kp_cap);
+  if (rc) return rc;
+  {
+    dim3 grid((ts->kp_cap + 255) / 256, B);
+    kp_lookup_kernel<<<grid, 256, 0, s>>>(ts->d_kp, ts->d_nkp, ts->kp_cap, c.width, c.height, d_depth, d_flow, d_mask, px,
+                                          c.choose_data, c.depth_map_factor, c.bf, ctx->mscale, ts->d_kpmask, ts->d_kpdepth, ts->d_kpflow);
+    ctx->launches++;
+  }
+  cudaEventRecord(ctx->ev1, s);
+  VIDO_CUDA(cudaGetLastError());
+  std::vector<int32_t> nkp(B), asn(B);
+  VIDO_CUDA(cudaMemcpyAsync(nkp.data(), ts->d_nkp, 4 * B, cudaMemcpyDeviceToHost, s));
+  VIDO_CUDA(cudaMemcpyAsync(asn.data(), ts->d_asn, 4 * B, cudaMemcpyDeviceToHost, s));
+  int32_t flag = 0;
+  VIDO_CUDA(cudaMemcpyAsync(&flag, ctx->d_err, 4, cudaMemcpyDeviceToHost, s));
+  VIDO_CUDA(cudaStreamSynchronize(s));
+  if (flag) { ctx->err = "ORB front-end capacity flag set"; cudaMemsetAsync(ctx->d_err, 0, 4, s); return VIDO_ERR_CAPACITY; }
+  {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) { ctx->t_ms[0] += ms; ctx->t_n[0] += B; }
+  }
+  out.resize(B);
+  for (int b = 0; b < B; b++) {
+    FrontFrame& f = out[b];
+    const int n = nkp[b], m = std::min(asn[b], ts->kp_cap);
+    const size_t o = (size_t)b * ts->kp_cap;
+    f.kps.resize(n); f.kp_mask.resize(n); f.kp_depth.resize(n); f.kp_flow.resize(2 * (size_t)n);
+    f.as_idx.resize(m); f.as_corres.resize(2 * (size_t)m); f.as_flow.resize(2 * (size_t)m); f.as_depth.resize(m);
+    if (n) {
+      VIDO_CUDA(cudaMemcpyAsync(f.kps.data(), ts->d_kp + o, sizeof(vido_keypoint) * n, cudaMemcpyDeviceToHost, s));
+      VIDO_CUDA(cudaMemcpyAsync(f.kp_mask.data(), ts->d_kpmask + o, 4 * n, cudaMemcpyDeviceToHost, s));
+      VIDO_CUDA(cudaMemcpyAsync(f.kp_depth.data(), ts->d_kpdepth + o, 4 * n, cudaMemcpyDeviceToHost, s));
+      VIDO_CUDA(cudaMemcpyAsync(f.kp_flow.data(), ts->d_kpflow + 2 * o, 8 * n, cudaMemcpyDeviceToHost, s));
+    }
+    if (m) {
+      VIDO_CUDA(cudaMemcpyAsync(f.as_idx.data(), ts->d_asidx + o, 4 * m, cudaMemcpyDeviceToHost, s));
+      VIDO_CUDA(cudaMemcpyAsync(f.as_corres.data(), ts->d_ascor + 2 * o, 8 * m, cudaMemcpyDeviceToHost, s));
+      VIDO_CUDA(cudaMemcpyAsync(f.as_flow.data(), ts->d_asflow + 2 * o, 8 * m, cudaMemcpyDeviceToHost, s));
+      VIDO_CUDA(cudaMemcpyAsync(f.as_depth.data(), ts->d_asdepth + o, 4 * m, cudaMemcpyDeviceToHost, s));
+    }
+  }
+  VIDO_CUDA(cudaStreamSynchronize(s));
+  return VIDO_OK;
+}
+
+// (mask, depth, flow) of frame `slot` of the resident chunk at n query positions
+static int query_maps(vido_ctx* ctx, const float* d_depth, const float* d_flow, const int32_t* d_mask, int slot, const float* xy,
+                      int n, int32_t* omask, float* odepth, float* oflow) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  if (n <= 0) return VIDO_OK;
+  if (n > ts->q_cap) { ctx->err = "too many map queries"; return VIDO_ERR_CAPACITY; }
+  cudaStream_t s = ctx->stream;
+  VIDO_CUDA(cudaMemcpyAsync(ts->d_q, xy, 8 * (size_t)n, cudaMemcpyHostToDevice, s));
+  int rc = assoc_gather(ctx, d_depth, d_flow, d_mask, slot, 1, ts->d_q, n, ts->d_qmask, ts->d_qdepth, ts->d_qflow);
+  if (rc) return rc;
+  VIDO_CUDA(cudaMemcpyAsync(omask, ts->d_qmask, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
+  VIDO_CUDA(cudaMemcpyAsync(odepth, ts->d_qdepth, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
+  VIDO_CUDA(cudaMemcpyAsync(oflow, ts->d_qflow, 8 * (size_t)n, cudaMemcpyDeviceToHost, s));
+  VIDO_CUDA(cudaStreamSynchronize(s));
+  return VIDO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// window graph from the flat map (Optimizer.cc:220-362) + solve + write-back (:1056-1142)
+// ---------------------------------------------------------------------------------------------------------
+static int partial_batch(vido_ctx* ctx, int WINDOW, vido_track_stats* st) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  const int N = (int)ts->map.size();
+  if (st) { st->ba_iterations = -1; st->ba_points = 0; st->ba_obs = 0; st->ba_trials = 0; }
+  if (WINDOW <= 0) return VIDO_OK;
+  const int start = N - WINDOW;
+  std::vector<float> poses(16 * (size_t)WINDOW), rel(16 * (size_t)std::max(WINDOW - 1, 0)), pts, oxyz;
+  std::vector<int> op, ol;
+  std::vector<int> pid_of_track;  // lazily sized
+  std::vector<std::pair<int, int>> owner;
+  std::vector<int> tid_list;
+  const float invfx = 1.0f / ctx->cfg.fx, invfy = 1.0f / ctx->cfg.fy;
+  // a track enters the window graph iff it is at least 3 long and was born inside the window
+  pid_of_track.assign(ts->tracks.size(), -1);
+  for (int i = start; i < N; i++) {
+    MapFrame& F = ts->map[i];
+    memcpy(&poses[16 * (size_t)(i - start)], F.Twc, sizeof(float) * 16);
+    if (i != start) memcpy(&rel[16 * (size_t)(i - start - 1)], F.rel, sizeof(float) * 16);
+    const int n = (int)F.depth.size();
+    for (int j = 0; j < n; j++) {
+      const int t = F.track[j];
+      if (t < 0) continue;
+      const TrackInfo& T = ts->tracks[t];
+      if (T.len < 3 || T.first_frame < start) continue;
+      int pid = pid_of_track[t];
+      if (F.pos[j] == 0) {
+        pid = (int)owner.size();
+        pid_of_track[t] = pid;
+        owner.push_back({i, j});
+        pts.push_back(F.p3[3 * j]); pts.push_back(F.p3[3 * j + 1]); pts.push_back(F.p3[3 * j + 2]);
+      }
+      if (pid < 0) continue;
+      const float z = F.depth[j], u = F.xy[2 * j], v = F.xy[2 * j + 1];
+      op.push_back(i - start); ol.push_back(pid);
+      oxyz.push_back((u - ctx->cfg.cx) * z * invfx); oxyz.push_back((v - ctx->cfg.cy) * z * invfy); oxyz.push_back(z);
+    }
+  }
+  vido_ba_problem pr;
+  memset(&pr, 0, sizeof pr);
+  vido_ba_default_params(&pr);
+  pr.n_poses = WINDOW; pr.n_points = (int)owner.size(); pr.n_obs = (int)op.size();
+  pr.poses = poses.data(); pr.rel_motion = rel.data(); pr.points = pts.data();
+  pr.obs_pose = op.data(); pr.obs_point = ol.data(); pr.obs_xyz = oxyz.data();
+  vido_lm_stats ls;
+  int rc = ba_partial_host(ctx, &pr, &ls);
+  if (rc) return rc;
+  if (st) { st->ba_iterations = ls.iterations; st->ba_points = pr.n_points; st->ba_obs = pr.n_obs; st->ba_trials = ls.total_trials; }
+  for (int i = start; i < N; i++) {
+    memcpy(ts->map[i].Twc, &poses[16 * (size_t)(i - start)], sizeof(float) * 16);
+    if (i > start) memcpy(ts->map[i].rel, &rel[16 * (size_t)(i - start - 1)], sizeof(float) * 16);
+  }
+  // every observation of an optimised point receives the optimised position (Optimizer.cc:1107-1122)
+  {
+    for (int i = start; i < N; i++) {
+      MapFrame& F = ts->map[i];
+      const int n = (int)F.depth.size();
+      for (int j = 0; j < n; j++) {
+        const int t = F.track[j];
+        if (t < 0) continue;
+        const TrackInfo& T = ts->tracks[t];
+        if (T.len < 3 || T.first_frame < start) continue;
+        const int pid = pid_of_track[t];
+        if (pid < 0) continue;
+        F.p3[3 * j] = pts[3 * (size_t)pid]; F.p3[3 * j + 1] = pts[3 * (size_t)pid + 1]; F.p3[3 * j + 2] = pts[3 * (size_t)pid + 2];
+      }
+    }
+  }
+  return VIDO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// back-end of one frame (sequential)
+// ---------------------------------------------------------------------------------------------------------
+static int back_end(vido_ctx* ctx, const FrontFrame& ff, int slot, const float* d_depth, const float* d_flow,
+                    const int32_t* d_mask, float* Tcw_out, vido_track_stats* st) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  const vido_config& c = ctx->cfg;
+  const int W = c.width, H = c.height;
+  cudaStream_t s = ctx->stream;
+  const float invfx = 1.0f / c.fx, invfy = 1.0f / c.fy;
+  float curTcw[16];
+  eye44(curTcw);
+  if (st) { memset(st, 0, sizeof *st); st->n_keypoints = (int)ff.kps.size(); }
+  int skipped = 0;
+  double t0 = now_ms();
+  if (!ts->initialised) {
+    // ---- Tracking::Initialization: features leaving frame 0 are the associated detections
+    MapFrame F;
+    const int m = (int)ff.as_idx.size();
+    F.xy.resize(2 * (size_t)m); F.depth = ff.as_depth; F.p3.resize(3 * (size_t)m);
+    F.asso.assign(m, -1); F.track.assign(m, -1); F.pos.assign(m, 0);
+    for (int i = 0; i < m; i++) {
+      const vido_keypoint& kp = ff.kps[ff.as_idx[i]];
+      F.xy[2 * i] = kp.x; F.xy[2 * i + 1] = kp.y;
+      const float z = F.depth[i];
+      F.p3[3 * i] = (kp.x - c.cx) * z * invfx; F.p3[3 * i + 1] = (kp.y - c.cy) * z * invfy; F.p3[3 * i + 2] = z;
+    }
+    eye44(F.Twc); eye44(F.rel);
+    ts->last_keys = F.xy; ts->last_depth = F.depth; ts->last_corres = ff.as_corres; ts->last_flow = ff.as_flow;
+    memcpy(ts->lastTcw, curTcw, sizeof curTcw);
+    ts->map.push_back(std::move(F));
+    ts->initialised = true;
+  } else {
+    const int Ns = (int)(ts->last_corres.size() / 2);
+    if (Ns < 2) skipped = 1;
+    else {
+      // ---- mvStatKeys = last mvCorres; depth lookups with the 1-px border rule (Tracking.cc:369-389)
+      std::vector<float> keys = ts->last_corres, kdepth(Ns, -1.f), qflow(2 * (size_t)Ns);
+      std::vector<int32_t> qmask(Ns);
+      {
+        std::vector<float> qd(Ns);
+        int rc = query_maps(ctx, d_depth, d_flow, d_mask, slot, keys.data(), Ns, qmask.data(), qd.data(), qflow.data());
+        if (rc) return rc;
+        for (int i = 0; i < Ns; i++) {
+          const int v = (int)keys[2 * i + 1], u = (int)keys[2 * i];
+          if (u < (W - 1) && u > 0 && v < (H - 1) && v > 0 && qd[i] > 0) kdepth[i] = qd[i];
+        }
+      }
+      // ---- GetInitModelCam: 3-D points of the last frame, constant-velocity model, PnP-RANSAC
+      std::vector<float> p3d(3 * (size_t)Ns, 0.f);
+      std::vector<int32_t> valid(Ns, 1), ids(Ns);
+      float Twl[16];
+      inv44(ts->lastTcw, Twl);
+      for (int i = 0; i < Ns; i++) {
+        const float z = ts->last_depth[i];
+        if (z < 0) { valid[i] = 0; continue; }
+        const float xc[3] = {(ts->last_keys[2 * i] - c.cx) * z * invfx, (ts->last_keys[2 * i + 1] - c.cy) * z * invfy, z};
+        for (int r = 0; r < 3; r++)
+          p3d[3 * i + r] = (float)((double)Twl[4 * r] * xc[0] + (double)Twl[4 * r + 1] * xc[1] + (double)Twl[4 * r + 2] * xc[2]) + Twl[4 * r + 3];
+      }
+      vido_pnp_problem pp;
+      memset(&pp, 0, sizeof pp);
+      vido_pnp_default_params(&pp);
+      pp.n = Ns; pp.cur_xy = keys.data(); pp.pts3d = p3d.data(); pp.valid = valid.data(); pp.inlier_ids = ids.data();
+      if (ts->has_velocity) mul44(ts->mVelocity, ts->lastTcw, pp.Tcw_motion);
+      else memcpy(pp.Tcw_motion, ts->lastTcw, sizeof(float) * 16);
+      pp.fx = c.fx; pp.fy = c.fy; pp.cx = c.cx; pp.cy = c.cy;
+      int rc = pnp_init_model_host(ctx, &pp);
+      if (rc) return rc;
+      std::vector<int> TM(ids.begin(), ids.begin() + pp.n_inliers);
+      memcpy(curTcw, pp.Tcw_out, sizeof curTcw);
+      double t1 = now_ms();
+      // ---- PoseOptimizationFlow2Cam
+      const int n = (int)TM.size();
+      std::vector<float> obs(2 * (size_t)n), fl(2 * (size_t)n), dep(n), fo(2 * (size_t)n);
+      std::vector<int32_t> inl(n);
+      for (int i = 0; i < n; i++) {
+        const int k = TM[i];
+        obs[2 * i] = ts->last_keys[2 * k]; obs[2 * i + 1] = ts->last_keys[2 * k + 1];
+        fl[2 * i] = ts->last_flow[2 * k]; fl[2 * i + 1] = ts->last_flow[2 * k + 1];
+        dep[i] = ts->last_depth[k];
+      }
+      vido_poseopt_problem po;
+      memset(&po, 0, sizeof po);
+      vido_poseopt_default_params(&po);
+      po.n = n; po.obs_xy = obs.data(); po.flow_xy = fl.data(); po.depth = dep.data();
+      memcpy(po.Tcw_init, curTcw, sizeof curTcw);
+      memcpy(po.Tcw_last, ts->lastTcw, sizeof curTcw);
+      po.fx = c.fx; po.fy = c.fy; po.cx = c.cx; po.cy = c.cy;
+      po.flow_out = fo.data(); po.inlier = inl.data();
+      rc = po_flow2_host(ctx, &po, 1, nullptr);
+      if (rc) return rc;
+      memcpy(curTcw, po.Tcw_out, sizeof curTcw);
+      if (n >= 3) {
+        for (int i = 0; i < n; i++) {
+          if (inl[i]) {
+            const int k = TM[i];
+            keys[2 * k] = (float)((double)ts->last_keys[2 * k] + (double)fo[2 * i]);
+            keys[2 * k + 1] = (float)((double)ts->last_keys[2 * k + 1] + (double)fo[2 * i + 1]);
+          } else TM[i] = -1;
+        }
+      }
+      double t2 = now_ms();
+      // ---- motion model: mVelocity = Tcw * LastTwc
+      float LastTwc[16];
+      inv44(ts->lastTcw, LastTwc);
+      mul44(curTcw, LastTwc, ts->mVelocity);
+      ts->has_velocity = true;
+      // ---- RenewFrameInfo (static part).  (1) surviving inliers at their refined positions
+      MapFrame F;
+      std::vector<float> ncorres, nflow;
+      const int maxn = c.max_track_bg;
+      {
+        std::vector<float> qxy;
+        std::vector<int> qk;
+        for (int i = 0; i < n; i++)
+          if (TM[i] != -1) { qxy.push_back(keys[2 * TM[i]]); qxy.push_back(keys[2 * TM[i] + 1]); qk.push_back(TM[i]); }
+        const int nq = (int)qk.size();
+        std::vector<int32_t> m2(nq);
+        std::vector<float> d2(nq), f2(2 * (size_t)nq);
+        rc = query_maps(ctx, d_depth, d_flow, d_mask, slot, qxy.data(), nq, m2.data(), d2.data(), f2.data());
+        if (rc) return rc;
+        for (int i = 0; i < nq; i++) {
+          const float px = qxy[2 * i], py = qxy[2 * i + 1];
+          const int x = (int)px, y = (int)py;
+          bool ok = !(x >= W || y >= H || x <= 0 || y <= 0) && m2[i] == 0 && !(d2[i] > 40 || d2[i] <= 0);
+          const float fx = f2[2 * i], fy = f2[2 * i + 1];
+          if (ok && fx != 0 && fy != 0 && px + fx < W && py + fy < H && px + fx > 0 && py + fy > 0) {
+            F.xy.push_back(px); F.xy.push_back(py);
+            ncorres.push_back(px + fx); ncorres.push_back(py + fy);
+            nflow.push_back(fx); nflow.push_back(fy);
+            F.depth.push_back(d2[i] > 0 ? d2[i] : -1.f);
+            F.asso.push_back(qk[i]);
+          }
+          if ((int)F.asso.size() > maxn) break;
+        }
+      }
+      // (2) top-up from the detected keypoints in 20 interleaved passes, skipping those within 1 px of a kept feature
+      int tot = (int)F.asso.size();
+      if (tot < maxn && !ff.kps.empty()) {
+        const int nk = (int)ff.kps.size(), mcheck = tot;
+        std::vector<uint8_t> used(nk, 0);
+        if (mcheck > 0) {
+          if (mcheck > ts->q_cap) { ctx->err = "renewal check list too long"; return VIDO_ERR_CAPACITY; }
+          VIDO_CUDA(cudaMemcpyAsync(ts->d_check, F.xy.data(), 8 * (size_t)mcheck, cudaMemcpyHostToDevice, s));
+          topup_used_kernel<<<(nk + 127) / 128, 128, 0, s>>>(ts->d_kp + (size_t)slot * ts->kp_cap, nk, ts->d_check, mcheck, ts->d_used);
+          ctx->launches++;
+          VIDO_CUDA(cudaMemcpyAsync(used.data(), ts->d_used, nk, cudaMemcpyDeviceToHost, s));
+          VIDO_CUDA(cudaStreamSynchronize(s));
+        }
+        int start_id = 0;
+        const int step = 20;
+        while (tot < maxn) {
+          if (start_id == step) break;
+          for (int i = start_id; i < nk; i += step) {
+            if (used[i]) continue;
+            const float px = ff.kps[i].x, py = ff.kps[i].y;
+            const int x = (int)px, y = (int)py;
+            if (x >= W || y >= H || x <= 0 || y <= 0) continue;
+            if (ff.kp_mask[i] != 0) continue;
+            const float d = ff.kp_depth[i];
+            if (d > 40 || d <= 0) continue;
+            const float fx = ff.kp_flow[2 * i], fy = ff.kp_flow[2 * i + 1];
+            if (fx != 0 && fy != 0 && px + fx < W && py + fy < H && px + fx > 0 && py + fy > 0) {
+              F.xy.push_back(px); F.xy.push_back(py);
+              ncorres.push_back(px + fx); ncorres.push_back(py + fy);
+              nflow.push_back(fx); nflow.push_back(fy);
+              F.depth.push_back(d);
+              F.asso.push_back(-1);
+              tot++;
+            }
+            if (tot >= maxn) break;
+          }
+          start_id++;
+        }
+      }
+      // (3)(4) world points through the current pose (Optimizer::Get3DinWorld)
+      const int nf = (int)F.asso.size();
+      float Twc[16];
+      inv44(curTcw, Twc);
+      F.p3.resize(3 * (size_t)nf);
+      for (int i = 0; i < nf; i++) {
+        const float z = F.depth[i];
+        const float xc[3] = {(F.xy[2 * i] - c.cx) * z * invfx, (F.xy[2 * i + 1] - c.cy) * z * invfy, z};
+        for (int r = 0; r < 3; r++)
+          F.p3[3 * i + r] = (float)((double)Twc[4 * r] * xc[0] + (double)Twc[4 * r + 1] * xc[1] + (double)Twc[4 * r + 2] * xc[2]) + Twc[4 * r + 3];
+      }
+      // ---- tracklets, incrementally (same chains as Tracking::GetStaticTrack)
+      F.track.assign(nf, -1); F.pos.assign(nf, 0);
+      MapFrame& P = ts->map.back();
+      const int fcur = (int)ts->map.size();
+      for (int j = 0; j < nf; j++) {
+        const int p = F.asso[j];
+        if (p < 0) continue;
+        if (P.track[p] >= 0) {
+          TrackInfo& T = ts->tracks[P.track[p]];
+          F.track[j] = P.track[p];
+          F.pos[j] = T.len;
+          T.len++;
+        } else {
+          const int t = (int)ts->tracks.size();
+          ts->tracks.push_back({fcur - 1, 2});
+          P.track[p] = t; P.pos[p] = 0;
+          F.track[j] = t; F.pos[j] = 1;
+        }
+      }
+      memcpy(F.Twc, Twc, sizeof Twc);
+      inv44(ts->mVelocity, F.rel);
+      ts->last_keys = F.xy; ts->last_depth = F.depth; ts->last_corres = ncorres; ts->last_flow = nflow;
+      memcpy(ts->lastTcw, curTcw, sizeof curTcw);
+      ts->map.push_back(std::move(F));
+      double t3 = now_ms();
+      if (st) {
+        st->ms_init = t1 - t0; st->ms_poseopt = t2 - t1; st->ms_renew = t3 - t2;
+        st->n_matches = Ns; st->n_init_inliers = pp.n_inliers; st->init_winner = pp.winner; st->n_pose_inliers = po.n_inliers;
+        st->n_static = nf;
+      }
+    }
+  }
+  memcpy(Tcw_out, curTcw, sizeof(float) * 16);
+  double t4 = now_ms();
+  const int window = ts->f_id < c.window_size ? ts->f_id : c.window_size;
+  int rc = skipped ? VIDO_OK : partial_batch(ctx, window, st);
+  if (st) st->ms_ba = now_ms() - t4;
+  ts->f_id++;
+  if (rc) return rc;
+  return skipped ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+int trk_track_chunk(vido_ctx* ctx, const vido_frame_inputs* in, int nframes, float* Tcw_out, vido_track_stats* stats) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  const vido_config& c = ctx->cfg;
+  cudaStream_t s = ctx->stream;
+  const size_t px = (size_t)c.width * c.height;
+  int done = 0;
+  while (done < nframes) {
+    const int B = std::min(ts->capB, nframes - done);
+    const vido_frame_inputs* f0 = in + done;
+    const int channels = f0->channels;
+    const uint8_t* d_img; const float* d_depth; const float* d_flow; const int32_t* d_mask;
+    bool contiguous_dev = f0->on_device != 0;
+    for (int b = 0; b < B; b++) {
+      const vido_frame_inputs& f = in[done + b];
+      if (f.channels != channels || (f.on_device != 0) != contiguous_dev || (channels != 1 && channels != 3)) { ctx->err = "inconsistent frame inputs"; return VIDO_ERR_ARG; }
+      if (f.on_device) {
+        // device-resident frames must be consecutive slices of one allocation (frame k at base + k*frame_bytes)
+        if (f.image != f0->image + (size_t)b * px * channels || f.depth != f0->depth + (size_t)b * px ||
+            f.flow != f0->flow + (size_t)b * px * 2 || f.mask != f0->mask + (size_t)b * px) contiguous_dev = false;
+      }
+    }
+    double tf0 = now_ms();
+    if (f0->on_device && contiguous_dev) {
+      d_img = f0->image; d_depth = f0->depth; d_flow = f0->flow; d_mask = f0->mask;
+    } else {
+      const cudaMemcpyKind kind = f0->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+      for (int b = 0; b < B; b++) {
+        const vido_frame_inputs& f = in[done + b];
+        VIDO_CUDA(cudaMemcpyAsync(ts->d_img + (size_t)b * px * channels, f.image, px * channels, kind, s));
+        VIDO_CUDA(cudaMemcpyAsync(ts->d_depth + (size_t)b * px, f.depth, px * 4, kind, s));
+        VIDO_CUDA(cudaMemcpyAsync(ts->d_flow + (size_t)b * px * 2, f.flow, px * 8, kind, s));
+        VIDO_CUDA(cudaMemcpyAsync(ts->d_mask + (size_t)b * px, f.mask, px * 4, kind, s));
+      }
+      d_img = ts->d_img; d_depth = ts->d_depth; d_flow = ts->d_flow; d_mask = ts->d_mask;
+    }
+    std::vector<FrontFrame> ff;
+    int rc = front_end(ctx, B, d_img, channels, d_depth, d_flow, d_mask, ff);
+    if (rc) return rc;
+    const double front_ms = (now_ms() - tf0) / B;
+    for (int b = 0; b < B; b++) {
+      vido_track_stats* st = stats ? stats + done + b : nullptr;
+      rc = back_end(ctx, ff[b], b, d_depth, d_flow, d_mask, Tcw_out + 16 * (size_t)(done + b), st);
+      if (rc < 0) return rc;
+      if (st) { st->ms_orb = front_ms; st->ms_assoc = 0; }
+      // the reference pre-scales the caller's depth map in place (Tracking.cc:299-322): reproduce on request
+      const vido_frame_inputs& f = in[done + b];
+      if (f.write_back_depth) {
+        rc = assoc_depth_prep(ctx, (float*)d_depth + (size_t)b * px, 1, px, c.width);
+        if (rc) return rc;
+        if (!f.on_device) VIDO_CUDA(cudaMemcpyAsync((void*)f.depth, d_depth + (size_t)b * px, px * 4, cudaMemcpyDeviceToHost, s));
+        else if (d_depth != f.depth) VIDO_CUDA(cudaMemcpyAsync((void*)f.depth, d_depth + (size_t)b * px, px * 4, cudaMemcpyDeviceToDevice, s));
+        VIDO_CUDA(cudaStreamSynchronize(s));
+      }
+    }
+    done += B;
+  }
+  return VIDO_OK;
+}
+
+int trk_num_frames(vido_ctx* ctx) { return (int)((TrackState*)ctx->trk)->map.size(); }
+
+int trk_get_map_poses(vido_ctx* ctx, float* poses, int cap) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  const int n = (int)ts->map.size();
+  for (int i = 0; i < n && i < cap; i++) memcpy(poses + 16 * (size_t)i, ts->map[i].Twc, sizeof(float) * 16);
+  return n;
+}
+
+int trk_get_static(vido_ctx* ctx, int frame, float* xy, float* depth, float* p3, int32_t* asso, int cap) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  if (frame < 0 || frame >= (int)ts->map.size()) return -1;
+  const MapFrame& F = ts->map[frame];
+  const int n = (int)F.depth.size();
+  for (int i = 0; i < n && i < cap; i++) {
+    xy[2 * i] = F.xy[2 * i]; xy[2 * i + 1] = F.xy[2 * i + 1];
+    depth[i] = F.depth[i];
+    p3[3 * i] = F.p3[3 * i]; p3[3 * i + 1] = F.p3[3 * i + 1]; p3[3 * i + 2] = F.p3[3 * i + 2];
+    asso[i] = F.asso[i];
+  }
+  return n;
+}
