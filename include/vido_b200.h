@@ -228,6 +228,26 @@ int vido_map_num_frames(vido_ctx* ctx);
 int vido_map_get_poses(vido_ctx* ctx, float* poses, int cap);
 int vido_map_get_static(vido_ctx* ctx, int frame, float* xy, float* depth, float* p3, int32_t* asso, int cap);
 
+
+/*
+ * IMU preintegration: replaces Tracking::PreintegrateIMU (src/Tracking.cc:784-887) + IMU::Preintegrated::
+ * IntegrateNewMeasurement (src/ImuTypes.cc:245-300) for njobs frame intervals at once.  samples = the IMU queue
+ * (ascending t, System::TrackRGBD's vImuMeas / IMU::Point); job j integrates (t_prev[j], t_cur[j]]; bias[j] =
+ * (bax,bay,baz,bwx,bwy,bwz) of the previous frame; noise = (ng, na, ngw, naw) as given to IMU::Calib::Set.
+ * Fields mirror IMU::Preintegrated (include/ImuTypes.h:120-233), float32.  Host pointers.
+ */
+typedef struct vido_imu_sample { double t; float ax, ay, az, wx, wy, wz; } vido_imu_sample;
+typedef struct vido_imu_preint {
+  float dT;
+  float dR[9], dV[3], dP[3];
+  float JRg[9], JVg[9], JVa[9], JPg[9], JPa[9];
+  float C[225];
+  float avgA[3], avgW[3];
+  int32_t n_steps, n_consumed;
+} vido_imu_preint;
+int vido_imu_preintegrate(vido_ctx* ctx, const vido_imu_sample* samples, int n, const double* t_prev, const double* t_cur,
+                          int njobs, const float* bias, const float* noise, vido_imu_preint* out);
+
 /* accumulated device time (CUDA events on the context stream) of the kernel groups: ms[0] ORB front-end launches,
  * ms[1] init-model kernels, ms[2] pose-optimisation kernel, ms[3] window-BA kernel; launches[k] = timed regions;
  * ba_alg_bytes = algorithmic bytes of the BA launches (296 B per edge per linearisation + 152 B per edge per

@@ -178,6 +178,22 @@ int vo_tracker_num_frames(void* h);
 int vo_tracker_get_map_poses(void* h, float* poses /* [n][16] Map::vmCameraPose (Twc, BA-refined) */, int cap);
 int vo_tracker_get_static(void* h, int frame, float* xy, float* depth, float* p3, int32_t* asso, int cap);
 
+/* ---- IMU preintegration: Tracking::PreintegrateIMU (src/Tracking.cc:784-887) + IMU::Preintegrated (src/ImuTypes.cc:143-300) ---- */
+typedef struct vo_imu_sample { double t; float ax, ay, az, wx, wy, wz; } vo_imu_sample;
+typedef struct vo_imu_preint {
+  float dT;
+  float dR[9], dV[3], dP[3];
+  float JRg[9], JVg[9], JVa[9], JPg[9], JPa[9];
+  float C[225];
+  float avgA[3], avgW[3];
+  int32_t n_steps, n_consumed; /* integrated steps; samples popped from the queue (the last used sample stays) */
+} vo_imu_preint;
+/* samples: the IMU queue (ascending t); bias = (bax,bay,baz,bwx,bwy,bwz); noise = (ng, na, ngw, naw) as passed to
+ * IMU::Calib::Set.  All arithmetic float32 like the reference's cv::Mat code (products accumulated in double and
+ * rounded once, as cv::gemm does for CV_32F); cv::SVDecomp-based NormalizeRotation is replaced by the polar factor. */
+int vo_imu_preintegrate(const vo_imu_sample* samples, int n, double t_prev, double t_cur, const float* bias,
+                        const float* noise, vo_imu_preint* out);
+
 #ifdef __cplusplus
 }
 #endif

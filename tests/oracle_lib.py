@@ -321,3 +321,20 @@ class OracleTracker:
         if self.h:
             lib().vo_tracker_destroy(self.h)
             self.h = None
+
+
+# ---------------------------------------------------------------- IMU preintegration oracle
+IMU_SAMPLE = np.dtype([("t", "<f8"), ("ax", "<f4"), ("ay", "<f4"), ("az", "<f4"), ("wx", "<f4"), ("wy", "<f4"), ("wz", "<f4")])
+IMU_PREINT = np.dtype([("dT", "<f4"), ("dR", "<f4", 9), ("dV", "<f4", 3), ("dP", "<f4", 3), ("JRg", "<f4", 9),
+                       ("JVg", "<f4", 9), ("JVa", "<f4", 9), ("JPg", "<f4", 9), ("JPa", "<f4", 9), ("C", "<f4", 225),
+                       ("avgA", "<f4", 3), ("avgW", "<f4", 3), ("n_steps", "<i4"), ("n_consumed", "<i4")])
+
+
+def imu_preintegrate(samples, t_prev, t_cur, bias, noise):
+    s = np.ascontiguousarray(samples, IMU_SAMPLE)
+    b = np.ascontiguousarray(bias, np.float32); nz = np.ascontiguousarray(noise, np.float32)
+    out = np.zeros(1, IMU_PREINT)
+    L = lib()
+    L.vo_imu_preintegrate.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.vo_imu_preintegrate(_p(s), len(s), float(t_prev), float(t_cur), _p(b), _p(nz), _p(out))
+    return out[0]

@@ -22,12 +22,14 @@ def _compare(ctx, pr, **params):
     args = (pr["poses"], pr["rel"], pr["points"], pr["obs_pose"], pr["obs_point"], pr["obs_xyz"])
     rp, rr, rpts, rits, rst = ol.ba_partial(*args, **params)
     gp, gr, gpts, gits, gst = ctx.ba_partial(*args, **params)
-    assert gits == rits, (gits, rits, gst.records(), rst.records())
-    assert gst.total_trials == rst.total_trials
-    for (c1, l1, t1), (c2, l2, t2) in zip(gst.records(), rst.records()):
-        assert t1 == t2
-        assert abs(c1 - c2) <= REL_TOL * max(abs(c2), 1e-12)
-        assert abs(l1 - l2) <= 1e-3 * abs(l2)
+    if len(pr["obs_pose"]):  # an odometry-only graph is solved exactly: its chi2 ends at round-off (1e-30) and the
+        # stop decisions below that level are noise, so the LM trajectory is only compared for real graphs
+        assert gits == rits, (gits, rits, gst.records(), rst.records())
+        assert gst.total_trials == rst.total_trials
+        for (c1, l1, t1), (c2, l2, t2) in zip(gst.records(), rst.records()):
+            assert t1 == t2
+            assert abs(c1 - c2) <= REL_TOL * max(abs(c2), 1e-12)
+            assert abs(l1 - l2) <= 1e-3 * abs(l2)
     scale_p = max(np.abs(rp).max(), 1.0)
     assert np.abs(gp - rp).max() <= REL_TOL * scale_p
     assert np.abs(gr - rr).max() <= REL_TOL * max(np.abs(rr).max(), 1.0)

@@ -82,6 +82,12 @@ class TrackStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+IMU_SAMPLE = np.dtype([("t", "<f8"), ("ax", "<f4"), ("ay", "<f4"), ("az", "<f4"), ("wx", "<f4"), ("wy", "<f4"), ("wz", "<f4")])
+IMU_PREINT = np.dtype([("dT", "<f4"), ("dR", "<f4", 9), ("dV", "<f4", 3), ("dP", "<f4", 3), ("JRg", "<f4", 9),
+                       ("JVg", "<f4", 9), ("JVa", "<f4", 9), ("JPg", "<f4", 9), ("JPa", "<f4", 9), ("C", "<f4", 225),
+                       ("avgA", "<f4", 3), ("avgW", "<f4", 3), ("n_steps", "<i4"), ("n_consumed", "<i4")])
+
+
 class VidoError(RuntimeError):
     pass
 
@@ -116,6 +122,7 @@ def load_library():
     lib.vido_bgr_to_gray_dev.argtypes = [vp, vp, C.c_int, C.c_size_t, C.c_int, vp, C.c_size_t, C.c_int]
     lib.vido_orb_get_level.argtypes = [vp, C.c_int, C.c_int, vp]
     lib.vido_orb_get_candidates.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp]
+    lib.vido_imu_preintegrate.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp]
     lib.vido_get_kernel_times.argtypes = [vp, vp, vp, vp]
     lib.vido_track_frames.argtypes = [vp, C.POINTER(FrameInputs), C.c_int, vp, C.POINTER(TrackStats)]
     lib.vido_track_reset.argtypes = [vp]
@@ -336,3 +343,14 @@ class Context:
         ms = np.zeros(4, np.float64); n = np.zeros(4, np.int64); b = np.zeros(1, np.float64)
         self._check(self.lib.vido_get_kernel_times(self.h, _ptr(ms), _ptr(n), _ptr(b)))
         return ms, n, float(b[0])
+
+    def imu_preintegrate(self, samples, t_prev, t_cur, bias, noise):
+        """batched IMU preintegration: t_prev/t_cur arrays of length njobs, bias [njobs,6]; returns IMU_PREINT array"""
+        s = np.ascontiguousarray(samples, IMU_SAMPLE)
+        tp = np.ascontiguousarray(np.atleast_1d(t_prev), np.float64); tc = np.ascontiguousarray(np.atleast_1d(t_cur), np.float64)
+        nj = len(tp)
+        b = np.ascontiguousarray(np.broadcast_to(np.asarray(bias, np.float32).reshape(-1, 6), (nj, 6)))
+        nz = np.ascontiguousarray(noise, np.float32)
+        out = np.zeros(nj, IMU_PREINT)
+        self._check(self.lib.vido_imu_preintegrate(self.h, _ptr(s), len(s), _ptr(tp), _ptr(tc), nj, _ptr(b), _ptr(nz), _ptr(out)))
+        return out

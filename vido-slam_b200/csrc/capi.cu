@@ -306,4 +306,11 @@ int vido_get_kernel_times(vido_ctx* ctx, double* ms, int64_t* launches, double* 
   return VIDO_OK;
 }
 
+int vido_imu_preintegrate(vido_ctx* ctx, const vido_imu_sample* samples, int n, const double* t_prev, const double* t_cur,
+                          int njobs, const float* bias, const float* noise, vido_imu_preint* out) {
+  if (!ctx || !t_prev || !t_cur || !bias || !noise || !out || (n > 0 && !samples)) return VIDO_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  return imu_preintegrate_host(ctx, samples, n, t_prev, t_cur, njobs, bias, noise, out);
+}
+
 }  // extern "C"

@@ -145,3 +145,7 @@ int trk_track_chunk(vido_ctx* ctx, const vido_frame_inputs* in, int nframes, flo
 int trk_num_frames(vido_ctx* ctx);
 int trk_get_map_poses(vido_ctx* ctx, float* poses, int cap);
 int trk_get_static(vido_ctx* ctx, int frame, float* xy, float* depth, float* p3, int32_t* asso, int cap);
+
+// imu_kernels.cu
+int imu_preintegrate_host(vido_ctx* ctx, const vido_imu_sample* samples, int n, const double* t_prev, const double* t_cur,
+                          int njobs, const float* bias, const float* noise, vido_imu_preint* out);
