@@ -1,0 +1,77 @@
+"""CPU: the C-ABI library loads without a GPU, exports every symbol include/vido_b200.h declares, refuses to create a
+context without a device (no CPU fallback), and the C++ facade (host/System.h) compiles and links against it."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "vido_b200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vido_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = pkg.load_library()
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} is declared in include/vido_b200.h but not exported"
+    assert lib.vido_version() >= 100
+
+
+def test_default_config_matches_reference_yaml(pkg):
+    cfg = pkg.default_config()
+    assert (cfg.width, cfg.height, cfg.nfeatures, cfg.nlevels, cfg.ini_th_fast, cfg.min_th_fast) == (1242, 375, 2500, 8, 20, 7)
+    assert (cfg.window_size, cfg.max_track_bg, cfg.max_track_obj, cfg.choose_data) == (20, 1000, 500, 2)
+    assert abs(cfg.scale_factor - 1.2) < 1e-6 and abs(cfg.depth_map_factor - 256) < 1e-6
+
+
+def test_no_cpu_fallback(pkg, have_gpu):
+    if have_gpu:
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.VidoError) as ei:
+        pkg.Context(pkg.default_config())
+    assert "CUDA" in str(ei.value)
+
+
+def test_product_does_not_reference_the_oracle():
+    """only tests/, __graft_entry__.smoke() and bench.py may touch oracle/"""
+    for base, _, files in os.walk(os.path.join(ROOT, "vido-slam_b200")):
+        for f in files:
+            if f.endswith((".cu", ".h", ".py", ".cc", "Makefile")):
+                txt = open(os.path.join(base, f), errors="ignore").read()
+                assert "liboracle" not in txt and "vo_" + "tracker" not in txt and "#include \"../oracle" not in txt, f
+
+
+def test_cpp_facade_compiles_and_links(tmp_path, pkg):
+    pkg.load_library()
+    src = tmp_path / "main.cc"
+    src.write_text(r'''
+#include "System.h"
+int main(int argc, char** argv) {
+  VIDO_SLAM::System sys;
+  if (argc > 1) {  // only with a GPU
+    sys.Init(argv[1], VIDO_SLAM::System::RGBD);
+    VIDO_SLAM::Mat im = VIDO_SLAM::Mat::create(375, 1242, VIDO_SLAM::CV_8UC1), d = VIDO_SLAM::Mat::create(375, 1242, VIDO_SLAM::CV_32FC1),
+                   f = VIDO_SLAM::Mat::create(375, 1242, VIDO_SLAM::CV_32FC2), m = VIDO_SLAM::Mat::create(375, 1242, VIDO_SLAM::CV_32SC1), gt, traj;
+    std::vector<std::vector<float> > obj;
+    VIDO_SLAM::Mat T = sys.TrackRGBD(im, d, f, m, gt, obj, 0.0, traj, 10);
+    return T.rows == 4 ? 0 : 1;
+  }
+  vido_config c;
+  vido_default_config(&c);
+  return c.nfeatures == 2500 ? 0 : 1;
+}
+''')
+    exe = tmp_path / "facade"
+    libdir = os.path.join(ROOT, "vido-slam_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(libdir, "host"), str(src), "-o", str(exe),
+                           "-L", libdir, "-lvido_b200", "-Wl,-rpath," + libdir, "-ldl", "-lpthread", "-lrt"])
+    assert subprocess.call([str(exe)]) == 0

@@ -14,11 +14,14 @@
 //     Cholesky-factored in shared memory.  Same linear system, same positive-definiteness test.
 // Everything is FP64 (g2o is built in double); inputs/outputs are the float32 Map fields.
 //
-// Data layout (HBM/L2 resident, a few MB): points are sorted by (first observing pose, track length descending) and
-// every track observes consecutive poses (true for the reference's graph by construction), so
-//   - the observations of point l are obs[pt_start[l] .. ), observation of pose p = pt_start[l] + (p - first[l]);
-//   - the points seen by both poses p1 <= p2 are, for every birth pose f <= p1, a PREFIX of group f
-//     (those with length > p2 - f): no index lists, no searches, no atomics.
+// Data layout (HBM/L2 resident, a few MB): points are sorted by (first observing pose f, track length descending) and
+// every track observes consecutive poses (true for the reference's graph by construction).  Group f = points born
+// at pose f; the points of group f seen by pose p are the PREFIX of the group with length > p - f.  Observations are
+// stored POSE-MAJOR: pose p owns the contiguous range [pose_base[p], pose_base[p+1]) holding, group after group, the
+// prefixes it sees; per-observation arrays (measurement, the 6x3 block Hpl) are struct-of-arrays over that index.
+//   - observation of point (f, i) in pose p:  q = pose_base[p] + off[p][f] + i            (i < cnt[f][p-f])
+//   - points common to poses p1 <= p2: for every f <= p1 the first cnt[f][p2-f] points of group f, found at the SAME
+//     i in both poses' ranges -> every warp access is coalesced, no index lists, no searches, no atomics.
 // Since J_point = R^T, the point block is (sum_o w_o) * I3: its inverse is a scalar and is applied on the fly.
 #include <cooperative_groups.h>
 
@@ -33,7 +36,7 @@
 namespace cg = cooperative_groups;
 using namespace vb;
 
-#define BA_THREADS 512
+#define BA_THREADS 256
 #define BA_MAX_W 24
 #define BA_MAX_CLUSTER 16
 #define BA_PCHUNK 8   // chunks per pose in the pose-block reduction
@@ -46,13 +49,15 @@ struct BaArgs {
   const float* poses_f32;   // [W][16]
   const float* rel_f32;     // [W-1][16]
   const float* points_f32;  // [P][3]  (sorted order)
-  const int* obs_pose;      // [M]
-  const int* obs_point;     // [M]
-  const float* obs_xyz;     // [M][3]
-  const int* pt_start;      // [P+1]
+  const int* obs_pose;      // [M]  pose-major observation index -> pose
+  const int* obs_point;     // [M]  -> point
+  const float* obs_xyz;     // [3][M] struct-of-arrays
+  const int* pt_len;        // [P]
   const int* pt_first;      // [P]
   const int* grp_start;     // [W+1]
   const int* cnt_gt;        // [W][W+1]: #points of group f with track length > L
+  const int* off;           // [W][W+1]: offset of group f inside pose p's range
+  const int* pose_base;     // [W+1]
   // state
   Pose* X;        // [2][W]
   Pose* Zinv;     // [W-1]
@@ -60,7 +65,7 @@ struct BaArgs {
   // system
   double* hl;     // [P]     point block = hl * I3
   double* bl;     // [P][3]
-  double* Hpl;    // [M][18] (6x3)
+  double* Hpl;    // [18][M] (6x3 block per observation, struct-of-arrays)
   double* Hpp;    // [W][36] diagonal blocks (points + odometry)
   double* Hoff;   // [W-1][36] blocks (i, i+1)
   double* bp;     // [W][6]
@@ -137,7 +142,7 @@ __device__ void phase_init(const BaArgs& a, int G, int GT) {
 }
 
 __device__ __forceinline__ double obs_chi(const BaArgs& a, const Pose& Xp, const double* p, int o, double* zc, double* e, double& w) {
-  const double z[3] = {(double)a.obs_xyz[3 * o], (double)a.obs_xyz[3 * o + 1], (double)a.obs_xyz[3 * o + 2]};
+  const double z[3] = {(double)a.obs_xyz[o], (double)a.obs_xyz[a.M + o], (double)a.obs_xyz[2 * (size_t)a.M + o]};
   edge_xyz(Xp, p, z, zc, e);
   double r0;
   huber((e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) * a.info_3d, a.d_3d, r0, w);
@@ -178,18 +183,19 @@ __device__ void phase_lin_obs(const BaArgs& a, int st, int G, int GT) {
     obs_chi(a, Xp, pts + 3 * (size_t)a.obs_point[o], o, zc, e, w);
     w *= a.info_3d;
     // Hpl = w * J_pose^T J_point, J_pose = [-I | Q(zc)], J_point = R^T
-    double* hp = a.Hpl + 18 * (size_t)o;
+    double* hp = a.Hpl + o;
+    const size_t M = a.M;
     const double* R = Xp.R;
     const double qx = 2 * zc[0], qy = 2 * zc[1], qz = 2 * zc[2];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
       const double r0c = R[3 * c], r1c = R[3 * c + 1], r2c = R[3 * c + 2];
-      hp[c] = -w * r0c;
-      hp[3 + c] = -w * r1c;
-      hp[6 + c] = -w * r2c;
-      hp[9 + c] = w * (qz * r1c - qy * r2c);
-      hp[12 + c] = w * (-qz * r0c + qx * r2c);
-      hp[15 + c] = w * (qy * r0c - qx * r1c);
+      hp[(c)*M] = -w * r0c;
+      hp[(3 + c) * M] = -w * r1c;
+      hp[(6 + c) * M] = -w * r2c;
+      hp[(9 + c) * M] = w * (qz * r1c - qy * r2c);
+      hp[(12 + c) * M] = w * (-qz * r0c + qx * r2c);
+      hp[(15 + c) * M] = w * (qy * r0c - qx * r1c);
     }
   }
   for (int i = G; i < a.W - 1; i += GT) {
@@ -208,8 +214,11 @@ __device__ void phase_lin_obs(const BaArgs& a, int st, int G, int GT) {
 }
 
 // linearisation, step 2: point blocks (thread per point) and partial pose blocks (warp per (pose, chunk))
-__device__ void phase_lin_blocks(const BaArgs& a, int st, int G, int GT, int rank, int nranks, double* red,
-                                 const int* s_grp, const int* s_cnt) {
+struct BaTab {  // shared-memory copies of the small layout tables
+  int grp[BA_MAX_W + 1], cnt[BA_MAX_W * (BA_MAX_W + 1)], off[BA_MAX_W * (BA_MAX_W + 1)], base[BA_MAX_W + 1];
+};
+
+__device__ void phase_lin_blocks(const BaArgs& a, int st, int G, int GT, int rank, int nranks, double* red, const BaTab& tb) {
   const Pose* X = a.X + (size_t)st * a.W;
   const double* pts = a.pts + (size_t)st * 3 * a.P;
   const int W = a.W;
@@ -217,15 +226,17 @@ __device__ void phase_lin_blocks(const BaArgs& a, int st, int G, int GT, int ran
   for (int l = G; l < a.P; l += GT) {
     double h = 0, b[3] = {0, 0, 0};
     const double* p = pts + 3 * (size_t)l;
-    const int f = a.pt_first[l], o0 = a.pt_start[l], o1 = a.pt_start[l + 1];
-    for (int o = o0; o < o1; o++) {
-      const Pose& Xp = X[f + (o - o0)];
+    const int f = a.pt_first[l], len = a.pt_len[l], i = l - tb.grp[f];
+    for (int k = 0; k < len; k++) {
+      const int pp = f + k;
+      const int o = tb.base[pp] + tb.off[pp * (W + 1) + f] + i;
+      const Pose& Xp = X[pp];
       double zc[3], e[3], w;
       obs_chi(a, Xp, p, o, zc, e, w);
       w *= a.info_3d;
       h += w;  // J_point^T J_point = R R^T = I
       const double* R = Xp.R;
-      for (int i = 0; i < 3; i++) b[i] -= w * (R[3 * i] * e[0] + R[3 * i + 1] * e[1] + R[3 * i + 2] * e[2]);
+      for (int r = 0; r < 3; r++) b[r] -= w * (R[3 * r] * e[0] + R[3 * r + 1] * e[1] + R[3 * r + 2] * e[2]);
     }
     a.hl[l] = h;
     for (int k = 0; k < 3; k++) a.bl[3 * (size_t)l + k] = b[k];
@@ -236,8 +247,7 @@ __device__ void phase_lin_blocks(const BaArgs& a, int st, int G, int GT, int ran
     block_reduce<1, true>(v, red);
     if (threadIdx.x == 0) a.part[rank * 4 + 2] = red[0];
   }
-  // pose blocks: job = (pose p, chunk c); the observations of pose p are, for every birth pose f <= p, the prefix of
-  // group f with length > p - f.  Lanes take points, 27 sums per lane, warp-shuffle reduction.
+  // pose blocks: job = (pose p, chunk c) over the pose's contiguous observation range; 27 sums per lane, shuffles
   const int lane = threadIdx.x & 31;
   const int gw = rank * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = nranks * (blockDim.x >> 5);
   for (int job = gw; job < W * BA_PCHUNK; job += nw) {
@@ -246,30 +256,20 @@ __device__ void phase_lin_blocks(const BaArgs& a, int st, int G, int GT, int ran
     double acc[27];
 #pragma unroll
     for (int k = 0; k < 27; k++) acc[k] = 0;
-    int idx0 = 0;  // running block index over the concatenated ranges, blocks dealt round-robin to the chunks
-    for (int f = 0; f <= p; f++) {
-      const int cntf = s_cnt[f * (W + 1) + (p - f)], base = s_grp[f];
-      const int nb = (cntf + 31) >> 5;
-      for (int b = 0; b < nb; b++) {
-        if (((idx0 + b) % BA_PCHUNK) != ch) continue;
-        const int i = (b << 5) + lane;
-        if (i >= cntf) continue;
-        const int l = base + i;
-        const int o = a.pt_start[l] + (p - f);
-        double zc[3], e[3], w;
-        obs_chi(a, Xp, pts + 3 * (size_t)l, o, zc, e, w);
-        w *= a.info_3d;
-        const double qx = 2 * zc[0], qy = 2 * zc[1], qz = 2 * zc[2];
-        const double J[3][6] = {{-1, 0, 0, 0, -qz, qy}, {0, -1, 0, qz, 0, -qx}, {0, 0, -1, -qy, qx, 0}};
-        int idx = 0;
+    const int q0 = tb.base[p], q1 = tb.base[p + 1];
+    for (int o = q0 + ch * 32 + lane; o < q1; o += 32 * BA_PCHUNK) {
+      double zc[3], e[3], w;
+      obs_chi(a, Xp, pts + 3 * (size_t)a.obs_point[o], o, zc, e, w);
+      w *= a.info_3d;
+      const double qx = 2 * zc[0], qy = 2 * zc[1], qz = 2 * zc[2];
+      const double J[3][6] = {{-1, 0, 0, 0, -qz, qy}, {0, -1, 0, qz, 0, -qx}, {0, 0, -1, -qy, qx, 0}};
+      int idx = 0;
 #pragma unroll
-        for (int r = 0; r < 6; r++) {
-          acc[21 + r] -= w * (J[0][r] * e[0] + J[1][r] * e[1] + J[2][r] * e[2]);
+      for (int r = 0; r < 6; r++) {
+        acc[21 + r] -= w * (J[0][r] * e[0] + J[1][r] * e[1] + J[2][r] * e[2]);
 #pragma unroll
-          for (int c = r; c < 6; c++) acc[idx++] += w * (J[0][r] * J[0][c] + J[1][r] * J[1][c] + J[2][r] * J[2][c]);
-        }
+        for (int c = r; c < 6; c++) acc[idx++] += w * (J[0][r] * J[0][c] + J[1][r] * J[1][c] + J[2][r] * J[2][c]);
       }
-      idx0 += nb;
     }
 #pragma unroll
     for (int k = 0; k < 27; k++) acc[k] = warp_sum(acc[k]);
@@ -336,14 +336,16 @@ __device__ void phase_lin_poses(const BaArgs& a, int G, int GT, int rank, double
   if (threadIdx.x == 0) a.part[rank * 4 + 3] = red[0];
 }
 
-// reduced camera system: S(p1,p2) = Hpp(p1,p2) + lambda I - sum_l Hpl(p1,l) Hpl(p2,l)^T / (hl + lambda); warp per pair
-__device__ void phase_schur(const BaArgs& a, double lambda, int rank, int nranks, const int* s_grp, const int* s_cnt) {
+// reduced camera system: S(p1,p2) = Hpp(p1,p2) + lambda I - sum_l Hpl(p1,l) Hpl(p2,l)^T / (hl + lambda).
+// Job = pose pair, dealt round-robin to the CTAs (ordered by distance so that every CTA gets the same mix of big and
+// small pairs); all threads of the CTA share the pair's common points (coalesced struct-of-arrays loads), 36-value
+// warp-shuffle reduction, then a fixed-order sum over the warps in shared memory (deterministic, no atomics).
+__device__ void phase_schur(const BaArgs& a, double lambda, int rank, int nranks, const BaTab& tb, double* sred /* [warps][36] */) {
   const int W = a.W, n = 6 * W;
-  const int lane = threadIdx.x & 31;
-  const int gw = rank * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = nranks * (blockDim.x >> 5);
+  const size_t M = a.M;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
   const int npairs = W * (W + 1) / 2;
-  // heavy jobs first: pairs ordered by distance d = p2 - p1 (d = 0 has the most common points)
-  for (int job = gw; job < npairs + W; job += nw) {
+  for (int job = rank; job < npairs + W; job += nranks) {
     if (job < npairs) {
       int d = 0, rem = job;
       while (rem >= W - d) { rem -= W - d; d++; }
@@ -352,16 +354,15 @@ __device__ void phase_schur(const BaArgs& a, double lambda, int rank, int nranks
 #pragma unroll
       for (int k = 0; k < 36; k++) acc[k] = 0;
       for (int f = 0; f <= p1; f++) {
-        const int cntf = s_cnt[f * (W + 1) + (p2 - f)], base = s_grp[f];
-        for (int i = lane; i < cntf; i += 32) {
-          const int l = base + i;
-          const int o0 = a.pt_start[l];
-          const double s = 1.0 / (a.hl[l] + lambda);
-          const double* h1 = a.Hpl + 18 * (size_t)(o0 + (p1 - f));
-          const double* h2 = a.Hpl + 18 * (size_t)(o0 + (p2 - f));
+        const int cntf = tb.cnt[f * (W + 1) + (p2 - f)];
+        const int q1 = tb.base[p1] + tb.off[p1 * (W + 1) + f], q2 = tb.base[p2] + tb.off[p2 * (W + 1) + f], l0 = tb.grp[f];
+        for (int i = tid; i < cntf; i += blockDim.x) {
+          const double s = 1.0 / (a.hl[l0 + i] + lambda);
+          const double* h1 = a.Hpl + (q1 + i);
+          const double* h2 = a.Hpl + (q2 + i);
           double t[18], g[18];
 #pragma unroll
-          for (int k = 0; k < 18; k++) { t[k] = h1[k] * s; g[k] = h2[k]; }
+          for (int k = 0; k < 18; k++) { t[k] = h1[k * M] * s; g[k] = h2[k * M]; }
 #pragma unroll
           for (int r = 0; r < 6; r++)
 #pragma unroll
@@ -370,43 +371,52 @@ __device__ void phase_schur(const BaArgs& a, double lambda, int rank, int nranks
       }
 #pragma unroll
       for (int k = 0; k < 36; k++) acc[k] = warp_sum(acc[k]);
-      if (lane == 0) {
-        for (int r = 0; r < 6; r++)
-          for (int c = 0; c < 6; c++) {
-            double h = 0;
-            if (p2 == p1) h = a.Hpp[36 * (size_t)p1 + 6 * r + c] + ((r == c) ? lambda : 0.0);
-            else if (p2 == p1 + 1) h = a.Hoff[36 * (size_t)p1 + 6 * r + c];
-            // block (p1,p2), p1 <= p2, stored transposed in the lower triangle
-            a.S[(size_t)(6 * p2 + c) * n + 6 * p1 + r] = h - acc[6 * r + c];
-          }
+      __syncthreads();  // sred free (previous job consumed)
+      if (lane == 0)
+        for (int k = 0; k < 36; k++) sred[warp * 36 + k] = acc[k];
+      __syncthreads();
+      if (tid < 36) {
+        double t = 0;
+        for (int w = 0; w < nwarp; w++) t += sred[w * 36 + tid];
+        const int r = tid / 6, c = tid - 6 * r;
+        double h = 0;
+        if (p2 == p1) h = a.Hpp[36 * (size_t)p1 + tid] + ((r == c) ? lambda : 0.0);
+        else if (p2 == p1 + 1) h = a.Hoff[36 * (size_t)p1 + tid];
+        a.S[(size_t)(6 * p2 + c) * n + 6 * p1 + r] = h - t;  // block (p1,p2), p1 <= p2, transposed into the lower triangle
       }
     } else {
       const int p = job - npairs;
       double acc[6] = {0, 0, 0, 0, 0, 0};
-      for (int f = 0; f <= p; f++) {
-        const int cntf = s_cnt[f * (W + 1) + (p - f)], base = s_grp[f];
-        for (int i = lane; i < cntf; i += 32) {
-          const int l = base + i;
-          const double s = 1.0 / (a.hl[l] + lambda);
-          const double* h = a.Hpl + 18 * (size_t)(a.pt_start[l] + (p - f));
-          const double* b = a.bl + 3 * (size_t)l;
-          const double c0 = s * b[0], c1 = s * b[1], c2 = s * b[2];
+      for (int o = tb.base[p] + tid; o < tb.base[p + 1]; o += blockDim.x) {
+        const int l = a.obs_point[o];
+        const double s = 1.0 / (a.hl[l] + lambda);
+        const double* b = a.bl + 3 * (size_t)l;
+        const double c0 = s * b[0], c1 = s * b[1], c2 = s * b[2];
+        const double* h = a.Hpl + o;
 #pragma unroll
-          for (int r = 0; r < 6; r++) acc[r] += h[3 * r] * c0 + h[3 * r + 1] * c1 + h[3 * r + 2] * c2;
-        }
+        for (int r = 0; r < 6; r++) acc[r] += h[(3 * r) * M] * c0 + h[(3 * r + 1) * M] * c1 + h[(3 * r + 2) * M] * c2;
       }
 #pragma unroll
       for (int r = 0; r < 6; r++) acc[r] = warp_sum(acc[r]);
+      __syncthreads();
       if (lane == 0)
-        for (int r = 0; r < 6; r++) a.bred[6 * p + r] = a.bp[6 * p + r] - acc[r];
+        for (int r = 0; r < 6; r++) sred[warp * 36 + r] = acc[r];
+      __syncthreads();
+      if (tid < 6) {
+        double t = 0;
+        for (int w = 0; w < nwarp; w++) t += sred[w * 36 + tid];
+        a.bred[6 * p + tid] = a.bp[6 * p + tid] - t;
+      }
     }
   }
 }
 
 // blocked (6x6) LL^T of the reduced system in shared memory + block substitutions; one CTA.  ld is odd to avoid
-// bank conflicts on column accesses.  Also applies the pose increments (trial poses) and their part of the scale.
-__device__ void phase_chol(const BaArgs& a, double lambda, int cur, double* Ls, double* ys, double* red) {
+// bank conflicts on column accesses.  The inverse of every diagonal block is kept (Li), so panels and substitutions
+// are plain products.  Also applies the pose increments (trial poses) and their part of the scale.
+__device__ void phase_chol(const BaArgs& a, double lambda, int cur, double* Ls, double* ys, double* Li, double* red) {
   const int n = 6 * a.W, ld = n + 1, tid = threadIdx.x, nt = blockDim.x, nb = a.W;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
   __shared__ int s_bad;
   if (tid == 0) s_bad = 0;
   for (int i = tid; i < n * n; i += nt) {
@@ -417,59 +427,94 @@ __device__ void phase_chol(const BaArgs& a, double lambda, int cur, double* Ls, 
   __syncthreads();
   for (int jb = 0; jb < nb; jb++) {
     const int j0 = 6 * jb;
-    // (1) factor the diagonal block (thread 0; 6x6)
+    // (1) diagonal block: L11 and its inverse, fully unrolled so that everything stays in registers (thread 0)
     if (tid == 0) {
+      double L[36], Iv[36];
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int c = 0; c < 6; c++) { L[6 * r + c] = (c <= r) ? Ls[(j0 + r) * ld + j0 + c] : 0.0; Iv[6 * r + c] = 0.0; }
+      bool ok = true;
+#pragma unroll
       for (int j = 0; j < 6; j++) {
-        double d = Ls[(j0 + j) * ld + j0 + j];
-        for (int k = 0; k < j; k++) d -= Ls[(j0 + j) * ld + j0 + k] * Ls[(j0 + j) * ld + j0 + k];
-        if (!(d > 0)) { s_bad = 1; break; }
-        const double ljj = sqrt(d);
-        Ls[(j0 + j) * ld + j0 + j] = ljj;
+        double d = L[7 * j];
+#pragma unroll
+        for (int k = 0; k < j; k++) d -= L[6 * j + k] * L[6 * j + k];
+        ok = ok && (d > 0);
+        const double ljj = sqrt(d), inv = 1.0 / ljj;
+        L[7 * j] = ljj;
+        Iv[7 * j] = inv;
+#pragma unroll
         for (int i = j + 1; i < 6; i++) {
-          double s = Ls[(j0 + i) * ld + j0 + j];
-          for (int k = 0; k < j; k++) s -= Ls[(j0 + i) * ld + j0 + k] * Ls[(j0 + j) * ld + j0 + k];
-          Ls[(j0 + i) * ld + j0 + j] = s / ljj;
+          double t = L[6 * i + j];
+#pragma unroll
+          for (int k = 0; k < j; k++) t -= L[6 * i + k] * L[6 * j + k];
+          L[6 * i + j] = t * inv;
         }
+      }
+      if (!ok) s_bad = 1;
+      else {
+#pragma unroll
+        for (int c = 0; c < 6; c++)  // Iv = L^-1 (lower), column by column
+#pragma unroll
+          for (int r = c + 1; r < 6; r++) {
+            double t = 0;
+#pragma unroll
+            for (int k = c; k < r; k++) t += L[6 * r + k] * Iv[6 * k + c];
+            Iv[6 * r + c] = -t * Iv[7 * r];
+          }
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+          for (int c = 0; c <= r; c++) Ls[(j0 + r) * ld + j0 + c] = L[6 * r + c];
+#pragma unroll
+        for (int k = 0; k < 36; k++) Li[36 * jb + k] = Iv[k];
       }
     }
     __syncthreads();
     if (s_bad) break;
-    // (2) panel: rows below the block, L21 = A21 * L11^-T (thread per row)
+    // (2) panel: rows below the block, L21 = A21 * L11^-T  =>  row'[j] = sum_{k<=j} row[k] * Iv[j][k]
     for (int i = j0 + 6 + tid; i < n; i += nt) {
-      double row[6];
+      double row[6], o[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) row[k] = Ls[i * ld + j0 + k];
+      const double* Iv = Li + 36 * jb;
 #pragma unroll
       for (int j = 0; j < 6; j++) {
-        double s = Ls[i * ld + j0 + j];
-        for (int k = 0; k < j; k++) s -= row[k] * Ls[(j0 + j) * ld + j0 + k];
-        row[j] = s / Ls[(j0 + j) * ld + j0 + j];
+        double t = 0;
+#pragma unroll
+        for (int k = 0; k <= j; k++) t += row[k] * Iv[6 * j + k];
+        o[j] = t;
       }
 #pragma unroll
-      for (int j = 0; j < 6; j++) Ls[i * ld + j0 + j] = row[j];
+      for (int j = 0; j < 6; j++) Ls[i * ld + j0 + j] = o[j];
     }
     __syncthreads();
-    // (3) trailing update A22 -= L21 L21^T (lower triangle), element per thread
+    // (3) trailing update A22 -= L21 L21^T (lower triangle): warp per row, lanes over the columns <= row
     const int m = n - j0 - 6;
-    for (int e = tid; e < m * m; e += nt) {
-      const int r = e / m, c = e - r * m;
-      if (c > r) continue;
+    for (int r = warp; r < m; r += nwarp) {
       const double* lr = Ls + (j0 + 6 + r) * ld + j0;
-      const double* lc = Ls + (j0 + 6 + c) * ld + j0;
-      Ls[(j0 + 6 + r) * ld + j0 + 6 + c] -= lr[0] * lc[0] + lr[1] * lc[1] + lr[2] * lc[2] + lr[3] * lc[3] + lr[4] * lc[4] + lr[5] * lc[5];
+      const double r0 = lr[0], r1 = lr[1], r2 = lr[2], r3 = lr[3], r4 = lr[4], r5 = lr[5];
+      for (int c = lane; c <= r; c += 32) {
+        const double* lc = Ls + (j0 + 6 + c) * ld + j0;
+        Ls[(j0 + 6 + r) * ld + j0 + 6 + c] -= r0 * lc[0] + r1 * lc[1] + r2 * lc[2] + r3 * lc[3] + r4 * lc[4] + r5 * lc[5];
+      }
     }
     __syncthreads();
   }
   __syncthreads();
   const int failed = s_bad;
   if (!failed) {
-    // forward substitution, block by block
+    // forward substitution: y_b = Iv_b * rhs_b, then rhs_below -= L21 * y_b
     for (int jb = 0; jb < nb; jb++) {
       const int j0 = 6 * jb;
-      if (tid == 0)
-        for (int j = 0; j < 6; j++) {
-          double s = ys[j0 + j];
-          for (int k = 0; k < j; k++) s -= Ls[(j0 + j) * ld + j0 + k] * ys[j0 + k];
-          ys[j0 + j] = s / Ls[(j0 + j) * ld + j0 + j];
-        }
+      double yb = 0;
+      if (tid < 6) {
+        const double* Iv = Li + 36 * jb;
+        for (int k = 0; k <= tid; k++) yb += Iv[6 * tid + k] * ys[j0 + k];
+      }
+      __syncthreads();
+      if (tid < 6) ys[j0 + tid] = yb;
       __syncthreads();
       for (int i = j0 + 6 + tid; i < n; i += nt) {
         const double* li = Ls + i * ld + j0;
@@ -477,21 +522,22 @@ __device__ void phase_chol(const BaArgs& a, double lambda, int cur, double* Ls, 
       }
       __syncthreads();
     }
-    // backward substitution with L^T
+    // backward substitution with L^T: x_b = Iv_b^T * rhs_b, then rhs_above -= L(b, above)^T x_b
     for (int jb = nb - 1; jb >= 0; jb--) {
       const int j0 = 6 * jb;
-      if (tid == 0)
-        for (int j = 5; j >= 0; j--) {
-          double s = ys[j0 + j];
-          for (int k = j + 1; k < 6; k++) s -= Ls[(j0 + k) * ld + j0 + j] * ys[j0 + k];
-          ys[j0 + j] = s / Ls[(j0 + j) * ld + j0 + j];
-        }
+      double xb = 0;
+      if (tid < 6) {
+        const double* Iv = Li + 36 * jb;
+        for (int k = tid; k < 6; k++) xb += Iv[6 * k + tid] * ys[j0 + k];
+      }
+      __syncthreads();
+      if (tid < 6) ys[j0 + tid] = xb;
       __syncthreads();
       for (int i = tid; i < j0; i += nt) {
-        double s = 0;
+        double t = 0;
 #pragma unroll
-        for (int k = 0; k < 6; k++) s += Ls[(j0 + k) * ld + i] * ys[j0 + k];
-        ys[i] -= s;
+        for (int k = 0; k < 6; k++) t += Ls[(j0 + k) * ld + i] * ys[j0 + k];
+        ys[i] -= t;
       }
       __syncthreads();
     }
@@ -516,24 +562,27 @@ __device__ void phase_chol(const BaArgs& a, double lambda, int cur, double* Ls, 
 }
 
 // back-substitution of the points (thread per point), trial points, scale, robust chi2 of the trial state
-__device__ void phase_update(const BaArgs& a, double lambda, int cur, int failed, int G, int GT, int rank, double* red) {
-  const int trial = cur ^ 1;
+__device__ void phase_update(const BaArgs& a, double lambda, int cur, int failed, int G, int GT, int rank, double* red,
+                             const BaTab& tb) {
+  const int trial = cur ^ 1, W = a.W;
+  const size_t M = a.M;
   const Pose* Xt = a.X + (size_t)trial * a.W;
   const double* pts = a.pts + (size_t)cur * 3 * a.P;
   double* ptt = a.pts + (size_t)trial * 3 * a.P;
   double scale = 0, chi = 0;
   for (int l = G; l < a.P; l += GT) {
     const double* b = a.bl + 3 * (size_t)l;
-    const int o0 = a.pt_start[l], o1 = a.pt_start[l + 1], f = a.pt_first[l];
+    const int f = a.pt_first[l], len = a.pt_len[l], i = l - tb.grp[f];
     double x[3];
     if (failed) { x[0] = b[0]; x[1] = b[1]; x[2] = b[2]; }
     else {
       double c0 = b[0], c1 = b[1], c2 = b[2];
-      for (int o = o0; o < o1; o++) {
-        const double* h = a.Hpl + 18 * (size_t)o;
-        const double* xp = a.xp + 6 * (f + (o - o0));
+      for (int k = 0; k < len; k++) {
+        const int pp = f + k;
+        const double* h = a.Hpl + (tb.base[pp] + tb.off[pp * (W + 1) + f] + i);
+        const double* xp = a.xp + 6 * pp;
 #pragma unroll
-        for (int r = 0; r < 6; r++) { c0 -= h[3 * r] * xp[r]; c1 -= h[3 * r + 1] * xp[r]; c2 -= h[3 * r + 2] * xp[r]; }
+        for (int r = 0; r < 6; r++) { c0 -= h[(3 * r) * M] * xp[r]; c1 -= h[(3 * r + 1) * M] * xp[r]; c2 -= h[(3 * r + 2) * M] * xp[r]; }
       }
       const double s = 1.0 / (a.hl[l] + lambda);
       x[0] = s * c0; x[1] = s * c1; x[2] = s * c2;
@@ -544,9 +593,10 @@ __device__ void phase_update(const BaArgs& a, double lambda, int cur, int failed
       ptt[3 * (size_t)l + k] = pn[k];
       scale += x[k] * (lambda * x[k] + b[k]);
     }
-    for (int o = o0; o < o1; o++) {
+    for (int k = 0; k < len; k++) {
+      const int pp = f + k;
       double zc[3], e[3], w;
-      chi += obs_chi(a, Xt[f + (o - o0)], pn, o, zc, e, w);
+      chi += obs_chi(a, Xt[pp], pn, tb.base[pp] + tb.off[pp * (W + 1) + f] + i, zc, e, w);
     }
   }
   for (int i = G; i < a.W - 1; i += GT) chi += se3_chi(a, Xt, i);
@@ -592,10 +642,11 @@ __device__ void phase_output_rel(const BaArgs& a, int G, int GT) {
 // the cluster kernel (cluster size set at launch: 16 CTAs when the device allows it, else 8)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BA_THREADS, 1) ba_window_kernel(BaArgs a) {
-  extern __shared__ __align__(16) double dsm[];  // (6W)(6W+1) + 6W doubles for the dense factorisation (CTA 0)
+  extern __shared__ __align__(16) double dsm[];  // (6W)(6W+1) + 6W + 36W doubles for the dense factorisation (CTA 0)
   __shared__ double red[16 * 2 + 32];
+  __shared__ double sred[(BA_THREADS / 32) * 36];
   __shared__ LmCtl ctl;  // every CTA keeps an identical copy: decisions are recomputed from the same partial sums
-  __shared__ int s_grp[BA_MAX_W + 1], s_cnt[BA_MAX_W * (BA_MAX_W + 1)];
+  __shared__ BaTab tb;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank(), nranks = (int)cluster.num_blocks();
   const int G = rank * blockDim.x + threadIdx.x, GT = nranks * blockDim.x;
@@ -605,8 +656,8 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_window_kernel(BaArgs a) {
   const unsigned long long t_start = t0;
 #define TOC(slot) do { if (G == 0) { unsigned long long t1_ = gtime(); tph[slot] += t1_ - t0; t0 = t1_; } } while (0)
 
-  for (int i = tid; i <= a.W; i += blockDim.x) s_grp[i] = a.grp_start[i];
-  for (int i = tid; i < a.W * (a.W + 1); i += blockDim.x) s_cnt[i] = a.cnt_gt[i];
+  for (int i = tid; i <= a.W; i += blockDim.x) { tb.grp[i] = a.grp_start[i]; tb.base[i] = a.pose_base[i]; }
+  for (int i = tid; i < a.W * (a.W + 1); i += blockDim.x) { tb.cnt[i] = a.cnt_gt[i]; tb.off[i] = a.off[i]; }
   if (tid == 0) lm_reset(&ctl);
   phase_init(a, G, GT);
   cluster.sync();
@@ -632,7 +683,7 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_window_kernel(BaArgs a) {
     const int cur = ctl.cur;
     phase_lin_obs(a, cur, G, GT);
     cluster.sync();
-    phase_lin_blocks(a, cur, G, GT, rank, nranks, red, s_grp, s_cnt);
+    phase_lin_blocks(a, cur, G, GT, rank, nranks, red, tb);
     cluster.sync();
     phase_lin_poses(a, G, GT, rank, red);
     cluster.sync();
@@ -645,14 +696,17 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_window_kernel(BaArgs a) {
     TOC(0);
     while (true) {
       const double lambda = ctl.lambda;
-      phase_schur(a, lambda, rank, nranks, s_grp, s_cnt);
+      phase_schur(a, lambda, rank, nranks, tb, sred);
       cluster.sync();
       TOC(2);
-      if (rank == 0) phase_chol(a, lambda, cur, dsm, dsm + (size_t)(6 * a.W) * (6 * a.W + 1), red);
+      if (rank == 0) {
+        double* ysm = dsm + (size_t)(6 * a.W) * (6 * a.W + 1);
+        phase_chol(a, lambda, cur, dsm, ysm, ysm + 6 * a.W, red);
+      }
       cluster.sync();
       TOC(3);
       const int failed = a.cinfo[1] != 0.0;
-      phase_update(a, lambda, cur, failed, G, GT, rank, red);
+      phase_update(a, lambda, cur, failed, G, GT, rank, red, tb);
       cluster.sync();
       TOC(4);
       if (tid == 0) {
@@ -685,10 +739,13 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_window_kernel(BaArgs a) {
 struct BaWorkspace {
   int capW = 0, capP = 0, capM = 0;
   int cluster = 8;
-  char* d_base = nullptr;
+  char* d_base = nullptr;            // solver workspace
+  char* d_in = nullptr;              // input block
+  char* d_out = nullptr;             // output block
   BaArgs args;
-  char* h_base = nullptr;
-  size_t h_bytes = 0;
+  char* h_in = nullptr;              // pinned mirrors
+  char* h_out = nullptr;
+  size_t in_bytes = 0, out_bytes = 0;
 };
 
 static size_t al(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -700,12 +757,23 @@ static T* carve(char*& p, size_t n) {
   return r;
 }
 
+// input block: carved identically on the pinned host staging buffer and on the device, so one H2D copy moves it all
+static void carve_inputs(char*& p, BaArgs& a, int W, int P, int M) {
+  a.poses_f32 = carve<float>(p, 16 * W); a.rel_f32 = carve<float>(p, 16 * W);
+  a.points_f32 = carve<float>(p, 3 * (size_t)P);
+  a.obs_pose = carve<int>(p, M); a.obs_point = carve<int>(p, M); a.obs_xyz = carve<float>(p, 3 * (size_t)M);
+  a.pt_len = carve<int>(p, P); a.pt_first = carve<int>(p, P);
+  a.grp_start = carve<int>(p, W + 1); a.cnt_gt = carve<int>(p, W * (W + 1));
+  a.off = carve<int>(p, W * (W + 1)); a.pose_base = carve<int>(p, W + 1);
+}
+// output block: one D2H copy
+static void carve_outputs(char*& p, BaArgs& a, int W, int P) {
+  a.ctl_out = carve<LmCtl>(p, 1); a.t_phase = carve<unsigned long long>(p, 8);
+  a.out_poses = carve<float>(p, 16 * W); a.out_rel = carve<float>(p, 16 * W); a.out_points = carve<float>(p, 3 * (size_t)P);
+  a.rec = carve<LmRec>(p, VIDO_LM_REC);
+}
+
 static void carve_all(char*& p, BaArgs& a, int capW, int capP, int capM) {
-  a.poses_f32 = carve<float>(p, 16 * capW); a.rel_f32 = carve<float>(p, 16 * capW);
-  a.points_f32 = carve<float>(p, 3 * (size_t)capP);
-  a.obs_pose = carve<int>(p, capM); a.obs_point = carve<int>(p, capM); a.obs_xyz = carve<float>(p, 3 * (size_t)capM);
-  a.pt_start = carve<int>(p, capP + 1); a.pt_first = carve<int>(p, capP);
-  a.grp_start = carve<int>(p, capW + 1); a.cnt_gt = carve<int>(p, capW * (capW + 1));
   a.X = carve<Pose>(p, 2 * capW); a.Zinv = carve<Pose>(p, capW); a.pts = carve<double>(p, 6 * (size_t)capP);
   a.hl = carve<double>(p, capP); a.bl = carve<double>(p, 3 * (size_t)capP); a.Hpl = carve<double>(p, 18 * (size_t)capM);
   a.Hpp = carve<double>(p, 36 * capW); a.Hoff = carve<double>(p, 36 * capW); a.bp = carve<double>(p, 6 * capW);
@@ -713,8 +781,6 @@ static void carve_all(char*& p, BaArgs& a, int capW, int capP, int capM) {
   a.S = carve<double>(p, 36 * (size_t)capW * capW); a.bred = carve<double>(p, 6 * capW); a.xp = carve<double>(p, 6 * capW);
   a.part = carve<double>(p, 4 * BA_MAX_CLUSTER); a.cinfo = carve<double>(p, 4);
   a.seJ = carve<double>(p, 72 * capW); a.seE = carve<double>(p, 8 * capW);
-  a.ctl_out = carve<LmCtl>(p, 1); a.rec = carve<LmRec>(p, VIDO_LM_REC); a.t_phase = carve<unsigned long long>(p, 8);
-  a.out_poses = carve<float>(p, 16 * capW); a.out_rel = carve<float>(p, 16 * capW); a.out_points = carve<float>(p, 3 * (size_t)capP);
 }
 
 int ba_setup(vido_ctx* ctx, int capW, int capP, int capM) {
@@ -726,20 +792,18 @@ int ba_setup(vido_ctx* ctx, int capW, int capP, int capM) {
   char* p = nullptr;
   carve_all(p, tmp, capW, capP, capM);
   const size_t need = (size_t)p;
+  p = nullptr; carve_inputs(p, tmp, capW, capP, capM); ws->in_bytes = (size_t)p;
+  p = nullptr; carve_outputs(p, tmp, capW, capP); ws->out_bytes = (size_t)p;
   VIDO_CUDA(cudaMalloc(&ws->d_base, need));
   VIDO_CUDA(cudaMemset(ws->d_base, 0, need));
+  VIDO_CUDA(cudaMalloc(&ws->d_in, ws->in_bytes));
+  VIDO_CUDA(cudaMalloc(&ws->d_out, ws->out_bytes));
+  VIDO_CUDA(cudaMallocHost(&ws->h_in, ws->in_bytes));
+  VIDO_CUDA(cudaMallocHost(&ws->h_out, ws->out_bytes));
   memset(&ws->args, 0, sizeof ws->args);
   p = ws->d_base;
   carve_all(p, ws->args, capW, capP, capM);
-  {
-    char* hp = nullptr;
-    carve<int>(hp, capM); carve<int>(hp, capM); carve<float>(hp, 3 * (size_t)capM);
-    carve<int>(hp, capP + 1); carve<int>(hp, capP); carve<float>(hp, 3 * (size_t)capP);
-    carve<int>(hp, capW + 1); carve<int>(hp, capW * (capW + 1));
-    ws->h_bytes = (size_t)hp + 4096;
-  }
-  VIDO_CUDA(cudaMallocHost(&ws->h_base, ws->h_bytes));
-  const size_t smem = sizeof(double) * ((size_t)(6 * capW) * (6 * capW + 1) + 6 * capW);
+  const size_t smem = sizeof(double) * ((size_t)(6 * capW) * (6 * capW + 1) + 6 * capW + 36 * capW);
   if (smem > 200 * 1024) { ctx->err = "BA window too large for the shared-memory Cholesky"; return VIDO_ERR_ARG; }
   VIDO_CUDA(cudaFuncSetAttribute(ba_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // 16-CTA clusters are a non-portable size: opt in, and verify that one fits
@@ -762,8 +826,8 @@ int ba_setup(vido_ctx* ctx, int capW, int capP, int capM) {
 void ba_teardown(vido_ctx* ctx) {
   BaWorkspace* ws = (BaWorkspace*)ctx->ba;
   if (!ws) return;
-  cudaFree(ws->d_base);
-  cudaFreeHost(ws->h_base);
+  cudaFree(ws->d_base); cudaFree(ws->d_in); cudaFree(ws->d_out);
+  cudaFreeHost(ws->h_in); cudaFreeHost(ws->h_out);
   delete ws;
   ctx->ba = nullptr;
 }
@@ -782,16 +846,19 @@ int ba_partial_host(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st) {
   a.d_cam = (double)pr->huber_cam;
   a.d_3d = (double)pr->huber_3d;
   a.gain_threshold = (double)pr->gain_threshold;
-  // ---- host-side layout: tracks sorted by (first pose, length descending), observations contiguous per track
-  char* hp = ws->h_base;
-  int* h_obs_pose = carve<int>(hp, M);
-  int* h_obs_point = carve<int>(hp, M);
-  float* h_xyz = carve<float>(hp, 3 * (size_t)M);
-  int* h_pt_start = carve<int>(hp, P + 1);
-  int* h_pt_first = carve<int>(hp, P);
-  float* h_pts = carve<float>(hp, 3 * (size_t)P);
-  int* h_grp = carve<int>(hp, W + 1);
-  int* h_cnt = carve<int>(hp, W * (W + 1));
+  // ---- host-side layout: tracks sorted by (first pose, length descending); observations pose-major (see the header)
+  BaArgs h;  // host view of the input block (same carving as the device view)
+  {
+    char* hp = ws->h_in; carve_inputs(hp, h, W, P, M);
+    char* dp = ws->d_in; carve_inputs(dp, a, W, P, M);
+    char* dq = ws->d_out; carve_outputs(dq, a, W, P);
+  }
+  float* h_poses = (float*)h.poses_f32; float* h_rel = (float*)h.rel_f32;
+  int* h_obs_pose = (int*)h.obs_pose; int* h_obs_point = (int*)h.obs_point; float* h_xyz = (float*)h.obs_xyz;
+  int* h_pt_len = (int*)h.pt_len; int* h_pt_first = (int*)h.pt_first; float* h_pts = (float*)h.points_f32;
+  int* h_grp = (int*)h.grp_start; int* h_cnt = (int*)h.cnt_gt; int* h_off = (int*)h.off; int* h_base = (int*)h.pose_base;
+  memcpy(h_poses, pr->poses, sizeof(float) * 16 * W);
+  if (W > 1) memcpy(h_rel, pr->rel_motion, sizeof(float) * 16 * (W - 1));
   std::vector<int> first(P, 1 << 30), len(P, 0), last(P, -1);
   for (int o = 0; o < M; o++) {
     const int l = pr->obs_point[o], p = pr->obs_pose[o];
@@ -814,42 +881,38 @@ int ba_partial_host(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st) {
     newid[l] = n;
     oldid[n] = l;
   }
-  h_pt_start[0] = 0;
-  for (int n = 0; n < P; n++) {
-    const int l = oldid[n];
-    h_pt_start[n + 1] = h_pt_start[n] + len[l];
-    h_pt_first[n] = first[l];
-    h_pts[3 * n] = pr->points[3 * l]; h_pts[3 * n + 1] = pr->points[3 * l + 1]; h_pts[3 * n + 2] = pr->points[3 * l + 2];
-  }
-  for (int o = 0; o < M; o++) {
-    const int l = pr->obs_point[o], p = pr->obs_pose[o], n = newid[l];
-    const int k = h_pt_start[n] + (p - first[l]);
-    h_obs_pose[k] = p;
-    h_obs_point[k] = n;
-    h_xyz[3 * k] = pr->obs_xyz[3 * o]; h_xyz[3 * k + 1] = pr->obs_xyz[3 * o + 1]; h_xyz[3 * k + 2] = pr->obs_xyz[3 * o + 2];
-  }
   for (int f = 0; f <= W; f++) h_grp[f] = 0;
-  for (int i = 0; i < W * (W + 1); i++) h_cnt[i] = 0;
+  for (int i = 0; i < W * (W + 1); i++) { h_cnt[i] = 0; h_off[i] = 0; }
   for (int l = 0; l < P; l++) {
     h_grp[first[l] + 1]++;
     for (int L = 0; L < len[l] && L <= W; L++) h_cnt[first[l] * (W + 1) + L]++;  // length > L
   }
   for (int f = 0; f < W; f++) h_grp[f + 1] += h_grp[f];
-  VIDO_CUDA(cudaMemcpyAsync((void*)a.poses_f32, pr->poses, sizeof(float) * 16 * W, cudaMemcpyHostToDevice, s));
-  if (W > 1) VIDO_CUDA(cudaMemcpyAsync((void*)a.rel_f32, pr->rel_motion, sizeof(float) * 16 * (W - 1), cudaMemcpyHostToDevice, s));
-  if (P) {
-    VIDO_CUDA(cudaMemcpyAsync((void*)a.points_f32, h_pts, sizeof(float) * 3 * P, cudaMemcpyHostToDevice, s));
-    VIDO_CUDA(cudaMemcpyAsync((void*)a.pt_first, h_pt_first, sizeof(int) * P, cudaMemcpyHostToDevice, s));
+  h_base[0] = 0;
+  for (int p = 0; p < W; p++) {
+    int acc = 0;
+    for (int f = 0; f <= p; f++) { h_off[p * (W + 1) + f] = acc; acc += h_cnt[f * (W + 1) + (p - f)]; }
+    h_off[p * (W + 1) + p + 1] = acc;
+    h_base[p + 1] = h_base[p] + acc;
   }
-  if (M) {
-    VIDO_CUDA(cudaMemcpyAsync((void*)a.obs_pose, h_obs_pose, sizeof(int) * M, cudaMemcpyHostToDevice, s));
-    VIDO_CUDA(cudaMemcpyAsync((void*)a.obs_point, h_obs_point, sizeof(int) * M, cudaMemcpyHostToDevice, s));
-    VIDO_CUDA(cudaMemcpyAsync((void*)a.obs_xyz, h_xyz, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, s));
+  for (int n = 0; n < P; n++) {
+    const int l = oldid[n];
+    h_pt_len[n] = len[l];
+    h_pt_first[n] = first[l];
+    h_pts[3 * n] = pr->points[3 * l]; h_pts[3 * n + 1] = pr->points[3 * l + 1]; h_pts[3 * n + 2] = pr->points[3 * l + 2];
   }
-  VIDO_CUDA(cudaMemcpyAsync((void*)a.pt_start, h_pt_start, sizeof(int) * (P + 1), cudaMemcpyHostToDevice, s));
-  VIDO_CUDA(cudaMemcpyAsync((void*)a.grp_start, h_grp, sizeof(int) * (W + 1), cudaMemcpyHostToDevice, s));
-  if (W) VIDO_CUDA(cudaMemcpyAsync((void*)a.cnt_gt, h_cnt, sizeof(int) * W * (W + 1), cudaMemcpyHostToDevice, s));
-  const size_t smem = sizeof(double) * ((size_t)(6 * W) * (6 * W + 1) + 6 * W);
+  for (int o = 0; o < M; o++) {
+    const int l = pr->obs_point[o], p = pr->obs_pose[o], n = newid[l], f = first[l];
+    const int q = h_base[p] + h_off[p * (W + 1) + f] + (n - h_grp[f]);
+    h_obs_pose[q] = p;
+    h_obs_point[q] = n;
+    h_xyz[q] = pr->obs_xyz[3 * o]; h_xyz[(size_t)M + q] = pr->obs_xyz[3 * o + 1]; h_xyz[2 * (size_t)M + q] = pr->obs_xyz[3 * o + 2];
+  }
+  {
+    char* hp = ws->h_in; BaArgs t2; carve_inputs(hp, t2, W, P, M);
+    VIDO_CUDA(cudaMemcpyAsync(ws->d_in, ws->h_in, (size_t)(hp - ws->h_in), cudaMemcpyHostToDevice, s));
+  }
+  const size_t smem = sizeof(double) * ((size_t)(6 * W) * (6 * W + 1) + 6 * W + 36 * W);
   {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ws->cluster); cfg.blockDim = dim3(BA_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -862,17 +925,21 @@ int ba_partial_host(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st) {
     cudaEventRecord(ctx->ev1, s);
     ctx->launches++;
   }
-  LmCtl ctl;
-  unsigned long long tph[8];
-  std::vector<float> opts(3 * (size_t)P);
-  VIDO_CUDA(cudaMemcpyAsync(&ctl, a.ctl_out, sizeof ctl, cudaMemcpyDeviceToHost, s));
-  VIDO_CUDA(cudaMemcpyAsync(tph, a.t_phase, sizeof tph, cudaMemcpyDeviceToHost, s));
-  VIDO_CUDA(cudaMemcpyAsync(pr->poses, a.out_poses, sizeof(float) * 16 * W, cudaMemcpyDeviceToHost, s));
-  if (W > 1) VIDO_CUDA(cudaMemcpyAsync(pr->rel_motion, a.out_rel, sizeof(float) * 16 * (W - 1), cudaMemcpyDeviceToHost, s));
-  if (P) VIDO_CUDA(cudaMemcpyAsync(opts.data(), a.out_points, sizeof(float) * 3 * P, cudaMemcpyDeviceToHost, s));
-  static LmRec recs[VIDO_LM_REC];
-  if (st) VIDO_CUDA(cudaMemcpyAsync(recs, a.rec, sizeof(LmRec) * VIDO_LM_REC, cudaMemcpyDeviceToHost, s));
+  BaArgs ho;
+  size_t out_used;
+  {
+    char* hq = ws->h_out; carve_outputs(hq, ho, W, P);
+    // the LM records sit at the end of the block: copy them only when asked for
+    out_used = st ? (size_t)(hq - ws->h_out) : (size_t)((char*)ho.rec - ws->h_out);
+  }
+  VIDO_CUDA(cudaMemcpyAsync(ws->h_out, ws->d_out, out_used, cudaMemcpyDeviceToHost, s));
   VIDO_CUDA(cudaStreamSynchronize(s));
+  const LmCtl ctl = *ho.ctl_out;
+  const unsigned long long* tph = ho.t_phase;
+  const LmRec* recs = ho.rec;
+  memcpy(pr->poses, ho.out_poses, sizeof(float) * 16 * W);
+  if (W > 1) memcpy(pr->rel_motion, ho.out_rel, sizeof(float) * 16 * (W - 1));
+  const float* opts = ho.out_points;
   for (int l = 0; l < P; l++) {
     const int n = newid[l];
     pr->points[3 * l] = opts[3 * n]; pr->points[3 * l + 1] = opts[3 * n + 1]; pr->points[3 * l + 2] = opts[3 * n + 2];

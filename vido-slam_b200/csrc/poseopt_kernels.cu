@@ -465,15 +465,17 @@ __global__ void __launch_bounds__(PO_THREADS) poseopt_flow2_kernel(const PoArgs*
 // =========================================================================================================
 struct PoWorkspace {
   int capN = 0, capProblems = 0;
-  char* d_base = nullptr;
-  PoArgs* d_args = nullptr;
-  // per-slot device arrays
-  float *obs, *flow_in, *depth, *Tinit, *Tlast, *Tout, *flow_out;
-  double *Xw, *flow, *xl, *eProj;
-  int *level, *inlier, *ninl;
-  LmCtl* ctl;
-  LmRec* rec;
+  // input block (one H2D): PoArgs[capProblems] then per problem obs | flow | depth | Tinit | Tlast
+  // output block (one D2H): per problem Tout | n_inliers | flow_out | inlier, then LmCtl[4] per problem, then records
+  char *d_in = nullptr, *d_out = nullptr, *h_in = nullptr, *h_out = nullptr;
+  size_t in_bytes = 0, out_bytes = 0;
+  double *Xw = nullptr, *flow = nullptr, *xl = nullptr, *eProj = nullptr;
+  int* level = nullptr;
 };
+
+static size_t pal(size_t v) { return (v + 63) & ~(size_t)63; }
+template <class T>
+static T* pcarve(char*& p, size_t n) { T* r = (T*)p; p += pal(sizeof(T) * n); return r; }
 
 int po_setup(vido_ctx* ctx, int capN, int capProblems) {
   PoWorkspace* ws = new PoWorkspace();
@@ -481,33 +483,26 @@ int po_setup(vido_ctx* ctx, int capN, int capProblems) {
   ws->capN = capN;
   ws->capProblems = capProblems;
   const size_t N = (size_t)capN * capProblems;
-  VIDO_CUDA(cudaMalloc(&ws->d_args, sizeof(PoArgs) * capProblems));
-  VIDO_CUDA(cudaMalloc(&ws->obs, sizeof(float) * 2 * N));
-  VIDO_CUDA(cudaMalloc(&ws->flow_in, sizeof(float) * 2 * N));
-  VIDO_CUDA(cudaMalloc(&ws->depth, sizeof(float) * N));
-  VIDO_CUDA(cudaMalloc(&ws->Tinit, sizeof(float) * 16 * capProblems));
-  VIDO_CUDA(cudaMalloc(&ws->Tlast, sizeof(float) * 16 * capProblems));
-  VIDO_CUDA(cudaMalloc(&ws->Tout, sizeof(float) * 16 * capProblems));
-  VIDO_CUDA(cudaMalloc(&ws->flow_out, sizeof(float) * 2 * N));
+  ws->in_bytes = pal(sizeof(PoArgs) * capProblems) + capProblems * (pal(8 * (size_t)capN) * 2 + pal(4 * (size_t)capN) + 2 * pal(64));
+  ws->out_bytes = capProblems * (pal(64) + pal(4) + pal(8 * (size_t)capN) + pal(4 * (size_t)capN)) + pal(sizeof(LmCtl) * 4 * capProblems) +
+                  pal(sizeof(LmRec) * VIDO_LM_REC * 4 * capProblems);
+  VIDO_CUDA(cudaMalloc(&ws->d_in, ws->in_bytes));
+  VIDO_CUDA(cudaMalloc(&ws->d_out, ws->out_bytes));
+  VIDO_CUDA(cudaMallocHost(&ws->h_in, ws->in_bytes));
+  VIDO_CUDA(cudaMallocHost(&ws->h_out, ws->out_bytes));
   VIDO_CUDA(cudaMalloc(&ws->Xw, sizeof(double) * 3 * N));
   VIDO_CUDA(cudaMalloc(&ws->flow, sizeof(double) * 4 * N));
   VIDO_CUDA(cudaMalloc(&ws->xl, sizeof(double) * 2 * N));
   VIDO_CUDA(cudaMalloc(&ws->eProj, sizeof(double) * 2 * N));
   VIDO_CUDA(cudaMalloc(&ws->level, sizeof(int) * N));
-  VIDO_CUDA(cudaMalloc(&ws->inlier, sizeof(int) * N));
-  VIDO_CUDA(cudaMalloc(&ws->ninl, sizeof(int) * capProblems));
-  VIDO_CUDA(cudaMalloc(&ws->ctl, sizeof(LmCtl) * 4 * capProblems));
-  VIDO_CUDA(cudaMalloc(&ws->rec, sizeof(LmRec) * VIDO_LM_REC * 4 * capProblems));
   return VIDO_OK;
 }
 
 void po_teardown(vido_ctx* ctx) {
   PoWorkspace* ws = (PoWorkspace*)ctx->po;
   if (!ws) return;
-  cudaFree(ws->d_args); cudaFree(ws->obs); cudaFree(ws->flow_in); cudaFree(ws->depth); cudaFree(ws->Tinit);
-  cudaFree(ws->Tlast); cudaFree(ws->Tout); cudaFree(ws->flow_out); cudaFree(ws->Xw); cudaFree(ws->flow);
-  cudaFree(ws->xl); cudaFree(ws->eProj); cudaFree(ws->level); cudaFree(ws->inlier); cudaFree(ws->ninl);
-  cudaFree(ws->ctl); cudaFree(ws->rec);
+  cudaFree(ws->d_in); cudaFree(ws->d_out); cudaFreeHost(ws->h_in); cudaFreeHost(ws->h_out);
+  cudaFree(ws->Xw); cudaFree(ws->flow); cudaFree(ws->xl); cudaFree(ws->eProj); cudaFree(ws->level);
   delete ws;
   ctx->po = nullptr;
 }
@@ -516,16 +511,31 @@ int po_flow2_host(vido_ctx* ctx, vido_poseopt_problem* prs, int nproblems, vido_
   PoWorkspace* ws = (PoWorkspace*)ctx->po;
   if (nproblems < 1 || nproblems > ws->capProblems) { ctx->err = "too many pose problems"; return VIDO_ERR_CAPACITY; }
   cudaStream_t s = ctx->stream;
-  std::vector<PoArgs> h(nproblems);
+  // identical carving of the host (pinned) and device blocks
+  char *hi = ws->h_in, *di = ws->d_in, *ho = ws->h_out, *dq = ws->d_out;
+  PoArgs* h_args = pcarve<PoArgs>(hi, nproblems);
+  PoArgs* d_args = pcarve<PoArgs>(di, nproblems);
+  struct Out { float* T; int* ninl; float* flow; int* inl; };
+  std::vector<Out> outs(nproblems);
   for (int k = 0; k < nproblems; k++) {
     vido_poseopt_problem& p = prs[k];
     if (p.n > ws->capN || p.n < 0 || p.rounds > 4 || p.rounds < 1) { ctx->err = "pose problem exceeds capacity"; return VIDO_ERR_CAPACITY; }
     const size_t off = (size_t)k * ws->capN;
-    PoArgs& a = h[k];
+    PoArgs& a = h_args[k];
     memset(&a, 0, sizeof a);
     a.n = p.n;
-    a.obs_xy = ws->obs + 2 * off; a.flow_xy = ws->flow_in + 2 * off; a.depth = ws->depth + off;
-    a.Tcw_init = ws->Tinit + 16 * k; a.Tcw_last = ws->Tlast + 16 * k;
+    float* h_obs = pcarve<float>(hi, 2 * (size_t)p.n);   a.obs_xy = pcarve<float>(di, 2 * (size_t)p.n);
+    float* h_flow = pcarve<float>(hi, 2 * (size_t)p.n);  a.flow_xy = pcarve<float>(di, 2 * (size_t)p.n);
+    float* h_dep = pcarve<float>(hi, p.n);               a.depth = pcarve<float>(di, p.n);
+    float* h_Ti = pcarve<float>(hi, 16);                 a.Tcw_init = pcarve<float>(di, 16);
+    float* h_Tl = pcarve<float>(hi, 16);                 a.Tcw_last = pcarve<float>(di, 16);
+    if (p.n) {
+      memcpy(h_obs, p.obs_xy, sizeof(float) * 2 * p.n);
+      memcpy(h_flow, p.flow_xy, sizeof(float) * 2 * p.n);
+      memcpy(h_dep, p.depth, sizeof(float) * p.n);
+    }
+    memcpy(h_Ti, p.Tcw_init, sizeof(float) * 16);
+    memcpy(h_Tl, p.Tcw_last, sizeof(float) * 16);
     a.fx = p.fx; a.fy = p.fy; a.cx = p.cx; a.cy = p.cy;
     a.info_f = (p.info_flow == 0.1f) ? 0.1 : (double)p.info_flow;   // Matrix2d literals of the reference are doubles
     a.info_p = (p.info_prior == 0.3f) ? 0.3 : (p.info_prior == 0.5f ? 0.5 : (double)p.info_prior);
@@ -534,51 +544,47 @@ int po_flow2_host(vido_ctx* ctx, vido_poseopt_problem* prs, int nproblems, vido_
     a.rounds = p.rounds; a.its = p.its;
     a.Xw = ws->Xw + 3 * off; a.flow = ws->flow + 4 * off; a.xl = ws->xl + 2 * off; a.eProj = ws->eProj + 2 * off;
     a.level = ws->level + off;
-    a.Tcw_out = ws->Tout + 16 * k; a.flow_out = ws->flow_out + 2 * off; a.inlier = ws->inlier + off; a.n_inliers = ws->ninl + k;
-    a.ctl = ws->ctl + 4 * k;
-    a.rec = stats ? ws->rec + (size_t)4 * VIDO_LM_REC * k : nullptr;
-    if (p.n) {
-      VIDO_CUDA(cudaMemcpyAsync((void*)a.obs_xy, p.obs_xy, sizeof(float) * 2 * p.n, cudaMemcpyHostToDevice, s));
-      VIDO_CUDA(cudaMemcpyAsync((void*)a.flow_xy, p.flow_xy, sizeof(float) * 2 * p.n, cudaMemcpyHostToDevice, s));
-      VIDO_CUDA(cudaMemcpyAsync((void*)a.depth, p.depth, sizeof(float) * p.n, cudaMemcpyHostToDevice, s));
-    }
-    VIDO_CUDA(cudaMemcpyAsync((void*)a.Tcw_init, p.Tcw_init, sizeof(float) * 16, cudaMemcpyHostToDevice, s));
-    VIDO_CUDA(cudaMemcpyAsync((void*)a.Tcw_last, p.Tcw_last, sizeof(float) * 16, cudaMemcpyHostToDevice, s));
+    outs[k].T = pcarve<float>(ho, 16);                    a.Tcw_out = pcarve<float>(dq, 16);
+    outs[k].ninl = pcarve<int>(ho, 1);                    a.n_inliers = pcarve<int>(dq, 1);
+    outs[k].flow = pcarve<float>(ho, 2 * (size_t)p.n);    a.flow_out = pcarve<float>(dq, 2 * (size_t)p.n);
+    outs[k].inl = pcarve<int>(ho, p.n);                   a.inlier = pcarve<int>(dq, p.n);
   }
-  VIDO_CUDA(cudaMemcpyAsync(ws->d_args, h.data(), sizeof(PoArgs) * nproblems, cudaMemcpyHostToDevice, s));
+  LmCtl* h_ctl = pcarve<LmCtl>(ho, 4 * (size_t)nproblems);
+  LmCtl* d_ctl = pcarve<LmCtl>(dq, 4 * (size_t)nproblems);
+  const size_t out_small = (size_t)(ho - ws->h_out);
+  LmRec* h_rec = pcarve<LmRec>(ho, (size_t)4 * VIDO_LM_REC * nproblems);
+  LmRec* d_rec = pcarve<LmRec>(dq, (size_t)4 * VIDO_LM_REC * nproblems);
+  for (int k = 0; k < nproblems; k++) {
+    h_args[k].ctl = d_ctl + 4 * k;
+    h_args[k].rec = stats ? d_rec + (size_t)4 * VIDO_LM_REC * k : nullptr;
+  }
+  VIDO_CUDA(cudaMemcpyAsync(ws->d_in, ws->h_in, (size_t)(hi - ws->h_in), cudaMemcpyHostToDevice, s));
   cudaEventRecord(ctx->ev0, s);
-  poseopt_flow2_kernel<<<nproblems, PO_THREADS, 0, s>>>(ws->d_args);
+  poseopt_flow2_kernel<<<nproblems, PO_THREADS, 0, s>>>(d_args);
   cudaEventRecord(ctx->ev1, s);
   ctx->launches++;
   VIDO_CUDA(cudaGetLastError());
-  std::vector<LmCtl> ctls(4 * nproblems);
-  std::vector<LmRec> recs;
-  for (int k = 0; k < nproblems; k++) {
-    vido_poseopt_problem& p = prs[k];
-    const PoArgs& a = h[k];
-    VIDO_CUDA(cudaMemcpyAsync(p.Tcw_out, a.Tcw_out, sizeof(float) * 16, cudaMemcpyDeviceToHost, s));
-    if (p.n && p.flow_out) VIDO_CUDA(cudaMemcpyAsync(p.flow_out, a.flow_out, sizeof(float) * 2 * p.n, cudaMemcpyDeviceToHost, s));
-    if (p.n && p.inlier) VIDO_CUDA(cudaMemcpyAsync(p.inlier, a.inlier, sizeof(int) * p.n, cudaMemcpyDeviceToHost, s));
-    VIDO_CUDA(cudaMemcpyAsync(&p.n_inliers, a.n_inliers, sizeof(int), cudaMemcpyDeviceToHost, s));
-  }
-  if (stats) {
-    recs.resize((size_t)4 * VIDO_LM_REC * nproblems);
-    VIDO_CUDA(cudaMemcpyAsync(ctls.data(), ws->ctl, sizeof(LmCtl) * 4 * nproblems, cudaMemcpyDeviceToHost, s));
-    VIDO_CUDA(cudaMemcpyAsync(recs.data(), ws->rec, sizeof(LmRec) * recs.size(), cudaMemcpyDeviceToHost, s));
-  }
+  VIDO_CUDA(cudaMemcpyAsync(ws->h_out, ws->d_out, stats ? (size_t)(ho - ws->h_out) : out_small, cudaMemcpyDeviceToHost, s));
   VIDO_CUDA(cudaStreamSynchronize(s));
   {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) { ctx->t_ms[2] += ms; ctx->t_n[2]++; }
   }
+  for (int k = 0; k < nproblems; k++) {
+    vido_poseopt_problem& p = prs[k];
+    memcpy(p.Tcw_out, outs[k].T, sizeof(float) * 16);
+    p.n_inliers = *outs[k].ninl;
+    if (p.n && p.flow_out) memcpy(p.flow_out, outs[k].flow, sizeof(float) * 2 * p.n);
+    if (p.n && p.inlier) memcpy(p.inlier, outs[k].inl, sizeof(int) * p.n);
+  }
   if (stats) {
     for (int k = 0; k < nproblems; k++)
       for (int r = 0; r < prs[k].rounds; r++) {
         vido_lm_stats& st = stats[4 * k + r];
-        const LmCtl& c = ctls[4 * k + r];
+        const LmCtl& c = h_ctl[4 * k + r];
         st.iterations = c.iterations; st.n_records = c.n_records; st.total_trials = c.total_trials;
         for (int i = 0; i < c.n_records && i < VIDO_LM_MAX_RECORDS; i++) {
-          const LmRec& rr = recs[((size_t)4 * k + r) * VIDO_LM_REC + i];
+          const LmRec& rr = h_rec[((size_t)4 * k + r) * VIDO_LM_REC + i];
           st.rec[i].chi2 = rr.chi2; st.rec[i].lambda = rr.lambda; st.rec[i].trials = rr.trials;
         }
       }

@@ -53,7 +53,7 @@ struct MapFrame {           // Map::vpFeatSta / vfDepSta / vp3DPointSta / vnAsso
   float Twc[16];            // vmCameraPose
   float rel[16];            // vmRigidMotion[f-1][0]
 };
-struct TrackInfo { int first_frame, len; };
+struct TrackInfo { int first_frame, len, pid, epoch; };  // pid valid for the window graph built in `epoch`
 
 struct FrontFrame {         // front-end results of one frame, on the host
   std::vector<vido_keypoint> kps;
@@ -74,6 +74,7 @@ struct TrackState {
   float lastTcw[16];
   std::vector<float> last_keys, last_depth, last_corres, last_flow;  // mpLastFrame mvStatKeys / mvStatDepth / mvCorres / mvFlowNext
   int f_id = 0;
+  int ba_epoch = 0;
   // device buffers of one chunk
   int capB = 0;
   uint8_t* d_img = nullptr;      // [B][H][W*3] or gray
@@ -169,7 +170,7 @@ void trk_teardown(vido_ctx* ctx) {
 int trk_reset(vido_ctx* ctx) {
   TrackState* ts = (TrackState*)ctx->trk;
   ts->map.clear(); ts->tracks.clear();
-  ts->initialised = false; ts->has_velocity = false; ts->f_id = 0;
+  ts->initialised = false; ts->has_velocity = false; ts->f_id = 0; ts->ba_epoch = 0;
   ts->last_keys.clear(); ts->last_depth.clear(); ts->last_corres.clear(); ts->last_flow.clear();
   return VIDO_OK;
 }
@@ -266,12 +267,11 @@ static int partial_batch(vido_ctx* ctx, int WINDOW, vido_track_stats* st) {
   const int start = N - WINDOW;
   std::vector<float> poses(16 * (size_t)WINDOW), rel(16 * (size_t)std::max(WINDOW - 1, 0)), pts, oxyz;
   std::vector<int> op, ol;
-  std::vector<int> pid_of_track;  // lazily sized
   std::vector<std::pair<int, int>> owner;
+  const int epoch = ++ts->ba_epoch;
   std::vector<int> tid_list;
   const float invfx = 1.0f / ctx->cfg.fx, invfy = 1.0f / ctx->cfg.fy;
   // a track enters the window graph iff it is at least 3 long and was born inside the window
-  pid_of_track.assign(ts->tracks.size(), -1);
   for (int i = start; i < N; i++) {
     MapFrame& F = ts->map[i];
     memcpy(&poses[16 * (size_t)(i - start)], F.Twc, sizeof(float) * 16);
@@ -280,12 +280,12 @@ static int partial_batch(vido_ctx* ctx, int WINDOW, vido_track_stats* st) {
     for (int j = 0; j < n; j++) {
       const int t = F.track[j];
       if (t < 0) continue;
-      const TrackInfo& T = ts->tracks[t];
+      TrackInfo& T = ts->tracks[t];
       if (T.len < 3 || T.first_frame < start) continue;
-      int pid = pid_of_track[t];
+      int pid = (T.epoch == epoch) ? T.pid : -1;
       if (F.pos[j] == 0) {
         pid = (int)owner.size();
-        pid_of_track[t] = pid;
+        T.pid = pid; T.epoch = epoch;
         owner.push_back({i, j});
         pts.push_back(F.p3[3 * j]); pts.push_back(F.p3[3 * j + 1]); pts.push_back(F.p3[3 * j + 2]);
       }
@@ -319,7 +319,7 @@ static int partial_batch(vido_ctx* ctx, int WINDOW, vido_track_stats* st) {
         if (t < 0) continue;
         const TrackInfo& T = ts->tracks[t];
         if (T.len < 3 || T.first_frame < start) continue;
-        const int pid = pid_of_track[t];
+        const int pid = (T.epoch == epoch) ? T.pid : -1;
         if (pid < 0) continue;
         F.p3[3 * j] = pts[3 * (size_t)pid]; F.p3[3 * j + 1] = pts[3 * (size_t)pid + 1]; F.p3[3 * j + 2] = pts[3 * (size_t)pid + 2];
       }
@@ -529,7 +529,7 @@ static int back_end(vido_ctx* ctx, const FrontFrame& ff, int slot, const float* 
           T.len++;
         } else {
           const int t = (int)ts->tracks.size();
-          ts->tracks.push_back({fcur - 1, 2});
+          ts->tracks.push_back({fcur - 1, 2, -1, -1});
           P.track[p] = t; P.pos[p] = 0;
           F.track[j] = t; F.pos[j] = 1;
         }
