@@ -39,11 +39,15 @@ using namespace vb;
 #define BA_THREADS 256
 #define BA_MAX_W 24
 #define BA_MAX_CLUSTER 16
-#define BA_PCHUNK 8   // chunks per pose in the pose-block reduction
+#define BA_PCHUNK 8   // max chunks per pose in the pose-block reduction
+#define BA_MAX_JOBS (BA_MAX_W * (BA_MAX_W + 1) / 2 + BA_MAX_W)   // Schur jobs: pose pairs + gradient jobs
+#define BA_MAX_SLOTS (BA_MAX_CLUSTER * BA_THREADS / 32)            // partial sums per job: at most one per warp
+#define BA_JOB_PAD 2   // fixed cost of entering a job (decode, prefix scan, flush), in units, for the load balance
 
 struct BaArgs {
   int W, P, M;
   int max_iterations;
+  int t_detail;   // debug: extra phase time stamps (VIDO_BA_TIMING=2)
   double info_cam, info_3d, d_cam, d_3d, gain_threshold;
   // graph (device)
   const float* poses_f32;   // [W][16]
@@ -65,29 +69,75 @@ struct BaArgs {
   // system
   double* hl;     // [P]     point block = hl * I3
   double* bl;     // [P][3]
-  double* Hpl;    // [18][M] (6x3 block per observation, struct-of-arrays)
+  // linearisation buffers, one per state buffer (index = state index): the trial state's observation pass fills the
+  // other one, an accepted trial makes it current
+  double* ow;     // [2][M]    robust weight * information of every observation   } the 6x3 block Hpl = ow * [-I | Q(zc)]^T R^T
+  double* ozc;    // [2][3][M] point in the camera frame (struct-of-arrays)         } is never formed (see phase_schur_units)
+  double* og;     // [2][3][M] ow * R * error: the point gradient is -sum og
+  double* ohb;    // [4][M] per observation: its point's hl and bl (written by phase_blocks, read coalesced by the gradient jobs)
   double* Hpp;    // [W][36] diagonal blocks (points + odometry)
   double* Hoff;   // [W-1][36] blocks (i, i+1)
   double* bp;     // [W][6]
-  double* ppart;  // [W][BA_PCHUNK][28] partial pose blocks (27 sums)
-  double* S;      // [6W][6W] reduced camera system (lower triangle)
-  double* bred;   // [6W]
+  double* ppart;  // [2][W][BA_PCHUNK][28] partial pose blocks (27 sums)
+  double* spart;  // [jobs][BA_MAX_SLOTS][16] partial Schur moment sums
+  double* pmax;   // [W] max |diagonal| of every pose block
   double* xp;     // [6W]
   double* part;   // [BA_MAX_CLUSTER][4]: chi2, scale, max point diag, max pose diag
   double* cinfo;  // [4]: pose part of the scale, solver failure flag
-  double* seJ;    // [W-1][72]
-  double* seE;    // [W-1][8]
+  double* seJ;    // [2][W][72]
+  double* seE;    // [2][W][8]
   LmCtl* ctl_out;
   LmRec* rec;
-  unsigned long long* t_phase;  // [8]
+  unsigned long long* t_phase;  // [24]
   float* out_poses; float* out_rel; float* out_points;
 };
 
+__device__ __forceinline__ double div_pos(double a, double x);
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// Sum 36 per-lane values over the warp with 54 shuffles instead of 180: two halving steps (lane pairs trade halves of
+// their value sets), then a butterfly inside the 8-lane groups.  Afterwards v[j], j < 9, of lane L holds the sum of
+// value 18*((L>>4)&1) + 9*((L>>3)&1) + j.  Fixed order, deterministic.
+__device__ __forceinline__ void warp_sum36(double* v) {
+  const int lane = threadIdx.x & 31;
+  const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+#pragma unroll
+  for (int k = 0; k < 18; k++) {
+    const double send = hi16 ? v[k] : v[k + 18], keep = hi16 ? v[k + 18] : v[k];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    const double send = hi8 ? v[k] : v[k + 9], keep = hi8 ? v[k + 9] : v[k];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    v[k] += __shfl_xor_sync(0xffffffffu, v[k], 4);
+    v[k] += __shfl_xor_sync(0xffffffffu, v[k], 2);
+    v[k] += __shfl_xor_sync(0xffffffffu, v[k], 1);
+  }
+}
+
+// Same idea for 16 values with 16 shuffles: afterwards v[0] of lane L holds the sum of value 8*b4 + 4*b3 + 2*b2 + b1
+// (b_i = bit i of L).
+__device__ __forceinline__ void warp_sum16(double* v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int h = 8, m = 16; h >= 1; h >>= 1, m >>= 1) {
+    const bool hi = (lane & m) != 0;
+#pragma unroll
+    for (int k = 0; k < h; k++) {
+      const double send = hi ? v[k] : v[k + h], keep = hi ? v[k + h] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -112,6 +162,8 @@ __device__ __forceinline__ void block_reduce(double* v, double* sm) {
   __syncthreads();
 }
 
+__device__ __forceinline__ unsigned long long gtime();
+__device__ __forceinline__ void ba_tick(unsigned long long* tp, int slot);
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -119,6 +171,10 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ba_tick(unsigned long long* tp, int slot) {
+  if (tp) { const unsigned long long t = gtime(); tp[slot] += t - tp[15]; tp[15] = t; }
+}
+
 __device__ void phase_init(const BaArgs& a, int G, int GT) {
   for (int i = G; i < a.W; i += GT) {
     Pose X;
@@ -149,118 +205,53 @@ __device__ __forceinline__ double obs_chi(const BaArgs& a, const Pose& Xp, const
   return r0;
 }
 
-__device__ __forceinline__ double se3_chi(const BaArgs& a, const Pose* X, int i) {
-  double e[6], r0, w;
-  edge_se3(X[i], X[i + 1], a.Zinv[i], e, nullptr, nullptr);
-  double c = 0;
-  for (int k = 0; k < 6; k++) c += e[k] * e[k];
-  huber(c * a.info_cam, a.d_cam, r0, w);
-  return r0;
-}
-
-// robust chi2 of state `st` (thread per observation) -> part[rank][0]
-__device__ void phase_errors(const BaArgs& a, int st, int G, int GT, int rank, double* red) {
-  const Pose* X = a.X + (size_t)st * a.W;
-  const double* pts = a.pts + (size_t)st * 3 * a.P;
-  double chi = 0;
-  for (int o = G; o < a.M; o += GT) {
-    double zc[3], e[3], w;
-    chi += obs_chi(a, X[a.obs_pose[o]], pts + 3 * (size_t)a.obs_point[o], o, zc, e, w);
-  }
-  for (int i = G; i < a.W - 1; i += GT) chi += se3_chi(a, X, i);
-  double v[1] = {chi};
-  block_reduce<1, false>(v, red);
-  if (threadIdx.x == 0) a.part[rank * 4 + 0] = red[0];
-}
-
-// linearisation, step 1: thread per observation -> Hpl; thread per odometry edge -> Jacobians
-__device__ void phase_lin_obs(const BaArgs& a, int st, int G, int GT) {
-  const Pose* X = a.X + (size_t)st * a.W;
-  const double* pts = a.pts + (size_t)st * 3 * a.P;
-  for (int o = G; o < a.M; o += GT) {
-    const Pose& Xp = X[a.obs_pose[o]];
-    double zc[3], e[3], w;
-    obs_chi(a, Xp, pts + 3 * (size_t)a.obs_point[o], o, zc, e, w);
-    w *= a.info_3d;
-    // Hpl = w * J_pose^T J_point, J_pose = [-I | Q(zc)], J_point = R^T
-    double* hp = a.Hpl + o;
-    const size_t M = a.M;
-    const double* R = Xp.R;
-    const double qx = 2 * zc[0], qy = 2 * zc[1], qz = 2 * zc[2];
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      const double r0c = R[3 * c], r1c = R[3 * c + 1], r2c = R[3 * c + 2];
-      hp[(c)*M] = -w * r0c;
-      hp[(3 + c) * M] = -w * r1c;
-      hp[(6 + c) * M] = -w * r2c;
-      hp[(9 + c) * M] = w * (qz * r1c - qy * r2c);
-      hp[(12 + c) * M] = w * (-qz * r0c + qx * r2c);
-      hp[(15 + c) * M] = w * (qy * r0c - qx * r1c);
-    }
-  }
-  for (int i = G; i < a.W - 1; i += GT) {
-    double e[6], Ji[36], Jj[36], r0, w;
-    edge_se3(X[i], X[i + 1], a.Zinv[i], e, Ji, Jj);
-    double c = 0;
-    for (int k = 0; k < 6; k++) c += e[k] * e[k];
-    huber(c * a.info_cam, a.d_cam, r0, w);
-    w *= a.info_cam;
-    double* J = a.seJ + 72 * (size_t)i;
-    for (int k = 0; k < 36; k++) { J[k] = Ji[k]; J[36 + k] = Jj[k]; }
-    double* E = a.seE + 8 * (size_t)i;
-    for (int k = 0; k < 6; k++) E[k] = e[k];
-    E[6] = w;
-  }
-}
-
-// linearisation, step 2: point blocks (thread per point) and partial pose blocks (warp per (pose, chunk))
-struct BaTab {  // shared-memory copies of the small layout tables
+// shared-memory copies of the small layout tables
+struct BaTab {
   int grp[BA_MAX_W + 1], cnt[BA_MAX_W * (BA_MAX_W + 1)], off[BA_MAX_W * (BA_MAX_W + 1)], base[BA_MAX_W + 1];
+  int ustart[BA_MAX_JOBS + 1];  // Schur work units (32 point-pairs each) + BA_JOB_PAD per non-empty job: prefix over the jobs
+  unsigned char jp1[BA_MAX_JOBS], jp2[BA_MAX_JOBS];  // pose pair of every pair job
+  int nch;                      // chunks per pose in the pose-block reduction
+  int uq;                       // Schur units per warp
 };
 
-__device__ void phase_lin_blocks(const BaArgs& a, int st, int G, int GT, int rank, int nranks, double* red, const BaTab& tb) {
+// The observation pass: ONE coalesced sweep over the observations (pose-major) at state `st`, written into the
+// linearisation buffer of the same index.  It serves two purposes at once: the robust chi2 of the state (what the LM
+// driver needs to accept or reject a trial) and the linearisation at that state (what the next iteration needs if the
+// trial is accepted -- the reference recomputes both, g2o/core/sparse_optimizer.cpp:377-380 + block_solver.hpp:502).
+//   warp per (pose, chunk): robust weight w, camera-frame point zc and gradient term g = w R e of every observation,
+//                           the 27 sums of the pose block, the chi2;
+//   thread per odometry edge: error, Jacobians, chi2.
+// Output: ow/ozc/og[st], ppart[st], seJ/seE[st], part[rank][0] = chi2 partial.
+__device__ void phase_obs(const BaArgs& a, int st, int G, int GT, int rank, int nranks, double* red, const BaTab& tb) {
   const Pose* X = a.X + (size_t)st * a.W;
   const double* pts = a.pts + (size_t)st * 3 * a.P;
   const int W = a.W;
-  double mx = 0;
-  for (int l = G; l < a.P; l += GT) {
-    double h = 0, b[3] = {0, 0, 0};
-    const double* p = pts + 3 * (size_t)l;
-    const int f = a.pt_first[l], len = a.pt_len[l], i = l - tb.grp[f];
-    for (int k = 0; k < len; k++) {
-      const int pp = f + k;
-      const int o = tb.base[pp] + tb.off[pp * (W + 1) + f] + i;
-      const Pose& Xp = X[pp];
-      double zc[3], e[3], w;
-      obs_chi(a, Xp, p, o, zc, e, w);
-      w *= a.info_3d;
-      h += w;  // J_point^T J_point = R R^T = I
-      const double* R = Xp.R;
-      for (int r = 0; r < 3; r++) b[r] -= w * (R[3 * r] * e[0] + R[3 * r + 1] * e[1] + R[3 * r + 2] * e[2]);
-    }
-    a.hl[l] = h;
-    for (int k = 0; k < 3; k++) a.bl[3 * (size_t)l + k] = b[k];
-    mx = fmax(mx, h);
-  }
-  {
-    double v[1] = {mx};
-    block_reduce<1, true>(v, red);
-    if (threadIdx.x == 0) a.part[rank * 4 + 2] = red[0];
-  }
-  // pose blocks: job = (pose p, chunk c) over the pose's contiguous observation range; 27 sums per lane, shuffles
+  const size_t M = a.M;
+  double* ow = a.ow + (size_t)st * M;
+  double* ozc = a.ozc + (size_t)st * 3 * M;
+  double* og = a.og + (size_t)st * 3 * M;
   const int lane = threadIdx.x & 31;
   const int gw = rank * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = nranks * (blockDim.x >> 5);
-  for (int job = gw; job < W * BA_PCHUNK; job += nw) {
-    const int p = job / BA_PCHUNK, ch = job % BA_PCHUNK;
+  const int nch = tb.nch;
+  double chi = 0;
+  for (int job = gw; job < W * nch; job += nw) {
+    const int p = job / nch, ch = job - p * nch;
     const Pose Xp = X[p];
+    const double* R = Xp.R;
     double acc[27];
 #pragma unroll
     for (int k = 0; k < 27; k++) acc[k] = 0;
     const int q0 = tb.base[p], q1 = tb.base[p + 1];
-    for (int o = q0 + ch * 32 + lane; o < q1; o += 32 * BA_PCHUNK) {
+    for (int o = q0 + ch * 32 + lane; o < q1; o += 32 * nch) {
       double zc[3], e[3], w;
-      obs_chi(a, Xp, pts + 3 * (size_t)a.obs_point[o], o, zc, e, w);
+      chi += obs_chi(a, Xp, pts + 3 * (size_t)a.obs_point[o], o, zc, e, w);
       w *= a.info_3d;
+      // Hpl = w * J_pose^T J_point with J_pose = [-I | Q(zc)], J_point = R^T is a function of (w, zc) and the pose's
+      // rotation only: keep those four numbers, every consumer rebuilds what it needs.  g = w R e: bl = -sum g.
+      ow[o] = w;
+      ozc[o] = zc[0]; ozc[M + o] = zc[1]; ozc[2 * M + o] = zc[2];
+#pragma unroll
+      for (int r = 0; r < 3; r++) og[r * M + o] = w * (R[3 * r] * e[0] + R[3 * r + 1] * e[1] + R[3 * r + 2] * e[2]);
       const double qx = 2 * zc[0], qy = 2 * zc[1], qz = 2 * zc[2];
       const double J[3][6] = {{-1, 0, 0, 0, -qz, qy}, {0, -1, 0, qz, 0, -qx}, {0, 0, -1, -qy, qx, 0}};
       int idx = 0;
@@ -274,274 +265,524 @@ __device__ void phase_lin_blocks(const BaArgs& a, int st, int G, int GT, int ran
 #pragma unroll
     for (int k = 0; k < 27; k++) acc[k] = warp_sum(acc[k]);
     if (lane == 0) {
-      double* o = a.ppart + ((size_t)p * BA_PCHUNK + ch) * 28;
+      double* o = a.ppart + (((size_t)st * W + p) * BA_PCHUNK + ch) * 28;
       for (int k = 0; k < 27; k++) o[k] = acc[k];
     }
   }
+  // odometry edges: the lanes of the LAST warp of the cluster (normally without a pose job, so the long Jacobian
+  // evaluation overlaps the observation sweep instead of following it)
+  for (int i = (gw == nw - 1) ? lane : W; i < W - 1; i += 32) {
+    double e[6], Ji[36], Jj[36], r0, w;
+    edge_se3(X[i], X[i + 1], a.Zinv[i], e, Ji, Jj);
+    double c = 0;
+    for (int k = 0; k < 6; k++) c += e[k] * e[k];
+    huber(c * a.info_cam, a.d_cam, r0, w);
+    chi += r0;
+    w *= a.info_cam;
+    double* J = a.seJ + 72 * ((size_t)st * W + i);
+    for (int k = 0; k < 36; k++) { J[k] = Ji[k]; J[36 + k] = Jj[k]; }
+    double* E = a.seE + 8 * ((size_t)st * W + i);
+    for (int k = 0; k < 6; k++) E[k] = e[k];
+    E[6] = w;
+  }
+  double v[1] = {chi};
+  block_reduce<1, false>(v, red);
+  if (threadIdx.x == 0) a.part[rank * 4 + 0] = red[0];
 }
 
-// linearisation, step 3 (after a barrier): sum the partial pose blocks in fixed order, add the odometry edges
-__device__ void phase_lin_poses(const BaArgs& a, int G, int GT, int rank, double* red) {
+// System blocks from the linearisation buffer `st` (after a barrier):
+//   warp per pose:    sum the partial pose blocks in fixed order, add the odometry edges; lanes own the 36 entries of
+//                     the block (two passes) and the 6 gradient entries;
+//   thread per point: the point block (a scalar: J_point^T J_point = R R^T = I) and its gradient are plain sums of
+//                     the stored per-observation terms; the loads of four observations are in flight together.
+__device__ void phase_blocks(const BaArgs& a, int st, int G, int GT, int rank, int nranks, double* red, const BaTab& tb) {
+  const int lane = threadIdx.x & 31;
+  const int gw = rank * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = nranks * (blockDim.x >> 5);
+  const int W = a.W, nch = tb.nch;
+  const size_t M = a.M;
+  for (int p = gw; p < W; p += nw) {
+    const double* Ji = a.seJ + 72 * ((size_t)st * W + p);          // edge p ("from" vertex), valid when p < W-1
+    const double* Jj = Ji + 36;
+    const double* Jt = a.seJ + 72 * ((size_t)st * W + p - 1) + 36;  // edge p-1 ("to" vertex), valid when p > 0
+    const double* Ee = a.seE + 8 * ((size_t)st * W + p);
+    const double* Et = a.seE + 8 * ((size_t)st * W + p - 1);
+    const double we = (p < W - 1) ? Ee[6] : 0.0, wt = (p > 0) ? Et[6] : 0.0;
+    const double* pp = a.ppart + ((size_t)st * W + p) * BA_PCHUNK * 28;
+    double dmax = 0;
+    for (int e = lane; e < 36; e += 32) {
+      const int r = e / 6, c = e - 6 * r;
+      const int lo = r < c ? r : c, hi = r < c ? c : r;
+      const int idx = lo * 6 - (lo * (lo - 1)) / 2 + (hi - lo);
+      double h = 0;
+      for (int ch = 0; ch < nch; ch++) h += pp[ch * 28 + idx];
+      if (p < W - 1) {
+        double t = 0, to = 0;
+        for (int k = 0; k < 6; k++) { t += Ji[6 * k + r] * Ji[6 * k + c]; to += Ji[6 * k + r] * Jj[6 * k + c]; }
+        h += we * t;
+        a.Hoff[36 * (size_t)p + e] = we * to;
+      }
+      if (p > 0) {
+        double t = 0;
+        for (int k = 0; k < 6; k++) t += Jt[6 * k + r] * Jt[6 * k + c];
+        h += wt * t;
+      }
+      a.Hpp[36 * (size_t)p + e] = h;
+      if (r == c) dmax = fmax(dmax, fabs(h));
+    }
+    if (lane < 6) {
+      double b = 0;
+      for (int ch = 0; ch < nch; ch++) b += pp[ch * 28 + 21 + lane];
+      if (p < W - 1) {
+        double t = 0;
+        for (int k = 0; k < 6; k++) t += Ji[6 * k + lane] * Ee[k];
+        b -= we * t;
+      }
+      if (p > 0) {
+        double t = 0;
+        for (int k = 0; k < 6; k++) t += Jt[6 * k + lane] * Et[k];
+        b -= wt * t;
+      }
+      a.bp[6 * p + lane] = b;
+    }
+    dmax = warp_max(dmax);
+    if (lane == 0) a.pmax[p] = dmax;
+  }
+  const double* ow = a.ow + (size_t)st * M;
+  const double* og = a.og + (size_t)st * 3 * M;
   double mx = 0;
-  for (int p = G; p < a.W; p += GT) {
-    double H[36], b[6], s[27];
-    for (int k = 0; k < 27; k++) s[k] = 0;
-    for (int ch = 0; ch < BA_PCHUNK; ch++) {
-      const double* o = a.ppart + ((size_t)p * BA_PCHUNK + ch) * 28;
-      for (int k = 0; k < 27; k++) s[k] += o[k];
-    }
-    int idx = 0;
-    for (int r = 0; r < 6; r++) {
-      b[r] = s[21 + r];
-      for (int c = r; c < 6; c++) { H[6 * r + c] = s[idx]; H[6 * c + r] = s[idx]; idx++; }
-    }
-    if (p < a.W - 1) {  // edge p: this pose is the "from" vertex
-      const double* Ji = a.seJ + 72 * (size_t)p;
-      const double* Jj = Ji + 36;
-      const double* E = a.seE + 8 * (size_t)p;
-      const double w = E[6];
-      double* off = a.Hoff + 36 * (size_t)p;
-      for (int r = 0; r < 6; r++) {
-        double t = 0;
-        for (int k = 0; k < 6; k++) t += Ji[6 * k + r] * E[k];
-        b[r] -= w * t;
-        for (int c = 0; c < 6; c++) {
-          double h = 0, ho = 0;
-          for (int k = 0; k < 6; k++) { h += Ji[6 * k + r] * Ji[6 * k + c]; ho += Ji[6 * k + r] * Jj[6 * k + c]; }
-          H[6 * r + c] += w * h;
-          off[6 * r + c] = w * ho;
-        }
+  for (int l = G; l < a.P; l += GT) {
+    const int f = a.pt_first[l], len = a.pt_len[l], i = l - tb.grp[f];
+    double h = 0, b0 = 0, b1 = 0, b2 = 0;
+    for (int k0 = 0; k0 < len; k0 += 4) {
+      double w[4], g0[4], g1[4], g2[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const bool on = k0 + j < len;
+        const int pp = on ? f + k0 + j : f;
+        const size_t o = (size_t)tb.base[pp] + tb.off[pp * (W + 1) + f] + i;
+        w[j] = on ? ow[o] : 0.0;
+        g0[j] = on ? og[o] : 0.0; g1[j] = on ? og[M + o] : 0.0; g2[j] = on ? og[2 * M + o] : 0.0;
       }
+#pragma unroll
+      for (int j = 0; j < 4; j++) { h += w[j]; b0 -= g0[j]; b1 -= g1[j]; b2 -= g2[j]; }
     }
-    if (p > 0) {  // edge p-1: "to" vertex
-      const double* Jj = a.seJ + 72 * (size_t)(p - 1) + 36;
-      const double* E = a.seE + 8 * (size_t)(p - 1);
-      const double w = E[6];
-      for (int r = 0; r < 6; r++) {
-        double t = 0;
-        for (int k = 0; k < 6; k++) t += Jj[6 * k + r] * E[k];
-        b[r] -= w * t;
-        for (int c = 0; c < 6; c++) {
-          double h = 0;
-          for (int k = 0; k < 6; k++) h += Jj[6 * k + r] * Jj[6 * k + c];
-          H[6 * r + c] += w * h;
-        }
-      }
+    a.hl[l] = h;
+    a.bl[3 * (size_t)l] = b0; a.bl[3 * (size_t)l + 1] = b1; a.bl[3 * (size_t)l + 2] = b2;
+    for (int k = 0; k < len; k++) {
+      const int pp = f + k;
+      const size_t o = (size_t)tb.base[pp] + tb.off[pp * (W + 1) + f] + i;
+      a.ohb[o] = h; a.ohb[M + o] = b0; a.ohb[2 * M + o] = b1; a.ohb[3 * M + o] = b2;
     }
-    for (int k = 0; k < 36; k++) a.Hpp[36 * (size_t)p + k] = H[k];
-    for (int r = 0; r < 6; r++) { a.bp[6 * p + r] = b[r]; mx = fmax(mx, fabs(H[7 * r])); }
+    mx = fmax(mx, h);
   }
   double v[1] = {mx};
   block_reduce<1, true>(v, red);
-  if (threadIdx.x == 0) a.part[rank * 4 + 3] = red[0];
+  if (threadIdx.x == 0) a.part[rank * 4 + 2] = red[0];
 }
 
-// reduced camera system: S(p1,p2) = Hpp(p1,p2) + lambda I - sum_l Hpl(p1,l) Hpl(p2,l)^T / (hl + lambda).
-// Job = pose pair, dealt round-robin to the CTAs (ordered by distance so that every CTA gets the same mix of big and
-// small pairs); all threads of the CTA share the pair's common points (coalesced struct-of-arrays loads), 36-value
-// warp-shuffle reduction, then a fixed-order sum over the warps in shared memory (deterministic, no atomics).
-__device__ void phase_schur(const BaArgs& a, double lambda, int rank, int nranks, const BaTab& tb, double* sred /* [warps][36] */) {
-  const int W = a.W, n = 6 * W;
+// reduced camera system: S(p1,p2) = Hpp(p1,p2) + lambda I - sum_l Hpl(p1,l) Hpl(p2,l)^T / (hl + lambda), and the
+// reduced gradient b(p) = bp(p) - sum_o Hpl(o) bl / (hl + lambda).
+//
+// Structure used: Hpl(p,l) = w [-I | Q]^T R_p^T with Q = [2 zc]x, so for a pose pair
+//   Hpl(p1,l) Hpl(p2,l)^T = w1 w2 [ R12, -R12 Q2 ; -Q1^T R12, Q1^T R12 Q2 ],  R12 = R_p1^T R_p2 (constant over the pair).
+// Every entry is linear in (1, zc1, zc2, zc1 zc2^T): a pair needs only the 16 moment sums
+//   C0 = sum c, A1 = sum c zc1, A2 = sum c zc2, Mz = sum c zc1 zc2^T,  c = w1 w2 / (hl + lambda),
+// i.e. 9 loads and ~20 FMAs per common point instead of 37 loads and 108 FMAs, and a 16-value reduction.  The 6x6 block
+// is assembled from the moments once per pair (phase_schur_reduce).
+//
+// Jobs: the W(W+1)/2 pose pairs (ordered by distance) followed by the W gradient jobs.  A job's terms are cut into
+// UNITS of 32 (one per lane); the flat unit list is dealt in equal contiguous runs to the warps of the whole cluster,
+// so the load is balanced whatever the track-length distribution.  A warp accumulates while it stays inside a job and
+// flushes a partial when the job changes; phase_schur_reduce adds the partials of every job in slot order
+// (deterministic, no atomics) and writes the system straight into CTA 0's shared memory (DSMEM).
+__device__ __forceinline__ void job_pair(int job, int W, int& p1, int& p2) {
+  int d = 0, rem = job;
+  while (rem >= W - d) { rem -= W - d; d++; }
+  p1 = rem; p2 = rem + d;
+}
+
+__device__ void phase_schur_units(const BaArgs& a, double lambda, int st, int rank, int nranks, const BaTab& tb) {
+  const int W = a.W;
   const size_t M = a.M;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-  const int npairs = W * (W + 1) / 2;
-  for (int job = rank; job < npairs + W; job += nranks) {
+  const int lane = threadIdx.x & 31;
+  const int gw = rank * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int npairs = W * (W + 1) / 2, njobs = npairs + W;
+  const int U = tb.ustart[njobs], q = tb.uq;
+  const double* ow = a.ow + (size_t)st * M;
+  const double* ozc = a.ozc + (size_t)st * 3 * M;
+  int u = gw * q;
+  const int ue = min(u + q, U);
+  if (u >= ue) return;
+  int job;
+  {  // last job whose first unit is <= u (empty jobs share their start with the next one and are skipped below)
+    int lo = 0, hi = njobs;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (tb.ustart[mid] <= u) lo = mid; else hi = mid;
+    }
+    job = lo;
+  }
+  while (u < ue) {
+    const int js = tb.ustart[job], je = tb.ustart[job + 1];
+    if (je <= u) { job++; continue; }
+    const int uend = min(ue, je - BA_JOB_PAD);  // the last BA_JOB_PAD units of a job are padding (no terms)
+    const int unext = min(ue, je);
+    const int slot = gw - js / q;
+    double* out = a.spart + ((size_t)job * BA_MAX_SLOTS + slot) * 16;
     if (job < npairs) {
-      int d = 0, rem = job;
-      while (rem >= W - d) { rem -= W - d; d++; }
-      const int p1 = rem, p2 = rem + d;
-      double acc[36];
+      const int p1 = tb.jp1[job], p2 = tb.jp2[job];
+      // the pair's common points are the first cnt[f][p2-f] points of every group f <= p1: lane f holds the group's
+      // count and inclusive prefix, the owner group of a flat index is found with p1 shuffles
+      const int cf = (lane <= p1) ? tb.cnt[lane * (W + 1) + (p2 - lane)] : 0;
+      int incl = cf;
 #pragma unroll
-      for (int k = 0; k < 36; k++) acc[k] = 0;
-      for (int f = 0; f <= p1; f++) {
-        const int cntf = tb.cnt[f * (W + 1) + (p2 - f)];
-        const int q1 = tb.base[p1] + tb.off[p1 * (W + 1) + f], q2 = tb.base[p2] + tb.off[p2 * (W + 1) + f], l0 = tb.grp[f];
-        for (int i = tid; i < cntf; i += blockDim.x) {
-          const double s = 1.0 / (a.hl[l0 + i] + lambda);
-          const double* h1 = a.Hpl + (q1 + i);
-          const double* h2 = a.Hpl + (q2 + i);
-          double t[18], g[18];
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      double acc[16];
 #pragma unroll
-          for (int k = 0; k < 18; k++) { t[k] = h1[k * M] * s; g[k] = h2[k * M]; }
+      for (int k = 0; k < 16; k++) acc[k] = 0;
+      // four units per trip: the group search is shared, and the 36 loads of the four terms are in flight together
+      // (the warp's unit run is the critical path of this phase, so latency per unit is what counts)
+      for (; u < uend; u += 4) {
+        int t[4], f[4] = {0, 0, 0, 0};
 #pragma unroll
-          for (int r = 0; r < 6; r++)
+        for (int j = 0; j < 4; j++) t[j] = (u + j < uend) ? (u + j - js) * 32 + lane : total;
+        // f = number of groups k < p1 with incl_k <= t (incl is non-decreasing): binary search with per-lane shuffles
 #pragma unroll
-            for (int c = 0; c < 6; c++) acc[6 * r + c] += t[3 * r] * g[3 * c] + t[3 * r + 1] * g[3 * c + 1] + t[3 * r + 2] * g[3 * c + 2];
+        for (int step = 16; step >= 1; step >>= 1) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int cand = f[j] + step;
+            const int v = __shfl_sync(0xffffffffu, incl, (cand - 1) & 31);
+            if (cand <= p1 && t[j] >= v) f[j] = cand;
+          }
+        }
+        double c[4], x1[4], y1[4], z1[4], x2[4], y2[4], z2[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int excl = __shfl_sync(0xffffffffu, incl - cf, f[j]);
+          const bool on = t[j] < total;
+          const int fj = on ? f[j] : 0, i = on ? t[j] - excl : 0;
+          const size_t q1 = tb.base[p1] + tb.off[p1 * (W + 1) + fj] + i, q2 = tb.base[p2] + tb.off[p2 * (W + 1) + fj] + i;
+          const double hl = on ? a.hl[tb.grp[fj] + i] : 1.0;
+          const double w12 = on ? ow[q1] * ow[q2] : 0.0;
+          x1[j] = on ? ozc[q1] : 0.0; y1[j] = on ? ozc[M + q1] : 0.0; z1[j] = on ? ozc[2 * M + q1] : 0.0;
+          x2[j] = on ? ozc[q2] : 0.0; y2[j] = on ? ozc[M + q2] : 0.0; z2[j] = on ? ozc[2 * M + q2] : 0.0;
+          c[j] = div_pos(w12, hl + lambda);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const double cx = c[j] * x1[j], cy = c[j] * y1[j], cz = c[j] * z1[j];
+          acc[0] += c[j];
+          acc[1] += cx; acc[2] += cy; acc[3] += cz;
+          acc[4] += c[j] * x2[j]; acc[5] += c[j] * y2[j]; acc[6] += c[j] * z2[j];
+          acc[7] += cx * x2[j]; acc[8] += cx * y2[j]; acc[9] += cx * z2[j];
+          acc[10] += cy * x2[j]; acc[11] += cy * y2[j]; acc[12] += cy * z2[j];
+          acc[13] += cz * x2[j]; acc[14] += cz * y2[j]; acc[15] += cz * z2[j];
         }
       }
+      u = unext;
+      warp_sum16(acc);
+      if ((lane & 1) == 0) out[lane >> 1] = acc[0];  // lane bits 4..1 = moment index
+    } else {
+      const int p = job - npairs;
+      const double* R = a.X[(size_t)st * W + p].R;
+      double acc[6] = {0, 0, 0, 0, 0, 0};
+      const int qe = tb.base[p + 1];
+      for (; u < uend; u += 4) {
+        // Hpl v = w [-u ; u x 2 zc],  u = R^T v,  v = bl / (hl + lambda); four units per trip (see above)
+        double sc[4], b0[4], b1[4], b2[4], w[4], qx[4], qy[4], qz[4];
 #pragma unroll
-      for (int k = 0; k < 36; k++) acc[k] = warp_sum(acc[k]);
-      __syncthreads();  // sred free (previous job consumed)
+        for (int j = 0; j < 4; j++) {
+          const size_t o = (size_t)tb.base[p] + (size_t)(u + j - js) * 32 + lane;
+          const bool on = (u + j < uend) && o < (size_t)qe;
+          sc[j] = on ? a.ohb[o] : 1.0;
+          b0[j] = on ? a.ohb[M + o] : 0.0; b1[j] = on ? a.ohb[2 * M + o] : 0.0; b2[j] = on ? a.ohb[3 * M + o] : 0.0;
+          w[j] = on ? ow[o] : 0.0;
+          qx[j] = on ? ozc[o] : 0.0; qy[j] = on ? ozc[M + o] : 0.0; qz[j] = on ? ozc[2 * M + o] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const double s1 = div_pos(w[j], sc[j] + lambda);
+          const double v0 = s1 * b0[j], v1 = s1 * b1[j], v2 = s1 * b2[j];
+          const double u0 = R[0] * v0 + R[3] * v1 + R[6] * v2, u1 = R[1] * v0 + R[4] * v1 + R[7] * v2, u2 = R[2] * v0 + R[5] * v1 + R[8] * v2;
+          const double ax = 2 * qx[j], ay = 2 * qy[j], az = 2 * qz[j];
+          acc[0] -= u0; acc[1] -= u1; acc[2] -= u2;
+          acc[3] += u1 * az - u2 * ay; acc[4] += u2 * ax - u0 * az; acc[5] += u0 * ay - u1 * ax;
+        }
+      }
+      u = unext;
+#pragma unroll
+      for (int r = 0; r < 6; r++) acc[r] = warp_sum(acc[r]);
       if (lane == 0)
-        for (int k = 0; k < 36; k++) sred[warp * 36 + k] = acc[k];
-      __syncthreads();
-      if (tid < 36) {
+        for (int r = 0; r < 6; r++) out[r] = acc[r];
+    }
+    job++;
+  }
+}
+
+__device__ __forceinline__ int eps3(int x, int y) { return ((y - x + 3) % 3 == 1) ? 1 : -1; }  // eps_{x y (3-x-y)}, x != y
+
+// warp per job: lanes 0..15 add the job's partial moment sums in slot order, the block is assembled from the moments
+// and written (with the pose-pose Hessian block and the damping) into the solver's buffer
+__device__ void phase_schur_reduce(const BaArgs& a, double lambda, int st, int rank, int nranks, const BaTab& tb, double* Ls0,
+                                   double* smr /* [warps][32] shared scratch */) {
+  const int W = a.W, n = 6 * W, ld = n + 1;
+  const int npairs = W * (W + 1) / 2, njobs = npairs + W, q = tb.uq;
+  const int lane = threadIdx.x & 31;
+  const int gw = rank * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = nranks * (blockDim.x >> 5);
+  for (int job = gw; job < njobs; job += nw) {
+    const int js = tb.ustart[job], je = tb.ustart[job + 1];
+    const int nslots = (je > js) ? (je - 1) / q - js / q + 1 : 0;
+    double mom = 0;
+    if (lane < 16) {
+      const double* sp = a.spart + (size_t)job * BA_MAX_SLOTS * 16 + lane;
+      for (int sl = 0; sl < nslots; sl++) mom += sp[16 * sl];
+    }
+    if (job < npairs) {
+      const int p1 = tb.jp1[job], p2 = tb.jp2[job];
+      // moments (lanes 0..15) and R12 = R_p1^T R_p2 (lanes 16..24) go through a per-warp shared scratch: they are
+      // indexed by run-time (r, c) below, which as register arrays would live in local memory
+      double* m = smr + 32 * (threadIdx.x >> 5);
+      double* R12 = m + 16;
+      __syncwarp();
+      if (lane < 16) m[lane] = mom;
+      else if (lane < 25) {
+        const double* R1 = a.X[(size_t)st * W + p1].R;
+        const double* R2 = a.X[(size_t)st * W + p2].R;
+        const int i = (lane - 16) / 3, j = (lane - 16) - 3 * i;
+        R12[lane - 16] = R1[i] * R2[j] + R1[3 + i] * R2[3 + j] + R1[6 + i] * R2[6 + j];
+      }
+      __syncwarp();
+      // m[0] = C0, m[1..3] = A1, m[4..6] = A2, m[7..15] = Mz (row = zc1 component)
+      for (int e = lane; e < 36; e += 32) {
+        const int r = e / 6, c = e - 6 * r;
         double t = 0;
-        for (int w = 0; w < nwarp; w++) t += sred[w * 36 + tid];
-        const int r = tid / 6, c = tid - 6 * r;
+        if (r < 3 && c < 3) t = m[0] * R12[3 * r + c];
+        else if (r < 3) {
+          const int j = c - 3;
+          for (int b = 0; b < 3; b++)
+            if (b != j) { const int k = 3 - b - j; t -= R12[3 * r + b] * (double)eps3(b, k) * 2.0 * m[4 + k]; }
+        } else if (c < 3) {
+          const int i = r - 3;
+          for (int b = 0; b < 3; b++)
+            if (b != i) { const int k = 3 - i - b; t += (double)eps3(i, k) * 2.0 * m[1 + k] * R12[3 * b + c]; }
+        } else {
+          const int i = r - 3, j = c - 3;
+          for (int k = 0; k < 3; k++) {
+            if (k == i) continue;
+            const int aa = 3 - i - k;
+            for (int mm = 0; mm < 3; mm++) {
+              if (mm == j) continue;
+              const int bb = 3 - mm - j;
+              t -= 4.0 * (double)(eps3(i, k) * eps3(bb, mm)) * m[7 + 3 * k + mm] * R12[3 * aa + bb];
+            }
+          }
+        }
         double h = 0;
-        if (p2 == p1) h = a.Hpp[36 * (size_t)p1 + tid] + ((r == c) ? lambda : 0.0);
-        else if (p2 == p1 + 1) h = a.Hoff[36 * (size_t)p1 + tid];
-        a.S[(size_t)(6 * p2 + c) * n + 6 * p1 + r] = h - t;  // block (p1,p2), p1 <= p2, transposed into the lower triangle
+        if (p2 == p1) h = a.Hpp[36 * (size_t)p1 + e] + ((r == c) ? lambda : 0.0);
+        else if (p2 == p1 + 1) h = a.Hoff[36 * (size_t)p1 + e];
+        // block (p1,p2), p1 <= p2, transposed into the lower triangle of the solver's buffer in CTA 0's shared memory
+        if (p1 != p2 || r <= c) Ls0[(6 * p2 + c) * ld + 6 * p1 + r] = h - t;
       }
     } else {
       const int p = job - npairs;
-      double acc[6] = {0, 0, 0, 0, 0, 0};
-      for (int o = tb.base[p] + tid; o < tb.base[p + 1]; o += blockDim.x) {
-        const int l = a.obs_point[o];
-        const double s = 1.0 / (a.hl[l] + lambda);
-        const double* b = a.bl + 3 * (size_t)l;
-        const double c0 = s * b[0], c1 = s * b[1], c2 = s * b[2];
-        const double* h = a.Hpl + o;
-#pragma unroll
-        for (int r = 0; r < 6; r++) acc[r] += h[(3 * r) * M] * c0 + h[(3 * r + 1) * M] * c1 + h[(3 * r + 2) * M] * c2;
-      }
-#pragma unroll
-      for (int r = 0; r < 6; r++) acc[r] = warp_sum(acc[r]);
-      __syncthreads();
-      if (lane == 0)
-        for (int r = 0; r < 6; r++) sred[warp * 36 + r] = acc[r];
-      __syncthreads();
-      if (tid < 6) {
-        double t = 0;
-        for (int w = 0; w < nwarp; w++) t += sred[w * 36 + tid];
-        a.bred[6 * p + tid] = a.bp[6 * p + tid] - t;
-      }
+      if (lane < 6) Ls0[n * ld + 6 * p + lane] = a.bp[6 * p + lane] - mom;  // right-hand side = row n
     }
   }
 }
 
-// blocked (6x6) LL^T of the reduced system in shared memory + block substitutions; one CTA.  ld is odd to avoid
-// bank conflicts on column accesses.  The inverse of every diagonal block is kept (Li), so panels and substitutions
-// are plain products.  Also applies the pose increments (trial poses) and their part of the scale.
-__device__ void phase_chol(const BaArgs& a, double lambda, int cur, double* Ls, double* ys, double* Li, double* red) {
+// blocked (6x6) LL^T of the reduced system in shared memory; one CTA.  ld is odd to avoid bank conflicts on column
+// accesses.  Layout: rows 0..n-1 = lower triangle of S, row n = the right-hand side: carrying b as an extra row of the
+// matrix turns the forward substitution into part of the panel/trailing steps (row n of L is y = L^-1 b).
+// The factorisation is latency-bound (one rsqrt + a short FMA chain per pivot), so the critical path is kept short:
+// the 6x6 diagonal block is factored in registers by one lane (reciprocal diagonal kept in Li), panels and the back
+// substitution are 6-step triangular solves against it, and while warps 1.. apply column jb's trailing update, warp 0
+// already updates and factors the next diagonal block (look-ahead).
+// Also applies the pose increments (trial poses) and their part of the scale.
+// 1/sqrt(d) for a positive normal d: the library fast path (MUFU.RSQ64H + one third-order correction) without its
+// special-case subroutine -- a CALL inside a latency-critical chain makes the compiler park live values in local memory
+__device__ __forceinline__ double rsqrt_pos(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double e = fma(d, -(y * y), 1.0);
+  return fma(fma(e, 0.375, 0.5), y * e, y);
+}
+
+// a / x for a positive normal x without the library's special-case subroutine (see rsqrt_pos)
+__device__ __forceinline__ double div_pos(double a, double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  const double q = a * y;
+  return fma(fma(-x, q, a), y, q);
+}
+
+// 6x6 Cholesky of a diagonal block by one lane, straight-line scalar code (no local arrays, no subroutine calls: either
+// would put local-memory round trips into this latency-critical chain).  Writes L in place and 1/L_jj to dinv.
+__device__ __forceinline__ bool chol_diag6(double* Ls, int ld, int j0, double* dinv) {
+  double* r0 = Ls + (size_t)j0 * ld + j0;
+  double *r1 = r0 + ld, *r2 = r1 + ld, *r3 = r2 + ld, *r4 = r3 + ld, *r5 = r4 + ld;
+  const double a00 = r0[0];
+  const double a10 = r1[0], a11 = r1[1];
+  const double a20 = r2[0], a21 = r2[1], a22 = r2[2];
+  const double a30 = r3[0], a31 = r3[1], a32 = r3[2], a33 = r3[3];
+  const double a40 = r4[0], a41 = r4[1], a42 = r4[2], a43 = r4[3], a44 = r4[4];
+  const double a50 = r5[0], a51 = r5[1], a52 = r5[2], a53 = r5[3], a54 = r5[4], a55 = r5[5];
+  const double i0 = rsqrt_pos(a00), l00 = a00 * i0;
+  const double l10 = a10 * i0, l20 = a20 * i0, l30 = a30 * i0, l40 = a40 * i0, l50 = a50 * i0;
+  const double d1 = a11 - l10 * l10;
+  const double i1 = rsqrt_pos(d1), l11 = d1 * i1;
+  const double l21 = (a21 - l20 * l10) * i1, l31 = (a31 - l30 * l10) * i1, l41 = (a41 - l40 * l10) * i1, l51 = (a51 - l50 * l10) * i1;
+  const double d2 = a22 - l20 * l20 - l21 * l21;
+  const double i2 = rsqrt_pos(d2), l22 = d2 * i2;
+  const double l32 = (a32 - l30 * l20 - l31 * l21) * i2, l42 = (a42 - l40 * l20 - l41 * l21) * i2, l52 = (a52 - l50 * l20 - l51 * l21) * i2;
+  const double d3 = a33 - l30 * l30 - l31 * l31 - l32 * l32;
+  const double i3 = rsqrt_pos(d3), l33 = d3 * i3;
+  const double l43 = (a43 - l40 * l30 - l41 * l31 - l42 * l32) * i3, l53 = (a53 - l50 * l30 - l51 * l31 - l52 * l32) * i3;
+  const double d4 = a44 - l40 * l40 - l41 * l41 - l42 * l42 - l43 * l43;
+  const double i4 = rsqrt_pos(d4), l44 = d4 * i4;
+  const double l54 = (a54 - l50 * l40 - l51 * l41 - l52 * l42 - l53 * l43) * i4;
+  const double d5 = a55 - l50 * l50 - l51 * l51 - l52 * l52 - l53 * l53 - l54 * l54;
+  const double i5 = rsqrt_pos(d5), l55 = d5 * i5;
+  if (!(a00 > 0 && d1 > 0 && d2 > 0 && d3 > 0 && d4 > 0 && d5 > 0)) return false;
+  r0[0] = l00;
+  r1[0] = l10; r1[1] = l11;
+  r2[0] = l20; r2[1] = l21; r2[2] = l22;
+  r3[0] = l30; r3[1] = l31; r3[2] = l32; r3[3] = l33;
+  r4[0] = l40; r4[1] = l41; r4[2] = l42; r4[3] = l43; r4[4] = l44;
+  r5[0] = l50; r5[1] = l51; r5[2] = l52; r5[3] = l53; r5[4] = l54; r5[5] = l55;
+  dinv[0] = i0; dinv[1] = i1; dinv[2] = i2; dinv[3] = i3; dinv[4] = i4; dinv[5] = i5;
+  return true;
+}
+
+__device__ void phase_chol(const BaArgs& a, double lambda, int cur, double* Ls, double* Li, double* red, unsigned long long* tp) {
   const int n = 6 * a.W, ld = n + 1, tid = threadIdx.x, nt = blockDim.x, nb = a.W;
   const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
   __shared__ int s_bad;
   if (tid == 0) s_bad = 0;
-  for (int i = tid; i < n * n; i += nt) {
-    const int r = i / n, c = i - r * n;
-    if (c <= r) Ls[r * ld + c] = a.S[i];
-  }
-  for (int i = tid; i < n; i += nt) ys[i] = a.bred[i];
+  double* ys = Ls + (size_t)n * ld;  // row n: right-hand side -> y -> x (phase_schur_reduce wrote S and b here)
   __syncthreads();
+  if (tid == 0 && !chol_diag6(Ls, ld, 0, Li)) s_bad = 1;
+  __syncthreads();
+  ba_tick(tp, 11);
   for (int jb = 0; jb < nb; jb++) {
+    if (s_bad) break;
     const int j0 = 6 * jb;
-    // (1) diagonal block: L11 and its inverse, fully unrolled so that everything stays in registers (thread 0)
-    if (tid == 0) {
-      double L[36], Iv[36];
-#pragma unroll
-      for (int r = 0; r < 6; r++)
-#pragma unroll
-        for (int c = 0; c < 6; c++) { L[6 * r + c] = (c <= r) ? Ls[(j0 + r) * ld + j0 + c] : 0.0; Iv[6 * r + c] = 0.0; }
-      bool ok = true;
-#pragma unroll
-      for (int j = 0; j < 6; j++) {
-        double d = L[7 * j];
-#pragma unroll
-        for (int k = 0; k < j; k++) d -= L[6 * j + k] * L[6 * j + k];
-        ok = ok && (d > 0);
-        const double ljj = sqrt(d), inv = 1.0 / ljj;
-        L[7 * j] = ljj;
-        Iv[7 * j] = inv;
-#pragma unroll
-        for (int i = j + 1; i < 6; i++) {
-          double t = L[6 * i + j];
-#pragma unroll
-          for (int k = 0; k < j; k++) t -= L[6 * i + k] * L[6 * j + k];
-          L[6 * i + j] = t * inv;
-        }
+    // (1) panel: rows below the block (and the rhs row): solve row' L11^T = row
+    {
+      const double* D = Ls + j0 * ld + j0;
+      const double* dv = Li + 6 * jb;
+      const double l10 = D[ld], l20 = D[2 * ld], l21 = D[2 * ld + 1], l30 = D[3 * ld], l31 = D[3 * ld + 1], l32 = D[3 * ld + 2];
+      const double l40 = D[4 * ld], l41 = D[4 * ld + 1], l42 = D[4 * ld + 2], l43 = D[4 * ld + 3];
+      const double l50 = D[5 * ld], l51 = D[5 * ld + 1], l52 = D[5 * ld + 2], l53 = D[5 * ld + 3], l54 = D[5 * ld + 4];
+      const double d0 = dv[0], d1 = dv[1], d2 = dv[2], d3 = dv[3], d4 = dv[4], d5 = dv[5];
+      for (int i = j0 + 6 + tid; i <= n; i += nt) {
+        double* row = Ls + i * ld + j0;
+        const double o0 = row[0] * d0;
+        const double o1 = (row[1] - o0 * l10) * d1;
+        const double o2 = (row[2] - o0 * l20 - o1 * l21) * d2;
+        const double o3 = (row[3] - o0 * l30 - o1 * l31 - o2 * l32) * d3;
+        const double o4 = (row[4] - o0 * l40 - o1 * l41 - o2 * l42 - o3 * l43) * d4;
+        const double o5 = (row[5] - o0 * l50 - o1 * l51 - o2 * l52 - o3 * l53 - o4 * l54) * d5;
+        row[0] = o0; row[1] = o1; row[2] = o2; row[3] = o3; row[4] = o4; row[5] = o5;
       }
-      if (!ok) s_bad = 1;
-      else {
+    }
+    __syncthreads();
+    ba_tick(tp, 16);
+    // (2) trailing update A22 -= L21 L21^T (lower triangle, plus the rhs row).  Warp 0: the next diagonal block and
+    //     its factorisation; warps 1..: one row each, lanes over the columns <= row.
+    const int m = n - j0 - 6;  // trailing matrix rows; local row m is the rhs
+    if (warp == 0) {
+      if (jb + 1 < nb) {
+        if (lane < 21) {
+          int r = 0, c = lane;
+          while (c > r) { c -= r + 1; r++; }
+          const double* lr = Ls + (j0 + 6 + r) * ld + j0;
+          const double* lc = Ls + (j0 + 6 + c) * ld + j0;
+          Ls[(j0 + 6 + r) * ld + j0 + 6 + c] -= lr[0] * lc[0] + lr[1] * lc[1] + lr[2] * lc[2] + lr[3] * lc[3] + lr[4] * lc[4] + lr[5] * lc[5];
+        }
+        __syncwarp();
+        if (lane == 0 && !chol_diag6(Ls, ld, j0 + 6, Li + 6 * (jb + 1))) s_bad = 1;
+        ba_tick(tp, 17);
+      }
+    } else {
+      // groups of 8 rows (8 independent FMA chains per lane, the column operand is loaded once per group)
+      const int ngroups = (m - 5 + 7) >> 3;  // local rows 6..m
+      for (int g = warp - 1; g < ngroups; g += nwarp - 1) {
+        const int r0 = 6 + 8 * g;
+        double rv[8][6];
 #pragma unroll
-        for (int c = 0; c < 6; c++)  // Iv = L^-1 (lower), column by column
+        for (int i = 0; i < 8; i++) {
+          const int r = min(r0 + i, m);
+          const double* lr = Ls + (j0 + 6 + r) * ld + j0;
 #pragma unroll
-          for (int r = c + 1; r < 6; r++) {
-            double t = 0;
+          for (int k = 0; k < 6; k++) rv[i][k] = lr[k];
+        }
+        const int rmax = min(r0 + 7, m), cmax = min(rmax, m - 1);
+        for (int c = lane; c <= cmax; c += 32) {
+          const double* lc = Ls + (j0 + 6 + c) * ld + j0;
+          const double l0 = lc[0], l1 = lc[1], l2 = lc[2], l3 = lc[3], l4 = lc[4], l5 = lc[5];
+          // load the 8 destinations, update, store: 8 independent chains (a read-modify-write per row would serialise
+          // on the possible aliasing of consecutive rows)
+          double cv[8];
 #pragma unroll
-            for (int k = c; k < r; k++) t += L[6 * r + k] * Iv[6 * k + c];
-            Iv[6 * r + c] = -t * Iv[7 * r];
+          for (int i = 0; i < 8; i++) {
+            const int r = r0 + i;
+            cv[i] = (r <= m && c <= r) ? Ls[(j0 + 6 + r) * ld + j0 + 6 + c] : 0.0;
           }
 #pragma unroll
-        for (int r = 0; r < 6; r++)
+          for (int i = 0; i < 8; i++)
+            cv[i] -= rv[i][0] * l0 + rv[i][1] * l1 + rv[i][2] * l2 + rv[i][3] * l3 + rv[i][4] * l4 + rv[i][5] * l5;
 #pragma unroll
-          for (int c = 0; c <= r; c++) Ls[(j0 + r) * ld + j0 + c] = L[6 * r + c];
-#pragma unroll
-        for (int k = 0; k < 36; k++) Li[36 * jb + k] = Iv[k];
+          for (int i = 0; i < 8; i++) {
+            const int r = r0 + i;
+            if (r <= m && c <= r) Ls[(j0 + 6 + r) * ld + j0 + 6 + c] = cv[i];
+          }
+        }
       }
     }
     __syncthreads();
-    if (s_bad) break;
-    // (2) panel: rows below the block, L21 = A21 * L11^-T  =>  row'[j] = sum_{k<=j} row[k] * Iv[j][k]
-    for (int i = j0 + 6 + tid; i < n; i += nt) {
-      double row[6], o[6];
-#pragma unroll
-      for (int k = 0; k < 6; k++) row[k] = Ls[i * ld + j0 + k];
-      const double* Iv = Li + 36 * jb;
-#pragma unroll
-      for (int j = 0; j < 6; j++) {
-        double t = 0;
-#pragma unroll
-        for (int k = 0; k <= j; k++) t += row[k] * Iv[6 * j + k];
-        o[j] = t;
-      }
-#pragma unroll
-      for (int j = 0; j < 6; j++) Ls[i * ld + j0 + j] = o[j];
-    }
-    __syncthreads();
-    // (3) trailing update A22 -= L21 L21^T (lower triangle): warp per row, lanes over the columns <= row
-    const int m = n - j0 - 6;
-    for (int r = warp; r < m; r += nwarp) {
-      const double* lr = Ls + (j0 + 6 + r) * ld + j0;
-      const double r0 = lr[0], r1 = lr[1], r2 = lr[2], r3 = lr[3], r4 = lr[4], r5 = lr[5];
-      for (int c = lane; c <= r; c += 32) {
-        const double* lc = Ls + (j0 + 6 + c) * ld + j0;
-        Ls[(j0 + 6 + r) * ld + j0 + 6 + c] -= r0 * lc[0] + r1 * lc[1] + r2 * lc[2] + r3 * lc[3] + r4 * lc[4] + r5 * lc[5];
-      }
-    }
-    __syncthreads();
+    ba_tick(tp, 18);
   }
   __syncthreads();
+  ba_tick(tp, 12);
   const int failed = s_bad;
-  if (!failed) {
-    // forward substitution: y_b = Iv_b * rhs_b, then rhs_below -= L21 * y_b
-    for (int jb = 0; jb < nb; jb++) {
-      const int j0 = 6 * jb;
-      double yb = 0;
-      if (tid < 6) {
-        const double* Iv = Li + 36 * jb;
-        for (int k = 0; k <= tid; k++) yb += Iv[6 * tid + k] * ys[j0 + k];
-      }
-      __syncthreads();
-      if (tid < 6) ys[j0 + tid] = yb;
-      __syncthreads();
-      for (int i = j0 + 6 + tid; i < n; i += nt) {
-        const double* li = Ls + i * ld + j0;
-        ys[i] -= li[0] * ys[j0] + li[1] * ys[j0 + 1] + li[2] * ys[j0 + 2] + li[3] * ys[j0 + 3] + li[4] * ys[j0 + 4] + li[5] * ys[j0 + 5];
-      }
-      __syncthreads();
-    }
-    // backward substitution with L^T: x_b = Iv_b^T * rhs_b, then rhs_above -= L(b, above)^T x_b
+  if (!failed && warp == 0) {
+    // back substitution with L^T by one warp (no block barriers): lane 0 solves L11^T x_b = y_b (6 steps), the block is
+    // broadcast with shuffles, every lane then updates its rows above (loads issued before x_b is known)
     for (int jb = nb - 1; jb >= 0; jb--) {
       const int j0 = 6 * jb;
-      double xb = 0;
-      if (tid < 6) {
-        const double* Iv = Li + 36 * jb;
-        for (int k = tid; k < 6; k++) xb += Iv[6 * k + tid] * ys[j0 + k];
+      const double* D = Ls + j0 * ld + j0;
+      const double* dv = Li + 6 * jb;
+      double x0, x1, x2, x3, x4, x5;
+      {
+        const double y0 = ys[j0], y1 = ys[j0 + 1], y2 = ys[j0 + 2], y3 = ys[j0 + 3], y4 = ys[j0 + 4], y5 = ys[j0 + 5];
+        // the most recent unknown enters last: one FMA + one product per step on the critical path
+        x5 = y5 * dv[5];
+        x4 = (y4 - D[5 * ld + 4] * x5) * dv[4];
+        x3 = (y3 - D[5 * ld + 3] * x5 - D[4 * ld + 3] * x4) * dv[3];
+        x2 = (y2 - D[5 * ld + 2] * x5 - D[4 * ld + 2] * x4 - D[3 * ld + 2] * x3) * dv[2];
+        x1 = (y1 - D[5 * ld + 1] * x5 - D[4 * ld + 1] * x4 - D[3 * ld + 1] * x3 - D[2 * ld + 1] * x2) * dv[1];
+        x0 = (y0 - D[5 * ld] * x5 - D[4 * ld] * x4 - D[3 * ld] * x3 - D[2 * ld] * x2 - D[ld] * x1) * dv[0];
       }
-      __syncthreads();
-      if (tid < 6) ys[j0 + tid] = xb;
-      __syncthreads();
-      for (int i = tid; i < j0; i += nt) {
-        double t = 0;
-#pragma unroll
-        for (int k = 0; k < 6; k++) t += Ls[(j0 + k) * ld + i] * ys[j0 + k];
-        ys[i] -= t;
-      }
-      __syncthreads();
+      // every lane computed the same x_b (broadcast loads): no exchange needed
+      if (lane < 6) ys[j0 + lane] = lane == 0 ? x0 : lane == 1 ? x1 : lane == 2 ? x2 : lane == 3 ? x3 : lane == 4 ? x4 : x5;
+#pragma unroll 5
+      for (int i = lane; i < j0; i += 32)
+        ys[i] -= D[i - j0] * x0 + D[ld + i - j0] * x1 + D[2 * ld + i - j0] * x2 + D[3 * ld + i - j0] * x3 +
+                 D[4 * ld + i - j0] * x4 + D[5 * ld + i - j0] * x5;
+      __syncwarp();
     }
   }
+  __syncthreads();
+  ba_tick(tp, 13);
   // increments, trial poses, pose part of the scale (x = b when the solver failed, like LinearSolverCSparse)
   const int trial = cur ^ 1;
   double sc = 0;
@@ -561,15 +802,28 @@ __device__ void phase_chol(const BaArgs& a, double lambda, int cur, double* Ls, 
   if (tid == 0) { a.cinfo[0] = red[0]; a.cinfo[1] = failed ? 1.0 : 0.0; }
 }
 
-// back-substitution of the points (thread per point), trial points, scale, robust chi2 of the trial state
+// back-substitution of the points (thread per point): x_l = (bl - sum_o Hpl(o)^T xp) / (hl + lambda) with
+// Hpl^T xp = w R (-x_t + 2 zc x x_r); trial points, point part of the scale.  The chi2 of the trial state comes from
+// the observation pass that follows.
 __device__ void phase_update(const BaArgs& a, double lambda, int cur, int failed, int G, int GT, int rank, double* red,
-                             const BaTab& tb) {
+                             const BaTab& tb, double* spose /* [W][16] shared scratch */) {
   const int trial = cur ^ 1, W = a.W;
   const size_t M = a.M;
-  const Pose* Xt = a.X + (size_t)trial * a.W;
   const double* pts = a.pts + (size_t)cur * 3 * a.P;
   double* ptt = a.pts + (size_t)trial * 3 * a.P;
-  double scale = 0, chi = 0;
+  const double* ow = a.ow + (size_t)cur * M;
+  const double* ozc = a.ozc + (size_t)cur * 3 * M;
+  // per pose: rotation (9), -x_t (3), x_r (3) in shared memory
+  for (int i = threadIdx.x; i < W * 16; i += blockDim.x) {
+    const int p = i >> 4, k = i & 15;
+    double v = 0;
+    if (k < 9) v = a.X[(size_t)cur * W + p].R[k];
+    else if (k < 12) v = -a.xp[6 * p + (k - 9)];
+    else if (k < 15) v = a.xp[6 * p + 3 + (k - 12)];
+    spose[i] = v;
+  }
+  __syncthreads();
+  double scale = 0;
   for (int l = G; l < a.P; l += GT) {
     const double* b = a.bl + 3 * (size_t)l;
     const int f = a.pt_first[l], len = a.pt_len[l], i = l - tb.grp[f];
@@ -577,32 +831,39 @@ __device__ void phase_update(const BaArgs& a, double lambda, int cur, int failed
     if (failed) { x[0] = b[0]; x[1] = b[1]; x[2] = b[2]; }
     else {
       double c0 = b[0], c1 = b[1], c2 = b[2];
-      for (int k = 0; k < len; k++) {
-        const int pp = f + k;
-        const double* h = a.Hpl + (tb.base[pp] + tb.off[pp * (W + 1) + f] + i);
-        const double* xp = a.xp + 6 * pp;
+      for (int k0 = 0; k0 < len; k0 += 4) {
+        double w[4], zx[4], zy[4], zz[4];
 #pragma unroll
-        for (int r = 0; r < 6; r++) { c0 -= h[(3 * r) * M] * xp[r]; c1 -= h[(3 * r + 1) * M] * xp[r]; c2 -= h[(3 * r + 2) * M] * xp[r]; }
+        for (int j = 0; j < 4; j++) {
+          const bool on = k0 + j < len;
+          const int pp = on ? f + k0 + j : f;
+          const size_t o = (size_t)tb.base[pp] + tb.off[pp * (W + 1) + f] + i;
+          w[j] = on ? ow[o] : 0.0;
+          zx[j] = on ? ozc[o] : 0.0; zy[j] = on ? ozc[M + o] : 0.0; zz[j] = on ? ozc[2 * M + o] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int pp = (k0 + j < len) ? f + k0 + j : f;
+          const double* sp = spose + 16 * pp;
+          const double qx = 2 * zx[j], qy = 2 * zy[j], qz = 2 * zz[j];
+          const double g0 = w[j] * (qy * sp[14] - qz * sp[13] + sp[9]), g1 = w[j] * (qz * sp[12] - qx * sp[14] + sp[10]),
+                       g2 = w[j] * (qx * sp[13] - qy * sp[12] + sp[11]);
+          c0 -= sp[0] * g0 + sp[1] * g1 + sp[2] * g2;
+          c1 -= sp[3] * g0 + sp[4] * g1 + sp[5] * g2;
+          c2 -= sp[6] * g0 + sp[7] * g1 + sp[8] * g2;
+        }
       }
-      const double s = 1.0 / (a.hl[l] + lambda);
+      const double s = div_pos(1.0, a.hl[l] + lambda);
       x[0] = s * c0; x[1] = s * c1; x[2] = s * c2;
     }
-    double pn[3];
     for (int k = 0; k < 3; k++) {
-      pn[k] = pts[3 * (size_t)l + k] + x[k];
-      ptt[3 * (size_t)l + k] = pn[k];
+      ptt[3 * (size_t)l + k] = pts[3 * (size_t)l + k] + x[k];
       scale += x[k] * (lambda * x[k] + b[k]);
     }
-    for (int k = 0; k < len; k++) {
-      const int pp = f + k;
-      double zc[3], e[3], w;
-      chi += obs_chi(a, Xt[pp], pn, tb.base[pp] + tb.off[pp * (W + 1) + f] + i, zc, e, w);
-    }
   }
-  for (int i = G; i < a.W - 1; i += GT) chi += se3_chi(a, Xt, i);
-  double v[2] = {chi, scale};
-  block_reduce<2, false>(v, red);
-  if (threadIdx.x == 0) { a.part[rank * 4 + 0] = red[0]; a.part[rank * 4 + 1] = red[1]; }
+  double v[1] = {scale};
+  block_reduce<1, false>(v, red);
+  if (threadIdx.x == 0) a.part[rank * 4 + 1] = red[0];
 }
 
 __device__ void phase_output(const BaArgs& a, int cur, int G, int GT) {
@@ -642,23 +903,53 @@ __device__ void phase_output_rel(const BaArgs& a, int G, int GT) {
 // the cluster kernel (cluster size set at launch: 16 CTAs when the device allows it, else 8)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BA_THREADS, 1) ba_window_kernel(BaArgs a) {
-  extern __shared__ __align__(16) double dsm[];  // (6W)(6W+1) + 6W + 36W doubles for the dense factorisation (CTA 0)
+  extern __shared__ __align__(16) double dsm[];  // (6W+1)^2 + 36W doubles for the dense factorisation (CTA 0)
   __shared__ double red[16 * 2 + 32];
-  __shared__ double sred[(BA_THREADS / 32) * 36];
   __shared__ LmCtl ctl;  // every CTA keeps an identical copy: decisions are recomputed from the same partial sums
   __shared__ BaTab tb;
+  __shared__ double spose[BA_MAX_W * 16];
+  __shared__ double smr[(BA_THREADS / 32) * 32];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank(), nranks = (int)cluster.num_blocks();
+  double* const Ls0 = cluster.map_shared_rank(dsm, 0);
   const int G = rank * blockDim.x + threadIdx.x, GT = nranks * blockDim.x;
   const int tid = threadIdx.x;
-  unsigned long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  unsigned long long t0 = (G == 0) ? gtime() : 0;
-  const unsigned long long t_start = t0;
-#define TOC(slot) do { if (G == 0) { unsigned long long t1_ = gtime(); tph[slot] += t1_ - t0; t0 = t1_; } } while (0)
+  // phase timers (thread 0 of CTA 0 only): slots 0 linearise, 2 schur, 3 solve, 4 update, 5 init, 6 LM bookkeeping, 7 total,
+  // 8-10 linearise sub-steps, 11-14 solve sub-steps; slot 15 is the running time stamp
+  __shared__ unsigned long long tph[24];
+  if (G == 0) { for (int k = 0; k < 24; k++) tph[k] = 0; tph[15] = gtime(); }
+  const unsigned long long t_start = (G == 0) ? tph[15] : 0;
+  unsigned long long* const tp = (G == 0) ? tph : nullptr;
+#define TOC(slot) ba_tick(tp, slot)
 
   for (int i = tid; i <= a.W; i += blockDim.x) { tb.grp[i] = a.grp_start[i]; tb.base[i] = a.pose_base[i]; }
   for (int i = tid; i < a.W * (a.W + 1); i += blockDim.x) { tb.cnt[i] = a.cnt_gt[i]; tb.off[i] = a.off[i]; }
   if (tid == 0) lm_reset(&ctl);
+  __syncthreads();
+  {  // Schur work units per job (the structure is fixed for the whole solve), then their prefix
+    const int W = a.W, npairs = W * (W + 1) / 2, njobs = npairs + W;
+    for (int job = tid; job < njobs; job += blockDim.x) {
+      int terms = 0;
+      if (job < npairs) {
+        int p1, p2;
+        job_pair(job, W, p1, p2);
+        for (int f = 0; f <= p1; f++) terms += tb.cnt[f * (W + 1) + (p2 - f)];
+      } else terms = tb.base[job - npairs + 1] - tb.base[job - npairs];
+      tb.ustart[job + 1] = terms > 0 ? ((terms + 31) >> 5) + BA_JOB_PAD : 0;
+      if (job < npairs) { int p1, p2; job_pair(job, W, p1, p2); tb.jp1[job] = (unsigned char)p1; tb.jp2[job] = (unsigned char)p2; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      tb.ustart[0] = 0;
+      for (int j = 0; j < njobs; j++) tb.ustart[j + 1] += tb.ustart[j];
+      const int nw = nranks * (blockDim.x >> 5);
+      const int q = (tb.ustart[njobs] + nw - 1) / nw;
+      tb.uq = q > 0 ? q : 1;
+      int nch = W > 0 ? nw / W : 1;
+      tb.nch = nch < 1 ? 1 : (nch > BA_PCHUNK ? BA_PCHUNK : nch);
+    }
+    __syncthreads();
+  }
   phase_init(a, G, GT);
   cluster.sync();
   if (a.W + a.P == 0 || a.max_iterations <= 0) {
@@ -668,7 +959,7 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_window_kernel(BaArgs a) {
     phase_output_rel(a, G, GT);
     return;
   }
-  phase_errors(a, 0, G, GT, rank, red);
+  phase_obs(a, 0, G, GT, rank, nranks, red, tb);  // chi2 and linearisation of the initial state
   cluster.sync();
   if (tid == 0) {
     double c = 0;
@@ -680,42 +971,48 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_window_kernel(BaArgs a) {
 
   for (int it = 0; it < a.max_iterations; it++) {
     if (ctl.stop_flag || !ctl.ok) break;
-    const int cur = ctl.cur;
-    phase_lin_obs(a, cur, G, GT);
+    const int cur = ctl.cur;  // state buffer == linearisation buffer
+    phase_blocks(a, cur, G, GT, rank, nranks, red, tb);
     cluster.sync();
-    phase_lin_blocks(a, cur, G, GT, rank, nranks, red, tb);
-    cluster.sync();
-    phase_lin_poses(a, G, GT, rank, red);
-    cluster.sync();
+    TOC(10);
     if (tid == 0) {
       double m = 0;
-      for (int r = 0; r < nranks; r++) m = fmax(m, fmax(a.part[r * 4 + 2], a.part[r * 4 + 3]));
+      for (int r = 0; r < nranks; r++) m = fmax(m, a.part[r * 4 + 2]);
+      for (int p = 0; p < a.W; p++) m = fmax(m, a.pmax[p]);
       lm_begin_iteration(&ctl, it, m, -1.0);
     }
     __syncthreads();
     TOC(0);
     while (true) {
       const double lambda = ctl.lambda;
-      phase_schur(a, lambda, rank, nranks, tb, sred);
+      phase_schur_units(a, lambda, cur, rank, nranks, tb);
+      if (a.t_detail) { __syncthreads(); TOC(19); }
+      cluster.sync();
+      TOC(1);
+      phase_schur_reduce(a, lambda, cur, rank, nranks, tb, Ls0, smr);
       cluster.sync();
       TOC(2);
       if (rank == 0) {
-        double* ysm = dsm + (size_t)(6 * a.W) * (6 * a.W + 1);
-        phase_chol(a, lambda, cur, dsm, ysm, ysm + 6 * a.W, red);
+        phase_chol(a, lambda, cur, dsm, dsm + (size_t)(6 * a.W + 1) * (6 * a.W + 1), red, tp);
       }
       cluster.sync();
       TOC(3);
       const int failed = a.cinfo[1] != 0.0;
-      phase_update(a, lambda, cur, failed, G, GT, rank, red, tb);
+      phase_update(a, lambda, cur, failed, G, GT, rank, red, tb, spose);
+      if (a.t_detail) { __syncthreads(); TOC(21); }
       cluster.sync();
       TOC(4);
+      phase_obs(a, cur ^ 1, G, GT, rank, nranks, red, tb);  // chi2 of the trial state + its linearisation
+      if (a.t_detail) { __syncthreads(); TOC(20); }
+      cluster.sync();
+      TOC(9);
       if (tid == 0) {
         double chi = 0, scale = a.cinfo[0];
         for (int r = 0; r < nranks; r++) { chi += a.part[r * 4]; scale += a.part[r * 4 + 1]; }
         lm_trial(&ctl, chi, scale, failed);
       }
       __syncthreads();
-      // the partial sums are next overwritten in phase_update, two cluster barriers later: no race with slower CTAs
+      // part[] is next written two cluster barriers later (phase_update / phase_obs): no race with slower CTAs
       if (!lm_more_trials(&ctl)) break;
     }
     if (tid == 0) lm_end_iteration(&ctl, it, a.gain_threshold, rank == 0 ? a.rec : nullptr);
@@ -728,7 +1025,7 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_window_kernel(BaArgs a) {
   if (G == 0) {
     *a.ctl_out = ctl;
     tph[7] = gtime() - t_start;
-    for (int k = 0; k < 8; k++) a.t_phase[k] = tph[k];
+    for (int k = 0; k < 24; k++) a.t_phase[k] = tph[k];
   }
 #undef TOC
 }
@@ -746,6 +1043,13 @@ struct BaWorkspace {
   char* h_in = nullptr;              // pinned mirrors
   char* h_out = nullptr;
   size_t in_bytes = 0, out_bytes = 0;
+  // the solve runs on its own stream so that a caller may overlap it with other work (ba_submit ... ba_collect)
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool pending = false;
+  bool want_records = false;
+  int W = 0, P = 0, M = 0;
+  std::vector<int> newid, oldid, first, len, last, keycnt;
 };
 
 static size_t al(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -768,19 +1072,19 @@ static void carve_inputs(char*& p, BaArgs& a, int W, int P, int M) {
 }
 // output block: one D2H copy
 static void carve_outputs(char*& p, BaArgs& a, int W, int P) {
-  a.ctl_out = carve<LmCtl>(p, 1); a.t_phase = carve<unsigned long long>(p, 8);
+  a.ctl_out = carve<LmCtl>(p, 1); a.t_phase = carve<unsigned long long>(p, 24);
   a.out_poses = carve<float>(p, 16 * W); a.out_rel = carve<float>(p, 16 * W); a.out_points = carve<float>(p, 3 * (size_t)P);
   a.rec = carve<LmRec>(p, VIDO_LM_REC);
 }
 
 static void carve_all(char*& p, BaArgs& a, int capW, int capP, int capM) {
   a.X = carve<Pose>(p, 2 * capW); a.Zinv = carve<Pose>(p, capW); a.pts = carve<double>(p, 6 * (size_t)capP);
-  a.hl = carve<double>(p, capP); a.bl = carve<double>(p, 3 * (size_t)capP); a.Hpl = carve<double>(p, 18 * (size_t)capM);
+  a.hl = carve<double>(p, capP); a.bl = carve<double>(p, 3 * (size_t)capP); a.ow = carve<double>(p, 2 * (size_t)capM); a.ozc = carve<double>(p, 6 * (size_t)capM); a.og = carve<double>(p, 6 * (size_t)capM); a.ohb = carve<double>(p, 4 * (size_t)capM);
   a.Hpp = carve<double>(p, 36 * capW); a.Hoff = carve<double>(p, 36 * capW); a.bp = carve<double>(p, 6 * capW);
-  a.ppart = carve<double>(p, (size_t)capW * BA_PCHUNK * 28);
-  a.S = carve<double>(p, 36 * (size_t)capW * capW); a.bred = carve<double>(p, 6 * capW); a.xp = carve<double>(p, 6 * capW);
+  a.ppart = carve<double>(p, 2 * (size_t)capW * BA_PCHUNK * 28);
+  a.spart = carve<double>(p, (size_t)BA_MAX_JOBS * BA_MAX_SLOTS * 16); a.pmax = carve<double>(p, capW); a.xp = carve<double>(p, 6 * capW);
   a.part = carve<double>(p, 4 * BA_MAX_CLUSTER); a.cinfo = carve<double>(p, 4);
-  a.seJ = carve<double>(p, 72 * capW); a.seE = carve<double>(p, 8 * capW);
+  a.seJ = carve<double>(p, 2 * 72 * capW); a.seE = carve<double>(p, 2 * 8 * capW);
 }
 
 int ba_setup(vido_ctx* ctx, int capW, int capP, int capM) {
@@ -803,7 +1107,7 @@ int ba_setup(vido_ctx* ctx, int capW, int capP, int capM) {
   memset(&ws->args, 0, sizeof ws->args);
   p = ws->d_base;
   carve_all(p, ws->args, capW, capP, capM);
-  const size_t smem = sizeof(double) * ((size_t)(6 * capW) * (6 * capW + 1) + 6 * capW + 36 * capW);
+  const size_t smem = sizeof(double) * ((size_t)(6 * capW + 1) * (6 * capW + 1) + 36 * capW);
   if (smem > 200 * 1024) { ctx->err = "BA window too large for the shared-memory Cholesky"; return VIDO_ERR_ARG; }
   VIDO_CUDA(cudaFuncSetAttribute(ba_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // 16-CTA clusters are a non-portable size: opt in, and verify that one fits
@@ -820,27 +1124,38 @@ int ba_setup(vido_ctx* ctx, int capW, int capP, int capM) {
   }
   cudaGetLastError();
   if (getenv("VIDO_BA_CLUSTER") && atoi(getenv("VIDO_BA_CLUSTER")) == 8) ws->cluster = 8;
+  VIDO_CUDA(cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking));
+  VIDO_CUDA(cudaEventCreate(&ws->ev0));
+  VIDO_CUDA(cudaEventCreate(&ws->ev1));
   return VIDO_OK;
 }
 
 void ba_teardown(vido_ctx* ctx) {
   BaWorkspace* ws = (BaWorkspace*)ctx->ba;
   if (!ws) return;
+  if (ws->stream) { cudaStreamSynchronize(ws->stream); cudaStreamDestroy(ws->stream); }
+  if (ws->ev0) cudaEventDestroy(ws->ev0);
+  if (ws->ev1) cudaEventDestroy(ws->ev1);
   cudaFree(ws->d_base); cudaFree(ws->d_in); cudaFree(ws->d_out);
   cudaFreeHost(ws->h_in); cudaFreeHost(ws->h_out);
   delete ws;
   ctx->ba = nullptr;
 }
 
-int ba_partial_host(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st) {
+// ba_submit: lay the problem out, copy it to the device and launch the solve on the BA stream (returns at once);
+// ba_collect: wait for it and write the results back into the problem's arrays, which must stay alive in between.
+int ba_submit(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records) {
   BaWorkspace* ws = (BaWorkspace*)ctx->ba;
+  if (ws->pending) { ctx->err = "a window BA is already in flight"; return VIDO_ERR_ARG; }
   const int W = pr->n_poses, P = pr->n_points, M = pr->n_obs;
   if (W < 0 || P < 0 || M < 0) return VIDO_ERR_ARG;
   if (W > ws->capW || P > ws->capP || M > ws->capM) { ctx->err = "BA problem exceeds the context capacity"; return VIDO_ERR_CAPACITY; }
-  cudaStream_t s = ctx->stream;
+  cudaStream_t s = ws->stream;
+  ws->W = W; ws->P = P; ws->M = M; ws->want_records = want_records;
   BaArgs a = ws->args;
   a.W = W; a.P = P; a.M = M;
   a.max_iterations = pr->max_iterations;
+  a.t_detail = (getenv("VIDO_BA_TIMING") && atoi(getenv("VIDO_BA_TIMING")) > 1) ? 1 : 0;
   a.info_cam = 1.0 / (double)pr->sigma2_cam;
   a.info_3d = 1.0 / (double)pr->sigma2_3d;
   a.d_cam = (double)pr->huber_cam;
@@ -859,7 +1174,8 @@ int ba_partial_host(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st) {
   int* h_grp = (int*)h.grp_start; int* h_cnt = (int*)h.cnt_gt; int* h_off = (int*)h.off; int* h_base = (int*)h.pose_base;
   memcpy(h_poses, pr->poses, sizeof(float) * 16 * W);
   if (W > 1) memcpy(h_rel, pr->rel_motion, sizeof(float) * 16 * (W - 1));
-  std::vector<int> first(P, 1 << 30), len(P, 0), last(P, -1);
+  std::vector<int>&first = ws->first, &len = ws->len, &last = ws->last, &keycnt = ws->keycnt, &newid = ws->newid, &oldid = ws->oldid;
+  first.assign(P, 1 << 30); len.assign(P, 0); last.assign(P, -1);
   for (int o = 0; o < M; o++) {
     const int l = pr->obs_point[o], p = pr->obs_pose[o];
     if (l < 0 || l >= P || p < 0 || p >= W) { ctx->err = "BA observation index out of range"; return VIDO_ERR_ARG; }
@@ -873,7 +1189,7 @@ int ba_partial_host(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st) {
       return VIDO_ERR_ARG;
     }
   // counting sort of the points by key = first * (W+1) + (W - len)
-  std::vector<int> keycnt((size_t)W * (W + 1) + 2, 0), newid(P), oldid(P);
+  keycnt.assign((size_t)W * (W + 1) + 2, 0); newid.resize(P); oldid.resize(P);
   for (int l = 0; l < P; l++) keycnt[(size_t)first[l] * (W + 1) + (W - len[l]) + 1]++;
   for (size_t k = 1; k < keycnt.size(); k++) keycnt[k] += keycnt[k - 1];
   for (int l = 0; l < P; l++) {
@@ -912,7 +1228,7 @@ int ba_partial_host(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st) {
     char* hp = ws->h_in; BaArgs t2; carve_inputs(hp, t2, W, P, M);
     VIDO_CUDA(cudaMemcpyAsync(ws->d_in, ws->h_in, (size_t)(hp - ws->h_in), cudaMemcpyHostToDevice, s));
   }
-  const size_t smem = sizeof(double) * ((size_t)(6 * W) * (6 * W + 1) + 6 * W + 36 * W);
+  const size_t smem = sizeof(double) * ((size_t)(6 * W + 1) * (6 * W + 1) + 36 * W);
   {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ws->cluster); cfg.blockDim = dim3(BA_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -920,20 +1236,31 @@ int ba_partial_host(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = ws->cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaEventRecord(ctx->ev0, s);
+    cudaEventRecord(ws->ev0, s);
     VIDO_CUDA(cudaLaunchKernelEx(&cfg, ba_window_kernel, a));
-    cudaEventRecord(ctx->ev1, s);
+    cudaEventRecord(ws->ev1, s);
     ctx->launches++;
   }
-  BaArgs ho;
-  size_t out_used;
   {
+    BaArgs ho;
     char* hq = ws->h_out; carve_outputs(hq, ho, W, P);
     // the LM records sit at the end of the block: copy them only when asked for
-    out_used = st ? (size_t)(hq - ws->h_out) : (size_t)((char*)ho.rec - ws->h_out);
+    const size_t out_used = want_records ? (size_t)(hq - ws->h_out) : (size_t)((char*)ho.rec - ws->h_out);
+    VIDO_CUDA(cudaMemcpyAsync(ws->h_out, ws->d_out, out_used, cudaMemcpyDeviceToHost, s));
   }
-  VIDO_CUDA(cudaMemcpyAsync(ws->h_out, ws->d_out, out_used, cudaMemcpyDeviceToHost, s));
-  VIDO_CUDA(cudaStreamSynchronize(s));
+  ws->pending = true;
+  return VIDO_OK;
+}
+
+int ba_collect(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st) {
+  BaWorkspace* ws = (BaWorkspace*)ctx->ba;
+  if (!ws->pending) { ctx->err = "no window BA in flight"; return VIDO_ERR_ARG; }
+  ws->pending = false;
+  const int W = ws->W, P = ws->P, M = ws->M;
+  const std::vector<int>& newid = ws->newid;
+  VIDO_CUDA(cudaStreamSynchronize(ws->stream));
+  BaArgs ho;
+  { char* hq = ws->h_out; carve_outputs(hq, ho, W, P); }
   const LmCtl ctl = *ho.ctl_out;
   const unsigned long long* tph = ho.t_phase;
   const LmRec* recs = ho.rec;
@@ -946,22 +1273,33 @@ int ba_partial_host(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st) {
   }
   {
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) { ctx->t_ms[3] += ms; ctx->t_n[3]++; }
+    if (cudaEventElapsedTime(&ms, ws->ev0, ws->ev1) == cudaSuccess) { ctx->t_ms[3] += ms; ctx->t_n[3]++; }
     const double edges = (double)M + (double)std::max(W - 1, 0);
     ctx->ba_alg_bytes += edges * (296.0 * std::max(ctl.iterations, 0) + 152.0 * (ctl.total_trials + 1));
   }
   if (getenv("VIDO_BA_TIMING"))
     fprintf(stderr, "[ba] cluster=%d W=%d P=%d M=%d its=%d trials=%d ns: linearize=%llu schur=%llu chol=%llu update=%llu init=%llu end=%llu total=%llu\n",
-            ws->cluster, W, P, M, ctl.iterations, ctl.total_trials, tph[0], tph[2], tph[3], tph[4], tph[5], tph[6], tph[7]);
+            ws->cluster, W, P, M, ctl.iterations, ctl.total_trials, tph[0] + tph[8] + tph[9] + tph[10] + tph[20], tph[1] + tph[2] + tph[19], tph[3] + tph[11] + tph[12] + tph[13] + tph[16] + tph[17] + tph[18], tph[4] + tph[21], tph[5], tph[6], tph[7]);
+  if (getenv("VIDO_BA_TIMING") && atoi(getenv("VIDO_BA_TIMING")) > 1)
+    fprintf(stderr, "[ba]   cta0 own time: obs_pass=%llu units=%llu update=%llu\n", tph[20], tph[19], tph[21]);
+  if (getenv("VIDO_BA_TIMING") && atoi(getenv("VIDO_BA_TIMING")) > 1)
+    fprintf(stderr, "[ba]   obs_wait=%llu blocks=%llu lm_begin=%llu | schur: units=%llu reduce=%llu | chol: diag0=%llu panel=%llu diag=%llu trail_wait=%llu backsub=%llu epilogue=%llu\n",
+            tph[9], tph[10], tph[0], tph[1], tph[2], tph[11], tph[16], tph[17], tph[18] + tph[12], tph[13], tph[3]);
   if (st) {
     st->iterations = ctl.iterations;
-    st->n_records = ctl.n_records;
+    st->n_records = ws->want_records ? ctl.n_records : 0;
     st->total_trials = ctl.total_trials;
-    for (int i = 0; i < ctl.n_records && i < VIDO_LM_MAX_RECORDS; i++) {
+    for (int i = 0; i < st->n_records && i < VIDO_LM_MAX_RECORDS; i++) {
       st->rec[i].chi2 = recs[i].chi2;
       st->rec[i].lambda = recs[i].lambda;
       st->rec[i].trials = recs[i].trials;
     }
   }
   return VIDO_OK;
+}
+
+int ba_partial_host(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st) {
+  int rc = ba_submit(ctx, pr, st != nullptr);
+  if (rc) return rc;
+  return ba_collect(ctx, pr, st);
 }

@@ -57,14 +57,30 @@ VHD void quat_from_R(const double* R, double* q) {
   } else {
     int i = 0;
     if (R[4] > R[0]) i = 1;
-    if (R[8] > R[4 * i]) i = 2;
-    const int j = (i + 1) % 3, k = (j + 1) % 3;
-    t = sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
-    q[1 + i] = 0.5 * t;
-    t = 0.5 / t;
-    q[0] = (R[3 * k + j] - R[3 * j + k]) * t;
-    q[1 + j] = (R[3 * j + i] + R[3 * i + j]) * t;
-    q[1 + k] = (R[3 * k + i] + R[3 * i + k]) * t;
+    if (R[8] > (i == 0 ? R[0] : R[4])) i = 2;
+    // the three cases spelled out with constant indices (a run-time index would push R and q into local memory)
+    if (i == 0) {  // j = 1, k = 2
+      t = sqrt(R[0] - R[4] - R[8] + 1.0);
+      q[1] = 0.5 * t;
+      t = 0.5 / t;
+      q[0] = (R[7] - R[5]) * t;
+      q[2] = (R[3] + R[1]) * t;
+      q[3] = (R[6] + R[2]) * t;
+    } else if (i == 1) {  // j = 2, k = 0
+      t = sqrt(R[4] - R[8] - R[0] + 1.0);
+      q[2] = 0.5 * t;
+      t = 0.5 / t;
+      q[0] = (R[2] - R[6]) * t;
+      q[3] = (R[7] + R[5]) * t;
+      q[1] = (R[1] + R[3]) * t;
+    } else {  // j = 0, k = 1
+      t = sqrt(R[8] - R[0] - R[4] + 1.0);
+      q[3] = 0.5 * t;
+      t = 0.5 / t;
+      q[0] = (R[3] - R[1]) * t;
+      q[1] = (R[2] + R[6]) * t;
+      q[2] = (R[5] + R[7]) * t;
+    }
   }
 }
 VHD void R_from_quat(const double* q, double* R) {

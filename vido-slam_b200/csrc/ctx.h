@@ -116,6 +116,8 @@ int orb_bgr_to_gray(vido_ctx* ctx, const uint8_t* d_bgr, int nframes, size_t fra
 int ba_setup(vido_ctx* ctx, int capW, int capP, int capM);
 void ba_teardown(vido_ctx* ctx);
 int ba_partial_host(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st);
+int ba_submit(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records);
+int ba_collect(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st);
 
 // poseopt_kernels.cu
 int po_setup(vido_ctx* ctx, int capN, int capProblems);

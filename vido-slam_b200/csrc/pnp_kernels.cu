@@ -67,25 +67,148 @@ __device__ __forceinline__ bool pnp_row(const PnpPose& T, const float* X3, const
   return true;
 }
 
+// H d = b by LDL^T, straight-line scalar code with exactly the operation order of the reference loops (the file is built
+// with -fmad=false: results are bit-identical to the CPU restatement); false if a pivot is <= 1e-12
+__device__ __forceinline__ bool ldlt6_solve(const double* H, const double* b, double* d) {
+  double v0 = H[0];
+  if (!(v0 > 1e-12)) return false;
+  const double D0 = v0;
+  double l10 = H[6];
+  l10 = l10 / v0;
+  double l20 = H[12];
+  l20 = l20 / v0;
+  double l30 = H[18];
+  l30 = l30 / v0;
+  double l40 = H[24];
+  l40 = l40 / v0;
+  double l50 = H[30];
+  l50 = l50 / v0;
+  double v1 = H[7];
+  v1 -= l10 * l10 * D0;
+  if (!(v1 > 1e-12)) return false;
+  const double D1 = v1;
+  double l21 = H[13];
+  l21 -= l20 * l10 * D0;
+  l21 = l21 / v1;
+  double l31 = H[19];
+  l31 -= l30 * l10 * D0;
+  l31 = l31 / v1;
+  double l41 = H[25];
+  l41 -= l40 * l10 * D0;
+  l41 = l41 / v1;
+  double l51 = H[31];
+  l51 -= l50 * l10 * D0;
+  l51 = l51 / v1;
+  double v2 = H[14];
+  v2 -= l20 * l20 * D0;
+  v2 -= l21 * l21 * D1;
+  if (!(v2 > 1e-12)) return false;
+  const double D2 = v2;
+  double l32 = H[20];
+  l32 -= l30 * l20 * D0;
+  l32 -= l31 * l21 * D1;
+  l32 = l32 / v2;
+  double l42 = H[26];
+  l42 -= l40 * l20 * D0;
+  l42 -= l41 * l21 * D1;
+  l42 = l42 / v2;
+  double l52 = H[32];
+  l52 -= l50 * l20 * D0;
+  l52 -= l51 * l21 * D1;
+  l52 = l52 / v2;
+  double v3 = H[21];
+  v3 -= l30 * l30 * D0;
+  v3 -= l31 * l31 * D1;
+  v3 -= l32 * l32 * D2;
+  if (!(v3 > 1e-12)) return false;
+  const double D3 = v3;
+  double l43 = H[27];
+  l43 -= l40 * l30 * D0;
+  l43 -= l41 * l31 * D1;
+  l43 -= l42 * l32 * D2;
+  l43 = l43 / v3;
+  double l53 = H[33];
+  l53 -= l50 * l30 * D0;
+  l53 -= l51 * l31 * D1;
+  l53 -= l52 * l32 * D2;
+  l53 = l53 / v3;
+  double v4 = H[28];
+  v4 -= l40 * l40 * D0;
+  v4 -= l41 * l41 * D1;
+  v4 -= l42 * l42 * D2;
+  v4 -= l43 * l43 * D3;
+  if (!(v4 > 1e-12)) return false;
+  const double D4 = v4;
+  double l54 = H[34];
+  l54 -= l50 * l40 * D0;
+  l54 -= l51 * l41 * D1;
+  l54 -= l52 * l42 * D2;
+  l54 -= l53 * l43 * D3;
+  l54 = l54 / v4;
+  double v5 = H[35];
+  v5 -= l50 * l50 * D0;
+  v5 -= l51 * l51 * D1;
+  v5 -= l52 * l52 * D2;
+  v5 -= l53 * l53 * D3;
+  v5 -= l54 * l54 * D4;
+  if (!(v5 > 1e-12)) return false;
+  const double D5 = v5;
+  double y0 = b[0];
+  double y1 = b[1];
+  y1 -= l10 * y0;
+  double y2 = b[2];
+  y2 -= l20 * y0;
+  y2 -= l21 * y1;
+  double y3 = b[3];
+  y3 -= l30 * y0;
+  y3 -= l31 * y1;
+  y3 -= l32 * y2;
+  double y4 = b[4];
+  y4 -= l40 * y0;
+  y4 -= l41 * y1;
+  y4 -= l42 * y2;
+  y4 -= l43 * y3;
+  double y5 = b[5];
+  y5 -= l50 * y0;
+  y5 -= l51 * y1;
+  y5 -= l52 * y2;
+  y5 -= l53 * y3;
+  y5 -= l54 * y4;
+  y0 /= D0;
+  y1 /= D1;
+  y2 /= D2;
+  y3 /= D3;
+  y4 /= D4;
+  y5 /= D5;
+  double d5 = y5;
+  double d4 = y4;
+  d4 -= l54 * d5;
+  double d3 = y3;
+  d3 -= l43 * d4;
+  d3 -= l53 * d5;
+  double d2 = y2;
+  d2 -= l32 * d3;
+  d2 -= l42 * d4;
+  d2 -= l52 * d5;
+  double d1 = y1;
+  d1 -= l21 * d2;
+  d1 -= l31 * d3;
+  d1 -= l41 * d4;
+  d1 -= l51 * d5;
+  double d0 = y0;
+  d0 -= l10 * d1;
+  d0 -= l20 * d2;
+  d0 -= l30 * d3;
+  d0 -= l40 * d4;
+  d0 -= l50 * d5;
+  d[0] = d0; d[1] = d1; d[2] = d2; d[3] = d3; d[4] = d4; d[5] = d5;
+  return true;
+}
+
 // solve H d = b (6x6, LDL^T) and apply the left-multiplicative update; false if H is not positive definite
-__device__ bool pnp_step(const double* H, const double* b, PnpPose& T) {
-  double L[36], D[6], y[6], d[6];
-  for (int k = 0; k < 36; k++) L[k] = 0;
-  for (int j = 0; j < 6; j++) {
-    double v = H[7 * j];
-    for (int k = 0; k < j; k++) v -= L[6 * j + k] * L[6 * j + k] * D[k];
-    if (!(v > 1e-12)) return false;
-    D[j] = v;
-    L[7 * j] = 1;
-    for (int i = j + 1; i < 6; i++) {
-      double s = H[6 * i + j];
-      for (int k = 0; k < j; k++) s -= L[6 * i + k] * L[6 * j + k] * D[k];
-      L[6 * i + j] = s / v;
-    }
-  }
-  for (int i = 0; i < 6; i++) { double s = b[i]; for (int k = 0; k < i; k++) s -= L[6 * i + k] * y[k]; y[i] = s; }
-  for (int i = 0; i < 6; i++) y[i] /= D[i];
-  for (int i = 5; i >= 0; i--) { double s = y[i]; for (int k = i + 1; k < 6; k++) s -= L[6 * k + i] * d[k]; d[i] = s; }
+__device__ __forceinline__ bool pnp_step(const double* H, const double* b, PnpPose& T) {
+  double d[6];
+  if (!ldlt6_solve(H, b, d)) return false;
   double q[4] = {1.0, 0.5 * d[0], 0.5 * d[1], 0.5 * d[2]};
   const double nq = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
   for (int k = 0; k < 4; k++) q[k] /= nq;
@@ -323,26 +446,28 @@ __global__ void __launch_bounds__(PNP_THREADS) pnp_select_kernel(const PnpArgs* 
 // =========================================================================================================
 struct PnpWorkspace {
   int capN = 0, capIters = 0;
-  PnpArgs* d_args = nullptr;
-  float *cur, *pts, *Tm, *Tout;
-  int *good, *ids, *tmp, *cnt, *result;
-  PnpPose* hyp;
+  // one pinned staging block each way: [PnpArgs | Tcw_motion | cur_xy | pts3d | good] -> device, [result | Tcw_out | ids] <- device
+  char *d_in = nullptr, *h_in = nullptr, *d_out = nullptr, *h_out = nullptr;
+  size_t in_bytes = 0, out_bytes = 0;
+  int *tmp = nullptr, *cnt = nullptr;
+  PnpPose* hyp = nullptr;
 };
 
+static constexpr size_t PNP_ARGS_SLOT = 256;   // PnpArgs padded so the float arrays behind it stay 16-byte aligned
+
 int pnp_setup(vido_ctx* ctx, int capN, int capIters) {
+  static_assert(sizeof(PnpArgs) <= PNP_ARGS_SLOT, "PnpArgs slot");
   PnpWorkspace* ws = new PnpWorkspace();
   ctx->pnp = ws;
   ws->capN = capN; ws->capIters = capIters;
-  VIDO_CUDA(cudaMalloc(&ws->d_args, sizeof(PnpArgs)));
-  VIDO_CUDA(cudaMalloc(&ws->cur, sizeof(float) * 2 * capN));
-  VIDO_CUDA(cudaMalloc(&ws->pts, sizeof(float) * 3 * capN));
-  VIDO_CUDA(cudaMalloc(&ws->Tm, sizeof(float) * 16));
-  VIDO_CUDA(cudaMalloc(&ws->Tout, sizeof(float) * 16));
-  VIDO_CUDA(cudaMalloc(&ws->good, sizeof(int) * capN));
-  VIDO_CUDA(cudaMalloc(&ws->ids, sizeof(int) * capN));
+  ws->in_bytes = PNP_ARGS_SLOT + sizeof(float) * 16 + sizeof(float) * 5 * (size_t)capN + sizeof(int) * (size_t)capN;
+  ws->out_bytes = sizeof(int) * 4 + sizeof(float) * 16 + sizeof(int) * (size_t)capN;
+  VIDO_CUDA(cudaMalloc(&ws->d_in, ws->in_bytes));
+  VIDO_CUDA(cudaMalloc(&ws->d_out, ws->out_bytes));
+  VIDO_CUDA(cudaMallocHost(&ws->h_in, ws->in_bytes));
+  VIDO_CUDA(cudaMallocHost(&ws->h_out, ws->out_bytes));
   VIDO_CUDA(cudaMalloc(&ws->tmp, sizeof(int) * capN));
   VIDO_CUDA(cudaMalloc(&ws->cnt, sizeof(int) * capIters));
-  VIDO_CUDA(cudaMalloc(&ws->result, sizeof(int) * 4));
   VIDO_CUDA(cudaMalloc(&ws->hyp, sizeof(PnpPose) * capIters));
   return VIDO_OK;
 }
@@ -350,8 +475,8 @@ int pnp_setup(vido_ctx* ctx, int capN, int capIters) {
 void pnp_teardown(vido_ctx* ctx) {
   PnpWorkspace* ws = (PnpWorkspace*)ctx->pnp;
   if (!ws) return;
-  cudaFree(ws->d_args); cudaFree(ws->cur); cudaFree(ws->pts); cudaFree(ws->Tm); cudaFree(ws->Tout); cudaFree(ws->good);
-  cudaFree(ws->ids); cudaFree(ws->tmp); cudaFree(ws->cnt); cudaFree(ws->result); cudaFree(ws->hyp);
+  cudaFree(ws->d_in); cudaFree(ws->d_out); cudaFreeHost(ws->h_in); cudaFreeHost(ws->h_out);
+  cudaFree(ws->tmp); cudaFree(ws->cnt); cudaFree(ws->hyp);
   delete ws;
   ctx->pnp = nullptr;
 }
@@ -360,44 +485,51 @@ int pnp_init_model_host(vido_ctx* ctx, vido_pnp_problem* p) {
   PnpWorkspace* ws = (PnpWorkspace*)ctx->pnp;
   if (p->n < 0 || p->n > ws->capN || p->iters > ws->capIters || p->iters < 1) { ctx->err = "PnP problem exceeds capacity"; return VIDO_ERR_CAPACITY; }
   cudaStream_t s = ctx->stream;
-  std::vector<int> good;
-  good.reserve(p->n);
+  const size_t n = (size_t)p->n;
+  // carve the staging block (same offsets on both sides)
+  const size_t o_tm = PNP_ARGS_SLOT, o_cur = o_tm + sizeof(float) * 16, o_pts = o_cur + sizeof(float) * 2 * n,
+               o_good = o_pts + sizeof(float) * 3 * n;
+  int* hgood = (int*)(ws->h_in + o_good);
+  int M = 0;
   for (int i = 0; i < p->n; i++)
-    if (!p->valid || p->valid[i]) good.push_back(i);
+    if (!p->valid || p->valid[i]) hgood[M++] = i;
+  const size_t in_used = o_good + sizeof(int) * (size_t)M;
+  const size_t o_res = 0, o_T = sizeof(int) * 4, o_ids = o_T + sizeof(float) * 16;
   PnpArgs a;
   memset(&a, 0, sizeof a);
-  a.n = p->n; a.M = (int)good.size(); a.iters = p->iters;
-  a.cur_xy = ws->cur; a.pts3d = ws->pts; a.good = ws->good; a.Tcw_motion = ws->Tm;
+  a.n = p->n; a.M = M; a.iters = p->iters;
+  a.Tcw_motion = (const float*)(ws->d_in + o_tm); a.cur_xy = (const float*)(ws->d_in + o_cur);
+  a.pts3d = (const float*)(ws->d_in + o_pts); a.good = (const int*)(ws->d_in + o_good);
   a.fx = p->fx; a.fy = p->fy; a.cx = p->cx; a.cy = p->cy; a.thr = p->reproj_err; a.confidence = p->confidence;
-  a.hyp = ws->hyp; a.hyp_cnt = ws->cnt; a.Tcw_out = ws->Tout; a.inlier_ids = ws->ids; a.result = ws->result;
-  if (p->n) {
-    VIDO_CUDA(cudaMemcpyAsync(ws->cur, p->cur_xy, sizeof(float) * 2 * p->n, cudaMemcpyHostToDevice, s));
-    VIDO_CUDA(cudaMemcpyAsync(ws->pts, p->pts3d, sizeof(float) * 3 * p->n, cudaMemcpyHostToDevice, s));
+  a.hyp = ws->hyp; a.hyp_cnt = ws->cnt;
+  a.result = (int*)(ws->d_out + o_res); a.Tcw_out = (float*)(ws->d_out + o_T); a.inlier_ids = (int*)(ws->d_out + o_ids);
+  memcpy(ws->h_in, &a, sizeof a);
+  memcpy(ws->h_in + o_tm, p->Tcw_motion, sizeof(float) * 16);
+  if (n) {
+    memcpy(ws->h_in + o_cur, p->cur_xy, sizeof(float) * 2 * n);
+    memcpy(ws->h_in + o_pts, p->pts3d, sizeof(float) * 3 * n);
   }
-  if (a.M) VIDO_CUDA(cudaMemcpyAsync(ws->good, good.data(), sizeof(int) * a.M, cudaMemcpyHostToDevice, s));
-  VIDO_CUDA(cudaMemcpyAsync(ws->Tm, p->Tcw_motion, sizeof(float) * 16, cudaMemcpyHostToDevice, s));
-  VIDO_CUDA(cudaMemcpyAsync(ws->d_args, &a, sizeof a, cudaMemcpyHostToDevice, s));
+  VIDO_CUDA(cudaMemcpyAsync(ws->d_in, ws->h_in, in_used, cudaMemcpyHostToDevice, s));
+  const PnpArgs* d_args = (const PnpArgs*)ws->d_in;
   cudaEventRecord(ctx->ev0, s);
   if (a.M >= 4) {
-    pnp_hypotheses_kernel<<<(a.iters + PNP_THREADS / 32 - 1) / (PNP_THREADS / 32), PNP_THREADS, 0, s>>>(ws->d_args);
+    pnp_hypotheses_kernel<<<(a.iters + PNP_THREADS / 32 - 1) / (PNP_THREADS / 32), PNP_THREADS, 0, s>>>(d_args);
     ctx->launches++;
   }
-  pnp_select_kernel<<<1, PNP_THREADS, 0, s>>>(ws->d_args, ws->tmp);
+  pnp_select_kernel<<<1, PNP_THREADS, 0, s>>>(d_args, ws->tmp);
   cudaEventRecord(ctx->ev1, s);
   ctx->launches++;
   VIDO_CUDA(cudaGetLastError());
-  int res[4];
-  VIDO_CUDA(cudaMemcpyAsync(res, ws->result, sizeof res, cudaMemcpyDeviceToHost, s));
-  VIDO_CUDA(cudaMemcpyAsync(p->Tcw_out, ws->Tout, sizeof(float) * 16, cudaMemcpyDeviceToHost, s));
+  // the inlier list is at most n ints: fetch it with the result instead of paying a second round trip
+  VIDO_CUDA(cudaMemcpyAsync(ws->h_out, ws->d_out, o_ids + sizeof(int) * n, cudaMemcpyDeviceToHost, s));
   VIDO_CUDA(cudaStreamSynchronize(s));
   {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) { ctx->t_ms[1] += ms; ctx->t_n[1]++; }
   }
+  const int* res = (const int*)(ws->h_out + o_res);
   p->n_inliers = res[0]; p->winner = res[1]; p->ransac_inliers = res[2]; p->mm_inliers = res[3];
-  if (res[0] > 0 && p->inlier_ids) {
-    VIDO_CUDA(cudaMemcpyAsync(p->inlier_ids, ws->ids, sizeof(int) * res[0], cudaMemcpyDeviceToHost, s));
-    VIDO_CUDA(cudaStreamSynchronize(s));
-  }
+  memcpy(p->Tcw_out, ws->h_out + o_T, sizeof(float) * 16);
+  if (res[0] > 0 && p->inlier_ids) memcpy(p->inlier_ids, ws->h_out + o_ids, sizeof(int) * (size_t)res[0]);
   return VIDO_OK;
 }

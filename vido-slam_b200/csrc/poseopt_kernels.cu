@@ -10,6 +10,7 @@
 //                                         g2o/solvers/linear_solver_dense.h:65-116
 // Because both Jacobians w.r.t. the flow vertex are the identity, H_ll = (w + w_prior) I and the Schur complement
 // collapses to a weighted sum of J^T J: one 27-value block reduction (warp shuffles) per solve.
+#include <algorithm>
 #include <cstring>
 
 #include "ctx.h"
@@ -66,14 +67,20 @@ __device__ void quat_from_R_dev(const double* R, double* q) {
   } else {
     int i = 0;
     if (R[4] > R[0]) i = 1;
-    if (R[8] > R[4 * i]) i = 2;
-    const int j = (i + 1) % 3, k = (j + 1) % 3;
-    t = sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
-    q[1 + i] = 0.5 * t;
-    t = 0.5 / t;
-    q[0] = (R[3 * k + j] - R[3 * j + k]) * t;
-    q[1 + j] = (R[3 * j + i] + R[3 * i + j]) * t;
-    q[1 + k] = (R[3 * k + i] + R[3 * i + k]) * t;
+    if (R[8] > (i == 0 ? R[0] : R[4])) i = 2;
+    if (i == 0) {
+      t = sqrt(R[0] - R[4] - R[8] + 1.0);
+      q[1] = 0.5 * t; t = 0.5 / t;
+      q[0] = (R[7] - R[5]) * t; q[2] = (R[3] + R[1]) * t; q[3] = (R[6] + R[2]) * t;
+    } else if (i == 1) {
+      t = sqrt(R[4] - R[8] - R[0] + 1.0);
+      q[2] = 0.5 * t; t = 0.5 / t;
+      q[0] = (R[2] - R[6]) * t; q[3] = (R[7] + R[5]) * t; q[1] = (R[1] + R[3]) * t;
+    } else {
+      t = sqrt(R[8] - R[0] - R[4] + 1.0);
+      q[3] = 0.5 * t; t = 0.5 / t;
+      q[0] = (R[3] - R[1]) * t; q[1] = (R[2] + R[6]) * t; q[2] = (R[5] + R[7]) * t;
+    }
   }
   if (q[0] < 0) { q[0] = -q[0]; q[1] = -q[1]; q[2] = -q[2]; q[3] = -q[3]; }
   const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
@@ -460,6 +467,388 @@ __global__ void __launch_bounds__(PO_THREADS) poseopt_flow2_kernel(const PoArgs*
   }
 }
 
+
+// =========================================================================================================
+// Fast path (n <= PO_CACHE_CAP): 512 threads; the linearisation of every edge (error, robust weight, the ten non-zero
+// Jacobian entries) is computed ONCE per LM iteration and kept in shared memory (struct-of-arrays, conflict-free), so the
+// damped Schur pass of every trial and the flow back-substitution read 13 doubles instead of re-evaluating the
+// projection (two divisions, a quaternion rotation) -- 2 projections per iteration instead of 5.  The 27-value block
+// reductions use halving exchanges (31 shuffles instead of 135), the 6x6 solve is straight-line register code.
+// Same arithmetic as the generic kernel above up to summation order.
+// =========================================================================================================
+#define PO_FAST_THREADS 512
+#define PO_CACHE_CAP 1536
+#define PO_NC 13  // e0 e1 w J0 J1 J2 J3 J5 J6 J7 J8 J10 J11
+
+__device__ __forceinline__ double rsqrt_pos_po(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double e = fma(d, -(y * y), 1.0);
+  return fma(fma(e, 0.375, 0.5), y * e, y);
+}
+
+// 6x6 SPD solve S x = b by LL^T in straight-line scalar code (registers only); false if a pivot is not positive
+__device__ __forceinline__ bool solve6_spd(const double* S, const double* b, double* x) {
+  const double a00 = S[0];
+  const double a10 = S[6], a11 = S[7];
+  const double a20 = S[12], a21 = S[13], a22 = S[14];
+  const double a30 = S[18], a31 = S[19], a32 = S[20], a33 = S[21];
+  const double a40 = S[24], a41 = S[25], a42 = S[26], a43 = S[27], a44 = S[28];
+  const double a50 = S[30], a51 = S[31], a52 = S[32], a53 = S[33], a54 = S[34], a55 = S[35];
+  const double d0 = a00;
+  const double i0 = rsqrt_pos_po(d0);
+  const double l10 = (a10) * i0;
+  const double l20 = (a20) * i0;
+  const double l30 = (a30) * i0;
+  const double l40 = (a40) * i0;
+  const double l50 = (a50) * i0;
+  const double d1 = a11 - l10 * l10;
+  const double i1 = rsqrt_pos_po(d1);
+  const double l21 = (a21 - l20 * l10) * i1;
+  const double l31 = (a31 - l30 * l10) * i1;
+  const double l41 = (a41 - l40 * l10) * i1;
+  const double l51 = (a51 - l50 * l10) * i1;
+  const double d2 = a22 - l20 * l20 - l21 * l21;
+  const double i2 = rsqrt_pos_po(d2);
+  const double l32 = (a32 - l30 * l20 - l31 * l21) * i2;
+  const double l42 = (a42 - l40 * l20 - l41 * l21) * i2;
+  const double l52 = (a52 - l50 * l20 - l51 * l21) * i2;
+  const double d3 = a33 - l30 * l30 - l31 * l31 - l32 * l32;
+  const double i3 = rsqrt_pos_po(d3);
+  const double l43 = (a43 - l40 * l30 - l41 * l31 - l42 * l32) * i3;
+  const double l53 = (a53 - l50 * l30 - l51 * l31 - l52 * l32) * i3;
+  const double d4 = a44 - l40 * l40 - l41 * l41 - l42 * l42 - l43 * l43;
+  const double i4 = rsqrt_pos_po(d4);
+  const double l54 = (a54 - l50 * l40 - l51 * l41 - l52 * l42 - l53 * l43) * i4;
+  const double d5 = a55 - l50 * l50 - l51 * l51 - l52 * l52 - l53 * l53 - l54 * l54;
+  const double i5 = rsqrt_pos_po(d5);
+  if (!(d0 > 0 && d1 > 0 && d2 > 0 && d3 > 0 && d4 > 0 && d5 > 0)) return false;
+  const double y0 = (b[0]) * i0;
+  const double y1 = (b[1] - l10 * y0) * i1;
+  const double y2 = (b[2] - l20 * y0 - l21 * y1) * i2;
+  const double y3 = (b[3] - l30 * y0 - l31 * y1 - l32 * y2) * i3;
+  const double y4 = (b[4] - l40 * y0 - l41 * y1 - l42 * y2 - l43 * y3) * i4;
+  const double y5 = (b[5] - l50 * y0 - l51 * y1 - l52 * y2 - l53 * y3 - l54 * y4) * i5;
+  const double x5 = (y5) * i5;
+  const double x4 = (y4 - l54 * x5) * i4;
+  const double x3 = (y3 - l53 * x5 - l43 * x4) * i3;
+  const double x2 = (y2 - l52 * x5 - l42 * x4 - l32 * x3) * i2;
+  const double x1 = (y1 - l51 * x5 - l41 * x4 - l31 * x3 - l21 * x2) * i1;
+  const double x0 = (y0 - l50 * x5 - l40 * x4 - l30 * x3 - l20 * x2 - l10 * x1) * i0;
+  x[0] = x0; x[1] = x1; x[2] = x2; x[3] = x3; x[4] = x4; x[5] = x5;
+  return true;
+}
+
+// sum of 32 per-lane values over the warp with 31 shuffles; afterwards v[0] of lane L is the total of value L
+__device__ __forceinline__ void warp_sum32(double* v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int h = 16, m = 16; h >= 1; h >>= 1, m >>= 1) {
+    const bool hi = (lane & m) != 0;
+#pragma unroll
+    for (int k = 0; k < h; k++) {
+      const double send = hi ? v[k] : v[k + h], keep = hi ? v[k + h] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+    }
+  }
+}
+
+// block sum of 27 values per thread -> sm[0..26] (v is clobbered); sm must hold 32 * (#warps) doubles
+__device__ __forceinline__ void bsum27(double* v, double* sm) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  warp_sum32(v);
+  __syncthreads();
+  sm[warp * 32 + lane] = v[0];
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double s = 0;
+    for (int w = 0; w < nw; w++) s += sm[w * 32 + threadIdx.x];
+    v[0] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) sm[threadIdx.x] = v[0];
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(PO_FAST_THREADS) poseopt_flow2_fast_kernel(const PoArgs* __restrict__ problems) {
+  const PoArgs a = problems[blockIdx.x];
+  const int n = a.n, tid = threadIdx.x, NT = PO_FAST_THREADS;
+  extern __shared__ double cache[];  // [PO_NC][n]
+  __shared__ double red[(PO_FAST_THREADS / 32) * 32];
+  __shared__ PoseQ T[2];
+  __shared__ PoseQ Tinit;
+  __shared__ LmCtl ctl;
+  __shared__ double Hpp[36], bp[6], xp[6], Ss[36], bs[6];
+  __shared__ int s_robust, s_nbad;
+
+  if (n < 3) {  // "if(nInitialCorrespondences<3) return 0;" -- nothing is touched
+    for (int i = tid; i < 16; i += NT) a.Tcw_out[i] = a.Tcw_init[i];
+    for (int i = tid; i < n; i += NT) {
+      a.flow_out[2 * i] = a.flow_xy[2 * i]; a.flow_out[2 * i + 1] = a.flow_xy[2 * i + 1];
+      a.inlier[i] = 1;
+    }
+    if (tid == 0) *a.n_inliers = 0;
+    return;
+  }
+  if (tid == 0) {
+    const float* L = a.Tcw_init;
+    double R[9] = {L[0], L[1], L[2], L[4], L[5], L[6], L[8], L[9], L[10]};
+    quat_from_R_dev(R, Tinit.q);
+    Tinit.t[0] = L[3]; Tinit.t[1] = L[7]; Tinit.t[2] = L[11];
+    s_robust = 1;
+    for (int k = 0; k < 6; k++) xp[k] = 0;
+  }
+  {
+    const float* L = a.Tcw_last;
+    float Rwl[9], twl[3];
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) Rwl[3 * r + c] = L[4 * c + r];
+    for (int r = 0; r < 3; r++) {
+      float s = 0.f;
+      for (int k = 0; k < 3; k++) s = __fadd_rn(s, __fmul_rn(-Rwl[3 * r + k], L[4 * k + 3]));
+      twl[r] = s;
+    }
+    for (int i = tid; i < n; i += NT) {
+      const double ox = a.obs_xy[2 * i], oy = a.obs_xy[2 * i + 1], d = a.depth[i];
+      const double X[3] = {(ox - (double)a.cx) * d / (double)a.fx, (oy - (double)a.cy) * d / (double)a.fy, d};
+      for (int r = 0; r < 3; r++)
+        a.Xw[3 * (size_t)i + r] = (double)Rwl[3 * r] * X[0] + (double)Rwl[3 * r + 1] * X[1] + (double)Rwl[3 * r + 2] * X[2] + (double)twl[r];
+      a.flow[2 * i] = a.flow_xy[2 * i]; a.flow[2 * i + 1] = a.flow_xy[2 * i + 1];
+      a.xl[2 * i] = 0; a.xl[2 * i + 1] = 0;
+      a.level[i] = 0;
+    }
+  }
+  __syncthreads();
+
+  double* const flowbuf[2] = {a.flow, a.flow + 2 * (size_t)n};
+  double* const c_e0 = cache, *const c_e1 = cache + n, *const c_w = cache + 2 * (size_t)n, *const c_J = cache + 3 * (size_t)n;  // c_J[k*n + i], k < 10
+  for (int round = 0; round < a.rounds; round++) {
+    if (tid == 0) {
+      lm_reset(&ctl);
+      T[0] = Tinit;
+    }
+    __syncthreads();
+    const int robust = s_robust;
+    {  // robust chi2 at the start state (buffer 0)
+      double v[32];
+#pragma unroll
+      for (int k = 0; k < 32; k++) v[k] = 0;
+      const PoseQ T0 = T[0];
+      for (int i = tid; i < n; i += NT) {
+        const double* fl = flowbuf[0] + 2 * i;
+        if (a.level[i] == 0) {
+          double e[2], r0, w;
+          proj_edge(a, T0, i, fl, e, nullptr);
+          a.eProj[2 * i] = e[0]; a.eProj[2 * i + 1] = e[1];
+          const double c = (e[0] * e[0] + e[1] * e[1]) * a.info_f;
+          if (robust) { huber_dev(c, a.delta, r0, w); v[0] += r0; } else v[0] += c;
+        }
+        const double p0 = fl[0] - (double)a.flow_xy[2 * i], p1 = fl[1] - (double)a.flow_xy[2 * i + 1];
+        v[0] += (p0 * p0 + p1 * p1) * a.info_p;
+      }
+      bsum27(v, red);
+      if (tid == 0) ctl.currentChi = red[0];
+      __syncthreads();
+    }
+    for (int it = 0; it < a.its; it++) {
+      if (ctl.stop_flag || !ctl.ok) break;
+      const int cur = ctl.cur;
+      const PoseQ Tc = T[cur];
+      const double* fcur = flowbuf[cur];
+      double* ftrial = flowbuf[cur ^ 1];
+      // ---- build: linearise every active edge once (cached), H_pp, b_p and the diagonal maximum
+      double acc[32];
+#pragma unroll
+      for (int k = 0; k < 32; k++) acc[k] = 0;
+      double mx = 0;
+      for (int i = tid; i < n; i += NT) {
+        double h = a.info_p;
+        if (a.level[i] == 0) {
+          double e[2], J[12], r0, w = 1.0;
+          proj_edge(a, Tc, i, fcur + 2 * i, e, J);
+          a.eProj[2 * i] = e[0]; a.eProj[2 * i + 1] = e[1];
+          if (robust) huber_dev((e[0] * e[0] + e[1] * e[1]) * a.info_f, a.delta, r0, w);
+          w *= a.info_f;
+          h += w;
+          c_e0[i] = e[0]; c_e1[i] = e[1]; c_w[i] = w;
+          c_J[i] = J[0]; c_J[n + i] = J[1]; c_J[2 * n + i] = J[2]; c_J[3 * n + i] = J[3]; c_J[4 * n + i] = J[5];
+          c_J[5 * n + i] = J[6]; c_J[6 * n + i] = J[7]; c_J[7 * n + i] = J[8]; c_J[8 * n + i] = J[10]; c_J[9 * n + i] = J[11];
+          int idx = 0;
+#pragma unroll
+          for (int r = 0; r < 6; r++) {
+            acc[21 + r] -= w * (J[r] * e[0] + J[6 + r] * e[1]);
+#pragma unroll
+            for (int c = r; c < 6; c++) acc[idx++] += w * (J[r] * J[c] + J[6 + r] * J[6 + c]);
+          }
+        }
+        mx = fmax(mx, h);
+      }
+      bsum27(acc, red);
+      if (tid == 0) {
+        int idx = 0;
+        for (int r = 0; r < 6; r++) {
+          bp[r] = red[21 + r];
+          for (int c = r; c < 6; c++) { Hpp[6 * r + c] = red[idx]; Hpp[6 * c + r] = red[idx]; idx++; }
+        }
+      }
+      __syncthreads();
+      {  // block max
+        const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) red[warp] = mx;
+        __syncthreads();
+        if (tid == 0) {
+          double m = 0;
+          for (int w = 0; w < NT / 32; w++) m = fmax(m, red[w]);
+          for (int r = 0; r < 6; r++) m = fmax(m, fabs(Hpp[7 * r]));
+          lm_begin_iteration(&ctl, it, m, -1.0);
+        }
+        __syncthreads();
+      }
+      // ---- trials
+      while (true) {
+        const double lambda = ctl.lambda;
+#pragma unroll
+        for (int k = 0; k < 32; k++) acc[k] = 0;
+        for (int i = tid; i < n; i += NT) {
+          if (a.level[i] != 0) continue;
+          const double e0 = c_e0[i], e1 = c_e1[i], w = c_w[i];
+          const double J[12] = {c_J[i], c_J[n + i], c_J[2 * n + i], c_J[3 * n + i], 0.0, c_J[4 * n + i],
+                                c_J[5 * n + i], c_J[6 * n + i], c_J[7 * n + i], 0.0, c_J[8 * n + i], c_J[9 * n + i]};
+          const double h = w + a.info_p + lambda;
+          const double p0 = fcur[2 * i] - (double)a.flow_xy[2 * i], p1 = fcur[2 * i + 1] - (double)a.flow_xy[2 * i + 1];
+          const double bl0 = -w * e0 - a.info_p * p0, bl1 = -w * e1 - a.info_p * p1;
+          const double s = w * w / h, g = w / h;
+          int idx = 0;
+#pragma unroll
+          for (int r = 0; r < 6; r++) {
+            acc[21 + r] += g * (J[r] * bl0 + J[6 + r] * bl1);
+#pragma unroll
+            for (int c = r; c < 6; c++) acc[idx++] += s * (J[r] * J[c] + J[6 + r] * J[6 + c]);
+          }
+        }
+        bsum27(acc, red);
+        if (tid < 36) {  // reduced 6x6 system
+          const int r = tid / 6, c = tid - 6 * r;
+          const int lo = r < c ? r : c, hi = r < c ? c : r;
+          const int idx = lo * 6 - (lo * (lo - 1)) / 2 + (hi - lo);
+          Ss[tid] = Hpp[tid] - red[idx] + ((r == c) ? lambda : 0.0);
+          if (tid < 6) bs[tid] = bp[tid] - red[21 + tid];
+        }
+        __syncthreads();
+        if (tid == 0) {
+          double x[6];
+          const bool ok = solve6_spd(Ss, bs, x);
+          if (ok) for (int k = 0; k < 6; k++) xp[k] = x[k];
+          ctl.fail = ok ? 0 : 1;  // on failure x keeps its previous content
+          se3_exp_mul(xp, Tc, T[cur ^ 1]);
+        }
+        __syncthreads();
+        const int failed = ctl.fail;
+        const PoseQ Tt = T[cur ^ 1];
+        double xr[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) xr[k] = xp[k];
+        // ---- flow increments, trial state, chi2 and scale
+        double v[32];
+#pragma unroll
+        for (int k = 0; k < 32; k++) v[k] = 0;
+        for (int i = tid; i < n; i += NT) {
+          const double p0 = fcur[2 * i] - (double)a.flow_xy[2 * i], p1 = fcur[2 * i + 1] - (double)a.flow_xy[2 * i + 1];
+          double bl0 = -a.info_p * p0, bl1 = -a.info_p * p1, h = a.info_p + lambda;
+          double x0, x1;
+          const bool active = a.level[i] == 0;
+          if (active) {
+            const double e0 = c_e0[i], e1 = c_e1[i], w = c_w[i];
+            h += w;
+            bl0 -= w * e0; bl1 -= w * e1;
+            const double jx0 = c_J[i] * xr[0] + c_J[n + i] * xr[1] + c_J[2 * n + i] * xr[2] + c_J[3 * n + i] * xr[3] + c_J[4 * n + i] * xr[5];
+            const double jx1 = c_J[5 * n + i] * xr[0] + c_J[6 * n + i] * xr[1] + c_J[7 * n + i] * xr[2] + c_J[8 * n + i] * xr[4] + c_J[9 * n + i] * xr[5];
+            x0 = (bl0 - w * jx0) / h;
+            x1 = (bl1 - w * jx1) / h;
+          } else {
+            x0 = bl0 / h;
+            x1 = bl1 / h;
+          }
+          if (failed) { x0 = a.xl[2 * i]; x1 = a.xl[2 * i + 1]; }
+          else { a.xl[2 * i] = x0; a.xl[2 * i + 1] = x1; }
+          const double f0 = fcur[2 * i] + x0, f1 = fcur[2 * i + 1] + x1;
+          ftrial[2 * i] = f0; ftrial[2 * i + 1] = f1;
+          v[1] += x0 * (lambda * x0 + bl0) + x1 * (lambda * x1 + bl1);
+          if (active) {
+            double e[2], r0, w;
+            const double ft[2] = {f0, f1};
+            proj_edge(a, Tt, i, ft, e, nullptr);
+            a.eProj[2 * i] = e[0]; a.eProj[2 * i + 1] = e[1];
+            const double c = (e[0] * e[0] + e[1] * e[1]) * a.info_f;
+            if (robust) { huber_dev(c, a.delta, r0, w); v[0] += r0; } else v[0] += c;
+          }
+          const double q0 = f0 - (double)a.flow_xy[2 * i], q1 = f1 - (double)a.flow_xy[2 * i + 1];
+          v[0] += (q0 * q0 + q1 * q1) * a.info_p;
+        }
+        bsum27(v, red);
+        if (tid == 0) {
+          double sc = red[1];
+          for (int r = 0; r < 6; r++) sc += xp[r] * (lambda * xp[r] + bp[r]);
+          lm_trial(&ctl, red[0], sc, failed);
+        }
+        __syncthreads();
+        if (!lm_more_trials(&ctl)) break;
+      }
+      if (tid == 0) lm_end_iteration(&ctl, it, -1.0, a.rec ? a.rec + (size_t)round * VIDO_LM_REC : nullptr);
+      __syncthreads();
+    }
+    // ---- classify (src/Optimizer.cc:2751-2794); accepted state -> buffer 0 for the next round
+    const int cur = ctl.cur;
+    const float th = (round == 0) ? a.th0 : a.th1;
+    double vb[32];
+#pragma unroll
+    for (int k = 0; k < 32; k++) vb[k] = 0;
+    const PoseQ Tf = T[cur];
+    for (int i = tid; i < n; i += NT) {
+      const double f0 = flowbuf[cur][2 * i], f1 = flowbuf[cur][2 * i + 1];
+      if (a.level[i] != 0) {  // demoted edges are re-evaluated at the final estimate
+        double e[2];
+        const double ft[2] = {f0, f1};
+        proj_edge(a, Tf, i, ft, e, nullptr);
+        a.eProj[2 * i] = e[0]; a.eProj[2 * i + 1] = e[1];
+      }
+      const float chi2 = (float)((a.eProj[2 * i] * a.eProj[2 * i] + a.eProj[2 * i + 1] * a.eProj[2 * i + 1]) * a.info_f);
+      if (chi2 > th) { a.level[i] = 1; vb[0] += 1.0; }
+      else a.level[i] = 0;
+      flowbuf[0][2 * i] = f0; flowbuf[0][2 * i + 1] = f1;
+    }
+    bsum27(vb, red);
+    if (tid == 0) {
+      s_nbad = (int)(red[0] + 0.5);
+      if (round == 2) s_robust = 0;
+      if (a.ctl) a.ctl[round] = ctl;
+      T[0] = T[cur];  // keep the final pose of this round (overwritten by the reset unless it is the last round)
+    }
+    __syncthreads();
+  }
+  // ---- outputs: pose (SE3Quat -> homogeneous -> float), refined flows, inlier flags
+  if (tid == 0) {
+    const PoseQ& F = T[0];
+    const double w = F.q[0], x = F.q[1], y = F.q[2], z = F.q[3];
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z, twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x,
+                 txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    const double R[9] = {1 - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1 - (txx + tzz), tyz - twx, txz - twy, tyz + twx, 1 - (txx + tyy)};
+    for (int r = 0; r < 3; r++) {
+      for (int c = 0; c < 3; c++) a.Tcw_out[4 * r + c] = (float)R[3 * r + c];
+      a.Tcw_out[4 * r + 3] = (float)F.t[r];
+    }
+    a.Tcw_out[12] = 0.f; a.Tcw_out[13] = 0.f; a.Tcw_out[14] = 0.f; a.Tcw_out[15] = 1.f;
+    *a.n_inliers = n - s_nbad;
+  }
+  for (int i = tid; i < n; i += NT) {
+    a.flow_out[2 * i] = (float)flowbuf[0][2 * i];
+    a.flow_out[2 * i + 1] = (float)flowbuf[0][2 * i + 1];
+    a.inlier[i] = a.level[i] == 0;
+  }
+}
+
 // =========================================================================================================
 // host side
 // =========================================================================================================
@@ -495,6 +884,7 @@ int po_setup(vido_ctx* ctx, int capN, int capProblems) {
   VIDO_CUDA(cudaMalloc(&ws->xl, sizeof(double) * 2 * N));
   VIDO_CUDA(cudaMalloc(&ws->eProj, sizeof(double) * 2 * N));
   VIDO_CUDA(cudaMalloc(&ws->level, sizeof(int) * N));
+  VIDO_CUDA(cudaFuncSetAttribute(poseopt_flow2_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * PO_NC * PO_CACHE_CAP)));
   return VIDO_OK;
 }
 
@@ -560,7 +950,12 @@ int po_flow2_host(vido_ctx* ctx, vido_poseopt_problem* prs, int nproblems, vido_
   }
   VIDO_CUDA(cudaMemcpyAsync(ws->d_in, ws->h_in, (size_t)(hi - ws->h_in), cudaMemcpyHostToDevice, s));
   cudaEventRecord(ctx->ev0, s);
-  poseopt_flow2_kernel<<<nproblems, PO_THREADS, 0, s>>>(d_args);
+  int nmax = 0;
+  for (int k = 0; k < nproblems; k++) nmax = std::max(nmax, prs[k].n);
+  if (nmax <= PO_CACHE_CAP)
+    poseopt_flow2_fast_kernel<<<nproblems, PO_FAST_THREADS, sizeof(double) * PO_NC * (size_t)std::max(nmax, 1), s>>>(d_args);
+  else
+    poseopt_flow2_kernel<<<nproblems, PO_THREADS, 0, s>>>(d_args);
   cudaEventRecord(ctx->ev1, s);
   ctx->launches++;
   VIDO_CUDA(cudaGetLastError());

@@ -75,6 +75,14 @@ struct TrackState {
   std::vector<float> last_keys, last_depth, last_corres, last_flow;  // mpLastFrame mvStatKeys / mvStatDepth / mvCorres / mvFlowNext
   int f_id = 0;
   int ba_epoch = 0;
+  // window BA in flight (runs on its own stream while the next frame is tracked)
+  bool ba_pending = false;
+  int ba_start = 0, ba_end = 0;
+  vido_track_stats* ba_st = nullptr;
+  vido_ba_problem ba_pr;
+  std::vector<float> ba_poses, ba_rel, ba_pts, ba_oxyz;
+  std::vector<int> ba_op, ba_ol;
+  std::vector<int> ba_ofeat;   // per observation: feature index inside its frame, for the write-back
   // device buffers of one chunk
   int capB = 0;
   uint8_t* d_img = nullptr;      // [B][H][W*3] or gray
@@ -169,6 +177,7 @@ void trk_teardown(vido_ctx* ctx) {
 
 int trk_reset(vido_ctx* ctx) {
   TrackState* ts = (TrackState*)ctx->trk;
+  if (ts->ba_pending) { vido_lm_stats ls; ba_collect(ctx, &ts->ba_pr, &ls); ts->ba_pending = false; }
   ts->map.clear(); ts->tracks.clear();
   ts->initialised = false; ts->has_velocity = false; ts->f_id = 0; ts->ba_epoch = 0;
   ts->last_keys.clear(); ts->last_depth.clear(); ts->last_corres.clear(); ts->last_flow.clear();
@@ -259,18 +268,48 @@ static int query_maps(vido_ctx* ctx, const float* d_depth, const float* d_flow, 
 // ---------------------------------------------------------------------------------------------------------
 // window graph from the flat map (Optimizer.cc:220-362) + solve + write-back (:1056-1142)
 // ---------------------------------------------------------------------------------------------------------
-static int partial_batch(vido_ctx* ctx, int WINDOW, vido_track_stats* st) {
+// The solve is asynchronous: ba_start launches it on the BA stream, ba_finish waits and writes the map back.  Nothing
+// the tracker reads between the two (last-frame keys/depth/pose, velocity) is touched by the BA (Tracking.cc:1320-1500
+// uses mpLastFrame / mVelocity only), so tracking frame k+1 while frame k's window is optimised gives the same result
+// as the reference's strictly sequential order.
+static int ba_finish(vido_ctx* ctx) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  if (!ts->ba_pending) return VIDO_OK;
+  ts->ba_pending = false;
+  vido_lm_stats ls;
+  int rc = ba_collect(ctx, &ts->ba_pr, &ls);
+  if (rc) return rc;
+  vido_track_stats* st = ts->ba_st;
+  if (st) { st->ba_iterations = ls.iterations; st->ba_trials = ls.total_trials; }
+  const int start = ts->ba_start, N = ts->ba_end;
+  for (int i = start; i < N; i++) {
+    memcpy(ts->map[i].Twc, &ts->ba_poses[16 * (size_t)(i - start)], sizeof(float) * 16);
+    if (i > start) memcpy(ts->map[i].rel, &ts->ba_rel[16 * (size_t)(i - start - 1)], sizeof(float) * 16);
+  }
+  // every observation of an optimised point receives the optimised position (Optimizer.cc:1107-1122)
+  const size_t nobs = ts->ba_op.size();
+  const float* pts = ts->ba_pts.data();
+  for (size_t o = 0; o < nobs; o++) {
+    float* d = &ts->map[start + ts->ba_op[o]].p3[3 * (size_t)ts->ba_ofeat[o]];
+    const float* q = pts + 3 * (size_t)ts->ba_ol[o];
+    d[0] = q[0]; d[1] = q[1]; d[2] = q[2];
+  }
+  return VIDO_OK;
+}
+
+static int ba_start(vido_ctx* ctx, int WINDOW, vido_track_stats* st) {
   TrackState* ts = (TrackState*)ctx->trk;
   const int N = (int)ts->map.size();
   if (st) { st->ba_iterations = -1; st->ba_points = 0; st->ba_obs = 0; st->ba_trials = 0; }
   if (WINDOW <= 0) return VIDO_OK;
   const int start = N - WINDOW;
-  std::vector<float> poses(16 * (size_t)WINDOW), rel(16 * (size_t)std::max(WINDOW - 1, 0)), pts, oxyz;
-  std::vector<int> op, ol;
-  std::vector<std::pair<int, int>> owner;
+  std::vector<float>&poses = ts->ba_poses, &rel = ts->ba_rel, &pts = ts->ba_pts, &oxyz = ts->ba_oxyz;
+  std::vector<int>&op = ts->ba_op, &ol = ts->ba_ol, &ofeat = ts->ba_ofeat;
+  poses.resize(16 * (size_t)WINDOW); rel.resize(16 * (size_t)std::max(WINDOW - 1, 0));
+  pts.clear(); oxyz.clear(); op.clear(); ol.clear(); ofeat.clear();
   const int epoch = ++ts->ba_epoch;
-  std::vector<int> tid_list;
-  const float invfx = 1.0f / ctx->cfg.fx, invfy = 1.0f / ctx->cfg.fy;
+  const float invfx = 1.0f / ctx->cfg.fx, invfy = 1.0f / ctx->cfg.fy, cx = ctx->cfg.cx, cy = ctx->cfg.cy;
+  int npts = 0;
   // a track enters the window graph iff it is at least 3 long and was born inside the window
   for (int i = start; i < N; i++) {
     MapFrame& F = ts->map[i];
@@ -284,47 +323,26 @@ static int partial_batch(vido_ctx* ctx, int WINDOW, vido_track_stats* st) {
       if (T.len < 3 || T.first_frame < start) continue;
       int pid = (T.epoch == epoch) ? T.pid : -1;
       if (F.pos[j] == 0) {
-        pid = (int)owner.size();
+        pid = npts++;
         T.pid = pid; T.epoch = epoch;
-        owner.push_back({i, j});
         pts.push_back(F.p3[3 * j]); pts.push_back(F.p3[3 * j + 1]); pts.push_back(F.p3[3 * j + 2]);
       }
       if (pid < 0) continue;
       const float z = F.depth[j], u = F.xy[2 * j], v = F.xy[2 * j + 1];
-      op.push_back(i - start); ol.push_back(pid);
-      oxyz.push_back((u - ctx->cfg.cx) * z * invfx); oxyz.push_back((v - ctx->cfg.cy) * z * invfy); oxyz.push_back(z);
+      op.push_back(i - start); ol.push_back(pid); ofeat.push_back(j);
+      oxyz.push_back((u - cx) * z * invfx); oxyz.push_back((v - cy) * z * invfy); oxyz.push_back(z);
     }
   }
-  vido_ba_problem pr;
+  vido_ba_problem& pr = ts->ba_pr;
   memset(&pr, 0, sizeof pr);
   vido_ba_default_params(&pr);
-  pr.n_poses = WINDOW; pr.n_points = (int)owner.size(); pr.n_obs = (int)op.size();
+  pr.n_poses = WINDOW; pr.n_points = npts; pr.n_obs = (int)op.size();
   pr.poses = poses.data(); pr.rel_motion = rel.data(); pr.points = pts.data();
   pr.obs_pose = op.data(); pr.obs_point = ol.data(); pr.obs_xyz = oxyz.data();
-  vido_lm_stats ls;
-  int rc = ba_partial_host(ctx, &pr, &ls);
+  if (st) { st->ba_points = pr.n_points; st->ba_obs = pr.n_obs; }
+  int rc = ba_submit(ctx, &pr, false);
   if (rc) return rc;
-  if (st) { st->ba_iterations = ls.iterations; st->ba_points = pr.n_points; st->ba_obs = pr.n_obs; st->ba_trials = ls.total_trials; }
-  for (int i = start; i < N; i++) {
-    memcpy(ts->map[i].Twc, &poses[16 * (size_t)(i - start)], sizeof(float) * 16);
-    if (i > start) memcpy(ts->map[i].rel, &rel[16 * (size_t)(i - start - 1)], sizeof(float) * 16);
-  }
-  // every observation of an optimised point receives the optimised position (Optimizer.cc:1107-1122)
-  {
-    for (int i = start; i < N; i++) {
-      MapFrame& F = ts->map[i];
-      const int n = (int)F.depth.size();
-      for (int j = 0; j < n; j++) {
-        const int t = F.track[j];
-        if (t < 0) continue;
-        const TrackInfo& T = ts->tracks[t];
-        if (T.len < 3 || T.first_frame < start) continue;
-        const int pid = (T.epoch == epoch) ? T.pid : -1;
-        if (pid < 0) continue;
-        F.p3[3 * j] = pts[3 * (size_t)pid]; F.p3[3 * j + 1] = pts[3 * (size_t)pid + 1]; F.p3[3 * j + 2] = pts[3 * (size_t)pid + 2];
-      }
-    }
-  }
+  ts->ba_pending = true; ts->ba_start = start; ts->ba_end = N; ts->ba_st = st;
   return VIDO_OK;
 }
 
@@ -364,18 +382,10 @@ static int back_end(vido_ctx* ctx, const FrontFrame& ff, int slot, const float* 
     const int Ns = (int)(ts->last_corres.size() / 2);
     if (Ns < 2) skipped = 1;
     else {
-      // ---- mvStatKeys = last mvCorres; depth lookups with the 1-px border rule (Tracking.cc:369-389)
-      std::vector<float> keys = ts->last_corres, kdepth(Ns, -1.f), qflow(2 * (size_t)Ns);
-      std::vector<int32_t> qmask(Ns);
-      {
-        std::vector<float> qd(Ns);
-        int rc = query_maps(ctx, d_depth, d_flow, d_mask, slot, keys.data(), Ns, qmask.data(), qd.data(), qflow.data());
-        if (rc) return rc;
-        for (int i = 0; i < Ns; i++) {
-          const int v = (int)keys[2 * i + 1], u = (int)keys[2 * i];
-          if (u < (W - 1) && u > 0 && v < (H - 1) && v > 0 && qd[i] > 0) kdepth[i] = qd[i];
-        }
-      }
+      // ---- mvStatKeys = last mvCorres.  The reference also samples the new depth map at these positions into
+      //      mvStatDepthTmp (Tracking.cc:369-389); in the static-only pipeline nothing reads that vector (RenewFrameInfo
+      //      re-samples at the refined positions, Tracking.cc:2970-3010), so the lookup round trip is not issued.
+      std::vector<float> keys = ts->last_corres;
       // ---- GetInitModelCam: 3-D points of the last frame, constant-velocity model, PnP-RANSAC
       std::vector<float> p3d(3 * (size_t)Ns, 0.f);
       std::vector<int32_t> valid(Ns, 1), ids(Ns);
@@ -550,7 +560,9 @@ static int back_end(vido_ctx* ctx, const FrontFrame& ff, int slot, const float* 
   memcpy(Tcw_out, curTcw, sizeof(float) * 16);
   double t4 = now_ms();
   const int window = ts->f_id < c.window_size ? ts->f_id : c.window_size;
-  int rc = skipped ? VIDO_OK : partial_batch(ctx, window, st);
+  int rc = ba_finish(ctx);  // the previous frame's window, solved while this frame was tracked
+  if (rc) return rc;
+  rc = skipped ? VIDO_OK : ba_start(ctx, window, st);
   if (st) st->ms_ba = now_ms() - t4;
   ts->f_id++;
   if (rc) return rc;
@@ -563,6 +575,7 @@ int trk_track_chunk(vido_ctx* ctx, const vido_frame_inputs* in, int nframes, flo
   const vido_config& c = ctx->cfg;
   cudaStream_t s = ctx->stream;
   const size_t px = (size_t)c.width * c.height;
+  if (ts->ba_pending) { vido_lm_stats ls; ba_collect(ctx, &ts->ba_pr, &ls); ts->ba_pending = false; }  // left by a failed call
   int done = 0;
   while (done < nframes) {
     const int B = std::min(ts->capB, nframes - done);
@@ -614,7 +627,7 @@ int trk_track_chunk(vido_ctx* ctx, const vido_frame_inputs* in, int nframes, flo
     }
     done += B;
   }
-  return VIDO_OK;
+  return ba_finish(ctx);  // drain: stats and map are final when the call returns
 }
 
 int trk_num_frames(vido_ctx* ctx) { return (int)((TrackState*)ctx->trk)->map.size(); }
