@@ -222,6 +222,12 @@ typedef struct vido_track_stats {
 /* Tcw_out: nframes x 16 floats (what TrackRGBD returns per frame); stats may be NULL.  Returns VIDO_OK or <0. */
 int vido_track_frames(vido_ctx* ctx, const vido_frame_inputs* frames, int nframes, float* Tcw_out, vido_track_stats* stats);
 int vido_track_reset(vido_ctx* ctx);
+/* Optional hint: start copying the HOST frames that the next vido_track_frames call will pass (at most max_batch of them are
+ * taken) while the context is busy with the current call.  The copy runs on its own stream into a second set of input
+ * buffers; vido_track_frames recognises the frames by the image pointer of the first one.  The host buffers must stay
+ * unchanged until that call returns.  No reference counterpart (the reference reads cv::Mat inputs synchronously,
+ * src/System.cc:51-63); results are identical with or without the hint. */
+int vido_track_prefetch(vido_ctx* ctx, const vido_frame_inputs* frames, int nframes);
 /* Map accessors (include/Map.h:44-97): number of frames, vmCameraPose (Twc, refined by the window optimisation),
  * per-frame static features vpFeatSta / vfDepSta / vp3DPointSta / vnAssoSta */
 int vido_map_num_frames(vido_ctx* ctx);

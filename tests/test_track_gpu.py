@@ -72,6 +72,25 @@ def test_chunking_does_not_change_results(pkg):
         assert np.array_equal(T, outs[0][0]) and np.array_equal(P, outs[0][1])
 
 
+def test_prefetch_hint_does_not_change_results(pkg):
+    """vido_track_prefetch only moves the host->device copy of the next call's frames onto the copy stream"""
+    cam = synth.SMALL
+    frames = _sequence(cam, 78, 8, flow_noise=0.05, depth_noise=0.005)
+    host = [dict(image=f["gray"].numpy().copy(), depth=f["depth_in"].numpy().copy(), flow=f["flow"].numpy().copy(),
+                 mask=f["mask"].numpy().copy()) for f in frames]
+    outs = []
+    for hint in (False, True):
+        ctx = pkg.Context(pkg.default_config(width=640, height=480, fx=cam["fx"], fy=cam["fy"], cx=cam["cx"], cy=cam["cy"],
+                                             bf=cam["bf"], max_batch=4))
+        if hint:
+            ctx.track_prefetch(host[4:8])
+        T0, _ = ctx.track_frames(host[0:4], want_stats=False)
+        T1, _ = ctx.track_frames(host[4:8], want_stats=False)
+        outs.append((np.concatenate([T0, T1]).copy(), ctx.map_poses().copy()))
+        ctx.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
 def test_rgb_input_and_depth_write_back(pkg):
     """3-channel input goes through the gray conversion kernel; write_back_depth reproduces the reference's in-place
     depth pre-scale"""

@@ -126,6 +126,8 @@ def load_library():
     lib.vido_get_kernel_times.argtypes = [vp, vp, vp, vp]
     lib.vido_track_frames.argtypes = [vp, C.POINTER(FrameInputs), C.c_int, vp, C.POINTER(TrackStats)]
     lib.vido_track_reset.argtypes = [vp]
+    lib.vido_track_prefetch.argtypes = [vp, C.POINTER(FrameInputs), C.c_int]
+    lib.vido_track_prefetch.restype = C.c_int
     lib.vido_map_num_frames.argtypes = [vp]
     lib.vido_map_get_poses.argtypes = [vp, vp, C.c_int]
     lib.vido_map_get_static.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int]
@@ -297,9 +299,7 @@ class Context:
                 pr.ransac_inliers, pr.mm_inliers)
 
     # ---- per-frame driver
-    def track_frames(self, frames, want_stats=True):
-        """frames: list of dicts {image, depth, flow, mask} holding either numpy host arrays or integer device
-        pointers (then pass on_device=True and channels).  Returns (Tcw [n,4,4] f32, [stats dict] or None)."""
+    def _frame_inputs(self, frames):
         n = len(frames)
         arr = (FrameInputs * n)()
         keep = []
@@ -308,6 +308,9 @@ class Context:
             if f.get("on_device"):
                 fi.image, fi.depth, fi.flow, fi.mask = f["image"], f["depth"], f["flow"], f["mask"]
                 fi.channels, fi.on_device = int(f["channels"]), 1
+            elif f.get("host_ptrs"):  # raw host pointers (e.g. pinned torch tensors): image, depth, flow, mask + channels
+                fi.image, fi.depth, fi.flow, fi.mask = f["image"], f["depth"], f["flow"], f["mask"]
+                fi.channels, fi.on_device = int(f["channels"]), 0
             else:
                 img = np.ascontiguousarray(f["image"], np.uint8); dep = np.ascontiguousarray(f["depth"], np.float32)
                 flo = np.ascontiguousarray(f["flow"], np.float32); msk = np.ascontiguousarray(f["mask"], np.int32)
@@ -316,10 +319,23 @@ class Context:
                 fi.channels, fi.on_device = (1 if img.ndim == 2 else img.shape[2]), 0
             fi.write_back_depth = int(f.get("write_back_depth", 0))
             fi.timestamp = float(f.get("timestamp", 0.1 * k))
+        return arr, keep
+
+    def track_frames(self, frames, want_stats=True):
+        """frames: list of dicts {image, depth, flow, mask} holding either numpy host arrays or integer device
+        pointers (then pass on_device=True and channels).  Returns (Tcw [n,4,4] f32, [stats dict] or None)."""
+        n = len(frames)
+        arr, keep = self._frame_inputs(frames)
         T = np.zeros((n, 16), np.float32)
         st = (TrackStats * n)() if want_stats else None
         self._check(self.lib.vido_track_frames(self.h, arr, n, _ptr(T), st))
         return T.reshape(n, 4, 4), ([s.as_dict() for s in st] if want_stats else None)
+
+    def track_prefetch(self, frames):
+        """Hint: start the host->device copy of the frames the NEXT track_frames call will pass (same buffers)."""
+        arr, keep = self._frame_inputs(frames)
+        self._prefetch_keep = keep  # the host arrays must outlive the copy
+        self._check(self.lib.vido_track_prefetch(self.h, arr, len(frames)))
 
     def track_reset(self):
         self._check(self.lib.vido_track_reset(self.h))

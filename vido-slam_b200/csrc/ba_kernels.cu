@@ -1037,11 +1037,14 @@ struct BaWorkspace {
   int capW = 0, capP = 0, capM = 0;
   int cluster = 8;
   char* d_base = nullptr;            // solver workspace
-  char* d_in = nullptr;              // input block
+  char* d_in2[2] = {nullptr, nullptr};  // input blocks (two: the next problem is staged while the current one is solved)
   char* d_out = nullptr;             // output block
   BaArgs args;
-  char* h_in = nullptr;              // pinned mirrors
+  char* h_in2[2] = {nullptr, nullptr};  // pinned mirrors
   char* h_out = nullptr;
+  int slot = 0;                      // staging slot of the problem being prepared / in flight
+  bool prepared = false;
+  BaArgs a_prep;                     // kernel arguments of the prepared problem
   size_t in_bytes = 0, out_bytes = 0;
   // the solve runs on its own stream so that a caller may overlap it with other work (ba_submit ... ba_collect)
   cudaStream_t stream = nullptr;
@@ -1049,7 +1052,8 @@ struct BaWorkspace {
   bool pending = false;
   bool want_records = false;
   int W = 0, P = 0, M = 0;
-  std::vector<int> newid, oldid, first, len, last, keycnt;
+  std::vector<int> newid2[2], oldid, first, len, last, keycnt;  // newid per staging slot (needed again at collect)
+  int inflight_slot = 0;
 };
 
 static size_t al(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -1100,9 +1104,11 @@ int ba_setup(vido_ctx* ctx, int capW, int capP, int capM) {
   p = nullptr; carve_outputs(p, tmp, capW, capP); ws->out_bytes = (size_t)p;
   VIDO_CUDA(cudaMalloc(&ws->d_base, need));
   VIDO_CUDA(cudaMemset(ws->d_base, 0, need));
-  VIDO_CUDA(cudaMalloc(&ws->d_in, ws->in_bytes));
+  for (int k = 0; k < 2; k++) {
+    VIDO_CUDA(cudaMalloc(&ws->d_in2[k], ws->in_bytes));
+    VIDO_CUDA(cudaMallocHost(&ws->h_in2[k], ws->in_bytes));
+  }
   VIDO_CUDA(cudaMalloc(&ws->d_out, ws->out_bytes));
-  VIDO_CUDA(cudaMallocHost(&ws->h_in, ws->in_bytes));
   VIDO_CUDA(cudaMallocHost(&ws->h_out, ws->out_bytes));
   memset(&ws->args, 0, sizeof ws->args);
   p = ws->d_base;
@@ -1136,22 +1142,27 @@ void ba_teardown(vido_ctx* ctx) {
   if (ws->stream) { cudaStreamSynchronize(ws->stream); cudaStreamDestroy(ws->stream); }
   if (ws->ev0) cudaEventDestroy(ws->ev0);
   if (ws->ev1) cudaEventDestroy(ws->ev1);
-  cudaFree(ws->d_base); cudaFree(ws->d_in); cudaFree(ws->d_out);
-  cudaFreeHost(ws->h_in); cudaFreeHost(ws->h_out);
+  cudaFree(ws->d_base); cudaFree(ws->d_in2[0]); cudaFree(ws->d_in2[1]); cudaFree(ws->d_out);
+  cudaFreeHost(ws->h_in2[0]); cudaFreeHost(ws->h_in2[1]); cudaFreeHost(ws->h_out);
   delete ws;
   ctx->ba = nullptr;
 }
 
-// ba_submit: lay the problem out, copy it to the device and launch the solve on the BA stream (returns at once);
-// ba_collect: wait for it and write the results back into the problem's arrays, which must stay alive in between.
-int ba_submit(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records) {
+// The solve is split in three host steps so that a caller can hide everything but the solve itself:
+//   ba_prepare: lay the problem's STRUCTURE and observations out in the free staging slot (may run while the previous
+//               problem is still being solved; pr->poses / rel_motion / points are not read);
+//   ba_launch:  add the state values (poses, odometry, points), copy the block and launch on the BA stream;
+//   ba_collect: wait and write the results back into the problem's arrays, which must stay alive in between.
+int ba_prepare(vido_ctx* ctx, const vido_ba_problem* pr) {
   BaWorkspace* ws = (BaWorkspace*)ctx->ba;
-  if (ws->pending) { ctx->err = "a window BA is already in flight"; return VIDO_ERR_ARG; }
+  ws->prepared = false;
   const int W = pr->n_poses, P = pr->n_points, M = pr->n_obs;
   if (W < 0 || P < 0 || M < 0) return VIDO_ERR_ARG;
   if (W > ws->capW || P > ws->capP || M > ws->capM) { ctx->err = "BA problem exceeds the context capacity"; return VIDO_ERR_CAPACITY; }
-  cudaStream_t s = ws->stream;
-  ws->W = W; ws->P = P; ws->M = M; ws->want_records = want_records;
+  const int slot = ws->pending ? (ws->inflight_slot ^ 1) : ws->slot;
+  ws->slot = slot;
+  char* const h_in = ws->h_in2[slot];
+  char* const d_in = ws->d_in2[slot];
   BaArgs a = ws->args;
   a.W = W; a.P = P; a.M = M;
   a.max_iterations = pr->max_iterations;
@@ -1164,17 +1175,14 @@ int ba_submit(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records) {
   // ---- host-side layout: tracks sorted by (first pose, length descending); observations pose-major (see the header)
   BaArgs h;  // host view of the input block (same carving as the device view)
   {
-    char* hp = ws->h_in; carve_inputs(hp, h, W, P, M);
-    char* dp = ws->d_in; carve_inputs(dp, a, W, P, M);
+    char* hp = h_in; carve_inputs(hp, h, W, P, M);
+    char* dp = d_in; carve_inputs(dp, a, W, P, M);
     char* dq = ws->d_out; carve_outputs(dq, a, W, P);
   }
-  float* h_poses = (float*)h.poses_f32; float* h_rel = (float*)h.rel_f32;
   int* h_obs_pose = (int*)h.obs_pose; int* h_obs_point = (int*)h.obs_point; float* h_xyz = (float*)h.obs_xyz;
   int* h_pt_len = (int*)h.pt_len; int* h_pt_first = (int*)h.pt_first; float* h_pts = (float*)h.points_f32;
   int* h_grp = (int*)h.grp_start; int* h_cnt = (int*)h.cnt_gt; int* h_off = (int*)h.off; int* h_base = (int*)h.pose_base;
-  memcpy(h_poses, pr->poses, sizeof(float) * 16 * W);
-  if (W > 1) memcpy(h_rel, pr->rel_motion, sizeof(float) * 16 * (W - 1));
-  std::vector<int>&first = ws->first, &len = ws->len, &last = ws->last, &keycnt = ws->keycnt, &newid = ws->newid, &oldid = ws->oldid;
+  std::vector<int>&first = ws->first, &len = ws->len, &last = ws->last, &keycnt = ws->keycnt, &newid = ws->newid2[slot], &oldid = ws->oldid;
   first.assign(P, 1 << 30); len.assign(P, 0); last.assign(P, -1);
   for (int o = 0; o < M; o++) {
     const int l = pr->obs_point[o], p = pr->obs_pose[o];
@@ -1215,7 +1223,6 @@ int ba_submit(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records) {
     const int l = oldid[n];
     h_pt_len[n] = len[l];
     h_pt_first[n] = first[l];
-    h_pts[3 * n] = pr->points[3 * l]; h_pts[3 * n + 1] = pr->points[3 * l + 1]; h_pts[3 * n + 2] = pr->points[3 * l + 2];
   }
   for (int o = 0; o < M; o++) {
     const int l = pr->obs_point[o], p = pr->obs_pose[o], n = newid[l], f = first[l];
@@ -1224,9 +1231,36 @@ int ba_submit(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records) {
     h_obs_point[q] = n;
     h_xyz[q] = pr->obs_xyz[3 * o]; h_xyz[(size_t)M + q] = pr->obs_xyz[3 * o + 1]; h_xyz[2 * (size_t)M + q] = pr->obs_xyz[3 * o + 2];
   }
+  ws->a_prep = a;
+  ws->prepared = true;
+  return VIDO_OK;
+}
+
+int ba_launch(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records) {
+  BaWorkspace* ws = (BaWorkspace*)ctx->ba;
+  if (ws->pending) { ctx->err = "a window BA is already in flight"; return VIDO_ERR_ARG; }
+  if (!ws->prepared) { ctx->err = "ba_launch without ba_prepare"; return VIDO_ERR_ARG; }
+  ws->prepared = false;
+  const int W = pr->n_poses, P = pr->n_points, M = pr->n_obs;
+  const int slot = ws->slot;
+  cudaStream_t s = ws->stream;
+  ws->W = W; ws->P = P; ws->M = M; ws->want_records = want_records;
+  const BaArgs a = ws->a_prep;
+  {  // state values
+    BaArgs h;
+    char* hp = ws->h_in2[slot]; carve_inputs(hp, h, W, P, M);
+    float* h_poses = (float*)h.poses_f32; float* h_rel = (float*)h.rel_f32; float* h_pts = (float*)h.points_f32;
+    memcpy(h_poses, pr->poses, sizeof(float) * 16 * W);
+    if (W > 1) memcpy(h_rel, pr->rel_motion, sizeof(float) * 16 * (W - 1));
+    const std::vector<int>& newid = ws->newid2[slot];
+    for (int l = 0; l < P; l++) {
+      const int n = newid[l];
+      h_pts[3 * n] = pr->points[3 * l]; h_pts[3 * n + 1] = pr->points[3 * l + 1]; h_pts[3 * n + 2] = pr->points[3 * l + 2];
+    }
+  }
   {
-    char* hp = ws->h_in; BaArgs t2; carve_inputs(hp, t2, W, P, M);
-    VIDO_CUDA(cudaMemcpyAsync(ws->d_in, ws->h_in, (size_t)(hp - ws->h_in), cudaMemcpyHostToDevice, s));
+    char* hp = ws->h_in2[slot]; BaArgs t2; carve_inputs(hp, t2, W, P, M);
+    VIDO_CUDA(cudaMemcpyAsync(ws->d_in2[slot], ws->h_in2[slot], (size_t)(hp - ws->h_in2[slot]), cudaMemcpyHostToDevice, s));
   }
   const size_t smem = sizeof(double) * ((size_t)(6 * W + 1) * (6 * W + 1) + 36 * W);
   {
@@ -1249,7 +1283,14 @@ int ba_submit(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records) {
     VIDO_CUDA(cudaMemcpyAsync(ws->h_out, ws->d_out, out_used, cudaMemcpyDeviceToHost, s));
   }
   ws->pending = true;
+  ws->inflight_slot = slot;
   return VIDO_OK;
+}
+
+int ba_submit(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records) {
+  int rc = ba_prepare(ctx, pr);
+  if (rc) return rc;
+  return ba_launch(ctx, pr, want_records);
 }
 
 int ba_collect(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st) {
@@ -1257,7 +1298,7 @@ int ba_collect(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st) {
   if (!ws->pending) { ctx->err = "no window BA in flight"; return VIDO_ERR_ARG; }
   ws->pending = false;
   const int W = ws->W, P = ws->P, M = ws->M;
-  const std::vector<int>& newid = ws->newid;
+  const std::vector<int>& newid = ws->newid2[ws->inflight_slot];
   VIDO_CUDA(cudaStreamSynchronize(ws->stream));
   BaArgs ho;
   { char* hq = ws->h_out; carve_outputs(hq, ho, W, P); }

@@ -131,6 +131,7 @@ int vido_orb_extract_dev(vido_ctx* ctx, const uint8_t* d_gray, int nframes, size
     return VIDO_ERR_ARG;
   }
   cudaSetDevice(ctx->device);
+  trk_quiesce(ctx);
   int rc = orb_run(ctx, d_gray, nframes, frame_stride, stride, d_out, cap_per_frame, d_n_out);
   if (rc != VIDO_OK) return rc;
   if (sync) return check_dev_err(ctx);
@@ -144,6 +145,7 @@ int vido_orb_extract(vido_ctx* ctx, const uint8_t* gray, int nframes, size_t fra
     return VIDO_ERR_ARG;
   }
   cudaSetDevice(ctx->device);
+  trk_quiesce(ctx);
   const vido_config& c = ctx->cfg;
   int done = 0;
   while (done < nframes) {
@@ -293,6 +295,12 @@ int vido_track_frames(vido_ctx* ctx, const vido_frame_inputs* frames, int nframe
   return trk_track_chunk(ctx, frames, nframes, Tcw_out, stats);
 }
 int vido_track_reset(vido_ctx* ctx) { return ctx ? trk_reset(ctx) : VIDO_ERR_ARG; }
+
+int vido_track_prefetch(vido_ctx* ctx, const vido_frame_inputs* frames, int nframes) {
+  if (!ctx || (!frames && nframes > 0)) return VIDO_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  return trk_prefetch(ctx, frames, nframes);
+}
 int vido_map_num_frames(vido_ctx* ctx) { return ctx ? trk_num_frames(ctx) : VIDO_ERR_ARG; }
 int vido_map_get_poses(vido_ctx* ctx, float* poses, int cap) { return (ctx && poses) ? trk_get_map_poses(ctx, poses, cap) : VIDO_ERR_ARG; }
 int vido_map_get_static(vido_ctx* ctx, int frame, float* xy, float* depth, float* p3, int32_t* asso, int cap) {

@@ -117,6 +117,8 @@ int ba_setup(vido_ctx* ctx, int capW, int capP, int capM);
 void ba_teardown(vido_ctx* ctx);
 int ba_partial_host(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st);
 int ba_submit(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records);
+int ba_prepare(vido_ctx* ctx, const vido_ba_problem* pr);
+int ba_launch(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records);
 int ba_collect(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st);
 
 // poseopt_kernels.cu
@@ -144,6 +146,8 @@ int trk_setup(vido_ctx* ctx);
 void trk_teardown(vido_ctx* ctx);
 int trk_reset(vido_ctx* ctx);
 int trk_track_chunk(vido_ctx* ctx, const vido_frame_inputs* in, int nframes, float* Tcw_out, vido_track_stats* stats);
+int trk_prefetch(vido_ctx* ctx, const vido_frame_inputs* in, int nframes);
+void trk_quiesce(vido_ctx* ctx);
 int trk_num_frames(vido_ctx* ctx);
 int trk_get_map_poses(vido_ctx* ctx, float* poses, int cap);
 int trk_get_static(vido_ctx* ctx, int frame, float* xy, float* depth, float* p3, int32_t* asso, int cap);

@@ -75,24 +75,44 @@ struct TrackState {
   std::vector<float> last_keys, last_depth, last_corres, last_flow;  // mpLastFrame mvStatKeys / mvStatDepth / mvCorres / mvFlowNext
   int f_id = 0;
   int ba_epoch = 0;
-  // window BA in flight (runs on its own stream while the next frame is tracked)
-  bool ba_pending = false;
-  int ba_start = 0, ba_end = 0;
-  vido_track_stats* ba_st = nullptr;
-  vido_ba_problem ba_pr;
-  std::vector<float> ba_poses, ba_rel, ba_pts, ba_oxyz;
-  std::vector<int> ba_op, ba_ol;
-  std::vector<int> ba_ofeat;   // per observation: feature index inside its frame, for the write-back
+  // window BA jobs: [fly] is being solved on the BA stream while the next frame is tracked and its job [fly ^ 1] is staged
+  struct BaJob {
+    int start = 0, end = 0;
+    vido_track_stats* st = nullptr;
+    vido_ba_problem pr;
+    std::vector<float> poses, rel, pts, oxyz;
+    std::vector<int> op, ol;
+    std::vector<int> ofeat;          // per observation: feature index inside its frame, for the write-back
+    std::vector<int> pframe, pfeat;  // per point: frame / feature of its first observation (initial position)
+  } job[2];
+  bool ba_pending = false, ba_staged = false;
+  int ba_fly = 0, ba_stage_slot = 0;
   // device buffers of one chunk
   int capB = 0;
-  uint8_t* d_img = nullptr;      // [B][H][W*3] or gray
-  uint8_t* d_gray = nullptr;     // [B][H][W]
-  float* d_depth = nullptr;      // [B][H][W]
-  float* d_flow = nullptr;       // [B][H][W][2]
-  int32_t* d_mask = nullptr;     // [B][H][W]
-  vido_keypoint* d_kp = nullptr; int32_t* d_nkp = nullptr;
-  int32_t* d_kpmask = nullptr; float* d_kpdepth = nullptr; float* d_kpflow = nullptr;
-  int32_t* d_asidx = nullptr; float* d_ascor = nullptr; float* d_asflow = nullptr; float* d_asdepth = nullptr; int32_t* d_asn = nullptr;
+  // Two pipeline slots.  A slot holds the inputs of one batch on the device, its front-end outputs on the device and
+  // their pinned host mirror.  While the back-end walks through the batch of slot s, the next batch (or the first batch
+  // of the next call, see vido_track_prefetch) is copied (copy stream) and run through the front-end (front-end stream)
+  // in slot s ^ 1.
+  struct FeSlot {
+    uint8_t* d_img = nullptr;   // [B][H][W*3] or gray   } own input buffers (host / scattered inputs are copied here)
+    float* d_depth = nullptr;   // [B][H][W]             }
+    float* d_flow = nullptr;    // [B][H][W][2]          }
+    int32_t* d_mask = nullptr;  // [B][H][W]             }
+    char* d_out = nullptr;      // front-end outputs, one block: kp | kpmask | kpdepth | kpflow | asidx | ascor | asflow | asdepth | nkp | asn | err
+    char* h_out = nullptr;      // pinned mirror
+    vido_keypoint* d_kp; int32_t* d_kpmask; float* d_kpdepth; float* d_kpflow;
+    int32_t* d_asidx; float* d_ascor; float* d_asflow; float* d_asdepth; int32_t* d_nkp; int32_t* d_asn; int32_t* d_flag;
+    cudaEvent_t copied = nullptr, done = nullptr, ev0 = nullptr, ev1 = nullptr;
+    bool launched = false;
+    int B = 0, channels = 0;
+    const void* key = nullptr;  // identity of the batch: image pointer of its first frame
+    const uint8_t* in_img = nullptr; const float* in_depth = nullptr; const float* in_flow = nullptr; const int32_t* in_mask = nullptr;  // inputs the kernels read
+  } fe[2];
+  size_t fe_out_bytes = 0;
+  int fe_cur = 0;
+  uint8_t* d_gray = nullptr;     // [B][H][W] (front-end stream only)
+  cudaStream_t copy_stream = nullptr, fe_stream = nullptr;
+  std::vector<vido_frame_inputs> hint;  // frames announced by vido_track_prefetch
   float* d_q = nullptr; int32_t* d_qmask = nullptr; float* d_qdepth = nullptr; float* d_qflow = nullptr;  // per-frame queries
   float* d_check = nullptr; uint8_t* d_used = nullptr;
   // pinned host mirrors
@@ -147,17 +167,33 @@ int trk_setup(vido_ctx* ctx) {
   ts->capB = B;
   ts->kp_cap = ctx->kp_cap;
   const size_t px = (size_t)c.width * c.height;
-  VIDO_CUDA(cudaMalloc(&ts->d_img, px * 3 * B));
-  VIDO_CUDA(cudaMalloc(&ts->d_gray, px * B));
-  VIDO_CUDA(cudaMalloc(&ts->d_depth, px * 4 * B));
-  VIDO_CUDA(cudaMalloc(&ts->d_flow, px * 8 * B));
-  VIDO_CUDA(cudaMalloc(&ts->d_mask, px * 4 * B));
   const size_t K = (size_t)ts->kp_cap * B;
-  VIDO_CUDA(cudaMalloc(&ts->d_kp, sizeof(vido_keypoint) * K));
-  VIDO_CUDA(cudaMalloc(&ts->d_nkp, sizeof(int32_t) * B));
-  VIDO_CUDA(cudaMalloc(&ts->d_kpmask, 4 * K)); VIDO_CUDA(cudaMalloc(&ts->d_kpdepth, 4 * K)); VIDO_CUDA(cudaMalloc(&ts->d_kpflow, 8 * K));
-  VIDO_CUDA(cudaMalloc(&ts->d_asidx, 4 * K)); VIDO_CUDA(cudaMalloc(&ts->d_ascor, 8 * K)); VIDO_CUDA(cudaMalloc(&ts->d_asflow, 8 * K));
-  VIDO_CUDA(cudaMalloc(&ts->d_asdepth, 4 * K)); VIDO_CUDA(cudaMalloc(&ts->d_asn, 4 * B));
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t o_kp = 0, o_kpmask = o_kp + al(sizeof(vido_keypoint) * K), o_kpdepth = o_kpmask + al(4 * K), o_kpflow = o_kpdepth + al(4 * K),
+               o_asidx = o_kpflow + al(8 * K), o_ascor = o_asidx + al(4 * K), o_asflow = o_ascor + al(8 * K), o_asdepth = o_asflow + al(8 * K),
+               o_nkp = o_asdepth + al(4 * K), o_asn = o_nkp + al(4 * (size_t)B), o_flag = o_asn + al(4 * (size_t)B);
+  ts->fe_out_bytes = o_flag + 256;
+  for (int k = 0; k < 2; k++) {
+    TrackState::FeSlot& F = ts->fe[k];
+    VIDO_CUDA(cudaMalloc(&F.d_img, px * 3 * B));
+    VIDO_CUDA(cudaMalloc(&F.d_depth, px * 4 * B));
+    VIDO_CUDA(cudaMalloc(&F.d_flow, px * 8 * B));
+    VIDO_CUDA(cudaMalloc(&F.d_mask, px * 4 * B));
+    VIDO_CUDA(cudaMalloc(&F.d_out, ts->fe_out_bytes));
+    VIDO_CUDA(cudaMemset(F.d_out, 0, ts->fe_out_bytes));
+    VIDO_CUDA(cudaMallocHost(&F.h_out, ts->fe_out_bytes));
+    F.d_kp = (vido_keypoint*)(F.d_out + o_kp); F.d_kpmask = (int32_t*)(F.d_out + o_kpmask); F.d_kpdepth = (float*)(F.d_out + o_kpdepth);
+    F.d_kpflow = (float*)(F.d_out + o_kpflow); F.d_asidx = (int32_t*)(F.d_out + o_asidx); F.d_ascor = (float*)(F.d_out + o_ascor);
+    F.d_asflow = (float*)(F.d_out + o_asflow); F.d_asdepth = (float*)(F.d_out + o_asdepth); F.d_nkp = (int32_t*)(F.d_out + o_nkp);
+    F.d_asn = (int32_t*)(F.d_out + o_asn); F.d_flag = (int32_t*)(F.d_out + o_flag);
+    VIDO_CUDA(cudaEventCreateWithFlags(&F.copied, cudaEventDisableTiming));
+    VIDO_CUDA(cudaEventCreateWithFlags(&F.done, cudaEventDisableTiming));
+    VIDO_CUDA(cudaEventCreate(&F.ev0));
+    VIDO_CUDA(cudaEventCreate(&F.ev1));
+  }
+  VIDO_CUDA(cudaMalloc(&ts->d_gray, px * B));
+  VIDO_CUDA(cudaStreamCreateWithFlags(&ts->copy_stream, cudaStreamNonBlocking));
+  VIDO_CUDA(cudaStreamCreateWithFlags(&ts->fe_stream, cudaStreamNonBlocking));
   VIDO_CUDA(cudaMalloc(&ts->d_q, 8 * ts->q_cap)); VIDO_CUDA(cudaMalloc(&ts->d_qmask, 4 * ts->q_cap));
   VIDO_CUDA(cudaMalloc(&ts->d_qdepth, 4 * ts->q_cap)); VIDO_CUDA(cudaMalloc(&ts->d_qflow, 8 * ts->q_cap));
   VIDO_CUDA(cudaMalloc(&ts->d_check, 8 * ts->q_cap)); VIDO_CUDA(cudaMalloc(&ts->d_used, ts->kp_cap));
@@ -167,9 +203,17 @@ int trk_setup(vido_ctx* ctx) {
 void trk_teardown(vido_ctx* ctx) {
   TrackState* ts = (TrackState*)ctx->trk;
   if (!ts) return;
-  cudaFree(ts->d_img); cudaFree(ts->d_gray); cudaFree(ts->d_depth); cudaFree(ts->d_flow); cudaFree(ts->d_mask);
-  cudaFree(ts->d_kp); cudaFree(ts->d_nkp); cudaFree(ts->d_kpmask); cudaFree(ts->d_kpdepth); cudaFree(ts->d_kpflow);
-  cudaFree(ts->d_asidx); cudaFree(ts->d_ascor); cudaFree(ts->d_asflow); cudaFree(ts->d_asdepth); cudaFree(ts->d_asn);
+  if (ts->copy_stream) { cudaStreamSynchronize(ts->copy_stream); cudaStreamDestroy(ts->copy_stream); }
+  if (ts->fe_stream) { cudaStreamSynchronize(ts->fe_stream); cudaStreamDestroy(ts->fe_stream); }
+  for (int k = 0; k < 2; k++) {
+    TrackState::FeSlot& F = ts->fe[k];
+    cudaFree(F.d_img); cudaFree(F.d_depth); cudaFree(F.d_flow); cudaFree(F.d_mask); cudaFree(F.d_out); cudaFreeHost(F.h_out);
+    if (F.copied) cudaEventDestroy(F.copied);
+    if (F.done) cudaEventDestroy(F.done);
+    if (F.ev0) cudaEventDestroy(F.ev0);
+    if (F.ev1) cudaEventDestroy(F.ev1);
+  }
+  cudaFree(ts->d_gray);
   cudaFree(ts->d_q); cudaFree(ts->d_qmask); cudaFree(ts->d_qdepth); cudaFree(ts->d_qflow); cudaFree(ts->d_check); cudaFree(ts->d_used);
   delete ts;
   ctx->trk = nullptr;
@@ -177,74 +221,128 @@ void trk_teardown(vido_ctx* ctx) {
 
 int trk_reset(vido_ctx* ctx) {
   TrackState* ts = (TrackState*)ctx->trk;
-  if (ts->ba_pending) { vido_lm_stats ls; ba_collect(ctx, &ts->ba_pr, &ls); ts->ba_pending = false; }
+  if (ts->ba_pending) { vido_lm_stats ls; ba_collect(ctx, &ts->job[ts->ba_fly].pr, &ls); ts->ba_pending = false; }
   ts->map.clear(); ts->tracks.clear();
   ts->initialised = false; ts->has_velocity = false; ts->f_id = 0; ts->ba_epoch = 0;
+  cudaStreamSynchronize(ts->copy_stream); cudaStreamSynchronize(ts->fe_stream);
+  ts->fe[0].launched = ts->fe[1].launched = false; ts->hint.clear();
   ts->last_keys.clear(); ts->last_depth.clear(); ts->last_corres.clear(); ts->last_flow.clear();
   return VIDO_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// front-end of a chunk: inputs resident on the device
+// front-end of a batch, asynchronous: fe_launch enqueues input copies (copy stream), gray conversion, ORB, association,
+// per-keypoint lookups and the device->host copy of the results (front-end stream); fe_collect waits and unpacks.
 // ---------------------------------------------------------------------------------------------------------
-static int front_end(vido_ctx* ctx, int B, const uint8_t* d_img, int channels, const float* d_depth, const float* d_flow,
-                     const int32_t* d_mask, std::vector<FrontFrame>& out) {
+__global__ void __launch_bounds__(256) h2d_stream_kernel(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, size_t bytes);
+static int prefetch_array(vido_ctx* ctx, cudaStream_t cs, void* dst, const void* src, size_t bytes);
+
+static int fe_launch(vido_ctx* ctx, TrackState::FeSlot& F, const vido_frame_inputs* in, int B) {
   TrackState* ts = (TrackState*)ctx->trk;
   const vido_config& c = ctx->cfg;
-  cudaStream_t s = ctx->stream;
   const size_t px = (size_t)c.width * c.height;
-  const uint8_t* d_gray = d_img;
-  cudaEventRecord(ctx->ev0, s);
-  if (channels == 3) {
-    int rc = orb_bgr_to_gray(ctx, d_img, B, px * 3, c.width * 3, ts->d_gray, px, c.width);
-    if (rc) return rc;
-    d_gray = ts->d_gray;
+  const vido_frame_inputs* f0 = in;
+  const int channels = f0->channels;
+  bool contiguous_dev = f0->on_device != 0;
+  for (int b = 0; b < B; b++) {
+    const vido_frame_inputs& f = in[b];
+    if (f.channels != channels || (f.on_device != 0) != (f0->on_device != 0) || (channels != 1 && channels != 3)) { ctx->err = "inconsistent frame inputs"; return VIDO_ERR_ARG; }
+    if (f.on_device) {
+      // device-resident frames are used in place when they are consecutive slices of one allocation
+      if (f.image != f0->image + (size_t)b * px * channels || f.depth != f0->depth + (size_t)b * px ||
+          f.flow != f0->flow + (size_t)b * px * 2 || f.mask != f0->mask + (size_t)b * px) contiguous_dev = false;
+    }
   }
-  int rc = orb_run(ctx, d_gray, B, px, c.width, ts->d_kp, ts->kp_cap, ts->d_nkp);
-  if (rc) return rc;
-  rc = assoc_frame_associate(ctx, ts->d_kp, ts->d_nkp, ts->kp_cap, d_depth, d_flow, d_mask, B, 1, ts->d_asidx, ts->d_ascor,
-                             ts->d_asflow, ts->d_asdepth, ts->d_asn, ts->kp_cap);
-  if (rc) return rc;
-  {
+  cudaStream_t fs = ts->fe_stream;
+  if (f0->on_device && contiguous_dev) {
+    F.in_img = f0->image; F.in_depth = f0->depth; F.in_flow = f0->flow; F.in_mask = f0->mask;
+  } else {
+    cudaStream_t cs = ts->copy_stream;
+    for (int b = 0; b < B; b++) {
+      const vido_frame_inputs& f = in[b];
+      if (f.on_device) {
+        VIDO_CUDA(cudaMemcpyAsync(F.d_img + (size_t)b * px * channels, f.image, px * channels, cudaMemcpyDeviceToDevice, cs));
+        VIDO_CUDA(cudaMemcpyAsync(F.d_depth + (size_t)b * px, f.depth, px * 4, cudaMemcpyDeviceToDevice, cs));
+        VIDO_CUDA(cudaMemcpyAsync(F.d_flow + (size_t)b * px * 2, f.flow, px * 8, cudaMemcpyDeviceToDevice, cs));
+        VIDO_CUDA(cudaMemcpyAsync(F.d_mask + (size_t)b * px, f.mask, px * 4, cudaMemcpyDeviceToDevice, cs));
+      } else {
+        int rc = prefetch_array(ctx, cs, F.d_img + (size_t)b * px * channels, f.image, px * channels);
+        if (!rc) rc = prefetch_array(ctx, cs, F.d_depth + (size_t)b * px, f.depth, px * 4);
+        if (!rc) rc = prefetch_array(ctx, cs, F.d_flow + (size_t)b * px * 2, f.flow, px * 8);
+        if (!rc) rc = prefetch_array(ctx, cs, F.d_mask + (size_t)b * px, f.mask, px * 4);
+        if (rc) return rc;
+      }
+    }
+    VIDO_CUDA(cudaEventRecord(F.copied, cs));
+    VIDO_CUDA(cudaStreamWaitEvent(fs, F.copied, 0));
+    F.in_img = F.d_img; F.in_depth = F.d_depth; F.in_flow = F.d_flow; F.in_mask = F.d_mask;
+  }
+  // the ORB / association entry points launch on ctx->stream: point it at the front-end stream for this section
+  cudaStream_t saved = ctx->stream;
+  ctx->stream = fs;
+  int rc = VIDO_OK;
+  do {
+    const uint8_t* d_gray = F.in_img;
+    cudaEventRecord(F.ev0, fs);
+    if (channels == 3) {
+      rc = orb_bgr_to_gray(ctx, F.in_img, B, px * 3, c.width * 3, ts->d_gray, px, c.width);
+      if (rc) break;
+      d_gray = ts->d_gray;
+    }
+    rc = orb_run(ctx, d_gray, B, px, c.width, F.d_kp, ts->kp_cap, F.d_nkp);
+    if (rc) break;
+    rc = assoc_frame_associate(ctx, F.d_kp, F.d_nkp, ts->kp_cap, F.in_depth, F.in_flow, F.in_mask, B, 1, F.d_asidx, F.d_ascor,
+                               F.d_asflow, F.d_asdepth, F.d_asn, ts->kp_cap);
+    if (rc) break;
     dim3 grid((ts->kp_cap + 255) / 256, B);
-    kp_lookup_kernel<<<grid, 256, 0, s>>>(ts->d_kp, ts->d_nkp, ts->kp_cap, c.width, c.height, d_depth, d_flow, d_mask, px,
-                                          c.choose_data, c.depth_map_factor, c.bf, ctx->mscale, ts->d_kpmask, ts->d_kpdepth, ts->d_kpflow);
+    kp_lookup_kernel<<<grid, 256, 0, fs>>>(F.d_kp, F.d_nkp, ts->kp_cap, c.width, c.height, F.in_depth, F.in_flow, F.in_mask, px,
+                                           c.choose_data, c.depth_map_factor, c.bf, ctx->mscale, F.d_kpmask, F.d_kpdepth, F.d_kpflow);
     ctx->launches++;
+    cudaEventRecord(F.ev1, fs);
+    if (cudaGetLastError() != cudaSuccess) { ctx->err = "front-end launch failed"; rc = VIDO_ERR_CUDA; break; }
+    if (cudaMemcpyAsync(F.d_flag, ctx->d_err, 4, cudaMemcpyDeviceToDevice, fs) != cudaSuccess ||
+        cudaMemcpyAsync(F.h_out, F.d_out, ts->fe_out_bytes, cudaMemcpyDeviceToHost, fs) != cudaSuccess ||
+        cudaEventRecord(F.done, fs) != cudaSuccess) { ctx->err = "front-end copy failed"; rc = VIDO_ERR_CUDA; break; }
+  } while (0);
+  ctx->stream = saved;
+  if (rc) return rc;
+  F.launched = true; F.B = B; F.channels = channels; F.key = (const void*)f0->image;
+  return VIDO_OK;
+}
+
+static int fe_collect(vido_ctx* ctx, TrackState::FeSlot& F, std::vector<FrontFrame>& out) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  VIDO_CUDA(cudaEventSynchronize(F.done));
+  F.launched = false;
+  const int B = F.B;
+  const size_t K = ts->kp_cap;
+  const char* h = F.h_out;
+  auto hp = [&](const void* dptr) { return h + ((const char*)dptr - F.d_out); };
+  if (*(const int32_t*)hp(F.d_flag)) {
+    ctx->err = "ORB front-end capacity flag set";
+    cudaMemsetAsync(ctx->d_err, 0, 4, ts->fe_stream);
+    return VIDO_ERR_CAPACITY;
   }
-  cudaEventRecord(ctx->ev1, s);
-  VIDO_CUDA(cudaGetLastError());
-  std::vector<int32_t> nkp(B), asn(B);
-  VIDO_CUDA(cudaMemcpyAsync(nkp.data(), ts->d_nkp, 4 * B, cudaMemcpyDeviceToHost, s));
-  VIDO_CUDA(cudaMemcpyAsync(asn.data(), ts->d_asn, 4 * B, cudaMemcpyDeviceToHost, s));
-  int32_t flag = 0;
-  VIDO_CUDA(cudaMemcpyAsync(&flag, ctx->d_err, 4, cudaMemcpyDeviceToHost, s));
-  VIDO_CUDA(cudaStreamSynchronize(s));
-  if (flag) { ctx->err = "ORB front-end capacity flag set"; cudaMemsetAsync(ctx->d_err, 0, 4, s); return VIDO_ERR_CAPACITY; }
   {
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) { ctx->t_ms[0] += ms; ctx->t_n[0] += B; }
+    if (cudaEventElapsedTime(&ms, F.ev0, F.ev1) == cudaSuccess) { ctx->t_ms[0] += ms; ctx->t_n[0] += B; }
   }
+  const int32_t* nkp = (const int32_t*)hp(F.d_nkp);
+  const int32_t* asn = (const int32_t*)hp(F.d_asn);
+  const vido_keypoint* kp = (const vido_keypoint*)hp(F.d_kp);
+  const int32_t* kpmask = (const int32_t*)hp(F.d_kpmask); const float* kpdepth = (const float*)hp(F.d_kpdepth);
+  const float* kpflow = (const float*)hp(F.d_kpflow); const int32_t* asidx = (const int32_t*)hp(F.d_asidx);
+  const float* ascor = (const float*)hp(F.d_ascor); const float* asflow = (const float*)hp(F.d_asflow); const float* asdepth = (const float*)hp(F.d_asdepth);
   out.resize(B);
   for (int b = 0; b < B; b++) {
     FrontFrame& f = out[b];
-    const int n = nkp[b], m = std::min(asn[b], ts->kp_cap);
-    const size_t o = (size_t)b * ts->kp_cap;
-    f.kps.resize(n); f.kp_mask.resize(n); f.kp_depth.resize(n); f.kp_flow.resize(2 * (size_t)n);
-    f.as_idx.resize(m); f.as_corres.resize(2 * (size_t)m); f.as_flow.resize(2 * (size_t)m); f.as_depth.resize(m);
-    if (n) {
-      VIDO_CUDA(cudaMemcpyAsync(f.kps.data(), ts->d_kp + o, sizeof(vido_keypoint) * n, cudaMemcpyDeviceToHost, s));
-      VIDO_CUDA(cudaMemcpyAsync(f.kp_mask.data(), ts->d_kpmask + o, 4 * n, cudaMemcpyDeviceToHost, s));
-      VIDO_CUDA(cudaMemcpyAsync(f.kp_depth.data(), ts->d_kpdepth + o, 4 * n, cudaMemcpyDeviceToHost, s));
-      VIDO_CUDA(cudaMemcpyAsync(f.kp_flow.data(), ts->d_kpflow + 2 * o, 8 * n, cudaMemcpyDeviceToHost, s));
-    }
-    if (m) {
-      VIDO_CUDA(cudaMemcpyAsync(f.as_idx.data(), ts->d_asidx + o, 4 * m, cudaMemcpyDeviceToHost, s));
-      VIDO_CUDA(cudaMemcpyAsync(f.as_corres.data(), ts->d_ascor + 2 * o, 8 * m, cudaMemcpyDeviceToHost, s));
-      VIDO_CUDA(cudaMemcpyAsync(f.as_flow.data(), ts->d_asflow + 2 * o, 8 * m, cudaMemcpyDeviceToHost, s));
-      VIDO_CUDA(cudaMemcpyAsync(f.as_depth.data(), ts->d_asdepth + o, 4 * m, cudaMemcpyDeviceToHost, s));
-    }
+    const size_t n = (size_t)std::min(std::max(nkp[b], 0), ts->kp_cap), m = (size_t)std::min(std::max(asn[b], 0), ts->kp_cap);
+    const size_t o = (size_t)b * K;
+    f.kps.assign(kp + o, kp + o + n); f.kp_mask.assign(kpmask + o, kpmask + o + n); f.kp_depth.assign(kpdepth + o, kpdepth + o + n);
+    f.kp_flow.assign(kpflow + 2 * o, kpflow + 2 * (o + n));
+    f.as_idx.assign(asidx + o, asidx + o + m); f.as_corres.assign(ascor + 2 * o, ascor + 2 * (o + m));
+    f.as_flow.assign(asflow + 2 * o, asflow + 2 * (o + m)); f.as_depth.assign(asdepth + o, asdepth + o + m);
   }
-  VIDO_CUDA(cudaStreamSynchronize(s));
   return VIDO_OK;
 }
 
@@ -268,53 +366,56 @@ static int query_maps(vido_ctx* ctx, const float* d_depth, const float* d_flow, 
 // ---------------------------------------------------------------------------------------------------------
 // window graph from the flat map (Optimizer.cc:220-362) + solve + write-back (:1056-1142)
 // ---------------------------------------------------------------------------------------------------------
-// The solve is asynchronous: ba_start launches it on the BA stream, ba_finish waits and writes the map back.  Nothing
-// the tracker reads between the two (last-frame keys/depth/pose, velocity) is touched by the BA (Tracking.cc:1320-1500
-// uses mpLastFrame / mVelocity only), so tracking frame k+1 while frame k's window is optimised gives the same result
-// as the reference's strictly sequential order.
+// The solve is asynchronous and its host work is split so that only the solve itself is serial:
+//   ba_stage(k)  -- graph STRUCTURE and observations of frame k's window (needs only the tracker's state) -- runs while the
+//                   window of frame k-1 is still being solved;
+//   ba_finish    -- waits for the window in flight and writes poses / points back into the map;
+//   ba_go(k)     -- reads the (just refined) poses and point positions and launches.
+// Nothing the tracker reads between launch and finish (last-frame keys / depth / pose, velocity) is touched by the BA
+// (Tracking.cc:1320-1500 uses mpLastFrame / mVelocity only), so the result equals the reference's sequential order.
 static int ba_finish(vido_ctx* ctx) {
   TrackState* ts = (TrackState*)ctx->trk;
   if (!ts->ba_pending) return VIDO_OK;
   ts->ba_pending = false;
+  TrackState::BaJob& J = ts->job[ts->ba_fly];
   vido_lm_stats ls;
-  int rc = ba_collect(ctx, &ts->ba_pr, &ls);
+  int rc = ba_collect(ctx, &J.pr, &ls);
   if (rc) return rc;
-  vido_track_stats* st = ts->ba_st;
-  if (st) { st->ba_iterations = ls.iterations; st->ba_trials = ls.total_trials; }
-  const int start = ts->ba_start, N = ts->ba_end;
+  if (J.st) { J.st->ba_iterations = ls.iterations; J.st->ba_trials = ls.total_trials; }
+  const int start = J.start, N = J.end;
   for (int i = start; i < N; i++) {
-    memcpy(ts->map[i].Twc, &ts->ba_poses[16 * (size_t)(i - start)], sizeof(float) * 16);
-    if (i > start) memcpy(ts->map[i].rel, &ts->ba_rel[16 * (size_t)(i - start - 1)], sizeof(float) * 16);
+    memcpy(ts->map[i].Twc, &J.poses[16 * (size_t)(i - start)], sizeof(float) * 16);
+    if (i > start) memcpy(ts->map[i].rel, &J.rel[16 * (size_t)(i - start - 1)], sizeof(float) * 16);
   }
   // every observation of an optimised point receives the optimised position (Optimizer.cc:1107-1122)
-  const size_t nobs = ts->ba_op.size();
-  const float* pts = ts->ba_pts.data();
+  const size_t nobs = J.op.size();
+  const float* pts = J.pts.data();
   for (size_t o = 0; o < nobs; o++) {
-    float* d = &ts->map[start + ts->ba_op[o]].p3[3 * (size_t)ts->ba_ofeat[o]];
-    const float* q = pts + 3 * (size_t)ts->ba_ol[o];
+    float* d = &ts->map[start + J.op[o]].p3[3 * (size_t)J.ofeat[o]];
+    const float* q = pts + 3 * (size_t)J.ol[o];
     d[0] = q[0]; d[1] = q[1]; d[2] = q[2];
   }
   return VIDO_OK;
 }
 
-static int ba_start(vido_ctx* ctx, int WINDOW, vido_track_stats* st) {
+static int ba_stage(vido_ctx* ctx, int WINDOW, vido_track_stats* st) {
   TrackState* ts = (TrackState*)ctx->trk;
+  ts->ba_staged = false;
   const int N = (int)ts->map.size();
   if (st) { st->ba_iterations = -1; st->ba_points = 0; st->ba_obs = 0; st->ba_trials = 0; }
   if (WINDOW <= 0) return VIDO_OK;
+  ts->ba_stage_slot = ts->ba_pending ? (ts->ba_fly ^ 1) : ts->ba_fly;
+  TrackState::BaJob& J = ts->job[ts->ba_stage_slot];
   const int start = N - WINDOW;
-  std::vector<float>&poses = ts->ba_poses, &rel = ts->ba_rel, &pts = ts->ba_pts, &oxyz = ts->ba_oxyz;
-  std::vector<int>&op = ts->ba_op, &ol = ts->ba_ol, &ofeat = ts->ba_ofeat;
-  poses.resize(16 * (size_t)WINDOW); rel.resize(16 * (size_t)std::max(WINDOW - 1, 0));
-  pts.clear(); oxyz.clear(); op.clear(); ol.clear(); ofeat.clear();
+  J.start = start; J.end = N; J.st = st;
+  J.poses.resize(16 * (size_t)WINDOW); J.rel.resize(16 * (size_t)std::max(WINDOW - 1, 0));
+  J.oxyz.clear(); J.op.clear(); J.ol.clear(); J.ofeat.clear(); J.pframe.clear(); J.pfeat.clear();
   const int epoch = ++ts->ba_epoch;
   const float invfx = 1.0f / ctx->cfg.fx, invfy = 1.0f / ctx->cfg.fy, cx = ctx->cfg.cx, cy = ctx->cfg.cy;
   int npts = 0;
   // a track enters the window graph iff it is at least 3 long and was born inside the window
   for (int i = start; i < N; i++) {
     MapFrame& F = ts->map[i];
-    memcpy(&poses[16 * (size_t)(i - start)], F.Twc, sizeof(float) * 16);
-    if (i != start) memcpy(&rel[16 * (size_t)(i - start - 1)], F.rel, sizeof(float) * 16);
     const int n = (int)F.depth.size();
     for (int j = 0; j < n; j++) {
       const int t = F.track[j];
@@ -325,31 +426,56 @@ static int ba_start(vido_ctx* ctx, int WINDOW, vido_track_stats* st) {
       if (F.pos[j] == 0) {
         pid = npts++;
         T.pid = pid; T.epoch = epoch;
-        pts.push_back(F.p3[3 * j]); pts.push_back(F.p3[3 * j + 1]); pts.push_back(F.p3[3 * j + 2]);
+        J.pframe.push_back(i); J.pfeat.push_back(j);
       }
       if (pid < 0) continue;
       const float z = F.depth[j], u = F.xy[2 * j], v = F.xy[2 * j + 1];
-      op.push_back(i - start); ol.push_back(pid); ofeat.push_back(j);
-      oxyz.push_back((u - cx) * z * invfx); oxyz.push_back((v - cy) * z * invfy); oxyz.push_back(z);
+      J.op.push_back(i - start); J.ol.push_back(pid); J.ofeat.push_back(j);
+      J.oxyz.push_back((u - cx) * z * invfx); J.oxyz.push_back((v - cy) * z * invfy); J.oxyz.push_back(z);
     }
   }
-  vido_ba_problem& pr = ts->ba_pr;
+  J.pts.resize(3 * (size_t)npts);
+  vido_ba_problem& pr = J.pr;
   memset(&pr, 0, sizeof pr);
   vido_ba_default_params(&pr);
-  pr.n_poses = WINDOW; pr.n_points = npts; pr.n_obs = (int)op.size();
-  pr.poses = poses.data(); pr.rel_motion = rel.data(); pr.points = pts.data();
-  pr.obs_pose = op.data(); pr.obs_point = ol.data(); pr.obs_xyz = oxyz.data();
+  pr.n_poses = WINDOW; pr.n_points = npts; pr.n_obs = (int)J.op.size();
+  pr.poses = J.poses.data(); pr.rel_motion = J.rel.data(); pr.points = J.pts.data();
+  pr.obs_pose = J.op.data(); pr.obs_point = J.ol.data(); pr.obs_xyz = J.oxyz.data();
   if (st) { st->ba_points = pr.n_points; st->ba_obs = pr.n_obs; }
-  int rc = ba_submit(ctx, &pr, false);
+  int rc = ba_prepare(ctx, &pr);
   if (rc) return rc;
-  ts->ba_pending = true; ts->ba_start = start; ts->ba_end = N; ts->ba_st = st;
+  ts->ba_staged = true;
+  return VIDO_OK;
+}
+
+static int ba_go(vido_ctx* ctx) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  if (!ts->ba_staged) return VIDO_OK;
+  ts->ba_staged = false;
+  const int slot = ts->ba_stage_slot;
+  TrackState::BaJob& J = ts->job[slot];
+  const int start = J.start, N = J.end;
+  for (int i = start; i < N; i++) {
+    const MapFrame& F = ts->map[i];
+    memcpy(&J.poses[16 * (size_t)(i - start)], F.Twc, sizeof(float) * 16);
+    if (i != start) memcpy(&J.rel[16 * (size_t)(i - start - 1)], F.rel, sizeof(float) * 16);
+  }
+  const size_t np = J.pframe.size();
+  for (size_t l = 0; l < np; l++) {
+    const float* q = &ts->map[J.pframe[l]].p3[3 * (size_t)J.pfeat[l]];
+    J.pts[3 * l] = q[0]; J.pts[3 * l + 1] = q[1]; J.pts[3 * l + 2] = q[2];
+  }
+  int rc = ba_launch(ctx, &J.pr, false);
+  if (rc) return rc;
+  ts->ba_pending = true;
+  ts->ba_fly = slot;
   return VIDO_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // back-end of one frame (sequential)
 // ---------------------------------------------------------------------------------------------------------
-static int back_end(vido_ctx* ctx, const FrontFrame& ff, int slot, const float* d_depth, const float* d_flow,
+static int back_end(vido_ctx* ctx, const FrontFrame& ff, int slot, const vido_keypoint* d_kp, const float* d_depth, const float* d_flow,
                     const int32_t* d_mask, float* Tcw_out, vido_track_stats* st) {
   TrackState* ts = (TrackState*)ctx->trk;
   const vido_config& c = ctx->cfg;
@@ -483,7 +609,7 @@ static int back_end(vido_ctx* ctx, const FrontFrame& ff, int slot, const float* 
         if (mcheck > 0) {
           if (mcheck > ts->q_cap) { ctx->err = "renewal check list too long"; return VIDO_ERR_CAPACITY; }
           VIDO_CUDA(cudaMemcpyAsync(ts->d_check, F.xy.data(), 8 * (size_t)mcheck, cudaMemcpyHostToDevice, s));
-          topup_used_kernel<<<(nk + 127) / 128, 128, 0, s>>>(ts->d_kp + (size_t)slot * ts->kp_cap, nk, ts->d_check, mcheck, ts->d_used);
+          topup_used_kernel<<<(nk + 127) / 128, 128, 0, s>>>(d_kp + (size_t)slot * ts->kp_cap, nk, ts->d_check, mcheck, ts->d_used);
           ctx->launches++;
           VIDO_CUDA(cudaMemcpyAsync(used.data(), ts->d_used, nk, cudaMemcpyDeviceToHost, s));
           VIDO_CUDA(cudaStreamSynchronize(s));
@@ -560,59 +686,102 @@ static int back_end(vido_ctx* ctx, const FrontFrame& ff, int slot, const float* 
   memcpy(Tcw_out, curTcw, sizeof(float) * 16);
   double t4 = now_ms();
   const int window = ts->f_id < c.window_size ? ts->f_id : c.window_size;
-  int rc = ba_finish(ctx);  // the previous frame's window, solved while this frame was tracked
+  int rc = skipped ? VIDO_OK : ba_stage(ctx, window, st);  // structure of this frame's window, staged while the previous
+  if (rc) return rc;                                        // frame's window is still being solved
+  rc = ba_finish(ctx);
   if (rc) return rc;
-  rc = skipped ? VIDO_OK : ba_start(ctx, window, st);
+  rc = ba_go(ctx);
   if (st) st->ms_ba = now_ms() - t4;
   ts->f_id++;
   if (rc) return rc;
   return skipped ? 1 : 0;
 }
 
+
+// Host->device copy done by SMs (the source is pinned host memory, directly addressable under UVA).  The prefetch of a
+// whole chunk is ~140 MB; issued as cudaMemcpyAsync it would sit in the copy-engine queue in front of the small,
+// latency-critical copies of the back-end (PnP / pose-opt / BA inputs) and delay each of them by up to one DMA
+// descriptor.  A few CTAs streaming it keep the DMA queues free.  src and dst must be congruent modulo 16.
+__global__ void __launch_bounds__(256) h2d_stream_kernel(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, size_t bytes) {
+  const size_t head = (16 - ((size_t)src & 15)) & 15;
+  const size_t h = head < bytes ? head : bytes;
+  const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gn = (size_t)gridDim.x * blockDim.x;
+  if (gtid < h) dst[gtid] = src[gtid];
+  const size_t body = (bytes - h) / 16;
+  const uint4* s4 = (const uint4*)(src + h);
+  uint4* d4 = (uint4*)(dst + h);
+  size_t i = gtid;
+  for (; i + 3 * gn < body; i += 4 * gn) {  // four independent 16-byte reads in flight per thread
+    const uint4 a = s4[i], b = s4[i + gn], c = s4[i + 2 * gn], d = s4[i + 3 * gn];
+    d4[i] = a; d4[i + gn] = b; d4[i + 2 * gn] = c; d4[i + 3 * gn] = d;
+  }
+  for (; i < body; i += gn) d4[i] = s4[i];
+  const size_t tail0 = h + body * 16;
+  if (tail0 + gtid < bytes) dst[tail0 + gtid] = src[tail0 + gtid];
+}
+
+static bool is_pinned_host(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
+// one array of one frame onto the copy stream: SM copy when possible, DMA otherwise
+static int prefetch_array(vido_ctx* ctx, cudaStream_t cs, void* dst, const void* src, size_t bytes) {
+  if ((((size_t)dst ^ (size_t)src) & 15) == 0 && is_pinned_host(src)) {
+    h2d_stream_kernel<<<8, 256, 0, cs>>>((uint8_t*)dst, (const uint8_t*)src, bytes);
+    ctx->launches++;
+    VIDO_CUDA(cudaGetLastError());
+  } else {
+    VIDO_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, cs));
+  }
+  return VIDO_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------
+// vido_track_prefetch: remember the frames the NEXT vido_track_frames call will start with.  While the back-end of the
+// current call works through its last batch, their copy and front-end already run in the idle pipeline slot.
+int trk_prefetch(vido_ctx* ctx, const vido_frame_inputs* in, int nframes) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  ts->hint.clear();
+  if (nframes <= 0) return VIDO_OK;
+  const int B = std::min(ts->capB, nframes);
+  ts->hint.assign(in, in + B);
+  return VIDO_OK;
+}
+
 int trk_track_chunk(vido_ctx* ctx, const vido_frame_inputs* in, int nframes, float* Tcw_out, vido_track_stats* stats) {
   TrackState* ts = (TrackState*)ctx->trk;
   const vido_config& c = ctx->cfg;
   cudaStream_t s = ctx->stream;
   const size_t px = (size_t)c.width * c.height;
-  if (ts->ba_pending) { vido_lm_stats ls; ba_collect(ctx, &ts->ba_pr, &ls); ts->ba_pending = false; }  // left by a failed call
+  if (ts->ba_pending) { vido_lm_stats ls; ba_collect(ctx, &ts->job[ts->ba_fly].pr, &ls); ts->ba_pending = false; }  // left by a failed call
   int done = 0;
   while (done < nframes) {
     const int B = std::min(ts->capB, nframes - done);
-    const vido_frame_inputs* f0 = in + done;
-    const int channels = f0->channels;
-    const uint8_t* d_img; const float* d_depth; const float* d_flow; const int32_t* d_mask;
-    bool contiguous_dev = f0->on_device != 0;
-    for (int b = 0; b < B; b++) {
-      const vido_frame_inputs& f = in[done + b];
-      if (f.channels != channels || (f.on_device != 0) != contiguous_dev || (channels != 1 && channels != 3)) { ctx->err = "inconsistent frame inputs"; return VIDO_ERR_ARG; }
-      if (f.on_device) {
-        // device-resident frames must be consecutive slices of one allocation (frame k at base + k*frame_bytes)
-        if (f.image != f0->image + (size_t)b * px * channels || f.depth != f0->depth + (size_t)b * px ||
-            f.flow != f0->flow + (size_t)b * px * 2 || f.mask != f0->mask + (size_t)b * px) contiguous_dev = false;
-      }
-    }
     double tf0 = now_ms();
-    if (f0->on_device && contiguous_dev) {
-      d_img = f0->image; d_depth = f0->depth; d_flow = f0->flow; d_mask = f0->mask;
-    } else {
-      const cudaMemcpyKind kind = f0->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-      for (int b = 0; b < B; b++) {
-        const vido_frame_inputs& f = in[done + b];
-        VIDO_CUDA(cudaMemcpyAsync(ts->d_img + (size_t)b * px * channels, f.image, px * channels, kind, s));
-        VIDO_CUDA(cudaMemcpyAsync(ts->d_depth + (size_t)b * px, f.depth, px * 4, kind, s));
-        VIDO_CUDA(cudaMemcpyAsync(ts->d_flow + (size_t)b * px * 2, f.flow, px * 8, kind, s));
-        VIDO_CUDA(cudaMemcpyAsync(ts->d_mask + (size_t)b * px, f.mask, px * 4, kind, s));
-      }
-      d_img = ts->d_img; d_depth = ts->d_depth; d_flow = ts->d_flow; d_mask = ts->d_mask;
+    TrackState::FeSlot& F = ts->fe[ts->fe_cur];
+    if (!(F.launched && F.key == (const void*)in[done].image && F.B == B && F.channels == in[done].channels)) {
+      int rc = fe_launch(ctx, F, in + done, B);  // not announced (first batch of a sequence, or the hint did not match)
+      if (rc) return rc;
     }
     std::vector<FrontFrame> ff;
-    int rc = front_end(ctx, B, d_img, channels, d_depth, d_flow, d_mask, ff);
+    int rc = fe_collect(ctx, F, ff);
     if (rc) return rc;
+    // look-ahead: the next batch of this call, or the announced first batch of the next call, goes through copy and
+    // front-end in the other slot while this batch's back-end runs
+    {
+      TrackState::FeSlot& N = ts->fe[ts->fe_cur ^ 1];
+      N.launched = false;
+      if (done + B < nframes) rc = fe_launch(ctx, N, in + done + B, std::min(ts->capB, nframes - done - B));
+      else if (!ts->hint.empty()) { rc = fe_launch(ctx, N, ts->hint.data(), (int)ts->hint.size()); ts->hint.clear(); }
+      if (rc) return rc;
+    }
+    const float* d_depth = F.in_depth; const float* d_flow = F.in_flow; const int32_t* d_mask = F.in_mask;
     const double front_ms = (now_ms() - tf0) / B;
     for (int b = 0; b < B; b++) {
       vido_track_stats* st = stats ? stats + done + b : nullptr;
-      rc = back_end(ctx, ff[b], b, d_depth, d_flow, d_mask, Tcw_out + 16 * (size_t)(done + b), st);
+      rc = back_end(ctx, ff[b], b, F.d_kp, d_depth, d_flow, d_mask, Tcw_out + 16 * (size_t)(done + b), st);
       if (rc < 0) return rc;
       if (st) { st->ms_orb = front_ms; st->ms_assoc = 0; }
       // the reference pre-scales the caller's depth map in place (Tracking.cc:299-322): reproduce on request
@@ -625,9 +794,16 @@ int trk_track_chunk(vido_ctx* ctx, const vido_frame_inputs* in, int nframes, flo
         VIDO_CUDA(cudaStreamSynchronize(s));
       }
     }
+    ts->fe_cur ^= 1;
     done += B;
   }
   return ba_finish(ctx);  // drain: stats and map are final when the call returns
+}
+
+// the ORB workspace is shared with the stand-alone extraction entry points: wait for a front-end running ahead
+void trk_quiesce(vido_ctx* ctx) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  if (ts && ts->fe_stream) cudaStreamSynchronize(ts->fe_stream);
 }
 
 int trk_num_frames(vido_ctx* ctx) { return (int)((TrackState*)ctx->trk)->map.size(); }
