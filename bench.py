@@ -223,6 +223,13 @@ def main():
         ba_ms = kms[3] / max(kn[3], 1)
         achieved = (kbytes / max(kn[3], 1)) / (ba_ms * 1e-3) / 1e9 if ba_ms > 0 else 0.0
         share = {n: float(v) for n, v in zip(("orb_front_end", "init_model", "pose_opt", "window_ba"), kms)}
+        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), if any
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_ba_traffic.json")) as fh:
+                traffic = float(json.load(fh)["dram_bytes_per_launch"])
+        except Exception:
+            pass
         # CPU baseline: oracle on a bounded sample of the same sequence (frames 0..cpu_sample-1, steady state at its end)
         import oracle_lib as ol
         tr = ol.OracleTracker(ol.track_config(CAM, rebuild=1))
@@ -247,7 +254,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": "ba_window_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_kind,
+                         "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_kind,
                          "avg_launch_ms": ba_ms, "device_ms_by_stage": share},
             "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": 1, "kind": "port",
                              "sample": f"frames {skip}..{ncpu - 1} of the same sequence through the CPU restatement (single thread, like the reference)"},

@@ -192,6 +192,14 @@ int vido_frame_sample_objects_dev(vido_ctx* ctx, const float* d_depth, const flo
  * queries outside the image return mask -1 */
 int vido_gather_dev(vido_ctx* ctx, const float* d_depth, const float* d_flow, const int32_t* d_mask, int frame, int raw_depth,
                     const float* d_xy, int n, int32_t* d_mask_out, float* d_depth_out, float* d_flow_out);
+/* Tracking::UpdateMask (src/Tracking.cc:3291-3357).  sem_label / corres_xy (HOST, n object features of the last frame:
+ * mpLastFrame->vSemObjLabel, mvObjCorres); d_mask_last / d_flow_last: last frame's mask and flow, d_mask_cur: the new
+ * frame's mask, updated in place (device, tight rows of cfg.width).  For every semantic label in ascending order the
+ * current mask votes at the predicted positions; a lost mask (majority 0 with >= 100 votes) is forward-warped from the
+ * last frame.  Labels must lie in [0, 4096).  Returns the number of unique labels (uniq_out / recovered, optional,
+ * receive them and whether each was warped) or a negative VIDO_ERR_*. */
+int vido_update_mask_dev(vido_ctx* ctx, const int32_t* sem_label, const float* corres_xy, int n, const int32_t* d_mask_last,
+                         const float* d_flow_last, int32_t* d_mask_cur, int32_t* uniq_out, int32_t* recovered, int cap);
 /* KAIST depth scale mScale (src/Tracking.cc:318), 1 by default */
 int vido_set_depth_scale(vido_ctx* ctx, float mscale);
 

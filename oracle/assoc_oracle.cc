@@ -2,6 +2,9 @@
 //   depth pre-scale           src/Tracking.cc:299-322
 //   static association        src/Frame.cc:72-100 (+ depth lookup :164-177)
 //   stride-4 object sampling  src/Frame.cc:184-211
+#include <algorithm>
+#include <map>
+#include <vector>
 #include <cstddef>
 #include "vido_oracle.h"
 
@@ -68,6 +71,46 @@ int vo_frame_sample_objects(const float* depth, const float* flow, const int32_t
       }
     }
   return m;
+}
+
+// Tracking::UpdateMask (src/Tracking.cc:3291-3357).  For every semantic label of the last frame's object features, in
+// ascending label order: the labels of the CURRENT mask at the features' predicted positions (int truncation, strictly
+// inside) vote; with >= 100 votes and label 0 winning (mask lost; ties go to the smaller label -- std::map order kept
+// by the insertion sort std::sort uses for so few entries) the last frame's pixels of that label are forward-warped
+// through the last flow (int truncation of the flow, strictly inside) into the current mask.  Labels are processed one
+// after the other on the mask as modified so far.  recovered[k] = 1 if the k-th unique label was warped.
+int vo_update_mask(const int32_t* sem_label, const float* corres_xy, int n, const int32_t* mask_last, const float* flow_last,
+                   int32_t* mask_cur, int W, int H, int32_t* uniq_out, int32_t* recovered, int cap) {
+  std::vector<int32_t> uni(sem_label, sem_label + n);
+  std::sort(uni.begin(), uni.end());
+  uni.erase(std::unique(uni.begin(), uni.end()), uni.end());
+  for (size_t k = 0; k < uni.size(); k++) {
+    const int32_t L = uni[k];
+    std::map<int, int> dups;
+    int votes = 0;
+    for (int i = 0; i < n; i++) {
+      if (sem_label[i] != L) continue;
+      const int u = (int)corres_xy[2 * i], v = (int)corres_xy[2 * i + 1];
+      if (u < W && u > 0 && v < H && v > 0) { ++dups[mask_cur[(size_t)v * W + u]]; votes++; }
+    }
+    int rec = 0;
+    if (votes >= 100) {
+      int best = 0, best_cnt = -1;
+      for (auto& kv : dups)
+        if (kv.second > best_cnt) { best_cnt = kv.second; best = kv.first; }  // first (smallest) label among equals
+      if (best == 0) {
+        rec = 1;
+        for (int j = 0; j < H; j++)
+          for (int kx = 0; kx < W; kx++)
+            if (mask_last[(size_t)j * W + kx] == L) {
+              const int fx = (int)flow_last[2 * ((size_t)j * W + kx)], fy = (int)flow_last[2 * ((size_t)j * W + kx) + 1];
+              if (kx + fx < W && kx + fx > 0 && j + fy < H && j + fy > 0) mask_cur[(size_t)(j + fy) * W + kx + fx] = L;
+            }
+      }
+    }
+    if ((int)k < cap) { if (uniq_out) uniq_out[k] = L; if (recovered) recovered[k] = rec; }
+  }
+  return (int)uni.size();
 }
 
 }  // extern "C"

@@ -135,7 +135,15 @@ int fast_roi(const uint8_t* img, int w, int h, int stride, int thr, std::vector<
   std::vector<int> S((size_t)w * h, 0);
   for (int y = 3; y < h - 3; y++)
     for (int x = 3; x < w - 3; x++) {
-      int s = fast_score_at(img + (size_t)y * stride + x, stride);
+      // exact early rejection (the usual FAST high-speed test): 9 contiguous ring pixels always contain at least two of
+      // the compass pixels 0, 4, 8, 12, so a corner at threshold thr needs two of them brighter than c + thr or two darker
+      // than c - thr; everything else has score < thr and never reaches the full score
+      const uint8_t* pc = img + (size_t)y * stride + x;
+      const int c = pc[0], hi = c + thr, lo = c - thr;
+      const int p0 = pc[3 * stride], p4 = pc[3], p8 = pc[-3 * stride], p12 = pc[-3];
+      const int nb = (p0 > hi) + (p4 > hi) + (p8 > hi) + (p12 > hi), nd = (p0 < lo) + (p4 < lo) + (p8 < lo) + (p12 < lo);
+      if (nb < 2 && nd < 2) continue;
+      int s = fast_score_at(pc, stride);
       S[(size_t)y * w + x] = (s >= thr) ? s : 0;
     }
   for (int y = 3; y < h - 3; y++)

@@ -109,6 +109,12 @@ int vo_frame_associate(const vo_keypoint* kps, int n, const float* depth, const 
 int vo_frame_sample_objects(const float* depth, const float* flow, const int32_t* mask, int W, int H, float th_depth_obj,
                             float* keys_xy, float* corres_xy, float* flow_xy, float* depth_out, int32_t* label, int cap);
 
+/* Tracking::UpdateMask (src/Tracking.cc:3291-3357): majority vote of the current mask at the predicted object-feature positions
+ * per semantic label; a label whose mask was lost (majority 0, >= 100 votes) is forward-warped from the last mask through
+ * the last flow.  mask_cur is modified in place; returns the number of unique labels (ascending in uniq_out). */
+int vo_update_mask(const int32_t* sem_label, const float* corres_xy, int n, const int32_t* mask_last, const float* flow_last,
+                   int32_t* mask_cur, int W, int H, int32_t* uniq_out, int32_t* recovered, int cap);
+
 /*
  * Per-frame camera pose optimisation Optimizer::PoseOptimizationFlow2Cam (src/Optimizer.cc:2622-2824):
  * one VertexSE3Expmap + n marginalised VertexSBAFlow, EdgeSE3ProjectFlow2 + EdgeFlowPrior per match, 4 rounds.

@@ -190,6 +190,16 @@ def frame_sample_objects(depth, flow, mask, th_depth_obj):
     return keys[:n].copy(), cor[:n].copy(), fl[:n].copy(), dep[:n].copy(), lab[:n].copy()
 
 
+def update_mask(sem_label, corres_xy, mask_last, flow_last, mask_cur):
+    sem = np.ascontiguousarray(sem_label, np.int32); cor = np.ascontiguousarray(corres_xy, np.float32)
+    ml = np.ascontiguousarray(mask_last, np.int32); fl = np.ascontiguousarray(flow_last, np.float32)
+    mc = np.ascontiguousarray(mask_cur, np.int32).copy()
+    H, W = ml.shape
+    uniq = np.zeros(256, np.int32); rec = np.zeros(256, np.int32)
+    k = lib().vo_update_mask(_p(sem), _p(cor), len(sem), _p(ml), _p(fl), _p(mc), W, H, _p(uniq), _p(rec), 256)
+    return mc, uniq[:k].copy(), rec[:k].copy()
+
+
 class PoseOptProblem(C.Structure):
     _fields_ = [("n", C.c_int32), ("pad", C.c_int32), ("obs_xy", C.c_void_p), ("flow_xy", C.c_void_p),
                 ("depth", C.c_void_p), ("Tcw_init", C.c_float * 16), ("Tcw_last", C.c_float * 16),

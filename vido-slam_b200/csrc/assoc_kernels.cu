@@ -11,6 +11,9 @@
 // the depth map is only needed when the caller wants the reference's in-place side effect.
 #include <cstring>
 
+#include <algorithm>
+#include <vector>
+
 #include "ctx.h"
 
 struct DepthConv {
@@ -220,4 +223,103 @@ int assoc_gather(vido_ctx* ctx, const float* d_depth, const float* d_flow, const
   ctx->launches++;
   VIDO_CUDA(cudaGetLastError());
   return VIDO_OK;
+}
+
+// =========================================================================================================
+// Tracking::UpdateMask (src/Tracking.cc:3291-3357): per semantic label (ascending, one after the other on the mask as
+// modified so far) a vote of the current mask at the predicted object-feature positions; a lost mask (label 0 wins with
+// >= 100 votes; ties go to the smaller label) is forward-warped from the last frame through its flow.
+// Three small kernels per label, all on the context stream; the decision stays on the device.
+// =========================================================================================================
+#define UM_BINS 4096  // labels must be in [0, UM_BINS)
+
+__global__ void um_vote_kernel(const int32_t* __restrict__ sem, const float* __restrict__ cor, int n, int32_t label,
+                               const int32_t* __restrict__ mask_cur, int W, int H, int32_t* __restrict__ hist /* [UM_BINS + 2] */,
+                               int32_t* __restrict__ err) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || sem[i] != label) return;
+  const int u = (int)cor[2 * i], v = (int)cor[2 * i + 1];
+  if (u < W && u > 0 && v < H && v > 0) {
+    const int32_t l = mask_cur[(size_t)v * W + u];
+    if (l < 0 || l >= UM_BINS) { atomicExch(err, 2); return; }
+    atomicAdd(&hist[l], 1);
+    atomicAdd(&hist[UM_BINS], 1);  // number of votes
+  }
+}
+
+// winner of the vote -> hist[UM_BINS + 1] = 1 when the mask has to be recovered; clears the histogram for the next label
+__global__ void um_decide_kernel(int32_t* __restrict__ hist, int32_t* __restrict__ recovered_k) {
+  __shared__ int s_cnt[256], s_lab[256];
+  const int tid = threadIdx.x;
+  int best = -1, lab = 0;
+  for (int l = tid; l < UM_BINS; l += blockDim.x) {
+    const int c = hist[l];
+    if (c > best) { best = c; lab = l; }  // ascending l per thread: the smaller label is kept among equals
+  }
+  s_cnt[tid] = best; s_lab[tid] = lab;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) {
+      const int c2 = s_cnt[tid + o], l2 = s_lab[tid + o];
+      if (c2 > s_cnt[tid] || (c2 == s_cnt[tid] && l2 < s_lab[tid])) { s_cnt[tid] = c2; s_lab[tid] = l2; }
+    }
+    __syncthreads();
+  }
+  const int votes = hist[UM_BINS];
+  __syncthreads();
+  for (int l = tid; l < UM_BINS; l += blockDim.x) hist[l] = 0;
+  if (tid == 0) {
+    const int rec = (votes >= 100 && s_lab[0] == 0 && s_cnt[0] > 0) ? 1 : 0;
+    hist[UM_BINS] = 0;
+    hist[UM_BINS + 1] = rec;
+    *recovered_k = rec;
+  }
+}
+
+__global__ void um_warp_kernel(const int32_t* __restrict__ flag, int32_t label, const int32_t* __restrict__ mask_last,
+                               const float* __restrict__ flow_last, int32_t* __restrict__ mask_cur, int W, int H) {
+  if (*flag == 0) return;
+  const size_t px = (size_t)W * H;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < px; k += (size_t)gridDim.x * blockDim.x) {
+    if (mask_last[k] != label) continue;
+    const int j = (int)(k / W), kx = (int)(k - (size_t)j * W);
+    const int fx = (int)flow_last[2 * k], fy = (int)flow_last[2 * k + 1];  // truncation, like the reference's int conversion
+    if (kx + fx < W && kx + fx > 0 && j + fy < H && j + fy > 0) mask_cur[(size_t)(j + fy) * W + kx + fx] = label;  // same value from every writer
+  }
+}
+
+int assoc_update_mask(vido_ctx* ctx, const int32_t* sem_label, const float* corres_xy, int n, const int32_t* d_mask_last,
+                      const float* d_flow_last, int32_t* d_mask_cur, int32_t* uniq_out, int32_t* recovered, int cap) {
+  if (n <= 0) return 0;
+  const int W = ctx->cfg.width, H = ctx->cfg.height;
+  cudaStream_t s = ctx->stream;
+  std::vector<int32_t> uni(sem_label, sem_label + n);
+  std::sort(uni.begin(), uni.end());
+  uni.erase(std::unique(uni.begin(), uni.end()), uni.end());
+  const int nl = (int)uni.size();
+  int32_t *d_sem = nullptr, *d_hist = nullptr, *d_rec = nullptr;
+  float* d_cor = nullptr;
+  VIDO_CUDA(cudaMallocAsync(&d_sem, sizeof(int32_t) * n, s));
+  VIDO_CUDA(cudaMallocAsync(&d_cor, sizeof(float) * 2 * n, s));
+  VIDO_CUDA(cudaMallocAsync(&d_hist, sizeof(int32_t) * (UM_BINS + 2), s));
+  VIDO_CUDA(cudaMallocAsync(&d_rec, sizeof(int32_t) * nl, s));
+  VIDO_CUDA(cudaMemcpyAsync(d_sem, sem_label, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
+  VIDO_CUDA(cudaMemcpyAsync(d_cor, corres_xy, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, s));
+  VIDO_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(int32_t) * (UM_BINS + 2), s));
+  for (int k = 0; k < nl; k++) {
+    um_vote_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_sem, d_cor, n, uni[k], d_mask_cur, W, H, d_hist, ctx->d_err);
+    um_decide_kernel<<<1, 256, 0, s>>>(d_hist, d_rec + k);
+    um_warp_kernel<<<148 * 4, 256, 0, s>>>(d_hist + UM_BINS + 1, uni[k], d_mask_last, d_flow_last, d_mask_cur, W, H);
+    ctx->launches += 3;
+  }
+  VIDO_CUDA(cudaGetLastError());
+  std::vector<int32_t> rec(nl);
+  int32_t flag = 0;
+  VIDO_CUDA(cudaMemcpyAsync(rec.data(), d_rec, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost, s));
+  VIDO_CUDA(cudaMemcpyAsync(&flag, ctx->d_err, 4, cudaMemcpyDeviceToHost, s));
+  cudaFreeAsync(d_sem, s); cudaFreeAsync(d_cor, s); cudaFreeAsync(d_hist, s); cudaFreeAsync(d_rec, s);
+  VIDO_CUDA(cudaStreamSynchronize(s));
+  if (flag) { cudaMemsetAsync(ctx->d_err, 0, 4, s); ctx->err = "UpdateMask: mask label outside [0, 4096)"; return VIDO_ERR_ARG; }
+  for (int k = 0; k < nl && k < cap; k++) { if (uniq_out) uniq_out[k] = uni[k]; if (recovered) recovered[k] = rec[k]; }
+  return nl;
 }

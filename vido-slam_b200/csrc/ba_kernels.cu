@@ -1048,6 +1048,9 @@ struct BaWorkspace {
   size_t in_bytes = 0, out_bytes = 0;
   // the solve runs on its own stream so that a caller may overlap it with other work (ba_submit ... ba_collect)
   cudaStream_t stream = nullptr;
+  cudaStream_t up_stream = nullptr;  // uploads the structure part of a staged problem while the previous one is solved
+  cudaEvent_t up_done = nullptr;
+  size_t values_bytes = 0;           // leading part of the input block holding poses | odometry | points
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool pending = false;
   bool want_records = false;
@@ -1130,7 +1133,9 @@ int ba_setup(vido_ctx* ctx, int capW, int capP, int capM) {
   }
   cudaGetLastError();
   if (getenv("VIDO_BA_CLUSTER") && atoi(getenv("VIDO_BA_CLUSTER")) == 8) ws->cluster = 8;
-  VIDO_CUDA(cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking));
+  VIDO_CUDA(vido_create_stream(&ws->stream, true));
+  VIDO_CUDA(vido_create_stream(&ws->up_stream, true));
+  VIDO_CUDA(cudaEventCreateWithFlags(&ws->up_done, cudaEventDisableTiming));
   VIDO_CUDA(cudaEventCreate(&ws->ev0));
   VIDO_CUDA(cudaEventCreate(&ws->ev1));
   return VIDO_OK;
@@ -1140,6 +1145,8 @@ void ba_teardown(vido_ctx* ctx) {
   BaWorkspace* ws = (BaWorkspace*)ctx->ba;
   if (!ws) return;
   if (ws->stream) { cudaStreamSynchronize(ws->stream); cudaStreamDestroy(ws->stream); }
+  if (ws->up_stream) { cudaStreamSynchronize(ws->up_stream); cudaStreamDestroy(ws->up_stream); }
+  if (ws->up_done) cudaEventDestroy(ws->up_done);
   if (ws->ev0) cudaEventDestroy(ws->ev0);
   if (ws->ev1) cudaEventDestroy(ws->ev1);
   cudaFree(ws->d_base); cudaFree(ws->d_in2[0]); cudaFree(ws->d_in2[1]); cudaFree(ws->d_out);
@@ -1231,6 +1238,14 @@ int ba_prepare(vido_ctx* ctx, const vido_ba_problem* pr) {
     h_obs_point[q] = n;
     h_xyz[q] = pr->obs_xyz[3 * o]; h_xyz[(size_t)M + q] = pr->obs_xyz[3 * o + 1]; h_xyz[2 * (size_t)M + q] = pr->obs_xyz[3 * o + 2];
   }
+  {  // everything behind the state values is final: upload it now (own stream, other staging slot than the solve in flight)
+    char* hp = h_in; BaArgs t2; carve_inputs(hp, t2, W, P, M);
+    const size_t used = (size_t)(hp - h_in);
+    const size_t vb = (size_t)((const char*)h.obs_pose - h_in);  // poses_f32 | rel_f32 | points_f32 come first
+    ws->values_bytes = vb;
+    VIDO_CUDA(cudaMemcpyAsync(d_in + vb, h_in + vb, used - vb, cudaMemcpyHostToDevice, ws->up_stream));
+    VIDO_CUDA(cudaEventRecord(ws->up_done, ws->up_stream));
+  }
   ws->a_prep = a;
   ws->prepared = true;
   return VIDO_OK;
@@ -1258,10 +1273,8 @@ int ba_launch(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records) {
       h_pts[3 * n] = pr->points[3 * l]; h_pts[3 * n + 1] = pr->points[3 * l + 1]; h_pts[3 * n + 2] = pr->points[3 * l + 2];
     }
   }
-  {
-    char* hp = ws->h_in2[slot]; BaArgs t2; carve_inputs(hp, t2, W, P, M);
-    VIDO_CUDA(cudaMemcpyAsync(ws->d_in2[slot], ws->h_in2[slot], (size_t)(hp - ws->h_in2[slot]), cudaMemcpyHostToDevice, s));
-  }
+  VIDO_CUDA(cudaMemcpyAsync(ws->d_in2[slot], ws->h_in2[slot], ws->values_bytes, cudaMemcpyHostToDevice, s));
+  VIDO_CUDA(cudaStreamWaitEvent(s, ws->up_done, 0));
   const size_t smem = sizeof(double) * ((size_t)(6 * W + 1) * (6 * W + 1) + 36 * W);
   {
     cudaLaunchConfig_t cfg = {};

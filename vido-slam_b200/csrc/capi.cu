@@ -51,7 +51,7 @@ vido_ctx* vido_create(const vido_config* cfg) {
   if (ctx->cfg.max_batch < 1) ctx->cfg.max_batch = 1;
   ctx->device = cfg->device;
   ctx->num_sms = prop.multiProcessorCount;
-  if (cudaSetDevice(cfg->device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaSetDevice(cfg->device) != cudaSuccess || vido_create_stream(&ctx->stream, true) != cudaSuccess) {
     g_create_err = "cudaSetDevice/cudaStreamCreate failed";
     delete ctx;
     return nullptr;
@@ -250,6 +250,13 @@ int vido_init_model(vido_ctx* ctx, vido_pnp_problem* p) {
   if (!ctx || !p) return VIDO_ERR_ARG;
   cudaSetDevice(ctx->device);
   return pnp_init_model_host(ctx, p);
+}
+
+int vido_update_mask_dev(vido_ctx* ctx, const int32_t* sem_label, const float* corres_xy, int n, const int32_t* d_mask_last,
+                         const float* d_flow_last, int32_t* d_mask_cur, int32_t* uniq_out, int32_t* recovered, int cap) {
+  if (!ctx || n < 0 || (n > 0 && (!sem_label || !corres_xy || !d_mask_last || !d_flow_last || !d_mask_cur))) return VIDO_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  return assoc_update_mask(ctx, sem_label, corres_xy, n, d_mask_last, d_flow_last, d_mask_cur, uniq_out, recovered, cap);
 }
 
 int vido_depth_prep_dev(vido_ctx* ctx, float* d_depth, int nframes, size_t frame_stride_elems, int stride_elems) {

@@ -112,6 +112,8 @@ int orb_run(vido_ctx* ctx, const uint8_t* d_gray, int nframes, size_t frame_stri
 int orb_bgr_to_gray(vido_ctx* ctx, const uint8_t* d_bgr, int nframes, size_t frame_stride, int stride,
                     uint8_t* d_gray, size_t gray_frame_stride, int gray_stride);
 
+cudaError_t vido_create_stream(cudaStream_t* s, bool high_priority);  // track.cu
+
 // ba_kernels.cu
 int ba_setup(vido_ctx* ctx, int capW, int capP, int capM);
 void ba_teardown(vido_ctx* ctx);
@@ -133,6 +135,8 @@ int pnp_init_model_host(vido_ctx* ctx, vido_pnp_problem* p);
 
 // assoc_kernels.cu
 int assoc_depth_prep(vido_ctx* ctx, float* d_depth, int nframes, size_t frame_stride, int stride);
+int assoc_update_mask(vido_ctx* ctx, const int32_t* sem_label, const float* corres_xy, int n, const int32_t* d_mask_last,
+                      const float* d_flow_last, int32_t* d_mask_cur, int32_t* uniq_out, int32_t* recovered, int cap);
 int assoc_frame_associate(vido_ctx* ctx, const vido_keypoint* d_kps, const int32_t* d_nkp, int kp_cap, const float* d_depth,
                           const float* d_flow, const int32_t* d_mask, int nframes, int raw, int32_t* d_idx, float* d_corres,
                           float* d_oflow, float* d_odepth, int32_t* d_n, int out_cap);

@@ -86,7 +86,7 @@ struct TrackState {
     std::vector<int> pframe, pfeat;  // per point: frame / feature of its first observation (initial position)
   } job[2];
   bool ba_pending = false, ba_staged = false;
-  int ba_fly = 0, ba_stage_slot = 0;
+  int ba_fly = 0, ba_stage_slot = 0, ba_rest = -1;
   // device buffers of one chunk
   int capB = 0;
   // Two pipeline slots.  A slot holds the inputs of one batch on the device, its front-end outputs on the device and
@@ -159,6 +159,14 @@ __global__ void topup_used_kernel(const vido_keypoint* __restrict__ kps, int n, 
   used[i] = u ? 1 : 0;
 }
 
+// latency-critical streams (per-frame back-end, window BA) get the highest priority, the run-ahead streams (input copies,
+// front-end of the next batch) the lowest: when both have blocks ready the back-end's short kernels are scheduled first
+cudaError_t vido_create_stream(cudaStream_t* s, bool high) {
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);  // lo = least priority (numerically greatest)
+  return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, high ? hi : lo);
+}
+
 int trk_setup(vido_ctx* ctx) {
   TrackState* ts = new TrackState();
   ctx->trk = ts;
@@ -192,8 +200,8 @@ int trk_setup(vido_ctx* ctx) {
     VIDO_CUDA(cudaEventCreate(&F.ev1));
   }
   VIDO_CUDA(cudaMalloc(&ts->d_gray, px * B));
-  VIDO_CUDA(cudaStreamCreateWithFlags(&ts->copy_stream, cudaStreamNonBlocking));
-  VIDO_CUDA(cudaStreamCreateWithFlags(&ts->fe_stream, cudaStreamNonBlocking));
+  VIDO_CUDA(vido_create_stream(&ts->copy_stream, false));
+  VIDO_CUDA(vido_create_stream(&ts->fe_stream, false));
   VIDO_CUDA(cudaMalloc(&ts->d_q, 8 * ts->q_cap)); VIDO_CUDA(cudaMalloc(&ts->d_qmask, 4 * ts->q_cap));
   VIDO_CUDA(cudaMalloc(&ts->d_qdepth, 4 * ts->q_cap)); VIDO_CUDA(cudaMalloc(&ts->d_qflow, 8 * ts->q_cap));
   VIDO_CUDA(cudaMalloc(&ts->d_check, 8 * ts->q_cap)); VIDO_CUDA(cudaMalloc(&ts->d_used, ts->kp_cap));
@@ -225,7 +233,7 @@ int trk_reset(vido_ctx* ctx) {
   ts->map.clear(); ts->tracks.clear();
   ts->initialised = false; ts->has_velocity = false; ts->f_id = 0; ts->ba_epoch = 0;
   cudaStreamSynchronize(ts->copy_stream); cudaStreamSynchronize(ts->fe_stream);
-  ts->fe[0].launched = ts->fe[1].launched = false; ts->hint.clear();
+  ts->fe[0].launched = ts->fe[1].launched = false; ts->hint.clear(); ts->ba_rest = -1; ts->ba_staged = false;
   ts->last_keys.clear(); ts->last_depth.clear(); ts->last_corres.clear(); ts->last_flow.clear();
   return VIDO_OK;
 }
@@ -387,15 +395,31 @@ static int ba_finish(vido_ctx* ctx) {
     memcpy(ts->map[i].Twc, &J.poses[16 * (size_t)(i - start)], sizeof(float) * 16);
     if (i > start) memcpy(ts->map[i].rel, &J.rel[16 * (size_t)(i - start - 1)], sizeof(float) * 16);
   }
-  // every observation of an optimised point receives the optimised position (Optimizer.cc:1107-1122)
+  // Every observation of an optimised point receives the optimised position (Optimizer.cc:1107-1122).  Only the FIRST
+  // observation of each point is read again before the next solve is launched (its initial position): write those now,
+  // the rest in ba_writeback_rest, after the launch.
+  const size_t np = J.pframe.size();
+  const float* pts = J.pts.data();
+  for (size_t l = 0; l < np; l++) {
+    float* d = &ts->map[J.pframe[l]].p3[3 * (size_t)J.pfeat[l]];
+    d[0] = pts[3 * l]; d[1] = pts[3 * l + 1]; d[2] = pts[3 * l + 2];
+  }
+  ts->ba_rest = (int)(&J - ts->job);
+  return VIDO_OK;
+}
+
+static void ba_writeback_rest(vido_ctx* ctx) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  if (ts->ba_rest < 0) return;
+  TrackState::BaJob& J = ts->job[ts->ba_rest];
+  ts->ba_rest = -1;
   const size_t nobs = J.op.size();
   const float* pts = J.pts.data();
   for (size_t o = 0; o < nobs; o++) {
-    float* d = &ts->map[start + J.op[o]].p3[3 * (size_t)J.ofeat[o]];
+    float* d = &ts->map[J.start + J.op[o]].p3[3 * (size_t)J.ofeat[o]];
     const float* q = pts + 3 * (size_t)J.ol[o];
     d[0] = q[0]; d[1] = q[1]; d[2] = q[2];
   }
-  return VIDO_OK;
 }
 
 static int ba_stage(vido_ctx* ctx, int WINDOW, vido_track_stats* st) {
@@ -691,6 +715,7 @@ static int back_end(vido_ctx* ctx, const FrontFrame& ff, int slot, const vido_ke
   rc = ba_finish(ctx);
   if (rc) return rc;
   rc = ba_go(ctx);
+  ba_writeback_rest(ctx);  // off the critical path: the next solve is already running
   if (st) st->ms_ba = now_ms() - t4;
   ts->f_id++;
   if (rc) return rc;
@@ -797,7 +822,11 @@ int trk_track_chunk(vido_ctx* ctx, const vido_frame_inputs* in, int nframes, flo
     ts->fe_cur ^= 1;
     done += B;
   }
-  return ba_finish(ctx);  // drain: stats and map are final when the call returns
+  {
+    int rc = ba_finish(ctx);  // drain: stats and map are final when the call returns
+    ba_writeback_rest(ctx);
+    return rc;
+  }
 }
 
 // the ORB workspace is shared with the stand-alone extraction entry points: wait for a front-end running ahead
