@@ -144,19 +144,25 @@ __global__ void kp_lookup_kernel(const vido_keypoint* __restrict__ kps, const in
   oflow[2 * o + 1] = flow[2 * k + 1];
 }
 
-// used[i] = 1 if keypoint i lies within 1 px (Euclidean, float) of any already selected feature (Tracking.cc:3030-3040)
-__global__ void topup_used_kernel(const vido_keypoint* __restrict__ kps, int n, const float* __restrict__ check, int m,
-                                  uint8_t* __restrict__ used) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// used[i] = 1 if keypoint i lies within 1 px (Euclidean, float) of any already selected feature (Tracking.cc:3030-3040).
+// One warp per keypoint: the lanes stride over the selected features, any hit ends the search (2.5 k x 1 k distance tests
+// per frame; a thread per keypoint walking the whole list serially was the longest kernel of the tracking path).
+__global__ void __launch_bounds__(256) topup_used_kernel(const vido_keypoint* __restrict__ kps, int n, const float* __restrict__ check, int m,
+                                                         uint8_t* __restrict__ used) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (i >= n) return;
   const float sx = kps[i].x, sy = kps[i].y;
   bool u = false;
-  for (int j = 0; j < m && !u; j++) {
-    const float dx = __fsub_rn(check[2 * j], sx), dy = __fsub_rn(check[2 * j + 1], sy);
-    const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
-    u = d < 1.0f;
+  for (int j0 = 0; j0 < m; j0 += 32) {
+    const int j = j0 + lane;
+    bool hit = false;
+    if (j < m) {
+      const float dx = __fsub_rn(check[2 * j], sx), dy = __fsub_rn(check[2 * j + 1], sy);
+      hit = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))) < 1.0f;
+    }
+    if (__any_sync(0xffffffffu, hit)) { u = true; break; }
   }
-  used[i] = u ? 1 : 0;
+  if (lane == 0) used[i] = u ? 1 : 0;
 }
 
 // latency-critical streams (per-frame back-end, window BA) get the highest priority, the run-ahead streams (input copies,
@@ -633,7 +639,7 @@ static int back_end(vido_ctx* ctx, const FrontFrame& ff, int slot, const vido_ke
         if (mcheck > 0) {
           if (mcheck > ts->q_cap) { ctx->err = "renewal check list too long"; return VIDO_ERR_CAPACITY; }
           VIDO_CUDA(cudaMemcpyAsync(ts->d_check, F.xy.data(), 8 * (size_t)mcheck, cudaMemcpyHostToDevice, s));
-          topup_used_kernel<<<(nk + 127) / 128, 128, 0, s>>>(d_kp + (size_t)slot * ts->kp_cap, nk, ts->d_check, mcheck, ts->d_used);
+          topup_used_kernel<<<(nk + 7) / 8, 256, 0, s>>>(d_kp + (size_t)slot * ts->kp_cap, nk, ts->d_check, mcheck, ts->d_used);
           ctx->launches++;
           VIDO_CUDA(cudaMemcpyAsync(used.data(), ts->d_used, nk, cudaMemcpyDeviceToHost, s));
           VIDO_CUDA(cudaStreamSynchronize(s));
