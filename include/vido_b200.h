@@ -52,6 +52,8 @@ typedef struct vido_config {
   int32_t rgb;                    /* Camera.RGB: 1 = RGB order, 0 = BGR (3-channel input only) */
   int32_t max_batch;              /* frames the ORB front-end processes per launch (>=1) */
   int32_t device;                 /* CUDA device ordinal */
+  float sf_mg_thres, sf_ds_thres; /* SFMgThres / SFDsThres: scene-flow magnitude and distribution thresholds of
+                                     Tracking::DynObjTracking (src/Tracking.cc:159-160, 1746-1783) */
 } vido_config;
 
 void vido_default_config(vido_config* cfg);  /* reference's kitti_config.yaml values at 1242x375 */
@@ -155,7 +157,9 @@ int vido_pose_opt_flow2(vido_ctx* ctx, vido_poseopt_problem* problems, int nprob
  * cv::solvePnPRansac internals are un-vendored and not reproducible bit for bit).  Host pointers.
  */
 typedef struct vido_pnp_problem {
-  int32_t n, pad;
+  int32_t n;
+  int32_t no_motion_model; /* 1: GetInitModelObj for an object without a previous motion (src/Tracking.cc:2143-2151): the RANSAC
+                              model is returned whatever its support; Tcw_motion only seeds the minimal solver */
   const float* cur_xy;     /* [n][2] current keypoints */
   const float* pts3d;      /* [n][3] world points of the last frame (Frame::UnprojectStereoStat) */
   const int32_t* valid;    /* [n] 0 where the depth was negative (excluded from RANSAC); may be NULL */
@@ -207,7 +211,10 @@ int vido_set_depth_scale(vido_ctx* ctx, float mscale);
 /*
  * Per-frame driver: replaces System::TrackRGBD -> Tracking::GrabImageRGBD -> Tracking::Track
  * (src/System.cc:51-63, src/Tracking.cc:283-456, 1081-1509) including the PartialBatchOptimization of every frame.
- * This version covers sensor = RGBD (VO), bJoint = true, UseSampleFeature = 0 and a static scene (all-zero mask).
+ * This version covers sensor = RGBD (VO), bJoint = true, UseSampleFeature = 0; static scenes and scenes with dynamic
+ * objects (UpdateMask, GetSceneFlowObj, DynObjTracking, GetInitModelObj, PoseOptimizationFlow2, object part of
+ * RenewFrameInfo, GetDynamicTrackNew: src/Tracking.cc:1160-1308, 1582-1912, 2030-2162, 2615-2720, 3112-3357).  Like the
+ * reference (mSegMap is a shallow copy of the caller's mask), a lost object mask is re-warped IN the frame's mask buffer.
  * A chunk of frames is passed at once so that the frame-independent front-end (gray conversion, ORB, association)
  * runs batched; results are identical to calling it frame by frame.
  */
@@ -226,6 +233,8 @@ typedef struct vido_track_stats {
   double ms_orb, ms_assoc, ms_init, ms_poseopt, ms_renew, ms_ba; /* host wall time per stage (ms_orb: front-end share) */
   int32_t n_keypoints, n_matches, n_init_inliers, init_winner, n_pose_inliers, n_static;
   int32_t ba_iterations, ba_trials, ba_points, ba_obs;
+  int32_t n_dyn_features, n_objects, n_objects_ok, n_masks_recovered; /* object features leaving the frame; objects found by
+                                DynObjTracking; objects with an estimated motion (bObjStat); labels re-warped by UpdateMask */
 } vido_track_stats;
 /* Tcw_out: nframes x 16 floats (what TrackRGBD returns per frame); stats may be NULL.  Returns VIDO_OK or <0. */
 int vido_track_frames(vido_ctx* ctx, const vido_frame_inputs* frames, int nframes, float* Tcw_out, vido_track_stats* stats);
@@ -241,6 +250,14 @@ int vido_track_prefetch(vido_ctx* ctx, const vido_frame_inputs* frames, int nfra
 int vido_map_num_frames(vido_ctx* ctx);
 int vido_map_get_poses(vido_ctx* ctx, float* poses, int cap);
 int vido_map_get_static(vido_ctx* ctx, int frame, float* xy, float* depth, float* p3, int32_t* asso, int cap);
+/* Map::vpFeatDyn / vfDepDyn / vp3DPointDyn / vnAssoDyn[frame-1] / vnFeatLabel[frame-1]; returns the count */
+int vido_map_get_dynamic(vido_ctx* ctx, int frame, float* xy, float* depth, float* p3, int32_t* asso, int32_t* label, int cap);
+/* objects with an estimated motion in frame >= 1: Map::vnRMLabel / vnSMLabel / vmRigidMotion / vmRigidCentre [frame-1][1..]
+ * (the camera entry 0 is vido_map_get_poses); motion = world-frame rigid motion H (4x4 float), centre = last-frame centroid */
+int vido_map_get_objects(vido_ctx* ctx, int frame, int32_t* label, int32_t* sem_label, float* motion, float* centre, int cap);
+/* Map::TrackletDyn / nObjID (Tracking::GetDynamicTrackNew, src/Tracking.cc:2615-2720): per track its length, object id and the
+ * (frame, feature) of its first element; returns the number of tracks */
+int vido_map_get_dyn_tracks(vido_ctx* ctx, int32_t* len, int32_t* obj_id, int32_t* first_frame, int32_t* first_feat, int cap);
 
 
 /*

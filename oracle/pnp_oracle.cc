@@ -183,7 +183,7 @@ int vo_init_model_cam(vo_pnp_problem* p) {
     if (rpe < p->reproj_err) mm.push_back(i);
   }
   p->mm_inliers = (int)mm.size();
-  if ((int)best_in.size() > (int)mm.size()) {
+  if (p->no_motion_model || (int)best_in.size() > (int)mm.size()) {  // GetInitModelObj without PreObjID (:2143-2151)
     p->winner = 0;
     float* o = p->Tcw_out;
     for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) o[4 * r + c] = (float)best.R[3 * r + c]; o[4 * r + 3] = (float)best.t[r]; }

@@ -1,6 +1,6 @@
-// track_oracle.cc -- CPU restatement of the per-frame driver (VO, static scene).  TEST INFRASTRUCTURE ONLY.
+// track_oracle.cc -- CPU restatement of the per-frame driver (VO, static + dynamic objects).  TEST INFRASTRUCTURE ONLY.
 //
-// Follows, for sensor = RGBD, bJoint = true, UseSampleFeature = 0 and an all-zero object mask:
+// Follows, for sensor = RGBD, bJoint = true, UseSampleFeature = 0:
 //   Tracking::GrabImageRGBD          src/Tracking.cc:283-456   (depth pre-scale, Frame, carry-over of correspondences)
 //   Frame::Frame                     src/Frame.cc:36-241       (ORB, static association)
 //   Tracking::Track                  src/Tracking.cc:1081-1509 (init model, pose optimisation, motion model, renewal,
@@ -9,11 +9,18 @@
 //   Tracking::RenewFrameInfo         src/Tracking.cc:2959-3135 (static part)
 //   Tracking::GetStaticTrack         src/Tracking.cc:2514-2613 (rebuilt from frame 0 every frame, like the reference)
 //   Optimizer::PartialBatchOptimization graph construction   src/Optimizer.cc:43-362, write-back :1056-1142
-// Not covered (documented in DESIGN.md): dynamic objects (DynObjTracking, object motion), IMU, FullBatch.
+//   Tracking::UpdateMask             src/Tracking.cc:3291-3357 ; object carry-over src/Tracking.cc:391-421
+//   Tracking::GetSceneFlowObj        src/Tracking.cc:1582-1668 ; Tracking::DynObjTracking src/Tracking.cc:1670-1912
+//   Tracking::GetInitModelObj        src/Tracking.cc:2030-2162 ; Optimizer::PoseOptimizationFlow2 src/Optimizer.cc:3037-3253
+//   Tracking::RenewFrameInfo         src/Tracking.cc:3112-3289 (object part) ; GetDynamicTrackNew src/Tracking.cc:2615-2720
+// Not covered (documented in DESIGN.md): IMU, FullBatch.
 // float 4x4 products follow cv::Mat CV_32F gemm (double accumulation, one rounding).
+#include <algorithm>
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <vector>
 
 #include "vido_oracle.h"
@@ -56,6 +63,17 @@ struct Frame {
   std::vector<P3> mvStat3DPointTmp;
   std::vector<int> nStaInlierID;
   float Tcw[16];
+  // object features (Frame.h: mvObjKeys, mvObjDepth, mvObjCorres, mvObjFlowNext, vSemObjLabel, vObjLabel, nDynInlierID,
+  // mvObj3DPoint) and per-object results (nModLabel, nSemPosition, bObjStat, vObjMod, vObjCentre3D, vnObjID, vnObjInlierID)
+  std::vector<P2> mvObjKeys, mvObjCorres, mvObjFlowNext;
+  std::vector<float> mvObjDepth;
+  std::vector<int> vSemObjLabel, vObjLabel, nDynInlierID;
+  std::vector<P3> mvObj3DPoint, vFlow_3d;
+  std::vector<int> nModLabel, nSemPosition;
+  std::vector<char> bObjStat;
+  std::vector<std::array<float, 16>> vObjMod;
+  std::vector<P3> vObjCentre3D;
+  std::vector<std::vector<int>> vnObjID, vnObjInlierID;
 };
 
 struct Map {
@@ -66,6 +84,16 @@ struct Map {
   std::vector<std::vector<std::pair<int, int>>> TrackletSta;
   std::vector<std::vector<float>> vmCameraPose;   // 16 floats each (Twc)
   std::vector<std::vector<float>> vmRigidMotion;  // camera motion [f-1][0]
+  // dynamic part
+  std::vector<std::vector<P2>> vpFeatDyn;
+  std::vector<std::vector<float>> vfDepDyn;
+  std::vector<std::vector<P3>> vp3DPointDyn;
+  std::vector<std::vector<int>> vnAssoDyn, vnFeatLabel;
+  std::vector<std::vector<std::pair<int, int>>> TrackletDyn;
+  std::vector<int> nObjID;
+  std::vector<std::vector<std::array<float, 16>>> vmObjMotion;  // vmRigidMotion[f-1][1..]
+  std::vector<std::vector<int>> vnRMLabel, vnSMLabel;            // without the camera entry
+  std::vector<std::vector<P3>> vmRigidCentre;
 };
 
 double now_ms() {
@@ -82,7 +110,15 @@ struct Tracker {
   int f_id = 0;
   bool initialised = false;
   // incremental tracklet state (rebuild_tracklets == 0)
-  std::vector<int> trackOfPrev;
+  std::vector<int> trackOfPrev, dynTrackOfPrev;
+  int max_id = 1;
+  // mSegMapLast / mFlowMapLast (src/Tracking.cc:777-780), kept only while the last frame carries object features
+  std::vector<int32_t> segLast, segCur;
+  std::vector<float> flowLast;
+  // object samples of the current Frame ctor (mvTmpObjKeys ... of src/Tracking.cc:395-399)
+  std::vector<P2> tmpKeys, tmpCorres, tmpFlow;
+  std::vector<float> tmpDepth;
+  std::vector<int> tmpSem;
 
   ~Tracker() { delete last; if (cur != last) delete cur; }
 
@@ -135,6 +171,321 @@ struct Tracker {
       }
     }
     trackOfPrev = curc;
+  }
+
+
+  // ---- Frame::UnprojectStereoObject(i, 0) (src/Frame.cc:735-769): world point of object feature i of frame f
+  P3 unproject_obj(const Frame& f, int i) const {
+    float Twf[16];
+    inv44(f.Tcw, Twf);
+    return to_world(unproject_cam(f.mvObjKeys[i], f.mvObjDepth[i]), Twf);
+  }
+
+  // ---- Tracking::GetSceneFlowObj (src/Tracking.cc:1582-1668)
+  void scene_flow() {
+    const int N = (int)cur->mvObjKeys.size();
+    cur->vFlow_3d.assign(N, P3{0.f, 0.f, 0.f});
+    float Twl[16], Twc[16];
+    inv44(last->Tcw, Twl);
+    inv44(cur->Tcw, Twc);
+    for (int i = 0; i < N; i++) {
+      if (cur->vSemObjLabel[i] <= 0 || last->vSemObjLabel[i] <= 0) { cur->vObjLabel[i] = -1; continue; }
+      const P3 xp = to_world(unproject_cam(last->mvObjKeys[i], last->mvObjDepth[i]), Twl);
+      const P3 xc = to_world(unproject_cam(cur->mvObjKeys[i], cur->mvObjDepth[i]), Twc);
+      cur->vFlow_3d[i] = {xc.x - xp.x, xc.y - xp.y, xc.z - xp.z};
+    }
+  }
+
+  // most frequent value; ties -> smallest value (std::map order + insertion sort of SortPairInt, src/Tracking.cc:1853-1863)
+  static int majority(const std::vector<int>& v) {
+    std::map<int, int> dups;
+    for (int k : v) ++dups[k];
+    int best = 0, cnt = -1;
+    for (auto& k : dups)
+      if (k.second > cnt) { cnt = k.second; best = k.first; }
+    return best;
+  }
+
+  // ---- Tracking::DynObjTracking (src/Tracking.cc:1670-1912)
+  std::vector<std::vector<int>> dyn_obj_tracking() {
+    const int W = cfg.width, H = cfg.height;
+    std::vector<int> UniLab = cur->vSemObjLabel;
+    std::sort(UniLab.begin(), UniLab.end());
+    UniLab.erase(std::unique(UniLab.begin(), UniLab.end()), UniLab.end());
+    std::vector<std::vector<int>> Posi(UniLab.size());
+    for (size_t i = 0; i < cur->vSemObjLabel.size(); i++) {
+      if (cur->vObjLabel[i] == -1) continue;
+      for (size_t j = 0; j < UniLab.size(); j++)
+        if (cur->vSemObjLabel[i] == UniLab[j]) { Posi[j].push_back((int)i); break; }
+    }
+    // objects mostly on the image boundary are dropped
+    std::vector<std::vector<int>> ObjId;
+    std::vector<int> sem_posi;
+    const int shrin_thr_row = 10, shrin_thr_col = 20;
+    for (size_t i = 0; i < Posi.size(); i++) {
+      float count = 0;
+      const float count_thres = 0.5f;
+      for (int id : Posi[i]) {
+        const float u = cur->mvObjKeys[id].x, v = cur->mvObjKeys[id].y;
+        if (v < shrin_thr_row || v > (H - shrin_thr_row) || u < shrin_thr_col || u > (W - shrin_thr_col)) count = count + 1;
+      }
+      if (count / Posi[i].size() > count_thres) {
+        for (int id : Posi[i]) cur->vObjLabel[id] = -1;
+        continue;
+      }
+      ObjId.push_back(Posi[i]);
+      sem_posi.push_back(UniLab[i]);
+    }
+    // static / far / small objects
+    std::vector<std::vector<int>> ObjIdNew;
+    std::vector<int> SemPosNew;
+    for (size_t i = 0; i < ObjId.size(); i++) {
+      float obj_center_depth = 0, sf_count = 0;
+      for (int id : ObjId[i]) {
+        obj_center_depth = obj_center_depth + cur->mvObjDepth[id];
+        const P3& f = cur->vFlow_3d[id];
+        const float sf_norm = std::sqrt(f.x * f.x + f.z * f.z);
+        if (sf_norm < cfg.sf_mg_thres) sf_count = sf_count + 1;
+      }
+      if (sf_count / ObjId[i].size() > cfg.sf_ds_thres) {
+        for (int id : ObjId[i]) cur->vObjLabel[id] = 0;
+        continue;
+      } else if (obj_center_depth / ObjId[i].size() > cfg.th_depth_obj || ObjId[i].size() < 150) {
+        for (int id : ObjId[i]) cur->vObjLabel[id] = -1;
+        continue;
+      }
+      ObjIdNew.push_back(ObjId[i]);
+      SemPosNew.push_back(sem_posi[i]);
+    }
+    // tracking ids: same semantic label as an object with a valid motion in the last frame -> same id, else a new one
+    if (f_id == 1) max_id = 1;
+    std::vector<int> LabId(ObjIdNew.size());
+    for (size_t i = 0; i < ObjIdNew.size(); i++) {
+      std::vector<int> Lb_last;
+      for (int id : ObjIdNew[i]) Lb_last.push_back(last->vSemObjLabel[id]);
+      const int New_lab = majority(Lb_last);
+      bool exist = false;
+      if (max_id != 1) {
+        for (size_t k = 0; k < last->nSemPosition.size(); k++)
+          if (last->nSemPosition[k] == New_lab && last->bObjStat[k]) { LabId[i] = last->nModLabel[k]; exist = true; break; }
+      }
+      if (!exist) { LabId[i] = max_id; max_id = max_id + 1; }
+      for (int id : ObjIdNew[i]) cur->vObjLabel[id] = LabId[i];
+    }
+    cur->nModLabel = LabId;
+    cur->nSemPosition = SemPosNew;
+    return ObjIdNew;
+  }
+
+  // ---- object loop of Tracking::Track (src/Tracking.cc:1179-1308): GetInitModelObj + PoseOptimizationFlow2 per object
+  void object_motions(const std::vector<std::vector<int>>& ObjIdNew) {
+    const size_t no = ObjIdNew.size();
+    cur->bObjStat.assign(no, 1);
+    cur->vObjMod.resize(no);
+    cur->vObjCentre3D.assign(no, P3{0.f, 0.f, 0.f});
+    cur->vnObjID.resize(no);
+    cur->vnObjInlierID.resize(no);
+    float Twl[16], Twc[16];
+    inv44(last->Tcw, Twl);
+    inv44(cur->Tcw, Twc);
+    for (size_t i = 0; i < no; i++) {
+      const std::vector<int>& ObjId = ObjIdNew[i];
+      const int N = (int)ObjId.size();
+      cur->vnObjID[i] = ObjId;
+      // centroid of the object's points in the last frame (cv::Mat float sums)
+      std::vector<float> cur2d(2 * (size_t)N), p3d(3 * (size_t)N);
+      P3 c = {0.f, 0.f, 0.f};
+      for (int j = 0; j < N; j++) {
+        const P3 xp = to_world(unproject_cam(last->mvObjKeys[ObjId[j]], last->mvObjDepth[ObjId[j]]), Twl);
+        c.x += xp.x; c.y += xp.y; c.z += xp.z;
+        p3d[3 * j] = xp.x; p3d[3 * j + 1] = xp.y; p3d[3 * j + 2] = xp.z;
+        cur2d[2 * j] = cur->mvObjKeys[ObjId[j]].x; cur2d[2 * j + 1] = cur->mvObjKeys[ObjId[j]].y;
+      }
+      const float invn = (float)(1.0 / (double)N);
+      cur->vObjCentre3D[i] = {c.x * invn, c.y * invn, c.z * invn};
+      // ---- GetInitModelObj
+      int PreObjID = -1;
+      for (size_t k = 0; k < last->nModLabel.size(); k++)
+        if (last->nModLabel[k] == cur->nModLabel[i]) { PreObjID = (int)k; break; }
+      vo_pnp_problem pp;
+      memset(&pp, 0, sizeof pp);
+      vo_pnp_default_params(&pp);
+      std::vector<int> ids(N);
+      pp.n = N; pp.cur_xy = cur2d.data(); pp.pts3d = p3d.data(); pp.valid = nullptr; pp.inlier_ids = ids.data();
+      if (PreObjID != -1) mul44(cur->Tcw, last->vObjMod[PreObjID].data(), pp.Tcw_motion);
+      else { memcpy(pp.Tcw_motion, cur->Tcw, sizeof(float) * 16); pp.no_motion_model = 1; }
+      pp.fx = cfg.fx; pp.fy = cfg.fy; pp.cx = cfg.cx; pp.cy = cfg.cy;
+      vo_init_model_cam(&pp);
+      std::vector<int> in_ids(pp.n_inliers);
+      std::vector<char> keep(N, 0);
+      for (int k = 0; k < pp.n_inliers; k++) { in_ids[k] = ObjId[ids[k]]; keep[ids[k]] = 1; }
+      for (int j = 0; j < N; j++)
+        if (!keep[j]) cur->vObjLabel[ObjId[j]] = -1;
+      if (in_ids.size() < 50) {
+        cur->bObjStat[i] = 0;
+        eye44(cur->vObjMod[i].data());
+        cur->vObjCentre3D[i] = {0.f, 0.f, 0.f};
+        cur->vnObjInlierID[i] = in_ids;
+        continue;
+      }
+      // ---- PoseOptimizationFlow2
+      const int n = (int)in_ids.size();
+      std::vector<float> obs(2 * (size_t)n), fl(2 * (size_t)n), dep(n), fo(2 * (size_t)n);
+      std::vector<int> inl(n);
+      for (int k = 0; k < n; k++) {
+        const int id = in_ids[k];
+        obs[2 * k] = last->mvObjKeys[id].x; obs[2 * k + 1] = last->mvObjKeys[id].y;
+        fl[2 * k] = last->mvObjFlowNext[id].x; fl[2 * k + 1] = last->mvObjFlowNext[id].y;
+        dep[k] = last->mvObjDepth[id];
+      }
+      vo_poseopt_problem po;
+      memset(&po, 0, sizeof po);
+      vo_poseopt_default_params(&po);
+      po.n = n; po.obs_xy = obs.data(); po.flow_xy = fl.data(); po.depth = dep.data();
+      memcpy(po.Tcw_init, pp.Tcw_out, sizeof(float) * 16);
+      memcpy(po.Tcw_last, last->Tcw, sizeof(float) * 16);
+      po.fx = cfg.fx; po.fy = cfg.fy; po.cx = cfg.cx; po.cy = cfg.cy;
+      po.flow_out = fo.data(); po.inlier = inl.data();
+      po.info_prior = 0.5f; po.rounds = 1; po.its = 200;
+      vo_poseopt_flow2cam(&po, nullptr);
+      mul44(Twc, po.Tcw_out, cur->vObjMod[i].data());  // vObjMod = inv(Tcw) * Obj_X
+      std::vector<int> InlierID;
+      for (int k = 0; k < n; k++) {
+        const int id = in_ids[k];
+        if (inl[k]) {
+          cur->mvObjKeys[id].x = (float)((double)last->mvObjKeys[id].x + (double)fo[2 * k]);
+          cur->mvObjKeys[id].y = (float)((double)last->mvObjKeys[id].y + (double)fo[2 * k + 1]);
+          InlierID.push_back(id);
+        } else cur->vObjLabel[id] = -1;
+      }
+      cur->vnObjInlierID[i] = InlierID;
+    }
+  }
+
+  // ---- Tracking::RenewFrameInfo, object part (src/Tracking.cc:3112-3289)
+  void renew_objects(const float* depth, const float* flow, const int32_t* mask) {
+    const int W = cfg.width, H = cfg.height, max_num_obj = cfg.max_track_obj;
+    std::vector<P2> keys, corres, fl;
+    std::vector<float> dep;
+    std::vector<int> sem, inl, lab;
+    const size_t no = cur->vnObjInlierID.size();
+    std::vector<int> ObjFeaCount(no);
+    for (size_t i = 0; i < no; i++) {
+      if (!cur->bObjStat[i]) { ObjFeaCount[i] = -1; continue; }
+      int count = 0;
+      for (int id : cur->vnObjInlierID[i]) {
+        const int x = (int)cur->mvObjKeys[id].x, y = (int)cur->mvObjKeys[id].y;
+        if (x >= W || y >= H || x <= 0 || y <= 0) continue;
+        const size_t k = (size_t)y * W + x;
+        if (mask[k] != 0 && depth[k] < 25 && depth[k] > 0) {
+          const float fx = flow[2 * k], fy = flow[2 * k + 1];
+          if (x + fx < W && y + fy < H && x + fx > 0 && y + fy > 0) {
+            keys.push_back({(float)x, (float)y});
+            dep.push_back(depth[k]);
+            sem.push_back(mask[k]);
+            fl.push_back({fx, fy});
+            corres.push_back({x + fx, y + fy});
+            inl.push_back(id);
+            lab.push_back(cur->vObjLabel[id]);
+            count = count + 1;
+          }
+        }
+      }
+      ObjFeaCount[i] = count;
+    }
+    // top-up per tracked object from this frame's samples, 15 interleaved passes, >= 1 px away from the kept inliers
+    const std::vector<P2> check = keys;
+    for (size_t i = 0; i < no; i++) {
+      if (!cur->bObjStat[i]) continue;
+      const int SemLabel = cur->nSemPosition[i];
+      int tot_num = ObjFeaCount[i], start_id = 0;
+      const int step = 15;
+      while (tot_num < max_num_obj) {
+        if (start_id == step) break;
+        for (size_t j = start_id; j < tmpSem.size(); j += step) {
+          if (tmpSem[j] != SemLabel) continue;
+          float min_dist = 100;
+          bool used = false;
+          for (size_t k = 0; k < check.size(); k++) {
+            const float d = std::sqrt((check[k].x - tmpKeys[j].x) * (check[k].x - tmpKeys[j].x) +
+                                      (check[k].y - tmpKeys[j].y) * (check[k].y - tmpKeys[j].y));
+            if (d < min_dist) min_dist = d;
+            if (min_dist < 1.0) { used = true; break; }
+          }
+          if (used) continue;
+          keys.push_back(tmpKeys[j]); dep.push_back(tmpDepth[j]); sem.push_back(tmpSem[j]); fl.push_back(tmpFlow[j]);
+          corres.push_back(tmpCorres[j]); inl.push_back(-1); lab.push_back(cur->nModLabel[i]);
+          tot_num = tot_num + 1;
+          if (tot_num >= max_num_obj) break;
+        }
+        start_id = start_id + 1;
+      }
+    }
+    // semantic labels without a tracked object: all their samples, label -2
+    std::vector<int> UniLab = tmpSem;
+    std::sort(UniLab.begin(), UniLab.end());
+    UniLab.erase(std::unique(UniLab.begin(), UniLab.end()), UniLab.end());
+    std::vector<char> NewLab(UniLab.size(), 0);
+    for (size_t i = 0; i < cur->nSemPosition.size(); i++)
+      for (size_t j = 0; j < UniLab.size(); j++)
+        if (UniLab[j] == cur->nSemPosition[i] && cur->bObjStat[i]) { NewLab[j] = 1; break; }
+    for (size_t i = 0; i < NewLab.size(); i++) {
+      if (NewLab[i]) continue;
+      for (size_t j = 0; j < tmpSem.size(); j++) {
+        if (UniLab[i] != tmpSem[j]) continue;
+        keys.push_back(tmpKeys[j]); dep.push_back(tmpDepth[j]); sem.push_back(tmpSem[j]); fl.push_back(tmpFlow[j]);
+        corres.push_back(tmpCorres[j]); inl.push_back(-1); lab.push_back(-2);
+      }
+    }
+    float Twc[16];
+    inv44(cur->Tcw, Twc);
+    std::vector<P3> p3(keys.size());
+    for (size_t i = 0; i < keys.size(); i++) p3[i] = to_world(unproject_cam(keys[i], dep[i]), Twc);
+    cur->mvObjKeys = keys; cur->mvObjDepth = dep; cur->mvObj3DPoint = p3; cur->mvObjCorres = corres; cur->mvObjFlowNext = fl;
+    cur->vSemObjLabel = sem; cur->nDynInlierID = inl; cur->vObjLabel = lab;
+  }
+
+  // ---- Tracking::GetDynamicTrackNew (src/Tracking.cc:2615-2720), from frame 0 or incrementally (same chains)
+  void rebuild_dyn_tracklets() {
+    const auto& TM = map.vnAssoDyn;
+    const auto& OL = map.vnFeatLabel;
+    std::vector<int> pre;
+    std::vector<std::vector<std::pair<int, int>>> T;
+    std::vector<int> oid;
+    for (int i = 0; i < (int)TM.size(); i++) {
+      std::vector<int> curc(TM[i].size(), -1);
+      for (size_t j = 0; j < TM[i].size(); j++) {
+        if (TM[i][j] == -1) continue;
+        if (i > 0 && pre[TM[i][j]] != -1) {
+          T[pre[TM[i][j]]].push_back({i + 1, (int)j});
+          curc[j] = pre[TM[i][j]];
+        } else {
+          T.push_back({{i, TM[i][j]}, {i + 1, (int)j}});
+          oid.push_back(OL[i][j]);
+          curc[j] = (int)T.size() - 1;
+        }
+      }
+      pre = curc;
+    }
+    map.TrackletDyn.swap(T);
+    map.nObjID.swap(oid);
+  }
+  void extend_dyn_tracklets() {
+    const auto& TM = map.vnAssoDyn;
+    const int i = (int)TM.size() - 1;
+    std::vector<int> curc(TM[i].size(), -1);
+    for (size_t j = 0; j < TM[i].size(); j++) {
+      if (TM[i][j] == -1) continue;
+      if (i > 0 && dynTrackOfPrev[TM[i][j]] != -1) {
+        map.TrackletDyn[dynTrackOfPrev[TM[i][j]]].push_back({i + 1, (int)j});
+        curc[j] = dynTrackOfPrev[TM[i][j]];
+      } else {
+        map.TrackletDyn.push_back({{i, TM[i][j]}, {i + 1, (int)j}});
+        map.nObjID.push_back(map.vnFeatLabel[i][j]);
+        curc[j] = (int)map.TrackletDyn.size() - 1;
+      }
+    }
+    dynTrackOfPrev = curc;
   }
 
   // ---- Optimizer::PartialBatchOptimization
@@ -268,6 +619,17 @@ struct Tracker {
     if (st) memset(st, 0, sizeof *st);
     double t0 = now_ms();
     vo_depth_prep(depth, W, H, W, cfg.choose_data, cfg.depth_map_factor, cfg.bf, 1.0f);
+    // ---- UpdateMask (src/Tracking.cc:353-364): the reference edits the caller's mask in place; the oracle edits a copy
+    if (initialised && !last->vSemObjLabel.empty() && !segLast.empty()) {
+      segCur.assign(mask, mask + (size_t)W * H);
+      std::vector<float> cor(2 * last->mvObjCorres.size());
+      for (size_t i = 0; i < last->mvObjCorres.size(); i++) { cor[2 * i] = last->mvObjCorres[i].x; cor[2 * i + 1] = last->mvObjCorres[i].y; }
+      std::vector<int32_t> uniq(last->vSemObjLabel.size() + 1), rec(last->vSemObjLabel.size() + 1);
+      const int nu = vo_update_mask(last->vSemObjLabel.data(), cor.data(), (int)last->vSemObjLabel.size(), segLast.data(), flowLast.data(),
+                                    segCur.data(), W, H, uniq.data(), rec.data(), (int)uniq.size());
+      if (st) for (int i = 0; i < nu; i++) st->n_masks_recovered += rec[i] ? 1 : 0;
+      mask = segCur.data();
+    }
     cur = new Frame();
     eye44(cur->Tcw);
     cur->mvKeys.resize(cfg.orb.nfeatures + 64);
@@ -286,6 +648,35 @@ struct Tracker {
         cur->mvFlowNext.push_back({fl[2 * i], fl[2 * i + 1]});
         cur->mvStatDepthTmp.push_back(dep[i]);
       }
+    }
+    {  // Frame ctor: stride-4 object sampling (src/Frame.cc:184-211)
+      const int cap = ((W + 3) / 4) * ((H + 3) / 4);
+      std::vector<float> k2(2 * (size_t)cap), c2(2 * (size_t)cap), f2(2 * (size_t)cap), d1(cap);
+      std::vector<int32_t> l1(cap);
+      const int m = vo_frame_sample_objects(depth, flow, mask, W, H, cfg.th_depth_obj, k2.data(), c2.data(), f2.data(), d1.data(), l1.data(), cap);
+      tmpKeys.resize(m); tmpCorres.resize(m); tmpFlow.resize(m); tmpDepth.assign(d1.begin(), d1.begin() + m); tmpSem.assign(l1.begin(), l1.begin() + m);
+      for (int i = 0; i < m; i++) { tmpKeys[i] = {k2[2 * i], k2[2 * i + 1]}; tmpCorres[i] = {c2[2 * i], c2[2 * i + 1]}; tmpFlow[i] = {f2[2 * i], f2[2 * i + 1]}; }
+    }
+    if (initialised) {  // GrabImageRGBD :391-421: object features = last frame's correspondences, fresh depth / label lookups
+      cur->mvObjKeys = last->mvObjCorres;
+      const size_t no = cur->mvObjKeys.size();
+      cur->mvObjDepth.assign(no, -1.f);
+      cur->vSemObjLabel.assign(no, -1);
+      for (size_t i = 0; i < no; i++) {
+        const int u = (int)cur->mvObjKeys[i].x, v = (int)cur->mvObjKeys[i].y;
+        if (u < (W - 1) && u > 0 && v < (H - 1) && v > 0 && depth[(size_t)v * W + u] < cfg.th_depth_obj && depth[(size_t)v * W + u] > 0) {
+          cur->mvObjDepth[i] = depth[(size_t)v * W + u];
+          cur->vSemObjLabel[i] = mask[(size_t)v * W + u];
+        } else {
+          cur->mvObjDepth[i] = 0.1f;
+          cur->vSemObjLabel[i] = 0;
+        }
+      }
+      cur->vObjLabel.assign(no, -2);
+    } else {
+      cur->mvObjKeys = tmpKeys; cur->mvObjCorres = tmpCorres; cur->mvObjFlowNext = tmpFlow; cur->mvObjDepth = tmpDepth;
+      cur->vSemObjLabel = tmpSem;
+      cur->vObjLabel.assign(tmpKeys.size(), -2);
     }
     if (initialised) {  // GrabImageRGBD :369-389
       cur->mvStatKeys = last->mvCorres;
@@ -308,6 +699,11 @@ struct Tracker {
       map.vpFeatSta.push_back(cur->mvStatKeysTmp);
       map.vfDepSta.push_back(cur->mvStatDepthTmp);
       map.vp3DPointSta.push_back(cur->mvStat3DPointTmp);
+      for (size_t i = 0; i < cur->mvObjKeys.size(); i++) cur->mvObj3DPoint.push_back(unproject_cam(cur->mvObjKeys[i], cur->mvObjDepth[i]));
+      map.vpFeatDyn.push_back(cur->mvObjKeys);
+      map.vfDepDyn.push_back(cur->mvObjDepth);
+      map.vp3DPointDyn.push_back(cur->mvObj3DPoint);
+      if (st) st->n_dyn_features = (int)cur->mvObjKeys.size();
       std::vector<float> I(16, 0.f);
       I[0] = I[5] = I[10] = I[15] = 1.f;
       map.vmCameraPose.push_back(I);
@@ -378,8 +774,17 @@ struct Tracker {
         inv44(last->Tcw, LastTwc);
         mul44(cur->Tcw, LastTwc, mVelocity);
         has_velocity = true;
+        // ---- scene flow, object tracking, object motions (src/Tracking.cc:1160-1308)
+        std::vector<std::vector<int>> ObjIdNew;
+        if (!cur->mvObjKeys.empty()) {
+          scene_flow();
+          ObjIdNew = dyn_obj_tracking();
+          object_motions(ObjIdNew);
+        }
+        double t4b = now_ms();
         // ---- RenewFrameInfo + map bookkeeping
         renew(TM_sub, depth, flow, mask);
+        renew_objects(depth, flow, mask);
         Frame* old = last;
         last = cur;
         last->mvStatKeys = cur->mvStatKeysTmp;
@@ -389,8 +794,24 @@ struct Tracker {
         map.vfDepSta.push_back(cur->mvStatDepthTmp);
         map.vp3DPointSta.push_back(cur->mvStat3DPointTmp);
         map.vnAssoSta.push_back(cur->nStaInlierID);
-        if (cfg.rebuild_tracklets) rebuild_tracklets();
-        else extend_tracklets();
+        map.vpFeatDyn.push_back(cur->mvObjKeys);
+        map.vfDepDyn.push_back(cur->mvObjDepth);
+        map.vp3DPointDyn.push_back(cur->mvObj3DPoint);
+        map.vnAssoDyn.push_back(cur->nDynInlierID);
+        map.vnFeatLabel.push_back(cur->vObjLabel);
+        if (cfg.rebuild_tracklets) { rebuild_tracklets(); rebuild_dyn_tracklets(); }
+        else { extend_tracklets(); extend_dyn_tracklets(); }
+        {  // (6.2) object motions and labels, (10) centres (src/Tracking.cc:1390-1422)
+          std::vector<std::array<float, 16>> mot_o;
+          std::vector<int> rml, sml;
+          std::vector<P3> cen;
+          for (size_t i = 0; i < cur->vObjMod.size(); i++) {
+            if (!cur->bObjStat[i]) continue;
+            mot_o.push_back(cur->vObjMod[i]); rml.push_back(cur->nModLabel[i]); sml.push_back(cur->nSemPosition[i]);
+            cen.push_back(cur->vObjCentre3D[i]);
+          }
+          map.vmObjMotion.push_back(mot_o); map.vnRMLabel.push_back(rml); map.vnSMLabel.push_back(sml); map.vmRigidCentre.push_back(cen);
+        }
         std::vector<float> Twc(16), mot(16);
         inv44(cur->Tcw, Twc.data());
         inv44(mVelocity, mot.data());
@@ -398,13 +819,20 @@ struct Tracker {
         map.vmRigidMotion.push_back(mot);
         double t5 = now_ms();
         if (st) {
-          st->ms_init = t3 - t2; st->ms_poseopt = t4 - t3; st->ms_renew = t5 - t4;
+          st->ms_init = t3 - t2; st->ms_poseopt = t4 - t3; st->ms_renew = t5 - t4; (void)t4b;
+          st->n_dyn_features = (int)cur->mvObjKeys.size(); st->n_objects = (int)cur->vObjMod.size();
+          for (char b : cur->bObjStat) st->n_objects_ok += b ? 1 : 0;
           st->n_matches = Ns; st->n_init_inliers = pp.n_inliers; st->init_winner = pp.winner; st->n_pose_inliers = ninl;
           st->n_static = (int)cur->mvStatKeysTmp.size();
         }
       }
     }
     memcpy(Tcw_out, cur->Tcw, sizeof(float) * 16);
+    // mSegMapLast / mFlowMapLast (src/Tracking.cc:777-780); only needed while object features are alive
+    if (rc == 0 && !last->vSemObjLabel.empty()) {
+      segLast.assign(mask, mask + (size_t)W * H);
+      flowLast.assign(flow, flow + 2 * (size_t)W * H);
+    } else if (rc == 0) { segLast.clear(); flowLast.clear(); }
     // ---- PartialBatchOptimization, every frame (src/Tracking.cc:1428-1451)
     double t6 = now_ms();
     const int window = f_id < cfg.window_size ? f_id : cfg.window_size;
@@ -446,6 +874,42 @@ int vo_tracker_get_static(void* h, int frame, float* xy, float* depth, float* p3
     depth[i] = t->map.vfDepSta[frame][i];
     p3[3 * i] = t->map.vp3DPointSta[frame][i].x; p3[3 * i + 1] = t->map.vp3DPointSta[frame][i].y; p3[3 * i + 2] = t->map.vp3DPointSta[frame][i].z;
     asso[i] = frame > 0 ? t->map.vnAssoSta[frame - 1][i] : -1;
+  }
+  return n;
+}
+
+int vo_tracker_get_dynamic(void* h, int frame, float* xy, float* depth, float* p3, int32_t* asso, int32_t* label, int cap) {
+  Tracker* t = (Tracker*)h;
+  if (frame < 0 || frame >= (int)t->map.vpFeatDyn.size()) return -1;
+  const int n = (int)t->map.vpFeatDyn[frame].size();
+  for (int i = 0; i < n && i < cap; i++) {
+    xy[2 * i] = t->map.vpFeatDyn[frame][i].x; xy[2 * i + 1] = t->map.vpFeatDyn[frame][i].y;
+    depth[i] = t->map.vfDepDyn[frame][i];
+    p3[3 * i] = t->map.vp3DPointDyn[frame][i].x; p3[3 * i + 1] = t->map.vp3DPointDyn[frame][i].y; p3[3 * i + 2] = t->map.vp3DPointDyn[frame][i].z;
+    asso[i] = frame > 0 ? t->map.vnAssoDyn[frame - 1][i] : -1;
+    label[i] = frame > 0 ? t->map.vnFeatLabel[frame - 1][i] : -2;
+  }
+  return n;
+}
+int vo_tracker_get_objects(void* h, int frame, int32_t* label, int32_t* sem_label, float* motion, float* centre, int cap) {
+  Tracker* t = (Tracker*)h;
+  if (frame < 1 || frame > (int)t->map.vmObjMotion.size()) return -1;
+  const auto& M = t->map.vmObjMotion[frame - 1];
+  const int n = (int)M.size();
+  for (int i = 0; i < n && i < cap; i++) {
+    label[i] = t->map.vnRMLabel[frame - 1][i]; sem_label[i] = t->map.vnSMLabel[frame - 1][i];
+    memcpy(motion + 16 * i, M[i].data(), sizeof(float) * 16);
+    centre[3 * i] = t->map.vmRigidCentre[frame - 1][i].x; centre[3 * i + 1] = t->map.vmRigidCentre[frame - 1][i].y;
+    centre[3 * i + 2] = t->map.vmRigidCentre[frame - 1][i].z;
+  }
+  return n;
+}
+int vo_tracker_get_dyn_tracks(void* h, int32_t* len, int32_t* obj_id, int32_t* first_frame, int32_t* first_feat, int cap) {
+  Tracker* t = (Tracker*)h;
+  const int n = (int)t->map.TrackletDyn.size();
+  for (int i = 0; i < n && i < cap; i++) {
+    len[i] = (int)t->map.TrackletDyn[i].size(); obj_id[i] = t->map.nObjID[i];
+    first_frame[i] = t->map.TrackletDyn[i][0].first; first_feat[i] = t->map.TrackletDyn[i][0].second;
   }
   return n;
 }

@@ -145,7 +145,9 @@ int vo_poseopt_flow2cam(vo_poseopt_problem* p, vo_lm_stats* stats /* [rounds] or
  * iteration count, refit on the consensus set.  Cross-checked loosely against cv2.solvePnPRansac in the tests.
  */
 typedef struct vo_pnp_problem {
-  int32_t n, pad;
+  int32_t n;
+  int32_t no_motion_model; /* 1: GetInitModelObj without a previous motion of the object (src/Tracking.cc:2143-2151): the RANSAC
+                              model is returned whatever its support; Tcw_motion only seeds the minimal solver */
   const float* cur_xy;     /* [n][2] current keypoints */
   const float* pts3d;      /* [n][3] world points of the last frame (UnprojectStereoStat, float) */
   const int32_t* valid;    /* [n] 0 where the depth was negative (excluded from RANSAC) */
@@ -160,7 +162,7 @@ typedef struct vo_pnp_problem {
 void vo_pnp_default_params(vo_pnp_problem* p);
 int vo_init_model_cam(vo_pnp_problem* p);
 
-/* ---- per-frame driver (VO, static scene): System::TrackRGBD -> Tracking::GrabImageRGBD -> Track ---- */
+/* ---- per-frame driver (VO, static + dynamic objects): System::TrackRGBD -> Tracking::GrabImageRGBD -> Track ---- */
 typedef struct vo_track_config {
   int32_t width, height;
   float fx, fy, cx, cy, bf;
@@ -169,11 +171,15 @@ typedef struct vo_track_config {
   int32_t max_track_bg, window_size;
   vo_orb_params orb;
   int32_t rebuild_tracklets; /* 1: rebuild all tracklets from frame 0 every frame like the reference (O(T)/frame) */
+  int32_t max_track_obj;     /* MaxTrackPointOBJ (500) */
+  float sf_mg_thres, sf_ds_thres; /* SFMgThres 0.12 / SFDsThres 0.3 (src/Tracking.cc:159-160) */
 } vo_track_config;
 typedef struct vo_track_stats {
   double ms_orb, ms_assoc, ms_init, ms_poseopt, ms_renew, ms_ba;
   int32_t n_keypoints, n_matches, n_init_inliers, init_winner, n_pose_inliers, n_static;
   int32_t ba_iterations, ba_trials, ba_points, ba_obs;
+  int32_t n_dyn_features, n_objects, n_objects_ok, n_masks_recovered; /* object features leaving the frame; objects found by
+                                DynObjTracking; objects with an estimated motion (bObjStat); labels re-warped by UpdateMask */
 } vo_track_stats;
 void* vo_tracker_create(const vo_track_config* cfg);
 void vo_tracker_destroy(void* h);
@@ -183,6 +189,14 @@ int vo_tracker_track(void* h, const uint8_t* gray, float* depth, const float* fl
 int vo_tracker_num_frames(void* h);
 int vo_tracker_get_map_poses(void* h, float* poses /* [n][16] Map::vmCameraPose (Twc, BA-refined) */, int cap);
 int vo_tracker_get_static(void* h, int frame, float* xy, float* depth, float* p3, int32_t* asso, int cap);
+/* Map::vpFeatDyn / vfDepDyn / vp3DPointDyn / vnAssoDyn[frame-1] / vnFeatLabel[frame-1] (include/Map.h:44-97) */
+int vo_tracker_get_dynamic(void* h, int frame, float* xy, float* depth, float* p3, int32_t* asso, int32_t* label, int cap);
+/* objects of frame >= 1: Map::vnRMLabel / vnSMLabel / vmRigidMotion / vmRigidCentre [frame-1][1..] (camera entry 0 skipped) */
+int vo_tracker_get_objects(void* h, int frame, int32_t* label, int32_t* sem_label, float* motion /* [n][16] */,
+                           float* centre /* [n][3] */, int cap);
+/* Map::TrackletDyn / nObjID (Tracking::GetDynamicTrackNew, src/Tracking.cc:2615-2720): per track its length, object id and
+ * first (frame, feature) */
+int vo_tracker_get_dyn_tracks(void* h, int32_t* len, int32_t* obj_id, int32_t* first_frame, int32_t* first_feat, int cap);
 
 /* ---- IMU preintegration: Tracking::PreintegrateIMU (src/Tracking.cc:784-887) + IMU::Preintegrated (src/ImuTypes.cc:143-300) ---- */
 typedef struct vo_imu_sample { double t; float ax, ay, az, wx, wy, wz; } vo_imu_sample;

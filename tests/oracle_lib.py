@@ -231,7 +231,7 @@ def poseopt_flow2cam(obs_xy, flow_xy, depth, Tcw_init, Tcw_last, K, **params):
 
 
 class PnpProblem(C.Structure):
-    _fields_ = [("n", C.c_int32), ("pad", C.c_int32), ("cur_xy", C.c_void_p), ("pts3d", C.c_void_p),
+    _fields_ = [("n", C.c_int32), ("no_motion_model", C.c_int32), ("cur_xy", C.c_void_p), ("pts3d", C.c_void_p),
                 ("valid", C.c_void_p), ("Tcw_motion", C.c_float * 16),
                 ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
                 ("iters", C.c_int32), ("reproj_err", C.c_float), ("confidence", C.c_float),
@@ -267,7 +267,8 @@ class TrackConfig(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float),
                 ("cy", C.c_float), ("bf", C.c_float), ("choose_data", C.c_int32), ("depth_map_factor", C.c_float),
                 ("th_depth_bg", C.c_float), ("th_depth_obj", C.c_float), ("max_track_bg", C.c_int32),
-                ("window_size", C.c_int32), ("orb", OrbParams), ("rebuild_tracklets", C.c_int32)]
+                ("window_size", C.c_int32), ("orb", OrbParams), ("rebuild_tracklets", C.c_int32),
+                ("max_track_obj", C.c_int32), ("sf_mg_thres", C.c_float), ("sf_ds_thres", C.c_float)]
 
 
 class TrackStats(C.Structure):
@@ -275,14 +276,16 @@ class TrackStats(C.Structure):
                 ("ms_renew", C.c_double), ("ms_ba", C.c_double),
                 ("n_keypoints", C.c_int32), ("n_matches", C.c_int32), ("n_init_inliers", C.c_int32),
                 ("init_winner", C.c_int32), ("n_pose_inliers", C.c_int32), ("n_static", C.c_int32),
-                ("ba_iterations", C.c_int32), ("ba_trials", C.c_int32), ("ba_points", C.c_int32), ("ba_obs", C.c_int32)]
+                ("ba_iterations", C.c_int32), ("ba_trials", C.c_int32), ("ba_points", C.c_int32), ("ba_obs", C.c_int32),
+                ("n_dyn_features", C.c_int32), ("n_objects", C.c_int32), ("n_objects_ok", C.c_int32),
+                ("n_masks_recovered", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 def track_config(cam, nfeatures=2500, window=20, max_track_bg=1000, rebuild=1, choose_data=2, depth_map_factor=256.0,
-                 th_depth_bg=5000.0, th_depth_obj=25.0):
+                 th_depth_bg=5000.0, th_depth_obj=25.0, max_track_obj=500, sf_mg_thres=0.12, sf_ds_thres=0.3):
     c = TrackConfig()
     c.width, c.height = cam["width"], cam["height"]
     c.fx, c.fy, c.cx, c.cy, c.bf = cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["bf"]
@@ -290,6 +293,7 @@ def track_config(cam, nfeatures=2500, window=20, max_track_bg=1000, rebuild=1, c
     c.max_track_bg, c.window_size = max_track_bg, window
     c.orb = default_orb_params(nfeatures)
     c.rebuild_tracklets = rebuild
+    c.max_track_obj, c.sf_mg_thres, c.sf_ds_thres = max_track_obj, sf_mg_thres, sf_ds_thres
     return c
 
 
@@ -303,6 +307,9 @@ class OracleTracker:
         L.vo_tracker_get_map_poses.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.vo_tracker_num_frames.argtypes = [C.c_void_p]
         L.vo_tracker_get_static.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int]
+        L.vo_tracker_get_dynamic.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_int]
+        L.vo_tracker_get_objects.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int]
+        L.vo_tracker_get_dyn_tracks.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_int]
         self.cfg = cfg
         self.h = L.vo_tracker_create(C.byref(cfg))
 
@@ -326,6 +333,25 @@ class OracleTracker:
         asso = np.zeros(cap, np.int32)
         n = lib().vo_tracker_get_static(self.h, frame, _p(xy), _p(dep), _p(p3), _p(asso), cap)
         return xy[:n].copy(), dep[:n].copy(), p3[:n].copy(), asso[:n].copy()
+
+    def dynamic_features(self, frame, cap=32768):
+        """Map::vpFeatDyn / vfDepDyn / vp3DPointDyn / vnAssoDyn / vnFeatLabel of one frame"""
+        xy = np.zeros((cap, 2), np.float32); dep = np.zeros(cap, np.float32); p3 = np.zeros((cap, 3), np.float32)
+        asso = np.zeros(cap, np.int32); lab = np.zeros(cap, np.int32)
+        n = lib().vo_tracker_get_dynamic(self.h, frame, _p(xy), _p(dep), _p(p3), _p(asso), _p(lab), cap)
+        return xy[:n].copy(), dep[:n].copy(), p3[:n].copy(), asso[:n].copy(), lab[:n].copy()
+
+    def objects(self, frame, cap=64):
+        """(tracking label, semantic label, motion 4x4, centre) of the objects with an estimated motion in `frame` (>= 1)"""
+        lab = np.zeros(cap, np.int32); sem = np.zeros(cap, np.int32); mot = np.zeros((cap, 16), np.float32)
+        cen = np.zeros((cap, 3), np.float32)
+        n = max(lib().vo_tracker_get_objects(self.h, frame, _p(lab), _p(sem), _p(mot), _p(cen), cap), 0)
+        return lab[:n].copy(), sem[:n].copy(), mot[:n].reshape(n, 4, 4).copy(), cen[:n].copy()
+
+    def dyn_tracks(self, cap=1 << 20):
+        ln = np.zeros(cap, np.int32); oid = np.zeros(cap, np.int32); ff = np.zeros(cap, np.int32); fj = np.zeros(cap, np.int32)
+        n = lib().vo_tracker_get_dyn_tracks(self.h, _p(ln), _p(oid), _p(ff), _p(fj), cap)
+        return ln[:n].copy(), oid[:n].copy(), ff[:n].copy(), fj[:n].copy()
 
     def close(self):
         if self.h:

@@ -1,0 +1,63 @@
+"""GPU: vido_track_frames on scenes with dynamic objects against the oracle (same frames, same order): object bookkeeping
+is exact (counts, labels, associations, tracklets), object motions / refined features within the float tolerance."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import synth
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-4
+CAM = synth.KITTI
+
+
+def _both(pkg, n, batch, **kw):
+    sc = synth.Scene(cam=CAM, seed=1234, flow_noise=0.1, depth_noise=0.01, n_objects=5, **kw)
+    frames = [sc.frame(k) for k in range(n)]
+    otr = ol.OracleTracker(ol.track_config(CAM))
+    ref = [otr.track(f["gray"].numpy(), f["depth_in"].numpy(), f["flow"].numpy(), f["mask"].numpy()) for f in frames]
+    ctx = pkg.Context(pkg.default_config(width=CAM["width"], height=CAM["height"], fx=CAM["fx"], fy=CAM["fy"], cx=CAM["cx"],
+                                         cy=CAM["cy"], bf=CAM["bf"], max_batch=batch))
+    T, st = ctx.track_frames([dict(image=f["gray"].numpy(), depth=f["depth_in"].numpy(), flow=f["flow"].numpy(),
+                                   mask=f["mask"].numpy().copy()) for f in frames])
+    return otr, ref, ctx, T, st
+
+
+def _compare(otr, ref, ctx, T, st, n):
+    for k in range(n):
+        T0, s0, rc0 = ref[k]
+        assert rc0 == 0
+        for key in ("n_keypoints", "n_matches", "n_init_inliers", "n_pose_inliers", "n_static", "ba_points", "ba_obs",
+                    "n_dyn_features", "n_objects", "n_objects_ok", "n_masks_recovered"):
+            assert st[k][key] == s0[key], (k, key, st[k][key], s0[key])
+        assert np.abs(T[k] - T0).max() <= REL_TOL * max(np.abs(T0).max(), 1.0), k
+        a, b = ctx.map_dynamic(k), otr.dynamic_features(k)
+        assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4]), k      # vnAssoDyn, vnFeatLabel
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), k      # vpFeatDyn (integer pixels / samples), vfDepDyn
+        assert np.abs(a[2] - b[2]).max() <= REL_TOL * max(np.abs(b[2]).max(), 1.0), k
+        if k >= 1:
+            la, sa, ma, ca = ctx.map_objects(k)
+            lb, sb, mb, cb = otr.objects(k)
+            assert np.array_equal(la, lb) and np.array_equal(sa, sb), k
+            assert np.abs(ma - mb).max() <= REL_TOL * max(np.abs(mb).max(), 1.0), k
+            assert np.abs(ca - cb).max() <= 1e-4 * max(np.abs(cb).max(), 1.0), k
+    for x, y in zip(ctx.map_dyn_tracks(), otr.dyn_tracks()):
+        assert np.array_equal(x, y)
+    P0, P = otr.map_poses(), ctx.map_poses()
+    assert np.abs(P - P0).max() <= REL_TOL * max(np.abs(P0).max(), 1.0)
+
+
+def test_dynamic_sequence_matches_oracle(pkg):
+    n = 12
+    otr, ref, ctx, T, st = _both(pkg, n, 4)
+    assert all(s["n_objects"] == 5 for s in st[1:])
+    _compare(otr, ref, ctx, T, st, n)
+    otr.close(); ctx.close()
+
+
+def test_lost_mask_recovered_like_oracle(pkg):
+    n = 6
+    otr, ref, ctx, T, st = _both(pkg, n, 3, drop_mask=((3, 2), (4, 5)))
+    assert [s["n_masks_recovered"] for s in st] == [0, 0, 0, 1, 1, 0]
+    _compare(otr, ref, ctx, T, st, n)
+    otr.close(); ctx.close()

@@ -23,7 +23,7 @@ class VidoConfig(C.Structure):
                 ("max_track_bg", C.c_int32), ("max_track_obj", C.c_int32), ("window_size", C.c_int32),
                 ("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
                 ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32), ("rgb", C.c_int32),
-                ("max_batch", C.c_int32), ("device", C.c_int32)]
+                ("max_batch", C.c_int32), ("device", C.c_int32), ("sf_mg_thres", C.c_float), ("sf_ds_thres", C.c_float)]
 
 
 class LmRecord(C.Structure):
@@ -57,7 +57,7 @@ class PoseOptProblem(C.Structure):
 
 
 class PnpProblem(C.Structure):
-    _fields_ = [("n", C.c_int32), ("pad", C.c_int32), ("cur_xy", C.c_void_p), ("pts3d", C.c_void_p),
+    _fields_ = [("n", C.c_int32), ("no_motion_model", C.c_int32), ("cur_xy", C.c_void_p), ("pts3d", C.c_void_p),
                 ("valid", C.c_void_p), ("Tcw_motion", C.c_float * 16),
                 ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
                 ("iters", C.c_int32), ("reproj_err", C.c_float), ("confidence", C.c_float),
@@ -76,7 +76,9 @@ class TrackStats(C.Structure):
                 ("ms_renew", C.c_double), ("ms_ba", C.c_double),
                 ("n_keypoints", C.c_int32), ("n_matches", C.c_int32), ("n_init_inliers", C.c_int32),
                 ("init_winner", C.c_int32), ("n_pose_inliers", C.c_int32), ("n_static", C.c_int32),
-                ("ba_iterations", C.c_int32), ("ba_trials", C.c_int32), ("ba_points", C.c_int32), ("ba_obs", C.c_int32)]
+                ("ba_iterations", C.c_int32), ("ba_trials", C.c_int32), ("ba_points", C.c_int32), ("ba_obs", C.c_int32),
+                ("n_dyn_features", C.c_int32), ("n_objects", C.c_int32), ("n_objects_ok", C.c_int32),
+                ("n_masks_recovered", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -131,6 +133,9 @@ def load_library():
     lib.vido_map_num_frames.argtypes = [vp]
     lib.vido_map_get_poses.argtypes = [vp, vp, C.c_int]
     lib.vido_map_get_static.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int]
+    lib.vido_map_get_dynamic.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, C.c_int]
+    lib.vido_map_get_objects.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int]
+    lib.vido_map_get_dyn_tracks.argtypes = [vp, vp, vp, vp, vp, C.c_int]
     lib.vido_pnp_default_params.argtypes = [C.POINTER(PnpProblem)]
     lib.vido_init_model.argtypes = [vp, C.POINTER(PnpProblem)]
     lib.vido_poseopt_default_params.argtypes = [C.POINTER(PoseOptProblem)]
@@ -353,6 +358,27 @@ class Context:
         if n < 0:
             raise VidoError("bad frame index")
         return xy[:n].copy(), dep[:n].copy(), p3[:n].copy(), asso[:n].copy()
+
+    def map_dynamic(self, frame, cap=32768):
+        """Map::vpFeatDyn / vfDepDyn / vp3DPointDyn / vnAssoDyn / vnFeatLabel of one frame"""
+        xy = np.zeros((cap, 2), np.float32); dep = np.zeros(cap, np.float32); p3 = np.zeros((cap, 3), np.float32)
+        asso = np.zeros(cap, np.int32); lab = np.zeros(cap, np.int32)
+        n = self.lib.vido_map_get_dynamic(self.h, frame, _ptr(xy), _ptr(dep), _ptr(p3), _ptr(asso), _ptr(lab), cap)
+        if n < 0:
+            raise VidoError("bad frame index")
+        return xy[:n].copy(), dep[:n].copy(), p3[:n].copy(), asso[:n].copy(), lab[:n].copy()
+
+    def map_objects(self, frame, cap=64):
+        """(tracking label, semantic label, motion 4x4, centre) of the objects with an estimated motion in `frame` (>= 1)"""
+        lab = np.zeros(cap, np.int32); sem = np.zeros(cap, np.int32); mot = np.zeros((cap, 16), np.float32)
+        cen = np.zeros((cap, 3), np.float32)
+        n = max(self.lib.vido_map_get_objects(self.h, frame, _ptr(lab), _ptr(sem), _ptr(mot), _ptr(cen), cap), 0)
+        return lab[:n].copy(), sem[:n].copy(), mot[:n].reshape(n, 4, 4).copy(), cen[:n].copy()
+
+    def map_dyn_tracks(self, cap=1 << 20):
+        ln = np.zeros(cap, np.int32); oid = np.zeros(cap, np.int32); ff = np.zeros(cap, np.int32); fj = np.zeros(cap, np.int32)
+        n = self.lib.vido_map_get_dyn_tracks(self.h, _ptr(ln), _ptr(oid), _ptr(ff), _ptr(fj), cap)
+        return ln[:n].copy(), oid[:n].copy(), ff[:n].copy(), fj[:n].copy()
 
     def kernel_times(self):
         """device ms / timed regions of (ORB front-end, init model, pose optimisation, window BA) + BA algorithmic bytes"""

@@ -20,6 +20,7 @@ void vido_default_config(vido_config* c) {
   c->depth_map_factor = 256.f;
   c->th_depth_bg = 5000.f; c->th_depth_obj = 25.f;
   c->max_track_bg = 1000; c->max_track_obj = 500;
+  c->sf_mg_thres = 0.12f; c->sf_ds_thres = 0.3f;
   c->window_size = 20;
   c->nfeatures = 2500; c->scale_factor = 1.2f; c->nlevels = 8; c->ini_th_fast = 20; c->min_th_fast = 7;
   c->rgb = 0;
@@ -60,7 +61,7 @@ vido_ctx* vido_create(const vido_config* cfg) {
   cudaEventCreate(&ctx->ev1);
   int rc = orb_setup(ctx);
   if (rc == VIDO_OK) rc = ba_setup(ctx, 24, 16384, 131072);
-  if (rc == VIDO_OK) rc = po_setup(ctx, 4096, 16);
+  if (rc == VIDO_OK) rc = po_setup(ctx, 8192, 16);
   if (rc == VIDO_OK) rc = pnp_setup(ctx, 8192, 2048);
   if (rc == VIDO_OK) rc = trk_setup(ctx);
   if (rc != VIDO_OK) {
@@ -312,6 +313,16 @@ int vido_map_num_frames(vido_ctx* ctx) { return ctx ? trk_num_frames(ctx) : VIDO
 int vido_map_get_poses(vido_ctx* ctx, float* poses, int cap) { return (ctx && poses) ? trk_get_map_poses(ctx, poses, cap) : VIDO_ERR_ARG; }
 int vido_map_get_static(vido_ctx* ctx, int frame, float* xy, float* depth, float* p3, int32_t* asso, int cap) {
   return ctx ? trk_get_static(ctx, frame, xy, depth, p3, asso, cap) : VIDO_ERR_ARG;
+}
+
+int vido_map_get_dynamic(vido_ctx* ctx, int frame, float* xy, float* depth, float* p3, int32_t* asso, int32_t* label, int cap) {
+  return ctx ? trk_get_dynamic(ctx, frame, xy, depth, p3, asso, label, cap) : VIDO_ERR_ARG;
+}
+int vido_map_get_objects(vido_ctx* ctx, int frame, int32_t* label, int32_t* sem_label, float* motion, float* centre, int cap) {
+  return ctx ? trk_get_objects(ctx, frame, label, sem_label, motion, centre, cap) : VIDO_ERR_ARG;
+}
+int vido_map_get_dyn_tracks(vido_ctx* ctx, int32_t* len, int32_t* obj_id, int32_t* first_frame, int32_t* first_feat, int cap) {
+  return ctx ? trk_get_dyn_tracks(ctx, len, obj_id, first_frame, first_feat, cap) : VIDO_ERR_ARG;
 }
 
 int vido_get_kernel_times(vido_ctx* ctx, double* ms, int64_t* launches, double* ba_alg_bytes) {

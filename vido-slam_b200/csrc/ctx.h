@@ -155,6 +155,9 @@ void trk_quiesce(vido_ctx* ctx);
 int trk_num_frames(vido_ctx* ctx);
 int trk_get_map_poses(vido_ctx* ctx, float* poses, int cap);
 int trk_get_static(vido_ctx* ctx, int frame, float* xy, float* depth, float* p3, int32_t* asso, int cap);
+int trk_get_dynamic(vido_ctx* ctx, int frame, float* xy, float* depth, float* p3, int32_t* asso, int32_t* label, int cap);
+int trk_get_objects(vido_ctx* ctx, int frame, int32_t* label, int32_t* sem_label, float* motion, float* centre, int cap);
+int trk_get_dyn_tracks(vido_ctx* ctx, int32_t* len, int32_t* obj_id, int32_t* first_frame, int32_t* first_feat, int cap);
 
 // imu_kernels.cu
 int imu_preintegrate_host(vido_ctx* ctx, const vido_imu_sample* samples, int n, const double* t_prev, const double* t_cur,

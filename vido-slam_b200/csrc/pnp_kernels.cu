@@ -19,7 +19,7 @@ struct PnpPose {
 };
 
 struct PnpArgs {
-  int n, M, iters;
+  int n, M, iters, no_mm;   // no_mm: GetInitModelObj without a previous object motion (the RANSAC model always wins)
   const float* cur_xy;   // [n][2]
   const float* pts3d;    // [n][3]
   const int* good;       // [M] indices with valid depth
@@ -426,14 +426,18 @@ __global__ void __launch_bounds__(PNP_THREADS) pnp_select_kernel(const PnpArgs* 
   }
   const int nm = s_base;
   // ---- winner (src/Tracking.cc:2006-2025)
-  if (nr > nm) {
+  if (a.no_mm || nr > nm) {
     for (int k = tid; k < nr; k += PNP_THREADS) a.inlier_ids[k] = tmp_ids[k];  // position inside the valid list, as the reference does
     if (tid == 0) {
-      for (int r = 0; r < 3; r++) {
-        for (int c = 0; c < 3; c++) a.Tcw_out[4 * r + c] = (float)T.R[3 * r + c];
-        a.Tcw_out[4 * r + 3] = (float)T.t[r];
+      if (s_best >= 0) {
+        for (int r = 0; r < 3; r++) {
+          for (int c = 0; c < 3; c++) a.Tcw_out[4 * r + c] = (float)T.R[3 * r + c];
+          a.Tcw_out[4 * r + 3] = (float)T.t[r];
+        }
+        a.Tcw_out[12] = 0.f; a.Tcw_out[13] = 0.f; a.Tcw_out[14] = 0.f; a.Tcw_out[15] = 1.f;
+      } else {
+        for (int k = 0; k < 16; k++) a.Tcw_out[k] = Tm[k];   // no consensus at all: the seed pose, zero inliers
       }
-      a.Tcw_out[12] = 0.f; a.Tcw_out[13] = 0.f; a.Tcw_out[14] = 0.f; a.Tcw_out[15] = 1.f;
       a.result[0] = nr; a.result[1] = 0;
     }
   } else if (tid == 0) {
@@ -497,7 +501,7 @@ int pnp_init_model_host(vido_ctx* ctx, vido_pnp_problem* p) {
   const size_t o_res = 0, o_T = sizeof(int) * 4, o_ids = o_T + sizeof(float) * 16;
   PnpArgs a;
   memset(&a, 0, sizeof a);
-  a.n = p->n; a.M = M; a.iters = p->iters;
+  a.n = p->n; a.M = M; a.iters = p->iters; a.no_mm = p->no_motion_model;
   a.Tcw_motion = (const float*)(ws->d_in + o_tm); a.cur_xy = (const float*)(ws->d_in + o_cur);
   a.pts3d = (const float*)(ws->d_in + o_pts); a.good = (const int*)(ws->d_in + o_good);
   a.fx = p->fx; a.fy = p->fy; a.cx = p->cx; a.cy = p->cy; a.thr = p->reproj_err; a.confidence = p->confidence;

@@ -9,11 +9,17 @@
 //   Optimizer::PartialBatchOptimization graph construction / write-back  Optimizer.cc:43-362, 1056-1142
 // The front-end (gray conversion, pyramid, FAST, quad-tree, orientation, association, per-keypoint map lookups) is run
 // for a whole chunk of frames at once -- it has no inter-frame dependency -- the back-end is sequential per frame.
-// Scope of this version: sensor RGBD, bJoint = true, UseSampleFeature = 0, all-zero object mask (no dynamic objects),
-// no IMU.  float 4x4 products use double accumulation + one rounding like cv::Mat CV_32F gemm.
+// Dynamic objects (non-zero mask): Tracking::UpdateMask Tracking.cc:3291-3357, object carry-over :391-421,
+//   GetSceneFlowObj :1582-1668, DynObjTracking :1670-1912, GetInitModelObj :2030-2162 + Optimizer::PoseOptimizationFlow2
+//   Optimizer.cc:3037-3253 (one launch for all objects of a frame), object part of RenewFrameInfo :3112-3289,
+//   GetDynamicTrackNew :2615-2720 (incremental).  A static sequence (all-zero mask) never enters these branches.
+// Scope of this version: sensor RGBD, bJoint = true, UseSampleFeature = 0, no IMU.
+// float 4x4 products use double accumulation + one rounding like cv::Mat CV_32F gemm.
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cstring>
+#include <map>
 
 #include "ctx.h"
 
@@ -47,11 +53,17 @@ void inv44(const float* T, float* Ti) {
 }
 void eye44(float* T) { memset(T, 0, sizeof(float) * 16); T[0] = T[5] = T[10] = T[15] = 1.f; }
 
+struct ObjEntry { int label, sem; float motion[16]; float centre[3]; };  // vnRMLabel / vnSMLabel / vmRigidMotion[f-1][j>=1] / vmRigidCentre
+struct DynTrack { int first_frame, first_feat, len, obj_id; };          // TrackletDyn / nObjID
 struct MapFrame {           // Map::vpFeatSta / vfDepSta / vp3DPointSta / vnAssoSta of one frame + its pose
   std::vector<float> xy, depth, p3;
   std::vector<int> asso, track, pos;
   float Twc[16];            // vmCameraPose
   float rel[16];            // vmRigidMotion[f-1][0]
+  // Map::vpFeatDyn / vfDepDyn / vp3DPointDyn / vnAssoDyn / vnFeatLabel + the objects with an estimated motion
+  std::vector<float> dxy, ddepth, dp3;
+  std::vector<int> dasso, dlabel, dtrack;
+  std::vector<ObjEntry> objects;
 };
 struct TrackInfo { int first_frame, len, pid, epoch; };  // pid valid for the window graph built in `epoch`
 
@@ -61,6 +73,8 @@ struct FrontFrame {         // front-end results of one frame, on the host
   std::vector<float> kp_depth, kp_flow;
   std::vector<int32_t> as_idx;           // Frame-ctor association
   std::vector<float> as_corres, as_flow, as_depth;
+  std::vector<float> ob_keys, ob_corres, ob_flow, ob_depth;  // Frame-ctor object samples (mvObjKeys ... of Frame.cc:184-211)
+  std::vector<int32_t> ob_sem;
 };
 
 }  // namespace
@@ -75,6 +89,20 @@ struct TrackState {
   std::vector<float> last_keys, last_depth, last_corres, last_flow;  // mpLastFrame mvStatKeys / mvStatDepth / mvCorres / mvFlowNext
   int f_id = 0;
   int ba_epoch = 0;
+  // object state of mpLastFrame: mvObjKeys / mvObjDepth / mvObjCorres / mvObjFlowNext / vSemObjLabel and nModLabel /
+  // nSemPosition / bObjStat / vObjMod
+  std::vector<float> lo_keys, lo_depth, lo_corres, lo_flow;
+  std::vector<int32_t> lo_sem;
+  std::vector<int> l_mod_label, l_sem_pos;
+  std::vector<char> l_obj_stat;
+  std::vector<std::array<float, 16>> l_obj_mod;
+  std::vector<DynTrack> dyn_tracks;
+  int max_id = 1;
+  int obj_cap = 0;                 // stride-4 sampling grid = upper bound of the object samples of a frame
+  bool dyn_seen = false;           // a frame with object samples was seen: their device->host copy rides with the front-end
+  int32_t* d_last_mask = nullptr;  // mSegMapLast / mFlowMapLast (Tracking.cc:777-780), kept while object features are alive
+  float* d_last_flow = nullptr;
+  bool have_last_maps = false;
   // window BA jobs: [fly] is being solved on the BA stream while the next frame is tracked and its job [fly ^ 1] is staged
   struct BaJob {
     int start = 0, end = 0;
@@ -102,13 +130,18 @@ struct TrackState {
     char* h_out = nullptr;      // pinned mirror
     vido_keypoint* d_kp; int32_t* d_kpmask; float* d_kpdepth; float* d_kpflow;
     int32_t* d_asidx; float* d_ascor; float* d_asflow; float* d_asdepth; int32_t* d_nkp; int32_t* d_asn; int32_t* d_flag;
+    int32_t* d_obn;             // object samples per frame (inside d_out)
+    char* d_obj = nullptr;      // object samples, one block: keys | corres | flow | depth | label, each [B][obj_cap]
+    char* h_obj = nullptr;      // pinned mirror
+    float* d_obkeys; float* d_obcorres; float* d_obflow; float* d_obdepth; int32_t* d_obsem;
+    bool obj_copied = false;
     cudaEvent_t copied = nullptr, done = nullptr, ev0 = nullptr, ev1 = nullptr;
     bool launched = false;
     int B = 0, channels = 0;
     const void* key = nullptr;  // identity of the batch: image pointer of its first frame
     const uint8_t* in_img = nullptr; const float* in_depth = nullptr; const float* in_flow = nullptr; const int32_t* in_mask = nullptr;  // inputs the kernels read
   } fe[2];
-  size_t fe_out_bytes = 0;
+  size_t fe_out_bytes = 0, fe_obj_bytes = 0;
   int fe_cur = 0;
   uint8_t* d_gray = nullptr;     // [B][H][W] (front-end stream only)
   cudaStream_t copy_stream = nullptr, fe_stream = nullptr;
@@ -185,8 +218,14 @@ int trk_setup(vido_ctx* ctx) {
   auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
   const size_t o_kp = 0, o_kpmask = o_kp + al(sizeof(vido_keypoint) * K), o_kpdepth = o_kpmask + al(4 * K), o_kpflow = o_kpdepth + al(4 * K),
                o_asidx = o_kpflow + al(8 * K), o_ascor = o_asidx + al(4 * K), o_asflow = o_ascor + al(8 * K), o_asdepth = o_asflow + al(8 * K),
-               o_nkp = o_asdepth + al(4 * K), o_asn = o_nkp + al(4 * (size_t)B), o_flag = o_asn + al(4 * (size_t)B);
+               o_nkp = o_asdepth + al(4 * K), o_asn = o_nkp + al(4 * (size_t)B), o_obn = o_asn + al(4 * (size_t)B),
+               o_flag = o_obn + al(4 * (size_t)B);
   ts->fe_out_bytes = o_flag + 256;
+  ts->obj_cap = ((c.width + 3) / 4) * ((c.height + 3) / 4);
+  ts->q_cap = std::max(ts->q_cap, ts->obj_cap + 64);
+  const size_t OC = (size_t)ts->obj_cap * B;
+  const size_t q_keys = 0, q_corres = q_keys + al(8 * OC), q_flow = q_corres + al(8 * OC), q_depth = q_flow + al(8 * OC), q_sem = q_depth + al(4 * OC);
+  ts->fe_obj_bytes = q_sem + al(4 * OC);
   for (int k = 0; k < 2; k++) {
     TrackState::FeSlot& F = ts->fe[k];
     VIDO_CUDA(cudaMalloc(&F.d_img, px * 3 * B));
@@ -199,7 +238,11 @@ int trk_setup(vido_ctx* ctx) {
     F.d_kp = (vido_keypoint*)(F.d_out + o_kp); F.d_kpmask = (int32_t*)(F.d_out + o_kpmask); F.d_kpdepth = (float*)(F.d_out + o_kpdepth);
     F.d_kpflow = (float*)(F.d_out + o_kpflow); F.d_asidx = (int32_t*)(F.d_out + o_asidx); F.d_ascor = (float*)(F.d_out + o_ascor);
     F.d_asflow = (float*)(F.d_out + o_asflow); F.d_asdepth = (float*)(F.d_out + o_asdepth); F.d_nkp = (int32_t*)(F.d_out + o_nkp);
-    F.d_asn = (int32_t*)(F.d_out + o_asn); F.d_flag = (int32_t*)(F.d_out + o_flag);
+    F.d_asn = (int32_t*)(F.d_out + o_asn); F.d_flag = (int32_t*)(F.d_out + o_flag); F.d_obn = (int32_t*)(F.d_out + o_obn);
+    VIDO_CUDA(cudaMalloc(&F.d_obj, ts->fe_obj_bytes));
+    VIDO_CUDA(cudaMallocHost(&F.h_obj, ts->fe_obj_bytes));
+    F.d_obkeys = (float*)(F.d_obj + q_keys); F.d_obcorres = (float*)(F.d_obj + q_corres); F.d_obflow = (float*)(F.d_obj + q_flow);
+    F.d_obdepth = (float*)(F.d_obj + q_depth); F.d_obsem = (int32_t*)(F.d_obj + q_sem);
     VIDO_CUDA(cudaEventCreateWithFlags(&F.copied, cudaEventDisableTiming));
     VIDO_CUDA(cudaEventCreateWithFlags(&F.done, cudaEventDisableTiming));
     VIDO_CUDA(cudaEventCreate(&F.ev0));
@@ -210,7 +253,9 @@ int trk_setup(vido_ctx* ctx) {
   VIDO_CUDA(vido_create_stream(&ts->fe_stream, false));
   VIDO_CUDA(cudaMalloc(&ts->d_q, 8 * ts->q_cap)); VIDO_CUDA(cudaMalloc(&ts->d_qmask, 4 * ts->q_cap));
   VIDO_CUDA(cudaMalloc(&ts->d_qdepth, 4 * ts->q_cap)); VIDO_CUDA(cudaMalloc(&ts->d_qflow, 8 * ts->q_cap));
-  VIDO_CUDA(cudaMalloc(&ts->d_check, 8 * ts->q_cap)); VIDO_CUDA(cudaMalloc(&ts->d_used, ts->kp_cap));
+  VIDO_CUDA(cudaMalloc(&ts->d_check, 8 * ts->q_cap)); VIDO_CUDA(cudaMalloc(&ts->d_used, std::max(ts->kp_cap, ts->obj_cap)));
+  VIDO_CUDA(cudaMalloc(&ts->d_last_mask, px * 4));
+  VIDO_CUDA(cudaMalloc(&ts->d_last_flow, px * 8));
   return VIDO_OK;
 }
 
@@ -222,12 +267,13 @@ void trk_teardown(vido_ctx* ctx) {
   for (int k = 0; k < 2; k++) {
     TrackState::FeSlot& F = ts->fe[k];
     cudaFree(F.d_img); cudaFree(F.d_depth); cudaFree(F.d_flow); cudaFree(F.d_mask); cudaFree(F.d_out); cudaFreeHost(F.h_out);
+    cudaFree(F.d_obj); cudaFreeHost(F.h_obj);
     if (F.copied) cudaEventDestroy(F.copied);
     if (F.done) cudaEventDestroy(F.done);
     if (F.ev0) cudaEventDestroy(F.ev0);
     if (F.ev1) cudaEventDestroy(F.ev1);
   }
-  cudaFree(ts->d_gray);
+  cudaFree(ts->d_gray); cudaFree(ts->d_last_mask); cudaFree(ts->d_last_flow);
   cudaFree(ts->d_q); cudaFree(ts->d_qmask); cudaFree(ts->d_qdepth); cudaFree(ts->d_qflow); cudaFree(ts->d_check); cudaFree(ts->d_used);
   delete ts;
   ctx->trk = nullptr;
@@ -241,6 +287,9 @@ int trk_reset(vido_ctx* ctx) {
   cudaStreamSynchronize(ts->copy_stream); cudaStreamSynchronize(ts->fe_stream);
   ts->fe[0].launched = ts->fe[1].launched = false; ts->hint.clear(); ts->ba_rest = -1; ts->ba_staged = false;
   ts->last_keys.clear(); ts->last_depth.clear(); ts->last_corres.clear(); ts->last_flow.clear();
+  ts->lo_keys.clear(); ts->lo_depth.clear(); ts->lo_corres.clear(); ts->lo_flow.clear(); ts->lo_sem.clear();
+  ts->l_mod_label.clear(); ts->l_sem_pos.clear(); ts->l_obj_stat.clear(); ts->l_obj_mod.clear();
+  ts->dyn_tracks.clear(); ts->max_id = 1; ts->have_last_maps = false;
   return VIDO_OK;
 }
 
@@ -308,6 +357,9 @@ static int fe_launch(vido_ctx* ctx, TrackState::FeSlot& F, const vido_frame_inpu
     rc = assoc_frame_associate(ctx, F.d_kp, F.d_nkp, ts->kp_cap, F.in_depth, F.in_flow, F.in_mask, B, 1, F.d_asidx, F.d_ascor,
                                F.d_asflow, F.d_asdepth, F.d_asn, ts->kp_cap);
     if (rc) break;
+    rc = assoc_sample_objects(ctx, F.in_depth, F.in_flow, F.in_mask, B, 1, F.d_obkeys, F.d_obcorres, F.d_obflow, F.d_obdepth, F.d_obsem,
+                              F.d_obn, ts->obj_cap);
+    if (rc) break;
     dim3 grid((ts->kp_cap + 255) / 256, B);
     kp_lookup_kernel<<<grid, 256, 0, fs>>>(F.d_kp, F.d_nkp, ts->kp_cap, c.width, c.height, F.in_depth, F.in_flow, F.in_mask, px,
                                            c.choose_data, c.depth_map_factor, c.bf, ctx->mscale, F.d_kpmask, F.d_kpdepth, F.d_kpflow);
@@ -316,7 +368,9 @@ static int fe_launch(vido_ctx* ctx, TrackState::FeSlot& F, const vido_frame_inpu
     if (cudaGetLastError() != cudaSuccess) { ctx->err = "front-end launch failed"; rc = VIDO_ERR_CUDA; break; }
     if (cudaMemcpyAsync(F.d_flag, ctx->d_err, 4, cudaMemcpyDeviceToDevice, fs) != cudaSuccess ||
         cudaMemcpyAsync(F.h_out, F.d_out, ts->fe_out_bytes, cudaMemcpyDeviceToHost, fs) != cudaSuccess ||
+        (ts->dyn_seen && cudaMemcpyAsync(F.h_obj, F.d_obj, ts->fe_obj_bytes, cudaMemcpyDeviceToHost, fs) != cudaSuccess) ||
         cudaEventRecord(F.done, fs) != cudaSuccess) { ctx->err = "front-end copy failed"; rc = VIDO_ERR_CUDA; break; }
+    F.obj_copied = ts->dyn_seen;
   } while (0);
   ctx->stream = saved;
   if (rc) return rc;
@@ -347,9 +401,31 @@ static int fe_collect(vido_ctx* ctx, TrackState::FeSlot& F, std::vector<FrontFra
   const int32_t* kpmask = (const int32_t*)hp(F.d_kpmask); const float* kpdepth = (const float*)hp(F.d_kpdepth);
   const float* kpflow = (const float*)hp(F.d_kpflow); const int32_t* asidx = (const int32_t*)hp(F.d_asidx);
   const float* ascor = (const float*)hp(F.d_ascor); const float* asflow = (const float*)hp(F.d_asflow); const float* asdepth = (const float*)hp(F.d_asdepth);
+  const int32_t* obn = (const int32_t*)hp(F.d_obn);
+  bool any_obj = false;
+  for (int b = 0; b < B; b++) {
+    if (obn[b] > ts->obj_cap) { ctx->err = "object samples exceed the sampling grid"; return VIDO_ERR_CAPACITY; }
+    any_obj |= obn[b] > 0;
+  }
+  if (any_obj && !F.obj_copied) {  // first batch with objects: fetch the samples now; later batches carry them along
+    ts->dyn_seen = true;
+    VIDO_CUDA(cudaMemcpyAsync(F.h_obj, F.d_obj, ts->fe_obj_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    VIDO_CUDA(cudaStreamSynchronize(ctx->stream));
+    F.obj_copied = true;
+  }
+  auto ho = [&](const void* dptr) { return F.h_obj + ((const char*)dptr - F.d_obj); };
+  const float* obkeys = (const float*)ho(F.d_obkeys); const float* obcorres = (const float*)ho(F.d_obcorres);
+  const float* obflow = (const float*)ho(F.d_obflow); const float* obdepth = (const float*)ho(F.d_obdepth);
+  const int32_t* obsem = (const int32_t*)ho(F.d_obsem);
   out.resize(B);
   for (int b = 0; b < B; b++) {
     FrontFrame& f = out[b];
+    {
+      const size_t no = (size_t)std::max(obn[b], 0), oo = (size_t)b * ts->obj_cap;
+      f.ob_keys.assign(obkeys + 2 * oo, obkeys + 2 * (oo + no)); f.ob_corres.assign(obcorres + 2 * oo, obcorres + 2 * (oo + no));
+      f.ob_flow.assign(obflow + 2 * oo, obflow + 2 * (oo + no)); f.ob_depth.assign(obdepth + oo, obdepth + oo + no);
+      f.ob_sem.assign(obsem + oo, obsem + oo + no);
+    }
     const size_t n = (size_t)std::min(std::max(nkp[b], 0), ts->kp_cap), m = (size_t)std::min(std::max(asn[b], 0), ts->kp_cap);
     const size_t o = (size_t)b * K;
     f.kps.assign(kp + o, kp + o + n); f.kp_mask.assign(kpmask + o, kpmask + o + n); f.kp_depth.assign(kpdepth + o, kpdepth + o + n);
@@ -374,6 +450,439 @@ static int query_maps(vido_ctx* ctx, const float* d_depth, const float* d_flow, 
   VIDO_CUDA(cudaMemcpyAsync(odepth, ts->d_qdepth, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
   VIDO_CUDA(cudaMemcpyAsync(oflow, ts->d_qflow, 8 * (size_t)n, cudaMemcpyDeviceToHost, s));
   VIDO_CUDA(cudaStreamSynchronize(s));
+  return VIDO_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// dynamic objects
+// ---------------------------------------------------------------------------------------------------------
+// used[i] = 1 if object sample i (xy) lies within 1 px of an already kept object feature (Tracking.cc:3186-3200); the kept
+// list is the same for every object of the frame, so one pass over all samples answers every later query
+__global__ void __launch_bounds__(256) topup_used_xy_kernel(const float* __restrict__ xy, int n, const float* __restrict__ check, int m,
+                                                            uint8_t* __restrict__ used) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const float sx = xy[2 * i], sy = xy[2 * i + 1];
+  bool u = false;
+  for (int j0 = 0; j0 < m; j0 += 32) {
+    const int j = j0 + lane;
+    bool hit = false;
+    if (j < m) {
+      const float dx = __fsub_rn(check[2 * j], sx), dy = __fsub_rn(check[2 * j + 1], sy);
+      hit = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))) < 1.0f;
+    }
+    if (__any_sync(0xffffffffu, hit)) { u = true; break; }
+  }
+  if (lane == 0) used[i] = u ? 1 : 0;
+}
+
+// Frame::UnprojectStereoObject / Optimizer::Get3DinWorld: pixel + depth through Twc (float, cv::Mat gemm rounding)
+static inline void px_to_world(const vido_config& c, float u, float v, float z, const float* Twc, float* o) {
+  const float invfx = 1.0f / c.fx, invfy = 1.0f / c.fy;
+  const float xc[3] = {(u - c.cx) * z * invfx, (v - c.cy) * z * invfy, z};
+  for (int r = 0; r < 3; r++)
+    o[r] = (float)((double)Twc[4 * r] * xc[0] + (double)Twc[4 * r + 1] * xc[1] + (double)Twc[4 * r + 2] * xc[2]) + Twc[4 * r + 3];
+}
+
+// The object mask of frame b was re-warped by UpdateMask: the Frame-ctor stages that read the mask (static association,
+// object sampling, per-keypoint lookups) are repeated for that frame on the back-end stream (rare path).
+static int fe_redo_frame(vido_ctx* ctx, TrackState::FeSlot& F, int b, FrontFrame& f) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  const vido_config& c = ctx->cfg;
+  const size_t px = (size_t)c.width * c.height, K = ts->kp_cap, OC = ts->obj_cap;
+  cudaStream_t s = ctx->stream;
+  const float* dd = F.in_depth + b * px; const float* df = F.in_flow + 2 * b * px; const int32_t* dm = F.in_mask + b * px;
+  int rc = assoc_frame_associate(ctx, F.d_kp + b * K, F.d_nkp + b, ts->kp_cap, dd, df, dm, 1, 1, F.d_asidx + b * K, F.d_ascor + 2 * b * K,
+                                 F.d_asflow + 2 * b * K, F.d_asdepth + b * K, F.d_asn + b, ts->kp_cap);
+  if (rc) return rc;
+  rc = assoc_sample_objects(ctx, dd, df, dm, 1, 1, F.d_obkeys + 2 * b * OC, F.d_obcorres + 2 * b * OC, F.d_obflow + 2 * b * OC,
+                            F.d_obdepth + b * OC, F.d_obsem + b * OC, F.d_obn + b, ts->obj_cap);
+  if (rc) return rc;
+  dim3 grid((ts->kp_cap + 255) / 256, 1);
+  kp_lookup_kernel<<<grid, 256, 0, s>>>(F.d_kp + b * K, F.d_nkp + b, ts->kp_cap, c.width, c.height, dd, df, dm, px, c.choose_data,
+                                        c.depth_map_factor, c.bf, ctx->mscale, F.d_kpmask + b * K, F.d_kpdepth + b * K, F.d_kpflow + 2 * b * K);
+  ctx->launches++;
+  VIDO_CUDA(cudaGetLastError());
+  int32_t cnt[2] = {0, 0};
+  VIDO_CUDA(cudaMemcpyAsync(&cnt[0], F.d_asn + b, 4, cudaMemcpyDeviceToHost, s));
+  VIDO_CUDA(cudaMemcpyAsync(&cnt[1], F.d_obn + b, 4, cudaMemcpyDeviceToHost, s));
+  VIDO_CUDA(cudaStreamSynchronize(s));
+  const size_t n = f.kps.size(), m = (size_t)std::min(std::max(cnt[0], 0), ts->kp_cap), no = (size_t)std::min(std::max(cnt[1], 0), ts->obj_cap);
+  f.as_idx.resize(m); f.as_corres.resize(2 * m); f.as_flow.resize(2 * m); f.as_depth.resize(m);
+  f.ob_keys.resize(2 * no); f.ob_corres.resize(2 * no); f.ob_flow.resize(2 * no); f.ob_depth.resize(no); f.ob_sem.resize(no);
+  auto back = [&](void* dst, const void* src, size_t bytes) { return bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s) : cudaSuccess; };
+  VIDO_CUDA(back(f.kp_mask.data(), F.d_kpmask + b * K, 4 * n));
+  VIDO_CUDA(back(f.kp_depth.data(), F.d_kpdepth + b * K, 4 * n));
+  VIDO_CUDA(back(f.kp_flow.data(), F.d_kpflow + 2 * b * K, 8 * n));
+  VIDO_CUDA(back(f.as_idx.data(), F.d_asidx + b * K, 4 * m));
+  VIDO_CUDA(back(f.as_corres.data(), F.d_ascor + 2 * b * K, 8 * m));
+  VIDO_CUDA(back(f.as_flow.data(), F.d_asflow + 2 * b * K, 8 * m));
+  VIDO_CUDA(back(f.as_depth.data(), F.d_asdepth + b * K, 4 * m));
+  VIDO_CUDA(back(f.ob_keys.data(), F.d_obkeys + 2 * b * OC, 8 * no));
+  VIDO_CUDA(back(f.ob_corres.data(), F.d_obcorres + 2 * b * OC, 8 * no));
+  VIDO_CUDA(back(f.ob_flow.data(), F.d_obflow + 2 * b * OC, 8 * no));
+  VIDO_CUDA(back(f.ob_depth.data(), F.d_obdepth + b * OC, 4 * no));
+  VIDO_CUDA(back(f.ob_sem.data(), F.d_obsem + b * OC, 4 * no));
+  VIDO_CUDA(cudaStreamSynchronize(s));
+  return VIDO_OK;
+}
+
+// per-frame object state while the frame is tracked (mpCurrentFrame's object members)
+struct DynFrame {
+  std::vector<float> keys, depth;       // mvObjKeys (refined in place by the object pose optimisation), mvObjDepth
+  std::vector<int32_t> sem;             // vSemObjLabel
+  std::vector<int> label;               // vObjLabel
+  std::vector<float> flow3;             // vFlow_3d
+  std::vector<int> mod_label, sem_pos;  // nModLabel, nSemPosition
+  std::vector<char> stat;               // bObjStat
+  std::vector<std::array<float, 16>> mod;  // vObjMod
+  std::vector<std::array<float, 3>> centre;
+  std::vector<std::vector<int>> obj_id, inlier_id;  // vnObjID, vnObjInlierID
+};
+
+static int majority_label(const std::vector<int>& v) {  // std::map order + stable descending count (Tracking.cc:1853-1863)
+  std::map<int, int> dups;
+  for (int k : v) ++dups[k];
+  int best = 0, cnt = -1;
+  for (auto& k : dups)
+    if (k.second > cnt) { cnt = k.second; best = k.first; }
+  return best;
+}
+
+// GrabImageRGBD :391-421 -- object features of the new frame = last frame's correspondences + fresh depth / label lookups
+static int dyn_carry_over(vido_ctx* ctx, const float* d_depth, const float* d_flow, const int32_t* d_mask, int slot, DynFrame& D) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  const vido_config& c = ctx->cfg;
+  const int W = c.width, H = c.height;
+  const int n = (int)(ts->lo_corres.size() / 2);
+  D.keys = ts->lo_corres;
+  D.depth.assign(n, -1.f); D.sem.assign(n, -1); D.label.assign(n, -2);
+  if (n == 0) return VIDO_OK;
+  std::vector<int32_t> m2(n);
+  std::vector<float> d2(n), f2(2 * (size_t)n);
+  int rc = query_maps(ctx, d_depth, d_flow, d_mask, slot, D.keys.data(), n, m2.data(), d2.data(), f2.data());
+  if (rc) return rc;
+  for (int i = 0; i < n; i++) {
+    const int u = (int)D.keys[2 * i], v = (int)D.keys[2 * i + 1];
+    if (u < (W - 1) && u > 0 && v < (H - 1) && v > 0 && d2[i] < c.th_depth_obj && d2[i] > 0) { D.depth[i] = d2[i]; D.sem[i] = m2[i]; }
+    else { D.depth[i] = 0.1f; D.sem[i] = 0; }
+  }
+  return VIDO_OK;
+}
+
+// GetSceneFlowObj (Tracking.cc:1582-1668) + DynObjTracking (:1670-1912); returns the feature index lists of the objects
+static std::vector<std::vector<int>> dyn_track_objects(vido_ctx* ctx, const float* curTcw, DynFrame& D) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  const vido_config& c = ctx->cfg;
+  const int W = c.width, H = c.height;
+  const int N = (int)D.sem.size();
+  float Twl[16], Twc[16];
+  inv44(ts->lastTcw, Twl);
+  inv44(curTcw, Twc);
+  D.flow3.assign(3 * (size_t)N, 0.f);
+  for (int i = 0; i < N; i++) {
+    if (D.sem[i] <= 0 || ts->lo_sem[i] <= 0) { D.label[i] = -1; continue; }
+    float xp[3], xc[3];
+    px_to_world(c, ts->lo_keys[2 * i], ts->lo_keys[2 * i + 1], ts->lo_depth[i], Twl, xp);
+    px_to_world(c, D.keys[2 * i], D.keys[2 * i + 1], D.depth[i], Twc, xc);
+    for (int r = 0; r < 3; r++) D.flow3[3 * i + r] = xc[r] - xp[r];
+  }
+  std::vector<int> UniLab(D.sem.begin(), D.sem.end());
+  std::sort(UniLab.begin(), UniLab.end());
+  UniLab.erase(std::unique(UniLab.begin(), UniLab.end()), UniLab.end());
+  std::vector<std::vector<int>> Posi(UniLab.size());
+  for (int i = 0; i < N; i++) {
+    if (D.label[i] == -1) continue;
+    const size_t j = std::lower_bound(UniLab.begin(), UniLab.end(), (int)D.sem[i]) - UniLab.begin();
+    Posi[j].push_back(i);
+  }
+  std::vector<std::vector<int>> ObjId;
+  std::vector<int> sem_posi;
+  const int shrin_thr_row = 10, shrin_thr_col = 20;
+  for (size_t i = 0; i < Posi.size(); i++) {
+    float count = 0;
+    for (int id : Posi[i]) {
+      const float u = D.keys[2 * id], v = D.keys[2 * id + 1];
+      if (v < shrin_thr_row || v > (H - shrin_thr_row) || u < shrin_thr_col || u > (W - shrin_thr_col)) count = count + 1;
+    }
+    if (count / Posi[i].size() > 0.5f) {
+      for (int id : Posi[i]) D.label[id] = -1;
+      continue;
+    }
+    ObjId.push_back(Posi[i]);
+    sem_posi.push_back(UniLab[i]);
+  }
+  std::vector<std::vector<int>> ObjIdNew;
+  std::vector<int> SemPosNew;
+  for (size_t i = 0; i < ObjId.size(); i++) {
+    float obj_center_depth = 0, sf_count = 0;
+    for (int id : ObjId[i]) {
+      obj_center_depth = obj_center_depth + D.depth[id];
+      const float fx = D.flow3[3 * id], fz = D.flow3[3 * id + 2];
+      const float sf_norm = std::sqrt(fx * fx + fz * fz);
+      if (sf_norm < c.sf_mg_thres) sf_count = sf_count + 1;
+    }
+    if (sf_count / ObjId[i].size() > c.sf_ds_thres) {
+      for (int id : ObjId[i]) D.label[id] = 0;
+      continue;
+    } else if (obj_center_depth / ObjId[i].size() > c.th_depth_obj || ObjId[i].size() < 150) {
+      for (int id : ObjId[i]) D.label[id] = -1;
+      continue;
+    }
+    ObjIdNew.push_back(ObjId[i]);
+    SemPosNew.push_back(sem_posi[i]);
+  }
+  if (ts->f_id == 1) ts->max_id = 1;
+  std::vector<int> LabId(ObjIdNew.size());
+  for (size_t i = 0; i < ObjIdNew.size(); i++) {
+    std::vector<int> Lb_last;
+    for (int id : ObjIdNew[i]) Lb_last.push_back(ts->lo_sem[id]);
+    const int New_lab = majority_label(Lb_last);
+    bool exist = false;
+    if (ts->max_id != 1) {
+      for (size_t k = 0; k < ts->l_sem_pos.size(); k++)
+        if (ts->l_sem_pos[k] == New_lab && ts->l_obj_stat[k]) { LabId[i] = ts->l_mod_label[k]; exist = true; break; }
+    }
+    if (!exist) { LabId[i] = ts->max_id; ts->max_id = ts->max_id + 1; }
+    for (int id : ObjIdNew[i]) D.label[id] = LabId[i];
+  }
+  D.mod_label = LabId;
+  D.sem_pos = SemPosNew;
+  return ObjIdNew;
+}
+
+// object loop of Tracking::Track (Tracking.cc:1179-1308): GetInitModelObj per object (PnP kernels), then ONE pose-optimisation
+// launch for all objects that kept >= 50 inliers (the objects use disjoint feature sets, so the order does not matter)
+static int dyn_object_motions(vido_ctx* ctx, const float* curTcw, const std::vector<std::vector<int>>& ObjIdNew, DynFrame& D) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  const vido_config& c = ctx->cfg;
+  const size_t no = ObjIdNew.size();
+  D.stat.assign(no, 1); D.mod.resize(no); D.centre.assign(no, std::array<float, 3>{0.f, 0.f, 0.f});
+  D.obj_id = ObjIdNew; D.inlier_id.assign(no, std::vector<int>());
+  float Twl[16], Twc[16];
+  inv44(ts->lastTcw, Twl);
+  inv44(curTcw, Twc);
+  struct Job { size_t obj; std::vector<int> ids; std::vector<float> obs, fl, dep, fo; std::vector<int32_t> inl; float init[16]; };
+  std::vector<Job> jobs;
+  for (size_t i = 0; i < no; i++) {
+    const std::vector<int>& ObjId = ObjIdNew[i];
+    const int N = (int)ObjId.size();
+    std::vector<float> cur2d(2 * (size_t)N), p3d(3 * (size_t)N);
+    float cs[3] = {0.f, 0.f, 0.f};
+    for (int j = 0; j < N; j++) {
+      const int id = ObjId[j];
+      float xp[3];
+      px_to_world(c, ts->lo_keys[2 * id], ts->lo_keys[2 * id + 1], ts->lo_depth[id], Twl, xp);
+      for (int r = 0; r < 3; r++) { cs[r] += xp[r]; p3d[3 * j + r] = xp[r]; }
+      cur2d[2 * j] = D.keys[2 * id]; cur2d[2 * j + 1] = D.keys[2 * id + 1];
+    }
+    const float invn = (float)(1.0 / (double)N);
+    D.centre[i] = {cs[0] * invn, cs[1] * invn, cs[2] * invn};
+    int PreObjID = -1;
+    for (size_t k = 0; k < ts->l_mod_label.size(); k++)
+      if (ts->l_mod_label[k] == D.mod_label[i]) { PreObjID = (int)k; break; }
+    vido_pnp_problem pp;
+    memset(&pp, 0, sizeof pp);
+    vido_pnp_default_params(&pp);
+    std::vector<int32_t> ids(N);
+    pp.n = N; pp.cur_xy = cur2d.data(); pp.pts3d = p3d.data(); pp.valid = nullptr; pp.inlier_ids = ids.data();
+    if (PreObjID != -1) mul44(curTcw, ts->l_obj_mod[PreObjID].data(), pp.Tcw_motion);
+    else { memcpy(pp.Tcw_motion, curTcw, sizeof(float) * 16); pp.no_motion_model = 1; }
+    pp.fx = c.fx; pp.fy = c.fy; pp.cx = c.cx; pp.cy = c.cy;
+    int rc = pnp_init_model_host(ctx, &pp);
+    if (rc) return rc;
+    std::vector<int> in_ids(pp.n_inliers);
+    std::vector<char> keep(N, 0);
+    for (int k = 0; k < pp.n_inliers; k++) { in_ids[k] = ObjId[ids[k]]; keep[ids[k]] = 1; }
+    for (int j = 0; j < N; j++)
+      if (!keep[j]) D.label[ObjId[j]] = -1;
+    if (in_ids.size() < 50) {
+      D.stat[i] = 0;
+      eye44(D.mod[i].data());
+      D.centre[i] = {0.f, 0.f, 0.f};
+      D.inlier_id[i] = in_ids;
+      continue;
+    }
+    Job J;
+    J.obj = i; J.ids = in_ids;
+    const size_t n = in_ids.size();
+    J.obs.resize(2 * n); J.fl.resize(2 * n); J.dep.resize(n); J.fo.resize(2 * n); J.inl.resize(n);
+    for (size_t k = 0; k < n; k++) {
+      const int id = in_ids[k];
+      J.obs[2 * k] = ts->lo_keys[2 * id]; J.obs[2 * k + 1] = ts->lo_keys[2 * id + 1];
+      J.fl[2 * k] = ts->lo_flow[2 * id]; J.fl[2 * k + 1] = ts->lo_flow[2 * id + 1];
+      J.dep[k] = ts->lo_depth[id];
+    }
+    memcpy(J.init, pp.Tcw_out, sizeof J.init);
+    jobs.push_back(std::move(J));
+  }
+  // ---- PoseOptimizationFlow2 for all objects of the frame: one CTA per object, 16 objects per launch
+  for (size_t j0 = 0; j0 < jobs.size(); j0 += 16) {
+    const int nb = (int)std::min<size_t>(16, jobs.size() - j0);
+    std::vector<vido_poseopt_problem> pr(nb);
+    for (int k = 0; k < nb; k++) {
+      Job& J = jobs[j0 + k];
+      vido_poseopt_problem& po = pr[k];
+      memset(&po, 0, sizeof po);
+      vido_poseopt_default_params(&po);
+      po.n = (int)J.ids.size(); po.obs_xy = J.obs.data(); po.flow_xy = J.fl.data(); po.depth = J.dep.data();
+      memcpy(po.Tcw_init, J.init, sizeof J.init);
+      memcpy(po.Tcw_last, ts->lastTcw, sizeof(float) * 16);
+      po.fx = c.fx; po.fy = c.fy; po.cx = c.cx; po.cy = c.cy;
+      po.flow_out = J.fo.data(); po.inlier = J.inl.data();
+      po.info_prior = 0.5f; po.rounds = 1; po.its = 200;
+    }
+    int rc = po_flow2_host(ctx, pr.data(), nb, nullptr);
+    if (rc) return rc;
+    for (int k = 0; k < nb; k++) {
+      Job& J = jobs[j0 + k];
+      mul44(Twc, pr[k].Tcw_out, D.mod[J.obj].data());  // vObjMod = inv(Tcw) * Obj_X  (Tracking.cc:1271)
+      std::vector<int> InlierID;
+      for (size_t q = 0; q < J.ids.size(); q++) {
+        const int id = J.ids[q];
+        if (J.inl[q]) {
+          D.keys[2 * id] = (float)((double)ts->lo_keys[2 * id] + (double)J.fo[2 * q]);
+          D.keys[2 * id + 1] = (float)((double)ts->lo_keys[2 * id + 1] + (double)J.fo[2 * q + 1]);
+          InlierID.push_back(id);
+        } else D.label[id] = -1;
+      }
+      D.inlier_id[J.obj] = InlierID;
+    }
+  }
+  return VIDO_OK;
+}
+
+// object part of Tracking::RenewFrameInfo (Tracking.cc:3112-3289) + Map bookkeeping (:1351-1355, 1390-1422) + dynamic
+// tracklets (GetDynamicTrackNew, incremental); F is the MapFrame of the current frame
+static int dyn_renew(vido_ctx* ctx, const FrontFrame& ff, const float* curTcw, const float* d_obkeys, const float* d_depth,
+                     const float* d_flow, const int32_t* d_mask, int slot, DynFrame& D, MapFrame& F) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  const vido_config& c = ctx->cfg;
+  const int W = c.width, H = c.height, max_num_obj = c.max_track_obj;
+  cudaStream_t s = ctx->stream;
+  std::vector<float> keys, corres, fl, dep;
+  std::vector<int32_t> sem;
+  std::vector<int> inl, lab;
+  const size_t no = D.inlier_id.size();
+  std::vector<int> ObjFeaCount(no, -1);
+  {  // (1) inliers of the tracked objects at their refined (then truncated) positions
+    std::vector<float> qxy;
+    for (size_t i = 0; i < no; i++)
+      if (D.stat[i]) for (int id : D.inlier_id[i]) { qxy.push_back(D.keys[2 * id]); qxy.push_back(D.keys[2 * id + 1]); }
+    const int nq = (int)(qxy.size() / 2);
+    std::vector<int32_t> m2(nq);
+    std::vector<float> d2(nq), f2(2 * (size_t)nq);
+    int rc = query_maps(ctx, d_depth, d_flow, d_mask, slot, qxy.data(), nq, m2.data(), d2.data(), f2.data());
+    if (rc) return rc;
+    int q = 0;
+    for (size_t i = 0; i < no; i++) {
+      if (!D.stat[i]) continue;
+      int count = 0;
+      for (int id : D.inlier_id[i]) {
+        const int k = q++;
+        const int x = (int)D.keys[2 * id], y = (int)D.keys[2 * id + 1];
+        if (x >= W || y >= H || x <= 0 || y <= 0) continue;
+        if (m2[k] != 0 && d2[k] < 25 && d2[k] > 0) {
+          const float fx = f2[2 * k], fy = f2[2 * k + 1];
+          if (x + fx < W && y + fy < H && x + fx > 0 && y + fy > 0) {
+            keys.push_back((float)x); keys.push_back((float)y);
+            dep.push_back(d2[k]); sem.push_back(m2[k]);
+            fl.push_back(fx); fl.push_back(fy);
+            corres.push_back(x + fx); corres.push_back(y + fy);
+            inl.push_back(id); lab.push_back(D.label[id]);
+            count = count + 1;
+          }
+        }
+      }
+      ObjFeaCount[i] = count;
+    }
+  }
+  // (2) top-up per tracked object from this frame's samples (15 interleaved passes), >= 1 px from every kept inlier
+  const int nt = (int)ff.ob_sem.size(), mcheck = (int)(keys.size() / 2);
+  bool need_topup = false;
+  for (size_t i = 0; i < no; i++) need_topup |= D.stat[i] && ObjFeaCount[i] < max_num_obj;
+  std::vector<uint8_t> used(nt, 0);
+  if (need_topup && nt > 0 && mcheck > 0) {
+    if (mcheck > ts->q_cap) { ctx->err = "object renewal check list too long"; return VIDO_ERR_CAPACITY; }
+    VIDO_CUDA(cudaMemcpyAsync(ts->d_check, keys.data(), 8 * (size_t)mcheck, cudaMemcpyHostToDevice, s));
+    topup_used_xy_kernel<<<(nt + 7) / 8, 256, 0, s>>>(d_obkeys, nt, ts->d_check, mcheck, ts->d_used);
+    ctx->launches++;
+    VIDO_CUDA(cudaGetLastError());
+    VIDO_CUDA(cudaMemcpyAsync(used.data(), ts->d_used, nt, cudaMemcpyDeviceToHost, s));
+    VIDO_CUDA(cudaStreamSynchronize(s));
+  }
+  auto push_sample = [&](int j, int label) {
+    keys.push_back(ff.ob_keys[2 * j]); keys.push_back(ff.ob_keys[2 * j + 1]);
+    dep.push_back(ff.ob_depth[j]); sem.push_back(ff.ob_sem[j]);
+    fl.push_back(ff.ob_flow[2 * j]); fl.push_back(ff.ob_flow[2 * j + 1]);
+    corres.push_back(ff.ob_corres[2 * j]); corres.push_back(ff.ob_corres[2 * j + 1]);
+    inl.push_back(-1); lab.push_back(label);
+  };
+  for (size_t i = 0; i < no; i++) {
+    if (!D.stat[i]) continue;
+    const int SemLabel = D.sem_pos[i];
+    int tot_num = ObjFeaCount[i], start_id = 0;
+    const int step = 15;
+    while (tot_num < max_num_obj) {
+      if (start_id == step) break;
+      for (int j = start_id; j < nt; j += step) {
+        if (ff.ob_sem[j] != SemLabel) continue;
+        if (used[j]) continue;
+        push_sample(j, D.mod_label[i]);
+        tot_num = tot_num + 1;
+        if (tot_num >= max_num_obj) break;
+      }
+      start_id = start_id + 1;
+    }
+  }
+  // (3) semantic labels without a tracked object: all their samples, tracking label -2
+  std::vector<int> UniLab(ff.ob_sem.begin(), ff.ob_sem.end());
+  std::sort(UniLab.begin(), UniLab.end());
+  UniLab.erase(std::unique(UniLab.begin(), UniLab.end()), UniLab.end());
+  std::vector<char> NewLab(UniLab.size(), 0);
+  for (size_t i = 0; i < D.sem_pos.size(); i++)
+    for (size_t j = 0; j < UniLab.size(); j++)
+      if (UniLab[j] == D.sem_pos[i] && D.stat[i]) { NewLab[j] = 1; break; }
+  for (size_t i = 0; i < NewLab.size(); i++) {
+    if (NewLab[i]) continue;
+    for (int j = 0; j < nt; j++)
+      if (UniLab[i] == ff.ob_sem[j]) push_sample(j, -2);
+  }
+  // (4) world points, Map arrays
+  const size_t nf = dep.size();
+  float Twc[16];
+  inv44(curTcw, Twc);
+  F.dxy = keys; F.ddepth = dep; F.dasso = inl; F.dlabel = lab;
+  F.dp3.resize(3 * nf);
+  for (size_t i = 0; i < nf; i++) px_to_world(c, keys[2 * i], keys[2 * i + 1], dep[i], Twc, &F.dp3[3 * i]);
+  for (size_t i = 0; i < D.mod.size(); i++) {
+    if (!D.stat[i]) continue;
+    ObjEntry e;
+    e.label = D.mod_label[i]; e.sem = D.sem_pos[i];
+    memcpy(e.motion, D.mod[i].data(), sizeof e.motion);
+    memcpy(e.centre, D.centre[i].data(), sizeof e.centre);
+    F.objects.push_back(e);
+  }
+  // (5) dynamic tracklets, incrementally (same chains as Tracking::GetDynamicTrackNew)
+  F.dtrack.assign(nf, -1);
+  MapFrame& P = ts->map.back();
+  const int fcur = (int)ts->map.size();
+  for (size_t j = 0; j < nf; j++) {
+    const int p = inl[j];
+    if (p < 0) continue;
+    if (P.dtrack[p] >= 0) {
+      F.dtrack[j] = P.dtrack[p];
+      ts->dyn_tracks[P.dtrack[p]].len++;
+    } else {
+      const int t = (int)ts->dyn_tracks.size();
+      ts->dyn_tracks.push_back({fcur - 1, p, 2, lab[j]});
+      F.dtrack[j] = t;   // (the predecessor keeps -1: only the newest element of a chain is looked up again)
+    }
+  }
+  // (6) becomes mpLastFrame
+  ts->lo_keys = keys; ts->lo_depth = dep; ts->lo_corres = corres; ts->lo_flow = fl; ts->lo_sem = sem;
+  ts->l_mod_label = D.mod_label; ts->l_sem_pos = D.sem_pos; ts->l_obj_stat = D.stat; ts->l_obj_mod = D.mod;
   return VIDO_OK;
 }
 
@@ -505,18 +1014,33 @@ static int ba_go(vido_ctx* ctx) {
 // ---------------------------------------------------------------------------------------------------------
 // back-end of one frame (sequential)
 // ---------------------------------------------------------------------------------------------------------
-static int back_end(vido_ctx* ctx, const FrontFrame& ff, int slot, const vido_keypoint* d_kp, const float* d_depth, const float* d_flow,
-                    const int32_t* d_mask, float* Tcw_out, vido_track_stats* st) {
+static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int slot, float* Tcw_out, vido_track_stats* st) {
   TrackState* ts = (TrackState*)ctx->trk;
   const vido_config& c = ctx->cfg;
   const int W = c.width, H = c.height;
   cudaStream_t s = ctx->stream;
+  const vido_keypoint* d_kp = FS.d_kp;
+  const float* d_depth = FS.in_depth; const float* d_flow = FS.in_flow; const int32_t* d_mask = FS.in_mask;
+  const size_t px = (size_t)W * H;
   const float invfx = 1.0f / c.fx, invfy = 1.0f / c.fy;
   float curTcw[16];
   eye44(curTcw);
   if (st) { memset(st, 0, sizeof *st); st->n_keypoints = (int)ff.kps.size(); }
   int skipped = 0;
   double t0 = now_ms();
+  // ---- Tracking::UpdateMask (Tracking.cc:353-364): votes of the last frame's object features in the new mask; a lost mask is
+  //      re-warped in place and the mask-dependent Frame-ctor stages of this frame are repeated
+  if (ts->initialised && !ts->lo_sem.empty() && ts->have_last_maps) {
+    const int nl = (int)ts->lo_sem.size();
+    std::vector<int32_t> uniq(nl), rec(nl);
+    const int nu = assoc_update_mask(ctx, ts->lo_sem.data(), ts->lo_corres.data(), nl, ts->d_last_mask, ts->d_last_flow,
+                                     (int32_t*)d_mask + (size_t)slot * px, uniq.data(), rec.data(), nl);
+    if (nu < 0) return nu;
+    int nrec = 0;
+    for (int k = 0; k < nu; k++) nrec += rec[k] ? 1 : 0;
+    if (st) st->n_masks_recovered = nrec;
+    if (nrec) { int rc = fe_redo_frame(ctx, FS, slot, ff); if (rc) return rc; }
+  }
   if (!ts->initialised) {
     // ---- Tracking::Initialization: features leaving frame 0 are the associated detections
     MapFrame F;
@@ -532,6 +1056,18 @@ static int back_end(vido_ctx* ctx, const FrontFrame& ff, int slot, const vido_ke
     eye44(F.Twc); eye44(F.rel);
     ts->last_keys = F.xy; ts->last_depth = F.depth; ts->last_corres = ff.as_corres; ts->last_flow = ff.as_flow;
     memcpy(ts->lastTcw, curTcw, sizeof curTcw);
+    {  // object samples of frame 0 (Frame.cc:184-211, Tracking.cc:1524-1541)
+      const size_t no = ff.ob_sem.size();
+      F.dxy = ff.ob_keys; F.ddepth = ff.ob_depth; F.dp3.resize(3 * no);
+      F.dasso.assign(no, -1); F.dlabel.assign(no, -2); F.dtrack.assign(no, -1);
+      for (size_t i = 0; i < no; i++) {
+        const float z = F.ddepth[i], u = F.dxy[2 * i], v = F.dxy[2 * i + 1];
+        F.dp3[3 * i] = (u - c.cx) * z * invfx; F.dp3[3 * i + 1] = (v - c.cy) * z * invfy; F.dp3[3 * i + 2] = z;
+      }
+      ts->lo_keys = ff.ob_keys; ts->lo_depth = ff.ob_depth; ts->lo_corres = ff.ob_corres; ts->lo_flow = ff.ob_flow; ts->lo_sem = ff.ob_sem;
+      ts->l_mod_label.clear(); ts->l_sem_pos.clear(); ts->l_obj_stat.clear(); ts->l_obj_mod.clear();
+      if (st) st->n_dyn_features = (int)no;
+    }
     ts->map.push_back(std::move(F));
     ts->initialised = true;
   } else {
@@ -602,6 +1138,17 @@ static int back_end(vido_ctx* ctx, const FrontFrame& ff, int slot, const vido_ke
       inv44(ts->lastTcw, LastTwc);
       mul44(curTcw, LastTwc, ts->mVelocity);
       ts->has_velocity = true;
+      // ---- dynamic objects: carry-over, scene flow, object tracking, object motions (Tracking.cc:391-421, 1160-1308)
+      DynFrame D;
+      const bool dyn = !ts->lo_corres.empty() || !ff.ob_sem.empty();
+      if (!ts->lo_corres.empty()) {
+        rc = dyn_carry_over(ctx, d_depth, d_flow, d_mask, slot, D);
+        if (rc) return rc;
+        const std::vector<std::vector<int>> ObjIdNew = dyn_track_objects(ctx, curTcw, D);
+        rc = dyn_object_motions(ctx, curTcw, ObjIdNew, D);
+        if (rc) return rc;
+        if (st) { st->n_objects = (int)ObjIdNew.size(); for (char b : D.stat) st->n_objects_ok += b ? 1 : 0; }
+      }
       // ---- RenewFrameInfo (static part).  (1) surviving inliers at their refined positions
       MapFrame F;
       std::vector<float> ncorres, nflow;
@@ -702,6 +1249,11 @@ static int back_end(vido_ctx* ctx, const FrontFrame& ff, int slot, const vido_ke
       }
       memcpy(F.Twc, Twc, sizeof Twc);
       inv44(ts->mVelocity, F.rel);
+      if (dyn) {  // RenewFrameInfo (object part), Map bookkeeping, dynamic tracklets
+        rc = dyn_renew(ctx, ff, curTcw, FS.d_obkeys + 2 * (size_t)slot * ts->obj_cap, d_depth, d_flow, d_mask, slot, D, F);
+        if (rc) return rc;
+        if (st) st->n_dyn_features = (int)F.ddepth.size();
+      }
       ts->last_keys = F.xy; ts->last_depth = F.depth; ts->last_corres = ncorres; ts->last_flow = nflow;
       memcpy(ts->lastTcw, curTcw, sizeof curTcw);
       ts->map.push_back(std::move(F));
@@ -711,6 +1263,16 @@ static int back_end(vido_ctx* ctx, const FrontFrame& ff, int slot, const vido_ke
         st->n_matches = Ns; st->n_init_inliers = pp.n_inliers; st->init_winner = pp.winner; st->n_pose_inliers = po.n_inliers;
         st->n_static = nf;
       }
+    }
+  }
+  // mSegMapLast / mFlowMapLast (Tracking.cc:777-780): the slot buffers are recycled by the look-ahead front-end, so the maps
+  // of the frame that becomes mpLastFrame are kept in private copies -- only while it carries object features
+  if (!skipped) {
+    ts->have_last_maps = false;
+    if (!ts->lo_sem.empty()) {
+      VIDO_CUDA(cudaMemcpyAsync(ts->d_last_mask, d_mask + (size_t)slot * px, px * 4, cudaMemcpyDeviceToDevice, s));
+      VIDO_CUDA(cudaMemcpyAsync(ts->d_last_flow, d_flow + 2 * (size_t)slot * px, px * 8, cudaMemcpyDeviceToDevice, s));
+      ts->have_last_maps = true;
     }
   }
   memcpy(Tcw_out, curTcw, sizeof(float) * 16);
@@ -808,11 +1370,11 @@ int trk_track_chunk(vido_ctx* ctx, const vido_frame_inputs* in, int nframes, flo
       else if (!ts->hint.empty()) { rc = fe_launch(ctx, N, ts->hint.data(), (int)ts->hint.size()); ts->hint.clear(); }
       if (rc) return rc;
     }
-    const float* d_depth = F.in_depth; const float* d_flow = F.in_flow; const int32_t* d_mask = F.in_mask;
+    const float* d_depth = F.in_depth;
     const double front_ms = (now_ms() - tf0) / B;
     for (int b = 0; b < B; b++) {
       vido_track_stats* st = stats ? stats + done + b : nullptr;
-      rc = back_end(ctx, ff[b], b, F.d_kp, d_depth, d_flow, d_mask, Tcw_out + 16 * (size_t)(done + b), st);
+      rc = back_end(ctx, F, ff[b], b, Tcw_out + 16 * (size_t)(done + b), st);
       if (rc < 0) return rc;
       if (st) { st->ms_orb = front_ms; st->ms_assoc = 0; }
       // the reference pre-scales the caller's depth map in place (Tracking.cc:299-322): reproduce on request
@@ -860,6 +1422,44 @@ int trk_get_static(vido_ctx* ctx, int frame, float* xy, float* depth, float* p3,
     depth[i] = F.depth[i];
     p3[3 * i] = F.p3[3 * i]; p3[3 * i + 1] = F.p3[3 * i + 1]; p3[3 * i + 2] = F.p3[3 * i + 2];
     asso[i] = F.asso[i];
+  }
+  return n;
+}
+
+int trk_get_dynamic(vido_ctx* ctx, int frame, float* xy, float* depth, float* p3, int32_t* asso, int32_t* label, int cap) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  if (frame < 0 || frame >= (int)ts->map.size()) return -1;
+  const MapFrame& F = ts->map[frame];
+  const int n = (int)F.ddepth.size();
+  for (int i = 0; i < n && i < cap; i++) {
+    xy[2 * i] = F.dxy[2 * i]; xy[2 * i + 1] = F.dxy[2 * i + 1];
+    depth[i] = F.ddepth[i];
+    p3[3 * i] = F.dp3[3 * i]; p3[3 * i + 1] = F.dp3[3 * i + 1]; p3[3 * i + 2] = F.dp3[3 * i + 2];
+    asso[i] = F.dasso[i];
+    label[i] = F.dlabel[i];
+  }
+  return n;
+}
+
+int trk_get_objects(vido_ctx* ctx, int frame, int32_t* label, int32_t* sem_label, float* motion, float* centre, int cap) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  if (frame < 1 || frame >= (int)ts->map.size()) return -1;
+  const MapFrame& F = ts->map[frame];
+  const int n = (int)F.objects.size();
+  for (int i = 0; i < n && i < cap; i++) {
+    label[i] = F.objects[i].label; sem_label[i] = F.objects[i].sem;
+    memcpy(motion + 16 * (size_t)i, F.objects[i].motion, sizeof(float) * 16);
+    memcpy(centre + 3 * (size_t)i, F.objects[i].centre, sizeof(float) * 3);
+  }
+  return n;
+}
+
+int trk_get_dyn_tracks(vido_ctx* ctx, int32_t* len, int32_t* obj_id, int32_t* first_frame, int32_t* first_feat, int cap) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  const int n = (int)ts->dyn_tracks.size();
+  for (int i = 0; i < n && i < cap; i++) {
+    len[i] = ts->dyn_tracks[i].len; obj_id[i] = ts->dyn_tracks[i].obj_id;
+    first_frame[i] = ts->dyn_tracks[i].first_frame; first_feat[i] = ts->dyn_tracks[i].first_feat;
   }
   return n;
 }
