@@ -126,6 +126,43 @@ int vido_ba_partial(vido_ctx* ctx, vido_ba_problem* p, vido_lm_stats* stats);
 
 
 /*
+ * Full-sequence graph optimisation: replaces Optimizer::FullBatchOptimization (src/Optimizer.cc:1235-2178) for the flat graph
+ * the reference builds at :1318-1745.  SE3 vertices: n_poses camera poses (estimate = Map::vmCameraPose, Twc) followed by
+ * n_motions object motions (identity at :1597).  Point vertices: one per static tracklet, one per element of a dynamic
+ * tracklet.  Edges: EdgeSE3Prior on SE3 vertex 0 (information prior_info, no kernel, :1336-1345); EdgeSE3 kind 0 = camera
+ * odometry (Map::vmRigidMotion[i-1][0]), kind 1 = object smoothness (identity, :1611-1638); EdgeSE3PointXYZ kind 0 = static,
+ * kind 1 = dynamic (measurement = Optimizer::Get3DinCamera); LandmarkMotionTernaryEdge (p1, p2, H).  Every point may be the
+ * p2 of at most one and the p1 of at most one ternary edge (the elements of a tracklet form a chain).
+ * This flat graph is also the wire format of the keyframe-factor all-gather of the multi-GPU configuration (one sequence per
+ * GPU; see vido_fba_pack / INTEGRATION.md).  Host pointers; se3 / points are float32 in/out like the Map
+ * (:2090-2176).  Returns VIDO_OK; the iteration count is in stats->iterations.
+ */
+typedef struct vido_fba_problem {
+  int32_t n_poses, n_motions, n_points, n_obs, n_e6, n_tern;
+  float* se3;               /* [n_poses + n_motions][16] in/out */
+  float* points;            /* [n_points][3] in/out */
+  const int32_t* e6_i;      /* [n_e6] SE3 vertex indices */
+  const int32_t* e6_j;
+  const int32_t* e6_kind;   /* 0 odometry, 1 smoothness */
+  const float* e6_meas;     /* [n_e6][16] */
+  const int32_t* obs_se3;   /* [n_obs] */
+  const int32_t* obs_point;
+  const int32_t* obs_kind;  /* 0 static, 1 dynamic */
+  const float* obs_xyz;     /* [n_obs][3] */
+  const int32_t* tern_p1;   /* [n_tern] point vertex of the previous frame */
+  const int32_t* tern_p2;   /* point vertex of the current frame */
+  const int32_t* tern_h;    /* SE3 vertex of the object motion */
+  int32_t max_iterations;   /* 300 (:1941) */
+  float sigma2_cam, sigma2_3d_sta, sigma2_3d_dyn, sigma2_obj, sigma2_smooth; /* 0.0001, 80, 80, 100, 0.001 (:1290-1295) */
+  float huber_cam, huber_obj, huber_3d;  /* 0.01 each (:1312) */
+  float gain_threshold;     /* SparseOptimizerTerminateAction gain 1e-4 (:1283) */
+  float prior_info;         /* 100000 (:1341) */
+} vido_fba_problem;
+void vido_fba_default_params(vido_fba_problem* p);
+int vido_ba_full(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* stats);
+
+
+/*
  * Per-frame joint optical-flow + pose optimisation: replaces Optimizer::PoseOptimizationFlow2Cam
  * (src/Optimizer.cc:2622-2824; camera) and Optimizer::PoseOptimizationFlow2 (:3037-3253; one call per object, with
  * Tcw_init = mInitModel, info_prior = 0.5, rounds = 1, its = 200).  One problem = one SE3 vertex + n flow vertices.
@@ -258,6 +295,23 @@ int vido_map_get_objects(vido_ctx* ctx, int frame, int32_t* label, int32_t* sem_
 /* Map::TrackletDyn / nObjID (Tracking::GetDynamicTrackNew, src/Tracking.cc:2615-2720): per track its length, object id and the
  * (frame, feature) of its first element; returns the number of tracks */
 int vido_map_get_dyn_tracks(vido_ctx* ctx, int32_t* len, int32_t* obj_id, int32_t* first_frame, int32_t* first_feat, int cap);
+
+
+/*
+ * Optimizer::FullBatchOptimization on the context's Map (what Tracking::Track does at the stop frame, src/Tracking.cc:
+ * 1490-1498): builds the flat graph (vido_fba_problem), solves it on the device and writes the results back like
+ * src/Optimizer.cc:2090-2176: refined camera poses (Map::vmCameraPose_RF, vido_map_get_poses_rf), refined object motions
+ * (Map::vmRigidMotion_RF, vido_map_get_objects_rf), static and dynamic 3-D points in place (vido_map_get_static / _dynamic).
+ * sizes (optional, 6 ints): poses, motions, points, observations, SE3 edges, ternary edges.
+ */
+int vido_full_batch(vido_ctx* ctx, vido_lm_stats* stats, int32_t* sizes);
+int vido_map_get_poses_rf(vido_ctx* ctx, float* poses, int cap);
+int vido_map_get_objects_rf(vido_ctx* ctx, int frame, float* motion, int cap);
+/* The flat FullBatch graph of the context's Map ("keyframe factors").  Call with se3 == NULL to get the sizes, then with
+ * arrays of those sizes.  The index arrays are relative to this sequence; vido_fba_problem documents every field. */
+int vido_map_export_full_graph(vido_ctx* ctx, int32_t* sizes, float* se3, float* points, int32_t* e6_i, int32_t* e6_j,
+                               int32_t* e6_kind, float* e6_meas, int32_t* obs_se3, int32_t* obs_point, int32_t* obs_kind,
+                               float* obs_xyz, int32_t* tern_p1, int32_t* tern_p2, int32_t* tern_h);
 
 
 /*

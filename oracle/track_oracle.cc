@@ -614,6 +614,147 @@ struct Tracker {
     cur->mvCorres = corres;
   }
 
+
+  // ---- Optimizer::FullBatchOptimization, graph construction (src/Optimizer.cc:1235-1745) in flat form
+  struct FullGraph {
+    std::vector<float> se3, points, e6_meas, obs_xyz;
+    std::vector<int> e6_i, e6_j, e6_kind, obs_se3, obs_point, obs_kind, tern_p1, tern_p2, tern_h;
+    int n_poses = 0, n_motions = 0;
+    std::vector<std::vector<int>> VertexID;        // [frame-1][object entry] -> SE3 vertex (camera entry excluded)
+    std::vector<std::vector<int>> makSta, makDyn;  // per frame, per feature: point vertex or -1
+  };
+  FullGraph build_full_graph() {
+    FullGraph G;
+    const int N = (int)map.vpFeatSta.size();
+    const auto& StaTracks = map.TrackletSta;
+    const auto& DynTracks = map.TrackletDyn;
+    std::vector<std::vector<int>> labSta(N), labDyn(N), posSta(N), posDyn(N);
+    G.makSta.resize(N); G.makDyn.resize(N);
+    for (int i = 0; i < N; i++) {
+      labSta[i].assign(map.vpFeatSta[i].size(), -1); posSta[i] = labSta[i]; G.makSta[i] = labSta[i];
+      labDyn[i].assign(map.vpFeatDyn[i].size(), -1); posDyn[i] = labDyn[i]; G.makDyn[i] = labDyn[i];
+    }
+    for (size_t t = 0; t < StaTracks.size(); t++) {
+      if (StaTracks[t].size() < 3) continue;
+      for (size_t k = 0; k < StaTracks[t].size(); k++) { labSta[StaTracks[t][k].first][StaTracks[t][k].second] = (int)t; posSta[StaTracks[t][k].first][StaTracks[t][k].second] = (int)k; }
+    }
+    for (size_t t = 0; t < DynTracks.size(); t++) {
+      if (DynTracks[t].size() < 3) continue;
+      for (size_t k = 0; k < DynTracks[t].size(); k++) { labDyn[DynTracks[t][k].first][DynTracks[t][k].second] = (int)t; posDyn[DynTracks[t][k].first][DynTracks[t][k].second] = (int)k; }
+    }
+    G.n_poses = N;
+    for (int i = 0; i < N; i++) G.se3.insert(G.se3.end(), map.vmCameraPose[i].begin(), map.vmCameraPose[i].end());
+    G.VertexID.resize(std::max(N - 1, 0));
+    int next_se3 = N;
+    float I16[16];
+    eye44(I16);
+    auto add_point = [&](const P3& Xw) { G.points.push_back(Xw.x); G.points.push_back(Xw.y); G.points.push_back(Xw.z); return (int)(G.points.size() / 3) - 1; };
+    auto add_obs = [&](int se3v, int pt, int kind, const P3& xc) {
+      G.obs_se3.push_back(se3v); G.obs_point.push_back(pt); G.obs_kind.push_back(kind);
+      G.obs_xyz.push_back(xc.x); G.obs_xyz.push_back(xc.y); G.obs_xyz.push_back(xc.z);
+    };
+    for (int i = 0; i < N; i++) {
+      if (i != 0) {
+        G.e6_i.push_back(i - 1); G.e6_j.push_back(i); G.e6_kind.push_back(0);
+        G.e6_meas.insert(G.e6_meas.end(), map.vmRigidMotion[i - 1].begin(), map.vmRigidMotion[i - 1].end());
+      }
+      // static features
+      for (size_t j = 0; j < labSta[i].size(); j++) {
+        const int t = labSta[i][j];
+        if (t == -1) continue;
+        const int pos = i == 0 ? 0 : posSta[i][j];
+        int pid;
+        if (pos == 0) pid = add_point(map.vp3DPointSta[i][j]);
+        else pid = G.makSta[StaTracks[t][pos - 1].first][StaTracks[t][pos - 1].second];
+        if (pid == -1) continue;
+        add_obs(i, pid, 0, unproject_cam(map.vpFeatSta[i][j], map.vfDepSta[i][j]));
+        G.makSta[i][j] = pid;
+      }
+      // dynamic part
+      if (i == 0) {
+        for (size_t j = 0; j < labDyn[i].size(); j++) {
+          if (labDyn[i][j] == -1) continue;
+          const int pid = add_point(map.vp3DPointDyn[i][j]);
+          add_obs(i, pid, 1, unproject_cam(map.vpFeatDyn[i][j], map.vfDepDyn[i][j]));
+          G.makDyn[i][j] = pid;
+        }
+        continue;
+      }
+      const auto& labels = map.vnRMLabel[i - 1];
+      std::vector<int> ObjUniqueID(labels.size(), -1);
+      G.VertexID[i - 1].assign(labels.size(), -1);
+      for (size_t j = 0; j < labels.size(); j++) {
+        G.se3.insert(G.se3.end(), I16, I16 + 16);   // object motions start from identity (:1597)
+        const int vid = next_se3++;
+        if (i > 2) {  // smoothness w.r.t. the same object's motion in the previous frame (SMOOTH_CONSTRAINT && i>2)
+          int TraceID = -1;
+          for (size_t k = 0; k < map.vnRMLabel[i - 2].size(); k++)
+            if (map.vnRMLabel[i - 2][k] == labels[j]) { TraceID = (int)k; break; }
+          if (TraceID != -1) {
+            G.e6_i.push_back(G.VertexID[i - 2][TraceID]); G.e6_j.push_back(vid); G.e6_kind.push_back(1);
+            G.e6_meas.insert(G.e6_meas.end(), I16, I16 + 16);
+          }
+        }
+        ObjUniqueID[j] = vid;
+        G.VertexID[i - 1][j] = vid;
+      }
+      for (size_t j = 0; j < labDyn[i].size(); j++) {
+        const int t = labDyn[i][j];
+        if (t == -1) continue;
+        const int pos = posDyn[i][j];
+        int ObjPositionID = -1;
+        for (size_t k = 0; k < labels.size(); k++)
+          if (labels[k] == map.nObjID[t]) { ObjPositionID = ObjUniqueID[k]; break; }
+        if (ObjPositionID == -1 && pos != 0) continue;
+        int prev = -1;
+        if (pos != 0) {
+          prev = G.makDyn[DynTracks[t][pos - 1].first][DynTracks[t][pos - 1].second];
+          if (prev == -1) continue;  // (the reference would dereference a null vertex here; cannot happen for chains built by Track())
+        }
+        const int pid = add_point(map.vp3DPointDyn[i][j]);
+        add_obs(i, pid, 1, unproject_cam(map.vpFeatDyn[i][j], map.vfDepDyn[i][j]));
+        if (pos != 0) { G.tern_p1.push_back(prev); G.tern_p2.push_back(pid); G.tern_h.push_back(ObjPositionID); }
+        G.makDyn[i][j] = pid;
+      }
+    }
+    G.n_motions = next_se3 - N;
+    return G;
+  }
+  void fill_problem(FullGraph& G, vo_fba_problem& pr) {
+    memset(&pr, 0, sizeof pr);
+    vo_fba_default_params(&pr);
+    pr.n_poses = G.n_poses; pr.n_motions = G.n_motions; pr.n_points = (int)(G.points.size() / 3);
+    pr.n_obs = (int)G.obs_se3.size(); pr.n_e6 = (int)G.e6_i.size(); pr.n_tern = (int)G.tern_p1.size();
+    pr.se3 = G.se3.data(); pr.points = G.points.data();
+    pr.e6_i = G.e6_i.data(); pr.e6_j = G.e6_j.data(); pr.e6_kind = G.e6_kind.data(); pr.e6_meas = G.e6_meas.data();
+    pr.obs_se3 = G.obs_se3.data(); pr.obs_point = G.obs_point.data(); pr.obs_kind = G.obs_kind.data(); pr.obs_xyz = G.obs_xyz.data();
+    pr.tern_p1 = G.tern_p1.data(); pr.tern_p2 = G.tern_p2.data(); pr.tern_h = G.tern_h.data();
+  }
+  std::vector<std::vector<float>> vmCameraPose_RF;
+  std::vector<std::vector<std::array<float, 16>>> vmObjMotion_RF;
+  int full_batch(vo_lm_stats* stats, int32_t* sizes) {
+    if (cfg.rebuild_tracklets == 0) { rebuild_tracklets(); rebuild_dyn_tracklets(); }
+    FullGraph G = build_full_graph();
+    vo_fba_problem pr;
+    fill_problem(G, pr);
+    if (sizes) { sizes[0] = pr.n_poses; sizes[1] = pr.n_motions; sizes[2] = pr.n_points; sizes[3] = pr.n_obs; sizes[4] = pr.n_e6; sizes[5] = pr.n_tern; }
+    const int its = vo_ba_full(&pr, stats);
+    // write-back (src/Optimizer.cc:2090-2176): refined poses of frames >= 1, refined object motions, points in place
+    const int N = G.n_poses;
+    vmCameraPose_RF = map.vmCameraPose;
+    vmObjMotion_RF = map.vmObjMotion;
+    for (int i = 1; i < N; i++) std::copy(G.se3.begin() + 16 * (size_t)i, G.se3.begin() + 16 * (size_t)(i + 1), vmCameraPose_RF[i].begin());
+    for (int i = 0; i + 1 < N; i++)
+      for (size_t j = 0; j < G.VertexID[i].size(); j++) memcpy(vmObjMotion_RF[i][j].data(), &G.se3[16 * (size_t)G.VertexID[i][j]], sizeof(float) * 16);
+    for (int i = 0; i < N; i++) {
+      for (size_t j = 0; j < G.makSta[i].size(); j++)
+        if (G.makSta[i][j] != -1) map.vp3DPointSta[i][j] = {G.points[3 * (size_t)G.makSta[i][j]], G.points[3 * (size_t)G.makSta[i][j] + 1], G.points[3 * (size_t)G.makSta[i][j] + 2]};
+      for (size_t j = 0; j < G.makDyn[i].size(); j++)
+        if (G.makDyn[i][j] != -1) map.vp3DPointDyn[i][j] = {G.points[3 * (size_t)G.makDyn[i][j]], G.points[3 * (size_t)G.makDyn[i][j] + 1], G.points[3 * (size_t)G.makDyn[i][j] + 2]};
+    }
+    return its;
+  }
+
   int track(const uint8_t* gray, float* depth, const float* flow, const int32_t* mask, float* Tcw_out, vo_track_stats* st) {
     const int W = cfg.width, H = cfg.height;
     if (st) memset(st, 0, sizeof *st);
@@ -912,6 +1053,36 @@ int vo_tracker_get_dyn_tracks(void* h, int32_t* len, int32_t* obj_id, int32_t* f
     first_frame[i] = t->map.TrackletDyn[i][0].first; first_feat[i] = t->map.TrackletDyn[i][0].second;
   }
   return n;
+}
+
+int vo_tracker_full_batch(void* h, vo_lm_stats* stats, int32_t* sizes) { return ((Tracker*)h)->full_batch(stats, sizes); }
+int vo_tracker_get_map_poses_rf(void* h, float* poses, int cap) {
+  Tracker* t = (Tracker*)h;
+  const int n = (int)t->vmCameraPose_RF.size();
+  for (int i = 0; i < n && i < cap; i++) memcpy(poses + 16 * i, t->vmCameraPose_RF[i].data(), sizeof(float) * 16);
+  return n;
+}
+int vo_tracker_get_objects_rf(void* h, int frame, float* motion, int cap) {
+  Tracker* t = (Tracker*)h;
+  if (frame < 1 || frame > (int)t->vmObjMotion_RF.size()) return -1;
+  const auto& M = t->vmObjMotion_RF[frame - 1];
+  for (int i = 0; i < (int)M.size() && i < cap; i++) memcpy(motion + 16 * i, M[i].data(), sizeof(float) * 16);
+  return (int)M.size();
+}
+int vo_tracker_export_full_graph(void* h, int32_t* sizes, float* se3, float* points, int32_t* e6_i, int32_t* e6_j, int32_t* e6_kind,
+                                 float* e6_meas, int32_t* obs_se3, int32_t* obs_point, int32_t* obs_kind, float* obs_xyz,
+                                 int32_t* tern_p1, int32_t* tern_p2, int32_t* tern_h) {
+  Tracker* t = (Tracker*)h;
+  if (t->cfg.rebuild_tracklets == 0) { t->rebuild_tracklets(); t->rebuild_dyn_tracklets(); }
+  auto G = t->build_full_graph();
+  sizes[0] = G.n_poses; sizes[1] = G.n_motions; sizes[2] = (int)(G.points.size() / 3); sizes[3] = (int)G.obs_se3.size();
+  sizes[4] = (int)G.e6_i.size(); sizes[5] = (int)G.tern_p1.size();
+  if (!se3) return 0;
+  auto cp = [](auto* dst, const auto& v) { if (!v.empty()) memcpy(dst, v.data(), sizeof(v[0]) * v.size()); };
+  cp(se3, G.se3); cp(points, G.points); cp(e6_i, G.e6_i); cp(e6_j, G.e6_j); cp(e6_kind, G.e6_kind); cp(e6_meas, G.e6_meas);
+  cp(obs_se3, G.obs_se3); cp(obs_point, G.obs_point); cp(obs_kind, G.obs_kind); cp(obs_xyz, G.obs_xyz);
+  cp(tern_p1, G.tern_p1); cp(tern_p2, G.tern_p2); cp(tern_h, G.tern_h);
+  return 0;
 }
 
 }  // extern "C"

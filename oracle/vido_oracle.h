@@ -98,6 +98,44 @@ void vo_edge_se3(const double* Xi /*R row-major 9 + t 3*/, const double* Xj, con
 void vo_se3_oplus(const double* X, const double* upd6, double* Xout); /* VertexSE3::oplusImpl */
 void vo_edge_se3_pointxyz(const double* X, const double* p, const double* z, double err[3], double Ji[18], double Jj[9]);
 
+/*
+ * Full-sequence graph of Optimizer::FullBatchOptimization (src/Optimizer.cc:1235-2178) in flat form.
+ * SE3 vertices: n_poses camera poses (VertexSE3, estimate = Map::vmCameraPose, Twc) followed by n_motions object motions
+ * (VertexSE3, initialised to identity, :1594-1598).  Point vertices: one per static track, one per element of a dynamic
+ * track.  Edges: EdgeSE3Prior on SE3 vertex 0 (information 1e5, no kernel, :1336-1345); EdgeSE3 kind 0 = camera odometry
+ * (sigma2_cam), kind 1 = object smoothness (identity measurement, sigma2_smooth, :1611-1638); EdgeSE3PointXYZ kind 0 =
+ * static (sigma2_3d_sta), kind 1 = dynamic (sigma2_3d_dyn); LandmarkMotionTernaryEdge (p1, p2, H), sigma2_obj.
+ * Every point is the p2 of at most one and the p1 of at most one ternary edge (the elements of a tracklet form a chain).
+ */
+typedef struct vo_fba_problem {
+  int32_t n_poses, n_motions, n_points, n_obs, n_e6, n_tern;
+  float* se3;               /* [n_poses + n_motions][16] in/out */
+  float* points;            /* [n_points][3] in/out */
+  const int32_t* e6_i;      /* [n_e6] SE3 vertex indices */
+  const int32_t* e6_j;
+  const int32_t* e6_kind;   /* 0 odometry, 1 smoothness */
+  const float* e6_meas;     /* [n_e6][16] */
+  const int32_t* obs_se3;   /* [n_obs] */
+  const int32_t* obs_point;
+  const int32_t* obs_kind;  /* 0 static, 1 dynamic */
+  const float* obs_xyz;     /* [n_obs][3] camera-frame measurement (Optimizer::Get3DinCamera) */
+  const int32_t* tern_p1;   /* [n_tern] point of the previous frame */
+  const int32_t* tern_p2;   /* point of the current frame */
+  const int32_t* tern_h;    /* SE3 vertex index of the object motion */
+  int32_t max_iterations;   /* 300 (:1941) */
+  float sigma2_cam, sigma2_3d_sta, sigma2_3d_dyn, sigma2_obj, sigma2_smooth; /* 0.0001, 80, 80, 100, 0.001 (:1290-1295) */
+  float huber_cam, huber_obj, huber_3d;  /* 0.01 each (:1312) */
+  float gain_threshold;     /* 1e-4 (:1283) */
+  float prior_info;         /* 100000 (:1341) */
+} vo_fba_problem;
+void vo_fba_default_params(vo_fba_problem* p);
+int vo_ba_full(vo_fba_problem* p, vo_lm_stats* stats);
+/* LandmarkMotionTernaryEdge (g2o/types/types_dyn_slam3d.cpp:53-85): err = p1 - H^-1 p2; J1 = I, J2 (3x3), JH (3x6) */
+void vo_edge_landmark_motion(const double* H /*R 9 + t 3*/, const double* p1, const double* p2, double err[3], double J2[9],
+                             double JH[18]);
+/* EdgeSE3Prior with identity offset (g2o/types/edge_se3_prior.cpp:89-102, isometry3d_gradients.h:265-325) */
+void vo_edge_se3_prior(const double* X, const double* Z, double err[6], double J[36]);
+
 /* ---- per-frame stages of Tracking::GrabImageRGBD / Frame::Frame ---- */
 /* depth pre-scale, in place (src/Tracking.cc:299-322): negatives -> 0; OMD d/f; KITTI bf/(d/f); KAIST mScale*bf/(d/f) */
 void vo_depth_prep(float* depth, int W, int H, int stride_elems, int choose_data, float depth_map_factor, float bf, float mscale);
@@ -197,6 +235,16 @@ int vo_tracker_get_objects(void* h, int frame, int32_t* label, int32_t* sem_labe
 /* Map::TrackletDyn / nObjID (Tracking::GetDynamicTrackNew, src/Tracking.cc:2615-2720): per track its length, object id and
  * first (frame, feature) */
 int vo_tracker_get_dyn_tracks(void* h, int32_t* len, int32_t* obj_id, int32_t* first_frame, int32_t* first_feat, int cap);
+/* Optimizer::FullBatchOptimization on the tracker's Map (src/Tracking.cc:1490-1498): results in vmCameraPose_RF /
+ * vmRigidMotion_RF, points refined in place.  sizes (optional, 6 ints): poses, motions, points, obs, e6, tern.  Returns the
+ * iteration count. */
+int vo_tracker_full_batch(void* h, vo_lm_stats* stats, int32_t* sizes);
+int vo_tracker_get_map_poses_rf(void* h, float* poses, int cap);
+int vo_tracker_get_objects_rf(void* h, int frame, float* motion, int cap);
+/* the flat FullBatch graph the tracker would solve (arrays sized by a first call with NULL pointers -> sizes) */
+int vo_tracker_export_full_graph(void* h, int32_t* sizes, float* se3, float* points, int32_t* e6_i, int32_t* e6_j, int32_t* e6_kind,
+                                 float* e6_meas, int32_t* obs_se3, int32_t* obs_point, int32_t* obs_kind, float* obs_xyz,
+                                 int32_t* tern_p1, int32_t* tern_p2, int32_t* tern_h);
 
 /* ---- IMU preintegration: Tracking::PreintegrateIMU (src/Tracking.cc:784-887) + IMU::Preintegrated (src/ImuTypes.cc:143-300) ---- */
 typedef struct vo_imu_sample { double t; float ax, ay, az, wx, wy, wz; } vo_imu_sample;

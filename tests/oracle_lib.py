@@ -262,6 +262,64 @@ def init_model_cam(cur_xy, pts3d, valid, Tcw_motion, K, **params):
             pr.mm_inliers)
 
 
+# ---------------------------------------------------------------- full-sequence graph (FullBatchOptimization)
+class FbaProblem(C.Structure):
+    _fields_ = [("n_poses", C.c_int32), ("n_motions", C.c_int32), ("n_points", C.c_int32), ("n_obs", C.c_int32),
+                ("n_e6", C.c_int32), ("n_tern", C.c_int32),
+                ("se3", C.c_void_p), ("points", C.c_void_p),
+                ("e6_i", C.c_void_p), ("e6_j", C.c_void_p), ("e6_kind", C.c_void_p), ("e6_meas", C.c_void_p),
+                ("obs_se3", C.c_void_p), ("obs_point", C.c_void_p), ("obs_kind", C.c_void_p), ("obs_xyz", C.c_void_p),
+                ("tern_p1", C.c_void_p), ("tern_p2", C.c_void_p), ("tern_h", C.c_void_p),
+                ("max_iterations", C.c_int32),
+                ("sigma2_cam", C.c_float), ("sigma2_3d_sta", C.c_float), ("sigma2_3d_dyn", C.c_float),
+                ("sigma2_obj", C.c_float), ("sigma2_smooth", C.c_float),
+                ("huber_cam", C.c_float), ("huber_obj", C.c_float), ("huber_3d", C.c_float),
+                ("gain_threshold", C.c_float), ("prior_info", C.c_float)]
+
+
+FBA_KEYS = ("se3", "points", "e6_i", "e6_j", "e6_kind", "e6_meas", "obs_se3", "obs_point", "obs_kind", "obs_xyz",
+            "tern_p1", "tern_p2", "tern_h")
+
+
+def fill_fba(pr, g, n_poses):
+    """g: dict of numpy arrays (FBA_KEYS); the arrays se3 / points are updated in place by the solver"""
+    f32 = ("se3", "points", "e6_meas", "obs_xyz")
+    keep = {k: np.ascontiguousarray(g[k], np.float32 if k in f32 else np.int32) for k in FBA_KEYS}
+    pr.n_poses = n_poses
+    pr.n_motions = keep["se3"].reshape(-1, 16).shape[0] - n_poses
+    pr.n_points = keep["points"].reshape(-1, 3).shape[0]
+    pr.n_obs, pr.n_e6, pr.n_tern = len(keep["obs_se3"]), len(keep["e6_i"]), len(keep["tern_p1"])
+    for k in FBA_KEYS:
+        setattr(pr, k, _p(keep[k]).value if keep[k].size else None)
+    return keep
+
+
+def ba_full(g, n_poses, **params):
+    """Optimizer::FullBatchOptimization on a flat graph; returns (se3 [n,4,4], points, iterations, LmStats)"""
+    pr = FbaProblem()
+    lib().vo_fba_default_params(C.byref(pr))
+    keep = fill_fba(pr, {k: np.array(g[k], copy=True) for k in FBA_KEYS}, n_poses)
+    for k, v in params.items():
+        setattr(pr, k, v)
+    st = LmStats()
+    its = lib().vo_ba_full(C.byref(pr), C.byref(st))
+    return keep["se3"].reshape(-1, 4, 4), keep["points"].reshape(-1, 3), its, st
+
+
+def edge_landmark_motion(H, p1, p2):
+    H = np.ascontiguousarray(H, np.float64); p1 = np.ascontiguousarray(p1, np.float64); p2 = np.ascontiguousarray(p2, np.float64)
+    e = np.zeros(3); J2 = np.zeros((3, 3)); JH = np.zeros((3, 6))
+    lib().vo_edge_landmark_motion(_p(H), _p(p1), _p(p2), _p(e), _p(J2), _p(JH))
+    return e, J2, JH
+
+
+def edge_se3_prior(X, Z):
+    X = np.ascontiguousarray(X, np.float64); Z = np.ascontiguousarray(Z, np.float64)
+    e = np.zeros(6); J = np.zeros((6, 6))
+    lib().vo_edge_se3_prior(_p(X), _p(Z), _p(e), _p(J))
+    return e, J
+
+
 # ---------------------------------------------------------------- tracking pipeline oracle
 class TrackConfig(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float),
@@ -310,6 +368,10 @@ class OracleTracker:
         L.vo_tracker_get_dynamic.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_int]
         L.vo_tracker_get_objects.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int]
         L.vo_tracker_get_dyn_tracks.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_int]
+        L.vo_tracker_full_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.vo_tracker_get_map_poses_rf.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.vo_tracker_get_objects_rf.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.vo_tracker_export_full_graph.argtypes = [C.c_void_p] + [C.c_void_p] * 14
         self.cfg = cfg
         self.h = L.vo_tracker_create(C.byref(cfg))
 
@@ -352,6 +414,36 @@ class OracleTracker:
         ln = np.zeros(cap, np.int32); oid = np.zeros(cap, np.int32); ff = np.zeros(cap, np.int32); fj = np.zeros(cap, np.int32)
         n = lib().vo_tracker_get_dyn_tracks(self.h, _p(ln), _p(oid), _p(ff), _p(fj), cap)
         return ln[:n].copy(), oid[:n].copy(), ff[:n].copy(), fj[:n].copy()
+
+    def full_batch(self):
+        """Optimizer::FullBatchOptimization on the map; returns (iterations, LmStats, sizes[6])"""
+        st = LmStats(); sizes = np.zeros(6, np.int32)
+        its = lib().vo_tracker_full_batch(self.h, C.byref(st), _p(sizes))
+        return its, st, sizes
+
+    def map_poses_rf(self):
+        n = lib().vo_tracker_num_frames(self.h)
+        P = np.zeros((n, 16), np.float32)
+        lib().vo_tracker_get_map_poses_rf(self.h, _p(P), n)
+        return P.reshape(n, 4, 4)
+
+    def objects_rf(self, frame, cap=64):
+        mot = np.zeros((cap, 16), np.float32)
+        n = max(lib().vo_tracker_get_objects_rf(self.h, frame, _p(mot), cap), 0)
+        return mot[:n].reshape(n, 4, 4).copy()
+
+    def export_full_graph(self):
+        """the flat FullBatch graph of the current map: (dict of arrays keyed by FBA_KEYS, n_poses)"""
+        sizes = np.zeros(6, np.int32)
+        lib().vo_tracker_export_full_graph(self.h, _p(sizes), *([None] * 13))
+        npo, nmo, npt, nob, ne6, nte = [int(v) for v in sizes]
+        g = dict(se3=np.zeros((npo + nmo, 16), np.float32), points=np.zeros((npt, 3), np.float32),
+                 e6_i=np.zeros(ne6, np.int32), e6_j=np.zeros(ne6, np.int32), e6_kind=np.zeros(ne6, np.int32),
+                 e6_meas=np.zeros((ne6, 16), np.float32), obs_se3=np.zeros(nob, np.int32), obs_point=np.zeros(nob, np.int32),
+                 obs_kind=np.zeros(nob, np.int32), obs_xyz=np.zeros((nob, 3), np.float32), tern_p1=np.zeros(nte, np.int32),
+                 tern_p2=np.zeros(nte, np.int32), tern_h=np.zeros(nte, np.int32))
+        lib().vo_tracker_export_full_graph(self.h, _p(sizes), *[_p(g[k]) if g[k].size else None for k in FBA_KEYS])
+        return g, npo
 
     def close(self):
         if self.h:

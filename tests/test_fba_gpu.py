@@ -1,0 +1,87 @@
+"""GPU: vido_ba_full / vido_full_batch (Optimizer::FullBatchOptimization, src/Optimizer.cc:1235-2178) against the oracle:
+same LM trajectory (iterations, trials, robust chi2 per iteration), estimates within 1e-4 relative."""
+import numpy as np
+import pytest
+
+import fba_synth
+import oracle_lib as ol
+import synth
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-4
+CAM = synth.KITTI
+
+
+def _same_lm(st_gpu, st_ref, rel=1e-6):
+    a, b = st_gpu.records(), st_ref.records()
+    assert st_gpu.iterations == st_ref.iterations and st_gpu.total_trials == st_ref.total_trials, (st_gpu.iterations, st_ref.iterations)
+    assert len(a) == len(b)
+    for (c1, l1, t1), (c2, l2, t2) in zip(a, b):
+        assert t1 == t2
+        assert abs(c1 - c2) <= rel * max(abs(c2), 1e-12) and abs(l1 - l2) <= 1e-6 * abs(l2)
+
+
+@pytest.mark.parametrize("n_frames,n_objects,seed", [(6, 2, 3), (5, 0, 5), (9, 3, 11)])
+def test_flat_graph_matches_oracle(pkg, n_frames, n_objects, seed):
+    g, n_poses, truth = fba_synth.make_graph(n_frames=n_frames, n_objects=n_objects, seed=seed)
+    se3_ref, pts_ref, its, st_ref = ol.ba_full(g, n_poses)
+    ctx = pkg.Context(pkg.default_config(width=640, height=480, max_batch=1))
+    se3, pts, st = ctx.ba_full(g, n_poses)
+    _same_lm(st, st_ref)
+    assert np.abs(se3 - se3_ref).max() <= REL_TOL * max(np.abs(se3_ref).max(), 1.0)
+    assert np.abs(pts - pts_ref).max() <= REL_TOL * max(np.abs(pts_ref).max(), 1.0)
+    assert np.abs(se3[:n_poses, :3, 3] - truth["Twc"][:, :3, 3]).max() < 0.02      # and right in absolute terms
+    ctx.close()
+
+
+def test_bad_graphs_are_rejected(pkg):
+    g, n_poses, _ = fba_synth.make_graph(n_frames=4, n_objects=1, seed=2)
+    ctx = pkg.Context(pkg.default_config(width=640, height=480, max_batch=1))
+    bad = dict(g); bad["obs_point"] = g["obs_point"].copy(); bad["obs_point"][0] = 10 ** 6
+    with pytest.raises(pkg.VidoError):
+        ctx.ba_full(bad, n_poses)
+    bad = dict(g); bad["tern_p1"] = g["tern_p1"].copy(); bad["tern_p1"][1] = g["tern_p1"][0]   # two successors of one point
+    with pytest.raises(pkg.VidoError):
+        ctx.ba_full(bad, n_poses)
+    ctx.close()
+
+
+def test_pipeline_full_batch_matches_oracle(pkg):
+    """track a dynamic sequence, then FullBatch on the Map: same flat graph as the oracle's tracker, same solution"""
+    n = 6
+    sc = synth.Scene(cam=CAM, seed=1234, flow_noise=0.1, depth_noise=0.01, n_objects=5)
+    frames = [sc.frame(k) for k in range(n)]
+    otr = ol.OracleTracker(ol.track_config(CAM))
+    for f in frames:
+        otr.track(f["gray"].numpy(), f["depth_in"].numpy(), f["flow"].numpy(), f["mask"].numpy())
+    ctx = pkg.Context(pkg.default_config(width=CAM["width"], height=CAM["height"], fx=CAM["fx"], fy=CAM["fy"], cx=CAM["cx"],
+                                         cy=CAM["cy"], bf=CAM["bf"], max_batch=3))
+    ctx.track_frames([dict(image=f["gray"].numpy(), depth=f["depth_in"].numpy(), flow=f["flow"].numpy(),
+                           mask=f["mask"].numpy().copy()) for f in frames], want_stats=False)
+    # (1) the keyframe-factor graph: identical structure, float payload within the tracking tolerance
+    g0, np0 = otr.export_full_graph()
+    g1, np1 = ctx.export_full_graph()
+    assert np0 == np1 == n
+    for k in ol.FBA_KEYS:
+        assert g0[k].shape == g1[k].shape, k
+        if g0[k].dtype == np.int32:
+            assert np.array_equal(g0[k], g1[k]), k
+        elif g0[k].size:
+            assert np.abs(g0[k] - g1[k]).max() <= REL_TOL * max(np.abs(g0[k]).max(), 1.0), k
+    assert len(g0["tern_p1"]) > 1000 and len(g0["obs_se3"]) > 5000
+    # (2) the solver on the SAME graph (the oracle's), bounded to a few iterations to keep the CPU side short
+    se3_ref, pts_ref, its, st_ref = ol.ba_full(g0, np0, max_iterations=6)
+    se3, pts, st = ctx.ba_full(g0, np0, max_iterations=6)
+    _same_lm(st, st_ref)
+    assert np.abs(se3 - se3_ref).max() <= REL_TOL * max(np.abs(se3_ref).max(), 1.0)
+    assert np.abs(pts - pts_ref).max() <= REL_TOL * max(np.abs(pts_ref).max(), 1.0)
+    # (3) vido_full_batch on the context's own Map runs to the reference's stop rule and improves the robust chi2
+    st_full, sizes = ctx.full_batch()
+    rec = st_full.records()
+    assert list(sizes) == [np0, g0["se3"].shape[0] - np0, g0["points"].shape[0], len(g0["obs_se3"]), len(g0["e6_i"]), len(g0["tern_p1"])]
+    assert st_full.iterations >= 5 and rec[-1][0] < rec[0][0]
+    P, Prf = ctx.map_poses(), ctx.map_poses_rf()
+    assert np.array_equal(P[0], Prf[0]) and np.isfinite(Prf).all() and np.abs(P - Prf).max() < 0.2
+    for k in range(1, n):
+        assert ctx.map_objects_rf(k).shape == ctx.map_objects(k)[2].shape
+    otr.close(); ctx.close()

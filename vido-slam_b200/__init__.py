@@ -65,6 +65,27 @@ class PnpProblem(C.Structure):
                 ("n_inliers", C.c_int32), ("winner", C.c_int32), ("ransac_inliers", C.c_int32), ("mm_inliers", C.c_int32)]
 
 
+class FbaProblem(C.Structure):
+    """vido_fba_problem (include/vido_b200.h): flat graph of Optimizer::FullBatchOptimization"""
+    _fields_ = [("n_poses", C.c_int32), ("n_motions", C.c_int32), ("n_points", C.c_int32), ("n_obs", C.c_int32),
+                ("n_e6", C.c_int32), ("n_tern", C.c_int32),
+                ("se3", C.c_void_p), ("points", C.c_void_p),
+                ("e6_i", C.c_void_p), ("e6_j", C.c_void_p), ("e6_kind", C.c_void_p), ("e6_meas", C.c_void_p),
+                ("obs_se3", C.c_void_p), ("obs_point", C.c_void_p), ("obs_kind", C.c_void_p), ("obs_xyz", C.c_void_p),
+                ("tern_p1", C.c_void_p), ("tern_p2", C.c_void_p), ("tern_h", C.c_void_p),
+                ("max_iterations", C.c_int32),
+                ("sigma2_cam", C.c_float), ("sigma2_3d_sta", C.c_float), ("sigma2_3d_dyn", C.c_float),
+                ("sigma2_obj", C.c_float), ("sigma2_smooth", C.c_float),
+                ("huber_cam", C.c_float), ("huber_obj", C.c_float), ("huber_3d", C.c_float),
+                ("gain_threshold", C.c_float), ("prior_info", C.c_float)]
+
+
+FBA_KEYS = ("se3", "points", "e6_i", "e6_j", "e6_kind", "e6_meas", "obs_se3", "obs_point", "obs_kind", "obs_xyz",
+            "tern_p1", "tern_p2", "tern_h")
+FBA_F32 = ("se3", "points", "e6_meas", "obs_xyz")
+FBA_WIDTH = dict(se3=16, points=3, e6_meas=16, obs_xyz=3)
+
+
 class FrameInputs(C.Structure):
     _fields_ = [("image", C.c_void_p), ("channels", C.c_int32), ("on_device", C.c_int32), ("depth", C.c_void_p),
                 ("flow", C.c_void_p), ("mask", C.c_void_p), ("write_back_depth", C.c_int32), ("pad", C.c_int32),
@@ -136,6 +157,12 @@ def load_library():
     lib.vido_map_get_dynamic.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, C.c_int]
     lib.vido_map_get_objects.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int]
     lib.vido_map_get_dyn_tracks.argtypes = [vp, vp, vp, vp, vp, C.c_int]
+    lib.vido_fba_default_params.argtypes = [C.POINTER(FbaProblem)]
+    lib.vido_ba_full.argtypes = [vp, C.POINTER(FbaProblem), C.POINTER(LmStats)]
+    lib.vido_full_batch.argtypes = [vp, C.POINTER(LmStats), vp]
+    lib.vido_map_get_poses_rf.argtypes = [vp, vp, C.c_int]
+    lib.vido_map_get_objects_rf.argtypes = [vp, C.c_int, vp, C.c_int]
+    lib.vido_map_export_full_graph.argtypes = [vp] + [vp] * 14
     lib.vido_pnp_default_params.argtypes = [C.POINTER(PnpProblem)]
     lib.vido_init_model.argtypes = [vp, C.POINTER(PnpProblem)]
     lib.vido_poseopt_default_params.argtypes = [C.POINTER(PoseOptProblem)]
@@ -379,6 +406,54 @@ class Context:
         ln = np.zeros(cap, np.int32); oid = np.zeros(cap, np.int32); ff = np.zeros(cap, np.int32); fj = np.zeros(cap, np.int32)
         n = self.lib.vido_map_get_dyn_tracks(self.h, _ptr(ln), _ptr(oid), _ptr(ff), _ptr(fj), cap)
         return ln[:n].copy(), oid[:n].copy(), ff[:n].copy(), fj[:n].copy()
+
+    # ---- full-sequence optimisation (Optimizer::FullBatchOptimization)
+    def ba_full(self, g, n_poses, **params):
+        """solve a flat graph (dict keyed by FBA_KEYS); returns (se3 [n,4,4], points [m,3], LmStats)"""
+        keep = {k: np.array(g[k], dtype=np.float32 if k in FBA_F32 else np.int32, copy=True, order="C") for k in FBA_KEYS}
+        pr = FbaProblem()
+        self.lib.vido_fba_default_params(C.byref(pr))
+        pr.n_poses = n_poses
+        pr.n_motions = keep["se3"].reshape(-1, 16).shape[0] - n_poses
+        pr.n_points = keep["points"].reshape(-1, 3).shape[0]
+        pr.n_obs, pr.n_e6, pr.n_tern = len(keep["obs_se3"]), len(keep["e6_i"]), len(keep["tern_p1"])
+        for k in FBA_KEYS:
+            setattr(pr, k, _ptr(keep[k]).value if keep[k].size else None)
+        for k, v in params.items():
+            setattr(pr, k, v)
+        st = LmStats()
+        self._check(self.lib.vido_ba_full(self.h, C.byref(pr), C.byref(st)))
+        return keep["se3"].reshape(-1, 4, 4), keep["points"].reshape(-1, 3), st
+
+    def full_batch(self):
+        """FullBatchOptimization on the context's map; returns (LmStats, sizes[6])"""
+        st = LmStats(); sizes = np.zeros(6, np.int32)
+        self._check(self.lib.vido_full_batch(self.h, C.byref(st), _ptr(sizes)))
+        return st, sizes
+
+    def map_poses_rf(self):
+        n = self.lib.vido_map_num_frames(self.h)
+        P = np.zeros((max(n, 1), 16), np.float32)
+        self.lib.vido_map_get_poses_rf(self.h, _ptr(P), n)
+        return P[:n].reshape(n, 4, 4)
+
+    def map_objects_rf(self, frame, cap=64):
+        mot = np.zeros((cap, 16), np.float32)
+        n = max(self.lib.vido_map_get_objects_rf(self.h, frame, _ptr(mot), cap), 0)
+        return mot[:n].reshape(n, 4, 4).copy()
+
+    def export_full_graph(self):
+        """flat FullBatch graph ("keyframe factors") of the map: (dict keyed by FBA_KEYS, n_poses)"""
+        sizes = np.zeros(6, np.int32)
+        self._check(self.lib.vido_map_export_full_graph(self.h, _ptr(sizes), *([None] * 13)))
+        npo, nmo, npt, nob, ne6, nte = [int(v) for v in sizes]
+        g = dict(se3=np.zeros((npo + nmo, 16), np.float32), points=np.zeros((npt, 3), np.float32),
+                 e6_i=np.zeros(ne6, np.int32), e6_j=np.zeros(ne6, np.int32), e6_kind=np.zeros(ne6, np.int32),
+                 e6_meas=np.zeros((ne6, 16), np.float32), obs_se3=np.zeros(nob, np.int32), obs_point=np.zeros(nob, np.int32),
+                 obs_kind=np.zeros(nob, np.int32), obs_xyz=np.zeros((nob, 3), np.float32), tern_p1=np.zeros(nte, np.int32),
+                 tern_p2=np.zeros(nte, np.int32), tern_h=np.zeros(nte, np.int32))
+        self._check(self.lib.vido_map_export_full_graph(self.h, _ptr(sizes), *[_ptr(g[k]) if g[k].size else None for k in FBA_KEYS]))
+        return g, npo
 
     def kernel_times(self):
         """device ms / timed regions of (ORB front-end, init model, pose optimisation, window BA) + BA algorithmic bytes"""

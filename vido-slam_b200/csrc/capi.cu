@@ -325,6 +325,23 @@ int vido_map_get_dyn_tracks(vido_ctx* ctx, int32_t* len, int32_t* obj_id, int32_
   return ctx ? trk_get_dyn_tracks(ctx, len, obj_id, first_frame, first_feat, cap) : VIDO_ERR_ARG;
 }
 
+void vido_fba_default_params(vido_fba_problem* p) { if (p) vido_fba_default_params_impl(p); }
+int vido_ba_full(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* stats) {
+  if (!ctx || !p) return VIDO_ERR_ARG;
+  if (p->n_poses < 0 || p->n_motions < 0 || p->n_points < 0 || p->n_obs < 0 || p->n_e6 < 0 || p->n_tern < 0) { ctx->err = "negative size"; return VIDO_ERR_ARG; }
+  return fba_solve_host(ctx, p, stats);
+}
+int vido_full_batch(vido_ctx* ctx, vido_lm_stats* stats, int32_t* sizes) { return ctx ? trk_full_batch(ctx, stats, sizes) : VIDO_ERR_ARG; }
+int vido_map_get_poses_rf(vido_ctx* ctx, float* poses, int cap) { return (ctx && poses) ? trk_get_map_poses_rf(ctx, poses, cap) : VIDO_ERR_ARG; }
+int vido_map_get_objects_rf(vido_ctx* ctx, int frame, float* motion, int cap) { return ctx ? trk_get_objects_rf(ctx, frame, motion, cap) : VIDO_ERR_ARG; }
+int vido_map_export_full_graph(vido_ctx* ctx, int32_t* sizes, float* se3, float* points, int32_t* e6_i, int32_t* e6_j, int32_t* e6_kind,
+                               float* e6_meas, int32_t* obs_se3, int32_t* obs_point, int32_t* obs_kind, float* obs_xyz,
+                               int32_t* tern_p1, int32_t* tern_p2, int32_t* tern_h) {
+  if (!ctx || !sizes) return VIDO_ERR_ARG;
+  return trk_export_full_graph(ctx, sizes, se3, points, e6_i, e6_j, e6_kind, e6_meas, obs_se3, obs_point, obs_kind, obs_xyz, tern_p1,
+                               tern_p2, tern_h);
+}
+
 int vido_get_kernel_times(vido_ctx* ctx, double* ms, int64_t* launches, double* ba_alg_bytes) {
   if (!ctx) return VIDO_ERR_ARG;
   for (int k = 0; k < 4; k++) { if (ms) ms[k] = ctx->t_ms[k]; if (launches) launches[k] = ctx->t_n[k]; }

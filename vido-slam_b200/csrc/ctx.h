@@ -159,6 +159,17 @@ int trk_get_dynamic(vido_ctx* ctx, int frame, float* xy, float* depth, float* p3
 int trk_get_objects(vido_ctx* ctx, int frame, int32_t* label, int32_t* sem_label, float* motion, float* centre, int cap);
 int trk_get_dyn_tracks(vido_ctx* ctx, int32_t* len, int32_t* obj_id, int32_t* first_frame, int32_t* first_feat, int cap);
 
+int trk_full_batch(vido_ctx* ctx, vido_lm_stats* stats, int32_t* sizes);
+int trk_get_map_poses_rf(vido_ctx* ctx, float* poses, int cap);
+int trk_get_objects_rf(vido_ctx* ctx, int frame, float* motion, int cap);
+int trk_export_full_graph(vido_ctx* ctx, int32_t* sizes, float* se3, float* points, int32_t* e6_i, int32_t* e6_j, int32_t* e6_kind,
+                          float* e6_meas, int32_t* obs_se3, int32_t* obs_point, int32_t* obs_kind, float* obs_xyz, int32_t* tern_p1,
+                          int32_t* tern_p2, int32_t* tern_h);
+
+// fba_kernels.cu
+void vido_fba_default_params_impl(vido_fba_problem* p);
+int fba_solve_host(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* st);
+
 // imu_kernels.cu
 int imu_preintegrate_host(vido_ctx* ctx, const vido_imu_sample* samples, int n, const double* t_prev, const double* t_cur,
                           int njobs, const float* bias, const float* noise, vido_imu_preint* out);

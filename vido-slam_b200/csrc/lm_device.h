@@ -1,5 +1,5 @@
 // lm_device.h -- the reference's Levenberg-Marquardt driver as a device-side state machine, executed by ONE thread
-// of the solver kernel between barriers (no host round trips).
+// of the solver kernel between barriers (no host round trips), or by the host between launches (full-sequence graph).
 //
 //   SparseOptimizer::optimize           g2o/core/sparse_optimizer.cpp:354-427 (local chi2_check patch :393-396)
 //   OptimizationAlgorithmLevenberg      g2o/core/optimization_algorithm_levenberg.cpp:61-189 (nBad patch :154-161)
@@ -9,6 +9,13 @@
 #include <math.h>
 
 #define VIDO_LM_REC 320
+// the same state machine drives the in-kernel solvers (window BA, pose optimisation) and the host-side loop of the
+// full-sequence optimisation (fba_kernels.cu)
+#if defined(__CUDACC__)
+#define LMHD __host__ __device__ __forceinline__
+#else
+#define LMHD inline
+#endif
 
 struct LmRec {
   double chi2, lambda;
@@ -21,7 +28,7 @@ struct LmCtl {
   int iterations, n_records, total_trials, pad;
 };
 
-__device__ __forceinline__ void lm_reset(LmCtl* c) {
+LMHD void lm_reset(LmCtl* c) {
   c->lambda = -1; c->ni = 2; c->currentChi = 0; c->iniChi = 0; c->tempChi = 0; c->lastTrialChi = 0;
   c->chi2_check = 0; c->lastChi = 0; c->rho = 0;
   c->it = 0; c->qmax = 0; c->nBad = 0; c->stop_flag = 0; c->ok = 1; c->accepted = 0; c->fail = 0; c->cur = 0;
@@ -29,7 +36,7 @@ __device__ __forceinline__ void lm_reset(LmCtl* c) {
 }
 
 // start of Levenberg::solve(it): system has just been built; maxdiag only needed at it == 0
-__device__ __forceinline__ void lm_begin_iteration(LmCtl* c, int it, double maxdiag, double user_lambda) {
+LMHD void lm_begin_iteration(LmCtl* c, int it, double maxdiag, double user_lambda) {
   c->iniChi = c->currentChi;
   c->tempChi = c->currentChi;
   if (it == 0) {
@@ -43,7 +50,7 @@ __device__ __forceinline__ void lm_begin_iteration(LmCtl* c, int it, double maxd
 
 // after one trial: chi = robust chi2 at the trial state, scale = x^T(lambda x + b), failed = linear solver failed.
 // Sets c->accepted and flips c->cur on acceptance.  Continue trying while (rho < 0 && qmax < 10).
-__device__ __forceinline__ void lm_trial(LmCtl* c, double chi, double scale, int failed) {
+LMHD void lm_trial(LmCtl* c, double chi, double scale, int failed) {
   c->lastTrialChi = chi;
   const double tempChi = failed ? DBL_MAX : chi;
   double rho = c->currentChi - tempChi;
@@ -70,11 +77,11 @@ __device__ __forceinline__ void lm_trial(LmCtl* c, double chi, double scale, int
   c->fail = 0;
 }
 
-__device__ __forceinline__ bool lm_more_trials(const LmCtl* c) { return c->rho < 0 && c->qmax < 10; }
+LMHD bool lm_more_trials(const LmCtl* c) { return c->rho < 0 && c->qmax < 10; }
 
 // end of the iteration: stop rules of solve(), the chi2_check patch of optimize(), statistics, terminate action.
 // gain_threshold < 0: no terminate action registered.
-__device__ __forceinline__ void lm_end_iteration(LmCtl* c, int it, double gain_threshold, LmRec* rec) {
+LMHD void lm_end_iteration(LmCtl* c, int it, double gain_threshold, LmRec* rec) {
   int result_ok;
   if (c->qmax == 10 || c->rho == 0) result_ok = 0;
   else {

@@ -53,13 +53,14 @@ void inv44(const float* T, float* Ti) {
 }
 void eye44(float* T) { memset(T, 0, sizeof(float) * 16); T[0] = T[5] = T[10] = T[15] = 1.f; }
 
-struct ObjEntry { int label, sem; float motion[16]; float centre[3]; };  // vnRMLabel / vnSMLabel / vmRigidMotion[f-1][j>=1] / vmRigidCentre
+struct ObjEntry { int label, sem; float motion[16]; float centre[3]; float motion_rf[16]; };  // vnRMLabel / vnSMLabel / vmRigidMotion[f-1][j>=1] / vmRigidCentre
 struct DynTrack { int first_frame, first_feat, len, obj_id; };          // TrackletDyn / nObjID
 struct MapFrame {           // Map::vpFeatSta / vfDepSta / vp3DPointSta / vnAssoSta of one frame + its pose
   std::vector<float> xy, depth, p3;
   std::vector<int> asso, track, pos;
   float Twc[16];            // vmCameraPose
   float rel[16];            // vmRigidMotion[f-1][0]
+  float Twc_rf[16];         // vmCameraPose_RF (refined by the full-sequence optimisation)
   // Map::vpFeatDyn / vfDepDyn / vp3DPointDyn / vnAssoDyn / vnFeatLabel + the objects with an estimated motion
   std::vector<float> dxy, ddepth, dp3;
   std::vector<int> dasso, dlabel, dtrack;
@@ -861,6 +862,7 @@ static int dyn_renew(vido_ctx* ctx, const FrontFrame& ff, const float* curTcw, c
     ObjEntry e;
     e.label = D.mod_label[i]; e.sem = D.sem_pos[i];
     memcpy(e.motion, D.mod[i].data(), sizeof e.motion);
+    memcpy(e.motion_rf, e.motion, sizeof e.motion);
     memcpy(e.centre, D.centre[i].data(), sizeof e.centre);
     F.objects.push_back(e);
   }
@@ -877,7 +879,8 @@ static int dyn_renew(vido_ctx* ctx, const FrontFrame& ff, const float* curTcw, c
     } else {
       const int t = (int)ts->dyn_tracks.size();
       ts->dyn_tracks.push_back({fcur - 1, p, 2, lab[j]});
-      F.dtrack[j] = t;   // (the predecessor keeps -1: only the newest element of a chain is looked up again)
+      F.dtrack[j] = t;
+      P.dtrack[p] = t;   // first element of the chain (read by the full-sequence graph builder)
     }
   }
   // (6) becomes mpLastFrame
@@ -1053,7 +1056,7 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
       const float z = F.depth[i];
       F.p3[3 * i] = (kp.x - c.cx) * z * invfx; F.p3[3 * i + 1] = (kp.y - c.cy) * z * invfy; F.p3[3 * i + 2] = z;
     }
-    eye44(F.Twc); eye44(F.rel);
+    eye44(F.Twc); eye44(F.rel); eye44(F.Twc_rf);
     ts->last_keys = F.xy; ts->last_depth = F.depth; ts->last_corres = ff.as_corres; ts->last_flow = ff.as_flow;
     memcpy(ts->lastTcw, curTcw, sizeof curTcw);
     {  // object samples of frame 0 (Frame.cc:184-211, Tracking.cc:1524-1541)
@@ -1248,6 +1251,7 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
         }
       }
       memcpy(F.Twc, Twc, sizeof Twc);
+      memcpy(F.Twc_rf, Twc, sizeof Twc);
       inv44(ts->mVelocity, F.rel);
       if (dyn) {  // RenewFrameInfo (object part), Map bookkeeping, dynamic tracklets
         rc = dyn_renew(ctx, ff, curTcw, FS.d_obkeys + 2 * (size_t)slot * ts->obj_cap, d_depth, d_flow, d_mask, slot, D, F);
@@ -1462,4 +1466,172 @@ int trk_get_dyn_tracks(vido_ctx* ctx, int32_t* len, int32_t* obj_id, int32_t* fi
     first_frame[i] = ts->dyn_tracks[i].first_frame; first_feat[i] = ts->dyn_tracks[i].first_feat;
   }
   return n;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Optimizer::FullBatchOptimization on the Map: flat graph (Optimizer.cc:1235-1745), device solve (fba_kernels.cu),
+// write-back (Optimizer.cc:2090-2176)
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct FullGraph {
+  std::vector<float> se3, points, e6_meas, obs_xyz;
+  std::vector<int32_t> e6_i, e6_j, e6_kind, obs_se3, obs_point, obs_kind, tern_p1, tern_p2, tern_h;
+  int n_poses = 0, n_motions = 0;
+  std::vector<std::vector<int>> VertexID;        // [frame][object entry] -> SE3 vertex
+  std::vector<std::vector<int>> makSta, makDyn;  // per frame, per feature: point vertex or -1
+};
+
+void build_full_graph(TrackState* ts, const vido_config& c, FullGraph& G) {
+  const int N = (int)ts->map.size();
+  const float invfx = 1.0f / c.fx, invfy = 1.0f / c.fy;
+  G.n_poses = N;
+  G.VertexID.assign(N, std::vector<int>());
+  G.makSta.resize(N); G.makDyn.resize(N);
+  for (int i = 0; i < N; i++) G.se3.insert(G.se3.end(), ts->map[i].Twc, ts->map[i].Twc + 16);
+  int next_se3 = N;
+  float I16[16];
+  eye44(I16);
+  auto add_point = [&](const float* Xw) { G.points.push_back(Xw[0]); G.points.push_back(Xw[1]); G.points.push_back(Xw[2]); return (int)(G.points.size() / 3) - 1; };
+  auto add_obs = [&](int se3v, int pt, int kind, float u, float v, float z) {
+    G.obs_se3.push_back(se3v); G.obs_point.push_back(pt); G.obs_kind.push_back(kind);
+    G.obs_xyz.push_back((u - c.cx) * z * invfx); G.obs_xyz.push_back((v - c.cy) * z * invfy); G.obs_xyz.push_back(z);
+  };
+  for (int i = 0; i < N; i++) {
+    const MapFrame& F = ts->map[i];
+    if (i != 0) {
+      G.e6_i.push_back(i - 1); G.e6_j.push_back(i); G.e6_kind.push_back(0);
+      G.e6_meas.insert(G.e6_meas.end(), F.rel, F.rel + 16);
+    }
+    // static tracklets of length >= 3: one point per tracklet, one observation per element
+    const int ns = (int)F.depth.size();
+    G.makSta[i].assign(ns, -1);
+    for (int j = 0; j < ns; j++) {
+      const int t = F.track[j];
+      if (t < 0 || ts->tracks[t].len < 3) continue;
+      int pid;
+      if (F.pos[j] == 0) pid = add_point(&F.p3[3 * (size_t)j]);
+      else pid = G.makSta[i - 1][F.asso[j]];
+      if (pid == -1) continue;
+      add_obs(i, pid, 0, F.xy[2 * j], F.xy[2 * j + 1], F.depth[j]);
+      G.makSta[i][j] = pid;
+    }
+    // dynamic tracklets: every element is its own point; consecutive elements are tied by the object's motion
+    const int nd = (int)F.ddepth.size();
+    G.makDyn[i].assign(nd, -1);
+    if (i == 0) {
+      for (int j = 0; j < nd; j++) {
+        const int t = F.dtrack[j];
+        if (t < 0 || ts->dyn_tracks[t].len < 3) continue;
+        const int pid = add_point(&F.dp3[3 * (size_t)j]);
+        add_obs(i, pid, 1, F.dxy[2 * j], F.dxy[2 * j + 1], F.ddepth[j]);
+        G.makDyn[i][j] = pid;
+      }
+      continue;
+    }
+    const size_t nobj = F.objects.size();
+    G.VertexID[i].assign(nobj, -1);
+    for (size_t j = 0; j < nobj; j++) {
+      G.se3.insert(G.se3.end(), I16, I16 + 16);   // object motions start from identity (Optimizer.cc:1597)
+      const int vid = next_se3++;
+      if (i > 2) {  // SMOOTH_CONSTRAINT && i>2 (Optimizer.cc:1611-1638)
+        const MapFrame& Pf = ts->map[i - 1];
+        int TraceID = -1;
+        for (size_t k = 0; k < Pf.objects.size(); k++)
+          if (Pf.objects[k].label == F.objects[j].label) { TraceID = (int)k; break; }
+        if (TraceID != -1) {
+          G.e6_i.push_back(G.VertexID[i - 1][TraceID]); G.e6_j.push_back(vid); G.e6_kind.push_back(1);
+          G.e6_meas.insert(G.e6_meas.end(), I16, I16 + 16);
+        }
+      }
+      G.VertexID[i][j] = vid;
+    }
+    for (int j = 0; j < nd; j++) {
+      const int t = F.dtrack[j];
+      if (t < 0 || ts->dyn_tracks[t].len < 3) continue;
+      const int pos = i - ts->dyn_tracks[t].first_frame;
+      int ObjPositionID = -1;
+      for (size_t k = 0; k < nobj; k++)
+        if (F.objects[k].label == ts->dyn_tracks[t].obj_id) { ObjPositionID = G.VertexID[i][k]; break; }
+      if (ObjPositionID == -1 && pos != 0) continue;
+      int prev = -1;
+      if (pos != 0) {
+        prev = G.makDyn[i - 1][F.dasso[j]];
+        if (prev == -1) continue;
+      }
+      const int pid = add_point(&F.dp3[3 * (size_t)j]);
+      add_obs(i, pid, 1, F.dxy[2 * j], F.dxy[2 * j + 1], F.ddepth[j]);
+      if (pos != 0) { G.tern_p1.push_back(prev); G.tern_p2.push_back(pid); G.tern_h.push_back(ObjPositionID); }
+      G.makDyn[i][j] = pid;
+    }
+  }
+  G.n_motions = next_se3 - N;
+}
+
+void fill_problem(FullGraph& G, vido_fba_problem& pr) {
+  memset(&pr, 0, sizeof pr);
+  vido_fba_default_params_impl(&pr);
+  pr.n_poses = G.n_poses; pr.n_motions = G.n_motions; pr.n_points = (int)(G.points.size() / 3);
+  pr.n_obs = (int)G.obs_se3.size(); pr.n_e6 = (int)G.e6_i.size(); pr.n_tern = (int)G.tern_p1.size();
+  pr.se3 = G.se3.data(); pr.points = G.points.data();
+  pr.e6_i = G.e6_i.data(); pr.e6_j = G.e6_j.data(); pr.e6_kind = G.e6_kind.data(); pr.e6_meas = G.e6_meas.data();
+  pr.obs_se3 = G.obs_se3.data(); pr.obs_point = G.obs_point.data(); pr.obs_kind = G.obs_kind.data(); pr.obs_xyz = G.obs_xyz.data();
+  pr.tern_p1 = G.tern_p1.data(); pr.tern_p2 = G.tern_p2.data(); pr.tern_h = G.tern_h.data();
+}
+}  // namespace
+
+int trk_full_batch(vido_ctx* ctx, vido_lm_stats* stats, int32_t* sizes) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  int rc = ba_finish(ctx);   // a window solve left in flight by a failed call
+  if (rc) return rc;
+  ba_writeback_rest(ctx);
+  FullGraph G;
+  build_full_graph(ts, ctx->cfg, G);
+  vido_fba_problem pr;
+  fill_problem(G, pr);
+  if (sizes) { sizes[0] = pr.n_poses; sizes[1] = pr.n_motions; sizes[2] = pr.n_points; sizes[3] = pr.n_obs; sizes[4] = pr.n_e6; sizes[5] = pr.n_tern; }
+  rc = fba_solve_host(ctx, &pr, stats);
+  if (rc) return rc;
+  const int N = G.n_poses;
+  for (int i = 1; i < N; i++) memcpy(ts->map[i].Twc_rf, &G.se3[16 * (size_t)i], sizeof(float) * 16);
+  for (int i = 1; i < N; i++)
+    for (size_t j = 0; j < G.VertexID[i].size(); j++) memcpy(ts->map[i].objects[j].motion_rf, &G.se3[16 * (size_t)G.VertexID[i][j]], sizeof(float) * 16);
+  for (int i = 0; i < N; i++) {
+    MapFrame& F = ts->map[i];
+    for (size_t j = 0; j < G.makSta[i].size(); j++)
+      if (G.makSta[i][j] != -1) memcpy(&F.p3[3 * j], &G.points[3 * (size_t)G.makSta[i][j]], sizeof(float) * 3);
+    for (size_t j = 0; j < G.makDyn[i].size(); j++)
+      if (G.makDyn[i][j] != -1) memcpy(&F.dp3[3 * j], &G.points[3 * (size_t)G.makDyn[i][j]], sizeof(float) * 3);
+  }
+  return VIDO_OK;
+}
+
+int trk_get_map_poses_rf(vido_ctx* ctx, float* poses, int cap) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  const int n = (int)ts->map.size();
+  for (int i = 0; i < n && i < cap; i++) memcpy(poses + 16 * (size_t)i, ts->map[i].Twc_rf, sizeof(float) * 16);
+  return n;
+}
+
+int trk_get_objects_rf(vido_ctx* ctx, int frame, float* motion, int cap) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  if (frame < 1 || frame >= (int)ts->map.size()) return -1;
+  const MapFrame& F = ts->map[frame];
+  for (int i = 0; i < (int)F.objects.size() && i < cap; i++) memcpy(motion + 16 * (size_t)i, F.objects[i].motion_rf, sizeof(float) * 16);
+  return (int)F.objects.size();
+}
+
+int trk_export_full_graph(vido_ctx* ctx, int32_t* sizes, float* se3, float* points, int32_t* e6_i, int32_t* e6_j, int32_t* e6_kind,
+                          float* e6_meas, int32_t* obs_se3, int32_t* obs_point, int32_t* obs_kind, float* obs_xyz, int32_t* tern_p1,
+                          int32_t* tern_p2, int32_t* tern_h) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  FullGraph G;
+  build_full_graph(ts, ctx->cfg, G);
+  sizes[0] = G.n_poses; sizes[1] = G.n_motions; sizes[2] = (int)(G.points.size() / 3); sizes[3] = (int)G.obs_se3.size();
+  sizes[4] = (int)G.e6_i.size(); sizes[5] = (int)G.tern_p1.size();
+  if (!se3) return VIDO_OK;
+  auto cp = [](auto* dst, const auto& v) { if (dst && !v.empty()) memcpy(dst, v.data(), sizeof(v[0]) * v.size()); };
+  cp(se3, G.se3); cp(points, G.points); cp(e6_i, G.e6_i); cp(e6_j, G.e6_j); cp(e6_kind, G.e6_kind); cp(e6_meas, G.e6_meas);
+  cp(obs_se3, G.obs_se3); cp(obs_point, G.obs_point); cp(obs_kind, G.obs_kind); cp(obs_xyz, G.obs_xyz);
+  cp(tern_p1, G.tern_p1); cp(tern_p2, G.tern_p2); cp(tern_h, G.tern_h);
+  return VIDO_OK;
 }
