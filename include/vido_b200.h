@@ -333,6 +333,28 @@ typedef struct vido_imu_preint {
 int vido_imu_preintegrate(vido_ctx* ctx, const vido_imu_sample* samples, int n, const double* t_prev, const double* t_cur,
                           int njobs, const float* bias, const float* noise, vido_imu_preint* out);
 
+/*
+ * Inertial-only optimisation of the VIO initialisation: replaces Optimizer::InertialOptimization (src/Optimizer.cc:2441-2620,
+ * called from Tracking::InitializeIMU, src/Tracking.cc:937-1044) with EdgeInertialGS (src/G2oTypes.cc:357-482).  Poses are
+ * fixed; unknowns: one velocity per frame, gyro / acc bias (priors prior_g / prior_a), gravity direction Rwg, scale.
+ * preint[i] = preintegration from frame i to i+1 (frame i+1's mpImuPreintegrated, e.g. from vido_imu_preintegrate),
+ * bias_lin[i] = the bias it was integrated with; Rwb / twb = Frame::GetImuRotation / GetImuPosition (float32).  Host pointers.
+ */
+typedef struct vido_inertial_problem {
+  int32_t n_frames, its;          /* its = 200 (:2444) */
+  const float* Rwb;               /* [n][9] */
+  const float* twb;               /* [n][3] */
+  float* velocity;                /* [n][3] in/out (Frame::mVw) */
+  const vido_imu_preint* preint;  /* [n-1] */
+  const float* bias_lin;          /* [n-1][6] bax,bay,baz,bwx,bwy,bwz */
+  double Rwg[9];                  /* in/out (Eigen::Matrix3d mRwg) */
+  double scale;                   /* in/out (mScale) */
+  double bg[3], ba[3];            /* in/out (mbg, mba) */
+  float prior_g, prior_a;         /* 1e2, 1e9 (src/Tracking.cc:1453) */
+} vido_inertial_problem;
+void vido_inertial_default_params(vido_inertial_problem* p);
+int vido_inertial_opt(vido_ctx* ctx, vido_inertial_problem* p, vido_lm_stats* stats);
+
 /* accumulated device time (CUDA events on the context stream) of the kernel groups: ms[0] ORB front-end launches,
  * ms[1] init-model kernels, ms[2] pose-optimisation kernel, ms[3] window-BA kernel; launches[k] = timed regions;
  * ba_alg_bytes = algorithmic bytes of the BA launches (296 B per edge per linearisation + 152 B per edge per

@@ -262,6 +262,29 @@ typedef struct vo_imu_preint {
 int vo_imu_preintegrate(const vo_imu_sample* samples, int n, double t_prev, double t_cur, const float* bias,
                         const float* noise, vo_imu_preint* out);
 
+/*
+ * Inertial-only optimisation of the VIO initialisation: Optimizer::InertialOptimization (src/Optimizer.cc:2441-2620) with
+ * EdgeInertialGS (src/G2oTypes.cc:357-482).  Poses are fixed; unknowns: one velocity per frame, gyro / acc bias, gravity
+ * direction Rwg (2 dof), scale.  preint[i] is the preintegration from frame i to frame i+1 (frame i+1's mpImuPreintegrated),
+ * bias_lin[i] the bias it was integrated with.  Rwb / twb: body poses (Frame::GetImuRotation / GetImuPosition, float32).
+ */
+typedef struct vo_inertial_problem {
+  int32_t n_frames, its;       /* its = 200 (:2444) */
+  const float* Rwb;            /* [n][9] */
+  const float* twb;            /* [n][3] */
+  float* velocity;             /* [n][3] in/out (Frame::mVw) */
+  const vo_imu_preint* preint; /* [n-1] */
+  const float* bias_lin;       /* [n-1][6] bax,bay,baz,bwx,bwy,bwz */
+  double Rwg[9];               /* in/out */
+  double scale;                /* in/out */
+  double bg[3], ba[3];         /* in/out */
+  float prior_g, prior_a;      /* 1e2, 1e9 (src/Tracking.cc:1453) */
+} vo_inertial_problem;
+void vo_inertial_default_params(vo_inertial_problem* p);
+int vo_inertial_optimization(vo_inertial_problem* p, vo_lm_stats* stats);
+/* information matrix of an EdgeInertialGS from the 15x15 float32 preintegration covariance (src/G2oTypes.cc:363-375) */
+void vo_inertial_edge_information(const float* C15, double* info81);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,3 +41,58 @@ def integrate_f64(steps, bias):
         dR = dR @ dRi
         dT += dt
     return dR, dV, dP, dT
+
+
+# ---------------------------------------------------------------- a consistent body trajectory for the inertial-only optimisation
+def _exp(w):
+    th = np.linalg.norm(w)
+    return ba_synth.rot(w, th) if th > 1e-12 else np.eye(3)
+
+
+def make_vio_case(n_frames=12, seed=0, fps=10.0, scale_true=1.25, bg_true=(0.002, -0.001, 0.0015), tilt=(0.15, -0.1)):
+    """Body trajectory p(t), R(t) in a world whose gravity is tilted by `tilt` (rad about x, y) from -z; 200 Hz IMU samples
+    (specific force R^T (a - g), body rates + bias), frames at `fps`.  Returns the inputs of Optimizer::InertialOptimization as
+    Tracking::InitializeIMU prepares them (src/Tracking.cc:937-1000): positions in visual units (metric / scale_true), velocities
+    from finite differences, Rwg from the summed delta-velocities, zero biases."""
+    rng = np.random.default_rng(seed)
+    Rg = _exp(np.array([tilt[0], 0, 0])) @ _exp(np.array([0, tilt[1], 0]))
+    g_w = Rg @ np.array([0, 0, -9.79])
+    h = 1.0 / 2000.0
+    T_end = (n_frames - 1) / fps + 0.05
+    n_fine = int(T_end / h) + 2
+    tf = np.arange(n_fine) * h
+    p = np.stack([1.5 * tf + 0.3 * np.sin(1.1 * tf), 0.4 * np.sin(0.8 * tf), 0.2 * np.cos(0.9 * tf) - 0.2], 1)
+    v = np.stack([1.5 + 0.33 * np.cos(1.1 * tf), 0.32 * np.cos(0.8 * tf), -0.18 * np.sin(0.9 * tf)], 1)
+    a = np.stack([-0.363 * np.sin(1.1 * tf), -0.256 * np.sin(0.8 * tf), -0.162 * np.cos(0.9 * tf)], 1)
+    w_body = np.stack([0.10 * np.sin(1.7 * tf), 0.15 * np.cos(1.2 * tf), 0.08 * np.sin(0.9 * tf + 0.3)], 1)
+    R = np.zeros((n_fine, 3, 3)); R[0] = _exp(np.array([0.05, -0.02, 0.1]))
+    for i in range(1, n_fine):
+        R[i] = R[i - 1] @ _exp(0.5 * (w_body[i - 1] + w_body[i]) * h)
+    step = int(round(1.0 / FREQ / h))
+    idx = np.arange(0, n_fine, step)
+    s = np.zeros(len(idx), ol.IMU_SAMPLE)
+    s["t"] = tf[idx]
+    f_body = np.einsum("nji,nj->ni", R[idx], a[idx] - g_w)            # R^T (a - g)
+    f_body += rng.normal(size=f_body.shape) * 2.0e-3 * np.sqrt(FREQ) * 0.1
+    w_meas = w_body[idx] + np.asarray(bg_true) + rng.normal(size=f_body.shape) * 1.7e-4 * np.sqrt(FREQ) * 0.1
+    for k, nm in enumerate(("ax", "ay", "az")):
+        s[nm] = f_body[:, k]
+    for k, nm in enumerate(("wx", "wy", "wz")):
+        s[nm] = w_meas[:, k]
+    fidx = np.array([int(round((k / fps + 0.01) / h)) for k in range(n_frames)])
+    ft = tf[fidx]
+    Rwb = R[fidx].astype(np.float32)
+    twb = (p[fidx] / scale_true).astype(np.float32)
+    pre = np.array([ol.imu_preintegrate(s, ft[k], ft[k + 1], np.zeros(6, np.float32), NOISE) for k in range(n_frames - 1)], ol.IMU_PREINT).reshape(-1)
+    # Tracking::InitializeIMU: gravity direction from the summed delta-velocities, velocities from finite differences
+    dirG = np.zeros(3, np.float32); vel = np.zeros((n_frames, 3), np.float32)
+    for k in range(n_frames - 1):
+        dirG -= Rwb[k] @ pre[k]["dV"]
+        vk = (twb[k + 1] - twb[k]) / pre[k]["dT"]
+        vel[k + 1] = vk; vel[k] = vk
+    dirG = dirG / np.linalg.norm(dirG)
+    gI = np.array([0, 0, -1.0], np.float32)
+    vv = np.cross(gI, dirG); nv = np.linalg.norm(vv); ang = np.arccos(np.dot(gI, dirG))
+    Rwg = _exp((vv * ang / nv).astype(np.float64))
+    truth = dict(scale=scale_true, bg=np.asarray(bg_true), g_dir=g_w / 9.79, vel=v[fidx])
+    return dict(Rwb=Rwb, twb=twb, vel=vel, preint=pre, bias_lin=np.zeros((n_frames - 1, 6), np.float32), Rwg=Rwg), truth

@@ -466,3 +466,43 @@ def imu_preintegrate(samples, t_prev, t_cur, bias, noise):
     L.vo_imu_preintegrate.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
     L.vo_imu_preintegrate(_p(s), len(s), float(t_prev), float(t_cur), _p(b), _p(nz), _p(out))
     return out[0]
+
+
+# ---------------------------------------------------------------- inertial-only optimisation (VIO initialisation)
+class InertialProblem(C.Structure):
+    _fields_ = [("n_frames", C.c_int32), ("its", C.c_int32), ("Rwb", C.c_void_p), ("twb", C.c_void_p), ("velocity", C.c_void_p),
+                ("preint", C.c_void_p), ("bias_lin", C.c_void_p), ("Rwg", C.c_double * 9), ("scale", C.c_double),
+                ("bg", C.c_double * 3), ("ba", C.c_double * 3), ("prior_g", C.c_float), ("prior_a", C.c_float)]
+
+
+def fill_inertial(pr, Rwb, twb, vel, preint, bias_lin, Rwg, scale, bg, ba):
+    keep = [np.ascontiguousarray(Rwb, np.float32).reshape(-1, 9), np.ascontiguousarray(twb, np.float32).reshape(-1, 3),
+            np.array(vel, np.float32).reshape(-1, 3).copy(), np.ascontiguousarray(preint, IMU_PREINT),
+            np.ascontiguousarray(bias_lin, np.float32).reshape(-1, 6)]
+    pr.n_frames = keep[0].shape[0]
+    pr.Rwb, pr.twb, pr.velocity, pr.preint, pr.bias_lin = [_p(a).value for a in keep]
+    pr.Rwg[:] = [float(v) for v in np.asarray(Rwg, np.float64).reshape(9)]
+    pr.scale = float(scale)
+    pr.bg[:] = [float(v) for v in bg]
+    pr.ba[:] = [float(v) for v in ba]
+    return keep
+
+
+def inertial_optimization(Rwb, twb, vel, preint, bias_lin, Rwg, scale=1.0, bg=(0, 0, 0), ba=(0, 0, 0), **params):
+    """Optimizer::InertialOptimization; returns dict(velocity, Rwg, scale, bg, ba, iterations, stats)"""
+    pr = InertialProblem()
+    lib().vo_inertial_default_params(C.byref(pr))
+    keep = fill_inertial(pr, Rwb, twb, vel, preint, bias_lin, Rwg, scale, bg, ba)
+    for k, v in params.items():
+        setattr(pr, k, v)
+    st = LmStats()
+    its = lib().vo_inertial_optimization(C.byref(pr), C.byref(st))
+    return dict(velocity=keep[2], Rwg=np.array(pr.Rwg[:]).reshape(3, 3), scale=pr.scale, bg=np.array(pr.bg[:]), ba=np.array(pr.ba[:]),
+                iterations=its, stats=st)
+
+
+def inertial_edge_information(C15):
+    Cm = np.ascontiguousarray(C15, np.float32).reshape(15, 15)
+    out = np.zeros((9, 9))
+    lib().vo_inertial_edge_information(_p(Cm), _p(out))
+    return out

@@ -86,6 +86,13 @@ FBA_F32 = ("se3", "points", "e6_meas", "obs_xyz")
 FBA_WIDTH = dict(se3=16, points=3, e6_meas=16, obs_xyz=3)
 
 
+class InertialProblem(C.Structure):
+    """vido_inertial_problem (include/vido_b200.h)"""
+    _fields_ = [("n_frames", C.c_int32), ("its", C.c_int32), ("Rwb", C.c_void_p), ("twb", C.c_void_p), ("velocity", C.c_void_p),
+                ("preint", C.c_void_p), ("bias_lin", C.c_void_p), ("Rwg", C.c_double * 9), ("scale", C.c_double),
+                ("bg", C.c_double * 3), ("ba", C.c_double * 3), ("prior_g", C.c_float), ("prior_a", C.c_float)]
+
+
 class FrameInputs(C.Structure):
     _fields_ = [("image", C.c_void_p), ("channels", C.c_int32), ("on_device", C.c_int32), ("depth", C.c_void_p),
                 ("flow", C.c_void_p), ("mask", C.c_void_p), ("write_back_depth", C.c_int32), ("pad", C.c_int32),
@@ -163,6 +170,8 @@ def load_library():
     lib.vido_map_get_poses_rf.argtypes = [vp, vp, C.c_int]
     lib.vido_map_get_objects_rf.argtypes = [vp, C.c_int, vp, C.c_int]
     lib.vido_map_export_full_graph.argtypes = [vp] + [vp] * 14
+    lib.vido_inertial_default_params.argtypes = [C.POINTER(InertialProblem)]
+    lib.vido_inertial_opt.argtypes = [vp, C.POINTER(InertialProblem), C.POINTER(LmStats)]
     lib.vido_pnp_default_params.argtypes = [C.POINTER(PnpProblem)]
     lib.vido_init_model.argtypes = [vp, C.POINTER(PnpProblem)]
     lib.vido_poseopt_default_params.argtypes = [C.POINTER(PoseOptProblem)]
@@ -454,6 +463,26 @@ class Context:
                  tern_p2=np.zeros(nte, np.int32), tern_h=np.zeros(nte, np.int32))
         self._check(self.lib.vido_map_export_full_graph(self.h, _ptr(sizes), *[_ptr(g[k]) if g[k].size else None for k in FBA_KEYS]))
         return g, npo
+
+    def inertial_opt(self, Rwb, twb, vel, preint, bias_lin, Rwg, scale=1.0, bg=(0, 0, 0), ba=(0, 0, 0), **params):
+        """Optimizer::InertialOptimization; returns dict(velocity, Rwg, scale, bg, ba, stats)"""
+        keep = [np.ascontiguousarray(Rwb, np.float32).reshape(-1, 9), np.ascontiguousarray(twb, np.float32).reshape(-1, 3),
+                np.array(vel, np.float32).reshape(-1, 3).copy(), np.ascontiguousarray(preint, IMU_PREINT),
+                np.ascontiguousarray(bias_lin, np.float32).reshape(-1, 6)]
+        pr = InertialProblem()
+        self.lib.vido_inertial_default_params(C.byref(pr))
+        pr.n_frames = keep[0].shape[0]
+        pr.Rwb, pr.twb, pr.velocity, pr.preint, pr.bias_lin = [_ptr(a).value for a in keep]
+        pr.Rwg[:] = [float(v) for v in np.asarray(Rwg, np.float64).reshape(9)]
+        pr.scale = float(scale)
+        pr.bg[:] = [float(v) for v in bg]
+        pr.ba[:] = [float(v) for v in ba]
+        for k, v in params.items():
+            setattr(pr, k, v)
+        st = LmStats()
+        self._check(self.lib.vido_inertial_opt(self.h, C.byref(pr), C.byref(st)))
+        return dict(velocity=keep[2], Rwg=np.array(pr.Rwg[:]).reshape(3, 3), scale=pr.scale, bg=np.array(pr.bg[:]),
+                    ba=np.array(pr.ba[:]), stats=st)
 
     def kernel_times(self):
         """device ms / timed regions of (ORB front-end, init model, pose optimisation, window BA) + BA algorithmic bytes"""

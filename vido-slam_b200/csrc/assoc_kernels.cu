@@ -299,10 +299,20 @@ int assoc_update_mask(vido_ctx* ctx, const int32_t* sem_label, const float* corr
   const int nl = (int)uni.size();
   int32_t *d_sem = nullptr, *d_hist = nullptr, *d_rec = nullptr;
   float* d_cor = nullptr;
-  VIDO_CUDA(cudaMallocAsync(&d_sem, sizeof(int32_t) * n, s));
-  VIDO_CUDA(cudaMallocAsync(&d_cor, sizeof(float) * 2 * n, s));
-  VIDO_CUDA(cudaMallocAsync(&d_hist, sizeof(int32_t) * (UM_BINS + 2), s));
-  VIDO_CUDA(cudaMallocAsync(&d_rec, sizeof(int32_t) * nl, s));
+  {
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_cor = al(sizeof(int32_t) * n), o_hist = o_cor + al(sizeof(float) * 2 * n),
+                 o_rec = o_hist + al(sizeof(int32_t) * (UM_BINS + 2)), need = o_rec + al(sizeof(int32_t) * nl);
+    if (need > ctx->um_ws_bytes) {
+      VIDO_CUDA(cudaStreamSynchronize(s));
+      if (ctx->um_ws) cudaFree(ctx->um_ws);
+      ctx->um_ws = nullptr; ctx->um_ws_bytes = 0;
+      VIDO_CUDA(cudaMalloc(&ctx->um_ws, 2 * need));
+      ctx->um_ws_bytes = 2 * need;
+    }
+    d_sem = (int32_t*)ctx->um_ws; d_cor = (float*)(ctx->um_ws + o_cor); d_hist = (int32_t*)(ctx->um_ws + o_hist);
+    d_rec = (int32_t*)(ctx->um_ws + o_rec);
+  }
   VIDO_CUDA(cudaMemcpyAsync(d_sem, sem_label, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
   VIDO_CUDA(cudaMemcpyAsync(d_cor, corres_xy, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, s));
   VIDO_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(int32_t) * (UM_BINS + 2), s));
@@ -317,7 +327,6 @@ int assoc_update_mask(vido_ctx* ctx, const int32_t* sem_label, const float* corr
   int32_t flag = 0;
   VIDO_CUDA(cudaMemcpyAsync(rec.data(), d_rec, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost, s));
   VIDO_CUDA(cudaMemcpyAsync(&flag, ctx->d_err, 4, cudaMemcpyDeviceToHost, s));
-  cudaFreeAsync(d_sem, s); cudaFreeAsync(d_cor, s); cudaFreeAsync(d_hist, s); cudaFreeAsync(d_rec, s);
   VIDO_CUDA(cudaStreamSynchronize(s));
   if (flag) { cudaMemsetAsync(ctx->d_err, 0, 4, s); ctx->err = "UpdateMask: mask label outside [0, 4096)"; return VIDO_ERR_ARG; }
   for (int k = 0; k < nl && k < cap; k++) { if (uniq_out) uniq_out[k] = uni[k]; if (recovered) recovered[k] = rec[k]; }

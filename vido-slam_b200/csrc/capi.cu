@@ -87,6 +87,7 @@ void vido_destroy(vido_ctx* ctx) {
   po_teardown(ctx);
   ba_teardown(ctx);
   orb_teardown(ctx);
+  if (ctx->um_ws) cudaFree(ctx->um_ws);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -340,6 +341,13 @@ int vido_map_export_full_graph(vido_ctx* ctx, int32_t* sizes, float* se3, float*
   if (!ctx || !sizes) return VIDO_ERR_ARG;
   return trk_export_full_graph(ctx, sizes, se3, points, e6_i, e6_j, e6_kind, e6_meas, obs_se3, obs_point, obs_kind, obs_xyz, tern_p1,
                                tern_p2, tern_h);
+}
+
+void vido_inertial_default_params(vido_inertial_problem* p) { if (p) inertial_default_params(p); }
+int vido_inertial_opt(vido_ctx* ctx, vido_inertial_problem* p, vido_lm_stats* stats) {
+  if (!ctx || !p) return VIDO_ERR_ARG;
+  if (p->n_frames < 0 || (p->n_frames >= 2 && (!p->Rwb || !p->twb || !p->velocity || !p->preint || !p->bias_lin))) { ctx->err = "inertial: null input"; return VIDO_ERR_ARG; }
+  return inertial_opt_host(ctx, p, stats);
 }
 
 int vido_get_kernel_times(vido_ctx* ctx, double* ms, int64_t* launches, double* ba_alg_bytes) {

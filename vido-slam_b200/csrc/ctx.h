@@ -91,6 +91,8 @@ struct vido_ctx {
   void* po = nullptr;  // PoWorkspace (poseopt_kernels.cu)
   void* pnp = nullptr; // PnpWorkspace (pnp_kernels.cu)
   void* trk = nullptr; // TrackState (track.cu)
+  char* um_ws = nullptr;   // UpdateMask workspace (assoc_kernels.cu), grown on demand: cudaMalloc is expensive once peer
+  size_t um_ws_bytes = 0;  // access is enabled (NCCL), so nothing on the per-frame path allocates
 };
 
 #define VIDO_CUDA(call)                                                                     \
@@ -169,6 +171,10 @@ int trk_export_full_graph(vido_ctx* ctx, int32_t* sizes, float* se3, float* poin
 // fba_kernels.cu
 void vido_fba_default_params_impl(vido_fba_problem* p);
 int fba_solve_host(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* st);
+
+// inertial_kernels.cu
+void inertial_default_params(vido_inertial_problem* p);
+int inertial_opt_host(vido_ctx* ctx, vido_inertial_problem* p, vido_lm_stats* st);
 
 // imu_kernels.cu
 int imu_preintegrate_host(vido_ctx* ctx, const vido_imu_sample* samples, int n, const double* t_prev, const double* t_cur,

@@ -587,24 +587,29 @@ __global__ void __launch_bounds__(256) fba_update_kernel(FbaDev d, int cur, doub
   block_sum_store(acc, d.partial);
 }
 
+// One device allocation per solve, carved by a bump allocator: cudaMalloc / cudaFree are expensive (and synchronise peers)
+// once NCCL has enabled peer access, so the solver makes exactly one of each.  Pass 1 (base == nullptr) only adds up sizes.
+struct Arena {
+  char* base = nullptr;
+  size_t off = 0;
+  template <class T>
+  T* take(size_t count) {
+    const size_t bytes = (std::max<size_t>(sizeof(T) * count, 16) + 255) & ~(size_t)255;
+    T* p = base ? (T*)(base + off) : nullptr;
+    off += bytes;
+    return p;
+  }
+};
 template <class T>
-int dev_upload(vido_ctx* ctx, std::vector<void*>& pool, const T* src, size_t count, T** out) {
-  *out = nullptr;
-  void* p = nullptr;
-  VIDO_CUDA(cudaMalloc(&p, std::max<size_t>(sizeof(T) * count, 16)));
-  pool.push_back(p);
-  if (count) VIDO_CUDA(cudaMemcpy(p, src, sizeof(T) * count, cudaMemcpyHostToDevice));
-  *out = (T*)p;
+int dev_upload(vido_ctx* ctx, Arena& A, const T* src, size_t count, T** out) {
+  *out = A.take<T>(count);
+  if (A.base && count) VIDO_CUDA(cudaMemcpyAsync(*out, src, sizeof(T) * count, cudaMemcpyHostToDevice, ctx->stream));
   return VIDO_OK;
 }
 template <class T>
-int dev_alloc(vido_ctx* ctx, std::vector<void*>& pool, size_t count, T** out, bool zero = true) {
-  *out = nullptr;
-  void* p = nullptr;
-  VIDO_CUDA(cudaMalloc(&p, std::max<size_t>(sizeof(T) * count, 16)));
-  pool.push_back(p);
-  if (zero) VIDO_CUDA(cudaMemset(p, 0, std::max<size_t>(sizeof(T) * count, 16)));
-  *out = (T*)p;
+int dev_alloc(vido_ctx* ctx, Arena& A, size_t count, T** out) {
+  *out = A.take<T>(count);
+  if (A.base) VIDO_CUDA(cudaMemsetAsync(*out, 0, std::max<size_t>(sizeof(T) * count, 16), ctx->stream));
   return VIDO_OK;
 }
 
@@ -618,7 +623,7 @@ void vido_fba_default_params_impl(vido_fba_problem* p) {
   p->prior_info = 100000.f;
 }
 
-static int fba_run(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* st, std::vector<void*>& pool) {
+static int fba_run(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* st, char** arena_base) {
   cudaStream_t s = ctx->stream;
   FbaDev d;
   memset(&d, 0, sizeof d);
@@ -679,8 +684,19 @@ static int fba_run(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* st, std::v
     int k = fill[p->tern_p1[t]]++; cpl_v[k] = p->tern_h[t]; cpl_kind[k] = 1; cpl_e[k] = t;
     k = fill[p->tern_p2[t]]++; cpl_v[k] = p->tern_h[t]; cpl_kind[k] = 2; cpl_e[k] = t;
   }
-  // ---- device buffers
+  // ---- device buffers: pass 0 sizes the arena, pass 1 carves and uploads (pageable host memory: the async copies are
+  //      staged by the runtime before the call returns, so the host vectors may go out of scope afterwards)
   int rc;
+  Arena pool;
+  const size_t nn = (size_t)d.n * d.n;
+  const int RB = 1024;   // reduction blocks
+  for (int pass = 0; pass < 2; pass++) {
+  if (pass == 1) {
+    void* base = nullptr;
+    VIDO_CUDA(cudaMalloc(&base, pool.off + 256));
+    *arena_base = (char*)base;
+    pool.base = (char*)base; pool.off = 0;
+  }
 #define UP(vec, field) if ((rc = dev_upload(ctx, pool, (vec).data(), (vec).size(), &field))) return rc
 #define UPC(ptr, count, field) if ((rc = dev_upload(ctx, pool, ptr, (size_t)(count), &field))) return rc
   Pose* dX0; Pose* dX1; double* dP0; double* dP1;
@@ -696,15 +712,14 @@ static int fba_run(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* st, std::v
   UP(cpl_start, tmp); d.cpl_start = tmp; UP(cpl_v, tmp); d.cpl_v = tmp; UP(cpl_kind, tmp); d.cpl_kind = tmp; UP(cpl_e, tmp); d.cpl_e = tmp;
 #undef UP
 #undef UPC
-  const size_t nn = (size_t)d.n * d.n;
 #define AL(field, count) if ((rc = dev_alloc(ctx, pool, (size_t)(count), &field))) return rc
   AL(d.Hss, nn); AL(d.bs, d.n); AL(d.hl, d.NP); AL(d.bl, 3 * (size_t)d.NP);
   AL(d.Bo, 18 * (size_t)d.NO); AL(d.B1, 18 * (size_t)d.NT); AL(d.B2, 18 * (size_t)d.NT); AL(d.Ot, 9 * (size_t)d.NT);
   AL(d.S, nn); AL(d.bp, d.n); AL(d.x, d.n + 3 * (size_t)d.NP);
   AL(d.Lkk, 6 * (size_t)d.NP); AL(d.Lk1, 9 * (size_t)d.NP);
-  const int RB = 1024;   // reduction blocks
   AL(d.partial, RB + 8); AL(d.fail, 4);
 #undef AL
+  }  // pass
   double* d_scalar = d.partial + RB;   // [0] chi2, [1] scale, [2] maxdiag
   const int n_edges = 1 + d.NE + d.NO + d.NT;
   const int red_blocks = std::min(RB, (std::max(n_edges, d.NS + d.NP) + 255) / 256);
@@ -800,9 +815,9 @@ static int fba_run(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* st, std::v
 }
 
 int fba_solve_host(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* st) {
-  std::vector<void*> pool;
-  const int rc = fba_run(ctx, p, st, pool);
+  char* arena = nullptr;
+  const int rc = fba_run(ctx, p, st, &arena);
   cudaStreamSynchronize(ctx->stream);
-  for (void* q : pool) cudaFree(q);
+  if (arena) cudaFree(arena);
   return rc;
 }
