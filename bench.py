@@ -258,6 +258,7 @@ def main():
         dtd = time.perf_counter() - t0
         extra["dynamic_objects"] = {"value": 2 * CHUNK / dtd, "unit": "frames/s", "objects_per_frame": float(np.mean([x["n_objects_ok"] for x in sd])),
                                     "object_features_per_frame": float(np.mean([x["n_dyn_features"] for x in sd])),
+                                    "host_ms_per_frame": {k: float(np.mean([x[k] for x in sd])) for k in ("ms_init", "ms_poseopt", "ms_renew", "ms_ba")},
                                     "workload": "5 moving objects / frame, masks + flow (BASELINE.json configs[3]), inputs resident in HBM"}
     except Exception as e:
         extra["dynamic_objects"] = {"error": str(e)[:200]}

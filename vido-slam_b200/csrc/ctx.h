@@ -134,6 +134,7 @@ int po_flow2_host(vido_ctx* ctx, vido_poseopt_problem* prs, int nproblems, vido_
 int pnp_setup(vido_ctx* ctx, int capN, int capIters);
 void pnp_teardown(vido_ctx* ctx);
 int pnp_init_model_host(vido_ctx* ctx, vido_pnp_problem* p);
+int pnp_init_model_batch(vido_ctx* ctx, vido_pnp_problem* ps, int nproblems);  // all problems of a frame in one launch pair
 
 // assoc_kernels.cu
 int assoc_depth_prep(vido_ctx* ctx, float* d_depth, int nframes, size_t frame_stride, int stride);

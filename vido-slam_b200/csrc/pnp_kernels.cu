@@ -32,6 +32,7 @@ struct PnpArgs {
   float* Tcw_out;   // [16]
   int* inlier_ids;  // [n]
   int* result;      // n_inliers, winner, ransac_inliers, mm_inliers
+  int* tmp_ids;     // [n] scratch of the selection kernel
 };
 
 __device__ __forceinline__ unsigned long long splitmix(unsigned long long x) {
@@ -231,8 +232,14 @@ __device__ __forceinline__ bool pnp_inlier(const PnpPose& T, const float* X3, co
 }
 
 // ---- kernel 1: one warp per hypothesis
+// PnpArgs are laid out in PNP_ARGS_SLOT-byte slots: problem k of a batched launch is blockIdx.y (hypotheses) / blockIdx.x (select)
+static constexpr size_t PNP_ARGS_SLOT = 256;
+__device__ __forceinline__ const PnpArgs& pnp_args(const PnpArgs* ap, int k) {
+  return *(const PnpArgs*)((const char*)ap + (size_t)k * PNP_ARGS_SLOT);
+}
+
 __global__ void __launch_bounds__(PNP_THREADS) pnp_hypotheses_kernel(const PnpArgs* __restrict__ ap) {
-  const PnpArgs a = *ap;
+  const PnpArgs a = pnp_args(ap, blockIdx.y);
   const int lane = threadIdx.x & 31;
   const int iter = blockIdx.x * (PNP_THREADS / 32) + (threadIdx.x >> 5);
   if (iter >= a.iters || a.M < 4) return;
@@ -300,8 +307,9 @@ __device__ int ransac_update_iters(double p, double ep, int modelPoints, int max
 }
 
 // ---- kernel 2: replay the sequential selection, consensus set, refit, motion model, winner (one CTA)
-__global__ void __launch_bounds__(PNP_THREADS) pnp_select_kernel(const PnpArgs* __restrict__ ap, int* __restrict__ tmp_ids) {
-  const PnpArgs a = *ap;
+__global__ void __launch_bounds__(PNP_THREADS) pnp_select_kernel(const PnpArgs* __restrict__ ap) {
+  const PnpArgs a = pnp_args(ap, blockIdx.x);
+  int* __restrict__ tmp_ids = a.tmp_ids;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double fx = a.fx, fy = a.fy, cx = a.cx, cy = a.cy;
   __shared__ int s_best, s_cnt, s_warp[PNP_THREADS / 32], s_base, s_ok, s_nr, s_nm;
@@ -448,31 +456,33 @@ __global__ void __launch_bounds__(PNP_THREADS) pnp_select_kernel(const PnpArgs* 
 }
 
 // =========================================================================================================
+static constexpr int PNP_MAX_BATCH = 8;   // problems per launch (the objects of one frame)
+
 struct PnpWorkspace {
   int capN = 0, capIters = 0;
-  // one pinned staging block each way: [PnpArgs | Tcw_motion | cur_xy | pts3d | good] -> device, [result | Tcw_out | ids] <- device
+  // one pinned staging block each way: [PnpArgs slots | per problem: Tcw_motion | cur_xy | pts3d | good] -> device,
+  // [per problem: result | Tcw_out | ids] <- device
   char *d_in = nullptr, *h_in = nullptr, *d_out = nullptr, *h_out = nullptr;
   size_t in_bytes = 0, out_bytes = 0;
-  int *tmp = nullptr, *cnt = nullptr;
-  PnpPose* hyp = nullptr;
+  int *tmp = nullptr, *cnt = nullptr;   // [PNP_MAX_BATCH][capN], [PNP_MAX_BATCH][capIters]
+  PnpPose* hyp = nullptr;               // [PNP_MAX_BATCH][capIters]
 };
-
-static constexpr size_t PNP_ARGS_SLOT = 256;   // PnpArgs padded so the float arrays behind it stay 16-byte aligned
 
 int pnp_setup(vido_ctx* ctx, int capN, int capIters) {
   static_assert(sizeof(PnpArgs) <= PNP_ARGS_SLOT, "PnpArgs slot");
   PnpWorkspace* ws = new PnpWorkspace();
   ctx->pnp = ws;
   ws->capN = capN; ws->capIters = capIters;
-  ws->in_bytes = PNP_ARGS_SLOT + sizeof(float) * 16 + sizeof(float) * 5 * (size_t)capN + sizeof(int) * (size_t)capN;
-  ws->out_bytes = sizeof(int) * 4 + sizeof(float) * 16 + sizeof(int) * (size_t)capN;
+  // the batch shares one data region of capN points in total (a frame's objects partition its features)
+  ws->in_bytes = PNP_ARGS_SLOT * PNP_MAX_BATCH + PNP_MAX_BATCH * (sizeof(float) * 16 + 64) + sizeof(float) * 5 * (size_t)capN + sizeof(int) * (size_t)capN;
+  ws->out_bytes = PNP_MAX_BATCH * (sizeof(int) * 4 + sizeof(float) * 16 + 64) + sizeof(int) * (size_t)capN;
   VIDO_CUDA(cudaMalloc(&ws->d_in, ws->in_bytes));
   VIDO_CUDA(cudaMalloc(&ws->d_out, ws->out_bytes));
   VIDO_CUDA(cudaMallocHost(&ws->h_in, ws->in_bytes));
   VIDO_CUDA(cudaMallocHost(&ws->h_out, ws->out_bytes));
-  VIDO_CUDA(cudaMalloc(&ws->tmp, sizeof(int) * capN));
-  VIDO_CUDA(cudaMalloc(&ws->cnt, sizeof(int) * capIters));
-  VIDO_CUDA(cudaMalloc(&ws->hyp, sizeof(PnpPose) * capIters));
+  VIDO_CUDA(cudaMalloc(&ws->tmp, sizeof(int) * (size_t)capN));
+  VIDO_CUDA(cudaMalloc(&ws->cnt, sizeof(int) * (size_t)capIters * PNP_MAX_BATCH));
+  VIDO_CUDA(cudaMalloc(&ws->hyp, sizeof(PnpPose) * (size_t)capIters * PNP_MAX_BATCH));
   return VIDO_OK;
 }
 
@@ -485,55 +495,89 @@ void pnp_teardown(vido_ctx* ctx) {
   ctx->pnp = nullptr;
 }
 
-int pnp_init_model_host(vido_ctx* ctx, vido_pnp_problem* p) {
+// up to PNP_MAX_BATCH problems in one pair of launches (one H2D block, one D2H block, one synchronisation)
+static int pnp_batch(vido_ctx* ctx, vido_pnp_problem* ps, int nb) {
   PnpWorkspace* ws = (PnpWorkspace*)ctx->pnp;
-  if (p->n < 0 || p->n > ws->capN || p->iters > ws->capIters || p->iters < 1) { ctx->err = "PnP problem exceeds capacity"; return VIDO_ERR_CAPACITY; }
   cudaStream_t s = ctx->stream;
-  const size_t n = (size_t)p->n;
-  // carve the staging block (same offsets on both sides)
-  const size_t o_tm = PNP_ARGS_SLOT, o_cur = o_tm + sizeof(float) * 16, o_pts = o_cur + sizeof(float) * 2 * n,
-               o_good = o_pts + sizeof(float) * 3 * n;
-  int* hgood = (int*)(ws->h_in + o_good);
-  int M = 0;
-  for (int i = 0; i < p->n; i++)
-    if (!p->valid || p->valid[i]) hgood[M++] = i;
-  const size_t in_used = o_good + sizeof(int) * (size_t)M;
-  const size_t o_res = 0, o_T = sizeof(int) * 4, o_ids = o_T + sizeof(float) * 16;
-  PnpArgs a;
-  memset(&a, 0, sizeof a);
-  a.n = p->n; a.M = M; a.iters = p->iters; a.no_mm = p->no_motion_model;
-  a.Tcw_motion = (const float*)(ws->d_in + o_tm); a.cur_xy = (const float*)(ws->d_in + o_cur);
-  a.pts3d = (const float*)(ws->d_in + o_pts); a.good = (const int*)(ws->d_in + o_good);
-  a.fx = p->fx; a.fy = p->fy; a.cx = p->cx; a.cy = p->cy; a.thr = p->reproj_err; a.confidence = p->confidence;
-  a.hyp = ws->hyp; a.hyp_cnt = ws->cnt;
-  a.result = (int*)(ws->d_out + o_res); a.Tcw_out = (float*)(ws->d_out + o_T); a.inlier_ids = (int*)(ws->d_out + o_ids);
-  memcpy(ws->h_in, &a, sizeof a);
-  memcpy(ws->h_in + o_tm, p->Tcw_motion, sizeof(float) * 16);
-  if (n) {
-    memcpy(ws->h_in + o_cur, p->cur_xy, sizeof(float) * 2 * n);
-    memcpy(ws->h_in + o_pts, p->pts3d, sizeof(float) * 3 * n);
+  auto a16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+  size_t in_off = PNP_ARGS_SLOT * (size_t)nb, out_off = 0, tmp_off = 0;
+  size_t o_res[PNP_MAX_BATCH], o_T[PNP_MAX_BATCH], o_ids[PNP_MAX_BATCH];
+  int max_iters = 1, any_ransac = 0;
+  for (int k = 0; k < nb; k++) {
+    vido_pnp_problem* p = &ps[k];
+    const size_t n = (size_t)p->n;
+    const size_t o_tm = in_off, o_cur = o_tm + sizeof(float) * 16, o_pts = a16(o_cur + sizeof(float) * 2 * n), o_good = a16(o_pts + sizeof(float) * 3 * n);
+    if (o_good + sizeof(int) * n > ws->in_bytes || tmp_off + n > (size_t)ws->capN) { ctx->err = "PnP batch exceeds capacity"; return VIDO_ERR_CAPACITY; }
+    int* hgood = (int*)(ws->h_in + o_good);
+    int M = 0;
+    for (int i = 0; i < p->n; i++)
+      if (!p->valid || p->valid[i]) hgood[M++] = i;
+    in_off = a16(o_good + sizeof(int) * (size_t)M);
+    o_res[k] = out_off; o_T[k] = out_off + sizeof(int) * 4; o_ids[k] = o_T[k] + sizeof(float) * 16;
+    out_off = a16(o_ids[k] + sizeof(int) * n);
+    if (out_off > ws->out_bytes) { ctx->err = "PnP batch exceeds capacity"; return VIDO_ERR_CAPACITY; }
+    PnpArgs a;
+    memset(&a, 0, sizeof a);
+    a.n = p->n; a.M = M; a.iters = p->iters; a.no_mm = p->no_motion_model;
+    a.Tcw_motion = (const float*)(ws->d_in + o_tm); a.cur_xy = (const float*)(ws->d_in + o_cur);
+    a.pts3d = (const float*)(ws->d_in + o_pts); a.good = (const int*)(ws->d_in + o_good);
+    a.fx = p->fx; a.fy = p->fy; a.cx = p->cx; a.cy = p->cy; a.thr = p->reproj_err; a.confidence = p->confidence;
+    a.hyp = ws->hyp + (size_t)k * ws->capIters; a.hyp_cnt = ws->cnt + (size_t)k * ws->capIters;
+    a.result = (int*)(ws->d_out + o_res[k]); a.Tcw_out = (float*)(ws->d_out + o_T[k]); a.inlier_ids = (int*)(ws->d_out + o_ids[k]);
+    a.tmp_ids = ws->tmp + tmp_off;
+    tmp_off += n;
+    memcpy(ws->h_in + PNP_ARGS_SLOT * (size_t)k, &a, sizeof a);
+    memcpy(ws->h_in + o_tm, p->Tcw_motion, sizeof(float) * 16);
+    if (n) {
+      memcpy(ws->h_in + o_cur, p->cur_xy, sizeof(float) * 2 * n);
+      memcpy(ws->h_in + o_pts, p->pts3d, sizeof(float) * 3 * n);
+    }
+    max_iters = std::max(max_iters, p->iters);
+    any_ransac |= (M >= 4);
   }
-  VIDO_CUDA(cudaMemcpyAsync(ws->d_in, ws->h_in, in_used, cudaMemcpyHostToDevice, s));
+  VIDO_CUDA(cudaMemcpyAsync(ws->d_in, ws->h_in, in_off, cudaMemcpyHostToDevice, s));
   const PnpArgs* d_args = (const PnpArgs*)ws->d_in;
   cudaEventRecord(ctx->ev0, s);
-  if (a.M >= 4) {
-    pnp_hypotheses_kernel<<<(a.iters + PNP_THREADS / 32 - 1) / (PNP_THREADS / 32), PNP_THREADS, 0, s>>>(d_args);
+  if (any_ransac) {
+    pnp_hypotheses_kernel<<<dim3((max_iters + PNP_THREADS / 32 - 1) / (PNP_THREADS / 32), nb), PNP_THREADS, 0, s>>>(d_args);
     ctx->launches++;
   }
-  pnp_select_kernel<<<1, PNP_THREADS, 0, s>>>(d_args, ws->tmp);
+  pnp_select_kernel<<<nb, PNP_THREADS, 0, s>>>(d_args);
   cudaEventRecord(ctx->ev1, s);
   ctx->launches++;
   VIDO_CUDA(cudaGetLastError());
-  // the inlier list is at most n ints: fetch it with the result instead of paying a second round trip
-  VIDO_CUDA(cudaMemcpyAsync(ws->h_out, ws->d_out, o_ids + sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+  // the inlier lists are at most n ints each: fetch them with the results instead of paying a second round trip
+  VIDO_CUDA(cudaMemcpyAsync(ws->h_out, ws->d_out, out_off, cudaMemcpyDeviceToHost, s));
   VIDO_CUDA(cudaStreamSynchronize(s));
   {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) { ctx->t_ms[1] += ms; ctx->t_n[1]++; }
   }
-  const int* res = (const int*)(ws->h_out + o_res);
-  p->n_inliers = res[0]; p->winner = res[1]; p->ransac_inliers = res[2]; p->mm_inliers = res[3];
-  memcpy(p->Tcw_out, ws->h_out + o_T, sizeof(float) * 16);
-  if (res[0] > 0 && p->inlier_ids) memcpy(p->inlier_ids, ws->h_out + o_ids, sizeof(int) * (size_t)res[0]);
+  for (int k = 0; k < nb; k++) {
+    vido_pnp_problem* p = &ps[k];
+    const int* res = (const int*)(ws->h_out + o_res[k]);
+    p->n_inliers = res[0]; p->winner = res[1]; p->ransac_inliers = res[2]; p->mm_inliers = res[3];
+    memcpy(p->Tcw_out, ws->h_out + o_T[k], sizeof(float) * 16);
+    if (res[0] > 0 && p->inlier_ids) memcpy(p->inlier_ids, ws->h_out + o_ids[k], sizeof(int) * (size_t)res[0]);
+  }
   return VIDO_OK;
 }
+
+int pnp_init_model_batch(vido_ctx* ctx, vido_pnp_problem* ps, int nproblems) {
+  PnpWorkspace* ws = (PnpWorkspace*)ctx->pnp;
+  for (int k = 0; k < nproblems; k++)
+    if (ps[k].n < 0 || ps[k].n > ws->capN || ps[k].iters > ws->capIters || ps[k].iters < 1) { ctx->err = "PnP problem exceeds capacity"; return VIDO_ERR_CAPACITY; }
+  // greedy packing: as many consecutive problems per launch as the shared point capacity allows
+  int k0 = 0;
+  while (k0 < nproblems) {
+    int nb = 0;
+    size_t pts = 0;
+    while (k0 + nb < nproblems && nb < PNP_MAX_BATCH && (nb == 0 || pts + (size_t)ps[k0 + nb].n <= (size_t)ws->capN)) { pts += (size_t)ps[k0 + nb].n; nb++; }
+    const int rc = pnp_batch(ctx, ps + k0, nb);
+    if (rc) return rc;
+    k0 += nb;
+  }
+  return VIDO_OK;
+}
+
+int pnp_init_model_host(vido_ctx* ctx, vido_pnp_problem* p) { return pnp_init_model_batch(ctx, p, 1); }

@@ -666,33 +666,45 @@ static int dyn_object_motions(vido_ctx* ctx, const float* curTcw, const std::vec
   inv44(curTcw, Twc);
   struct Job { size_t obj; std::vector<int> ids; std::vector<float> obs, fl, dep, fo; std::vector<int32_t> inl; float init[16]; };
   std::vector<Job> jobs;
+  // ---- GetInitModelObj for all objects of the frame: the PnP problems are independent (disjoint feature sets), so they go
+  //      through the RANSAC kernels together (one H2D block, one launch pair, one D2H block)
+  std::vector<vido_pnp_problem> pps(no);
+  std::vector<std::vector<float>> cur2d(no), p3d(no);
+  std::vector<std::vector<int32_t>> idsv(no);
   for (size_t i = 0; i < no; i++) {
     const std::vector<int>& ObjId = ObjIdNew[i];
     const int N = (int)ObjId.size();
-    std::vector<float> cur2d(2 * (size_t)N), p3d(3 * (size_t)N);
+    cur2d[i].resize(2 * (size_t)N); p3d[i].resize(3 * (size_t)N); idsv[i].resize(N);
     float cs[3] = {0.f, 0.f, 0.f};
     for (int j = 0; j < N; j++) {
       const int id = ObjId[j];
       float xp[3];
       px_to_world(c, ts->lo_keys[2 * id], ts->lo_keys[2 * id + 1], ts->lo_depth[id], Twl, xp);
-      for (int r = 0; r < 3; r++) { cs[r] += xp[r]; p3d[3 * j + r] = xp[r]; }
-      cur2d[2 * j] = D.keys[2 * id]; cur2d[2 * j + 1] = D.keys[2 * id + 1];
+      for (int r = 0; r < 3; r++) { cs[r] += xp[r]; p3d[i][3 * j + r] = xp[r]; }
+      cur2d[i][2 * j] = D.keys[2 * id]; cur2d[i][2 * j + 1] = D.keys[2 * id + 1];
     }
     const float invn = (float)(1.0 / (double)N);
     D.centre[i] = {cs[0] * invn, cs[1] * invn, cs[2] * invn};
     int PreObjID = -1;
     for (size_t k = 0; k < ts->l_mod_label.size(); k++)
       if (ts->l_mod_label[k] == D.mod_label[i]) { PreObjID = (int)k; break; }
-    vido_pnp_problem pp;
+    vido_pnp_problem& pp = pps[i];
     memset(&pp, 0, sizeof pp);
     vido_pnp_default_params(&pp);
-    std::vector<int32_t> ids(N);
-    pp.n = N; pp.cur_xy = cur2d.data(); pp.pts3d = p3d.data(); pp.valid = nullptr; pp.inlier_ids = ids.data();
+    pp.n = N; pp.cur_xy = cur2d[i].data(); pp.pts3d = p3d[i].data(); pp.valid = nullptr; pp.inlier_ids = idsv[i].data();
     if (PreObjID != -1) mul44(curTcw, ts->l_obj_mod[PreObjID].data(), pp.Tcw_motion);
     else { memcpy(pp.Tcw_motion, curTcw, sizeof(float) * 16); pp.no_motion_model = 1; }
     pp.fx = c.fx; pp.fy = c.fy; pp.cx = c.cx; pp.cy = c.cy;
-    int rc = pnp_init_model_host(ctx, &pp);
+  }
+  if (no) {
+    const int rc = pnp_init_model_batch(ctx, pps.data(), (int)no);
     if (rc) return rc;
+  }
+  for (size_t i = 0; i < no; i++) {
+    const std::vector<int>& ObjId = ObjIdNew[i];
+    const int N = (int)ObjId.size();
+    const vido_pnp_problem& pp = pps[i];
+    const std::vector<int32_t>& ids = idsv[i];
     std::vector<int> in_ids(pp.n_inliers);
     std::vector<char> keep(N, 0);
     for (int k = 0; k < pp.n_inliers; k++) { in_ids[k] = ObjId[ids[k]]; keep[ids[k]] = 1; }
