@@ -5,7 +5,9 @@
 //   cv::Mat System::TrackRGBD(..., vImuMeas, ...)                 src/System.cc:65-78 (IMU samples are preintegrated
 //                                                                 on the GPU; the pose path is the VO one, like the
 //                                                                 reference whose LocalInertialBA is empty, F6)
-//   void System::SaveResultsIJRR2020(dir)                         src/System.cc:80-198 (camera trajectories)
+//   void System::SaveResultsIJRR2020(dir)                         src/System.cc:80-198 (object motions, camera trajectory after
+//                                                                 the window optimisation and after FullBatch)
+// The call with index nImage-1 also runs Optimizer::FullBatchOptimization when ChooseData == 2 (src/Tracking.cc:1490-1498).
 // With OpenCV available define VIDO_HAVE_OPENCV before including: the signatures then use cv::Mat exactly like the
 // reference.  Without OpenCV (this image has no OpenCV C++), VIDO_SLAM::Mat below is a minimal view type with the same
 // fields the path touches (rows, cols, type, data, step).
@@ -119,6 +121,7 @@ class System {
     c.scale_factor = (float)num("ORBextractor.scaleFactor", c.scale_factor);
     c.nlevels = (int)num("ORBextractor.nLevels", c.nlevels);
     c.ini_th_fast = (int)num("ORBextractor.iniThFAST", c.ini_th_fast); c.min_th_fast = (int)num("ORBextractor.minThFAST", c.min_th_fast);
+    c.sf_mg_thres = (float)num("SFMgThres", c.sf_mg_thres); c.sf_ds_thres = (float)num("SFDsThres", c.sf_ds_thres);
     imu_noise_[0] = (float)num("IMU.NoiseGyro", 1.7e-4); imu_noise_[1] = (float)num("IMU.NoiseAcc", 2.0e-3);
     imu_noise_[2] = (float)num("IMU.GyroWalk", 1.9393e-05); imu_noise_[3] = (float)num("IMU.AccWalk", 3.0e-03);
     const float freq = (float)num("IMU.Frequency", 200.0), sf = sqrtf(freq);  // Tracking::ParseIMUParamFile (Tracking.cc:174-275)
@@ -136,7 +139,7 @@ class System {
   // depthmap is modified in place (pre-scaled) exactly like the reference (src/Tracking.cc:299-322)
   Mat TrackRGBD(const Mat& im, Mat& depthmap, const Mat& flowmap, const Mat& maskmap, const Mat& /*mTcw_gt*/,
                 const std::vector<std::vector<float> >& /*vObjPose_gt*/, const double& timestamp, Mat& /*imTraj*/,
-                const int& /*nImage*/) {
+                const int& nImage) {
     if (sensor_ != RGBD && sensor_ != IMU_RGBD) {  // src/System.cc:55-59
       std::cerr << "ERROR: you called TrackRGBD but input sensor was not set to RGBD." << std::endl;
       exit(-1);
@@ -152,6 +155,14 @@ class System {
     if (rc < 0) std::cerr << "vido_b200: " << vido_last_error(ctx_) << std::endl;  // the reference prints and continues
     trajectory_.insert(trajectory_.end(), Tcw, Tcw + 16);
     last_t_ = timestamp;
+    // f_id == StopFrame (= nImage - 1): the joint optimisation over the whole sequence, KITTI-style data only
+    // (src/Tracking.cc:288, 1490-1498); results are read by SaveResultsIJRR2020
+    if (frame_id_ == nImage - 1 && cfg_.choose_data == 2) {
+      vido_lm_stats st;
+      if (vido_full_batch(ctx_, &st, nullptr) < 0) std::cerr << "vido_b200: " << vido_last_error(ctx_) << std::endl;
+      else full_batch_done_ = true;
+    }
+    frame_id_++;
     return make_pose_mat(Tcw);
   }
 
@@ -181,30 +192,37 @@ class System {
     return TrackRGBD(im, depthmap, flowmap, maskmap, mTcw_gt, vObjPose_gt, timestamp, imTraj, nImage);
   }
 
-  // initial_rgbd_new.txt = per-frame tracking poses, refined_rgbd_new.txt = Map::vmCameraPose after the window BA;
-  // 12 floats per row, 9 decimals, like src/System.cc:80-198
+  // obj_mot_rgbd_new.txt: "frame label m00 .. m33" per estimated object motion (Map::vmRigidMotion[f][j>=1]);
+  // initial_rgbd_new.txt: "frame m00 .. m33" of Map::vmCameraPose (Twc, refined by the window optimisation);
+  // refined_rgbd_new.txt: Map::vmCameraPose_RF (after FullBatchOptimization; equal to the initial one if it never ran).
+  // Layout and precision of src/System.cc:80-160; the ground-truth files of the reference are not written.
   void SaveResultsIJRR2020(const std::string& filename) {
-    auto dump = [&](const std::string& path, const float* T, int n, bool invert) {
-      std::ofstream f(path.c_str());
-      f << std::fixed;
-      for (int i = 0; i < n; i++) {
-        float M[16];
-        memcpy(M, T + 16 * i, sizeof M);
-        if (invert) {  // stored Tcw -> the reference writes Twc
-          float R[9] = {M[0], M[4], M[8], M[1], M[5], M[9], M[2], M[6], M[10]};
-          float t[3];
-          for (int r = 0; r < 3; r++) t[r] = -(R[3 * r] * M[3] + R[3 * r + 1] * M[7] + R[3 * r + 2] * M[11]);
-          for (int r = 0; r < 3; r++) { M[4 * r] = R[3 * r]; M[4 * r + 1] = R[3 * r + 1]; M[4 * r + 2] = R[3 * r + 2]; M[4 * r + 3] = t[r]; }
-        }
-        for (int r = 0; r < 3; r++)
-          for (int c = 0; c < 4; c++) f << std::setprecision(9) << M[4 * r + c] << ((r == 2 && c == 3) ? "\n" : " ");
-      }
+    auto row16 = [](std::ofstream& f, const float* M) {
+      f << std::fixed << std::setprecision(9);
+      for (int k = 0; k < 12; k++) f << M[k] << " ";
+      f << 0.0 << " " << 0.0 << " " << 0.0 << " " << 1.0 << std::endl;
     };
-    dump(filename + "initial_rgbd_new.txt", trajectory_.data(), (int)(trajectory_.size() / 16), true);
     const int n = vido_map_num_frames(ctx_);
+    {
+      std::ofstream f((filename + "obj_mot_rgbd_new.txt").c_str(), std::ios::trunc);
+      for (int i = 1; i < n; i++) {
+        int32_t label[64], sem[64];
+        float motion[64 * 16], centre[64 * 3];
+        const int m = vido_map_get_objects(ctx_, i, label, sem, motion, centre, 64);
+        for (int j = 0; j < m && j < 64; j++) { f << i << " " << label[j] << " "; row16(f, motion + 16 * j); }
+      }
+    }
     std::vector<float> P(16 * (size_t)(n > 0 ? n : 1));
-    if (n > 0) vido_map_get_poses(ctx_, P.data(), n);
-    dump(filename + "refined_rgbd_new.txt", P.data(), n > 0 ? n : 0, false);
+    {
+      std::ofstream f((filename + "initial_rgbd_new.txt").c_str(), std::ios::trunc);
+      if (n > 0) vido_map_get_poses(ctx_, P.data(), n);
+      for (int i = 0; i < n; i++) { f << i << " "; row16(f, P.data() + 16 * (size_t)i); }
+    }
+    {
+      std::ofstream f((filename + "refined_rgbd_new.txt").c_str(), std::ios::trunc);
+      if (n > 0) vido_map_get_poses_rf(ctx_, P.data(), n);
+      for (int i = 0; i < n; i++) { f << i << " "; row16(f, P.data() + 16 * (size_t)i); }
+    }
   }
 
   vido_ctx* context() { return ctx_; }
@@ -219,7 +237,8 @@ class System {
   std::vector<vido_imu_preint> preint_;
   float imu_noise_[4] = {0, 0, 0, 0};
   double last_t_ = 0;
-  bool have_last_t_ = false;
+  bool have_last_t_ = false, full_batch_done_ = false;
+  int frame_id_ = 0;
 };
 
 }  // namespace VIDO_SLAM
