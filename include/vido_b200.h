@@ -157,6 +157,9 @@ typedef struct vido_fba_problem {
   float huber_cam, huber_obj, huber_3d;  /* 0.01 each (:1312) */
   float gain_threshold;     /* SparseOptimizerTerminateAction gain 1e-4 (:1283) */
   float prior_info;         /* 100000 (:1341) */
+  int32_t solver;           /* linear solver of (H + lambda I) x = b: 0 automatic, 1 direct (explicit Schur complement +
+                               banded tiled Cholesky), 2 matrix-free (implicit Schur complement, preconditioned CG; for long
+                               dynamic tracklets / thousands of SE3 vertices).  With solver 2 stats->pad = CG iterations. */
 } vido_fba_problem;
 void vido_fba_default_params(vido_fba_problem* p);
 int vido_ba_full(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* stats);

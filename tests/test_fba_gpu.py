@@ -34,6 +34,21 @@ def test_flat_graph_matches_oracle(pkg, n_frames, n_objects, seed):
     ctx.close()
 
 
+@pytest.mark.parametrize("n_frames,n_objects,seed", [(6, 2, 3), (9, 3, 11)])
+def test_matrix_free_solver_matches_oracle(pkg, n_frames, n_objects, seed):
+    """solver = 2: implicit Schur complement + preconditioned CG instead of the explicit reduced system; the linear systems are
+    solved to 1e-13, so the LM trajectory is the oracle's as well"""
+    g, n_poses, truth = fba_synth.make_graph(n_frames=n_frames, n_objects=n_objects, seed=seed)
+    se3_ref, pts_ref, its, st_ref = ol.ba_full(g, n_poses)
+    ctx = pkg.Context(pkg.default_config(width=640, height=480, max_batch=1))
+    se3, pts, st = ctx.ba_full(g, n_poses, solver=2)
+    assert st.pad > 0                                  # CG iterations were spent
+    _same_lm(st, st_ref, rel=1e-5)
+    assert np.abs(se3 - se3_ref).max() <= REL_TOL * max(np.abs(se3_ref).max(), 1.0)
+    assert np.abs(pts - pts_ref).max() <= REL_TOL * max(np.abs(pts_ref).max(), 1.0)
+    ctx.close()
+
+
 def test_bad_graphs_are_rejected(pkg):
     g, n_poses, _ = fba_synth.make_graph(n_frames=4, n_objects=1, seed=2)
     ctx = pkg.Context(pkg.default_config(width=640, height=480, max_batch=1))
@@ -75,6 +90,10 @@ def test_pipeline_full_batch_matches_oracle(pkg):
     _same_lm(st, st_ref)
     assert np.abs(se3 - se3_ref).max() <= REL_TOL * max(np.abs(se3_ref).max(), 1.0)
     assert np.abs(pts - pts_ref).max() <= REL_TOL * max(np.abs(pts_ref).max(), 1.0)
+    se3_cg, pts_cg, st_cg = ctx.ba_full(g0, np0, max_iterations=6, solver=2)
+    assert st_cg.iterations == st_ref.iterations and st_cg.total_trials == st_ref.total_trials
+    assert np.abs(se3_cg - se3_ref).max() <= REL_TOL * max(np.abs(se3_ref).max(), 1.0)
+    assert np.abs(pts_cg - pts_ref).max() <= REL_TOL * max(np.abs(pts_ref).max(), 1.0)
     # (3) vido_full_batch on the context's own Map runs to the reference's stop rule and improves the robust chi2
     st_full, sizes = ctx.full_batch()
     rec = st_full.records()

@@ -23,5 +23,5 @@ st, sizes = ctx.full_batch()
 t2 = time.perf_counter()
 rec = st.records()
 print(f"tracked {n} frames in {1e3 * (t1 - t0):.1f} ms; full batch: sizes {list(sizes)} iterations {st.iterations} trials {st.total_trials} "
-      f"{1e3 * (t2 - t1):.1f} ms chi2 {rec[0][0]:.4f} -> {rec[-1][0]:.4f}")
+      f"{1e3 * (t2 - t1):.1f} ms chi2 {rec[0][0]:.4f} -> {rec[-1][0]:.4f}  (CG iterations of the matrix-free path: {st.pad})")
 ctx.close()

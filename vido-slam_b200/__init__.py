@@ -77,7 +77,7 @@ class FbaProblem(C.Structure):
                 ("sigma2_cam", C.c_float), ("sigma2_3d_sta", C.c_float), ("sigma2_3d_dyn", C.c_float),
                 ("sigma2_obj", C.c_float), ("sigma2_smooth", C.c_float),
                 ("huber_cam", C.c_float), ("huber_obj", C.c_float), ("huber_3d", C.c_float),
-                ("gain_threshold", C.c_float), ("prior_info", C.c_float)]
+                ("gain_threshold", C.c_float), ("prior_info", C.c_float), ("solver", C.c_int32)]
 
 
 FBA_KEYS = ("se3", "points", "e6_i", "e6_j", "e6_kind", "e6_meas", "obs_se3", "obs_point", "obs_kind", "obs_xyz",

@@ -31,8 +31,8 @@ namespace {
 
 using vb::Pose;
 
-constexpr int FBA_MAX_ACTIVE = 128;   // SE3 vertices coupled to one chain (tracklet length * 2 + 1 for dynamic chains)
-constexpr int FBA_CHAIN_WARPS = 2;    // chains per CTA of the elimination kernel
+constexpr int FBA_MAX_ACTIVE = 256;   // SE3 vertices coupled to one chain (tracklet length * 2 + 1 for dynamic chains)
+constexpr int FBA_CHAIN_WARPS = 1;    // chains per CTA of the elimination kernel (36 KB of running blocks per chain)
 constexpr int FBA_TB = 48;            // Cholesky tile (8 SE3 blocks)
 
 struct FbaDev {
@@ -57,6 +57,22 @@ struct FbaDev {
   const int *cpl_start, *cpl_v, *cpl_kind, *cpl_e;
   double* partial;                     // reduction scratch
   int* fail;
+  // ---- matrix-free path (pcg != 0): the SE3 block is kept as diagonal blocks + one block per SE3 edge, the Schur
+  //      complement is applied implicitly (B T^-1 B^T through the factored chains), solved by preconditioned CG
+  int pcg;
+  double *Hd, *He6;                    // [NS][36], [NE][36] (block row = e6i, column = e6j)
+  const int *cpl_pt;                   // [ncpl] point of a coupling
+  const int *vc_start, *vc_ci;         // SE3 vertex -> its couplings
+  const int *ve_start, *ve_e, *ve_side;// SE3 vertex -> its SE3 edges (side 0: vertex is e6i, 1: e6j)
+  double *cg_r, *cg_z, *cg_p, *cg_q;   // [n]
+  double *cg_t;                        // [NP][3]
+  double *cg_M;                        // [NS][21] lower Cholesky factors of the preconditioner's diagonal pivots
+  double *cg_A;                        // [NS][36] preconditioner diagonal blocks before factorisation
+  double *cg_W;                        // [NS][36] sub-diagonal factor blocks along the SE3-edge paths
+  const int *path_start, *path_v, *path_e;  // paths of the SE3-edge graph (odometry chain, one smoothness chain per object)
+  int NPATH;
+  double *cg_part;                     // [2][NS] per-vertex partial dot products
+  double *cg_s;                        // scalars: 0 rz, 1 pq, 2 rr, 3 alpha, 4 beta, 5 rz_new, 6 bnorm2
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -138,13 +154,24 @@ __global__ void __launch_bounds__(256) fba_chi2_kernel(FbaDev d, int sel) {
 }
 
 // H[a][c] += w Ja^T Jc for 6-column Jacobians with `rows` rows; only blocks on or below the diagonal are kept
-__device__ __forceinline__ void add_block(double* H, int n, int a, int c, const double* Ja, const double* Jc, int rows, double w) {
+__device__ __forceinline__ void add_block(const FbaDev& d, int a, int c, const double* Ja, const double* Jc, int rows, double w) {
+  if (d.pcg) {
+    if (a != c) return;   // off-diagonal SE3 blocks only come from SE3 edges and are stored per edge (He6)
+    for (int r = 0; r < 6; r++)
+      for (int q = 0; q < 6; q++) {
+        double s = 0;
+        for (int k = 0; k < rows; k++) s += Ja[6 * k + r] * Jc[6 * k + q];
+        atomicAdd(&d.Hd[36 * (size_t)a + 6 * r + q], w * s);
+      }
+    return;
+  }
   if (a < c) return;
+  const int n = d.n;
   for (int r = 0; r < 6; r++)
     for (int q = 0; q < 6; q++) {
       double s = 0;
       for (int k = 0; k < rows; k++) s += Ja[6 * k + r] * Jc[6 * k + q];
-      atomicAdd(&H[(size_t)(6 * a + r) * n + 6 * c + q], w * s);
+      atomicAdd(&d.Hss[(size_t)(6 * a + r) * n + 6 * c + q], w * s);
     }
 }
 
@@ -169,7 +196,7 @@ __global__ void __launch_bounds__(128) fba_linearize_kernel(FbaDev d, int sel) {
       for (int k = 0; k < 6; k++) s += Jj[6 * k + r] * e[k];
       atomicAdd(&d.bs[r], -w * s);
     }
-    add_block(d.Hss, n, 0, 0, Jj, Jj, 6, w);
+    add_block(d, 0, 0, Jj, Jj, 6, w);
   } else if (i <= d.NE) {
     const int ed = i - 1, k6 = d.e6k[ed], a = d.e6i[ed], c = d.e6j[ed];
     double e[6], Ji[36], Jj[36];
@@ -185,10 +212,19 @@ __global__ void __launch_bounds__(128) fba_linearize_kernel(FbaDev d, int sel) {
       atomicAdd(&d.bs[6 * a + r], -w * si);
       atomicAdd(&d.bs[6 * c + r], -w * sj);
     }
-    add_block(d.Hss, n, a, a, Ji, Ji, 6, w);
-    add_block(d.Hss, n, c, c, Jj, Jj, 6, w);
-    add_block(d.Hss, n, a, c, Ji, Jj, 6, w);
-    add_block(d.Hss, n, c, a, Jj, Ji, 6, w);
+    add_block(d, a, a, Ji, Ji, 6, w);
+    add_block(d, c, c, Jj, Jj, 6, w);
+    add_block(d, a, c, Ji, Jj, 6, w);
+    add_block(d, c, a, Jj, Ji, 6, w);
+    if (d.pcg) {
+      double* Hb = d.He6 + 36 * (size_t)ed;
+      for (int r = 0; r < 6; r++)
+        for (int q = 0; q < 6; q++) {
+          double s3 = 0;
+          for (int k = 0; k < 6; k++) s3 += Ji[6 * k + r] * Jj[6 * k + q];
+          Hb[6 * r + q] = w * s3;
+        }
+    }
   } else if (i <= d.NE + d.NO) {
     const int o = i - 1 - d.NE, a = d.os[o], l = d.op[o];
     const Pose& Xa = X[a];
@@ -215,7 +251,7 @@ __global__ void __launch_bounds__(128) fba_linearize_kernel(FbaDev d, int sel) {
         B[3 * r + q] = w * h;
       }
     }
-    add_block(d.Hss, n, a, a, Ji, Ji, 3, w);
+    add_block(d, a, a, Ji, Ji, 3, w);
     for (int r = 0; r < 3; r++) {
       double s = 0;
       for (int k = 0; k < 3; k++) s += Xa.R[3 * r + k] * e[k];
@@ -258,7 +294,7 @@ __global__ void __launch_bounds__(128) fba_linearize_kernel(FbaDev d, int sel) {
         b2[3 * r + qq] = w * h;
       }
     }
-    add_block(d.Hss, n, hv, hv, JH, JH, 3, w);
+    add_block(d, hv, hv, JH, JH, 3, w);
     double* O = d.Ot + 9 * (size_t)t;
     for (int r = 0; r < 3; r++)
       for (int qq = 0; qq < 3; qq++) O[3 * r + qq] = w * (-H.R[3 * qq + r]);   // J1^T J2 = J2
@@ -268,7 +304,7 @@ __global__ void __launch_bounds__(128) fba_linearize_kernel(FbaDev d, int sel) {
 __global__ void __launch_bounds__(256) fba_maxdiag_kernel(FbaDev d) {
   double m = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.n + d.NP; i += gridDim.x * blockDim.x)
-    m = fmax(m, fabs(i < d.n ? d.Hss[(size_t)i * d.n + i] : d.hl[i - d.n]));
+    m = fmax(m, fabs(i < d.n ? (d.pcg ? d.Hd[36 * (size_t)(i / 6) + 7 * (i % 6)] : d.Hss[(size_t)i * d.n + i]) : d.hl[i - d.n]));
   __shared__ double sm[32];
   for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
@@ -411,15 +447,21 @@ __global__ void __launch_bounds__(32 * FBA_CHAIN_WARPS) fba_chain_kernel(FbaDev 
       const double* y = Y + 3 * idx;
       atomicAdd(&d.bp[6 * V[idx / 6] + idx % 6], -(y[0] * ck[0] + y[1] * ck[1] + y[2] * ck[2]));
     }
+    // one lane per vertex pair: the two 6x3 blocks go to registers once, then 36 accumulations (no per-entry index math)
     const int npair = nact * nact;
-    for (int idx = lane; idx < npair * 36; idx += 32) {
-      const int pr = idx / 36, rq = idx % 36, a = pr / nact, b = pr % nact;
+    for (int pr = lane; pr < npair; pr += 32) {
+      const int a = pr / nact, b = pr - a * nact;
       const int va = V[a], vb2 = V[b];
       if (va < vb2) continue;
-      const int r = rq / 6, q = rq % 6;
-      const double* ya = Y + 18 * a + 3 * r;
-      const double* yb = Y + 18 * b + 3 * q;
-      atomicAdd(&d.S[(size_t)(6 * va + r) * n + 6 * vb2 + q], -(ya[0] * yb[0] + ya[1] * yb[1] + ya[2] * yb[2]));
+      double ya[18], yb[18];
+#pragma unroll
+      for (int q = 0; q < 18; q++) { ya[q] = Y[18 * a + q]; yb[q] = Y[18 * b + q]; }
+      double* Sb = d.S + (size_t)(6 * va) * n + 6 * vb2;
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int q = 0; q < 6; q++)
+          atomicAdd(Sb + (size_t)r * n + q, -(ya[3 * r] * yb[3 * q] + ya[3 * r + 1] * yb[3 * q + 1] + ya[3 * r + 2] * yb[3 * q + 2]));
     }
     __syncwarp();
     for (int q = 0; q < 6; q++) Lp[q] = L[q];
@@ -457,12 +499,13 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ A, 
 }
 
 // rows below the diagonal tile: A[i][j0..j0+jb) <- A[i][..] L^-T  (one thread per row)
-__global__ void __launch_bounds__(128) chol_panel_kernel(double* __restrict__ A, int n, int j0, int jb) {
+// (`rows` = rows below the panel that can be non-zero: the factor keeps the envelope of the matrix, see fba_run)
+__global__ void __launch_bounds__(128) chol_panel_kernel(double* __restrict__ A, int n, int j0, int jb, int rows) {
   __shared__ double T[FBA_TB][FBA_TB + 1];
   for (int i = threadIdx.x; i < jb * jb; i += blockDim.x) T[i / jb][i % jb] = A[(size_t)(j0 + i / jb) * n + j0 + i % jb];
   __syncthreads();
   const int i = j0 + jb + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= j0 + jb + rows) return;
   double* row = A + (size_t)i * n + j0;
   double y[FBA_TB];
   for (int c = 0; c < jb; c++) {
@@ -474,20 +517,22 @@ __global__ void __launch_bounds__(128) chol_panel_kernel(double* __restrict__ A,
 }
 
 // trailing update: A[i][k] -= sum_m P[i][m] P[k][m] for i >= k >= j0+jb, 32x32 tiles (lower tiles only)
-__global__ void __launch_bounds__(256) chol_update_kernel(double* __restrict__ A, int n, int j0, int jb) {
+__global__ void __launch_bounds__(256) chol_update_kernel(double* __restrict__ A, int n_full, int j0, int jb, int rows) {
   if (blockIdx.x > blockIdx.y) return;   // tile column <= tile row
   __shared__ double Pi[32][FBA_TB + 1], Pk[32][FBA_TB + 1];
   const int base = j0 + jb, i0 = base + blockIdx.y * 32, k0 = base + blockIdx.x * 32;
+  const size_t n = (size_t)n_full;
+  const int lim = base + rows;            // rows / columns beyond the envelope are untouched
   for (int idx = threadIdx.x; idx < 32 * jb; idx += blockDim.x) {
     const int r = idx / jb, m = idx % jb;
-    Pi[r][m] = (i0 + r < n) ? A[(size_t)(i0 + r) * n + j0 + m] : 0.0;
-    Pk[r][m] = (k0 + r < n) ? A[(size_t)(k0 + r) * n + j0 + m] : 0.0;
+    Pi[r][m] = (i0 + r < lim) ? A[(size_t)(i0 + r) * n + j0 + m] : 0.0;
+    Pk[r][m] = (k0 + r < lim) ? A[(size_t)(k0 + r) * n + j0 + m] : 0.0;
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < 32 * 32; idx += blockDim.x) {
     const int r = idx / 32, c = idx % 32;
     const int i = i0 + r, k = k0 + c;
-    if (i >= n || k >= n || k > i) continue;
+    if (i >= lim || k >= lim || k > i) continue;
     double s = 0;
     for (int m = 0; m < jb; m++) s += Pi[r][m] * Pk[c][m];
     A[(size_t)i * n + k] -= s;
@@ -495,13 +540,15 @@ __global__ void __launch_bounds__(256) chol_update_kernel(double* __restrict__ A
 }
 
 // L y = b (column-oriented), L^T x = y (row-oriented); one CTA, the vector stays in global memory
-__global__ void __launch_bounds__(1024) chol_solve_kernel(const double* __restrict__ L, int n, double* __restrict__ b) {
+// (`band`: L[i][j] = 0 for i - j > band)
+__global__ void __launch_bounds__(1024) chol_solve_kernel(const double* __restrict__ L, int n, double* __restrict__ b, int band) {
   for (int j = 0; j < n; j++) {
     __shared__ double xj;
     if (threadIdx.x == 0) { xj = b[j] / L[(size_t)j * n + j]; b[j] = xj; }
     __syncthreads();
     const double v = xj;
-    for (int i = j + 1 + threadIdx.x; i < n; i += blockDim.x) b[i] -= L[(size_t)i * n + j] * v;
+    const int hi = min(n, j + band + 1);
+    for (int i = j + 1 + threadIdx.x; i < hi; i += blockDim.x) b[i] -= L[(size_t)i * n + j] * v;
     __syncthreads();
   }
   for (int j = n - 1; j >= 0; j--) {
@@ -509,7 +556,7 @@ __global__ void __launch_bounds__(1024) chol_solve_kernel(const double* __restri
     if (threadIdx.x == 0) { xj2 = b[j] / L[(size_t)j * n + j]; b[j] = xj2; }
     __syncthreads();
     const double v = xj2;
-    for (int k = threadIdx.x; k < j; k += blockDim.x) b[k] -= L[(size_t)j * n + k] * v;
+    for (int k = max(0, j - band) + threadIdx.x; k < j; k += blockDim.x) b[k] -= L[(size_t)j * n + k] * v;
     __syncthreads();
   }
 }
@@ -555,6 +602,330 @@ __global__ void __launch_bounds__(128) fba_backsub_kernel(FbaDev d) {
     xn[0] = (r[0] - L[1] * xn[1] - L[3] * xn[2]) / L[0];
     xl[3 * (size_t)p] = xn[0]; xl[3 * (size_t)p + 1] = xn[1]; xl[3 * (size_t)p + 2] = xn[2];
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// matrix-free path: (Hss + lambda I - B (T + lambda I)^-1 B^T) x = bs - B (T + lambda I)^-1 bl by preconditioned CG
+// ---------------------------------------------------------------------------------------------------------
+// Cholesky of every chain's block-tridiagonal pivot (thread per chain): Lkk, Lk1
+__global__ void __launch_bounds__(128) pcg_chain_factor_kernel(FbaDev d, double lambda) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d.NCH) return;
+  double Lp[6] = {1, 0, 1, 0, 0, 1};
+  const int k0 = d.chain_start[c], k1 = d.chain_start[c + 1];
+  for (int k = k0; k < k1; k++) {
+    const int p = d.chain_pts[k];
+    const double hd = d.hl[p] + lambda;
+    double D[9] = {hd, 0, 0, 0, hd, 0, 0, 0, hd};
+    double M[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (k > k0) {
+      const double* O = d.Ot + 9 * (size_t)d.chain_link[k];
+      for (int r = 0; r < 3; r++) {
+        const double a0 = O[r], a1 = O[3 + r], a2 = O[6 + r];
+        const double y0 = a0 / Lp[0];
+        const double y1 = (a1 - y0 * Lp[1]) / Lp[2];
+        const double y2 = (a2 - y0 * Lp[3] - y1 * Lp[4]) / Lp[5];
+        M[3 * r] = y0; M[3 * r + 1] = y1; M[3 * r + 2] = y2;
+      }
+      for (int r = 0; r < 3; r++)
+        for (int q = 0; q < 3; q++) D[3 * r + q] -= M[3 * r] * M[3 * q] + M[3 * r + 1] * M[3 * q + 1] + M[3 * r + 2] * M[3 * q + 2];
+    }
+    double L[6];
+    double v = D[0];
+    bool bad = !(v > 0);
+    L[0] = sqrt(v); L[1] = D[3] / L[0]; L[3] = D[6] / L[0];
+    v = D[4] - L[1] * L[1];
+    bad |= !(v > 0);
+    L[2] = sqrt(v); L[4] = (D[7] - L[3] * L[1]) / L[2];
+    v = D[8] - L[3] * L[3] - L[4] * L[4];
+    bad |= !(v > 0);
+    L[5] = sqrt(v);
+    if (bad) { *d.fail = 1; return; }
+    for (int q = 0; q < 6; q++) { d.Lkk[6 * (size_t)p + q] = L[q]; Lp[q] = L[q]; }
+    for (int q = 0; q < 9; q++) d.Lk1[9 * (size_t)p + q] = M[q];
+  }
+}
+
+// in-place (T + lambda I) u = t for every chain (thread per chain), t / u = [NP][3]
+__global__ void __launch_bounds__(128) pcg_chain_solve_kernel(FbaDev d, double* __restrict__ t) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d.NCH) return;
+  const int k0 = d.chain_start[c], k1 = d.chain_start[c + 1];
+  double yp[3] = {0, 0, 0};
+  for (int k = k0; k < k1; k++) {
+    const int p = d.chain_pts[k];
+    const double* M = d.Lk1 + 9 * (size_t)p;
+    const double* L = d.Lkk + 6 * (size_t)p;
+    double r[3] = {t[3 * (size_t)p], t[3 * (size_t)p + 1], t[3 * (size_t)p + 2]};
+    if (k > k0)
+      for (int q = 0; q < 3; q++) r[q] -= M[3 * q] * yp[0] + M[3 * q + 1] * yp[1] + M[3 * q + 2] * yp[2];
+    yp[0] = r[0] / L[0];
+    yp[1] = (r[1] - L[1] * yp[0]) / L[2];
+    yp[2] = (r[2] - L[3] * yp[0] - L[4] * yp[1]) / L[5];
+    t[3 * (size_t)p] = yp[0]; t[3 * (size_t)p + 1] = yp[1]; t[3 * (size_t)p + 2] = yp[2];
+  }
+  double xn[3] = {0, 0, 0};
+  for (int k = k1 - 1; k >= k0; k--) {
+    const int p = d.chain_pts[k];
+    const double* L = d.Lkk + 6 * (size_t)p;
+    double r[3] = {t[3 * (size_t)p], t[3 * (size_t)p + 1], t[3 * (size_t)p + 2]};
+    if (k + 1 < k1) {
+      const double* Mn = d.Lk1 + 9 * (size_t)d.chain_pts[k + 1];
+      for (int q = 0; q < 3; q++) r[q] -= Mn[q] * xn[0] + Mn[3 + q] * xn[1] + Mn[6 + q] * xn[2];
+    }
+    xn[2] = r[2] / L[5];
+    xn[1] = (r[1] - L[4] * xn[2]) / L[2];
+    xn[0] = (r[0] - L[1] * xn[1] - L[3] * xn[2]) / L[0];
+    t[3 * (size_t)p] = xn[0]; t[3 * (size_t)p + 1] = xn[1]; t[3 * (size_t)p + 2] = xn[2];
+  }
+}
+
+// t_k = sum over the couplings of point k of B^T v_vertex (thread per point); v == nullptr: t = bl
+__global__ void __launch_bounds__(256) pcg_point_gather_kernel(FbaDev d, const double* __restrict__ v, double* __restrict__ t) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= d.NP) return;
+  double r[3] = {0, 0, 0};
+  if (!v) { r[0] = d.bl[3 * (size_t)p]; r[1] = d.bl[3 * (size_t)p + 1]; r[2] = d.bl[3 * (size_t)p + 2]; }
+  else
+    for (int ci = d.cpl_start[p]; ci < d.cpl_start[p + 1]; ci++) {
+      const double* B = cpl_block(d, ci);
+      const double* xv = v + 6 * d.cpl_v[ci];
+      for (int rr = 0; rr < 6; rr++) {
+        const double xr = xv[rr];
+        r[0] += B[3 * rr] * xr; r[1] += B[3 * rr + 1] * xr; r[2] += B[3 * rr + 2] * xr;
+      }
+    }
+  t[3 * (size_t)p] = r[0]; t[3 * (size_t)p + 1] = r[1]; t[3 * (size_t)p + 2] = r[2];
+}
+
+// warp per SE3 vertex.  mode 0: out_v = (Hd_v + lambda) in_v + sum_e6 He in_other - sum_cpl B u_pt, part[v] = in_v . out_v
+//                       mode 1: out_v = bs_v - sum_cpl B u_pt   (reduced right-hand side)
+__global__ void __launch_bounds__(128) pcg_vertex_kernel(FbaDev d, double lambda, int mode, const double* __restrict__ in,
+                                                          const double* __restrict__ u, double* __restrict__ out, double* __restrict__ part) {
+  const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (v >= d.NS) return;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  for (int k = d.vc_start[v] + lane; k < d.vc_start[v + 1]; k += 32) {
+    const int ci = d.vc_ci[k];
+    const double* B = cpl_block(d, ci);
+    const double* up = u + 3 * (size_t)d.cpl_pt[ci];
+    const double u0 = up[0], u1 = up[1], u2 = up[2];
+#pragma unroll
+    for (int r = 0; r < 6; r++) acc[r] -= B[3 * r] * u0 + B[3 * r + 1] * u1 + B[3 * r + 2] * u2;
+  }
+#pragma unroll
+  for (int r = 0; r < 6; r++)
+    for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+  if (lane != 0) return;
+  if (mode == 1) {
+    for (int r = 0; r < 6; r++) out[6 * (size_t)v + r] = d.bs[6 * (size_t)v + r] + acc[r];
+    return;
+  }
+  const double* xv = in + 6 * (size_t)v;
+  const double* Hv = d.Hd + 36 * (size_t)v;
+  for (int r = 0; r < 6; r++) {
+    double s = lambda * xv[r];
+    for (int q = 0; q < 6; q++) s += Hv[6 * r + q] * xv[q];
+    acc[r] += s;
+  }
+  for (int k = d.ve_start[v]; k < d.ve_start[v + 1]; k++) {
+    const int e = d.ve_e[k];
+    const double* Hb = d.He6 + 36 * (size_t)e;
+    if (d.ve_side[k] == 0) {
+      const double* xo = in + 6 * (size_t)d.e6j[e];
+      for (int r = 0; r < 6; r++)
+        for (int q = 0; q < 6; q++) acc[r] += Hb[6 * r + q] * xo[q];
+    } else {
+      const double* xo = in + 6 * (size_t)d.e6i[e];
+      for (int r = 0; r < 6; r++)
+        for (int q = 0; q < 6; q++) acc[r] += Hb[6 * q + r] * xo[q];
+    }
+  }
+  double dot = 0;
+  for (int r = 0; r < 6; r++) { out[6 * (size_t)v + r] = acc[r]; dot += xv[r] * acc[r]; }
+  part[v] = dot;
+}
+
+// block-Jacobi preconditioner: M_v = Hd_v + lambda I - sum_cpl B B^T / (hl_pt + lambda) (exact diagonal block of the Schur
+// complement for static points, point-diagonal approximation along dynamic chains); stored as its lower Cholesky factor
+__global__ void __launch_bounds__(128) pcg_precond_kernel(FbaDev d, double lambda) {
+  const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (v >= d.NS) return;
+  double acc[21];
+#pragma unroll
+  for (int k = 0; k < 21; k++) acc[k] = 0;
+  for (int k = d.vc_start[v] + lane; k < d.vc_start[v + 1]; k += 32) {
+    const int ci = d.vc_ci[k];
+    const double* B = cpl_block(d, ci);
+    const double w = 1.0 / (d.hl[d.cpl_pt[ci]] + lambda);
+    int idx = 0;
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+      for (int q = 0; q <= r; q++) acc[idx++] -= w * (B[3 * r] * B[3 * q] + B[3 * r + 1] * B[3 * q + 1] + B[3 * r + 2] * B[3 * q + 2]);
+  }
+#pragma unroll
+  for (int k = 0; k < 21; k++)
+    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+  if (lane != 0) return;
+  double* A = d.cg_A + 36 * (size_t)v;
+  int idx = 0;
+  for (int r = 0; r < 6; r++)
+    for (int q = 0; q <= r; q++) {
+      const double a = d.Hd[36 * (size_t)v + 6 * r + q] + acc[idx++] + (r == q ? lambda : 0.0);
+      A[6 * r + q] = a; A[6 * q + r] = a;
+    }
+}
+
+// The preconditioner M = blockdiag(A_v) + the SE3-edge blocks.  Every SE3 vertex has at most one incoming and one outgoing
+// SE3 edge (odometry: pose k-1 -> k; smoothness: an object's motion in consecutive frames), so M is block-tridiagonal along
+// disjoint paths and is factored exactly without fill (thread per path).  It carries the stiff couplings of the system
+// (information 1e4 / 1e3 against 1/80 for the points), which block-Jacobi alone leaves to CG.
+__global__ void __launch_bounds__(64) pcg_path_factor_kernel(FbaDev d) {
+  const int pth = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pth >= d.NPATH) return;
+  double Lp[36];
+  for (int k = d.path_start[pth]; k < d.path_start[pth + 1]; k++) {
+    const int v = d.path_v[k], e = d.path_e[k];
+    double D[36], W[36];
+    for (int q = 0; q < 36; q++) { D[q] = d.cg_A[36 * (size_t)v + q]; W[q] = 0; }
+    if (e >= 0) {
+      // T_{k,k-1} = He6^T (He6: rows = e6i = previous vertex, columns = e6j = this vertex);  W = T_{k,k-1} Lp^-T
+      const double* Hb = d.He6 + 36 * (size_t)e;
+      for (int r = 0; r < 6; r++) {
+        double y[6];
+        for (int c = 0; c < 6; c++) {
+          double s2 = Hb[6 * c + r];
+          for (int m = 0; m < c; m++) s2 -= y[m] * Lp[6 * c + m];
+          y[c] = s2 / Lp[6 * c + c];
+        }
+        for (int c = 0; c < 6; c++) W[6 * r + c] = y[c];
+      }
+      for (int r = 0; r < 6; r++)
+        for (int c = 0; c <= r; c++) {
+          double s2 = 0;
+          for (int m = 0; m < 6; m++) s2 += W[6 * r + m] * W[6 * c + m];
+          D[6 * r + c] -= s2;
+        }
+    }
+    double Lf[36];
+    bool bad = false;
+    for (int j = 0; j < 6; j++) {
+      double dd = D[6 * j + j];
+      for (int m = 0; m < j; m++) dd -= Lf[6 * j + m] * Lf[6 * j + m];
+      if (!(dd > 0)) { bad = true; dd = 1.0; }
+      Lf[6 * j + j] = sqrt(dd);
+      for (int i = j + 1; i < 6; i++) {
+        double s2 = D[6 * i + j];
+        for (int m = 0; m < j; m++) s2 -= Lf[6 * i + m] * Lf[6 * j + m];
+        Lf[6 * i + j] = s2 / Lf[6 * j + j];
+      }
+      for (int i = 0; i < j; i++) Lf[6 * i + j] = 0;
+    }
+    if (bad) *d.fail = 1;
+    int idx = 0;
+    for (int r = 0; r < 6; r++)
+      for (int c = 0; c <= r; c++) d.cg_M[21 * (size_t)v + idx++] = Lf[6 * r + c];
+    for (int q = 0; q < 36; q++) { d.cg_W[36 * (size_t)v + q] = W[q]; Lp[q] = Lf[q]; }
+  }
+}
+
+// z = M^-1 r along every path (forward with L / W, backward with their transposes) + the per-vertex partials r.z and r.r
+__global__ void __launch_bounds__(64) pcg_path_solve_kernel(FbaDev d) {
+  const int pth = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pth >= d.NPATH) return;
+  const int k0 = d.path_start[pth], k1 = d.path_start[pth + 1];
+  double yp[6] = {0, 0, 0, 0, 0, 0};
+  for (int k = k0; k < k1; k++) {
+    const int v = d.path_v[k];
+    const double* L = d.cg_M + 21 * (size_t)v;
+    const double* W = d.cg_W + 36 * (size_t)v;
+    double r[6];
+    for (int q = 0; q < 6; q++) r[q] = d.cg_r[6 * (size_t)v + q];
+    if (k > k0)
+      for (int q = 0; q < 6; q++)
+        for (int m = 0; m < 6; m++) r[q] -= W[6 * q + m] * yp[m];
+    int idx = 0;
+    for (int i = 0; i < 6; i++) {
+      double s2 = r[i];
+      for (int m = 0; m < i; m++) s2 -= L[idx + m] * yp[m];
+      yp[i] = s2 / L[idx + i];
+      idx += i + 1;
+    }
+    for (int q = 0; q < 6; q++) d.cg_z[6 * (size_t)v + q] = yp[q];
+  }
+  double zn[6] = {0, 0, 0, 0, 0, 0};
+  for (int k = k1 - 1; k >= k0; k--) {
+    const int v = d.path_v[k];
+    const double* L = d.cg_M + 21 * (size_t)v;
+    double y[6];
+    for (int q = 0; q < 6; q++) y[q] = d.cg_z[6 * (size_t)v + q];
+    if (k + 1 < k1) {
+      const double* Wn = d.cg_W + 36 * (size_t)d.path_v[k + 1];
+      for (int q = 0; q < 6; q++)
+        for (int m = 0; m < 6; m++) y[q] -= Wn[6 * m + q] * zn[m];
+    }
+    for (int i = 5; i >= 0; i--) {
+      double s2 = y[i];
+      for (int m = i + 1; m < 6; m++) s2 -= L[m * (m + 1) / 2 + i] * zn[m];
+      zn[i] = s2 / L[i * (i + 1) / 2 + i];
+    }
+    double rz = 0, rr = 0;
+    for (int q = 0; q < 6; q++) {
+      const double rq = d.cg_r[6 * (size_t)v + q];
+      d.cg_z[6 * (size_t)v + q] = zn[q];
+      rz += rq * zn[q]; rr += rq * rq;
+    }
+    d.cg_part[v] = rz; d.cg_part[d.NS + v] = rr;
+  }
+}
+
+// fixed-order sums of the per-vertex partials (one block); what = 0: pq -> alpha ; 1: rz_new, rr -> beta ; 2: init (rz, rr, bnorm2)
+__global__ void __launch_bounds__(256) pcg_scalar_kernel(FbaDev d, int what) {
+  __shared__ double sm[2][8];
+  double a = 0, b = 0;
+  for (int i = threadIdx.x; i < d.NS; i += 256) { a += d.cg_part[i]; b += d.cg_part[d.NS + i]; }
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = a; sm[1][threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  a = 0; b = 0;
+  for (int w = 0; w < 8; w++) { a += sm[0][w]; b += sm[1][w]; }
+  double* sc = d.cg_s;
+  if (what == 0) {
+    sc[1] = a;
+    if (!(a > 0)) { *d.fail = 1; sc[3] = 0; } else sc[3] = sc[0] / a;
+  } else if (what == 1) {
+    sc[5] = a; sc[2] = b;
+    sc[4] = sc[0] != 0 ? a / sc[0] : 0.0;
+    sc[0] = a;
+  } else {
+    sc[0] = a; sc[2] = b; sc[6] = b;
+  }
+}
+
+// x += alpha p ; r -= alpha q   (the preconditioner solve and the dot products follow in pcg_path_solve_kernel)
+__global__ void __launch_bounds__(256) pcg_step1_kernel(FbaDev d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.n) return;
+  const double alpha = d.cg_s[3];
+  d.x[i] += alpha * d.cg_p[i];
+  d.cg_r[i] -= alpha * d.cg_q[i];
+}
+// p = z + beta p
+__global__ void __launch_bounds__(256) pcg_step2_kernel(FbaDev d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.n) return;
+  d.cg_p[i] = d.cg_z[i] + d.cg_s[4] * d.cg_p[i];
+}
+// start: x = 0, p = 0 (then p = z + 0 * p), beta = 0
+__global__ void __launch_bounds__(256) pcg_init_kernel(FbaDev d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) d.cg_s[4] = 0.0;
+  if (i >= d.n) return;
+  d.x[i] = 0.0;
+  d.cg_p[i] = 0.0;
 }
 
 // a failed factorisation leaves x = b (linear_solver_csparse.h:126-133)
@@ -621,6 +992,7 @@ void vido_fba_default_params_impl(vido_fba_problem* p) {
   p->huber_cam = 0.01f; p->huber_obj = 0.01f; p->huber_3d = 0.01f;
   p->gain_threshold = 1e-4f;
   p->prior_info = 100000.f;
+  p->solver = 0;
 }
 
 static int fba_run(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* st, char** arena_base) {
@@ -684,11 +1056,114 @@ static int fba_run(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* st, char**
     int k = fill[p->tern_p1[t]]++; cpl_v[k] = p->tern_h[t]; cpl_kind[k] = 1; cpl_e[k] = t;
     k = fill[p->tern_p2[t]]++; cpl_v[k] = p->tern_h[t]; cpl_kind[k] = 2; cpl_e[k] = t;
   }
+  // ---- frame order of the SE3 vertices.  The reduced system couples a vertex only with vertices of nearby frames (odometry,
+  //      smoothness, the frames a tracklet spans), so with the object motions interleaved with the camera poses of their
+  //      frame it is banded; the Cholesky factor keeps the envelope, and the tiled factorisation / triangular solves below
+  //      only touch `band` rows below each panel.  perm maps the caller's vertex index to the solver's.
+  std::vector<int> perm(d.NS), inv_perm(d.NS);
+  {
+    std::vector<int> key(d.NS, -1), pt_pose(d.NP, -1);
+    for (int i = 0; i < p->n_poses; i++) key[i] = 2 * i;
+    for (int o = 0; o < d.NO; o++) pt_pose[p->obs_point[o]] = std::max(pt_pose[p->obs_point[o]], (int)p->obs_se3[o]);
+    for (int t = 0; t < d.NT; t++) {
+      const int h = p->tern_h[t], pp = pt_pose[p->tern_p2[t]];
+      if (h >= p->n_poses && pp >= 0 && pp < p->n_poses) key[h] = std::max(key[h], 2 * pp + 1);
+    }
+    for (int pass = 0; pass < 4; pass++)
+      for (int e = 0; e < d.NE; e++) {
+        const int a = p->e6_i[e], b2 = p->e6_j[e];
+        if (key[a] >= 0 && key[b2] < 0) key[b2] = key[a] + 2;
+        else if (key[b2] >= 0 && key[a] < 0) key[a] = std::max(key[b2] - 2, 1);
+      }
+    for (int v = 0; v < d.NS; v++) { if (key[v] < 0) key[v] = 2 * p->n_poses + 1; inv_perm[v] = v; }
+    std::stable_sort(inv_perm.begin(), inv_perm.end(), [&](int x, int y) { return key[x] < key[y]; });
+    for (int v = 0; v < d.NS; v++) perm[inv_perm[v]] = v;
+  }
+  std::vector<int> e6i(d.NE), e6j(d.NE), obs_se3(d.NO), tern_h(d.NT);
+  for (int e = 0; e < d.NE; e++) { e6i[e] = perm[p->e6_i[e]]; e6j[e] = perm[p->e6_j[e]]; }
+  for (int o = 0; o < d.NO; o++) obs_se3[o] = perm[p->obs_se3[o]];
+  for (int t = 0; t < d.NT; t++) tern_h[t] = perm[p->tern_h[t]];
+  for (int k = 0; k < ncpl; k++) cpl_v[k] = perm[cpl_v[k]];
+  {
+    std::vector<Pose> Xp(d.NS);
+    for (int v = 0; v < d.NS; v++) Xp[perm[v]] = X[v];
+    X.swap(Xp);
+  }
+  int band_v = 0;   // largest index distance between two coupled SE3 vertices
+  for (int e = 0; e < d.NE; e++) band_v = std::max(band_v, std::abs(e6i[e] - e6j[e]));
+  for (int ch = 0; ch < d.NCH; ch++) {
+    int lo = d.NS, hi = -1;
+    for (int k = chain_start[ch]; k < chain_start[ch + 1]; k++)
+      for (int ci = cpl_start[chain_pts[k]]; ci < cpl_start[chain_pts[k] + 1]; ci++) { lo = std::min(lo, cpl_v[ci]); hi = std::max(hi, cpl_v[ci]); }
+    if (hi >= 0) band_v = std::max(band_v, hi - lo);
+  }
+  const int band = std::min(d.n, 6 * (band_v + 1));
+  // ---- solver: the explicit Schur complement of a chain couples all the SE3 vertices it meets (A^2 blocks, A^3 work), fine
+  //      for tracklets of a few dozen frames; long dynamic tracklets and very large systems take the matrix-free path
+  int max_active = 0;
+  {
+    std::vector<int> seen(d.NS, -1);
+    for (int ch = 0; ch < d.NCH; ch++) {
+      int cnt = 0;
+      for (int k = chain_start[ch]; k < chain_start[ch + 1]; k++)
+        for (int ci = cpl_start[chain_pts[k]]; ci < cpl_start[chain_pts[k] + 1]; ci++)
+          if (seen[cpl_v[ci]] != ch) { seen[cpl_v[ci]] = ch; cnt++; }
+      max_active = std::max(max_active, cnt);
+    }
+  }
+  d.pcg = p->solver == 2 || (p->solver != 1 && (max_active > 96 || d.n > 16384)) ? 1 : 0;
+  if (!d.pcg && max_active > FBA_MAX_ACTIVE) { ctx->err = "FullBatch: a tracklet couples more SE3 vertices than the chain kernel holds (use the matrix-free solver)"; return VIDO_ERR_CAPACITY; }
+  std::vector<int> cpl_pt(ncpl), vc_start(d.NS + 1, 0), vc_ci(ncpl), ve_start(d.NS + 1, 0), ve_e(2 * (size_t)d.NE), ve_side(2 * (size_t)d.NE);
+  for (int q = 0; q < d.NP; q++)
+    for (int ci = cpl_start[q]; ci < cpl_start[q + 1]; ci++) { cpl_pt[ci] = q; vc_start[cpl_v[ci] + 1]++; }
+  for (int v = 0; v < d.NS; v++) vc_start[v + 1] += vc_start[v];
+  {
+    std::vector<int> f2(vc_start.begin(), vc_start.end() - 1);
+    for (int ci = 0; ci < ncpl; ci++) vc_ci[f2[cpl_v[ci]]++] = ci;
+  }
+  // paths of the SE3-edge graph for the preconditioner (every vertex: at most one incoming, one outgoing edge, no cycle;
+  // a graph that violates this falls back to single-vertex paths = block-Jacobi)
+  std::vector<int> path_start(1, 0), path_v, path_e;
+  {
+    std::vector<int> e_in(d.NS, -1), e_out(d.NS, -1);
+    bool ok = true;
+    for (int e = 0; e < d.NE && ok; e++) {
+      if (e6i[e] == e6j[e] || e_out[e6i[e]] != -1 || e_in[e6j[e]] != -1) ok = false;
+      else { e_out[e6i[e]] = e; e_in[e6j[e]] = e; }
+    }
+    if (ok) {
+      for (int v = 0; v < d.NS; v++) {
+        if (e_in[v] != -1) continue;
+        int u = v, le = -1;
+        while (true) {
+          path_v.push_back(u); path_e.push_back(le);
+          if (e_out[u] == -1) break;
+          le = e_out[u]; u = e6j[le];
+        }
+        path_start.push_back((int)path_v.size());
+      }
+      if ((int)path_v.size() != d.NS) ok = false;   // a cycle
+    }
+    if (!ok) {
+      path_start.assign(1, 0); path_v.clear(); path_e.clear();
+      for (int v = 0; v < d.NS; v++) { path_v.push_back(v); path_e.push_back(-1); path_start.push_back(v + 1); }
+    }
+  }
+  d.NPATH = (int)path_start.size() - 1;
+  for (int e = 0; e < d.NE; e++) { ve_start[e6i[e] + 1]++; ve_start[e6j[e] + 1]++; }
+  for (int v = 0; v < d.NS; v++) ve_start[v + 1] += ve_start[v];
+  {
+    std::vector<int> f3(ve_start.begin(), ve_start.end() - 1);
+    for (int e = 0; e < d.NE; e++) {
+      int k = f3[e6i[e]]++; ve_e[k] = e; ve_side[k] = 0;
+      k = f3[e6j[e]]++; ve_e[k] = e; ve_side[k] = 1;
+    }
+  }
   // ---- device buffers: pass 0 sizes the arena, pass 1 carves and uploads (pageable host memory: the async copies are
   //      staged by the runtime before the call returns, so the host vectors may go out of scope afterwards)
   int rc;
   Arena pool;
-  const size_t nn = (size_t)d.n * d.n;
+  const size_t nn = d.pcg ? 16 : (size_t)d.n * d.n;   // the dense system only exists on the direct path
   const int RB = 1024;   // reduction blocks
   for (int pass = 0; pass < 2; pass++) {
   if (pass == 1) {
@@ -704,12 +1179,15 @@ static int fba_run(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* st, char**
   d.X[0] = dX0; d.X[1] = dX1; d.P[0] = dP0; d.P[1] = dP1;
   Pose* dZ; UP(Zi, dZ); d.Z6inv = dZ;
   int* tmp;
-  UPC(p->e6_i, d.NE, tmp); d.e6i = tmp; UPC(p->e6_j, d.NE, tmp); d.e6j = tmp; UPC(p->e6_kind, d.NE, tmp); d.e6k = tmp;
-  UPC(p->obs_se3, d.NO, tmp); d.os = tmp; UPC(p->obs_point, d.NO, tmp); d.op = tmp; UPC(p->obs_kind, d.NO, tmp); d.ok = tmp;
+  UP(e6i, tmp); d.e6i = tmp; UP(e6j, tmp); d.e6j = tmp; UPC(p->e6_kind, d.NE, tmp); d.e6k = tmp;
+  UP(obs_se3, tmp); d.os = tmp; UPC(p->obs_point, d.NO, tmp); d.op = tmp; UPC(p->obs_kind, d.NO, tmp); d.ok = tmp;
   double* dm; UP(meas, dm); d.meas = dm;
-  UPC(p->tern_p1, d.NT, tmp); d.t1 = tmp; UPC(p->tern_p2, d.NT, tmp); d.t2 = tmp; UPC(p->tern_h, d.NT, tmp); d.th = tmp;
+  UPC(p->tern_p1, d.NT, tmp); d.t1 = tmp; UPC(p->tern_p2, d.NT, tmp); d.t2 = tmp; UP(tern_h, tmp); d.th = tmp;
   UP(chain_start, tmp); d.chain_start = tmp; UP(chain_pts, tmp); d.chain_pts = tmp; UP(chain_link, tmp); d.chain_link = tmp;
   UP(cpl_start, tmp); d.cpl_start = tmp; UP(cpl_v, tmp); d.cpl_v = tmp; UP(cpl_kind, tmp); d.cpl_kind = tmp; UP(cpl_e, tmp); d.cpl_e = tmp;
+  UP(cpl_pt, tmp); d.cpl_pt = tmp; UP(vc_start, tmp); d.vc_start = tmp; UP(vc_ci, tmp); d.vc_ci = tmp;
+  UP(ve_start, tmp); d.ve_start = tmp; UP(ve_e, tmp); d.ve_e = tmp; UP(ve_side, tmp); d.ve_side = tmp;
+  UP(path_start, tmp); d.path_start = tmp; UP(path_v, tmp); d.path_v = tmp; UP(path_e, tmp); d.path_e = tmp;
 #undef UP
 #undef UPC
 #define AL(field, count) if ((rc = dev_alloc(ctx, pool, (size_t)(count), &field))) return rc
@@ -718,6 +1196,12 @@ static int fba_run(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* st, char**
   AL(d.S, nn); AL(d.bp, d.n); AL(d.x, d.n + 3 * (size_t)d.NP);
   AL(d.Lkk, 6 * (size_t)d.NP); AL(d.Lk1, 9 * (size_t)d.NP);
   AL(d.partial, RB + 8); AL(d.fail, 4);
+  if (d.pcg) {
+    AL(d.Hd, 36 * (size_t)d.NS); AL(d.He6, 36 * (size_t)d.NE);
+    AL(d.cg_r, d.n); AL(d.cg_z, d.n); AL(d.cg_p, d.n); AL(d.cg_q, d.n); AL(d.cg_t, 3 * (size_t)d.NP);
+    AL(d.cg_M, 21 * (size_t)d.NS); AL(d.cg_A, 36 * (size_t)d.NS); AL(d.cg_W, 36 * (size_t)d.NS);
+    AL(d.cg_part, 2 * (size_t)d.NS); AL(d.cg_s, 8);
+  }
 #undef AL
   }  // pass
   double* d_scalar = d.partial + RB;   // [0] chi2, [1] scale, [2] maxdiag
@@ -737,12 +1221,14 @@ static int fba_run(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* st, char**
 
   LmCtl c;
   lm_reset(&c);
+  long cg_total = 0;
   std::vector<LmRec> rec(VIDO_LM_REC);
   const double gain = (double)p->gain_threshold;
   for (int it = 0; it < p->max_iterations && !c.stop_flag && c.ok; it++) {
     if (it == 0) { if ((rc = chi2_of(c.cur, &c.currentChi))) return rc; }
     // ---- buildSystem at the current state
-    VIDO_CUDA(cudaMemsetAsync(d.Hss, 0, sizeof(double) * nn, s));
+    if (d.pcg) VIDO_CUDA(cudaMemsetAsync(d.Hd, 0, sizeof(double) * 36 * (size_t)d.NS, s));
+    else VIDO_CUDA(cudaMemsetAsync(d.Hss, 0, sizeof(double) * nn, s));
     VIDO_CUDA(cudaMemsetAsync(d.bs, 0, sizeof(double) * d.n, s));
     VIDO_CUDA(cudaMemsetAsync(d.hl, 0, sizeof(double) * std::max(d.NP, 1), s));
     VIDO_CUDA(cudaMemsetAsync(d.bl, 0, sizeof(double) * 3 * std::max<size_t>(d.NP, 1), s));
@@ -761,33 +1247,84 @@ static int fba_run(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* st, char**
     do {
       const double lambda = c.lambda;
       VIDO_CUDA(cudaMemsetAsync(d.fail, 0, sizeof(int) * 4, s));
-      fba_prepare_trial_kernel<<<148 * 4, 256, 0, s>>>(d, lambda);
-      if (d.NCH > 0) fba_chain_kernel<<<(d.NCH + FBA_CHAIN_WARPS - 1) / FBA_CHAIN_WARPS, 32 * FBA_CHAIN_WARPS, 0, s>>>(d, lambda);
-      ctx->launches += 2;
-      for (int j0 = 0; j0 < d.n; j0 += FBA_TB) {
-        const int jb = std::min(FBA_TB, d.n - j0), rest = d.n - j0 - jb;
-        chol_diag_kernel<<<1, 256, 0, s>>>(d.S, d.n, j0, jb, d.fail);
-        ctx->launches++;
-        if (rest > 0) {
-          chol_panel_kernel<<<(rest + 127) / 128, 128, 0, s>>>(d.S, d.n, j0, jb);
-          const int tiles = (rest + 31) / 32;
-          chol_update_kernel<<<dim3(tiles, tiles), 256, 0, s>>>(d.S, d.n, j0, jb);
-          ctx->launches += 2;
-        }
-      }
-      if ((rc = launch_ok())) return rc;
       int fail = 0;
-      VIDO_CUDA(cudaMemcpyAsync(&fail, d.fail, sizeof(int), cudaMemcpyDeviceToHost, s));
-      VIDO_CUDA(cudaStreamSynchronize(s));
-      if (fail == 2) { ctx->err = "FullBatch: a tracklet couples more SE3 vertices than the chain kernel holds"; return VIDO_ERR_CAPACITY; }
-      if (fail) {
-        fba_x_from_b_kernel<<<148, 256, 0, s>>>(d);
-        ctx->launches++;
+      if (!d.pcg) {
+        fba_prepare_trial_kernel<<<148 * 4, 256, 0, s>>>(d, lambda);
+        if (d.NCH > 0) fba_chain_kernel<<<(d.NCH + FBA_CHAIN_WARPS - 1) / FBA_CHAIN_WARPS, 32 * FBA_CHAIN_WARPS, 0, s>>>(d, lambda);
+        ctx->launches += 2;
+        for (int j0 = 0; j0 < d.n; j0 += FBA_TB) {
+          const int jb = std::min(FBA_TB, d.n - j0), rest = std::min(d.n - j0 - jb, band);
+          chol_diag_kernel<<<1, 256, 0, s>>>(d.S, d.n, j0, jb, d.fail);
+          ctx->launches++;
+          if (rest > 0) {
+            chol_panel_kernel<<<(rest + 127) / 128, 128, 0, s>>>(d.S, d.n, j0, jb, rest);
+            const int tiles = (rest + 31) / 32;
+            chol_update_kernel<<<dim3(tiles, tiles), 256, 0, s>>>(d.S, d.n, j0, jb, rest);
+            ctx->launches += 2;
+          }
+        }
+        if ((rc = launch_ok())) return rc;
+        VIDO_CUDA(cudaMemcpyAsync(&fail, d.fail, sizeof(int), cudaMemcpyDeviceToHost, s));
+        VIDO_CUDA(cudaStreamSynchronize(s));
+        if (fail == 2) { ctx->err = "FullBatch: a tracklet couples more SE3 vertices than the chain kernel holds"; return VIDO_ERR_CAPACITY; }
+        if (fail) {
+          fba_x_from_b_kernel<<<148, 256, 0, s>>>(d);
+          ctx->launches++;
+        } else {
+          fba_copy_bp_kernel<<<148, 256, 0, s>>>(d);
+          chol_solve_kernel<<<1, 1024, 0, s>>>(d.S, d.n, d.x, band);
+          if (d.NCH > 0) fba_backsub_kernel<<<(d.NCH + 127) / 128, 128, 0, s>>>(d);
+          ctx->launches += 3;
+        }
       } else {
-        fba_copy_bp_kernel<<<148, 256, 0, s>>>(d);
-        chol_solve_kernel<<<1, 1024, 0, s>>>(d.S, d.n, d.x);
-        if (d.NCH > 0) fba_backsub_kernel<<<(d.NCH + 127) / 128, 128, 0, s>>>(d);
-        ctx->launches += 3;
+        // ---- matrix-free: factor the chains, preconditioner, reduced right-hand side, then CG on the SE3 unknowns
+        const int vb = (d.NS + 3) / 4, cb = (d.NCH + 127) / 128, pb = (d.NP + 255) / 256;
+        if (d.NCH > 0) pcg_chain_factor_kernel<<<cb, 128, 0, s>>>(d, lambda);
+        const int ptb = (d.NPATH + 63) / 64, nb256 = (d.n + 255) / 256;
+        pcg_precond_kernel<<<vb, 128, 0, s>>>(d, lambda);
+        pcg_path_factor_kernel<<<ptb, 64, 0, s>>>(d);
+        if (d.NP > 0) pcg_point_gather_kernel<<<pb, 256, 0, s>>>(d, nullptr, d.cg_t);
+        if (d.NCH > 0) pcg_chain_solve_kernel<<<cb, 128, 0, s>>>(d, d.cg_t);
+        pcg_vertex_kernel<<<vb, 128, 0, s>>>(d, lambda, 1, nullptr, d.cg_t, d.cg_r, d.cg_part);
+        pcg_init_kernel<<<nb256, 256, 0, s>>>(d);
+        pcg_path_solve_kernel<<<ptb, 64, 0, s>>>(d);
+        pcg_scalar_kernel<<<1, 256, 0, s>>>(d, 2);
+        pcg_step2_kernel<<<nb256, 256, 0, s>>>(d);
+        ctx->launches += 9;
+        if ((rc = launch_ok())) return rc;
+        double sc[8];
+        VIDO_CUDA(cudaMemcpyAsync(&fail, d.fail, sizeof(int), cudaMemcpyDeviceToHost, s));
+        VIDO_CUDA(cudaMemcpyAsync(sc, d.cg_s, sizeof sc, cudaMemcpyDeviceToHost, s));
+        VIDO_CUDA(cudaStreamSynchronize(s));
+        const double bnorm2 = sc[6];
+        const int max_cg = std::max(400, 6 * d.n);
+        int cg_it = 0;
+        while (!fail && bnorm2 > 0 && cg_it < max_cg) {
+          for (int k = 0; k < 16; k++, cg_it++) {
+            if (d.NP > 0) pcg_point_gather_kernel<<<pb, 256, 0, s>>>(d, d.cg_p, d.cg_t);
+            if (d.NCH > 0) pcg_chain_solve_kernel<<<cb, 128, 0, s>>>(d, d.cg_t);
+            pcg_vertex_kernel<<<vb, 128, 0, s>>>(d, lambda, 0, d.cg_p, d.cg_t, d.cg_q, d.cg_part);
+            pcg_scalar_kernel<<<1, 256, 0, s>>>(d, 0);
+            pcg_step1_kernel<<<nb256, 256, 0, s>>>(d);
+            pcg_path_solve_kernel<<<ptb, 64, 0, s>>>(d);
+            pcg_scalar_kernel<<<1, 256, 0, s>>>(d, 1);
+            pcg_step2_kernel<<<nb256, 256, 0, s>>>(d);
+            ctx->launches += 8;
+          }
+          if ((rc = launch_ok())) return rc;
+          VIDO_CUDA(cudaMemcpyAsync(&fail, d.fail, sizeof(int), cudaMemcpyDeviceToHost, s));
+          VIDO_CUDA(cudaMemcpyAsync(sc, d.cg_s, sizeof sc, cudaMemcpyDeviceToHost, s));
+          VIDO_CUDA(cudaStreamSynchronize(s));
+          if (!(sc[2] > 1e-26 * bnorm2)) break;   // |r| <= 1e-13 |b|
+        }
+        cg_total += cg_it;
+        if (fail) {
+          fba_x_from_b_kernel<<<148, 256, 0, s>>>(d);
+          ctx->launches++;
+        } else {
+          if (d.NCH > 0) fba_backsub_kernel<<<(d.NCH + 127) / 128, 128, 0, s>>>(d);
+          ctx->launches++;
+        }
       }
       fba_update_kernel<<<red_blocks, 256, 0, s>>>(d, c.cur, lambda);
       fba_final_sum_kernel<<<1, 32, 0, s>>>(d.partial, red_blocks, d_scalar + 1);
@@ -803,10 +1340,11 @@ static int fba_run(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* st, char**
   // ---- results: float32 like Converter::toCvSE3 / toCvMat (src/Optimizer.cc:2090-2176)
   VIDO_CUDA(cudaMemcpy(X.data(), d.X[c.cur], sizeof(Pose) * d.NS, cudaMemcpyDeviceToHost));
   VIDO_CUDA(cudaMemcpy(P.data(), d.P[c.cur], sizeof(double) * 3 * d.NP, cudaMemcpyDeviceToHost));
-  for (int i = 0; i < d.NS; i++) vb::pose_to_f32(X[i], p->se3 + 16 * (size_t)i);
+  for (int i = 0; i < d.NS; i++) vb::pose_to_f32(X[perm[i]], p->se3 + 16 * (size_t)i);
   for (size_t i = 0; i < P.size(); i++) p->points[i] = (float)P[i];
   if (st) {
     st->iterations = c.iterations; st->n_records = c.n_records; st->total_trials = c.total_trials;
+    st->pad = d.pcg ? (int32_t)std::min<long>(cg_total, 0x7fffffff) : 0;   // CG iterations of the matrix-free path
     for (int k = 0; k < c.n_records && k < VIDO_LM_MAX_RECORDS; k++) {
       st->rec[k].chi2 = rec[k].chi2; st->rec[k].lambda = rec[k].lambda; st->rec[k].trials = rec[k].trials;
     }
