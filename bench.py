@@ -260,6 +260,17 @@ def main():
                                     "object_features_per_frame": float(np.mean([x["n_dyn_features"] for x in sd])),
                                     "host_ms_per_frame": {k: float(np.mean([x[k] for x in sd])) for k in ("ms_init", "ms_poseopt", "ms_renew", "ms_ba")},
                                     "workload": "5 moving objects / frame, masks + flow (BASELINE.json configs[3]), inputs resident in HBM"}
+        # joint FullBatch (camera poses, static points, object points, object motions) over the 96 dynamic frames just tracked
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        st_d, sz_d = ctx.full_batch()
+        dt_d = time.perf_counter() - t0
+        recd = st_d.records()
+        extra["dynamic_objects"]["full_batch"] = {"frames": int(sz_d[0]), "object_motions": int(sz_d[1]), "points": int(sz_d[2]),
+                                                  "observations": int(sz_d[3]), "ternary_edges": int(sz_d[5]),
+                                                  "iterations": int(st_d.iterations), "trials": int(st_d.total_trials),
+                                                  "cg_iterations": int(st_d.pad), "ms": dt_d * 1e3,
+                                                  "chi2_first": recd[0][0] if recd else None, "chi2_last": recd[-1][0] if recd else None}
     except Exception as e:
         extra["dynamic_objects"] = {"error": str(e)[:200]}
     frames_total = args.steps * CHUNK * world
