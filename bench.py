@@ -318,6 +318,7 @@ def main():
             "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": 1, "kind": "port",
                              "sample": f"frames {skip}..{ncpu - 1} of the same sequence through the CPU restatement (single thread, like the reference)"},
             **extra,
+            "host_ms_per_frame": {k: float(np.mean([x[k] for x in stats])) for k in ("ms_orb", "ms_init", "ms_poseopt", "ms_renew", "ms_ba")},
             "ba_per_frame": {"iterations": float(np.mean([s["ba_iterations"] for s in stats])), "obs": float(np.mean([s["ba_obs"] for s in stats])),
                              "points": float(np.mean([s["ba_points"] for s in stats]))},
         }

@@ -1038,10 +1038,19 @@ struct BaWorkspace {
   int cluster = 8;
   char* d_base = nullptr;            // solver workspace
   char* d_in2[2] = {nullptr, nullptr};  // input blocks (two: the next problem is staged while the current one is solved)
-  char* d_out = nullptr;             // output block
+  char* d_out2[2] = {nullptr, nullptr}; // output blocks (two: a solve may be queued behind the one in flight)
   BaArgs args;
   char* h_in2[2] = {nullptr, nullptr};  // pinned mirrors
-  char* h_out = nullptr;
+  char* h_out2[2] = {nullptr, nullptr};
+  // chaining: a window queued behind the previous one takes the poses / odometry / points they share straight from the
+  // previous solve's output block on the device (gather kernel on the BA stream), so consecutive solves run back to back
+  int* d_chain2[2] = {nullptr, nullptr};   // [capW + capP]: source index in the previous output per pose / sorted point, -1 = host value
+  int* h_chain2[2] = {nullptr, nullptr};
+  bool chained2[2] = {false, false};
+  cudaEvent_t out_done[2] = {nullptr, nullptr};
+  struct Flight { int slot, W, P, M; bool want_records; };
+  Flight flight[2];
+  int nflight = 0;
   int slot = 0;                      // staging slot of the problem being prepared / in flight
   bool prepared = false;
   BaArgs a_prep;                     // kernel arguments of the prepared problem
@@ -1051,12 +1060,8 @@ struct BaWorkspace {
   cudaStream_t up_stream = nullptr;  // uploads the structure part of a staged problem while the previous one is solved
   cudaEvent_t up_done = nullptr;
   size_t values_bytes = 0;           // leading part of the input block holding poses | odometry | points
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  bool pending = false;
-  bool want_records = false;
-  int W = 0, P = 0, M = 0;
+  cudaEvent_t ev0[2] = {nullptr, nullptr}, ev1[2] = {nullptr, nullptr};
   std::vector<int> newid2[2], oldid, first, len, last, keycnt;  // newid per staging slot (needed again at collect)
-  int inflight_slot = 0;
 };
 
 static size_t al(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -1111,8 +1116,15 @@ int ba_setup(vido_ctx* ctx, int capW, int capP, int capM) {
     VIDO_CUDA(cudaMalloc(&ws->d_in2[k], ws->in_bytes));
     VIDO_CUDA(cudaMallocHost(&ws->h_in2[k], ws->in_bytes));
   }
-  VIDO_CUDA(cudaMalloc(&ws->d_out, ws->out_bytes));
-  VIDO_CUDA(cudaMallocHost(&ws->h_out, ws->out_bytes));
+  for (int k = 0; k < 2; k++) {
+    VIDO_CUDA(cudaMalloc(&ws->d_out2[k], ws->out_bytes));
+    VIDO_CUDA(cudaMallocHost(&ws->h_out2[k], ws->out_bytes));
+    VIDO_CUDA(cudaMalloc(&ws->d_chain2[k], sizeof(int) * (size_t)(capW + capP)));
+    VIDO_CUDA(cudaMallocHost(&ws->h_chain2[k], sizeof(int) * (size_t)(capW + capP)));
+    VIDO_CUDA(cudaEventCreateWithFlags(&ws->out_done[k], cudaEventDisableTiming));
+    VIDO_CUDA(cudaEventCreate(&ws->ev0[k]));
+    VIDO_CUDA(cudaEventCreate(&ws->ev1[k]));
+  }
   memset(&ws->args, 0, sizeof ws->args);
   p = ws->d_base;
   carve_all(p, ws->args, capW, capP, capM);
@@ -1136,8 +1148,6 @@ int ba_setup(vido_ctx* ctx, int capW, int capP, int capM) {
   VIDO_CUDA(vido_create_stream(&ws->stream, true));
   VIDO_CUDA(vido_create_stream(&ws->up_stream, true));
   VIDO_CUDA(cudaEventCreateWithFlags(&ws->up_done, cudaEventDisableTiming));
-  VIDO_CUDA(cudaEventCreate(&ws->ev0));
-  VIDO_CUDA(cudaEventCreate(&ws->ev1));
   return VIDO_OK;
 }
 
@@ -1147,10 +1157,14 @@ void ba_teardown(vido_ctx* ctx) {
   if (ws->stream) { cudaStreamSynchronize(ws->stream); cudaStreamDestroy(ws->stream); }
   if (ws->up_stream) { cudaStreamSynchronize(ws->up_stream); cudaStreamDestroy(ws->up_stream); }
   if (ws->up_done) cudaEventDestroy(ws->up_done);
-  if (ws->ev0) cudaEventDestroy(ws->ev0);
-  if (ws->ev1) cudaEventDestroy(ws->ev1);
-  cudaFree(ws->d_base); cudaFree(ws->d_in2[0]); cudaFree(ws->d_in2[1]); cudaFree(ws->d_out);
-  cudaFreeHost(ws->h_in2[0]); cudaFreeHost(ws->h_in2[1]); cudaFreeHost(ws->h_out);
+  for (int k = 0; k < 2; k++) {
+    if (ws->ev0[k]) cudaEventDestroy(ws->ev0[k]);
+    if (ws->ev1[k]) cudaEventDestroy(ws->ev1[k]);
+    if (ws->out_done[k]) cudaEventDestroy(ws->out_done[k]);
+    cudaFree(ws->d_out2[k]); cudaFreeHost(ws->h_out2[k]); cudaFree(ws->d_chain2[k]); cudaFreeHost(ws->h_chain2[k]);
+  }
+  cudaFree(ws->d_base); cudaFree(ws->d_in2[0]); cudaFree(ws->d_in2[1]);
+  cudaFreeHost(ws->h_in2[0]); cudaFreeHost(ws->h_in2[1]);
   delete ws;
   ctx->ba = nullptr;
 }
@@ -1160,13 +1174,39 @@ void ba_teardown(vido_ctx* ctx) {
 //               problem is still being solved; pr->poses / rel_motion / points are not read);
 //   ba_launch:  add the state values (poses, odometry, points), copy the block and launch on the BA stream;
 //   ba_collect: wait and write the results back into the problem's arrays, which must stay alive in between.
-int ba_prepare(vido_ctx* ctx, const vido_ba_problem* pr) {
+// values of window k+1 that are outputs of window k, copied on the device (same float32 bits as the host round trip)
+__global__ void __launch_bounds__(256) ba_chain_kernel(const int* __restrict__ chain, int W, int P, const float* __restrict__ prev_poses,
+                                                       const float* __restrict__ prev_rel, const float* __restrict__ prev_points,
+                                                       float* __restrict__ poses, float* __restrict__ rel, float* __restrict__ points) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int np = 16 * W, nr = 16 * (W - 1);
+  if (i < np) {
+    const int src = chain[i >> 4];
+    if (src >= 0) poses[i] = prev_poses[16 * src + (i & 15)];
+  } else if (i < np + nr) {
+    const int k = i - np, j = k >> 4;
+    const int a = chain[j], b = chain[j + 1];
+    if (a >= 0 && b == a + 1) rel[k] = prev_rel[16 * a + (k & 15)];
+  } else if (i < np + nr + 3 * P) {
+    const int k = i - np - nr, n = k / 3;
+    const int src = chain[W + n];
+    if (src >= 0) points[k] = prev_points[3 * src + (k - 3 * n)];
+  }
+}
+
+int ba_prepare_chained(vido_ctx* ctx, const vido_ba_problem* pr, const int* prev_pose, const int* prev_point);
+int ba_prepare(vido_ctx* ctx, const vido_ba_problem* pr) { return ba_prepare_chained(ctx, pr, nullptr, nullptr); }
+
+// prev_pose[i] / prev_point[l]: index of pose i / point l (caller numbering) in the problem that is IN FLIGHT right now, or -1;
+// nullptr: no chaining (every value comes from pr at launch time)
+int ba_prepare_chained(vido_ctx* ctx, const vido_ba_problem* pr, const int* prev_pose, const int* prev_point) {
   BaWorkspace* ws = (BaWorkspace*)ctx->ba;
   ws->prepared = false;
   const int W = pr->n_poses, P = pr->n_points, M = pr->n_obs;
   if (W < 0 || P < 0 || M < 0) return VIDO_ERR_ARG;
   if (W > ws->capW || P > ws->capP || M > ws->capM) { ctx->err = "BA problem exceeds the context capacity"; return VIDO_ERR_CAPACITY; }
-  const int slot = ws->pending ? (ws->inflight_slot ^ 1) : ws->slot;
+  if (ws->nflight >= 2) { ctx->err = "two window solves are already queued"; return VIDO_ERR_STATE; }
+  const int slot = ws->nflight ? (ws->flight[ws->nflight - 1].slot ^ 1) : ws->slot;
   ws->slot = slot;
   char* const h_in = ws->h_in2[slot];
   char* const d_in = ws->d_in2[slot];
@@ -1184,7 +1224,7 @@ int ba_prepare(vido_ctx* ctx, const vido_ba_problem* pr) {
   {
     char* hp = h_in; carve_inputs(hp, h, W, P, M);
     char* dp = d_in; carve_inputs(dp, a, W, P, M);
-    char* dq = ws->d_out; carve_outputs(dq, a, W, P);
+    char* dq = ws->d_out2[slot]; carve_outputs(dq, a, W, P);
   }
   int* h_obs_pose = (int*)h.obs_pose; int* h_obs_point = (int*)h.obs_point; float* h_xyz = (float*)h.obs_xyz;
   int* h_pt_len = (int*)h.pt_len; int* h_pt_first = (int*)h.pt_first; float* h_pts = (float*)h.points_f32;
@@ -1244,6 +1284,16 @@ int ba_prepare(vido_ctx* ctx, const vido_ba_problem* pr) {
     const size_t vb = (size_t)((const char*)h.obs_pose - h_in);  // poses_f32 | rel_f32 | points_f32 come first
     ws->values_bytes = vb;
     VIDO_CUDA(cudaMemcpyAsync(d_in + vb, h_in + vb, used - vb, cudaMemcpyHostToDevice, ws->up_stream));
+    ws->chained2[slot] = false;
+    if (prev_pose && (prev_point || P == 0) && ws->nflight == 1) {
+      const BaWorkspace::Flight& Fp = ws->flight[0];
+      const std::vector<int>& pnew = ws->newid2[Fp.slot];
+      int* hc = ws->h_chain2[slot];
+      for (int i = 0; i < W; i++) hc[i] = (prev_pose[i] >= 0 && prev_pose[i] < Fp.W) ? prev_pose[i] : -1;
+      for (int l = 0; l < P; l++) hc[W + newid[l]] = (prev_point[l] >= 0 && prev_point[l] < Fp.P) ? pnew[prev_point[l]] : -1;
+      VIDO_CUDA(cudaMemcpyAsync(ws->d_chain2[slot], hc, sizeof(int) * (size_t)(W + P), cudaMemcpyHostToDevice, ws->up_stream));
+      ws->chained2[slot] = true;
+    }
     VIDO_CUDA(cudaEventRecord(ws->up_done, ws->up_stream));
   }
   ws->a_prep = a;
@@ -1253,13 +1303,13 @@ int ba_prepare(vido_ctx* ctx, const vido_ba_problem* pr) {
 
 int ba_launch(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records) {
   BaWorkspace* ws = (BaWorkspace*)ctx->ba;
-  if (ws->pending) { ctx->err = "a window BA is already in flight"; return VIDO_ERR_ARG; }
   if (!ws->prepared) { ctx->err = "ba_launch without ba_prepare"; return VIDO_ERR_ARG; }
+  if (ws->nflight >= 2) { ctx->err = "two window solves are already queued"; return VIDO_ERR_STATE; }
+  if (ws->nflight == 1 && !ws->chained2[ws->slot]) { ctx->err = "a window BA is already in flight"; return VIDO_ERR_ARG; }
   ws->prepared = false;
   const int W = pr->n_poses, P = pr->n_points, M = pr->n_obs;
   const int slot = ws->slot;
   cudaStream_t s = ws->stream;
-  ws->W = W; ws->P = P; ws->M = M; ws->want_records = want_records;
   const BaArgs a = ws->a_prep;
   {  // state values
     BaArgs h;
@@ -1273,8 +1323,21 @@ int ba_launch(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records) {
       h_pts[3 * n] = pr->points[3 * l]; h_pts[3 * n + 1] = pr->points[3 * l + 1]; h_pts[3 * n + 2] = pr->points[3 * l + 2];
     }
   }
-  VIDO_CUDA(cudaMemcpyAsync(ws->d_in2[slot], ws->h_in2[slot], ws->values_bytes, cudaMemcpyHostToDevice, s));
+  // the state values travel on the upload stream too (behind the structure part): with a solve in flight the BA stream
+  // then only has to run the gather and the kernel
+  VIDO_CUDA(cudaMemcpyAsync(ws->d_in2[slot], ws->h_in2[slot], ws->values_bytes, cudaMemcpyHostToDevice, ws->up_stream));
+  VIDO_CUDA(cudaEventRecord(ws->up_done, ws->up_stream));
   VIDO_CUDA(cudaStreamWaitEvent(s, ws->up_done, 0));
+  if (ws->nflight == 1 && ws->chained2[slot]) {
+    // queued behind the solve in flight (same stream, so it runs after it): shared values come from its output block
+    const BaWorkspace::Flight& Fp = ws->flight[0];
+    BaArgs po;
+    { char* q = ws->d_out2[Fp.slot]; carve_outputs(q, po, Fp.W, Fp.P); }
+    const int total = 16 * W + 16 * std::max(W - 1, 0) + 3 * P;
+    ba_chain_kernel<<<(total + 255) / 256, 256, 0, s>>>(ws->d_chain2[slot], W, P, po.out_poses, po.out_rel, po.out_points,
+                                                        (float*)a.poses_f32, (float*)a.rel_f32, (float*)a.points_f32);
+    ctx->launches++;
+  }
   const size_t smem = sizeof(double) * ((size_t)(6 * W + 1) * (6 * W + 1) + 36 * W);
   {
     cudaLaunchConfig_t cfg = {};
@@ -1283,20 +1346,20 @@ int ba_launch(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = ws->cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaEventRecord(ws->ev0, s);
+    cudaEventRecord(ws->ev0[slot], s);
     VIDO_CUDA(cudaLaunchKernelEx(&cfg, ba_window_kernel, a));
-    cudaEventRecord(ws->ev1, s);
+    cudaEventRecord(ws->ev1[slot], s);
     ctx->launches++;
   }
   {
     BaArgs ho;
-    char* hq = ws->h_out; carve_outputs(hq, ho, W, P);
+    char* hq = ws->h_out2[slot]; carve_outputs(hq, ho, W, P);
     // the LM records sit at the end of the block: copy them only when asked for
-    const size_t out_used = want_records ? (size_t)(hq - ws->h_out) : (size_t)((char*)ho.rec - ws->h_out);
-    VIDO_CUDA(cudaMemcpyAsync(ws->h_out, ws->d_out, out_used, cudaMemcpyDeviceToHost, s));
+    const size_t out_used = want_records ? (size_t)(hq - ws->h_out2[slot]) : (size_t)((char*)ho.rec - ws->h_out2[slot]);
+    VIDO_CUDA(cudaMemcpyAsync(ws->h_out2[slot], ws->d_out2[slot], out_used, cudaMemcpyDeviceToHost, s));
+    VIDO_CUDA(cudaEventRecord(ws->out_done[slot], s));
   }
-  ws->pending = true;
-  ws->inflight_slot = slot;
+  ws->flight[ws->nflight++] = {slot, W, P, M, want_records};
   return VIDO_OK;
 }
 
@@ -1308,13 +1371,15 @@ int ba_submit(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records) {
 
 int ba_collect(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st) {
   BaWorkspace* ws = (BaWorkspace*)ctx->ba;
-  if (!ws->pending) { ctx->err = "no window BA in flight"; return VIDO_ERR_ARG; }
-  ws->pending = false;
-  const int W = ws->W, P = ws->P, M = ws->M;
-  const std::vector<int>& newid = ws->newid2[ws->inflight_slot];
-  VIDO_CUDA(cudaStreamSynchronize(ws->stream));
+  if (ws->nflight == 0) { ctx->err = "no window BA in flight"; return VIDO_ERR_ARG; }
+  const BaWorkspace::Flight F = ws->flight[0];   // the oldest
+  ws->flight[0] = ws->flight[1];
+  ws->nflight--;
+  const int W = F.W, P = F.P, M = F.M;
+  const std::vector<int>& newid = ws->newid2[F.slot];
+  VIDO_CUDA(cudaEventSynchronize(ws->out_done[F.slot]));
   BaArgs ho;
-  { char* hq = ws->h_out; carve_outputs(hq, ho, W, P); }
+  { char* hq = ws->h_out2[F.slot]; carve_outputs(hq, ho, W, P); }
   const LmCtl ctl = *ho.ctl_out;
   const unsigned long long* tph = ho.t_phase;
   const LmRec* recs = ho.rec;
@@ -1327,7 +1392,7 @@ int ba_collect(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st) {
   }
   {
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, ws->ev0, ws->ev1) == cudaSuccess) { ctx->t_ms[3] += ms; ctx->t_n[3]++; }
+    if (cudaEventElapsedTime(&ms, ws->ev0[F.slot], ws->ev1[F.slot]) == cudaSuccess) { ctx->t_ms[3] += ms; ctx->t_n[3]++; }
     const double edges = (double)M + (double)std::max(W - 1, 0);
     ctx->ba_alg_bytes += edges * (296.0 * std::max(ctl.iterations, 0) + 152.0 * (ctl.total_trials + 1));
   }
@@ -1341,7 +1406,7 @@ int ba_collect(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st) {
             tph[9], tph[10], tph[0], tph[1], tph[2], tph[11], tph[16], tph[17], tph[18] + tph[12], tph[13], tph[3]);
   if (st) {
     st->iterations = ctl.iterations;
-    st->n_records = ws->want_records ? ctl.n_records : 0;
+    st->n_records = F.want_records ? ctl.n_records : 0;
     st->total_trials = ctl.total_trials;
     for (int i = 0; i < st->n_records && i < VIDO_LM_MAX_RECORDS; i++) {
       st->rec[i].chi2 = recs[i].chi2;

@@ -122,6 +122,9 @@ void ba_teardown(vido_ctx* ctx);
 int ba_partial_host(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st);
 int ba_submit(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records);
 int ba_prepare(vido_ctx* ctx, const vido_ba_problem* pr);
+// same, for a problem that will be queued behind the solve in flight: prev_pose[i] / prev_point[l] = index of pose i / point l
+// in that solve's problem (or -1); those values are then taken from its output block on the device
+int ba_prepare_chained(vido_ctx* ctx, const vido_ba_problem* pr, const int* prev_pose, const int* prev_point);
 int ba_launch(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records);
 int ba_collect(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st);
 

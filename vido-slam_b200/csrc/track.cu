@@ -113,9 +113,15 @@ struct TrackState {
     std::vector<int> op, ol;
     std::vector<int> ofeat;          // per observation: feature index inside its frame, for the write-back
     std::vector<int> pframe, pfeat;  // per point: frame / feature of its first observation (initial position)
+    std::vector<int> prev_pose, prev_point;  // index of every pose / point in the previous window's problem (-1: not in it)
+    int epoch = 0;
   } job[2];
-  bool ba_pending = false, ba_staged = false;
-  int ba_fly = 0, ba_stage_slot = 0, ba_rest = -1;
+  // Up to two windows are queued on the BA stream: window k+1 is launched BEFORE window k has finished -- the values they
+  // share (19 of 20 poses, the odometry between them, every point that stays in the window) are gathered from window k's
+  // output on the device -- and window k's results are written back into the Map while window k+1 is already running.
+  bool ba_staged = false;
+  int ba_queue[2] = {0, 0}, ba_nq = 0;   // job slots in flight, oldest first
+  int ba_stage_slot = 0, ba_rest = -1;
   // device buffers of one chunk
   int capB = 0;
   // Two pipeline slots.  A slot holds the inputs of one batch on the device, its front-end outputs on the device and
@@ -282,7 +288,7 @@ void trk_teardown(vido_ctx* ctx) {
 
 int trk_reset(vido_ctx* ctx) {
   TrackState* ts = (TrackState*)ctx->trk;
-  if (ts->ba_pending) { vido_lm_stats ls; ba_collect(ctx, &ts->job[ts->ba_fly].pr, &ls); ts->ba_pending = false; }
+  while (ts->ba_nq > 0) { vido_lm_stats ls; ba_collect(ctx, &ts->job[ts->ba_queue[0]].pr, &ls); ts->ba_queue[0] = ts->ba_queue[1]; ts->ba_nq--; }
   ts->map.clear(); ts->tracks.clear();
   ts->initialised = false; ts->has_velocity = false; ts->f_id = 0; ts->ba_epoch = 0;
   cudaStreamSynchronize(ts->copy_stream); cudaStreamSynchronize(ts->fe_stream);
@@ -913,9 +919,10 @@ static int dyn_renew(vido_ctx* ctx, const FrontFrame& ff, const float* curTcw, c
 // (Tracking.cc:1320-1500 uses mpLastFrame / mVelocity only), so the result equals the reference's sequential order.
 static int ba_finish(vido_ctx* ctx) {
   TrackState* ts = (TrackState*)ctx->trk;
-  if (!ts->ba_pending) return VIDO_OK;
-  ts->ba_pending = false;
-  TrackState::BaJob& J = ts->job[ts->ba_fly];
+  if (ts->ba_nq == 0) return VIDO_OK;
+  TrackState::BaJob& J = ts->job[ts->ba_queue[0]];
+  ts->ba_queue[0] = ts->ba_queue[1];
+  ts->ba_nq--;
   vido_lm_stats ls;
   int rc = ba_collect(ctx, &J.pr, &ls);
   if (rc) return rc;
@@ -958,13 +965,24 @@ static int ba_stage(vido_ctx* ctx, int WINDOW, vido_track_stats* st) {
   const int N = (int)ts->map.size();
   if (st) { st->ba_iterations = -1; st->ba_points = 0; st->ba_obs = 0; st->ba_trials = 0; }
   if (WINDOW <= 0) return VIDO_OK;
-  ts->ba_stage_slot = ts->ba_pending ? (ts->ba_fly ^ 1) : ts->ba_fly;
+  if (ts->ba_nq == 2 || (ts->ba_nq == 1 && ts->job[ts->ba_queue[0]].epoch != ts->ba_epoch)) {  // cannot chain: drain first
+    while (ts->ba_nq > 0) { int rc0 = ba_finish(ctx); if (rc0) return rc0; }
+    ba_writeback_rest(ctx);
+  }
+  ts->ba_stage_slot = ts->ba_nq ? (ts->ba_queue[ts->ba_nq - 1] ^ 1) : ts->ba_stage_slot;
   TrackState::BaJob& J = ts->job[ts->ba_stage_slot];
+  const TrackState::BaJob* Jp = ts->ba_nq ? &ts->job[ts->ba_queue[0]] : nullptr;   // the window in flight, if any
   const int start = N - WINDOW;
   J.start = start; J.end = N; J.st = st;
   J.poses.resize(16 * (size_t)WINDOW); J.rel.resize(16 * (size_t)std::max(WINDOW - 1, 0));
   J.oxyz.clear(); J.op.clear(); J.ol.clear(); J.ofeat.clear(); J.pframe.clear(); J.pfeat.clear();
+  J.prev_pose.assign(WINDOW, -1); J.prev_point.clear();
+  if (Jp)
+    for (int i = start; i < N; i++)
+      if (i >= Jp->start && i < Jp->end) J.prev_pose[i - start] = i - Jp->start;
+  const int prev_epoch = ts->ba_epoch;
   const int epoch = ++ts->ba_epoch;
+  J.epoch = epoch;
   const float invfx = 1.0f / ctx->cfg.fx, invfy = 1.0f / ctx->cfg.fy, cx = ctx->cfg.cx, cy = ctx->cfg.cy;
   int npts = 0;
   // a track enters the window graph iff it is at least 3 long and was born inside the window
@@ -978,6 +996,7 @@ static int ba_stage(vido_ctx* ctx, int WINDOW, vido_track_stats* st) {
       if (T.len < 3 || T.first_frame < start) continue;
       int pid = (T.epoch == epoch) ? T.pid : -1;
       if (F.pos[j] == 0) {
+        J.prev_point.push_back((Jp && T.epoch == prev_epoch) ? T.pid : -1);   // same track, point of the window in flight
         pid = npts++;
         T.pid = pid; T.epoch = epoch;
         J.pframe.push_back(i); J.pfeat.push_back(j);
@@ -996,7 +1015,7 @@ static int ba_stage(vido_ctx* ctx, int WINDOW, vido_track_stats* st) {
   pr.poses = J.poses.data(); pr.rel_motion = J.rel.data(); pr.points = J.pts.data();
   pr.obs_pose = J.op.data(); pr.obs_point = J.ol.data(); pr.obs_xyz = J.oxyz.data();
   if (st) { st->ba_points = pr.n_points; st->ba_obs = pr.n_obs; }
-  int rc = ba_prepare(ctx, &pr);
+  int rc = Jp ? ba_prepare_chained(ctx, &pr, J.prev_pose.data(), J.prev_point.data()) : ba_prepare(ctx, &pr);
   if (rc) return rc;
   ts->ba_staged = true;
   return VIDO_OK;
@@ -1021,8 +1040,7 @@ static int ba_go(vido_ctx* ctx) {
   }
   int rc = ba_launch(ctx, &J.pr, false);
   if (rc) return rc;
-  ts->ba_pending = true;
-  ts->ba_fly = slot;
+  ts->ba_queue[ts->ba_nq++] = slot;
   return VIDO_OK;
 }
 
@@ -1294,12 +1312,17 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
   memcpy(Tcw_out, curTcw, sizeof(float) * 16);
   double t4 = now_ms();
   const int window = ts->f_id < c.window_size ? ts->f_id : c.window_size;
-  int rc = skipped ? VIDO_OK : ba_stage(ctx, window, st);  // structure of this frame's window, staged while the previous
-  if (rc) return rc;                                        // frame's window is still being solved
-  rc = ba_finish(ctx);
+  // This frame's window is staged AND queued on the BA stream while the previous frame's window is still being solved: what
+  // the two share comes from the previous output block on the device.  Only then are the previous results awaited and
+  // written back into the Map -- with the next solve already enqueued right behind it.
+  int rc = skipped ? VIDO_OK : ba_stage(ctx, window, st);
   if (rc) return rc;
-  rc = ba_go(ctx);
-  ba_writeback_rest(ctx);  // off the critical path: the next solve is already running
+  const bool queued_behind = ts->ba_staged && ts->ba_nq == 1;
+  if (queued_behind) rc = ba_go(ctx);
+  if (rc) return rc;
+  while (ts->ba_nq > (queued_behind ? 1 : 0)) { rc = ba_finish(ctx); if (rc) return rc; }
+  if (!queued_behind) rc = ba_go(ctx);
+  ba_writeback_rest(ctx);
   if (st) st->ms_ba = now_ms() - t4;
   ts->f_id++;
   if (rc) return rc;
@@ -1364,7 +1387,7 @@ int trk_track_chunk(vido_ctx* ctx, const vido_frame_inputs* in, int nframes, flo
   const vido_config& c = ctx->cfg;
   cudaStream_t s = ctx->stream;
   const size_t px = (size_t)c.width * c.height;
-  if (ts->ba_pending) { vido_lm_stats ls; ba_collect(ctx, &ts->job[ts->ba_fly].pr, &ls); ts->ba_pending = false; }  // left by a failed call
+  while (ts->ba_nq > 0) { vido_lm_stats ls; ba_collect(ctx, &ts->job[ts->ba_queue[0]].pr, &ls); ts->ba_queue[0] = ts->ba_queue[1]; ts->ba_nq--; }  // left by a failed call
   int done = 0;
   while (done < nframes) {
     const int B = std::min(ts->capB, nframes - done);
@@ -1407,8 +1430,8 @@ int trk_track_chunk(vido_ctx* ctx, const vido_frame_inputs* in, int nframes, flo
     done += B;
   }
   {
-    int rc = ba_finish(ctx);  // drain: stats and map are final when the call returns
-    ba_writeback_rest(ctx);
+    int rc = VIDO_OK;  // drain: stats and map are final when the call returns
+    while (ts->ba_nq > 0 && rc == VIDO_OK) { rc = ba_finish(ctx); ba_writeback_rest(ctx); }
     return rc;
   }
 }
@@ -1593,9 +1616,8 @@ void fill_problem(FullGraph& G, vido_fba_problem& pr) {
 
 int trk_full_batch(vido_ctx* ctx, vido_lm_stats* stats, int32_t* sizes) {
   TrackState* ts = (TrackState*)ctx->trk;
-  int rc = ba_finish(ctx);   // a window solve left in flight by a failed call
-  if (rc) return rc;
-  ba_writeback_rest(ctx);
+  int rc = VIDO_OK;   // window solves left in flight by a failed call
+  while (ts->ba_nq > 0) { rc = ba_finish(ctx); if (rc) return rc; ba_writeback_rest(ctx); }
   FullGraph G;
   build_full_graph(ts, ctx->cfg, G);
   vido_fba_problem pr;
