@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -91,6 +92,10 @@ struct vido_ctx {
   void* po = nullptr;  // PoWorkspace (poseopt_kernels.cu)
   void* pnp = nullptr; // PnpWorkspace (pnp_kernels.cu)
   void* trk = nullptr; // TrackState (track.cu)
+  // One-shot hook run by the synchronous PnP / pose-optimisation wrappers after their launches and before they wait for the
+  // results: the per-frame driver parks host work there (staging and queueing the previous frame's window solve, retiring
+  // the one before) so that it overlaps the kernels instead of extending the frame's serial path.
+  std::function<void()> idle_work;
   char* um_ws = nullptr;   // UpdateMask workspace (assoc_kernels.cu), grown on demand: cudaMalloc is expensive once peer
   size_t um_ws_bytes = 0;  // access is enabled (NCCL), so nothing on the per-frame path allocates
 };

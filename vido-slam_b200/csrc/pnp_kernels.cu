@@ -548,6 +548,7 @@ static int pnp_batch(vido_ctx* ctx, vido_pnp_problem* ps, int nb) {
   VIDO_CUDA(cudaGetLastError());
   // the inlier lists are at most n ints each: fetch them with the results instead of paying a second round trip
   VIDO_CUDA(cudaMemcpyAsync(ws->h_out, ws->d_out, out_off, cudaMemcpyDeviceToHost, s));
+  if (ctx->idle_work) { std::function<void()> f; f.swap(ctx->idle_work); f(); }   // host work hidden behind the kernels
   VIDO_CUDA(cudaStreamSynchronize(s));
   {
     float ms = 0;

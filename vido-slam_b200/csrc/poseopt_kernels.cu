@@ -960,6 +960,7 @@ int po_flow2_host(vido_ctx* ctx, vido_poseopt_problem* prs, int nproblems, vido_
   ctx->launches++;
   VIDO_CUDA(cudaGetLastError());
   VIDO_CUDA(cudaMemcpyAsync(ws->h_out, ws->d_out, stats ? (size_t)(ho - ws->h_out) : out_small, cudaMemcpyDeviceToHost, s));
+  if (ctx->idle_work) { std::function<void()> f; f.swap(ctx->idle_work); f(); }   // host work hidden behind the kernel
   VIDO_CUDA(cudaStreamSynchronize(s));
   {
     float ms = 0;

@@ -121,6 +121,9 @@ struct TrackState {
   // output on the device -- and window k's results are written back into the Map while window k+1 is already running.
   bool ba_staged = false;
   int ba_queue[2] = {0, 0}, ba_nq = 0;   // job slots in flight, oldest first
+  // the window of frame k is staged and queued while the camera PnP of frame k+1 runs on the GPU (ctx->idle_work)
+  struct { bool valid = false; int window = 0; vido_track_stats* st = nullptr; } ba_deferred;
+  int ba_deferred_rc = 0;
   int ba_stage_slot = 0, ba_rest = -1;
   // device buffers of one chunk
   int capB = 0;
@@ -289,6 +292,7 @@ void trk_teardown(vido_ctx* ctx) {
 int trk_reset(vido_ctx* ctx) {
   TrackState* ts = (TrackState*)ctx->trk;
   while (ts->ba_nq > 0) { vido_lm_stats ls; ba_collect(ctx, &ts->job[ts->ba_queue[0]].pr, &ls); ts->ba_queue[0] = ts->ba_queue[1]; ts->ba_nq--; }
+  ts->ba_deferred.valid = false;
   ts->map.clear(); ts->tracks.clear();
   ts->initialised = false; ts->has_velocity = false; ts->f_id = 0; ts->ba_epoch = 0;
   cudaStreamSynchronize(ts->copy_stream); cudaStreamSynchronize(ts->fe_stream);
@@ -965,8 +969,14 @@ static int ba_stage(vido_ctx* ctx, int WINDOW, vido_track_stats* st) {
   const int N = (int)ts->map.size();
   if (st) { st->ba_iterations = -1; st->ba_points = 0; st->ba_obs = 0; st->ba_trials = 0; }
   if (WINDOW <= 0) return VIDO_OK;
-  if (ts->ba_nq == 2 || (ts->ba_nq == 1 && ts->job[ts->ba_queue[0]].epoch != ts->ba_epoch)) {  // cannot chain: drain first
-    while (ts->ba_nq > 0) { int rc0 = ba_finish(ctx); if (rc0) return rc0; }
+  if (ts->ba_nq == 2) {   // retire the older of the two queued solves: the new one chains to the newer
+    int rc0 = ba_finish(ctx);
+    if (rc0) return rc0;
+    ba_writeback_rest(ctx);
+  }
+  if (ts->ba_nq == 1 && ts->job[ts->ba_queue[0]].epoch != ts->ba_epoch) {  // cannot chain: drain first
+    int rc0 = ba_finish(ctx);
+    if (rc0) return rc0;
     ba_writeback_rest(ctx);
   }
   ts->ba_stage_slot = ts->ba_nq ? (ts->ba_queue[ts->ba_nq - 1] ^ 1) : ts->ba_stage_slot;
@@ -1044,6 +1054,18 @@ static int ba_go(vido_ctx* ctx) {
   return VIDO_OK;
 }
 
+// stage + queue the window solve that was put off at the end of the previous frame
+static int ba_flush_deferred(vido_ctx* ctx) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  if (!ts->ba_deferred.valid) return VIDO_OK;
+  ts->ba_deferred.valid = false;
+  double t0 = now_ms();
+  int rc = ba_stage(ctx, ts->ba_deferred.window, ts->ba_deferred.st);
+  if (!rc) rc = ba_go(ctx);
+  if (ts->ba_deferred.st) ts->ba_deferred.st->ms_ba += now_ms() - t0;
+  return rc;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // back-end of one frame (sequential)
 // ---------------------------------------------------------------------------------------------------------
@@ -1075,6 +1097,7 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
     if (nrec) { int rc = fe_redo_frame(ctx, FS, slot, ff); if (rc) return rc; }
   }
   if (!ts->initialised) {
+    { int rc0 = ba_flush_deferred(ctx); if (rc0) return rc0; }
     // ---- Tracking::Initialization: features leaving frame 0 are the associated detections
     MapFrame F;
     const int m = (int)ff.as_idx.size();
@@ -1105,7 +1128,7 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
     ts->initialised = true;
   } else {
     const int Ns = (int)(ts->last_corres.size() / 2);
-    if (Ns < 2) skipped = 1;
+    if (Ns < 2) { skipped = 1; int rc0 = ba_flush_deferred(ctx); if (rc0) return rc0; }
     else {
       // ---- mvStatKeys = last mvCorres.  The reference also samples the new depth map at these positions into
       //      mvStatDepthTmp (Tracking.cc:369-389); in the static-only pipeline nothing reads that vector (RenewFrameInfo
@@ -1130,8 +1153,13 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
       if (ts->has_velocity) mul44(ts->mVelocity, ts->lastTcw, pp.Tcw_motion);
       else memcpy(pp.Tcw_motion, ts->lastTcw, sizeof(float) * 16);
       pp.fx = c.fx; pp.fy = c.fy; pp.cx = c.cx; pp.cy = c.cy;
+      // while the RANSAC kernels run: stage and queue the window solve of the previous frame
+      ts->ba_deferred_rc = VIDO_OK;
+      ctx->idle_work = [ctx, ts]() { ts->ba_deferred_rc = ba_flush_deferred(ctx); };
       int rc = pnp_init_model_host(ctx, &pp);
+      if (ctx->idle_work) { ctx->idle_work = nullptr; ts->ba_deferred_rc = ba_flush_deferred(ctx); }
       if (rc) return rc;
+      if (ts->ba_deferred_rc) return ts->ba_deferred_rc;
       std::vector<int> TM(ids.begin(), ids.begin() + pp.n_inliers);
       memcpy(curTcw, pp.Tcw_out, sizeof curTcw);
       double t1 = now_ms();
@@ -1153,8 +1181,14 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
       memcpy(po.Tcw_last, ts->lastTcw, sizeof curTcw);
       po.fx = c.fx; po.fy = c.fy; po.cx = c.cx; po.cy = c.cy;
       po.flow_out = fo.data(); po.inlier = inl.data();
+      // while the pose optimisation runs: retire the older queued window solve (its results go back into the Map)
+      ctx->idle_work = [ctx, ts]() {
+        while (ts->ba_nq > 1 && ts->ba_deferred_rc == VIDO_OK) { ts->ba_deferred_rc = ba_finish(ctx); ba_writeback_rest(ctx); }
+      };
       rc = po_flow2_host(ctx, &po, 1, nullptr);
+      ctx->idle_work = nullptr;
       if (rc) return rc;
+      if (ts->ba_deferred_rc) return ts->ba_deferred_rc;
       memcpy(curTcw, po.Tcw_out, sizeof curTcw);
       if (n >= 3) {
         for (int i = 0; i < n; i++) {
@@ -1312,17 +1346,11 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
   memcpy(Tcw_out, curTcw, sizeof(float) * 16);
   double t4 = now_ms();
   const int window = ts->f_id < c.window_size ? ts->f_id : c.window_size;
-  // This frame's window is staged AND queued on the BA stream while the previous frame's window is still being solved: what
-  // the two share comes from the previous output block on the device.  Only then are the previous results awaited and
-  // written back into the Map -- with the next solve already enqueued right behind it.
-  int rc = skipped ? VIDO_OK : ba_stage(ctx, window, st);
-  if (rc) return rc;
-  const bool queued_behind = ts->ba_staged && ts->ba_nq == 1;
-  if (queued_behind) rc = ba_go(ctx);
-  if (rc) return rc;
-  while (ts->ba_nq > (queued_behind ? 1 : 0)) { rc = ba_finish(ctx); if (rc) return rc; }
-  if (!queued_behind) rc = ba_go(ctx);
-  ba_writeback_rest(ctx);
+  // The window of this frame is staged and queued during the next frame's camera PnP (ba_flush_deferred): it chains to the
+  // solve in flight on the device, and the host work disappears behind kernels that had to be waited for anyway.
+  int rc = VIDO_OK;
+  if (st) { st->ba_iterations = -1; st->ba_points = 0; st->ba_obs = 0; st->ba_trials = 0; }
+  if (!skipped) { ts->ba_deferred.valid = true; ts->ba_deferred.window = window; ts->ba_deferred.st = st; }
   if (st) st->ms_ba = now_ms() - t4;
   ts->f_id++;
   if (rc) return rc;
@@ -1388,6 +1416,7 @@ int trk_track_chunk(vido_ctx* ctx, const vido_frame_inputs* in, int nframes, flo
   cudaStream_t s = ctx->stream;
   const size_t px = (size_t)c.width * c.height;
   while (ts->ba_nq > 0) { vido_lm_stats ls; ba_collect(ctx, &ts->job[ts->ba_queue[0]].pr, &ls); ts->ba_queue[0] = ts->ba_queue[1]; ts->ba_nq--; }  // left by a failed call
+  ts->ba_deferred.valid = false;   // (a successful call never leaves one behind)
   int done = 0;
   while (done < nframes) {
     const int B = std::min(ts->capB, nframes - done);
@@ -1430,7 +1459,7 @@ int trk_track_chunk(vido_ctx* ctx, const vido_frame_inputs* in, int nframes, flo
     done += B;
   }
   {
-    int rc = VIDO_OK;  // drain: stats and map are final when the call returns
+    int rc = ba_flush_deferred(ctx);  // drain: stats and map are final when the call returns
     while (ts->ba_nq > 0 && rc == VIDO_OK) { rc = ba_finish(ctx); ba_writeback_rest(ctx); }
     return rc;
   }
@@ -1616,7 +1645,8 @@ void fill_problem(FullGraph& G, vido_fba_problem& pr) {
 
 int trk_full_batch(vido_ctx* ctx, vido_lm_stats* stats, int32_t* sizes) {
   TrackState* ts = (TrackState*)ctx->trk;
-  int rc = VIDO_OK;   // window solves left in flight by a failed call
+  int rc = ba_flush_deferred(ctx);   // window solves left by a failed call
+  if (rc) return rc;
   while (ts->ba_nq > 0) { rc = ba_finish(ctx); if (rc) return rc; ba_writeback_rest(ctx); }
   FullGraph G;
   build_full_graph(ts, ctx->cfg, G);
