@@ -191,6 +191,32 @@ int vido_pose_opt_flow2(vido_ctx* ctx, vido_poseopt_problem* problems, int nprob
 
 
 /*
+ * Reprojection-only optimisers of the bJoint == false branch (src/Tracking.cc:1133-1136, 1268-1274):
+ *   kind 0 replaces Optimizer::PoseOptimizationNew    (src/Optimizer.cc:2180-2334): camera pose, Huber sqrt(rp_thres), 100 its
+ *   kind 1 replaces Optimizer::PoseOptimizationObjMot (src/Optimizer.cc:2826-3035): object motion with P = K * Tcw, 200 its
+ * One problem = one SE3 vertex + n reprojection edges, one CTA each, several problems per launch.  pts3d are the back-projected
+ * points of the last frame as the caller computed them (the reference's kind-0 call adds time-seeded depth noise there; that is
+ * the caller's business).  Outliers: chi2 > rp_thres after the optimisation.  Host pointers.
+ */
+typedef struct vido_projopt_problem {
+  int32_t n, kind;
+  const float* obs_xy;   /* [n][2] current keypoints */
+  const float* pts3d;    /* [n][3] */
+  float T_init[16];      /* kind 0: pCurFrame->mTcw; kind 1: inv(Tcw) * mInitModel */
+  float fx, fy, cx, cy;  /* kind 0 */
+  double P[12];          /* kind 1: 3x4 projection, row-major */
+  float rp_thres;        /* 0.01 */
+  int32_t its;           /* 100 / 200 */
+  float T_out[16];
+  int32_t* inlier;       /* [n] (may be NULL) */
+  int32_t n_inliers;
+} vido_projopt_problem;
+void vido_projopt_default_params(vido_projopt_problem* p, int kind);
+/* stats: NULL or nproblems entries */
+int vido_pose_opt_proj(vido_ctx* ctx, vido_projopt_problem* problems, int nproblems, vido_lm_stats* stats);
+
+
+/*
  * Initial camera / object model: replaces Tracking::GetInitModelCam (src/Tracking.cc:1914-2028) and GetInitModelObj
  * (:2030-2162): PnP-RANSAC (500 iterations, 0.4 px, confidence 0.98) against the constant-velocity model, the model
  * with more inliers wins.  The RANSAC is the deterministic variant documented in oracle/vido_oracle.h (OpenCV's

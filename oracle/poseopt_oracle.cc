@@ -186,6 +186,116 @@ struct Flow2System {
   }
 };
 
+// ---- one SE3Expmap vertex, n reprojection edges (PoseOptimizationNew / PoseOptimizationObjMot)
+struct ProjSystem {
+  int N = 0, kind = 0;
+  SE3Q T;
+  std::vector<V3> Xw;
+  std::vector<double> obs, err;
+  bool robust = true;
+  double fx, fy, cx, cy, delta, P[12];
+  double H[36], b[6], x[6];
+  std::vector<SE3Q> bk;
+
+  int num_vertices() const { return 1; }
+  void project(const V3& pc, double* uv) const {
+    if (kind == 0) { uv[0] = pc.x / pc.z * fx + cx; uv[1] = pc.y / pc.z * fy + cy; return; }
+    const double m1 = P[0] * pc.x + P[1] * pc.y + P[2] * pc.z + P[3], m2 = P[4] * pc.x + P[5] * pc.y + P[6] * pc.z + P[7],
+                 m3 = P[8] * pc.x + P[9] * pc.y + P[10] * pc.z + P[11];
+    const double invm3 = 1.0 / m3;
+    uv[0] = m1 * invm3; uv[1] = m2 * invm3;
+  }
+  void edge_error(int i, double* e) const {
+    double uv[2];
+    project(map_point(T, Xw[i]), uv);
+    e[0] = obs[2 * i] - uv[0]; e[1] = obs[2 * i + 1] - uv[1];
+  }
+  void compute_errors() { for (int i = 0; i < N; i++) edge_error(i, &err[2 * i]); }
+  double robust_chi2() const {
+    double chi = 0, rho[3];
+    for (int i = 0; i < N; i++) {
+      const double c = err[2 * i] * err[2 * i] + err[2 * i + 1] * err[2 * i + 1];
+      if (robust) { huber(c, delta, rho); chi += rho[0]; } else chi += c;
+    }
+    return chi;
+  }
+  void jacobian(int i, double J[2][6]) const {
+    const V3 pc = map_point(T, Xw[i]);
+    const double x = pc.x, y = pc.y, z = pc.z;
+    if (kind == 0) {
+      const double invz = 1.0 / z, invz_2 = invz * invz;
+      J[0][0] = x * y * invz_2 * fx; J[0][1] = -(1 + (x * x * invz_2)) * fx; J[0][2] = y * invz * fx;
+      J[0][3] = -invz * fx;          J[0][4] = 0;                            J[0][5] = x * invz_2 * fx;
+      J[1][0] = (1 + y * y * invz_2) * fy; J[1][1] = -x * y * invz_2 * fy;   J[1][2] = -x * invz * fy;
+      J[1][3] = 0;                   J[1][4] = -invz * fy;                   J[1][5] = y * invz_2 * fy;
+      return;
+    }
+    const double m1 = P[0] * x + P[1] * y + P[2] * z + P[3], m2 = P[4] * x + P[5] * y + P[6] * z + P[7],
+                 m3 = P[8] * x + P[9] * y + P[10] * z + P[11];
+    const double invm3 = 1.0 / m3, invm3_2 = invm3 * invm3;
+    double t[2][3];
+    for (int c = 0; c < 3; c++) {
+      t[0][c] = invm3_2 * (P[c] * m3 - P[8 + c] * m1);
+      t[1][c] = invm3_2 * (P[4 + c] * m3 - P[8 + c] * m2);
+    }
+    for (int r = 0; r < 2; r++) {
+      J[r][0] = -1.0 * (y * t[r][2] - z * t[r][1]);
+      J[r][1] = -1.0 * (z * t[r][0] - x * t[r][2]);
+      J[r][2] = -1.0 * (x * t[r][1] - y * t[r][0]);
+      J[r][3] = -1.0 * t[r][0]; J[r][4] = -1.0 * t[r][1]; J[r][5] = -1.0 * t[r][2];
+    }
+  }
+  void build_system() {
+    memset(H, 0, sizeof H);
+    memset(b, 0, sizeof b);
+    double rho[3];
+    for (int i = 0; i < N; i++) {
+      double J[2][6];
+      jacobian(i, J);
+      const double* e = &err[2 * i];
+      double w = 1.0;
+      if (robust) { huber(e[0] * e[0] + e[1] * e[1], delta, rho); w = rho[1]; }
+      for (int r = 0; r < 6; r++) {
+        b[r] += -w * (J[0][r] * e[0] + J[1][r] * e[1]);
+        for (int c = 0; c < 6; c++) H[6 * r + c] += w * (J[0][r] * J[0][c] + J[1][r] * J[1][c]);
+      }
+    }
+  }
+  double max_diag() const { double m = 0; for (int r = 0; r < 6; r++) m = std::max(m, std::fabs(H[7 * r])); return m; }
+  bool solve(double lambda) {
+    double S[36], L[36] = {0}, D[6], y[6];
+    memcpy(S, H, sizeof S);
+    for (int r = 0; r < 6; r++) S[7 * r] += lambda;
+    for (int j = 0; j < 6; j++) {
+      double d = S[7 * j];
+      for (int k = 0; k < j; k++) d -= L[6 * j + k] * L[6 * j + k] * D[k];
+      if (!(d > 0)) return false;   // x keeps its previous content
+      D[j] = d; L[7 * j] = 1;
+      for (int i = j + 1; i < 6; i++) {
+        double s = S[6 * i + j];
+        for (int k = 0; k < j; k++) s -= L[6 * i + k] * L[6 * j + k] * D[k];
+        L[6 * i + j] = s / d;
+      }
+    }
+    for (int i = 0; i < 6; i++) { double s = b[i]; for (int k = 0; k < i; k++) s -= L[6 * i + k] * y[k]; y[i] = s; }
+    for (int i = 0; i < 6; i++) y[i] /= D[i];
+    for (int i = 5; i >= 0; i--) { double s = y[i]; for (int k = i + 1; k < 6; k++) s -= L[6 * k + i] * x[k]; x[i] = s; }
+    return true;
+  }
+  void update() {
+    Quat dq; V3 dt;
+    se3_exp(x, dq, dt);
+    SE3Q n;
+    n.t = dt + quat_rotate(dq, T.t);
+    n.q = quat_normalized(quat_mul(dq, T.q));
+    T = n;
+  }
+  void push() { bk.push_back(T); }
+  void pop() { T = bk.back(); bk.pop_back(); }
+  void discard_top() { bk.pop_back(); }
+  double compute_scale(double lambda) const { double s = 0; for (int j = 0; j < 6; j++) s += x[j] * (lambda * x[j] + b[j]); return s; }
+};
+
 static SE3Q se3q_from_f32(const float* T) {
   M3 R = {{T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]}};
   return {quat_normalized(quat_from_R(R)), {T[3], T[7], T[11]}};
@@ -278,6 +388,51 @@ int vo_poseopt_flow2cam(vo_poseopt_problem* p, vo_lm_stats* stats) {
     if (p->inlier) p->inlier[i] = (N >= 3) ? (S.level[i] == 0) : 1;
   }
   return (N >= 3) ? N - nBad : 0;
+}
+
+void vo_projopt_default_params(vo_projopt_problem* p, int kind) {
+  p->kind = kind; p->rp_thres = 0.01f; p->its = kind == 0 ? 100 : 200;
+}
+
+int vo_pose_opt_proj(vo_projopt_problem* p, vo_lm_stats* stats) {
+  const int N = p->n;
+  if (N < 3) {  // "if(nInitialCorrespondences<3) return" -- kind 0 leaves the pose, kind 1 returns identity
+    if (p->kind == 0) memcpy(p->T_out, p->T_init, sizeof(float) * 16);
+    else { memset(p->T_out, 0, sizeof(float) * 16); p->T_out[0] = p->T_out[5] = p->T_out[10] = p->T_out[15] = 1.f; }
+    for (int i = 0; i < N; i++) if (p->inlier) p->inlier[i] = 1;
+    p->n_inliers = 0;
+    if (stats) { stats->iterations = -1; stats->n_records = 0; stats->total_trials = 0; }
+    return 0;
+  }
+  ProjSystem S;
+  S.N = N; S.kind = p->kind;
+  S.fx = p->fx; S.fy = p->fy; S.cx = p->cx; S.cy = p->cy;
+  memcpy(S.P, p->P, sizeof S.P);
+  S.robust = p->kind == 0;
+  S.delta = (double)sqrtf(p->rp_thres);
+  S.Xw.resize(N); S.obs.resize(2 * (size_t)N); S.err.assign(2 * (size_t)N, 0.0);
+  for (int i = 0; i < N; i++) {
+    S.Xw[i] = {p->pts3d[3 * i], p->pts3d[3 * i + 1], p->pts3d[3 * i + 2]};
+    S.obs[2 * i] = p->obs_xy[2 * i]; S.obs[2 * i + 1] = p->obs_xy[2 * i + 1];
+  }
+  memset(S.x, 0, sizeof S.x);
+  S.T = se3q_from_f32(p->T_init);
+  lm_optimize(S, p->its, -1.0, -1.0, stats);
+  int nBad = 0;
+  for (int i = 0; i < N; i++) {
+    const float chi2 = (float)(S.err[2 * i] * S.err[2 * i] + S.err[2 * i + 1] * S.err[2 * i + 1]);   // errors of the last evaluation
+    const bool out = chi2 > p->rp_thres;
+    if (p->inlier) p->inlier[i] = out ? 0 : 1;
+    nBad += out ? 1 : 0;
+  }
+  M3 R = quat_to_R(S.T.q);
+  float* o = p->T_out;
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) o[4 * r + c] = (float)R.m[3 * r + c];
+  o[3] = (float)S.T.t.x; o[7] = (float)S.T.t.y; o[11] = (float)S.T.t.z;
+  o[12] = o[13] = o[14] = 0.f; o[15] = 1.f;
+  p->n_inliers = N - nBad;
+  return p->n_inliers;
 }
 
 }  // extern "C"

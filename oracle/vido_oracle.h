@@ -175,6 +175,32 @@ void vo_poseopt_default_params(vo_poseopt_problem* p);
 int vo_poseopt_flow2cam(vo_poseopt_problem* p, vo_lm_stats* stats /* [rounds] or NULL */);
 
 /*
+ * Reprojection-only optimisers of the bJoint == false branch (src/Tracking.cc:1133-1136, 1268-1274):
+ *   kind 0  Optimizer::PoseOptimizationNew     (src/Optimizer.cc:2180-2334): camera pose, EdgeSE3ProjectXYZOnlyPose
+ *           (g2o/types/types_six_dof_expmap.cpp:266-296), information I, Huber delta = sqrt(rp_thres), optimize(100)
+ *   kind 1  Optimizer::PoseOptimizationObjMot  (src/Optimizer.cc:2826-3035): object motion, EdgeSE3ProjectXYZOnlyObjMotion
+ *           (types_six_dof_expmap.cpp:394-441) with P = K * Tcw, no kernel, optimize(200)
+ * One VertexSE3Expmap, n edges, one round; an edge whose chi2 exceeds rp_thres (0.01) afterwards is an outlier.  The
+ * reference feeds kind 0 with depth-noised points (Frame::UnprojectStereoStat(i, 1), time-seeded RNG): pts3d is whatever
+ * the caller back-projected, the noise is not part of this function.
+ */
+typedef struct vo_projopt_problem {
+  int32_t n, kind;
+  const float* obs_xy;   /* [n][2] current keypoints */
+  const float* pts3d;    /* [n][3] Xw (float, as stored in the edge from a float cv::Mat) */
+  float T_init[16];      /* vertex estimate at the start (kind 0: pCurFrame->mTcw; kind 1: inv(Tcw) * mInitModel) */
+  float fx, fy, cx, cy;  /* kind 0 */
+  double P[12];          /* kind 1: 3x4 projection K * Tcw (row-major) */
+  float rp_thres;        /* 0.01 */
+  int32_t its;           /* 100 / 200 */
+  float T_out[16];
+  int32_t* inlier;       /* [n] */
+  int32_t n_inliers;
+} vo_projopt_problem;
+void vo_projopt_default_params(vo_projopt_problem* p, int kind);
+int vo_pose_opt_proj(vo_projopt_problem* p, vo_lm_stats* stats);
+
+/*
  * Initial camera model of Tracking::GetInitModelCam (src/Tracking.cc:1914-2028): PnP-RANSAC over the previous frame's
  * 3-D points and the current 2-D points versus the constant-velocity model, the one with more inliers wins.
  * cv::solvePnPRansac(500, 0.4 px, 0.98, SOLVEPNP_P3P) lives in un-vendored OpenCV and is not reproducible bit for

@@ -506,3 +506,36 @@ def inertial_edge_information(C15):
     out = np.zeros((9, 9))
     lib().vo_inertial_edge_information(_p(Cm), _p(out))
     return out
+
+
+# ---------------------------------------------------------------- reprojection-only optimisers (bJoint == false)
+class ProjOptProblem(C.Structure):
+    _fields_ = [("n", C.c_int32), ("kind", C.c_int32), ("obs_xy", C.c_void_p), ("pts3d", C.c_void_p),
+                ("T_init", C.c_float * 16), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("P", C.c_double * 12), ("rp_thres", C.c_float), ("its", C.c_int32), ("T_out", C.c_float * 16),
+                ("inlier", C.c_void_p), ("n_inliers", C.c_int32)]
+
+
+def fill_projopt(pr, kind, obs_xy, pts3d, T_init, K=None, P=None):
+    keep = [np.ascontiguousarray(obs_xy, np.float32).reshape(-1, 2), np.ascontiguousarray(pts3d, np.float32).reshape(-1, 3)]
+    keep.append(np.zeros(len(keep[0]), np.int32))
+    pr.n = len(keep[0])
+    pr.obs_xy, pr.pts3d, pr.inlier = _p(keep[0]).value, _p(keep[1]).value, _p(keep[2]).value
+    pr.T_init[:] = [float(v) for v in np.asarray(T_init, np.float32).reshape(16)]
+    if K is not None:
+        pr.fx, pr.fy, pr.cx, pr.cy = K
+    if P is not None:
+        pr.P[:] = [float(v) for v in np.asarray(P, np.float64).reshape(12)]
+    return keep
+
+
+def pose_opt_proj(kind, obs_xy, pts3d, T_init, K=None, P=None, **params):
+    """kind 0: Optimizer::PoseOptimizationNew, kind 1: PoseOptimizationObjMot.  Returns (T 4x4, inlier flags, LmStats)"""
+    pr = ProjOptProblem()
+    lib().vo_projopt_default_params(C.byref(pr), kind)
+    keep = fill_projopt(pr, kind, obs_xy, pts3d, T_init, K, P)
+    for k, v in params.items():
+        setattr(pr, k, v)
+    st = LmStats()
+    lib().vo_pose_opt_proj(C.byref(pr), C.byref(st))
+    return np.array(pr.T_out[:], np.float32).reshape(4, 4), keep[2].copy(), st

@@ -86,6 +86,14 @@ FBA_F32 = ("se3", "points", "e6_meas", "obs_xyz")
 FBA_WIDTH = dict(se3=16, points=3, e6_meas=16, obs_xyz=3)
 
 
+class ProjOptProblem(C.Structure):
+    """vido_projopt_problem (include/vido_b200.h)"""
+    _fields_ = [("n", C.c_int32), ("kind", C.c_int32), ("obs_xy", C.c_void_p), ("pts3d", C.c_void_p),
+                ("T_init", C.c_float * 16), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("P", C.c_double * 12), ("rp_thres", C.c_float), ("its", C.c_int32), ("T_out", C.c_float * 16),
+                ("inlier", C.c_void_p), ("n_inliers", C.c_int32)]
+
+
 class InertialProblem(C.Structure):
     """vido_inertial_problem (include/vido_b200.h)"""
     _fields_ = [("n_frames", C.c_int32), ("its", C.c_int32), ("Rwb", C.c_void_p), ("twb", C.c_void_p), ("velocity", C.c_void_p),
@@ -170,6 +178,8 @@ def load_library():
     lib.vido_map_get_poses_rf.argtypes = [vp, vp, C.c_int]
     lib.vido_map_get_objects_rf.argtypes = [vp, C.c_int, vp, C.c_int]
     lib.vido_map_export_full_graph.argtypes = [vp] + [vp] * 14
+    lib.vido_projopt_default_params.argtypes = [C.POINTER(ProjOptProblem), C.c_int]
+    lib.vido_pose_opt_proj.argtypes = [vp, C.POINTER(ProjOptProblem), C.c_int, C.POINTER(LmStats)]
     lib.vido_inertial_default_params.argtypes = [C.POINTER(InertialProblem)]
     lib.vido_inertial_opt.argtypes = [vp, C.POINTER(InertialProblem), C.POINTER(LmStats)]
     lib.vido_pnp_default_params.argtypes = [C.POINTER(PnpProblem)]
@@ -463,6 +473,33 @@ class Context:
                  tern_p2=np.zeros(nte, np.int32), tern_h=np.zeros(nte, np.int32))
         self._check(self.lib.vido_map_export_full_graph(self.h, _ptr(sizes), *[_ptr(g[k]) if g[k].size else None for k in FBA_KEYS]))
         return g, npo
+
+    def pose_opt_proj(self, problems):
+        """problems: list of dicts(kind, obs_xy, pts3d, T_init, K=(fx,fy,cx,cy) | P=3x4, + optional rp_thres / its).
+        One launch for all.  Returns [(T 4x4, inlier flags, LmStats)]"""
+        n = len(problems)
+        arr = (ProjOptProblem * n)()
+        st = (LmStats * n)()
+        keep = []
+        for k, d in enumerate(problems):
+            pr = arr[k]
+            self.lib.vido_projopt_default_params(C.byref(pr), int(d["kind"]))
+            obs = np.ascontiguousarray(d["obs_xy"], np.float32).reshape(-1, 2)
+            pts = np.ascontiguousarray(d["pts3d"], np.float32).reshape(-1, 3)
+            inl = np.zeros(len(obs), np.int32)
+            keep.append((obs, pts, inl))
+            pr.n = len(obs)
+            pr.obs_xy, pr.pts3d, pr.inlier = _ptr(obs).value, _ptr(pts).value, _ptr(inl).value
+            pr.T_init[:] = [float(v) for v in np.asarray(d["T_init"], np.float32).reshape(16)]
+            if d.get("K") is not None:
+                pr.fx, pr.fy, pr.cx, pr.cy = d["K"]
+            if d.get("P") is not None:
+                pr.P[:] = [float(v) for v in np.asarray(d["P"], np.float64).reshape(12)]
+            for key in ("rp_thres", "its"):
+                if key in d:
+                    setattr(pr, key, d[key])
+        self._check(self.lib.vido_pose_opt_proj(self.h, arr, n, st))
+        return [(np.array(arr[k].T_out[:], np.float32).reshape(4, 4), keep[k][2].copy(), st[k]) for k in range(n)]
 
     def inertial_opt(self, Rwb, twb, vel, preint, bias_lin, Rwg, scale=1.0, bg=(0, 0, 0), ba=(0, 0, 0), **params):
         """Optimizer::InertialOptimization; returns dict(velocity, Rwg, scale, bg, ba, stats)"""

@@ -343,6 +343,12 @@ int vido_map_export_full_graph(vido_ctx* ctx, int32_t* sizes, float* se3, float*
                                tern_p2, tern_h);
 }
 
+void vido_projopt_default_params(vido_projopt_problem* p, int kind) { if (p) projopt_default_params(p, kind); }
+int vido_pose_opt_proj(vido_ctx* ctx, vido_projopt_problem* problems, int nproblems, vido_lm_stats* stats) {
+  if (!ctx || !problems || nproblems < 0) return VIDO_ERR_ARG;
+  return projopt_host(ctx, problems, nproblems, stats);
+}
+
 void vido_inertial_default_params(vido_inertial_problem* p) { if (p) inertial_default_params(p); }
 int vido_inertial_opt(vido_ctx* ctx, vido_inertial_problem* p, vido_lm_stats* stats) {
   if (!ctx || !p) return VIDO_ERR_ARG;

@@ -181,6 +181,10 @@ int trk_export_full_graph(vido_ctx* ctx, int32_t* sizes, float* se3, float* poin
 void vido_fba_default_params_impl(vido_fba_problem* p);
 int fba_solve_host(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* st);
 
+// projopt_kernels.cu
+void projopt_default_params(vido_projopt_problem* p, int kind);
+int projopt_host(vido_ctx* ctx, vido_projopt_problem* prs, int nproblems, vido_lm_stats* stats);
+
 // inertial_kernels.cu
 void inertial_default_params(vido_inertial_problem* p);
 int inertial_opt_host(vido_ctx* ctx, vido_inertial_problem* p, vido_lm_stats* st);
