@@ -54,6 +54,9 @@ typedef struct vido_config {
   int32_t device;                 /* CUDA device ordinal */
   float sf_mg_thres, sf_ds_thres; /* SFMgThres / SFDsThres: scene-flow magnitude and distribution thresholds of
                                      Tracking::DynObjTracking (src/Tracking.cc:159-160, 1746-1783) */
+  int32_t b_joint;                /* Tracking::bJoint (never initialised in the reference, include/Tracking.h:184; default 1):
+                                     1 = PoseOptimizationFlow2Cam / Flow2, 0 = PoseOptimizationNew / ObjMot (src/Tracking.cc:
+                                     1133-1136, 1268-1274) without the time-seeded depth noise of that branch */
 } vido_config;
 
 void vido_default_config(vido_config* cfg);  /* reference's kitti_config.yaml values at 1242x375 */

@@ -328,35 +328,66 @@ struct Tracker {
         cur->vnObjInlierID[i] = in_ids;
         continue;
       }
-      // ---- PoseOptimizationFlow2
-      const int n = (int)in_ids.size();
-      std::vector<float> obs(2 * (size_t)n), fl(2 * (size_t)n), dep(n), fo(2 * (size_t)n);
-      std::vector<int> inl(n);
-      for (int k = 0; k < n; k++) {
-        const int id = in_ids[k];
-        obs[2 * k] = last->mvObjKeys[id].x; obs[2 * k + 1] = last->mvObjKeys[id].y;
-        fl[2 * k] = last->mvObjFlowNext[id].x; fl[2 * k + 1] = last->mvObjFlowNext[id].y;
-        dep[k] = last->mvObjDepth[id];
-      }
-      vo_poseopt_problem po;
-      memset(&po, 0, sizeof po);
-      vo_poseopt_default_params(&po);
-      po.n = n; po.obs_xy = obs.data(); po.flow_xy = fl.data(); po.depth = dep.data();
-      memcpy(po.Tcw_init, pp.Tcw_out, sizeof(float) * 16);
-      memcpy(po.Tcw_last, last->Tcw, sizeof(float) * 16);
-      po.fx = cfg.fx; po.fy = cfg.fy; po.cx = cfg.cx; po.cy = cfg.cy;
-      po.flow_out = fo.data(); po.inlier = inl.data();
-      po.info_prior = 0.5f; po.rounds = 1; po.its = 200;
-      vo_poseopt_flow2cam(&po, nullptr);
-      mul44(Twc, po.Tcw_out, cur->vObjMod[i].data());  // vObjMod = inv(Tcw) * Obj_X
       std::vector<int> InlierID;
-      for (int k = 0; k < n; k++) {
-        const int id = in_ids[k];
-        if (inl[k]) {
-          cur->mvObjKeys[id].x = (float)((double)last->mvObjKeys[id].x + (double)fo[2 * k]);
-          cur->mvObjKeys[id].y = (float)((double)last->mvObjKeys[id].y + (double)fo[2 * k + 1]);
-          InlierID.push_back(id);
-        } else cur->vObjLabel[id] = -1;
+      if (cfg.b_joint) {
+        // ---- PoseOptimizationFlow2
+        const int n = (int)in_ids.size();
+        std::vector<float> obs(2 * (size_t)n), fl(2 * (size_t)n), dep(n), fo(2 * (size_t)n);
+        std::vector<int> inl(n);
+        for (int k = 0; k < n; k++) {
+          const int id = in_ids[k];
+          obs[2 * k] = last->mvObjKeys[id].x; obs[2 * k + 1] = last->mvObjKeys[id].y;
+          fl[2 * k] = last->mvObjFlowNext[id].x; fl[2 * k + 1] = last->mvObjFlowNext[id].y;
+          dep[k] = last->mvObjDepth[id];
+        }
+        vo_poseopt_problem po;
+        memset(&po, 0, sizeof po);
+        vo_poseopt_default_params(&po);
+        po.n = n; po.obs_xy = obs.data(); po.flow_xy = fl.data(); po.depth = dep.data();
+        memcpy(po.Tcw_init, pp.Tcw_out, sizeof(float) * 16);
+        memcpy(po.Tcw_last, last->Tcw, sizeof(float) * 16);
+        po.fx = cfg.fx; po.fy = cfg.fy; po.cx = cfg.cx; po.cy = cfg.cy;
+        po.flow_out = fo.data(); po.inlier = inl.data();
+        po.info_prior = 0.5f; po.rounds = 1; po.its = 200;
+        vo_poseopt_flow2cam(&po, nullptr);
+        mul44(Twc, po.Tcw_out, cur->vObjMod[i].data());  // vObjMod = inv(Tcw) * Obj_X
+        for (int k = 0; k < n; k++) {
+          const int id = in_ids[k];
+          if (inl[k]) {
+            cur->mvObjKeys[id].x = (float)((double)last->mvObjKeys[id].x + (double)fo[2 * k]);
+            cur->mvObjKeys[id].y = (float)((double)last->mvObjKeys[id].y + (double)fo[2 * k + 1]);
+            InlierID.push_back(id);
+          } else cur->vObjLabel[id] = -1;
+        }
+      } else {
+        // ---- PoseOptimizationObjMot (src/Optimizer.cc:2826-3035): world-frame motion H, projection P = K * Tcw
+        const int n = (int)in_ids.size();
+        std::vector<float> obs(2 * (size_t)n), p3(3 * (size_t)n);
+        std::vector<int> inl(n);
+        for (int k = 0; k < n; k++) {
+          const int id = in_ids[k];
+          const P3 xp = to_world(unproject_cam(last->mvObjKeys[id], last->mvObjDepth[id]), Twl);
+          obs[2 * k] = cur->mvObjKeys[id].x; obs[2 * k + 1] = cur->mvObjKeys[id].y;
+          p3[3 * k] = xp.x; p3[3 * k + 1] = xp.y; p3[3 * k + 2] = xp.z;
+        }
+        vo_projopt_problem pj;
+        memset(&pj, 0, sizeof pj);
+        vo_projopt_default_params(&pj, 1);
+        pj.n = n; pj.obs_xy = obs.data(); pj.pts3d = p3.data(); pj.inlier = inl.data();
+        mul44(Twc, pp.Tcw_out, pj.T_init);   // Init = inv(Tcw) * mInitModel
+        const double KK[12] = {cfg.fx, 0, cfg.cx, 0, 0, cfg.fy, cfg.cy, 0, 0, 0, 1, 0};
+        for (int r = 0; r < 3; r++)
+          for (int c = 0; c < 4; c++) {
+            double v = 0;
+            for (int m = 0; m < 4; m++) v += KK[4 * r + m] * (double)cur->Tcw[4 * m + c];
+            pj.P[4 * r + c] = v;
+          }
+        vo_pose_opt_proj(&pj, nullptr);
+        memcpy(cur->vObjMod[i].data(), pj.T_out, sizeof(float) * 16);
+        for (int k = 0; k < n; k++) {
+          if (inl[k]) InlierID.push_back(in_ids[k]);
+          else cur->vObjLabel[in_ids[k]] = -1;
+        }
       }
       cur->vnObjInlierID[i] = InlierID;
     }
@@ -880,34 +911,58 @@ struct Tracker {
         std::vector<int> TM_sub(ids.begin(), ids.begin() + pp.n_inliers);
         memcpy(cur->Tcw, pp.Tcw_out, sizeof(float) * 16);
         double t3 = now_ms();
-        // ---- PoseOptimizationFlow2Cam
-        const int n = (int)TM_sub.size();
-        std::vector<float> obs(2 * (size_t)n), fl(2 * (size_t)n), dep(n), fo(2 * (size_t)n);
-        std::vector<int> inl(n);
-        for (int i = 0; i < n; i++) {
-          const int k = TM_sub[i];
-          obs[2 * i] = last->mvStatKeys[k].x; obs[2 * i + 1] = last->mvStatKeys[k].y;
-          fl[2 * i] = last->mvFlowNext[k].x; fl[2 * i + 1] = last->mvFlowNext[k].y;
-          dep[i] = last->mvStatDepth[k];
-        }
-        vo_poseopt_problem po;
-        memset(&po, 0, sizeof po);
-        vo_poseopt_default_params(&po);
-        po.n = n; po.obs_xy = obs.data(); po.flow_xy = fl.data(); po.depth = dep.data();
-        memcpy(po.Tcw_init, cur->Tcw, sizeof(float) * 16);
-        memcpy(po.Tcw_last, last->Tcw, sizeof(float) * 16);
-        po.fx = cfg.fx; po.fy = cfg.fy; po.cx = cfg.cx; po.cy = cfg.cy;
-        po.flow_out = fo.data(); po.inlier = inl.data();
-        const int ninl = vo_poseopt_flow2cam(&po, nullptr);
-        memcpy(cur->Tcw, po.Tcw_out, sizeof(float) * 16);
-        if (n >= 3) {
+        int ninl = 0;
+        if (cfg.b_joint) {
+          // ---- PoseOptimizationFlow2Cam
+          const int n = (int)TM_sub.size();
+          std::vector<float> obs(2 * (size_t)n), fl(2 * (size_t)n), dep(n), fo(2 * (size_t)n);
+          std::vector<int> inl(n);
           for (int i = 0; i < n; i++) {
-            if (inl[i]) {
-              const int k = TM_sub[i];
-              cur->mvStatKeys[k].x = (float)((double)last->mvStatKeys[k].x + (double)fo[2 * i]);
-              cur->mvStatKeys[k].y = (float)((double)last->mvStatKeys[k].y + (double)fo[2 * i + 1]);
-            } else TM_sub[i] = -1;
+            const int k = TM_sub[i];
+            obs[2 * i] = last->mvStatKeys[k].x; obs[2 * i + 1] = last->mvStatKeys[k].y;
+            fl[2 * i] = last->mvFlowNext[k].x; fl[2 * i + 1] = last->mvFlowNext[k].y;
+            dep[i] = last->mvStatDepth[k];
           }
+          vo_poseopt_problem po;
+          memset(&po, 0, sizeof po);
+          vo_poseopt_default_params(&po);
+          po.n = n; po.obs_xy = obs.data(); po.flow_xy = fl.data(); po.depth = dep.data();
+          memcpy(po.Tcw_init, cur->Tcw, sizeof(float) * 16);
+          memcpy(po.Tcw_last, last->Tcw, sizeof(float) * 16);
+          po.fx = cfg.fx; po.fy = cfg.fy; po.cx = cfg.cx; po.cy = cfg.cy;
+          po.flow_out = fo.data(); po.inlier = inl.data();
+          ninl = vo_poseopt_flow2cam(&po, nullptr);
+          memcpy(cur->Tcw, po.Tcw_out, sizeof(float) * 16);
+          if (n >= 3) {
+            for (int i = 0; i < n; i++) {
+              if (inl[i]) {
+                const int k = TM_sub[i];
+                cur->mvStatKeys[k].x = (float)((double)last->mvStatKeys[k].x + (double)fo[2 * i]);
+                cur->mvStatKeys[k].y = (float)((double)last->mvStatKeys[k].y + (double)fo[2 * i + 1]);
+              } else TM_sub[i] = -1;
+            }
+          }
+        } else {
+          // ---- PoseOptimizationNew (src/Optimizer.cc:2180-2334): reprojection of the last frame's world points (no depth noise)
+          const int n = (int)TM_sub.size();
+          std::vector<float> obs(2 * (size_t)n), p3(3 * (size_t)n);
+          std::vector<int> inl(n);
+          for (int i = 0; i < n; i++) {
+            const int k = TM_sub[i];
+            obs[2 * i] = cur->mvStatKeys[k].x; obs[2 * i + 1] = cur->mvStatKeys[k].y;
+            p3[3 * i] = p3d[3 * k]; p3[3 * i + 1] = p3d[3 * k + 1]; p3[3 * i + 2] = p3d[3 * k + 2];
+          }
+          vo_projopt_problem pj;
+          memset(&pj, 0, sizeof pj);
+          vo_projopt_default_params(&pj, 0);
+          pj.n = n; pj.obs_xy = obs.data(); pj.pts3d = p3.data(); pj.inlier = inl.data();
+          memcpy(pj.T_init, cur->Tcw, sizeof(float) * 16);
+          pj.fx = cfg.fx; pj.fy = cfg.fy; pj.cx = cfg.cx; pj.cy = cfg.cy;
+          ninl = vo_pose_opt_proj(&pj, nullptr);
+          memcpy(cur->Tcw, pj.T_out, sizeof(float) * 16);
+          if (n >= 3)
+            for (int i = 0; i < n; i++)
+              if (!inl[i]) TM_sub[i] = -1;
         }
         double t4 = now_ms();
         // ---- motion model (src/Tracking.cc:1142-1148)

@@ -237,6 +237,9 @@ typedef struct vo_track_config {
   int32_t rebuild_tracklets; /* 1: rebuild all tracklets from frame 0 every frame like the reference (O(T)/frame) */
   int32_t max_track_obj;     /* MaxTrackPointOBJ (500) */
   float sf_mg_thres, sf_ds_thres; /* SFMgThres 0.12 / SFDsThres 0.3 (src/Tracking.cc:159-160) */
+  int32_t b_joint;           /* Tracking::bJoint (uninitialised in the reference): 1 = joint flow + pose optimisers
+                                (PoseOptimizationFlow2Cam / Flow2), 0 = reprojection-only (PoseOptimizationNew / ObjMot, without
+                                the time-seeded depth noise the reference adds in that branch) */
 } vo_track_config;
 typedef struct vo_track_stats {
   double ms_orb, ms_assoc, ms_init, ms_poseopt, ms_renew, ms_ba;

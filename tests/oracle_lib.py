@@ -326,7 +326,7 @@ class TrackConfig(C.Structure):
                 ("cy", C.c_float), ("bf", C.c_float), ("choose_data", C.c_int32), ("depth_map_factor", C.c_float),
                 ("th_depth_bg", C.c_float), ("th_depth_obj", C.c_float), ("max_track_bg", C.c_int32),
                 ("window_size", C.c_int32), ("orb", OrbParams), ("rebuild_tracklets", C.c_int32),
-                ("max_track_obj", C.c_int32), ("sf_mg_thres", C.c_float), ("sf_ds_thres", C.c_float)]
+                ("max_track_obj", C.c_int32), ("sf_mg_thres", C.c_float), ("sf_ds_thres", C.c_float), ("b_joint", C.c_int32)]
 
 
 class TrackStats(C.Structure):
@@ -343,7 +343,7 @@ class TrackStats(C.Structure):
 
 
 def track_config(cam, nfeatures=2500, window=20, max_track_bg=1000, rebuild=1, choose_data=2, depth_map_factor=256.0,
-                 th_depth_bg=5000.0, th_depth_obj=25.0, max_track_obj=500, sf_mg_thres=0.12, sf_ds_thres=0.3):
+                 th_depth_bg=5000.0, th_depth_obj=25.0, max_track_obj=500, sf_mg_thres=0.12, sf_ds_thres=0.3, b_joint=1):
     c = TrackConfig()
     c.width, c.height = cam["width"], cam["height"]
     c.fx, c.fy, c.cx, c.cy, c.bf = cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["bf"]
@@ -352,6 +352,7 @@ def track_config(cam, nfeatures=2500, window=20, max_track_bg=1000, rebuild=1, c
     c.orb = default_orb_params(nfeatures)
     c.rebuild_tracklets = rebuild
     c.max_track_obj, c.sf_mg_thres, c.sf_ds_thres = max_track_obj, sf_mg_thres, sf_ds_thres
+    c.b_joint = b_joint
     return c
 
 

@@ -11,13 +11,13 @@ REL_TOL = 1e-4
 CAM = synth.KITTI
 
 
-def _both(pkg, n, batch, **kw):
+def _both(pkg, n, batch, b_joint=1, **kw):
     sc = synth.Scene(cam=CAM, seed=1234, flow_noise=0.1, depth_noise=0.01, n_objects=5, **kw)
     frames = [sc.frame(k) for k in range(n)]
-    otr = ol.OracleTracker(ol.track_config(CAM))
+    otr = ol.OracleTracker(ol.track_config(CAM, b_joint=b_joint))
     ref = [otr.track(f["gray"].numpy(), f["depth_in"].numpy(), f["flow"].numpy(), f["mask"].numpy()) for f in frames]
     ctx = pkg.Context(pkg.default_config(width=CAM["width"], height=CAM["height"], fx=CAM["fx"], fy=CAM["fy"], cx=CAM["cx"],
-                                         cy=CAM["cy"], bf=CAM["bf"], max_batch=batch))
+                                         cy=CAM["cy"], bf=CAM["bf"], max_batch=batch, b_joint=b_joint))
     T, st = ctx.track_frames([dict(image=f["gray"].numpy(), depth=f["depth_in"].numpy(), flow=f["flow"].numpy(),
                                    mask=f["mask"].numpy().copy()) for f in frames])
     return otr, ref, ctx, T, st
@@ -59,5 +59,14 @@ def test_lost_mask_recovered_like_oracle(pkg):
     n = 6
     otr, ref, ctx, T, st = _both(pkg, n, 3, drop_mask=((3, 2), (4, 5)))
     assert [s["n_masks_recovered"] for s in st] == [0, 0, 0, 1, 1, 0]
+    _compare(otr, ref, ctx, T, st, n)
+    otr.close(); ctx.close()
+
+
+def test_reprojection_only_branch_matches_oracle(pkg):
+    """bJoint = false (src/Tracking.cc:1133-1136, 1268-1274): PoseOptimizationNew for the camera, PoseOptimizationObjMot per object"""
+    n = 8
+    otr, ref, ctx, T, st = _both(pkg, n, 4, b_joint=0)
+    assert sum(s["n_objects_ok"] for s in st) >= 5 * (n - 2)
     _compare(otr, ref, ctx, T, st, n)
     otr.close(); ctx.close()

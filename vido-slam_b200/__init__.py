@@ -23,7 +23,8 @@ class VidoConfig(C.Structure):
                 ("max_track_bg", C.c_int32), ("max_track_obj", C.c_int32), ("window_size", C.c_int32),
                 ("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
                 ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32), ("rgb", C.c_int32),
-                ("max_batch", C.c_int32), ("device", C.c_int32), ("sf_mg_thres", C.c_float), ("sf_ds_thres", C.c_float)]
+                ("max_batch", C.c_int32), ("device", C.c_int32), ("sf_mg_thres", C.c_float), ("sf_ds_thres", C.c_float),
+                ("b_joint", C.c_int32)]
 
 
 class LmRecord(C.Structure):

@@ -21,6 +21,7 @@ void vido_default_config(vido_config* c) {
   c->th_depth_bg = 5000.f; c->th_depth_obj = 25.f;
   c->max_track_bg = 1000; c->max_track_obj = 500;
   c->sf_mg_thres = 0.12f; c->sf_ds_thres = 0.3f;
+  c->b_joint = 1;
   c->window_size = 20;
   c->nfeatures = 2500; c->scale_factor = 1.2f; c->nlevels = 8; c->ini_th_fast = 20; c->min_th_fast = 7;
   c->rgb = 0;

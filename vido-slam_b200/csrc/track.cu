@@ -740,6 +740,51 @@ static int dyn_object_motions(vido_ctx* ctx, const float* curTcw, const std::vec
     memcpy(J.init, pp.Tcw_out, sizeof J.init);
     jobs.push_back(std::move(J));
   }
+  if (!c.b_joint) {
+    // ---- PoseOptimizationObjMot (Optimizer.cc:2826-3035) for all objects of the frame in one launch: world-frame motion H
+    //      (initialised with inv(Tcw) * mInitModel), reprojection through P = K * Tcw, no refinement of the keypoints
+    std::vector<vido_projopt_problem> pj(jobs.size());
+    std::vector<std::vector<float>> obs(jobs.size()), p3(jobs.size());
+    double P[12];
+    const double KK[12] = {c.fx, 0, c.cx, 0, 0, c.fy, c.cy, 0, 0, 0, 1, 0};
+    for (int r = 0; r < 3; r++)
+      for (int q = 0; q < 4; q++) {
+        double v = 0;
+        for (int m = 0; m < 4; m++) v += KK[4 * r + m] * (double)curTcw[4 * m + q];
+        P[4 * r + q] = v;
+      }
+    for (size_t k = 0; k < jobs.size(); k++) {
+      Job& J = jobs[k];
+      const size_t n = J.ids.size();
+      obs[k].resize(2 * n); p3[k].resize(3 * n);
+      for (size_t q = 0; q < n; q++) {
+        const int id = J.ids[q];
+        obs[k][2 * q] = D.keys[2 * id]; obs[k][2 * q + 1] = D.keys[2 * id + 1];
+        px_to_world(c, ts->lo_keys[2 * id], ts->lo_keys[2 * id + 1], ts->lo_depth[id], Twl, &p3[k][3 * q]);
+      }
+      vido_projopt_problem& pr = pj[k];
+      memset(&pr, 0, sizeof pr);
+      vido_projopt_default_params(&pr, 1);
+      pr.n = (int)n; pr.obs_xy = obs[k].data(); pr.pts3d = p3[k].data(); pr.inlier = J.inl.data();
+      mul44(Twc, J.init, pr.T_init);
+      memcpy(pr.P, P, sizeof P);
+    }
+    if (!jobs.empty()) {
+      const int rc = projopt_host(ctx, pj.data(), (int)jobs.size(), nullptr);
+      if (rc) return rc;
+    }
+    for (size_t k = 0; k < jobs.size(); k++) {
+      Job& J = jobs[k];
+      memcpy(D.mod[J.obj].data(), pj[k].T_out, sizeof(float) * 16);
+      std::vector<int> InlierID;
+      for (size_t q = 0; q < J.ids.size(); q++) {
+        if (J.inl[q]) InlierID.push_back(J.ids[q]);
+        else D.label[J.ids[q]] = -1;
+      }
+      D.inlier_id[J.obj] = InlierID;
+    }
+    return VIDO_OK;
+  }
   // ---- PoseOptimizationFlow2 for all objects of the frame: one CTA per object, 16 objects per launch
   for (size_t j0 = 0; j0 < jobs.size(); j0 += 16) {
     const int nb = (int)std::min<size_t>(16, jobs.size() - j0);
@@ -1163,41 +1208,69 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
       std::vector<int> TM(ids.begin(), ids.begin() + pp.n_inliers);
       memcpy(curTcw, pp.Tcw_out, sizeof curTcw);
       double t1 = now_ms();
-      // ---- PoseOptimizationFlow2Cam
+      int n_pose_inliers = 0;
       const int n = (int)TM.size();
-      std::vector<float> obs(2 * (size_t)n), fl(2 * (size_t)n), dep(n), fo(2 * (size_t)n);
-      std::vector<int32_t> inl(n);
-      for (int i = 0; i < n; i++) {
-        const int k = TM[i];
-        obs[2 * i] = ts->last_keys[2 * k]; obs[2 * i + 1] = ts->last_keys[2 * k + 1];
-        fl[2 * i] = ts->last_flow[2 * k]; fl[2 * i + 1] = ts->last_flow[2 * k + 1];
-        dep[i] = ts->last_depth[k];
-      }
-      vido_poseopt_problem po;
-      memset(&po, 0, sizeof po);
-      vido_poseopt_default_params(&po);
-      po.n = n; po.obs_xy = obs.data(); po.flow_xy = fl.data(); po.depth = dep.data();
-      memcpy(po.Tcw_init, curTcw, sizeof curTcw);
-      memcpy(po.Tcw_last, ts->lastTcw, sizeof curTcw);
-      po.fx = c.fx; po.fy = c.fy; po.cx = c.cx; po.cy = c.cy;
-      po.flow_out = fo.data(); po.inlier = inl.data();
-      // while the pose optimisation runs: retire the older queued window solve (its results go back into the Map)
-      ctx->idle_work = [ctx, ts]() {
-        while (ts->ba_nq > 1 && ts->ba_deferred_rc == VIDO_OK) { ts->ba_deferred_rc = ba_finish(ctx); ba_writeback_rest(ctx); }
-      };
-      rc = po_flow2_host(ctx, &po, 1, nullptr);
-      ctx->idle_work = nullptr;
-      if (rc) return rc;
-      if (ts->ba_deferred_rc) return ts->ba_deferred_rc;
-      memcpy(curTcw, po.Tcw_out, sizeof curTcw);
-      if (n >= 3) {
+      if (c.b_joint) {
+        // ---- PoseOptimizationFlow2Cam
+        std::vector<float> obs(2 * (size_t)n), fl(2 * (size_t)n), dep(n), fo(2 * (size_t)n);
+        std::vector<int32_t> inl(n);
         for (int i = 0; i < n; i++) {
-          if (inl[i]) {
-            const int k = TM[i];
-            keys[2 * k] = (float)((double)ts->last_keys[2 * k] + (double)fo[2 * i]);
-            keys[2 * k + 1] = (float)((double)ts->last_keys[2 * k + 1] + (double)fo[2 * i + 1]);
-          } else TM[i] = -1;
+          const int k = TM[i];
+          obs[2 * i] = ts->last_keys[2 * k]; obs[2 * i + 1] = ts->last_keys[2 * k + 1];
+          fl[2 * i] = ts->last_flow[2 * k]; fl[2 * i + 1] = ts->last_flow[2 * k + 1];
+          dep[i] = ts->last_depth[k];
         }
+        vido_poseopt_problem po;
+        memset(&po, 0, sizeof po);
+        vido_poseopt_default_params(&po);
+        po.n = n; po.obs_xy = obs.data(); po.flow_xy = fl.data(); po.depth = dep.data();
+        memcpy(po.Tcw_init, curTcw, sizeof curTcw);
+        memcpy(po.Tcw_last, ts->lastTcw, sizeof curTcw);
+        po.fx = c.fx; po.fy = c.fy; po.cx = c.cx; po.cy = c.cy;
+        po.flow_out = fo.data(); po.inlier = inl.data();
+        // while the pose optimisation runs: retire the older queued window solve (its results go back into the Map)
+        ctx->idle_work = [ctx, ts]() {
+          while (ts->ba_nq > 1 && ts->ba_deferred_rc == VIDO_OK) { ts->ba_deferred_rc = ba_finish(ctx); ba_writeback_rest(ctx); }
+        };
+        rc = po_flow2_host(ctx, &po, 1, nullptr);
+        ctx->idle_work = nullptr;
+        if (rc) return rc;
+        if (ts->ba_deferred_rc) return ts->ba_deferred_rc;
+        memcpy(curTcw, po.Tcw_out, sizeof curTcw);
+        if (n >= 3) {
+          for (int i = 0; i < n; i++) {
+            if (inl[i]) {
+              const int k = TM[i];
+              keys[2 * k] = (float)((double)ts->last_keys[2 * k] + (double)fo[2 * i]);
+              keys[2 * k + 1] = (float)((double)ts->last_keys[2 * k + 1] + (double)fo[2 * i + 1]);
+            } else TM[i] = -1;
+          }
+        }
+        n_pose_inliers = po.n_inliers;
+      } else {
+        // ---- PoseOptimizationNew (Optimizer.cc:2180-2334): reprojection of the last frame's world points; the retirement
+        //      of the older window solve still hides behind the kernel
+        std::vector<float> obs(2 * (size_t)n), p3(3 * (size_t)n);
+        std::vector<int32_t> inl(n);
+        for (int i = 0; i < n; i++) {
+          const int k = TM[i];
+          obs[2 * i] = keys[2 * k]; obs[2 * i + 1] = keys[2 * k + 1];
+          p3[3 * i] = p3d[3 * k]; p3[3 * i + 1] = p3d[3 * k + 1]; p3[3 * i + 2] = p3d[3 * k + 2];
+        }
+        vido_projopt_problem pj;
+        memset(&pj, 0, sizeof pj);
+        vido_projopt_default_params(&pj, 0);
+        pj.n = n; pj.obs_xy = obs.data(); pj.pts3d = p3.data(); pj.inlier = inl.data();
+        memcpy(pj.T_init, curTcw, sizeof curTcw);
+        pj.fx = c.fx; pj.fy = c.fy; pj.cx = c.cx; pj.cy = c.cy;
+        rc = projopt_host(ctx, &pj, 1, nullptr);
+        if (rc) return rc;
+        while (ts->ba_nq > 1) { rc = ba_finish(ctx); if (rc) return rc; ba_writeback_rest(ctx); }
+        memcpy(curTcw, pj.T_out, sizeof curTcw);
+        n_pose_inliers = pj.n_inliers;
+        if (n >= 3)
+          for (int i = 0; i < n; i++)
+            if (!inl[i]) TM[i] = -1;
       }
       double t2 = now_ms();
       // ---- motion model: mVelocity = Tcw * LastTwc
@@ -1328,7 +1401,7 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
       double t3 = now_ms();
       if (st) {
         st->ms_init = t1 - t0; st->ms_poseopt = t2 - t1; st->ms_renew = t3 - t2;
-        st->n_matches = Ns; st->n_init_inliers = pp.n_inliers; st->init_winner = pp.winner; st->n_pose_inliers = po.n_inliers;
+        st->n_matches = Ns; st->n_init_inliers = pp.n_inliers; st->init_winner = pp.winner; st->n_pose_inliers = n_pose_inliers;
         st->n_static = nf;
       }
     }
