@@ -383,9 +383,50 @@ typedef struct vido_inertial_problem {
   double scale;                   /* in/out (mScale) */
   double bg[3], ba[3];            /* in/out (mbg, mba) */
   float prior_g, prior_a;         /* 1e2, 1e9 (src/Tracking.cc:1453) */
+  int32_t mode;                   /* 0: the initialisation above (its 200, lambda 1e3); 1: Optimizer::InertialOptimization(Map*,
+                                     Rwg, scale) of Tracking::ScaleRefinement (src/Optimizer.cc:2336-2439, src/Tracking.cc:1046-
+                                     1077): velocities and biases fixed, no priors, only gravity direction and scale; its = 10 */
 } vido_inertial_problem;
 void vido_inertial_default_params(vido_inertial_problem* p);
 int vido_inertial_opt(vido_ctx* ctx, vido_inertial_problem* p, vido_lm_stats* stats);
+
+/*
+ * VIO mode of the per-frame driver (sensor = IMU_RGBD).  vido_track_set_imu replaces Tracking::ParseIMUParamFile (src/Tracking.cc:
+ * 174-275): Tbc = camera-to-body transform (row-major 4x4, "Tbc" of the YAML), noise = (ng, na, ngw, naw) as handed to IMU::Calib
+ * (already scaled by sqrt(IMU.Frequency), :258-262); must be called before the first frame (or after vido_track_reset).
+ * vido_track_grab_imu replaces Tracking::GrabImuData (:277-281) / the vImuMeas argument of System::TrackRGBD (src/System.cc:64-76):
+ * the samples System::TrackRGBD would receive together with the frame that lies `frames_ahead` frames after the next one to be
+ * tracked (0 = the next frame), so that a whole chunk can be announced before one vido_track_frames call; deliveries in frame order,
+ * ascending t.  vido_frame_inputs.timestamp is the frame's time stamp.
+ * With IMU data the driver then does what Tracking::Track does (src/Tracking.cc:1115-1119, 1452-1480, 1555-1561): preintegration of
+ * every frame against the last frame's bias (one kernel launch per front-end batch), InitializeIMU(1e2, 1e9) after the window
+ * optimisation of every frame until it succeeds (>= 10 map frames, >= 2 s; gravity direction from the summed delta-velocities,
+ * velocities from finite differences, the inertial-only optimisation above, bias write-back with Reintegrate when the gyro bias
+ * moved by > 0.01, Map::ApplyScaledRotation, Tracking::UpdateFrameIMU), and ScaleRefinement (mode 1) in the mTinit windows.
+ * The pose returned for a frame is mpCurrentFrame->mTcw after these steps, like System::TrackRGBD.
+ */
+typedef struct vido_imu_state {
+  int32_t initialized;     /* Tracking::mbImuInitialized */
+  int32_t status;          /* last InitializeIMU attempt: -1 none, 0 done, 1 too few frames / too little time, 2 scale < 0.1,
+                              3 a frame without preintegration breaks the chain (not initialised; the reference would skip the edge) */
+  int32_t init_frame;      /* frame id at which the initialisation succeeded */
+  int32_t n_refinements;   /* ScaleRefinement calls */
+  int32_t n_reintegrated;  /* IMU::Preintegrated::Reintegrate calls */
+  int32_t lm_iterations, lm_trials; /* of the initialisation's inertial-only optimisation */
+  float t_init;            /* mTinit */
+  double scale;            /* mScale of the last inertial-only optimisation */
+  double Rwg[9], bg[3], ba[3];
+} vido_imu_state;
+int vido_track_set_imu(vido_ctx* ctx, const float* Tbc, const float* noise);
+int vido_track_grab_imu(vido_ctx* ctx, const vido_imu_sample* samples, int n, int frames_ahead);
+int vido_track_get_imu_state(vido_ctx* ctx, vido_imu_state* out);
+/* per frame id (the initial frame included): Frame::mTcw (after ApplyScaledRotation / UpdateFrameIMU), mVw, mImuBias (bax..bwz);
+ * returns the number of frames */
+int vido_map_get_imu_frames(vido_ctx* ctx, float* Tcw, float* vel, float* bias, int cap);
+/* Map::ApplyScaledRotation(R, s, bScaledVel = true, t = 0) (src/Map.cc:55-119): every camera pose, rigid motion and 3-D point of
+ * the context's Map, the frame poses / velocities (VIO mode) or the last-frame pose, are scaled by s and rotated by R (row-major
+ * 3x3); pending window solves are retired first */
+int vido_map_apply_scaled_rotation(vido_ctx* ctx, const float* R, float s);
 
 /* accumulated device time (CUDA events on the context stream) of the kernel groups: ms[0] ORB front-end launches,
  * ms[1] init-model kernels, ms[2] pose-optimisation kernel, ms[3] window-BA kernel; launches[k] = timed regions;

@@ -192,7 +192,7 @@ void edge_information(const float* C15, double* Info) {
 }
 
 struct InertialSys {
-  int N = 0, dim = 0;
+  int N = 0, dim = 0, mode = 0;
   std::vector<double> Rwb, twb, V;     // [N][9], [N][3], [N][3]
   double bg[3], ba[3], Rwg[9], s;
   const vo_imu_preint* pre = nullptr;  // [N-1]
@@ -327,7 +327,8 @@ struct InertialSys {
       for (int i = 0; i < 9; i++)
         for (int j = 0; j < 9; j++) chi += r[i] * I9[9 * i + j] * r[j];
     }
-    for (int k = 0; k < 3; k++) chi += priorA * ba[k] * ba[k] + priorG * bg[k] * bg[k];
+    if (mode == 0)
+      for (int k = 0; k < 3; k++) chi += priorA * ba[k] * ba[k] + priorG * bg[k] * bg[k];
     return chi;
   }
   void build_system() {
@@ -361,7 +362,7 @@ struct InertialSys {
       }
     }
     // priors: error = 0 - estimate, Jacobian +I (as written in the reference)
-    for (int k = 0; k < 3; k++) {
+    for (int k = 0; k < 3 && mode == 0; k++) {
       H[(size_t)(3 * N + k) * dim + 3 * N + k] += priorG;
       b[3 * N + k] -= priorG * (0.0 - bg[k]);
       H[(size_t)(3 * N + 3 + k) * dim + 3 * N + 3 + k] += priorA;
@@ -370,10 +371,31 @@ struct InertialSys {
   }
   double max_diag() const {
     double m = 0;
-    for (int i = 0; i < dim; i++) m = std::max(m, std::fabs(H[(size_t)i * dim + i]));
+    for (int i = (mode == 1 ? 3 * N + 6 : 0); i < dim; i++) m = std::max(m, std::fabs(H[(size_t)i * dim + i]));
     return m;
   }
+  bool solve3(double lambda) {   // mode 1: only gravity direction (2) and scale (1) are free
+    const int o = 3 * N + 6;
+    double A[9], L[9] = {0}, y[3];
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) A[3 * r + c] = H[(size_t)(o + r) * dim + o + c] + (r == c ? lambda : 0.0);
+    for (int j = 0; j < 3; j++) {
+      double d = A[3 * j + j];
+      for (int k = 0; k < j; k++) d -= L[3 * j + k] * L[3 * j + k];
+      if (d <= 0) return false;
+      L[3 * j + j] = std::sqrt(d);
+      for (int i = j + 1; i < 3; i++) {
+        double s2 = A[3 * i + j];
+        for (int k = 0; k < j; k++) s2 -= L[3 * i + k] * L[3 * j + k];
+        L[3 * i + j] = s2 / L[3 * j + j];
+      }
+    }
+    for (int i = 0; i < 3; i++) { double s2 = b[o + i]; for (int k = 0; k < i; k++) s2 -= L[3 * i + k] * y[k]; y[i] = s2 / L[3 * i + i]; }
+    for (int i = 2; i >= 0; i--) { double s2 = y[i]; for (int k = i + 1; k < 3; k++) s2 -= L[3 * k + i] * x[o + k]; x[o + i] = s2 / L[3 * i + i]; }
+    return true;
+  }
   bool solve(double lambda) {
+    if (mode == 1) return solve3(lambda);
     std::vector<double> L(H);
     for (int i = 0; i < dim; i++) L[(size_t)i * dim + i] += lambda;
     for (int j = 0; j < dim; j++) {
@@ -414,7 +436,7 @@ struct InertialSys {
   void discard_top() { stack.pop_back(); }
   double compute_scale(double lambda) const {
     double sc = 0;
-    for (int j = 0; j < dim; j++) sc += x[j] * (lambda * x[j] + b[j]);
+    for (int j = (mode == 1 ? 3 * N + 6 : 0); j < dim; j++) sc += x[j] * (lambda * x[j] + b[j]);
     return sc;
   }
 };
@@ -423,13 +445,14 @@ struct InertialSys {
 
 extern "C" {
 
-void vo_inertial_default_params(vo_inertial_problem* p) { p->prior_g = 1e2f; p->prior_a = 1e9f; p->its = 200; }
+void vo_inertial_default_params(vo_inertial_problem* p) { p->prior_g = 1e2f; p->prior_a = 1e9f; p->its = 200; p->mode = 0; }
 
 void vo_inertial_edge_information(const float* C15, double* info81) { edge_information(C15, info81); }
 
 int vo_inertial_optimization(vo_inertial_problem* p, vo_lm_stats* stats) {
   InertialSys S;
   S.N = p->n_frames;
+  S.mode = p->mode;
   if (S.N < 2) { if (stats) { stats->iterations = -1; stats->n_records = 0; stats->total_trials = 0; } return -1; }
   S.dim = 3 * S.N + 9;
   S.Rwb.resize(9 * (size_t)S.N); S.twb.resize(3 * (size_t)S.N); S.V.resize(3 * (size_t)S.N);
@@ -444,12 +467,38 @@ int vo_inertial_optimization(vo_inertial_problem* p, vo_lm_stats* stats) {
   for (int e = 0; e + 1 < S.N; e++) edge_information(p->preint[e].C, &S.Info[81 * (size_t)e]);
   S.err.assign(9 * (size_t)(S.N - 1), 0.0);
   S.H.assign((size_t)S.dim * S.dim, 0.0); S.b.assign(S.dim, 0.0); S.x.assign(S.dim, 0.0);
-  const int its = vo::lm_optimize(S, p->its, -1.0, p->prior_g != 0.f ? 1e3 : -1.0, stats);
+  const int its = vo::lm_optimize(S, p->its, -1.0, (p->mode == 0 && p->prior_g != 0.f) ? 1e3 : -1.0, stats);
   for (size_t i = 0; i < S.V.size(); i++) p->velocity[i] = (float)S.V[i];
   for (int k = 0; k < 3; k++) { p->bg[k] = S.bg[k]; p->ba[k] = S.ba[k]; }
   for (int k = 0; k < 9; k++) p->Rwg[k] = S.Rwg[k];
   p->scale = S.s;
   return its;
+}
+
+// IMU::Preintegrated::GetUpdatedDeltaRotation / Velocity / Position (src/ImuTypes.cc:370-386) for db = (dbg, dba), and
+// IMU::ExpSO3(float) / NormalizeRotation for the tracker's VIO glue
+void vo_imu_updated_deltas(const vo_imu_preint* p, const float* dbg, const float* dba, float* dR, float* dV, float* dP) {
+  float rj[3];
+  for (int i = 0; i < 3; i++) rj[i] = (float)((double)p->JRg[3 * i] * dbg[0] + (double)p->JRg[3 * i + 1] * dbg[1] + (double)p->JRg[3 * i + 2] * dbg[2]);
+  double E[9], Rd[9], M[9], Rn[9];
+  exp_so3_f(rj[0], rj[1], rj[2], E);
+  for (int k = 0; k < 9; k++) Rd[k] = p->dR[k];
+  mul33(Rd, E, M);
+  normalize_rotation_f(M, Rn);
+  for (int k = 0; k < 9; k++) dR[k] = (float)Rn[k];
+  for (int i = 0; i < 3; i++) {
+    const float t1 = (float)((double)p->JVg[3 * i] * dbg[0] + (double)p->JVg[3 * i + 1] * dbg[1] + (double)p->JVg[3 * i + 2] * dbg[2]);
+    const float t2 = (float)((double)p->JVa[3 * i] * dba[0] + (double)p->JVa[3 * i + 1] * dba[1] + (double)p->JVa[3 * i + 2] * dba[2]);
+    dV[i] = (float)((float)(p->dV[i] + t1) + t2);
+    const float u1 = (float)((double)p->JPg[3 * i] * dbg[0] + (double)p->JPg[3 * i + 1] * dbg[1] + (double)p->JPg[3 * i + 2] * dbg[2]);
+    const float u2 = (float)((double)p->JPa[3 * i] * dba[0] + (double)p->JPa[3 * i + 1] * dba[1] + (double)p->JPa[3 * i + 2] * dba[2]);
+    dP[i] = (float)((float)(p->dP[i] + u1) + u2);
+  }
+}
+void vo_imu_exp_so3_f(const float* w, float* R) {
+  double Rd[9];
+  exp_so3_f(w[0], w[1], w[2], Rd);
+  for (int k = 0; k < 9; k++) R[k] = (float)Rd[k];
 }
 
 }  // extern "C"

@@ -13,7 +13,10 @@
 //   Tracking::GetSceneFlowObj        src/Tracking.cc:1582-1668 ; Tracking::DynObjTracking src/Tracking.cc:1670-1912
 //   Tracking::GetInitModelObj        src/Tracking.cc:2030-2162 ; Optimizer::PoseOptimizationFlow2 src/Optimizer.cc:3037-3253
 //   Tracking::RenewFrameInfo         src/Tracking.cc:3112-3289 (object part) ; GetDynamicTrackNew src/Tracking.cc:2615-2720
-// Not covered (documented in DESIGN.md): IMU, FullBatch.
+// VIO glue (sensor = IMU_RGBD): Tracking::ParseIMUParamFile / GrabImuData / PreintegrateIMU / UpdateFrameIMU / InitializeIMU /
+//   ScaleRefinement  src/Tracking.cc:174-281, 784-1077, 1115-1119, 1452-1480, 1555-1561 ; Frame IMU state src/Frame.cc:437-521,
+//   include/Frame.h:44-110 ; Map::ApplyScaledRotation src/Map.cc:55-119 ; the write-back of Optimizer::InertialOptimization
+//   src/Optimizer.cc:2589-2619
 // float 4x4 products follow cv::Mat CV_32F gemm (double accumulation, one rounding).
 #include <algorithm>
 #include <array>
@@ -55,6 +58,33 @@ void inv44(const float* T, float* Ti) {  // Converter::toInvMatrix (src/Converte
 }
 
 void eye44(float* T) { memset(T, 0, sizeof(float) * 16); T[0] = T[5] = T[10] = T[15] = 1.f; }
+
+
+// ---- float32 cv::Mat helpers of the VIO glue (gemm: double accumulation, one rounding per expression)
+void mm3(const float* A, const float* B, float* C) {
+  float o[9];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) o[3 * r + c] = (float)((double)A[3 * r] * B[c] + (double)A[3 * r + 1] * B[3 + c] + (double)A[3 * r + 2] * B[6 + c]);
+  memcpy(C, o, sizeof o);
+}
+// alpha * A * v + beta * w
+void mv3(const float* A, const float* v, float* o, double alpha = 1.0, const float* w = nullptr) {
+  float t[3];
+  for (int r = 0; r < 3; r++)
+    t[r] = (float)(alpha * ((double)A[3 * r] * v[0] + (double)A[3 * r + 1] * v[1] + (double)A[3 * r + 2] * v[2]) + (w ? (double)w[r] : 0.0));
+  memcpy(o, t, sizeof t);
+}
+
+struct ImuFrame {              // IMU members of Frame (include/Frame.h): mTcw, mVw, mImuBias, mpImuPreintegrated, mTimeStamp
+  float Tcw[16];
+  float vel[3] = {0.f, 0.f, 0.f};
+  float bias[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // bax, bay, baz, bwx, bwy, bwz
+  bool has_pre = false;
+  vo_imu_preint pre;           // integrated with pre_b; db = bu - b: gyro (0..2), acc (3..5) (IMU::Preintegrated::db)
+  float pre_b[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, db[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  size_t q0 = 0, q1 = 0;       // queue range the preintegration saw (Reintegrate)
+  double t = 0, t_prev = 0;
+};
 
 struct Frame {
   std::vector<vo_keypoint> mvKeys;
@@ -119,6 +149,223 @@ struct Tracker {
   std::vector<P2> tmpKeys, tmpCorres, tmpFlow;
   std::vector<float> tmpDepth;
   std::vector<int> tmpSem;
+
+
+  // ---- VIO state (Tracking: mpImuCalib, mlQueueImuData, mbImuInitialized, mScale, mRwg, mbg, mba, mTinit, mFirstTs)
+  bool vio = false;
+  float Tbc[16], Tcb[16], imu_noise[4];
+  std::vector<vo_imu_sample> imu_q;
+  size_t imu_head = 0;                 // queue front
+  std::vector<ImuFrame> fr;            // by frame id; fr[0] (the initial frame) is not in Map::vpFrames
+  double next_t = 0;
+  vo_imu_state ist;
+  vo_lm_stats imu_lm;
+
+  void set_imu(const float* Tbc_, const float* noise) {   // IMU::Calib::Set (src/ImuTypes.cc:476-500)
+    vio = true;
+    memcpy(Tbc, Tbc_, sizeof Tbc);
+    memcpy(imu_noise, noise, sizeof imu_noise);
+    eye44(Tcb);
+    float Rt[9], tb[3] = {Tbc[3], Tbc[7], Tbc[11]}, tc[3];
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) { Rt[3 * r + c] = Tbc[4 * c + r]; Tcb[4 * r + c] = Tbc[4 * c + r]; }
+    mv3(Rt, tb, tc, -1.0);
+    for (int r = 0; r < 3; r++) Tcb[4 * r + 3] = tc[r];
+    memset(&ist, 0, sizeof ist);
+    ist.scale = 1.0; ist.status = -1;
+    ist.Rwg[0] = ist.Rwg[4] = ist.Rwg[8] = 1.0;
+  }
+  void imu_rotation(const ImuFrame& f, float* Rwb) const {   // Frame::GetImuRotation: mRwc * Tcb.R
+    float Rwc[9], Rcb[9];
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) { Rwc[3 * r + c] = f.Tcw[4 * c + r]; Rcb[3 * r + c] = Tcb[4 * r + c]; }
+    mm3(Rwc, Rcb, Rwb);
+  }
+  void imu_position(const ImuFrame& f, float* twb) const {   // Frame::GetImuPosition: mOwb = mRwc * tcb + mOw, mOw = -mRcw.t() * mtcw
+    float Rwc[9], tcw[3] = {f.Tcw[3], f.Tcw[7], f.Tcw[11]}, tcb[3] = {Tcb[3], Tcb[7], Tcb[11]}, Ow[3];
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) Rwc[3 * r + c] = f.Tcw[4 * c + r];
+    mv3(Rwc, tcw, Ow, -1.0);
+    mv3(Rwc, tcb, twb, 1.0, Ow);
+  }
+  void set_imu_pose_velocity(ImuFrame& f, const float* Rwb, const float* twb, const float* Vwb) const {   // src/Frame.cc:510-521
+    memcpy(f.vel, Vwb, sizeof f.vel);
+    float Rbw[9], tbw[3], Tbw[16];
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) Rbw[3 * r + c] = Rwb[3 * c + r];
+    mv3(Rbw, twb, tbw, -1.0);
+    eye44(Tbw);
+    for (int r = 0; r < 3; r++) {
+      for (int c = 0; c < 3; c++) Tbw[4 * r + c] = Rbw[3 * r + c];
+      Tbw[4 * r + 3] = tbw[r];
+    }
+    mul44(Tcb, Tbw, f.Tcw);
+  }
+  static void set_new_bias(ImuFrame& f, const float* b) {   // Frame::SetNewBias + IMU::Preintegrated::SetNewBias (src/ImuTypes.cc:328-339)
+    memcpy(f.bias, b, sizeof f.bias);
+    if (f.has_pre)
+      for (int k = 0; k < 3; k++) { f.db[k] = b[3 + k] - f.pre_b[3 + k]; f.db[3 + k] = b[k] - f.pre_b[k]; }
+  }
+  static void pre_set_new_bias(ImuFrame& f, const float* b) {   // mpImuPreintegrated->SetNewBias only
+    if (f.has_pre)
+      for (int k = 0; k < 3; k++) { f.db[k] = b[3 + k] - f.pre_b[3 + k]; f.db[3 + k] = b[k] - f.pre_b[k]; }
+  }
+  void integrate(ImuFrame& f, const float* b) {   // new IMU::Preintegrated(b, calib) over the frame's queue range
+    vo_imu_preintegrate(imu_q.data() + f.q0, (int)(f.q1 - f.q0), f.t_prev, f.t, b, imu_noise, &f.pre);
+    memcpy(f.pre_b, b, sizeof f.pre_b);
+    for (int k = 0; k < 6; k++) f.db[k] = 0.f;
+    f.has_pre = true;
+  }
+  // Tracking::PreintegrateIMU (src/Tracking.cc:784-887) for the new frame, bias of the last frame
+  void preintegrate(ImuFrame& f, const ImuFrame& prev) {
+    f.has_pre = false;
+    if (imu_head >= imu_q.size()) return;   // "Not IMU data in mlQueueImuData"
+    f.q0 = imu_head; f.q1 = imu_q.size();
+    integrate(f, prev.bias);
+    imu_head += (size_t)f.pre.n_consumed;
+  }
+  // Tracking::UpdateFrameIMU (src/Tracking.cc:889-923); mpLastFrame == mpCurrentFrame == fr.back()
+  void update_frame_imu(const float* b) {
+    ImuFrame& c = fr.back();
+    const ImuFrame& p = fr[fr.size() - 2];
+    set_new_bias(c, b);
+    if (!c.has_pre) return;
+    const float Gz[3] = {0.f, 0.f, -9.79f};
+    float twb1[3], Rwb1[9], dR[9], dV[3], dP[3], Rwb[9], twb[3], Vwb[3];
+    imu_position(p, twb1);
+    imu_rotation(p, Rwb1);
+    vo_imu_updated_deltas(&c.pre, c.db, c.db + 3, dR, dV, dP);
+    const float t12 = c.pre.dT;
+    mm3(Rwb1, dR, Rwb);
+    const float ht2 = 0.5f * t12 * t12;
+    for (int r = 0; r < 3; r++) {
+      // twb1 + Vwb1*t12 + 0.5f*t12*t12*Gz + Rwb1*dP ; Vwb1 + Gz*t12 + Rwb1*dV  (left to right, one rounding per operator)
+      const float rp = (float)((double)Rwb1[3 * r] * dP[0] + (double)Rwb1[3 * r + 1] * dP[1] + (double)Rwb1[3 * r + 2] * dP[2]);
+      const float rv = (float)((double)Rwb1[3 * r] * dV[0] + (double)Rwb1[3 * r + 1] * dV[1] + (double)Rwb1[3 * r + 2] * dV[2]);
+      twb[r] = ((twb1[r] + (float)((double)p.vel[r] * (double)t12)) + (float)((double)ht2 * (double)Gz[r])) + rp;
+      Vwb[r] = (p.vel[r] + (float)((double)Gz[r] * (double)t12)) + rv;
+    }
+    set_imu_pose_velocity(c, Rwb, twb, Vwb);
+    memcpy(cur->Tcw, c.Tcw, sizeof c.Tcw);   // mpLastFrame = mpCurrentFrame
+  }
+  // Map::ApplyScaledRotation (src/Map.cc:55-119) with the frames of Map::vpFrames (fr[1..])
+  void apply_scaled_rotation(const float* R, float s);
+  // the inertial problem over Map::vpFrames = fr[1..N] (src/Optimizer.cc:2441-2560 / 2336-2425); false: a frame without preintegration
+  bool run_inertial(int mode, float priorG, float priorA) {
+    const int N = (int)fr.size() - 1;
+    std::vector<float> Rwb(9 * (size_t)N), twb(3 * (size_t)N), vel(3 * (size_t)N), blin(6 * (size_t)(N - 1));
+    std::vector<vo_imu_preint> pre(N - 1);
+    for (int i = 1; i <= N; i++) {
+      imu_rotation(fr[i], &Rwb[9 * (size_t)(i - 1)]);
+      imu_position(fr[i], &twb[3 * (size_t)(i - 1)]);
+      memcpy(&vel[3 * (size_t)(i - 1)], fr[i].vel, sizeof(float) * 3);
+      pre_set_new_bias(fr[i], fr[i - 1].bias);
+      if (i >= 2) {
+        if (!fr[i].has_pre) return false;
+        pre[i - 2] = fr[i].pre;
+        memcpy(&blin[6 * (size_t)(i - 2)], fr[i].pre_b, sizeof(float) * 6);
+      }
+    }
+    vo_inertial_problem p;
+    memset(&p, 0, sizeof p);
+    vo_inertial_default_params(&p);
+    p.n_frames = N; p.Rwb = Rwb.data(); p.twb = twb.data(); p.velocity = vel.data(); p.preint = pre.data(); p.bias_lin = blin.data();
+    p.mode = mode; p.its = mode == 0 ? 200 : 10;
+    p.prior_g = priorG; p.prior_a = priorA;
+    for (int k = 0; k < 9; k++) p.Rwg[k] = ist.Rwg[k];
+    p.scale = ist.scale;
+    for (int k = 0; k < 3; k++) { p.bg[k] = (double)fr[1].bias[3 + k]; p.ba[k] = (double)fr[1].bias[k]; }   // VertexGyroBias(vpFs.front())
+    vo_inertial_optimization(&p, &imu_lm);
+    for (int k = 0; k < 9; k++) ist.Rwg[k] = p.Rwg[k];
+    ist.scale = p.scale;
+    if (mode == 0) {   // write-back, src/Optimizer.cc:2589-2619
+      for (int k = 0; k < 3; k++) { ist.bg[k] = p.bg[k]; ist.ba[k] = p.ba[k]; }
+      const float b[6] = {(float)p.ba[0], (float)p.ba[1], (float)p.ba[2], (float)p.bg[0], (float)p.bg[1], (float)p.bg[2]};
+      for (int i = 1; i <= N; i++) {
+        memcpy(fr[i].vel, &vel[3 * (size_t)(i - 1)], sizeof(float) * 3);
+        double d2 = 0;
+        for (int k = 0; k < 3; k++) { const float d = fr[i].bias[3 + k] - b[3 + k]; d2 += (double)d * d; }
+        const bool re = std::sqrt(d2) > 0.01;
+        set_new_bias(fr[i], b);
+        if (re && fr[i].has_pre) { integrate(fr[i], b); ist.n_reintegrated++; }
+      }
+    }
+    return true;
+  }
+  void apply_and_update(const float* b) {   // tail shared by InitializeIMU / ScaleRefinement
+    if (std::fabs(ist.scale - 1.0) > 0.00001) {
+      float Rgw[9];
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) Rgw[3 * r + c] = (float)ist.Rwg[3 * c + r];   // Converter::toCvMat(mRwg).t()
+      apply_scaled_rotation(Rgw, (float)ist.scale);
+      update_frame_imu(b);
+    }
+  }
+  // Tracking::InitializeIMU(1e2, 1e9) (src/Tracking.cc:937-1044)
+  void initialize_imu() {
+    const int N = (int)fr.size() - 1;
+    if (N < 10) { ist.status = 1; return; }
+    const double first_ts = fr[1].t;
+    if (fr.back().t - first_ts < 2.0) { ist.status = 1; return; }
+    float dirG[3] = {0.f, 0.f, 0.f};
+    for (int i = 1; i <= N; i++) {
+      if (!fr[i].has_pre) continue;
+      float R[9], dR[9], dV[3], dP[3], p1[3], p0[3];
+      imu_rotation(fr[i - 1], R);
+      vo_imu_updated_deltas(&fr[i].pre, fr[i].db, fr[i].db + 3, dR, dV, dP);
+      imu_position(fr[i], p1);
+      imu_position(fr[i - 1], p0);
+      for (int r = 0; r < 3; r++) {
+        const float rv = (float)((double)R[3 * r] * dV[0] + (double)R[3 * r + 1] * dV[1] + (double)R[3 * r + 2] * dV[2]);
+        dirG[r] = dirG[r] - rv;
+        const float v = (float)((double)(p1[r] - p0[r]) * (1.0 / (double)fr[i].pre.dT));
+        fr[i].vel[r] = v;
+        fr[i - 1].vel[r] = v;
+      }
+    }
+    const double nrm = std::sqrt((double)dirG[0] * dirG[0] + (double)dirG[1] * dirG[1] + (double)dirG[2] * dirG[2]);
+    for (int r = 0; r < 3; r++) dirG[r] = (float)((double)dirG[r] * (1.0 / nrm));
+    const float gI[3] = {0.f, 0.f, -1.f};
+    const float v[3] = {gI[1] * dirG[2] - gI[2] * dirG[1], gI[2] * dirG[0] - gI[0] * dirG[2], gI[0] * dirG[1] - gI[1] * dirG[0]};
+    const float nv = (float)std::sqrt((double)v[0] * v[0] + (double)v[1] * v[1] + (double)v[2] * v[2]);
+    const float cosg = (float)((double)gI[0] * dirG[0] + (double)gI[1] * dirG[1] + (double)gI[2] * dirG[2]);
+    const float ang = (float)std::acos((double)cosg);
+    float vzg[3], Rwg[9];
+    for (int r = 0; r < 3; r++) vzg[r] = (float)((double)(float)((double)v[r] * (double)ang) * (1.0 / (double)nv));
+    vo_imu_exp_so3_f(vzg, Rwg);
+    for (int k = 0; k < 9; k++) ist.Rwg[k] = Rwg[k];
+    ist.t_init = (float)(fr.back().t - first_ts);
+    ist.scale = 1.0;
+    if (!run_inertial(0, 1e2f, 1e9f)) { ist.status = 3; return; }
+    ist.lm_iterations = imu_lm.iterations; ist.lm_trials = imu_lm.total_trials;
+    if (ist.scale < 1e-1) { ist.status = 2; return; }
+    float b[6];
+    memcpy(b, fr[1].bias, sizeof b);   // vpF[0]->GetImuBias()
+    apply_and_update(b);
+    ist.initialized = 1; ist.init_frame = N; ist.status = 0;
+  }
+  // Tracking::ScaleRefinement (src/Tracking.cc:1046-1077)
+  void scale_refinement() {
+    for (int k = 0; k < 9; k++) ist.Rwg[k] = (k % 4 == 0) ? 1.0 : 0.0;
+    ist.scale = 1.0;
+    if (!run_inertial(1, 0.f, 0.f)) return;
+    ist.n_refinements++;
+    if (ist.scale < 1e-1) return;
+    float b[6];
+    memcpy(b, fr.back().bias, sizeof b);
+    apply_and_update(b);
+  }
+  // the IMU part of Tracking::Track after the window optimisation (src/Tracking.cc:1452-1480)
+  void vio_after_ba() {
+    if (!ist.initialized) initialize_imu();
+    if (ist.initialized && ist.t_init < 100.0f) {
+      ist.t_init = (float)((double)ist.t_init + (fr.back().t - fr[fr.size() - 2].t));
+      const float T = ist.t_init;
+      const bool win = (T > 15.0f && T < 15.5f) || (T > 25.0f && T < 25.5f) || (T > 35.0f && T < 35.5f) || (T > 45.0f && T < 45.5f) ||
+                       (T > 55.0f && T < 55.5f) || (T > 65.0f && T < 65.5f) || (T > 75.0f && T < 75.5f);
+      if ((int)fr.size() - 1 <= 1000 && win) scale_refinement();
+    }
+  }
 
   ~Tracker() { delete last; if (cur != last) delete cur; }
 
@@ -880,6 +1127,22 @@ struct Tracker {
       I[0] = I[5] = I[10] = I[15] = 1.f;
       map.vmCameraPose.push_back(I);
       eye44(cur->Tcw);
+      if (vio) {   // src/Tracking.cc:1555-1561: IMU pose from Tcb, zero velocity, empty preintegration
+        ImuFrame f0;
+        float Rwb0[9], twb0[3], V0[3] = {0.f, 0.f, 0.f};
+        for (int r = 0; r < 3; r++) {
+          for (int c = 0; c < 3; c++) Rwb0[3 * r + c] = Tcb[4 * r + c];
+          twb0[r] = Tcb[4 * r + 3];
+        }
+        set_imu_pose_velocity(f0, Rwb0, twb0, V0);
+        memset(&f0.pre, 0, sizeof f0.pre);
+        f0.pre.dR[0] = f0.pre.dR[4] = f0.pre.dR[8] = 1.f;
+        f0.has_pre = true;
+        f0.t = f0.t_prev = next_t;
+        memcpy(cur->Tcw, f0.Tcw, sizeof f0.Tcw);
+        fr.clear();
+        fr.push_back(f0);
+      }
       last = cur;
       last->mvStatKeys = cur->mvStatKeysTmp;
       last->mvStatDepth = cur->mvStatDepthTmp;
@@ -888,6 +1151,15 @@ struct Tracker {
       const int Ns = (int)cur->mvStatKeys.size();
       if (Ns < 2) { rc = 1; }
       else {
+        if (vio) {   // src/Tracking.cc:1115-1119 (Frame ctor: mVw of the previous frame, src/Frame.cc:437-447)
+          ImuFrame f;
+          const ImuFrame& pf = fr.back();
+          f.t = next_t; f.t_prev = pf.t;
+          memcpy(f.vel, pf.vel, sizeof f.vel);
+          memcpy(f.bias, pf.bias, sizeof f.bias);
+          preintegrate(f, pf);
+          fr.push_back(f);
+        }
         // ---- GetInitModelCam
         std::vector<float> cur2d(2 * (size_t)Ns), p3d(3 * (size_t)Ns, 0.f);
         std::vector<int> valid(Ns, 1), ids(Ns);
@@ -1009,6 +1281,7 @@ struct Tracker {
           map.vmObjMotion.push_back(mot_o); map.vnRMLabel.push_back(rml); map.vnSMLabel.push_back(sml); map.vmRigidCentre.push_back(cen);
         }
         std::vector<float> Twc(16), mot(16);
+        if (vio) memcpy(fr.back().Tcw, cur->Tcw, sizeof(float) * 16);
         inv44(cur->Tcw, Twc.data());
         inv44(mVelocity, mot.data());
         map.vmCameraPose.push_back(Twc);
@@ -1034,11 +1307,60 @@ struct Tracker {
     const int window = f_id < cfg.window_size ? f_id : cfg.window_size;
     if (rc == 0) partial_batch(window, st);
     if (st) st->ms_ba = now_ms() - t6;
+    if (vio && rc == 0 && f_id > 0) {   // InitializeIMU / ScaleRefinement (src/Tracking.cc:1452-1480); TrackRGBD returns mTcw after them
+      vio_after_ba();
+      memcpy(Tcw_out, cur->Tcw, sizeof(float) * 16);
+    }
     f_id++;
     if (rc != 0 && cur != last) { delete cur; cur = last; }
     return rc;
   }
 };
+
+
+// Map::ApplyScaledRotation(R, s, bScaledVel = true, t = 0) (src/Map.cc:55-119)
+void Tracker::apply_scaled_rotation(const float* R, float s) {
+  float Tyw[16];
+  eye44(Tyw);
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) Tyw[4 * r + c] = R[3 * r + c];
+  auto rot_pt = [&](P3& p) {   // s * Ryw * p + tyw: one gemm with alpha = s, beta = 1 (tyw = 0)
+    const float x = p.x, y = p.y, z = p.z;
+    float o[3];
+    for (int r = 0; r < 3; r++)
+      o[r] = (float)((double)s * ((double)R[3 * r] * x + (double)R[3 * r + 1] * y + (double)R[3 * r + 2] * z) + 0.0);
+    p = {o[0], o[1], o[2]};
+  };
+  auto scale_pose = [&](float* pose) {   // pose.t *= s ; pose = Tyw * pose
+    pose[3] *= s; pose[7] *= s; pose[11] *= s;
+    mul44(Tyw, pose, pose);
+  };
+  auto frame_pose = [&](float* Tcw) {   // Twc.t *= s ; Tyc = Tyw * Twc ; SetPose(Tyc^-1)
+    float Twc[16], Tyc[16];
+    inv44(Tcw, Twc);
+    Twc[3] *= s; Twc[7] *= s; Twc[11] *= s;
+    mul44(Tyw, Twc, Tyc);
+    inv44(Tyc, Tcw);
+  };
+  if (vio) {
+    for (size_t i = 1; i < fr.size(); i++) {   // Map::vpFrames
+      frame_pose(fr[i].Tcw);
+      mv3(R, fr[i].vel, fr[i].vel, (double)s);   // Ryw * Vw * s
+    }
+    if (last && fr.size() > 1) memcpy(last->Tcw, fr.back().Tcw, sizeof(float) * 16);
+  } else if (last) {
+    frame_pose(last->Tcw);
+  }
+  if (last) {   // the tracker only keeps the last frame's feature lists alive
+    for (auto& p : last->mvStat3DPointTmp) rot_pt(p);
+    for (auto& p : last->mvObj3DPoint) rot_pt(p);
+  }
+  for (auto& f : map.vp3DPointSta) for (auto& p : f) rot_pt(p);
+  for (auto& f : map.vp3DPointDyn) for (auto& p : f) rot_pt(p);
+  for (auto& pose : map.vmCameraPose) scale_pose(pose.data());
+  for (auto& pose : map.vmRigidMotion) scale_pose(pose.data());
+  for (auto& f : map.vmObjMotion) for (auto& m : f) scale_pose(m.data());
+}
 
 }  // namespace
 
@@ -1106,6 +1428,26 @@ int vo_tracker_get_dyn_tracks(void* h, int32_t* len, int32_t* obj_id, int32_t* f
   for (int i = 0; i < n && i < cap; i++) {
     len[i] = (int)t->map.TrackletDyn[i].size(); obj_id[i] = t->map.nObjID[i];
     first_frame[i] = t->map.TrackletDyn[i][0].first; first_feat[i] = t->map.TrackletDyn[i][0].second;
+  }
+  return n;
+}
+
+int vo_tracker_apply_scaled_rotation(void* h, const float* R, float s) { ((Tracker*)h)->apply_scaled_rotation(R, s); return 0; }
+int vo_tracker_set_imu(void* h, const float* Tbc, const float* noise) { ((Tracker*)h)->set_imu(Tbc, noise); return 0; }
+int vo_tracker_grab_imu(void* h, const vo_imu_sample* smp, int n) {
+  Tracker* t = (Tracker*)h;
+  t->imu_q.insert(t->imu_q.end(), smp, smp + n);
+  return 0;
+}
+void vo_tracker_set_timestamp(void* h, double ts) { ((Tracker*)h)->next_t = ts; }
+int vo_tracker_get_imu_state(void* h, vo_imu_state* out) { *out = ((Tracker*)h)->ist; return 0; }
+int vo_tracker_get_imu_frames(void* h, float* Tcw, float* vel, float* bias, int cap) {
+  Tracker* t = (Tracker*)h;
+  const int n = (int)t->fr.size();
+  for (int i = 0; i < n && i < cap; i++) {
+    if (Tcw) memcpy(Tcw + 16 * (size_t)i, t->fr[i].Tcw, sizeof(float) * 16);
+    if (vel) memcpy(vel + 3 * (size_t)i, t->fr[i].vel, sizeof(float) * 3);
+    if (bias) memcpy(bias + 6 * (size_t)i, t->fr[i].bias, sizeof(float) * 6);
   }
   return n;
 }

@@ -308,9 +308,39 @@ typedef struct vo_inertial_problem {
   double scale;                /* in/out */
   double bg[3], ba[3];         /* in/out */
   float prior_g, prior_a;      /* 1e2, 1e9 (src/Tracking.cc:1453) */
+  int32_t mode;                /* 0: the initialisation above; 1: Optimizer::InertialOptimization(Map*, Rwg, scale) of
+                                  Tracking::ScaleRefinement (src/Optimizer.cc:2336-2439): velocities and biases fixed, no priors,
+                                  only gravity direction and scale, 10 iterations, default lambda */
 } vo_inertial_problem;
 void vo_inertial_default_params(vo_inertial_problem* p);
 int vo_inertial_optimization(vo_inertial_problem* p, vo_lm_stats* stats);
+/* IMU::Preintegrated::GetUpdatedDeltaRotation / Velocity / Position (src/ImuTypes.cc:370-386) for db = (dbg, dba) */
+void vo_imu_updated_deltas(const vo_imu_preint* p, const float* dbg, const float* dba, float* dR9, float* dV3, float* dP3);
+void vo_imu_exp_so3_f(const float* w3, float* R9); /* IMU::ExpSO3(float) (src/ImuTypes.cc:38-50) */
+/* Map::ApplyScaledRotation(R, s, bScaledVel = true, t = 0) (src/Map.cc:55-119) on the tracker's Map and last frame */
+int vo_tracker_apply_scaled_rotation(void* h, const float* R9, float s);
+/* ---- VIO mode of the tracker (sensor = IMU_RGBD): Tracking::ParseIMUParamFile / GrabImuData / PreintegrateIMU / InitializeIMU /
+ * ScaleRefinement / UpdateFrameIMU (src/Tracking.cc:174-281, 784-1077, 1452-1480).  set_imu: Tbc row-major 4x4, noise = (ng, na,
+ * ngw, naw) as given to IMU::Calib::Set.  grab_imu before each track call = System::TrackRGBD's vImuMeas; set_timestamp = its
+ * timestamp argument. */
+typedef struct vo_imu_state {
+  int32_t initialized;     /* Tracking::mbImuInitialized */
+  int32_t status;          /* last InitializeIMU attempt: -1 none, 0 done, 1 too few frames / too little time, 2 scale < 0.1,
+                              3 a frame without preintegration */
+  int32_t init_frame;      /* frame id at which the initialisation succeeded */
+  int32_t n_refinements;   /* ScaleRefinement calls */
+  int32_t n_reintegrated;  /* IMU::Preintegrated::Reintegrate calls (gyro bias moved by more than 0.01) */
+  int32_t lm_iterations, lm_trials; /* of the initialisation's inertial-only optimisation */
+  float t_init;            /* mTinit */
+  double scale;            /* mScale of the last inertial-only optimisation */
+  double Rwg[9], bg[3], ba[3];
+} vo_imu_state;
+int vo_tracker_set_imu(void* h, const float* Tbc16, const float* noise4);
+int vo_tracker_grab_imu(void* h, const vo_imu_sample* samples, int n);
+void vo_tracker_set_timestamp(void* h, double t);
+int vo_tracker_get_imu_state(void* h, vo_imu_state* out);
+/* per frame id (frame 0 included): Frame::mTcw, mVw, mImuBias (bax..bwz); returns the number of frames */
+int vo_tracker_get_imu_frames(void* h, float* Tcw, float* vel, float* bias, int cap);
 /* information matrix of an EdgeInertialGS from the 15x15 float32 preintegration covariance (src/G2oTypes.cc:363-375) */
 void vo_inertial_edge_information(const float* C15, double* info81);
 

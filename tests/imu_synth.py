@@ -96,3 +96,77 @@ def make_vio_case(n_frames=12, seed=0, fps=10.0, scale_true=1.25, bg_true=(0.002
     Rwg = _exp((vv * ang / nv).astype(np.float64))
     truth = dict(scale=scale_true, bg=np.asarray(bg_true), g_dir=g_w / 9.79, vel=v[fidx])
     return dict(Rwb=Rwb, twb=twb, vel=vel, preint=pre, bias_lin=np.zeros((n_frames - 1, 6), np.float32), Rwg=Rwg), truth
+
+
+# ---------------------------------------------------------------- a camera + IMU sequence for the VIO mode of the tracker
+TBC = np.array([[0.9998, -0.0175, 0.0100, 0.05], [0.0174, 0.9998, 0.0080, -0.03], [-0.0101, -0.0078, 0.9999, 0.02], [0, 0, 0, 1]])
+
+
+def _orthonormal(T):
+    u, _, vt = np.linalg.svd(T[:3, :3])
+    T = T.copy(); T[:3, :3] = u @ vt
+    return T
+
+
+def vio_camera_pose_np(k):
+    """Twc of (real-valued) frame index k: the canyon drive of synth.camera_pose with speed / height / lateral variation so that
+    the accelerometer sees the motion (y down: gravity is +y in this world)"""
+    yaw = np.radians(2.0) * np.sin(0.15 * k) + np.radians(1.0) * np.sin(0.5 * k)
+    pitch = np.radians(0.6) * np.sin(0.31 * k + 1.0)
+    cy, sy, cp, sp = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch)
+    Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    Rx = np.array([[1, 0, 0], [0, cp, -sp], [0, sp, cp]])
+    T = np.eye(4)
+    T[:3, :3] = Ry @ Rx
+    T[:3, 3] = [1.5 * np.sin(0.05 * k) + 0.3 * np.sin(0.4 * k), 0.12 * np.sin(0.5 * k), 1.0 * k + 0.4 * np.sin(0.6 * k)]
+    return T
+
+
+def vio_camera_pose(k):
+    import torch
+    return torch.from_numpy(vio_camera_pose_np(float(k)))
+
+
+def make_vio_sequence(n_frames, fps=2.5, bg_true=(0.002, -0.001, 0.0015), seed=0, noise=0.05, t0=10.0):
+    """200 Hz IMU samples of the body (Twb = Twc * Tcb) riding on vio_camera_pose(t * fps), frame k at t0 + k / fps.
+    Returns (samples, frame_t, Tbc float32 4x4, truth)"""
+    rng = np.random.default_rng(seed)
+    Tbc = _orthonormal(TBC)
+    Tcb = np.linalg.inv(Tbc)
+    g_w = np.array([0.0, 9.79, 0.0])
+    h = 1e-3
+    n = int((n_frames - 1) / fps * FREQ) + 12
+
+    def body(t):
+        Twc = vio_camera_pose_np(t * fps)
+        Twb = Twc @ Tcb
+        return Twb[:3, :3], Twb[:3, 3]
+
+    s = np.zeros(n, ol.IMU_SAMPLE)
+    ts = (np.arange(n) - 4) / FREQ + 0.0013
+    for i, t in enumerate(ts):
+        Rm, pm = body(t - h)
+        R0, p0 = body(t)
+        Rp, pp = body(t + h)
+        a = (pp - 2 * p0 + pm) / (h * h)
+        dR = Rm.T @ Rp
+        w = np.array([dR[2, 1] - dR[1, 2], dR[0, 2] - dR[2, 0], dR[1, 0] - dR[0, 1]]) / (4 * h)   # log(dR) / (2h), small angle
+        f = R0.T @ (a - g_w) + rng.normal(size=3) * 2.0e-3 * np.sqrt(FREQ) * noise
+        wm = w + np.asarray(bg_true) + rng.normal(size=3) * 1.7e-4 * np.sqrt(FREQ) * noise
+        s["t"][i] = t0 + t
+        s["ax"][i], s["ay"][i], s["az"][i] = f
+        s["wx"][i], s["wy"][i], s["wz"][i] = wm
+    frame_t = t0 + np.arange(n_frames) / fps
+    truth = dict(bg=np.asarray(bg_true), g_w=g_w, Tcb=Tcb)
+    return s, frame_t, Tbc.astype(np.float32), truth
+
+
+def imu_chunks(samples, frame_t):
+    """per frame k: the samples System::TrackRGBD would receive with it (those up to the frame's timestamp, plus the first later one)"""
+    out, lo = [], 0
+    for t in frame_t:
+        hi = int(np.searchsorted(samples["t"], t, side="right")) + 1
+        hi = min(max(hi, lo), len(samples))
+        out.append(samples[lo:hi])
+        lo = hi
+    return out

@@ -356,6 +356,13 @@ def track_config(cam, nfeatures=2500, window=20, max_track_bg=1000, rebuild=1, c
     return c
 
 
+class ImuState(C.Structure):
+    """vo_imu_state / vido_imu_state"""
+    _fields_ = [("initialized", C.c_int32), ("status", C.c_int32), ("init_frame", C.c_int32), ("n_refinements", C.c_int32),
+                ("n_reintegrated", C.c_int32), ("lm_iterations", C.c_int32), ("lm_trials", C.c_int32), ("t_init", C.c_float),
+                ("scale", C.c_double), ("Rwg", C.c_double * 9), ("bg", C.c_double * 3), ("ba", C.c_double * 3)]
+
+
 class OracleTracker:
     def __init__(self, cfg):
         L = lib()
@@ -373,11 +380,44 @@ class OracleTracker:
         L.vo_tracker_get_map_poses_rf.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.vo_tracker_get_objects_rf.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.vo_tracker_export_full_graph.argtypes = [C.c_void_p] + [C.c_void_p] * 14
+        L.vo_tracker_set_imu.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.vo_tracker_grab_imu.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.vo_tracker_set_timestamp.argtypes = [C.c_void_p, C.c_double]
+        L.vo_tracker_set_timestamp.restype = None
+        L.vo_tracker_get_imu_state.argtypes = [C.c_void_p, C.c_void_p]
+        L.vo_tracker_get_imu_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.vo_tracker_apply_scaled_rotation.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
         self.cfg = cfg
         self.h = L.vo_tracker_create(C.byref(cfg))
 
-    def track(self, gray, depth_in, flow, mask):
+    # ---- VIO mode (sensor = IMU_RGBD)
+    def set_imu(self, Tbc, noise):
+        T = np.ascontiguousarray(Tbc, np.float32).reshape(16); nz = np.ascontiguousarray(noise, np.float32)
+        lib().vo_tracker_set_imu(self.h, _p(T), _p(nz))
+
+    def grab_imu(self, samples):
+        s = np.ascontiguousarray(samples, IMU_SAMPLE)
+        lib().vo_tracker_grab_imu(self.h, _p(s), len(s))
+
+    def imu_state(self):
+        st = ImuState()
+        lib().vo_tracker_get_imu_state(self.h, C.byref(st))
+        return st
+
+    def imu_frames(self):
+        n = lib().vo_tracker_get_imu_frames(self.h, None, None, None, 0)
+        T = np.zeros((n, 16), np.float32); v = np.zeros((n, 3), np.float32); b = np.zeros((n, 6), np.float32)
+        lib().vo_tracker_get_imu_frames(self.h, _p(T), _p(v), _p(b), n)
+        return T.reshape(n, 4, 4), v, b
+
+    def apply_scaled_rotation(self, R, s):
+        Rm = np.ascontiguousarray(R, np.float32).reshape(9)
+        lib().vo_tracker_apply_scaled_rotation(self.h, _p(Rm), float(s))
+
+    def track(self, gray, depth_in, flow, mask, timestamp=None):
         """depth_in is copied (the oracle pre-scales its copy in place).  Returns (Tcw 4x4, stats dict, rc)."""
+        if timestamp is not None:
+            lib().vo_tracker_set_timestamp(self.h, float(timestamp))
         g = np.ascontiguousarray(gray, np.uint8); d = np.ascontiguousarray(depth_in, np.float32).copy()
         f = np.ascontiguousarray(flow, np.float32); m = np.ascontiguousarray(mask, np.int32)
         T = np.zeros(16, np.float32)
@@ -473,7 +513,8 @@ def imu_preintegrate(samples, t_prev, t_cur, bias, noise):
 class InertialProblem(C.Structure):
     _fields_ = [("n_frames", C.c_int32), ("its", C.c_int32), ("Rwb", C.c_void_p), ("twb", C.c_void_p), ("velocity", C.c_void_p),
                 ("preint", C.c_void_p), ("bias_lin", C.c_void_p), ("Rwg", C.c_double * 9), ("scale", C.c_double),
-                ("bg", C.c_double * 3), ("ba", C.c_double * 3), ("prior_g", C.c_float), ("prior_a", C.c_float)]
+                ("bg", C.c_double * 3), ("ba", C.c_double * 3), ("prior_g", C.c_float), ("prior_a", C.c_float),
+                ("mode", C.c_int32)]
 
 
 def fill_inertial(pr, Rwb, twb, vel, preint, bias_lin, Rwg, scale, bg, ba):

@@ -44,8 +44,9 @@ class Scene:
     """Canyon x in [-xw, xw], y in [-yh, yg] (y down, camera at y=0), infinite in z."""
 
     def __init__(self, cam=KITTI, seed=1234, xw=7.0, yg=1.65, yh=5.0, device="cpu",
-                 flow_noise=0.0, depth_noise=0.0, depth_map_factor=256.0, n_objects=0, drop_mask=()):
+                 flow_noise=0.0, depth_noise=0.0, depth_map_factor=256.0, n_objects=0, drop_mask=(), pose_fn=None):
         self.cam = dict(cam)
+        self.pose_fn = pose_fn or camera_pose   # k -> Twc (4x4 float64 tensor)
         self.n_objects = n_objects          # rigid textured billboards driving ahead of the camera (labels 1..n)
         self.drop_mask = set(drop_mask)     # (frame, label) pairs whose semantic mask is "lost" (exercises UpdateMask)
         self.seed = seed
@@ -144,8 +145,8 @@ class Scene:
         """dict: gray u8 [H,W], depth_in f32 [H,W] (reference input convention), depth_m f32 (metric),
         flow f32 [H,W,2], mask i32 [H,W], Twc (4x4 f64)"""
         cam = self.cam
-        Twc = camera_pose(k)
-        Tn = camera_pose(k + 1)
+        Twc = self.pose_fn(k)
+        Tn = self.pose_fn(k + 1)
         z, P, pid = self._intersect(Twc)
         gray = self._texture(P, pid)
         label = None

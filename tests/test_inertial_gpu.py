@@ -26,3 +26,17 @@ def test_inertial_opt_matches_oracle(pkg, n_frames, seed, scale):
     if n_frames >= 12:
         assert abs(out["scale"] - truth["scale"]) < 0.03 * truth["scale"]
     ctx.close()
+
+
+def test_scale_refinement_mode_matches_oracle(pkg):
+    case, truth = imu_synth.make_vio_case(n_frames=14, seed=2)
+    full = ol.inertial_optimization(**case)
+    args = (case["Rwb"], case["twb"], full["velocity"], case["preint"], case["bias_lin"], full["Rwg"])
+    kw = dict(scale=0.9 * full["scale"], bg=full["bg"], ba=full["ba"], mode=1, its=10)
+    ref = ol.inertial_optimization(*args, **kw)
+    ctx = pkg.Context(pkg.default_config(width=640, height=480, max_batch=1))
+    out = ctx.inertial_opt(*args, **kw)
+    assert out["stats"].iterations == ref["stats"].iterations and out["stats"].total_trials == ref["stats"].total_trials
+    assert abs(out["scale"] - ref["scale"]) <= 1e-6 * abs(ref["scale"]) and np.abs(out["Rwg"] - ref["Rwg"]).max() <= 1e-6
+    assert np.array_equal(out["velocity"], ref["velocity"])
+    ctx.close()

@@ -27,3 +27,16 @@ def test_recovers_scale_gravity_and_gyro_bias():
     assert np.abs(out["bg"] - truth["bg"]).max() < 6e-4, out["bg"]
     assert np.abs(out["ba"]).max() < 1e-3                              # pinned by the 1e9 prior
     assert np.abs(out["velocity"] * out["scale"] - truth["vel"]).max() < 0.08
+
+
+def test_scale_refinement_mode():
+    """Optimizer::InertialOptimization(Map*, Rwg, scale) of Tracking::ScaleRefinement: only gravity direction and scale move"""
+    case, truth = imu_synth.make_vio_case(n_frames=14, seed=2)
+    full = ol.inertial_optimization(**case)
+    # refine from the initialised state with a deliberately wrong scale, velocities / biases fixed
+    out = ol.inertial_optimization(case["Rwb"], case["twb"], full["velocity"], case["preint"], case["bias_lin"], full["Rwg"],
+                                   scale=0.9 * full["scale"], bg=full["bg"], ba=full["ba"], mode=1, its=10)
+    rec = out["stats"].records()
+    assert rec[-1][0] < rec[0][0]
+    assert np.array_equal(out["velocity"], full["velocity"]) and np.array_equal(out["bg"], full["bg"])
+    assert abs(out["scale"] - full["scale"]) < 0.02 * full["scale"]

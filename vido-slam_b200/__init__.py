@@ -99,7 +99,15 @@ class InertialProblem(C.Structure):
     """vido_inertial_problem (include/vido_b200.h)"""
     _fields_ = [("n_frames", C.c_int32), ("its", C.c_int32), ("Rwb", C.c_void_p), ("twb", C.c_void_p), ("velocity", C.c_void_p),
                 ("preint", C.c_void_p), ("bias_lin", C.c_void_p), ("Rwg", C.c_double * 9), ("scale", C.c_double),
-                ("bg", C.c_double * 3), ("ba", C.c_double * 3), ("prior_g", C.c_float), ("prior_a", C.c_float)]
+                ("bg", C.c_double * 3), ("ba", C.c_double * 3), ("prior_g", C.c_float), ("prior_a", C.c_float),
+                ("mode", C.c_int32)]
+
+
+class ImuState(C.Structure):
+    """vido_imu_state (include/vido_b200.h)"""
+    _fields_ = [("initialized", C.c_int32), ("status", C.c_int32), ("init_frame", C.c_int32), ("n_refinements", C.c_int32),
+                ("n_reintegrated", C.c_int32), ("lm_iterations", C.c_int32), ("lm_trials", C.c_int32), ("t_init", C.c_float),
+                ("scale", C.c_double), ("Rwg", C.c_double * 9), ("bg", C.c_double * 3), ("ba", C.c_double * 3)]
 
 
 class FrameInputs(C.Structure):
@@ -183,6 +191,11 @@ def load_library():
     lib.vido_pose_opt_proj.argtypes = [vp, C.POINTER(ProjOptProblem), C.c_int, C.POINTER(LmStats)]
     lib.vido_inertial_default_params.argtypes = [C.POINTER(InertialProblem)]
     lib.vido_inertial_opt.argtypes = [vp, C.POINTER(InertialProblem), C.POINTER(LmStats)]
+    lib.vido_track_set_imu.argtypes = [vp, vp, vp]
+    lib.vido_track_grab_imu.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.vido_track_get_imu_state.argtypes = [vp, C.POINTER(ImuState)]
+    lib.vido_map_get_imu_frames.argtypes = [vp, vp, vp, vp, C.c_int]
+    lib.vido_map_apply_scaled_rotation.argtypes = [vp, vp, C.c_float]
     lib.vido_pnp_default_params.argtypes = [C.POINTER(PnpProblem)]
     lib.vido_init_model.argtypes = [vp, C.POINTER(PnpProblem)]
     lib.vido_poseopt_default_params.argtypes = [C.POINTER(PoseOptProblem)]
@@ -373,10 +386,42 @@ class Context:
             fi.timestamp = float(f.get("timestamp", 0.1 * k))
         return arr, keep
 
-    def track_frames(self, frames, want_stats=True):
+    # ---- VIO mode (sensor = IMU_RGBD)
+    def track_set_imu(self, Tbc, noise):
+        """Tracking::ParseIMUParamFile: Tbc 4x4, noise (ng, na, ngw, naw) as given to IMU::Calib"""
+        T = np.ascontiguousarray(Tbc, np.float32).reshape(16); nz = np.ascontiguousarray(noise, np.float32)
+        self._check(self.lib.vido_track_set_imu(self.h, _ptr(T), _ptr(nz)))
+
+    def track_grab_imu(self, samples, frames_ahead=0):
+        """Tracking::GrabImuData for the frame `frames_ahead` frames after the next one to be tracked"""
+        s = np.ascontiguousarray(samples, IMU_SAMPLE)
+        self._check(self.lib.vido_track_grab_imu(self.h, _ptr(s), len(s), int(frames_ahead)))
+
+    def imu_state(self):
+        st = ImuState()
+        self._check(self.lib.vido_track_get_imu_state(self.h, C.byref(st)))
+        return st
+
+    def map_imu_frames(self):
+        n = self.lib.vido_map_get_imu_frames(self.h, None, None, None, 0)
+        T = np.zeros((max(n, 0), 16), np.float32); v = np.zeros((max(n, 0), 3), np.float32); b = np.zeros((max(n, 0), 6), np.float32)
+        if n > 0:
+            self.lib.vido_map_get_imu_frames(self.h, _ptr(T), _ptr(v), _ptr(b), n)
+        return T.reshape(-1, 4, 4), v, b
+
+    def map_apply_scaled_rotation(self, R, s):
+        """Map::ApplyScaledRotation(R, s)"""
+        Rm = np.ascontiguousarray(R, np.float32).reshape(9)
+        self._check(self.lib.vido_map_apply_scaled_rotation(self.h, _ptr(Rm), float(s)))
+
+    def track_frames(self, frames, want_stats=True, imu=None):
         """frames: list of dicts {image, depth, flow, mask} holding either numpy host arrays or integer device
-        pointers (then pass on_device=True and channels).  Returns (Tcw [n,4,4] f32, [stats dict] or None)."""
+        pointers (then pass on_device=True and channels).  imu (VIO mode): per frame the IMU samples System::TrackRGBD would
+        receive with it.  Returns (Tcw [n,4,4] f32, [stats dict] or None)."""
         n = len(frames)
+        if imu is not None:
+            for k, smp in enumerate(imu):
+                self.track_grab_imu(smp, k)
         arr, keep = self._frame_inputs(frames)
         T = np.zeros((n, 16), np.float32)
         st = (TrackStats * n)() if want_stats else None

@@ -357,6 +357,15 @@ int vido_inertial_opt(vido_ctx* ctx, vido_inertial_problem* p, vido_lm_stats* st
   return inertial_opt_host(ctx, p, stats);
 }
 
+int vido_track_set_imu(vido_ctx* ctx, const float* Tbc, const float* noise) { return (ctx && Tbc && noise) ? trk_set_imu(ctx, Tbc, noise) : VIDO_ERR_ARG; }
+int vido_track_grab_imu(vido_ctx* ctx, const vido_imu_sample* samples, int n, int frames_ahead) {
+  if (!ctx || n < 0 || (n > 0 && !samples) || frames_ahead < 0) return VIDO_ERR_ARG;
+  return trk_grab_imu(ctx, samples, n, frames_ahead);
+}
+int vido_track_get_imu_state(vido_ctx* ctx, vido_imu_state* out) { return (ctx && out) ? trk_get_imu_state(ctx, out) : VIDO_ERR_ARG; }
+int vido_map_get_imu_frames(vido_ctx* ctx, float* Tcw, float* vel, float* bias, int cap) { return ctx ? trk_get_imu_frames(ctx, Tcw, vel, bias, cap) : VIDO_ERR_ARG; }
+int vido_map_apply_scaled_rotation(vido_ctx* ctx, const float* R, float s) { return (ctx && R) ? trk_apply_scaled_rotation(ctx, R, s) : VIDO_ERR_ARG; }
+
 int vido_get_kernel_times(vido_ctx* ctx, double* ms, int64_t* launches, double* ba_alg_bytes) {
   if (!ctx) return VIDO_ERR_ARG;
   for (int k = 0; k < 4; k++) { if (ms) ms[k] = ctx->t_ms[k]; if (launches) launches[k] = ctx->t_n[k]; }

@@ -170,6 +170,11 @@ int trk_get_dynamic(vido_ctx* ctx, int frame, float* xy, float* depth, float* p3
 int trk_get_objects(vido_ctx* ctx, int frame, int32_t* label, int32_t* sem_label, float* motion, float* centre, int cap);
 int trk_get_dyn_tracks(vido_ctx* ctx, int32_t* len, int32_t* obj_id, int32_t* first_frame, int32_t* first_feat, int cap);
 
+int trk_apply_scaled_rotation(vido_ctx* ctx, const float* R, float s);
+int trk_set_imu(vido_ctx* ctx, const float* Tbc, const float* noise);
+int trk_grab_imu(vido_ctx* ctx, const vido_imu_sample* smp, int n, int frames_ahead);
+int trk_get_imu_state(vido_ctx* ctx, vido_imu_state* out);
+int trk_get_imu_frames(vido_ctx* ctx, float* Tcw, float* vel, float* bias, int cap);
 int trk_full_batch(vido_ctx* ctx, vido_lm_stats* stats, int32_t* sizes);
 int trk_get_map_poses_rf(vido_ctx* ctx, float* poses, int cap);
 int trk_get_objects_rf(vido_ctx* ctx, int frame, float* motion, int cap);
@@ -191,4 +196,4 @@ int inertial_opt_host(vido_ctx* ctx, vido_inertial_problem* p, vido_lm_stats* st
 
 // imu_kernels.cu
 int imu_preintegrate_host(vido_ctx* ctx, const vido_imu_sample* samples, int n, const double* t_prev, const double* t_cur,
-                          int njobs, const float* bias, const float* noise, vido_imu_preint* out);
+                          int njobs, const float* bias, const float* noise, vido_imu_preint* out, const int32_t* nvis = nullptr);

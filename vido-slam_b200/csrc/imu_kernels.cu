@@ -133,11 +133,13 @@ __device__ void imu_step(ImuState& s, float* C /* 225, global */, const float* b
   s.dT = (float)(T + t);
 }
 
-__global__ void imu_preint_kernel(const vido_imu_sample* __restrict__ q, int n, const double* __restrict__ t_prev,
-                                  const double* __restrict__ t_cur, int njobs, const float* __restrict__ bias,
-                                  float ng, float na, float ngw, float naw, vido_imu_preint* __restrict__ out) {
+__global__ void imu_preint_kernel(const vido_imu_sample* __restrict__ q, int n_all, const int32_t* __restrict__ nvis,
+                                  const double* __restrict__ t_prev, const double* __restrict__ t_cur, int njobs,
+                                  const float* __restrict__ bias, float ng, float na, float ngw, float naw,
+                                  vido_imu_preint* __restrict__ out) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= njobs) return;
+  const int n = nvis ? min(nvis[j], n_all) : n_all;   // samples delivered before this frame (the queue the reference would see)
   const double tp = t_prev[j], tc = t_cur[j];
   vido_imu_preint* o = out + j;
   float Nga[36], NgaWalk[36];
@@ -197,23 +199,28 @@ __global__ void imu_preint_kernel(const vido_imu_sample* __restrict__ q, int n, 
 }
 
 int imu_preintegrate_host(vido_ctx* ctx, const vido_imu_sample* samples, int n, const double* t_prev, const double* t_cur,
-                          int njobs, const float* bias, const float* noise, vido_imu_preint* out) {
+                          int njobs, const float* bias, const float* noise, vido_imu_preint* out, const int32_t* nvis) {
   if (n < 0 || njobs < 1) return VIDO_ERR_ARG;
   cudaStream_t s = ctx->stream;
-  vido_imu_sample* d_s = nullptr; double* d_t = nullptr; float* d_b = nullptr; vido_imu_preint* d_o = nullptr;
+  vido_imu_sample* d_s = nullptr; double* d_t = nullptr; float* d_b = nullptr; vido_imu_preint* d_o = nullptr; int32_t* d_n = nullptr;
   VIDO_CUDA(cudaMallocAsync(&d_s, sizeof(vido_imu_sample) * std::max(n, 1), s));
   VIDO_CUDA(cudaMallocAsync(&d_t, sizeof(double) * 2 * njobs, s));
   VIDO_CUDA(cudaMallocAsync(&d_b, sizeof(float) * 6 * njobs, s));
   VIDO_CUDA(cudaMallocAsync(&d_o, sizeof(vido_imu_preint) * njobs, s));
+  if (nvis) {
+    VIDO_CUDA(cudaMallocAsync(&d_n, sizeof(int32_t) * njobs, s));
+    VIDO_CUDA(cudaMemcpyAsync(d_n, nvis, sizeof(int32_t) * njobs, cudaMemcpyHostToDevice, s));
+  }
   if (n) VIDO_CUDA(cudaMemcpyAsync(d_s, samples, sizeof(vido_imu_sample) * n, cudaMemcpyHostToDevice, s));
   VIDO_CUDA(cudaMemcpyAsync(d_t, t_prev, sizeof(double) * njobs, cudaMemcpyHostToDevice, s));
   VIDO_CUDA(cudaMemcpyAsync(d_t + njobs, t_cur, sizeof(double) * njobs, cudaMemcpyHostToDevice, s));
   VIDO_CUDA(cudaMemcpyAsync(d_b, bias, sizeof(float) * 6 * njobs, cudaMemcpyHostToDevice, s));
-  imu_preint_kernel<<<(njobs + 63) / 64, 64, 0, s>>>(d_s, n, d_t, d_t + njobs, njobs, d_b, noise[0], noise[1], noise[2], noise[3], d_o);
+  imu_preint_kernel<<<(njobs + 63) / 64, 64, 0, s>>>(d_s, n, d_n, d_t, d_t + njobs, njobs, d_b, noise[0], noise[1], noise[2], noise[3], d_o);
   ctx->launches++;
   VIDO_CUDA(cudaGetLastError());
   VIDO_CUDA(cudaMemcpyAsync(out, d_o, sizeof(vido_imu_preint) * njobs, cudaMemcpyDeviceToHost, s));
   VIDO_CUDA(cudaStreamSynchronize(s));
   cudaFreeAsync(d_s, s); cudaFreeAsync(d_t, s); cudaFreeAsync(d_b, s); cudaFreeAsync(d_o, s);
+  if (d_n) cudaFreeAsync(d_n, s);
   return VIDO_OK;
 }

@@ -26,7 +26,7 @@ constexpr int IN_THREADS = 256;
 #define GRAVITY_VALUE ((double)9.79f)   // include/ImuTypes.h:29 (a float constant)
 
 struct InertialArgs {
-  int N, its;
+  int N, its, mode;
   const double* Rwb;   // [N][9]
   const double* twb;   // [N][3]
   const vido_imu_preint* pre;  // [N-1]
@@ -272,7 +272,7 @@ __device__ double chi2_of(const InertialArgs& a, int sel, double* sm) {
     for (int i = 0; i < 9; i++)
       for (int j = 0; j < 9; j++) acc += r[i] * I9[9 * i + j] * r[j];
   }
-  if (threadIdx.x == 0)
+  if (threadIdx.x == 0 && a.mode == 0)
     for (int k = 0; k < 3; k++) acc += a.priorA * glob[3 + k] * glob[3 + k] + a.priorG * glob[k] * glob[k];
   return block_sum(acc, sm);
 }
@@ -375,21 +375,24 @@ __global__ void __launch_bounds__(IN_THREADS) inertial_opt_kernel(InertialArgs a
       if (tid < 81) {
         const int r = bcol[tid / 9], q = bcol[tid % 9];
         for (int e = 0; e < E; e++) s += a.He[225 * (size_t)e + 15 * r + q];
-        if (tid / 9 == tid % 9) { if (tid / 9 < 3) s += a.priorG; else if (tid / 9 < 6) s += a.priorA; }
+        if (tid / 9 == tid % 9 && a.mode == 0) { if (tid / 9 < 3) s += a.priorG; else if (tid / 9 < 6) s += a.priorA; }
         Hbb[tid] = s;
       } else {
         const int r = tid - 81;
         for (int e = 0; e < E; e++) s += a.be[15 * (size_t)e + bcol[r]];
-        if (r < 3) s -= a.priorG * (0.0 - glob[r]);
-        else if (r < 6) s -= a.priorA * (0.0 - glob[r]);
+        if (a.mode == 0) {
+          if (r < 3) s -= a.priorG * (0.0 - glob[r]);
+          else if (r < 6) s -= a.priorA * (0.0 - glob[r]);
+        }
         bb[r] = s;
       }
     }
     __syncthreads();
     if (it == 0 && !(a.user_lambda > 0)) {
       double m = 0;
-      for (int i = tid; i < 3 * N; i += IN_THREADS) m = fmax(m, fabs(a.D[9 * (size_t)(i / 3) + 4 * (i % 3)]));
-      if (tid < 9) m = fmax(m, fabs(Hbb[10 * tid]));
+      if (a.mode == 0)
+        for (int i = tid; i < 3 * N; i += IN_THREADS) m = fmax(m, fabs(a.D[9 * (size_t)(i / 3) + 4 * (i % 3)]));
+      if (tid < 9 && (a.mode == 0 || tid >= 6)) m = fmax(m, fabs(Hbb[10 * tid]));
       for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
       __syncthreads();
       if ((tid & 31) == 0) sm[tid >> 5] = m;
@@ -400,7 +403,30 @@ __global__ void __launch_bounds__(IN_THREADS) inertial_opt_kernel(InertialArgs a
     // ---- trials
     while (true) {
       const double lambda = c->lambda;
-      if (tid == 0) {
+      if (tid == 0 && a.mode == 1) {
+        // only gravity direction and scale are free: 3x3 system on the border entries 6..8, every other increment stays 0
+        s_fail = 0;
+        double A3[9], L3[9], y3[3], x3[3] = {a.x[3 * (size_t)N + 6], a.x[3 * (size_t)N + 7], a.x[3 * (size_t)N + 8]};
+        for (int r = 0; r < 3; r++)
+          for (int q = 0; q < 3; q++) { A3[3 * r + q] = Hbb[9 * (6 + r) + 6 + q] + (r == q ? lambda : 0.0); L3[3 * r + q] = 0; }
+        for (int j = 0; j < 3 && !s_fail; j++) {
+          double dd = A3[3 * j + j];
+          for (int k = 0; k < j; k++) dd -= L3[3 * j + k] * L3[3 * j + k];
+          if (!(dd > 0)) { s_fail = 1; break; }
+          L3[3 * j + j] = sqrt(dd);
+          for (int i = j + 1; i < 3; i++) {
+            double s2 = A3[3 * i + j];
+            for (int k = 0; k < j; k++) s2 -= L3[3 * i + k] * L3[3 * j + k];
+            L3[3 * i + j] = s2 / L3[3 * j + j];
+          }
+        }
+        if (!s_fail) {
+          for (int i = 0; i < 3; i++) { double s2 = bb[6 + i]; for (int k = 0; k < i; k++) s2 -= L3[3 * i + k] * y3[k]; y3[i] = s2 / L3[3 * i + i]; }
+          for (int i = 2; i >= 0; i--) { double s2 = y3[i]; for (int k = i + 1; k < 3; k++) s2 -= L3[3 * k + i] * x3[k]; x3[i] = s2 / L3[3 * i + i]; }
+          for (int k = 0; k < 3; k++) a.x[3 * (size_t)N + 6 + k] = x3[k];
+        }
+      }
+      if (tid == 0 && a.mode == 0) {
         // forward elimination of the velocity chain; border Schur complement in Sbb / x[3N..]
         s_fail = 0;
         for (int k = 0; k < 81; k++) Sbb[k] = Hbb[k] + ((k / 9 == k % 9) ? lambda : 0.0);
@@ -503,18 +529,18 @@ __global__ void __launch_bounds__(IN_THREADS) inertial_opt_kernel(InertialArgs a
       double* gt = a.glob + 16 * (cur ^ 1);
       double sc = 0;
       for (int i = tid; i < 3 * N; i += IN_THREADS) {
-        const double xi = a.x[i];
+        const double xi = a.mode == 0 ? a.x[i] : 0.0;
         Vt[i] = V[i] + xi;
         sc += xi * (lambda * xi + a.bv[i]);
       }
       if (tid == 0) {
         const double* xb = a.x + 3 * (size_t)N;
-        for (int k = 0; k < 6; k++) gt[k] = glob[k] + xb[k];
+        for (int k = 0; k < 6; k++) gt[k] = glob[k] + (a.mode == 0 ? xb[k] : 0.0);
         double Ex[9];
         exp_so3(xb[6], xb[7], 0.0, Ex);
         mul33(glob + 6, Ex, gt + 6);
         gt[15] = glob[15] * exp(xb[8]);
-        for (int k = 0; k < 9; k++) sc += xb[k] * (lambda * xb[k] + bb[k]);
+        for (int k = (a.mode == 0 ? 0 : 6); k < 9; k++) sc += xb[k] * (lambda * xb[k] + bb[k]);
       }
       const double scale = block_sum(sc, sm);
       const double chi = chi2_of(a, cur ^ 1, sm);
@@ -592,7 +618,7 @@ void edge_information(const float* C15, double* Info) {
 
 }  // namespace
 
-void inertial_default_params(vido_inertial_problem* p) { p->prior_g = 1e2f; p->prior_a = 1e9f; p->its = 200; }
+void inertial_default_params(vido_inertial_problem* p) { p->prior_g = 1e2f; p->prior_a = 1e9f; p->its = 200; p->mode = 0; }
 
 int inertial_opt_host(vido_ctx* ctx, vido_inertial_problem* p, vido_lm_stats* st) {
   if (st) { st->iterations = -1; st->n_records = 0; st->total_trials = 0; }
@@ -628,10 +654,10 @@ int inertial_opt_host(vido_ctx* ctx, vido_inertial_problem* p, vido_lm_stats* st
     if (cudaMemsetAsync(base + o_x, 0, 8 * (3 * (size_t)N + 9), s) != cudaSuccess) { ctx->err = "inertial: memset failed"; rc = VIDO_ERR_CUDA; break; }
     InertialArgs a;
     memset(&a, 0, sizeof a);
-    a.N = N; a.its = p->its;
+    a.N = N; a.its = p->its; a.mode = p->mode;
     a.Rwb = (const double*)(base + o_Rwb); a.twb = (const double*)(base + o_twb); a.pre = (const vido_imu_preint*)(base + o_pre);
     a.blin = (const float*)(base + o_blin); a.Info = (const double*)(base + o_Info);
-    a.priorG = (double)p->prior_g; a.priorA = (double)p->prior_a; a.user_lambda = p->prior_g != 0.f ? 1e3 : -1.0;   // :2456-2458
+    a.priorG = (double)p->prior_g; a.priorA = (double)p->prior_a; a.user_lambda = (p->mode == 0 && p->prior_g != 0.f) ? 1e3 : -1.0;   // :2456-2458
     a.V = (double*)(base + o_V); a.glob = (double*)(base + o_glob);
     a.He = (double*)(base + o_He); a.be = (double*)(base + o_be); a.D = (double*)(base + o_D); a.O = (double*)(base + o_O);
     a.Bv = (double*)(base + o_Bv); a.bv = (double*)(base + o_bv); a.x = (double*)(base + o_x); a.L = (double*)(base + o_L);

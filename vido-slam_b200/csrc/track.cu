@@ -13,11 +13,16 @@
 //   GetSceneFlowObj :1582-1668, DynObjTracking :1670-1912, GetInitModelObj :2030-2162 + Optimizer::PoseOptimizationFlow2
 //   Optimizer.cc:3037-3253 (one launch for all objects of a frame), object part of RenewFrameInfo :3112-3289,
 //   GetDynamicTrackNew :2615-2720 (incremental).  A static sequence (all-zero mask) never enters these branches.
-// Scope of this version: sensor RGBD, bJoint = true, UseSampleFeature = 0, no IMU.
+// VIO mode (sensor = IMU_RGBD, after vido_track_set_imu): Tracking::ParseIMUParamFile / GrabImuData / PreintegrateIMU (the
+//   preintegration kernel, one launch per front-end batch) / InitializeIMU + Optimizer::InertialOptimization (the inertial
+//   kernel) / ScaleRefinement / UpdateFrameIMU  Tracking.cc:174-281, 784-1077, 1115-1119, 1452-1480, 1555-1561; the IMU state of
+//   Frame  Frame.cc:437-521, Frame.h:44-110; Map::ApplyScaledRotation  Map.cc:55-119.
+// Scope of this version: sensor RGBD / IMU_RGBD, UseSampleFeature = 0.
 // float 4x4 products use double accumulation + one rounding like cv::Mat CV_32F gemm.
 #include <algorithm>
 #include <array>
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <map>
 
@@ -66,6 +71,75 @@ struct MapFrame {           // Map::vpFeatSta / vfDepSta / vp3DPointSta / vnAsso
   std::vector<int> dasso, dlabel, dtrack;
   std::vector<ObjEntry> objects;
 };
+
+// ---- float32 cv::Mat helpers of the VIO glue (gemm: double accumulation, one rounding per expression)
+void mm3(const float* A, const float* B, float* C) {
+  float o[9];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) o[3 * r + c] = (float)((double)A[3 * r] * B[c] + (double)A[3 * r + 1] * B[3 + c] + (double)A[3 * r + 2] * B[6 + c]);
+  memcpy(C, o, sizeof o);
+}
+void mv3(const float* A, const float* v, float* o, double alpha = 1.0, const float* w = nullptr) {   // alpha * A * v + w
+  float t[3];
+  for (int r = 0; r < 3; r++)
+    t[r] = (float)(alpha * ((double)A[3 * r] * v[0] + (double)A[3 * r + 1] * v[1] + (double)A[3 * r + 2] * v[2]) + (w ? (double)w[r] : 0.0));
+  memcpy(o, t, sizeof t);
+}
+void inv33d(const double* m, double* o) {
+  const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+  const double id = 1.0 / (m[0] * c00 + m[1] * c01 + m[2] * c02);
+  o[0] = c00 * id; o[1] = (m[2] * m[7] - m[1] * m[8]) * id; o[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+  o[3] = c01 * id; o[4] = (m[0] * m[8] - m[2] * m[6]) * id; o[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+  o[6] = c02 * id; o[7] = (m[1] * m[6] - m[0] * m[7]) * id; o[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+}
+// IMU::ExpSO3(float) (ImuTypes.cc:38-50), entries rounded to float32
+void exp_so3_host(const float* w, float* R) {
+  const float x = w[0], y = w[1], z = w[2];
+  const float d2 = x * x + y * y + z * z;
+  const float d = std::sqrt(d2);
+  const double W[9] = {0, -z, y, z, 0, -x, -y, x, 0};
+  for (int k = 0; k < 9; k++) {
+    const int i = k / 3, j = k % 3;
+    const double w2 = W[3 * i] * W[j] + W[3 * i + 1] * W[3 + j] + W[3 * i + 2] * W[6 + j];
+    const double I = (i == j) ? 1.0 : 0.0;
+    const double v = d < 1e-4f ? I + W[k] + 0.5 * (double)(float)w2
+                               : I + W[k] * std::sin((double)d) / d + (double)(float)w2 * (1.0 - std::cos((double)d)) / d2;
+    R[k] = (float)v;
+  }
+}
+// IMU::Preintegrated::GetUpdatedDeltaRotation / Velocity / Position (ImuTypes.cc:370-386): db = (gyro, acc) bias deltas;
+// NormalizeRotation (cv::SVDecomp U * Vt) = orthogonal polar factor
+void updated_deltas(const vido_imu_preint& p, const float* db, float* dR, float* dV, float* dP) {
+  const float* dbg = db; const float* dba = db + 3;
+  float rj[3], E[9];
+  mv3(p.JRg, dbg, rj);
+  exp_so3_host(rj, E);
+  double X[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+      X[3 * i + j] = (double)(float)((double)p.dR[3 * i] * E[j] + (double)p.dR[3 * i + 1] * E[3 + j] + (double)p.dR[3 * i + 2] * E[6 + j]);
+  for (int it = 0; it < 8; it++) {
+    double Xi[9];
+    inv33d(X, Xi);
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) X[3 * i + j] = 0.5 * (X[3 * i + j] + Xi[3 * j + i]);
+  }
+  for (int k = 0; k < 9; k++) dR[k] = (float)X[k];
+  float t1[3], t2[3], u1[3], u2[3];
+  mv3(p.JVg, dbg, t1); mv3(p.JVa, dba, t2); mv3(p.JPg, dbg, u1); mv3(p.JPa, dba, u2);
+  for (int i = 0; i < 3; i++) { dV[i] = (p.dV[i] + t1[i]) + t2[i]; dP[i] = (p.dP[i] + u1[i]) + u2[i]; }
+}
+
+struct ImuFrame {              // IMU members of Frame (Frame.h): mTcw, mVw, mImuBias, mpImuPreintegrated, mTimeStamp
+  float Tcw[16];
+  float vel[3] = {0.f, 0.f, 0.f};
+  float bias[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // bax, bay, baz, bwx, bwy, bwz
+  bool has_pre = false;
+  vido_imu_preint pre;         // integrated with pre_b; db = bu - b: gyro (0..2), acc (3..5) (IMU::Preintegrated::db)
+  float pre_b[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, db[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  size_t q1 = 0;               // queue samples delivered when the frame was preintegrated (Reintegrate)
+  double t = 0, t_prev = 0;
+};
 struct TrackInfo { int first_frame, len, pid, epoch; };  // pid valid for the window graph built in `epoch`
 
 struct FrontFrame {         // front-end results of one frame, on the host
@@ -81,6 +155,18 @@ struct FrontFrame {         // front-end results of one frame, on the host
 }  // namespace
 
 struct TrackState {
+  // ---- VIO state (Tracking: mpImuCalib, mlQueueImuData, mbImuInitialized, mScale, mRwg, mbg, mba, mTinit)
+  bool vio = false;
+  float Tbc[16], Tcb[16], imu_noise[4];
+  std::vector<vido_imu_sample> imu_q;    // every delivered sample (kept: Reintegrate re-reads its range)
+  std::vector<int64_t> imu_q_frame;      // frame counter before which each sample was delivered (nondecreasing)
+  size_t imu_head = 0;                   // queue front (mlQueueImuData.front())
+  int64_t frames_seen = 0;               // frames handed to the back-end (tracked or skipped)
+  std::vector<ImuFrame> fr;              // by frame id; fr[0] (the initial frame) is not in Map::vpFrames
+  struct PreCache { bool valid = false; double t_prev = 0, t = 0; float bias[6]; size_t q1 = 0; vido_imu_preint pre; };
+  std::vector<PreCache> pre_cache;       // preintegrations of the current front-end batch (one launch)
+  double cur_t = 0;                      // timestamp of the frame in the back-end
+  vido_imu_state ist;
   // sequence state
   std::vector<MapFrame> map;
   std::vector<TrackInfo> tracks;
@@ -301,6 +387,12 @@ int trk_reset(vido_ctx* ctx) {
   ts->lo_keys.clear(); ts->lo_depth.clear(); ts->lo_corres.clear(); ts->lo_flow.clear(); ts->lo_sem.clear();
   ts->l_mod_label.clear(); ts->l_sem_pos.clear(); ts->l_obj_stat.clear(); ts->l_obj_mod.clear();
   ts->dyn_tracks.clear(); ts->max_id = 1; ts->have_last_maps = false;
+  ts->fr.clear(); ts->imu_q.clear(); ts->imu_q_frame.clear(); ts->imu_head = 0; ts->frames_seen = 0; ts->pre_cache.clear();
+  if (ts->vio) {
+    memset(&ts->ist, 0, sizeof ts->ist);
+    ts->ist.scale = 1.0; ts->ist.status = -1;
+    ts->ist.Rwg[0] = ts->ist.Rwg[4] = ts->ist.Rwg[8] = 1.0;
+  }
   return VIDO_OK;
 }
 
@@ -1111,6 +1203,305 @@ static int ba_flush_deferred(vido_ctx* ctx) {
   return rc;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// VIO glue (sensor = IMU_RGBD): the host side of Tracking's IMU path around the preintegration / inertial kernels
+// ---------------------------------------------------------------------------------------------------------
+static int trk_apply_scaled_rotation_impl(vido_ctx* ctx, const float* R, float s);
+
+static void vio_imu_rotation(const TrackState* ts, const ImuFrame& f, float* Rwb) {   // Frame::GetImuRotation: mRwc * Tcb.R
+  float Rwc[9], Rcb[9];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) { Rwc[3 * r + c] = f.Tcw[4 * c + r]; Rcb[3 * r + c] = ts->Tcb[4 * r + c]; }
+  mm3(Rwc, Rcb, Rwb);
+}
+static void vio_imu_position(const TrackState* ts, const ImuFrame& f, float* twb) {   // mOwb = mRwc * tcb + mOw, mOw = -mRcw.t() * mtcw
+  float Rwc[9], tcw[3] = {f.Tcw[3], f.Tcw[7], f.Tcw[11]}, tcb[3] = {ts->Tcb[3], ts->Tcb[7], ts->Tcb[11]}, Ow[3];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) Rwc[3 * r + c] = f.Tcw[4 * c + r];
+  mv3(Rwc, tcw, Ow, -1.0);
+  mv3(Rwc, tcb, twb, 1.0, Ow);
+}
+static void vio_set_imu_pose_velocity(const TrackState* ts, ImuFrame& f, const float* Rwb, const float* twb, const float* Vwb) {  // Frame.cc:510-521
+  memcpy(f.vel, Vwb, sizeof f.vel);
+  float Rbw[9], tbw[3], Tbw[16];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) Rbw[3 * r + c] = Rwb[3 * c + r];
+  mv3(Rbw, twb, tbw, -1.0);
+  eye44(Tbw);
+  for (int r = 0; r < 3; r++) {
+    for (int c = 0; c < 3; c++) Tbw[4 * r + c] = Rbw[3 * r + c];
+    Tbw[4 * r + 3] = tbw[r];
+  }
+  mul44(ts->Tcb, Tbw, f.Tcw);
+}
+static void vio_pre_set_new_bias(ImuFrame& f, const float* b) {   // IMU::Preintegrated::SetNewBias (ImuTypes.cc:328-339)
+  if (f.has_pre)
+    for (int k = 0; k < 3; k++) { f.db[k] = b[3 + k] - f.pre_b[3 + k]; f.db[3 + k] = b[k] - f.pre_b[k]; }
+}
+static void vio_set_new_bias(ImuFrame& f, const float* b) {       // Frame::SetNewBias (Frame.cc:464-469)
+  memcpy(f.bias, b, sizeof f.bias);
+  vio_pre_set_new_bias(f, b);
+}
+// queue window handed to the kernel: everything from the current queue front on (older samples lie before every interval)
+static int vio_run_jobs(vido_ctx* ctx, size_t base, int njobs, const double* tp, const double* tc, const float* bias, const size_t* q1,
+                        vido_imu_preint* out) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  size_t hi = base;
+  std::vector<int32_t> nvis(njobs);
+  for (int j = 0; j < njobs; j++) { hi = std::max(hi, q1[j]); nvis[j] = (int32_t)(q1[j] > base ? q1[j] - base : 0); }
+  int rc = imu_preintegrate_host(ctx, ts->imu_q.data() + base, (int)(hi - base), tp, tc, njobs, bias, ts->imu_noise, out, nvis.data());
+  if (rc) return rc;
+  for (int j = 0; j < njobs; j++) out[j].n_consumed += (int32_t)base;   // absolute queue index
+  return VIDO_OK;
+}
+static size_t vio_visible(const TrackState* ts, int64_t frame_counter) {
+  return (size_t)(std::upper_bound(ts->imu_q_frame.begin(), ts->imu_q_frame.end(), frame_counter) - ts->imu_q_frame.begin());
+}
+// Tracking::PreintegrateIMU for the B frames of a front-end batch in ONE launch: they all integrate with the bias of the last
+// tracked frame (it only changes at the initialisation / a reintegration, which invalidates the rest of the cache)
+static int vio_preintegrate_batch(vido_ctx* ctx, const vido_frame_inputs* in, int B) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  ts->pre_cache.assign(B, TrackState::PreCache());
+  if (!ts->vio || ts->fr.empty()) {   // frame 0 of the sequence is in this batch: its successors are cached from b = 1 on
+    if (!ts->vio || B < 2) return VIDO_OK;
+  }
+  const int b0 = ts->fr.empty() ? 1 : 0;
+  const int nj = B - b0;
+  if (nj <= 0) return VIDO_OK;
+  std::vector<double> tp(nj), tc(nj);
+  std::vector<float> bias(6 * (size_t)nj, 0.f);
+  std::vector<size_t> q1(nj);
+  std::vector<vido_imu_preint> out(nj);
+  for (int j = 0; j < nj; j++) {
+    const int b = b0 + j;
+    tp[j] = b == 0 ? ts->fr.back().t : in[b - 1].timestamp;
+    tc[j] = in[b].timestamp;
+    if (!ts->fr.empty()) memcpy(&bias[6 * (size_t)j], ts->fr.back().bias, sizeof(float) * 6);
+    q1[j] = vio_visible(ts, ts->frames_seen + b);
+  }
+  int rc = vio_run_jobs(ctx, ts->imu_head, nj, tp.data(), tc.data(), bias.data(), q1.data(), out.data());
+  if (rc) return rc;
+  for (int j = 0; j < nj; j++) {
+    TrackState::PreCache& C = ts->pre_cache[b0 + j];
+    C.valid = true; C.t_prev = tp[j]; C.t = tc[j]; C.q1 = q1[j]; C.pre = out[j];
+    memcpy(C.bias, &bias[6 * (size_t)j], sizeof C.bias);
+  }
+  return VIDO_OK;
+}
+// the new frame's IMU state (Frame ctor Frame.cc:437-447, Tracking.cc:1115-1119): velocity / bias of the last frame, preintegration
+static int vio_new_frame(vido_ctx* ctx, int slot) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  ImuFrame f;
+  const ImuFrame& pf = ts->fr.back();
+  f.t = ts->cur_t; f.t_prev = pf.t;
+  memcpy(f.vel, pf.vel, sizeof f.vel);
+  memcpy(f.bias, pf.bias, sizeof f.bias);
+  f.q1 = vio_visible(ts, ts->frames_seen);
+  f.has_pre = false;
+  if (ts->imu_head < f.q1) {   // else: "Not IMU data in mlQueueImuData"
+    const TrackState::PreCache* C = (slot >= 0 && slot < (int)ts->pre_cache.size()) ? &ts->pre_cache[slot] : nullptr;
+    if (C && C->valid && C->t_prev == f.t_prev && C->t == f.t && C->q1 == f.q1 && memcmp(C->bias, pf.bias, sizeof C->bias) == 0) {
+      f.pre = C->pre;
+    } else {
+      int rc = vio_run_jobs(ctx, ts->imu_head, 1, &f.t_prev, &f.t, pf.bias, &f.q1, &f.pre);
+      if (rc) return rc;
+    }
+    memcpy(f.pre_b, pf.bias, sizeof f.pre_b);
+    f.has_pre = true;
+    ts->imu_head = (size_t)f.pre.n_consumed;
+  }
+  ts->fr.push_back(f);
+  return VIDO_OK;
+}
+// Tracking::UpdateFrameIMU (Tracking.cc:889-923); mpLastFrame == mpCurrentFrame == fr.back()
+static void vio_update_frame_imu(TrackState* ts, const float* b) {
+  ImuFrame& c = ts->fr.back();
+  const ImuFrame& p = ts->fr[ts->fr.size() - 2];
+  vio_set_new_bias(c, b);
+  if (!c.has_pre) return;
+  const float Gz[3] = {0.f, 0.f, -9.79f};
+  float twb1[3], Rwb1[9], dR[9], dV[3], dP[3], Rwb[9], twb[3], Vwb[3], rp[3], rv[3];
+  vio_imu_position(ts, p, twb1);
+  vio_imu_rotation(ts, p, Rwb1);
+  updated_deltas(c.pre, c.db, dR, dV, dP);
+  const float t12 = c.pre.dT;
+  mm3(Rwb1, dR, Rwb);
+  mv3(Rwb1, dP, rp);
+  mv3(Rwb1, dV, rv);
+  const float ht2 = 0.5f * t12 * t12;
+  for (int r = 0; r < 3; r++) {
+    twb[r] = ((twb1[r] + (float)((double)p.vel[r] * (double)t12)) + (float)((double)ht2 * (double)Gz[r])) + rp[r];
+    Vwb[r] = (p.vel[r] + (float)((double)Gz[r] * (double)t12)) + rv[r];
+  }
+  vio_set_imu_pose_velocity(ts, c, Rwb, twb, Vwb);
+  memcpy(ts->lastTcw, c.Tcw, sizeof c.Tcw);
+}
+// the inertial problem over Map::vpFrames = fr[1..N] (Optimizer.cc:2441-2560 / 2336-2425) on the inertial kernel, and the
+// write-back of mode 0 (Optimizer.cc:2589-2619).  *ok = false: a frame without preintegration breaks the chain.
+static int vio_run_inertial(vido_ctx* ctx, int mode, float priorG, float priorA, bool* ok) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  std::vector<ImuFrame>& fr = ts->fr;
+  const int N = (int)fr.size() - 1;
+  *ok = false;
+  std::vector<float> Rwb(9 * (size_t)N), twb(3 * (size_t)N), vel(3 * (size_t)N), blin(6 * (size_t)(N - 1));
+  std::vector<vido_imu_preint> pre(N - 1);
+  for (int i = 1; i <= N; i++) {
+    vio_imu_rotation(ts, fr[i], &Rwb[9 * (size_t)(i - 1)]);
+    vio_imu_position(ts, fr[i], &twb[3 * (size_t)(i - 1)]);
+    memcpy(&vel[3 * (size_t)(i - 1)], fr[i].vel, sizeof(float) * 3);
+    vio_pre_set_new_bias(fr[i], fr[i - 1].bias);
+    if (i >= 2) {
+      if (!fr[i].has_pre) return VIDO_OK;
+      pre[i - 2] = fr[i].pre;
+      memcpy(&blin[6 * (size_t)(i - 2)], fr[i].pre_b, sizeof(float) * 6);
+    }
+  }
+  vido_inertial_problem p;
+  memset(&p, 0, sizeof p);
+  inertial_default_params(&p);
+  p.n_frames = N; p.Rwb = Rwb.data(); p.twb = twb.data(); p.velocity = vel.data(); p.preint = pre.data(); p.bias_lin = blin.data();
+  p.mode = mode; p.its = mode == 0 ? 200 : 10;
+  p.prior_g = priorG; p.prior_a = priorA;
+  for (int k = 0; k < 9; k++) p.Rwg[k] = ts->ist.Rwg[k];
+  p.scale = ts->ist.scale;
+  for (int k = 0; k < 3; k++) { p.bg[k] = (double)fr[1].bias[3 + k]; p.ba[k] = (double)fr[1].bias[k]; }   // VertexGyroBias(vpFs.front())
+  vido_lm_stats lm;
+  int rc = inertial_opt_host(ctx, &p, &lm);
+  if (rc) return rc;
+  if (mode == 0) { ts->ist.lm_iterations = lm.iterations; ts->ist.lm_trials = lm.total_trials; }
+  for (int k = 0; k < 9; k++) ts->ist.Rwg[k] = p.Rwg[k];
+  ts->ist.scale = p.scale;
+  if (mode == 0) {
+    for (int k = 0; k < 3; k++) { ts->ist.bg[k] = p.bg[k]; ts->ist.ba[k] = p.ba[k]; }
+    const float b[6] = {(float)p.ba[0], (float)p.ba[1], (float)p.ba[2], (float)p.bg[0], (float)p.bg[1], (float)p.bg[2]};
+    std::vector<int> redo;
+    for (int i = 1; i <= N; i++) {
+      memcpy(fr[i].vel, &vel[3 * (size_t)(i - 1)], sizeof(float) * 3);
+      double d2 = 0;
+      for (int k = 0; k < 3; k++) { const float d = fr[i].bias[3 + k] - b[3 + k]; d2 += (double)d * d; }
+      const bool re = std::sqrt(d2) > 0.01;
+      vio_set_new_bias(fr[i], b);
+      if (re && fr[i].has_pre) redo.push_back(i);
+    }
+    if (!redo.empty()) {   // IMU::Preintegrated::Reintegrate (ImuTypes.cc:236-243): the same samples with the new bias, one launch
+      const int nj = (int)redo.size();
+      std::vector<double> tp(nj), tc(nj);
+      std::vector<float> bias(6 * (size_t)nj);
+      std::vector<size_t> q1(nj);
+      std::vector<vido_imu_preint> out(nj);
+      for (int j = 0; j < nj; j++) {
+        tp[j] = fr[redo[j]].t_prev; tc[j] = fr[redo[j]].t; q1[j] = fr[redo[j]].q1;
+        memcpy(&bias[6 * (size_t)j], b, sizeof b);
+      }
+      rc = vio_run_jobs(ctx, 0, nj, tp.data(), tc.data(), bias.data(), q1.data(), out.data());
+      if (rc) return rc;
+      for (int j = 0; j < nj; j++) {
+        ImuFrame& f = fr[redo[j]];
+        f.pre = out[j];
+        memcpy(f.pre_b, b, sizeof b);
+        for (int k = 0; k < 6; k++) f.db[k] = 0.f;
+        ts->ist.n_reintegrated++;
+      }
+    }
+    ts->pre_cache.clear();   // the bias of the last frame changed: the batch's remaining preintegrations are redone
+  }
+  *ok = true;
+  return VIDO_OK;
+}
+static int vio_apply_and_update(vido_ctx* ctx, const float* b) {   // tail shared by InitializeIMU / ScaleRefinement
+  TrackState* ts = (TrackState*)ctx->trk;
+  if (std::fabs(ts->ist.scale - 1.0) > 0.00001) {
+    float Rgw[9];
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) Rgw[3 * r + c] = (float)ts->ist.Rwg[3 * c + r];   // Converter::toCvMat(mRwg).t()
+    int rc = trk_apply_scaled_rotation_impl(ctx, Rgw, (float)ts->ist.scale);
+    if (rc) return rc;
+    vio_update_frame_imu(ts, b);
+  }
+  return VIDO_OK;
+}
+// Tracking::InitializeIMU(1e2, 1e9) (Tracking.cc:937-1044)
+static int vio_initialize_imu(vido_ctx* ctx) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  std::vector<ImuFrame>& fr = ts->fr;
+  vido_imu_state& ist = ts->ist;
+  const int N = (int)fr.size() - 1;
+  if (N < 10) { ist.status = 1; return VIDO_OK; }
+  const double first_ts = fr[1].t;
+  if (fr.back().t - first_ts < 2.0) { ist.status = 1; return VIDO_OK; }
+  float dirG[3] = {0.f, 0.f, 0.f};
+  for (int i = 1; i <= N; i++) {
+    if (!fr[i].has_pre) continue;
+    float R[9], dR[9], dV[3], dP[3], p1[3], p0[3], rv[3];
+    vio_imu_rotation(ts, fr[i - 1], R);
+    updated_deltas(fr[i].pre, fr[i].db, dR, dV, dP);
+    vio_imu_position(ts, fr[i], p1);
+    vio_imu_position(ts, fr[i - 1], p0);
+    mv3(R, dV, rv);
+    for (int r = 0; r < 3; r++) {
+      dirG[r] = dirG[r] - rv[r];
+      const float v = (float)((double)(p1[r] - p0[r]) * (1.0 / (double)fr[i].pre.dT));
+      fr[i].vel[r] = v;
+      fr[i - 1].vel[r] = v;
+    }
+  }
+  const double nrm = std::sqrt((double)dirG[0] * dirG[0] + (double)dirG[1] * dirG[1] + (double)dirG[2] * dirG[2]);
+  for (int r = 0; r < 3; r++) dirG[r] = (float)((double)dirG[r] * (1.0 / nrm));
+  const float gI[3] = {0.f, 0.f, -1.f};
+  const float v[3] = {gI[1] * dirG[2] - gI[2] * dirG[1], gI[2] * dirG[0] - gI[0] * dirG[2], gI[0] * dirG[1] - gI[1] * dirG[0]};
+  const float nv = (float)std::sqrt((double)v[0] * v[0] + (double)v[1] * v[1] + (double)v[2] * v[2]);
+  const float cosg = (float)((double)gI[0] * dirG[0] + (double)gI[1] * dirG[1] + (double)gI[2] * dirG[2]);
+  const float ang = (float)std::acos((double)cosg);
+  float vzg[3], Rwg[9];
+  for (int r = 0; r < 3; r++) vzg[r] = (float)((double)(float)((double)v[r] * (double)ang) * (1.0 / (double)nv));
+  exp_so3_host(vzg, Rwg);
+  for (int k = 0; k < 9; k++) ist.Rwg[k] = Rwg[k];
+  ist.t_init = (float)(fr.back().t - first_ts);
+  ist.scale = 1.0;
+  bool ok = false;
+  int rc = vio_run_inertial(ctx, 0, 1e2f, 1e9f, &ok);
+  if (rc) return rc;
+  if (!ok) { ist.status = 3; return VIDO_OK; }
+  if (ist.scale < 1e-1) { ist.status = 2; return VIDO_OK; }
+  float b[6];
+  memcpy(b, fr[1].bias, sizeof b);   // vpF[0]->GetImuBias()
+  rc = vio_apply_and_update(ctx, b);
+  if (rc) return rc;
+  ist.initialized = 1; ist.init_frame = N; ist.status = 0;
+  return VIDO_OK;
+}
+// Tracking::ScaleRefinement (Tracking.cc:1046-1077)
+static int vio_scale_refinement(vido_ctx* ctx) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  for (int k = 0; k < 9; k++) ts->ist.Rwg[k] = (k % 4 == 0) ? 1.0 : 0.0;
+  ts->ist.scale = 1.0;
+  bool ok = false;
+  int rc = vio_run_inertial(ctx, 1, 0.f, 0.f, &ok);
+  if (rc || !ok) return rc;
+  ts->ist.n_refinements++;
+  if (ts->ist.scale < 1e-1) return VIDO_OK;
+  float b[6];
+  memcpy(b, ts->fr.back().bias, sizeof b);
+  return vio_apply_and_update(ctx, b);
+}
+// the IMU part of Tracking::Track after the window optimisation (Tracking.cc:1452-1480)
+static int vio_after_ba(vido_ctx* ctx) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  vido_imu_state& ist = ts->ist;
+  int rc = VIDO_OK;
+  if (!ist.initialized) rc = vio_initialize_imu(ctx);
+  if (rc) return rc;
+  if (ist.initialized && ist.t_init < 100.0f) {
+    ist.t_init = (float)((double)ist.t_init + (ts->fr.back().t - ts->fr[ts->fr.size() - 2].t));
+    const float T = ist.t_init;
+    const bool win = (T > 15.0f && T < 15.5f) || (T > 25.0f && T < 25.5f) || (T > 35.0f && T < 35.5f) || (T > 45.0f && T < 45.5f) ||
+                     (T > 55.0f && T < 55.5f) || (T > 65.0f && T < 65.5f) || (T > 75.0f && T < 75.5f);
+    if ((int)ts->fr.size() - 1 <= 1000 && win) rc = vio_scale_refinement(ctx);
+  }
+  return rc;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // back-end of one frame (sequential)
 // ---------------------------------------------------------------------------------------------------------
@@ -1155,6 +1546,22 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
       F.p3[3 * i] = (kp.x - c.cx) * z * invfx; F.p3[3 * i + 1] = (kp.y - c.cy) * z * invfy; F.p3[3 * i + 2] = z;
     }
     eye44(F.Twc); eye44(F.rel); eye44(F.Twc_rf);
+    if (ts->vio) {   // Tracking.cc:1555-1561: IMU pose from Tcb, zero velocity, empty preintegration
+      ImuFrame f0;
+      float Rwb0[9], twb0[3], V0[3] = {0.f, 0.f, 0.f};
+      for (int r = 0; r < 3; r++) {
+        for (int cc = 0; cc < 3; cc++) Rwb0[3 * r + cc] = ts->Tcb[4 * r + cc];
+        twb0[r] = ts->Tcb[4 * r + 3];
+      }
+      vio_set_imu_pose_velocity(ts, f0, Rwb0, twb0, V0);
+      memset(&f0.pre, 0, sizeof f0.pre);
+      f0.pre.dR[0] = f0.pre.dR[4] = f0.pre.dR[8] = 1.f;
+      f0.has_pre = true;
+      f0.t = f0.t_prev = ts->cur_t;
+      memcpy(curTcw, f0.Tcw, sizeof f0.Tcw);
+      ts->fr.clear();
+      ts->fr.push_back(f0);
+    }
     ts->last_keys = F.xy; ts->last_depth = F.depth; ts->last_corres = ff.as_corres; ts->last_flow = ff.as_flow;
     memcpy(ts->lastTcw, curTcw, sizeof curTcw);
     {  // object samples of frame 0 (Frame.cc:184-211, Tracking.cc:1524-1541)
@@ -1179,6 +1586,7 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
       //      mvStatDepthTmp (Tracking.cc:369-389); in the static-only pipeline nothing reads that vector (RenewFrameInfo
       //      re-samples at the refined positions, Tracking.cc:2970-3010), so the lookup round trip is not issued.
       std::vector<float> keys = ts->last_corres;
+      if (ts->vio) { int rcv = vio_new_frame(ctx, slot); if (rcv) return rcv; }
       // ---- GetInitModelCam: 3-D points of the last frame, constant-velocity model, PnP-RANSAC
       std::vector<float> p3d(3 * (size_t)Ns, 0.f);
       std::vector<int32_t> valid(Ns, 1), ids(Ns);
@@ -1389,6 +1797,7 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
       }
       memcpy(F.Twc, Twc, sizeof Twc);
       memcpy(F.Twc_rf, Twc, sizeof Twc);
+      if (ts->vio) memcpy(ts->fr.back().Tcw, curTcw, sizeof curTcw);
       inv44(ts->mVelocity, F.rel);
       if (dyn) {  // RenewFrameInfo (object part), Map bookkeeping, dynamic tracklets
         rc = dyn_renew(ctx, ff, curTcw, FS.d_obkeys + 2 * (size_t)slot * ts->obj_cap, d_depth, d_flow, d_mask, slot, D, F);
@@ -1424,8 +1833,13 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
   int rc = VIDO_OK;
   if (st) { st->ba_iterations = -1; st->ba_points = 0; st->ba_obs = 0; st->ba_trials = 0; }
   if (!skipped) { ts->ba_deferred.valid = true; ts->ba_deferred.window = window; ts->ba_deferred.st = st; }
+  if (ts->vio && !skipped && ts->f_id > 0) {   // InitializeIMU / ScaleRefinement (Tracking.cc:1452-1480); TrackRGBD returns mTcw after them
+    rc = vio_after_ba(ctx);
+    memcpy(Tcw_out, ts->lastTcw, sizeof(float) * 16);
+  }
   if (st) st->ms_ba = now_ms() - t4;
   ts->f_id++;
+  ts->frames_seen++;
   if (rc) return rc;
   return skipped ? 1 : 0;
 }
@@ -1513,8 +1927,10 @@ int trk_track_chunk(vido_ctx* ctx, const vido_frame_inputs* in, int nframes, flo
     }
     const float* d_depth = F.in_depth;
     const double front_ms = (now_ms() - tf0) / B;
+    if (ts->vio) { rc = vio_preintegrate_batch(ctx, in + done, B); if (rc) return rc; }
     for (int b = 0; b < B; b++) {
       vido_track_stats* st = stats ? stats + done + b : nullptr;
+      ts->cur_t = in[done + b].timestamp;
       rc = back_end(ctx, F, ff[b], b, Tcw_out + 16 * (size_t)(done + b), st);
       if (rc < 0) return rc;
       if (st) { st->ms_orb = front_ms; st->ms_assoc = 0; }
@@ -1771,4 +2187,99 @@ int trk_export_full_graph(vido_ctx* ctx, int32_t* sizes, float* se3, float* poin
   cp(obs_se3, G.obs_se3); cp(obs_point, G.obs_point); cp(obs_kind, G.obs_kind); cp(obs_xyz, G.obs_xyz);
   cp(tern_p1, G.tern_p1); cp(tern_p2, G.tern_p2); cp(tern_h, G.tern_h);
   return VIDO_OK;
+}
+
+// Map::ApplyScaledRotation(R, s, bScaledVel = true, t = 0) (src/Map.cc:55-119): camera poses, rigid motions and points of the
+// Map, pose and velocity of the frames of Map::vpFrames.  Every queued window solve is retired first: the reference calls this
+// after the PartialBatchOptimization of the frame.
+static int trk_apply_scaled_rotation_impl(vido_ctx* ctx, const float* R, float s) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  int rc = ba_flush_deferred(ctx);
+  while (ts->ba_nq > 0 && rc == VIDO_OK) { rc = ba_finish(ctx); ba_writeback_rest(ctx); }
+  if (rc) return rc;
+  float Tyw[16];
+  eye44(Tyw);
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) Tyw[4 * r + c] = R[3 * r + c];
+  auto rot_pts = [&](std::vector<float>& P) {   // s * Ryw * p + tyw: one gemm with alpha = s, beta = 1 (tyw = 0)
+    for (size_t i = 0; i + 2 < P.size(); i += 3) {
+      const float x = P[i], y = P[i + 1], z = P[i + 2];
+      for (int r = 0; r < 3; r++)
+        P[i + r] = (float)((double)s * ((double)R[3 * r] * x + (double)R[3 * r + 1] * y + (double)R[3 * r + 2] * z) + 0.0);
+    }
+  };
+  auto scale_pose = [&](float* pose) {   // pose.t *= s ; pose = Tyw * pose
+    pose[3] *= s; pose[7] *= s; pose[11] *= s;
+    mul44(Tyw, pose, pose);
+  };
+  auto frame_pose = [&](float* Tcw) {   // Twc.t *= s ; Tyc = Tyw * Twc ; SetPose(Tyc^-1)
+    float Twc[16], Tyc[16];
+    inv44(Tcw, Twc);
+    Twc[3] *= s; Twc[7] *= s; Twc[11] *= s;
+    mul44(Tyw, Twc, Tyc);
+    inv44(Tyc, Tcw);
+  };
+  if (ts->vio) {
+    for (size_t i = 1; i < ts->fr.size(); i++) {
+      frame_pose(ts->fr[i].Tcw);
+      mv3(R, ts->fr[i].vel, ts->fr[i].vel, (double)s);   // Ryw * Vw * s
+    }
+    if (ts->fr.size() > 1) memcpy(ts->lastTcw, ts->fr.back().Tcw, sizeof(float) * 16);
+  } else if (ts->initialised) {
+    frame_pose(ts->lastTcw);
+  }
+  for (size_t f = 0; f < ts->map.size(); f++) {
+    MapFrame& F = ts->map[f];
+    rot_pts(F.p3); rot_pts(F.dp3);
+    scale_pose(F.Twc);
+    if (f > 0) scale_pose(F.rel);
+    for (ObjEntry& o : F.objects) scale_pose(o.motion);
+  }
+  return VIDO_OK;
+}
+int trk_apply_scaled_rotation(vido_ctx* ctx, const float* R, float s) { return trk_apply_scaled_rotation_impl(ctx, R, s); }
+
+// Tracking::ParseIMUParamFile (Tracking.cc:174-275) -> IMU::Calib::Set (ImuTypes.cc:476-500): switches the driver to IMU_RGBD
+int trk_set_imu(vido_ctx* ctx, const float* Tbc, const float* noise) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  if (ts->initialised) { ctx->err = "set_imu: the sequence has already started (call vido_track_reset first)"; return VIDO_ERR_STATE; }
+  ts->vio = true;
+  memcpy(ts->Tbc, Tbc, sizeof ts->Tbc);
+  memcpy(ts->imu_noise, noise, sizeof ts->imu_noise);
+  eye44(ts->Tcb);
+  float Rt[9], tb[3] = {Tbc[3], Tbc[7], Tbc[11]}, tc[3];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) { Rt[3 * r + c] = Tbc[4 * c + r]; ts->Tcb[4 * r + c] = Tbc[4 * c + r]; }
+  mv3(Rt, tb, tc, -1.0);
+  for (int r = 0; r < 3; r++) ts->Tcb[4 * r + 3] = tc[r];
+  memset(&ts->ist, 0, sizeof ts->ist);
+  ts->ist.scale = 1.0; ts->ist.status = -1;
+  ts->ist.Rwg[0] = ts->ist.Rwg[4] = ts->ist.Rwg[8] = 1.0;
+  return VIDO_OK;
+}
+// Tracking::GrabImuData (Tracking.cc:277-281)
+int trk_grab_imu(vido_ctx* ctx, const vido_imu_sample* smp, int n, int frames_ahead) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  if (!ts->vio) { ctx->err = "grab_imu: not in IMU mode (vido_track_set_imu)"; return VIDO_ERR_STATE; }
+  const int64_t target = ts->frames_seen + frames_ahead;
+  if (!ts->imu_q_frame.empty() && target < ts->imu_q_frame.back()) { ctx->err = "grab_imu: deliveries must be in frame order"; return VIDO_ERR_ARG; }
+  ts->imu_q.insert(ts->imu_q.end(), smp, smp + n);
+  ts->imu_q_frame.insert(ts->imu_q_frame.end(), (size_t)n, target);
+  return VIDO_OK;
+}
+int trk_get_imu_state(vido_ctx* ctx, vido_imu_state* out) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  if (!ts->vio) { ctx->err = "not in IMU mode"; return VIDO_ERR_STATE; }
+  *out = ts->ist;
+  return VIDO_OK;
+}
+int trk_get_imu_frames(vido_ctx* ctx, float* Tcw, float* vel, float* bias, int cap) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  const int n = (int)ts->fr.size();
+  for (int i = 0; i < n && i < cap; i++) {
+    if (Tcw) memcpy(Tcw + 16 * (size_t)i, ts->fr[i].Tcw, sizeof(float) * 16);
+    if (vel) memcpy(vel + 3 * (size_t)i, ts->fr[i].vel, sizeof(float) * 3);
+    if (bias) memcpy(bias + 6 * (size_t)i, ts->fr[i].bias, sizeof(float) * 6);
+  }
+  return n;
 }

@@ -2,9 +2,9 @@
 // C-ABI of libvido_b200.so.  Header-only.  Same names, argument meaning and error behaviour:
 //   VIDO_SLAM::System::Init(yaml, sensor)                         src/System.cc:23-48
 //   cv::Mat System::TrackRGBD(im, depth, flow, mask, Tcw_gt, objPose_gt, t, imTraj, nImage)   src/System.cc:51-63
-//   cv::Mat System::TrackRGBD(..., vImuMeas, ...)                 src/System.cc:65-78 (IMU samples are preintegrated
-//                                                                 on the GPU; the pose path is the VO one, like the
-//                                                                 reference whose LocalInertialBA is empty, F6)
+//   cv::Mat System::TrackRGBD(..., vImuMeas, ...)                 src/System.cc:65-78: GrabImuData for every measurement, then the
+//                                                                 frame; sensor IMU_RGBD runs the VIO mode of the driver
+//                                                                 (preintegration, InitializeIMU, ScaleRefinement)
 //   void System::SaveResultsIJRR2020(dir)                         src/System.cc:80-198 (object motions, camera trajectory after
 //                                                                 the window optimisation and after FullBatch)
 // The call with index nImage-1 also runs Optimizer::FullBatchOptimization when ChooseData == 2 (src/Tracking.cc:1490-1498).
@@ -95,9 +95,32 @@ class System {
     }
     std::map<std::string, std::string> kv;
     std::string line;
+    std::vector<float> tbc;   // "Tbc: !!opencv-matrix ... data: [ 16 values ]" (Tracking::ParseIMUParamFile, src/Tracking.cc:174-196)
+    int in_tbc = 0;           // 1: inside the Tbc node, 2: inside its data list
     while (std::getline(f, line)) {
       const size_t h = line.find('#');
       if (h != std::string::npos) line = line.substr(0, h);
+      if (line.compare(0, 4, "Tbc:") == 0) { in_tbc = 1; continue; }
+      if (in_tbc) {
+        size_t pos = 0;
+        if (in_tbc == 1) {
+          const size_t d = line.find("data:");
+          if (d == std::string::npos) { if (!line.empty() && line[0] != ' ') in_tbc = 0; else continue; }
+          else { in_tbc = 2; pos = line.find('[', d); pos = (pos == std::string::npos) ? line.size() : pos + 1; }
+        }
+        if (in_tbc == 2) {
+          std::string body = line.substr(pos);
+          const size_t e = body.find(']');
+          const bool last = e != std::string::npos;
+          if (last) body = body.substr(0, e);
+          for (char& ch : body) if (ch == ',') ch = ' ';
+          std::istringstream is(body);
+          float v;
+          while (is >> v) tbc.push_back(v);
+          if (last) in_tbc = 0;
+          continue;
+        }
+      }
       const size_t c = line.find(':');
       if (c == std::string::npos || line[0] == '%') continue;
       std::string k = line.substr(0, c), v = line.substr(c + 1);
@@ -133,6 +156,14 @@ class System {
     if (!ctx_) {
       std::cerr << "vido_b200: " << vido_last_error(nullptr) << std::endl;
       exit(-1);
+    }
+    if (sensor == IMU_RGBD) {   // src/Tracking.cc:111-121
+      if (tbc.size() != 16) {
+        std::cerr << "*Tbc matrix have to be a 4x4 transformation matrix*" << std::endl;
+        std::cout << "*Error with the IMU parameters in the config file*" << std::endl;
+      } else if (vido_track_set_imu(ctx_, tbc.data(), imu_noise_) < 0) {
+        std::cerr << "vido_b200: " << vido_last_error(ctx_) << std::endl;
+      }
     }
   }
 
@@ -173,22 +204,13 @@ class System {
       std::cerr << "ERROR: you called TrackRGBD(IMU) but input sensor was not set to IMU_RGBD." << std::endl;
       exit(-1);
     }
+    std::vector<vido_imu_sample> q(vImuMeas.size());
     for (size_t i = 0; i < vImuMeas.size(); i++) {
-      vido_imu_sample s;
+      vido_imu_sample& s = q[i];
       s.t = vImuMeas[i].t; s.ax = vImuMeas[i].ax; s.ay = vImuMeas[i].ay; s.az = vImuMeas[i].az;
       s.wx = vImuMeas[i].wx; s.wy = vImuMeas[i].wy; s.wz = vImuMeas[i].wz;
-      imu_queue_.push_back(s);
     }
-    if (have_last_t_ && !imu_queue_.empty()) {
-      const float bias[6] = {0, 0, 0, 0, 0, 0};
-      vido_imu_preint pre;
-      const double t0 = last_t_, t1 = timestamp;
-      if (vido_imu_preintegrate(ctx_, imu_queue_.data(), (int)imu_queue_.size(), &t0, &t1, 1, bias, imu_noise_, &pre) == VIDO_OK) {
-        preint_.push_back(pre);
-        imu_queue_.erase(imu_queue_.begin(), imu_queue_.begin() + pre.n_consumed);
-      }
-    }
-    have_last_t_ = true;
+    if (vido_track_grab_imu(ctx_, q.data(), (int)q.size(), 0) < 0) std::cerr << "vido_b200: " << vido_last_error(ctx_) << std::endl;
     return TrackRGBD(im, depthmap, flowmap, maskmap, mTcw_gt, vObjPose_gt, timestamp, imTraj, nImage);
   }
 
@@ -226,18 +248,17 @@ class System {
   }
 
   vido_ctx* context() { return ctx_; }
-  const std::vector<vido_imu_preint>& preintegrations() const { return preint_; }
+  // Tracking::isImuInitialized / mScale
+  bool isImuInitialized() { vido_imu_state st; return vido_track_get_imu_state(ctx_, &st) == VIDO_OK && st.initialized; }
 
  private:
   vido_ctx* ctx_ = nullptr;
   vido_config cfg_;
   eSensor sensor_ = RGBD;
   std::vector<float> trajectory_;
-  std::vector<vido_imu_sample> imu_queue_;
-  std::vector<vido_imu_preint> preint_;
   float imu_noise_[4] = {0, 0, 0, 0};
   double last_t_ = 0;
-  bool have_last_t_ = false, full_batch_done_ = false;
+  bool full_batch_done_ = false;
   int frame_id_ = 0;
 };
 
