@@ -393,7 +393,8 @@ int vido_inertial_opt(vido_ctx* ctx, vido_inertial_problem* p, vido_lm_stats* st
 /*
  * VIO mode of the per-frame driver (sensor = IMU_RGBD).  vido_track_set_imu replaces Tracking::ParseIMUParamFile (src/Tracking.cc:
  * 174-275): Tbc = camera-to-body transform (row-major 4x4, "Tbc" of the YAML), noise = (ng, na, ngw, naw) as handed to IMU::Calib
- * (already scaled by sqrt(IMU.Frequency), :258-262); must be called before the first frame (or after vido_track_reset).
+ * (already scaled by sqrt(IMU.Frequency), :258-262); must be called before the first frame (or after vido_track_reset);
+ * Tbc = noise = NULL switches back to sensor = RGBD.
  * vido_track_grab_imu replaces Tracking::GrabImuData (:277-281) / the vImuMeas argument of System::TrackRGBD (src/System.cc:64-76):
  * the samples System::TrackRGBD would receive together with the frame that lies `frames_ahead` frames after the next one to be
  * tracked (0 = the next frame), so that a whole chunk can be announced before one vido_track_frames call; deliveries in frame order,

@@ -127,9 +127,28 @@ def vio_camera_pose(k):
     return torch.from_numpy(vio_camera_pose_np(float(k)))
 
 
-def make_vio_sequence(n_frames, fps=2.5, bg_true=(0.002, -0.001, 0.0015), seed=0, noise=0.05, t0=10.0):
-    """200 Hz IMU samples of the body (Twb = Twc * Tcb) riding on vio_camera_pose(t * fps), frame k at t0 + k / fps.
-    Returns (samples, frame_t, Tbc float32 4x4, truth)"""
+def vio_camera_pose_10fps_np(k):
+    """the same drive for 10 frames/s (bench.py's VIO leg): accelerations of a car (< 2 m/s^2) at 1 m / frame"""
+    yaw = np.radians(2.0) * np.sin(0.15 * k)
+    pitch = np.radians(0.3) * np.sin(0.11 * k + 1.0)
+    cy, sy, cp, sp = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch)
+    Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    Rx = np.array([[1, 0, 0], [0, cp, -sp], [0, sp, cp]])
+    T = np.eye(4)
+    T[:3, :3] = Ry @ Rx
+    T[:3, 3] = [1.5 * np.sin(0.05 * k) + 0.6 * np.sin(0.1 * k), 0.25 * np.sin(0.13 * k), 1.0 * k + 1.2 * np.sin(0.12 * k)]
+    return T
+
+
+def vio_camera_pose_10fps(k):
+    import torch
+    return torch.from_numpy(vio_camera_pose_10fps_np(float(k)))
+
+
+def make_vio_sequence(n_frames, fps=2.5, bg_true=(0.002, -0.001, 0.0015), seed=0, noise=0.05, t0=10.0, pose_np=None):
+    """200 Hz IMU samples of the body (Twb = Twc * Tcb) riding on pose_np(t * fps) (default vio_camera_pose_np), frame k at
+    t0 + k / fps.  Returns (samples, frame_t, Tbc float32 4x4, truth)"""
+    pose_np = pose_np or vio_camera_pose_np
     rng = np.random.default_rng(seed)
     Tbc = _orthonormal(TBC)
     Tcb = np.linalg.inv(Tbc)
@@ -138,7 +157,7 @@ def make_vio_sequence(n_frames, fps=2.5, bg_true=(0.002, -0.001, 0.0015), seed=0
     n = int((n_frames - 1) / fps * FREQ) + 12
 
     def body(t):
-        Twc = vio_camera_pose_np(t * fps)
+        Twc = pose_np(t * fps)
         Twb = Twc @ Tcb
         return Twb[:3, :3], Twb[:3, 3]
 

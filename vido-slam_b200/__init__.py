@@ -389,6 +389,9 @@ class Context:
     # ---- VIO mode (sensor = IMU_RGBD)
     def track_set_imu(self, Tbc, noise):
         """Tracking::ParseIMUParamFile: Tbc 4x4, noise (ng, na, ngw, naw) as given to IMU::Calib"""
+        if Tbc is None:   # back to sensor = RGBD
+            self._check(self.lib.vido_track_set_imu(self.h, None, None))
+            return
         T = np.ascontiguousarray(Tbc, np.float32).reshape(16); nz = np.ascontiguousarray(noise, np.float32)
         self._check(self.lib.vido_track_set_imu(self.h, _ptr(T), _ptr(nz)))
 

@@ -357,7 +357,7 @@ int vido_inertial_opt(vido_ctx* ctx, vido_inertial_problem* p, vido_lm_stats* st
   return inertial_opt_host(ctx, p, stats);
 }
 
-int vido_track_set_imu(vido_ctx* ctx, const float* Tbc, const float* noise) { return (ctx && Tbc && noise) ? trk_set_imu(ctx, Tbc, noise) : VIDO_ERR_ARG; }
+int vido_track_set_imu(vido_ctx* ctx, const float* Tbc, const float* noise) { return (ctx && ((Tbc && noise) || (!Tbc && !noise))) ? trk_set_imu(ctx, Tbc, noise) : VIDO_ERR_ARG; }
 int vido_track_grab_imu(vido_ctx* ctx, const vido_imu_sample* samples, int n, int frames_ahead) {
   if (!ctx || n < 0 || (n > 0 && !samples) || frames_ahead < 0) return VIDO_ERR_ARG;
   return trk_grab_imu(ctx, samples, n, frames_ahead);

@@ -2243,6 +2243,7 @@ int trk_apply_scaled_rotation(vido_ctx* ctx, const float* R, float s) { return t
 int trk_set_imu(vido_ctx* ctx, const float* Tbc, const float* noise) {
   TrackState* ts = (TrackState*)ctx->trk;
   if (ts->initialised) { ctx->err = "set_imu: the sequence has already started (call vido_track_reset first)"; return VIDO_ERR_STATE; }
+  if (!Tbc) { ts->vio = false; return VIDO_OK; }   // back to sensor = RGBD
   ts->vio = true;
   memcpy(ts->Tbc, Tbc, sizeof ts->Tbc);
   memcpy(ts->imu_noise, noise, sizeof ts->imu_noise);
