@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256, 1) chol_kernel(const double* S, const dou
   const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
   double* Li = Ls + (size_t)(n + 1) * ld;
   __shared__ int s_bad;
-  long long c_diag = 0, c_panel = 0, c_trail = 0, c_back = 0, c_tot = 0;
+  long long c_diag = 0, c_panel = 0, c_trail = 0, c_back = 0, c_tot = 0, c_w = 0;
   for (int rep = 0; rep < reps; rep++) {
     for (int i = tid; i < n * n; i += nt) { const int r = i / n, c = i - r * n; if (c <= r) Ls[r * ld + c] = S[i]; }
     double* ys = Ls + (size_t)n * ld;
@@ -106,7 +106,16 @@ __global__ void __launch_bounds__(256, 1) chol_kernel(const double* S, const dou
       const int m = n - j0 - 6;
       if (warp == 0) {
         if (jb + 1 < nb) {
-          if (lane < 21) {
+          if ((VARIANT & 16) && lane < 21) {
+            // row of lane l in the packed lower triangle: 3 bits per lane in one constant; the 6-term dot as a tree
+            const int r = (int)((0x5b6db2491b6d2448ull >> (3 * lane)) & 7ull), c = lane - ((r * (r + 1)) >> 1);
+            const double* lr = Ls + (j0 + 6 + r) * ld + j0;
+            const double* lc = Ls + (j0 + 6 + c) * ld + j0;
+            double* dst = Ls + (j0 + 6 + r) * ld + j0 + 6 + c;
+            const double s01 = fma(lr[1], lc[1], lr[0] * lc[0]), s23 = fma(lr[3], lc[3], lr[2] * lc[2]), s45 = fma(lr[5], lc[5], lr[4] * lc[4]);
+            *dst = *dst - ((s01 + s23) + s45);
+          }
+          if (!(VARIANT & 16) && lane < 21) {
             int r = 0, c = lane;
             while (c > r) { c -= r + 1; r++; }
             const double* lr = Ls + (j0 + 6 + r) * ld + j0;
@@ -114,7 +123,7 @@ __global__ void __launch_bounds__(256, 1) chol_kernel(const double* S, const dou
             Ls[(j0 + 6 + r) * ld + j0 + 6 + c] -= lr[0] * lc[0] + lr[1] * lc[1] + lr[2] * lc[2] + lr[3] * lc[3] + lr[4] * lc[4] + lr[5] * lc[5];
           }
           __syncwarp();
-          if (VARIANT == 0) {
+          if (!(VARIANT & 1)) {
             if (lane == 0 && !chol_diag6(Ls, ld, j0 + 6, Li + 6 * (jb + 1))) s_bad = 1;
           } else {
             // lane r (< 6) owns row r of the block; column j: pivot from lane j, broadcast by shuffle
@@ -158,8 +167,58 @@ __global__ void __launch_bounds__(256, 1) chol_kernel(const double* S, const dou
         }
         t1 = clock64(); c_diag += t1 - t0; t0 = t1;
       } else {
+        const long long tw0 = clock64();
         const int ngroups = (m - 5 + 7) >> 3;
-        for (int g = warp - 1; g < ngroups; g += nwarp - 1) {
+        // VARIANT & 2: the warp that shares warp 0's scheduler (warp 4) stays idle, so the critical chain owns its FP64 pipe
+        const int widx = (VARIANT & 2) ? (warp < 4 ? warp - 1 : warp - 2) : warp - 1;
+        const int nwork = (VARIANT & 2) ? nwarp - 2 : nwarp - 1;
+        const bool idle = (VARIANT & 2) && warp == 4;
+        if (VARIANT & 64) {
+          // 8-row x 32-column tiles dealt round-robin to the workers (the triangle makes the groups unequal: 1..4 tiles)
+          int t = 0;
+          for (int g = 0; g < ngroups && !idle; g++) {
+            const int r0 = 6 + 8 * g;
+            const int rmax = min(r0 + 7, m), cmax = min(rmax, m - 1);
+            const int nch = (cmax >> 5) + 1;
+            bool have = false;
+            double rv[8][6];
+            for (int ch = 0; ch < nch; ch++, t++) {
+              if (t % nwork != widx) continue;
+              if (!have) {
+                have = true;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                  const int r = min(r0 + i, m);
+                  const double* lr = Ls + (j0 + 6 + r) * ld + j0;
+#pragma unroll
+                  for (int k = 0; k < 6; k++) rv[i][k] = lr[k];
+                }
+              }
+              const int c = lane + 32 * ch;
+              if (c <= cmax) {
+                const double* lc = Ls + (j0 + 6 + c) * ld + j0;
+                const double l0 = lc[0], l1 = lc[1], l2 = lc[2], l3 = lc[3], l4 = lc[4], l5 = lc[5];
+                double cv[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) { const int r = r0 + i; cv[i] = (r <= m && c <= r) ? Ls[(j0 + 6 + r) * ld + j0 + 6 + c] : 0.0; }
+#pragma unroll
+                for (int i = 0; i < 8; i++) cv[i] -= rv[i][0] * l0 + rv[i][1] * l1 + rv[i][2] * l2 + rv[i][3] * l3 + rv[i][4] * l4 + rv[i][5] * l5;
+#pragma unroll
+                for (int i = 0; i < 8; i++) { const int r = r0 + i; if (r <= m && c <= r) Ls[(j0 + 6 + r) * ld + j0 + 6 + c] = cv[i]; }
+              }
+            }
+          }
+        } else
+        for (int pass = 0; pass * nwork < ngroups && !idle; pass++) {
+          int g;
+          if (VARIANT & 128) {   // heaviest groups first, alternating direction over the workers
+            const int gp = pass * nwork + ((pass & 1) ? nwork - 1 - widx : widx);
+            if (gp >= ngroups) continue;
+            g = ngroups - 1 - gp;
+          } else {
+            g = widx + pass * nwork;
+            if (g >= ngroups) continue;
+          }
           const int r0 = 6 + 8 * g;
           double rv[8][6];
 #pragma unroll
@@ -182,13 +241,32 @@ __global__ void __launch_bounds__(256, 1) chol_kernel(const double* S, const dou
             for (int i = 0; i < 8; i++) { const int r = r0 + i; if (r <= m && c <= r) Ls[(j0 + 6 + r) * ld + j0 + 6 + c] = cv[i]; }
           }
         }
+        c_w += clock64() - tw0;
       }
       __syncthreads();
       t1 = clock64(); c_trail += t1 - t0; t0 = t1;
     }
     __syncthreads();
     t0 = clock64();
-    if (!s_bad && warp == 0) {
+    if ((VARIANT & 8) && !s_bad) {
+      // inverse of every diagonal block (lower triangular 6x6), one thread per block: Linv stored row-major in Lv[36*jb]
+      double* Lv = Li + 6 * nb;
+      if (tid < nb) {
+        const double* D = Ls + (6 * tid) * ld + 6 * tid;
+        const double* dv = Li + 6 * tid;
+        double* V = Lv + 36 * tid;
+        for (int c = 0; c < 6; c++) {
+          V[7 * c] = dv[c];
+          for (int r = c + 1; r < 6; r++) {
+            double sacc = 0;
+            for (int k = c; k < r; k++) sacc += D[r * ld + k] * V[6 * k + c];
+            V[6 * r + c] = -sacc * dv[r];
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (!s_bad && warp == 0 && !(VARIANT & (12 | 32))) {
       for (int jb = nb - 1; jb >= 0; jb--) {
         const int j0 = 6 * jb;
         const double* D = Ls + j0 * ld + j0;
@@ -204,24 +282,110 @@ __global__ void __launch_bounds__(256, 1) chol_kernel(const double* S, const dou
           x0 = (y0 - D[5 * ld] * x5 - D[4 * ld] * x4 - D[3 * ld] * x3 - D[2 * ld] * x2 - D[ld] * x1) * dv[0];
         }
         if (lane < 6) ys[j0 + lane] = lane == 0 ? x0 : lane == 1 ? x1 : lane == 2 ? x2 : lane == 3 ? x3 : lane == 4 ? x4 : x5;
-        if (VARIANT == 0) {
 #pragma unroll 5
-          for (int i = lane; i < j0; i += 32)
-            ys[i] -= D[i - j0] * x0 + D[ld + i - j0] * x1 + D[2 * ld + i - j0] * x2 + D[3 * ld + i - j0] * x3 + D[4 * ld + i - j0] * x4 + D[5 * ld + i - j0] * x5;
-        } else {
-          double yv[5];
+        for (int i = lane; i < j0; i += 32)
+          ys[i] -= D[i - j0] * x0 + D[ld + i - j0] * x1 + D[2 * ld + i - j0] * x2 + D[3 * ld + i - j0] * x3 + D[4 * ld + i - j0] * x4 + D[5 * ld + i - j0] * x5;
+        __syncwarp();
+      }
+    }
+    if (!s_bad && warp == 0 && (VARIANT & 32)) {
+      // every load of a block step is issued before the 6-step solve (the stores of the previous step forbid the compiler to
+      // hoist them itself), the rows above are updated as independent chains that end with the unknown known last
+      for (int jb = nb - 1; jb >= 0; jb--) {
+        const int j0 = 6 * jb;
+        const double* D = Ls + j0 * ld + j0;
+        const double* dv = Li + 6 * jb;
+        const double y0 = ys[j0], y1 = ys[j0 + 1], y2 = ys[j0 + 2], y3 = ys[j0 + 3], y4 = ys[j0 + 4], y5 = ys[j0 + 5];
+        const double d0 = dv[0], d1 = dv[1], d2 = dv[2], d3 = dv[3], d4 = dv[4], d5 = dv[5];
+        const double l10 = D[ld], l20 = D[2 * ld], l21 = D[2 * ld + 1], l30 = D[3 * ld], l31 = D[3 * ld + 1], l32 = D[3 * ld + 2];
+        const double l40 = D[4 * ld], l41 = D[4 * ld + 1], l42 = D[4 * ld + 2], l43 = D[4 * ld + 3];
+        const double l50 = D[5 * ld], l51 = D[5 * ld + 1], l52 = D[5 * ld + 2], l53 = D[5 * ld + 3], l54 = D[5 * ld + 4];
+        double dl[4][6], yv[4];
 #pragma unroll
-          for (int u = 0; u < 5; u++) { const int i = lane + 32 * u; yv[u] = (i < j0) ? ys[i] : 0.0; }
+        for (int u = 0; u < 4; u++) {
+          const int i = lane + 32 * u;
+          const bool on = i < j0;
+          yv[u] = on ? ys[i] : 0.0;
 #pragma unroll
-          for (int u = 0; u < 5; u++) {
-            const int i = lane + 32 * u;
-            if (i < j0) yv[u] -= D[i - j0] * x0 + D[ld + i - j0] * x1 + D[2 * ld + i - j0] * x2 + D[3 * ld + i - j0] * x3 + D[4 * ld + i - j0] * x4 + D[5 * ld + i - j0] * x5;
-          }
+          for (int k = 0; k < 6; k++) dl[u][k] = on ? D[k * ld + i - j0] : 0.0;
+        }
+        const double x5 = y5 * d5;
+        const double x4 = (y4 - l54 * x5) * d4;
+        const double x3 = ((y3 - l53 * x5) - l43 * x4) * d3;
+        const double x2 = (((y2 - l52 * x5) - l42 * x4) - l32 * x3) * d2;
+        const double x1 = ((((y1 - l51 * x5) - l41 * x4) - l31 * x3) - l21 * x2) * d1;
+        const double x0 = (((((y0 - l50 * x5) - l40 * x4) - l30 * x3) - l20 * x2) - l10 * x1) * d0;
 #pragma unroll
-          for (int u = 0; u < 5; u++) { const int i = lane + 32 * u; if (i < j0) ys[i] = yv[u]; }
+        for (int u = 0; u < 4; u++) {
+          const int i = lane + 32 * u;
+          double t = yv[u];
+          t = fma(-dl[u][5], x5, t); t = fma(-dl[u][4], x4, t); t = fma(-dl[u][3], x3, t);
+          t = fma(-dl[u][2], x2, t); t = fma(-dl[u][1], x1, t); t = fma(-dl[u][0], x0, t);
+          if (i < j0) ys[i] = t;
+        }
+        if (lane < 6) {
+          double xv = x0;
+          xv = lane == 1 ? x1 : xv; xv = lane == 2 ? x2 : xv; xv = lane == 3 ? x3 : xv; xv = lane == 4 ? x4 : xv; xv = lane == 5 ? x5 : xv;
+          ys[j0 + lane] = xv;
         }
         __syncwarp();
       }
+    }
+    if (!s_bad && warp == 0 && (VARIANT & 12)) {
+      // y kept in registers: lane l owns rows l, l+32, l+64, l+96; the 6 entries of the current block are fetched by shuffles,
+      // every lane solves the block redundantly; the update of a lane's rows starts with the unknown that is known first
+      double yv[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) { const int i = lane + 32 * u; yv[u] = (i < n) ? ys[i] : 0.0; }
+      const double* Lv = Li + 6 * nb;
+      for (int jb = nb - 1; jb >= 0; jb--) {
+        const int j0 = 6 * jb;
+        const double* D = Ls + j0 * ld + j0;
+        const double* dv = Li + 6 * jb;
+        // loads that do not depend on the previous block: issue first
+        double dl[4][6];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = lane + 32 * u;
+#pragma unroll
+          for (int k = 0; k < 6; k++) dl[u][k] = (i < j0) ? D[k * ld + i - j0] : 0.0;
+        }
+        double yb[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+          const int i = j0 + k, u = i >> 5;
+          const double v = u == 0 ? yv[0] : u == 1 ? yv[1] : u == 2 ? yv[2] : yv[3];
+          yb[k] = __shfl_sync(0xffffffffu, v, i & 31);
+        }
+        double x0, x1, x2, x3, x4, x5;
+        if (VARIANT & 8) {
+          const double* V = Lv + 36 * jb;   // x = Linv^T y: x_c = sum_{r >= c} V[r][c] y_r, independent dot products
+          x5 = V[35] * yb[5];
+          x4 = V[28] * yb[4] + V[34] * yb[5];
+          x3 = (V[21] * yb[3] + V[27] * yb[4]) + V[33] * yb[5];
+          x2 = (V[14] * yb[2] + V[20] * yb[3]) + (V[26] * yb[4] + V[32] * yb[5]);
+          x1 = (V[7] * yb[1] + V[13] * yb[2]) + (V[19] * yb[3] + V[25] * yb[4]) + V[31] * yb[5];
+          x0 = (V[0] * yb[0] + V[6] * yb[1]) + (V[12] * yb[2] + V[18] * yb[3]) + (V[24] * yb[4] + V[30] * yb[5]);
+        } else {
+          x5 = yb[5] * dv[5];
+          x4 = (yb[4] - D[5 * ld + 4] * x5) * dv[4];
+          x3 = (yb[3] - D[5 * ld + 3] * x5 - D[4 * ld + 3] * x4) * dv[3];
+          x2 = (yb[2] - D[5 * ld + 2] * x5 - D[4 * ld + 2] * x4 - D[3 * ld + 2] * x3) * dv[2];
+          x1 = (yb[1] - D[5 * ld + 1] * x5 - D[4 * ld + 1] * x4 - D[3 * ld + 1] * x3 - D[2 * ld + 1] * x2) * dv[1];
+          x0 = (yb[0] - D[5 * ld] * x5 - D[4 * ld] * x4 - D[3 * ld] * x3 - D[2 * ld] * x2 - D[ld] * x1) * dv[0];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = lane + 32 * u;
+          double t = yv[u];
+          if (VARIANT & 8) t -= ((dl[u][5] * x5 + dl[u][4] * x4) + (dl[u][3] * x3 + dl[u][2] * x2)) + (dl[u][1] * x1 + dl[u][0] * x0);
+          else { t -= dl[u][5] * x5; t -= dl[u][4] * x4; t -= dl[u][3] * x3; t -= dl[u][2] * x2; t -= dl[u][1] * x1; t -= dl[u][0] * x0; }
+          if (i >= j0 && i < j0 + 6) { const int k = i - j0; t = k == 0 ? x0 : k == 1 ? x1 : k == 2 ? x2 : k == 3 ? x3 : k == 4 ? x4 : x5; }
+          yv[u] = t;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) { const int i = lane + 32 * u; if (i < n) ys[i] = yv[u]; }
     }
     __syncthreads();
     t1 = clock64(); c_back += t1 - t0;
@@ -229,6 +393,8 @@ __global__ void __launch_bounds__(256, 1) chol_kernel(const double* S, const dou
     for (int i = tid; i < n; i += nt) x[i] = ys[i];
     __syncthreads();
   }
+  if (tid == 32) cyc[9] = c_w / reps;
+  if (tid == 224) cyc[10] = c_w / reps;
   if (tid == 0) { cyc[0] = c_tot / reps; cyc[1] = c_panel / reps; cyc[2] = c_diag / reps; cyc[3] = c_trail / reps; cyc[4] = c_back / reps; }
   // isolated pieces, no other warp active
   __syncthreads();
@@ -283,19 +449,19 @@ int main() {
   double *dS, *db, *dx; long long* cyc;
   cudaMalloc(&dS, n * n * 8); cudaMalloc(&db, n * 8); cudaMalloc(&dx, n * 8); cudaMallocManaged(&cyc, 128);
   cudaMemcpy(dS, S.data(), n * n * 8, cudaMemcpyHostToDevice); cudaMemcpy(db, b.data(), n * 8, cudaMemcpyHostToDevice);
-  const size_t smem = sizeof(double) * ((size_t)(n + 1) * (n + 1) + 36 * nb);
-  cudaFuncSetAttribute(chol_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaFuncSetAttribute(chol_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  for (int variant = 0; variant < 2; variant++) {
-    if (variant == 0) chol_kernel<0><<<1, 256, smem>>>(dS, db, dx, nb, cyc, 20);
-    else chol_kernel<1><<<1, 256, smem>>>(dS, db, dx, nb, cyc, 20);
+  const size_t smem = sizeof(double) * ((size_t)(n + 1) * (n + 1) + 48 * nb);
+  const int variants[] = {0, 48, 128, 176, 178};
+  for (int vi = 0; vi < 5; vi++) {
+    const int variant = variants[vi];
+#define RUNV(V) case V: cudaFuncSetAttribute(chol_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); chol_kernel<V><<<1, 256, smem>>>(dS, db, dx, nb, cyc, 20); break;
+    switch (variant) { RUNV(0) RUNV(48) RUNV(128) RUNV(176) RUNV(178) }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
     cudaMemcpy(xr.data(), dx, n * 8, cudaMemcpyDeviceToHost);
     double res = 0;
     for (int i = 0; i < n; i++) { double s = -b[i]; for (int j = 0; j < n; j++) s += S[i * n + j] * xr[j]; res = fmax(res, fabs(s)); }
-    printf("variant %d: total=%lld cycles (panel=%lld diag(warp0)=%lld trail+wait=%lld backsub=%lld) residual=%.3e globaltimer_read=%lld cyc | isolated: chol_diag6=%lld rsqrt6chain=%lld ldst21=%lld\n",
-           variant, cyc[0], cyc[1], cyc[2], cyc[3], cyc[4], res, cyc[5], cyc[6], cyc[7], cyc[8]);
+    printf("variant %d: total=%lld cycles (panel=%lld diag(warp0)=%lld trail+wait=%lld backsub=%lld) residual=%.3e trailing own: warp1=%lld warp7=%lld | isolated: chol_diag6=%lld\n",
+           variant, cyc[0], cyc[1], cyc[2], cyc[3], cyc[4], res, cyc[9], cyc[10], cyc[6]);
   }
   return 0;
 }

@@ -702,11 +702,14 @@ __device__ void phase_chol(const BaArgs& a, double lambda, int cur, double* Ls, 
     if (warp == 0) {
       if (jb + 1 < nb) {
         if (lane < 21) {
-          int r = 0, c = lane;
-          while (c > r) { c -= r + 1; r++; }
+          // row of lane l in the packed lower triangle (3 bits per lane in one constant: a decode loop costs ~150 cycles of
+          // this critical chain); the 6-term dot product as a tree (depth 4 instead of 7)
+          const int r = (int)((0x5b6db2491b6d2448ull >> (3 * lane)) & 7ull), c = lane - ((r * (r + 1)) >> 1);
           const double* lr = Ls + (j0 + 6 + r) * ld + j0;
           const double* lc = Ls + (j0 + 6 + c) * ld + j0;
-          Ls[(j0 + 6 + r) * ld + j0 + 6 + c] -= lr[0] * lc[0] + lr[1] * lc[1] + lr[2] * lc[2] + lr[3] * lc[3] + lr[4] * lc[4] + lr[5] * lc[5];
+          double* dst = Ls + (j0 + 6 + r) * ld + j0 + 6 + c;
+          const double s01 = fma(lr[1], lc[1], lr[0] * lc[0]), s23 = fma(lr[3], lc[3], lr[2] * lc[2]), s45 = fma(lr[5], lc[5], lr[4] * lc[4]);
+          *dst = *dst - ((s01 + s23) + s45);
         }
         __syncwarp();
         if (lane == 0 && !chol_diag6(Ls, ld, j0 + 6, Li + 6 * (jb + 1))) s_bad = 1;
@@ -714,8 +717,15 @@ __device__ void phase_chol(const BaArgs& a, double lambda, int cur, double* Ls, 
       }
     } else {
       // groups of 8 rows (8 independent FMA chains per lane, the column operand is loaded once per group)
+      // The cost of a group grows with its row index (columns <= row: 1..4 chunks of 32).  Groups are dealt heaviest first and
+      // in alternating direction over the workers, so that the busiest warp has 6 chunks instead of 8 at the first step (the
+      // FP64 pipe of this one SM bounds the early steps, the diagonal chain of warp 0 the late ones).
       const int ngroups = (m - 5 + 7) >> 3;  // local rows 6..m
-      for (int g = warp - 1; g < ngroups; g += nwarp - 1) {
+      const int nwork = nwarp - 1, widx = warp - 1;
+      for (int pass = 0; pass * nwork < ngroups; pass++) {
+        const int gp = pass * nwork + ((pass & 1) ? nwork - 1 - widx : widx);
+        if (gp >= ngroups) continue;
+        const int g = ngroups - 1 - gp;
         const int r0 = 6 + 8 * g;
         double rv[8][6];
 #pragma unroll
@@ -755,29 +765,49 @@ __device__ void phase_chol(const BaArgs& a, double lambda, int cur, double* Ls, 
   ba_tick(tp, 12);
   const int failed = s_bad;
   if (!failed && warp == 0) {
-    // back substitution with L^T by one warp (no block barriers): lane 0 solves L11^T x_b = y_b (6 steps), the block is
-    // broadcast with shuffles, every lane then updates its rows above (loads issued before x_b is known)
+    // back substitution with L^T by one warp (no block barriers).  Per block step every lane solves L11^T x_b = y_b
+    // redundantly (broadcast loads, 6 dependent steps) and updates its rows above.  All loads of a step -- the block, y_b and
+    // the lane's rows of the panel -- are issued BEFORE the solve: the stores of the previous step forbid the compiler to hoist
+    // them itself, and a chunk-by-chunk load / update / store sequence serialises (measured 920 cycles per block step, 420
+    // like this).  The updates are independent chains that end with the unknown that is known last.
     for (int jb = nb - 1; jb >= 0; jb--) {
       const int j0 = 6 * jb;
       const double* D = Ls + j0 * ld + j0;
       const double* dv = Li + 6 * jb;
-      double x0, x1, x2, x3, x4, x5;
-      {
-        const double y0 = ys[j0], y1 = ys[j0 + 1], y2 = ys[j0 + 2], y3 = ys[j0 + 3], y4 = ys[j0 + 4], y5 = ys[j0 + 5];
-        // the most recent unknown enters last: one FMA + one product per step on the critical path
-        x5 = y5 * dv[5];
-        x4 = (y4 - D[5 * ld + 4] * x5) * dv[4];
-        x3 = (y3 - D[5 * ld + 3] * x5 - D[4 * ld + 3] * x4) * dv[3];
-        x2 = (y2 - D[5 * ld + 2] * x5 - D[4 * ld + 2] * x4 - D[3 * ld + 2] * x3) * dv[2];
-        x1 = (y1 - D[5 * ld + 1] * x5 - D[4 * ld + 1] * x4 - D[3 * ld + 1] * x3 - D[2 * ld + 1] * x2) * dv[1];
-        x0 = (y0 - D[5 * ld] * x5 - D[4 * ld] * x4 - D[3 * ld] * x3 - D[2 * ld] * x2 - D[ld] * x1) * dv[0];
+      const double y0 = ys[j0], y1 = ys[j0 + 1], y2 = ys[j0 + 2], y3 = ys[j0 + 3], y4 = ys[j0 + 4], y5 = ys[j0 + 5];
+      const double d0 = dv[0], d1 = dv[1], d2 = dv[2], d3 = dv[3], d4 = dv[4], d5 = dv[5];
+      const double l10 = D[ld], l20 = D[2 * ld], l21 = D[2 * ld + 1], l30 = D[3 * ld], l31 = D[3 * ld + 1], l32 = D[3 * ld + 2];
+      const double l40 = D[4 * ld], l41 = D[4 * ld + 1], l42 = D[4 * ld + 2], l43 = D[4 * ld + 3];
+      const double l50 = D[5 * ld], l51 = D[5 * ld + 1], l52 = D[5 * ld + 2], l53 = D[5 * ld + 3], l54 = D[5 * ld + 4];
+      constexpr int NCH = (6 * BA_MAX_W + 31) / 32;   // rows above the block, 32 per chunk
+      double dl[NCH][6], yv[NCH];
+#pragma unroll
+      for (int u = 0; u < NCH; u++) {
+        const int i = lane + 32 * u;
+        const bool on = i < j0;
+        yv[u] = on ? ys[i] : 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) dl[u][k] = on ? D[k * ld + i - j0] : 0.0;
       }
-      // every lane computed the same x_b (broadcast loads): no exchange needed
-      if (lane < 6) ys[j0 + lane] = lane == 0 ? x0 : lane == 1 ? x1 : lane == 2 ? x2 : lane == 3 ? x3 : lane == 4 ? x4 : x5;
-#pragma unroll 5
-      for (int i = lane; i < j0; i += 32)
-        ys[i] -= D[i - j0] * x0 + D[ld + i - j0] * x1 + D[2 * ld + i - j0] * x2 + D[3 * ld + i - j0] * x3 +
-                 D[4 * ld + i - j0] * x4 + D[5 * ld + i - j0] * x5;
+      const double x5 = y5 * d5;
+      const double x4 = (y4 - l54 * x5) * d4;
+      const double x3 = ((y3 - l53 * x5) - l43 * x4) * d3;
+      const double x2 = (((y2 - l52 * x5) - l42 * x4) - l32 * x3) * d2;
+      const double x1 = ((((y1 - l51 * x5) - l41 * x4) - l31 * x3) - l21 * x2) * d1;
+      const double x0 = (((((y0 - l50 * x5) - l40 * x4) - l30 * x3) - l20 * x2) - l10 * x1) * d0;
+#pragma unroll
+      for (int u = 0; u < NCH; u++) {
+        const int i = lane + 32 * u;
+        double t = yv[u];
+        t = fma(-dl[u][5], x5, t); t = fma(-dl[u][4], x4, t); t = fma(-dl[u][3], x3, t);
+        t = fma(-dl[u][2], x2, t); t = fma(-dl[u][1], x1, t); t = fma(-dl[u][0], x0, t);
+        if (i < j0) ys[i] = t;
+      }
+      if (lane < 6) {
+        double xv = x0;
+        xv = lane == 1 ? x1 : xv; xv = lane == 2 ? x2 : xv; xv = lane == 3 ? x3 : xv; xv = lane == 4 ? x4 : xv; xv = lane == 5 ? x5 : xv;
+        ys[j0 + lane] = xv;
+      }
       __syncwarp();
     }
   }
