@@ -98,6 +98,35 @@ def test_vio_scale_refinement_matches_oracle(pkg):
     otr.close(); ctx.close()
 
 
+def test_vio_with_dynamic_objects_matches_oracle(pkg):
+    """1242x375, 3 moving objects: Map::ApplyScaledRotation also rotates / scales the object points (vp3DPointDyn) and the object
+    motions (vmRigidMotion[f][j >= 1]); the object state of mpLastFrame (vObjMod, centres) stays as it is, like the reference"""
+    n, cam = 13, synth.KITTI
+    frames, chunks, ft, Tbc, truth = vio_synth.sequence(n, cam=cam, seed=1234, flow_noise=0.05, depth_noise=0.005, n_objects=3)
+    otr, poses, states = vio_synth.run_oracle(frames, chunks, ft, Tbc, cam=cam, cfg_kw={})
+    assert otr.imu_state().initialized == 1
+    ctx = pkg.Context(pkg.default_config(width=cam["width"], height=cam["height"], fx=cam["fx"], fy=cam["fy"], cx=cam["cx"],
+                                         cy=cam["cy"], bf=cam["bf"], max_batch=5))
+    ctx.track_set_imu(Tbc, imu_synth.NOISE)
+    inp = _inputs(frames, ft)
+    for d in inp:
+        d["mask"] = d["mask"].copy()
+    T, st = ctx.track_frames(inp, imu=chunks)
+    # after the initialisation the world's z axis points up: the scene-flow test of DynObjTracking (x / z components only,
+    # src/Tracking.cc:1746-1751) no longer sees the objects move -- reference behaviour, identical on both sides
+    assert sum(s["n_objects_ok"] for s in st[:11]) >= 3 * 9
+    _compare(ctx, T, otr, poses, n)
+    for k in (2, 9, 10, n - 1):
+        a, b = ctx.map_dynamic(k), otr.dynamic_features(k)
+        assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4]), k
+        assert np.abs(a[2] - b[2]).max() <= REL_TOL * max(np.abs(b[2]).max(), 1.0), k
+        la, sa, ma, ca = ctx.map_objects(k)
+        lb, sb, mb, cb = otr.objects(k)
+        assert np.array_equal(la, lb) and np.array_equal(sa, sb), k
+        assert np.abs(ma - mb).max() <= REL_TOL * max(np.abs(mb).max(), 1.0), k
+    otr.close(); ctx.close()
+
+
 def test_apply_scaled_rotation_matches_oracle(pkg):
     sc = synth.Scene(cam=synth.SMALL, seed=5)
     frames = [sc.frame(k) for k in range(4)]

@@ -8,16 +8,16 @@ import synth
 CFG = dict(nfeatures=1200, window=8, max_track_bg=400)
 
 
-def sequence(n_frames, fps=2.5, bg_true=(0.002, -0.001, 0.0015), seed=77):
+def sequence(n_frames, fps=2.5, bg_true=(0.002, -0.001, 0.0015), seed=77, cam=synth.SMALL, **scene_kw):
     samples, ft, Tbc, truth = imu_synth.make_vio_sequence(n_frames, fps=fps, bg_true=bg_true)
     chunks = imu_synth.imu_chunks(samples, ft)
-    sc = synth.Scene(cam=synth.SMALL, seed=seed, pose_fn=imu_synth.vio_camera_pose)
+    sc = synth.Scene(cam=cam, seed=seed, pose_fn=imu_synth.vio_camera_pose, **scene_kw)
     frames = [sc.frame(k) for k in range(n_frames)]
     return frames, chunks, ft, Tbc, truth
 
 
-def run_oracle(frames, chunks, ft, Tbc):
-    cfg = ol.track_config(synth.SMALL, rebuild=0, **CFG)
+def run_oracle(frames, chunks, ft, Tbc, cam=synth.SMALL, cfg_kw=None):
+    cfg = ol.track_config(cam, rebuild=0, **(CFG if cfg_kw is None else cfg_kw))
     tr = ol.OracleTracker(cfg)
     tr.set_imu(Tbc, imu_synth.NOISE)
     poses, states = [], []
