@@ -429,6 +429,19 @@ int vido_map_get_imu_frames(vido_ctx* ctx, float* Tcw, float* vel, float* bias, 
  * 3x3); pending window solves are retired first */
 int vido_map_apply_scaled_rotation(vido_ctx* ctx, const float* R, float s);
 
+/*
+ * Accuracy against ground truth: replaces Tracking::GetMetricError (src/Tracking.cc:3531-3674, bRMSError = false) on the context's
+ * Map.  Camera: for every frame i >= 1 the relative pose error  CamPose[i] CamPose[i-1]^-1 * CamPose_gt[i-1] CamPose_gt[i]^-1
+ * (translation norm, rotation angle in degrees with the reference's clamped-trace rule), averaged; cam_pose_gt = Map::
+ * vmCameraPose_GT (Twc, n_gt >= map frames), refined != 0 evaluates vmCameraPose_RF instead of vmCameraPose.  Objects: for the
+ * n_obj estimated object motions in the order vido_map_get_objects returns them over frames 1, 2, ... (refined: the _RF motions),
+ * RigMotBody = ObjPosePre^-1 * RigMot * ObjPosePre against RigMot_gt (Map::vmObjPosePre / vmRigidMotion_GT, supplied by the
+ * caller; NULL / 0 skips the object part).  per_item (optional): (t, r) of every camera pair, then of every object.
+ */
+typedef struct vido_metric { float cam_t, cam_r, obj_t, obj_r; int32_t n_cam, n_obj; } vido_metric;
+int vido_metric_error(vido_ctx* ctx, const float* cam_pose_gt, int n_gt, int refined, const float* obj_pose_pre,
+                      const float* obj_motion_gt, int n_obj, vido_metric* out, float* per_item);
+
 /* accumulated device time (CUDA events on the context stream) of the kernel groups: ms[0] ORB front-end launches,
  * ms[1] init-model kernels, ms[2] pose-optimisation kernel, ms[3] window-BA kernel; launches[k] = timed regions;
  * ba_alg_bytes = algorithmic bytes of the BA launches (296 B per edge per linearisation + 152 B per edge per

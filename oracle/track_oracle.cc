@@ -1482,4 +1482,64 @@ int vo_tracker_export_full_graph(void* h, int32_t* sizes, float* se3, float* poi
   return 0;
 }
 
+// Tracking::GetMetricError (src/Tracking.cc:3531-3674), bRMSError = false
+static void metric_pair(const float* E, float* t_err, float* r_err) {
+  *t_err = std::sqrt(E[3] * E[3] + E[7] * E[7] + E[11] * E[11]);
+  float tr = 0;
+  for (int j = 0; j < 3; j++) {
+    const float d = E[5 * j];
+    if (d > 1.0) tr = (float)((double)tr + 1.0 - ((double)d - 1.0));
+    else tr = tr + d;
+  }
+  *r_err = (float)(std::acos(((double)tr - 1.0) / 2.0) * 180.0 / 3.1415926);
+}
+int vo_tracker_metric_error(void* h, const float* cam_gt, int n_gt, int refined, const float* pose_pre, const float* mot_gt, int n_obj,
+                            vo_metric* out, float* per_item) {
+  Tracker* t = (Tracker*)h;
+  const auto& cam = (refined && !t->vmCameraPose_RF.empty()) ? t->vmCameraPose_RF : t->map.vmCameraPose;
+  const int n = (int)cam.size();
+  if (n_gt < n) return -1;
+  memset(out, 0, sizeof *out);
+  float ts = 0, rs = 0;
+  int k = 0;
+  for (int i = 1; i < n; i++) {
+    float A[16], B[16], C[16], E[16], te, re;
+    inv44(cam[i - 1].data(), A);
+    mul44(cam[i].data(), A, B);
+    inv44(cam_gt + 16 * (size_t)i, A);
+    mul44(cam_gt + 16 * (size_t)(i - 1), A, C);
+    mul44(B, C, E);
+    metric_pair(E, &te, &re);
+    ts = ts + te; rs = rs + re;
+    if (per_item) { per_item[2 * k] = te; per_item[2 * k + 1] = re; }
+    k++;
+  }
+  out->n_cam = n > 1 ? n - 1 : 0;
+  if (out->n_cam) { out->cam_t = ts / (float)out->n_cam; out->cam_r = rs / (float)out->n_cam; }
+  ts = 0; rs = 0;
+  int o = 0;
+  if (n_obj > 0) {
+    for (size_t f = 0; f < t->map.vmObjMotion.size(); f++)
+      for (size_t j = 0; j < t->map.vmObjMotion[f].size(); j++) {
+        if (o >= n_obj) return -2;
+        const float* M = (refined && !t->vmObjMotion_RF.empty()) ? t->vmObjMotion_RF[f][j].data() : t->map.vmObjMotion[f][j].data();
+        const float* P = pose_pre + 16 * (size_t)o;
+        float A[16], B[16], C[16], E[16], te, re;
+        inv44(P, A);
+        mul44(A, M, B);
+        mul44(B, P, C);
+        inv44(C, A);
+        mul44(A, mot_gt + 16 * (size_t)o, E);
+        metric_pair(E, &te, &re);
+        ts = ts + te; rs = rs + re;
+        if (per_item) { per_item[2 * k] = te; per_item[2 * k + 1] = re; }
+        k++; o++;
+      }
+    if (o != n_obj) return -2;
+    out->n_obj = n_obj;
+    out->obj_t = ts / (float)n_obj; out->obj_r = rs / (float)n_obj;
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -335,6 +335,10 @@ typedef struct vo_imu_state {
   double scale;            /* mScale of the last inertial-only optimisation */
   double Rwg[9], bg[3], ba[3];
 } vo_imu_state;
+/* Tracking::GetMetricError (src/Tracking.cc:3531-3674, bRMSError = false) on the tracker's Map; see vido_metric_error */
+typedef struct vo_metric { float cam_t, cam_r, obj_t, obj_r; int32_t n_cam, n_obj; } vo_metric;
+int vo_tracker_metric_error(void* h, const float* cam_pose_gt, int n_gt, int refined, const float* obj_pose_pre,
+                            const float* obj_motion_gt, int n_obj, vo_metric* out, float* per_item);
 int vo_tracker_set_imu(void* h, const float* Tbc16, const float* noise4);
 int vo_tracker_grab_imu(void* h, const vo_imu_sample* samples, int n);
 void vo_tracker_set_timestamp(void* h, double t);

@@ -356,6 +356,12 @@ def track_config(cam, nfeatures=2500, window=20, max_track_bg=1000, rebuild=1, c
     return c
 
 
+class Metric(C.Structure):
+    """vo_metric / vido_metric"""
+    _fields_ = [("cam_t", C.c_float), ("cam_r", C.c_float), ("obj_t", C.c_float), ("obj_r", C.c_float), ("n_cam", C.c_int32),
+                ("n_obj", C.c_int32)]
+
+
 class ImuState(C.Structure):
     """vo_imu_state / vido_imu_state"""
     _fields_ = [("initialized", C.c_int32), ("status", C.c_int32), ("init_frame", C.c_int32), ("n_refinements", C.c_int32),
@@ -413,6 +419,22 @@ class OracleTracker:
     def apply_scaled_rotation(self, R, s):
         Rm = np.ascontiguousarray(R, np.float32).reshape(9)
         lib().vo_tracker_apply_scaled_rotation(self.h, _p(Rm), float(s))
+
+    def metric_error(self, cam_gt, obj_pose_pre=None, obj_motion_gt=None, refined=False):
+        """Tracking::GetMetricError; returns (Metric, per-item (t, r) array)"""
+        L = lib()
+        L.vo_tracker_metric_error.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                              C.POINTER(Metric), C.c_void_p]
+        g = np.ascontiguousarray(cam_gt, np.float32).reshape(-1, 16)
+        no = 0 if obj_pose_pre is None else len(obj_pose_pre)
+        pp = np.ascontiguousarray(obj_pose_pre, np.float32).reshape(-1, 16) if no else None
+        mg = np.ascontiguousarray(obj_motion_gt, np.float32).reshape(-1, 16) if no else None
+        m = Metric()
+        per = np.zeros((max(len(g) - 1, 0) + no, 2), np.float32)
+        rc = L.vo_tracker_metric_error(self.h, _p(g), len(g), int(refined), _p(pp) if no else None, _p(mg) if no else None, no,
+                                       C.byref(m), _p(per))
+        assert rc == 0, rc
+        return m, per
 
     def track(self, gray, depth_in, flow, mask, timestamp=None):
         """depth_in is copied (the oracle pre-scales its copy in place).  Returns (Tcw 4x4, stats dict, rc)."""

@@ -3,6 +3,7 @@ is exact (counts, labels, associations, tracklets), object motions / refined fea
 import numpy as np
 import pytest
 
+import metric_synth
 import oracle_lib as ol
 import synth
 
@@ -69,4 +70,31 @@ def test_reprojection_only_branch_matches_oracle(pkg):
     otr, ref, ctx, T, st = _both(pkg, n, 4, b_joint=0)
     assert sum(s["n_objects_ok"] for s in st) >= 5 * (n - 2)
     _compare(otr, ref, ctx, T, st, n)
+    otr.close(); ctx.close()
+
+
+def test_metric_error_matches_oracle(pkg):
+    """vido_metric_error (Tracking::GetMetricError as a device-side evaluation) on the tracked dynamic sequence, before and after
+    the full-sequence optimisation"""
+    n = 7
+    sc = synth.Scene(cam=CAM, seed=1234, flow_noise=0.1, depth_noise=0.01, n_objects=5)
+    frames = [sc.frame(k) for k in range(n)]
+    otr = ol.OracleTracker(ol.track_config(CAM, rebuild=0))
+    for f in frames:
+        otr.track(f["gray"].numpy(), f["depth_in"].numpy(), f["flow"].numpy(), f["mask"].numpy())
+    ctx = pkg.Context(pkg.default_config(width=CAM["width"], height=CAM["height"], fx=CAM["fx"], fy=CAM["fy"], cx=CAM["cx"],
+                                         cy=CAM["cy"], bf=CAM["bf"], max_batch=4))
+    ctx.track_frames([dict(image=f["gray"].numpy(), depth=f["depth_in"].numpy(), flow=f["flow"].numpy(),
+                           mask=f["mask"].numpy().copy()) for f in frames])
+    cam_gt, pre, mgt = metric_synth.ground_truth(sc, frames, lambda f: otr.objects(f)[1])
+    for refined in (False, True):
+        if refined:
+            otr.full_batch(); ctx.full_batch()
+        m0, per0 = otr.metric_error(cam_gt, pre, mgt, refined=refined)
+        m1, per1 = ctx.metric_error(cam_gt, pre, mgt, refined=refined)
+        assert (m1.n_cam, m1.n_obj) == (m0.n_cam, m0.n_obj) == (n - 1, 5 * (n - 1))
+        assert np.abs(per1[:, 0] - per0[:, 0]).max() < 2e-4          # metres
+        assert np.abs(per1[:, 1] - per0[:, 1]).max() < 0.06          # degrees (float32 acos near 1: steps of ~0.03 degree)
+        assert abs(m1.cam_t - m0.cam_t) < 1e-4 and abs(m1.obj_t - m0.obj_t) < 1e-4
+        assert m1.cam_t < 0.02 and m1.obj_t < 0.03
     otr.close(); ctx.close()

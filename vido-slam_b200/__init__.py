@@ -103,6 +103,12 @@ class InertialProblem(C.Structure):
                 ("mode", C.c_int32)]
 
 
+class Metric(C.Structure):
+    """vido_metric (include/vido_b200.h)"""
+    _fields_ = [("cam_t", C.c_float), ("cam_r", C.c_float), ("obj_t", C.c_float), ("obj_r", C.c_float), ("n_cam", C.c_int32),
+                ("n_obj", C.c_int32)]
+
+
 class ImuState(C.Structure):
     """vido_imu_state (include/vido_b200.h)"""
     _fields_ = [("initialized", C.c_int32), ("status", C.c_int32), ("init_frame", C.c_int32), ("n_refinements", C.c_int32),
@@ -192,6 +198,7 @@ def load_library():
     lib.vido_inertial_default_params.argtypes = [C.POINTER(InertialProblem)]
     lib.vido_inertial_opt.argtypes = [vp, C.POINTER(InertialProblem), C.POINTER(LmStats)]
     lib.vido_track_set_imu.argtypes = [vp, vp, vp]
+    lib.vido_metric_error.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, C.POINTER(Metric), vp]
     lib.vido_track_grab_imu.argtypes = [vp, vp, C.c_int, C.c_int]
     lib.vido_track_get_imu_state.argtypes = [vp, C.POINTER(ImuState)]
     lib.vido_map_get_imu_frames.argtypes = [vp, vp, vp, vp, C.c_int]
@@ -411,6 +418,18 @@ class Context:
         if n > 0:
             self.lib.vido_map_get_imu_frames(self.h, _ptr(T), _ptr(v), _ptr(b), n)
         return T.reshape(-1, 4, 4), v, b
+
+    def metric_error(self, cam_gt, obj_pose_pre=None, obj_motion_gt=None, refined=False):
+        """Tracking::GetMetricError on the context's Map; returns (Metric, per-item (t, r) array)"""
+        g = np.ascontiguousarray(cam_gt, np.float32).reshape(-1, 16)
+        no = 0 if obj_pose_pre is None else len(obj_pose_pre)
+        pp = np.ascontiguousarray(obj_pose_pre, np.float32).reshape(-1, 16) if no else None
+        mg = np.ascontiguousarray(obj_motion_gt, np.float32).reshape(-1, 16) if no else None
+        m = Metric()
+        per = np.zeros((max(len(g) - 1, 0) + no, 2), np.float32)
+        self._check(self.lib.vido_metric_error(self.h, _ptr(g), len(g), int(refined), _ptr(pp) if no else None,
+                                               _ptr(mg) if no else None, no, C.byref(m), _ptr(per)))
+        return m, per
 
     def map_apply_scaled_rotation(self, R, s):
         """Map::ApplyScaledRotation(R, s)"""

@@ -366,6 +366,12 @@ int vido_track_get_imu_state(vido_ctx* ctx, vido_imu_state* out) { return (ctx &
 int vido_map_get_imu_frames(vido_ctx* ctx, float* Tcw, float* vel, float* bias, int cap) { return ctx ? trk_get_imu_frames(ctx, Tcw, vel, bias, cap) : VIDO_ERR_ARG; }
 int vido_map_apply_scaled_rotation(vido_ctx* ctx, const float* R, float s) { return (ctx && R) ? trk_apply_scaled_rotation(ctx, R, s) : VIDO_ERR_ARG; }
 
+int vido_metric_error(vido_ctx* ctx, const float* cam_pose_gt, int n_gt, int refined, const float* obj_pose_pre,
+                      const float* obj_motion_gt, int n_obj, vido_metric* out, float* per_item) {
+  if (!ctx || !out || !cam_pose_gt || n_gt < 0 || n_obj < 0 || (n_obj > 0 && (!obj_pose_pre || !obj_motion_gt))) return VIDO_ERR_ARG;
+  return trk_metric_error(ctx, cam_pose_gt, n_gt, refined, obj_pose_pre, obj_motion_gt, n_obj, out, per_item);
+}
+
 int vido_get_kernel_times(vido_ctx* ctx, double* ms, int64_t* launches, double* ba_alg_bytes) {
   if (!ctx) return VIDO_ERR_ARG;
   for (int k = 0; k < 4; k++) { if (ms) ms[k] = ctx->t_ms[k]; if (launches) launches[k] = ctx->t_n[k]; }

@@ -194,6 +194,12 @@ int projopt_host(vido_ctx* ctx, vido_projopt_problem* prs, int nproblems, vido_l
 void inertial_default_params(vido_inertial_problem* p);
 int inertial_opt_host(vido_ctx* ctx, vido_inertial_problem* p, vido_lm_stats* st);
 
+// metric_kernels.cu
+int metric_error_host(vido_ctx* ctx, const float* cam, const float* cam_gt, int n, const float* mot, const float* pose_pre,
+                      const float* mot_gt, int n_obj, vido_metric* out, float* per_item);
+int trk_metric_error(vido_ctx* ctx, const float* cam_gt, int n_gt, int refined, const float* pose_pre, const float* mot_gt, int n_obj,
+                     vido_metric* out, float* per_item);   // track.cu
+
 // imu_kernels.cu
 int imu_preintegrate_host(vido_ctx* ctx, const vido_imu_sample* samples, int n, const double* t_prev, const double* t_cur,
                           int njobs, const float* bias, const float* noise, vido_imu_preint* out, const int32_t* nvis = nullptr);

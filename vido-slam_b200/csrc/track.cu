@@ -2284,3 +2284,18 @@ int trk_get_imu_frames(vido_ctx* ctx, float* Tcw, float* vel, float* bias, int c
   }
   return n;
 }
+
+// Tracking::GetMetricError on the Map (metric_kernels.cu): camera poses and the estimated object motions in Map order
+int trk_metric_error(vido_ctx* ctx, const float* cam_gt, int n_gt, int refined, const float* pose_pre, const float* mot_gt, int n_obj,
+                     vido_metric* out, float* per_item) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  const int n = (int)ts->map.size();
+  if (n_gt < n) { ctx->err = "metric: fewer ground-truth poses than map frames"; return VIDO_ERR_ARG; }
+  std::vector<float> cam(16 * (size_t)std::max(n, 1)), mot;
+  for (int i = 0; i < n; i++) memcpy(&cam[16 * (size_t)i], refined ? ts->map[i].Twc_rf : ts->map[i].Twc, sizeof(float) * 16);
+  for (int i = 1; i < n; i++)
+    for (const ObjEntry& o : ts->map[i].objects) mot.insert(mot.end(), refined ? o.motion_rf : o.motion, (refined ? o.motion_rf : o.motion) + 16);
+  const int have = (int)(mot.size() / 16);
+  if (n_obj > 0 && n_obj != have) { ctx->err = "metric: object ground truth does not match the number of estimated object motions"; return VIDO_ERR_ARG; }
+  return metric_error_host(ctx, cam.data(), cam_gt, n, mot.data(), pose_pre, mot_gt, n_obj, out, per_item);
+}
