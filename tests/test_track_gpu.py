@@ -110,3 +110,30 @@ def test_rgb_input_and_depth_write_back(pkg):
     ref = ol.depth_prep(frames[1]["depth_in"].numpy(), 2, 256.0, cam["bf"])
     assert np.array_equal(deps[1], ref)
     ctx.close()
+
+
+def test_lost_tracking_skips_frames_like_oracle(pkg):
+    """a frame whose flow throws every correspondence out of the image leaves mpLastFrame without features: Tracking::Track returns
+    early for every later frame (src/Tracking.cc:1110-1113, "Temperal Match size is < 2"), nothing is added to the Map"""
+    cam = synth.SMALL
+    frames = _sequence(cam, 9, 5)
+    flows = [f["flow"].numpy().copy() for f in frames]
+    flows[2][:] = 1e4
+    otr = ol.OracleTracker(ol.track_config(cam, nfeatures=1200, window=8))
+    ref = [otr.track(f["gray"].numpy(), f["depth_in"].numpy(), fl, f["mask"].numpy()) for f, fl in zip(frames, flows)]
+    assert [r[2] for r in ref] == [0, 0, 0, 1, 1]
+    ctx = pkg.Context(pkg.default_config(width=cam["width"], height=cam["height"], fx=cam["fx"], fy=cam["fy"], cx=cam["cx"],
+                                         cy=cam["cy"], bf=cam["bf"], max_batch=2, nfeatures=1200, window_size=8))
+    T, st = ctx.track_frames([dict(image=f["gray"].numpy(), depth=f["depth_in"].numpy(), flow=fl, mask=f["mask"].numpy())
+                              for f, fl in zip(frames, flows)])
+    for k in range(5):
+        assert np.abs(T[k] - ref[k][0]).max() <= REL_TOL * max(np.abs(ref[k][0]).max(), 1.0), k
+        assert st[k]["n_matches"] == ref[k][1]["n_matches"] and st[k]["n_static"] == ref[k][1]["n_static"], k
+    P0, P = otr.map_poses(), ctx.map_poses()
+    assert P.shape == P0.shape == (3, 4, 4) and np.abs(P - P0).max() <= REL_TOL
+    # the context stays usable: a reset starts a new sequence
+    ctx.track_reset()
+    T2, _ = ctx.track_frames([dict(image=f["gray"].numpy(), depth=f["depth_in"].numpy(), flow=f["flow"].numpy(), mask=f["mask"].numpy())
+                              for f in frames[:3]])
+    assert np.abs(T2[1] - ref[1][0]).max() <= REL_TOL
+    otr.close(); ctx.close()
