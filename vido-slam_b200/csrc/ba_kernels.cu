@@ -29,151 +29,15 @@
 #include <cstdlib>
 #include <cstring>
 
-#include "ba_math.h"
-#include "ctx.h"
-#include "lm_device.h"
+#include "ba_common.h"
 
 namespace cg = cooperative_groups;
-using namespace vb;
 
-#define BA_THREADS 256
-#define BA_MAX_W 24
-#define BA_MAX_CLUSTER 16
-#define BA_PCHUNK 8   // max chunks per pose in the pose-block reduction
-#define BA_MAX_JOBS (BA_MAX_W * (BA_MAX_W + 1) / 2 + BA_MAX_W)   // Schur jobs: pose pairs + gradient jobs
-#define BA_MAX_SLOTS (BA_MAX_CLUSTER * BA_THREADS / 32)            // partial sums per job: at most one per warp
-#define BA_JOB_PAD 2   // fixed cost of entering a job (decode, prefix scan, flush), in units, for the load balance
-
-struct BaArgs {
-  int W, P, M;
-  int max_iterations;
-  int t_detail;   // debug: extra phase time stamps (VIDO_BA_TIMING=2)
-  double info_cam, info_3d, d_cam, d_3d, gain_threshold;
-  // graph (device)
-  const float* poses_f32;   // [W][16]
-  const float* rel_f32;     // [W-1][16]
-  const float* points_f32;  // [P][3]  (sorted order)
-  const int* obs_pose;      // [M]  pose-major observation index -> pose
-  const int* obs_point;     // [M]  -> point
-  const float* obs_xyz;     // [3][M] struct-of-arrays
-  const int* pt_len;        // [P]
-  const int* pt_first;      // [P]
-  const int* grp_start;     // [W+1]
-  const int* cnt_gt;        // [W][W+1]: #points of group f with track length > L
-  const int* off;           // [W][W+1]: offset of group f inside pose p's range
-  const int* pose_base;     // [W+1]
-  // state
-  Pose* X;        // [2][W]
-  Pose* Zinv;     // [W-1]
-  double* pts;    // [2][P][3]
-  // system
-  double* hl;     // [P]     point block = hl * I3
-  double* bl;     // [P][3]
-  // linearisation buffers, one per state buffer (index = state index): the trial state's observation pass fills the
-  // other one, an accepted trial makes it current
-  double* ow;     // [2][M]    robust weight * information of every observation   } the 6x3 block Hpl = ow * [-I | Q(zc)]^T R^T
-  double* ozc;    // [2][3][M] point in the camera frame (struct-of-arrays)         } is never formed (see phase_schur_units)
-  double* og;     // [2][3][M] ow * R * error: the point gradient is -sum og
-  double* ohb;    // [4][M] per observation: its point's hl and bl (written by phase_blocks, read coalesced by the gradient jobs)
-  double* Hpp;    // [W][36] diagonal blocks (points + odometry)
-  double* Hoff;   // [W-1][36] blocks (i, i+1)
-  double* bp;     // [W][6]
-  double* ppart;  // [2][W][BA_PCHUNK][28] partial pose blocks (27 sums)
-  double* spart;  // [jobs][BA_MAX_SLOTS][16] partial Schur moment sums
-  double* pmax;   // [W] max |diagonal| of every pose block
-  double* xp;     // [6W]
-  double* part;   // [BA_MAX_CLUSTER][4]: chi2, scale, max point diag, max pose diag
-  double* cinfo;  // [4]: pose part of the scale, solver failure flag
-  double* seJ;    // [2][W][72]
-  double* seE;    // [2][W][8]
-  LmCtl* ctl_out;
-  LmRec* rec;
-  unsigned long long* t_phase;  // [24]
-  float* out_poses; float* out_rel; float* out_points;
-};
-
-__device__ __forceinline__ double div_pos(double a, double x);
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-// Sum 36 per-lane values over the warp with 54 shuffles instead of 180: two halving steps (lane pairs trade halves of
-// their value sets), then a butterfly inside the 8-lane groups.  Afterwards v[j], j < 9, of lane L holds the sum of
-// value 18*((L>>4)&1) + 9*((L>>3)&1) + j.  Fixed order, deterministic.
-__device__ __forceinline__ void warp_sum36(double* v) {
-  const int lane = threadIdx.x & 31;
-  const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
-#pragma unroll
-  for (int k = 0; k < 18; k++) {
-    const double send = hi16 ? v[k] : v[k + 18], keep = hi16 ? v[k + 18] : v[k];
-    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int k = 0; k < 9; k++) {
-    const double send = hi8 ? v[k] : v[k + 9], keep = hi8 ? v[k + 9] : v[k];
-    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int k = 0; k < 9; k++) {
-    v[k] += __shfl_xor_sync(0xffffffffu, v[k], 4);
-    v[k] += __shfl_xor_sync(0xffffffffu, v[k], 2);
-    v[k] += __shfl_xor_sync(0xffffffffu, v[k], 1);
-  }
-}
-
-// Same idea for 16 values with 16 shuffles: afterwards v[0] of lane L holds the sum of value 8*b4 + 4*b3 + 2*b2 + b1
-// (b_i = bit i of L).
-__device__ __forceinline__ void warp_sum16(double* v) {
-  const int lane = threadIdx.x & 31;
-#pragma unroll
-  for (int h = 8, m = 16; h >= 1; h >>= 1, m >>= 1) {
-    const bool hi = (lane & m) != 0;
-#pragma unroll
-    for (int k = 0; k < h; k++) {
-      const double send = hi ? v[k] : v[k + h], keep = hi ? v[k + h] : v[k];
-      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, m);
-    }
-  }
-  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
-
-__device__ __forceinline__ double warp_max(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-
-// block-wide reduction of NV values per thread; results in sm[0..NV) (valid after the call for every thread)
-template <int NV, bool MAX>
-__device__ __forceinline__ void block_reduce(double* v, double* sm) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-#pragma unroll
-  for (int k = 0; k < NV; k++) v[k] = MAX ? warp_max(v[k]) : warp_sum(v[k]);
-  __syncthreads();
-  if (lane == 0)
-    for (int k = 0; k < NV; k++) sm[warp * NV + k] = v[k];
-  __syncthreads();
-  if (threadIdx.x < NV) {
-    double s = sm[threadIdx.x];
-    for (int w = 1; w < nw; w++) s = MAX ? fmax(s, sm[w * NV + threadIdx.x]) : s + sm[w * NV + threadIdx.x];
-    sm[threadIdx.x] = s;
-  }
-  __syncthreads();
-}
-
-__device__ __forceinline__ unsigned long long gtime();
-__device__ __forceinline__ void ba_tick(unsigned long long* tp, int slot);
-__device__ __forceinline__ unsigned long long gtime() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-
-// ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void ba_tick(unsigned long long* tp, int slot) {
-  if (tp) { const unsigned long long t = gtime(); tp[slot] += t - tp[15]; tp[15] = t; }
-}
+// ba_window.cu
+size_t ba_window_smem(int W, int capO, int capPt);
+size_t ba_window_smem_limit();
+int ba_window_configure(size_t max_smem, int* cluster_out);
+cudaError_t ba_window_launch(const BaArgs& a, int cluster, size_t smem, cudaStream_t s);
 
 __device__ void phase_init(const BaArgs& a, int G, int GT) {
   for (int i = G; i < a.W; i += GT) {
@@ -612,18 +476,6 @@ __device__ __forceinline__ double rsqrt_pos(double d) {
   return fma(fma(e, 0.375, 0.5), y * e, y);
 }
 
-// a / x for a positive normal x without the library's special-case subroutine (see rsqrt_pos)
-__device__ __forceinline__ double div_pos(double a, double x) {
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  const double q = a * y;
-  return fma(fma(-x, q, a), y, q);
-}
-
 // 6x6 Cholesky of a diagonal block by one lane, straight-line scalar code (no local arrays, no subroutine calls: either
 // would put local-memory round trips into this latency-critical chain).  Writes L in place and 1/L_jj to dinv.
 __device__ __forceinline__ bool chol_diag6(double* Ls, int ld, int j0, double* dinv) {
@@ -932,7 +784,7 @@ __device__ void phase_output_rel(const BaArgs& a, int G, int GT) {
 // ---------------------------------------------------------------------------------------------------------
 // the cluster kernel (cluster size set at launch: 16 CTAs when the device allows it, else 8)
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BA_THREADS, 1) ba_window_kernel(BaArgs a) {
+__global__ void __launch_bounds__(BA_THREADS, 1) ba_window_big_kernel(BaArgs a) {
   extern __shared__ __align__(16) double dsm[];  // (6W+1)^2 + 36W doubles for the dense factorisation (CTA 0)
   __shared__ double red[16 * 2 + 32];
   __shared__ LmCtl ctl;  // every CTA keeps an identical copy: decisions are recomputed from the same partial sums
@@ -1066,6 +918,13 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_window_kernel(BaArgs a) {
 struct BaWorkspace {
   int capW = 0, capP = 0, capM = 0;
   int cluster = 8;
+  // shared-memory resident kernel (ba_window.cu): cluster size, dynamic shared memory it may use; per staging slot whether the
+  // problem fits and what it needs.  Oversized windows fall back to the L2-resident kernel of this file.
+  int cluster_sm = 8;
+  size_t smem_limit = 0;
+  bool use_sm2[2] = {false, false};
+  size_t smem2[2] = {0, 0};
+  std::vector<int> wk_obs;
   char* d_base = nullptr;            // solver workspace
   char* d_in2[2] = {nullptr, nullptr};  // input blocks (two: the next problem is staged while the current one is solved)
   char* d_out2[2] = {nullptr, nullptr}; // output blocks (two: a solve may be queued behind the one in flight)
@@ -1078,7 +937,7 @@ struct BaWorkspace {
   int* h_chain2[2] = {nullptr, nullptr};
   bool chained2[2] = {false, false};
   cudaEvent_t out_done[2] = {nullptr, nullptr};
-  struct Flight { int slot, W, P, M; bool want_records; };
+  struct Flight { int slot, W, P, M; bool want_records; bool sm; };
   Flight flight[2];
   int nflight = 0;
   int slot = 0;                      // staging slot of the problem being prepared / in flight
@@ -1127,6 +986,9 @@ static void carve_all(char*& p, BaArgs& a, int capW, int capP, int capM) {
   a.spart = carve<double>(p, (size_t)BA_MAX_JOBS * BA_MAX_SLOTS * 16); a.pmax = carve<double>(p, capW); a.xp = carve<double>(p, 6 * capW);
   a.part = carve<double>(p, 4 * BA_MAX_CLUSTER); a.cinfo = carve<double>(p, 4);
   a.seJ = carve<double>(p, 2 * 72 * capW); a.seE = carve<double>(p, 2 * 8 * capW);
+  a.wmom = carve<double>(p, (size_t)(BA_MAX_CLUSTER - 1) * BA_MAX_JOBS * 16);
+  a.wpsum = carve<double>(p, (size_t)2 * (BA_MAX_CLUSTER - 1) * capW * 28);
+  a.eH = carve<double>(p, (size_t)2 * capW * 120);
 }
 
 int ba_setup(vido_ctx* ctx, int capW, int capP, int capM) {
@@ -1160,10 +1022,10 @@ int ba_setup(vido_ctx* ctx, int capW, int capP, int capM) {
   carve_all(p, ws->args, capW, capP, capM);
   const size_t smem = sizeof(double) * ((size_t)(6 * capW + 1) * (6 * capW + 1) + 36 * capW);
   if (smem > 200 * 1024) { ctx->err = "BA window too large for the shared-memory Cholesky"; return VIDO_ERR_ARG; }
-  VIDO_CUDA(cudaFuncSetAttribute(ba_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VIDO_CUDA(cudaFuncSetAttribute(ba_window_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // 16-CTA clusters are a non-portable size: opt in, and verify that one fits
   ws->cluster = 8;
-  if (cudaFuncSetAttribute(ba_window_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+  if (cudaFuncSetAttribute(ba_window_big_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(16); cfg.blockDim = dim3(BA_THREADS); cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute at[1];
@@ -1171,10 +1033,13 @@ int ba_setup(vido_ctx* ctx, int capW, int capP, int capM) {
     at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int nclusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&nclusters, ba_window_kernel, &cfg) == cudaSuccess && nclusters >= 1) ws->cluster = 16;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, ba_window_big_kernel, &cfg) == cudaSuccess && nclusters >= 1) ws->cluster = 16;
   }
   cudaGetLastError();
   if (getenv("VIDO_BA_CLUSTER") && atoi(getenv("VIDO_BA_CLUSTER")) == 8) ws->cluster = 8;
+  ws->smem_limit = ba_window_smem_limit();
+  if (ws->smem_limit == 0 || ba_window_configure(ws->smem_limit, &ws->cluster_sm) != 0) { ctx->err = "cannot configure the window-BA kernel"; return VIDO_ERR_CUDA; }
+  if (getenv("VIDO_BA_CLUSTER") && atoi(getenv("VIDO_BA_CLUSTER")) == 8) ws->cluster_sm = 8;
   VIDO_CUDA(vido_create_stream(&ws->stream, true));
   VIDO_CUDA(vido_create_stream(&ws->up_stream, true));
   VIDO_CUDA(cudaEventCreateWithFlags(&ws->up_done, cudaEventDisableTiming));
@@ -1326,6 +1191,19 @@ int ba_prepare_chained(vido_ctx* ctx, const vido_ba_problem* pr, const int* prev
     }
     VIDO_CUDA(cudaEventRecord(ws->up_done, ws->up_stream));
   }
+  {  // does the window fit the shared-memory resident kernel?  Points are dealt round-robin (sorted order) to the workers.
+    const int nwk = ws->cluster_sm - 1;
+    ws->wk_obs.assign(nwk, 0);
+    for (int n = 0; n < P; n++) ws->wk_obs[n % nwk] += h_pt_len[n];
+    int capO = 0;
+    for (int c = 0; c < nwk; c++) capO = std::max(capO, ws->wk_obs[c]);
+    const int capPt = (P + nwk - 1) / nwk;
+    a.capO = (capO + 7) & ~7; a.capPt = (capPt + 7) & ~7;
+    const size_t need = ba_window_smem(W, a.capO, a.capPt);
+    const char* force = getenv("VIDO_BA_KERNEL");   // debug: "l2" forces the L2-resident kernel
+    ws->use_sm2[slot] = need <= ws->smem_limit && capO < 65536 && !(force && !strcmp(force, "l2"));
+    ws->smem2[slot] = need;
+  }
   ws->a_prep = a;
   ws->prepared = true;
   return VIDO_OK;
@@ -1369,7 +1247,12 @@ int ba_launch(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records) {
     ctx->launches++;
   }
   const size_t smem = sizeof(double) * ((size_t)(6 * W + 1) * (6 * W + 1) + 36 * W);
-  {
+  if (ws->use_sm2[slot]) {
+    cudaEventRecord(ws->ev0[slot], s);
+    VIDO_CUDA(ba_window_launch(a, ws->cluster_sm, ws->smem2[slot], s));
+    cudaEventRecord(ws->ev1[slot], s);
+    ctx->launches++;
+  } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ws->cluster); cfg.blockDim = dim3(BA_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute at[1];
@@ -1377,7 +1260,7 @@ int ba_launch(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records) {
     at[0].val.clusterDim.x = ws->cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     cudaEventRecord(ws->ev0[slot], s);
-    VIDO_CUDA(cudaLaunchKernelEx(&cfg, ba_window_kernel, a));
+    VIDO_CUDA(cudaLaunchKernelEx(&cfg, ba_window_big_kernel, a));
     cudaEventRecord(ws->ev1[slot], s);
     ctx->launches++;
   }
@@ -1389,7 +1272,7 @@ int ba_launch(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records) {
     VIDO_CUDA(cudaMemcpyAsync(ws->h_out2[slot], ws->d_out2[slot], out_used, cudaMemcpyDeviceToHost, s));
     VIDO_CUDA(cudaEventRecord(ws->out_done[slot], s));
   }
-  ws->flight[ws->nflight++] = {slot, W, P, M, want_records};
+  ws->flight[ws->nflight++] = {slot, W, P, M, want_records, ws->use_sm2[slot]};
   return VIDO_OK;
 }
 
@@ -1426,12 +1309,15 @@ int ba_collect(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st) {
     const double edges = (double)M + (double)std::max(W - 1, 0);
     ctx->ba_alg_bytes += edges * (296.0 * std::max(ctl.iterations, 0) + 152.0 * (ctl.total_trials + 1));
   }
-  if (getenv("VIDO_BA_TIMING"))
+  if (getenv("VIDO_BA_TIMING") && F.sm)
+    fprintf(stderr, "[ba-sm] cluster=%d W=%d P=%d M=%d its=%d trials=%d ns: init=%llu schur=%llu reduce=%llu solve=%llu update+obs=%llu lm=%llu total=%llu\n",
+            ws->cluster_sm, W, P, M, ctl.iterations, ctl.total_trials, tph[5], tph[0], tph[1], tph[2], tph[3], tph[4], tph[7]);
+  else if (getenv("VIDO_BA_TIMING"))
     fprintf(stderr, "[ba] cluster=%d W=%d P=%d M=%d its=%d trials=%d ns: linearize=%llu schur=%llu chol=%llu update=%llu init=%llu end=%llu total=%llu\n",
             ws->cluster, W, P, M, ctl.iterations, ctl.total_trials, tph[0] + tph[8] + tph[9] + tph[10] + tph[20], tph[1] + tph[2] + tph[19], tph[3] + tph[11] + tph[12] + tph[13] + tph[16] + tph[17] + tph[18], tph[4] + tph[21], tph[5], tph[6], tph[7]);
-  if (getenv("VIDO_BA_TIMING") && atoi(getenv("VIDO_BA_TIMING")) > 1)
+  if (!F.sm && getenv("VIDO_BA_TIMING") && atoi(getenv("VIDO_BA_TIMING")) > 1)
     fprintf(stderr, "[ba]   cta0 own time: obs_pass=%llu units=%llu update=%llu\n", tph[20], tph[19], tph[21]);
-  if (getenv("VIDO_BA_TIMING") && atoi(getenv("VIDO_BA_TIMING")) > 1)
+  if (!F.sm && getenv("VIDO_BA_TIMING") && atoi(getenv("VIDO_BA_TIMING")) > 1)
     fprintf(stderr, "[ba]   obs_wait=%llu blocks=%llu lm_begin=%llu | schur: units=%llu reduce=%llu | chol: diag0=%llu panel=%llu diag=%llu trail_wait=%llu backsub=%llu epilogue=%llu\n",
             tph[9], tph[10], tph[0], tph[1], tph[2], tph[11], tph[16], tph[17], tph[18] + tph[12], tph[13], tph[3]);
   if (st) {

@@ -51,6 +51,11 @@ vido_ctx* vido_create(const vido_config* cfg) {
   if (!ctx) { g_create_err = "out of memory"; return nullptr; }
   ctx->cfg = *cfg;
   if (ctx->cfg.max_batch < 1) ctx->cfg.max_batch = 1;
+  if (cfg->window_size < 1 || cfg->window_size > 24) {   // the window solver keeps the reduced system in shared memory (BA_MAX_W)
+    g_create_err = "window_size must be in 1..24";
+    delete ctx;
+    return nullptr;
+  }
   ctx->device = cfg->device;
   ctx->num_sms = prop.multiProcessorCount;
   if (cudaSetDevice(cfg->device) != cudaSuccess || vido_create_stream(&ctx->stream, true) != cudaSuccess) {
@@ -72,6 +77,8 @@ vido_ctx* vido_create(const vido_config* cfg) {
     po_teardown(ctx);
     ba_teardown(ctx);
     orb_teardown(ctx);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return nullptr;
@@ -89,6 +96,8 @@ void vido_destroy(vido_ctx* ctx) {
   ba_teardown(ctx);
   orb_teardown(ctx);
   if (ctx->um_ws) cudaFree(ctx->um_ws);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -98,6 +107,7 @@ void* vido_stream(vido_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 int vido_sync(vido_ctx* ctx) {
   if (!ctx) return VIDO_ERR_ARG;
+  cudaSetDevice(ctx->device);
   VIDO_CUDA(cudaStreamSynchronize(ctx->stream));
   return VIDO_OK;
 }
@@ -304,7 +314,11 @@ int vido_track_frames(vido_ctx* ctx, const vido_frame_inputs* frames, int nframe
   cudaSetDevice(ctx->device);
   return trk_track_chunk(ctx, frames, nframes, Tcw_out, stats);
 }
-int vido_track_reset(vido_ctx* ctx) { return ctx ? trk_reset(ctx) : VIDO_ERR_ARG; }
+int vido_track_reset(vido_ctx* ctx) {
+  if (!ctx) return VIDO_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  return trk_reset(ctx);
+}
 
 int vido_track_prefetch(vido_ctx* ctx, const vido_frame_inputs* frames, int nframes) {
   if (!ctx || (!frames && nframes > 0)) return VIDO_ERR_ARG;
@@ -331,9 +345,14 @@ void vido_fba_default_params(vido_fba_problem* p) { if (p) vido_fba_default_para
 int vido_ba_full(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* stats) {
   if (!ctx || !p) return VIDO_ERR_ARG;
   if (p->n_poses < 0 || p->n_motions < 0 || p->n_points < 0 || p->n_obs < 0 || p->n_e6 < 0 || p->n_tern < 0) { ctx->err = "negative size"; return VIDO_ERR_ARG; }
+  cudaSetDevice(ctx->device);
   return fba_solve_host(ctx, p, stats);
 }
-int vido_full_batch(vido_ctx* ctx, vido_lm_stats* stats, int32_t* sizes) { return ctx ? trk_full_batch(ctx, stats, sizes) : VIDO_ERR_ARG; }
+int vido_full_batch(vido_ctx* ctx, vido_lm_stats* stats, int32_t* sizes) {
+  if (!ctx) return VIDO_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  return trk_full_batch(ctx, stats, sizes);
+}
 int vido_map_get_poses_rf(vido_ctx* ctx, float* poses, int cap) { return (ctx && poses) ? trk_get_map_poses_rf(ctx, poses, cap) : VIDO_ERR_ARG; }
 int vido_map_get_objects_rf(vido_ctx* ctx, int frame, float* motion, int cap) { return ctx ? trk_get_objects_rf(ctx, frame, motion, cap) : VIDO_ERR_ARG; }
 int vido_map_export_full_graph(vido_ctx* ctx, int32_t* sizes, float* se3, float* points, int32_t* e6_i, int32_t* e6_j, int32_t* e6_kind,
@@ -347,6 +366,7 @@ int vido_map_export_full_graph(vido_ctx* ctx, int32_t* sizes, float* se3, float*
 void vido_projopt_default_params(vido_projopt_problem* p, int kind) { if (p) projopt_default_params(p, kind); }
 int vido_pose_opt_proj(vido_ctx* ctx, vido_projopt_problem* problems, int nproblems, vido_lm_stats* stats) {
   if (!ctx || !problems || nproblems < 0) return VIDO_ERR_ARG;
+  cudaSetDevice(ctx->device);
   return projopt_host(ctx, problems, nproblems, stats);
 }
 
@@ -354,21 +374,28 @@ void vido_inertial_default_params(vido_inertial_problem* p) { if (p) inertial_de
 int vido_inertial_opt(vido_ctx* ctx, vido_inertial_problem* p, vido_lm_stats* stats) {
   if (!ctx || !p) return VIDO_ERR_ARG;
   if (p->n_frames < 0 || (p->n_frames >= 2 && (!p->Rwb || !p->twb || !p->velocity || !p->preint || !p->bias_lin))) { ctx->err = "inertial: null input"; return VIDO_ERR_ARG; }
+  cudaSetDevice(ctx->device);
   return inertial_opt_host(ctx, p, stats);
 }
 
 int vido_track_set_imu(vido_ctx* ctx, const float* Tbc, const float* noise) { return (ctx && ((Tbc && noise) || (!Tbc && !noise))) ? trk_set_imu(ctx, Tbc, noise) : VIDO_ERR_ARG; }
 int vido_track_grab_imu(vido_ctx* ctx, const vido_imu_sample* samples, int n, int frames_ahead) {
   if (!ctx || n < 0 || (n > 0 && !samples) || frames_ahead < 0) return VIDO_ERR_ARG;
+  cudaSetDevice(ctx->device);
   return trk_grab_imu(ctx, samples, n, frames_ahead);
 }
 int vido_track_get_imu_state(vido_ctx* ctx, vido_imu_state* out) { return (ctx && out) ? trk_get_imu_state(ctx, out) : VIDO_ERR_ARG; }
 int vido_map_get_imu_frames(vido_ctx* ctx, float* Tcw, float* vel, float* bias, int cap) { return ctx ? trk_get_imu_frames(ctx, Tcw, vel, bias, cap) : VIDO_ERR_ARG; }
-int vido_map_apply_scaled_rotation(vido_ctx* ctx, const float* R, float s) { return (ctx && R) ? trk_apply_scaled_rotation(ctx, R, s) : VIDO_ERR_ARG; }
+int vido_map_apply_scaled_rotation(vido_ctx* ctx, const float* R, float s) {
+  if (!ctx || !R) return VIDO_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  return trk_apply_scaled_rotation(ctx, R, s);
+}
 
 int vido_metric_error(vido_ctx* ctx, const float* cam_pose_gt, int n_gt, int refined, const float* obj_pose_pre,
                       const float* obj_motion_gt, int n_obj, vido_metric* out, float* per_item) {
   if (!ctx || !out || !cam_pose_gt || n_gt < 0 || n_obj < 0 || (n_obj > 0 && (!obj_pose_pre || !obj_motion_gt))) return VIDO_ERR_ARG;
+  cudaSetDevice(ctx->device);
   return trk_metric_error(ctx, cam_pose_gt, n_gt, refined, obj_pose_pre, obj_motion_gt, n_obj, out, per_item);
 }
 

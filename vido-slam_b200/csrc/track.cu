@@ -1822,6 +1822,9 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
     if (!ts->lo_sem.empty()) {
       VIDO_CUDA(cudaMemcpyAsync(ts->d_last_mask, d_mask + (size_t)slot * px, px * 4, cudaMemcpyDeviceToDevice, s));
       VIDO_CUDA(cudaMemcpyAsync(ts->d_last_flow, d_flow + 2 * (size_t)slot * px, px * 8, cudaMemcpyDeviceToDevice, s));
+      // the slot (or, with zero-copy device inputs, the caller's buffer) is recycled by the run-ahead front-end on other
+      // streams and may be reused by the caller once the call returns: the private copies must be complete before either
+      VIDO_CUDA(cudaStreamSynchronize(s));
       ts->have_last_maps = true;
     }
   }
@@ -1897,7 +1900,7 @@ int trk_prefetch(vido_ctx* ctx, const vido_frame_inputs* in, int nframes) {
   return VIDO_OK;
 }
 
-int trk_track_chunk(vido_ctx* ctx, const vido_frame_inputs* in, int nframes, float* Tcw_out, vido_track_stats* stats) {
+static int trk_track_chunk_impl(vido_ctx* ctx, const vido_frame_inputs* in, int nframes, float* Tcw_out, vido_track_stats* stats) {
   TrackState* ts = (TrackState*)ctx->trk;
   const vido_config& c = ctx->cfg;
   cudaStream_t s = ctx->stream;
@@ -1952,6 +1955,19 @@ int trk_track_chunk(vido_ctx* ctx, const vido_frame_inputs* in, int nframes, flo
     while (ts->ba_nq > 0 && rc == VIDO_OK) { rc = ba_finish(ctx); ba_writeback_rest(ctx); }
     return rc;
   }
+}
+
+// The caller's per-frame statistics array only lives for the duration of the call: whatever a failed call leaves queued
+// (a deferred window, solves in flight) must not keep pointers into it -- later entry points (the next chunk, FullBatch,
+// ApplyScaledRotation) retire that work and would otherwise write through them.
+int trk_track_chunk(vido_ctx* ctx, const vido_frame_inputs* in, int nframes, float* Tcw_out, vido_track_stats* stats) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  const int rc = trk_track_chunk_impl(ctx, in, nframes, Tcw_out, stats);
+  ts->ba_deferred.st = nullptr;
+  ts->job[0].st = nullptr;
+  ts->job[1].st = nullptr;
+  if (rc < 0) cudaStreamSynchronize(ctx->stream);   // nothing of a failed call may still read the caller's buffers
+  return rc;
 }
 
 // the ORB workspace is shared with the stand-alone extraction entry points: wait for a front-end running ahead
