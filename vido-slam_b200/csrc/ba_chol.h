@@ -6,7 +6,7 @@
 // and the reduced 6W x 6W system is factored densely.  Same linear system, same positive-definiteness test (all pivots > 0).
 //
 // Structure (right-looking LL^T, block size 8 = one FP64 tensor-core tile):
-//   * the trailing matrix lives in REGISTERS for the whole factorisation: every 8x8 tile is owned by one of the 15 "bulk"
+//   * the trailing matrix lives in REGISTERS for the whole factorisation: every 8x8 tile is owned by one of the 12 "bulk"
 //     warps as an m8n8k4 accumulator fragment (2 doubles per lane); the rank-8 trailing update of a tile is two
 //     mma.sync.m8n8k4.f64 (DMMA) whose A/B fragments come from the 8-wide panel buffer Lp.  Only the tiles of the next
 //     block column are written back to shared memory after a step (they are final), so the shared-memory traffic per step
@@ -25,8 +25,9 @@
 #define BC_LPS 12        // row stride of the panel buffer in doubles: the 8 rows x 4 doubles of a fragment load then touch every
                          // bank exactly twice (stride 8 or 9 would give 4-way conflicts)
 #define BC_MAXT 18       // block rows at the largest window (W = 24: n = 144)
-#define BC_BULK_WARPS 15
-#define BC_MAX_SLOTS 11  // tiles per bulk warp at BC_MAXT: ceil(152 / 15)
+#define BC_BULK_WARPS 12 // warps 0,1,2, 4,5,6, 8,9,10, 12,13,14: the scheduler of warps 3,7,11,15 belongs to the chain warp (15) alone
+#define BC_MAX_SLOTS 13  // tiles per bulk warp at BC_MAXT: ceil(152 / 12)
+#define BC_ACTIVE ((BC_BULK_WARPS + 1) * 32)   // threads taking part in the factorisation barriers
 
 struct CholSm {
   double* S;     // (np + 1) x ld: lower triangle of the system, row np = right-hand side
@@ -116,28 +117,65 @@ __device__ __forceinline__ void bc_trsm_row(const double* D, int ld, const doubl
 
 // Factor S = L L^T in place (lower triangle) and carry the right-hand side (row np) through the forward substitution.
 // Called by all BC_THREADS threads of the CTA.  s_bad: shared flag, set when a pivot is not positive.
-// tk: optional cycle counters of thread 0 (chain warp) and thread 32 (bulk) for the probe: [0] diag0, [1] chain work per
-// step, [2] chain waiting at the step barrier, [3] bulk panel, [4] bulk trailing, [5] bulk waiting.
-// The chain warp and the bulk warps run two separate loops (warp specialisation: the register files of the two roles --
-// the 8x8 block being factored vs. the accumulator tiles -- never coexist) that meet at two named barriers per step.
+// tk: optional cycle counters (probe): [0] diag0, [1] chain work per step, [2] chain waiting at the step barrier, [3] bulk
+// panel, [4] bulk trailing, [5] bulk waiting, [6] chain trsm, [7] chain diagonal update; [16 + 8 jb ..] per-step trace.
+//
+// Warp roles (warp specialisation: the register files of the roles never coexist):
+//   chain  (warp 15)  the pivot chain, one block ahead of everybody else: panel rows of block jb+1 (8 lanes, scalar), their
+//                     update of the diagonal block jb+1 (two DMMA), its 8x8 factorisation (one lane, in registers);
+//   helper (warp 11)  the inverse of every freshly factored diagonal block (8 lanes, one 8-step chain), which turns the
+//                     panel of the bulk warps and the back substitution into matrix products;
+//   bulk   (12 warps: 0,1,2, 4,5,6, 8,9,10, 12,13,14)  panel L21 = A21 L11^-T as two DMMA per 8-row tile, trailing update
+//                     of the register-resident tiles (two DMMA per tile, two tiles interleaved), write-back of final tiles.
+// The scheduler of warps 3, 7, 11, 15 serves the chain (and the short helper bursts) only; the issue arbiter prefers high
+// warp ids.  Barriers: STEP (chain + bulk, end of a step), PANEL (panel complete; the chain only arrives), LINV (chain ->
+// helper: block factored), LREADY (helper -> bulk: inverse stored).
 #define BC_BAR_PANEL 1
 #define BC_BAR_STEP 2
-__device__ __forceinline__ void bc_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(BC_THREADS) : "memory"); }
-__device__ __forceinline__ void bc_bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(BC_THREADS) : "memory"); }
+#define BC_BAR_BULK 3
+#define BC_BAR_LINV 4
+#define BC_BAR_LREADY 5
+#define BC_CHAIN_WARP 15
+#define BC_HELPER_WARP 11
+__device__ __forceinline__ void bc_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(BC_ACTIVE) : "memory"); }
+__device__ __forceinline__ void bc_bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(BC_ACTIVE) : "memory"); }
 
-__device__ __forceinline__ void bc_factor(const CholSm cs, int* s_bad, long long* tk) {
+// first tile id of block column c (tiles (R, C), R >= C >= 1, without (1,1), numbered column by column)
+__device__ __forceinline__ int bc_tile_off(int c, int T) {
+  return (c <= 1) ? 0 : (T - 2) + (c - 2) * T - ((c - 1) * c / 2 - 1);
+}
+
+// What the factorisation needs in shared memory before it starts, copied from the global copy Sg (same layout): block
+// column 0 (the first panel, with the diagonal block 0), the diagonal block 1 (the chain warp's first look-ahead) and the
+// right-hand side row.  Everything else goes straight from Sg into the accumulator registers of the bulk warps.
+__device__ __forceinline__ void bc_stage(const CholSm cs, const double* __restrict__ Sg) {
+  const int np = cs.np, ld = cs.ld;
+  for (int i = threadIdx.x; i < 8 * np; i += BC_THREADS) {
+    const int r = i >> 3, c = i & 7;
+    if (c <= r) cs.S[r * ld + c] = Sg[r * ld + c];
+  }
+  for (int i = threadIdx.x; i < np; i += BC_THREADS) cs.S[np * ld + i] = Sg[np * ld + i];
+  if (np > 8 && threadIdx.x >= BC_THREADS - 64) {
+    const int i = threadIdx.x - (BC_THREADS - 64), r = 8 + (i >> 3), c = 8 + (i & 7);
+    if (c <= r) cs.S[r * ld + c] = Sg[r * ld + c];
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void bc_factor(const CholSm cs, int* s_bad, long long* tk, const double* __restrict__ Sg = nullptr) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int np = cs.np, ld = cs.ld, T = np >> 3;
   double* const S = cs.S;
   double* const Lp = cs.Lp;
-  if (tid == 0) *s_bad = 0;
-  if (warp == 0) {
+  const int fr = lane >> 2, fk = lane & 3;
+  if (warp == BC_CHAIN_WARP) {
     // =========================== chain warp ===========================
-    __syncwarp();
     long long t0 = 0;
     if (tk) t0 = clock64();
-    if (lane == 0 && !bc_chol8(S, ld, cs.dinv)) *s_bad = 1;
-    bc_bar_sync(BC_BAR_STEP);   // the bulk warps have loaded their tiles, block 0 is factored
+    if (lane == 0) *s_bad = bc_chol8(S, ld, cs.dinv) ? 0 : 1;
+    __syncwarp();
+    asm volatile("bar.arrive %0, 64;" ::"n"(BC_BAR_LINV) : "memory");
+    bc_bar_sync(BC_BAR_STEP);   // block 0 is factored, the bulk warps have loaded their tiles
     if (tk && lane == 0) { const long long t1 = clock64(); tk[0] += t1 - t0; t0 = t1; }
     for (int jb = 0; jb < T; jb++) {
       if (*s_bad) break;
@@ -151,67 +189,37 @@ __device__ __forceinline__ void bc_factor(const CholSm cs, int* s_bad, long long
       }
       __syncwarp();
       bc_bar_arrive(BC_BAR_PANEL);
+      long long t6 = 0;
+      if (tk && lane == 0) { t6 = clock64(); tk[6] += t6 - t0; }
       if (more) {
-        // update of the diagonal block jb+1: 36 entries of the lower triangle over the 32 lanes (lanes 0..3 take a second
-        // one); 8-term dot as a tree
-        for (int e = lane; e < 36; e += 32) {
-          const int r = (e >= 1) + (e >= 3) + (e >= 6) + (e >= 10) + (e >= 15) + (e >= 21) + (e >= 28), c = e - ((r * (r + 1)) >> 1);
-          const double* lr = Lp + (j0 + 8 + r) * BC_LPS;
-          const double* lc = Lp + (j0 + 8 + c) * BC_LPS;
-          const double s01 = fma(lr[1], lc[1], lr[0] * lc[0]), s23 = fma(lr[3], lc[3], lr[2] * lc[2]);
-          const double s45 = fma(lr[5], lc[5], lr[4] * lc[4]), s67 = fma(lr[7], lc[7], lr[6] * lc[6]);
-          double* dst = S + (j0 + 8 + r) * ld + j0 + 8 + c;
-          *dst = *dst - ((s01 + s23) + (s45 + s67));
-        }
+        // update of the diagonal block jb+1, D -= L L^T, as two DMMA: the A and the B fragment of L(jb+1, jb) are the same
+        // registers (B[k][c] = L(c, k)).  The tile is symmetric; its upper half is carried along and never read.
+        double* dp = S + (j0 + 8 + fr) * ld + j0 + 8 + 2 * fk;
+        const double* pl = Lp + (j0 + 8 + fr) * BC_LPS + fk;
+        double d0 = dp[0], d1 = dp[1];
+        const double a0 = pl[0], a1 = pl[4];
+        bc_dmma(d0, d1, -a0, a0);
+        bc_dmma(d0, d1, -a1, a1);
+        dp[0] = d0; dp[1] = d1;
         __syncwarp();
+        if (tk && lane == 0) tk[7] += clock64() - t6;
         if (lane == 0 && !bc_chol8(S + (j0 + 8) * ld + j0 + 8, ld, cs.dinv + j0 + 8)) *s_bad = 1;
+        __syncwarp();
+        asm volatile("bar.arrive %0, 64;" ::"n"(BC_BAR_LINV) : "memory");
       }
-      if (tk && lane == 0) { const long long t1 = clock64(); tk[1] += t1 - t0; t0 = t1; }
+      if (tk && lane == 0) { const long long t1 = clock64(); tk[1] += t1 - t0; tk[16 + 8 * jb] = t1 - t0; t0 = t1; }
       bc_bar_sync(BC_BAR_STEP);
-      if (tk && lane == 0) { const long long t1 = clock64(); tk[2] += t1 - t0; t0 = t1; }
+      if (tk && lane == 0) { const long long t1 = clock64(); tk[2] += t1 - t0; tk[17 + 8 * jb] = t1 - t0; t0 = t1; }
     }
-  } else {
-    // =========================== bulk warps ===========================
-    // tile ownership: tiles (R, C), R >= C >= 1, without (1,1), numbered column by column and dealt round-robin, so that
-    // the tiles still active at any step are spread evenly over the warps.  packed = R | C << 8, -1 = no tile.
-    double c0[BC_MAX_SLOTS], c1[BC_MAX_SLOTS];
-    int tRC[BC_MAX_SLOTS];
-    const int fr = lane >> 2, fk = lane & 3;
-#pragma unroll
-    for (int s = 0; s < BC_MAX_SLOTS; s++) {
-      int t = (warp - 1) + BC_BULK_WARPS * s;
-      int c = 1, R = -1;
-      while (c < T) {
-        const int cnt = (c == 1) ? T - 2 : T - c;
-        if (t < cnt) { R = ((c == 1) ? 2 : c) + t; break; }
-        t -= cnt; c++;
-      }
-      tRC[s] = (R >= 0) ? (R | (c << 8)) : -1;
-      c0[s] = 0; c1[s] = 0;
-      if (R >= 0) {
-        const int row = 8 * R + fr, col = 8 * c + 2 * fk;
-        c0[s] = (row >= col) ? S[row * ld + col] : S[col * ld + row];
-        c1[s] = (row >= col + 1) ? S[row * ld + col + 1] : S[(col + 1) * ld + row];
-      }
-    }
-    bc_bar_sync(BC_BAR_STEP);
-    long long t0 = 0;
-    if (tk && tid == 32) t0 = clock64();
+  } else if (warp == BC_HELPER_WARP) {
+    // =========================== helper warp ===========================
     for (int jb = 0; jb < T; jb++) {
-      if (*s_bad) break;
-      const int j0 = 8 * jb;
-      const double* D = S + j0 * ld + j0;
-      const double* dv = cs.dinv + j0;
-      const bool more = jb + 1 < T;
-      // ---- panel rows of the blocks >= jb+2 and the right-hand side row
-      {
-        const int b = tid - 32, i = j0 + 16 + b;
-        if (i < np) bc_trsm_row(D, ld, dv, S + i * ld + j0, Lp + i * BC_LPS);
-        else if (b == BC_THREADS - 33) bc_trsm_row(D, ld, dv, S + np * ld + j0, nullptr);
-      }
-      if (warp == BC_BULK_WARPS && lane >= 8 && lane < 16) {
-        // inverse of the diagonal factor (column c by one lane) for the back substitution: X = L11^-1
-        const int c = lane - 8;
+      asm volatile("bar.sync %0, 64;" ::"n"(BC_BAR_LINV) : "memory");
+      const int bad = *s_bad;
+      if (!bad && lane < 8) {   // X = L11^-1, column c by lane c
+        const int c = lane, j0 = 8 * jb;
+        const double* D = S + j0 * ld + j0;
+        const double* dv = cs.dinv + j0;
         double x[8];
 #pragma unroll
         for (int m = 0; m < 8; m++) {
@@ -223,21 +231,125 @@ __device__ __forceinline__ void bc_factor(const CholSm cs, int* s_bad, long long
 #pragma unroll
         for (int m = 0; m < 8; m++) cs.Linv[jb * 64 + m * 8 + c] = x[m];
       }
-      if (tk && tid == 32) { const long long t1 = clock64(); tk[3] += t1 - t0; t0 = t1; }
-      bc_bar_sync(BC_BAR_PANEL);
-      if (more) {
-        // ---- trailing update of the owned tiles: C -= L(R,jb) L(C,jb)^T as two DMMA (k = 0..3, 4..7)
-#pragma unroll
-        for (int s = 0; s < BC_MAX_SLOTS; s++) {
-          const int R = tRC[s] & 255, C = tRC[s] >> 8;
-          if (tRC[s] < 0 || C <= jb || (R == C && C == jb + 1)) continue;
-          const double* pa = Lp + (8 * R + fr) * BC_LPS + fk;
-          const double* pb = Lp + (8 * C + fr) * BC_LPS + fk;
-          const double a0 = -pa[0], a1 = -pa[4], b0 = pb[0], b1 = pb[4];
-          bc_dmma(c0[s], c1[s], a0, b0);
-          bc_dmma(c0[s], c1[s], a1, b1);
+      __syncwarp();
+      bc_bar_arrive(BC_BAR_LREADY);
+      if (bad) break;
+    }
+  } else if ((warp & 3) != 3) {
+    // =========================== bulk warps ===========================
+    const int bw = warp - (warp >> 2), btid = bw * 32 + lane;   // bulk warp / thread index
+    // tile ownership: tile id = bw + 12 * slot, ids run column by column, so the tiles still active at a step are the
+    // slots >= smin(step) of every warp: the update below jumps into an unrolled slot sequence (no per-slot activity test
+    // for retired tiles).  packed = R | C << 8.
+    double c0[BC_MAX_SLOTS + 1], c1[BC_MAX_SLOTS + 1];
+    int tRC[BC_MAX_SLOTS + 1];
+    const int ntiles = bc_tile_off(T, T);
+    const int nsl = (ntiles > bw) ? (ntiles - bw + BC_BULK_WARPS - 1) / BC_BULK_WARPS : 0;
+    {  // tile table: one thread per tile decodes its (R, C); the panel buffer is free until the first step
+      int* tab = (int*)Lp;
+      if (btid < BC_BULK_WARPS * (BC_MAX_SLOTS + 1)) {
+        int t = btid, c = 1, R = -1;
+        while (c < T) {
+          const int cnt = (c == 1) ? T - 2 : T - c;
+          if (t < cnt) { R = ((c == 1) ? 2 : c) + t; break; }
+          t -= cnt; c++;
         }
-        if (warp == BC_BULK_WARPS) {  // right-hand side row: y(c) -= L(rhs, jb) . L(c, jb)
+        tab[btid] = (R >= 0) ? (R | (c << 8)) : 0;
+      }
+      asm volatile("bar.sync %0, %1;" ::"n"(BC_BAR_BULK), "n"(BC_BULK_WARPS * 32) : "memory");
+#pragma unroll
+      for (int s = 0; s <= BC_MAX_SLOTS; s++) tRC[s] = tab[bw + BC_BULK_WARPS * s];
+      asm volatile("bar.sync %0, %1;" ::"n"(BC_BAR_BULK), "n"(BC_BULK_WARPS * 32) : "memory");
+    }
+    const double* src = Sg ? Sg : S;
+#pragma unroll
+    for (int s = 0; s <= BC_MAX_SLOTS; s++) {
+      const int R = tRC[s] & 255, c = tRC[s] >> 8;
+      c0[s] = 0; c1[s] = 0;
+      if (s < nsl) {
+        const int row = 8 * R + fr, col = 8 * c + 2 * fk;
+        c0[s] = (row >= col) ? src[row * ld + col] : src[col * ld + row];
+        c1[s] = (row >= col + 1) ? src[row * ld + col + 1] : src[(col + 1) * ld + row];
+      }
+    }
+    bc_bar_sync(BC_BAR_STEP);
+    long long t0 = 0;
+    if (tk && btid == 0) t0 = clock64();
+    const double* const lpf = Lp + fr * BC_LPS + fk;   // fragment base of this lane
+    for (int jb = 0; jb < T; jb++) {
+      bc_bar_sync(BC_BAR_LREADY);
+      if (*s_bad) break;
+      const int j0 = 8 * jb;
+      const bool more = jb + 1 < T;
+      const double* Li = cs.Linv + jb * 64;
+      // ---- panel: L21 = A21 L11^-T for the 8-row tiles of the blocks >= jb+2 (two DMMA each), and the right-hand side row
+      {
+        const double b0 = Li[fr * 8 + fk], b1 = Li[fr * 8 + 4 + fk];   // B[k][c] = Linv[c][k]
+        for (int rt = jb + 2 + bw; rt < T; rt += BC_BULK_WARPS) {
+          double* ar = S + (8 * rt + fr) * ld + j0;
+          double r0 = 0, r1 = 0;
+          bc_dmma(r0, r1, ar[fk], b0);
+          bc_dmma(r0, r1, ar[4 + fk], b1);
+          __syncwarp();
+          ar[2 * fk] = r0; ar[2 * fk + 1] = r1;
+          double* lp = Lp + (8 * rt + fr) * BC_LPS + 2 * fk;
+          lp[0] = r0; lp[1] = r1;
+        }
+        if (bw == BC_BULK_WARPS - 1 && lane < 8) {
+          double* yr = S + np * ld + j0;
+          double sa = 0, sb = 0;
+#pragma unroll
+          for (int m = 0; m < 8; m += 2) {
+            sa = fma(yr[m], Li[lane * 8 + m], sa);
+            sb = fma(yr[m + 1], Li[lane * 8 + m + 1], sb);
+          }
+          __syncwarp(0xffu);
+          yr[lane] = sa + sb;
+        }
+      }
+      if (tk && btid == 0) { const long long t1 = clock64(); tk[3] += t1 - t0; tk[18 + 8 * jb] = t1 - t0; t0 = t1; }
+      bc_bar_sync(BC_BAR_PANEL);
+      if (tk && btid == 0) { const long long t1 = clock64(); tk[19 + 8 * jb] = t1 - t0; }
+      if (more) {
+        // ---- trailing update of the owned tiles, C -= L(R,jb) L(C,jb)^T as two DMMA (k = 0..3, 4..7), two tiles interleaved
+        //      (the two DMMA of a tile depend on each other); tiles that received their last update go back to shared
+        //      memory: block column jb+1 (the next panel) and the diagonal tile jb+2.  Active tile ids at step jb: >= fa(jb)
+        //      = first id of column jb+1, +1 for its diagonal tile (the chain warp owns it by now); the ones below fa(jb+1)
+        //      are final.  The pair that contains slot smin may start one slot early: that tile is retired, its registers
+        //      are dead, updating them is harmless (it is not written back: s >= smin).
+        const int fa = (jb == 0) ? 0 : bc_tile_off(jb + 1, T) + 1;
+        const int fn = bc_tile_off(jb + 2, T) + 1;
+        const int smin = (fa > bw) ? (fa - bw + BC_BULK_WARPS - 1) / BC_BULK_WARPS : 0;
+        const int sfl = (fn > bw) ? (fn - bw + BC_BULK_WARPS - 1) / BC_BULK_WARPS : 0;
+#define BC_UPD2(s)                                                                                         \
+  case (s) / 2: {                                                                                          \
+    if ((s) >= nsl) break;                                                                                 \
+    const int Ra_ = tRC[s] & 255, Ca_ = tRC[s] >> 8, Rb_ = tRC[(s) + 1] & 255, Cb_ = tRC[(s) + 1] >> 8;    \
+    const double* paa_ = lpf + Ra_ * (8 * BC_LPS);                                                         \
+    const double* pba_ = lpf + Ca_ * (8 * BC_LPS);                                                         \
+    const double* pab_ = lpf + Rb_ * (8 * BC_LPS);                                                         \
+    const double* pbb_ = lpf + Cb_ * (8 * BC_LPS);                                                         \
+    const double a0_ = paa_[0], a1_ = paa_[4], b0_ = pba_[0], b1_ = pba_[4];                               \
+    const double e0_ = pab_[0], e1_ = pab_[4], f0_ = pbb_[0], f1_ = pbb_[4];                               \
+    bc_dmma(c0[s], c1[s], -a0_, b0_);                                                                      \
+    bc_dmma(c0[(s) + 1], c1[(s) + 1], -e0_, f0_);                                                          \
+    bc_dmma(c0[s], c1[s], -a1_, b1_);                                                                      \
+    bc_dmma(c0[(s) + 1], c1[(s) + 1], -e1_, f1_);                                                          \
+    if ((s) >= smin && (s) < sfl) {                                                                        \
+      double* dst_ = S + (8 * Ra_ + fr) * ld + 8 * Ca_ + 2 * fk;                                           \
+      dst_[0] = c0[s]; dst_[1] = c1[s];                                                                    \
+    }                                                                                                      \
+    if ((s) + 1 < sfl && (s) + 1 < nsl) {                                                                  \
+      double* dst_ = S + (8 * Rb_ + fr) * ld + 8 * Cb_ + 2 * fk;                                           \
+      dst_[0] = c0[(s) + 1]; dst_[1] = c1[(s) + 1];                                                        \
+    }                                                                                                      \
+  }
+        switch (smin >> 1) {
+          BC_UPD2(0) BC_UPD2(2) BC_UPD2(4) BC_UPD2(6) BC_UPD2(8) BC_UPD2(10) BC_UPD2(12)
+          default: break;
+        }
+#undef BC_UPD2
+        if (bw == BC_BULK_WARPS - 1) {  // right-hand side row: y(c) -= L(rhs, jb) . L(c, jb)
           const double* lr = S + np * ld + j0;
           const double r0 = lr[0], r1 = lr[1], r2 = lr[2], r3 = lr[3], r4 = lr[4], r5 = lr[5], r6 = lr[6], r7 = lr[7];
           for (int c = j0 + 8 + lane; c < np; c += 32) {
@@ -247,69 +359,62 @@ __device__ __forceinline__ void bc_factor(const CholSm cs, int* s_bad, long long
             S[np * ld + c] -= (s01 + s23) + (s45 + s67);
           }
         }
-        // ---- tiles that are final now go back to shared memory: block column jb+1 (next panel) and the diagonal tile jb+2
-#pragma unroll
-        for (int s = 0; s < BC_MAX_SLOTS; s++) {
-          const int R = tRC[s] & 255, C = tRC[s] >> 8;
-          if (tRC[s] < 0) continue;
-          if ((C == jb + 1 && R > C) || (R == C && C == jb + 2)) {
-            const int row = 8 * R + fr, col = 8 * C + 2 * fk;
-            S[row * ld + col] = c0[s];
-            S[row * ld + col + 1] = c1[s];
-          }
-        }
       }
-      if (tk && tid == 32) { const long long t1 = clock64(); tk[4] += t1 - t0; t0 = t1; }
+      if (tk && btid == 0) { const long long t1 = clock64(); tk[4] += t1 - t0; tk[20 + 8 * jb] = t1 - t0; t0 = t1; }
       bc_bar_sync(BC_BAR_STEP);
-      if (tk && tid == 32) { const long long t1 = clock64(); tk[5] += t1 - t0; t0 = t1; }
+      if (tk && btid == 0) { const long long t1 = clock64(); tk[5] += t1 - t0; tk[21 + 8 * jb] = t1 - t0; t0 = t1; }
     }
   }
   __syncthreads();
 }
 
-// Back substitution L^T x = y by warp 0 (the other warps return at once): x overwrites row np.  Per block step the 8
-// unknowns are a matrix-vector product with the precomputed inverse of the diagonal factor; every lane then updates its
-// rows above the block.
+// Back substitution L^T x = y by the chain warp (the other warps return at once): x overwrites row np.  Per block step
+// lane k (mod 8) forms unknown k as a row of the matrix-vector product with the precomputed inverse of the diagonal
+// factor, a shuffle broadcast hands the 8 unknowns to every lane, and the lanes update their rows above the block.  The
+// rows of L a lane needs for that are loaded BEFORE the unknowns are formed (they do not depend on them).
 __device__ __forceinline__ void bc_backsolve(const CholSm cs) {
-  if (threadIdx.x >= 32) return;
-  const int lane = threadIdx.x, np = cs.np, ld = cs.ld, T = np >> 3;
+  if ((threadIdx.x >> 5) != BC_CHAIN_WARP) return;
+  const int lane = threadIdx.x & 31, np = cs.np, ld = cs.ld, T = np >> 3;
   double* const ys = cs.S + (size_t)np * ld;
   const double* const S = cs.S;
+  constexpr int NCH = (BC_MAXT * 8 + 31) / 32;
+  const int k8 = lane & 7;
   for (int jb = T - 1; jb >= 0; jb--) {
     const int j0 = 8 * jb;
     const double* Li = cs.Linv + jb * 64;
-    // rows of L of this block, at the columns this lane owns (issued before the solve: independent of it)
-    constexpr int NCH = (BC_MAXT * 8 + 31) / 32;
-    double x[8];
-    {
-      double y[8];
-#pragma unroll
-      for (int m = 0; m < 8; m++) y[m] = ys[j0 + m];
-      // x = L11^-T y: x_k = sum_{m >= k} Linv[m][k] y_m
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        double s = 0;
-#pragma unroll
-        for (int m = k; m < 8; m++) s = fma(Li[m * 8 + k], y[m], s);
-        x[k] = s;
-      }
-    }
+    double lv[NCH][8], yv[NCH];
 #pragma unroll
     for (int u = 0; u < NCH; u++) {
       const int i = lane + 32 * u;
-      if (i < j0) {
-        double t = ys[i];
+      const bool on = i < j0;
+      const double* col = S + j0 * ld + (on ? i : 0);
+      yv[u] = on ? ys[i] : 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; k++) t = fma(-S[(j0 + k) * ld + i], x[k], t);
-        ys[i] = t;
+      for (int k = 0; k < 8; k++) lv[u][k] = on ? col[k * ld] : 0.0;
+    }
+    // x_k = sum_{m >= k} Linv[m][k] y_m (two partial sums to halve the dependent chain); Linv is stored with its zeros
+    double sa = 0, sb = 0;
+#pragma unroll
+    for (int m = 0; m < 8; m += 2) {
+      sa = fma(Li[m * 8 + k8], ys[j0 + m], sa);
+      sb = fma(Li[(m + 1) * 8 + k8], ys[j0 + m + 1], sb);
+    }
+    const double xk = sa + sb;
+    double x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = __shfl_sync(0xffffffffu, xk, k);
+#pragma unroll
+    for (int u = 0; u < NCH; u++) {
+      const int i = lane + 32 * u;
+      double ta = yv[u], tb = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k += 2) {
+        ta = fma(-lv[u][k], x[k], ta);
+        tb = fma(-lv[u][k + 1], x[k + 1], tb);
       }
+      if (i < j0) ys[i] = ta + tb;
     }
-    if (lane < 8) {
-      double xv = x[0];
-#pragma unroll
-      for (int k = 1; k < 8; k++) xv = (lane == k) ? x[k] : xv;
-      ys[j0 + lane] = xv;
-    }
+    if (lane < 8) ys[j0 + lane] = xk;
     __syncwarp();
   }
 }

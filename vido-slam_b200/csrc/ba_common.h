@@ -24,6 +24,21 @@ __device__ __forceinline__ double div_pos(double a, double x) {
 }
 
 
+// Huber rho(e) and weight rho'(e) like vb::huber, with sqrt and the division replaced by one reciprocal square root
+// (MUFU.RSQ64H + one third-order correction, ~1 ulp): s = e rsqrt(e), delta / s = delta rsqrt(e)
+__device__ __forceinline__ void huber_fast(double e, double delta, double& rho0, double& w) {
+  const double dsqr = delta * delta;
+  if (e <= dsqr) { rho0 = e; w = 1.0; }
+  else {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(e));
+    const double c = fma(e, -(y * y), 1.0);
+    y = fma(fma(c, 0.375, 0.5), y * c, y);
+    rho0 = 2 * (e * y) * delta - dsqr;
+    w = delta * y;
+  }
+}
+
 #define BA_THREADS 256
 #define BA_MAX_W 24
 #define BA_MAX_CLUSTER 16
@@ -82,7 +97,8 @@ struct BaArgs {
   double* wmom;   // [workers][jobs][16] Schur moment sums of every worker CTA
   double* wpsum;  // [2][workers][W][28] pose-block sums of every worker CTA, per linearisation buffer
   double* eH;     // [2][W][120] odometry edges: w Ji^T Ji | w Ji^T Jj | w Jj^T Jj | -w Ji^T e | -w Jj^T e, per linearisation buffer
-  int capO, capPt;  // observation / point capacity of a worker CTA (shared-memory carving)
+  double* Sg;     // [(np+1) x (np+1)] reduced camera system (lower triangle, row np = right-hand side), assembled by all CTAs
+  int capO, capPt, capT;  // observation / point / Schur-term capacity of a worker CTA (shared-memory carving)
 };
 
 __device__ __forceinline__ double warp_sum(double v) {

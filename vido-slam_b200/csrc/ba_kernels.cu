@@ -34,7 +34,7 @@
 namespace cg = cooperative_groups;
 
 // ba_window.cu
-size_t ba_window_smem(int W, int capO, int capPt);
+size_t ba_window_smem(int W, int capO, int capPt, int capT);
 size_t ba_window_smem_limit();
 int ba_window_configure(size_t max_smem, int* cluster_out);
 cudaError_t ba_window_launch(const BaArgs& a, int cluster, size_t smem, cudaStream_t s);
@@ -989,6 +989,7 @@ static void carve_all(char*& p, BaArgs& a, int capW, int capP, int capM) {
   a.wmom = carve<double>(p, (size_t)(BA_MAX_CLUSTER - 1) * BA_MAX_JOBS * 16);
   a.wpsum = carve<double>(p, (size_t)2 * (BA_MAX_CLUSTER - 1) * capW * 28);
   a.eH = carve<double>(p, (size_t)2 * capW * 120);
+  a.Sg = carve<double>(p, (size_t)(6 * capW + 9) * (6 * capW + 9));
 }
 
 int ba_setup(vido_ctx* ctx, int capW, int capP, int capM) {
@@ -1193,13 +1194,17 @@ int ba_prepare_chained(vido_ctx* ctx, const vido_ba_problem* pr, const int* prev
   }
   {  // does the window fit the shared-memory resident kernel?  Points are dealt round-robin (sorted order) to the workers.
     const int nwk = ws->cluster_sm - 1;
-    ws->wk_obs.assign(nwk, 0);
-    for (int n = 0; n < P; n++) ws->wk_obs[n % nwk] += h_pt_len[n];
-    int capO = 0;
-    for (int c = 0; c < nwk; c++) capO = std::max(capO, ws->wk_obs[c]);
+    ws->wk_obs.assign(2 * (size_t)nwk, 0);
+    for (int n = 0; n < P; n++) {
+      const int L = h_pt_len[n];
+      ws->wk_obs[n % nwk] += L;
+      ws->wk_obs[nwk + n % nwk] += L * (L + 1) / 2;   // Schur terms: pose pairs of the track
+    }
+    int capO = 0, capT = 0;
+    for (int c = 0; c < nwk; c++) { capO = std::max(capO, ws->wk_obs[c]); capT = std::max(capT, ws->wk_obs[nwk + c]); }
     const int capPt = (P + nwk - 1) / nwk;
-    a.capO = (capO + 7) & ~7; a.capPt = (capPt + 7) & ~7;
-    const size_t need = ba_window_smem(W, a.capO, a.capPt);
+    a.capO = (capO + 7) & ~7; a.capPt = (capPt + 7) & ~7; a.capT = (capT + 7) & ~7;
+    const size_t need = ba_window_smem(W, a.capO, a.capPt, a.capT);
     const char* force = getenv("VIDO_BA_KERNEL");   // debug: "l2" forces the L2-resident kernel
     ws->use_sm2[slot] = need <= ws->smem_limit && capO < 65536 && !(force && !strcmp(force, "l2"));
     ws->smem2[slot] = need;
@@ -1310,8 +1315,8 @@ int ba_collect(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st) {
     ctx->ba_alg_bytes += edges * (296.0 * std::max(ctl.iterations, 0) + 152.0 * (ctl.total_trials + 1));
   }
   if (getenv("VIDO_BA_TIMING") && F.sm)
-    fprintf(stderr, "[ba-sm] cluster=%d W=%d P=%d M=%d its=%d trials=%d ns: init=%llu schur=%llu reduce=%llu solve=%llu update+obs=%llu lm=%llu total=%llu\n",
-            ws->cluster_sm, W, P, M, ctl.iterations, ctl.total_trials, tph[5], tph[0], tph[1], tph[2], tph[3], tph[4], tph[7]);
+    fprintf(stderr, "[ba-sm] cluster=%d W=%d P=%d M=%d its=%d trials=%d ns: init=%llu schur=%llu reduce=%llu stage=%llu solve=%llu update+obs=%llu lm=%llu total=%llu | worker 0 own: schur=%llu reduce=%llu load=%llu update=%llu obs=%llu\n",
+            ws->cluster_sm, W, P, M, ctl.iterations, ctl.total_trials, tph[5], tph[0], tph[1], tph[6], tph[2], tph[3], tph[4], tph[7], tph[8], tph[9], tph[10], tph[11], tph[12]);
   else if (getenv("VIDO_BA_TIMING"))
     fprintf(stderr, "[ba] cluster=%d W=%d P=%d M=%d its=%d trials=%d ns: linearize=%llu schur=%llu chol=%llu update=%llu init=%llu end=%llu total=%llu\n",
             ws->cluster, W, P, M, ctl.iterations, ctl.total_trials, tph[0] + tph[8] + tph[9] + tph[10] + tph[20], tph[1] + tph[2] + tph[19], tph[3] + tph[11] + tph[12] + tph[13] + tph[16] + tph[17] + tph[18], tph[4] + tph[21], tph[5], tph[6], tph[7]);

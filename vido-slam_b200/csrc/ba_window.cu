@@ -39,6 +39,8 @@ struct BwShared {
   int lbase[BW_TAB];          // [f][k]: first local observation of segment (f, k); pose of the segment = f + k
   int pbase[BA_MAX_W + 1];    // pose-major observation list: first entry of pose p
   unsigned char jp1[BW_NPAIRS_MAX], jp2[BW_NPAIRS_MAX];
+  int tstart[BW_NPAIRS_MAX + 1];             // first Schur term of every pair job in this worker's term list
+  unsigned short jorder[BW_NPAIRS_MAX];      // pair jobs by descending term count (lane = job: similar trip counts per warp)
   int Mc, Pc;
   Pose X[2][BA_MAX_W];        // poses of both state buffers (every CTA keeps a copy)
   Pose Zinv[BA_MAX_W];        // inverse odometry measurements (CTA 0)
@@ -52,33 +54,49 @@ struct BwShared {
   int s_bad;
 };
 
-// worker-side view of the dynamic shared memory
+// worker-side view of the dynamic shared memory.  Only scalar members: a pointer ARRAY indexed by the run-time buffer index
+// would put the whole struct into local memory and turn every access into LDL + generic LD (measured in the first version).
 struct BwObs {
-  double *w[2], *zx[2], *zy[2], *zz[2];   // robust weight * information and camera-frame point, per linearisation buffer
+  double* lin;      // [2][4][capO]: w | zx | zy | zz per linearisation buffer (robust weight * information, camera-frame point)
   double *gx, *gy, *gz;                   // transient per-observation 3-vectors (gradient terms)
+  double* pts;      // [2][7][capPt]: px | py | pz | hl | bx | by | bz per state / linearisation buffer
+  double* inv;      // 1 / (hl + lambda) of the trial
   float *mx, *my, *mz;                    // measurement
+  unsigned int* t12;                      // Schur terms: observation in the job's first pose | in its second pose << 16
+  unsigned short* tj;                     // Schur terms: local point
   unsigned short *opt, *plist;            // local point of an observation; pose-major observation list
   unsigned char* opo;                     // pose of an observation
-  double *px[2], *py[2], *pz[2], *hl[2], *bx[2], *by[2], *bz[2], *inv;
   unsigned char *pf, *plen;
+  int capO, capPt;
+  __device__ __forceinline__ double* w(int b) const { return lin + (size_t)b * 4 * capO; }
+  __device__ __forceinline__ double* zx(int b) const { return lin + ((size_t)b * 4 + 1) * capO; }
+  __device__ __forceinline__ double* zy(int b) const { return lin + ((size_t)b * 4 + 2) * capO; }
+  __device__ __forceinline__ double* zz(int b) const { return lin + ((size_t)b * 4 + 3) * capO; }
+  __device__ __forceinline__ double* px(int b) const { return pts + (size_t)b * 7 * capPt; }
+  __device__ __forceinline__ double* py(int b) const { return pts + ((size_t)b * 7 + 1) * capPt; }
+  __device__ __forceinline__ double* pz(int b) const { return pts + ((size_t)b * 7 + 2) * capPt; }
+  __device__ __forceinline__ double* hl(int b) const { return pts + ((size_t)b * 7 + 3) * capPt; }
+  __device__ __forceinline__ double* bx(int b) const { return pts + ((size_t)b * 7 + 4) * capPt; }
+  __device__ __forceinline__ double* by(int b) const { return pts + ((size_t)b * 7 + 5) * capPt; }
+  __device__ __forceinline__ double* bz(int b) const { return pts + ((size_t)b * 7 + 6) * capPt; }
 };
 
-__host__ __device__ inline size_t bw_worker_bytes(int capO, int capPt) {
-  return (size_t)capO * (11 * 8 + 3 * 4 + 2 * 2 + 1) + (size_t)capPt * (15 * 8 + 2) + 64;
+__host__ __device__ inline size_t bw_worker_bytes(int capO, int capPt, int capT) {
+  return (size_t)capO * (11 * 8 + 3 * 4 + 2 * 2 + 1) + (size_t)capPt * (15 * 8 + 2) + (size_t)capT * 6 + 64;
 }
 
-__device__ __forceinline__ void bw_carve(char* base, int capO, int capPt, BwObs& o) {
+__device__ __forceinline__ void bw_carve(char* base, int capO, int capPt, int capT, BwObs& o) {
   double* d = (double*)base;
-  for (int b = 0; b < 2; b++) { o.w[b] = d; d += capO; o.zx[b] = d; d += capO; o.zy[b] = d; d += capO; o.zz[b] = d; d += capO; }
+  o.capO = capO; o.capPt = capPt;
+  o.lin = d; d += 8 * (size_t)capO;
   o.gx = d; d += capO; o.gy = d; d += capO; o.gz = d; d += capO;
-  for (int b = 0; b < 2; b++) {
-    o.px[b] = d; d += capPt; o.py[b] = d; d += capPt; o.pz[b] = d; d += capPt; o.hl[b] = d; d += capPt;
-    o.bx[b] = d; d += capPt; o.by[b] = d; d += capPt; o.bz[b] = d; d += capPt;
-  }
+  o.pts = d; d += 14 * (size_t)capPt;
   o.inv = d; d += capPt;
   float* f = (float*)d;
   o.mx = f; f += capO; o.my = f; f += capO; o.mz = f; f += capO;
+  o.t12 = (unsigned int*)f; f += capT;
   unsigned short* u = (unsigned short*)f;
+  o.tj = u; u += capT;
   o.opt = u; u += capO; o.plist = u; u += capO;
   unsigned char* c = (unsigned char*)u;
   o.opo = c; c += capO; o.pf = c; c += capPt; o.plen = c;
@@ -107,13 +125,13 @@ __device__ __forceinline__ double bw_block_reduce(double v, double* sm) {
 __device__ __forceinline__ void bw_obs_pass(const BaArgs& a, BwShared& sh, const BwObs& ob, int st, int wk, int nwk, double& chi_out,
                                             double& hmax_out) {
   const int tid = threadIdx.x, W = a.W, Mc = sh.Mc, Pc = sh.Pc;
-  double* const ow = ob.w[st];
-  double* const zx = ob.zx[st];
-  double* const zy = ob.zy[st];
-  double* const zz = ob.zz[st];
-  const double* px = ob.px[st];
-  const double* py = ob.py[st];
-  const double* pz = ob.pz[st];
+  double* const ow = ob.w(st);
+  double* const zx = ob.zx(st);
+  double* const zy = ob.zy(st);
+  double* const zz = ob.zz(st);
+  const double* px = ob.px(st);
+  const double* py = ob.py(st);
+  const double* pz = ob.pz(st);
   double chi = 0;
   for (int o = tid; o < Mc; o += BW_THREADS) {
     const int j = ob.opt[o], p = ob.opo[o];
@@ -124,7 +142,7 @@ __device__ __forceinline__ void bw_obs_pass(const BaArgs& a, BwShared& sh, const
     const double z2 = Xp.R[2] * d0 + Xp.R[5] * d1 + Xp.R[8] * d2;
     const double e0 = z0 - (double)ob.mx[o], e1 = z1 - (double)ob.my[o], e2 = z2 - (double)ob.mz[o];
     double r0, w;
-    huber((e0 * e0 + e1 * e1 + e2 * e2) * a.info_3d, a.d_3d, r0, w);
+    huber_fast((e0 * e0 + e1 * e1 + e2 * e2) * a.info_3d, a.d_3d, r0, w);
     chi += r0;
     w *= a.info_3d;
     ow[o] = w; zx[o] = z0; zy[o] = z1; zz[o] = z2;
@@ -142,7 +160,7 @@ __device__ __forceinline__ void bw_obs_pass(const BaArgs& a, BwShared& sh, const
       const int o = lb[k] + i;
       h += ow[o]; b0 -= ob.gx[o]; b1 -= ob.gy[o]; b2 -= ob.gz[o];
     }
-    ob.hl[st][j] = h; ob.bx[st][j] = b0; ob.by[st][j] = b1; ob.bz[st][j] = b2;
+    ob.hl(st)[j] = h; ob.bx(st)[j] = b0; ob.by(st)[j] = b1; ob.bz(st)[j] = b2;
     hmax = fmax(hmax, h);
   }
   // pose-block sums: the last 8 W threads, 8 lanes per pose (the point loop above occupies the first warps).  Whole warps
@@ -169,16 +187,36 @@ __device__ __forceinline__ void bw_obs_pass(const BaArgs& a, BwShared& sh, const
         for (int cc = r; cc < 6; cc++) acc[idx++] += w * (J[0][r] * J[0][cc] + J[1][r] * J[1][cc] + J[2][r] * J[2][cc]);
       }
     }
+    // 27 (padded to 28) sums over the 8 lanes of a pose with 14 + 7 + 4 = 25 shuffles instead of 81: lane pairs trade halves
+    // of their value sets at every step.  Afterwards lane c holds the sums 14 b2 + 7 b1 + 4 b0' ... of its slice:
+    //   step 1 (xor 4): b2 = c >> 2 keeps values [14 b2, 14 b2 + 14);  step 2 (xor 2): b1 keeps 7 of them;  step 3 (xor 1):
+    //   b0 = 0 keeps 4, b0 = 1 keeps 3 (+1 padding)
+    double v14[14], v7[7], v4[4];
+    {
+      const bool h2 = (c & 4) != 0, h1 = (c & 2) != 0, h0 = (c & 1) != 0;
 #pragma unroll
-    for (int k = 0; k < 27; k++) {
-      acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 4);
-      acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 2);
-      acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1);
+      for (int k = 0; k < 14; k++) {
+        const double lo = acc[k], hi = (k + 14 < 27) ? acc[k + 14] : 0.0;
+        const double send = h2 ? lo : hi, keep = h2 ? hi : lo;
+        v14[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+#pragma unroll
+      for (int k = 0; k < 7; k++) {
+        const double send = h1 ? v14[k] : v14[k + 7], keep = h1 ? v14[k + 7] : v14[k];
+        v7[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const double lo = v7[k], hi = (k + 4 < 7) ? v7[k + 4] : 0.0;
+        const double send = h0 ? lo : hi, keep = h0 ? hi : lo;
+        v4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+      }
     }
-    if (valid && c == 0) {
-      double* out = a.wpsum + (((size_t)st * nwk + wk) * W + p) * 28;
-#pragma unroll
-      for (int k = 0; k < 27; k++) out[k] = acc[k];
+    if (valid) {
+      // lane c holds sums base .. base + n - 1 with base = 14 (c >> 2) + 7 ((c >> 1) & 1) + 4 (c & 1), n = 4 or 3
+      double* out = a.wpsum + (((size_t)st * nwk + wk) * W + p) * 28 + 14 * (c >> 2) + 7 * ((c >> 1) & 1) + 4 * (c & 1);
+      out[0] = v4[0]; out[1] = v4[1]; out[2] = v4[2];
+      if (!(c & 1)) out[3] = v4[3];
     }
   }
   chi_out = bw_block_reduce<false>(chi, sh.red);
@@ -192,10 +230,10 @@ __device__ __forceinline__ void bw_obs_pass(const BaArgs& a, BwShared& sh, const
 __device__ __forceinline__ double bw_update(const BaArgs& a, BwShared& sh, const BwObs& ob, int cur, double lambda, int failed) {
   const int tid = threadIdx.x, W = a.W, Mc = sh.Mc, Pc = sh.Pc, trial = cur ^ 1;
   if (!failed) {
-    const double* ow = ob.w[cur];
-    const double* zx = ob.zx[cur];
-    const double* zy = ob.zy[cur];
-    const double* zz = ob.zz[cur];
+    const double* ow = ob.w(cur);
+    const double* zx = ob.zx(cur);
+    const double* zy = ob.zy(cur);
+    const double* zz = ob.zz(cur);
     for (int o = tid; o < Mc; o += BW_THREADS) {
       const int p = ob.opo[o];
       const double* R = sh.X[cur][p].R;
@@ -210,7 +248,7 @@ __device__ __forceinline__ double bw_update(const BaArgs& a, BwShared& sh, const
   __syncthreads();
   double scale = 0;
   for (int j = tid; j < Pc; j += BW_THREADS) {
-    const double b0 = ob.bx[cur][j], b1 = ob.by[cur][j], b2 = ob.bz[cur][j];
+    const double b0 = ob.bx(cur)[j], b1 = ob.by(cur)[j], b2 = ob.bz(cur)[j];
     double x0 = b0, x1 = b1, x2 = b2;
     if (!failed) {
       const int f = ob.pf[j], len = ob.plen[j], i = j - sh.lgrp[f];
@@ -223,9 +261,9 @@ __device__ __forceinline__ double bw_update(const BaArgs& a, BwShared& sh, const
       const double s = ob.inv[j];
       x0 = s * c0; x1 = s * c1; x2 = s * c2;
     }
-    ob.px[trial][j] = ob.px[cur][j] + x0;
-    ob.py[trial][j] = ob.py[cur][j] + x1;
-    ob.pz[trial][j] = ob.pz[cur][j] + x2;
+    ob.px(trial)[j] = ob.px(cur)[j] + x0;
+    ob.py(trial)[j] = ob.py(cur)[j] + x1;
+    ob.pz(trial)[j] = ob.pz(cur)[j] + x2;
     scale += x0 * (lambda * x0 + b0) + x1 * (lambda * x1 + b1) + x2 * (lambda * x2 + b2);
   }
   __syncthreads();
@@ -234,55 +272,56 @@ __device__ __forceinline__ double bw_update(const BaArgs& a, BwShared& sh, const
 
 // ---------------------------------------------------------------------------------------------------------
 // worker: Schur moment sums of this worker's points (see phase_schur_units of ba_kernels.cu for the algebra).
-// Job = pose pair (p1 <= p2) or gradient of a pose; 4 adjacent lanes per job stride over the job's terms and
-// combine their sums with a fixed shuffle tree (deterministic, no atomics).
+//   4 adjacent lanes per job stride over the job's FLAT term list (built once per launch; pair jobs sorted by term count so
+//   that the 8 jobs of a warp have similar trip counts) and combine their 16 moment sums with a fixed shuffle tree -- no
+//   atomics, deterministic.  Measured alternatives: walking the (group, prefix) structure per job (segments hold ~4
+//   observations once the points are dealt over 15 CTAs: the lanes idle in the walk), and one lane per job (32 unrelated
+//   gathers per load instruction: ~5 shared-memory wavefronts each, the phase became LSU-bound).  With 4 lanes per job the
+//   lanes of a job read 4 consecutive terms, i.e. mostly one 32-byte segment per array.
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void bw_schur(const BaArgs& a, BwShared& sh, const BwObs& ob, int cur, double lambda, int wk) {
   const int tid = threadIdx.x, W = a.W, Pc = sh.Pc;
   const int npairs = W * (W + 1) / 2, njobs = npairs + W;
-  for (int j = tid; j < Pc; j += BW_THREADS) ob.inv[j] = div_pos(1.0, ob.hl[cur][j] + lambda);
+  for (int j = tid; j < Pc; j += BW_THREADS) ob.inv[j] = div_pos(1.0, ob.hl(cur)[j] + lambda);
   __syncthreads();
-  const double* ow = ob.w[cur];
-  const double* zx = ob.zx[cur];
-  const double* zy = ob.zy[cur];
-  const double* zz = ob.zz[cur];
+  const double* ow = ob.w(cur);
+  const double* zx = ob.zx(cur);
+  const double* zy = ob.zy(cur);
+  const double* zz = ob.zz(cur);
+  double* const wm = a.wmom + (size_t)wk * njobs * 16;
   const int s = tid & 3;
   const bool hi2 = (s & 2) != 0, hi1 = (s & 1) != 0;
-  double* const wm = a.wmom + (size_t)wk * njobs * 16;
-  for (int job0 = 0; job0 < njobs; job0 += BW_THREADS / 4) {
-    const int job = job0 + (tid >> 2);
+  for (int r0 = 0; r0 < njobs; r0 += BW_THREADS / 4) {
+    const int rk = r0 + (tid >> 2);   // rank in the sorted job order; the gradient jobs follow the pair jobs
     double acc[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) acc[k] = 0;
-    if (job < npairs) {
-      const int p1 = sh.jp1[job], p2 = sh.jp2[job];
-      int i = s;
-      for (int f = 0; f <= p1; f++) {
-        const int n = sh.lcnt[f * (W + 1) + (p2 - f)];
-        if (n == 0) continue;
-        const int b1 = sh.lbase[f * (W + 1) + (p1 - f)], b2 = sh.lbase[f * (W + 1) + (p2 - f)], g0 = sh.lgrp[f];
-        for (; i < n; i += 4) {
-          const int o1 = b1 + i, o2 = b2 + i;
-          const double c = ow[o1] * ow[o2] * ob.inv[g0 + i];
-          const double x1 = zx[o1], y1 = zy[o1], z1 = zz[o1], x2 = zx[o2], y2 = zy[o2], z2 = zz[o2];
-          const double cx = c * x1, cy = c * y1, cz = c * z1;
-          acc[0] += c;
-          acc[1] += cx; acc[2] += cy; acc[3] += cz;
-          acc[4] += c * x2; acc[5] += c * y2; acc[6] += c * z2;
-          acc[7] += cx * x2; acc[8] += cx * y2; acc[9] += cx * z2;
-          acc[10] += cy * x2; acc[11] += cy * y2; acc[12] += cy * z2;
-          acc[13] += cz * x2; acc[14] += cz * y2; acc[15] += cz * z2;
-        }
-        i -= n;
+    int job = -1;
+    if (rk < npairs) {
+      job = sh.jorder[rk];
+      const int k1 = sh.tstart[job + 1];
+      for (int k = sh.tstart[job] + s; k < k1; k += 4) {
+        const unsigned int t = ob.t12[k];
+        const int o1 = (int)(t & 0xffffu), o2 = (int)(t >> 16);
+        const double c = ow[o1] * ow[o2] * ob.inv[ob.tj[k]];
+        const double x1 = zx[o1], y1 = zy[o1], z1 = zz[o1], x2 = zx[o2], y2 = zy[o2], z2 = zz[o2];
+        const double cx = c * x1, cy = c * y1, cz = c * z1;
+        acc[0] += c;
+        acc[1] += cx; acc[2] += cy; acc[3] += cz;
+        acc[4] += c * x2; acc[5] += c * y2; acc[6] += c * z2;
+        acc[7] += cx * x2; acc[8] += cx * y2; acc[9] += cx * z2;
+        acc[10] += cy * x2; acc[11] += cy * y2; acc[12] += cy * z2;
+        acc[13] += cz * x2; acc[14] += cz * y2; acc[15] += cz * z2;
       }
-    } else if (job < njobs) {
+    } else if (rk < njobs) {
       // gradient job: sum_o Hpl(o) v,  v = bl / (hl + lambda);  Hpl v = w [-u ; u x 2 zc],  u = R^T v
-      const int p = job - npairs;
+      job = rk;
+      const int p = rk - npairs;
       const double* R = sh.X[cur][p].R;
       for (int t = sh.pbase[p] + s; t < sh.pbase[p + 1]; t += 4) {
         const int o = ob.plist[t], j = ob.opt[o];
         const double s1 = ow[o] * ob.inv[j];
-        const double v0 = s1 * ob.bx[cur][j], v1 = s1 * ob.by[cur][j], v2 = s1 * ob.bz[cur][j];
+        const double v0 = s1 * ob.bx(cur)[j], v1 = s1 * ob.by(cur)[j], v2 = s1 * ob.bz(cur)[j];
         const double u0 = R[0] * v0 + R[3] * v1 + R[6] * v2, u1 = R[1] * v0 + R[4] * v1 + R[7] * v2, u2 = R[2] * v0 + R[5] * v1 + R[8] * v2;
         const double ax = 2 * zx[o], ay = 2 * zy[o], az = 2 * zz[o];
         acc[0] -= u0; acc[1] -= u1; acc[2] -= u2;
@@ -302,7 +341,7 @@ __device__ __forceinline__ void bw_schur(const BaArgs& a, BwShared& sh, const Bw
       const double send = hi1 ? v[k] : v[k + 4], keep = hi1 ? v[k + 4] : v[k];
       u[k] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
     }
-    if (job < njobs) {
+    if (job >= 0) {
       double* out = wm + (size_t)job * 16 + 8 * (s >> 1) + 4 * (s & 1);
       out[0] = u[0]; out[1] = u[1]; out[2] = u[2]; out[3] = u[3];
     }
@@ -313,10 +352,11 @@ __device__ __forceinline__ int bw_eps3(int x, int y) { return ((y - x + 3) % 3 =
 
 // ---------------------------------------------------------------------------------------------------------
 // every CTA (reducer r): sum the worker partials of the pair jobs j == r (mod C) and of the poses p == r (mod C), assemble
-// the blocks of the reduced system and store them into CTA 0's shared memory.
+// the blocks of the reduced system and store them into the global copy of the system (L2).  (Storing straight into CTA 0's
+// shared memory through DSMEM was the first version: 16 CTAs x 4 KB into ONE receiver at ~20 B/clk cost 3.5 k cycles.)
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void bw_reduce_assemble(const BaArgs& a, BwShared& sh, int cur, double lambda, int rank, int nranks, int nwk,
-                                                   double* S0 /* CTA 0's system (DSMEM) */, int ld, int np) {
+                                                   double* S0 /* the system in global memory */, int ld, int np) {
   const int tid = threadIdx.x, W = a.W;
   const int npairs = W * (W + 1) / 2, njobs = npairs + W;
   const int nslots = (npairs > rank) ? (npairs - rank + nranks - 1) / nranks : 0;
@@ -325,23 +365,32 @@ __device__ __forceinline__ void bw_reduce_assemble(const BaArgs& a, BwShared& sh
   for (int idx = tid; idx < nslots * 16; idx += BW_THREADS) {
     const int slot = idx >> 4, v = idx & 15, job = rank + slot * nranks;
     const double* src = a.wmom + (size_t)job * 16 + v;
+    double t[BA_MAX_CLUSTER - 1];
+#pragma unroll
+    for (int c = 0; c < BA_MAX_CLUSTER - 1; c++) t[c] = (c < nwk) ? src[c * wstride] : 0.0;   // all loads in flight
     double s = 0;
-#pragma unroll 5
-    for (int c = 0; c < nwk; c++) s += src[c * wstride];
+#pragma unroll
+    for (int c = 0; c < BA_MAX_CLUSTER - 1; c++) s += t[c];
     sh.rmom[slot][v] = s;
   }
-  for (int idx = tid; idx < npslots * 33; idx += BW_THREADS) {
+  for (int idx = BW_THREADS - 1 - tid; idx < npslots * 33; idx += BW_THREADS) {   // from the top: overlaps the loop above
     const int ps = idx / 33, v = idx - 33 * ps, p = rank + ps * nranks;
     double s = 0;
     if (v < 27) {
       const double* src = a.wpsum + ((size_t)cur * nwk * W + p) * 28 + v;
-#pragma unroll 5
-      for (int c = 0; c < nwk; c++) s += src[(size_t)c * W * 28];
+      double t[BA_MAX_CLUSTER - 1];
+#pragma unroll
+      for (int c = 0; c < BA_MAX_CLUSTER - 1; c++) t[c] = (c < nwk) ? src[(size_t)c * W * 28] : 0.0;
+#pragma unroll
+      for (int c = 0; c < BA_MAX_CLUSTER - 1; c++) s += t[c];
       sh.rps[ps][v] = s;
     } else {
       const double* src = a.wmom + (size_t)(npairs + p) * 16 + (v - 27);
-#pragma unroll 5
-      for (int c = 0; c < nwk; c++) s += src[c * wstride];
+      double t[BA_MAX_CLUSTER - 1];
+#pragma unroll
+      for (int c = 0; c < BA_MAX_CLUSTER - 1; c++) t[c] = (c < nwk) ? src[c * wstride] : 0.0;
+#pragma unroll
+      for (int c = 0; c < BA_MAX_CLUSTER - 1; c++) s += t[c];
       sh.rgr[ps][v - 27] = s;
     }
   }
@@ -466,16 +515,20 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ba_window_kernel(BaArgs a) {
   const int nwk = nranks - 1, wk = rank - 1;   // workers are ranks 1..nranks-1
   const int tid = threadIdx.x, W = a.W, P = a.P;
   const int n = 6 * W, np = bc_np(n), ld = np + 1;
-  double* const S0 = cluster.map_shared_rank((double*)dsm_raw, 0);
   CholSm cs;
   bc_carve((double*)dsm_raw, n, cs);
   BwObs ob;
-  bw_carve(dsm_raw, a.capO, a.capPt, ob);
-  unsigned long long t_mark = 0, t_start = 0;
-  unsigned long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  bw_carve(dsm_raw, a.capO, a.capPt, a.capT, ob);
+  __shared__ unsigned long long tph[8], tq[8], t_mark, t_start, t_mark2;   // phase timers (thread 0 of CTA 0 / of worker 0)
   const bool timer = (rank == 0 && tid == 0);
+  if (tid < 8) { tph[tid] = 0; tq[tid] = 0; }
+  __syncthreads();
   if (timer) { t_start = gtime(); t_mark = t_start; }
 #define BW_TOC(slot) do { if (timer) { const unsigned long long t_ = gtime(); tph[slot] += t_ - t_mark; t_mark = t_; } } while (0)
+  // second timer on worker 0 (rank 1): its own time inside the phases, slots 8..15 of t_phase
+  const bool timer2 = (rank == 1 && tid == 0);
+#define BW_MARK2() do { if (timer2) t_mark2 = gtime(); } while (0)
+#define BW_TOC2(slot) do { if (timer2) { const unsigned long long t_ = gtime(); tq[slot] += t_ - t_mark2; t_mark2 = t_; } } while (0)
 
   // ---- tables
   const int npairs = W * (W + 1) / 2;
@@ -538,9 +591,9 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ba_window_kernel(BaArgs a) {
     for (int j = tid; j < Pc; j += BW_THREADS) {
       const int nidx = wk + j * nwk, f = a.pt_first[nidx], len = a.pt_len[nidx];
       ob.pf[j] = (unsigned char)f; ob.plen[j] = (unsigned char)len;
-      ob.px[0][j] = (double)a.points_f32[3 * (size_t)nidx];
-      ob.py[0][j] = (double)a.points_f32[3 * (size_t)nidx + 1];
-      ob.pz[0][j] = (double)a.points_f32[3 * (size_t)nidx + 2];
+      ob.px(0)[j] = (double)a.points_f32[3 * (size_t)nidx];
+      ob.py(0)[j] = (double)a.points_f32[3 * (size_t)nidx + 1];
+      ob.pz(0)[j] = (double)a.points_f32[3 * (size_t)nidx + 2];
       const int i = j - sh.lgrp[f], ig = nidx - a.grp_start[f];
       for (int k = 0; k < len; k++) {
         const int o = sh.lbase[f * (W + 1) + k] + i, p = f + k;
@@ -555,6 +608,46 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ba_window_kernel(BaArgs a) {
         const int e = f * (W + 1) + (p - f), b = sh.lbase[e], c = sh.lcnt[e];
         for (int i = 0; i < c; i++) ob.plist[pos++] = (unsigned short)(b + i);
       }
+    }
+    // Schur term lists: the points common to poses p1 <= p2 are, for every group f <= p1, the first lcnt[f][p2-f] local points
+    for (int job = tid; job < npairs; job += BW_THREADS) {
+      const int p1 = sh.jp1[job], p2 = sh.jp2[job];
+      int c = 0;
+      for (int f = 0; f <= p1; f++) c += sh.lcnt[f * (W + 1) + (p2 - f)];
+      sh.tstart[job + 1] = c;
+    }
+    __syncthreads();
+    if (tid < 32) {   // inclusive scan of the counts -> tstart (one warp, consecutive runs per lane)
+      const int per = (npairs + 31) / 32, e0 = tid * per, e1 = min(e0 + per, npairs);
+      int sum = 0;
+      for (int e = e0; e < e1; e++) sum += sh.tstart[e + 1];
+      int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (tid >= o) incl += v;
+      }
+      int run = incl - sum;
+      for (int e = e0; e < e1; e++) { const int c = sh.tstart[e + 1]; run += c; sh.tstart[e + 1] = run; }
+      if (tid == 0) sh.tstart[0] = 0;
+    }
+    __syncthreads();
+    for (int job = tid; job < npairs; job += BW_THREADS) {
+      const int p1 = sh.jp1[job], p2 = sh.jp2[job];
+      int k = sh.tstart[job];
+      const int cnt = sh.tstart[job + 1] - k;
+      for (int f = 0; f <= p1; f++) {
+        const int n = sh.lcnt[f * (W + 1) + (p2 - f)];
+        const int b1 = sh.lbase[f * (W + 1) + (p1 - f)], b2 = sh.lbase[f * (W + 1) + (p2 - f)], g0 = sh.lgrp[f];
+        for (int i = 0; i < n; i++, k++) { ob.t12[k] = (unsigned int)(b1 + i) | ((unsigned int)(b2 + i) << 16); ob.tj[k] = (unsigned short)(g0 + i); }
+      }
+      // rank of this job by descending term count (ties by job index)
+      int rk = 0;
+      for (int j2 = 0; j2 < npairs; j2++) {
+        const int c2 = sh.tstart[j2 + 1] - sh.tstart[j2];
+        rk += (c2 > cnt || (c2 == cnt && j2 < job)) ? 1 : 0;
+      }
+      sh.jorder[rk] = (unsigned short)job;
     }
   }
   __syncthreads();
@@ -600,17 +693,24 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ba_window_kernel(BaArgs a) {
       __syncthreads();
       while (true) {
         const double lambda = sh.ctl.lambda;
+        BW_MARK2();
         if (rank > 0) bw_schur(a, sh, ob, cur, lambda, wk);
+        BW_TOC2(0);
         cluster.sync();
         BW_TOC(0);
-        bw_reduce_assemble(a, sh, cur, lambda, rank, nranks, nwk, S0, ld, np);
+        BW_MARK2();
+        bw_reduce_assemble(a, sh, cur, lambda, rank, nranks, nwk, a.Sg, ld, np);
+        BW_TOC2(1);
         cluster.sync();
         BW_TOC(1);
         if (rank == 0) {
-          bc_factor(cs, &sh.s_bad, nullptr);
+          bc_stage(cs, a.Sg);
+          BW_TOC(6);
+          bc_factor(cs, &sh.s_bad, nullptr, a.Sg);
           const int failed = sh.s_bad;
           if (!failed) bc_backsolve(cs);
           __syncthreads();
+          BW_TOC(2);
           // increments (x = b when the solver failed, like LinearSolverCSparse), trial poses, pose part of the scale
           const double* ys = cs.S + (size_t)np * ld;
           double sc = 0;
@@ -637,14 +737,18 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ba_window_kernel(BaArgs a) {
           const double chi = bw_block_reduce<false>(bw_edges(a, sh, cur ^ 1, (double*)dsm_raw), sh.red);
           if (tid == 0) a.part[0] = chi;
         } else {
+          BW_MARK2();
           for (int i = tid; i < n; i += BW_THREADS) sh.xp[i] = a.xp[i];
           for (int p = tid; p < W; p += BW_THREADS) sh.X[cur ^ 1][p] = a.X[(size_t)(cur ^ 1) * W + p];
           __syncthreads();
+          BW_TOC2(2);
           double scale = bw_update(a, sh, ob, cur, lambda, failed);
           scale = bw_block_reduce<false>(scale, sh.red);
+          BW_TOC2(3);
           double chi, hmax;
           bw_obs_pass(a, sh, ob, cur ^ 1, wk, nwk, chi, hmax);
           if (tid == 0) { a.part[rank * 4 + 0] = chi; a.part[rank * 4 + 1] = scale; }
+          BW_TOC2(4);
         }
         cluster.sync();
         BW_TOC(3);
@@ -695,15 +799,16 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ba_window_kernel(BaArgs a) {
     if (tid == 0) {
       if (run) *a.ctl_out = sh.ctl;
       tph[7] = gtime() - t_start;
-      for (int k = 0; k < 24; k++) a.t_phase[k] = k < 8 ? tph[k] : 0;
+      for (int k = 0; k < 8; k++) a.t_phase[k] = tph[k];
     }
   } else {
+    if (timer2) for (int k = 0; k < 8; k++) a.t_phase[8 + k] = tq[k];
     const int Pc = sh.Pc;
     for (int j = tid; j < Pc; j += BW_THREADS) {
       const size_t nidx = (size_t)wk + (size_t)j * nwk;
-      a.out_points[3 * nidx] = (float)ob.px[fin][j];
-      a.out_points[3 * nidx + 1] = (float)ob.py[fin][j];
-      a.out_points[3 * nidx + 2] = (float)ob.pz[fin][j];
+      a.out_points[3 * nidx] = (float)ob.px(fin)[j];
+      a.out_points[3 * nidx + 1] = (float)ob.py(fin)[j];
+      a.out_points[3 * nidx + 2] = (float)ob.pz(fin)[j];
     }
   }
   cluster.sync();   // no CTA may exit while others can still address its shared memory
@@ -714,10 +819,10 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ba_window_kernel(BaArgs a) {
 // host side
 // =========================================================================================================
 // shared memory a launch needs (dynamic part), or 0 when the problem does not fit the shared-memory resident kernel
-size_t ba_window_smem(int W, int capO, int capPt) {
+size_t ba_window_smem(int W, int capO, int capPt, int capT) {
   const size_t solver = sizeof(double) * bc_smem_doubles(6 * W);
   const size_t edges = sizeof(double) * 80 * (size_t)W;
-  const size_t worker = bw_worker_bytes(capO, capPt);
+  const size_t worker = bw_worker_bytes(capO, capPt, capT);
   size_t need = solver > worker ? solver : worker;
   if (edges > need) need = edges;
   return need;
