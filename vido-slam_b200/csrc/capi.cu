@@ -70,8 +70,10 @@ vido_ctx* vido_create(const vido_config* cfg) {
   if (rc == VIDO_OK) rc = po_setup(ctx, 8192, 16);
   if (rc == VIDO_OK) rc = pnp_setup(ctx, 8192, 2048);
   if (rc == VIDO_OK) rc = trk_setup(ctx);
+  if (rc == VIDO_OK) rc = chain_setup(ctx, ctx->cfg.max_batch);
   if (rc != VIDO_OK) {
     g_create_err = ctx->err;
+    chain_teardown(ctx);
     trk_teardown(ctx);
     pnp_teardown(ctx);
     po_teardown(ctx);
@@ -90,6 +92,7 @@ void vido_destroy(vido_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  chain_teardown(ctx);
   trk_teardown(ctx);
   pnp_teardown(ctx);
   po_teardown(ctx);

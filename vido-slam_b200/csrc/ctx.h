@@ -92,6 +92,7 @@ struct vido_ctx {
   void* po = nullptr;  // PoWorkspace (poseopt_kernels.cu)
   void* pnp = nullptr; // PnpWorkspace (pnp_kernels.cu)
   void* trk = nullptr; // TrackState (track.cu)
+  void* chain = nullptr; // ChainWorkspace (chain_kernels.cu)
   // One-shot hook run by the synchronous PnP / pose-optimisation wrappers after their launches and before they wait for the
   // results: the per-frame driver parks host work there (staging and queueing the previous frame's window solve, retiring
   // the one before) so that it overlaps the kernels instead of extending the frame's serial path.
@@ -110,6 +111,31 @@ struct vido_ctx {
       return VIDO_ERR_CUDA;                                                                 \
     }                                                                                       \
   } while (0)
+
+// ---- device-resident tracker state of the static VO path (chain_kernels.cu): what Tracking keeps of mpLastFrame
+//      (mvStatKeys / mvStatDepth / mvCorres / mvFlowNext, mTcw) and the motion model (mVelocity), as device arrays, so that
+//      the per-frame kernels of frame k+1 can be queued behind those of frame k without a host round trip
+struct ChainStateDev {
+  int32_t* hdr;   // [0] number of features, [1] has_velocity, [2] frame was skipped (lost tracking)
+  float *Tcw, *vel, *keys, *depth, *corres, *flow;
+};
+struct ChainPnpOut { const float* T; const int32_t* ids; const int32_t* res; };   // init model: pose, inlier ids, (n, winner, nr, nm)
+struct ChainPoOut { const float* T; const float* flow; const int32_t* inl; const int32_t* ninl; const int32_t* n; };
+int pnp_chain_setup(vido_ctx* ctx, int cap);
+int pnp_chain_enqueue(vido_ctx* ctx, const ChainStateDev& st, int which, ChainPnpOut* out);
+int po_chain_setup(vido_ctx* ctx, int cap);
+int po_chain_enqueue(vido_ctx* ctx, const ChainStateDev& st, int which, const ChainPnpOut& pnp, ChainPoOut* out);
+
+// chain_kernels.cu
+int chain_setup(vido_ctx* ctx, int nslots);
+void chain_teardown(vido_ctx* ctx);
+int chain_capacity(vido_ctx* ctx);
+int chain_upload_state(vido_ctx* ctx, int n, const float* keys, const float* depth, const float* corres, const float* flow, const float* Tcw,
+                       const float* vel, int has_velocity);
+int chain_enqueue_frame(vido_ctx* ctx, const vido_keypoint* kp, const int32_t* nkp, const int32_t* kpmask, const float* kpdepth,
+                        const float* kpflow, const float* depth, const float* flow, const int32_t* mask, int slot);
+int chain_wait_record(vido_ctx* ctx, int slot, const int32_t** hdr, const float** Tcw, const float** Twc, const float** rel, const float** vel,
+                      const float** xy, const float** depth, const float** p3, const float** corres, const float** flow, const int32_t** asso);
 
 // orb_kernels.cu
 int orb_setup(vido_ctx* ctx);

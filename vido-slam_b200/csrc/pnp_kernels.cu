@@ -466,6 +466,13 @@ struct PnpWorkspace {
   size_t in_bytes = 0, out_bytes = 0;
   int *tmp = nullptr, *cnt = nullptr;   // [PNP_MAX_BATCH][capN], [PNP_MAX_BATCH][capIters]
   PnpPose* hyp = nullptr;               // [PNP_MAX_BATCH][capIters]
+  // device-chained camera problem (pnp_chain_enqueue): arguments per state buffer, inputs built on the device, outputs
+  char* c_block = nullptr;
+  PnpArgs* c_args[2] = {nullptr, nullptr};
+  float *c_p3d = nullptr, *c_tm = nullptr, *c_T = nullptr;
+  int *c_good = nullptr, *c_ids = nullptr, *c_res = nullptr, *c_tmp = nullptr;
+  int c_cap = 0;
+  bool c_ready[2] = {false, false};
 };
 
 int pnp_setup(vido_ctx* ctx, int capN, int capIters) {
@@ -490,7 +497,7 @@ void pnp_teardown(vido_ctx* ctx) {
   PnpWorkspace* ws = (PnpWorkspace*)ctx->pnp;
   if (!ws) return;
   cudaFree(ws->d_in); cudaFree(ws->d_out); cudaFreeHost(ws->h_in); cudaFreeHost(ws->h_out);
-  cudaFree(ws->tmp); cudaFree(ws->cnt); cudaFree(ws->hyp);
+  cudaFree(ws->tmp); cudaFree(ws->cnt); cudaFree(ws->hyp); cudaFree(ws->c_block);
   delete ws;
   ctx->pnp = nullptr;
 }
@@ -582,3 +589,117 @@ int pnp_init_model_batch(vido_ctx* ctx, vido_pnp_problem* ps, int nproblems) {
 }
 
 int pnp_init_model_host(vido_ctx* ctx, vido_pnp_problem* p) { return pnp_init_model_batch(ctx, p, 1); }
+
+// =========================================================================================================
+// device-chained camera init model: the problem is built from the device-resident tracker state (no host round trip)
+// =========================================================================================================
+// Tracking::GetInitModelCam prologue (src/Tracking.cc:1914-1965): 3-D points of the last frame through Twl (float, cv::Mat
+// gemm rounding: double accumulation, one rounding, then the float translation add), valid = depth >= 0, the constant-
+// velocity pose mVelocity * Tcw_last.  One CTA; writes n / M into the argument block of the two PnP kernels.
+__global__ void __launch_bounds__(1024) pnp_chain_prep_kernel(PnpArgs* __restrict__ args, int32_t* __restrict__ hdr, const float* __restrict__ Tcw,
+                                                              const float* __restrict__ vel, const float* __restrict__ keys,
+                                                              const float* __restrict__ depth, float fx, float fy, float cx, float cy,
+                                                              float* __restrict__ p3d, int* __restrict__ good, float* __restrict__ tm) {
+  __shared__ float Twl[16];
+  __shared__ int s_warp[32], s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = hdr[0];
+  const bool skip = n < 2;   // "if (Ns < 2) skipped" of the per-frame driver: lost tracking, the frame is not processed
+  if (tid == 0) {
+    hdr[2] = skip ? 1 : 0;
+    s_base = 0;
+    for (int k = 0; k < 16; k++) Twl[k] = 0.f;
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) Twl[4 * r + c] = Tcw[4 * c + r];
+    for (int r = 0; r < 3; r++) {
+      double s = 0;
+      for (int k = 0; k < 3; k++) s += (double)(-Twl[4 * r + k]) * (double)Tcw[4 * k + 3];
+      Twl[4 * r + 3] = (float)s;
+    }
+    Twl[15] = 1.f;
+  }
+  if (tid < 16) {
+    float v = Tcw[tid];
+    if (hdr[1]) {   // mVelocity * Tcw_last, double accumulation, one rounding (cv::Mat CV_32F product)
+      const int r = tid >> 2, c = tid & 3;
+      double s = 0;
+      for (int k = 0; k < 4; k++) s += (double)vel[4 * r + k] * (double)Tcw[4 * k + c];
+      v = (float)s;
+    }
+    tm[tid] = v;
+  }
+  __syncthreads();
+  const float invfx = __fdiv_rn(1.0f, fx), invfy = __fdiv_rn(1.0f, fy);
+  const int nn = skip ? 0 : n;
+  for (int i0 = 0; i0 < nn; i0 += 1024) {
+    const int i = i0 + tid;
+    bool ok = false;
+    if (i < nn) {
+      const float z = depth[i];
+      ok = !(z < 0);
+      float o[3] = {0.f, 0.f, 0.f};
+      if (ok) {
+        const float xc[3] = {__fmul_rn(__fmul_rn(__fsub_rn(keys[2 * i], cx), z), invfx), __fmul_rn(__fmul_rn(__fsub_rn(keys[2 * i + 1], cy), z), invfy), z};
+        for (int r = 0; r < 3; r++)
+          o[r] = __fadd_rn((float)((double)Twl[4 * r] * xc[0] + (double)Twl[4 * r + 1] * xc[1] + (double)Twl[4 * r + 2] * xc[2]), Twl[4 * r + 3]);
+      }
+      p3d[3 * i] = o[0]; p3d[3 * i + 1] = o[1]; p3d[3 * i + 2] = o[2];
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; w++) off += s_warp[w];
+    if (ok) good[off + __popc(m & ((1u << lane) - 1u))] = i;
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int w = 0; w < 32; w++) t += s_warp[w]; s_base += t; }
+    __syncthreads();
+  }
+  if (tid == 0) { args->n = nn; args->M = s_base; }
+}
+
+int pnp_chain_setup(vido_ctx* ctx, int cap) {
+  PnpWorkspace* ws = (PnpWorkspace*)ctx->pnp;
+  if (cap > ws->capN) { ctx->err = "chain capacity exceeds the PnP capacity"; return VIDO_ERR_CAPACITY; }
+  ws->c_cap = cap;
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t o_args = 0, o_p3d = o_args + 2 * PNP_ARGS_SLOT, o_tm = o_p3d + al(12 * (size_t)cap), o_T = o_tm + 256, o_good = o_T + 256,
+               o_ids = o_good + al(4 * (size_t)cap), o_res = o_ids + al(4 * (size_t)cap), o_tmp = o_res + 256, total = o_tmp + al(4 * (size_t)cap);
+  VIDO_CUDA(cudaMalloc(&ws->c_block, total));
+  VIDO_CUDA(cudaMemset(ws->c_block, 0, total));
+  ws->c_args[0] = (PnpArgs*)(ws->c_block + o_args); ws->c_args[1] = (PnpArgs*)(ws->c_block + o_args + PNP_ARGS_SLOT);
+  ws->c_p3d = (float*)(ws->c_block + o_p3d); ws->c_tm = (float*)(ws->c_block + o_tm); ws->c_T = (float*)(ws->c_block + o_T);
+  ws->c_good = (int*)(ws->c_block + o_good); ws->c_ids = (int*)(ws->c_block + o_ids); ws->c_res = (int*)(ws->c_block + o_res);
+  ws->c_tmp = (int*)(ws->c_block + o_tmp);
+  ws->c_ready[0] = ws->c_ready[1] = false;
+  return VIDO_OK;
+}
+
+// queue (no synchronisation): prologue, 500 hypotheses, selection.  `which` = index of the state buffer `st` (its pointers are
+// baked into that buffer's argument block the first time it is used).
+int pnp_chain_enqueue(vido_ctx* ctx, const ChainStateDev& st, int which, ChainPnpOut* out) {
+  PnpWorkspace* ws = (PnpWorkspace*)ctx->pnp;
+  cudaStream_t s = ctx->stream;
+  const vido_config& c = ctx->cfg;
+  vido_pnp_problem dp;
+  vido_pnp_default_params(&dp);
+  if (!ws->c_ready[which]) {
+    PnpArgs a;
+    memset(&a, 0, sizeof a);
+    a.iters = dp.iters; a.no_mm = 0;
+    a.cur_xy = st.corres; a.pts3d = ws->c_p3d; a.good = ws->c_good; a.Tcw_motion = ws->c_tm;
+    a.fx = c.fx; a.fy = c.fy; a.cx = c.cx; a.cy = c.cy; a.thr = dp.reproj_err; a.confidence = dp.confidence;
+    a.hyp = ws->hyp; a.hyp_cnt = ws->cnt;
+    a.Tcw_out = ws->c_T; a.inlier_ids = ws->c_ids; a.result = ws->c_res; a.tmp_ids = ws->c_tmp;
+    VIDO_CUDA(cudaMemcpyAsync(ws->c_args[which], &a, sizeof a, cudaMemcpyHostToDevice, s));   // pageable source: staged before return
+    ws->c_ready[which] = true;
+  }
+  pnp_chain_prep_kernel<<<1, 1024, 0, s>>>(ws->c_args[which], st.hdr, st.Tcw, st.vel, st.keys, st.depth, c.fx, c.fy, c.cx, c.cy, ws->c_p3d,
+                                           ws->c_good, ws->c_tm);
+  pnp_hypotheses_kernel<<<dim3((dp.iters + PNP_THREADS / 32 - 1) / (PNP_THREADS / 32), 1), PNP_THREADS, 0, s>>>(ws->c_args[which]);
+  pnp_select_kernel<<<1, PNP_THREADS, 0, s>>>(ws->c_args[which]);
+  ctx->launches += 3;
+  VIDO_CUDA(cudaGetLastError());
+  out->T = ws->c_T; out->ids = ws->c_ids; out->res = ws->c_res;
+  return VIDO_OK;
+}

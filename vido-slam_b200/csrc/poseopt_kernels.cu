@@ -860,6 +860,14 @@ struct PoWorkspace {
   size_t in_bytes = 0, out_bytes = 0;
   double *Xw = nullptr, *flow = nullptr, *xl = nullptr, *eProj = nullptr;
   int* level = nullptr;
+  // device-chained camera problem (po_chain_enqueue)
+  char* c_block = nullptr;
+  PoArgs* c_args[2] = {nullptr, nullptr};
+  float *c_obs = nullptr, *c_flow = nullptr, *c_dep = nullptr, *c_T = nullptr, *c_flowout = nullptr;
+  int *c_inl = nullptr, *c_ninl = nullptr, *c_n = nullptr;
+  LmCtl* c_ctl = nullptr;
+  int c_cap = 0;
+  bool c_ready[2] = {false, false};
 };
 
 static size_t pal(size_t v) { return (v + 63) & ~(size_t)63; }
@@ -892,7 +900,7 @@ void po_teardown(vido_ctx* ctx) {
   PoWorkspace* ws = (PoWorkspace*)ctx->po;
   if (!ws) return;
   cudaFree(ws->d_in); cudaFree(ws->d_out); cudaFreeHost(ws->h_in); cudaFreeHost(ws->h_out);
-  cudaFree(ws->Xw); cudaFree(ws->flow); cudaFree(ws->xl); cudaFree(ws->eProj); cudaFree(ws->level);
+  cudaFree(ws->Xw); cudaFree(ws->flow); cudaFree(ws->xl); cudaFree(ws->eProj); cudaFree(ws->level); cudaFree(ws->c_block);
   delete ws;
   ctx->po = nullptr;
 }
@@ -985,5 +993,73 @@ int po_flow2_host(vido_ctx* ctx, vido_poseopt_problem* prs, int nproblems, vido_
         }
       }
   }
+  return VIDO_OK;
+}
+
+// =========================================================================================================
+// device-chained camera pose optimisation: the problem is gathered on the device from the init-model inliers
+// =========================================================================================================
+// Tracking::Track between GetInitModelCam and PoseOptimizationFlow2Cam (src/Tracking.cc:1137-1160): the inliers' last-frame
+// key points, flows and depths, in inlier order
+__global__ void __launch_bounds__(1024) po_chain_prep_kernel(PoArgs* __restrict__ args, const int32_t* __restrict__ pnp_res,
+                                                             const int32_t* __restrict__ ids, const float* __restrict__ keys,
+                                                             const float* __restrict__ flow, const float* __restrict__ depth,
+                                                             float* __restrict__ obs, float* __restrict__ fl, float* __restrict__ dep,
+                                                             int32_t* __restrict__ n_out) {
+  const int n = pnp_res[0];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int k = ids[i];
+    obs[2 * i] = keys[2 * k]; obs[2 * i + 1] = keys[2 * k + 1];
+    fl[2 * i] = flow[2 * k]; fl[2 * i + 1] = flow[2 * k + 1];
+    dep[i] = depth[k];
+  }
+  if (threadIdx.x == 0) { args->n = n; *n_out = n; }
+}
+
+int po_chain_setup(vido_ctx* ctx, int cap) {
+  PoWorkspace* ws = (PoWorkspace*)ctx->po;
+  if (cap > ws->capN || cap > PO_CACHE_CAP) { ctx->err = "chain capacity exceeds the pose-optimisation capacity"; return VIDO_ERR_CAPACITY; }
+  ws->c_cap = cap;
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t o_args = 0, o_obs = o_args + al(2 * sizeof(PoArgs)), o_flow = o_obs + al(8 * (size_t)cap), o_dep = o_flow + al(8 * (size_t)cap),
+               o_T = o_dep + al(4 * (size_t)cap), o_fo = o_T + 256, o_inl = o_fo + al(8 * (size_t)cap), o_ninl = o_inl + al(4 * (size_t)cap),
+               o_n = o_ninl + 256, o_ctl = o_n + 256, total = o_ctl + al(sizeof(LmCtl) * 4);
+  VIDO_CUDA(cudaMalloc(&ws->c_block, total));
+  VIDO_CUDA(cudaMemset(ws->c_block, 0, total));
+  ws->c_args[0] = (PoArgs*)(ws->c_block + o_args); ws->c_args[1] = ws->c_args[0] + 1;
+  ws->c_obs = (float*)(ws->c_block + o_obs); ws->c_flow = (float*)(ws->c_block + o_flow); ws->c_dep = (float*)(ws->c_block + o_dep);
+  ws->c_T = (float*)(ws->c_block + o_T); ws->c_flowout = (float*)(ws->c_block + o_fo); ws->c_inl = (int*)(ws->c_block + o_inl);
+  ws->c_ninl = (int*)(ws->c_block + o_ninl); ws->c_n = (int*)(ws->c_block + o_n); ws->c_ctl = (LmCtl*)(ws->c_block + o_ctl);
+  ws->c_ready[0] = ws->c_ready[1] = false;
+  return VIDO_OK;
+}
+
+int po_chain_enqueue(vido_ctx* ctx, const ChainStateDev& st, int which, const ChainPnpOut& pnp, ChainPoOut* out) {
+  PoWorkspace* ws = (PoWorkspace*)ctx->po;
+  cudaStream_t s = ctx->stream;
+  const vido_config& c = ctx->cfg;
+  if (!ws->c_ready[which]) {
+    vido_poseopt_problem p;
+    vido_poseopt_default_params(&p);
+    PoArgs a;
+    memset(&a, 0, sizeof a);
+    a.obs_xy = ws->c_obs; a.flow_xy = ws->c_flow; a.depth = ws->c_dep; a.Tcw_init = pnp.T; a.Tcw_last = st.Tcw;
+    a.fx = c.fx; a.fy = c.fy; a.cx = c.cx; a.cy = c.cy;
+    a.info_f = (p.info_flow == 0.1f) ? 0.1 : (double)p.info_flow;
+    a.info_p = (p.info_prior == 0.3f) ? 0.3 : (p.info_prior == 0.5f ? 0.5 : (double)p.info_prior);
+    a.delta = (double)sqrtf(p.rp_thres);
+    a.th0 = p.rp_thres; a.th1 = p.chi2_th;
+    a.rounds = p.rounds; a.its = p.its;
+    a.Xw = ws->Xw; a.flow = ws->flow; a.xl = ws->xl; a.eProj = ws->eProj; a.level = ws->level;
+    a.Tcw_out = ws->c_T; a.n_inliers = ws->c_ninl; a.flow_out = ws->c_flowout; a.inlier = ws->c_inl;
+    a.ctl = ws->c_ctl; a.rec = nullptr;
+    VIDO_CUDA(cudaMemcpyAsync(ws->c_args[which], &a, sizeof a, cudaMemcpyHostToDevice, s));
+    ws->c_ready[which] = true;
+  }
+  po_chain_prep_kernel<<<1, 1024, 0, s>>>(ws->c_args[which], pnp.res, pnp.ids, st.keys, st.flow, st.depth, ws->c_obs, ws->c_flow, ws->c_dep, ws->c_n);
+  poseopt_flow2_fast_kernel<<<1, PO_FAST_THREADS, sizeof(double) * PO_NC * (size_t)ws->c_cap, s>>>(ws->c_args[which]);
+  ctx->launches += 2;
+  VIDO_CUDA(cudaGetLastError());
+  out->T = ws->c_T; out->flow = ws->c_flowout; out->inl = ws->c_inl; out->ninl = ws->c_ninl; out->n = ws->c_n;
   return VIDO_OK;
 }

@@ -176,6 +176,7 @@ struct TrackState {
   std::vector<float> last_keys, last_depth, last_corres, last_flow;  // mpLastFrame mvStatKeys / mvStatDepth / mvCorres / mvFlowNext
   int f_id = 0;
   int ba_epoch = 0;
+  bool chain_active = false;   // the static tracker state lives on the device (chain_kernels.cu); the host vectors mirror it
   // object state of mpLastFrame: mvObjKeys / mvObjDepth / mvObjCorres / mvObjFlowNext / vSemObjLabel and nModLabel /
   // nSemPosition / bObjStat / vObjMod
   std::vector<float> lo_keys, lo_depth, lo_corres, lo_flow;
@@ -379,6 +380,7 @@ int trk_reset(vido_ctx* ctx) {
   TrackState* ts = (TrackState*)ctx->trk;
   while (ts->ba_nq > 0) { vido_lm_stats ls; ba_collect(ctx, &ts->job[ts->ba_queue[0]].pr, &ls); ts->ba_queue[0] = ts->ba_queue[1]; ts->ba_nq--; }
   ts->ba_deferred.valid = false;
+  ts->chain_active = false;
   ts->map.clear(); ts->tracks.clear();
   ts->initialised = false; ts->has_velocity = false; ts->f_id = 0; ts->ba_epoch = 0;
   cudaStreamSynchronize(ts->copy_stream); cudaStreamSynchronize(ts->fe_stream);
@@ -1505,6 +1507,30 @@ static int vio_after_ba(vido_ctx* ctx) {
 // ---------------------------------------------------------------------------------------------------------
 // back-end of one frame (sequential)
 // ---------------------------------------------------------------------------------------------------------
+// tracklets of the static features, incrementally (same chains as Tracking::GetStaticTrack, src/Tracking.cc:2514-2613): every
+// feature of the new frame F continues the track of its predecessor in the last Map frame, or starts one with it
+static void link_static_tracks(TrackState* ts, MapFrame& F) {
+  const int nf = (int)F.asso.size();
+  F.track.assign(nf, -1); F.pos.assign(nf, 0);
+  MapFrame& P = ts->map.back();
+  const int fcur = (int)ts->map.size();
+  for (int j = 0; j < nf; j++) {
+    const int p = F.asso[j];
+    if (p < 0) continue;
+    if (P.track[p] >= 0) {
+      TrackInfo& T = ts->tracks[P.track[p]];
+      F.track[j] = P.track[p];
+      F.pos[j] = T.len;
+      T.len++;
+    } else {
+      const int t = (int)ts->tracks.size();
+      ts->tracks.push_back({fcur - 1, 2, -1, -1});
+      P.track[p] = t; P.pos[p] = 0;
+      F.track[j] = t; F.pos[j] = 1;
+    }
+  }
+}
+
 static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int slot, float* Tcw_out, vido_track_stats* st) {
   TrackState* ts = (TrackState*)ctx->trk;
   const vido_config& c = ctx->cfg;
@@ -1777,24 +1803,7 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
           F.p3[3 * i + r] = (float)((double)Twc[4 * r] * xc[0] + (double)Twc[4 * r + 1] * xc[1] + (double)Twc[4 * r + 2] * xc[2]) + Twc[4 * r + 3];
       }
       // ---- tracklets, incrementally (same chains as Tracking::GetStaticTrack)
-      F.track.assign(nf, -1); F.pos.assign(nf, 0);
-      MapFrame& P = ts->map.back();
-      const int fcur = (int)ts->map.size();
-      for (int j = 0; j < nf; j++) {
-        const int p = F.asso[j];
-        if (p < 0) continue;
-        if (P.track[p] >= 0) {
-          TrackInfo& T = ts->tracks[P.track[p]];
-          F.track[j] = P.track[p];
-          F.pos[j] = T.len;
-          T.len++;
-        } else {
-          const int t = (int)ts->tracks.size();
-          ts->tracks.push_back({fcur - 1, 2, -1, -1});
-          P.track[p] = t; P.pos[p] = 0;
-          F.track[j] = t; F.pos[j] = 1;
-        }
-      }
+      link_static_tracks(ts, F);
       memcpy(F.Twc, Twc, sizeof Twc);
       memcpy(F.Twc_rf, Twc, sizeof Twc);
       if (ts->vio) memcpy(ts->fr.back().Tcw, curTcw, sizeof curTcw);
@@ -1891,6 +1900,60 @@ static int prefetch_array(vido_ctx* ctx, cudaStream_t cs, void* dst, const void*
 // ---------------------------------------------------------------------------------------------------------
 // vido_track_prefetch: remember the frames the NEXT vido_track_frames call will start with.  While the back-end of the
 // current call works through its last batch, their copy and front-end already run in the idle pipeline slot.
+// ---------------------------------------------------------------------------------------------------------
+// device-chained static back-end (chain_kernels.cu): eligibility, queueing, consumption of the finished records
+// ---------------------------------------------------------------------------------------------------------
+// A frame can go through the chain when nothing of the object / inertial machinery is involved and the tracker state fits the
+// chain's buffers (always true from the second tracked frame on: RenewFrameInfo caps the static features at MaxTrackPointBG+1).
+static bool chain_eligible(vido_ctx* ctx, const FrontFrame& ff, const vido_frame_inputs& in) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  const vido_config& c = ctx->cfg;
+  if (getenv("VIDO_NO_CHAIN")) return false;   // debug: host-driven path only
+  if (!ts->initialised || ts->vio || !c.b_joint || in.write_back_depth) return false;
+  if (!ts->lo_corres.empty() || !ff.ob_sem.empty() || !ts->lo_sem.empty()) return false;
+  return (int)(ts->last_corres.size() / 2) <= chain_capacity(ctx);
+}
+
+// the record of frame `slot` -> Map frame, host mirrors of the tracker state, per-frame outputs; then the window solve of the
+// frame is staged and queued at once (the host-driven path defers it to the next frame's kernels to hide it; here the device
+// is already busy with the following frames)
+static int chain_consume(vido_ctx* ctx, int slot, const FrontFrame& ff, float* Tcw_out, vido_track_stats* st) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  const vido_config& c = ctx->cfg;
+  const int32_t* hdr; const float *Tcw, *Twc, *rel, *vel, *xy, *depth, *p3, *corres, *flow; const int32_t* asso;
+  int rc = chain_wait_record(ctx, slot, &hdr, &Tcw, &Twc, &rel, &vel, &xy, &depth, &p3, &corres, &flow, &asso);
+  if (rc) return rc;
+  if (st) { memset(st, 0, sizeof *st); st->n_keypoints = (int)ff.kps.size(); st->ba_iterations = -1; }
+  memcpy(Tcw_out, Tcw, sizeof(float) * 16);
+  if (hdr[0] == 1) {   // lost tracking: nothing was processed (see back_end)
+    rc = ba_flush_deferred(ctx);
+    ts->f_id++; ts->frames_seen++;
+    return rc ? rc : 1;
+  }
+  const int nf = hdr[7];
+  MapFrame F;
+  F.xy.assign(xy, xy + 2 * (size_t)nf); F.depth.assign(depth, depth + nf); F.p3.assign(p3, p3 + 3 * (size_t)nf);
+  F.asso.assign(asso, asso + nf);
+  link_static_tracks(ts, F);
+  memcpy(F.Twc, Twc, sizeof(float) * 16); memcpy(F.Twc_rf, Twc, sizeof(float) * 16); memcpy(F.rel, rel, sizeof(float) * 16);
+  ts->last_keys = F.xy; ts->last_depth = F.depth;
+  ts->last_corres.assign(corres, corres + 2 * (size_t)nf); ts->last_flow.assign(flow, flow + 2 * (size_t)nf);
+  memcpy(ts->lastTcw, Tcw, sizeof(float) * 16);
+  memcpy(ts->mVelocity, vel, sizeof(float) * 16);
+  ts->has_velocity = true;
+  ts->map.push_back(std::move(F));
+  ts->have_last_maps = false;
+  if (st) {
+    st->n_matches = hdr[1]; st->n_init_inliers = hdr[2]; st->init_winner = hdr[3]; st->n_pose_inliers = hdr[6]; st->n_static = nf;
+  }
+  const int window = ts->f_id < c.window_size ? ts->f_id : c.window_size;
+  ts->ba_deferred.valid = true; ts->ba_deferred.window = window; ts->ba_deferred.st = st;
+  ts->f_id++; ts->frames_seen++;
+  rc = ba_flush_deferred(ctx);
+  while (ts->ba_nq > 1 && rc == VIDO_OK) { rc = ba_finish(ctx); ba_writeback_rest(ctx); }
+  return rc;
+}
+
 int trk_prefetch(vido_ctx* ctx, const vido_frame_inputs* in, int nframes) {
   TrackState* ts = (TrackState*)ctx->trk;
   ts->hint.clear();
@@ -1934,6 +1997,33 @@ static int trk_track_chunk_impl(vido_ctx* ctx, const vido_frame_inputs* in, int 
     for (int b = 0; b < B; b++) {
       vido_track_stats* st = stats ? stats + done + b : nullptr;
       ts->cur_t = in[done + b].timestamp;
+      if (chain_eligible(ctx, ff[b], in[done + b])) {
+        // a run of consecutive eligible frames: queue the kernels of all of them, then consume the records in order
+        int e = b;
+        if (!ts->chain_active) {
+          rc = chain_upload_state(ctx, (int)(ts->last_corres.size() / 2), ts->last_keys.data(), ts->last_depth.data(), ts->last_corres.data(),
+                                  ts->last_flow.data(), ts->lastTcw, ts->mVelocity, ts->has_velocity ? 1 : 0);
+          if (rc) return rc;
+          ts->chain_active = true;
+        }
+        const size_t K = ts->kp_cap;
+        while (e < B && !in[done + e].write_back_depth && ff[e].ob_sem.empty()) {
+          rc = chain_enqueue_frame(ctx, F.d_kp + e * K, F.d_nkp + e, F.d_kpmask + e * K, F.d_kpdepth + e * K, F.d_kpflow + 2 * e * K,
+                                   F.in_depth + (size_t)e * px, F.in_flow + 2 * (size_t)e * px, F.in_mask + (size_t)e * px, e);
+          if (rc) return rc;
+          e++;
+        }
+        for (int k = b; k < e; k++) {
+          vido_track_stats* sk = stats ? stats + done + k : nullptr;
+          ts->cur_t = in[done + k].timestamp;
+          rc = chain_consume(ctx, k, ff[k], Tcw_out + 16 * (size_t)(done + k), sk);
+          if (rc < 0) return rc;
+          if (sk) { sk->ms_orb = front_ms; sk->ms_assoc = 0; }
+        }
+        b = e - 1;
+        continue;
+      }
+      ts->chain_active = false;   // the host-driven path owns the state again (its vectors mirror the device state)
       rc = back_end(ctx, F, ff[b], b, Tcw_out + 16 * (size_t)(done + b), st);
       if (rc < 0) return rc;
       if (st) { st->ms_orb = front_ms; st->ms_assoc = 0; }
@@ -2210,6 +2300,7 @@ int trk_export_full_graph(vido_ctx* ctx, int32_t* sizes, float* se3, float* poin
 // after the PartialBatchOptimization of the frame.
 static int trk_apply_scaled_rotation_impl(vido_ctx* ctx, const float* R, float s) {
   TrackState* ts = (TrackState*)ctx->trk;
+  ts->chain_active = false;   // the last-frame pose changes below: a chained run re-uploads the state
   int rc = ba_flush_deferred(ctx);
   while (ts->ba_nq > 0 && rc == VIDO_OK) { rc = ba_finish(ctx); ba_writeback_rest(ctx); }
   if (rc) return rc;
