@@ -1,0 +1,120 @@
+"""CPU: an independent re-solve of the sliding-window graph, the way the reference's linear solver sees it.
+
+The reference hands the FULL system (poses + points, no Schur complement) to CSparse's sparse Cholesky
+(3rdparty/g2o/g2o/solvers/linear_solver_csparse.h:108-141).  The oracle (oracle/ba_oracle.cc) and the product eliminate the
+points first.  Here one Levenberg-Marquardt trial is restated with numpy / scipy.sparse only: the full H = sum rho' J^T Omega J
+and b = -sum rho' J^T Omega e are assembled edge by edge (block_solver.hpp:502-560, base_binary_edge.hpp:55-120, Huber
+robust_kernel_impl.cpp:78-91), damped with lambda = tau max|H_jj| (optimization_algorithm_levenberg.cpp:61-120), solved with a
+sparse direct solver, applied with the vertices' oplus, and the robust chi2 / gain ratio / next lambda are evaluated -- and
+compared with the oracle's first iteration.  Only the per-edge error / Jacobian functions are shared with the oracle (they are
+checked against central differences in test_ba_oracle.py)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+import ba_synth
+import oracle_lib as ol
+
+
+def quat_from_R(R):  # Eigen::Quaterniond(Matrix3d)
+    t = R[0, 0] + R[1, 1] + R[2, 2]
+    if t > 0:
+        s = np.sqrt(t + 1.0)
+        w = 0.5 * s; s = 0.5 / s
+        return np.array([w, (R[2, 1] - R[1, 2]) * s, (R[0, 2] - R[2, 0]) * s, (R[1, 0] - R[0, 1]) * s])
+    i = int(np.argmax([R[0, 0], R[1, 1], R[2, 2]]))
+    j, k = (i + 1) % 3, (i + 2) % 3
+    s = np.sqrt(R[i, i] - R[j, j] - R[k, k] + 1.0)
+    q = np.zeros(4)
+    q[1 + i] = 0.5 * s; s = 0.5 / s
+    q[0] = (R[k, j] - R[j, k]) * s; q[1 + j] = (R[j, i] + R[i, j]) * s; q[1 + k] = (R[k, i] + R[i, k]) * s
+    return q
+
+
+def R_from_quat(q):
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def pose_from_f32(T):  # Converter::toSE3Quat: rotation through a unit quaternion with w >= 0
+    T = np.asarray(T, np.float32).reshape(4, 4).astype(np.float64)
+    q = quat_from_R(T[:3, :3])
+    if q[0] < 0:
+        q = -q
+    q /= np.linalg.norm(q)
+    return np.concatenate([R_from_quat(q).reshape(-1), T[:3, 3]])
+
+
+def huber(e, delta):
+    d2 = delta * delta
+    if e <= d2:
+        return e, 1.0
+    s = np.sqrt(e)
+    return 2 * s * delta - d2, delta / s
+
+
+def robust_chi2(X, Z, pts, op, olp, meas, info_cam, info_3d, d_cam, d_3d):
+    chi = 0.0
+    for i in range(len(X) - 1):
+        e, _, _ = ol.edge_se3(X[i], X[i + 1], Z[i])
+        chi += huber(info_cam * e @ e, d_cam)[0]
+    for o in range(len(op)):
+        e, _, _ = ol.edge_se3_pointxyz(X[op[o]], pts[olp[o]], meas[o])
+        chi += huber(info_3d * e @ e, d_3d)[0]
+    return chi
+
+
+@pytest.mark.parametrize("W,P,seed", [(6, 60, 1), (10, 150, 2)])
+def test_full_system_sparse_solve_matches_oracle_first_iteration(W, P, seed):
+    pr = ba_synth.make_window(W=W, P=P, seed=seed, pose_noise=0.03, obs_noise=0.03)
+    info_cam, info_3d = 1.0 / float(np.float32(0.0001)), 1.0 / float(np.float32(16.0))
+    d_cam = d_3d = float(np.float32(0.01))
+    X = [pose_from_f32(T) for T in pr["poses"]]
+    Z = [pose_from_f32(T) for T in pr["rel"]]
+    pts = pr["points"].astype(np.float64)
+    op, olp, meas = pr["obs_pose"], pr["obs_point"], pr["obs_xyz"].astype(np.float64)
+    n = 6 * W + 3 * P
+    rows, cols, vals = [], [], []
+    b = np.zeros(n)
+
+    def add(i0, j0, B):
+        for r in range(B.shape[0]):
+            for c in range(B.shape[1]):
+                rows.append(i0 + r); cols.append(j0 + c); vals.append(B[r, c])
+
+    for i in range(W - 1):
+        e, Ji, Jj = ol.edge_se3(X[i], X[i + 1], Z[i])
+        w = huber(info_cam * e @ e, d_cam)[1] * info_cam
+        a, c = 6 * i, 6 * (i + 1)
+        add(a, a, w * Ji.T @ Ji); add(c, c, w * Jj.T @ Jj); add(a, c, w * Ji.T @ Jj); add(c, a, w * Jj.T @ Ji)
+        b[a:a + 6] -= w * Ji.T @ e; b[c:c + 6] -= w * Jj.T @ e
+    for o in range(len(op)):
+        e, Jp, Jl = ol.edge_se3_pointxyz(X[op[o]], pts[olp[o]], meas[o])
+        w = huber(info_3d * e @ e, d_3d)[1] * info_3d
+        a, c = 6 * int(op[o]), 6 * W + 3 * int(olp[o])
+        add(a, a, w * Jp.T @ Jp); add(c, c, w * Jl.T @ Jl); add(a, c, w * Jp.T @ Jl); add(c, a, w * Jl.T @ Jp)
+        b[a:a + 6] -= w * Jp.T @ e; b[c:c + 3] -= w * Jl.T @ e
+    H = sp.coo_matrix((vals, (rows, cols)), shape=(n, n)).tocsc()
+    chi0 = robust_chi2(X, Z, pts, op, olp, meas, info_cam, info_3d, d_cam, d_3d)
+    lam = 1e-5 * np.abs(H.diagonal()).max()
+    x = spla.spsolve((H + lam * sp.identity(n, format="csc")).tocsc(), b)
+    Xn = [ol.se3_oplus(X[i], x[6 * i:6 * i + 6]) for i in range(W)]
+    ptn = pts + x[6 * W:].reshape(-1, 3)
+    chi1 = robust_chi2(Xn, Z, ptn, op, olp, meas, info_cam, info_3d, d_cam, d_3d)
+    rho = (chi0 - chi1) / (x @ (lam * x + b) + 1e-3)
+    assert rho > 0 and chi1 < chi0            # the first trial is accepted on these graphs
+    alpha = min(1.0 - (2 * rho - 1) ** 3, 2.0 / 3.0)
+    lam1 = lam * max(1.0 / 3.0, alpha)
+    # ---- the oracle's first LM iteration (Schur complement + dense Cholesky of the reduced system)
+    poses, rel, opts, its, st = ol.ba_partial(pr["poses"], pr["rel"], pr["points"], op, olp, pr["obs_xyz"], max_iterations=1)
+    c, l, trials = st.records()[0]
+    assert its == 1 and trials == 1
+    assert abs(c - chi1) <= 1e-7 * chi1        # same step => same robust chi2 after it
+    assert abs(l - lam1) <= 1e-6 * lam1        # same gain ratio => same damping for the next iteration
+    got = np.stack([pose_from_f32(T) for T in poses])
+    want = np.stack(Xn)
+    assert np.abs(got - want).max() <= 2e-5 * max(np.abs(want).max(), 1.0)   # outputs are float32 matrices
+    assert np.abs(opts - ptn).max() <= 2e-5 * max(np.abs(ptn).max(), 1.0)

@@ -43,3 +43,11 @@ def test_invalid_depths_and_tiny_inputs(ctx):
     r0 = ol.init_model_cam(pr["cur"], pr["pts"], None, pr["Tcw_motion"], pr["K"])
     r1 = ctx.init_model(pr["cur"], pr["pts"], None, pr["Tcw_motion"], pr["K"])
     assert r1[2] == r0[2] == 1 and np.array_equal(r1[0], r0[0]) and np.array_equal(r1[1], r0[1])
+
+
+@pytest.mark.parametrize("k", range(8))
+def test_init_model_matches_opencv_golden(ctx, k):
+    """the product against the OpenCV goldens (same rule as the CPU test of the oracle), incl. badly wrong motion priors"""
+    import test_pnp_golden as tg
+    g = np.load(tg.GOLD)
+    tg.check_case(g, k, ctx.init_model)

@@ -25,7 +25,8 @@
 #define BC_LPS 12        // row stride of the panel buffer in doubles: the 8 rows x 4 doubles of a fragment load then touch every
                          // bank exactly twice (stride 8 or 9 would give 4-way conflicts)
 #define BC_MAXT 18       // block rows at the largest window (W = 24: n = 144)
-#define BC_BULK_WARPS 12 // warps 0,1,2, 4,5,6, 8,9,10, 12,13,14: the scheduler of warps 3,7,11,15 belongs to the chain warp (15) alone
+#define BC_BULK_WARPS 12 // warps 0,1,2, 4,5,6, 8,9,10, 12,13,14: the scheduler of warps 3,7,11,15 serves the chain (15) and the helper (11)
+                         // only (measured: with bulk warps on that scheduler the chain's step grows from 1650 to 2100-2500 cycles)
 #define BC_MAX_SLOTS 13  // tiles per bulk warp at BC_MAXT: ceil(152 / 12)
 #define BC_ACTIVE ((BC_BULK_WARPS + 1) * 32)   // threads taking part in the factorisation barriers
 
