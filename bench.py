@@ -9,7 +9,10 @@ frame).  The sequence continues across steps, so after the warm-up the sliding w
   e2e   : the same call with HOST buffers (pinned): H2D copies of image+depth+flow+mask and the D2H of the poses are
           inside the timed region
   roofline : dominant kernel (ba_window_kernel), algorithmic bytes / CUDA-event time against MEASURED_PEAKS.json
-  cpu_baseline : the oracle (CPU restatement of the reference path) on a bounded sample of the same sequence, rank 0 only
+  cpu_baseline : the oracle (CPU restatement of the reference path), built ON THIS BOX with the reference's -O3 -march=native,
+          single thread like the reference, on bounded samples of the same sequence, with its stage buckets
+  vio / dynamic_objects : BASELINE.json configs[2] / configs[3] through the same driver, each with its own resident / end-to-end
+          / CPU numbers (measured after the headline arms, outside their timed regions)
 
   --impl reference : times only the CPU restatement (the reference itself cannot be built here: no OpenCV/Eigen/CSparse
                      C++ in the image) on bounded samples.
@@ -31,8 +34,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 CHUNK = 32   # frames per step (one vido_track_frames call)
 BATCH = 16   # frames per front-end batch inside the call (ctx max_batch)
 REF_CHUNK = 4
+LEG_WARM, LEG_TIMED = 32, 320   # frames of the VIO / dynamic-object legs (warm-up chunk contains the IMU initialisation)
 CAM = dict(width=1242, height=375, fx=718.856, fy=718.856, cx=607.1928, cy=185.2157, bf=386.1448)
 METRIC = "frames/s Tracking+PartialBA on 1242x375 synth seq"
+ORACLE_FLAGS = "-O3 -march=native -ffp-contract=off (oracle/Makefile `native`, built on this box)"
 
 
 def load_pkg():
@@ -42,6 +47,16 @@ def load_pkg():
     sys.modules["vido_slam_b200"] = mod
     spec.loader.exec_module(mod)
     return mod
+
+
+def native_oracle():
+    """the CPU baseline is compiled on the box it is measured on, with the reference's flags (vido_slam/CMakeLists.txt:13-14)"""
+    try:
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "native"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        os.environ["VIDO_ORACLE_LIB"] = os.path.join(ROOT, "oracle", "liboracle_native.so")
+        return ORACLE_FLAGS
+    except Exception:
+        return "-O3 -ffp-contract=off (portable build: `make native` failed on this box)"
 
 
 class ClockSampler(threading.Thread):
@@ -84,36 +99,90 @@ def measured_peak():
     return 6650.0, "fallback"
 
 
+STAGES = ("ms_orb", "ms_assoc", "ms_init", "ms_poseopt", "ms_renew", "ms_ba")
+
+
+def cpu_sample(host_frames, prime, timed, rebuild=1, imu=None, n_objects=0):
+    """the CPU restatement over host frames [0, prime + timed): `prime` untimed, `timed` timed.  Returns frames/s and the mean
+    stage buckets (feature extraction, association, init model, pose optimisation, map update, local BA -- the reference's
+    timing table, src/System.cc:200-233 / src/Tracking.cc:348-359,1121-1139,1319-1330,1451, plus the Frame constructor)"""
+    import oracle_lib as ol
+    tr = ol.OracleTracker(ol.track_config(CAM, rebuild=rebuild))
+    if imu is not None:
+        tr.set_imu(imu["Tbc"], imu["noise"])
+    k = 0
+
+    def one(k):
+        if imu is not None:
+            tr.grab_imu(imu["chunks"][k])
+            return tr.track(*host_frames(k), timestamp=float(imu["t"][k]))
+        return tr.track(*host_frames(k))
+    for _ in range(prime):
+        one(k); k += 1
+    acc = {s: 0.0 for s in STAGES}
+    t0 = time.perf_counter()
+    for _ in range(timed):
+        _, st, _ = one(k); k += 1
+        for s in STAGES:
+            acc[s] += st[s]
+    dt = time.perf_counter() - t0
+    tr.close()
+    return timed / dt, {s: acc[s] / timed for s in STAGES}
+
+
+def cv2_front_end_ms(gray):
+    """cross-check of the oracle's scalar FAST / resize: OpenCV's own (SIMD) cv::resize pyramid + per-cell cv::FAST loop of
+    ORBextractor::ComputeKeyPointsOctTree on one frame, single thread"""
+    try:
+        import cv2
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        import oracle_lib as ol
+        from make_orb_golden import cv_level_candidates
+        cv2.setNumThreads(1)
+        p = ol.default_orb_params()
+        H, W = gray.shape
+        w, h, _ = ol.level_sizes(W, H, p)
+        best = 1e9
+        for _ in range(3):
+            t0 = time.perf_counter()
+            cur = gray
+            for l in range(p.nlevels):
+                if l > 0:
+                    cur = cv2.resize(cur, (int(w[l]), int(h[l])), interpolation=cv2.INTER_LINEAR)
+                cv_level_candidates(cur)
+            best = min(best, (time.perf_counter() - t0) * 1e3)
+        return {"ms_per_frame": best, "what": "cv2.resize x7 + 1231 cv2 FAST calls from a Python loop (its interpreter overhead included), 1 thread",
+                "cv2": cv2.__version__}
+    except Exception as e:
+        return {"error": str(e)[:120]}
+
+
 def reference_arm(args, rank, world):
-    """CPU restatement of the reference path, single thread like the reference (g2o OpenMP off)."""
+    """CPU restatement of the reference path, single thread like the reference (g2o OpenMP off, Tracking is serial: one
+    sequence cannot use more than one core)."""
     if rank != 0:
         return
-    import oracle_lib as ol
+    flags = native_oracle()
     import synth
     sc = synth.Scene(cam=CAM, seed=1234, flow_noise=0.1, depth_noise=0.01)
-    tr = ol.OracleTracker(ol.track_config(CAM, rebuild=1))
     # the window BA reaches its steady-state size (20 poses) after 20 frames: prime at least 24 frames untimed so that
     # the timed sample is the same workload as the GPU arm's (whose warm-up steps cover 96 frames)
     prime = max(args.warmup * REF_CHUNK, 24)
-    steps = min(args.steps, 8)   # bounded sample: <= 32 timed frames (about 2-3 s of CPU work)
+    steps = max(1, min(args.steps, 8))   # bounded sample: <= 32 timed frames (about 2-3 s of CPU work)
     total = prime + steps * REF_CHUNK
     frames = [sc.frame(k) for k in range(total)]
     host = [(f["gray"].numpy(), f["depth_in"].numpy(), f["flow"].numpy(), f["mask"].numpy()) for f in frames]
-    k = 0
-    for _ in range(prime):
-        tr.track(*host[k]); k += 1
     t0 = time.perf_counter()
-    for _ in range(steps * REF_CHUNK):
-        tr.track(*host[k]); k += 1
-    dt = time.perf_counter() - t0
-    fps = steps * REF_CHUNK / dt
-    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+    fps, stage = cpu_sample(lambda k: host[k], prime, steps * REF_CHUNK)
+    dt = steps * REF_CHUNK / fps
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
+            "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "1242x375 KITTI-shape mono VO, synthetic sequence, ORB + PartialBatchOptimization every frame",
                        "frames_per_step": REF_CHUNK, "window": 20, "nfeatures": 2500},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "port",
-                             "sample": f"frames {prime}..{total - 1} of the seed-1234 sequence (CPU restatement; the reference needs OpenCV/Eigen/CSparse C++ which are absent)"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "port", "flags": flags, "stage_ms": stage,
+                             "host_cores": os.cpu_count(),
+                             "sample": f"frames {prime}..{total - 1} of the seed-1234 sequence ({steps} steps of {REF_CHUNK} frames; CPU restatement; the reference needs OpenCV/Eigen/CSparse C++ which are absent)"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -124,7 +193,9 @@ def main():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--cpu-sample", type=int, default=40, help="frames of the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=40, help="frames of the early CPU baseline sample (24 of them untimed)")
+    ap.add_argument("--cpu-late", type=int, default=224, help="frame at which the second CPU sample (16 frames) starts; 0 = skip")
+    ap.add_argument("--no-legs", action="store_true", help="skip the VIO / dynamic-object / FullBatch legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -149,65 +220,79 @@ def main():
 
     # ---- synthetic sequence of this rank (one independent sequence per GPU: weak scaling, no data-path collective)
     total = (args.warmup + args.steps) * CHUNK
-    sc = synth.Scene(cam=CAM, seed=1234 + rank, flow_noise=0.1, depth_noise=0.01, device=str(dev))
+    legs = rank == 0 and world == 1 and not args.no_legs   # the other configurations are measured at N = 1 only
+    nbuf = max(total, LEG_WARM + LEG_TIMED if legs else 0)
     H, W = CAM["height"], CAM["width"]
-    img = torch.empty((total, H, W, 3), dtype=torch.uint8, device=dev)
-    dep = torch.empty((total, H, W), dtype=torch.float32, device=dev)
-    flo = torch.empty((total, H, W, 2), dtype=torch.float32, device=dev)
-    msk = torch.zeros((total, H, W), dtype=torch.int32, device=dev)
-    for k in range(total):
-        f = sc.frame(k)
-        img[k] = f["gray"].unsqueeze(-1).expand(H, W, 3)
-        dep[k] = f["depth_in"]
-        flo[k] = f["flow"]
-    torch.cuda.synchronize()
+    img = torch.empty((nbuf, H, W, 3), dtype=torch.uint8, device=dev)
+    dep = torch.empty((nbuf, H, W), dtype=torch.float32, device=dev)
+    flo = torch.empty((nbuf, H, W, 2), dtype=torch.float32, device=dev)
+    msk = torch.zeros((nbuf, H, W), dtype=torch.int32, device=dev)
+    h_img, h_dep, h_flo, h_msk = (torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (img, dep, flo, msk))
+
+    def fill(scene, n):
+        for k in range(n):
+            f = scene.frame(k)
+            img[k] = f["gray"].unsqueeze(-1).expand(H, W, 3)
+            dep[k] = f["depth_in"]
+            flo[k] = f["flow"]
+            msk[k] = f["mask"]
+        torch.cuda.synchronize()
+        for d, s in ((h_img, img), (h_dep, dep), (h_flo, flo), (h_msk, msk)):
+            d[:n].copy_(s[:n])
+        torch.cuda.synchronize()
+
+    fill(synth.Scene(cam=CAM, seed=1234 + rank, flow_noise=0.1, depth_noise=0.01, device=str(dev)), total)
     bytes_frame = H * W * (3 + 4 + 8 + 4)
-    # pinned host copies for the end-to-end arm
-    h_img, h_dep, h_flo, h_msk = (t.cpu().pin_memory() for t in (img, dep, flo, msk))
 
-    def dev_frames(k0, n):
+    def dev_frames(k0, n, ts=None):
         return [dict(image=img[k].data_ptr(), depth=dep[k].data_ptr(), flow=flo[k].data_ptr(), mask=msk[k].data_ptr(),
-                     channels=3, on_device=True) for k in range(k0, k0 + n)]
+                     channels=3, on_device=True, **({"timestamp": float(ts[k])} if ts is not None else {})) for k in range(k0, k0 + n)]
 
-    def host_frames(k0, n):
-        return [dict(image=h_img[k].numpy(), depth=h_dep[k].numpy(), flow=h_flo[k].numpy(), mask=h_msk[k].numpy())
-                for k in range(k0, k0 + n)]
+    def host_frames(k0, n, ts=None):
+        return [dict(image=h_img[k].numpy(), depth=h_dep[k].numpy(), flow=h_flo[k].numpy(), mask=h_msk[k].numpy(),
+                     **({"timestamp": float(ts[k])} if ts is not None else {})) for k in range(k0, k0 + n)]
 
-    def barrier():
-        if dist is not None:
+    def host_gray(k):
+        return (h_img[k, :, :, 0].numpy().copy(), h_dep[k].numpy(), h_flo[k].numpy(), h_msk[k].numpy())
+
+    def barrier(collective=True):
+        if dist is not None and collective:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_arm(make_frames):
+    def run_arm(make_frames, n_warm, n_steps, ts=None, imu=None, collective=True, before=None):
+        """n_warm + n_steps chunks of CHUNK frames through the public API; the copy (host arm) and the front-end of the next chunk
+        are announced with vido_track_prefetch and run ahead; everything is inside the timed region"""
         ctx.track_reset()
+        if before:
+            before()
         k = 0
-        # while a chunk is processed, the copy (host arm) and the front-end of the next one already run
-        # (vido_track_prefetch); everything stays inside the timed region and goes through the same public API
-        pf = True  # both arms announce the next chunk (vido_track_prefetch): copy + front-end run ahead of the back-end
+        last = (n_warm + n_steps) * CHUNK
+
         def step(kk, want_stats):
-            if pf and kk + 2 * CHUNK <= total:
-                ctx.track_prefetch(make_frames(kk + CHUNK, CHUNK))
-            return ctx.track_frames(make_frames(kk, CHUNK), want_stats=want_stats)
-        for _ in range(args.warmup):
+            if kk + 2 * CHUNK <= last:
+                ctx.track_prefetch(make_frames(kk + CHUNK, CHUNK, ts))
+            return ctx.track_frames(make_frames(kk, CHUNK, ts), want_stats=want_stats, imu=(imu[kk:kk + CHUNK] if imu is not None else None))
+        for _ in range(n_warm):
             step(k, False); k += CHUNK
         ms0, n0, b0 = ctx.kernel_times()
         l0 = ctx.launches
-        barrier()
+        barrier(collective)
         t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         stream = torch.cuda.ExternalStream(ctx.stream)
         e0.record(stream)
         stats = []
-        for _ in range(args.steps):
+        for _ in range(n_steps):
             _, st = step(k, True); k += CHUNK
             stats += st
         e1.record(stream)
-        barrier()
+        barrier(collective)
         wall = time.perf_counter() - t0
         dev_ms = e0.elapsed_time(e1)
         ms1, n1, b1 = ctx.kernel_times()
         elapsed = max(wall, dev_ms * 1e-3)
-        if dist is not None:
+        if dist is not None and collective:
             t = torch.tensor([elapsed], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             elapsed = float(t.item())
@@ -215,8 +300,8 @@ def main():
 
     sampler = ClockSampler(local)
     sampler.start()
-    el_dev, kms, kn, kbytes, launches, stats = run_arm(dev_frames)
-    el_e2e, _, _, _, _, _ = run_arm(host_frames)
+    el_dev, kms, kn, kbytes, launches, stats = run_arm(dev_frames, args.warmup, args.steps)
+    el_e2e, _, _, _, _, _ = run_arm(host_frames, args.warmup, args.steps)
     sampler.stop_flag = True
 
     # ---- outside the timed region: the once-per-sequence stages --------------------------------------------------
@@ -239,79 +324,81 @@ def main():
         extra["full_batch"] = {"frames": int(sizes[0]), "points": int(sizes[2]), "observations": int(sizes[3]),
                                "iterations": int(st_fb.iterations), "trials": int(st_fb.total_trials), "ms": dt_fb * 1e3,
                                "chi2_first": rec[0][0] if rec else None, "chi2_last": rec[-1][0] if rec else None}
+        if legs:   # the same graph through the CPU restatement of FullBatchOptimization
+            import oracle_lib as ol
+            native_oracle()
+            t0 = time.perf_counter()
+            if int(sizes[3]) <= 600000:   # bounded: the CPU solve of larger graphs takes minutes
+                _, _, its_cpu, _ = ol.ba_full(g, npo)
+                extra["full_batch"]["cpu_port_ms"] = (time.perf_counter() - t0) * 1e3
+                extra["full_batch"]["cpu_port_iterations"] = int(its_cpu)
     except Exception as e:  # reported, never fatal for the headline metric
-        extra["full_batch"] = {"error": str(e)[:200]}
-    # (2b) the VIO mode of the driver (BASELINE.json configs[2]): 10 frames/s, 200 Hz IMU riding on the camera; preintegration of
-    #      every frame, InitializeIMU after frame 21 (10 map frames, 2 s), then tracking in the gravity-aligned metric map
-    try:
-        import imu_synth
-        nv = 3 * CHUNK
-        smp, ft, Tbc, _ = imu_synth.make_vio_sequence(nv, fps=10.0, pose_np=imu_synth.vio_camera_pose_10fps_np)
-        imu_chunks = imu_synth.imu_chunks(smp, ft)
-        scv = synth.Scene(cam=CAM, seed=777 + rank, device=str(dev), pose_fn=imu_synth.vio_camera_pose_10fps)
-        for k in range(nv):
-            f = scv.frame(k)
-            img[k] = f["gray"].unsqueeze(-1).expand(H, W, 3); dep[k] = f["depth_in"]; flo[k] = f["flow"]; msk[k] = 0
-        torch.cuda.synchronize()
-        ctx.track_reset()
-        ctx.track_set_imu(Tbc, imu_synth.NOISE)
+        extra.setdefault("full_batch", {})["error"] = str(e)[:200]
 
-        def vio_frames(k0, n):
-            fr = dev_frames(k0, n)
-            for j, d in enumerate(fr):
-                d["timestamp"] = float(ft[k0 + j])
-            return fr
-        ctx.track_frames(vio_frames(0, CHUNK), want_stats=False, imu=imu_chunks[:CHUNK])   # contains the initialisation (frame 21)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        ctx.track_frames(vio_frames(CHUNK, 2 * CHUNK), want_stats=False, imu=imu_chunks[CHUNK:nv])
-        torch.cuda.synchronize()
-        dtv = time.perf_counter() - t0
-        ist = ctx.imu_state()
-        extra["vio"] = {"value": 2 * CHUNK / dtv, "unit": "frames/s", "imu_hz": 200, "frames_per_s_input": 10,
-                        "imu_initialized": int(ist.initialized), "init_frame": int(ist.init_frame), "scale": float(ist.scale),
-                        "gyro_bias": [float(x) for x in ist.bg], "inertial_lm": [int(ist.lm_iterations), int(ist.lm_trials)],
-                        "workload": "VIO mode (BASELINE.json configs[2]): noise-free depth / flow, 20 IMU samples per frame, inputs resident in HBM; timed after the initialisation"}
-    except Exception as e:
-        extra["vio"] = {"error": str(e)[:200]}
-    finally:
+    flags = native_oracle() if rank == 0 else None
+
+    def leg(name, scene, workload, ts=None, imu=None, imu_cpu=None, before=None):
+        """one of BASELINE.json's other single-GPU configurations through the same driver: resident, end-to-end and CPU numbers"""
+        out = {"unit": "frames/s", "workload": workload, "frames_timed": LEG_TIMED}
         try:
+            fill(scene, LEG_WARM + LEG_TIMED)
+            nw, ns = LEG_WARM // CHUNK, LEG_TIMED // CHUNK
+            el, _, _, _, _, st = run_arm(dev_frames, nw, ns, ts=ts, imu=imu, collective=False, before=before)
+            out["value"] = LEG_TIMED / el
+            out["host_ms_per_frame"] = {k: float(np.mean([x[k] for x in st])) for k in ("ms_init", "ms_poseopt", "ms_renew", "ms_ba")}
+            out["objects_per_frame"] = float(np.mean([x["n_objects_ok"] for x in st]))
+            out["object_features_per_frame"] = float(np.mean([x["n_dyn_features"] for x in st]))
+            el2, _, _, _, _, _ = run_arm(host_frames, nw, ns, ts=ts, imu=imu, collective=False, before=before)
+            out["e2e"] = {"value": LEG_TIMED / el2, "unit": "frames/s", "h2d_bytes_per_step": bytes_frame * CHUNK, "d2h_bytes_per_step": 64 * CHUNK}
+            fps, stage = cpu_sample(host_gray, LEG_WARM, 16, imu=imu_cpu)
+            out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": 1, "kind": "port", "flags": flags, "stage_ms": stage,
+                                   "sample": f"frames {LEG_WARM}..{LEG_WARM + 15} of the same sequence"}
+            out["vs_cpu"] = {"resident": out["value"] / fps, "e2e": out["e2e"]["value"] / fps}
+        except Exception as e:
+            out["error"] = str(e)[:200]
+        return out
+
+    if legs:
+        # (2b) VIO mode (BASELINE.json configs[2]): 10 frames/s, 200 Hz IMU riding on the camera; preintegration of every
+        #      frame, InitializeIMU after frame 21 (inside the warm-up chunk), then tracking in the gravity-aligned metric map
+        try:
+            import imu_synth
+            nv = LEG_WARM + LEG_TIMED
+            smp, ft, Tbc, _ = imu_synth.make_vio_sequence(nv, fps=10.0, pose_np=imu_synth.vio_camera_pose_10fps_np)
+            chunks = imu_synth.imu_chunks(smp, ft)
+            extra["vio"] = leg("vio", synth.Scene(cam=CAM, seed=777, device=str(dev), pose_fn=imu_synth.vio_camera_pose_10fps),
+                               "VIO mode (BASELINE.json configs[2]): noise-free depth / flow, 20 IMU samples per frame (200 Hz at 10 frames/s); timed after the IMU initialisation",
+                               ts=ft, imu=chunks, imu_cpu={"Tbc": Tbc, "noise": imu_synth.NOISE, "chunks": chunks, "t": ft},
+                               before=lambda: ctx.track_set_imu(Tbc, imu_synth.NOISE))
+            ist = ctx.imu_state()
+            extra["vio"].update({"imu_hz": 200, "imu_initialized": int(ist.initialized), "init_frame": int(ist.init_frame), "scale": float(ist.scale),
+                                 "gyro_bias": [float(x) for x in ist.bg], "inertial_lm": [int(ist.lm_iterations), int(ist.lm_trials)]})
+        except Exception as e:
+            extra["vio"] = {"error": str(e)[:200]}
+        finally:
+            try:
+                ctx.track_reset()
+                ctx.track_set_imu(None, None)   # back to sensor = RGBD for the remaining legs
+            except Exception:
+                pass
+        # (3) the same driver on a scene with 5 moving objects (BASELINE.json configs[3])
+        extra["dynamic_objects"] = leg("dynamic_objects", synth.Scene(cam=CAM, seed=4321, flow_noise=0.1, depth_noise=0.01, device=str(dev), n_objects=5),
+                                       "5 moving objects / frame, masks + flow, joint static / object-motion tracking (BASELINE.json configs[3])")
+        try:   # joint FullBatch (camera poses, static points, object points, object motions) over the dynamic frames just tracked
             ctx.track_reset()
-            ctx.track_set_imu(None, None)   # back to sensor = RGBD for the remaining legs
-        except Exception:
-            pass
-    # (3) the same driver on a scene with 5 moving objects (BASELINE.json configs[3]); short, rank 0's number is reported
-    try:
-        nd = 3 * CHUNK
-        scd = synth.Scene(cam=CAM, seed=4321 + rank, flow_noise=0.1, depth_noise=0.01, device=str(dev), n_objects=5)
-        for k in range(nd):
-            f = scd.frame(k)
-            img[k] = f["gray"].unsqueeze(-1).expand(H, W, 3); dep[k] = f["depth_in"]; flo[k] = f["flow"]; msk[k] = f["mask"]
-        torch.cuda.synchronize()
-        ctx.track_reset()
-        ctx.track_frames(dev_frames(0, CHUNK), want_stats=False)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        _, sd = ctx.track_frames(dev_frames(CHUNK, 2 * CHUNK), want_stats=True)
-        torch.cuda.synchronize()
-        dtd = time.perf_counter() - t0
-        extra["dynamic_objects"] = {"value": 2 * CHUNK / dtd, "unit": "frames/s", "objects_per_frame": float(np.mean([x["n_objects_ok"] for x in sd])),
-                                    "object_features_per_frame": float(np.mean([x["n_dyn_features"] for x in sd])),
-                                    "host_ms_per_frame": {k: float(np.mean([x[k] for x in sd])) for k in ("ms_init", "ms_poseopt", "ms_renew", "ms_ba")},
-                                    "workload": "5 moving objects / frame, masks + flow (BASELINE.json configs[3]), inputs resident in HBM"}
-        # joint FullBatch (camera poses, static points, object points, object motions) over the 96 dynamic frames just tracked
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        st_d, sz_d = ctx.full_batch()
-        dt_d = time.perf_counter() - t0
-        recd = st_d.records()
-        extra["dynamic_objects"]["full_batch"] = {"frames": int(sz_d[0]), "object_motions": int(sz_d[1]), "points": int(sz_d[2]),
-                                                  "observations": int(sz_d[3]), "ternary_edges": int(sz_d[5]),
-                                                  "iterations": int(st_d.iterations), "trials": int(st_d.total_trials),
-                                                  "cg_iterations": int(st_d.pad), "ms": dt_d * 1e3,
-                                                  "chi2_first": recd[0][0] if recd else None, "chi2_last": recd[-1][0] if recd else None}
-    except Exception as e:
-        extra["dynamic_objects"] = {"error": str(e)[:200]}
+            ctx.track_frames(dev_frames(0, 3 * CHUNK), want_stats=False)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            st_d, sz_d = ctx.full_batch()
+            dt_d = time.perf_counter() - t0
+            recd = st_d.records()
+            extra["dynamic_objects"]["full_batch"] = {"frames": int(sz_d[0]), "object_motions": int(sz_d[1]), "points": int(sz_d[2]),
+                                                      "observations": int(sz_d[3]), "ternary_edges": int(sz_d[5]),
+                                                      "iterations": int(st_d.iterations), "trials": int(st_d.total_trials),
+                                                      "cg_iterations": int(st_d.pad), "ms": dt_d * 1e3,
+                                                      "chi2_first": recd[0][0] if recd else None, "chi2_last": recd[-1][0] if recd else None}
+        except Exception as e:
+            extra["dynamic_objects"]["full_batch"] = {"error": str(e)[:200]}
     frames_total = args.steps * CHUNK * world
     value = frames_total / el_dev
     e2e = frames_total / el_e2e
@@ -323,34 +410,26 @@ def main():
         share = {n: float(v) for n, v in zip(("orb_front_end", "init_model", "pose_opt", "window_ba"), kms)}
         # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), if any
         traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "r1_ba_traffic.json")) as fh:
-                traffic = float(json.load(fh)["dram_bytes_per_launch"])
-        except Exception:
-            pass
-        # CPU baseline: oracle on a bounded sample of the same sequence (frames 0..cpu_sample-1, steady state at its end)
-        import oracle_lib as ol
-        tr = ol.OracleTracker(ol.track_config(CAM, rebuild=1))
+        for name in ("r2_ba_traffic.json", "r1_ba_traffic.json"):
+            try:
+                with open(os.path.join(ROOT, "profiles", name)) as fh:
+                    traffic = float(json.load(fh)["dram_bytes_per_launch"])
+                break
+            except Exception:
+                pass
+        # CPU baseline: the headline sequence again (the legs reused the buffers)
+        fill(synth.Scene(cam=CAM, seed=1234, flow_noise=0.1, depth_noise=0.01, device=str(dev)), min(total, max(args.cpu_sample, args.cpu_late + 16)))
         ncpu = min(args.cpu_sample, total)
-        host = [(h_img[k, :, :, 0].numpy().copy(), h_dep[k].numpy(), h_flo[k].numpy(), h_msk[k].numpy()) for k in range(ncpu)]
         skip = min(24, ncpu // 2)
-        for k in range(skip):
-            tr.track(*host[k])
-        t0 = time.perf_counter()
-        for k in range(skip, ncpu):
-            tr.track(*host[k])
-        cpu_fps = (ncpu - skip) / (time.perf_counter() - t0)
-        tr.close()
+        cpu_fps, cpu_stage = cpu_sample(host_gray, skip, ncpu - skip, rebuild=1)
         # second number "for honesty" (SURVEY 8d): the same CPU path with incremental tracklet bookkeeping instead of the
         # reference's rebuild from frame 0 every frame (only matters for long sequences)
-        tr2 = ol.OracleTracker(ol.track_config(CAM, rebuild=0))
-        for k in range(skip):
-            tr2.track(*host[k])
-        t0 = time.perf_counter()
-        for k in range(skip, ncpu):
-            tr2.track(*host[k])
-        cpu_fps_inc = (ncpu - skip) / (time.perf_counter() - t0)
-        tr2.close()
+        cpu_fps_inc, _ = cpu_sample(host_gray, skip, ncpu - skip, rebuild=0)
+        late = None
+        if args.cpu_late and args.cpu_late + 16 <= total:   # the rebuild grows with the frame index: a second, later sample
+            fa, sa = cpu_sample(host_gray, args.cpu_late, 16, rebuild=1)
+            late = {"first_frame": args.cpu_late, "frames": 16, "value_rebuild": fa, "stage_ms_rebuild": sa}
+        cv2_ms = cv2_front_end_ms(h_img[skip, :, :, 0].numpy().copy())
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": el_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -358,17 +437,19 @@ def main():
             "config": {"workload": "1242x375 KITTI-shape mono VO, synthetic sequence, ORB + PartialBatchOptimization every frame (BASELINE.json configs[1])",
                        "frames_per_step": CHUNK, "front_end_batch": BATCH, "window": 20, "nfeatures": 2500, "max_track_bg": 1000,
                        "sequences": "one per GPU (seed 1234+rank)", "l2": f"inputs ({bytes_frame * CHUNK / 1e6:.0f} MB per step) exceed the 126 MB L2",
-                       "scope": "static scene, VO (the headline); full_batch / dynamic_objects / factor_allgather are measured outside the timed region"},
+                       "scope": "static scene, VO (the headline); vio / dynamic_objects / full_batch / factor_allgather are measured after the headline arms"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": bytes_frame * CHUNK, "d2h_bytes_per_step": 64 * CHUNK},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": "ba_window_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_kind,
-                         "avg_launch_ms": ba_ms, "device_ms_by_stage": share},
-            "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": 1, "kind": "port",
+                         "avg_launch_ms": ba_ms, "device_ms_by_stage": share,
+                         "note": "the window problem is shared-memory / L2 resident: the kernel is bound by FP64 issue and dependent-latency chains, not by HBM (DESIGN.md section 6)"},
+            "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": 1, "kind": "port", "flags": flags, "stage_ms": cpu_stage,
                              "sample": f"frames {skip}..{ncpu - 1} of the same sequence through the CPU restatement (single thread, like the reference)",
-                             "value_incremental_tracklets": cpu_fps_inc, "host_cores": os.cpu_count(),
-                             "one_sequence_per_core_estimate": cpu_fps * (os.cpu_count() or 1)},
+                             "value_incremental_tracklets": cpu_fps_inc, "late_sample": late, "host_cores": os.cpu_count(),
+                             "one_sequence_per_core_estimate": cpu_fps * (os.cpu_count() or 1),
+                             "cv2_front_end_cross_check": cv2_ms},
             **extra,
             "host_ms_per_frame": {k: float(np.mean([x[k] for x in stats])) for k in ("ms_orb", "ms_init", "ms_poseopt", "ms_renew", "ms_ba")},
             "ba_per_frame": {"iterations": float(np.mean([s["ba_iterations"] for s in stats])), "obs": float(np.mean([s["ba_obs"] for s in stats])),

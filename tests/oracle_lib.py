@@ -24,7 +24,7 @@ def default_orb_params(nfeatures=2500):
 def lib():
     global _LIB
     if _LIB is None:
-        path = os.path.join(ROOT, "oracle", "liboracle.so")
+        path = os.environ.get("VIDO_ORACLE_LIB") or os.path.join(ROOT, "oracle", "liboracle.so")   # bench.py: the -march=native build
         if not os.path.exists(path):
             subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
         _LIB = C.CDLL(path)

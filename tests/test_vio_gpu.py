@@ -212,5 +212,5 @@ int main(int argc, char** argv) {
     exe = tmp_path / "facade_vio"
     libdir = os.path.join(root, "vido-slam_b200")
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(libdir, "host"), str(src), "-o", str(exe),
-                           "-L", libdir, "-lvido_b200", "-Wl,-rpath," + libdir, "-ldl", "-lpthread", "-lrt"])
+                           "-L", libdir, "-lvido_slam", "-lvido_b200", "-Wl,-rpath," + libdir, "-ldl", "-lpthread", "-lrt"])
     assert subprocess.call([str(exe), str(yaml)]) == 0
