@@ -130,16 +130,16 @@ __device__ __forceinline__ void bc_trsm_row(const double* D, int ld, const doubl
 //                     of the register-resident tiles (two DMMA per tile, two tiles interleaved), write-back of final tiles.
 // The scheduler of warps 3, 7, 11, 15 serves the chain (and the short helper bursts) only; the issue arbiter prefers high
 // warp ids.  Barriers: STEP (chain + bulk, end of a step), PANEL (panel complete; the chain only arrives), LINV (chain ->
-// helper: block factored), LREADY (helper -> bulk: inverse stored).
+// helper: block factored).
 #define BC_BAR_PANEL 1
 #define BC_BAR_STEP 2
 #define BC_BAR_BULK 3
 #define BC_BAR_LINV 4
-#define BC_BAR_LREADY 5
 #define BC_CHAIN_WARP 15
 #define BC_HELPER_WARP 11
-__device__ __forceinline__ void bc_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(BC_ACTIVE) : "memory"); }
-__device__ __forceinline__ void bc_bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(BC_ACTIVE) : "memory"); }
+// barrier id and thread count are immediates (a register operand takes the slow dispatch path of BAR)
+#define bc_bar_sync(id) asm volatile("bar.sync %0, %1;" ::"n"(id), "n"(BC_ACTIVE) : "memory")
+#define bc_bar_arrive(id) asm volatile("bar.arrive %0, %1;" ::"n"(id), "n"(BC_ACTIVE) : "memory")
 
 // first tile id of block column c (tiles (R, C), R >= C >= 1, without (1,1), numbered column by column)
 __device__ __forceinline__ int bc_tile_off(int c, int T) {
@@ -232,124 +232,90 @@ __device__ __forceinline__ void bc_factor(const CholSm cs, int* s_bad, long long
 #pragma unroll
         for (int m = 0; m < 8; m++) cs.Linv[jb * 64 + m * 8 + c] = x[m];
       }
-      __syncwarp();
-      bc_bar_arrive(BC_BAR_LREADY);
       if (bad) break;
     }
   } else if ((warp & 3) != 3) {
     // =========================== bulk warps ===========================
+    // LEFT-looking for everything the chain does not need at once: at step jb only the tiles that become the next panel
+    // (block column jb+1, rows >= jb+2) and the diagonal tile jb+2 are brought up to date, with ALL the panels 0..jb.  The
+    // updates with the panels 0..jb-1 (already final in S) run while the helper inverts the diagonal factor and the panel of
+    // this step is formed; only the last rank-8 update (panel jb, from the conflict-free buffer Lp) follows the panel.
+    // A right-looking version (every trailing tile resident in registers, updated at every step) was measured first: its work
+    // is front-loaded (104 tiles at step 0, ~2300 cycles against ~1650 of the chain warp) and the first 8 of 15 steps were
+    // bound by it; left-looking the busiest step has 56 tile updates spread over 12 warps, most of them off the critical path.
     const int bw = warp - (warp >> 2), btid = bw * 32 + lane;   // bulk warp / thread index
-    // tile ownership: tile id = bw + 12 * slot, ids run column by column, so the tiles still active at a step are the
-    // slots >= smin(step) of every warp: the update below jumps into an unrolled slot sequence (no per-slot activity test
-    // for retired tiles).  packed = R | C << 8.
-    double c0[BC_MAX_SLOTS + 1], c1[BC_MAX_SLOTS + 1];
-    int tRC[BC_MAX_SLOTS + 1];
-    const int ntiles = bc_tile_off(T, T);
-    const int nsl = (ntiles > bw) ? (ntiles - bw + BC_BULK_WARPS - 1) / BC_BULK_WARPS : 0;
-    {  // tile table: one thread per tile decodes its (R, C); the panel buffer is free until the first step
-      int* tab = (int*)Lp;
-      if (btid < BC_BULK_WARPS * (BC_MAX_SLOTS + 1)) {
-        int t = btid, c = 1, R = -1;
-        while (c < T) {
-          const int cnt = (c == 1) ? T - 2 : T - c;
-          if (t < cnt) { R = ((c == 1) ? 2 : c) + t; break; }
-          t -= cnt; c++;
-        }
-        tab[btid] = (R >= 0) ? (R | (c << 8)) : 0;
-      }
-      asm volatile("bar.sync %0, %1;" ::"n"(BC_BAR_BULK), "n"(BC_BULK_WARPS * 32) : "memory");
-#pragma unroll
-      for (int s = 0; s <= BC_MAX_SLOTS; s++) tRC[s] = tab[bw + BC_BULK_WARPS * s];
-      asm volatile("bar.sync %0, %1;" ::"n"(BC_BAR_BULK), "n"(BC_BULK_WARPS * 32) : "memory");
-    }
-    const double* src = Sg ? Sg : S;
-#pragma unroll
-    for (int s = 0; s <= BC_MAX_SLOTS; s++) {
-      const int R = tRC[s] & 255, c = tRC[s] >> 8;
-      c0[s] = 0; c1[s] = 0;
-      if (s < nsl) {
-        const int row = 8 * R + fr, col = 8 * c + 2 * fk;
-        c0[s] = (row >= col) ? src[row * ld + col] : src[col * ld + row];
-        c1[s] = (row >= col + 1) ? src[row * ld + col + 1] : src[(col + 1) * ld + row];
-      }
-    }
     bc_bar_sync(BC_BAR_STEP);
     long long t0 = 0;
     if (tk && btid == 0) t0 = clock64();
-    const double* const lpf = Lp + fr * BC_LPS + fk;   // fragment base of this lane
+    const double* const lpf = Lp + fr * BC_LPS + fk;   // fragment base of this lane in the panel buffer
     for (int jb = 0; jb < T; jb++) {
-      bc_bar_sync(BC_BAR_LREADY);
-      if (*s_bad) break;
       const int j0 = 8 * jb;
       const bool more = jb + 1 < T;
-      const double* Li = cs.Linv + jb * 64;
-      // ---- panel: L21 = A21 L11^-T for the 8-row tiles of the blocks >= jb+2 (two DMMA each), and the right-hand side row
+      if (*s_bad) break;
+      // ---- panel: rows of the blocks >= jb+2 and the right-hand side row against L11 (thread per row).  (Forming the panel as
+      //      a DMMA product with the inverse of L11 was measured too: the bulk warps then wait for that inverse at every step.)
       {
-        const double b0 = Li[fr * 8 + fk], b1 = Li[fr * 8 + 4 + fk];   // B[k][c] = Linv[c][k]
-        for (int rt = jb + 2 + bw; rt < T; rt += BC_BULK_WARPS) {
-          double* ar = S + (8 * rt + fr) * ld + j0;
-          double r0 = 0, r1 = 0;
-          bc_dmma(r0, r1, ar[fk], b0);
-          bc_dmma(r0, r1, ar[4 + fk], b1);
-          __syncwarp();
-          ar[2 * fk] = r0; ar[2 * fk + 1] = r1;
-          double* lp = Lp + (8 * rt + fr) * BC_LPS + 2 * fk;
-          lp[0] = r0; lp[1] = r1;
-        }
-        if (bw == BC_BULK_WARPS - 1 && lane < 8) {
-          double* yr = S + np * ld + j0;
-          double sa = 0, sb = 0;
+        const double* D = S + j0 * ld + j0;
+        const double* dv = cs.dinv + j0;
+        const int i = j0 + 16 + btid;
+        if (i < np) bc_trsm_row(D, ld, dv, S + i * ld + j0, Lp + i * BC_LPS);
+        else if (btid == BC_BULK_WARPS * 32 - 1) bc_trsm_row(D, ld, dv, S + np * ld + j0, nullptr);
+      }
+      // ---- tiles of this step: (R, jb+1) for R = jb+2 .. T-1, then the diagonal tile (jb+2, jb+2); at most two per warp
+      const int ncol = T - jb - 2 > 0 ? T - jb - 2 : 0, nt = ncol + (jb + 2 < T ? 1 : 0);
+      double c0[2] = {0, 0}, c1[2] = {0, 0};
+      int tR[2] = {-1, -1}, tC[2] = {0, 0};
 #pragma unroll
-          for (int m = 0; m < 8; m += 2) {
-            sa = fma(yr[m], Li[lane * 8 + m], sa);
-            sb = fma(yr[m + 1], Li[lane * 8 + m + 1], sb);
-          }
-          __syncwarp(0xffu);
-          yr[lane] = sa + sb;
+      for (int q = 0; q < 2; q++) {
+        const int t = bw + BC_BULK_WARPS * q;
+        if (t >= nt) continue;
+        const int R = (t < ncol) ? jb + 2 + t : jb + 2, C = (t < ncol) ? jb + 1 : jb + 2;
+        tR[q] = R; tC[q] = C;
+        const int row = 8 * R + fr, col = 8 * C + 2 * fk;
+        // the tile's original value: from the global copy of the system when the caller staged only the first panel (its
+        // latency hides behind the updates below: it is added last)
+        const double* src = Sg ? Sg : S;
+        const double o0 = (row >= col) ? src[row * ld + col] : src[col * ld + row];
+        const double o1 = (row >= col + 1) ? src[row * ld + col + 1] : src[(col + 1) * ld + row];
+        double a0 = 0, a1 = 0;
+        double b0 = 0, b1 = 0, e0 = 0, e1 = 0, g0 = 0, g1 = 0;   // four accumulator pairs: the 2 jb DMMA of a tile form four
+                                                                  // chains instead of one (late steps: one tile, many panels)
+        const double* pa = S + (8 * R + fr) * ld + fk;
+        const double* pb = S + (8 * C + fr) * ld + fk;
+        int k = 0;
+        for (; k + 1 < jb; k += 2) {
+          const double x0 = pa[8 * k], x1 = pa[8 * k + 4], y0 = pb[8 * k], y1 = pb[8 * k + 4];
+          const double u0 = pa[8 * k + 8], u1 = pa[8 * k + 12], v0 = pb[8 * k + 8], v1 = pb[8 * k + 12];
+          bc_dmma(a0, a1, -x0, y0);
+          bc_dmma(b0, b1, -u0, v0);
+          bc_dmma(e0, e1, -x1, y1);
+          bc_dmma(g0, g1, -u1, v1);
         }
+        if (k < jb) {
+          const double x0 = pa[8 * k], x1 = pa[8 * k + 4], y0 = pb[8 * k], y1 = pb[8 * k + 4];
+          bc_dmma(a0, a1, -x0, y0);
+          bc_dmma(b0, b1, -x1, y1);
+        }
+        a0 += e0 + o0; a1 += e1 + o1; b0 += g0; b1 += g1;
+        c0[q] = a0 + b0; c1[q] = a1 + b1;
       }
       if (tk && btid == 0) { const long long t1 = clock64(); tk[3] += t1 - t0; tk[18 + 8 * jb] = t1 - t0; t0 = t1; }
       bc_bar_sync(BC_BAR_PANEL);
       if (tk && btid == 0) { const long long t1 = clock64(); tk[19 + 8 * jb] = t1 - t0; }
       if (more) {
-        // ---- trailing update of the owned tiles, C -= L(R,jb) L(C,jb)^T as two DMMA (k = 0..3, 4..7), two tiles interleaved
-        //      (the two DMMA of a tile depend on each other); tiles that received their last update go back to shared
-        //      memory: block column jb+1 (the next panel) and the diagonal tile jb+2.  Active tile ids at step jb: >= fa(jb)
-        //      = first id of column jb+1, +1 for its diagonal tile (the chain warp owns it by now); the ones below fa(jb+1)
-        //      are final.  The pair that contains slot smin may start one slot early: that tile is retired, its registers
-        //      are dead, updating them is harmless (it is not written back: s >= smin).
-        const int fa = (jb == 0) ? 0 : bc_tile_off(jb + 1, T) + 1;
-        const int fn = bc_tile_off(jb + 2, T) + 1;
-        const int smin = (fa > bw) ? (fa - bw + BC_BULK_WARPS - 1) / BC_BULK_WARPS : 0;
-        const int sfl = (fn > bw) ? (fn - bw + BC_BULK_WARPS - 1) / BC_BULK_WARPS : 0;
-#define BC_UPD2(s)                                                                                         \
-  case (s) / 2: {                                                                                          \
-    if ((s) >= nsl) break;                                                                                 \
-    const int Ra_ = tRC[s] & 255, Ca_ = tRC[s] >> 8, Rb_ = tRC[(s) + 1] & 255, Cb_ = tRC[(s) + 1] >> 8;    \
-    const double* paa_ = lpf + Ra_ * (8 * BC_LPS);                                                         \
-    const double* pba_ = lpf + Ca_ * (8 * BC_LPS);                                                         \
-    const double* pab_ = lpf + Rb_ * (8 * BC_LPS);                                                         \
-    const double* pbb_ = lpf + Cb_ * (8 * BC_LPS);                                                         \
-    const double a0_ = paa_[0], a1_ = paa_[4], b0_ = pba_[0], b1_ = pba_[4];                               \
-    const double e0_ = pab_[0], e1_ = pab_[4], f0_ = pbb_[0], f1_ = pbb_[4];                               \
-    bc_dmma(c0[s], c1[s], -a0_, b0_);                                                                      \
-    bc_dmma(c0[(s) + 1], c1[(s) + 1], -e0_, f0_);                                                          \
-    bc_dmma(c0[s], c1[s], -a1_, b1_);                                                                      \
-    bc_dmma(c0[(s) + 1], c1[(s) + 1], -e1_, f1_);                                                          \
-    if ((s) >= smin && (s) < sfl) {                                                                        \
-      double* dst_ = S + (8 * Ra_ + fr) * ld + 8 * Ca_ + 2 * fk;                                           \
-      dst_[0] = c0[s]; dst_[1] = c1[s];                                                                    \
-    }                                                                                                      \
-    if ((s) + 1 < sfl && (s) + 1 < nsl) {                                                                  \
-      double* dst_ = S + (8 * Rb_ + fr) * ld + 8 * Cb_ + 2 * fk;                                           \
-      dst_[0] = c0[(s) + 1]; dst_[1] = c1[(s) + 1];                                                        \
-    }                                                                                                      \
-  }
-        switch (smin >> 1) {
-          BC_UPD2(0) BC_UPD2(2) BC_UPD2(4) BC_UPD2(6) BC_UPD2(8) BC_UPD2(10) BC_UPD2(12)
-          default: break;
+        // ---- the last update of this step's tiles (panel jb, from Lp) and their write-back
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          if (tR[q] < 0) continue;
+          const double* pa = lpf + tR[q] * (8 * BC_LPS);
+          const double* pb = lpf + tC[q] * (8 * BC_LPS);
+          const double x0 = pa[0], x1 = pa[4], y0 = pb[0], y1 = pb[4];
+          double z0 = 0, z1 = 0;
+          bc_dmma(c0[q], c1[q], -x0, y0);
+          bc_dmma(z0, z1, -x1, y1);
+          double* dst = S + (8 * tR[q] + fr) * ld + 8 * tC[q] + 2 * fk;
+          dst[0] = c0[q] + z0; dst[1] = c1[q] + z1;
         }
-#undef BC_UPD2
         if (bw == BC_BULK_WARPS - 1) {  // right-hand side row: y(c) -= L(rhs, jb) . L(c, jb)
           const double* lr = S + np * ld + j0;
           const double r0 = lr[0], r1 = lr[1], r2 = lr[2], r3 = lr[3], r4 = lr[4], r5 = lr[5], r6 = lr[6], r7 = lr[7];
