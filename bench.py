@@ -320,6 +320,10 @@ def main():
         t0 = time.perf_counter()
         st_fb, sizes = ctx.full_batch()
         dt_fb = time.perf_counter() - t0
+        if dist is not None:   # what the gathered factors are for: solve the neighbour's block, compare with the neighbour's own result
+            diff, its = factors.cross_check(ctx, gathered, rank, ctx.map_poses_rf(), device=dev)
+            extra["factor_allgather"]["neighbour_block_max_abs_diff"] = diff
+            extra["factor_allgather"]["neighbour_block_iterations"] = its
         rec = st_fb.records()
         extra["full_batch"] = {"frames": int(sizes[0]), "points": int(sizes[2]), "observations": int(sizes[3]),
                                "iterations": int(st_fb.iterations), "trials": int(st_fb.total_trials), "ms": dt_fb * 1e3,

@@ -105,3 +105,51 @@ def test_pipeline_full_batch_matches_oracle(pkg):
     for k in range(1, n):
         assert ctx.map_objects_rf(k).shape == ctx.map_objects(k)[2].shape
     otr.close(); ctx.close()
+
+
+def _gathered_worker(rank, world, port, q):
+    import os
+    import sys
+    import torch.distributed as dist
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests"))
+    import __graft_entry__ as ge
+    pkg = ge._load_pkg()
+    from vido_slam_b200 import factors
+    import synth
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cam = synth.SMALL
+    sc = synth.Scene(cam=cam, seed=300 + rank, flow_noise=0.1, depth_noise=0.01, n_objects=rank)   # rank 1 has a moving object
+    frames = [sc.frame(k) for k in range(8 + 2 * rank)]
+    ctx = pkg.Context(pkg.default_config(width=cam["width"], height=cam["height"], fx=cam["fx"], fy=cam["fy"], cx=cam["cx"], cy=cam["cy"],
+                                         bf=cam["bf"], max_batch=4))
+    ctx.track_frames([dict(image=f["gray"].numpy(), depth=f["depth_in"].numpy(), flow=f["flow"].numpy(), mask=f["mask"].numpy()) for f in frames],
+                     want_stats=False)
+    g, npo = ctx.export_full_graph()
+    gathered, _ = factors.all_gather_factors(g, npo)
+    ctx.full_batch()
+    diff, its = factors.cross_check(ctx, gathered, rank, ctx.map_poses_rf())
+    q.put((rank, diff, its, len(gathered)))
+    ctx.close()
+    dist.destroy_process_group()
+
+
+def test_gathered_block_solves_like_its_owner():
+    """BASELINE.json configs[4]: after the keyframe-factor all-gather every rank holds every sequence's graph; rank r solves the
+    GATHERED block of rank r+1 and must reproduce that rank's own FullBatchOptimization (two processes share cuda:0 here, the
+    exchange runs over gloo; bench.py --gpus N does the same over NCCL)"""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mctx = mp.get_context("spawn")
+    q = mctx.Queue()
+    procs = [mctx.Process(target=_gathered_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    for rank, diff, its, n in res:
+        assert n == 2 and its >= 1
+        assert diff <= 1e-4, (rank, diff)

@@ -99,6 +99,18 @@ struct BaArgs {
   double* eH;     // [2][W][120] odometry edges: w Ji^T Ji | w Ji^T Jj | w Jj^T Jj | -w Ji^T e | -w Jj^T e, per linearisation buffer
   double* Sg;     // [(np+1) x (np+1)] reduced camera system (lower triangle, row np = right-hand side), assembled by all CTAs
   int capO, capPt, capT;  // observation / point / Schur-term capacity of a worker CTA (shared-memory carving)
+  // chaining inside the kernel: values this window shares with the solve queued in front of it come from that solve's output
+  // block (chain[i] = index of pose i / sorted point W + n in the previous problem, -1 = value from the input block)
+  const int* chain;
+  const float *prev_poses, *prev_rel, *prev_points;
+  // the output block is also written to its pinned host mirror (h_delta = host block - device block, in bytes) followed by a
+  // completion word: the host polls it, so that NOTHING but solver kernels sits on the solver's stream and consecutive
+  // solves can be launched with programmatic dependent launch (prologue of solve k+1 behind the tail of solve k)
+  const char* out_base;   // device output block
+  char* h_out;            // its pinned host mirror (nullptr: no mirror)
+  int out_bytes;
+  volatile int* h_flag;
+  int seq;
 };
 
 __device__ __forceinline__ double warp_sum(double v) {

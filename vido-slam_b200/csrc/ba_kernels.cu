@@ -25,6 +25,9 @@
 // Since J_point = R^T, the point block is (sum_o w_o) * I3: its inverse is a scalar and is applied on the fly.
 #include <cooperative_groups.h>
 
+#include <atomic>
+#include <string>
+
 #include <cfloat>
 #include <cstdlib>
 #include <cstring>
@@ -37,7 +40,7 @@ namespace cg = cooperative_groups;
 size_t ba_window_smem(int W, int capO, int capPt, int capT);
 size_t ba_window_smem_limit();
 int ba_window_configure(size_t max_smem, int* cluster_out);
-cudaError_t ba_window_launch(const BaArgs& a, int cluster, size_t smem, cudaStream_t s);
+cudaError_t ba_window_launch(const BaArgs& a, int cluster, size_t smem, cudaStream_t s, bool programmatic);
 
 __device__ void phase_init(const BaArgs& a, int G, int GT) {
   for (int i = G; i < a.W; i += GT) {
@@ -915,6 +918,7 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_window_big_kernel(BaArgs a) 
 // =========================================================================================================
 // host side
 // =========================================================================================================
+#define BA_DEPTH 3   // window solves that may be queued at once (staging slots)
 struct BaWorkspace {
   int capW = 0, capP = 0, capM = 0;
   int cluster = 8;
@@ -922,23 +926,25 @@ struct BaWorkspace {
   // problem fits and what it needs.  Oversized windows fall back to the L2-resident kernel of this file.
   int cluster_sm = 8;
   size_t smem_limit = 0;
-  bool use_sm2[2] = {false, false};
-  size_t smem2[2] = {0, 0};
+  bool use_sm2[BA_DEPTH] = {};
+  size_t smem2[BA_DEPTH] = {};
   std::vector<int> wk_obs;
+  int seq = 0;                       // launch counter of the shared-memory kernel (completion word in the pinned output mirror)
+  int seq2[BA_DEPTH] = {};
   char* d_base = nullptr;            // solver workspace
-  char* d_in2[2] = {nullptr, nullptr};  // input blocks (two: the next problem is staged while the current one is solved)
-  char* d_out2[2] = {nullptr, nullptr}; // output blocks (two: a solve may be queued behind the one in flight)
+  char* d_in2[BA_DEPTH] = {};  // input blocks (two: the next problem is staged while the current one is solved)
+  char* d_out2[BA_DEPTH] = {}; // output blocks (two: a solve may be queued behind the one in flight)
   BaArgs args;
-  char* h_in2[2] = {nullptr, nullptr};  // pinned mirrors
-  char* h_out2[2] = {nullptr, nullptr};
+  char* h_in2[BA_DEPTH] = {};  // pinned mirrors
+  char* h_out2[BA_DEPTH] = {};
   // chaining: a window queued behind the previous one takes the poses / odometry / points they share straight from the
   // previous solve's output block on the device (gather kernel on the BA stream), so consecutive solves run back to back
-  int* d_chain2[2] = {nullptr, nullptr};   // [capW + capP]: source index in the previous output per pose / sorted point, -1 = host value
-  int* h_chain2[2] = {nullptr, nullptr};
-  bool chained2[2] = {false, false};
-  cudaEvent_t out_done[2] = {nullptr, nullptr};
+  int* d_chain2[BA_DEPTH] = {};   // [capW + capP]: source index in the previous output per pose / sorted point, -1 = host value
+  int* h_chain2[BA_DEPTH] = {};
+  bool chained2[BA_DEPTH] = {};
+  cudaEvent_t out_done[BA_DEPTH] = {};
   struct Flight { int slot, W, P, M; bool want_records; bool sm; };
-  Flight flight[2];
+  Flight flight[BA_DEPTH];
   int nflight = 0;
   int slot = 0;                      // staging slot of the problem being prepared / in flight
   bool prepared = false;
@@ -949,8 +955,8 @@ struct BaWorkspace {
   cudaStream_t up_stream = nullptr;  // uploads the structure part of a staged problem while the previous one is solved
   cudaEvent_t up_done = nullptr;
   size_t values_bytes = 0;           // leading part of the input block holding poses | odometry | points
-  cudaEvent_t ev0[2] = {nullptr, nullptr}, ev1[2] = {nullptr, nullptr};
-  std::vector<int> newid2[2], oldid, first, len, last, keycnt;  // newid per staging slot (needed again at collect)
+  cudaEvent_t ev0[BA_DEPTH] = {}, ev1[BA_DEPTH] = {};
+  std::vector<int> newid2[BA_DEPTH], oldid, first, len, last, keycnt;  // newid per staging slot (needed again at collect)
 };
 
 static size_t al(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -1005,13 +1011,14 @@ int ba_setup(vido_ctx* ctx, int capW, int capP, int capM) {
   p = nullptr; carve_outputs(p, tmp, capW, capP); ws->out_bytes = (size_t)p;
   VIDO_CUDA(cudaMalloc(&ws->d_base, need));
   VIDO_CUDA(cudaMemset(ws->d_base, 0, need));
-  for (int k = 0; k < 2; k++) {
+  for (int k = 0; k < BA_DEPTH; k++) {
     VIDO_CUDA(cudaMalloc(&ws->d_in2[k], ws->in_bytes));
     VIDO_CUDA(cudaMallocHost(&ws->h_in2[k], ws->in_bytes));
   }
-  for (int k = 0; k < 2; k++) {
+  for (int k = 0; k < BA_DEPTH; k++) {
     VIDO_CUDA(cudaMalloc(&ws->d_out2[k], ws->out_bytes));
-    VIDO_CUDA(cudaMallocHost(&ws->h_out2[k], ws->out_bytes));
+    VIDO_CUDA(cudaMallocHost(&ws->h_out2[k], ws->out_bytes + 64));
+    memset(ws->h_out2[k], 0, ws->out_bytes + 64);
     VIDO_CUDA(cudaMalloc(&ws->d_chain2[k], sizeof(int) * (size_t)(capW + capP)));
     VIDO_CUDA(cudaMallocHost(&ws->h_chain2[k], sizeof(int) * (size_t)(capW + capP)));
     VIDO_CUDA(cudaEventCreateWithFlags(&ws->out_done[k], cudaEventDisableTiming));
@@ -1053,14 +1060,14 @@ void ba_teardown(vido_ctx* ctx) {
   if (ws->stream) { cudaStreamSynchronize(ws->stream); cudaStreamDestroy(ws->stream); }
   if (ws->up_stream) { cudaStreamSynchronize(ws->up_stream); cudaStreamDestroy(ws->up_stream); }
   if (ws->up_done) cudaEventDestroy(ws->up_done);
-  for (int k = 0; k < 2; k++) {
+  for (int k = 0; k < BA_DEPTH; k++) {
     if (ws->ev0[k]) cudaEventDestroy(ws->ev0[k]);
     if (ws->ev1[k]) cudaEventDestroy(ws->ev1[k]);
     if (ws->out_done[k]) cudaEventDestroy(ws->out_done[k]);
     cudaFree(ws->d_out2[k]); cudaFreeHost(ws->h_out2[k]); cudaFree(ws->d_chain2[k]); cudaFreeHost(ws->h_chain2[k]);
   }
-  cudaFree(ws->d_base); cudaFree(ws->d_in2[0]); cudaFree(ws->d_in2[1]);
-  cudaFreeHost(ws->h_in2[0]); cudaFreeHost(ws->h_in2[1]);
+  cudaFree(ws->d_base);
+  for (int k = 0; k < BA_DEPTH; k++) { cudaFree(ws->d_in2[k]); cudaFreeHost(ws->h_in2[k]); }
   delete ws;
   ctx->ba = nullptr;
 }
@@ -1101,8 +1108,8 @@ int ba_prepare_chained(vido_ctx* ctx, const vido_ba_problem* pr, const int* prev
   const int W = pr->n_poses, P = pr->n_points, M = pr->n_obs;
   if (W < 0 || P < 0 || M < 0) return VIDO_ERR_ARG;
   if (W > ws->capW || P > ws->capP || M > ws->capM) { ctx->err = "BA problem exceeds the context capacity"; return VIDO_ERR_CAPACITY; }
-  if (ws->nflight >= 2) { ctx->err = "two window solves are already queued"; return VIDO_ERR_STATE; }
-  const int slot = ws->nflight ? (ws->flight[ws->nflight - 1].slot ^ 1) : ws->slot;
+  if (ws->nflight >= BA_DEPTH) { ctx->err = "too many window solves are queued"; return VIDO_ERR_STATE; }
+  const int slot = ws->nflight ? (ws->flight[ws->nflight - 1].slot + 1) % BA_DEPTH : ws->slot;
   ws->slot = slot;
   char* const h_in = ws->h_in2[slot];
   char* const d_in = ws->d_in2[slot];
@@ -1181,8 +1188,8 @@ int ba_prepare_chained(vido_ctx* ctx, const vido_ba_problem* pr, const int* prev
     ws->values_bytes = vb;
     VIDO_CUDA(cudaMemcpyAsync(d_in + vb, h_in + vb, used - vb, cudaMemcpyHostToDevice, ws->up_stream));
     ws->chained2[slot] = false;
-    if (prev_pose && (prev_point || P == 0) && ws->nflight == 1) {
-      const BaWorkspace::Flight& Fp = ws->flight[0];
+    if (prev_pose && (prev_point || P == 0) && ws->nflight >= 1) {
+      const BaWorkspace::Flight& Fp = ws->flight[ws->nflight - 1];   // the newest solve in the queue
       const std::vector<int>& pnew = ws->newid2[Fp.slot];
       int* hc = ws->h_chain2[slot];
       for (int i = 0; i < W; i++) hc[i] = (prev_pose[i] >= 0 && prev_pose[i] < Fp.W) ? prev_pose[i] : -1;
@@ -1217,8 +1224,8 @@ int ba_prepare_chained(vido_ctx* ctx, const vido_ba_problem* pr, const int* prev
 int ba_launch(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records) {
   BaWorkspace* ws = (BaWorkspace*)ctx->ba;
   if (!ws->prepared) { ctx->err = "ba_launch without ba_prepare"; return VIDO_ERR_ARG; }
-  if (ws->nflight >= 2) { ctx->err = "two window solves are already queued"; return VIDO_ERR_STATE; }
-  if (ws->nflight == 1 && !ws->chained2[ws->slot]) { ctx->err = "a window BA is already in flight"; return VIDO_ERR_ARG; }
+  if (ws->nflight >= BA_DEPTH) { ctx->err = "too many window solves are queued"; return VIDO_ERR_STATE; }
+  if (ws->nflight >= 1 && !ws->chained2[ws->slot]) { ctx->err = "a window BA is already in flight"; return VIDO_ERR_ARG; }
   ws->prepared = false;
   const int W = pr->n_poses, P = pr->n_points, M = pr->n_obs;
   const int slot = ws->slot;
@@ -1240,10 +1247,36 @@ int ba_launch(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records) {
   // then only has to run the gather and the kernel
   VIDO_CUDA(cudaMemcpyAsync(ws->d_in2[slot], ws->h_in2[slot], ws->values_bytes, cudaMemcpyHostToDevice, ws->up_stream));
   VIDO_CUDA(cudaEventRecord(ws->up_done, ws->up_stream));
+  if (ws->use_sm2[slot]) {
+    // Shared-memory resident kernel: nothing but solver kernels on the solver's stream.  The uploads are awaited by the host
+    // (a few tens of microseconds, the host is about to launch anyway), the values shared with the solve in front are gathered
+    // inside the kernel, the results come back through the pinned mirror + completion word.  Consecutive solves are launched
+    // with programmatic stream serialisation: the prologue of this one overlaps the tail of the previous one.
+    VIDO_CUDA(cudaEventSynchronize(ws->up_done));
+    BaArgs b = a;
+    const bool chained = ws->nflight >= 1 && ws->chained2[slot];
+    if (chained) {
+      const BaWorkspace::Flight& Fp = ws->flight[ws->nflight - 1];
+      BaArgs po;
+      { char* q = ws->d_out2[Fp.slot]; carve_outputs(q, po, Fp.W, Fp.P); }
+      b.chain = ws->d_chain2[slot]; b.prev_poses = po.out_poses; b.prev_rel = po.out_rel; b.prev_points = po.out_points;
+    } else { b.chain = nullptr; b.prev_poses = b.prev_rel = b.prev_points = nullptr; }
+    BaArgs ho;
+    char* hq = ws->h_out2[slot]; carve_outputs(hq, ho, W, P);
+    const size_t out_used = want_records ? (size_t)(hq - ws->h_out2[slot]) : (size_t)((char*)ho.rec - ws->h_out2[slot]);
+    b.out_base = ws->d_out2[slot]; b.h_out = ws->h_out2[slot]; b.out_bytes = (int)((out_used + 15) & ~(size_t)15);
+    b.h_flag = (volatile int*)(ws->h_out2[slot] + ws->out_bytes);
+    b.seq = ++ws->seq;
+    ws->seq2[slot] = b.seq;
+    VIDO_CUDA(ba_window_launch(b, ws->cluster_sm, ws->smem2[slot], s, ws->nflight >= 1));
+    ctx->launches++;
+    ws->flight[ws->nflight++] = {slot, W, P, M, want_records, true};
+    return VIDO_OK;
+  }
   VIDO_CUDA(cudaStreamWaitEvent(s, ws->up_done, 0));
-  if (ws->nflight == 1 && ws->chained2[slot]) {
+  if (ws->nflight >= 1 && ws->chained2[slot]) {
     // queued behind the solve in flight (same stream, so it runs after it): shared values come from its output block
-    const BaWorkspace::Flight& Fp = ws->flight[0];
+    const BaWorkspace::Flight& Fp = ws->flight[ws->nflight - 1];
     BaArgs po;
     { char* q = ws->d_out2[Fp.slot]; carve_outputs(q, po, Fp.W, Fp.P); }
     const int total = 16 * W + 16 * std::max(W - 1, 0) + 3 * P;
@@ -1252,12 +1285,7 @@ int ba_launch(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records) {
     ctx->launches++;
   }
   const size_t smem = sizeof(double) * ((size_t)(6 * W + 1) * (6 * W + 1) + 36 * W);
-  if (ws->use_sm2[slot]) {
-    cudaEventRecord(ws->ev0[slot], s);
-    VIDO_CUDA(ba_window_launch(a, ws->cluster_sm, ws->smem2[slot], s));
-    cudaEventRecord(ws->ev1[slot], s);
-    ctx->launches++;
-  } else {
+  {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ws->cluster); cfg.blockDim = dim3(BA_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute at[1];
@@ -1291,11 +1319,26 @@ int ba_collect(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st) {
   BaWorkspace* ws = (BaWorkspace*)ctx->ba;
   if (ws->nflight == 0) { ctx->err = "no window BA in flight"; return VIDO_ERR_ARG; }
   const BaWorkspace::Flight F = ws->flight[0];   // the oldest
-  ws->flight[0] = ws->flight[1];
+  for (int k = 0; k + 1 < ws->nflight; k++) ws->flight[k] = ws->flight[k + 1];
   ws->nflight--;
   const int W = F.W, P = F.P, M = F.M;
   const std::vector<int>& newid = ws->newid2[F.slot];
-  VIDO_CUDA(cudaEventSynchronize(ws->out_done[F.slot]));
+  if (F.sm) {
+    // completion word of the pinned output mirror (written by the kernel after the mirror itself)
+    volatile int* flag = (volatile int*)(ws->h_out2[F.slot] + ws->out_bytes);
+    const int want = ws->seq2[F.slot];
+    long spins = 0;
+    while (*flag != want) {
+      if ((++spins & 0xfff) == 0) {
+        const cudaError_t q = cudaStreamQuery(ws->stream);
+        if (q != cudaSuccess && q != cudaErrorNotReady) { ctx->err = std::string("window BA kernel failed: ") + cudaGetErrorString(q); return VIDO_ERR_CUDA; }
+        if (q == cudaSuccess && *flag != want) { ctx->err = "window BA finished without publishing its results"; return VIDO_ERR_CUDA; }
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+  } else {
+    VIDO_CUDA(cudaEventSynchronize(ws->out_done[F.slot]));
+  }
   BaArgs ho;
   { char* hq = ws->h_out2[F.slot]; carve_outputs(hq, ho, W, P); }
   const LmCtl ctl = *ho.ctl_out;
@@ -1310,7 +1353,8 @@ int ba_collect(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st) {
   }
   {
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, ws->ev0[F.slot], ws->ev1[F.slot]) == cudaSuccess) { ctx->t_ms[3] += ms; ctx->t_n[3]++; }
+    if (F.sm) { ctx->t_ms[3] += (double)tph[7] * 1e-6; ctx->t_n[3]++; }   // the kernel's own %globaltimer span (no events on its stream)
+    else if (cudaEventElapsedTime(&ms, ws->ev0[F.slot], ws->ev1[F.slot]) == cudaSuccess) { ctx->t_ms[3] += ms; ctx->t_n[3]++; }
     const double edges = (double)M + (double)std::max(W - 1, 0);
     ctx->ba_alg_bytes += edges * (296.0 * std::max(ctl.iterations, 0) + 152.0 * (ctl.total_trials + 1));
   }
@@ -1336,6 +1380,15 @@ int ba_collect(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st) {
     }
   }
   return VIDO_OK;
+}
+
+// true when the oldest queued solve has finished (ba_collect will not block)
+bool ba_oldest_done(vido_ctx* ctx) {
+  BaWorkspace* ws = (BaWorkspace*)ctx->ba;
+  if (ws->nflight == 0) return false;
+  const BaWorkspace::Flight& F = ws->flight[0];
+  if (F.sm) return *(volatile int*)(ws->h_out2[F.slot] + ws->out_bytes) == ws->seq2[F.slot];
+  return cudaEventQuery(ws->out_done[F.slot]) == cudaSuccess;
 }
 
 int ba_partial_host(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st) {

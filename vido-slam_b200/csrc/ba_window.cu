@@ -530,6 +530,9 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ba_window_kernel(BaArgs a) {
 #define BW_MARK2() do { if (timer2) t_mark2 = gtime(); } while (0)
 #define BW_TOC2(slot) do { if (timer2) { const unsigned long long t_ = gtime(); tq[slot] += t_ - t_mark2; t_mark2 = t_; } } while (0)
 
+  // programmatic dependent launch: let the solve queued behind this one start its prologue (tables, term lists) right away;
+  // it blocks at griddepcontrol.wait below until this grid has completed and flushed its results
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // ---- tables
   const int npairs = W * (W + 1) / 2;
   if (tid == 0) lm_reset(&sh.ctl);
@@ -538,21 +541,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ba_window_kernel(BaArgs a) {
     while (rem >= W - d) { rem -= W - d; d++; }
     sh.jp1[job] = (unsigned char)rem; sh.jp2[job] = (unsigned char)(rem + d);
   }
-  for (int p = tid; p < W; p += BW_THREADS) {
-    Pose X;
-    pose_from_f32(a.poses_f32 + 16 * p, X);
-    sh.X[0][p] = X;
-    sh.X[1][p] = X;
-  }
   if (rank == 0) {
-    for (int i = tid; i < W - 1; i += BW_THREADS) {
-      Pose Z, I, Zi;
-      pose_from_f32(a.rel_f32 + 16 * i, Z);
-      for (int k = 0; k < 9; k++) I.R[k] = (k % 4 == 0) ? 1.0 : 0.0;
-      I.t[0] = I.t[1] = I.t[2] = 0;
-      pose_inv_mul(Z, I, Zi);
-      sh.Zinv[i] = Zi;
-    }
     if (tid == 0) { sh.Mc = 0; sh.Pc = 0; }
   } else {
     // local point c + j * nwk <-> sorted point index; counts of the round-robin deal in closed form
@@ -591,9 +580,6 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ba_window_kernel(BaArgs a) {
     for (int j = tid; j < Pc; j += BW_THREADS) {
       const int nidx = wk + j * nwk, f = a.pt_first[nidx], len = a.pt_len[nidx];
       ob.pf[j] = (unsigned char)f; ob.plen[j] = (unsigned char)len;
-      ob.px(0)[j] = (double)a.points_f32[3 * (size_t)nidx];
-      ob.py(0)[j] = (double)a.points_f32[3 * (size_t)nidx + 1];
-      ob.pz(0)[j] = (double)a.points_f32[3 * (size_t)nidx + 2];
       const int i = j - sh.lgrp[f], ig = nidx - a.grp_start[f];
       for (int k = 0; k < len; k++) {
         const int o = sh.lbase[f * (W + 1) + k] + i, p = f + k;
@@ -648,6 +634,38 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ba_window_kernel(BaArgs a) {
         rk += (c2 > cnt || (c2 == cnt && j2 < job)) ? 1 : 0;
       }
       sh.jorder[rk] = (unsigned short)job;
+    }
+  }
+  // ---- state values.  Everything above depends on the STRUCTURE of the window only; the values may be outputs of the solve in
+  //      front of this one (same float32 bits as a round trip through the host Map): wait for it here.
+  unsigned long long t_w0 = 0;
+  if (timer) t_w0 = gtime();
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (timer) { const unsigned long long t_ = gtime(); t_start += t_ - t_w0; t_mark = t_; tq[7] = t_ - t_w0; }   // the span excludes the time blocked behind the solve in front
+  for (int p = tid; p < W; p += BW_THREADS) {
+    const int src = a.chain ? a.chain[p] : -1;
+    Pose X;
+    pose_from_f32(src >= 0 ? a.prev_poses + 16 * src : a.poses_f32 + 16 * p, X);
+    sh.X[0][p] = X;
+    sh.X[1][p] = X;
+  }
+  if (rank == 0) {
+    for (int i = tid; i < W - 1; i += BW_THREADS) {
+      const int s0 = a.chain ? a.chain[i] : -1, s1 = a.chain ? a.chain[i + 1] : -1;
+      Pose Z, I, Zi;
+      pose_from_f32((s0 >= 0 && s1 == s0 + 1) ? a.prev_rel + 16 * s0 : a.rel_f32 + 16 * i, Z);
+      for (int k = 0; k < 9; k++) I.R[k] = (k % 4 == 0) ? 1.0 : 0.0;
+      I.t[0] = I.t[1] = I.t[2] = 0;
+      pose_inv_mul(Z, I, Zi);
+      sh.Zinv[i] = Zi;
+    }
+  } else {
+    const int Pc = sh.Pc;
+    for (int j = tid; j < Pc; j += BW_THREADS) {
+      const int nidx = wk + j * nwk;
+      const int src = a.chain ? a.chain[W + nidx] : -1;
+      const float* q = src >= 0 ? a.prev_points + 3 * (size_t)src : a.points_f32 + 3 * (size_t)nidx;
+      ob.px(0)[j] = (double)q[0]; ob.py(0)[j] = (double)q[1]; ob.pz(0)[j] = (double)q[2];
     }
   }
   __syncthreads();
@@ -811,7 +829,18 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ba_window_kernel(BaArgs a) {
       a.out_points[3 * nidx + 2] = (float)ob.pz(fin)[j];
     }
   }
-  cluster.sync();   // no CTA may exit while others can still address its shared memory
+  cluster.sync();   // every CTA's results are in the device block (and no CTA exits while others may address its shared memory)
+  if (rank == 0 && a.h_out) {
+    // mirror the output block into pinned host memory (posted writes over PCIe, ~30 KB) and publish the completion word: the
+    // host polls it instead of waiting on a stream event
+    const int n16 = a.out_bytes >> 4;
+    const uint4* srcv = (const uint4*)a.out_base;
+    uint4* dstv = (uint4*)a.h_out;
+    for (int i = tid; i < n16; i += BW_THREADS) dstv[i] = srcv[i];
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) { *a.h_flag = a.seq; __threadfence_system(); }
+  }
 #undef BW_TOC
 }
 
@@ -852,12 +881,19 @@ int ba_window_configure(size_t max_smem, int* cluster_out) {
   return 0;
 }
 
-cudaError_t ba_window_launch(const BaArgs& a, int cluster, size_t smem, cudaStream_t s) {
+// programmatic: the previous operation on the stream is a solve of this kernel that may still be running -- launch with
+// programmatic stream serialisation (the kernel orders itself behind it with griddepcontrol.wait)
+cudaError_t ba_window_launch(const BaArgs& a, int cluster, size_t smem, cudaStream_t s, bool programmatic) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cluster); cfg.blockDim = dim3(BW_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
+  if (programmatic && !getenv("VIDO_BA_NO_PDL")) {
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   return cudaLaunchKernelEx(&cfg, ba_window_kernel, a);
 }

@@ -158,6 +158,7 @@ int ba_prepare(vido_ctx* ctx, const vido_ba_problem* pr);
 int ba_prepare_chained(vido_ctx* ctx, const vido_ba_problem* pr, const int* prev_pose, const int* prev_point);
 int ba_launch(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records);
 int ba_collect(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st);
+bool ba_oldest_done(vido_ctx* ctx);
 
 // poseopt_kernels.cu
 int po_setup(vido_ctx* ctx, int capN, int capProblems);

@@ -176,6 +176,8 @@ struct TrackState {
   std::vector<float> last_keys, last_depth, last_corres, last_flow;  // mpLastFrame mvStatKeys / mvStatDepth / mvCorres / mvFlowNext
   int f_id = 0;
   int ba_epoch = 0;
+  double ht[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // debug (VIDO_HOST_TIMING): host ms in record wait / consume / BA stage+go / BA retire / enqueue / front-end
+  long hn = 0;
   bool chain_active = false;   // the static tracker state lives on the device (chain_kernels.cu); the host vectors mirror it
   // object state of mpLastFrame: mvObjKeys / mvObjDepth / mvObjCorres / mvObjFlowNext / vSemObjLabel and nModLabel /
   // nSemPosition / bObjStat / vObjMod
@@ -202,12 +204,12 @@ struct TrackState {
     std::vector<int> pframe, pfeat;  // per point: frame / feature of its first observation (initial position)
     std::vector<int> prev_pose, prev_point;  // index of every pose / point in the previous window's problem (-1: not in it)
     int epoch = 0;
-  } job[2];
+  } job[3];
   // Up to two windows are queued on the BA stream: window k+1 is launched BEFORE window k has finished -- the values they
   // share (19 of 20 poses, the odometry between them, every point that stays in the window) are gathered from window k's
   // output on the device -- and window k's results are written back into the Map while window k+1 is already running.
   bool ba_staged = false;
-  int ba_queue[2] = {0, 0}, ba_nq = 0;   // job slots in flight, oldest first
+  int ba_queue[3] = {0, 0, 0}, ba_nq = 0;   // job slots in flight, oldest first
   // the window of frame k is staged and queued while the camera PnP of frame k+1 runs on the GPU (ctx->idle_work)
   struct { bool valid = false; int window = 0; vido_track_stats* st = nullptr; } ba_deferred;
   int ba_deferred_rc = 0;
@@ -378,7 +380,7 @@ void trk_teardown(vido_ctx* ctx) {
 
 int trk_reset(vido_ctx* ctx) {
   TrackState* ts = (TrackState*)ctx->trk;
-  while (ts->ba_nq > 0) { vido_lm_stats ls; ba_collect(ctx, &ts->job[ts->ba_queue[0]].pr, &ls); ts->ba_queue[0] = ts->ba_queue[1]; ts->ba_nq--; }
+  while (ts->ba_nq > 0) { vido_lm_stats ls; ba_collect(ctx, &ts->job[ts->ba_queue[0]].pr, &ls); ts->ba_queue[0] = ts->ba_queue[1]; ts->ba_queue[1] = ts->ba_queue[2]; ts->ba_nq--; }
   ts->ba_deferred.valid = false;
   ts->chain_active = false;
   ts->map.clear(); ts->tracks.clear();
@@ -1064,7 +1066,7 @@ static int ba_finish(vido_ctx* ctx) {
   TrackState* ts = (TrackState*)ctx->trk;
   if (ts->ba_nq == 0) return VIDO_OK;
   TrackState::BaJob& J = ts->job[ts->ba_queue[0]];
-  ts->ba_queue[0] = ts->ba_queue[1];
+  ts->ba_queue[0] = ts->ba_queue[1]; ts->ba_queue[1] = ts->ba_queue[2];
   ts->ba_nq--;
   vido_lm_stats ls;
   int rc = ba_collect(ctx, &J.pr, &ls);
@@ -1108,19 +1110,19 @@ static int ba_stage(vido_ctx* ctx, int WINDOW, vido_track_stats* st) {
   const int N = (int)ts->map.size();
   if (st) { st->ba_iterations = -1; st->ba_points = 0; st->ba_obs = 0; st->ba_trials = 0; }
   if (WINDOW <= 0) return VIDO_OK;
-  if (ts->ba_nq == 2) {   // retire the older of the two queued solves: the new one chains to the newer
+  while (ts->ba_nq == 3 || (ts->ba_nq > 0 && ba_oldest_done(ctx))) {   // retire finished solves; the oldest one when every slot is taken
     int rc0 = ba_finish(ctx);
     if (rc0) return rc0;
     ba_writeback_rest(ctx);
   }
-  if (ts->ba_nq == 1 && ts->job[ts->ba_queue[0]].epoch != ts->ba_epoch) {  // cannot chain: drain first
+  while (ts->ba_nq >= 1 && ts->job[ts->ba_queue[ts->ba_nq - 1]].epoch != ts->ba_epoch) {  // cannot chain to the newest: drain first
     int rc0 = ba_finish(ctx);
     if (rc0) return rc0;
     ba_writeback_rest(ctx);
   }
-  ts->ba_stage_slot = ts->ba_nq ? (ts->ba_queue[ts->ba_nq - 1] ^ 1) : ts->ba_stage_slot;
+  ts->ba_stage_slot = ts->ba_nq ? (ts->ba_queue[ts->ba_nq - 1] + 1) % 3 : ts->ba_stage_slot;
   TrackState::BaJob& J = ts->job[ts->ba_stage_slot];
-  const TrackState::BaJob* Jp = ts->ba_nq ? &ts->job[ts->ba_queue[0]] : nullptr;   // the window in flight, if any
+  const TrackState::BaJob* Jp = ts->ba_nq ? &ts->job[ts->ba_queue[ts->ba_nq - 1]] : nullptr;   // the newest window in the queue: chain to it
   const int start = N - WINDOW;
   J.start = start; J.end = N; J.st = st;
   J.poses.resize(16 * (size_t)WINDOW); J.rel.resize(16 * (size_t)std::max(WINDOW - 1, 0));
@@ -1921,8 +1923,10 @@ static int chain_consume(vido_ctx* ctx, int slot, const FrontFrame& ff, float* T
   TrackState* ts = (TrackState*)ctx->trk;
   const vido_config& c = ctx->cfg;
   const int32_t* hdr; const float *Tcw, *Twc, *rel, *vel, *xy, *depth, *p3, *corres, *flow; const int32_t* asso;
+  const double th0 = now_ms();
   int rc = chain_wait_record(ctx, slot, &hdr, &Tcw, &Twc, &rel, &vel, &xy, &depth, &p3, &corres, &flow, &asso);
   if (rc) return rc;
+  const double th1 = now_ms();
   if (st) { memset(st, 0, sizeof *st); st->n_keypoints = (int)ff.kps.size(); st->ba_iterations = -1; }
   memcpy(Tcw_out, Tcw, sizeof(float) * 16);
   if (hdr[0] == 1) {   // lost tracking: nothing was processed (see back_end)
@@ -1949,8 +1953,14 @@ static int chain_consume(vido_ctx* ctx, int slot, const FrontFrame& ff, float* T
   const int window = ts->f_id < c.window_size ? ts->f_id : c.window_size;
   ts->ba_deferred.valid = true; ts->ba_deferred.window = window; ts->ba_deferred.st = st;
   ts->f_id++; ts->frames_seen++;
+  const double th2 = now_ms();
   rc = ba_flush_deferred(ctx);
-  while (ts->ba_nq > 1 && rc == VIDO_OK) { rc = ba_finish(ctx); ba_writeback_rest(ctx); }
+  const double th3 = now_ms();
+  // finished solves are retired without blocking (ba_stage blocks only when all three slots are taken): the host stays ahead
+  // of the solver stream instead of waiting for the solve before last after every frame
+  while (ts->ba_nq > 0 && rc == VIDO_OK && ba_oldest_done(ctx)) { rc = ba_finish(ctx); ba_writeback_rest(ctx); }
+  const double th4 = now_ms();
+  ts->ht[0] += th1 - th0; ts->ht[1] += th2 - th1; ts->ht[2] += th3 - th2; ts->ht[3] += th4 - th3; ts->hn++;
   return rc;
 }
 
@@ -1968,7 +1978,7 @@ static int trk_track_chunk_impl(vido_ctx* ctx, const vido_frame_inputs* in, int 
   const vido_config& c = ctx->cfg;
   cudaStream_t s = ctx->stream;
   const size_t px = (size_t)c.width * c.height;
-  while (ts->ba_nq > 0) { vido_lm_stats ls; ba_collect(ctx, &ts->job[ts->ba_queue[0]].pr, &ls); ts->ba_queue[0] = ts->ba_queue[1]; ts->ba_nq--; }  // left by a failed call
+  while (ts->ba_nq > 0) { vido_lm_stats ls; ba_collect(ctx, &ts->job[ts->ba_queue[0]].pr, &ls); ts->ba_queue[0] = ts->ba_queue[1]; ts->ba_queue[1] = ts->ba_queue[2]; ts->ba_nq--; }  // left by a failed call
   ts->ba_deferred.valid = false;   // (a successful call never leaves one behind)
   int done = 0;
   while (done < nframes) {
@@ -1993,6 +2003,7 @@ static int trk_track_chunk_impl(vido_ctx* ctx, const vido_frame_inputs* in, int 
     }
     const float* d_depth = F.in_depth;
     const double front_ms = (now_ms() - tf0) / B;
+    ts->ht[5] += now_ms() - tf0;
     if (ts->vio) { rc = vio_preintegrate_batch(ctx, in + done, B); if (rc) return rc; }
     for (int b = 0; b < B; b++) {
       vido_track_stats* st = stats ? stats + done + b : nullptr;
@@ -2007,12 +2018,14 @@ static int trk_track_chunk_impl(vido_ctx* ctx, const vido_frame_inputs* in, int 
           ts->chain_active = true;
         }
         const size_t K = ts->kp_cap;
+        const double te0 = now_ms();
         while (e < B && !in[done + e].write_back_depth && ff[e].ob_sem.empty()) {
           rc = chain_enqueue_frame(ctx, F.d_kp + e * K, F.d_nkp + e, F.d_kpmask + e * K, F.d_kpdepth + e * K, F.d_kpflow + 2 * e * K,
                                    F.in_depth + (size_t)e * px, F.in_flow + 2 * (size_t)e * px, F.in_mask + (size_t)e * px, e);
           if (rc) return rc;
           e++;
         }
+        ts->ht[4] += now_ms() - te0;
         for (int k = b; k < e; k++) {
           vido_track_stats* sk = stats ? stats + done + k : nullptr;
           ts->cur_t = in[done + k].timestamp;
@@ -2040,6 +2053,12 @@ static int trk_track_chunk_impl(vido_ctx* ctx, const vido_frame_inputs* in, int 
     ts->fe_cur ^= 1;
     done += B;
   }
+  if (getenv("VIDO_HOST_TIMING") && ts->hn > 0) {
+    fprintf(stderr, "[host] per frame ms over %ld frames: record wait %.3f, consume %.3f, BA stage+launch %.3f, BA retire wait %.3f, chain enqueue %.3f, front-end collect+launch %.3f\n",
+            ts->hn, ts->ht[0] / ts->hn, ts->ht[1] / ts->hn, ts->ht[2] / ts->hn, ts->ht[3] / ts->hn, ts->ht[4] / ts->hn, ts->ht[5] / ts->hn);
+    for (int k = 0; k < 8; k++) ts->ht[k] = 0;
+    ts->hn = 0;
+  }
   {
     int rc = ba_flush_deferred(ctx);  // drain: stats and map are final when the call returns
     while (ts->ba_nq > 0 && rc == VIDO_OK) { rc = ba_finish(ctx); ba_writeback_rest(ctx); }
@@ -2056,6 +2075,7 @@ int trk_track_chunk(vido_ctx* ctx, const vido_frame_inputs* in, int nframes, flo
   ts->ba_deferred.st = nullptr;
   ts->job[0].st = nullptr;
   ts->job[1].st = nullptr;
+  ts->job[2].st = nullptr;
   if (rc < 0) cudaStreamSynchronize(ctx->stream);   // nothing of a failed call may still read the caller's buffers
   return rc;
 }

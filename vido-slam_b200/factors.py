@@ -75,3 +75,25 @@ def all_gather_factors(g, n_poses, device=None, group=None):
     host = recv.cpu().numpy()
     out = [unpack_graph(host[r * cap:r * cap + sizes[r]]) for r in range(world)]
     return out, dict(bytes_per_rank=sizes, padded_bytes=cap, allgather_ms=ms)
+
+
+def cross_check(ctx, gathered, rank, own_refined, device=None, group=None):
+    """What the gathered factors are for: rank r solves the block of rank (r + 1) % N from the GATHERED graph with the flat-graph
+    solver (vido_ba_full) and compares the refined camera poses with the ones that rank obtained from its own Map
+    (vido_full_batch).  The refined poses of every rank travel in a second, small all-gather.  Returns the largest absolute
+    difference this rank saw (the joint system is block-diagonal by sequence: it must be solver round-off)."""
+    world = dist.get_world_size(group)
+    dev = torch.device(device) if device is not None else torch.device("cpu")
+    counts = [int(n) for _, n in gathered]
+    cap = max(counts)
+    mine = torch.zeros(cap * 16, dtype=torch.float32, device=dev)
+    own = torch.from_numpy(np.ascontiguousarray(own_refined, np.float32).reshape(-1))
+    mine[:own.numel()] = own.to(dev)
+    allp = torch.empty(world * cap * 16, dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(allp, mine, group=group)
+    nb = (rank + 1) % world
+    g, npo = gathered[nb]
+    se3, _, st = ctx.ba_full(g, npo)
+    want = allp.cpu().numpy().reshape(world, cap, 16)[nb, :npo]
+    got = se3[:npo].reshape(npo, 16)
+    return float(np.abs(got - want).max()), int(st.iterations)
