@@ -166,6 +166,11 @@ typedef struct vido_fba_problem {
 } vido_fba_problem;
 void vido_fba_default_params(vido_fba_problem* p);
 int vido_ba_full(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* stats);
+/* The graph as g2o text -- replaces optimizer.save("dynamic_slam_graph_before_opt.g2o" / "..._after_opt.g2o"),
+ * src/Optimizer.cc:1937,1939 (g2o/core/optimizable_graph.cpp:589-622; tags g2o/types/types_slam3d.cpp:37-45).  Host only, no
+ * context.  precision <= 0: 6 digits like the reference's default std::ostream.  vido_full_batch writes both files into the
+ * working directory like the reference when the environment has VIDO_SAVE_G2O=1. */
+int vido_fba_save_g2o(const vido_fba_problem* p, const char* path, int precision);
 
 
 /*

@@ -190,6 +190,7 @@ def load_library():
     lib.vido_fba_default_params.argtypes = [C.POINTER(FbaProblem)]
     lib.vido_ba_full.argtypes = [vp, C.POINTER(FbaProblem), C.POINTER(LmStats)]
     lib.vido_full_batch.argtypes = [vp, C.POINTER(LmStats), vp]
+    lib.vido_fba_save_g2o.argtypes = [C.POINTER(FbaProblem), C.c_char_p, C.c_int]
     lib.vido_map_get_poses_rf.argtypes = [vp, vp, C.c_int]
     lib.vido_map_get_objects_rf.argtypes = [vp, C.c_int, vp, C.c_int]
     lib.vido_map_export_full_graph.argtypes = [vp] + [vp] * 14
@@ -221,6 +222,26 @@ def default_config(**kw):
             raise KeyError(k)
         setattr(cfg, k, v)
     return cfg
+
+
+def save_g2o(path, g, n_poses, precision=0, **params):
+    """the flat FullBatch graph `g` (dict keyed by FBA_KEYS) as g2o text through the C-ABI (vido_fba_save_g2o; host only) --
+    the files of src/Optimizer.cc:1937,1939.  precision 0 = 6 digits like the reference's std::ostream."""
+    lib = load_library()
+    keep = {k: np.array(g[k], dtype=np.float32 if k in FBA_F32 else np.int32, copy=True, order="C") for k in FBA_KEYS}
+    pr = FbaProblem()
+    lib.vido_fba_default_params(C.byref(pr))
+    pr.n_poses = n_poses
+    pr.n_motions = keep["se3"].reshape(-1, 16).shape[0] - n_poses
+    pr.n_points = keep["points"].reshape(-1, 3).shape[0]
+    pr.n_obs, pr.n_e6, pr.n_tern = len(keep["obs_se3"]), len(keep["e6_i"]), len(keep["tern_p1"])
+    for k in FBA_KEYS:
+        setattr(pr, k, keep[k].ctypes.data if keep[k].size else None)
+    for k, v in params.items():
+        setattr(pr, k, v)
+    rc = lib.vido_fba_save_g2o(C.byref(pr), str(path).encode(), precision)
+    if rc != 0:
+        raise VidoError(f"vido_fba_save_g2o({path}) failed: {rc}")
 
 
 def _ptr(a):

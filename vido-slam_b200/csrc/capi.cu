@@ -351,6 +351,11 @@ int vido_ba_full(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* stats) {
   cudaSetDevice(ctx->device);
   return fba_solve_host(ctx, p, stats);
 }
+int vido_fba_save_g2o(const vido_fba_problem* p, const char* path, int precision) {
+  if (!p || !path) return VIDO_ERR_ARG;
+  if (p->n_poses < 0 || p->n_motions < 0 || p->n_points < 0 || p->n_obs < 0 || p->n_e6 < 0 || p->n_tern < 0) return VIDO_ERR_ARG;
+  return fba_save_g2o(p, path, precision);
+}
 int vido_full_batch(vido_ctx* ctx, vido_lm_stats* stats, int32_t* sizes) {
   if (!ctx) return VIDO_ERR_ARG;
   cudaSetDevice(ctx->device);

@@ -159,6 +159,7 @@ int ba_prepare_chained(vido_ctx* ctx, const vido_ba_problem* pr, const int* prev
 int ba_launch(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records);
 int ba_collect(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st);
 bool ba_oldest_done(vido_ctx* ctx);
+int fba_save_g2o(const vido_fba_problem* p, const char* path, int precision);
 
 // poseopt_kernels.cu
 int po_setup(vido_ctx* ctx, int capN, int capProblems);

@@ -2268,8 +2268,12 @@ int trk_full_batch(vido_ctx* ctx, vido_lm_stats* stats, int32_t* sizes) {
   vido_fba_problem pr;
   fill_problem(G, pr);
   if (sizes) { sizes[0] = pr.n_poses; sizes[1] = pr.n_motions; sizes[2] = pr.n_points; sizes[3] = pr.n_obs; sizes[4] = pr.n_e6; sizes[5] = pr.n_tern; }
+  const char* save = getenv("VIDO_SAVE_G2O");   // the two graph files of src/Optimizer.cc:1937,1939, on request
+  const bool save_files = save && save[0] == '1';
+  if (save_files) fba_save_g2o(&pr, "dynamic_slam_graph_before_opt.g2o", 0);
   rc = fba_solve_host(ctx, &pr, stats);
   if (rc) return rc;
+  if (save_files) fba_save_g2o(&pr, "dynamic_slam_graph_after_opt.g2o", 0);
   const int N = G.n_poses;
   for (int i = 1; i < N; i++) memcpy(ts->map[i].Twc_rf, &G.se3[16 * (size_t)i], sizeof(float) * 16);
   for (int i = 1; i < N; i++)
