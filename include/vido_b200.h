@@ -310,9 +310,33 @@ typedef struct vido_track_stats {
   int32_t n_dyn_features, n_objects, n_objects_ok, n_masks_recovered; /* object features leaving the frame; objects found by
                                 DynObjTracking; objects with an estimated motion (bObjStat); labels re-warped by UpdateMask */
 } vido_track_stats;
-/* Tcw_out: nframes x 16 floats (what TrackRGBD returns per frame); stats may be NULL.  Returns VIDO_OK or <0. */
+/* Tcw_out: nframes x 16 floats (what TrackRGBD returns per frame); stats may be NULL.  Returns VIDO_OK or <0.
+ * With a stats array every window optimisation of the call has finished when it returns.  With stats == NULL the last (up to
+ * three) window solves may still be queued on the solver stream: the next call continues behind them, so a stream of calls never
+ * empties the pipeline; vido_sync, every vido_map_* accessor, vido_full_batch, vido_metric_error and vido_ba_partial retire them
+ * first, so no caller can observe a Map that is not final. */
 int vido_track_frames(vido_ctx* ctx, const vido_frame_inputs* frames, int nframes, float* Tcw_out, vido_track_stats* stats);
 int vido_track_reset(vido_ctx* ctx);
+/* Input staging of the demo (vido_slam/demo/run_vido_slam.cc:114-122) on the device, for nframes tightly packed width x height
+ * images each: raw Bayer RG mosaic (8 bit) -> BGR like cv::cvtColor(COLOR_BayerRG2BGR); 16-bit depth -> float like
+ * convertTo(CV_32F); 8-bit mask -> int32 like convertTo(CV_32SC1).  Sources: host or device pointers (NULL = skip that
+ * conversion); destinations: device pointers (3 * width * height bytes / width * height floats / ints per frame), usable as
+ * vido_frame_inputs with on_device = 1 (channels = 3 for the BGR image).  Asynchronous on the context's stream; host sources
+ * must stay unchanged until vido_sync or the next synchronising call. */
+int vido_convert_raw(vido_ctx* ctx, const uint8_t* bayer, const uint16_t* depth16, const uint8_t* mask8, int nframes, uint8_t* d_bgr,
+                     float* d_depth, int32_t* d_mask);
+/* The demo's per-frame sequence in one call (vido_slam/demo/run_vido_slam.cc:112-137): raw inputs as the files hold them (HOST
+ * pointers: Bayer RG mosaic, 16-bit depth, float32 flow, 8-bit mask) -> vido_convert_raw into buffers the context owns ->
+ * vido_track_frames on the device copies (image = the demosaiced BGR, 3 channels).  Same results as converting with OpenCV and
+ * calling vido_track_frames; the host->device traffic is 5.6 instead of 8.9 MB per 1280 x 560 frame. */
+typedef struct vido_raw_inputs {
+  const uint8_t* bayer;      /* height x width */
+  const uint16_t* depth16;   /* height x width */
+  const float* flow;         /* height x width x 2 */
+  const uint8_t* mask8;      /* height x width */
+  double timestamp;
+} vido_raw_inputs;
+int vido_track_raw_frames(vido_ctx* ctx, const vido_raw_inputs* frames, int nframes, float* Tcw_out, vido_track_stats* stats);
 /* Optional hint: start copying the HOST frames that the next vido_track_frames call will pass (at most max_batch of them are
  * taken) while the context is busy with the current call.  The copy runs on its own stream into a second set of input
  * buffers; vido_track_frames recognises the frames by the image pointer of the first one.  The host buffers must stay

@@ -191,6 +191,7 @@ def load_library():
     lib.vido_ba_full.argtypes = [vp, C.POINTER(FbaProblem), C.POINTER(LmStats)]
     lib.vido_full_batch.argtypes = [vp, C.POINTER(LmStats), vp]
     lib.vido_fba_save_g2o.argtypes = [C.POINTER(FbaProblem), C.c_char_p, C.c_int]
+    lib.vido_convert_raw.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp]
     lib.vido_map_get_poses_rf.argtypes = [vp, vp, C.c_int]
     lib.vido_map_get_objects_rf.argtypes = [vp, C.c_int, vp, C.c_int]
     lib.vido_map_export_full_graph.argtypes = [vp] + [vp] * 14
@@ -246,6 +247,15 @@ def save_g2o(path, g, n_poses, precision=0, **params):
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+class PackedFrames:
+    """a marshalled vido_frame_inputs array (Context.pack_frames)"""
+    def __init__(self, arr, keep, n):
+        self.arr, self.keep, self.n = arr, keep, n
+
+    def __len__(self):
+        return self.n
 
 
 class Context:
@@ -392,7 +402,15 @@ class Context:
                 pr.ransac_inliers, pr.mm_inliers)
 
     # ---- per-frame driver
+    def pack_frames(self, frames):
+        """marshal a list of frame dicts once (vido_frame_inputs array); the result can be passed to track_frames /
+        track_prefetch any number of times -- a streaming caller then pays no Python marshalling per call"""
+        arr, keep = self._frame_inputs(frames)
+        return PackedFrames(arr, keep, len(frames))
+
     def _frame_inputs(self, frames):
+        if isinstance(frames, PackedFrames):
+            return frames.arr, frames.keep
         n = len(frames)
         arr = (FrameInputs * n)()
         keep = []
@@ -415,6 +433,21 @@ class Context:
         return arr, keep
 
     # ---- VIO mode (sensor = IMU_RGBD)
+    def convert_raw(self, nframes, d_bgr=None, d_depth=None, d_mask=None, bayer=None, depth16=None, mask8=None):
+        """vido_convert_raw: raw Bayer RG / u16 depth / u8 mask (numpy host arrays or integer device pointers) -> device
+        buffers (integer device pointers) in the tracker's input types; asynchronous on the context's stream"""
+        def src(a):
+            if a is None:
+                return None, None
+            if isinstance(a, int):
+                return a, None
+            a = np.ascontiguousarray(a)
+            return a.ctypes.data, a
+        pb, kb = src(bayer); pd, kd = src(depth16); pm, km = src(mask8)
+        self._check(self.lib.vido_convert_raw(self.h, pb, pd, pm, nframes, d_bgr, d_depth, d_mask))
+        self.sync()   # the host sources (kb, kd, km) may go away after the call
+        return kb, kd, km
+
     def track_set_imu(self, Tbc, noise):
         """Tracking::ParseIMUParamFile: Tbc 4x4, noise (ng, na, ngw, naw) as given to IMU::Calib"""
         if Tbc is None:   # back to sensor = RGBD
@@ -626,3 +659,66 @@ class Context:
         out = np.zeros(nj, IMU_PREINT)
         self._check(self.lib.vido_imu_preintegrate(self.h, _ptr(s), len(s), _ptr(tp), _ptr(tc), nj, _ptr(b), _ptr(nz), _ptr(out)))
         return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# on-disk input formats of the demo (host/InputDecode.h, built into libvido_slam.so)
+_io = None
+
+
+def _io_lib():
+    global _io
+    if _io is None:
+        load_library()   # libvido_slam.so links libvido_b200.so
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libvido_slam.so")
+        if not os.path.exists(path):
+            raise VidoError(f"{path} is missing: run __graft_entry__.build()")
+        _io = C.CDLL(path)
+        _io.vido_io_read_png.argtypes = [C.c_char_p] + [C.POINTER(C.c_int32)] * 4 + [C.c_void_p, C.c_size_t]
+        _io.vido_io_read_flo.argtypes = [C.c_char_p] + [C.POINTER(C.c_int32)] * 2 + [C.c_void_p, C.c_size_t]
+        _io.vido_io_load_kaist_imu.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
+        _io.vido_io_load_kaist_timestamps.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_int]
+    return _io
+
+
+def read_png(path):
+    """cv::imread(path, IMREAD_UNCHANGED) for 8 / 16-bit grey, grey-alpha, RGB(A) PNGs (channels in FILE order, i.e. RGB)"""
+    lib = _io_lib()
+    w, h, ch, bd = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+    if lib.vido_io_read_png(str(path).encode(), C.byref(w), C.byref(h), C.byref(ch), C.byref(bd), None, 0) != 0:
+        raise VidoError(f"cannot decode {path}")
+    a = np.zeros((h.value, w.value, ch.value), np.uint8 if bd.value == 8 else np.uint16)
+    if lib.vido_io_read_png(str(path).encode(), None, None, None, None, a.ctypes.data, a.nbytes) != 0:
+        raise VidoError(f"cannot decode {path}")
+    return a[:, :, 0] if ch.value == 1 else a
+
+
+def read_flo(path):
+    """cv::optflow::readOpticalFlow: [H, W, 2] float32"""
+    lib = _io_lib()
+    w, h = C.c_int32(), C.c_int32()
+    if lib.vido_io_read_flo(str(path).encode(), C.byref(w), C.byref(h), None, 0) != 0:
+        raise VidoError(f"cannot read {path}")
+    a = np.zeros((h.value, w.value, 2), np.float32)
+    if lib.vido_io_read_flo(str(path).encode(), None, None, a.ctypes.data, a.size) != 0:
+        raise VidoError(f"cannot read {path}")
+    return a
+
+
+def load_kaist_imu(path, cap=1 << 21):
+    """LoadIMU of the demo: rows (t [s], ax, ay, az, wx, wy, wz)"""
+    a = np.zeros((cap, 7), np.float64)
+    n = _io_lib().vido_io_load_kaist_imu(str(path).encode(), a.ctypes.data, cap)
+    if n < 0:
+        raise VidoError(f"cannot read {path}")
+    return a[:n].copy()
+
+
+def load_kaist_timestamps(image_dir, cap=1 << 18):
+    """LoadKaistImg of the demo: (file stems [19 characters], times [s])"""
+    t = np.zeros(cap, np.float64)
+    names = C.create_string_buffer(20 * cap)
+    n = _io_lib().vido_io_load_kaist_timestamps(str(image_dir).encode(), t.ctypes.data, names, cap)
+    if n < 0:
+        raise VidoError(f"cannot read {image_dir}/../vTimestampsImage.txt")
+    return [names.raw[20 * i:20 * i + 20].split(b"\0")[0].decode() for i in range(n)], t[:n].copy()

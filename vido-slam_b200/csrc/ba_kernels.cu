@@ -1358,6 +1358,23 @@ int ba_collect(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st) {
     const double edges = (double)M + (double)std::max(W - 1, 0);
     ctx->ba_alg_bytes += edges * (296.0 * std::max(ctl.iterations, 0) + 152.0 * (ctl.total_trials + 1));
   }
+  if (getenv("VIDO_BA_TIMING") && F.sm) {   // gap on the solver stream between the end of the solve in front and this one's release
+    static unsigned long long last_end = 0, gap_sum = 0, blocked_sum = 0, sync_sum = 0, mirror_sum = 0; static int gap_n = 0;
+    if (last_end && tph[16] > last_end && tph[16] - last_end < 5000000ull) {
+      gap_sum += tph[16] - last_end; blocked_sum += tph[18]; gap_n++;
+      sync_sum += tph[19] - tph[17]; mirror_sum += tph[20] - tph[19];
+    }
+    last_end = tph[17];
+    if (atoi(getenv("VIDO_BA_TIMING")) > 1) {
+      static unsigned long long t0 = 0;
+      if (!t0) t0 = tph[21];
+      fprintf(stderr, "[ba-line] seq %d its %d: begin %.1f wait-enter %.1f release %.1f end %.1f mirrored %.1f us\n", ws->seq2[F.slot], ctl.iterations,
+              1e-3 * (double)(tph[21] - t0), 1e-3 * (double)(tph[22] - t0), 1e-3 * (double)(tph[16] - t0), 1e-3 * (double)(tph[17] - t0), 1e-3 * (double)(tph[20] - t0));
+    }
+    if (gap_n && gap_n % 64 == 0)
+      fprintf(stderr, "[ba-gap] mean gap end->release %.1f us (own tail: closing barrier %.1f us, mirror copy %.1f us), blocked in griddepcontrol.wait %.1f us over %d solves\n",
+              1e-3 * gap_sum / gap_n, 1e-3 * sync_sum / gap_n, 1e-3 * mirror_sum / gap_n, 1e-3 * blocked_sum / gap_n, gap_n);
+  }
   if (getenv("VIDO_BA_TIMING") && F.sm)
     fprintf(stderr, "[ba-sm] cluster=%d W=%d P=%d M=%d its=%d trials=%d ns: init=%llu schur=%llu reduce=%llu stage=%llu solve=%llu update+obs=%llu lm=%llu total=%llu | worker 0 own: schur=%llu reduce=%llu load=%llu update=%llu obs=%llu\n",
             ws->cluster_sm, W, P, M, ctl.iterations, ctl.total_trials, tph[5], tph[0], tph[1], tph[6], tph[2], tph[3], tph[4], tph[7], tph[8], tph[9], tph[10], tph[11], tph[12]);

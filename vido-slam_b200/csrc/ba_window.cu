@@ -641,7 +641,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ba_window_kernel(BaArgs a) {
   unsigned long long t_w0 = 0;
   if (timer) t_w0 = gtime();
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (timer) { const unsigned long long t_ = gtime(); t_start += t_ - t_w0; t_mark = t_; tq[7] = t_ - t_w0; }   // the span excludes the time blocked behind the solve in front
+  if (timer) { const unsigned long long t_ = gtime(); tq[4] = t_start; tq[5] = t_w0; t_start += t_ - t_w0; t_mark = t_; tq[7] = t_ - t_w0; tq[6] = t_; }   // the span excludes the time blocked behind the solve in front
   for (int p = tid; p < W; p += BW_THREADS) {
     const int src = a.chain ? a.chain[p] : -1;
     Pose X;
@@ -816,8 +816,10 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ba_window_kernel(BaArgs a) {
     }
     if (tid == 0) {
       if (run) *a.ctl_out = sh.ctl;
-      tph[7] = gtime() - t_start;
+      const unsigned long long t_end = gtime();
+      tph[7] = t_end - t_start;
       for (int k = 0; k < 8; k++) a.t_phase[k] = tph[k];
+      a.t_phase[16] = tq[6]; a.t_phase[17] = t_end; a.t_phase[18] = tq[7]; a.t_phase[21] = tq[4]; a.t_phase[22] = tq[5];   // absolute: released behind the solve in front, end; time blocked
     }
   } else {
     if (timer2) for (int k = 0; k < 8; k++) a.t_phase[8 + k] = tq[k];
@@ -830,6 +832,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ba_window_kernel(BaArgs a) {
     }
   }
   cluster.sync();   // every CTA's results are in the device block (and no CTA exits while others may address its shared memory)
+  const unsigned long long t_sync = timer ? gtime() : 0;
   if (rank == 0 && a.h_out) {
     // mirror the output block into pinned host memory (posted writes over PCIe, ~30 KB) and publish the completion word: the
     // host polls it instead of waiting on a stream event
@@ -839,7 +842,13 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ba_window_kernel(BaArgs a) {
     for (int i = tid; i < n16; i += BW_THREADS) dstv[i] = srcv[i];
     __threadfence_system();
     __syncthreads();
-    if (tid == 0) { *a.h_flag = a.seq; __threadfence_system(); }
+    if (tid == 0) {
+      // debug stamps straight into the mirror (t_phase[19], [20]): after the closing cluster barrier, after the mirror copy
+      unsigned long long* ht = (unsigned long long*)((char*)a.h_out + ((const char*)a.t_phase - (const char*)a.out_base));
+      ht[19] = t_sync; ht[20] = gtime();
+      __threadfence_system();
+      *a.h_flag = a.seq; __threadfence_system();
+    }
   }
 #undef BW_TOC
 }

@@ -99,6 +99,8 @@ void vido_destroy(vido_ctx* ctx) {
   ba_teardown(ctx);
   orb_teardown(ctx);
   if (ctx->um_ws) cudaFree(ctx->um_ws);
+  for (int k = 0; k < 3; k++) if (ctx->raw_stage[k]) cudaFree(ctx->raw_stage[k]);
+  for (int k = 0; k < 4; k++) if (ctx->raw_dev[k]) cudaFree(ctx->raw_dev[k]);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
@@ -111,6 +113,7 @@ void* vido_stream(vido_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int vido_sync(vido_ctx* ctx) {
   if (!ctx) return VIDO_ERR_ARG;
   cudaSetDevice(ctx->device);
+  { int rc = trk_drain(ctx); if (rc) return rc; }   // window solves a vido_track_frames call without statistics left queued
   VIDO_CUDA(cudaStreamSynchronize(ctx->stream));
   return VIDO_OK;
 }
@@ -246,6 +249,7 @@ void vido_ba_default_params(vido_ba_problem* p) {
 int vido_ba_partial(vido_ctx* ctx, vido_ba_problem* p, vido_lm_stats* stats) {
   if (!ctx || !p) return VIDO_ERR_ARG;
   cudaSetDevice(ctx->device);
+  { int rc = trk_drain(ctx); if (rc) return rc; }   // the solver workspace is shared with the tracker's queued window solves
   return ba_partial_host(ctx, p, stats);
 }
 
@@ -350,6 +354,48 @@ int vido_ba_full(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* stats) {
   if (p->n_poses < 0 || p->n_motions < 0 || p->n_points < 0 || p->n_obs < 0 || p->n_e6 < 0 || p->n_tern < 0) { ctx->err = "negative size"; return VIDO_ERR_ARG; }
   cudaSetDevice(ctx->device);
   return fba_solve_host(ctx, p, stats);
+}
+int vido_convert_raw(vido_ctx* ctx, const uint8_t* bayer, const uint16_t* depth16, const uint8_t* mask8, int nframes, uint8_t* d_bgr,
+                     float* d_depth, int32_t* d_mask) {
+  if (!ctx || nframes < 1) return VIDO_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  return input_convert_raw(ctx, bayer, depth16, mask8, nframes, d_bgr, d_depth, d_mask);
+}
+int vido_track_raw_frames(vido_ctx* ctx, const vido_raw_inputs* frames, int nframes, float* Tcw_out, vido_track_stats* stats) {
+  if (!ctx || !frames || !Tcw_out || nframes < 1) return VIDO_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  const size_t px = (size_t)ctx->cfg.width * ctx->cfg.height;
+  const int cap = std::max(1, ctx->cfg.max_batch);
+  if (ctx->raw_dev_frames < cap) {
+    for (int k = 0; k < 4; k++) { if (ctx->raw_dev[k]) cudaFree(ctx->raw_dev[k]); ctx->raw_dev[k] = nullptr; }
+    ctx->raw_dev_frames = 0;
+    const size_t bytes[4] = {3 * px, 4 * px, 8 * px, 4 * px};
+    for (int k = 0; k < 4; k++) VIDO_CUDA(cudaMalloc(&ctx->raw_dev[k], bytes[k] * cap));
+    ctx->raw_dev_frames = cap;
+  }
+  uint8_t* d_bgr = (uint8_t*)ctx->raw_dev[0]; float* d_depth = (float*)ctx->raw_dev[1];
+  float* d_flow = (float*)ctx->raw_dev[2]; int32_t* d_mask = (int32_t*)ctx->raw_dev[3];
+  std::vector<vido_frame_inputs> in(cap);
+  for (int done = 0; done < nframes; done += cap) {
+    const int B = std::min(cap, nframes - done);
+    for (int b = 0; b < B; b++) {
+      const vido_raw_inputs& r = frames[done + b];
+      if (!r.bayer || !r.depth16 || !r.flow || !r.mask8) { ctx->err = "vido_track_raw_frames: a frame has a NULL input"; return VIDO_ERR_ARG; }
+      int rc = input_convert_raw(ctx, r.bayer, r.depth16, r.mask8, 1, d_bgr + 3 * px * b, d_depth + px * b, d_mask + px * b);
+      if (rc) return rc;
+      VIDO_CUDA(cudaMemcpyAsync(d_flow + 2 * px * b, r.flow, 8 * px, cudaMemcpyHostToDevice, ctx->stream));
+      // (one frame at a time: the staging buffers of vido_convert_raw hold a single frame here)
+      vido_frame_inputs& f = in[b];
+      memset(&f, 0, sizeof f);
+      f.image = d_bgr + 3 * px * b; f.channels = 3; f.on_device = 1;
+      f.depth = d_depth + px * b; f.flow = d_flow + 2 * px * b; f.mask = d_mask + px * b;
+      f.timestamp = r.timestamp;
+    }
+    VIDO_CUDA(cudaStreamSynchronize(ctx->stream));   // the front-end reads the converted frames on its own stream
+    int rc = trk_track_chunk(ctx, in.data(), B, Tcw_out + 16 * (size_t)done, stats ? stats + done : nullptr);
+    if (rc < 0) return rc;
+  }
+  return VIDO_OK;
 }
 int vido_fba_save_g2o(const vido_fba_problem* p, const char* path, int precision) {
   if (!p || !path) return VIDO_ERR_ARG;

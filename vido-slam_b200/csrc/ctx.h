@@ -53,6 +53,10 @@ struct vido_ctx {
   double t_ms[4] = {0, 0, 0, 0};   // 0 ORB front-end, 1 init model, 2 pose optimisation, 3 window BA
   int64_t t_n[4] = {0, 0, 0, 0};
   double ba_alg_bytes = 0;         // algorithmic bytes of the BA launches so far (SURVEY.md 8d accounting)
+  void* raw_stage[3] = {nullptr, nullptr, nullptr};   // vido_convert_raw: device staging of host raw image / depth / mask
+  size_t raw_cap[3] = {0, 0, 0};
+  void* raw_dev[4] = {nullptr, nullptr, nullptr, nullptr};   // vido_track_raw_frames: converted BGR / depth / flow / mask of one batch
+  int raw_dev_frames = 0;
 
   // ---- ORB front-end ----
   int nlevels = 0;
@@ -160,6 +164,8 @@ int ba_launch(vido_ctx* ctx, const vido_ba_problem* pr, bool want_records);
 int ba_collect(vido_ctx* ctx, vido_ba_problem* pr, vido_lm_stats* st);
 bool ba_oldest_done(vido_ctx* ctx);
 int fba_save_g2o(const vido_fba_problem* p, const char* path, int precision);
+int input_convert_raw(vido_ctx* ctx, const uint8_t* bayer, const uint16_t* depth16, const uint8_t* mask8, int nframes, uint8_t* d_bgr,
+                      float* d_depth, int32_t* d_mask);
 
 // poseopt_kernels.cu
 int po_setup(vido_ctx* ctx, int capN, int capProblems);
@@ -191,6 +197,7 @@ int trk_reset(vido_ctx* ctx);
 int trk_track_chunk(vido_ctx* ctx, const vido_frame_inputs* in, int nframes, float* Tcw_out, vido_track_stats* stats);
 int trk_prefetch(vido_ctx* ctx, const vido_frame_inputs* in, int nframes);
 void trk_quiesce(vido_ctx* ctx);
+int trk_drain(vido_ctx* ctx);   // retire every queued window solve (Map and solver workspace final afterwards)
 int trk_num_frames(vido_ctx* ctx);
 int trk_get_map_poses(vido_ctx* ctx, float* poses, int cap);
 int trk_get_static(vido_ctx* ctx, int frame, float* xy, float* depth, float* p3, int32_t* asso, int cap);

@@ -178,6 +178,9 @@ struct TrackState {
   int ba_epoch = 0;
   double ht[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // debug (VIDO_HOST_TIMING): host ms in record wait / consume / BA stage+go / BA retire / enqueue / front-end
   long hn = 0;
+  double dt[12] = {0};   // debug (VIDO_HOST_TIMING): host-path ms in mask update / PnP / pose-opt / carry-over / object tracking / object motions / static renewal / object renewal / last-map copies
+  long dn = 0;
+  bool call_failed = false;    // the last vido_track_frames call returned an error: whatever it left queued is discarded
   bool chain_active = false;   // the static tracker state lives on the device (chain_kernels.cu); the host vectors mirror it
   // object state of mpLastFrame: mvObjKeys / mvObjDepth / mvObjCorres / mvObjFlowNext / vSemObjLabel and nModLabel /
   // nSemPosition / bObjStat / vObjMod
@@ -1549,6 +1552,9 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
   double t0 = now_ms();
   // ---- Tracking::UpdateMask (Tracking.cc:353-364): votes of the last frame's object features in the new mask; a lost mask is
   //      re-warped in place and the mask-dependent Frame-ctor stages of this frame are repeated
+  const bool htime = getenv("VIDO_HOST_TIMING") != nullptr;
+  double tm = htime ? now_ms() : 0;
+  auto lap = [&](int k) { if (htime) { const double t_ = now_ms(); ts->dt[k] += t_ - tm; tm = t_; } };
   if (ts->initialised && !ts->lo_sem.empty() && ts->have_last_maps) {
     const int nl = (int)ts->lo_sem.size();
     std::vector<int32_t> uniq(nl), rec(nl);
@@ -1627,6 +1633,7 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
         for (int r = 0; r < 3; r++)
           p3d[3 * i + r] = (float)((double)Twl[4 * r] * xc[0] + (double)Twl[4 * r + 1] * xc[1] + (double)Twl[4 * r + 2] * xc[2]) + Twl[4 * r + 3];
       }
+      lap(0);
       vido_pnp_problem pp;
       memset(&pp, 0, sizeof pp);
       vido_pnp_default_params(&pp);
@@ -1644,6 +1651,7 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
       std::vector<int> TM(ids.begin(), ids.begin() + pp.n_inliers);
       memcpy(curTcw, pp.Tcw_out, sizeof curTcw);
       double t1 = now_ms();
+      lap(1);
       int n_pose_inliers = 0;
       const int n = (int)TM.size();
       if (c.b_joint) {
@@ -1709,6 +1717,7 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
             if (!inl[i]) TM[i] = -1;
       }
       double t2 = now_ms();
+      lap(2);
       // ---- motion model: mVelocity = Tcw * LastTwc
       float LastTwc[16];
       inv44(ts->lastTcw, LastTwc);
@@ -1720,9 +1729,12 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
       if (!ts->lo_corres.empty()) {
         rc = dyn_carry_over(ctx, d_depth, d_flow, d_mask, slot, D);
         if (rc) return rc;
+        lap(3);
         const std::vector<std::vector<int>> ObjIdNew = dyn_track_objects(ctx, curTcw, D);
+        lap(4);
         rc = dyn_object_motions(ctx, curTcw, ObjIdNew, D);
         if (rc) return rc;
+        lap(5);
         if (st) { st->n_objects = (int)ObjIdNew.size(); for (char b : D.stat) st->n_objects_ok += b ? 1 : 0; }
       }
       // ---- RenewFrameInfo (static part).  (1) surviving inliers at their refined positions
@@ -1810,6 +1822,7 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
       memcpy(F.Twc_rf, Twc, sizeof Twc);
       if (ts->vio) memcpy(ts->fr.back().Tcw, curTcw, sizeof curTcw);
       inv44(ts->mVelocity, F.rel);
+      lap(6);
       if (dyn) {  // RenewFrameInfo (object part), Map bookkeeping, dynamic tracklets
         rc = dyn_renew(ctx, ff, curTcw, FS.d_obkeys + 2 * (size_t)slot * ts->obj_cap, d_depth, d_flow, d_mask, slot, D, F);
         if (rc) return rc;
@@ -1819,6 +1832,7 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
       memcpy(ts->lastTcw, curTcw, sizeof curTcw);
       ts->map.push_back(std::move(F));
       double t3 = now_ms();
+      lap(7);
       if (st) {
         st->ms_init = t1 - t0; st->ms_poseopt = t2 - t1; st->ms_renew = t3 - t2;
         st->n_matches = Ns; st->n_init_inliers = pp.n_inliers; st->init_winner = pp.winner; st->n_pose_inliers = n_pose_inliers;
@@ -1841,6 +1855,8 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
   }
   memcpy(Tcw_out, curTcw, sizeof(float) * 16);
   double t4 = now_ms();
+  lap(8);
+  if (htime) ts->dn++;
   const int window = ts->f_id < c.window_size ? ts->f_id : c.window_size;
   // The window of this frame is staged and queued during the next frame's camera PnP (ba_flush_deferred): it chains to the
   // solve in flight on the device, and the host work disappears behind kernels that had to be waited for anyway.
@@ -1978,7 +1994,10 @@ static int trk_track_chunk_impl(vido_ctx* ctx, const vido_frame_inputs* in, int 
   const vido_config& c = ctx->cfg;
   cudaStream_t s = ctx->stream;
   const size_t px = (size_t)c.width * c.height;
-  while (ts->ba_nq > 0) { vido_lm_stats ls; ba_collect(ctx, &ts->job[ts->ba_queue[0]].pr, &ls); ts->ba_queue[0] = ts->ba_queue[1]; ts->ba_queue[1] = ts->ba_queue[2]; ts->ba_nq--; }  // left by a failed call
+  if (ts->call_failed) {   // left by a failed call: discarded.  (Solves a successful call without statistics left queued keep running.)
+    while (ts->ba_nq > 0) { vido_lm_stats ls; ba_collect(ctx, &ts->job[ts->ba_queue[0]].pr, &ls); ts->ba_queue[0] = ts->ba_queue[1]; ts->ba_queue[1] = ts->ba_queue[2]; ts->ba_nq--; }
+    ts->call_failed = false;
+  }
   ts->ba_deferred.valid = false;   // (a successful call never leaves one behind)
   int done = 0;
   while (done < nframes) {
@@ -1994,13 +2013,21 @@ static int trk_track_chunk_impl(vido_ctx* ctx, const vido_frame_inputs* in, int 
     if (rc) return rc;
     // look-ahead: the next batch of this call, or the announced first batch of the next call, goes through copy and
     // front-end in the other slot while this batch's back-end runs
-    {
+    // (On the device-chained path the launch waits until this batch's tracker kernels are queued: they feed the window solver,
+    // whose queue of three solves must not run dry at the batch boundary; the look-ahead has the whole batch to finish.)
+    bool ahead_done = false;
+    auto launch_ahead = [&]() -> int {
+      if (ahead_done) return VIDO_OK;
+      ahead_done = true;
+      const double ta0 = now_ms();
       TrackState::FeSlot& N = ts->fe[ts->fe_cur ^ 1];
       N.launched = false;
-      if (done + B < nframes) rc = fe_launch(ctx, N, in + done + B, std::min(ts->capB, nframes - done - B));
-      else if (!ts->hint.empty()) { rc = fe_launch(ctx, N, ts->hint.data(), (int)ts->hint.size()); ts->hint.clear(); }
-      if (rc) return rc;
-    }
+      int r = VIDO_OK;
+      if (done + B < nframes) r = fe_launch(ctx, N, in + done + B, std::min(ts->capB, nframes - done - B));
+      else if (!ts->hint.empty()) { r = fe_launch(ctx, N, ts->hint.data(), (int)ts->hint.size()); ts->hint.clear(); }
+      ts->ht[5] += now_ms() - ta0;
+      return r;
+    };
     const float* d_depth = F.in_depth;
     const double front_ms = (now_ms() - tf0) / B;
     ts->ht[5] += now_ms() - tf0;
@@ -2026,6 +2053,8 @@ static int trk_track_chunk_impl(vido_ctx* ctx, const vido_frame_inputs* in, int 
           e++;
         }
         ts->ht[4] += now_ms() - te0;
+        rc = launch_ahead();
+        if (rc) return rc;
         for (int k = b; k < e; k++) {
           vido_track_stats* sk = stats ? stats + done + k : nullptr;
           ts->cur_t = in[done + k].timestamp;
@@ -2037,6 +2066,8 @@ static int trk_track_chunk_impl(vido_ctx* ctx, const vido_frame_inputs* in, int 
         continue;
       }
       ts->chain_active = false;   // the host-driven path owns the state again (its vectors mirror the device state)
+      rc = launch_ahead();
+      if (rc) return rc;
       rc = back_end(ctx, F, ff[b], b, Tcw_out + 16 * (size_t)(done + b), st);
       if (rc < 0) return rc;
       if (st) { st->ms_orb = front_ms; st->ms_assoc = 0; }
@@ -2050,6 +2081,8 @@ static int trk_track_chunk_impl(vido_ctx* ctx, const vido_frame_inputs* in, int 
         VIDO_CUDA(cudaStreamSynchronize(s));
       }
     }
+    rc = launch_ahead();
+    if (rc) return rc;
     ts->fe_cur ^= 1;
     done += B;
   }
@@ -2059,11 +2092,30 @@ static int trk_track_chunk_impl(vido_ctx* ctx, const vido_frame_inputs* in, int 
     for (int k = 0; k < 8; k++) ts->ht[k] = 0;
     ts->hn = 0;
   }
+  if (getenv("VIDO_HOST_TIMING") && ts->dn > 0) {
+    fprintf(stderr, "[host-path] per frame ms over %ld frames: mask update %.3f, PnP %.3f, pose-opt %.3f, carry-over %.3f, object tracking %.3f, object motions %.3f, static renewal %.3f, object renewal %.3f, last-map copies %.3f\n",
+            ts->dn, ts->dt[0] / ts->dn, ts->dt[1] / ts->dn, ts->dt[2] / ts->dn, ts->dt[3] / ts->dn, ts->dt[4] / ts->dn, ts->dt[5] / ts->dn, ts->dt[6] / ts->dn, ts->dt[7] / ts->dn, ts->dt[8] / ts->dn);
+    for (int k = 0; k < 12; k++) ts->dt[k] = 0;
+    ts->dn = 0;
+  }
   {
-    int rc = ba_flush_deferred(ctx);  // drain: stats and map are final when the call returns
-    while (ts->ba_nq > 0 && rc == VIDO_OK) { rc = ba_finish(ctx); ba_writeback_rest(ctx); }
+    // With a statistics array the call drains the solver queue: stats and Map are final when it returns.  Without one the last
+    // (up to three) window solves stay queued on the solver stream and the next call continues behind them -- a stream of calls
+    // then never empties the pipeline; every Map accessor, vido_sync, FullBatch and the stand-alone BA entry drain first.
+    int rc = ba_flush_deferred(ctx);
+    if (stats || ts->vio)
+      while (ts->ba_nq > 0 && rc == VIDO_OK) { rc = ba_finish(ctx); ba_writeback_rest(ctx); }
     return rc;
   }
+}
+
+int trk_drain(vido_ctx* ctx) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  if (!ts) return VIDO_OK;
+  if (ts->call_failed) return VIDO_OK;   // the next call discards what the failed one left
+  int rc = ba_flush_deferred(ctx);
+  while (ts->ba_nq > 0 && rc == VIDO_OK) { rc = ba_finish(ctx); ba_writeback_rest(ctx); }
+  return rc;
 }
 
 // The caller's per-frame statistics array only lives for the duration of the call: whatever a failed call leaves queued
@@ -2076,7 +2128,7 @@ int trk_track_chunk(vido_ctx* ctx, const vido_frame_inputs* in, int nframes, flo
   ts->job[0].st = nullptr;
   ts->job[1].st = nullptr;
   ts->job[2].st = nullptr;
-  if (rc < 0) cudaStreamSynchronize(ctx->stream);   // nothing of a failed call may still read the caller's buffers
+  if (rc < 0) { cudaStreamSynchronize(ctx->stream); ts->call_failed = true; }   // nothing of a failed call may still read the caller's buffers
   return rc;
 }
 
@@ -2090,6 +2142,7 @@ int trk_num_frames(vido_ctx* ctx) { return (int)((TrackState*)ctx->trk)->map.siz
 
 int trk_get_map_poses(vido_ctx* ctx, float* poses, int cap) {
   TrackState* ts = (TrackState*)ctx->trk;
+  trk_drain(ctx);
   const int n = (int)ts->map.size();
   for (int i = 0; i < n && i < cap; i++) memcpy(poses + 16 * (size_t)i, ts->map[i].Twc, sizeof(float) * 16);
   return n;
@@ -2097,6 +2150,7 @@ int trk_get_map_poses(vido_ctx* ctx, float* poses, int cap) {
 
 int trk_get_static(vido_ctx* ctx, int frame, float* xy, float* depth, float* p3, int32_t* asso, int cap) {
   TrackState* ts = (TrackState*)ctx->trk;
+  trk_drain(ctx);
   if (frame < 0 || frame >= (int)ts->map.size()) return -1;
   const MapFrame& F = ts->map[frame];
   const int n = (int)F.depth.size();
@@ -2111,6 +2165,7 @@ int trk_get_static(vido_ctx* ctx, int frame, float* xy, float* depth, float* p3,
 
 int trk_get_dynamic(vido_ctx* ctx, int frame, float* xy, float* depth, float* p3, int32_t* asso, int32_t* label, int cap) {
   TrackState* ts = (TrackState*)ctx->trk;
+  trk_drain(ctx);
   if (frame < 0 || frame >= (int)ts->map.size()) return -1;
   const MapFrame& F = ts->map[frame];
   const int n = (int)F.ddepth.size();
@@ -2126,6 +2181,7 @@ int trk_get_dynamic(vido_ctx* ctx, int frame, float* xy, float* depth, float* p3
 
 int trk_get_objects(vido_ctx* ctx, int frame, int32_t* label, int32_t* sem_label, float* motion, float* centre, int cap) {
   TrackState* ts = (TrackState*)ctx->trk;
+  trk_drain(ctx);
   if (frame < 1 || frame >= (int)ts->map.size()) return -1;
   const MapFrame& F = ts->map[frame];
   const int n = (int)F.objects.size();
@@ -2138,6 +2194,7 @@ int trk_get_objects(vido_ctx* ctx, int frame, int32_t* label, int32_t* sem_label
 }
 
 int trk_get_dyn_tracks(vido_ctx* ctx, int32_t* len, int32_t* obj_id, int32_t* first_frame, int32_t* first_feat, int cap) {
+  trk_drain(ctx);
   TrackState* ts = (TrackState*)ctx->trk;
   const int n = (int)ts->dyn_tracks.size();
   for (int i = 0; i < n && i < cap; i++) {
@@ -2307,6 +2364,7 @@ int trk_export_full_graph(vido_ctx* ctx, int32_t* sizes, float* se3, float* poin
                           float* e6_meas, int32_t* obs_se3, int32_t* obs_point, int32_t* obs_kind, float* obs_xyz, int32_t* tern_p1,
                           int32_t* tern_p2, int32_t* tern_h) {
   TrackState* ts = (TrackState*)ctx->trk;
+  { int rc = trk_drain(ctx); if (rc) return rc; }
   FullGraph G;
   build_full_graph(ts, ctx->cfg, G);
   sizes[0] = G.n_poses; sizes[1] = G.n_motions; sizes[2] = (int)(G.points.size() / 3); sizes[3] = (int)G.obs_se3.size();
@@ -2420,6 +2478,7 @@ int trk_get_imu_frames(vido_ctx* ctx, float* Tcw, float* vel, float* bias, int c
 int trk_metric_error(vido_ctx* ctx, const float* cam_gt, int n_gt, int refined, const float* pose_pre, const float* mot_gt, int n_obj,
                      vido_metric* out, float* per_item) {
   TrackState* ts = (TrackState*)ctx->trk;
+  { int rc = trk_drain(ctx); if (rc) return rc; }
   const int n = (int)ts->map.size();
   if (n_gt < n) { ctx->err = "metric: fewer ground-truth poses than map frames"; return VIDO_ERR_ARG; }
   std::vector<float> cam(16 * (size_t)std::max(n, 1)), mot;

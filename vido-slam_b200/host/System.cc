@@ -112,6 +112,7 @@ void System::Init(const std::string& strSettingsFile, const eSensor sensor) {
 // one frame through the driver (Tracking::GrabImageRGBD, src/Tracking.cc:283-456)
 cv::Mat System::track(const cv::Mat& im, cv::Mat& depthmap, const cv::Mat& flowmap, const cv::Mat& masksem, const cv::Mat& mTcw_gt,
                       const double& timestamp, const int& nImage) {
+  (void)mTcw_gt;   // see after_track
   vido_frame_inputs in;
   memset(&in, 0, sizeof in);
   in.image = im.data; in.channels = mat_channels(im); in.on_device = 0;
@@ -121,6 +122,34 @@ cv::Mat System::track(const cv::Mat& im, cv::Mat& depthmap, const cv::Mat& flowm
   float Tcw[16];
   vido_track_stats st;
   const int rc = vido_track_frames(ctx_, &in, 1, Tcw, &st);
+  return after_track(rc, Tcw, st, timestamp, nImage);
+}
+
+// the demo's per-frame sequence (demo/run_vido_slam.cc:112-137) with the pixel conversions on the device
+cv::Mat System::TrackRaw(const uint8_t* bayer, const uint16_t* depth16, const float* flow, const uint8_t* mask8,
+                         const std::vector<IMU::Point>* vImuMeas, const double& timestamp, const int& nImage) {
+  if ((sensor_ == IMU_RGBD) != (vImuMeas != nullptr)) {
+    std::cerr << "ERROR: TrackRaw needs IMU measurements exactly when the sensor is IMU_RGBD." << std::endl;
+    exit(-1);
+  }
+  if (vImuMeas) {
+    std::vector<vido_imu_sample> q(vImuMeas->size());
+    for (size_t i = 0; i < q.size(); i++) {
+      const IMU::Point& m = (*vImuMeas)[i];
+      q[i].t = m.t; q[i].ax = m.ax; q[i].ay = m.ay; q[i].az = m.az; q[i].wx = m.wx; q[i].wy = m.wy; q[i].wz = m.wz;
+    }
+    if (vido_track_grab_imu(ctx_, q.data(), (int)q.size(), 0) < 0) std::cerr << "vido_b200: " << vido_last_error(ctx_) << std::endl;
+  }
+  vido_raw_inputs in;
+  in.bayer = bayer; in.depth16 = depth16; in.flow = flow; in.mask8 = mask8; in.timestamp = timestamp;
+  float Tcw[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  vido_track_stats st;
+  memset(&st, 0, sizeof st);
+  const int rc = vido_track_raw_frames(ctx_, &in, 1, Tcw, &st);
+  return after_track(rc, Tcw, st, timestamp, nImage);
+}
+
+cv::Mat System::after_track(int rc, const float* Tcw, const vido_track_stats& st, double timestamp, int nImage) {
   if (rc < 0) std::cerr << "vido_b200: " << vido_last_error(ctx_) << std::endl;  // the reference prints and continues
   else {
     // the reference's timing table (src/Tracking.cc:348-359,1121-1139,1177-1330,1451): mask update, camera pose estimation,
@@ -132,7 +161,6 @@ cv::Mat System::track(const cv::Mat& im, cv::Mat& depthmap, const cv::Mat& flowm
   trajectory_.insert(trajectory_.end(), Tcw, Tcw + 16);
   // Map::vmCameraPose_GT: the reference only ever stores the identity of the first frame (src/Tracking.cc:1546; the per-frame
   // assignment at :436-444 is commented out), so does this facade -- mTcw_gt is accepted and otherwise unused, like there
-  (void)mTcw_gt;
   if (frame_id_ == 0) { const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}; cam_gt_.assign(I, I + 16); }
   last_t_ = timestamp;
   // f_id == StopFrame (= nImage - 1): the joint optimisation over the whole sequence, KITTI-style data only

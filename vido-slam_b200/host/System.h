@@ -95,11 +95,17 @@ class System {
 
   // ---- additions of this library (no reference counterpart)
   vido_ctx* context() { return ctx_; }
+  // What the demo does per frame (demo/run_vido_slam.cc:112-137) with the pixel conversions on the device: the raw Bayer RG
+  // image, the 16-bit depth, the flow and the 8-bit mask exactly as the files hold them (host/InputDecode.h reads them).
+  // vImuMeas: NULL for an RGBD system, the frame's IMU samples for an IMU_RGBD one.
+  cv::Mat TrackRaw(const uint8_t* bayer, const uint16_t* depth16, const float* flow, const uint8_t* mask8,
+                   const std::vector<IMU::Point>* vImuMeas, const double& timestamp, const int& nImage);
   bool isImuInitialized();   // Tracking::isImuInitialized
 
  private:
   cv::Mat track(const cv::Mat& im, cv::Mat& depthmap, const cv::Mat& flowmap, const cv::Mat& masksem, const cv::Mat& mTcw_gt,
                 const double& timestamp, const int& nImage);
+  cv::Mat after_track(int rc, const float* Tcw, const vido_track_stats& st, double timestamp, int nImage);
   vido_ctx* ctx_ = nullptr;
   vido_config cfg_;
   eSensor sensor_ = RGBD;
