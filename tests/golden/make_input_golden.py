@@ -9,7 +9,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 rng = np.random.default_rng(2024)
 out = {}
-for name, shape in (("a", (23, 38)), ("b", (24, 40)), ("c", (9, 7))):
+for name, shape in (("a", (65, 131)), ("b", (64, 200)), ("c", (71, 96))):   # sizes a context accepts (>= 64)
     raw = rng.integers(0, 256, shape, dtype=np.uint8)
     if name == "b":   # a smooth image too: small differences that rounding must get right
         yy, xx = np.mgrid[0:shape[0], 0:shape[1]]

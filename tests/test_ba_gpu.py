@@ -67,3 +67,14 @@ def test_single_pose_and_empty(ctx):
     rp, rr, rpts, rits, rst = ol.ba_partial(pr["poses"], pr["rel"], pr["points"], pr["obs_pose"], pr["obs_point"], pr["obs_xyz"])
     assert gits == rits
     assert np.abs(gp - rp).max() <= 1e-6
+
+
+def test_largest_window_matches_oracle(pkg):
+    """window_size 24 (n = 144 unknowns: the fifth 32-row chunk of the back substitution, 18 block steps)"""
+    c = pkg.Context(pkg.default_config(width=640, height=480, max_batch=1, window_size=24))
+    try:
+        pr = ba_synth.make_window(W=24, P=1200, seed=11)
+        its, st = _compare(c, pr)
+        assert its >= 2
+    finally:
+        c.close()

@@ -46,7 +46,7 @@ def test_demosaic_equals_cv2_golden(pkg, name):
     assert np.array_equal(bgr[0], GOLD["bgr_" + name])
 
 
-@pytest.mark.parametrize("shape,on_device", [((560, 1280), False), ((375, 1242), True), ((37, 51), False)])
+@pytest.mark.parametrize("shape,on_device", [((560, 1280), False), ((375, 1242), True), ((67, 129), False)])
 def test_full_size_conversions_equal_oracle(pkg, shape, on_device):
     rng = np.random.default_rng(7)
     n = 3

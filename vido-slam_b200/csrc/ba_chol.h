@@ -244,6 +244,23 @@ __device__ __forceinline__ void bc_factor(const CholSm cs, int* s_bad, long long
     // is front-loaded (104 tiles at step 0, ~2300 cycles against ~1650 of the chain warp) and the first 8 of 15 steps were
     // bound by it; left-looking the busiest step has 56 tile updates spread over 12 warps, most of them off the critical path.
     const int bw = warp - (warp >> 2), btid = bw * 32 + lane;   // bulk warp / thread index
+    // The original value of a tile (from the global copy Sg when the caller staged only the first panel) is fetched one step
+    // AHEAD of its use: an L2 round trip is several hundred cycles, more than the early steps' few DMMA can hide.
+    const double* const src = Sg ? Sg : S;
+    double on0[2] = {0, 0}, on1[2] = {0, 0};
+    auto fetch = [&](int jn) {
+      const int ncol = T - jn - 2 > 0 ? T - jn - 2 : 0, nt = ncol + (jn + 2 < T ? 1 : 0);
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const int t = bw + BC_BULK_WARPS * q;
+        if (t >= nt) continue;
+        const int R = (t < ncol) ? jn + 2 + t : jn + 2, C = (t < ncol) ? jn + 1 : jn + 2;
+        const int row = 8 * R + fr, col = 8 * C + 2 * fk;
+        on0[q] = (row >= col) ? src[row * ld + col] : src[col * ld + row];
+        on1[q] = (row >= col + 1) ? src[row * ld + col + 1] : src[(col + 1) * ld + row];
+      }
+    };
+    fetch(0);
     bc_bar_sync(BC_BAR_STEP);
     long long t0 = 0;
     if (tk && btid == 0) t0 = clock64();
@@ -265,18 +282,15 @@ __device__ __forceinline__ void bc_factor(const CholSm cs, int* s_bad, long long
       const int ncol = T - jb - 2 > 0 ? T - jb - 2 : 0, nt = ncol + (jb + 2 < T ? 1 : 0);
       double c0[2] = {0, 0}, c1[2] = {0, 0};
       int tR[2] = {-1, -1}, tC[2] = {0, 0};
+      const double oc0[2] = {on0[0], on0[1]}, oc1[2] = {on1[0], on1[1]};
+      if (jb + 1 < T) fetch(jb + 1);
 #pragma unroll
       for (int q = 0; q < 2; q++) {
         const int t = bw + BC_BULK_WARPS * q;
         if (t >= nt) continue;
         const int R = (t < ncol) ? jb + 2 + t : jb + 2, C = (t < ncol) ? jb + 1 : jb + 2;
         tR[q] = R; tC[q] = C;
-        const int row = 8 * R + fr, col = 8 * C + 2 * fk;
-        // the tile's original value: from the global copy of the system when the caller staged only the first panel (its
-        // latency hides behind the updates below: it is added last)
-        const double* src = Sg ? Sg : S;
-        const double o0 = (row >= col) ? src[row * ld + col] : src[col * ld + row];
-        const double o1 = (row >= col + 1) ? src[row * ld + col + 1] : src[(col + 1) * ld + row];
+        const double o0 = oc0[q], o1 = oc1[q];   // the tile's original value, fetched during the previous step
         double a0 = 0, a1 = 0;
         double b0 = 0, b1 = 0, e0 = 0, e1 = 0, g0 = 0, g1 = 0;   // four accumulator pairs: the 2 jb DMMA of a tile form four
                                                                   // chains instead of one (late steps: one tile, many panels)
@@ -335,53 +349,57 @@ __device__ __forceinline__ void bc_factor(const CholSm cs, int* s_bad, long long
   __syncthreads();
 }
 
-// Back substitution L^T x = y by the chain warp (the other warps return at once): x overwrites row np.  Per block step
-// lane k (mod 8) forms unknown k as a row of the matrix-vector product with the precomputed inverse of the diagonal
-// factor, a shuffle broadcast hands the 8 unknowns to every lane, and the lanes update their rows above the block.  The
-// rows of L a lane needs for that are loaded BEFORE the unknowns are formed (they do not depend on them).
+// Back substitution L^T x = y by FIVE warps (11..15; the other warps return at once): x overwrites row np.
+// Warp u owns the rows 32u .. 32u+31 (np <= 144 at the largest window) and keeps their y in registers (lane = row).  Per block step, from the last block up:
+// the warp that owns the block gathers its 8 values with shuffles, forms the 8 unknowns as a matrix-vector product with the
+// precomputed inverse of the diagonal factor and publishes them in a 2 x 8 shared buffer (the dinv array, dead by now); one
+// named barrier later every warp subtracts their contribution from its rows above the block -- 8 FMAs in two chains, the
+// rows of L loaded before the barrier.  The single-warp version this replaces issued ~120 instructions per step and was
+// bound by that (650 cycles per step measured); here a step is ~35 instructions per warp on its own scheduler.
+#define BC_BAR_BACK 5
 __device__ __forceinline__ void bc_backsolve(const CholSm cs) {
-  if ((threadIdx.x >> 5) != BC_CHAIN_WARP) return;
-  const int lane = threadIdx.x & 31, np = cs.np, ld = cs.ld, T = np >> 3;
+  const int warp = threadIdx.x >> 5;
+  if (warp < 11) return;
+  const int lane = threadIdx.x & 31, u = warp - 11, np = cs.np, ld = cs.ld, T = np >> 3;
   double* const ys = cs.S + (size_t)np * ld;
   const double* const S = cs.S;
-  constexpr int NCH = (BC_MAXT * 8 + 31) / 32;
+  double* const xbuf = cs.dinv;
+  const int i = 32 * u + lane;
+  const bool mine = i < np;
+  double y = mine ? ys[i] : 0.0;
   const int k8 = lane & 7;
   for (int jb = T - 1; jb >= 0; jb--) {
     const int j0 = 8 * jb;
-    const double* Li = cs.Linv + jb * 64;
-    double lv[NCH][8], yv[NCH];
+    const bool above = i < j0;   // this row still receives the block's contribution
+    double lv[8];
+    {
+      const double* col = S + (size_t)j0 * ld + (above ? i : 0);
 #pragma unroll
-    for (int u = 0; u < NCH; u++) {
-      const int i = lane + 32 * u;
-      const bool on = i < j0;
-      const double* col = S + j0 * ld + (on ? i : 0);
-      yv[u] = on ? ys[i] : 0.0;
-#pragma unroll
-      for (int k = 0; k < 8; k++) lv[u][k] = on ? col[k * ld] : 0.0;
+      for (int k = 0; k < 8; k++) lv[k] = above ? col[k * ld] : 0.0;
     }
-    // x_k = sum_{m >= k} Linv[m][k] y_m (two partial sums to halve the dependent chain); Linv is stored with its zeros
-    double sa = 0, sb = 0;
+    if (u == (j0 >> 5)) {
+      const double* Li = cs.Linv + jb * 64;
+      const int l0 = j0 & 31;
+      double sa = 0, sb = 0;
 #pragma unroll
-    for (int m = 0; m < 8; m += 2) {
-      sa = fma(Li[m * 8 + k8], ys[j0 + m], sa);
-      sb = fma(Li[(m + 1) * 8 + k8], ys[j0 + m + 1], sb);
-    }
-    const double xk = sa + sb;
-    double x[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) x[k] = __shfl_sync(0xffffffffu, xk, k);
-#pragma unroll
-    for (int u = 0; u < NCH; u++) {
-      const int i = lane + 32 * u;
-      double ta = yv[u], tb = 0;
-#pragma unroll
-      for (int k = 0; k < 8; k += 2) {
-        ta = fma(-lv[u][k], x[k], ta);
-        tb = fma(-lv[u][k + 1], x[k + 1], tb);
+      for (int m = 0; m < 8; m += 2) {   // x_k = sum_{m >= k} Linv[m][k] y_m; Linv is stored with its zeros
+        const double y0 = __shfl_sync(0xffffffffu, y, l0 + m), y1 = __shfl_sync(0xffffffffu, y, l0 + m + 1);
+        sa = fma(Li[m * 8 + k8], y0, sa);
+        sb = fma(Li[(m + 1) * 8 + k8], y1, sb);
       }
-      if (i < j0) ys[i] = ta + tb;
+      const double xk = sa + sb;
+      if (lane < 8) xbuf[8 * (jb & 1) + lane] = xk;
+      if (lane >= l0 && lane < l0 + 8) y = xk;   // l0 is a multiple of 8: lane l0 + k formed unknown k
     }
-    if (lane < 8) ys[j0 + lane] = xk;
-    __syncwarp();
+    asm volatile("bar.sync %0, 160;" ::"n"(BC_BAR_BACK) : "memory");
+    const double* xb = xbuf + 8 * (jb & 1);
+    double ta = 0, tb = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+      ta = fma(lv[k], xb[k], ta);
+      tb = fma(lv[k + 1], xb[k + 1], tb);
+    }
+    y -= ta + tb;
   }
+  if (mine) ys[i] = y;
 }

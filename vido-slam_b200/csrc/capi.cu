@@ -107,7 +107,7 @@ void vido_destroy(vido_ctx* ctx) {
   delete ctx;
 }
 
-int64_t vido_kernel_launches(vido_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t vido_kernel_launches(vido_ctx* ctx) { return ctx ? ctx->launches.load() : (int64_t)0; }
 void* vido_stream(vido_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 int vido_sync(vido_ctx* ctx) {

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <functional>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -46,7 +47,7 @@ struct vido_ctx {
   int num_sms = 0;
   cudaStream_t stream = nullptr;
   std::string err;
-  int64_t launches = 0;
+  std::atomic<int64_t> launches{0};   // kernels launched (the window-solver host thread counts too)
   float mscale = 1.f;  // Tracking::mScale (KAIST depth scale)
   // device-time accounting (CUDA events on `stream`), see vido_get_kernel_times
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

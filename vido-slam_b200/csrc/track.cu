@@ -24,7 +24,11 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
 #include <map>
+#include <mutex>
+#include <thread>
 
 #include "ctx.h"
 
@@ -180,6 +184,20 @@ struct TrackState {
   long hn = 0;
   double dt[12] = {0};   // debug (VIDO_HOST_TIMING): host-path ms in mask update / PnP / pose-opt / carry-over / object tracking / object motions / static renewal / object renewal / last-map copies
   long dn = 0;
+  // ---- window-solver host thread (device-chained path): tracklet linking, staging, launch and retirement of the window solves
+  //      run beside the tracker thread.  It owns `tracks`, MapFrame::track / pos, the solver queue and (while jobs are pending)
+  //      the Twc / rel / p3 write-back of Map frames; the tracker thread only appends frames (capacity reserved up front, so the
+  //      elements never move) and joins (ba_async_join) before anything else touches that state.
+  struct BaAsyncJob { int N, window; vido_track_stats* st; };
+  std::thread ba_thread;
+  std::mutex ba_mu;
+  std::condition_variable ba_cv_job, ba_cv_idle;
+  std::deque<BaAsyncJob> ba_jobs;
+  bool ba_thread_on = false, ba_thread_stop = false, ba_thread_busy = false;
+  int ba_async_rc = VIDO_OK;          // sticky: first error of a job
+  std::string ba_async_err;
+  int ba_N_override = 0;              // Map size the job being staged was posted for (0: the current size)
+  double bt[2] = {0, 0};              // debug (VIDO_HOST_TIMING): solver-thread ms in stage+launch / retirement
   bool call_failed = false;    // the last vido_track_frames call returned an error: whatever it left queued is discarded
   bool chain_active = false;   // the static tracker state lives on the device (chain_kernels.cu); the host vectors mirror it
   // object state of mpLastFrame: mvObjKeys / mvObjDepth / mvObjCorres / mvObjFlowNext / vSemObjLabel and nModLabel /
@@ -308,8 +326,12 @@ cudaError_t vido_create_stream(cudaStream_t* s, bool high) {
   return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, high ? hi : lo);
 }
 
+static int ba_async_join(vido_ctx* ctx);
+static void ba_async_shutdown(vido_ctx* ctx);
+
 int trk_setup(vido_ctx* ctx) {
   TrackState* ts = new TrackState();
+  ts->map.reserve(4096);   // the solver thread indexes Map frames while the tracker appends: no reallocation under it (chain_consume)
   ctx->trk = ts;
   const vido_config& c = ctx->cfg;
   const int B = c.max_batch;
@@ -363,6 +385,7 @@ int trk_setup(vido_ctx* ctx) {
 
 void trk_teardown(vido_ctx* ctx) {
   TrackState* ts = (TrackState*)ctx->trk;
+  if (ts) ba_async_shutdown(ctx);
   if (!ts) return;
   if (ts->copy_stream) { cudaStreamSynchronize(ts->copy_stream); cudaStreamDestroy(ts->copy_stream); }
   if (ts->fe_stream) { cudaStreamSynchronize(ts->fe_stream); cudaStreamDestroy(ts->fe_stream); }
@@ -383,6 +406,7 @@ void trk_teardown(vido_ctx* ctx) {
 
 int trk_reset(vido_ctx* ctx) {
   TrackState* ts = (TrackState*)ctx->trk;
+  ba_async_join(ctx);   // (an error of the abandoned sequence is dropped with it)
   while (ts->ba_nq > 0) { vido_lm_stats ls; ba_collect(ctx, &ts->job[ts->ba_queue[0]].pr, &ls); ts->ba_queue[0] = ts->ba_queue[1]; ts->ba_queue[1] = ts->ba_queue[2]; ts->ba_nq--; }
   ts->ba_deferred.valid = false;
   ts->chain_active = false;
@@ -1110,7 +1134,7 @@ static void ba_writeback_rest(vido_ctx* ctx) {
 static int ba_stage(vido_ctx* ctx, int WINDOW, vido_track_stats* st) {
   TrackState* ts = (TrackState*)ctx->trk;
   ts->ba_staged = false;
-  const int N = (int)ts->map.size();
+  const int N = ts->ba_N_override > 0 ? ts->ba_N_override : (int)ts->map.size();
   if (st) { st->ba_iterations = -1; st->ba_points = 0; st->ba_obs = 0; st->ba_trials = 0; }
   if (WINDOW <= 0) return VIDO_OK;
   while (ts->ba_nq == 3 || (ts->ba_nq > 0 && ba_oldest_done(ctx))) {   // retire finished solves; the oldest one when every slot is taken
@@ -1208,6 +1232,77 @@ static int ba_flush_deferred(vido_ctx* ctx) {
   if (!rc) rc = ba_go(ctx);
   if (ts->ba_deferred.st) ts->ba_deferred.st->ms_ba += now_ms() - t0;
   return rc;
+}
+
+// ---- the window-solver host thread (see TrackState::ba_thread).  One job per tracked frame, in frame order: link the frame's
+//      static tracklets, stage its window (ba_stage retires finished solves / the oldest one when the three slots are taken),
+//      launch, then retire whatever has finished meanwhile.
+static void link_static_tracks_at(TrackState* ts, MapFrame& F, MapFrame& P, int fcur);
+static void ba_async_main(vido_ctx* ctx) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  cudaSetDevice(ctx->device);
+  for (;;) {
+    TrackState::BaAsyncJob job;
+    {
+      std::unique_lock<std::mutex> lk(ts->ba_mu);
+      ts->ba_thread_busy = false;
+      if (ts->ba_jobs.empty()) ts->ba_cv_idle.notify_all();
+      ts->ba_cv_job.wait(lk, [ts] { return ts->ba_thread_stop || !ts->ba_jobs.empty(); });
+      if (ts->ba_jobs.empty()) return;   // stop requested and nothing left
+      job = ts->ba_jobs.front();
+      ts->ba_jobs.pop_front();
+      ts->ba_thread_busy = true;
+      if (ts->ba_async_rc != VIDO_OK) continue;   // after an error the remaining jobs are dropped (the call fails at its next join)
+    }
+    const double t0 = now_ms();
+    link_static_tracks_at(ts, ts->map[job.N - 1], ts->map[job.N - 2], job.N - 1);
+    ts->ba_N_override = job.N;
+    int rc = ba_stage(ctx, job.window, job.st);
+    if (!rc) rc = ba_go(ctx);
+    ts->ba_N_override = 0;
+    const double t1 = now_ms();
+    if (job.st) job.st->ms_ba += t1 - t0;
+    while (ts->ba_nq > 0 && rc == VIDO_OK && ba_oldest_done(ctx)) { rc = ba_finish(ctx); ba_writeback_rest(ctx); }
+    ts->bt[0] += t1 - t0; ts->bt[1] += now_ms() - t1;
+    if (rc != VIDO_OK) {
+      std::lock_guard<std::mutex> lk(ts->ba_mu);
+      if (ts->ba_async_rc == VIDO_OK) { ts->ba_async_rc = rc; ts->ba_async_err = ctx->err; }
+    }
+  }
+}
+
+// wait until the solver thread has worked off every posted job (solves may still be queued on the DEVICE); returns the sticky error
+static int ba_async_join(vido_ctx* ctx) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  if (!ts->ba_thread_on) return VIDO_OK;
+  std::unique_lock<std::mutex> lk(ts->ba_mu);
+  ts->ba_cv_idle.wait(lk, [ts] { return ts->ba_jobs.empty() && !ts->ba_thread_busy; });
+  const int rc = ts->ba_async_rc;
+  if (rc != VIDO_OK) { ctx->err = ts->ba_async_err; ts->ba_async_rc = VIDO_OK; }
+  return rc;
+}
+
+static int ba_async_post(vido_ctx* ctx, int N, int window, vido_track_stats* st) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  if (!ts->ba_thread_on) {
+    ts->ba_thread_stop = false; ts->ba_thread_busy = false;
+    ts->ba_thread = std::thread(ba_async_main, ctx);
+    ts->ba_thread_on = true;
+  }
+  std::lock_guard<std::mutex> lk(ts->ba_mu);
+  if (ts->ba_async_rc != VIDO_OK) { const int rc = ts->ba_async_rc; ctx->err = ts->ba_async_err; ts->ba_async_rc = VIDO_OK; return rc; }
+  ts->ba_jobs.push_back({N, window, st});
+  ts->ba_cv_job.notify_one();
+  return VIDO_OK;
+}
+
+static void ba_async_shutdown(vido_ctx* ctx) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  if (!ts->ba_thread_on) return;
+  { std::lock_guard<std::mutex> lk(ts->ba_mu); ts->ba_thread_stop = true; }
+  ts->ba_cv_job.notify_all();
+  ts->ba_thread.join();
+  ts->ba_thread_on = false;
 }
 
 
@@ -1514,11 +1609,12 @@ static int vio_after_ba(vido_ctx* ctx) {
 // ---------------------------------------------------------------------------------------------------------
 // tracklets of the static features, incrementally (same chains as Tracking::GetStaticTrack, src/Tracking.cc:2514-2613): every
 // feature of the new frame F continues the track of its predecessor in the last Map frame, or starts one with it
-static void link_static_tracks(TrackState* ts, MapFrame& F) {
+static void link_static_tracks_at(TrackState* ts, MapFrame& F, MapFrame& P, int fcur);
+static void link_static_tracks(TrackState* ts, MapFrame& F) { link_static_tracks_at(ts, F, ts->map.back(), (int)ts->map.size()); }
+// F = the frame with Map index fcur (not necessarily pushed yet), P = the frame in front of it
+static void link_static_tracks_at(TrackState* ts, MapFrame& F, MapFrame& P, int fcur) {
   const int nf = (int)F.asso.size();
   F.track.assign(nf, -1); F.pos.assign(nf, 0);
-  MapFrame& P = ts->map.back();
-  const int fcur = (int)ts->map.size();
   for (int j = 0; j < nf; j++) {
     const int p = F.asso[j];
     if (p < 0) continue;
@@ -1547,6 +1643,7 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
   const float invfx = 1.0f / c.fx, invfy = 1.0f / c.fy;
   float curTcw[16];
   eye44(curTcw);
+  { int rcj = ba_async_join(ctx); if (rcj) return rcj; }   // the host-driven path stages its window solves on this thread
   if (st) { memset(st, 0, sizeof *st); st->n_keypoints = (int)ff.kps.size(); }
   int skipped = 0;
   double t0 = now_ms();
@@ -1946,7 +2043,8 @@ static int chain_consume(vido_ctx* ctx, int slot, const FrontFrame& ff, float* T
   if (st) { memset(st, 0, sizeof *st); st->n_keypoints = (int)ff.kps.size(); st->ba_iterations = -1; }
   memcpy(Tcw_out, Tcw, sizeof(float) * 16);
   if (hdr[0] == 1) {   // lost tracking: nothing was processed (see back_end)
-    rc = ba_flush_deferred(ctx);
+    rc = ba_async_join(ctx);
+    if (!rc) rc = ba_flush_deferred(ctx);
     ts->f_id++; ts->frames_seen++;
     return rc ? rc : 1;
   }
@@ -1954,27 +2052,39 @@ static int chain_consume(vido_ctx* ctx, int slot, const FrontFrame& ff, float* T
   MapFrame F;
   F.xy.assign(xy, xy + 2 * (size_t)nf); F.depth.assign(depth, depth + nf); F.p3.assign(p3, p3 + 3 * (size_t)nf);
   F.asso.assign(asso, asso + nf);
-  link_static_tracks(ts, F);
+  const bool async = !getenv("VIDO_BA_INLINE");   // debug: VIDO_BA_INLINE=1 stages the window solves on this thread
+  if (!async) link_static_tracks(ts, F);
   memcpy(F.Twc, Twc, sizeof(float) * 16); memcpy(F.Twc_rf, Twc, sizeof(float) * 16); memcpy(F.rel, rel, sizeof(float) * 16);
   ts->last_keys = F.xy; ts->last_depth = F.depth;
   ts->last_corres.assign(corres, corres + 2 * (size_t)nf); ts->last_flow.assign(flow, flow + 2 * (size_t)nf);
   memcpy(ts->lastTcw, Tcw, sizeof(float) * 16);
   memcpy(ts->mVelocity, vel, sizeof(float) * 16);
   ts->has_velocity = true;
+  if (ts->map.size() == ts->map.capacity()) {   // the solver thread indexes Map frames: they must not move under it
+    rc = ba_async_join(ctx);
+    if (rc) return rc;
+    ts->map.reserve(std::max<size_t>(4096, 2 * ts->map.capacity()));
+  }
   ts->map.push_back(std::move(F));
   ts->have_last_maps = false;
   if (st) {
     st->n_matches = hdr[1]; st->n_init_inliers = hdr[2]; st->init_winner = hdr[3]; st->n_pose_inliers = hdr[6]; st->n_static = nf;
   }
   const int window = ts->f_id < c.window_size ? ts->f_id : c.window_size;
-  ts->ba_deferred.valid = true; ts->ba_deferred.window = window; ts->ba_deferred.st = st;
   ts->f_id++; ts->frames_seen++;
   const double th2 = now_ms();
-  rc = ba_flush_deferred(ctx);
-  const double th3 = now_ms();
-  // finished solves are retired without blocking (ba_stage blocks only when all three slots are taken): the host stays ahead
-  // of the solver stream instead of waiting for the solve before last after every frame
-  while (ts->ba_nq > 0 && rc == VIDO_OK && ba_oldest_done(ctx)) { rc = ba_finish(ctx); ba_writeback_rest(ctx); }
+  double th3 = th2;
+  if (async) {
+    // tracklet linking, staging, launch and retirement of this frame's window solve: the solver thread's job
+    rc = ba_async_post(ctx, (int)ts->map.size(), window, st);
+  } else {
+    ts->ba_deferred.valid = true; ts->ba_deferred.window = window; ts->ba_deferred.st = st;
+    rc = ba_flush_deferred(ctx);
+    th3 = now_ms();
+    // finished solves are retired without blocking (ba_stage blocks only when all three slots are taken): the host stays ahead
+    // of the solver stream instead of waiting for the solve before last after every frame
+    while (ts->ba_nq > 0 && rc == VIDO_OK && ba_oldest_done(ctx)) { rc = ba_finish(ctx); ba_writeback_rest(ctx); }
+  }
   const double th4 = now_ms();
   ts->ht[0] += th1 - th0; ts->ht[1] += th2 - th1; ts->ht[2] += th3 - th2; ts->ht[3] += th4 - th3; ts->hn++;
   return rc;
@@ -1995,6 +2105,7 @@ static int trk_track_chunk_impl(vido_ctx* ctx, const vido_frame_inputs* in, int 
   cudaStream_t s = ctx->stream;
   const size_t px = (size_t)c.width * c.height;
   if (ts->call_failed) {   // left by a failed call: discarded.  (Solves a successful call without statistics left queued keep running.)
+    ba_async_join(ctx);
     while (ts->ba_nq > 0) { vido_lm_stats ls; ba_collect(ctx, &ts->job[ts->ba_queue[0]].pr, &ls); ts->ba_queue[0] = ts->ba_queue[1]; ts->ba_queue[1] = ts->ba_queue[2]; ts->ba_nq--; }
     ts->call_failed = false;
   }
@@ -2038,6 +2149,11 @@ static int trk_track_chunk_impl(vido_ctx* ctx, const vido_frame_inputs* in, int 
       if (chain_eligible(ctx, ff[b], in[done + b])) {
         // a run of consecutive eligible frames: queue the kernels of all of them, then consume the records in order
         int e = b;
+        if (ts->ba_deferred.valid) {   // a window the host-driven path put off: queue it before the solver thread takes over
+          rc = ba_async_join(ctx);
+          if (!rc) rc = ba_flush_deferred(ctx);
+          if (rc) return rc;
+        }
         if (!ts->chain_active) {
           rc = chain_upload_state(ctx, (int)(ts->last_corres.size() / 2), ts->last_keys.data(), ts->last_depth.data(), ts->last_corres.data(),
                                   ts->last_flow.data(), ts->lastTcw, ts->mVelocity, ts->has_velocity ? 1 : 0);
@@ -2087,9 +2203,12 @@ static int trk_track_chunk_impl(vido_ctx* ctx, const vido_frame_inputs* in, int 
     done += B;
   }
   if (getenv("VIDO_HOST_TIMING") && ts->hn > 0) {
-    fprintf(stderr, "[host] per frame ms over %ld frames: record wait %.3f, consume %.3f, BA stage+launch %.3f, BA retire wait %.3f, chain enqueue %.3f, front-end collect+launch %.3f\n",
-            ts->hn, ts->ht[0] / ts->hn, ts->ht[1] / ts->hn, ts->ht[2] / ts->hn, ts->ht[3] / ts->hn, ts->ht[4] / ts->hn, ts->ht[5] / ts->hn);
+    ba_async_join(ctx);   // (debug output only: the solver thread's counters are read below)
+    fprintf(stderr, "[host] per frame ms over %ld frames: record wait %.3f, consume %.3f, BA stage+launch %.3f, BA retire wait %.3f, chain enqueue %.3f, front-end collect+launch %.3f | solver thread: link+stage+launch %.3f, retirement %.3f\n",
+            ts->hn, ts->ht[0] / ts->hn, ts->ht[1] / ts->hn, ts->ht[2] / ts->hn, ts->ht[3] / ts->hn, ts->ht[4] / ts->hn, ts->ht[5] / ts->hn,
+            ts->bt[0] / ts->hn, ts->bt[1] / ts->hn);
     for (int k = 0; k < 8; k++) ts->ht[k] = 0;
+    ts->bt[0] = ts->bt[1] = 0;
     ts->hn = 0;
   }
   if (getenv("VIDO_HOST_TIMING") && ts->dn > 0) {
@@ -2102,9 +2221,14 @@ static int trk_track_chunk_impl(vido_ctx* ctx, const vido_frame_inputs* in, int 
     // With a statistics array the call drains the solver queue: stats and Map are final when it returns.  Without one the last
     // (up to three) window solves stay queued on the solver stream and the next call continues behind them -- a stream of calls
     // then never empties the pipeline; every Map accessor, vido_sync, FullBatch and the stand-alone BA entry drain first.
-    int rc = ba_flush_deferred(ctx);
-    if (stats || ts->vio)
-      while (ts->ba_nq > 0 && rc == VIDO_OK) { rc = ba_finish(ctx); ba_writeback_rest(ctx); }
+    if (!(stats || ts->vio)) {
+      if (!ts->ba_deferred.valid) return VIDO_OK;   // (only the host-driven path leaves a deferred window; the solver thread is idle then)
+      int rc = ba_async_join(ctx);
+      return rc ? rc : ba_flush_deferred(ctx);
+    }
+    int rc = ba_async_join(ctx);
+    if (!rc) rc = ba_flush_deferred(ctx);
+    while (ts->ba_nq > 0 && rc == VIDO_OK) { rc = ba_finish(ctx); ba_writeback_rest(ctx); }
     return rc;
   }
 }
@@ -2112,8 +2236,9 @@ static int trk_track_chunk_impl(vido_ctx* ctx, const vido_frame_inputs* in, int 
 int trk_drain(vido_ctx* ctx) {
   TrackState* ts = (TrackState*)ctx->trk;
   if (!ts) return VIDO_OK;
-  if (ts->call_failed) return VIDO_OK;   // the next call discards what the failed one left
-  int rc = ba_flush_deferred(ctx);
+  if (ts->call_failed) { ba_async_join(ctx); return VIDO_OK; }   // the next call discards what the failed one left
+  int rc = ba_async_join(ctx);
+  if (!rc) rc = ba_flush_deferred(ctx);
   while (ts->ba_nq > 0 && rc == VIDO_OK) { rc = ba_finish(ctx); ba_writeback_rest(ctx); }
   return rc;
 }
@@ -2124,11 +2249,18 @@ int trk_drain(vido_ctx* ctx) {
 int trk_track_chunk(vido_ctx* ctx, const vido_frame_inputs* in, int nframes, float* Tcw_out, vido_track_stats* stats) {
   TrackState* ts = (TrackState*)ctx->trk;
   const int rc = trk_track_chunk_impl(ctx, in, nframes, Tcw_out, stats);
-  ts->ba_deferred.st = nullptr;
-  ts->job[0].st = nullptr;
-  ts->job[1].st = nullptr;
-  ts->job[2].st = nullptr;
-  if (rc < 0) { cudaStreamSynchronize(ctx->stream); ts->call_failed = true; }   // nothing of a failed call may still read the caller's buffers
+  if (rc < 0) {   // nothing of a failed call may still read the caller's buffers or write its statistics
+    { std::lock_guard<std::mutex> lk(ts->ba_mu); ts->ba_jobs.clear(); }
+    ba_async_join(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    ts->call_failed = true;
+  }
+  if (stats || rc < 0) {   // (without a statistics array every queued pointer is null already and the solver thread may be running)
+    ts->ba_deferred.st = nullptr;
+    ts->job[0].st = nullptr;
+    ts->job[1].st = nullptr;
+    ts->job[2].st = nullptr;
+  }
   return rc;
 }
 
@@ -2317,7 +2449,8 @@ void fill_problem(FullGraph& G, vido_fba_problem& pr) {
 
 int trk_full_batch(vido_ctx* ctx, vido_lm_stats* stats, int32_t* sizes) {
   TrackState* ts = (TrackState*)ctx->trk;
-  int rc = ba_flush_deferred(ctx);   // window solves left by a failed call
+  int rc = ba_async_join(ctx);
+  if (!rc) rc = ba_flush_deferred(ctx);   // window solves left by a failed call
   if (rc) return rc;
   while (ts->ba_nq > 0) { rc = ba_finish(ctx); if (rc) return rc; ba_writeback_rest(ctx); }
   FullGraph G;
@@ -2383,7 +2516,8 @@ int trk_export_full_graph(vido_ctx* ctx, int32_t* sizes, float* se3, float* poin
 static int trk_apply_scaled_rotation_impl(vido_ctx* ctx, const float* R, float s) {
   TrackState* ts = (TrackState*)ctx->trk;
   ts->chain_active = false;   // the last-frame pose changes below: a chained run re-uploads the state
-  int rc = ba_flush_deferred(ctx);
+  int rc = ba_async_join(ctx);
+  if (!rc) rc = ba_flush_deferred(ctx);
   while (ts->ba_nq > 0 && rc == VIDO_OK) { rc = ba_finish(ctx); ba_writeback_rest(ctx); }
   if (rc) return rc;
   float Tyw[16];
