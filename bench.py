@@ -346,6 +346,27 @@ def main():
     except Exception as e:  # reported, never fatal for the headline metric
         extra.setdefault("full_batch", {})["error"] = str(e)[:200]
 
+    # ---- the reference's own call pattern: one frame per call, window optimisation finished before the call returns (what the
+    #      C++ facade System::TrackRGBD does, host buffers in, pose out) -- latency-bound, no look-ahead, no pipelining across frames
+    frame_at_a_time = None
+    if world == 1 and legs:
+        try:
+            n_w, n_t = 32, 96
+            singles = [ctx.pack_frames(host_frames(k, 1)) for k in range(n_w + n_t)]
+            ctx.track_reset()
+            for k in range(n_w):
+                ctx.track_frames(singles[k], want_stats=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for k in range(n_w, n_w + n_t):
+                ctx.track_frames(singles[k], want_stats=True)
+            dt1 = time.perf_counter() - t0
+            frame_at_a_time = {"value": n_t / dt1, "unit": "frames/s", "frames_timed": n_t, "ms_per_frame": 1e3 * dt1 / n_t,
+                               "what": "one vido_track_frames call per frame with statistics (= System::TrackRGBD of the C++ facade): host buffers in, "
+                                       "front-end, tracking and the frame's window optimisation all finished when the call returns"}
+        except Exception as e:
+            frame_at_a_time = {"error": str(e)[:200]}
+
     flags = native_oracle() if rank == 0 else None
 
     def leg(name, scene, workload, ts=None, imu=None, imu_cpu=None, before=None):
@@ -461,6 +482,7 @@ def main():
                              "value_incremental_tracklets": cpu_fps_inc, "late_sample": late, "host_cores": os.cpu_count(),
                              "one_sequence_per_core_estimate": cpu_fps * (os.cpu_count() or 1),
                              "cv2_front_end_cross_check": cv2_ms},
+            **({"frame_at_a_time": frame_at_a_time} if frame_at_a_time else {}),
             **extra,
             "host_ms_per_frame": {k: float(np.mean([x[k] for x in stats])) for k in ("ms_orb", "ms_init", "ms_poseopt", "ms_renew", "ms_ba")},
             "ba_per_frame": {"iterations": float(np.mean([s["ba_iterations"] for s in stats])), "obs": float(np.mean([s["ba_obs"] for s in stats])),

@@ -28,38 +28,64 @@ __global__ void bgr2gray_kernel(const uint8_t* __restrict__ src, size_t sfs, int
 }
 
 // =====================================================================================================
-// K1: one pyramid level from the previous one.  Each thread produces 4 horizontally adjacent pixels.
+// K1: one pyramid level from the previous one (cv::resize INTER_LINEAR, fixed point: horizontal pass with 11-bit
+// coefficients, vertical pass (by * (r >> 4)) >> 16, + 2 >> 2).  A thread owns 4 adjacent output columns and walks down a
+// strip of PYR_ROWS output rows: the column tables (source offset, coefficients) stay in registers for the whole strip, and
+// the horizontal interpolation of a source row is reused when the next output row's upper source row is this row's lower
+// one (5 rows out of 6 at scale 1.2) -- 2 byte loads and ~10 integer instructions per output pixel instead of 4 loads + 2
+// table loads and ~50 instructions when every pixel was computed from scratch (round 1: issue-bound at 16 % of HBM peak).
 // =====================================================================================================
+#define PYR_ROWS 8
 __global__ void __launch_bounds__(128) pyr_down_kernel(const uint8_t* __restrict__ src, int spitch, size_t sfs, int sw,
                                                        int sh, uint8_t* __restrict__ dst, int dpitch, size_t dfs, int dw,
                                                        int dh, const int32_t* __restrict__ xofs,
                                                        const short2* __restrict__ xa, const int32_t* __restrict__ yofs,
                                                        const short2* __restrict__ ya) {
-  int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  int y = blockIdx.y;
-  int b = blockIdx.z;
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y0 = blockIdx.y * PYR_ROWS;
+  const int b = blockIdx.z;
   if (x4 >= dw) return;
-  int sy = yofs[y];
-  short2 by = ya[y];
-  const uint8_t* s0 = src + b * sfs + (size_t)sy * spitch;
-  const uint8_t* s1 = src + b * sfs + (size_t)min(sy + 1, sh - 1) * spitch;
-  uint32_t packed = 0;
+  int sx0[4], sx1[4], a0[4], a1[4];
 #pragma unroll
   for (int i = 0; i < 4; i++) {
-    int x = x4 + i;
-    int v = 0;
-    if (x < dw) {
-      int sx = xofs[x];
-      short2 ax = xa[x];
-      int sx1 = min(sx + 1, sw - 1);
-      int r0 = s0[sx] * ax.x + s0[sx1] * ax.y;
-      int r1 = s1[sx] * ax.x + s1[sx1] * ax.y;
-      v = (((by.x * (r0 >> 4)) >> 16) + ((by.y * (r1 >> 4)) >> 16) + 2) >> 2;
-      v = min(max(v, 0), 255);
-    }
-    packed |= (uint32_t)v << (8 * i);
+    const int x = min(x4 + i, dw - 1);
+    const int sx = xofs[x];
+    const short2 ax = xa[x];
+    sx0[i] = sx; sx1[i] = min(sx + 1, sw - 1);
+    a0[i] = ax.x; a1[i] = ax.y;
   }
-  *reinterpret_cast<uint32_t*>(dst + b * dfs + (size_t)y * dpitch + x4) = packed;  // pitch is a multiple of 64
+  const uint8_t* const sb = src + b * sfs;
+  uint8_t* const db = dst + b * dfs;
+  auto hrow = [&](int sy, int* r) {   // horizontal pass of source row sy for the 4 columns
+    const uint8_t* p = sb + (size_t)sy * spitch;
+#pragma unroll
+    for (int i = 0; i < 4; i++) r[i] = (p[sx0[i]] * a0[i] + p[sx1[i]] * a1[i]) >> 4;
+  };
+  int lo[4] = {0, 0, 0, 0}, lo_row = -1;   // horizontal result of the lower source row of the previous output row
+  const int yend = min(y0 + PYR_ROWS, dh);
+  for (int y = y0; y < yend; y++) {
+    const int sy = yofs[y], sy1 = min(sy + 1, sh - 1);
+    const short2 by = ya[y];
+    int r0[4], r1[4];
+    if (sy == lo_row) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) r0[i] = lo[i];
+    } else hrow(sy, r0);
+    if (sy1 == sy) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) r1[i] = r0[i];
+    } else hrow(sy1, r1);
+    uint32_t packed = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int v = (((by.x * r0[i]) >> 16) + ((by.y * r1[i]) >> 16) + 2) >> 2;
+      v = min(max(v, 0), 255);
+      packed |= (x4 + i < dw ? (uint32_t)v : 0u) << (8 * i);
+      lo[i] = r1[i];
+    }
+    lo_row = sy1;
+    *reinterpret_cast<uint32_t*>(db + (size_t)y * dpitch + x4) = packed;  // pitch is a multiple of 64
+  }
 }
 
 // =====================================================================================================
@@ -198,8 +224,8 @@ __global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(const CUtensor
         "l"(maps + level), "r"(x0a), "r"(cell.y0), "r"(b), "r"(smem_u32(&bar))
         : "memory");
   }
-  // zero the score array while the tile is in flight
-  for (int i = tid; i < rw * rh; i += FAST_THREADS) score[i] = 0;
+  // (no zero fill of the score array: the score pass below writes the one-pixel ring around the detection zone, which is all
+  //  the non-maximum suppression reads outside it)
   {
     uint32_t done = 0;
     while (!done) {
@@ -226,12 +252,14 @@ __global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(const CUtensor
   }
   __syncthreads();
 #endif
-  // ---- scores of the detection zone [3, rw-3) x [3, rh-3)
+  // ---- scores of the detection zone [3, rw-3) x [3, rh-3), zeros on the one-pixel ring around it
   const int iw = rw - 6, ih = rh - 6;
   if (iw > 0 && ih > 0) {
-    for (int y = warp; y < ih; y += FAST_THREADS / 32) {
-      for (int x = lane; x < iw; x += 32) {
-        int s = fast_score(tile + (y + 3) * bw + (x + 3), bw, P.min_thr);
+    for (int y = warp - 1; y <= ih; y += FAST_THREADS / 32) {
+      const bool yin = y >= 0 && y < ih;
+      for (int x = lane - 1; x <= iw; x += 32) {
+        int s = 0;
+        if (yin && x >= 0 && x < iw) s = fast_score(tile + (y + 3) * bw + (x + 3), bw, P.min_thr);
         score[(y + 3) * rw + (x + 3)] = (uint8_t)s;
       }
     }
@@ -1116,7 +1144,7 @@ int orb_run(vido_ctx* ctx, const uint8_t* d_gray, int nframes, size_t frame_stri
   for (int l = 1; l < c.nlevels; l++) {
     const OrbLevel& S = ctx->lv[l - 1];
     const OrbLevel& D = ctx->lv[l];
-    dim3 grid((D.w + 511) / 512, D.h, B);
+    dim3 grid((D.w + 511) / 512, (D.h + PYR_ROWS - 1) / PYR_ROWS, B);
     pyr_down_kernel<<<grid, 128, 0, st>>>(ctx->d_pyr + S.base, S.pitch, S.frame_stride, S.w, S.h, ctx->d_pyr + D.base,
                                           D.pitch, D.frame_stride, D.w, D.h, ctx->d_xofs[l], (const short2*)ctx->d_xa[l],
                                           ctx->d_yofs[l], (const short2*)ctx->d_ya[l]);
