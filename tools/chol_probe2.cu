@@ -85,7 +85,7 @@ int main() {
     for (int i = 0; i < n; i++) { err = fmax(err, fabs(x[i] - xr[i])); nx = fmax(nx, fabs(xr[i])); }
     printf("W=%d n=%d smem=%zu: %s bad=%d rel.err=%.3e | cycles total=%lld backsolve=%lld diag0=%lld chain_work=%lld chain_wait=%lld bulk_panel=%lld bulk_trail=%lld bulk_wait=%lld | chain: trsm=%lld diag_update=%lld backsolve(chain warp)=%lld\n",
            W, n, smem, cudaGetErrorString(e), bad, err / nx, c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8], c[9], c[10]);
-    if (W == 20) for (int jb = 0; jb < 15; jb++) printf("   step %2d: chain work=%lld wait=%lld | bulk panel=%lld panel-barrier=%lld trailing(incl. barrier)=%lld step-barrier=%lld\n", jb, c[16 + 8 * jb], c[17 + 8 * jb], c[18 + 8 * jb], c[19 + 8 * jb], c[20 + 8 * jb], c[21 + 8 * jb]);
+    if (W == 20) for (int jb = 0; jb < 15; jb++) printf("   step %2d: chain work=%lld wait=%lld | bulk panel=%lld (rows done at %lld, prefetch at %lld) panel-barrier=%lld trailing(incl. barrier)=%lld step-barrier=%lld\n", jb, c[16 + 8 * jb], c[17 + 8 * jb], c[18 + 8 * jb], c[22 + 8 * jb], c[23 + 8 * jb], c[19 + 8 * jb], c[20 + 8 * jb], c[21 + 8 * jb]);
     cudaFree(dA); cudaFree(db); cudaFree(dx); cudaFree(dc); cudaFree(dbad);
   }
   return 0;

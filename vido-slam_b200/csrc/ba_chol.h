@@ -278,12 +278,14 @@ __device__ __forceinline__ void bc_factor(const CholSm cs, int* s_bad, long long
         if (i < np) bc_trsm_row(D, ld, dv, S + i * ld + j0, Lp + i * BC_LPS);
         else if (btid == BC_BULK_WARPS * 32 - 1) bc_trsm_row(D, ld, dv, S + np * ld + j0, nullptr);
       }
+      if (tk && btid == 0) tk[22 + 8 * jb] = clock64() - t0;   // probe: warp 0 behind the panel rows
       // ---- tiles of this step: (R, jb+1) for R = jb+2 .. T-1, then the diagonal tile (jb+2, jb+2); at most two per warp
       const int ncol = T - jb - 2 > 0 ? T - jb - 2 : 0, nt = ncol + (jb + 2 < T ? 1 : 0);
       double c0[2] = {0, 0}, c1[2] = {0, 0};
       int tR[2] = {-1, -1}, tC[2] = {0, 0};
       const double oc0[2] = {on0[0], on0[1]}, oc1[2] = {on1[0], on1[1]};
       if (jb + 1 < T) fetch(jb + 1);
+      if (tk && btid == 0) tk[23 + 8 * jb] = clock64() - t0;   // probe: ... and behind the prefetch of the next step's tiles
 #pragma unroll
       for (int q = 0; q < 2; q++) {
         const int t = bw + BC_BULK_WARPS * q;

@@ -179,6 +179,67 @@ __device__ __forceinline__ int fast_score(const uint8_t* t, int bw, int thrMin) 
   return max(best_b, -best_d) - 1;
 }
 
+// The same score for TWO horizontally adjacent pixels at once, packed as signed 16-bit pairs: sm_100 has single-instruction
+// 2 x 16-bit min / max with three inputs (SASS VIMNMX.S16x2 / VIMNMX3.S16x2; the byte-wise __vminu4 family is emulated, ~6
+// instructions each).  d = ring - centre fits 16 bits; min over a 9-arc = min3 of three min3 (32 instructions for the 16
+// arcs), max over the arcs = a max3 tree.  Returns score(pixel 0) | score(pixel 1) << 16, each 0 below thrMin -- the same
+// value as fast_score (corner at threshold t  <=>  score >= t).  ~85 instructions per pixel instead of ~400 when most
+// pixels pass the 4-point pre-test (textured images); the pre-test still rejects flat pixel pairs after 10 byte loads.
+__device__ __forceinline__ uint32_t fast_score_pair(const uint8_t* t, int bw, int thrMin) {
+  auto pk = [](uint32_t a, uint32_t b) { return a | (b << 16); };
+  const uint32_t c = pk(t[0], t[1]);
+  const uint32_t nc = __vneg2(c);
+  // compass points first: a 9-arc contains at least one pixel of every opposite pair
+  const uint32_t e0 = t[3 * bw], e1 = t[3 * bw + 1], w0 = t[-3 * bw], w1 = t[-3 * bw + 1];
+  const uint32_t r3 = t[3], r4 = t[4], l3 = t[-3], l2 = t[-2];
+  uint32_t d[16];
+  d[0] = __vadd2(pk(e0, e1), nc);
+  d[8] = __vadd2(pk(w0, w1), nc);
+  d[4] = __vadd2(pk(r3, r4), nc);
+  d[12] = __vadd2(pk(l3, l2), nc);
+  {
+    const uint32_t mb = __vmins2(__vmaxs2(d[0], d[8]), __vmaxs2(d[4], d[12]));   // > thr  <=> a bright arc is possible
+    const uint32_t md = __vmaxs2(__vmins2(d[0], d[8]), __vmins2(d[4], d[12]));   // < -thr <=> a dark arc is possible
+    const int b0 = (short)(mb & 0xffffu), b1 = (short)(mb >> 16), k0 = (short)(md & 0xffffu), k1 = (short)(md >> 16);
+    if (b0 <= thrMin && b1 <= thrMin && k0 >= -thrMin && k1 >= -thrMin) return 0u;
+  }
+  {
+    const uint32_t a = t[3 * bw - 1], b = t[3 * bw + 2];                 // row +3: dx -1 .. 2
+    d[15] = __vadd2(pk(a, e0), nc); d[1] = __vadd2(pk(e1, b), nc);
+    const uint32_t g = t[-3 * bw - 1], h = t[-3 * bw + 2];               // row -3
+    d[9] = __vadd2(pk(g, w0), nc); d[7] = __vadd2(pk(w1, h), nc);
+    const uint32_t p2 = t[2 * bw + 2], p3 = t[2 * bw + 3], q2 = t[2 * bw - 2], q1 = t[2 * bw - 1];   // row +2
+    d[2] = __vadd2(pk(p2, p3), nc); d[14] = __vadd2(pk(q2, q1), nc);
+    const uint32_t u2 = t[-2 * bw + 2], u3 = t[-2 * bw + 3], v2 = t[-2 * bw - 2], v1 = t[-2 * bw - 1];   // row -2
+    d[6] = __vadd2(pk(u2, u3), nc); d[10] = __vadd2(pk(v2, v1), nc);
+    const uint32_t i3 = t[bw + 3], i4 = t[bw + 4], j3 = t[bw - 3], j2 = t[bw - 2];                     // row +1
+    d[3] = __vadd2(pk(i3, i4), nc); d[13] = __vadd2(pk(j3, j2), nc);
+    const uint32_t m3 = t[-bw + 3], m4 = t[-bw + 4], n3 = t[-bw - 3], n2 = t[-bw - 2];                 // row -1
+    d[5] = __vadd2(pk(m3, m4), nc); d[11] = __vadd2(pk(n3, n2), nc);
+  }
+  uint32_t lo3[16], hi3[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    lo3[k] = __vimin3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+    hi3[k] = __vimax3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+  }
+  uint32_t bb = 0x80008000u, bd = 0x7fff7fffu;   // max over the arcs of their min / min over the arcs of their max
+#pragma unroll
+  for (int k = 0; k < 16; k += 2) {
+    const uint32_t mnA = __vimin3_s16x2(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
+    const uint32_t mnB = __vimin3_s16x2(lo3[k + 1], lo3[(k + 4) & 15], lo3[(k + 7) & 15]);
+    bb = __vimax3_s16x2(bb, mnA, mnB);
+    const uint32_t mxA = __vimax3_s16x2(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
+    const uint32_t mxB = __vimax3_s16x2(hi3[k + 1], hi3[(k + 4) & 15], hi3[(k + 7) & 15]);
+    bd = __vimin3_s16x2(bd, mxA, mxB);
+  }
+  const int sb0 = (short)(bb & 0xffffu), sb1 = (short)(bb >> 16), sd0 = (short)(bd & 0xffffu), sd1 = (short)(bd >> 16);
+  int s0 = max(sb0, -sd0) - 1, s1 = max(sb1, -sd1) - 1;
+  s0 = s0 >= thrMin ? s0 : 0;
+  s1 = s1 >= thrMin ? s1 : 0;
+  return (uint32_t)s0 | ((uint32_t)s1 << 16);
+}
+
 #define FAST_MAXDIM 80  // max ROI edge (wCell+6); cells are 30..59 px by construction (src/ORBextractor.cc:773-776)
 #define FAST_THREADS 256
 
@@ -255,12 +316,20 @@ __global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(const CUtensor
   // ---- scores of the detection zone [3, rw-3) x [3, rh-3), zeros on the one-pixel ring around it
   const int iw = rw - 6, ih = rh - 6;
   if (iw > 0 && ih > 0) {
+    const int npair = (iw + 1) >> 1;
     for (int y = warp - 1; y <= ih; y += FAST_THREADS / 32) {
-      const bool yin = y >= 0 && y < ih;
-      for (int x = lane - 1; x <= iw; x += 32) {
-        int s = 0;
-        if (yin && x >= 0 && x < iw) s = fast_score(tile + (y + 3) * bw + (x + 3), bw, P.min_thr);
-        score[(y + 3) * rw + (x + 3)] = (uint8_t)s;
+      uint8_t* srow = score + (y + 3) * rw + 3;
+      if (y < 0 || y >= ih) {
+        for (int x = lane - 1; x <= iw; x += 32) srow[x] = 0;
+        continue;
+      }
+      if (lane == 0) { srow[-1] = 0; srow[iw] = 0; }
+      const uint8_t* trow = tile + (y + 3) * bw + 3;
+      for (int p = lane; p < npair; p += 32) {   // two pixels per lane (the odd one out of an odd-width zone is computed, not stored)
+        const int x = 2 * p;
+        const uint32_t s2 = fast_score_pair(trow + x, bw, P.min_thr);
+        srow[x] = (uint8_t)(s2 & 0xffu);
+        if (x + 1 < iw) srow[x + 1] = (uint8_t)(s2 >> 16);
       }
     }
   }
