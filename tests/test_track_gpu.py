@@ -209,3 +209,34 @@ int main(int argc, char** argv) {
     # an IMU_RGBD system must be driven through the IMU overload: the plain overload exits like the reference
     bad = subprocess.run(args + ["imu"], capture_output=True, text=True)
     assert bad.returncode != 0 and "input sensor was not set to RGBD" in bad.stderr
+
+
+def test_streaming_calls_without_statistics_match_drained_calls(pkg):
+    """Calls without a statistics array leave window solves queued (solver host thread + device queue) and the next call
+    continues behind them; every observer drains first.  Same Map as one drained call; destroying or resetting a context with
+    work still queued neither hangs nor leaks into the next sequence."""
+    cam, n = synth.KITTI, 40
+    frames = _sequence(cam, 99, n, flow_noise=0.1, depth_noise=0.01)
+    host = [dict(image=f["gray"].numpy(), depth=f["depth_in"].numpy(), flow=f["flow"].numpy(), mask=f["mask"].numpy()) for f in frames]
+    cfg = dict(width=cam["width"], height=cam["height"], fx=cam["fx"], fy=cam["fy"], cx=cam["cx"], cy=cam["cy"], bf=cam["bf"], max_batch=8)
+    ref = pkg.Context(pkg.default_config(**cfg))
+    T0, st0 = ref.track_frames([dict(h, depth=h["depth"].copy()) for h in host])
+    P0 = ref.map_poses()
+    ref.close()
+    ctx = pkg.Context(pkg.default_config(**cfg))
+    T = []
+    for k0 in range(0, n, 5):   # odd chunking, no statistics: nothing is drained between the calls
+        t, st = ctx.track_frames([dict(h, depth=h["depth"].copy()) for h in host[k0:k0 + 5]], want_stats=False)
+        assert st is None
+        T.append(t)
+    assert np.array_equal(np.concatenate(T), T0)
+    assert np.array_equal(ctx.map_poses(), P0)            # the accessor retires the queued solves first
+    a, b = ctx.map_static(n - 1), None
+    ctx.track_reset()                                       # reset right after streaming
+    t, _ = ctx.track_frames([dict(h, depth=h["depth"].copy()) for h in host[:12]], want_stats=False)
+    assert np.array_equal(t, T0[:12])
+    ctx.close()                                             # destroy with solves still queued
+    ctx2 = pkg.Context(pkg.default_config(**cfg))
+    t2, st2 = ctx2.track_frames([dict(h, depth=h["depth"].copy()) for h in host[:12]])
+    assert np.array_equal(t2, T0[:12]) and [s["ba_iterations"] for s in st2] == [s["ba_iterations"] for s in st0[:12]]
+    ctx2.close()

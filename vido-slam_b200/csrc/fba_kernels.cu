@@ -175,6 +175,54 @@ __device__ __forceinline__ void add_block(const FbaDev& d, int a, int c, const d
     }
 }
 
+// Diagonal-block and gradient contribution of a 3-row edge (J: 3 x 6, residual e) to SE3 vertex a, aggregated over the warp
+// when all 32 lanes hold edges of the SAME vertex: the edges are stored vertex by vertex (observations frame by frame, motion
+// edges object by object), so that is the common case, and 32 x 42 FP64 atomics on the same 42 addresses (the round-1
+// kernel: ~20 % of its samples were L2 atomic serialisation) become one butterfly reduction of the 27 unique sums and 42
+// single-lane atomics.  Returns false when the warp is not uniform: the caller then adds per thread.
+__device__ __forceinline__ bool add_diag_warp(const FbaDev& d, int a, const double* J, const double* e, double w) {
+  const unsigned act = __activemask();
+  if (act != 0xffffffffu) return false;
+  const int a0 = __shfl_sync(0xffffffffu, a, 0);
+  if (!__all_sync(0xffffffffu, a == a0)) return false;
+  const int lane = threadIdx.x & 31;
+  double hc[21], bc[6];
+  {
+    int idx = 0;
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+#pragma unroll
+      for (int c = r; c < 6; c++) hc[idx++] = w * (J[r] * J[c] + J[6 + r] * J[6 + c] + J[12 + r] * J[12 + c]);
+      bc[r] = -w * (J[r] * e[0] + J[6 + r] * e[1] + J[12 + r] * e[2]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 21; k++) hc[k] += __shfl_xor_sync(0xffffffffu, hc[k], o);
+#pragma unroll
+    for (int k = 0; k < 6; k++) bc[k] += __shfl_xor_sync(0xffffffffu, bc[k], o);
+  }
+  double* const Hb = d.pcg ? d.Hd + 36 * (size_t)a : d.Hss + (size_t)(6 * a) * d.n + 6 * a;
+  const int ldh = d.pcg ? 6 : d.n;
+  {
+    int idx = 0;
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+#pragma unroll
+      for (int c = r; c < 6; c++) {
+        if (lane == idx) {
+          atomicAdd(&Hb[(size_t)r * ldh + c], hc[idx]);
+          if (r != c) atomicAdd(&Hb[(size_t)c * ldh + r], hc[idx]);
+        }
+        idx++;
+      }
+      if (lane == 21 + r) atomicAdd(&d.bs[6 * a + r], bc[r]);
+    }
+  }
+  return true;
+}
+
 // buildSystem: one thread per edge.  Contributions to the SE3 block / rhs and to the point diagonals / rhs are summed with
 // FP64 atomics; the pose-point and point-point blocks belong to exactly one edge and are plain stores.
 __global__ void __launch_bounds__(128) fba_linearize_kernel(FbaDev d, int sel) {
@@ -227,7 +275,7 @@ __global__ void __launch_bounds__(128) fba_linearize_kernel(FbaDev d, int sel) {
     }
   } else if (i <= d.NE + d.NO) {
     const int o = i - 1 - d.NE, a = d.os[o], l = d.op[o];
-    const Pose& Xa = X[a];
+    const Pose Xa = X[a];   // a private copy: the stores below may alias X for all the compiler knows, and it re-read R per use
     double zc[3], e[3];
     vb::edge_xyz(Xa, P + 3 * (size_t)l, d.meas + 3 * (size_t)o, zc, e);
     double hw;
@@ -241,17 +289,20 @@ __global__ void __launch_bounds__(128) fba_linearize_kernel(FbaDev d, int sel) {
     Ji[9] = 2 * zc[2];  Ji[11] = -2 * zc[0];
     Ji[15] = -2 * zc[1]; Ji[16] = 2 * zc[0];
     double* B = d.Bo + 18 * (size_t)o;
+    const bool agg = add_diag_warp(d, a, Ji, e, w);
     for (int r = 0; r < 6; r++) {
-      double s = 0;
-      for (int k = 0; k < 3; k++) s += Ji[6 * k + r] * e[k];
-      atomicAdd(&d.bs[6 * a + r], -w * s);
+      if (!agg) {
+        double s = 0;
+        for (int k = 0; k < 3; k++) s += Ji[6 * k + r] * e[k];
+        atomicAdd(&d.bs[6 * a + r], -w * s);
+      }
       for (int q = 0; q < 3; q++) {
         double h = 0;
         for (int k = 0; k < 3; k++) h += Ji[6 * k + r] * Xa.R[3 * q + k];   // J_point[k][q] = R[q][k]
         B[3 * r + q] = w * h;
       }
     }
-    add_block(d, a, a, Ji, Ji, 3, w);
+    if (!agg) add_block(d, a, a, Ji, Ji, 3, w);
     for (int r = 0; r < 3; r++) {
       double s = 0;
       for (int k = 0; k < 3; k++) s += Xa.R[3 * r + k] * e[k];
@@ -260,7 +311,7 @@ __global__ void __launch_bounds__(128) fba_linearize_kernel(FbaDev d, int sel) {
     atomicAdd(&d.hl[l], w);
   } else {
     const int t = i - 1 - d.NE - d.NO, a = d.t1[t], c = d.t2[t], hv = d.th[t];
-    const Pose& H = X[hv];
+    const Pose H = X[hv];   // private copy, see above
     double q[3], e[3];
     tern_error(H, P + 3 * (size_t)a, P + 3 * (size_t)c, q, e);
     double hw;
@@ -283,10 +334,13 @@ __global__ void __launch_bounds__(128) fba_linearize_kernel(FbaDev d, int sel) {
     atomicAdd(&d.hl[c], w);
     double* b1 = d.B1 + 18 * (size_t)t;
     double* b2 = d.B2 + 18 * (size_t)t;
+    const bool agg = add_diag_warp(d, hv, JH, e, w);
     for (int r = 0; r < 6; r++) {
-      double s = 0;
-      for (int k = 0; k < 3; k++) s += JH[6 * k + r] * e[k];
-      atomicAdd(&d.bs[6 * hv + r], -w * s);
+      if (!agg) {
+        double s = 0;
+        for (int k = 0; k < 3; k++) s += JH[6 * k + r] * e[k];
+        atomicAdd(&d.bs[6 * hv + r], -w * s);
+      }
       for (int qq = 0; qq < 3; qq++) {
         b1[3 * r + qq] = w * JH[6 * qq + r];
         double h = 0;
@@ -294,7 +348,7 @@ __global__ void __launch_bounds__(128) fba_linearize_kernel(FbaDev d, int sel) {
         b2[3 * r + qq] = w * h;
       }
     }
-    add_block(d, hv, hv, JH, JH, 3, w);
+    if (!agg) add_block(d, hv, hv, JH, JH, 3, w);
     double* O = d.Ot + 9 * (size_t)t;
     for (int r = 0; r < 3; r++)
       for (int qq = 0; qq < 3; qq++) O[3 * r + qq] = w * (-H.R[3 * qq + r]);   // J1^T J2 = J2
