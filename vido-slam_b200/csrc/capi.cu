@@ -101,6 +101,7 @@ void vido_destroy(vido_ctx* ctx) {
   if (ctx->um_ws) cudaFree(ctx->um_ws);
   for (int k = 0; k < 3; k++) if (ctx->raw_stage[k]) cudaFree(ctx->raw_stage[k]);
   for (int k = 0; k < 4; k++) if (ctx->raw_dev[k]) cudaFree(ctx->raw_dev[k]);
+  if (ctx->fba_arena) cudaFree(ctx->fba_arena);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);

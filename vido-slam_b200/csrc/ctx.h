@@ -56,6 +56,8 @@ struct vido_ctx {
   double ba_alg_bytes = 0;         // algorithmic bytes of the BA launches so far (SURVEY.md 8d accounting)
   void* raw_stage[3] = {nullptr, nullptr, nullptr};   // vido_convert_raw: device staging of host raw image / depth / mask
   size_t raw_cap[3] = {0, 0, 0};
+  void* fba_arena = nullptr;       // FullBatch device arena, grow-only (fba_kernels.cu)
+  size_t fba_arena_bytes = 0;
   void* raw_dev[4] = {nullptr, nullptr, nullptr, nullptr};   // vido_track_raw_frames: converted BGR / depth / flow / mask of one batch
   int raw_dev_frames = 0;
 

@@ -24,6 +24,8 @@
 #include <vector>
 
 #include "ba_math.h"
+#include <chrono>
+
 #include "ctx.h"
 #include "lm_device.h"
 
@@ -1050,6 +1052,10 @@ void vido_fba_default_params_impl(vido_fba_problem* p) {
 }
 
 static int fba_run(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* st, char** arena_base) {
+  const bool tdbg = getenv("VIDO_FBA_TIMING") != nullptr;   // debug: host wall time of the phases of a solve
+  auto tnow = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double tt0 = tnow();
+  double tt_alloc0 = 0, tt_alloc1 = 0, tt_loop0 = 0;
   cudaStream_t s = ctx->stream;
   FbaDev d;
   memset(&d, 0, sizeof d);
@@ -1222,7 +1228,17 @@ static int fba_run(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* st, char**
   for (int pass = 0; pass < 2; pass++) {
   if (pass == 1) {
     void* base = nullptr;
-    VIDO_CUDA(cudaMalloc(&base, pool.off + 256));
+    tt_alloc0 = tnow();
+    // grow-only arena kept by the context: a fresh cudaMalloc of ~100 MB costs anything from 1 to several hundred ms
+    // (measured: bimodal, driver-side), a second solve on the same context none
+    const size_t need = pool.off + 256;
+    if (ctx->fba_arena_bytes < need) {
+      if (ctx->fba_arena) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->fba_arena); ctx->fba_arena = nullptr; ctx->fba_arena_bytes = 0; }
+      VIDO_CUDA(cudaMalloc(&ctx->fba_arena, need));
+      ctx->fba_arena_bytes = need;
+    }
+    base = ctx->fba_arena;
+    tt_alloc1 = tnow();
     *arena_base = (char*)base;
     pool.base = (char*)base; pool.off = 0;
   }
@@ -1278,6 +1294,7 @@ static int fba_run(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* st, char**
   long cg_total = 0;
   std::vector<LmRec> rec(VIDO_LM_REC);
   const double gain = (double)p->gain_threshold;
+  tt_loop0 = tnow();
   for (int it = 0; it < p->max_iterations && !c.stop_flag && c.ok; it++) {
     if (it == 0) { if ((rc = chi2_of(c.cur, &c.currentChi))) return rc; }
     // ---- buildSystem at the current state
@@ -1392,8 +1409,12 @@ static int fba_run(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* st, char**
     lm_end_iteration(&c, it, gain, rec.data());
   }
   // ---- results: float32 like Converter::toCvSE3 / toCvMat (src/Optimizer.cc:2090-2176)
+  const double tt_loop1 = tnow();
   VIDO_CUDA(cudaMemcpy(X.data(), d.X[c.cur], sizeof(Pose) * d.NS, cudaMemcpyDeviceToHost));
   VIDO_CUDA(cudaMemcpy(P.data(), d.P[c.cur], sizeof(double) * 3 * d.NP, cudaMemcpyDeviceToHost));
+  if (tdbg)
+    fprintf(stderr, "[fba] host ms: graph preparation %.1f, cudaMalloc %.1f (%.1f MB), upload + set-up %.1f, LM loop %.1f, download %.1f\n",
+            tt_alloc0 - tt0, tt_alloc1 - tt_alloc0, (double)pool.off / 1e6, tt_loop0 - tt_alloc1, tt_loop1 - tt_loop0, tnow() - tt_loop1);
   for (int i = 0; i < d.NS; i++) vb::pose_to_f32(X[perm[i]], p->se3 + 16 * (size_t)i);
   for (size_t i = 0; i < P.size(); i++) p->points[i] = (float)P[i];
   if (st) {
@@ -1410,6 +1431,6 @@ int fba_solve_host(vido_ctx* ctx, vido_fba_problem* p, vido_lm_stats* st) {
   char* arena = nullptr;
   const int rc = fba_run(ctx, p, st, &arena);
   cudaStreamSynchronize(ctx->stream);
-  if (arena) cudaFree(arena);
+  (void)arena;   // the arena belongs to the context (freed by vido_destroy)
   return rc;
 }
