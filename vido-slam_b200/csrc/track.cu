@@ -2161,17 +2161,29 @@ static int trk_track_chunk_impl(vido_ctx* ctx, const vido_frame_inputs* in, int 
           ts->chain_active = true;
         }
         const size_t K = ts->kp_cap;
-        const double te0 = now_ms();
-        while (e < B && !in[done + e].write_back_depth && ff[e].ob_sem.empty()) {
-          rc = chain_enqueue_frame(ctx, F.d_kp + e * K, F.d_nkp + e, F.d_kpmask + e * K, F.d_kpdepth + e * K, F.d_kpflow + 2 * e * K,
-                                   F.in_depth + (size_t)e * px, F.in_flow + 2 * (size_t)e * px, F.in_mask + (size_t)e * px, e);
-          if (rc) return rc;
-          e++;
-        }
-        ts->ht[4] += now_ms() - te0;
+        while (e < B && !in[done + e].write_back_depth && ff[e].ob_sem.empty()) e++;   // the run [b, e)
+        // The tracker kernels are queued a few frames ahead of the record being consumed, not the whole run at once: the first
+        // record of a batch is then ~0.5 ms away instead of ~1.3 ms (16 enqueues + the look-ahead launch), short enough for
+        // the window solver's queue of three to bridge the batch boundary.
+        const int AHEAD = 6;
+        int enq = b;
+        auto enqueue_upto = [&](int upto) -> int {
+          const double te0 = now_ms();
+          for (; enq < upto && enq < e; enq++) {
+            int r = chain_enqueue_frame(ctx, F.d_kp + enq * K, F.d_nkp + enq, F.d_kpmask + enq * K, F.d_kpdepth + enq * K, F.d_kpflow + 2 * enq * K,
+                                        F.in_depth + (size_t)enq * px, F.in_flow + 2 * (size_t)enq * px, F.in_mask + (size_t)enq * px, enq);
+            if (r) return r;
+          }
+          ts->ht[4] += now_ms() - te0;
+          return VIDO_OK;
+        };
+        rc = enqueue_upto(b + 3);
+        if (rc) return rc;
         rc = launch_ahead();
         if (rc) return rc;
         for (int k = b; k < e; k++) {
+          rc = enqueue_upto(k + 1 + AHEAD);
+          if (rc) return rc;
           vido_track_stats* sk = stats ? stats + done + k : nullptr;
           ts->cur_t = in[done + k].timestamp;
           rc = chain_consume(ctx, k, ff[k], Tcw_out + 16 * (size_t)(done + k), sk);
