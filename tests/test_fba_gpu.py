@@ -153,3 +153,33 @@ def test_gathered_block_solves_like_its_owner():
     for rank, diff, its, n in res:
         assert n == 2 and its >= 1
         assert diff <= 1e-4, (rank, diff)
+
+
+def test_full_batch_writes_the_reference_graph_files(pkg, tmp_path, monkeypatch):
+    """VIDO_SAVE_G2O=1: vido_full_batch writes dynamic_slam_graph_before_opt.g2o / ..._after_opt.g2o into the working directory like
+    Optimizer::FullBatchOptimization does (src/Optimizer.cc:1937,1939); the 'after' file holds the refined camera poses"""
+    import importlib
+    import synth
+    g2o_text = importlib.import_module("vido-slam_b200.g2o_text")
+    cam, n = synth.SMALL, 8
+    sc = synth.Scene(cam=cam, seed=5, flow_noise=0.1, depth_noise=0.01, n_objects=2)
+    frames = [sc.frame(k) for k in range(n)]
+    ctx = pkg.Context(pkg.default_config(width=cam["width"], height=cam["height"], fx=cam["fx"], fy=cam["fy"], cx=cam["cx"], cy=cam["cy"],
+                                         bf=cam["bf"], max_batch=4))
+    ctx.track_frames([dict(image=f["gray"].numpy(), depth=f["depth_in"].numpy(), flow=f["flow"].numpy(), mask=f["mask"].numpy().copy())
+                      for f in frames], want_stats=False)
+    g, n_poses = ctx.export_full_graph()
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setenv("VIDO_SAVE_G2O", "1")
+    st, sizes = ctx.full_batch()
+    before = g2o_text.read_g2o(tmp_path / "dynamic_slam_graph_before_opt.g2o")
+    after = g2o_text.read_g2o(tmp_path / "dynamic_slam_graph_after_opt.g2o")
+    assert len(before["se3"]) == len(g["se3"]) == sizes[0] + sizes[1] and len(before["points"]) == len(g["points"])
+    assert len(before["obs"]) == len(g["obs_se3"]) and len(before["tern"]) == len(g["tern_p1"]) and len(before["prior"]) == 1
+    T0 = np.asarray(g["se3"], np.float64).reshape(-1, 4, 4)
+    for k in (0, n_poses - 1, len(T0) - 1):
+        assert np.abs(before["se3"][g2o_text.FIRST_ID + k] - T0[k]).max() < 2e-5 * max(np.abs(T0[k]).max(), 1.0)   # 6 printed digits
+    P = ctx.map_poses_rf()
+    for k in (1, n_poses - 1):
+        assert np.abs(after["se3"][g2o_text.FIRST_ID + k] - P[k]).max() < 2e-5 * max(np.abs(P[k]).max(), 1.0)
+    ctx.close()

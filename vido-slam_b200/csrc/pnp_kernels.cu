@@ -466,6 +466,8 @@ struct PnpWorkspace {
   size_t in_bytes = 0, out_bytes = 0;
   int *tmp = nullptr, *cnt = nullptr;   // [PNP_MAX_BATCH][capN], [PNP_MAX_BATCH][capIters]
   PnpPose* hyp = nullptr;               // [PNP_MAX_BATCH][capIters]
+  PnpPose* c_hyp = nullptr;             // the device-chained tracker's own hypothesis scratch (it may run beside a host-driven batch)
+  int* c_cnt = nullptr;
   // device-chained camera problem (pnp_chain_enqueue): arguments per state buffer, inputs built on the device, outputs
   char* c_block = nullptr;
   PnpArgs* c_args[2] = {nullptr, nullptr};
@@ -497,7 +499,7 @@ void pnp_teardown(vido_ctx* ctx) {
   PnpWorkspace* ws = (PnpWorkspace*)ctx->pnp;
   if (!ws) return;
   cudaFree(ws->d_in); cudaFree(ws->d_out); cudaFreeHost(ws->h_in); cudaFreeHost(ws->h_out);
-  cudaFree(ws->tmp); cudaFree(ws->cnt); cudaFree(ws->hyp); cudaFree(ws->c_block);
+  cudaFree(ws->tmp); cudaFree(ws->cnt); cudaFree(ws->hyp); cudaFree(ws->c_block); cudaFree(ws->c_hyp); cudaFree(ws->c_cnt);
   delete ws;
   ctx->pnp = nullptr;
 }
@@ -667,6 +669,8 @@ int pnp_chain_setup(vido_ctx* ctx, int cap) {
                o_ids = o_good + al(4 * (size_t)cap), o_res = o_ids + al(4 * (size_t)cap), o_tmp = o_res + 256, total = o_tmp + al(4 * (size_t)cap);
   VIDO_CUDA(cudaMalloc(&ws->c_block, total));
   VIDO_CUDA(cudaMemset(ws->c_block, 0, total));
+  VIDO_CUDA(cudaMalloc(&ws->c_cnt, sizeof(int) * (size_t)ws->capIters));
+  VIDO_CUDA(cudaMalloc(&ws->c_hyp, sizeof(PnpPose) * (size_t)ws->capIters));
   ws->c_args[0] = (PnpArgs*)(ws->c_block + o_args); ws->c_args[1] = (PnpArgs*)(ws->c_block + o_args + PNP_ARGS_SLOT);
   ws->c_p3d = (float*)(ws->c_block + o_p3d); ws->c_tm = (float*)(ws->c_block + o_tm); ws->c_T = (float*)(ws->c_block + o_T);
   ws->c_good = (int*)(ws->c_block + o_good); ws->c_ids = (int*)(ws->c_block + o_ids); ws->c_res = (int*)(ws->c_block + o_res);
@@ -689,7 +693,7 @@ int pnp_chain_enqueue(vido_ctx* ctx, const ChainStateDev& st, int which, ChainPn
     a.iters = dp.iters; a.no_mm = 0;
     a.cur_xy = st.corres; a.pts3d = ws->c_p3d; a.good = ws->c_good; a.Tcw_motion = ws->c_tm;
     a.fx = c.fx; a.fy = c.fy; a.cx = c.cx; a.cy = c.cy; a.thr = dp.reproj_err; a.confidence = dp.confidence;
-    a.hyp = ws->hyp; a.hyp_cnt = ws->cnt;
+    a.hyp = ws->c_hyp; a.hyp_cnt = ws->c_cnt;
     a.Tcw_out = ws->c_T; a.inlier_ids = ws->c_ids; a.result = ws->c_res; a.tmp_ids = ws->c_tmp;
     VIDO_CUDA(cudaMemcpyAsync(ws->c_args[which], &a, sizeof a, cudaMemcpyHostToDevice, s));   // pageable source: staged before return
     ws->c_ready[which] = true;

@@ -862,6 +862,8 @@ struct PoWorkspace {
   int* level = nullptr;
   // device-chained camera problem (po_chain_enqueue)
   char* c_block = nullptr;
+  double *c_Xw = nullptr, *c_flowd = nullptr, *c_xl = nullptr, *c_eProj = nullptr;   // chain-private scratch
+  int* c_level = nullptr;
   PoArgs* c_args[2] = {nullptr, nullptr};
   float *c_obs = nullptr, *c_flow = nullptr, *c_dep = nullptr, *c_T = nullptr, *c_flowout = nullptr;
   int *c_inl = nullptr, *c_ninl = nullptr, *c_n = nullptr;
@@ -901,6 +903,7 @@ void po_teardown(vido_ctx* ctx) {
   if (!ws) return;
   cudaFree(ws->d_in); cudaFree(ws->d_out); cudaFreeHost(ws->h_in); cudaFreeHost(ws->h_out);
   cudaFree(ws->Xw); cudaFree(ws->flow); cudaFree(ws->xl); cudaFree(ws->eProj); cudaFree(ws->level); cudaFree(ws->c_block);
+  cudaFree(ws->c_Xw); cudaFree(ws->c_flowd); cudaFree(ws->c_xl); cudaFree(ws->c_eProj); cudaFree(ws->c_level);
   delete ws;
   ctx->po = nullptr;
 }
@@ -1026,6 +1029,12 @@ int po_chain_setup(vido_ctx* ctx, int cap) {
                o_n = o_ninl + 256, o_ctl = o_n + 256, total = o_ctl + al(sizeof(LmCtl) * 4);
   VIDO_CUDA(cudaMalloc(&ws->c_block, total));
   VIDO_CUDA(cudaMemset(ws->c_block, 0, total));
+  // the chain's own per-vertex scratch: it may run beside a host-driven batch (the objects of a frame)
+  VIDO_CUDA(cudaMalloc(&ws->c_Xw, sizeof(double) * 3 * (size_t)cap));
+  VIDO_CUDA(cudaMalloc(&ws->c_flowd, sizeof(double) * 4 * (size_t)cap));
+  VIDO_CUDA(cudaMalloc(&ws->c_xl, sizeof(double) * 2 * (size_t)cap));
+  VIDO_CUDA(cudaMalloc(&ws->c_eProj, sizeof(double) * 2 * (size_t)cap));
+  VIDO_CUDA(cudaMalloc(&ws->c_level, sizeof(int) * (size_t)cap));
   ws->c_args[0] = (PoArgs*)(ws->c_block + o_args); ws->c_args[1] = ws->c_args[0] + 1;
   ws->c_obs = (float*)(ws->c_block + o_obs); ws->c_flow = (float*)(ws->c_block + o_flow); ws->c_dep = (float*)(ws->c_block + o_dep);
   ws->c_T = (float*)(ws->c_block + o_T); ws->c_flowout = (float*)(ws->c_block + o_fo); ws->c_inl = (int*)(ws->c_block + o_inl);
@@ -1050,7 +1059,7 @@ int po_chain_enqueue(vido_ctx* ctx, const ChainStateDev& st, int which, const Ch
     a.delta = (double)sqrtf(p.rp_thres);
     a.th0 = p.rp_thres; a.th1 = p.chi2_th;
     a.rounds = p.rounds; a.its = p.its;
-    a.Xw = ws->Xw; a.flow = ws->flow; a.xl = ws->xl; a.eProj = ws->eProj; a.level = ws->level;
+    a.Xw = ws->c_Xw; a.flow = ws->c_flowd; a.xl = ws->c_xl; a.eProj = ws->c_eProj; a.level = ws->c_level;
     a.Tcw_out = ws->c_T; a.n_inliers = ws->c_ninl; a.flow_out = ws->c_flowout; a.inlier = ws->c_inl;
     a.ctl = ws->c_ctl; a.rec = nullptr;
     VIDO_CUDA(cudaMemcpyAsync(ws->c_args[which], &a, sizeof a, cudaMemcpyHostToDevice, s));

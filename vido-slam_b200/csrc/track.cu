@@ -265,6 +265,7 @@ struct TrackState {
   int fe_cur = 0;
   uint8_t* d_gray = nullptr;     // [B][H][W] (front-end stream only)
   cudaStream_t copy_stream = nullptr, fe_stream = nullptr;
+  cudaStream_t obj_stream = nullptr;   // object part of a frame whose static part runs on the device chain (hybrid_consume)
   std::vector<vido_frame_inputs> hint;  // frames announced by vido_track_prefetch
   float* d_q = nullptr; int32_t* d_qmask = nullptr; float* d_qdepth = nullptr; float* d_qflow = nullptr;  // per-frame queries
   float* d_check = nullptr; uint8_t* d_used = nullptr;
@@ -375,6 +376,7 @@ int trk_setup(vido_ctx* ctx) {
   VIDO_CUDA(cudaMalloc(&ts->d_gray, px * B));
   VIDO_CUDA(vido_create_stream(&ts->copy_stream, false));
   VIDO_CUDA(vido_create_stream(&ts->fe_stream, false));
+  VIDO_CUDA(vido_create_stream(&ts->obj_stream, true));
   VIDO_CUDA(cudaMalloc(&ts->d_q, 8 * ts->q_cap)); VIDO_CUDA(cudaMalloc(&ts->d_qmask, 4 * ts->q_cap));
   VIDO_CUDA(cudaMalloc(&ts->d_qdepth, 4 * ts->q_cap)); VIDO_CUDA(cudaMalloc(&ts->d_qflow, 8 * ts->q_cap));
   VIDO_CUDA(cudaMalloc(&ts->d_check, 8 * ts->q_cap)); VIDO_CUDA(cudaMalloc(&ts->d_used, std::max(ts->kp_cap, ts->obj_cap)));
@@ -389,6 +391,7 @@ void trk_teardown(vido_ctx* ctx) {
   if (!ts) return;
   if (ts->copy_stream) { cudaStreamSynchronize(ts->copy_stream); cudaStreamDestroy(ts->copy_stream); }
   if (ts->fe_stream) { cudaStreamSynchronize(ts->fe_stream); cudaStreamDestroy(ts->fe_stream); }
+  if (ts->obj_stream) { cudaStreamSynchronize(ts->obj_stream); cudaStreamDestroy(ts->obj_stream); }
   for (int k = 0; k < 2; k++) {
     TrackState::FeSlot& F = ts->fe[k];
     cudaFree(F.d_img); cudaFree(F.d_depth); cudaFree(F.d_flow); cudaFree(F.d_mask); cudaFree(F.d_out); cudaFreeHost(F.h_out);
@@ -1632,7 +1635,8 @@ static void link_static_tracks_at(TrackState* ts, MapFrame& F, MapFrame& P, int 
   }
 }
 
-static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int slot, float* Tcw_out, vido_track_stats* st) {
+// premask_nrec >= 0: UpdateMask (and the front-end redo it asked for) has been done by the caller, with that many recovered labels
+static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int slot, float* Tcw_out, vido_track_stats* st, int premask_nrec = -1) {
   TrackState* ts = (TrackState*)ctx->trk;
   const vido_config& c = ctx->cfg;
   const int W = c.width, H = c.height;
@@ -1652,7 +1656,9 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
   const bool htime = getenv("VIDO_HOST_TIMING") != nullptr;
   double tm = htime ? now_ms() : 0;
   auto lap = [&](int k) { if (htime) { const double t_ = now_ms(); ts->dt[k] += t_ - tm; tm = t_; } };
-  if (ts->initialised && !ts->lo_sem.empty() && ts->have_last_maps) {
+  if (premask_nrec >= 0) {
+    if (st) st->n_masks_recovered = premask_nrec;
+  } else if (ts->initialised && !ts->lo_sem.empty() && ts->have_last_maps) {
     const int nl = (int)ts->lo_sem.size();
     std::vector<int32_t> uniq(nl), rec(nl);
     const int nu = assoc_update_mask(ctx, ts->lo_sem.data(), ts->lo_corres.data(), nl, ts->d_last_mask, ts->d_last_flow,
@@ -2025,7 +2031,8 @@ static bool chain_eligible(vido_ctx* ctx, const FrontFrame& ff, const vido_frame
   const vido_config& c = ctx->cfg;
   if (getenv("VIDO_NO_CHAIN")) return false;   // debug: host-driven path only
   if (!ts->initialised || ts->vio || !c.b_joint || in.write_back_depth) return false;
-  if (!ts->lo_corres.empty() || !ff.ob_sem.empty() || !ts->lo_sem.empty()) return false;
+  // frames with object features: the static part on the chain, the object part on the host beside it (hybrid_consume)
+  if ((!ts->lo_corres.empty() || !ff.ob_sem.empty() || !ts->lo_sem.empty()) && getenv("VIDO_NO_HYBRID")) return false;
   return (int)(ts->last_corres.size() / 2) <= chain_capacity(ctx);
 }
 
@@ -2088,6 +2095,106 @@ static int chain_consume(vido_ctx* ctx, int slot, const FrontFrame& ff, float* T
   const double th4 = now_ms();
   ts->ht[0] += th1 - th0; ts->ht[1] += th2 - th1; ts->ht[2] += th3 - th2; ts->ht[3] += th4 - th3; ts->hn++;
   return rc;
+}
+
+// A frame with object features on the device-chained path.  Its static part (camera PnP, pose optimisation, static renewal)
+// was queued with the tracker chain on the context stream -- possibly several frames ago; the object part (Tracking::UpdateMask,
+// the carry-over of the object features, scene flow + DynObjTracking, the per-object PnP and motion optimisation, the object
+// part of RenewFrameInfo, the Map bookkeeping) runs here, with its kernels on a second stream and scratch the chain does not
+// share, in the order of the host-driven path (back_end).  The static part does not depend on the object part of the same or
+// of earlier frames except through UpdateMask: when that re-warps a lost label into this frame's mask the front-end products
+// the chain used are stale -- *fallback is set and the caller redoes the frame on the host-driven path (rare).
+static int hybrid_consume(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int slot, float* Tcw_out, vido_track_stats* st, int* fallback) {
+  TrackState* ts = (TrackState*)ctx->trk;
+  const vido_config& c = ctx->cfg;
+  const size_t px = (size_t)c.width * c.height;
+  const float* d_depth = FS.in_depth; const float* d_flow = FS.in_flow; const int32_t* d_mask = FS.in_mask;
+  *fallback = -1;
+  struct StreamSwap {   // the host-side helpers of the object path launch on ctx->stream
+    vido_ctx* c; cudaStream_t keep;
+    ~StreamSwap() { c->stream = keep; }
+  } swap{ctx, ctx->stream};
+  ctx->stream = ts->obj_stream;
+  const double th0 = now_ms();
+  if (st) { memset(st, 0, sizeof *st); st->n_keypoints = (int)ff.kps.size(); st->ba_iterations = -1; }
+  int nrec = 0;
+  if (!ts->lo_sem.empty() && ts->have_last_maps) {   // ---- Tracking::UpdateMask (see back_end)
+    const int nl = (int)ts->lo_sem.size();
+    std::vector<int32_t> uniq(nl), rec(nl);
+    const int nu = assoc_update_mask(ctx, ts->lo_sem.data(), ts->lo_corres.data(), nl, ts->d_last_mask, ts->d_last_flow,
+                                     (int32_t*)d_mask + (size_t)slot * px, uniq.data(), rec.data(), nl);
+    if (nu < 0) return nu;
+    for (int k = 0; k < nu; k++) nrec += rec[k] ? 1 : 0;
+    if (nrec) { *fallback = nrec; return VIDO_OK; }
+  }
+  DynFrame D;
+  int rc = VIDO_OK;
+  if (!ts->lo_corres.empty()) {
+    rc = dyn_carry_over(ctx, d_depth, d_flow, d_mask, slot, D);
+    if (rc) return rc;
+  }
+  // ---- the static part of the frame: the chain's record
+  const int32_t* hdr; const float *Tcw, *Twc, *rel, *vel, *xy, *depth, *p3, *corres, *flow; const int32_t* asso;
+  const double th1 = now_ms();
+  rc = chain_wait_record(ctx, slot, &hdr, &Tcw, &Twc, &rel, &vel, &xy, &depth, &p3, &corres, &flow, &asso);
+  if (rc) return rc;
+  const double th2 = now_ms();
+  memcpy(Tcw_out, Tcw, sizeof(float) * 16);
+  if (hdr[0] == 1) {   // lost tracking: nothing was processed (see back_end)
+    ts->f_id++; ts->frames_seen++;
+    return 1;
+  }
+  float curTcw[16];
+  memcpy(curTcw, Tcw, sizeof curTcw);
+  // ---- object tracking and motions against the LAST frame's pose (ts->lastTcw is updated below)
+  if (!ts->lo_corres.empty()) {
+    const std::vector<std::vector<int>> ObjIdNew = dyn_track_objects(ctx, curTcw, D);
+    rc = dyn_object_motions(ctx, curTcw, ObjIdNew, D);
+    if (rc) return rc;
+    if (st) { st->n_objects = (int)ObjIdNew.size(); for (char b : D.stat) st->n_objects_ok += b ? 1 : 0; }
+  }
+  const int nf = hdr[7];
+  MapFrame F;
+  F.xy.assign(xy, xy + 2 * (size_t)nf); F.depth.assign(depth, depth + nf); F.p3.assign(p3, p3 + 3 * (size_t)nf);
+  F.asso.assign(asso, asso + nf);
+  F.track.assign(nf, -1); F.pos.assign(nf, 0);   // linked by the solver thread
+  memcpy(F.Twc, Twc, sizeof(float) * 16); memcpy(F.Twc_rf, Twc, sizeof(float) * 16); memcpy(F.rel, rel, sizeof(float) * 16);
+  if (!ts->lo_corres.empty() || !ff.ob_sem.empty()) {   // RenewFrameInfo (object part), Map bookkeeping, dynamic tracklets
+    rc = dyn_renew(ctx, ff, curTcw, FS.d_obkeys + 2 * (size_t)slot * ts->obj_cap, d_depth, d_flow, d_mask, slot, D, F);
+    if (rc) return rc;
+    if (st) st->n_dyn_features = (int)F.ddepth.size();
+  }
+  ts->last_keys = F.xy; ts->last_depth = F.depth;
+  ts->last_corres.assign(corres, corres + 2 * (size_t)nf); ts->last_flow.assign(flow, flow + 2 * (size_t)nf);
+  memcpy(ts->lastTcw, Tcw, sizeof(float) * 16);
+  memcpy(ts->mVelocity, vel, sizeof(float) * 16);
+  ts->has_velocity = true;
+  if (ts->map.size() == ts->map.capacity()) {
+    rc = ba_async_join(ctx);
+    if (rc) return rc;
+    ts->map.reserve(std::max<size_t>(4096, 2 * ts->map.capacity()));
+  }
+  ts->map.push_back(std::move(F));
+  if (st) {
+    st->n_matches = hdr[1]; st->n_init_inliers = hdr[2]; st->init_winner = hdr[3]; st->n_pose_inliers = hdr[6]; st->n_static = nf;
+    st->n_masks_recovered = 0;
+  }
+  const int window = ts->f_id < c.window_size ? ts->f_id : c.window_size;
+  ts->f_id++; ts->frames_seen++;
+  rc = ba_async_post(ctx, (int)ts->map.size(), window, st);
+  if (rc) return rc;
+  // mSegMapLast / mFlowMapLast (see back_end): private copies while the frame carries object features
+  ts->have_last_maps = false;
+  if (!ts->lo_sem.empty()) {
+    cudaStream_t s = ctx->stream;
+    VIDO_CUDA(cudaMemcpyAsync(ts->d_last_mask, d_mask + (size_t)slot * px, px * 4, cudaMemcpyDeviceToDevice, s));
+    VIDO_CUDA(cudaMemcpyAsync(ts->d_last_flow, d_flow + 2 * (size_t)slot * px, px * 8, cudaMemcpyDeviceToDevice, s));
+    VIDO_CUDA(cudaStreamSynchronize(s));
+    ts->have_last_maps = true;
+  }
+  const double th3 = now_ms();
+  ts->ht[0] += th2 - th1; ts->ht[1] += (th1 - th0) + (th3 - th2); ts->hn++;
+  return VIDO_OK;
 }
 
 int trk_prefetch(vido_ctx* ctx, const vido_frame_inputs* in, int nframes) {
@@ -2161,7 +2268,8 @@ static int trk_track_chunk_impl(vido_ctx* ctx, const vido_frame_inputs* in, int 
           ts->chain_active = true;
         }
         const size_t K = ts->kp_cap;
-        while (e < B && !in[done + e].write_back_depth && ff[e].ob_sem.empty()) e++;   // the run [b, e)
+        const bool hybrid_ok = !getenv("VIDO_NO_HYBRID");
+        while (e < B && !in[done + e].write_back_depth && (hybrid_ok || ff[e].ob_sem.empty())) e++;   // the run [b, e)
         // The tracker kernels are queued a few frames ahead of the record being consumed, not the whole run at once: the first
         // record of a batch is then ~0.5 ms away instead of ~1.3 ms (16 enqueues + the look-ahead launch), short enough for
         // the window solver's queue of three to bridge the batch boundary.
@@ -2186,8 +2294,29 @@ static int trk_track_chunk_impl(vido_ctx* ctx, const vido_frame_inputs* in, int 
           if (rc) return rc;
           vido_track_stats* sk = stats ? stats + done + k : nullptr;
           ts->cur_t = in[done + k].timestamp;
-          rc = chain_consume(ctx, k, ff[k], Tcw_out + 16 * (size_t)(done + k), sk);
-          if (rc < 0) return rc;
+          if (!ts->lo_corres.empty() || !ts->lo_sem.empty() || !ff[k].ob_sem.empty()) {
+            int nrec = -1;
+            rc = hybrid_consume(ctx, F, ff[k], k, Tcw_out + 16 * (size_t)(done + k), sk, &nrec);
+            if (rc < 0) return rc;
+            if (nrec >= 0) {
+              // UpdateMask re-warped a label into this frame's mask: what the chain computed for this and the queued frames
+              // used stale front-end products.  Drop it, repeat the mask-dependent front-end stages and the whole frame on the
+              // host-driven path; the next frame starts a new run from the host mirrors (unchanged since the last consume).
+              const int32_t* hdr; const float *a0, *a1, *a2, *a3, *a4, *a5, *a6, *a7, *a8; const int32_t* a9;
+              for (int j = k; j < enq; j++) { rc = chain_wait_record(ctx, j, &hdr, &a0, &a1, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &a9); if (rc) return rc; }
+              ts->chain_active = false;
+              rc = fe_redo_frame(ctx, F, k, ff[k]);
+              if (rc) return rc;
+              rc = back_end(ctx, F, ff[k], k, Tcw_out + 16 * (size_t)(done + k), sk, nrec);
+              if (rc < 0) return rc;
+              if (sk) { sk->ms_orb = front_ms; sk->ms_assoc = 0; }
+              e = k + 1;
+              break;
+            }
+          } else {
+            rc = chain_consume(ctx, k, ff[k], Tcw_out + 16 * (size_t)(done + k), sk);
+            if (rc < 0) return rc;
+          }
           if (sk) { sk->ms_orb = front_ms; sk->ms_assoc = 0; }
         }
         b = e - 1;
