@@ -266,6 +266,7 @@ struct TrackState {
   uint8_t* d_gray = nullptr;     // [B][H][W] (front-end stream only)
   cudaStream_t copy_stream = nullptr, fe_stream = nullptr;
   cudaStream_t obj_stream = nullptr;   // object part of a frame whose static part runs on the device chain (hybrid_consume)
+  bool obj_stream_pending = false;     // copies queued on obj_stream that nobody has waited for yet
   std::vector<vido_frame_inputs> hint;  // frames announced by vido_track_prefetch
   float* d_q = nullptr; int32_t* d_qmask = nullptr; float* d_qdepth = nullptr; float* d_qflow = nullptr;  // per-frame queries
   float* d_check = nullptr; uint8_t* d_used = nullptr;
@@ -410,6 +411,8 @@ void trk_teardown(vido_ctx* ctx) {
 int trk_reset(vido_ctx* ctx) {
   TrackState* ts = (TrackState*)ctx->trk;
   ba_async_join(ctx);   // (an error of the abandoned sequence is dropped with it)
+  if (ts->obj_stream) cudaStreamSynchronize(ts->obj_stream);
+  ts->obj_stream_pending = false;
   while (ts->ba_nq > 0) { vido_lm_stats ls; ba_collect(ctx, &ts->job[ts->ba_queue[0]].pr, &ls); ts->ba_queue[0] = ts->ba_queue[1]; ts->ba_queue[1] = ts->ba_queue[2]; ts->ba_nq--; }
   ts->ba_deferred.valid = false;
   ts->chain_active = false;
@@ -1648,6 +1651,7 @@ static int back_end(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff, int s
   float curTcw[16];
   eye44(curTcw);
   { int rcj = ba_async_join(ctx); if (rcj) return rcj; }   // the host-driven path stages its window solves on this thread
+  if (ts->obj_stream_pending) { VIDO_CUDA(cudaStreamSynchronize(ts->obj_stream)); ts->obj_stream_pending = false; }
   if (st) { memset(st, 0, sizeof *st); st->n_keypoints = (int)ff.kps.size(); }
   int skipped = 0;
   double t0 = now_ms();
@@ -2189,7 +2193,9 @@ static int hybrid_consume(vido_ctx* ctx, TrackState::FeSlot& FS, FrontFrame& ff,
     cudaStream_t s = ctx->stream;
     VIDO_CUDA(cudaMemcpyAsync(ts->d_last_mask, d_mask + (size_t)slot * px, px * 4, cudaMemcpyDeviceToDevice, s));
     VIDO_CUDA(cudaMemcpyAsync(ts->d_last_flow, d_flow + 2 * (size_t)slot * px, px * 8, cudaMemcpyDeviceToDevice, s));
-    VIDO_CUDA(cudaStreamSynchronize(s));
+    // not waited for here: the only reader is the next frame's UpdateMask on this same stream; the slot is not recycled before
+    // the next batch, and the host-driven path and the end of the call synchronise this stream first (obj_stream_pending)
+    ts->obj_stream_pending = true;
     ts->have_last_maps = true;
   }
   const double th3 = now_ms();
@@ -2340,6 +2346,7 @@ static int trk_track_chunk_impl(vido_ctx* ctx, const vido_frame_inputs* in, int 
     }
     rc = launch_ahead();
     if (rc) return rc;
+    if (ts->obj_stream_pending) { VIDO_CUDA(cudaStreamSynchronize(ts->obj_stream)); ts->obj_stream_pending = false; }   // before the slot (or the caller's buffer) is reused
     ts->fe_cur ^= 1;
     done += B;
   }
@@ -2394,6 +2401,8 @@ int trk_track_chunk(vido_ctx* ctx, const vido_frame_inputs* in, int nframes, flo
     { std::lock_guard<std::mutex> lk(ts->ba_mu); ts->ba_jobs.clear(); }
     ba_async_join(ctx);
     cudaStreamSynchronize(ctx->stream);
+    if (ts->obj_stream) cudaStreamSynchronize(ts->obj_stream);
+    ts->obj_stream_pending = false;
     ts->call_failed = true;
   }
   if (stats || rc < 0) {   // (without a statistics array every queued pointer is null already and the solver thread may be running)
