@@ -5,19 +5,20 @@
 // the reference factors the full (poses + points) H with CSparse; here the points are eliminated first (Schur complement)
 // and the reduced 6W x 6W system is factored densely.  Same linear system, same positive-definiteness test (all pivots > 0).
 //
-// Structure (right-looking LL^T, block size 8 = one FP64 tensor-core tile):
-//   * the trailing matrix lives in REGISTERS for the whole factorisation: every 8x8 tile is owned by one of the 12 "bulk"
-//     warps as an m8n8k4 accumulator fragment (2 doubles per lane); the rank-8 trailing update of a tile is two
-//     mma.sync.m8n8k4.f64 (DMMA) whose A/B fragments come from the 8-wide panel buffer Lp.  Only the tiles of the next
-//     block column are written back to shared memory after a step (they are final), so the shared-memory traffic per step
-//     is the panel, not the trailing matrix (the scalar version of round 1 was bound by exactly that traffic).
-//   * warp 0 is the "chain" warp: the pivot chain (8 x (rsqrt + dependent FMA) per block) is the critical path of the
-//     factorisation, so warp 0 runs one block ahead -- it solves the 8 panel rows of block jb+1, applies their update to
-//     the diagonal block jb+1 and factors it while the bulk warps are still busy with step jb.
-//   * one named barrier (panel complete; the chain warp only arrives) and one CTA barrier per block step.
-//   * the right-hand side rides along as row np of the matrix (forward substitution = part of the panel steps); the
-//     8x8 inverses of the diagonal factors are computed off the critical path and turn the back substitution into
-//     matrix-vector products.
+// Structure (LL^T, block size 8 = one FP64 tensor-core tile, mma.sync.m8n8k4.f64 = SASS DMMA.8x8x4):
+//   * warp 15 is the "chain" warp: the pivot chain (8 x (rsqrt + dependent FMA) per block) is the critical path of the
+//     factorisation, so it runs one block ahead -- it solves the 8 panel rows of block jb+1, applies their update to the
+//     diagonal block jb+1 (two DMMA) and factors it (one lane, in registers) while the bulk warps are busy with step jb;
+//   * twelve "bulk" warps form the panel (thread per row) and update tiles LEFT-looking: at step jb only the tiles of block
+//     column jb+1 and the diagonal tile jb+2 are brought up to date, with all panels 0..jb, as chains of DMMA over four
+//     accumulator pairs; the tile's original value comes from the global copy of the system, fetched a step ahead;
+//   * warp 11 inverts every freshly factored diagonal block off the critical path: the back substitution then is a
+//     matrix-vector product per block;
+//   * named barriers with immediate ids (panel complete; end of step; block factored) instead of CTA barriers;
+//   * the right-hand side rides along as row np of the matrix (forward substitution = part of the panel steps).
+// Measured alternatives are recorded next to the code they lost against (right-looking register-resident trailing matrix, panel
+// as a DMMA product with the inverse factor, 14 bulk warps, software-pipelined tile loop, one barrier per 32-row chunk in the
+// back substitution): profiles/r2_chol_probe.txt, tools/chol_probe2.cu.
 #pragma once
 #include <cuda_runtime.h>
 
