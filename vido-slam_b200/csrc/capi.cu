@@ -102,6 +102,7 @@ void vido_destroy(vido_ctx* ctx) {
   for (int k = 0; k < 3; k++) if (ctx->raw_stage[k]) cudaFree(ctx->raw_stage[k]);
   for (int k = 0; k < 4; k++) if (ctx->raw_dev[k]) cudaFree(ctx->raw_dev[k]);
   if (ctx->fba_arena) cudaFree(ctx->fba_arena);
+  for (int k = 0; k < 3; k++) if (ctx->scratch[k]) cudaFree(ctx->scratch[k]);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);

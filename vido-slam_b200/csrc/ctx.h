@@ -56,6 +56,8 @@ struct vido_ctx {
   double ba_alg_bytes = 0;         // algorithmic bytes of the BA launches so far (SURVEY.md 8d accounting)
   void* raw_stage[3] = {nullptr, nullptr, nullptr};   // vido_convert_raw: device staging of host raw image / depth / mask
   size_t raw_cap[3] = {0, 0, 0};
+  void* scratch[3] = {nullptr, nullptr, nullptr};   // grow-only device scratch of the per-call entry points (0 inertial, 1 projection-only, 2 IMU preintegration): vido_scratch()
+  size_t scratch_bytes[3] = {0, 0, 0};
   void* fba_arena = nullptr;       // FullBatch device arena, grow-only (fba_kernels.cu)
   size_t fba_arena_bytes = 0;
   void* raw_dev[4] = {nullptr, nullptr, nullptr, nullptr};   // vido_track_raw_frames: converted BGR / depth / flow / mask of one batch
@@ -107,6 +109,20 @@ struct vido_ctx {
   char* um_ws = nullptr;   // UpdateMask workspace (assoc_kernels.cu), grown on demand: cudaMalloc is expensive once peer
   size_t um_ws_bytes = 0;  // access is enabled (NCCL), so nothing on the per-frame path allocates
 };
+
+// Grow-only device scratch kept by the context (freed by vido_destroy): a cudaMalloc / cudaFree pair per call costs anything from
+// a millisecond to several hundred (measured, driver-side) and synchronises the device.  Doubles on growth.
+inline void* vido_scratch(vido_ctx* ctx, int slot, size_t bytes) {
+  if (ctx->scratch_bytes[slot] < bytes) {
+    if (ctx->scratch[slot]) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->scratch[slot]); }
+    ctx->scratch[slot] = nullptr; ctx->scratch_bytes[slot] = 0;
+    const size_t want = bytes * 2;
+    if (cudaMalloc(&ctx->scratch[slot], want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    ctx->scratch_bytes[slot] = want;
+  }
+  return ctx->scratch[slot];
+}
+
 
 #define VIDO_CUDA(call)                                                                     \
   do {                                                                                      \

@@ -202,13 +202,17 @@ int imu_preintegrate_host(vido_ctx* ctx, const vido_imu_sample* samples, int n, 
                           int njobs, const float* bias, const float* noise, vido_imu_preint* out, const int32_t* nvis) {
   if (n < 0 || njobs < 1) return VIDO_ERR_ARG;
   cudaStream_t s = ctx->stream;
-  vido_imu_sample* d_s = nullptr; double* d_t = nullptr; float* d_b = nullptr; vido_imu_preint* d_o = nullptr; int32_t* d_n = nullptr;
-  VIDO_CUDA(cudaMallocAsync(&d_s, sizeof(vido_imu_sample) * std::max(n, 1), s));
-  VIDO_CUDA(cudaMallocAsync(&d_t, sizeof(double) * 2 * njobs, s));
-  VIDO_CUDA(cudaMallocAsync(&d_b, sizeof(float) * 6 * njobs, s));
-  VIDO_CUDA(cudaMallocAsync(&d_o, sizeof(vido_imu_preint) * njobs, s));
+  // one carved block of the context's grow-only scratch (stream-ordered allocations come from a pool that hands its memory back to
+  // the OS at every synchronisation by default: five of them per call made this entry point erratic, 0.1 .. 20 ms)
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t o_s = 0, o_t = o_s + al(sizeof(vido_imu_sample) * (size_t)std::max(n, 1)), o_b = o_t + al(sizeof(double) * 2 * njobs),
+               o_o = o_b + al(sizeof(float) * 6 * njobs), o_n = o_o + al(sizeof(vido_imu_preint) * njobs), total = o_n + al(sizeof(int32_t) * njobs);
+  char* base = (char*)vido_scratch(ctx, 2, total);
+  if (!base) { ctx->err = "imu preintegration: device allocation failed"; return VIDO_ERR_CUDA; }
+  vido_imu_sample* d_s = (vido_imu_sample*)(base + o_s); double* d_t = (double*)(base + o_t); float* d_b = (float*)(base + o_b);
+  vido_imu_preint* d_o = (vido_imu_preint*)(base + o_o); int32_t* d_n = nullptr;
   if (nvis) {
-    VIDO_CUDA(cudaMallocAsync(&d_n, sizeof(int32_t) * njobs, s));
+    d_n = (int32_t*)(base + o_n);
     VIDO_CUDA(cudaMemcpyAsync(d_n, nvis, sizeof(int32_t) * njobs, cudaMemcpyHostToDevice, s));
   }
   if (n) VIDO_CUDA(cudaMemcpyAsync(d_s, samples, sizeof(vido_imu_sample) * n, cudaMemcpyHostToDevice, s));
@@ -220,7 +224,5 @@ int imu_preintegrate_host(vido_ctx* ctx, const vido_imu_sample* samples, int n, 
   VIDO_CUDA(cudaGetLastError());
   VIDO_CUDA(cudaMemcpyAsync(out, d_o, sizeof(vido_imu_preint) * njobs, cudaMemcpyDeviceToHost, s));
   VIDO_CUDA(cudaStreamSynchronize(s));
-  cudaFreeAsync(d_s, s); cudaFreeAsync(d_t, s); cudaFreeAsync(d_b, s); cudaFreeAsync(d_o, s);
-  if (d_n) cudaFreeAsync(d_n, s);
   return VIDO_OK;
 }

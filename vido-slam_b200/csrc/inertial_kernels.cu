@@ -643,8 +643,8 @@ int inertial_opt_host(vido_ctx* ctx, vido_inertial_problem* p, vido_lm_stats* st
                o_D = take(8 * 9 * N), o_O = take(8 * 9 * N), o_Bv = take(8 * 27 * N), o_bv = take(8 * 3 * N), o_x = take(8 * (3 * N + 9)),
                o_L = take(8 * 9 * N), o_M = take(8 * 9 * N), o_Y = take(8 * 27 * N), o_cc = take(8 * 3 * N), o_ctl = take(sizeof(LmCtl)),
                o_rec = take(sizeof(LmRec) * VIDO_LM_REC);
-  char* base = nullptr;
-  VIDO_CUDA(cudaMalloc(&base, off));
+  char* base = (char*)vido_scratch(ctx, 0, off);
+  if (!base) { ctx->err = "inertial: device allocation failed"; return VIDO_ERR_CUDA; }
   int rc = VIDO_OK;
   do {
 #define CP(o, src, bytes) if (cudaMemcpyAsync(base + (o), src, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) { ctx->err = "inertial: upload failed"; rc = VIDO_ERR_CUDA; break; }
@@ -684,7 +684,6 @@ int inertial_opt_host(vido_ctx* ctx, vido_inertial_problem* p, vido_lm_stats* st
       for (int k = 0; k < c.n_records && k < VIDO_LM_MAX_RECORDS; k++) { st->rec[k].chi2 = rec[k].chi2; st->rec[k].lambda = rec[k].lambda; st->rec[k].trials = rec[k].trials; }
     }
   } while (0);
-  cudaStreamSynchronize(s);
-  cudaFree(base);
+  cudaStreamSynchronize(s);   // (the scratch belongs to the context)
   return rc;
 }

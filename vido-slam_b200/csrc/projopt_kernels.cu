@@ -283,8 +283,8 @@ int projopt_host(vido_ctx* ctx, vido_projopt_problem* prs, int nproblems, vido_l
     o_ctl[k] = off; off += al(sizeof(LmCtl)); o_rec[k] = off; off += al(sizeof(LmRec) * VIDO_LM_REC);
   }
   if (active.empty()) return VIDO_OK;
-  char* base = nullptr;
-  VIDO_CUDA(cudaMalloc(&base, off));
+  char* base = (char*)vido_scratch(ctx, 1, off);
+  if (!base) { ctx->err = "projection-only optimisation: device allocation failed"; return VIDO_ERR_CUDA; }
   std::vector<char> host(off, 0);
   ProjArgs* ha = (ProjArgs*)host.data();
   for (size_t q = 0; q < active.size(); q++) {
@@ -326,7 +326,6 @@ int projopt_host(vido_ctx* ctx, vido_projopt_problem* prs, int nproblems, vido_l
       }
     }
   } while (0);
-  cudaStreamSynchronize(s);
-  cudaFree(base);
+  cudaStreamSynchronize(s);   // (the scratch belongs to the context)
   return rc;
 }

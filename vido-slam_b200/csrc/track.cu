@@ -2030,13 +2030,33 @@ static int prefetch_array(vido_ctx* ctx, cudaStream_t cs, void* dst, const void*
 // ---------------------------------------------------------------------------------------------------------
 // A frame can go through the chain when nothing of the object / inertial machinery is involved and the tracker state fits the
 // chain's buffers (always true from the second tracked frame on: RenewFrameInfo caps the static features at MaxTrackPointBG+1).
+// VIO mode on the device-chained path: only frames whose Tracking::Track tail is bookkeeping -- the IMU is initialised and the
+// frame does not fall into one of the ScaleRefinement windows of mTinit (vio_after_ba); T is advanced like there (float sum).
+static bool vio_frame_is_plain(const TrackState* ts, float* T, double t_prev, double t, int ahead /* frames queued in front of this one */) {
+  const vido_imu_state& ist = ts->ist;
+  if (!ist.initialized) return false;
+  if (*T >= 100.0f) return true;
+  const float Tn = (float)((double)*T + (t - t_prev));
+  const bool win = (Tn > 15.0f && Tn < 15.5f) || (Tn > 25.0f && Tn < 25.5f) || (Tn > 35.0f && Tn < 35.5f) || (Tn > 45.0f && Tn < 45.5f) ||
+                   (Tn > 55.0f && Tn < 55.5f) || (Tn > 65.0f && Tn < 65.5f) || (Tn > 75.0f && Tn < 75.5f);
+  if (win && (int)ts->fr.size() + ahead <= 1000) return false;   // (fr.size() - 1 <= 1000 once this frame has been appended)
+  *T = Tn;
+  return true;
+}
+
 static bool chain_eligible(vido_ctx* ctx, const FrontFrame& ff, const vido_frame_inputs& in) {
   TrackState* ts = (TrackState*)ctx->trk;
   const vido_config& c = ctx->cfg;
   if (getenv("VIDO_NO_CHAIN")) return false;   // debug: host-driven path only
-  if (!ts->initialised || ts->vio || !c.b_joint || in.write_back_depth) return false;
+  if (!ts->initialised || !c.b_joint || in.write_back_depth) return false;
+  const bool objects = !ts->lo_corres.empty() || !ff.ob_sem.empty() || !ts->lo_sem.empty();
+  if (ts->vio) {
+    if (objects || ts->fr.empty() || getenv("VIDO_NO_VIO_CHAIN")) return false;
+    float T = ts->ist.t_init;
+    if (!vio_frame_is_plain(ts, &T, ts->fr.back().t, in.timestamp, 0)) return false;
+  }
   // frames with object features: the static part on the chain, the object part on the host beside it (hybrid_consume)
-  if ((!ts->lo_corres.empty() || !ff.ob_sem.empty() || !ts->lo_sem.empty()) && getenv("VIDO_NO_HYBRID")) return false;
+  if (objects && getenv("VIDO_NO_HYBRID")) return false;
   return (int)(ts->last_corres.size() / 2) <= chain_capacity(ctx);
 }
 
@@ -2058,6 +2078,13 @@ static int chain_consume(vido_ctx* ctx, int slot, const FrontFrame& ff, float* T
     if (!rc) rc = ba_flush_deferred(ctx);
     ts->f_id++; ts->frames_seen++;
     return rc ? rc : 1;
+  }
+  if (ts->vio) {   // the frame's IMU members (back_end: vio_new_frame before the PnP, mTcw after the pose optimisation, mTinit in vio_after_ba)
+    rc = vio_new_frame(ctx, slot);
+    if (rc) return rc;
+    memcpy(ts->fr.back().Tcw, Tcw, sizeof(float) * 16);
+    vido_imu_state& ist = ts->ist;
+    if (ist.initialized && ist.t_init < 100.0f) ist.t_init = (float)((double)ist.t_init + (ts->fr.back().t - ts->fr[ts->fr.size() - 2].t));
   }
   const int nf = hdr[7];
   MapFrame F;
@@ -2275,7 +2302,18 @@ static int trk_track_chunk_impl(vido_ctx* ctx, const vido_frame_inputs* in, int 
         }
         const size_t K = ts->kp_cap;
         const bool hybrid_ok = !getenv("VIDO_NO_HYBRID");
-        while (e < B && !in[done + e].write_back_depth && (hybrid_ok || ff[e].ob_sem.empty())) e++;   // the run [b, e)
+        {
+          float Tv = ts->ist.t_init;
+          double tp = ts->vio ? ts->fr.back().t : 0.0;
+          while (e < B && !in[done + e].write_back_depth && (hybrid_ok || ff[e].ob_sem.empty())) {   // the run [b, e)
+            if (ts->vio) {
+              if (!ff[e].ob_sem.empty() || !vio_frame_is_plain(ts, &Tv, tp, in[done + e].timestamp, e - b)) break;
+              tp = in[done + e].timestamp;
+            }
+            e++;
+          }
+          if (e == b) e = b + 1;   // (chain_eligible accepted frame b under the same rule)
+        }
         // The tracker kernels are queued a few frames ahead of the record being consumed, not the whole run at once: the first
         // record of a batch is then ~0.5 ms away instead of ~1.3 ms (16 enqueues + the look-ahead launch), short enough for
         // the window solver's queue of three to bridge the batch boundary.
