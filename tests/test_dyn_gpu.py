@@ -99,3 +99,38 @@ def test_metric_error_matches_oracle(pkg):
         if not refined:   # (the smoothness edges of the full-sequence optimisation pull the object motions: parity only)
             assert m1.cam_t < 0.02 and m1.obj_t < 0.03
     otr.close(); ctx.close()
+
+
+@pytest.mark.parametrize("switch", ["VIDO_NO_CHAIN", "VIDO_NO_HYBRID", "VIDO_BA_INLINE"])
+def test_paths_agree_under_debug_switches(pkg, monkeypatch, switch):
+    """the device-chained tracker, the hybrid object path and the solver host thread are optimisations of the host-driven
+    sequential order: switching each of them off gives the same Map (integer bookkeeping equal, floats to 1e-5)"""
+    n = 14
+    sc = synth.Scene(cam=CAM, seed=777, flow_noise=0.1, depth_noise=0.01, n_objects=3)
+    frames = [sc.frame(k) for k in range(n)]
+
+    def run():
+        ctx = pkg.Context(pkg.default_config(width=CAM["width"], height=CAM["height"], fx=CAM["fx"], fy=CAM["fy"], cx=CAM["cx"],
+                                             cy=CAM["cy"], bf=CAM["bf"], max_batch=4))
+        T, st = ctx.track_frames([dict(image=f["gray"].numpy(), depth=f["depth_in"].numpy().copy(), flow=f["flow"].numpy(),
+                                       mask=f["mask"].numpy().copy()) for f in frames])
+        out = dict(T=T, st=st, P=ctx.map_poses(), dyn=[ctx.map_dynamic(k) for k in (1, n // 2, n - 1)],
+                   obj=[ctx.map_objects(k) for k in (1, n // 2, n - 1)], sta=ctx.map_static(n - 1))
+        ctx.close()
+        return out
+
+    a = run()
+    monkeypatch.setenv(switch, "1")
+    b = run()
+    keys = ("n_keypoints", "n_matches", "n_init_inliers", "n_pose_inliers", "n_static", "ba_points", "ba_obs", "ba_iterations",
+            "n_dyn_features", "n_objects", "n_objects_ok", "n_masks_recovered")
+    for k in range(n):
+        for key in keys:
+            assert a["st"][k][key] == b["st"][k][key], (switch, k, key)
+    tol = lambda x, y: np.abs(np.asarray(x, np.float64) - np.asarray(y, np.float64)).max() <= 1e-5 * max(np.abs(np.asarray(y)).max(), 1.0)
+    assert tol(a["T"], b["T"]) and tol(a["P"], b["P"])
+    for da, db in zip(a["dyn"], b["dyn"]):
+        assert np.array_equal(da[3], db[3]) and np.array_equal(da[4], db[4]) and np.array_equal(da[0], db[0]) and tol(da[2], db[2])
+    for oa, ob in zip(a["obj"], b["obj"]):
+        assert np.array_equal(oa[0], ob[0]) and tol(oa[2], ob[2])
+    assert np.array_equal(a["sta"][3], b["sta"][3]) and tol(a["sta"][2], b["sta"][2])
