@@ -1,0 +1,67 @@
+"""CPU: the per-frame joint flow + pose optimisation (Optimizer::PoseOptimizationFlow2Cam, src/Optimizer.cc:2622-2824) pinned by
+an independent statement of what its last round minimises.  Model (EdgeSE3ProjectFlow2, g2o/types/types_six_dof_expmap.h:436-456;
+EdgeFlowPrior; information 0.1 / 0.3; no robust kernel in the last round, src/Optimizer.cc:2788): per match i with key point
+obs_i of the last frame, its depth and measured flow f_i,
+
+    cost(T, phi) = sum_{i in level 0} 0.1 |obs_i + phi_i - pi(T X_i)|^2 + sum_i 0.3 |phi_i - f_i|^2,   X_i = Twl backproject(obs_i, depth_i).
+
+For a fixed pose every flow has the closed-form minimiser phi_i = (0.1 (pi(T X_i) - obs_i) + 0.3 f_i) / 0.4, so the cost reduces to a
+function of the 6 pose parameters.  Checks on the oracle's result: its refined flows are those closed-form minimisers at its pose,
+and its pose is a stationary point of the reduced cost (scipy started there does not move)."""
+import numpy as np
+import pytest
+import scipy.optimize
+
+import oracle_lib as ol
+import pose_synth
+
+
+def _exp_se3(x):
+    w, t = x[:3], x[3:]
+    th = np.linalg.norm(w)
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    R = np.eye(3) if th < 1e-12 else np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * K @ K
+    T = np.eye(4); T[:3, :3] = R; T[:3, 3] = t
+    return T
+
+
+def _project(T, X, K):
+    fx, fy, cx, cy = K
+    Xc = X @ T[:3, :3].T + T[:3, 3]
+    return np.stack([fx * Xc[:, 0] / Xc[:, 2] + cx, fy * Xc[:, 1] / Xc[:, 2] + cy], 1)
+
+
+@pytest.mark.parametrize("n,seed,noise,outl", [(600, 1, 0.1, 0.05), (301, 4, 0.3, 0.2)])
+def test_result_minimises_the_independent_cost(n, seed, noise, outl):
+    pr = pose_synth.make_poseopt(n=n, seed=seed, flow_noise=noise, outliers=outl)
+    T, fo, inl, ninl, st = ol.poseopt_flow2cam(pr["obs"], pr["flow"], pr["depth"], pr["Tcw_init"], pr["Tcw_last"], pr["K"])
+    assert ninl > 0.5 * n
+    K = [float(v) for v in pr["K"]]
+    fx, fy, cx, cy = K
+    obs = np.asarray(pr["obs"], np.float64); f = np.asarray(pr["flow"], np.float64); z = np.asarray(pr["depth"], np.float64)
+    Twl = np.linalg.inv(np.asarray(pr["Tcw_last"], np.float64))
+    Xl = np.stack([(obs[:, 0] - cx) * z / fx, (obs[:, 1] - cy) * z / fy, z], 1)
+    X = Xl @ Twl[:3, :3].T + Twl[:3, 3]
+    lev0 = inl.astype(bool)
+    T0 = np.asarray(T, np.float64)
+
+    def flows(Tm):
+        phi = f.copy()
+        phi[lev0] = (0.1 * (_project(Tm, X[lev0], K) - obs[lev0]) + 0.3 * f[lev0]) / 0.4
+        return phi
+
+    def reduced(x):   # whitened residuals of the reduced problem at T = Exp(x) T0
+        Tm = _exp_se3(x) @ T0
+        phi = flows(Tm)
+        e = obs[lev0] + phi[lev0] - _project(Tm, X[lev0], K)
+        return np.concatenate([np.sqrt(0.1) * e.reshape(-1), np.sqrt(0.3) * (phi[lev0] - f[lev0]).reshape(-1)])
+
+    # (1) the refined flows of the inliers are the closed-form minimisers at the returned pose
+    assert np.abs(fo[lev0] - flows(T0)[lev0]).max() < 2e-3
+    # (2) the returned pose is a stationary point of the reduced cost
+    r0 = reduced(np.zeros(6))
+    sol = scipy.optimize.least_squares(reduced, np.zeros(6), method="lm", xtol=1e-15, ftol=1e-15, gtol=1e-15)
+    c0, c1 = float(r0 @ r0), float(sol.fun @ sol.fun)
+    assert c1 <= c0 * (1 + 1e-12)
+    assert c0 - c1 <= 1e-6 * c0, (c0, c1)
+    assert np.abs(sol.x[:3]).max() < 1e-6 and np.abs(sol.x[3:]).max() < 1e-5, sol.x
