@@ -65,3 +65,35 @@ def test_result_minimises_the_independent_cost(n, seed, noise, outl):
     assert c1 <= c0 * (1 + 1e-12)
     assert c0 - c1 <= 1e-6 * c0, (c0, c1)
     assert np.abs(sol.x[:3]).max() < 1e-6 and np.abs(sol.x[3:]).max() < 1e-5, sol.x
+
+
+def test_reprojection_only_optimisers_minimise_the_independent_cost():
+    """PoseOptimizationNew (camera pose, src/Optimizer.cc:2180-2334) and PoseOptimizationObjMot (object motion H through
+    P = K Tcw, :2826-3035): the last round minimises the plain sum of squared reprojection errors of the level-0 edges."""
+    import proj_synth
+    for make, kw in ((proj_synth.camera_case, dict(seed=1)), (proj_synth.object_case, dict(seed=2, outliers=0.0, noise=0.02))):
+        case, _, _ = make(**kw)
+        d = dict(case)
+        kind = d.pop("kind")
+        T, inl, st = ol.pose_opt_proj(kind, d["obs_xy"], d["pts3d"], d["T_init"], K=d.get("K"), P=d.get("P"))
+        lev0 = inl.astype(bool)
+        assert lev0.sum() >= 20
+        obs = np.asarray(d["obs_xy"], np.float64)[lev0]; X = np.asarray(d["pts3d"], np.float64)[lev0]
+        T0 = np.asarray(T, np.float64)
+
+        def res(x):
+            Tm = _exp_se3(x) @ T0
+            if kind == 0:
+                return (obs - _project(Tm, X, [float(v) for v in d["K"]])).reshape(-1)
+            P = np.asarray(d["P"], np.float64).reshape(3, 4)
+            Xh = X @ Tm[:3, :3].T + Tm[:3, 3]
+            q = Xh @ P[:, :3].T + P[:, 3]
+            return (obs - q[:, :2] / q[:, 2:3]).reshape(-1)
+
+        r0 = res(np.zeros(6))
+        sol = scipy.optimize.least_squares(res, np.zeros(6), method="lm", xtol=1e-15, ftol=1e-15, gtol=1e-15)
+        c0, c1 = float(r0 @ r0), float(sol.fun @ sol.fun)
+        # the returned flags are the classification AFTER the last round, the last round itself ran on the classification before it
+        # (0.01 px^2 gate: a few edges change sides), so the returned pose minimises over a slightly different set: near-stationary
+        assert c1 <= c0 * (1 + 1e-12) and c0 - c1 <= 0.05 * c0, (kind, c0, c1)
+        assert np.abs(sol.x[:3]).max() < 2e-5 and np.abs(sol.x[3:]).max() < 2e-4, (kind, sol.x)
