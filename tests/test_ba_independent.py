@@ -118,3 +118,95 @@ def test_full_system_sparse_solve_matches_oracle_first_iteration(W, P, seed):
     want = np.stack(Xn)
     assert np.abs(got - want).max() <= 2e-5 * max(np.abs(want).max(), 1.0)   # outputs are float32 matrices
     assert np.abs(opts - ptn).max() <= 2e-5 * max(np.abs(ptn).max(), 1.0)
+
+
+def _assemble(X, Z, pts, op, olp, meas, W, P, info_cam, info_3d, d_cam, d_3d):
+    n = 6 * W + 3 * P
+    rows, cols, vals = [], [], []
+    b = np.zeros(n)
+
+    def add(i0, j0, B):
+        r, c = np.meshgrid(np.arange(B.shape[0]), np.arange(B.shape[1]), indexing="ij")
+        rows.extend((i0 + r).reshape(-1)); cols.extend((j0 + c).reshape(-1)); vals.extend(B.reshape(-1))
+
+    for i in range(W - 1):
+        e, Ji, Jj = ol.edge_se3(X[i], X[i + 1], Z[i])
+        w = huber(info_cam * e @ e, d_cam)[1] * info_cam
+        a, c = 6 * i, 6 * (i + 1)
+        add(a, a, w * Ji.T @ Ji); add(c, c, w * Jj.T @ Jj); add(a, c, w * Ji.T @ Jj); add(c, a, w * Jj.T @ Ji)
+        b[a:a + 6] -= w * Ji.T @ e; b[c:c + 6] -= w * Jj.T @ e
+    for o in range(len(op)):
+        e, Jp, Jl = ol.edge_se3_pointxyz(X[op[o]], pts[olp[o]], meas[o])
+        w = huber(info_3d * e @ e, d_3d)[1] * info_3d
+        a, c = 6 * int(op[o]), 6 * W + 3 * int(olp[o])
+        add(a, a, w * Jp.T @ Jp); add(c, c, w * Jl.T @ Jl); add(a, c, w * Jp.T @ Jl); add(c, a, w * Jl.T @ Jp)
+        b[a:a + 6] -= w * Jp.T @ e; b[c:c + 3] -= w * Jl.T @ e
+    return sp.coo_matrix((vals, (rows, cols)), shape=(n, n)).tocsc(), b
+
+
+@pytest.mark.parametrize("W,P,seed", [(6, 60, 1), (8, 100, 3)])
+def test_whole_lm_trajectory_replayed_with_a_sparse_full_system(W, P, seed):
+    """Every iteration of the window optimisation, not only the first: the Levenberg-Marquardt driver of g2o
+    (optimization_algorithm_levenberg.cpp:61-149: gain ratio, lambda * max(1/3, 1 - (2 rho - 1)^3) / lambda * ni, at most ten
+    trials), the reference's two stop patches and SparseOptimizerTerminateAction (gain threshold), replayed in Python on the full
+    un-Schur'd system with a sparse direct solver.  The oracle (Schur complement, dense LL^T) must report the same number of
+    iterations and trials and the same chi2 / lambda after every iteration."""
+    pr = ba_synth.make_window(W=W, P=P, seed=seed, pose_noise=0.03, obs_noise=0.03)
+    info_cam, info_3d = 1.0 / float(np.float32(0.0001)), 1.0 / float(np.float32(16.0))
+    d_cam = d_3d = float(np.float32(0.01))
+    X = [pose_from_f32(T) for T in pr["poses"]]
+    Z = [pose_from_f32(T) for T in pr["rel"]]
+    pts = pr["points"].astype(np.float64)
+    op, olp, meas = pr["obs_pose"], pr["obs_point"], pr["obs_xyz"].astype(np.float64)
+    n = 6 * W + 3 * P
+    chi = lambda Xs, ps: robust_chi2(Xs, Z, ps, op, olp, meas, info_cam, info_3d, d_cam, d_3d)
+    poses, rel, opts, its, st = ol.ba_partial(pr["poses"], pr["rel"], pr["points"], op, olp, pr["obs_xyz"])
+    want = st.records()
+    bp = ol.BaProblem(); ol.lib().vo_ba_default_params(__import__("ctypes").byref(bp))
+    max_it, gain_thr = bp.max_iterations, float(bp.gain_threshold)
+    lam, ni, nbad, chi_check, last_chi = -1.0, 2.0, 0, 0.0, 0.0
+    got, stop, ok, i = [], False, True, 0
+    while i < max_it and not stop and ok:
+        cur = ini = chi(X, pts)
+        H, b = _assemble(X, Z, pts, op, olp, meas, W, P, info_cam, info_3d, d_cam, d_3d)
+        if i == 0:
+            lam, ni, nbad = 1e-5 * np.abs(H.diagonal()).max(), 2.0, 0
+        rho, q = 0.0, 0
+        while True:
+            x = spla.spsolve((H + lam * sp.identity(n, format="csc")).tocsc(), b)
+            Xn = [ol.se3_oplus(X[k], x[6 * k:6 * k + 6]) for k in range(W)]
+            pn = pts + x[6 * W:].reshape(-1, 3)
+            tmp = chi(Xn, pn)
+            rho = (cur - tmp) / (x @ (lam * x + b) + 1e-3)
+            if rho > 0 and np.isfinite(tmp):
+                lam *= max(1.0 / 3.0, min(1.0 - (2 * rho - 1) ** 3, 2.0 / 3.0)); ni = 2.0
+                cur, X, pts = tmp, Xn, pn
+            else:
+                lam *= ni; ni *= 2
+            q += 1
+            if not (rho < 0 and q < 10):
+                break
+        if q == 10 or rho == 0:
+            ok = False
+        else:
+            nbad = nbad + 1 if (ini - cur) * 1e3 < ini else 0
+            ok = nbad < 3
+        arc = tmp                       # the errors as the last trial left them (a rejected trial is restored AFTER this is read)
+        if chi_check < arc and i > 0:
+            ok = False
+        chi_check = arc
+        got.append((cur, lam, q))
+        c = chi(X, pts)
+        if i == 0:
+            last_chi = c
+        else:
+            gain = (last_chi - c) / c
+            last_chi = c
+            if 0 <= gain < gain_thr:
+                stop = True
+        i += 1
+    assert its == len(got) == len(want) and its >= 3
+    for (c1, l1, t1), (c2, l2, t2) in zip(got, want):
+        assert t1 == t2
+        assert abs(c1 - c2) <= 1e-6 * max(c2, 1e-12), (c1, c2)
+        assert abs(l1 - l2) <= 1e-4 * l2, (l1, l2)
