@@ -1,0 +1,82 @@
+"""CPU: static tracklets and the selection of the window graph, restated independently in pure Python from the reference
+(Tracking::GetStaticTrack, src/Tracking.cc:2514-2613; the static part of Optimizer::PartialBatchOptimization's graph
+construction, src/Optimizer.cc:46-90, 220-362) and applied to the associations the oracle tracker stored in its Map: for every
+frame the number of point vertices and observation edges of the window graph must equal what the oracle (and, by the GPU parity
+tests, the product -- which builds tracklets incrementally and selects by 'born inside the window') reports."""
+import numpy as np
+
+import oracle_lib as ol
+import synth
+
+
+def get_static_track(temporal_match):
+    """temporal_match[i][j]: index in Map frame i of the predecessor of feature j of Map frame i+1 (-1: none)"""
+    tracklets, check_pre, ids = [], [], 0
+    for i, tm in enumerate(temporal_match):
+        check_cur = [-1] * len(tm)
+        for j, p in enumerate(tm):
+            if p == -1:
+                continue
+            if i > 0 and check_pre[p] != -1:
+                tracklets[check_pre[p]].append((i + 1, j))
+                check_cur[j] = check_pre[p]
+            else:
+                tracklets.append([(i, p), (i + 1, j)])
+                check_cur[j] = ids
+                ids += 1
+        check_pre = check_cur
+    return tracklets
+
+
+def window_graph_size(n_feat, tracklets, window):
+    """(point vertices, observation edges) of the window over the last `window` of the len(n_feat) Map frames"""
+    N = len(n_feat)
+    label = [[-1] * n for n in n_feat]
+    for t, tr in enumerate(tracklets):
+        if len(tr) < 3:
+            continue
+        for f, j in tr:
+            label[f][j] = t
+    mark = [[-1] * n for n in n_feat]
+    points = edges = 0
+    uid = 0
+    for i in range(N - window, N):
+        for j in range(n_feat[i]):
+            t = label[i][j]
+            if t == -1:
+                continue
+            pos = tracklets[t].index((i, j))
+            if pos == 0:
+                mark[i][j] = uid; uid += 1
+                points += 1; edges += 1
+            else:
+                pf, pj = tracklets[t][pos - 1]
+                if mark[pf][pj] == -1:
+                    continue
+                mark[i][j] = mark[pf][pj]
+                edges += 1
+    return points, edges
+
+
+def test_window_graph_sizes_follow_the_reference_rules():
+    cam, n, W = synth.SMALL, 28, 20
+    sc = synth.Scene(cam=cam, seed=21, flow_noise=0.1, depth_noise=0.01)
+    otr = ol.OracleTracker(ol.track_config(cam, nfeatures=1200, max_track_bg=400, window=W))
+    stats = []
+    for k in range(n):
+        f = sc.frame(k)
+        T, s, rc = otr.track(f["gray"].numpy(), f["depth_in"].numpy(), f["flow"].numpy(), f["mask"].numpy())
+        assert rc == 0
+        stats.append(s)
+    feats = [otr.static_features(k) for k in range(n)]
+    n_feat = [len(x[3]) for x in feats]
+    checked = 0
+    for k in range(1, n):
+        tm = [feats[f][3].tolist() for f in range(1, k + 1)]          # vnAssoSta as of frame k
+        tracklets = get_static_track(tm)
+        window = min(k, W)
+        pts, obs = window_graph_size(n_feat[:k + 1], tracklets, window)
+        assert (stats[k]["ba_points"], stats[k]["ba_obs"]) == (pts, obs), (k, stats[k]["ba_points"], stats[k]["ba_obs"], pts, obs)
+        checked += pts > 0
+    assert checked >= n - 4 and stats[-1]["ba_points"] > 100
+    otr.close()
