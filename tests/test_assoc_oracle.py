@@ -47,3 +47,45 @@ def test_object_sampling_order_and_gates():
     want = [(x, y) for y in range(0, H, 4) for x in range(0, W, 4) if mask[y, x] and (x, y) not in ((12, 8), (16, 4))]
     assert [tuple(k) for k in keys.astype(int)] == want and (lab == 2).all()
     assert np.array_equal(cor, keys + np.float32([1.5, 0.5]))
+
+
+def test_association_and_sampling_against_pure_python_restatements():
+    """Frame::Frame's static association (src/Frame.cc:72-100) and stride-4 object sampling (:184-211) restated line by line in
+    pure Python (float32 arithmetic, the same comparison order) on random maps: identical lists in identical order."""
+    rng = np.random.default_rng(5)
+    H, W = 61, 83
+    f32 = np.float32
+    for trial in range(3):
+        depth = rng.uniform(-2, 60, (H, W)).astype(f32)
+        mask = (rng.integers(0, 4, (H, W)) * (rng.random((H, W)) < 0.4)).astype(np.int32)
+        flow = rng.normal(0, 6, (H, W, 2)).astype(f32)
+        flow[rng.random((H, W)) < 0.1] = 0
+        n = 400
+        xy = np.stack([rng.uniform(0, W - 1, n), rng.uniform(0, H - 1, n)], 1).astype(f32)
+        kps = np.zeros(n, ol.KP_DTYPE)
+        kps["x"], kps["y"] = xy[:, 0], xy[:, 1]
+        th = 40.0
+        idx, cor, fl, dep = ol.frame_associate(kps, depth, flow, mask, th)
+        want = []
+        for i in range(n):
+            x, y = int(xy[i, 0]), int(xy[i, 1])
+            if mask[y, x] != 0:
+                continue
+            if depth[y, x] > f32(th) or depth[y, x] <= 0:
+                continue
+            fx, fy = flow[y, x]
+            if fx != 0 and fy != 0 and f32(xy[i, 0] + fx) < W and f32(xy[i, 1] + fy) < H and xy[i, 0] < W and xy[i, 1] < H:
+                want.append((i, f32(xy[i, 0] + fx), f32(xy[i, 1] + fy), fx, fy))
+        assert list(idx) == [w[0] for w in want]
+        assert np.array_equal(cor, np.array([[w[1], w[2]] for w in want], f32)) and np.array_equal(fl, np.array([[w[3], w[4]] for w in want], f32))
+        keys, ocor, ofl, odep, lab = ol.frame_sample_objects(depth, flow, mask, 25.0)
+        wk = []
+        for i in range(0, H, 4):
+            for j in range(0, W, 4):
+                if mask[i, j] != 0 and depth[i, j] < f32(25.0) and depth[i, j] > 0:
+                    fx, fy = flow[i, j]
+                    if f32(j + fx) < W and f32(j + fx) > 0 and f32(i + fy) < H and f32(i + fy) > 0:
+                        wk.append((j, i, f32(j + fx), f32(i + fy), depth[i, j], mask[i, j]))
+        assert [tuple(k) for k in keys.astype(int)] == [(w[0], w[1]) for w in wk]
+        assert np.array_equal(ocor, np.array([[w[2], w[3]] for w in wk], f32)) and np.array_equal(odep, np.array([w[4] for w in wk], f32))
+        assert np.array_equal(lab, np.array([w[5] for w in wk], np.int32))
