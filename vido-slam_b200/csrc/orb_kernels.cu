@@ -35,14 +35,14 @@ __global__ void bgr2gray_kernel(const uint8_t* __restrict__ src, size_t sfs, int
 // one (5 rows out of 6 at scale 1.2) -- 2 byte loads and ~10 integer instructions per output pixel instead of 4 loads + 2
 // table loads and ~50 instructions when every pixel was computed from scratch (round 1: issue-bound at 16 % of HBM peak).
 // =====================================================================================================
-#define PYR_ROWS 8
+#define PYR_ROWS 8   // strip height at large batches; smaller when the launch would not fill the machine (pyr_rows below)
 __global__ void __launch_bounds__(128) pyr_down_kernel(const uint8_t* __restrict__ src, int spitch, size_t sfs, int sw,
                                                        int sh, uint8_t* __restrict__ dst, int dpitch, size_t dfs, int dw,
                                                        int dh, const int32_t* __restrict__ xofs,
                                                        const short2* __restrict__ xa, const int32_t* __restrict__ yofs,
-                                                       const short2* __restrict__ ya) {
+                                                       const short2* __restrict__ ya, int rows) {
   const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const int y0 = blockIdx.y * PYR_ROWS;
+  const int y0 = blockIdx.y * rows;
   const int b = blockIdx.z;
   if (x4 >= dw) return;
   int sx0[4], sx1[4], a0[4], a1[4];
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(128) pyr_down_kernel(const uint8_t* __restrict
     for (int i = 0; i < 4; i++) r[i] = (p[sx0[i]] * a0[i] + p[sx1[i]] * a1[i]) >> 4;
   };
   int lo[4] = {0, 0, 0, 0}, lo_row = -1;   // horizontal result of the lower source row of the previous output row
-  const int yend = min(y0 + PYR_ROWS, dh);
+  const int yend = min(y0 + rows, dh);
   for (int y = y0; y < yend; y++) {
     const int sy = yofs[y], sy1 = min(sy + 1, sh - 1);
     const short2 by = ya[y];
@@ -1213,10 +1213,14 @@ int orb_run(vido_ctx* ctx, const uint8_t* d_gray, int nframes, size_t frame_stri
   for (int l = 1; l < c.nlevels; l++) {
     const OrbLevel& S = ctx->lv[l - 1];
     const OrbLevel& D = ctx->lv[l];
-    dim3 grid((D.w + 511) / 512, (D.h + PYR_ROWS - 1) / PYR_ROWS, B);
+    // strip height: as tall as possible (table and row reuse) while the launch still has ~4 resident waves of threads
+    const long long quads = (long long)((D.w + 3) / 4) * D.h * B;   // 4-pixel groups of the level
+    int rows = (int)(quads / ((long long)ctx->num_sms * 2048 * 2));
+    rows = rows < 1 ? 1 : (rows > PYR_ROWS ? PYR_ROWS : rows);
+    dim3 grid((D.w + 511) / 512, (D.h + rows - 1) / rows, B);
     pyr_down_kernel<<<grid, 128, 0, st>>>(ctx->d_pyr + S.base, S.pitch, S.frame_stride, S.w, S.h, ctx->d_pyr + D.base,
                                           D.pitch, D.frame_stride, D.w, D.h, ctx->d_xofs[l], (const short2*)ctx->d_xa[l],
-                                          ctx->d_yofs[l], (const short2*)ctx->d_ya[l]);
+                                          ctx->d_yofs[l], (const short2*)ctx->d_ya[l], rows);
     ctx->launches++;
   }
   if (ctx->cells_per_frame > 0) {
