@@ -89,3 +89,59 @@ def test_association_and_sampling_against_pure_python_restatements():
         assert [tuple(k) for k in keys.astype(int)] == [(w[0], w[1]) for w in wk]
         assert np.array_equal(ocor, np.array([[w[2], w[3]] for w in wk], f32)) and np.array_equal(odep, np.array([w[4] for w in wk], f32))
         assert np.array_equal(lab, np.array([w[5] for w in wk], np.int32))
+
+
+def test_update_mask_against_a_pure_python_restatement():
+    """Tracking::UpdateMask (src/Tracking.cc:3291-3357) line by line in pure Python on random scenes: labels processed in sorted
+    order, votes read from the mask AS MODIFIED by the labels before, int truncation of correspondences and flows, >= 100 votes,
+    majority with ties to the smaller label, in-place forward warp in raster order"""
+    rng = np.random.default_rng(11)
+    H, W = 48, 72
+    for trial in range(6):
+        mask_last = np.zeros((H, W), np.int32)
+        labels = [2, 5, 7]
+        boxes = [(4, 4, 18, 20), (20, 30, 40, 52), (8, 50, 24, 68)]
+        for lab, (y0, x0, y1, x1) in zip(labels, boxes):
+            mask_last[y0:y1, x0:x1] = lab
+        flow_last = rng.normal(0, 3, (H, W, 2)).astype(np.float32)
+        flow_last[..., 0] += rng.uniform(-4, 4); flow_last[..., 1] += rng.uniform(-3, 3)
+        ys, xs = np.nonzero(mask_last)
+        pick = rng.random(len(ys)) < 0.9
+        ys, xs = ys[pick], xs[pick]
+        order = rng.permutation(len(ys))
+        ys, xs = ys[order], xs[order]
+        sem = mask_last[ys, xs].astype(np.int32)
+        corres = np.stack([xs + flow_last[ys, xs, 0], ys + flow_last[ys, xs, 1]], 1).astype(np.float32)
+        mask_cur = np.zeros((H, W), np.int32)
+        for lab, (y0, x0, y1, x1) in zip(labels, boxes):
+            if rng.random() < 0.5:     # this label survives in the new frame (shifted), otherwise it is lost
+                dy, dx = int(rng.integers(-3, 4)), int(rng.integers(-3, 4))
+                mask_cur[max(y0 + dy, 0):y1 + dy, max(x0 + dx, 0):x1 + dx] = lab
+        got, uniq, rec = ol.update_mask(sem, corres, mask_last, flow_last, mask_cur.copy())
+        # ---- restatement
+        seg = mask_cur.copy()
+        uni = sorted(set(sem.tolist()))
+        want_rec = []
+        for lab in uni:
+            votes = []
+            for i in np.nonzero(sem == lab)[0]:
+                u, v = int(corres[i, 0]), int(corres[i, 1])
+                if 0 < u < W and 0 < v < H:
+                    votes.append(int(seg[v, u]))
+            r = 0
+            if len(votes) >= 100:
+                cnt = {}
+                for k in votes:
+                    cnt[k] = cnt.get(k, 0) + 1
+                best = sorted(cnt.items(), key=lambda kv: (-kv[1], kv[0]))[0][0]
+                if best == 0:
+                    r = 1
+                    for j in range(H):
+                        for k in range(W):
+                            if mask_last[j, k] == lab:
+                                fx, fy = int(flow_last[j, k, 0]), int(flow_last[j, k, 1])
+                                if 0 < k + fx < W and 0 < j + fy < H:
+                                    seg[j + fy, k + fx] = lab
+            want_rec.append(r)
+        assert list(uniq) == uni and list(rec) == want_rec, (trial, list(rec), want_rec)
+        assert np.array_equal(got, seg), trial
