@@ -145,3 +145,18 @@ def test_update_mask_against_a_pure_python_restatement():
             want_rec.append(r)
         assert list(uniq) == uni and list(rec) == want_rec, (trial, list(rec), want_rec)
         assert np.array_equal(got, seg), trial
+
+
+def test_depth_pre_scale_against_numpy():
+    """Tracking::GrabImageRGBD's in-place depth pre-scale (src/Tracking.cc:299-322): float32 operations in the reference's order"""
+    rng = np.random.default_rng(3)
+    d = rng.uniform(-50, 9000, (37, 53)).astype(np.float32)
+    d[rng.random(d.shape) < 0.05] = 0
+    f32 = np.float32
+    factor, bf, ms = f32(256.0), f32(386.1448), f32(0.93)
+    with np.errstate(divide="ignore"):
+        want = {1: np.where(d < 0, f32(0), d / factor), 2: np.where(d < 0, f32(0), bf / (d / factor)),
+                3: np.where(d < 0, f32(0), (ms * bf) / (d / factor))}
+    for mode in (1, 2, 3):
+        got = ol.depth_prep(d, mode, float(factor), float(bf), float(ms))
+        assert got.dtype == np.float32 and np.array_equal(got, want[mode].astype(np.float32)), mode
