@@ -187,6 +187,16 @@ def reference_arm(args, rank, world):
     print(json.dumps(line))
 
 
+def bandwidth_kernels():
+    """the bandwidth-shaped kernels of the path (front-end, FullBatch linearisation) against the HBM roofline: figures from the
+    committed ncu captures (profiles/), not measured by this run -- the line's own `roofline` object is measured live"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_bandwidth_kernels.json")) as fh:
+            return {"roofline_bandwidth_kernels": json.load(fh)}
+    except Exception:
+        return {}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -489,6 +499,7 @@ def main():
                              "one_sequence_per_core_estimate": cpu_fps * (os.cpu_count() or 1),
                              "cv2_front_end_cross_check": cv2_ms},
             **({"frame_at_a_time": frame_at_a_time} if frame_at_a_time else {}),
+            **bandwidth_kernels(),
             **extra,
             "host_ms_per_frame": {k: float(np.mean([x[k] for x in stats])) for k in ("ms_orb", "ms_init", "ms_poseopt", "ms_renew", "ms_ba")},
             "ba_per_frame": {"iterations": float(np.mean([s["ba_iterations"] for s in stats])), "obs": float(np.mean([s["ba_obs"] for s in stats])),
