@@ -80,3 +80,40 @@ def test_window_graph_sizes_follow_the_reference_rules():
         checked += pts > 0
     assert checked >= n - 4 and stats[-1]["ba_points"] > 100
     otr.close()
+
+
+def test_dynamic_tracklets_follow_the_reference_rules():
+    """Tracking::GetDynamicTrackNew (src/Tracking.cc:2615-2720) restated in pure Python on the object associations / labels the
+    oracle tracker stored (Map::vnAssoDyn, vnFeatLabel): the same tracklets -- length, object id, first (frame, feature) -- in the
+    same order as the oracle's incremental bookkeeping (Map::TrackletDyn, nObjID)"""
+    cam, n = synth.SMALL, 12
+    sc = synth.Scene(cam=cam, seed=8, flow_noise=0.1, depth_noise=0.01, n_objects=3)
+    otr = ol.OracleTracker(ol.track_config(cam, nfeatures=800, max_track_bg=250, max_track_obj=150))
+    for k in range(n):
+        f = sc.frame(k)
+        T, s, rc = otr.track(f["gray"].numpy(), f["depth_in"].numpy(), f["flow"].numpy(), f["mask"].numpy())
+        assert rc == 0
+    dyn = [otr.dynamic_features(k) for k in range(n)]
+    tracklets, obj, check_pre, ids = [], [], [], 0
+    for i in range(n - 1):
+        asso, lab = dyn[i + 1][3].tolist(), dyn[i + 1][4].tolist()      # vnAssoDyn[i], vnFeatLabel[i]: features of Map frame i + 1
+        check_cur = [-1] * len(asso)
+        for j, p in enumerate(asso):
+            if p == -1:
+                continue
+            if i > 0 and check_pre[p] != -1:
+                tracklets[check_pre[p]].append((i + 1, j))
+                check_cur[j] = check_pre[p]
+            else:
+                tracklets.append([(i, p), (i + 1, j)])
+                obj.append(lab[j])
+                check_cur[j] = ids
+                ids += 1
+        check_pre = check_cur
+    ln, oid, ff, fj = otr.dyn_tracks()
+    assert len(tracklets) == len(ln) and len(tracklets) > 100
+    assert [len(t) for t in tracklets] == ln.tolist()
+    assert obj == oid.tolist()
+    assert [t[0] for t in tracklets] == list(zip(ff.tolist(), fj.tolist()))
+    assert max(len(t) for t in tracklets) >= 5
+    otr.close()
