@@ -2092,6 +2092,7 @@ static int chain_consume(vido_ctx* ctx, int slot, const FrontFrame& ff, float* T
   F.asso.assign(asso, asso + nf);
   const bool async = !getenv("VIDO_BA_INLINE");   // debug: VIDO_BA_INLINE=1 stages the window solves on this thread
   if (!async) link_static_tracks(ts, F);
+  else { F.track.assign(nf, -1); F.pos.assign(nf, 0); }   // linked by the solver thread (left like this if its job is dropped after an error)
   memcpy(F.Twc, Twc, sizeof(float) * 16); memcpy(F.Twc_rf, Twc, sizeof(float) * 16); memcpy(F.rel, rel, sizeof(float) * 16);
   ts->last_keys = F.xy; ts->last_depth = F.depth;
   ts->last_corres.assign(corres, corres + 2 * (size_t)nf); ts->last_flow.assign(flow, flow + 2 * (size_t)nf);
