@@ -117,3 +117,65 @@ def test_dynamic_tracklets_follow_the_reference_rules():
     assert [t[0] for t in tracklets] == list(zip(ff.tolist(), fj.tolist()))
     assert max(len(t) for t in tracklets) >= 5
     otr.close()
+
+
+def test_full_batch_graph_sizes_follow_the_reference_rules():
+    """The graph of Optimizer::FullBatchOptimization (src/Optimizer.cc:1235-1760) counted by an independent pure-Python walk over the
+    oracle tracker's Map with the reference's rules: camera poses, one motion vertex per tracked object and frame, smoothness edges
+    where the label existed in the frame before, static tracklets of length >= 3 (one point, one observation per element), dynamic
+    tracklets of length >= 3 (a point and an observation per element, a ternary motion edge per element after the first whose
+    object has a motion vertex in that frame).  Must equal the sizes of the graph the oracle exports (and, by the GPU parity
+    tests, the product)."""
+    cam, n = synth.SMALL, 12
+    sc = synth.Scene(cam=cam, seed=8, flow_noise=0.1, depth_noise=0.01, n_objects=3)
+    otr = ol.OracleTracker(ol.track_config(cam, nfeatures=800, max_track_bg=250, max_track_obj=150))
+    for k in range(n):
+        f = sc.frame(k)
+        T, s, rc = otr.track(f["gray"].numpy(), f["depth_in"].numpy(), f["flow"].numpy(), f["mask"].numpy())
+        assert rc == 0
+    g, n_poses = otr.export_full_graph()
+    got = (n_poses, len(g["se3"]) - n_poses, len(g["points"]), len(g["obs_se3"]), len(g["e6_i"]), len(g["tern_p1"]))
+    # ---- static part
+    sta = [otr.static_features(k) for k in range(n)]
+    st_tracks = [t for t in get_static_track([sta[f][3].tolist() for f in range(1, n)]) if len(t) >= 3]
+    points = len(st_tracks)
+    obs = sum(len(t) for t in st_tracks)
+    # ---- object motions and smoothness edges
+    labels = [None] + [otr.objects(k)[0].tolist() for k in range(1, n)]     # labels[i] = vnRMLabel[i-1][1:], objects of Map frame i
+    motions = sum(len(labels[i]) for i in range(1, n))
+    smooth = 0
+    for i in range(3, n):
+        for lab in labels[i]:
+            if lab in labels[i - 1]:
+                smooth += 1
+    e6 = (n - 1) + smooth
+    # ---- dynamic part
+    dyn = [otr.dynamic_features(k) for k in range(n)]
+    ln, oid, ff, fj = otr.dyn_tracks()
+    tracklets, check_pre, ids = [], [], 0
+    for i in range(n - 1):
+        asso = dyn[i + 1][3].tolist()
+        check_cur = [-1] * len(asso)
+        for j, p in enumerate(asso):
+            if p == -1:
+                continue
+            if i > 0 and check_pre[p] != -1:
+                tracklets[check_pre[p]].append((i + 1, j)); check_cur[j] = check_pre[p]
+            else:
+                tracklets.append([(i, p), (i + 1, j)]); check_cur[j] = ids; ids += 1
+        check_pre = check_cur
+    tern = 0
+    for t, tr in enumerate(tracklets):
+        if len(tr) < 3:
+            continue
+        for pos, (fr, j) in enumerate(tr):
+            has_motion = fr >= 1 and int(oid[t]) in labels[fr]
+            if pos != 0 and not has_motion:
+                continue
+            points += 1; obs += 1
+            if pos != 0:
+                tern += 1
+    want = (n, motions, points, obs, e6, tern)
+    assert got == want, (got, want)
+    assert motions >= 2 * (n - 3) and tern > 100
+    otr.close()
