@@ -179,3 +179,34 @@ def test_full_batch_graph_sizes_follow_the_reference_rules():
     assert got == want, (got, want)
     assert motions >= 2 * (n - 3) and tern > 100
     otr.close()
+
+
+def test_apply_scaled_rotation_against_numpy():
+    """Map::ApplyScaledRotation (src/Map.cc:56-119) in numpy on the oracle tracker's Map: points p -> s R p, camera poses
+    Twc -> [R | 0] [Rwc | s twc], float32 results"""
+    cam, n = synth.SMALL, 5
+    sc = synth.Scene(cam=cam, seed=13, flow_noise=0.1, depth_noise=0.01, n_objects=2)
+    otr = ol.OracleTracker(ol.track_config(cam, nfeatures=600, max_track_bg=200, max_track_obj=100))
+    for k in range(n):
+        f = sc.frame(k)
+        otr.track(f["gray"].numpy(), f["depth_in"].numpy(), f["flow"].numpy(), f["mask"].numpy())
+    P0 = otr.map_poses().astype(np.float64)
+    S0 = [otr.static_features(k)[2].astype(np.float64) for k in range(n)]
+    D0 = [otr.dynamic_features(k)[2].astype(np.float64) for k in range(n)]
+    w = np.array([0.2, -0.1, 0.3]); th = np.linalg.norm(w); K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    R = (np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * K @ K).astype(np.float32)
+    s = np.float32(1.37)
+    otr.apply_scaled_rotation(R, float(s))
+    P1 = otr.map_poses()
+    Rd = R.astype(np.float64)
+    for k in range(n):
+        want = P0[k].copy()
+        want[:3, 3] *= float(s)
+        want = np.vstack([np.hstack([Rd, np.zeros((3, 1))]), [0, 0, 0, 1]]) @ want
+        assert np.abs(P1[k] - want).max() <= 2e-6 * max(np.abs(want).max(), 1.0), k
+        a = otr.static_features(k)[2]
+        assert np.abs(a - (float(s) * S0[k] @ Rd.T)).max() <= 4e-6 * max(np.abs(S0[k]).max() * float(s), 1.0), k
+        b = otr.dynamic_features(k)[2]
+        if len(b):
+            assert np.abs(b - (float(s) * D0[k] @ Rd.T)).max() <= 4e-6 * max(np.abs(D0[k]).max() * float(s), 1.0), k
+    otr.close()
