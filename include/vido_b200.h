@@ -94,6 +94,40 @@ int vido_orb_get_candidates(vido_ctx* ctx, int frame, int level, int32_t* xs, in
                             int cap, int32_t* n);
 
 
+/*
+ * Descriptor stage of ORBextractor::operator() -- optional: the reference blurs every level (src/ORBextractor.cc:1078-1079) but
+ * has the descriptor call commented out (:1086; its Frame::mDescriptors stays uninitialised) and contains no matcher; the
+ * tracking entry points below never call these.
+ * vido_orb_describe_dev: 7x7 sigma-2 GaussianBlur (BORDER_REFLECT_101, OpenCV's 8-bit fixed-point arithmetic) of every pyramid
+ * level of the LAST extraction, then computeOrbDescriptor (:98-137, pattern :140-398 = include/vido_orb_pattern.h) for the key
+ * points that extraction wrote: d_kps / d_nkp as filled by vido_orb_extract_dev (frame f at d_kps + f*cap_per_frame),
+ * d_desc[(f*cap_per_frame + k)*32 .. +32) = descriptor of key point k of frame f, row order of the reference's _descriptors.
+ * Rotated test points that leave the level's buffer (key points closer than 19 px to the top / bottom edge; undefined in the
+ * reference) read 0.
+ */
+int vido_orb_describe_dev(vido_ctx* ctx, const vido_keypoint* d_kps, const int32_t* d_nkp, int nframes, int cap_per_frame,
+                          uint8_t* d_desc, int sync);
+/* ORBextractor::operator()(image, mask, keypoints, descriptors) with host pointers: vido_orb_extract plus desc
+ * [nframes][cap_per_frame][32] */
+int vido_orb_extract_describe(vido_ctx* ctx, const uint8_t* gray, int nframes, size_t frame_stride, int stride,
+                              vido_keypoint* out, int cap_per_frame, int32_t* n_out, uint8_t* desc);
+/* debug/inspection: blurred pyramid level of batch slot `frame` of the last descriptor pass (tight rows) */
+int vido_orb_get_blurred_level(vido_ctx* ctx, int frame, int level, uint8_t* out);
+/*
+ * Brute-force Hamming matching of 256-bit descriptors (north_star's "Hamming match"; distance = ORB-SLAM's
+ * ORBmatcher::DescriptorDistance, i.e. the popcount of the XOR; result = cv::BFMatcher(NORM_HAMMING) with k = 2): for every query
+ * descriptor the train index of the smallest distance (the lowest index among equals), that distance and the second smallest
+ * distance.  VIDO_HAMMING_NONE (0x7fffffff) / index -1 where the train set has fewer than two / no entries.
+ * _dev: npairs independent (query set, train set) pairs, set p at d_query + p*query_stride with d_nq[p] descriptors (<= qcap),
+ * outputs at [p*qcap + q]; all pointers device memory, 4-byte aligned.
+ */
+#define VIDO_HAMMING_NONE 0x7fffffff
+int vido_hamming_match(vido_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train, int nt, int32_t* best_idx,
+                       int32_t* best_dist, int32_t* second_dist);
+int vido_hamming_match_dev(vido_ctx* ctx, const uint8_t* d_query, size_t query_stride, const int32_t* d_nq, const uint8_t* d_train,
+                           size_t train_stride, const int32_t* d_nt, int npairs, int qcap, int32_t* d_best_idx,
+                           int32_t* d_best_dist, int32_t* d_second_dist, int sync);
+
 /* ---- Levenberg-Marquardt statistics (g2o G2OBatchStatistics-like, used for parity checks) ---- */
 #define VIDO_LM_MAX_RECORDS 320
 typedef struct vido_lm_record { double chi2; double lambda; int32_t trials; int32_t pad; } vido_lm_record;

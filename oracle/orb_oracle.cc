@@ -418,7 +418,10 @@ int vo_orb_pyramid(const uint8_t* gray, int W, int H, int stride, const vo_orb_p
   return p->nlevels;
 }
 
-int vo_orb_extract(const uint8_t* gray, int W, int H, int stride, const vo_orb_params* p, vo_keypoint* out, int cap) {
+// ORBextractor::operator() (src/ORBextractor.cc:1034-1105).  desc != nullptr additionally does what the reference's loop at
+// :1067-1101 was written to do: blur a clone of the level (:1078-1079) and describe the level's key points at their LEVEL
+// coordinates (:1086, commented out in the reference) before they are scaled to level 0 (:1094-1100).
+static int extract_impl(const uint8_t* gray, int W, int H, int stride, const vo_orb_params* p, vo_keypoint* out, int cap, uint8_t* desc) {
   Levels L = make_levels(W, H, *p);
   int umax[kHalfPatch + 2];
   make_umax(umax);
@@ -426,12 +429,17 @@ int vo_orb_extract(const uint8_t* gray, int W, int H, int stride, const vo_orb_p
   build_pyramid(gray, W, H, stride, L, pyr);
   int total = 0;
   std::vector<Cand> cand;
+  std::vector<uint8_t> blurred;
   for (int l = 0; l < p->nlevels; l++) {
     int cols = L.w[l], rows = L.h[l];
     level_candidates(pyr[l].data(), cols, rows, cols, *p, cand);
     const int minBX = kEdge - 3, minBY = minBX, maxBX = cols - kEdge + 3, maxBY = rows - kEdge + 3;
     std::vector<int> keep = distribute_octtree(cand, minBX, maxBX, minBY, maxBY, L.quota[l]);
     const int scaledPatch = (int)(kPatch * L.scale[l]);
+    if (desc && !keep.empty()) {
+      blurred.resize((size_t)cols * rows);
+      vo_gauss7_u8(pyr[l].data(), cols, rows, cols, blurred.data(), cols);
+    }
     for (int id : keep) {
       if (total >= cap) return -1;
       vo_keypoint kp;
@@ -440,12 +448,22 @@ int vo_orb_extract(const uint8_t* gray, int W, int H, int stride, const vo_orb_p
       kp.size = (float)scaledPatch;
       kp.response = (float)cand[id].score;
       kp.angle = ic_angle(pyr[l].data(), cols, cv_round_f(x), cv_round_f(y), umax);
+      if (desc) vo_orb_describe_level(blurred.data(), cols, rows, &x, &y, &kp.angle, 1, desc + (size_t)total * 32);
       if (l != 0) { x *= L.scale[l]; y *= L.scale[l]; }       // ORBextractor.cc:1096-1099
       kp.x = x; kp.y = y;
       out[total++] = kp;
     }
   }
   return total;
+}
+
+int vo_orb_extract(const uint8_t* gray, int W, int H, int stride, const vo_orb_params* p, vo_keypoint* out, int cap) {
+  return extract_impl(gray, W, H, stride, p, out, cap, nullptr);
+}
+
+int vo_orb_extract_describe(const uint8_t* gray, int W, int H, int stride, const vo_orb_params* p, vo_keypoint* out, int cap,
+                            uint8_t* desc) {
+  return extract_impl(gray, W, H, stride, p, out, cap, desc);
 }
 
 }  // extern "C"

@@ -55,6 +55,18 @@ int vo_orb_level_candidates(const uint8_t* img, int w, int h, int stride, const 
 /* full ORBextractor::operator(): returns number of keypoints (<= cap); pyramid optional out */
 int vo_orb_extract(const uint8_t* gray, int W, int H, int stride, const vo_orb_params* p,
                    vo_keypoint* out, int cap);
+/* operator() with the descriptor call of src/ORBextractor.cc:1086 enabled: desc[k*32 .. +32) for key point k */
+int vo_orb_extract_describe(const uint8_t* gray, int W, int H, int stride, const vo_orb_params* p,
+                            vo_keypoint* out, int cap, uint8_t* desc);
+/* cv::GaussianBlur(src, dst, Size(7,7), 2, 2, BORDER_REFLECT_101) on CV_8UC1 (src/ORBextractor.cc:1079), OpenCV's fixed-point path */
+void vo_gauss7_u8(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride);
+/* computeDescriptors (src/ORBextractor.cc:1023-1031) on a blurred level with tight rows: key points in level coordinates */
+void vo_orb_describe_level(const uint8_t* blurred, int w, int h, const float* xs, const float* ys, const float* angles, int n,
+                           uint8_t* desc);
+/* brute-force Hamming matching (cv::BFMatcher(NORM_HAMMING), k = 2): best train index (first minimum), its distance, second distance;
+ * 0x7fffffff / -1 where absent */
+void vo_hamming_match(const uint8_t* query, int nq, const uint8_t* train, int nt, int32_t* best_idx, int32_t* best_dist,
+                      int32_t* second_dist);
 /* pyramid only: writes level l at out + offsets[l] (tight rows of width w[l]) */
 int vo_orb_pyramid(const uint8_t* gray, int W, int H, int stride, const vo_orb_params* p,
                    uint8_t* out, int64_t* offsets);

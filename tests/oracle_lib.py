@@ -95,6 +95,42 @@ def orb_extract(gray, p, cap=20000):
     return out[:n].copy()
 
 
+def orb_extract_describe(gray, p, cap=20000):
+    """operator() with the descriptor call enabled: (key points, [n][32] uint8)"""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    H, W = gray.shape
+    out = np.zeros(cap, KP_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    n = lib().vo_orb_extract_describe(_p(gray), W, H, W, C.byref(p), _p(out), cap, _p(desc))
+    assert n >= 0
+    return out[:n].copy(), desc[:n].copy()
+
+
+def gauss7(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.zeros_like(img)
+    lib().vo_gauss7_u8(_p(img), img.shape[1], img.shape[0], img.shape[1], _p(out), img.shape[1])
+    return out
+
+
+def describe_level(blurred, xs, ys, angles):
+    blurred = np.ascontiguousarray(blurred, np.uint8)
+    xs = np.ascontiguousarray(xs, np.float32); ys = np.ascontiguousarray(ys, np.float32)
+    angles = np.ascontiguousarray(angles, np.float32)
+    desc = np.zeros((len(xs), 32), np.uint8)
+    lib().vo_orb_describe_level(_p(blurred), blurred.shape[1], blurred.shape[0], _p(xs), _p(ys), _p(angles), len(xs), _p(desc))
+    return desc
+
+
+def hamming_match(query, train):
+    query = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)
+    train = np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+    nq = len(query)
+    bi = np.zeros(nq, np.int32); bd = np.zeros(nq, np.int32); sd = np.zeros(nq, np.int32)
+    lib().vo_hamming_match(_p(query), nq, _p(train), len(train), _p(bi), _p(bd), _p(sd))
+    return bi, bd, sd
+
+
 # ---------------------------------------------------------------- graph optimisation oracle
 class LmRecord(C.Structure):
     _fields_ = [("chi2", C.c_double), ("lam", C.c_double), ("trials", C.c_int32), ("pad", C.c_int32)]

@@ -97,6 +97,7 @@ void vido_destroy(vido_ctx* ctx) {
   pnp_teardown(ctx);
   po_teardown(ctx);
   ba_teardown(ctx);
+  desc_teardown(ctx);
   orb_teardown(ctx);
   if (ctx->um_ws) cudaFree(ctx->um_ws);
   for (int k = 0; k < 3; k++) if (ctx->raw_stage[k]) cudaFree(ctx->raw_stage[k]);
@@ -189,6 +190,92 @@ int vido_orb_extract(vido_ctx* ctx, const uint8_t* gray, int nframes, size_t fra
     VIDO_CUDA(cudaStreamSynchronize(ctx->stream));
     done += B;
   }
+  return VIDO_OK;
+}
+
+/* ---- descriptor stage (desc_kernels.cu) ---- */
+int vido_orb_describe_dev(vido_ctx* ctx, const vido_keypoint* d_kps, const int32_t* d_nkp, int nframes, int cap_per_frame,
+                          uint8_t* d_desc, int sync) {
+  if (!ctx || !d_kps || !d_nkp || !d_desc || cap_per_frame < 1) {
+    if (ctx) ctx->err = "vido_orb_describe_dev: bad argument";
+    return VIDO_ERR_ARG;
+  }
+  cudaSetDevice(ctx->device);
+  trk_quiesce(ctx);
+  int rc = desc_run(ctx, d_kps, d_nkp, nframes, cap_per_frame, d_desc);
+  if (rc != VIDO_OK) return rc;
+  if (sync) VIDO_CUDA(cudaStreamSynchronize(ctx->stream));
+  return VIDO_OK;
+}
+
+int vido_orb_extract_describe(vido_ctx* ctx, const uint8_t* gray, int nframes, size_t frame_stride, int stride, vido_keypoint* out,
+                              int cap_per_frame, int32_t* n_out, uint8_t* desc) {
+  if (!ctx || !gray || !out || !n_out || !desc || cap_per_frame < 1 || stride < ctx->cfg.width) {
+    if (ctx) ctx->err = "vido_orb_extract_describe: bad argument";
+    return VIDO_ERR_ARG;
+  }
+  cudaSetDevice(ctx->device);
+  trk_quiesce(ctx);
+  const vido_config& c = ctx->cfg;
+  uint8_t* d_desc = desc_staging(ctx);
+  if (!d_desc) return VIDO_ERR_CUDA;
+  int done = 0;
+  while (done < nframes) {
+    const int B = std::min(c.max_batch, nframes - done);
+    for (int b = 0; b < B; b++)
+      VIDO_CUDA(cudaMemcpy2DAsync(ctx->d_in + (size_t)b * ctx->in_pitch * c.height, ctx->in_pitch,
+                                  gray + (size_t)(done + b) * frame_stride, stride, c.width, c.height,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    int rc = orb_run(ctx, ctx->d_in, B, (size_t)ctx->in_pitch * c.height, ctx->in_pitch, ctx->d_kp, ctx->kp_cap, ctx->d_nkp);
+    if (rc != VIDO_OK) return rc;
+    rc = desc_run(ctx, ctx->d_kp, ctx->d_nkp, B, ctx->kp_cap, d_desc);
+    if (rc != VIDO_OK) return rc;
+    VIDO_CUDA(cudaMemcpyAsync(n_out + done, ctx->d_nkp, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, ctx->stream));
+    rc = check_dev_err(ctx);  // synchronises
+    if (rc != VIDO_OK) return rc;
+    for (int b = 0; b < B; b++) {
+      const int n = n_out[done + b];
+      if (n > cap_per_frame) { ctx->err = "vido_orb_extract_describe: cap_per_frame too small"; return VIDO_ERR_CAPACITY; }
+      VIDO_CUDA(cudaMemcpyAsync(out + (size_t)(done + b) * cap_per_frame, ctx->d_kp + (size_t)b * ctx->kp_cap,
+                                sizeof(vido_keypoint) * n, cudaMemcpyDeviceToHost, ctx->stream));
+      VIDO_CUDA(cudaMemcpyAsync(desc + (size_t)(done + b) * cap_per_frame * 32, d_desc + (size_t)b * ctx->kp_cap * 32, (size_t)n * 32,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    VIDO_CUDA(cudaStreamSynchronize(ctx->stream));
+    done += B;
+  }
+  return VIDO_OK;
+}
+
+int vido_orb_get_blurred_level(vido_ctx* ctx, int frame, int level, uint8_t* out) {
+  if (!ctx || !out || level < 0 || level >= ctx->nlevels || frame < 0 || frame >= ctx->cfg.max_batch) return VIDO_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  return desc_get_blurred_level(ctx, frame, level, out);
+}
+
+int vido_hamming_match(vido_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train, int nt, int32_t* best_idx, int32_t* best_dist,
+                       int32_t* second_dist) {
+  if (!ctx || nq < 0 || nt < 0 || (nq && (!query || !best_idx || !best_dist || !second_dist)) || (nt && !train)) {
+    if (ctx) ctx->err = "vido_hamming_match: bad argument";
+    return VIDO_ERR_ARG;
+  }
+  cudaSetDevice(ctx->device);
+  return desc_match_host(ctx, query, nq, train, nt, best_idx, best_dist, second_dist);
+}
+
+int vido_hamming_match_dev(vido_ctx* ctx, const uint8_t* d_query, size_t query_stride, const int32_t* d_nq, const uint8_t* d_train,
+                           size_t train_stride, const int32_t* d_nt, int npairs, int qcap, int32_t* d_best_idx, int32_t* d_best_dist,
+                           int32_t* d_second_dist, int sync) {
+  if (!ctx || !d_query || !d_nq || !d_train || !d_nt || npairs < 1 || qcap < 1 || !d_best_idx || !d_best_dist || !d_second_dist ||
+      ((size_t)d_query & 3) || ((size_t)d_train & 3) || (query_stride & 3) || (train_stride & 3)) {
+    if (ctx) ctx->err = "vido_hamming_match_dev: bad argument (descriptor arrays must be 4-byte aligned)";
+    return VIDO_ERR_ARG;
+  }
+  cudaSetDevice(ctx->device);
+  int rc = desc_match_device_api(ctx, d_query, query_stride, d_nq, d_train, train_stride, d_nt, npairs, qcap, d_best_idx, d_best_dist,
+                                 d_second_dist);
+  if (rc != VIDO_OK) return rc;
+  if (sync) VIDO_CUDA(cudaStreamSynchronize(ctx->stream));
   return VIDO_OK;
 }
 

@@ -102,6 +102,7 @@ struct vido_ctx {
   void* pnp = nullptr; // PnpWorkspace (pnp_kernels.cu)
   void* trk = nullptr; // TrackState (track.cu)
   void* chain = nullptr; // ChainWorkspace (chain_kernels.cu)
+  void* desc = nullptr;  // DescWorkspace (desc_kernels.cu), created by the first descriptor / matcher call
   // One-shot hook run by the synchronous PnP / pose-optimisation wrappers after their launches and before they wait for the
   // results: the per-frame driver parks host work there (staging and queueing the previous frame's window solve, retiring
   // the one before) so that it overlaps the kernels instead of extending the frame's serial path.
@@ -159,6 +160,16 @@ int chain_enqueue_frame(vido_ctx* ctx, const vido_keypoint* kp, const int32_t* n
                         const float* kpflow, const float* depth, const float* flow, const int32_t* mask, int slot);
 int chain_wait_record(vido_ctx* ctx, int slot, const int32_t** hdr, const float** Tcw, const float** Twc, const float** rel, const float** vel,
                       const float** xy, const float** depth, const float** p3, const float** corres, const float** flow, const int32_t** asso);
+
+// desc_kernels.cu
+void desc_teardown(vido_ctx* ctx);
+int desc_run(vido_ctx* ctx, const vido_keypoint* d_kps, const int32_t* d_nkp, int nframes, int cap_per_frame, uint8_t* d_desc);
+uint8_t* desc_staging(vido_ctx* ctx);   // [max_batch][kp_cap][32] bytes
+int desc_get_blurred_level(vido_ctx* ctx, int frame, int level, uint8_t* out);
+int desc_match_device_api(vido_ctx* ctx, const uint8_t* d_q, size_t q_stride, const int32_t* d_nq, const uint8_t* d_t, size_t t_stride,
+                          const int32_t* d_nt, int npairs, int qcap, int32_t* d_best_idx, int32_t* d_best_dist, int32_t* d_second_dist);
+int desc_match_host(vido_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* best_idx, int32_t* best_dist,
+                    int32_t* second_dist);
 
 // orb_kernels.cu
 int orb_setup(vido_ctx* ctx);
