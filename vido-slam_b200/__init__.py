@@ -175,6 +175,11 @@ def load_library():
     lib.vido_bgr_to_gray_dev.argtypes = [vp, vp, C.c_int, C.c_size_t, C.c_int, vp, C.c_size_t, C.c_int]
     lib.vido_orb_get_level.argtypes = [vp, C.c_int, C.c_int, vp]
     lib.vido_orb_get_candidates.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp]
+    lib.vido_orb_describe_dev.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, C.c_int]
+    lib.vido_orb_extract_describe.argtypes = [vp, vp, C.c_int, C.c_size_t, C.c_int, vp, C.c_int, vp, vp]
+    lib.vido_orb_get_blurred_level.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.vido_hamming_match.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp]
+    lib.vido_hamming_match_dev.argtypes = [vp, vp, C.c_size_t, vp, vp, C.c_size_t, vp, C.c_int, C.c_int, vp, vp, vp, C.c_int]
     lib.vido_imu_preintegrate.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp]
     lib.vido_get_kernel_times.argtypes = [vp, vp, vp, vp]
     lib.vido_track_frames.argtypes = [vp, C.POINTER(FrameInputs), C.c_int, vp, C.POINTER(TrackStats)]
@@ -312,6 +317,42 @@ class Context:
         n = np.zeros(B, np.int32)
         self._check(self.lib.vido_orb_extract(self.h, _ptr(g), B, H * W, W, _ptr(out), cap, _ptr(n)))
         return [out[b, :n[b]].copy() for b in range(B)]
+
+    def orb_extract_describe(self, gray, cap=None):
+        """ORBextractor::operator() with descriptors.  gray: [H,W] or [B,H,W] uint8 numpy (host).
+        Returns (list of keypoint arrays, list of [n][32] uint8 descriptor arrays)."""
+        g = np.ascontiguousarray(gray, np.uint8)
+        if g.ndim == 2:
+            g = g[None]
+        B, H, W = g.shape
+        assert H == self.cfg.height and W == self.cfg.width
+        cap = cap or (self.cfg.nfeatures + 64)
+        out = np.zeros((B, cap), KP_DTYPE)
+        desc = np.zeros((B, cap, 32), np.uint8)
+        n = np.zeros(B, np.int32)
+        self._check(self.lib.vido_orb_extract_describe(self.h, _ptr(g), B, H * W, W, _ptr(out), cap, _ptr(n), _ptr(desc)))
+        return [out[b, :n[b]].copy() for b in range(B)], [desc[b, :n[b]].copy() for b in range(B)]
+
+    def orb_describe_dev(self, d_kps_ptr, d_nkp_ptr, nframes, cap, d_desc_ptr, sync=False):
+        self._check(self.lib.vido_orb_describe_dev(self.h, d_kps_ptr, d_nkp_ptr, nframes, cap, d_desc_ptr, 1 if sync else 0))
+
+    def get_blurred_level(self, frame, level):
+        w, h, _, _ = self.level_info()
+        out = np.zeros((h[level], w[level]), np.uint8)
+        self._check(self.lib.vido_orb_get_blurred_level(self.h, frame, level, _ptr(out)))
+        return out
+
+    def hamming_match(self, query, train):
+        """brute-force Hamming matching of [n][32] uint8 descriptor arrays (host): best train index, its distance, second distance"""
+        q = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)
+        t = np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+        bi = np.zeros(len(q), np.int32); bd = np.zeros(len(q), np.int32); sd = np.zeros(len(q), np.int32)
+        self._check(self.lib.vido_hamming_match(self.h, _ptr(q), len(q), _ptr(t), len(t), _ptr(bi), _ptr(bd), _ptr(sd)))
+        return bi, bd, sd
+
+    def hamming_match_dev(self, d_q, q_stride, d_nq, d_t, t_stride, d_nt, npairs, qcap, d_best_idx, d_best_dist, d_second, sync=False):
+        self._check(self.lib.vido_hamming_match_dev(self.h, d_q, q_stride, d_nq, d_t, t_stride, d_nt, npairs, qcap, d_best_idx,
+                                                    d_best_dist, d_second, 1 if sync else 0))
 
     def orb_extract_dev(self, d_gray_ptr, nframes, frame_stride, stride, d_out_ptr, cap, d_n_ptr, sync=False):
         self._check(self.lib.vido_orb_extract_dev(self.h, d_gray_ptr, nframes, frame_stride, stride, d_out_ptr, cap,
