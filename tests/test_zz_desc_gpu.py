@@ -91,10 +91,11 @@ def test_device_pointers_extract_describe_match(pkg, gold):
     d_kp = torch.zeros((B, cap, 24), dtype=torch.uint8, device=dev)
     d_n = torch.zeros(B, dtype=torch.int32, device=dev)
     d_desc = torch.zeros((B, cap, 32), dtype=torch.uint8, device=dev)
+    bi = torch.full((B - 1, cap), -7, dtype=torch.int32, device=dev); bd = torch.full_like(bi, -7); sd = torch.full_like(bi, -7)
     vp = lambda t: C.c_void_p(t.data_ptr())
+    torch.cuda.synchronize()   # torch's fills run on its own stream, the library's kernels on the context stream
     ctx.orb_extract_dev(vp(d_gray), B, H * W, W, vp(d_kp), cap, vp(d_n), sync=False)
     ctx.orb_describe_dev(vp(d_kp), vp(d_n), B, cap, vp(d_desc), sync=False)
-    bi = torch.full((B - 1, cap), -7, dtype=torch.int32, device=dev); bd = torch.full_like(bi, -7); sd = torch.full_like(bi, -7)
     # pair p: query = frame p, train = frame p + 1 (the same arrays, shifted by one frame)
     ctx.hamming_match_dev(vp(d_desc), cap * 32, vp(d_n), C.c_void_p(d_desc.data_ptr() + cap * 32), cap * 32,
                           C.c_void_p(d_n.data_ptr() + 4), B - 1, cap, vp(bi), vp(bd), vp(sd), sync=True)
