@@ -197,6 +197,54 @@ def bandwidth_kernels():
         return {}
 
 
+def descriptor_leg(ctx, torch, dev, gray_host, iters=20):
+    """the optional descriptor stage (rBRIEF + Hamming matching; the reference computes no descriptors) beside the
+    extraction it builds on: a device-resident batch, extract -> blur + describe -> match every frame against the next one, timed
+    per stage with CUDA events on the context stream; the descriptors of frame 0 and its matches are checked against the oracle"""
+    import ctypes as C
+    import oracle_lib as ol   # the checker of this leg, not the thing measured
+    B, H, W = gray_host.shape
+    cap = 2564
+    d_gray = torch.from_numpy(gray_host).to(dev)
+    d_kp = torch.zeros((B, cap, 24), dtype=torch.uint8, device=dev)
+    d_n = torch.zeros(B, dtype=torch.int32, device=dev)
+    d_desc = torch.zeros((B, cap, 32), dtype=torch.uint8, device=dev)
+    out = torch.zeros((3, B, cap), dtype=torch.int32, device=dev)
+    vp = lambda t, off=0: C.c_void_p(t.data_ptr() + off)
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ms = np.zeros(3)
+    torch.cuda.synchronize()
+    for it in range(-3, iters):
+        ev[0].record(stream)
+        ctx.orb_extract_dev(vp(d_gray), B, H * W, W, vp(d_kp), cap, vp(d_n))
+        ev[1].record(stream)
+        ctx.orb_describe_dev(vp(d_kp), vp(d_n), B, cap, vp(d_desc))
+        ev[2].record(stream)
+        ctx.hamming_match_dev(vp(d_desc), cap * 32, vp(d_n), vp(d_desc, cap * 32), cap * 32, vp(d_n, 4), B - 1, cap, vp(out[0]), vp(out[1]), vp(out[2]))
+        ev[3].record(stream)
+        ctx.sync()
+        if it >= 0:
+            ms += [ev[k].elapsed_time(ev[k + 1]) for k in range(3)]
+    ms /= iters
+    n = d_n.cpu().numpy()
+    okp, odesc0 = ol.orb_extract_describe(gray_host[0], ol.default_orb_params())
+    _, odesc1 = ol.orb_extract_describe(gray_host[1], ol.default_orb_params())
+    same_desc = bool(n[0] == len(odesc0) and np.array_equal(d_desc[0, :n[0]].cpu().numpy(), odesc0))
+    obi, obd, osd = ol.hamming_match(odesc0, odesc1)
+    got = out[:, 0, :n[0]].cpu().numpy()
+    same_match = bool(np.array_equal(got[0], obi) and np.array_equal(got[1], obd) and np.array_equal(got[2], osd))
+    w, h, _, _ = ctx.level_info()
+    pyr_bytes = int((w.astype(np.int64) * h).sum())
+    peak, _ = measured_peak()
+    return {"what": "optional descriptor stage beside the extraction: device-resident batch, extract -> 7x7 Gaussian + rBRIEF -> Hamming match of every frame against the next",
+            "batch": int(B), "key_points_per_frame": float(n.mean()),
+            "ms_per_batch": {"extract": float(ms[0]), "blur_describe": float(ms[1]), "match": float(ms[2])},
+            "frames_per_s": {"extract": B / ms[0] * 1e3, "extract_describe": B / (ms[0] + ms[1]) * 1e3, "extract_describe_match": B / ms.sum() * 1e3},
+            "blur_describe_algorithmic_GBps": 2 * pyr_bytes * B / (ms[1] * 1e-3) / 1e9, "hbm_peak_GBps": peak,
+            "descriptors_equal_oracle": same_desc, "matches_equal_oracle": same_match}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -505,6 +553,11 @@ def main():
             "ba_per_frame": {"iterations": float(np.mean([s["ba_iterations"] for s in stats])), "obs": float(np.mean([s["ba_obs"] for s in stats])),
                              "points": float(np.mean([s["ba_points"] for s in stats]))},
         }
+        if legs:   # last: nothing of the headline depends on it
+            try:
+                line["descriptors"] = descriptor_leg(ctx, torch, dev, np.ascontiguousarray(h_img[:BATCH, :, :, 0].numpy()))
+            except Exception as e:
+                line["descriptors"] = {"error": str(e)[:200]}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
