@@ -126,6 +126,22 @@ static int time_chain(int W, int H, int B, int iters) {
       ms_ext += a; ms_desc += b; ms_match += c;
     }
   }
+  // the smoothing alone: the same call with all key-point counts zero (the descriptor threads leave at their first test)
+  float ms_blur = 0;
+  {
+    int32_t* d_zero;
+    cudaMalloc(&d_zero, 4 * B); cudaMemset(d_zero, 0, 4 * B);
+    for (int it = -3; it < iters; it++) {
+      cudaEventRecord(e[0], st);
+      VCALL(vido_orb_describe_dev(ctx, d_kp, d_zero, B, cap, d_desc, 0));
+      cudaEventRecord(e[1], st);
+      cudaStreamSynchronize(st);
+      float a; cudaEventElapsedTime(&a, e[0], e[1]);
+      if (it >= 0) ms_blur += a;
+    }
+    cudaFree(d_zero);
+    VCALL(vido_orb_describe_dev(ctx, d_kp, d_n, B, cap, d_desc, 1));   // descriptors back in place for the comparison below
+  }
   cudaError_t err = cudaGetLastError();
   CHECK(err == cudaSuccess, "CUDA error after the timed chain: %s", cudaGetErrorString(err));
   std::vector<int32_t> n(B);
@@ -147,6 +163,8 @@ static int time_chain(int W, int H, int B, int iters) {
   printf("  extraction            %.3f ms per batch (%.1f us per frame)\n", ms_ext / iters, 1e3 * ms_ext / iters / B);
   printf("  blur + rBRIEF         %.3f ms per batch (%.1f us per frame); blur traffic %.2f MB per frame (read + write)\n", ms_desc / iters,
          1e3 * ms_desc / iters / B, 2e-6 * pyr_px);
+  printf("  blur alone (+ an empty descriptor launch)  %.3f ms per batch: %.1f MB read + written = %.0f GB/s\n", ms_blur / iters,
+         2e-6 * pyr_px * B, 2e-9 * pyr_px * B / (ms_blur / iters * 1e-3));
   printf("  Hamming match         %.3f ms per %d pairs (%.1f us per pair of ~%d x %d descriptors)\n", ms_match / iters, B - 1,
          1e3 * ms_match / iters / (B - 1), n[0], n[1]);
   cudaFree(d_gray); cudaFree(d_kp); cudaFree(d_n); cudaFree(d_desc); cudaFree(d_out);
@@ -154,7 +172,12 @@ static int time_chain(int W, int H, int B, int iters) {
   return 0;
 }
 
-int main() {
+int main(int argc, char** argv) {
+  if (argc > 2 && !strcmp(argv[1], "time")) {   // timing only: desc_check time <batch>
+    if (time_chain(1242, 375, atoi(argv[2]), 20)) return 1;
+    printf(fails ? "DESC_CHECK FAILED (%d)\n" : "DESC_CHECK PASSED\n", fails);
+    return fails ? 2 : 0;
+  }
 #ifdef DRY_RUN   // no device: only show that the synthetic frames give the oracle something to describe
   for (int f = 0; f < 2; f++) {
     const int W = f ? 1242 : 333, H = f ? 375 : 211;
