@@ -130,7 +130,17 @@ double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// inputs and outputs of one Tracking::DynObjTracking call, kept when the test-suite asks for them (vo_tracker_dyn_log_*): an
+// independent restatement of src/Tracking.cc:1670-1912 in tests/test_dynobj_independent.py is run on the inputs
+struct DynRecord {
+  int f_id = 0, max_id_before = 0, max_id_after = 0;
+  std::vector<int> sem, lab_before, lab_after, last_sem, last_sem_pos, last_stat, last_mod, out_mod, out_sem_pos, out_len, out_ids;
+  std::vector<float> key_xy, depth, flow3;
+};
+
 struct Tracker {
+  bool dyn_log_on = false;
+  std::vector<DynRecord> dyn_log;
   vo_track_config cfg;
   Map map;
   Frame* last = nullptr;
@@ -1246,7 +1256,24 @@ struct Tracker {
         std::vector<std::vector<int>> ObjIdNew;
         if (!cur->mvObjKeys.empty()) {
           scene_flow();
+          DynRecord rec;
+          if (dyn_log_on) {
+            rec.f_id = f_id; rec.max_id_before = max_id;
+            rec.sem = cur->vSemObjLabel; rec.lab_before = cur->vObjLabel; rec.last_sem = last->vSemObjLabel;
+            rec.last_sem_pos = last->nSemPosition; rec.last_mod = last->nModLabel;
+            for (char b : last->bObjStat) rec.last_stat.push_back(b ? 1 : 0);
+            for (size_t i = 0; i < cur->mvObjKeys.size(); i++) {
+              rec.key_xy.push_back(cur->mvObjKeys[i].x); rec.key_xy.push_back(cur->mvObjKeys[i].y);
+              rec.depth.push_back(cur->mvObjDepth[i]);
+              rec.flow3.push_back(cur->vFlow_3d[i].x); rec.flow3.push_back(cur->vFlow_3d[i].y); rec.flow3.push_back(cur->vFlow_3d[i].z);
+            }
+          }
           ObjIdNew = dyn_obj_tracking();
+          if (dyn_log_on) {
+            rec.max_id_after = max_id; rec.lab_after = cur->vObjLabel; rec.out_mod = cur->nModLabel; rec.out_sem_pos = cur->nSemPosition;
+            for (auto& o : ObjIdNew) { rec.out_len.push_back((int)o.size()); rec.out_ids.insert(rec.out_ids.end(), o.begin(), o.end()); }
+            dyn_log.push_back(std::move(rec));
+          }
           object_motions(ObjIdNew);
         }
         double t4b = now_ms();
@@ -1376,6 +1403,64 @@ int vo_tracker_track(void* h, const uint8_t* gray, float* depth, const float* fl
                      vo_track_stats* st) {
   return ((Tracker*)h)->track(gray, depth, flow, mask, Tcw_out, st);
 }
+// ---- test hooks: the recorded DynObjTracking calls
+void vo_tracker_dyn_log_enable(void* h, int on) { ((Tracker*)h)->dyn_log_on = on != 0; }
+int vo_tracker_dyn_log_count(void* h) { return (int)((Tracker*)h)->dyn_log.size(); }
+int vo_tracker_dyn_log_sizes(void* h, int k, int32_t* sizes) {
+  const DynRecord& r = ((Tracker*)h)->dyn_log[k];
+  const int v[8] = {(int)r.sem.size(), (int)r.last_sem.size(), (int)r.last_mod.size(), (int)r.out_mod.size(), (int)r.out_ids.size(),
+                    r.f_id, r.max_id_before, r.max_id_after};
+  for (int i = 0; i < 8; i++) sizes[i] = v[i];
+  return 0;
+}
+int vo_tracker_dyn_log_get(void* h, int k, int32_t* sem, int32_t* lab_before, int32_t* lab_after, int32_t* last_sem, float* key_xy,
+                           float* depth, float* flow3, int32_t* last_sem_pos, int32_t* last_stat, int32_t* last_mod, int32_t* out_mod,
+                           int32_t* out_sem_pos, int32_t* out_len, int32_t* out_ids) {
+  const DynRecord& r = ((Tracker*)h)->dyn_log[k];
+  auto cp = [](auto* dst, const auto& v) { for (size_t i = 0; i < v.size(); i++) dst[i] = v[i]; };
+  cp(sem, r.sem); cp(lab_before, r.lab_before); cp(lab_after, r.lab_after); cp(last_sem, r.last_sem); cp(key_xy, r.key_xy);
+  cp(depth, r.depth); cp(flow3, r.flow3); cp(last_sem_pos, r.last_sem_pos); cp(last_stat, r.last_stat); cp(last_mod, r.last_mod);
+  cp(out_mod, r.out_mod); cp(out_sem_pos, r.out_sem_pos); cp(out_len, r.out_len); cp(out_ids, r.out_ids);
+  return 0;
+}
+
+// Tracking::DynObjTracking on caller-supplied frame state (test hook: randomised inputs reach the branches the synthetic sequences
+// never take -- objects on the image boundary, static / far / small objects, lost ids, ties of the majority vote)
+int vo_dyn_obj_tracking(const vo_track_config* cfg, int n, const int32_t* sem, int32_t* lab, const float* key_xy, const float* depth,
+                        const float* flow3, const int32_t* last_sem, int n_last_obj, const int32_t* last_sem_pos, const int32_t* last_stat,
+                        const int32_t* last_mod, int f_id, int32_t* max_id, int32_t* out_mod, int32_t* out_sem_pos, int32_t* out_len,
+                        int32_t* out_ids) {
+  Tracker t;
+  t.cfg = *cfg;
+  t.cur = new Frame();
+  t.last = new Frame();
+  t.f_id = f_id;
+  t.max_id = *max_id;
+  for (int i = 0; i < n; i++) {
+    t.cur->vSemObjLabel.push_back(sem[i]); t.cur->vObjLabel.push_back(lab[i]);
+    t.cur->mvObjKeys.push_back({key_xy[2 * i], key_xy[2 * i + 1]});
+    t.cur->mvObjDepth.push_back(depth[i]);
+    t.cur->vFlow_3d.push_back({flow3[3 * i], flow3[3 * i + 1], flow3[3 * i + 2]});
+    t.last->vSemObjLabel.push_back(last_sem[i]);
+  }
+  for (int k = 0; k < n_last_obj; k++) {
+    t.last->nSemPosition.push_back(last_sem_pos[k]); t.last->bObjStat.push_back((char)(last_stat[k] != 0)); t.last->nModLabel.push_back(last_mod[k]);
+  }
+  const std::vector<std::vector<int>> ids = t.dyn_obj_tracking();
+  for (int i = 0; i < n; i++) lab[i] = t.cur->vObjLabel[i];
+  *max_id = t.max_id;
+  int at = 0;
+  for (size_t o = 0; o < ids.size(); o++) {
+    out_mod[o] = t.cur->nModLabel[o]; out_sem_pos[o] = t.cur->nSemPosition[o]; out_len[o] = (int)ids[o].size();
+    for (int id : ids[o]) out_ids[at++] = id;
+  }
+  const int no = (int)ids.size();
+  if (t.cur != t.last) delete t.cur;
+  delete t.last;
+  t.cur = t.last = nullptr;
+  return no;
+}
+
 int vo_tracker_num_frames(void* h) { return (int)((Tracker*)h)->map.vmCameraPose.size(); }
 int vo_tracker_get_map_poses(void* h, float* poses, int cap) {
   Tracker* t = (Tracker*)h;

@@ -392,6 +392,27 @@ def track_config(cam, nfeatures=2500, window=20, max_track_bg=1000, rebuild=1, c
     return c
 
 
+def dyn_obj_tracking(cfg, sem, lab, key_xy, depth, flow3, last_sem, last_sem_pos, last_stat, last_mod, f_id, max_id):
+    """Tracking::DynObjTracking of the oracle on caller-supplied frame state: (labels after, max_id after, nModLabel, nSemPosition,
+    list of index arrays)"""
+    L = lib()
+    L.vo_dyn_obj_tracking.argtypes = [C.POINTER(TrackConfig), C.c_int] + [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 5
+    n = len(sem)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    sem, lab, last_sem = i32(sem), i32(lab).copy(), i32(last_sem)
+    key_xy, depth, flow3 = f32(key_xy), f32(depth), f32(flow3)
+    lsp, lst, lmd = i32(last_sem_pos), i32(last_stat), i32(last_mod)
+    mx = np.array([max_id], np.int32)
+    out_mod = np.zeros(n + 1, np.int32); out_sem = np.zeros(n + 1, np.int32); out_len = np.zeros(n + 1, np.int32); out_ids = np.zeros(n + 1, np.int32)
+    no = L.vo_dyn_obj_tracking(C.byref(cfg), n, _p(sem), _p(lab), _p(key_xy), _p(depth), _p(flow3), _p(last_sem), len(lsp), _p(lsp), _p(lst),
+                               _p(lmd), f_id, _p(mx), _p(out_mod), _p(out_sem), _p(out_len), _p(out_ids))
+    ids, at = [], 0
+    for o in range(no):
+        ids.append(out_ids[at:at + out_len[o]].copy()); at += out_len[o]
+    return lab, int(mx[0]), out_mod[:no].copy(), out_sem[:no].copy(), ids
+
+
 class Metric(C.Structure):
     """vo_metric / vido_metric"""
     _fields_ = [("cam_t", C.c_float), ("cam_r", C.c_float), ("obj_t", C.c_float), ("obj_r", C.c_float), ("n_cam", C.c_int32),
@@ -431,6 +452,35 @@ class OracleTracker:
         L.vo_tracker_apply_scaled_rotation.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
         self.cfg = cfg
         self.h = L.vo_tracker_create(C.byref(cfg))
+
+    # ---- recorded Tracking::DynObjTracking calls (inputs and outputs), for tests/test_dynobj_independent.py
+    def dyn_log_enable(self, on=True):
+        lib().vo_tracker_dyn_log_enable.argtypes = [C.c_void_p, C.c_int]
+        lib().vo_tracker_dyn_log_enable.restype = None
+        lib().vo_tracker_dyn_log_enable(self.h, 1 if on else 0)
+
+    def dyn_log(self):
+        L = lib()
+        L.vo_tracker_dyn_log_count.argtypes = [C.c_void_p]
+        L.vo_tracker_dyn_log_sizes.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.vo_tracker_dyn_log_get.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 14
+        out = []
+        for k in range(L.vo_tracker_dyn_log_count(self.h)):
+            sz = np.zeros(8, np.int32)
+            L.vo_tracker_dyn_log_sizes(self.h, k, _p(sz))
+            n, nl, nlo, no, nid = [int(v) for v in sz[:5]]
+            assert nl == n
+            r = dict(f_id=int(sz[5]), max_id_before=int(sz[6]), max_id_after=int(sz[7]),
+                     sem=np.zeros(n, np.int32), lab_before=np.zeros(n, np.int32), lab_after=np.zeros(n, np.int32),
+                     last_sem=np.zeros(n, np.int32), key_xy=np.zeros((n, 2), np.float32), depth=np.zeros(n, np.float32),
+                     flow3=np.zeros((n, 3), np.float32), last_sem_pos=np.zeros(nlo, np.int32), last_stat=np.zeros(nlo, np.int32),
+                     last_mod=np.zeros(nlo, np.int32), out_mod=np.zeros(no, np.int32), out_sem_pos=np.zeros(no, np.int32),
+                     out_len=np.zeros(no, np.int32), out_ids=np.zeros(nid, np.int32))
+            L.vo_tracker_dyn_log_get(self.h, k, *[_p(r[key]) for key in ("sem", "lab_before", "lab_after", "last_sem", "key_xy", "depth", "flow3",
+                                                                        "last_sem_pos", "last_stat", "last_mod", "out_mod", "out_sem_pos",
+                                                                        "out_len", "out_ids")])
+            out.append(r)
+        return out
 
     # ---- VIO mode (sensor = IMU_RGBD)
     def set_imu(self, Tbc, noise):
