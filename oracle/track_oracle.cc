@@ -1424,6 +1424,32 @@ int vo_tracker_dyn_log_get(void* h, int k, int32_t* sem, int32_t* lab_before, in
   return 0;
 }
 
+// static half of Tracking::RenewFrameInfo (src/Tracking.cc:2959-3110) on caller-supplied frame state (test hook for
+// tests/test_renew_independent.py); outputs sized for max_track_bg + 1 features; returns the count
+int vo_renew_static(const vo_track_config* cfg, const int32_t* TM_sta, int n_tm, const float* stat_keys, int n_stat, const vo_keypoint* kps,
+                    int n_kps, const float* depth, const float* flow, const int32_t* mask, const float* Tcw, float* keys, float* corres,
+                    float* flow_next, int32_t* inlier_id, float* out_depth, float* p3) {
+  Tracker t;
+  t.cfg = *cfg;
+  t.cur = new Frame();
+  t.last = t.cur;
+  for (int i = 0; i < n_stat; i++) t.cur->mvStatKeys.push_back({stat_keys[2 * i], stat_keys[2 * i + 1]});
+  t.cur->mvKeys.assign(kps, kps + n_kps);
+  memcpy(t.cur->Tcw, Tcw, sizeof(float) * 16);
+  t.renew(std::vector<int>(TM_sta, TM_sta + n_tm), depth, flow, mask);
+  const Frame& c = *t.cur;
+  const int n = (int)c.mvStatKeysTmp.size();
+  for (int i = 0; i < n; i++) {
+    keys[2 * i] = c.mvStatKeysTmp[i].x; keys[2 * i + 1] = c.mvStatKeysTmp[i].y;
+    corres[2 * i] = c.mvCorres[i].x; corres[2 * i + 1] = c.mvCorres[i].y;
+    flow_next[2 * i] = c.mvFlowNext[i].x; flow_next[2 * i + 1] = c.mvFlowNext[i].y;
+    inlier_id[i] = c.nStaInlierID[i];
+    out_depth[i] = c.mvStatDepthTmp[i];
+    p3[3 * i] = c.mvStat3DPointTmp[i].x; p3[3 * i + 1] = c.mvStat3DPointTmp[i].y; p3[3 * i + 2] = c.mvStat3DPointTmp[i].z;
+  }
+  return n;
+}
+
 // Tracking::DynObjTracking on caller-supplied frame state (test hook: randomised inputs reach the branches the synthetic sequences
 // never take -- objects on the image boundary, static / far / small objects, lost ids, ties of the majority vote)
 int vo_dyn_obj_tracking(const vo_track_config* cfg, int n, const int32_t* sem, int32_t* lab, const float* key_xy, const float* depth,

@@ -392,6 +392,22 @@ def track_config(cam, nfeatures=2500, window=20, max_track_bg=1000, rebuild=1, c
     return c
 
 
+def renew_static(cfg, TM_sta, stat_keys, kps, depth, flow, mask, Tcw):
+    """static half of Tracking::RenewFrameInfo of the oracle on caller-supplied state: keys, corres, flow, inlier ids, depth, 3-D points"""
+    L = lib()
+    L.vo_renew_static.argtypes = [C.POINTER(TrackConfig), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 10
+    tm = np.ascontiguousarray(TM_sta, np.int32); sk = np.ascontiguousarray(stat_keys, np.float32); kp = np.ascontiguousarray(kps, KP_DTYPE)
+    depth = np.ascontiguousarray(depth, np.float32); flow = np.ascontiguousarray(flow, np.float32); mask = np.ascontiguousarray(mask, np.int32)
+    T = np.ascontiguousarray(Tcw, np.float32).reshape(16)
+    cap = cfg.max_track_bg + 2
+    keys = np.zeros((cap, 2), np.float32); cor = np.zeros((cap, 2), np.float32); fl = np.zeros((cap, 2), np.float32)
+    inl = np.zeros(cap, np.int32); dep = np.zeros(cap, np.float32); p3 = np.zeros((cap, 3), np.float32)
+    n = L.vo_renew_static(C.byref(cfg), _p(tm), len(tm), _p(sk), len(sk), _p(kp), len(kp), _p(depth), _p(flow), _p(mask), _p(T), _p(keys),
+                          _p(cor), _p(fl), _p(inl), _p(dep), _p(p3))
+    assert n <= cap
+    return keys[:n], cor[:n], fl[:n], inl[:n], dep[:n], p3[:n]
+
+
 def dyn_obj_tracking(cfg, sem, lab, key_xy, depth, flow3, last_sem, last_sem_pos, last_stat, last_mod, f_id, max_id):
     """Tracking::DynObjTracking of the oracle on caller-supplied frame state: (labels after, max_id after, nModLabel, nSemPosition,
     list of index arrays)"""
