@@ -1450,6 +1450,45 @@ int vo_renew_static(const vo_track_config* cfg, const int32_t* TM_sta, int n_tm,
   return n;
 }
 
+// object half of Tracking::RenewFrameInfo (src/Tracking.cc:3112-3289) on caller-supplied frame state (test hook for
+// tests/test_renew_independent.py); inlier_ids = the objects' inlier lists back to back (inlier_len[o] each); returns the count
+int vo_renew_objects(const vo_track_config* cfg, int n_feat, const float* obj_keys, const int32_t* obj_label, int n_obj,
+                     const int32_t* inlier_len, const int32_t* inlier_ids, const int32_t* obj_stat, const int32_t* sem_pos,
+                     const int32_t* mod_label, int n_tmp, const float* tmp_keys, const float* tmp_depth, const int32_t* tmp_sem,
+                     const float* tmp_flow, const float* tmp_corres, const float* depth, const float* flow, const int32_t* mask,
+                     const float* Tcw, int cap, float* keys, float* out_depth, float* corres, float* flow_next, int32_t* sem,
+                     int32_t* inlier_id, int32_t* label, float* p3) {
+  Tracker t;
+  t.cfg = *cfg;
+  t.cur = new Frame();
+  t.last = t.cur;
+  Frame& c = *t.cur;
+  for (int i = 0; i < n_feat; i++) { c.mvObjKeys.push_back({obj_keys[2 * i], obj_keys[2 * i + 1]}); c.vObjLabel.push_back(obj_label[i]); }
+  int at = 0;
+  for (int o = 0; o < n_obj; o++) {
+    c.vnObjInlierID.push_back(std::vector<int>(inlier_ids + at, inlier_ids + at + inlier_len[o]));
+    at += inlier_len[o];
+    c.vnObjID.push_back({});
+    c.bObjStat.push_back((char)(obj_stat[o] != 0)); c.nSemPosition.push_back(sem_pos[o]); c.nModLabel.push_back(mod_label[o]);
+  }
+  for (int j = 0; j < n_tmp; j++) {
+    t.tmpKeys.push_back({tmp_keys[2 * j], tmp_keys[2 * j + 1]}); t.tmpDepth.push_back(tmp_depth[j]); t.tmpSem.push_back(tmp_sem[j]);
+    t.tmpFlow.push_back({tmp_flow[2 * j], tmp_flow[2 * j + 1]}); t.tmpCorres.push_back({tmp_corres[2 * j], tmp_corres[2 * j + 1]});
+  }
+  memcpy(c.Tcw, Tcw, sizeof(float) * 16);
+  t.renew_objects(depth, flow, mask);
+  const int n = (int)c.mvObjKeys.size();
+  if (n > cap) return -n;
+  for (int i = 0; i < n; i++) {
+    keys[2 * i] = c.mvObjKeys[i].x; keys[2 * i + 1] = c.mvObjKeys[i].y; out_depth[i] = c.mvObjDepth[i];
+    corres[2 * i] = c.mvObjCorres[i].x; corres[2 * i + 1] = c.mvObjCorres[i].y;
+    flow_next[2 * i] = c.mvObjFlowNext[i].x; flow_next[2 * i + 1] = c.mvObjFlowNext[i].y;
+    sem[i] = c.vSemObjLabel[i]; inlier_id[i] = c.nDynInlierID[i]; label[i] = c.vObjLabel[i];
+    p3[3 * i] = c.mvObj3DPoint[i].x; p3[3 * i + 1] = c.mvObj3DPoint[i].y; p3[3 * i + 2] = c.mvObj3DPoint[i].z;
+  }
+  return n;
+}
+
 // Tracking::DynObjTracking on caller-supplied frame state (test hook: randomised inputs reach the branches the synthetic sequences
 // never take -- objects on the image boundary, static / far / small objects, lost ids, ties of the majority vote)
 int vo_dyn_obj_tracking(const vo_track_config* cfg, int n, const int32_t* sem, int32_t* lab, const float* key_xy, const float* depth,

@@ -408,6 +408,28 @@ def renew_static(cfg, TM_sta, stat_keys, kps, depth, flow, mask, Tcw):
     return keys[:n], cor[:n], fl[:n], inl[:n], dep[:n], p3[:n]
 
 
+def renew_objects(cfg, obj_keys, obj_label, inlier_sets, obj_stat, sem_pos, mod_label, tmp, depth, flow, mask, Tcw, cap=1 << 16):
+    """object half of Tracking::RenewFrameInfo of the oracle on caller-supplied state; tmp = dict(keys, depth, sem, flow, corres) of the
+    frame's object samples.  Returns keys, depth, corres, flow, semantic label, inlier id, object label, 3-D points."""
+    L = lib()
+    L.vo_renew_objects.argtypes = ([C.POINTER(TrackConfig), C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_int] +
+                                   [C.c_void_p] * 9 + [C.c_int] + [C.c_void_p] * 8)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    ok, ol_ = f32(obj_keys), i32(obj_label)
+    ilen = i32([len(s) for s in inlier_sets]); iids = i32(np.concatenate([np.asarray(s, np.int32) for s in inlier_sets]) if len(inlier_sets) else [])
+    st, sp, ml = i32(obj_stat), i32(sem_pos), i32(mod_label)
+    tk, td, ts, tf, tc = f32(tmp["keys"]), f32(tmp["depth"]), i32(tmp["sem"]), f32(tmp["flow"]), f32(tmp["corres"])
+    depth, flow, mask, T = f32(depth), f32(flow), i32(mask), f32(Tcw).reshape(16)
+    keys = np.zeros((cap, 2), np.float32); dep = np.zeros(cap, np.float32); cor = np.zeros((cap, 2), np.float32); fl = np.zeros((cap, 2), np.float32)
+    sem = np.zeros(cap, np.int32); inl = np.zeros(cap, np.int32); lab = np.zeros(cap, np.int32); p3 = np.zeros((cap, 3), np.float32)
+    n = L.vo_renew_objects(C.byref(cfg), len(ol_), _p(ok), _p(ol_), len(ilen), _p(ilen), _p(iids), _p(st), _p(sp), _p(ml), len(ts), _p(tk),
+                           _p(td), _p(ts), _p(tf), _p(tc), _p(depth), _p(flow), _p(mask), _p(T), cap, _p(keys), _p(dep), _p(cor), _p(fl),
+                           _p(sem), _p(inl), _p(lab), _p(p3))
+    assert 0 <= n <= cap
+    return keys[:n], dep[:n], cor[:n], fl[:n], sem[:n], inl[:n], lab[:n], p3[:n]
+
+
 def dyn_obj_tracking(cfg, sem, lab, key_xy, depth, flow3, last_sem, last_sem_pos, last_stat, last_mod, f_id, max_id):
     """Tracking::DynObjTracking of the oracle on caller-supplied frame state: (labels after, max_id after, nModLabel, nSemPosition,
     list of index arrays)"""
