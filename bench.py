@@ -40,6 +40,15 @@ METRIC = "frames/s Tracking+PartialBA on 1242x375 synth seq"
 ORACLE_FLAGS = "-O3 -march=native -ffp-contract=off (oracle/Makefile `native`, built on this box)"
 
 
+def headline_config():
+    """`config` of the bench line, the same object for the GPU arm and the reference arm"""
+    bytes_frame = CAM["height"] * CAM["width"] * (3 + 4 + 8 + 4)
+    return {"workload": "1242x375 KITTI-shape mono VO, synthetic sequence, ORB + PartialBatchOptimization every frame (BASELINE.json configs[1])",
+            "frames_per_step": CHUNK, "front_end_batch": BATCH, "window": 20, "nfeatures": 2500, "max_track_bg": 1000,
+            "sequences": "one per GPU (seed 1234+rank)", "l2": f"inputs ({bytes_frame * CHUNK / 1e6:.0f} MB per step) exceed the 126 MB L2",
+            "scope": "static scene, VO (the headline); vio / dynamic_objects / full_batch / factor_allgather are measured after the headline arms"}
+
+
 def load_pkg():
     path = os.path.join(ROOT, "vido-slam_b200", "__init__.py")
     spec = importlib.util.spec_from_file_location("vido_slam_b200", path, submodule_search_locations=[os.path.dirname(path)])
@@ -178,11 +187,10 @@ def reference_arm(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
             "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "1242x375 KITTI-shape mono VO, synthetic sequence, ORB + PartialBatchOptimization every frame",
-                       "frames_per_step": REF_CHUNK, "window": 20, "nfeatures": 2500},
+            "config": headline_config(),   # the GPU arm's configuration; a step of this arm is a bounded sample of it (cpu_baseline.sample)
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "port", "flags": flags, "stage_ms": stage,
-                             "host_cores": os.cpu_count(),
-                             "sample": f"frames {prime}..{total - 1} of the seed-1234 sequence ({steps} steps of {REF_CHUNK} frames; CPU restatement; the reference needs OpenCV/Eigen/CSparse C++ which are absent)"},
+                             "host_cores": os.cpu_count(), "sample_frames_per_step": REF_CHUNK,
+                             "sample": f"frames {prime}..{total - 1} of the seed-1234 sequence ({steps} steps, each a {REF_CHUNK}-frame sample of the configuration's {CHUNK}-frame step; CPU restatement; the reference needs OpenCV/Eigen/CSparse C++ which are absent)"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -530,10 +538,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": el_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "1242x375 KITTI-shape mono VO, synthetic sequence, ORB + PartialBatchOptimization every frame (BASELINE.json configs[1])",
-                       "frames_per_step": CHUNK, "front_end_batch": BATCH, "window": 20, "nfeatures": 2500, "max_track_bg": 1000,
-                       "sequences": "one per GPU (seed 1234+rank)", "l2": f"inputs ({bytes_frame * CHUNK / 1e6:.0f} MB per step) exceed the 126 MB L2",
-                       "scope": "static scene, VO (the headline); vio / dynamic_objects / full_batch / factor_allgather are measured after the headline arms"},
+            "config": headline_config(),
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": bytes_frame * CHUNK, "d2h_bytes_per_step": 64 * CHUNK},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
