@@ -137,3 +137,135 @@ def test_static_sequence_composed_in_python_equals_the_oracle_tracker():
             assert np.array_equal(asso, ka), k
             assert st["n_static"] == len(kx) and len(kx) >= 900
     tr.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# the object path on top: UpdateMask, object samples and their carry-over (src/Tracking.cc:343-364, 391-421), GetSceneFlowObj
+# (:1582-1668), DynObjTracking (:1670-1912, the Python restatement of test_dynobj_independent), the per-object loop of Track
+# (:1179-1308) with GetInitModelObj (:2030-2162) and PoseOptimizationFlow2 (src/Optimizer.cc:3037), the object half of
+# RenewFrameInfo and the Map pushes (:1345-1422)
+# ---------------------------------------------------------------------------------------------------------------------------
+from test_dynobj_independent import dyn_obj_tracking_py  # noqa: E402
+
+
+class PyDynTracker(PyTracker):
+    def __init__(self, cam, cfg):
+        super().__init__(cam, cfg)
+        self.seg_last = self.flow_last = None
+        self.max_id = 1
+        self.f_id = 0
+        self.dyn_map = []     # per frame: (xy, depth, p3, asso, label)
+        self.obj_map = []     # per frame >= 1: (label, semantic label, motion, centre)
+
+    def world(self, key, z, Tcw):
+        return unproject_world(key, z, self.K, inv_pose(Tcw))
+
+    def track(self, gray, depth_in, flow, mask):
+        W, H = self.cam["width"], self.cam["height"]
+        cfg = self.cfg
+        last = self.last
+        depth = ol.depth_prep(depth_in, cfg.choose_data, cfg.depth_map_factor, cfg.bf)
+        if last is not None and len(last["obj_sem"]) and self.seg_last is not None:            # UpdateMask, :343-364
+            mask, _, _ = ol.update_mask(last["obj_sem"], last["obj_corres"], self.seg_last, self.flow_last, mask)
+        T = super().track(gray, depth_in, flow, mask)
+        cur = self.last
+        tk, tc, tf, td, ts = ol.frame_sample_objects(depth, flow, mask, cfg.th_depth_obj)       # Frame.cc:184-211
+        tmp = dict(keys=tk, corres=tc, flow=tf, depth=td, sem=ts)
+        if last is None:
+            cur.update(obj_keys=tk, obj_corres=tc, obj_flow_next=tf, obj_depth=td, obj_sem=ts, obj_label=np.full(len(tk), -2, np.int32),
+                       mod_label=np.zeros(0, np.int32), sem_pos=np.zeros(0, np.int32), obj_stat=np.zeros(0, np.int32), obj_mod=[])
+            fx, fy, cx, cy = self.K
+            self.dyn_map.append((tk, td, None, None, None))
+        else:
+            # :403-421 object features of this frame = the last frame's correspondences, fresh depth / label at the truncated position
+            ok = last["obj_corres"].copy()
+            n = len(ok)
+            od = np.zeros(n, np.float32); osem = np.zeros(n, np.int32)
+            for i in range(n):
+                u, v = int(ok[i, 0]), int(ok[i, 1])
+                if 0 < u < W - 1 and 0 < v < H - 1 and 0 < depth[v, u] < cfg.th_depth_obj:
+                    od[i] = depth[v, u]; osem[i] = mask[v, u]
+                else:
+                    od[i] = F(0.1); osem[i] = 0
+            lab = np.full(n, -2, np.int32)
+            inlier_sets, stat, mods, cents, mod_label, sem_pos = [], [], [], [], np.zeros(0, np.int32), np.zeros(0, np.int32)
+            if n:
+                # GetSceneFlowObj: world displacement of every feature with a semantic label in both frames
+                flow3 = np.zeros((n, 3), np.float32)
+                for i in range(n):
+                    if osem[i] <= 0 or last["obj_sem"][i] <= 0:
+                        lab[i] = -1
+                        continue
+                    flow3[i] = self.world(ok[i], od[i], T) - self.world(last["obj_keys"][i], last["obj_depth"][i], last["Tcw"])
+                lab, self.max_id, mod_label, sem_pos, ids = dyn_obj_tracking_py(
+                    W, H, cfg.sf_mg_thres, cfg.sf_ds_thres, cfg.th_depth_obj, osem, lab, ok, od, flow3, last["obj_sem"], last["sem_pos"],
+                    last["obj_stat"], last["mod_label"], self.f_id, self.max_id)
+                Twc = inv_pose(T)
+                for o, oid in enumerate(ids):                                                    # :1179-1308
+                    p3 = np.stack([self.world(last["obj_keys"][i], last["obj_depth"][i], last["Tcw"]) for i in oid])
+                    c = np.zeros(3, np.float32)
+                    for p in p3:
+                        c = (c + p).astype(np.float32)
+                    centre = (c * F(1.0 / np.float64(len(oid)))).astype(np.float32)
+                    pre = [k for k in range(len(last["mod_label"])) if last["mod_label"][k] == mod_label[o]]     # GetInitModelObj
+                    if pre:
+                        T0, sub, _, _, _ = ol.init_model_cam(ok[oid], p3, None, mat_mul(T, last["obj_mod"][pre[0]]), self.K)
+                    else:
+                        T0, sub, _, _, _ = ol.init_model_cam(ok[oid], p3, None, T, self.K, no_motion_model=1)
+                    keep = np.zeros(len(oid), bool); keep[sub] = True
+                    lab[oid[~keep]] = -1
+                    in_ids = oid[sub]
+                    if len(in_ids) < 50:
+                        stat.append(0); mods.append(np.eye(4, dtype=np.float32)); cents.append(np.zeros(3, np.float32)); inlier_sets.append(in_ids)
+                        continue
+                    Tx, fo, inl, _, _ = ol.poseopt_flow2cam(last["obj_keys"][in_ids], last["obj_flow_next"][in_ids], last["obj_depth"][in_ids], T0,
+                                                            last["Tcw"], self.K, info_prior=0.5, rounds=1, its=200)
+                    mods.append(mat_mul(Twc, Tx))                                                # vObjMod = inv(Tcw) * Obj_X
+                    good = []
+                    for k, i in enumerate(in_ids):
+                        if inl[k]:
+                            ok[i, 0] = F(np.float64(last["obj_keys"][i, 0]) + np.float64(fo[k, 0]))
+                            ok[i, 1] = F(np.float64(last["obj_keys"][i, 1]) + np.float64(fo[k, 1]))
+                            good.append(i)
+                        else:
+                            lab[i] = -1
+                    stat.append(1); cents.append(centre); inlier_sets.append(np.array(good, np.int32))
+            nk, nd, ncor, nfl, nsem, ninl, nlab, np3 = ol.renew_objects(cfg, ok, lab, inlier_sets, stat, sem_pos, mod_label, tmp, depth, flow, mask, T)
+            cur.update(obj_keys=nk, obj_depth=nd, obj_corres=ncor, obj_flow_next=nfl, obj_sem=nsem, obj_label=nlab, mod_label=mod_label,
+                       sem_pos=sem_pos, obj_stat=np.array(stat, np.int32), obj_mod=mods)
+            self.dyn_map.append((nk, nd, np3, ninl, nlab))
+            okk = [o for o in range(len(stat)) if stat[o]]
+            self.obj_map.append((mod_label[okk], sem_pos[okk], [mods[o] for o in okk], [cents[o] for o in okk]))
+        if len(cur["obj_sem"]):
+            self.seg_last, self.flow_last = mask.copy(), flow.copy()
+        else:
+            self.seg_last = self.flow_last = None
+        self.f_id += 1
+        return T
+
+
+def test_dynamic_sequence_composed_in_python_equals_the_oracle_tracker():
+    cam = synth.KITTI
+    sc = synth.Scene(cam=cam, seed=1234, flow_noise=0.05, depth_noise=0.005, n_objects=5, drop_mask=[(3, 2)])
+    cfg = ol.track_config(cam)
+    tr = ol.OracleTracker(cfg)
+    py = PyDynTracker(cam, cfg)
+    n = 6
+    for k in range(n):
+        f = sc.frame(k)
+        g, d, fl, m = f["gray"].numpy(), f["depth_in"].numpy(), f["flow"].numpy(), f["mask"].numpy()
+        T_or, st, rc = tr.track(g, d, fl, m)
+        assert rc == 0
+        T_py = py.track(g, d, fl, m)
+        assert np.array_equal(T_py, T_or), k
+        xy, dep, p3, asso, lab = tr.dynamic_features(k)
+        kx, kd, kp3, ka, kl = py.dyn_map[k]
+        assert len(xy) > 2000 and np.array_equal(xy, kx) and np.array_equal(dep, kd), k
+        if k > 0:
+            assert np.array_equal(asso, ka) and np.array_equal(lab, kl) and np.array_equal(p3, kp3), k
+            olab, osem, omot, ocen = tr.objects(k)
+            plab, psem, pmot, pcen = py.obj_map[k - 1]
+            assert len(olab) == 5 and np.array_equal(olab, plab) and np.array_equal(osem, psem), k
+            assert np.array_equal(omot, np.stack(pmot)) and np.array_equal(ocen, np.stack(pcen)), k
+            assert st["n_masks_recovered"] == (1 if k == 3 else 0)
+    tr.close()
