@@ -269,3 +269,103 @@ def test_dynamic_sequence_composed_in_python_equals_the_oracle_tracker():
             assert np.array_equal(omot, np.stack(pmot)) and np.array_equal(ocen, np.stack(pcen)), k
             assert st["n_masks_recovered"] == (1 if k == 3 else 0)
     tr.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# the window optimisation chained over the sequence: what Tracking::Track pushes into the Map (:1345-1422), GetStaticTrack, the
+# graph Optimizer::PartialBatchOptimization builds from it (src/Optimizer.cc:43-100, 218-362) and what it writes back
+# (:1056-1142) -- every window starts from the poses, relative motions and points the windows before it left in the Map
+# ---------------------------------------------------------------------------------------------------------------------------
+from test_tracklets_independent import get_static_track  # noqa: E402
+
+
+def camera_point(key, z, K):
+    """Optimizer::Get3DinCamera (src/Optimizer.cc:3277-3294)"""
+    fx, fy, cx, cy = K
+    invfx, invfy = F(F(1) / fx), F(F(1) / fy)
+    return np.array([F(F(F(key[0] - cx) * z) * invfx), F(F(F(key[1] - cy) * z) * invfy), z], np.float32)
+
+
+class PyMapTracker(PyTracker):
+    def __init__(self, cam, cfg):
+        super().__init__(cam, cfg)
+        self.poses, self.rel, self.p3 = [], [], []
+        self.ba = []
+
+    def track(self, gray, depth_in, flow, mask):
+        first = self.last is None
+        T = super().track(gray, depth_in, flow, mask)
+        xy, dep, asso = self.map[-1]
+        if first:                                                          # Initialization: camera-frame points, identity pose
+            self.p3.append(np.stack([camera_point(xy[i], dep[i], self.K) for i in range(len(xy))]))
+            self.poses.append(np.eye(4, dtype=np.float32))
+            return T
+        Twc = inv_pose(T)
+        self.p3.append(np.stack([unproject_world(xy[i], dep[i], self.K, Twc) for i in range(len(xy))]))   # RenewFrameInfo (4)
+        self.poses.append(Twc)                                             # vmCameraPose: Twc
+        self.rel.append(inv_pose(self.velocity))                           # vmRigidMotion[.][0]: inverse of the motion model
+        self.partial_batch(min(len(self.poses) - 1, self.cfg.window_size))
+        return T
+
+    def partial_batch(self, window):
+        N = len(self.poses)
+        tracks = get_static_track([m[2].tolist() for m in self.map[1:]])
+        label = [[-1] * len(m[0]) for m in self.map]
+        for t, tr in enumerate(tracks):
+            if len(tr) >= 3:
+                for f, j in tr:
+                    label[f][j] = t
+        mark = [[-1] * len(m[0]) for m in self.map]
+        start = N - window
+        pts, owner, op, opt, oxyz = [], [], [], [], []
+        for i in range(start, N):
+            xy, dep, _ = self.map[i]
+            for j in range(len(xy)):
+                t = label[i][j]
+                if t == -1:
+                    continue
+                pos = tracks[t].index((i, j))
+                if pos == 0:
+                    pid = len(pts)
+                    pts.append(self.p3[i][j]); owner.append((i, j))
+                else:
+                    pf, pj = tracks[t][pos - 1]
+                    pid = mark[pf][pj]
+                    if pid == -1:
+                        continue
+                mark[i][j] = pid
+                op.append(i - start); opt.append(pid); oxyz.append(camera_point(xy[j], dep[j], self.K))
+        poses, rel, points, its, st = ol.ba_partial(np.stack(self.poses[start:]).reshape(window, 16),
+                                                    np.stack(self.rel[start:]).reshape(-1, 16) if window > 1 else np.zeros((0, 16), np.float32),
+                                                    np.array(pts, np.float32).reshape(-1, 3), op, opt, np.array(oxyz, np.float32).reshape(-1, 3))
+        self.ba.append((len(pts), len(op), its, st.total_trials))
+        for i in range(start, N):                                          # write-back, :1056-1142
+            self.poses[i] = poses[i - start].reshape(4, 4)
+            if i > start:
+                self.rel[i - 1] = rel[i - start - 1].reshape(4, 4)
+            for j in range(len(mark[i])):
+                if mark[i][j] != -1:
+                    self.p3[i][j] = points[mark[i][j]]
+
+
+def test_window_optimisation_chain_composed_in_python_equals_the_oracle_tracker():
+    cam = synth.SMALL
+    W = 6                                                                  # the window slides from frame 7 on
+    sc = synth.Scene(cam=cam, seed=77, flow_noise=0.1, depth_noise=0.01)
+    cfg = ol.track_config(cam, nfeatures=1200, max_track_bg=400, window=W)
+    tr = ol.OracleTracker(cfg)
+    py = PyMapTracker(cam, cfg)
+    n = 12
+    for k in range(n):
+        f = sc.frame(k)
+        g, d, fl, m = f["gray"].numpy(), f["depth_in"].numpy(), f["flow"].numpy(), f["mask"].numpy()
+        T_or, st, rc = tr.track(g, d, fl, m)
+        assert rc == 0
+        assert np.array_equal(py.track(g, d, fl, m), T_or), k
+        if k > 0:
+            assert (st["ba_points"], st["ba_obs"], st["ba_iterations"], st["ba_trials"]) == py.ba[-1], k
+        assert np.array_equal(tr.map_poses(), np.stack(py.poses)), k                      # every Map pose after this frame's window
+        for j in range(k + 1):
+            assert np.array_equal(tr.static_features(j)[2], py.p3[j]), (k, j)             # and every Map point
+    assert py.ba[-1][0] > 100 and py.ba[-1][2] >= 2
+    tr.close()
