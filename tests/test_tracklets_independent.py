@@ -178,6 +178,44 @@ def test_full_batch_graph_sizes_follow_the_reference_rules():
     want = (n, motions, points, obs, e6, tern)
     assert got == want, (got, want)
     assert motions >= 2 * (n - 3) and tern > 100
+    # ---- content, independent of the order in which the vertices were numbered
+    K = tuple(np.float32(cam[k]) for k in ("fx", "fy", "cx", "cy"))
+
+    def cam_pt(xy, z):   # Optimizer::Get3DinCamera (src/Optimizer.cc:3277-3294)
+        return (np.float32(np.float32(np.float32(xy[0] - K[2]) * z) * np.float32(np.float32(1) / K[0])),
+                np.float32(np.float32(np.float32(xy[1] - K[3]) * z) * np.float32(np.float32(1) / K[1])), np.float32(z))
+
+    poses = otr.map_poses()
+    assert np.array_equal(g["se3"][:n].reshape(n, 4, 4), poses)                       # VertexSE3 estimates = Map::vmCameraPose
+    # one vertex per object motion, every one of them started from the identity (src/Optimizer.cc:1577-1583: the estimate of the
+    # tracker is commented out there)
+    assert np.array_equal(g["se3"][n:].reshape(-1, 16), np.tile(np.eye(4, dtype=np.float32).reshape(1, 16), (motions, 1)))
+    want_obs, want_pts = [], []
+    for t in st_tracks:                                                               # static tracklets: one point, an observation per element
+        f0, j0 = t[0]
+        want_pts.append(tuple(sta[f0][2][j0]))
+        for f, j in t:
+            want_obs.append((f,) + cam_pt(sta[f][0][j], sta[f][1][j]))
+    want_tern = []
+    for t, tr in enumerate(tracklets):                                                # dynamic tracklets: a point and an observation per element
+        if len(tr) < 3:
+            continue
+        for pos, (fr, j) in enumerate(tr):
+            has_motion = fr >= 1 and int(oid[t]) in labels[fr]
+            if pos != 0 and not has_motion:
+                continue
+            want_pts.append(tuple(dyn[fr][2][j]))
+            want_obs.append((fr,) + cam_pt(dyn[fr][0][j], dyn[fr][1][j]))
+            if pos != 0:
+                pf, pj = tr[pos - 1]
+                want_tern.append(tuple(dyn[pf][2][pj]) + tuple(dyn[fr][2][j]))
+    got_obs = sorted((int(a),) + tuple(x) for a, x in zip(g["obs_se3"], g["obs_xyz"].reshape(-1, 3)))
+    assert got_obs == sorted(want_obs)
+    assert sorted(tuple(x) for x in g["points"].reshape(-1, 3)) == sorted(want_pts)
+    P = g["points"].reshape(-1, 3)
+    got_tern = sorted(tuple(P[a]) + tuple(P[b]) for a, b in zip(g["tern_p1"], g["tern_p2"]))
+    assert got_tern == sorted(want_tern)                                              # ternary edges join point(t-1) and point(t) of a tracklet
+    assert (g["tern_h"] >= n).all() and (g["tern_h"] < n + motions).all()             # ... through a motion vertex
     otr.close()
 
 
