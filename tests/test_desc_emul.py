@@ -212,3 +212,15 @@ def test_hamming_threads_small_and_tied_sets(emul, nt):
     assert np.array_equal(bi[0, :33], obi) and np.array_equal(bd[0, :33], obd) and np.array_equal(sd[0, :33], osd)
     if nt >= 8:
         assert bi[0, 3] == 0 and bd[0, 3] == 0 and sd[0, 3] == 0
+
+
+def test_kernel_bodies_under_address_sanitizer(tmp_path):
+    """the same per-thread bodies walked over their launch grids on heap buffers of exactly the product's sizes, under
+    AddressSanitizer and with the 4-byte alignment of every vector access asserted (tests/desc_emul_asan.cc): nine image sizes,
+    key points on and outside the border, out-of-range octaves, the matcher's partial / output arrays without slack"""
+    exe = str(tmp_path / "desc_asan")
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address", "-fno-omit-frame-pointer", "-ffp-contract=off",
+                           "-Wno-unknown-pragmas", "-DVIDO_EMUL_CHECK_ALIGN", "-o", exe, os.path.join(ROOT, "tests", "desc_emul_asan.cc")])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "ASAN_WALK_OK" in out.stdout

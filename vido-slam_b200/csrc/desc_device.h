@@ -16,6 +16,7 @@
 #define VIDO_HD __host__ __device__ __forceinline__
 #else
 #include <math.h>
+#include <stdlib.h>
 #define VIDO_HD inline
 #endif
 
@@ -59,6 +60,9 @@ VIDO_HD uint32_t vd_load_u32(const uint8_t* p) {   // p is 4-byte aligned
 #ifdef __CUDA_ARCH__
   return *(const uint32_t*)p;
 #else
+#ifdef VIDO_EMUL_CHECK_ALIGN   // the CPU emulation under AddressSanitizer also checks what the device requires of a vector access
+  if ((uintptr_t)p & 3) abort();
+#endif
   uint32_t v; memcpy(&v, p, 4); return v;
 #endif
 }
@@ -66,6 +70,9 @@ VIDO_HD void vd_store_u32(uint8_t* p, uint32_t v) {
 #ifdef __CUDA_ARCH__
   *(uint32_t*)p = v;
 #else
+#ifdef VIDO_EMUL_CHECK_ALIGN
+  if ((uintptr_t)p & 3) abort();
+#endif
   memcpy(p, &v, 4);
 #endif
 }
