@@ -235,6 +235,19 @@ def descriptor_leg(ctx, torch, dev, gray_host, iters=20):
         if it >= 0:
             ms += [ev[k].elapsed_time(ev[k + 1]) for k in range(3)]
     ms /= iters
+    # the smoothing alone: the same call with all key-point counts zero (the descriptor threads leave at their first test)
+    d_zero = torch.zeros(B, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    ms_blur = 0.0
+    for it in range(-3, iters):
+        ev[0].record(stream)
+        ctx.orb_describe_dev(vp(d_kp), vp(d_zero), B, cap, vp(d_desc))
+        ev[1].record(stream)
+        ctx.sync()
+        if it >= 0:
+            ms_blur += ev[0].elapsed_time(ev[1])
+    ms_blur /= iters
+    ctx.orb_describe_dev(vp(d_kp), vp(d_n), B, cap, vp(d_desc), sync=True)   # descriptors back in place for the check below
     n = d_n.cpu().numpy()
     okp, odesc0 = ol.orb_extract_describe(gray_host[0], ol.default_orb_params())
     _, odesc1 = ol.orb_extract_describe(gray_host[1], ol.default_orb_params())
@@ -250,6 +263,9 @@ def descriptor_leg(ctx, torch, dev, gray_host, iters=20):
             "ms_per_batch": {"extract": float(ms[0]), "blur_describe": float(ms[1]), "match": float(ms[2])},
             "frames_per_s": {"extract": B / ms[0] * 1e3, "extract_describe": B / (ms[0] + ms[1]) * 1e3, "extract_describe_match": B / ms.sum() * 1e3},
             "blur_describe_algorithmic_GBps": 2 * pyr_bytes * B / (ms[1] * 1e-3) / 1e9, "hbm_peak_GBps": peak,
+            "blur_roofline": {"bound": "hbm", "kernel": "blur7_kernel (+ one empty rbrief launch)", "achieved": 2 * pyr_bytes * B / (ms_blur * 1e-3) / 1e9,
+                              "peak": peak, "unit": "GB/s", "frac": (2 * pyr_bytes * B / (ms_blur * 1e-3) / 1e9) / peak if peak else None,
+                              "avg_launch_ms": float(ms_blur), "algorithmic_bytes": int(2 * pyr_bytes * B)},
             "descriptors_equal_oracle": same_desc, "matches_equal_oracle": same_match}
 
 
@@ -563,6 +579,13 @@ def main():
                 line["descriptors"] = descriptor_leg(ctx, torch, dev, np.ascontiguousarray(h_img[:BATCH, :, :, 0].numpy()))
             except Exception as e:
                 line["descriptors"] = {"error": str(e)[:200]}
+            try:   # the same at a batch that fills the machine (a second context; the HBM-shaped kernel of the stage against its roofline)
+                nb = min(64, total)
+                ctx64 = pkg.Context(pkg.default_config(max_batch=nb, device=local, **{k: CAM[k] for k in ("width", "height", "fx", "fy", "cx", "cy", "bf")}))
+                line["descriptors_batch64"] = descriptor_leg(ctx64, torch, dev, np.ascontiguousarray(h_img[:nb, :, :, 0].numpy()))
+                ctx64.close()
+            except Exception as e:
+                line["descriptors_batch64"] = {"error": str(e)[:200]}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
