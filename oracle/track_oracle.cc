@@ -138,9 +138,18 @@ struct DynRecord {
   std::vector<float> key_xy, depth, flow3;
 };
 
+// inputs and outputs of the gravity-direction / velocity initialisation of Tracking::InitializeIMU (src/Tracking.cc:955-988), kept for
+// tests/test_vio_oracle.py when the test-suite asks for them (same switch as the DynObjTracking recorder)
+struct ImuInitRecord {
+  std::vector<float> Tcw, dV, dT, vel_out;   // per Map frame: 16 / 3 (updated delta velocity) / 1 / 3 floats
+  std::vector<int> has_pre;
+  float Tbc[16], Rwg[9];
+};
+
 struct Tracker {
   bool dyn_log_on = false;
   std::vector<DynRecord> dyn_log;
+  std::vector<ImuInitRecord> imu_init_log;
   vo_track_config cfg;
   Map map;
   Frame* last = nullptr;
@@ -318,6 +327,18 @@ struct Tracker {
     const double first_ts = fr[1].t;
     if (fr.back().t - first_ts < 2.0) { ist.status = 1; return; }
     float dirG[3] = {0.f, 0.f, 0.f};
+    ImuInitRecord irec;
+    if (dyn_log_on) {
+      memcpy(irec.Tbc, Tbc, sizeof irec.Tbc);
+      for (int i = 0; i <= N; i++) {
+        irec.Tcw.insert(irec.Tcw.end(), fr[i].Tcw, fr[i].Tcw + 16);
+        irec.has_pre.push_back(fr[i].has_pre ? 1 : 0);
+        float dR[9], dV[3] = {0.f, 0.f, 0.f}, dP[3];
+        if (fr[i].has_pre) vo_imu_updated_deltas(&fr[i].pre, fr[i].db, fr[i].db + 3, dR, dV, dP);
+        irec.dV.insert(irec.dV.end(), dV, dV + 3);
+        irec.dT.push_back(fr[i].has_pre ? fr[i].pre.dT : 0.f);
+      }
+    }
     for (int i = 1; i <= N; i++) {
       if (!fr[i].has_pre) continue;
       float R[9], dR[9], dV[3], dP[3], p1[3], p0[3];
@@ -344,6 +365,11 @@ struct Tracker {
     for (int r = 0; r < 3; r++) vzg[r] = (float)((double)(float)((double)v[r] * (double)ang) * (1.0 / (double)nv));
     vo_imu_exp_so3_f(vzg, Rwg);
     for (int k = 0; k < 9; k++) ist.Rwg[k] = Rwg[k];
+    if (dyn_log_on) {
+      memcpy(irec.Rwg, Rwg, sizeof irec.Rwg);
+      for (int i = 0; i <= N; i++) irec.vel_out.insert(irec.vel_out.end(), fr[i].vel, fr[i].vel + 3);
+      imu_init_log.push_back(irec);
+    }
     ist.t_init = (float)(fr.back().t - first_ts);
     ist.scale = 1.0;
     if (!run_inertial(0, 1e2f, 1e9f)) { ist.status = 3; return; }
@@ -1403,6 +1429,19 @@ int vo_tracker_track(void* h, const uint8_t* gray, float* depth, const float* fl
                      vo_track_stats* st) {
   return ((Tracker*)h)->track(gray, depth, flow, mask, Tcw_out, st);
 }
+// ---- test hooks: the recorded gravity initialisations (n = frames 0..N); returns the number of frames of record k, or the count for k < 0
+int vo_tracker_imu_init_log(void* h, int k, float* Tcw, int32_t* has_pre, float* dV, float* dT, float* Tbc, float* Rwg, float* vel_out) {
+  Tracker* t = (Tracker*)h;
+  if (k < 0) return (int)t->imu_init_log.size();
+  const ImuInitRecord& r = t->imu_init_log[k];
+  const int n = (int)r.has_pre.size();
+  if (!Tcw) return n;
+  auto cp = [](auto* dst, const auto& v) { for (size_t i = 0; i < v.size(); i++) dst[i] = v[i]; };
+  cp(Tcw, r.Tcw); cp(has_pre, r.has_pre); cp(dV, r.dV); cp(dT, r.dT); cp(vel_out, r.vel_out);
+  memcpy(Tbc, r.Tbc, sizeof r.Tbc); memcpy(Rwg, r.Rwg, sizeof r.Rwg);
+  return n;
+}
+
 // ---- test hooks: the recorded DynObjTracking calls
 void vo_tracker_dyn_log_enable(void* h, int on) { ((Tracker*)h)->dyn_log_on = on != 0; }
 int vo_tracker_dyn_log_count(void* h) { return (int)((Tracker*)h)->dyn_log.size(); }

@@ -520,6 +520,20 @@ class OracleTracker:
             out.append(r)
         return out
 
+    def imu_init_log(self):
+        """recorded gravity-direction / velocity initialisations of Tracking::InitializeIMU (needs dyn_log_enable before tracking)"""
+        L = lib()
+        L.vo_tracker_imu_init_log.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7
+        out = []
+        for k in range(L.vo_tracker_imu_init_log(self.h, -1, *([None] * 7))):
+            n = L.vo_tracker_imu_init_log(self.h, k, *([None] * 7))
+            r = dict(Tcw=np.zeros((n, 4, 4), np.float32), has_pre=np.zeros(n, np.int32), dV=np.zeros((n, 3), np.float32),
+                     dT=np.zeros(n, np.float32), Tbc=np.zeros((4, 4), np.float32), Rwg=np.zeros((3, 3), np.float32),
+                     vel_out=np.zeros((n, 3), np.float32))
+            L.vo_tracker_imu_init_log(self.h, k, *[_p(r[key]) for key in ("Tcw", "has_pre", "dV", "dT", "Tbc", "Rwg", "vel_out")])
+            out.append(r)
+        return out
+
     # ---- VIO mode (sensor = IMU_RGBD)
     def set_imu(self, Tbc, noise):
         T = np.ascontiguousarray(Tbc, np.float32).reshape(16); nz = np.ascontiguousarray(noise, np.float32)

@@ -72,3 +72,44 @@ def test_apply_scaled_rotation_keeps_the_map_consistent():
     for a, b in zip(P0, P1):
         assert np.abs(b[:3, :3] - R @ a[:3, :3]).max() < 1e-6 and np.abs(b[:3, 3] - 1.7 * R @ a[:3, 3]).max() < 1e-5
     tr.close()
+
+
+def test_gravity_initialisation_against_a_numpy_restatement():
+    """the first half of Tracking::InitializeIMU (src/Tracking.cc:955-988) restated in numpy on the frame states the oracle recorded
+    when it initialised: body rotation / position of every Map frame from its camera pose and Tcb (Frame::GetImuRotation /
+    GetImuPosition), the gravity direction as the negated sum of the world-frame preintegrated velocity increments, the finite-
+    difference velocities, and the rotation that takes (0, 0, -1) onto that direction (IMU::ExpSO3, src/ImuTypes.cc:38-50)"""
+    frames, chunks, ft, Tbc, truth = vio_synth.sequence(12)
+    tr, poses, states = vio_synth.run_oracle(frames, chunks, ft, Tbc, record=True)
+    log = tr.imu_init_log()
+    tr.close()
+    assert len(log) == 1
+    r = log[0]
+    n = len(r["has_pre"])
+    assert n == 11 and r["has_pre"][1:].all()
+    Tcb = np.linalg.inv(r["Tbc"].astype(np.float64))
+    Rwb, pwb = [], []
+    for T in r["Tcw"].astype(np.float64):
+        Rwc = T[:3, :3].T
+        Ow = -Rwc @ T[:3, 3]
+        Rwb.append(Rwc @ Tcb[:3, :3]); pwb.append(Rwc @ Tcb[:3, 3] + Ow)
+    dirG = np.zeros(3)
+    vel = np.zeros((n, 3))
+    for i in range(1, n):
+        if not r["has_pre"][i]:
+            continue
+        dirG -= Rwb[i - 1] @ r["dV"][i].astype(np.float64)
+        v = (pwb[i] - pwb[i - 1]) / float(r["dT"][i])
+        vel[i] = v; vel[i - 1] = v
+    dirG /= np.linalg.norm(dirG)
+    gI = np.array([0.0, 0.0, -1.0])
+    v = np.cross(gI, dirG)
+    ang = np.arccos(gI @ dirG)
+    w = v * ang / np.linalg.norm(v)
+    d = np.linalg.norm(w)
+    W = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    Rwg = np.eye(3) + W * np.sin(d) / d + W @ W * (1 - np.cos(d)) / (d * d)
+    assert np.abs(Rwg - r["Rwg"]).max() < 5e-6
+    assert np.abs(Rwg @ gI - dirG).max() < 1e-9                      # it does rotate "down" onto the estimated direction
+    assert np.abs(vel - r["vel_out"]).max() < 2e-4 * np.abs(vel).max()
+    assert np.degrees(np.arccos((Rwg @ gI) @ np.array([0, 1.0, 0]))) < 1.5   # the synthetic camera's y axis points down

@@ -16,9 +16,11 @@ def sequence(n_frames, fps=2.5, bg_true=(0.002, -0.001, 0.0015), seed=77, cam=sy
     return frames, chunks, ft, Tbc, truth
 
 
-def run_oracle(frames, chunks, ft, Tbc, cam=synth.SMALL, cfg_kw=None):
+def run_oracle(frames, chunks, ft, Tbc, cam=synth.SMALL, cfg_kw=None, record=False):
     cfg = ol.track_config(cam, rebuild=0, **(CFG if cfg_kw is None else cfg_kw))
     tr = ol.OracleTracker(cfg)
+    if record:
+        tr.dyn_log_enable()   # also records the inputs / outputs of the gravity initialisation (OracleTracker.imu_init_log)
     tr.set_imu(Tbc, imu_synth.NOISE)
     poses, states = [], []
     for k, f in enumerate(frames):
