@@ -61,8 +61,15 @@ def load_pkg():
 def native_oracle():
     """the CPU baseline is compiled on the box it is measured on, with the reference's flags (vido_slam/CMakeLists.txt:13-14)"""
     try:
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "native"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-        os.environ["VIDO_ORACLE_LIB"] = os.path.join(ROOT, "oracle", "liboracle_native.so")
+        # named after this host's CPU: a -march=native library built elsewhere (the authoring container's copy travels with the
+        # snapshot) must not be picked up here
+        import hashlib
+        with open("/proc/cpuinfo") as fh:
+            cpu = "".join(ln for ln in fh if ln.startswith(("model name", "flags")))[:20000]
+        name = "liboracle_native_" + hashlib.sha1(cpu.encode()).hexdigest()[:10] + ".so"
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "native", "NATIVE_OUT=" + name], stdout=subprocess.DEVNULL,
+                              stderr=subprocess.DEVNULL)
+        os.environ["VIDO_ORACLE_LIB"] = os.path.join(ROOT, "oracle", name)
         return ORACLE_FLAGS
     except Exception:
         return "-O3 -ffp-contract=off (portable build: `make native` failed on this box)"
