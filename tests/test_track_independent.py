@@ -97,15 +97,21 @@ class PyTracker:
         prior = mat_mul(self.velocity, last["Tcw"]) if self.velocity is not None else last["Tcw"]            # :1976
         T0, ids, winner, nr, nm = ol.init_model_cam(sk, p3d, valid, prior, self.K)
         TM = ids.copy()
-        # PoseOptimizationFlow2Cam (:1133): the last frame's features, their flow and depth; refined flow replaces the match
-        T1, fo, inl, ninl, _ = ol.poseopt_flow2cam(last["stat_keys"][TM], last["flow_next"][TM], last["stat_depth"][TM], T0, last["Tcw"], self.K)
-        if len(TM) >= 3:
-            for i, k in enumerate(TM):
-                if inl[i]:
-                    sk[k, 0] = F(np.float64(last["stat_keys"][k, 0]) + np.float64(fo[i, 0]))
-                    sk[k, 1] = F(np.float64(last["stat_keys"][k, 1]) + np.float64(fo[i, 1]))
-                else:
-                    TM[i] = -1
+        if cfg.b_joint:
+            # PoseOptimizationFlow2Cam (:1133): the last frame's features, their flow and depth; refined flow replaces the match
+            T1, fo, inl, ninl, _ = ol.poseopt_flow2cam(last["stat_keys"][TM], last["flow_next"][TM], last["stat_depth"][TM], T0, last["Tcw"], self.K)
+            if len(TM) >= 3:
+                for i, k in enumerate(TM):
+                    if inl[i]:
+                        sk[k, 0] = F(np.float64(last["stat_keys"][k, 0]) + np.float64(fo[i, 0]))
+                        sk[k, 1] = F(np.float64(last["stat_keys"][k, 1]) + np.float64(fo[i, 1]))
+                    else:
+                        TM[i] = -1
+        else:
+            # PoseOptimizationNew (:1135, src/Optimizer.cc:2180-2334): reprojection of the last frame's world points, matches untouched
+            T1, inl, _ = ol.pose_opt_proj(0, sk[TM], p3d[TM], T0, K=self.K)
+            if len(TM) >= 3:
+                TM[inl == 0] = -1
         cur["Tcw"] = T1
         self.velocity = mat_mul(T1, Twl)                                                                    # :1142-1148
         # RenewFrameInfo (:1320) and the hand-over (:1336-1340)
@@ -368,4 +374,24 @@ def test_window_optimisation_chain_composed_in_python_equals_the_oracle_tracker(
         for j in range(k + 1):
             assert np.array_equal(tr.static_features(j)[2], py.p3[j]), (k, j)             # and every Map point
     assert py.ba[-1][0] > 100 and py.ba[-1][2] >= 2
+    tr.close()
+
+
+def test_reprojection_only_branch_composed_in_python_equals_the_oracle_tracker():
+    """Tracking::bJoint = false: PoseOptimizationNew instead of the joint flow + pose optimisation (src/Tracking.cc:1133-1136)"""
+    cam = synth.SMALL
+    sc = synth.Scene(cam=cam, seed=31, flow_noise=0.1, depth_noise=0.01)
+    cfg = ol.track_config(cam, nfeatures=1200, max_track_bg=400, b_joint=0)
+    tr = ol.OracleTracker(cfg)
+    py = PyTracker(cam, cfg)
+    for k in range(6):
+        f = sc.frame(k)
+        g, d, fl, m = f["gray"].numpy(), f["depth_in"].numpy(), f["flow"].numpy(), f["mask"].numpy()
+        T_or, st, rc = tr.track(g, d, fl, m)
+        assert rc == 0
+        assert np.array_equal(py.track(g, d, fl, m), T_or), k
+        xy, dep, p3, asso = tr.static_features(k)
+        assert np.array_equal(xy, py.map[k][0]) and np.array_equal(dep, py.map[k][1]), k
+        if k > 0:
+            assert np.array_equal(asso, py.map[k][2]), k
     tr.close()
