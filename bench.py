@@ -593,6 +593,16 @@ def main():
                 ctx64.close()
             except Exception as e:
                 line["descriptors_batch64"] = {"error": str(e)[:200]}
+            try:   # the opt-in sliding-window variant of the smoothing kernel (VIDO_BLUR=v2; CPU-emulated only when it was committed):
+                   # measured and checked against the oracle here so that the round's record holds both numbers; last on purpose
+                os.environ["VIDO_BLUR"] = "v2"
+                ctx64 = pkg.Context(pkg.default_config(max_batch=nb, device=local, **{k: CAM[k] for k in ("width", "height", "fx", "fy", "cx", "cy", "bf")}))
+                line["descriptors_batch64_blur_v2"] = descriptor_leg(ctx64, torch, dev, np.ascontiguousarray(h_img[:nb, :, :, 0].numpy()))
+                ctx64.close()
+            except Exception as e:
+                line["descriptors_batch64_blur_v2"] = {"error": str(e)[:200]}
+            finally:
+                os.environ.pop("VIDO_BLUR", None)
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

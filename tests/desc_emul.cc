@@ -8,16 +8,27 @@
 extern "C" {
 
 // pyramid geometry as in orb_setup (vido-slam_b200/csrc/orb_kernels.cu): level l at base[l] + frame * frame_stride[l], rows `pitch[l]` apart
-void emul_blur(const uint8_t* pyr, uint8_t* out, int nlevels, const int* w, const int* h, const int* pitch, const long long* base,
-               const long long* frame_stride, int nframes) {
+void emul_blur_v(const uint8_t* pyr, uint8_t* out, int nlevels, const int* w, const int* h, const int* pitch, const long long* base,
+                 const long long* frame_stride, int nframes, int version) {
   BlurParams P;
   memset(&P, 0, sizeof P);
-  for (int l = 0; l < nlevels; l++) blur_params_add_level(P, l, w[l], h[l], pitch[l], base[l], frame_stride[l]);
+  for (int l = 0; l < nlevels; l++) {
+    if (version == 2) blur2_params_add_level(P, l, w[l], h[l], pitch[l], base[l], frame_stride[l]);
+    else blur_params_add_level(P, l, w[l], h[l], pitch[l], base[l], frame_stride[l]);
+  }
   P.nframes = nframes;
   const unsigned gx = blur_grid_x(P);
   for (int z = 0; z < nframes; z++)
     for (unsigned b = 0; b < gx; b++)
-      for (int t = 0; t < BLUR_THREADS; t++) blur7_thread((int)(b * BLUR_THREADS + t), z, P, pyr, out);
+      for (int t = 0; t < BLUR_THREADS; t++) {
+        if (version == 2) blur7_thread_v2((int)(b * BLUR_THREADS + t), z, P, pyr, out);
+        else blur7_thread((int)(b * BLUR_THREADS + t), z, P, pyr, out);
+      }
+}
+
+void emul_blur(const uint8_t* pyr, uint8_t* out, int nlevels, const int* w, const int* h, const int* pitch, const long long* base,
+               const long long* frame_stride, int nframes) {
+  emul_blur_v(pyr, out, nlevels, w, h, pitch, base, frame_stride, nframes, 1);
 }
 
 void emul_rbrief(const uint8_t* blurred, int nlevels, const int* w, const int* h, const int* pitch, const long long* base,

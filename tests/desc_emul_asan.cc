@@ -58,6 +58,19 @@ static int run_size(int W, int H, int nlevels, int nframes) {
   for (int z = 0; z < nframes; z++)
     for (unsigned b = 0; b < blur_grid_x(B); b++)
       for (int t = 0; t < BLUR_THREADS; t++) blur7_thread((int)(b * BLUR_THREADS + t), z, B, pyr, blur);
+  {   // variant 2 of the smoothing kernel into a second buffer: same bytes
+    uint8_t* blur2 = (uint8_t*)malloc(L.bytes);
+    memset(blur2, 0, L.bytes);
+    BlurParams B2;
+    memset(&B2, 0, sizeof B2);
+    for (int l = 0; l < L.n; l++) blur2_params_add_level(B2, l, L.w[l], L.h[l], L.pitch[l], L.base[l], L.fs[l]);
+    B2.nframes = nframes;
+    for (int z = 0; z < nframes; z++)
+      for (unsigned b = 0; b < blur_grid_x(B2); b++)
+        for (int t = 0; t < BLUR_THREADS; t++) blur7_thread_v2((int)(b * BLUR_THREADS + t), z, B2, pyr, blur2);
+    if (memcmp(blur, blur2, L.bytes) != 0) { printf("variant 2 differs at %dx%d\n", W, H); abort(); }
+    free(blur2);
+  }
   // key points everywhere, including the border and outside the image (foreign key points must not fault)
   const int cap = 257;
   DescKeyPoint* kp = (DescKeyPoint*)malloc(sizeof(DescKeyPoint) * cap * nframes);

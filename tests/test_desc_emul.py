@@ -78,20 +78,21 @@ class Layout:
         return v[:, :self.w[l]]
 
 
-def run_blur(emul, lay, buf):
+def run_blur(emul, lay, buf, version=1):
     out = np.full(lay.bytes, 0xEE, np.uint8)
-    emul.emul_blur(_p(buf), _p(out), lay.n, _p(lay.w), _p(lay.h), _p(lay.pitch), _p(lay.base), _p(lay.fs), lay.nframes)
+    emul.emul_blur_v(_p(buf), _p(out), lay.n, _p(lay.w), _p(lay.h), _p(lay.pitch), _p(lay.base), _p(lay.fs), lay.nframes, version)
     return out
 
 
-def test_blur_threads_match_cv2_and_oracle(emul, gold):
+@pytest.mark.parametrize("version", [1, 2])
+def test_blur_threads_match_cv2_and_oracle(emul, gold, version):
     p = ol.default_orb_params()
     imgs = [gold["kitti_scene_img"], gold["kitti_scene_next_img"]]
     w, h, s = ol.level_sizes(1242, 375, p)
     lay = Layout(list(zip(w, h)), 2, s)
     pyrs = [ol.orb_pyramid(im, p) for im in imgs]
     buf = lay.pack(pyrs, None)
-    out = run_blur(emul, lay, buf)
+    out = run_blur(emul, lay, buf, version)
     for f, name in enumerate(["kitti_scene", "kitti_scene_next"]):
         for l in range(lay.n):
             got = np.ascontiguousarray(lay.level(out, f, l))
@@ -105,14 +106,15 @@ def test_blur_threads_match_cv2_and_oracle(emul, gold):
     assert (out[mask] == 0xEE).all()
 
 
+@pytest.mark.parametrize("version", [1, 2])
 @pytest.mark.parametrize("size", [(8, 8), (9, 11), (13, 8), (64, 17), (67, 35), (131, 97), (333, 211), (12, 64)])
-def test_blur_threads_odd_sizes(emul, size):
+def test_blur_threads_odd_sizes(emul, size, version):
     """widths that are not multiples of 4, levels narrower than the vector path, heights that are not multiples of the strip"""
     rng = np.random.default_rng(size[0] * 1000 + size[1])
     w, h = size
     imgs = [rng.integers(0, 256, (h, w), dtype=np.uint8) for _ in range(3)]
     lay = Layout([(w, h)], 3, [1.0])
-    out = run_blur(emul, lay, lay.pack([[im] for im in imgs], None))
+    out = run_blur(emul, lay, lay.pack([[im] for im in imgs], None), version)
     for f in range(3):
         assert np.array_equal(lay.level(out, f, 0), ol.gauss7(imgs[f])), f
 

@@ -179,6 +179,59 @@ VIDO_HD void blur7_thread(int gx, int gz, const BlurParams& P, const uint8_t* sr
   }
 }
 
+// ---- variant 2 (opt-in, VIDO_BLUR=v2; measured beside variant 1 by bench.py, not yet the default: it was written after the round's
+// GPU budget was spent and has only run in the CPU emulation).  One thread = 4 consecutive pixels x BLUR2_ROWS rows, walking down its
+// column with the horizontal sums of the last seven source rows in a register ring: every source row is loaded and summed
+// (BLUR2_ROWS + 6) / BLUR2_ROWS = 1.4 times instead of 2.5, and the per-thread set-up (level search, division) is paid once per 16 rows.
+#define BLUR2_ROWS 16
+inline void blur2_params_add_level(BlurParams& P, int l, int w, int h, int pitch, long long base, long long frame_stride) {
+  BlurLevel& b = P.lv[l];
+  b.w = w; b.h = h; b.pitch = pitch;
+  b.quads = (w + 3) / 4;
+  b.strips = (h + BLUR2_ROWS - 1) / BLUR2_ROWS;
+  b.first = l ? P.lv[l - 1].first + P.lv[l - 1].quads * P.lv[l - 1].strips : 0;
+  b.base = base; b.frame_stride = frame_stride;
+  P.items_per_frame = b.first + b.quads * b.strips;
+  if (P.nlevels < l + 1) P.nlevels = l + 1;
+}
+
+VIDO_HD void blur7_thread_v2(int gx, int gz, const BlurParams& P, const uint8_t* src, uint8_t* dst) {
+  if (gx >= P.items_per_frame || gz >= P.nframes) return;
+  int l = 0;
+#pragma unroll
+  for (int k = 1; k < VIDO_DESC_MAX_LEVELS; k++)
+    if (k < P.nlevels && gx >= P.lv[k].first) l = k;
+  const BlurLevel& L = P.lv[l];
+  const int item = gx - L.first;
+  const int strip = item / L.quads, q = item - strip * L.quads;
+  const int x0 = 4 * q, y0 = strip * BLUR2_ROWS;
+  if (L.w < 4 || L.h < 4) return;
+  const uint8_t* s = src + L.base + (long long)gz * L.frame_stride;
+  uint8_t* d = dst + L.base + (long long)gz * L.frame_stride;
+  uint32_t ring[7][4];
+#pragma unroll
+  for (int r = 0; r < 6; r++) blur7_hrow(s + (long long)vd_reflect101(y0 - 3 + r, L.h) * L.pitch, x0, L.w, ring[r]);
+#pragma unroll
+  for (int r = 0; r < BLUR2_ROWS; r++) {
+    const int y = y0 + r;
+    if (y >= L.h) break;
+    blur7_hrow(s + (long long)vd_reflect101(y + 3, L.h) * L.pitch, x0, L.w, ring[(r + 6) % 7]);
+    uint32_t o[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const uint32_t v = 18u * (ring[r % 7][c] + ring[(r + 6) % 7][c]) + 34u * (ring[(r + 1) % 7][c] + ring[(r + 5) % 7][c]) +
+                         48u * (ring[(r + 2) % 7][c] + ring[(r + 4) % 7][c]) + 56u * ring[(r + 3) % 7][c];
+      o[c] = (v + 0x8000u) >> 16;
+    }
+    uint8_t* out = d + (long long)y * L.pitch + x0;
+    if (x0 + 4 <= L.w) {
+      vd_store_u32(out, o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24));
+    } else {
+      for (int c = 0; c < 4 && x0 + c < L.w; c++) out[c] = (uint8_t)o[c];
+    }
+  }
+}
+
 // ================================================================================================================
 // rBRIEF.  One thread = one byte (8 tests) of one key point's descriptor; the 32 lanes of a warp write the 32 bytes of one
 // descriptor.  Key points arrive as the extraction wrote them (level-0 coordinates, src/ORBextractor.cc:1094-1100); the level

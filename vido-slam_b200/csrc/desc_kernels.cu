@@ -5,6 +5,9 @@
 // beside the extraction; the tracking path does not call them -- like the reference's, it associates by optical flow.
 // The kernels are HBM / L1-bound byte and bit work; their per-thread bodies live in desc_device.h (shared with the CPU
 // emulation of the test-suite), this file holds the launch geometry and the workspace.
+#include <stdlib.h>
+#include <string.h>
+
 #include "ctx.h"
 #include "desc_device.h"
 #include "../../include/vido_orb_pattern.h"
@@ -19,10 +22,15 @@ struct DescWorkspace {
   size_t ham_bytes = 0;
   BlurParams blur;
   DescParams desc;
+  int blur_version = 1;           // VIDO_BLUR=v2 selects the sliding-window variant (desc_device.h), read when the workspace is created
 };
 
 __global__ void __launch_bounds__(BLUR_THREADS) blur7_kernel(BlurParams P, const uint8_t* __restrict__ src, uint8_t* __restrict__ dst) {
   blur7_thread(blockIdx.x * blockDim.x + threadIdx.x, blockIdx.z, P, src, dst);
+}
+
+__global__ void __launch_bounds__(BLUR_THREADS) blur7_v2_kernel(BlurParams P, const uint8_t* __restrict__ src, uint8_t* __restrict__ dst) {
+  blur7_thread_v2(blockIdx.x * blockDim.x + threadIdx.x, blockIdx.z, P, src, dst);
 }
 
 __global__ void __launch_bounds__(RBRIEF_THREADS) rbrief_kernel(DescParams P, const uint8_t* __restrict__ blurred, const DescKeyPoint* __restrict__ kps,
@@ -67,13 +75,18 @@ static int desc_workspace_build(vido_ctx* ctx, DescWorkspace* ws) {
   VIDO_CUDA(cudaMemcpy(ws->d_pattern, vido_orb_pattern_31, sizeof vido_orb_pattern_31, cudaMemcpyHostToDevice));
   memset(&ws->blur, 0, sizeof ws->blur);
   memset(&ws->desc, 0, sizeof ws->desc);
+  {
+    const char* v = getenv("VIDO_BLUR");
+    ws->blur_version = (v && !strcmp(v, "v2")) ? 2 : 1;
+  }
   for (int l = 0; l < ctx->nlevels; l++) {
     const OrbLevel& L = ctx->lv[l];
     if (L.w < 8 || L.h < 8 || (L.pitch & 3) || (L.base & 3) || (L.frame_stride & 3)) {
       ctx->err = "descriptor stage: pyramid level too small or misaligned";
       return VIDO_ERR_ARG;
     }
-    blur_params_add_level(ws->blur, l, L.w, L.h, L.pitch, (long long)L.base, (long long)L.frame_stride);
+    if (ws->blur_version == 2) blur2_params_add_level(ws->blur, l, L.w, L.h, L.pitch, (long long)L.base, (long long)L.frame_stride);
+    else blur_params_add_level(ws->blur, l, L.w, L.h, L.pitch, (long long)L.base, (long long)L.frame_stride);
     desc_params_add_level(ws->desc, l, L.w, L.h, L.pitch, (long long)L.base, (long long)L.frame_stride, L.scale);
   }
   return VIDO_OK;
@@ -112,7 +125,8 @@ int desc_run(vido_ctx* ctx, const vido_keypoint* d_kps, const int32_t* d_nkp, in
   ws->blur.nframes = nframes;
   {
     dim3 grid(blur_grid_x(ws->blur), 1, nframes);
-    blur7_kernel<<<grid, BLUR_THREADS, 0, st>>>(ws->blur, ctx->d_pyr, ws->d_blur);
+    if (ws->blur_version == 2) blur7_v2_kernel<<<grid, BLUR_THREADS, 0, st>>>(ws->blur, ctx->d_pyr, ws->d_blur);
+    else blur7_kernel<<<grid, BLUR_THREADS, 0, st>>>(ws->blur, ctx->d_pyr, ws->d_blur);
     ctx->launches++;
   }
   ws->desc.nframes = nframes;
