@@ -121,3 +121,23 @@ def test_device_pointers_extract_describe_match(pkg, gold):
     disp = np.hypot(k1["x"][i0[good]] - k0["x"][good], k1["y"][i0[good]] - k0["y"][good])
     assert (disp < 30).mean() > 0.5
     ctx.close()
+
+
+@pytest.mark.xfail(strict=False, reason="VIDO_BLUR=v2 (sliding-window smoothing kernel) had only run in the CPU emulation when it was "
+                                        "committed: an XPASS here is its first run on a B200, a failure does not fail the suite")
+def test_zzz_blur_variant_2_equals_the_default(pkg, gold):
+    """last test of the last file on purpose: the opt-in variant of the smoothing kernel against cv2's bytes and the oracle's descriptors"""
+    os.environ["VIDO_BLUR"] = "v2"
+    try:
+        names = ["kitti_scene", "kitti_scene_next"]
+        imgs = np.stack([gold[f"{n}_img"] for n in names])
+        ctx = _ctx(pkg, 1242, 375, max_batch=2)
+        kps, desc = ctx.orb_extract_describe(imgs)
+        p = ol.default_orb_params()
+        for b, n in enumerate(names):
+            for l in range(8):
+                assert hashlib.sha256(ctx.get_blurred_level(b, l).tobytes()).hexdigest() == str(gold[f"{n}_blur_sha"][l]), (n, l)
+            assert np.array_equal(desc[b], ol.orb_extract_describe(imgs[b], p)[1]), n
+        ctx.close()
+    finally:
+        os.environ.pop("VIDO_BLUR", None)
