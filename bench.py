@@ -544,6 +544,12 @@ def main():
                 break
             except Exception:
                 pass
+        yardstick = None   # what bounds the dominant kernel instead of HBM: committed probe figures (profiles/), not measured by this run
+        try:
+            with open(os.path.join(ROOT, "profiles", "r2_ba_yardstick.json")) as fh:
+                yardstick = json.load(fh)
+        except Exception:
+            pass
         # CPU baseline: the headline sequence again (the legs reused the buffers)
         fill(synth.Scene(cam=CAM, seed=1234, flow_noise=0.1, depth_noise=0.01, device=str(dev)), min(total, max(args.cpu_sample, args.cpu_late + 16)))
         ncpu = min(args.cpu_sample, total)
@@ -567,7 +573,7 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": "ba_window_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_kind,
-                         "avg_launch_ms": ba_ms, "device_ms_by_stage": share,
+                         "avg_launch_ms": ba_ms, "device_ms_by_stage": share, "latency_yardstick": yardstick,
                          "note": "the window problem is shared-memory / L2 resident: the kernel is bound by FP64 issue and dependent-latency chains, not by HBM (DESIGN.md section 6)"},
             "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": 1, "kind": "port", "flags": flags, "stage_ms": cpu_stage,
                              "sample": f"frames {skip}..{ncpu - 1} of the same sequence through the CPU restatement (single thread, like the reference)",
