@@ -146,7 +146,12 @@ struct ImuInitRecord {
   float Tbc[16], Rwg[9];
 };
 
+// inputs and outputs of Tracking::UpdateFrameIMU (src/Tracking.cc:889-925) for tests/test_vio_oracle.py (same switch)
+struct ImuUpdateRecord { float Rwb1[9], twb1[3], Vwb1[3], dR[9], dV[3], dP[3], t12, Rwb[9], twb[3], Vwb[3]; };
+static_assert(sizeof(ImuUpdateRecord) == 46 * sizeof(float), "record layout");
+
 struct Tracker {
+  std::vector<ImuUpdateRecord> imu_update_log;
   bool dyn_log_on = false;
   std::vector<DynRecord> dyn_log;
   std::vector<ImuInitRecord> imu_init_log;
@@ -263,6 +268,13 @@ struct Tracker {
       const float rv = (float)((double)Rwb1[3 * r] * dV[0] + (double)Rwb1[3 * r + 1] * dV[1] + (double)Rwb1[3 * r + 2] * dV[2]);
       twb[r] = ((twb1[r] + (float)((double)p.vel[r] * (double)t12)) + (float)((double)ht2 * (double)Gz[r])) + rp;
       Vwb[r] = (p.vel[r] + (float)((double)Gz[r] * (double)t12)) + rv;
+    }
+    if (dyn_log_on) {
+      ImuUpdateRecord u;
+      memcpy(u.Rwb1, Rwb1, sizeof u.Rwb1); memcpy(u.twb1, twb1, sizeof u.twb1); memcpy(u.Vwb1, p.vel, sizeof u.Vwb1);
+      memcpy(u.dR, dR, sizeof u.dR); memcpy(u.dV, dV, sizeof u.dV); memcpy(u.dP, dP, sizeof u.dP); u.t12 = t12;
+      memcpy(u.Rwb, Rwb, sizeof u.Rwb); memcpy(u.twb, twb, sizeof u.twb); memcpy(u.Vwb, Vwb, sizeof u.Vwb);
+      imu_update_log.push_back(u);
     }
     set_imu_pose_velocity(c, Rwb, twb, Vwb);
     memcpy(cur->Tcw, c.Tcw, sizeof c.Tcw);   // mpLastFrame = mpCurrentFrame
@@ -1439,6 +1451,14 @@ int vo_tracker_imu_init_log(void* h, int k, float* Tcw, int32_t* has_pre, float*
   auto cp = [](auto* dst, const auto& v) { for (size_t i = 0; i < v.size(); i++) dst[i] = v[i]; };
   cp(Tcw, r.Tcw); cp(has_pre, r.has_pre); cp(dV, r.dV); cp(dT, r.dT); cp(vel_out, r.vel_out);
   memcpy(Tbc, r.Tbc, sizeof r.Tbc); memcpy(Rwg, r.Rwg, sizeof r.Rwg);
+  return n;
+}
+
+// ---- test hooks: the recorded UpdateFrameIMU calls, 46 floats each in the order of ImuUpdateRecord; returns the count
+int vo_tracker_imu_update_log(void* h, float* out, int cap) {
+  Tracker* t = (Tracker*)h;
+  const int n = (int)t->imu_update_log.size();
+  for (int i = 0; i < n && i < cap; i++) memcpy(out + 46 * (size_t)i, &t->imu_update_log[i], sizeof(float) * 46);
   return n;
 }
 

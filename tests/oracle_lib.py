@@ -534,6 +534,18 @@ class OracleTracker:
             out.append(r)
         return out
 
+    def imu_update_log(self, cap=64):
+        """recorded Tracking::UpdateFrameIMU calls: dicts of Rwb1, twb1, Vwb1, dR, dV, dP, t12 (inputs) and Rwb, twb, Vwb (outputs)"""
+        L = lib()
+        L.vo_tracker_imu_update_log.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        buf = np.zeros((cap, 46), np.float32)
+        n = L.vo_tracker_imu_update_log(self.h, _p(buf), cap)
+        out = []
+        for r in buf[:n]:
+            out.append(dict(Rwb1=r[0:9].reshape(3, 3), twb1=r[9:12], Vwb1=r[12:15], dR=r[15:24].reshape(3, 3), dV=r[24:27], dP=r[27:30],
+                            t12=r[30], Rwb=r[31:40].reshape(3, 3), twb=r[40:43], Vwb=r[43:46]))
+        return out
+
     # ---- VIO mode (sensor = IMU_RGBD)
     def set_imu(self, Tbc, noise):
         T = np.ascontiguousarray(Tbc, np.float32).reshape(16); nz = np.ascontiguousarray(noise, np.float32)

@@ -113,3 +113,24 @@ def test_gravity_initialisation_against_a_numpy_restatement():
     assert np.abs(Rwg @ gI - dirG).max() < 1e-9                      # it does rotate "down" onto the estimated direction
     assert np.abs(vel - r["vel_out"]).max() < 2e-4 * np.abs(vel).max()
     assert np.degrees(np.arccos((Rwg @ gI) @ np.array([0, 1.0, 0]))) < 1.5   # the synthetic camera's y axis points down
+
+
+def test_update_frame_imu_against_numpy():
+    """Tracking::UpdateFrameIMU (src/Tracking.cc:889-925) on the states the oracle recorded after its initialisation and scale
+    refinements: the current frame's body pose and velocity predicted from the previous frame with the bias-corrected
+    preintegration, Rwb = Rwb1 dR, twb = twb1 + Vwb1 t + 1/2 t^2 g + Rwb1 dP, Vwb = Vwb1 + g t + Rwb1 dV, g = (0, 0, -9.79)"""
+    frames, chunks, ft, Tbc, truth = vio_synth.sequence(14)
+    tr, poses, states = vio_synth.run_oracle(frames, chunks, ft, Tbc, record=True)
+    log = tr.imu_update_log()
+    tr.close()
+    assert len(log) >= 1
+    g = np.array([0, 0, -9.79])
+    for r in log:
+        t = float(r["t12"])
+        assert 0.05 < t < 1.0
+        R1 = r["Rwb1"].astype(np.float64)
+        assert np.abs(R1 @ r["dR"].astype(np.float64) - r["Rwb"]).max() < 2e-6
+        tw = r["twb1"] + r["Vwb1"].astype(np.float64) * t + 0.5 * t * t * g + R1 @ r["dP"].astype(np.float64)
+        vw = r["Vwb1"] + g * t + R1 @ r["dV"].astype(np.float64)
+        assert np.abs(tw - r["twb"]).max() < 5e-6 * max(1.0, np.abs(tw).max())
+        assert np.abs(vw - r["Vwb"]).max() < 5e-6 * max(1.0, np.abs(vw).max())
