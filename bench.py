@@ -256,10 +256,14 @@ def descriptor_leg(ctx, torch, dev, gray_host, iters=20):
     ms_blur /= iters
     ctx.orb_describe_dev(vp(d_kp), vp(d_n), B, cap, vp(d_desc), sync=True)   # descriptors back in place for the check below
     n = d_n.cpu().numpy()
+    t_c0 = time.perf_counter()
     okp, odesc0 = ol.orb_extract_describe(gray_host[0], ol.default_orb_params())
+    t_c1 = time.perf_counter()
     _, odesc1 = ol.orb_extract_describe(gray_host[1], ol.default_orb_params())
     same_desc = bool(n[0] == len(odesc0) and np.array_equal(d_desc[0, :n[0]].cpu().numpy(), odesc0))
+    t_c2 = time.perf_counter()
     obi, obd, osd = ol.hamming_match(odesc0, odesc1)
+    t_c3 = time.perf_counter()
     got = out[:, 0, :n[0]].cpu().numpy()
     same_match = bool(np.array_equal(got[0], obi) and np.array_equal(got[1], obd) and np.array_equal(got[2], osd))
     w, h, _, _ = ctx.level_info()
@@ -273,6 +277,8 @@ def descriptor_leg(ctx, torch, dev, gray_host, iters=20):
             "blur_roofline": {"bound": "hbm", "kernel": "blur7_kernel (+ one empty rbrief launch)", "achieved": 2 * pyr_bytes * B / (ms_blur * 1e-3) / 1e9,
                               "peak": peak, "unit": "GB/s", "frac": (2 * pyr_bytes * B / (ms_blur * 1e-3) / 1e9) / peak if peak else None,
                               "avg_launch_ms": float(ms_blur), "algorithmic_bytes": int(2 * pyr_bytes * B)},
+            "cpu_port_ms": {"extract_describe_one_frame": (t_c1 - t_c0) * 1e3, "match_one_pair": (t_c3 - t_c2) * 1e3,
+                            "note": "the oracle's scalar restatement, one core (not OpenCV's SIMD code)"},
             "descriptors_equal_oracle": same_desc, "matches_equal_oracle": same_match}
 
 
